@@ -1,0 +1,224 @@
+/*
+ * rbd_b200.h — C ABI of the B200-native batched articulated-body dynamics back end
+ *              for the Sofa.RigidBodyDynamics plugin.
+ *
+ * This is the drop-in boundary.  It replaces, for N robot instances at once, the
+ * pinocchio calls and the per-frame Eigen loops inside the reference's
+ *   src/sofa/RigidBodyDynamics/KinematicChainMapping.inl   (short: KCM.inl)
+ * protected workers, and adds the Mass/ForceField quantities the north-star names (CRBA, RNEA).
+ * Each entry point below cites the reference interface it stands behind (file:line, relative to the
+ * reference root).  INTEGRATION.md shows the patched KCM.inl that binds them.
+ *
+ * Conventions (identical to the reference unless stated):
+ *   - spatial 6-vectors are [linear(3); angular(3)]                      (Conversions.h:80-93)
+ *   - rigid poses are [x y z qx qy qz qw]                                (Conversions.h:34-37,58-71)
+ *   - free-flyer configuration q = [x y z qx qy qz qw], velocity = 6-vector in the joint (body) frame
+ *   - SE3 placements in descriptors / oMi outputs: 12 doubles, R row-major (9) then p (3)
+ *   - inertia records: [m, cx, cy, cz, Ixx, Ixy, Iyy, Ixz, Iyz, Izz]      (I about the CoM; pinocchio order)
+ *   - joint 0 is pinocchio's "universe"; kSkipUniverse = 0 (Types.h:32) so it is also output body 0
+ *
+ * Memory layouts:
+ *   *_soa entry points take DEVICE pointers in batch-strided ("tiled SoA") layout: an array with K fields
+ *   per instance stores field k of instance i at
+ *        (i / tile) * K * tile  +  k * tile  +  (i % tile)            [doubles]
+ *   tile >= n gives the plain SoA x[k*tile + i]; tile = 32..256 gives AoSoA.  tile must be >= 1.
+ *   *_host entry points take HOST pointers in the reference's own instance-major ("SOFA AoS") layout,
+ *   i.e. exactly the bytes of N concatenated sofa VecCoord/VecDeriv vectors; copies to and from the
+ *   device happen inside the call.
+ *
+ * Error convention (replaces ComponentState::Invalid + msg_error, KCM.inl:114-139): every function
+ * returns 0 on success or a negative rbd_status; nothing throws or aborts across this boundary.
+ * rbd_last_error() returns a thread-local description of the last failure.
+ *
+ * Threading (KCM is single-threaded and not re-entrant, KCM.h:120-121): calls on one workspace must be
+ * serialised by the caller; distinct workspaces are independent.  Multi-GPU = one workspace per device.
+ *
+ * There is NO CPU fallback behind this ABI: without a CUDA device every compute call fails with
+ * RBD_ERR_CUDA.
+ */
+#ifndef RBD_B200_H
+#define RBD_B200_H
+
+#include <stdint.h>
+
+#if defined(_WIN32)
+#  define RBD_API __declspec(dllexport)
+#else
+#  define RBD_API __attribute__((visibility("default")))
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RBD_B200_VERSION 100 /* 0.1.0 */
+
+typedef enum rbd_status {
+  RBD_OK = 0,
+  RBD_ERR_INVALID_ARG = -1, /* null pointer, negative size, n > capacity ...                          */
+  RBD_ERR_MODEL = -2,       /* descriptor violates a model invariant (parents[i] < i, pre-order ...)   */
+  RBD_ERR_CUDA = -3,        /* CUDA runtime error (message in rbd_last_error)                         */
+  RBD_ERR_NO_APPLY = -4,    /* applyJ / applyJT called before apply (reference relies on the cached
+                               Jacobians of the previous apply, KCM.inl:365-372)                       */
+  RBD_ERR_UNSUPPORTED = -5, /* model too large for the staged-constant path, unknown joint type ...    */
+  RBD_ERR_ALLOC = -6
+} rbd_status;
+
+/* Joint type codes (pinocchio joint models reachable from URDF). */
+enum {
+  RBD_JOINT_UNIVERSE = 0,
+  RBD_JOINT_RX = 1, RBD_JOINT_RY = 2, RBD_JOINT_RZ = 3, RBD_JOINT_RU = 4,         /* revolute             */
+  RBD_JOINT_PX = 5, RBD_JOINT_PY = 6, RBD_JOINT_PZ = 7, RBD_JOINT_PU = 8,         /* prismatic            */
+  RBD_JOINT_RUBX = 9, RBD_JOINT_RUBY = 10, RBD_JOINT_RUBZ = 11, RBD_JOINT_RUBU = 12, /* q = (cos, sin)     */
+  RBD_JOINT_FF = 13                                                               /* free-flyer           */
+};
+
+/*
+ * Model descriptor: the constants of pinocchio::Model the hot path reads.  Stands for the
+ * std::shared_ptr<pinocchio::Model> handed over by KinematicChainMapping::setModel (KCM.inl:304-311)
+ * plus the two frame tables (setBodyCoMFrames KCM.inl:313-317; m_extraFrames KCM.h:95), as produced by
+ * URDFModelLoader::load() (URDFModelLoader.cpp:126-184, 263-268).  All arrays are copied by
+ * rbd_model_create; the caller keeps ownership.
+ */
+typedef struct rbd_model_desc {
+  int32_t njoints;                /* model.njoints, universe included                                    */
+  int32_t nq, nv;                 /* model.nq, model.nv                                                  */
+  const int32_t* parents;         /* [njoints]   model.parents; parents[0] = 0, parents[i] < i           */
+  const int32_t* jtype;           /* [njoints]   RBD_JOINT_*                                             */
+  const double* axis;             /* [njoints*3] unit joint axis in the joint frame                      */
+  const double* placement;        /* [njoints*12] model.jointPlacements                                  */
+  const int32_t* idx_q;           /* [njoints]   first configuration index of each joint                 */
+  const int32_t* idx_v;           /* [njoints]   first velocity index of each joint                      */
+  const double* inertia;          /* [njoints*10] model.inertias                                         */
+  int32_t nframes;                /* model.nframes after the CoM frames were appended                    */
+  const int32_t* frame_parent;    /* [nframes]   frames[f].parentJoint                                   */
+  const double* frame_placement;  /* [nframes*12] frames[f].placement                                    */
+  double gravity[3];              /* model.gravity.linear()                                              */
+  int32_t n_out;                  /* njoints + nframes0 (mappedDof size, URDFModelLoader.cpp:277)        */
+  const int32_t* out_frames;      /* [n_out] frame index of every mapped output:
+                                     bodyCoMFrames then extraFrames (KCM.inl:382-395)                    */
+} rbd_model_desc;
+
+typedef struct rbd_model rbd_model;         /* immutable, shareable between workspaces                   */
+typedef struct rbd_workspace rbd_workspace; /* per device / per calling thread; owns device buffers      */
+
+typedef struct rbd_model_info {
+  int32_t njoints, nq, nv, nframes, n_out;
+  int32_t has_freeflyer_root;   /* 1 when joint 1 is a free-flyer attached to the universe               */
+  int32_t nq_joints, nv_joints; /* sizes of SOFA input1: nq (-7), nv (-6)  (URDFModelLoader.cpp:200)      */
+  int32_t omi_fields;           /* 12*(njoints-1)                                                        */
+  int32_t jac_fields;           /* 6*nv                                                                  */
+  int32_t mass_fields;          /* nv*(nv+1)/2                                                           */
+  int32_t max_depth;            /* longest joint chain                                                   */
+  int32_t eval_smem_doubles;    /* shared-memory doubles per instance used by the fused eval kernel      */
+  int64_t eval_bytes;           /* algorithmic bytes per eval                          */
+} rbd_model_info;
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* library                                                                                              */
+RBD_API int rbd_version(void);
+RBD_API const char* rbd_last_error(void);
+RBD_API void rbd_clear_error(void);
+RBD_API int rbd_device_count(int* count); /* RBD_ERR_CUDA when no driver / device is present            */
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* model: replaces setModel / setBodyCoMFrames / m_extraFrames (KCM.inl:304-317, KCM.h:90-95)            */
+RBD_API int rbd_model_create(const rbd_model_desc* desc, rbd_model** out);
+RBD_API void rbd_model_destroy(rbd_model* model);
+RBD_API int rbd_model_get_info(const rbd_model* model, rbd_model_info* info);
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* workspace: replaces the pinocchio::Data owned by the mapping (KCM.h:121, KCM.inl:310).  `capacity` is  */
+/* the largest batch the workspace will see; `stream` is a cudaStream_t (NULL = default stream).          */
+RBD_API int rbd_workspace_create(const rbd_model* model, int device, int64_t capacity, void* stream,
+                                 rbd_workspace** out);
+RBD_API void rbd_workspace_destroy(rbd_workspace* ws);
+RBD_API int rbd_workspace_set_stream(rbd_workspace* ws, void* stream);
+RBD_API int rbd_workspace_synchronize(rbd_workspace* ws);
+/* Number of kernels this workspace has launched since creation (bench.py's "gpu_launches").              */
+RBD_API int64_t rbd_workspace_launch_count(const rbd_workspace* ws);
+/* Block size override for the fused eval kernel (0 = automatic).  Tuning knob, not part of the contract. */
+RBD_API int rbd_workspace_set_eval_block(rbd_workspace* ws, int threads);
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* Mapping path, device SoA.                                                                            */
+
+/* apply — KinematicChainMapping::apply worker (KCM.inl:338-396): q -> world poses of the n_out mapped
+ * bodies/frames, [x y z qx qy qz qw] each (Eigen's rotation->quaternion branch order, Conversions.h:60).
+ *   q_joints : nq_joints fields    root_pose : 7 fields or NULL (required iff has_freeflyer_root)
+ *   out      : n_out*7 fields (overwritten)
+ * Caches the assembled configuration in the workspace for applyJ / applyJT (KCM.inl:365-372).           */
+RBD_API int rbd_apply_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q_joints,
+                          const double* root_pose, double* out);
+
+/* applyJ — KCM.inl:398-448: out[k] = J_k(LOCAL_WORLD_ALIGNED) * dq for every mapped output k,
+ * evaluated matrix-free.  The root velocity is used verbatim as the free-flyer joint velocity, as the
+ * reference does (KCM.inl:417-418).   dq_joints: nv_joints fields; root_vel: 6 fields or NULL;
+ * out: n_out*6 fields (overwritten).                                                                    */
+RBD_API int rbd_applyJ_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* dq_joints,
+                           const double* root_vel, double* out);
+
+/* applyJT (vector) — KCM.inl:450-513: tau += sum_k J_k^T in[k].   in: n_out*6 fields;
+ * out_tau: nv_joints fields, ACCUMULATED (+=) as the reference does (KCM.inl:498-511);
+ * out_root: 6 fields accumulated, or NULL.                                                              */
+RBD_API int rbd_applyJT_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* in, double* out_tau,
+                            double* out_root);
+
+/* applyJT (MatrixDeriv) — KCM.inl:515-639: one dense nv-wide row per constraint row.
+ *   nrows rows in CSR form: row r owns non-zeros [row_ptr[r], row_ptr[r+1]); row_instance[r] selects the
+ *   robot instance (its cached configuration); col[j] is the mapped-output index (< n_out); val is
+ *   nnz x 6 instance-major ([lin; ang], Conversions.h:86-93).  All five arrays are DEVICE pointers.
+ *   out_rows: nrows x nv, row-major (root wrench first when has_freeflyer_root), overwritten.
+ *   keep[r] = 1 iff ||row||^2 > 1e-12 (kMinTorque^2, KCM.inl:43-45,587,605): the caller must only emit
+ *   kept rows into the SOFA MatrixDeriv.                                                                */
+RBD_API int rbd_applyJT_rows_dev(rbd_workspace* ws, int64_t nrows, const int32_t* row_ptr,
+                                 const int32_t* row_instance, const int32_t* col, const double* val,
+                                 double* out_rows, int32_t* keep);
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* Mass / ForceField path, device SoA (north-star additions; the reference reaches them matrix-free
+ * through UniformMass + applyJ/applyJT, URDFModelLoader.cpp:369-391).                                    */
+
+/* Fused evaluation = the BASELINE metric unit: forward kinematics + world joint Jacobian
+ * (pinocchio::computeJointJacobians, call site KCM.inl:373) + CRBA + RNEA.
+ *   q: nq fields (full configuration incl. free-flyer), v, a: nv fields.
+ *   oMi : 12*(njoints-1) fields — placement of joint i (1-based) at fields [12(i-1), 12i): R row-major, p
+ *   J   : 6*nv fields — column c at fields [6c, 6c+6): [lin; ang], world frame (pinocchio data.J)
+ *   M   : nv*(nv+1)/2 fields — upper triangle packed by columns: M(r,c), r <= c, at field c(c+1)/2 + r
+ *   tau : nv fields — rnea(q, v, a)
+ * Any output pointer may be NULL; the corresponding work is skipped.                                     */
+RBD_API int rbd_eval_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, const double* v,
+                         const double* a, double* oMi, double* J, double* M, double* tau);
+RBD_API int rbd_crba_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, double* M);
+RBD_API int rbd_rnea_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, const double* v,
+                         const double* a, double* tau);
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* Layout adapters (Conversions.h:58-119 at batch scale): instance-major [n][K] <-> tiled SoA, on device. */
+RBD_API int rbd_aos_to_soa_dev(rbd_workspace* ws, int64_t n, int32_t K, int64_t tile, const double* aos,
+                               double* soa);
+RBD_API int rbd_soa_to_aos_dev(rbd_workspace* ws, int64_t n, int32_t K, int64_t tile, const double* soa,
+                               double* aos);
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* Host (SOFA AoS) entry points — what the patched KinematicChainMapping calls.  Pointers are HOST
+ * pointers, instance-major: [n][nq_joints], [n][7], [n][n_out][7], [n][n_out][6] ...  Pinned memory
+ * makes the copies asynchronous; pageable memory works.  Each call returns after its outputs are ready. */
+RBD_API int rbd_apply_host(rbd_workspace* ws, int64_t n, const double* q_joints, const double* root_pose,
+                           double* out);
+RBD_API int rbd_applyJ_host(rbd_workspace* ws, int64_t n, const double* dq_joints, const double* root_vel,
+                            double* out);
+RBD_API int rbd_applyJT_host(rbd_workspace* ws, int64_t n, const double* in, double* out_tau,
+                             double* out_root);
+RBD_API int rbd_applyJT_rows_host(rbd_workspace* ws, int64_t nrows, const int32_t* row_ptr,
+                                  const int32_t* row_instance, const int32_t* col, const double* val,
+                                  double* out_rows, int32_t* keep);
+/* q [n][nq], v,a [n][nv] -> oMi [n][12(njoints-1)], J [n][6 nv], M [n][nv(nv+1)/2], tau [n][nv];
+ * outputs may be NULL.  Processed in pipelined chunks (H2D, kernels and D2H overlap).                    */
+RBD_API int rbd_eval_host(rbd_workspace* ws, int64_t n, const double* q, const double* v, const double* a,
+                          double* oMi, double* J, double* M, double* tau);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBD_B200_H */

@@ -1,0 +1,166 @@
+"""CPU oracle loader — TEST INFRASTRUCTURE ONLY (see ``oracle/rbd_oracle.c`` header; parity unpinned).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs
+may import this package.  Nothing under ``sofa/`` does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librbd_oracle.so")
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "rbd_oracle.c")
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "librbd_oracle.so"], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        l = C.CDLL(LIB_PATH)
+        vp, dp = C.c_void_p, C.c_void_p
+        l.orc_create.restype = vp; l.orc_create.argtypes = [vp]
+        l.orc_destroy.restype = None; l.orc_destroy.argtypes = [vp]
+        l.orc_compute_joint_jacobians.restype = None; l.orc_compute_joint_jacobians.argtypes = [vp, dp]
+        l.orc_update_frame_placements.restype = None; l.orc_update_frame_placements.argtypes = [vp]
+        l.orc_get_frame_jacobian_lwa.restype = None; l.orc_get_frame_jacobian_lwa.argtypes = [vp, C.c_int, dp]
+        l.orc_rot_to_quat.restype = None; l.orc_rot_to_quat.argtypes = [dp, dp]
+        l.orc_apply.restype = None; l.orc_apply.argtypes = [vp, dp, dp, dp]
+        l.orc_applyJ.restype = None; l.orc_applyJ.argtypes = [vp, dp, dp, dp]
+        l.orc_applyJT.restype = None; l.orc_applyJT.argtypes = [vp, dp, dp, dp]
+        l.orc_applyJT_row.restype = C.c_int; l.orc_applyJT_row.argtypes = [vp, C.c_int, vp, dp, dp]
+        l.orc_crba.restype = None; l.orc_crba.argtypes = [vp, dp, dp]
+        l.orc_rnea.restype = None; l.orc_rnea.argtypes = [vp, dp, dp, dp, dp]
+        l.orc_eval.restype = None; l.orc_eval.argtypes = [vp, dp, dp, dp, dp, dp, dp, dp]
+        l.orc_eval_batch.restype = C.c_int
+        l.orc_eval_batch.argtypes = [vp, C.c_long, dp, dp, dp, dp, dp, dp, dp, C.c_int]
+        l.orc_data_J.restype = C.POINTER(C.c_double); l.orc_data_J.argtypes = [vp]
+        l.orc_get_oMi.restype = None; l.orc_get_oMi.argtypes = [vp, C.c_int, dp]
+        l.orc_get_oMf.restype = None; l.orc_get_oMf.argtypes = [vp, C.c_int, dp]
+        l.orc_max_threads.restype = C.c_int; l.orc_max_threads.argtypes = []
+        _lib = l
+    return _lib
+
+
+def _p(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.flags.c_contiguous
+    return a.ctypes.data
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+class Oracle:
+    """Single-instance pinocchio-semantics oracle bound to one model descriptor."""
+
+    def __init__(self, desc):
+        from sofa.rigidbodydynamics_b200._capi import make_desc  # POD marshalling only
+        self.d = desc
+        self._cdesc, self._keep = make_desc(desc)
+        self._w = lib().orc_create(C.addressof(self._cdesc))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_w", None):
+                lib().orc_destroy(self._w); self._w = None
+        except Exception:
+            pass
+
+    # -- mapping path ------------------------------------------------------------------------------------
+    def apply(self, q_joints, root_pose=None):
+        q_joints = _f64(q_joints); root_pose = None if root_pose is None else _f64(root_pose)
+        out = np.zeros((self.d.n_out, 7))
+        lib().orc_apply(self._w, _p(q_joints), _p(root_pose), _p(out))
+        return out
+
+    def applyJ(self, dq_joints, root_vel=None):
+        dq_joints = _f64(dq_joints); root_vel = None if root_vel is None else _f64(root_vel)
+        out = np.zeros((self.d.n_out, 6))
+        lib().orc_applyJ(self._w, _p(dq_joints), _p(root_vel), _p(out))
+        return out
+
+    def applyJT(self, wrenches, out_tau=None, out_root=None):
+        """Returns (out_tau, out_root) after ``+=`` accumulation into the given arrays (zeros if omitted)."""
+        w = _f64(wrenches)
+        tau = np.zeros(self.d.nv_joints) if out_tau is None else _f64(out_tau).copy()
+        root = None
+        if self.d.has_freeflyer_root:
+            root = np.zeros(6) if out_root is None else _f64(out_root).copy()
+        lib().orc_applyJT(self._w, _p(w), _p(tau), _p(root))
+        return tau, root
+
+    def applyJT_row(self, cols, vals):
+        cols = np.ascontiguousarray(np.asarray(cols, dtype=np.int32)); vals = _f64(vals)
+        row = np.zeros(self.d.nv)
+        keep = lib().orc_applyJT_row(self._w, int(cols.shape[0]), cols.ctypes.data, _p(vals), _p(row))
+        return row, bool(keep)
+
+    def frame_jacobian_lwa(self, frame: int):
+        J = np.zeros((self.d.nv, 6))  # col-major 6 x nv == row-major nv x 6
+        lib().orc_get_frame_jacobian_lwa(self._w, int(frame), _p(J))
+        return J.T.copy()
+
+    # -- dynamics ----------------------------------------------------------------------------------------
+    def crba(self, q):
+        q = _f64(q); M = np.zeros((self.d.nv, self.d.nv))
+        lib().orc_crba(self._w, _p(q), _p(M))
+        return M
+
+    def rnea(self, q, v, a):
+        q, v, a = _f64(q), _f64(v), _f64(a); tau = np.zeros(self.d.nv)
+        lib().orc_rnea(self._w, _p(q), _p(v), _p(a), _p(tau))
+        return tau
+
+    def eval(self, q, v, a):
+        q, v, a = _f64(q), _f64(v), _f64(a)
+        d = self.d
+        oMi = np.zeros(12 * (d.njoints - 1)); J = np.zeros(6 * d.nv)
+        M = np.zeros(d.nv * (d.nv + 1) // 2); tau = np.zeros(d.nv)
+        lib().orc_eval(self._w, _p(q), _p(v), _p(a), _p(oMi), _p(J), _p(M), _p(tau))
+        return oMi, J, M, tau
+
+
+def eval_batch(desc, q, v, a, nthreads: int = 0, want=("oMi", "J", "M", "tau")):
+    """Instance-major batched eval on ``nthreads`` host threads.  Returns (dict of outputs, threads used)."""
+    from sofa.rigidbodydynamics_b200._capi import make_desc
+    cdesc, _keep = make_desc(desc)
+    q, v, a = _f64(q), _f64(v), _f64(a)
+    n = q.shape[0]
+    out = {"oMi": np.zeros((n, 12 * (desc.njoints - 1))) if "oMi" in want else None,
+           "J": np.zeros((n, 6 * desc.nv)) if "J" in want else None,
+           "M": np.zeros((n, desc.nv * (desc.nv + 1) // 2)) if "M" in want else None,
+           "tau": np.zeros((n, desc.nv)) if "tau" in want else None}
+    used = lib().orc_eval_batch(C.addressof(cdesc), n, _p(q), _p(v), _p(a), _p(out["oMi"]), _p(out["J"]),
+                                _p(out["M"]), _p(out["tau"]), int(nthreads))
+    return out, used
+
+
+def rot_to_quat(R):
+    R = _f64(R).reshape(9); out = np.zeros(4)
+    lib().orc_rot_to_quat(_p(R), _p(out))
+    return out
+
+
+def unpack_upper(Mp: np.ndarray, nv: int) -> np.ndarray:
+    """Packed-by-columns upper triangle -> full symmetric matrix."""
+    M = np.zeros((nv, nv))
+    for c in range(nv):
+        for r in range(c + 1):
+            M[r, c] = M[c, r] = Mp[c * (c + 1) // 2 + r]
+    return M
