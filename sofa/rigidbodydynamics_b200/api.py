@@ -1,0 +1,168 @@
+"""Host-side handles over the C ABI (``include/rbd_b200.h``).
+
+``Model`` / ``Workspace`` are thin RAII wrappers of ``rbd_model*`` / ``rbd_workspace*``.  Device entry points take
+anything exposing ``data_ptr()`` (torch CUDA tensors: PyTorch is only the allocator/stream provider here) or a raw
+integer device address; host entry points take C-contiguous float64 numpy arrays in the reference's own
+instance-major layout.  Every call goes through the shared library; there is no Python/torch arithmetic path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _capi
+from ._capi import RbdError, check
+from .model import ModelDescriptor
+
+
+def _dev_ptr(x) -> Optional[int]:
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        if hasattr(x, "is_cuda") and not x.is_cuda:
+            raise ValueError("device entry point got a CPU tensor")
+        if hasattr(x, "is_contiguous") and not x.is_contiguous():
+            raise ValueError("device entry point needs contiguous tensors")
+        return int(x.data_ptr())
+    raise TypeError(f"cannot take a device pointer from {type(x)}")
+
+
+def _host_ptr(x: Optional[np.ndarray], dtype=np.float64) -> Optional[int]:
+    if x is None:
+        return None
+    if hasattr(x, "data_ptr") and not isinstance(x, np.ndarray):   # pinned torch CPU tensor
+        if getattr(x, "is_cuda", False):
+            raise ValueError("host entry point got a CUDA tensor")
+        return int(x.data_ptr())
+    if not isinstance(x, np.ndarray) or x.dtype != dtype or not x.flags.c_contiguous:
+        raise ValueError(f"host entry point needs a C-contiguous {np.dtype(dtype).name} numpy array")
+    return int(x.ctypes.data)
+
+
+class Model:
+    """``rbd_model``: immutable tree constants (replaces ``KinematicChainMapping::setModel`` + frame tables,
+    reference KinematicChainMapping.inl:304-317)."""
+
+    def __init__(self, desc: ModelDescriptor):
+        self.desc = desc
+        self._lib = _capi.load()
+        cdesc, self._keep = _capi.make_desc(desc)
+        h = C.c_void_p()
+        check(self._lib.rbd_model_create(C.byref(cdesc), C.byref(h)))
+        self._h = h
+        info = _capi.RbdModelInfo()
+        check(self._lib.rbd_model_get_info(self._h, C.byref(info)))
+        self.info = info
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rbd_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Workspace:
+    """``rbd_workspace``: per-device buffers + cached configuration (replaces the mapping's ``pinocchio::Data``,
+    reference KinematicChainMapping.h:121)."""
+
+    def __init__(self, model: Model, capacity: int, device: int = 0, stream: Optional[int] = None):
+        self.model = model
+        self._lib = model._lib
+        h = C.c_void_p()
+        check(self._lib.rbd_workspace_create(model._h, int(device), int(capacity), C.c_void_p(stream or 0), C.byref(h)))
+        self._h = h
+        self.capacity = int(capacity)
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rbd_workspace_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing ------------------------------------------------------------------------------------------
+    def set_stream(self, stream: Optional[int]):
+        check(self._lib.rbd_workspace_set_stream(self._h, C.c_void_p(stream or 0)))
+
+    def synchronize(self):
+        check(self._lib.rbd_workspace_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.rbd_workspace_launch_count(self._h))
+
+    def set_eval_block(self, threads: int):
+        check(self._lib.rbd_workspace_set_eval_block(self._h, int(threads)))
+
+    # -- device tiled-SoA entry points ----------------------------------------------------------------------
+    def eval_soa(self, n, tile, q, v=None, a=None, oMi=None, J=None, M=None, tau=None):
+        check(self._lib.rbd_eval_soa(self._h, n, tile, _dev_ptr(q), _dev_ptr(v), _dev_ptr(a), _dev_ptr(oMi),
+                                     _dev_ptr(J), _dev_ptr(M), _dev_ptr(tau)))
+
+    def crba_soa(self, n, tile, q, M):
+        check(self._lib.rbd_crba_soa(self._h, n, tile, _dev_ptr(q), _dev_ptr(M)))
+
+    def rnea_soa(self, n, tile, q, v, a, tau):
+        check(self._lib.rbd_rnea_soa(self._h, n, tile, _dev_ptr(q), _dev_ptr(v), _dev_ptr(a), _dev_ptr(tau)))
+
+    def apply_soa(self, n, tile, q_joints, root_pose, out):
+        check(self._lib.rbd_apply_soa(self._h, n, tile, _dev_ptr(q_joints), _dev_ptr(root_pose), _dev_ptr(out)))
+
+    def applyJ_soa(self, n, tile, dq_joints, root_vel, out):
+        check(self._lib.rbd_applyJ_soa(self._h, n, tile, _dev_ptr(dq_joints), _dev_ptr(root_vel), _dev_ptr(out)))
+
+    def applyJT_soa(self, n, tile, wrenches, out_tau, out_root=None):
+        check(self._lib.rbd_applyJT_soa(self._h, n, tile, _dev_ptr(wrenches), _dev_ptr(out_tau), _dev_ptr(out_root)))
+
+    def applyJT_rows_dev(self, nrows, row_ptr, row_instance, col, val, out_rows, keep):
+        check(self._lib.rbd_applyJT_rows_dev(self._h, nrows, _dev_ptr(row_ptr), _dev_ptr(row_instance), _dev_ptr(col),
+                                             _dev_ptr(val), _dev_ptr(out_rows), _dev_ptr(keep)))
+
+    def aos_to_soa(self, n, K, tile, aos, soa):
+        check(self._lib.rbd_aos_to_soa_dev(self._h, n, K, tile, _dev_ptr(aos), _dev_ptr(soa)))
+
+    def soa_to_aos(self, n, K, tile, soa, aos):
+        check(self._lib.rbd_soa_to_aos_dev(self._h, n, K, tile, _dev_ptr(soa), _dev_ptr(aos)))
+
+    # -- host (SOFA instance-major) entry points --------------------------------------------------------------
+    def eval_host(self, n, q, v=None, a=None, oMi=None, J=None, M=None, tau=None):
+        check(self._lib.rbd_eval_host(self._h, n, _host_ptr(q), _host_ptr(v), _host_ptr(a), _host_ptr(oMi),
+                                      _host_ptr(J), _host_ptr(M), _host_ptr(tau)))
+
+    def apply_host(self, n, q_joints, root_pose, out):
+        check(self._lib.rbd_apply_host(self._h, n, _host_ptr(q_joints), _host_ptr(root_pose), _host_ptr(out)))
+
+    def applyJ_host(self, n, dq_joints, root_vel, out):
+        check(self._lib.rbd_applyJ_host(self._h, n, _host_ptr(dq_joints), _host_ptr(root_vel), _host_ptr(out)))
+
+    def applyJT_host(self, n, wrenches, out_tau, out_root=None):
+        check(self._lib.rbd_applyJT_host(self._h, n, _host_ptr(wrenches), _host_ptr(out_tau), _host_ptr(out_root)))
+
+    def applyJT_rows_host(self, nrows, row_ptr, row_instance, col, val, out_rows, keep):
+        check(self._lib.rbd_applyJT_rows_host(self._h, nrows, _host_ptr(row_ptr, np.int32),
+                                              _host_ptr(row_instance, np.int32), _host_ptr(col, np.int32),
+                                              _host_ptr(val), _host_ptr(out_rows), _host_ptr(keep, np.int32)))
+
+
+def device_count() -> int:
+    lib = _capi.load()
+    n = C.c_int(0)
+    rc = lib.rbd_device_count(C.byref(n))
+    return int(n.value) if rc == 0 else 0
+
+
+__all__ = ["Model", "Workspace", "RbdError", "device_count"]

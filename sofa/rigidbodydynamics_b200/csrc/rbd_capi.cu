@@ -1,0 +1,524 @@
+// rbd_capi.cu — implementation of the C ABI declared in include/rbd_b200.h.
+//
+// The boundary a patched KinematicChainMapping binds: opaque model / workspace handles,
+// int status codes, raw pointers and sizes, no exceptions, no CPU fallback.  Device-pointer (*_soa/_dev)
+// entry points only enqueue kernels on the workspace stream; host-pointer (*_host) entry points wrap them in
+// pipelined host<->device copies plus the instance-major <-> tiled-SoA adapters.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../../include/rbd_b200.h"
+#include "rbd_kernels.h"
+#include "rbd_model_build.h"
+
+using namespace rbd;
+
+// --------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int set_err(int code, const std::string& msg) { g_err = msg; return code; }
+static int cuda_fail(cudaError_t e, const char* what) {
+  // cudaGetLastError clears non-sticky launch errors so the next call starts clean
+  cudaGetLastError();
+  return set_err(RBD_ERR_CUDA, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+}
+#define CK(call)                                        \
+  do {                                                  \
+    cudaError_t e_ = (call);                            \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+  } while (0)
+
+struct rbd_model {
+  DevModel dm;
+  HostTables ht;
+  rbd_model_info info;
+};
+
+static const int kHostChunk = 16384;  // instances per pipelined chunk of the *_host entry points
+static const int kSlots = 2;
+
+struct HostSlot {
+  cudaStream_t st = nullptr;
+  double* aos = nullptr;  // device, instance-major staging
+  double* soa = nullptr;  // device, tiled-SoA staging (tile = chunk)
+};
+
+struct rbd_workspace {
+  const rbd_model* model = nullptr;
+  int device = 0;
+  long long capacity = 0;
+  cudaStream_t stream = nullptr;
+  // device copies of the per-output tables
+  int *d_sorted_k = nullptr, *d_outk_parent = nullptr;
+  double *d_sorted_pl = nullptr, *d_outk_pl = nullptr;
+  DevTables tb{};
+  double* qcache = nullptr;  // [nq][capacity] assembled configuration of the last apply
+  long long applied_n = 0;   // instances covered by the cache (0 = apply not called yet)
+  LaunchCfg cfg_eval[4], cfg_apply, cfg_applyJ, cfg_applyJT, cfg_rows;
+  int forced_eval_block = 0;
+  long long launches = 0;
+  // host-path staging
+  HostSlot slot[kSlots];
+  size_t slot_doubles = 0;  // capacity of each of aos / soa per slot
+  long long chunk = 0;
+  cudaEvent_t ev = nullptr;
+  // grow-only buffers for the rows entry point
+  void* rows_buf = nullptr;
+  size_t rows_bytes = 0;
+};
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err != cudaSuccess) { ok = false; return; }
+    if (prev != dev) {
+      err = cudaSetDevice(dev);
+      if (err != cudaSuccess) ok = false;
+    }
+  }
+  ~DeviceGuard() {
+    if (ok && prev >= 0) {
+      int cur = -1;
+      if (cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+  }
+};
+#define GUARD(ws)                                                        \
+  if (!(ws)) return set_err(RBD_ERR_INVALID_ARG, "null workspace");      \
+  DeviceGuard guard_((ws)->device);                                      \
+  if (!guard_.ok) return cuda_fail(guard_.err, "cudaSetDevice")
+
+// --------------------------------------------------------------------------------------------------------
+// All RBD_API functions below were declared extern "C" in include/rbd_b200.h, so they get C linkage.
+
+RBD_API int rbd_version(void) { return RBD_B200_VERSION; }
+RBD_API const char* rbd_last_error(void) { return g_err.c_str(); }
+RBD_API void rbd_clear_error(void) { g_err.clear(); }
+
+RBD_API int rbd_device_count(int* count) {
+  if (!count) return set_err(RBD_ERR_INVALID_ARG, "null count");
+  *count = 0;
+  cudaError_t e = cudaGetDeviceCount(count);
+  if (e != cudaSuccess) { *count = 0; return cuda_fail(e, "cudaGetDeviceCount"); }
+  return RBD_OK;
+}
+
+RBD_API int rbd_model_create(const rbd_model_desc* desc, rbd_model** out) {
+  if (!desc || !out) return set_err(RBD_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  rbd_model* m = new (std::nothrow) rbd_model();
+  if (!m) return set_err(RBD_ERR_ALLOC, "out of host memory");
+  std::string err;
+  int rc = build_dev_model(desc, &m->dm, &m->ht, &err);
+  if (rc != RBD_OK) { delete m; return set_err(rc, err); }
+  rbd_model_info& I = m->info;
+  const DevModel& d = m->dm;
+  I.njoints = d.njoints; I.nq = d.nq; I.nv = d.nv; I.nframes = desc->nframes; I.n_out = d.n_out;
+  I.has_freeflyer_root = d.has_ff_root; I.nq_joints = d.nq_joints; I.nv_joints = d.nv_joints;
+  I.omi_fields = 12 * (d.njoints - 1); I.jac_fields = 6 * d.nv; I.mass_fields = d.nv * (d.nv + 1) / 2;
+  I.max_depth = d.max_depth; I.eval_smem_doubles = smem_eval(d, true, true);
+  I.eval_bytes = 8LL * ((d.nq + 2 * d.nv) + I.omi_fields + I.jac_fields + I.mass_fields + d.nv);
+  *out = m;
+  return RBD_OK;
+}
+RBD_API void rbd_model_destroy(rbd_model* model) { delete model; }
+RBD_API int rbd_model_get_info(const rbd_model* model, rbd_model_info* info) {
+  if (!model || !info) return set_err(RBD_ERR_INVALID_ARG, "null argument");
+  *info = model->info;
+  return RBD_OK;
+}
+
+// ---- workspace ------------------------------------------------------------------------------------------
+static void ws_free(rbd_workspace* ws) {
+  if (!ws) return;
+  cudaFree(ws->d_sorted_k); cudaFree(ws->d_outk_parent); cudaFree(ws->d_sorted_pl); cudaFree(ws->d_outk_pl);
+  cudaFree(ws->qcache); cudaFree(ws->rows_buf);
+  for (int s = 0; s < kSlots; ++s) {
+    cudaFree(ws->slot[s].aos); cudaFree(ws->slot[s].soa);
+    if (ws->slot[s].st) cudaStreamDestroy(ws->slot[s].st);
+  }
+  if (ws->ev) cudaEventDestroy(ws->ev);
+  delete ws;
+}
+
+RBD_API int rbd_workspace_create(const rbd_model* model, int device, int64_t capacity, void* stream,
+                                 rbd_workspace** out) {
+  if (!model || !out) return set_err(RBD_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  if (capacity < 1) return set_err(RBD_ERR_INVALID_ARG, "capacity must be >= 1");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return e != cudaSuccess ? cuda_fail(e, "cudaGetDeviceCount")
+                            : set_err(RBD_ERR_CUDA, "no CUDA device present (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return set_err(RBD_ERR_INVALID_ARG, "device index out of range");
+  DeviceGuard g(device);
+  if (!g.ok) return cuda_fail(g.err, "cudaSetDevice");
+  rbd_workspace* ws = new (std::nothrow) rbd_workspace();
+  if (!ws) return set_err(RBD_ERR_ALLOC, "out of host memory");
+  ws->model = model; ws->device = device; ws->capacity = capacity; ws->stream = (cudaStream_t)stream;
+  const HostTables& ht = model->ht;
+  const size_t no = ht.outk_parent.size();
+#define WS_CK(call)                                                  \
+  do {                                                               \
+    cudaError_t e_ = (call);                                         \
+    if (e_ != cudaSuccess) { ws_free(ws); return cuda_fail(e_, #call); } \
+  } while (0)
+  if (no > 0) {
+    WS_CK(cudaMalloc(&ws->d_sorted_k, no * sizeof(int)));
+    WS_CK(cudaMalloc(&ws->d_outk_parent, no * sizeof(int)));
+    WS_CK(cudaMalloc(&ws->d_sorted_pl, no * 12 * sizeof(double)));
+    WS_CK(cudaMalloc(&ws->d_outk_pl, no * 12 * sizeof(double)));
+    WS_CK(cudaMemcpy(ws->d_sorted_k, ht.sorted_k.data(), no * sizeof(int), cudaMemcpyHostToDevice));
+    WS_CK(cudaMemcpy(ws->d_outk_parent, ht.outk_parent.data(), no * sizeof(int), cudaMemcpyHostToDevice));
+    WS_CK(cudaMemcpy(ws->d_sorted_pl, ht.sorted_pl.data(), no * 12 * sizeof(double), cudaMemcpyHostToDevice));
+    WS_CK(cudaMemcpy(ws->d_outk_pl, ht.outk_pl.data(), no * 12 * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  ws->tb.sorted_k = ws->d_sorted_k; ws->tb.sorted_pl = ws->d_sorted_pl;
+  ws->tb.outk_parent = ws->d_outk_parent; ws->tb.outk_pl = ws->d_outk_pl;
+  WS_CK(cudaMalloc(&ws->qcache, (size_t)(model->dm.nq > 0 ? model->dm.nq : 1) * (size_t)capacity * sizeof(double)));
+  WS_CK(cudaEventCreateWithFlags(&ws->ev, cudaEventDisableTiming));
+#undef WS_CK
+  *out = ws;
+  return RBD_OK;
+}
+
+RBD_API void rbd_workspace_destroy(rbd_workspace* ws) {
+  if (!ws) return;
+  DeviceGuard g(ws->device);
+  ws_free(ws);
+}
+RBD_API int rbd_workspace_set_stream(rbd_workspace* ws, void* stream) {
+  if (!ws) return set_err(RBD_ERR_INVALID_ARG, "null workspace");
+  ws->stream = (cudaStream_t)stream;
+  return RBD_OK;
+}
+RBD_API int rbd_workspace_synchronize(rbd_workspace* ws) {
+  GUARD(ws);
+  CK(cudaStreamSynchronize(ws->stream));
+  return RBD_OK;
+}
+RBD_API int64_t rbd_workspace_launch_count(const rbd_workspace* ws) { return ws ? ws->launches : 0; }
+RBD_API int rbd_workspace_set_eval_block(rbd_workspace* ws, int threads) {
+  if (!ws) return set_err(RBD_ERR_INVALID_ARG, "null workspace");
+  if (threads < 0 || threads > 256 || threads % 32 != 0) return set_err(RBD_ERR_INVALID_ARG, "block must be 0 or a multiple of 32 <= 256");
+  ws->forced_eval_block = threads;
+  return RBD_OK;
+}
+
+static int check_batch(const rbd_workspace* ws, int64_t n, int64_t tile) {
+  if (n < 0) return set_err(RBD_ERR_INVALID_ARG, "negative batch size");
+  if (n > ws->capacity) return set_err(RBD_ERR_INVALID_ARG, "batch size exceeds the workspace capacity");
+  if (tile < 1) return set_err(RBD_ERR_INVALID_ARG, "tile must be >= 1");
+  return RBD_OK;
+}
+
+// ---- device SoA entry points (enqueue only) -----------------------------------------------------------------
+static int eval_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, const double* q, const double* v,
+                   const double* a, double* oMi, double* J, double* M, double* tau) {
+  const DevModel& dm = ws->model->dm;
+  if (!q) return set_err(RBD_ERR_INVALID_ARG, "q is null");
+  if (tau && (!v || !a)) return set_err(RBD_ERR_INVALID_ARG, "rnea needs v and a");
+  EvalArgs A{n, tile, q, v, a, oMi, J, M, tau};
+  const int sd = smem_eval(dm, M != nullptr, tau != nullptr);
+  CK(launch_eval(dm, A, sd, ws->forced_eval_block, ws->cfg_eval, st));
+  if (n > 0) ws->launches++;
+  return RBD_OK;
+}
+
+RBD_API int rbd_eval_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, const double* v,
+                         const double* a, double* oMi, double* J, double* M, double* tau) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, tile);
+  if (rc) return rc;
+  return eval_on(ws, ws->stream, n, tile, q, v, a, oMi, J, M, tau);
+}
+RBD_API int rbd_crba_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, double* M) {
+  if (!M) return set_err(RBD_ERR_INVALID_ARG, "M is null");
+  return rbd_eval_soa(ws, n, tile, q, nullptr, nullptr, nullptr, nullptr, M, nullptr);
+}
+RBD_API int rbd_rnea_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, const double* v,
+                         const double* a, double* tau) {
+  if (!tau) return set_err(RBD_ERR_INVALID_ARG, "tau is null");
+  return rbd_eval_soa(ws, n, tile, q, v, a, nullptr, nullptr, nullptr, tau);
+}
+
+static int apply_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, long long inst0, const double* qj,
+                    const double* root, double* out) {
+  const DevModel& dm = ws->model->dm;
+  if (!qj || !out) return set_err(RBD_ERR_INVALID_ARG, "null q_joints / out");
+  if (root && !dm.has_ff_root) return set_err(RBD_ERR_INVALID_ARG, "root pose given but the model has no free-flyer root");
+  MapArgs A{n, tile, qj, root, nullptr, out, ws->qcache, ws->capacity, inst0};
+  CK(launch_apply(dm, ws->tb, A, smem_apply(dm), &ws->cfg_apply, st));
+  if (n > 0) ws->launches++;
+  return RBD_OK;
+}
+RBD_API int rbd_apply_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q_joints, const double* root_pose,
+                          double* out) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, tile);
+  if (rc) return rc;
+  rc = apply_on(ws, ws->stream, n, tile, 0, q_joints, root_pose, out);
+  if (rc == RBD_OK) ws->applied_n = n;
+  return rc;
+}
+
+static int applyJ_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, long long inst0, const double* dq,
+                     const double* rootv, double* out) {
+  const DevModel& dm = ws->model->dm;
+  if (!dq || !out) return set_err(RBD_ERR_INVALID_ARG, "null dq_joints / out");
+  if (rootv && !dm.has_ff_root) return set_err(RBD_ERR_INVALID_ARG, "root velocity given but the model has no free-flyer root");
+  MapArgs A{n, tile, dq, rootv, nullptr, out, ws->qcache, ws->capacity, inst0};
+  CK(launch_applyJ(dm, ws->tb, A, smem_applyJ(dm), &ws->cfg_applyJ, st));
+  if (n > 0) ws->launches++;
+  return RBD_OK;
+}
+RBD_API int rbd_applyJ_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* dq_joints, const double* root_vel,
+                           double* out) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, tile);
+  if (rc) return rc;
+  if (n > ws->applied_n) return set_err(RBD_ERR_NO_APPLY, "applyJ before apply: no cached configuration for these instances");
+  return applyJ_on(ws, ws->stream, n, tile, 0, dq_joints, root_vel, out);
+}
+
+static int applyJT_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, long long inst0, const double* in,
+                      double* out_tau, double* out_root) {
+  const DevModel& dm = ws->model->dm;
+  if (!in || !out_tau) return set_err(RBD_ERR_INVALID_ARG, "null in / out_tau");
+  if (out_root && !dm.has_ff_root) return set_err(RBD_ERR_INVALID_ARG, "root output given but the model has no free-flyer root");
+  MapArgs A{n, tile, out_tau, out_root, in, nullptr, ws->qcache, ws->capacity, inst0};
+  CK(launch_applyJT(dm, ws->tb, A, smem_applyJT(dm), &ws->cfg_applyJT, st));
+  if (n > 0) ws->launches++;
+  return RBD_OK;
+}
+RBD_API int rbd_applyJT_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* in, double* out_tau,
+                            double* out_root) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, tile);
+  if (rc) return rc;
+  if (n > ws->applied_n) return set_err(RBD_ERR_NO_APPLY, "applyJT before apply: no cached configuration for these instances");
+  return applyJT_on(ws, ws->stream, n, tile, 0, in, out_tau, out_root);
+}
+
+RBD_API int rbd_applyJT_rows_dev(rbd_workspace* ws, int64_t nrows, const int32_t* row_ptr, const int32_t* row_instance,
+                                 const int32_t* col, const double* val, double* out_rows, int32_t* keep) {
+  GUARD(ws);
+  if (nrows < 0) return set_err(RBD_ERR_INVALID_ARG, "negative row count");
+  if (nrows == 0) return RBD_OK;
+  if (!row_ptr || !row_instance || !out_rows || !keep) return set_err(RBD_ERR_INVALID_ARG, "null row arrays");
+  if (ws->applied_n <= 0) return set_err(RBD_ERR_NO_APPLY, "applyJT(rows) before apply: no cached configuration");
+  const DevModel& dm = ws->model->dm;
+  RowArgs A{nrows, row_ptr, row_instance, col, val, out_rows, keep, ws->qcache, ws->capacity};
+  CK(launch_applyJT_rows(dm, ws->tb, A, smem_applyJT(dm), &ws->cfg_rows, ws->stream));
+  ws->launches++;
+  return RBD_OK;
+}
+
+RBD_API int rbd_aos_to_soa_dev(rbd_workspace* ws, int64_t n, int32_t K, int64_t tile, const double* aos, double* soa) {
+  GUARD(ws);
+  if (n < 0 || K < 0 || tile < 1 || (n > 0 && K > 0 && (!aos || !soa))) return set_err(RBD_ERR_INVALID_ARG, "bad transpose arguments");
+  CK(launch_aos_to_soa(n, K, tile, aos, soa, ws->stream));
+  if (n > 0 && K > 0) ws->launches++;
+  return RBD_OK;
+}
+RBD_API int rbd_soa_to_aos_dev(rbd_workspace* ws, int64_t n, int32_t K, int64_t tile, const double* soa, double* aos) {
+  GUARD(ws);
+  if (n < 0 || K < 0 || tile < 1 || (n > 0 && K > 0 && (!aos || !soa))) return set_err(RBD_ERR_INVALID_ARG, "bad transpose arguments");
+  CK(launch_soa_to_aos(n, K, tile, soa, aos, ws->stream));
+  if (n > 0 && K > 0) ws->launches++;
+  return RBD_OK;
+}
+
+// ---- host (SOFA AoS) entry points ----------------------------------------------------------------------------
+// Each chunk of <= ws->chunk instances goes through one of two slots, each with its own stream:
+//   H2D (instance-major) -> aos_to_soa -> kernel -> soa_to_aos -> D2H.
+// Consecutive chunks alternate slots so that the copies of one overlap the kernels of the other.
+static int ensure_slots(rbd_workspace* ws, size_t fields_total) {
+  const long long chunk = ws->capacity < kHostChunk ? ws->capacity : kHostChunk;
+  const size_t need = fields_total * (size_t)chunk;
+  if (ws->slot[0].st && ws->slot_doubles >= need && ws->chunk == chunk) return RBD_OK;
+  for (int s = 0; s < kSlots; ++s) {
+    if (!ws->slot[s].st) CK(cudaStreamCreateWithFlags(&ws->slot[s].st, cudaStreamNonBlocking));
+    if (ws->slot_doubles < need) {
+      CK(cudaStreamSynchronize(ws->slot[s].st));
+      cudaFree(ws->slot[s].aos); cudaFree(ws->slot[s].soa);
+      ws->slot[s].aos = ws->slot[s].soa = nullptr;
+      CK(cudaMalloc(&ws->slot[s].aos, need * sizeof(double)));
+      CK(cudaMalloc(&ws->slot[s].soa, need * sizeof(double)));
+    }
+  }
+  if (ws->slot_doubles < need) ws->slot_doubles = need;
+  ws->chunk = chunk;
+  return RBD_OK;
+}
+
+struct Piece {  // one array of a host call: K fields, host pointer (may be null), direction
+  int K;
+  const double* h_in;
+  double* h_out;
+  bool load;   // copy host -> device before the kernel
+  bool store;  // copy device -> host after the kernel
+  double* d_soa = nullptr;
+  double* d_aos = nullptr;
+};
+
+template <class KernelFn>
+static int run_host_chunks(rbd_workspace* ws, int64_t n, std::vector<Piece>& pieces, KernelFn kernel) {
+  size_t fields = 0;
+  for (auto& p : pieces) fields += (size_t)p.K;
+  int rc = ensure_slots(ws, fields);
+  if (rc) return rc;
+  // order after whatever the caller queued on the workspace stream
+  CK(cudaEventRecord(ws->ev, ws->stream));
+  for (int s = 0; s < kSlots; ++s) CK(cudaStreamWaitEvent(ws->slot[s].st, ws->ev, 0));
+  const long long chunk = ws->chunk;
+  int which = 0;
+  for (long long i0 = 0; i0 < n; i0 += chunk, which ^= 1) {
+    const long long cn = (n - i0) < chunk ? (n - i0) : chunk;
+    HostSlot& sl = ws->slot[which];
+    size_t off = 0;
+    for (auto& p : pieces) {
+      p.d_aos = sl.aos + off;
+      p.d_soa = sl.soa + off;
+      off += (size_t)p.K * (size_t)chunk;
+      const bool present = p.h_in != nullptr || p.h_out != nullptr;
+      if (!present) { p.d_aos = p.d_soa = nullptr; continue; }
+      if (p.load && p.K > 0) {
+        CK(cudaMemcpyAsync(p.d_aos, p.h_in + (size_t)i0 * p.K, (size_t)cn * p.K * sizeof(double), cudaMemcpyHostToDevice, sl.st));
+        CK(launch_aos_to_soa(cn, p.K, chunk, p.d_aos, p.d_soa, sl.st));
+        ws->launches++;
+      }
+    }
+    rc = kernel(sl.st, i0, cn, chunk);
+    if (rc) return rc;
+    for (auto& p : pieces) {
+      if (p.store && p.h_out && p.K > 0) {
+        CK(launch_soa_to_aos(cn, p.K, chunk, p.d_soa, p.d_aos, sl.st));
+        ws->launches++;
+        CK(cudaMemcpyAsync(p.h_out + (size_t)i0 * p.K, p.d_aos, (size_t)cn * p.K * sizeof(double), cudaMemcpyDeviceToHost, sl.st));
+      }
+    }
+  }
+  for (int s = 0; s < kSlots; ++s) CK(cudaStreamSynchronize(ws->slot[s].st));
+  return RBD_OK;
+}
+
+RBD_API int rbd_eval_host(rbd_workspace* ws, int64_t n, const double* q, const double* v, const double* a, double* oMi,
+                          double* J, double* M, double* tau) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, 1);
+  if (rc) return rc;
+  if (!q) return set_err(RBD_ERR_INVALID_ARG, "q is null");
+  if (tau && (!v || !a)) return set_err(RBD_ERR_INVALID_ARG, "rnea needs v and a");
+  const rbd_model_info& I = ws->model->info;
+  std::vector<Piece> P = {{I.nq, q, nullptr, true, false},      {I.nv, v, nullptr, true, false},
+                          {I.nv, a, nullptr, true, false},      {I.omi_fields, nullptr, oMi, false, true},
+                          {I.jac_fields, nullptr, J, false, true}, {I.mass_fields, nullptr, M, false, true},
+                          {I.nv, nullptr, tau, false, true}};
+  return run_host_chunks(ws, n, P, [&](cudaStream_t st, long long, long long cn, long long tile) {
+    return eval_on(ws, st, cn, tile, P[0].d_soa, P[1].d_soa, P[2].d_soa, P[3].d_soa, P[4].d_soa, P[5].d_soa, P[6].d_soa);
+  });
+}
+
+RBD_API int rbd_apply_host(rbd_workspace* ws, int64_t n, const double* q_joints, const double* root_pose, double* out) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, 1);
+  if (rc) return rc;
+  if (!q_joints || !out) return set_err(RBD_ERR_INVALID_ARG, "null q_joints / out");
+  const rbd_model_info& I = ws->model->info;
+  if (root_pose && !I.has_freeflyer_root) return set_err(RBD_ERR_INVALID_ARG, "root pose given but the model has no free-flyer root");
+  const int kq = root_pose ? I.nq - 7 : I.nq;
+  std::vector<Piece> P = {{kq, q_joints, nullptr, true, false}, {7, root_pose, nullptr, true, false},
+                          {7 * I.n_out, nullptr, out, false, true}};
+  rc = run_host_chunks(ws, n, P, [&](cudaStream_t st, long long i0, long long cn, long long tile) {
+    return apply_on(ws, st, cn, tile, i0, P[0].d_soa, P[1].d_soa, P[2].d_soa);
+  });
+  if (rc == RBD_OK) ws->applied_n = n;
+  return rc;
+}
+
+RBD_API int rbd_applyJ_host(rbd_workspace* ws, int64_t n, const double* dq_joints, const double* root_vel, double* out) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, 1);
+  if (rc) return rc;
+  if (!dq_joints || !out) return set_err(RBD_ERR_INVALID_ARG, "null dq_joints / out");
+  if (n > ws->applied_n) return set_err(RBD_ERR_NO_APPLY, "applyJ before apply: no cached configuration for these instances");
+  const rbd_model_info& I = ws->model->info;
+  if (root_vel && !I.has_freeflyer_root) return set_err(RBD_ERR_INVALID_ARG, "root velocity given but the model has no free-flyer root");
+  const int kv = root_vel ? I.nv - 6 : I.nv;
+  std::vector<Piece> P = {{kv, dq_joints, nullptr, true, false}, {6, root_vel, nullptr, true, false},
+                          {6 * I.n_out, nullptr, out, false, true}};
+  return run_host_chunks(ws, n, P, [&](cudaStream_t st, long long i0, long long cn, long long tile) {
+    return applyJ_on(ws, st, cn, tile, i0, P[0].d_soa, P[1].d_soa, P[2].d_soa);
+  });
+}
+
+RBD_API int rbd_applyJT_host(rbd_workspace* ws, int64_t n, const double* in, double* out_tau, double* out_root) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, 1);
+  if (rc) return rc;
+  if (!in || !out_tau) return set_err(RBD_ERR_INVALID_ARG, "null in / out_tau");
+  if (n > ws->applied_n) return set_err(RBD_ERR_NO_APPLY, "applyJT before apply: no cached configuration for these instances");
+  const rbd_model_info& I = ws->model->info;
+  if (out_root && !I.has_freeflyer_root) return set_err(RBD_ERR_INVALID_ARG, "root output given but the model has no free-flyer root");
+  const int kv = out_root ? I.nv - 6 : I.nv;
+  // out_tau / out_root are accumulated (+=, reference KinematicChainMapping.inl:498-511): load, add, store
+  std::vector<Piece> P = {{6 * I.n_out, in, nullptr, true, false}, {kv, out_tau, out_tau, true, true},
+                          {6, out_root, out_root, true, true}};
+  return run_host_chunks(ws, n, P, [&](cudaStream_t st, long long i0, long long cn, long long tile) {
+    return applyJT_on(ws, st, cn, tile, i0, P[0].d_soa, P[1].d_soa, P[2].d_soa);
+  });
+}
+
+RBD_API int rbd_applyJT_rows_host(rbd_workspace* ws, int64_t nrows, const int32_t* row_ptr, const int32_t* row_instance,
+                                  const int32_t* col, const double* val, double* out_rows, int32_t* keep) {
+  GUARD(ws);
+  if (nrows < 0) return set_err(RBD_ERR_INVALID_ARG, "negative row count");
+  if (nrows == 0) return RBD_OK;
+  if (!row_ptr || !row_instance || !out_rows || !keep) return set_err(RBD_ERR_INVALID_ARG, "null row arrays");
+  if (ws->applied_n <= 0) return set_err(RBD_ERR_NO_APPLY, "applyJT(rows) before apply: no cached configuration");
+  const int nv = ws->model->info.nv;
+  const long long nnz = row_ptr[nrows];
+  if (nnz < 0 || (nnz > 0 && (!col || !val))) return set_err(RBD_ERR_INVALID_ARG, "bad CSR arrays");
+  for (int64_t r = 0; r < nrows; ++r)
+    if (row_instance[r] < 0 || row_instance[r] >= ws->applied_n) return set_err(RBD_ERR_INVALID_ARG, "row_instance out of the applied range");
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t b_rp = al((size_t)(nrows + 1) * 4), b_ri = al((size_t)nrows * 4), b_col = al((size_t)nnz * 4),
+               b_val = al((size_t)nnz * 48), b_out = al((size_t)nrows * nv * 8), b_keep = al((size_t)nrows * 4);
+  const size_t total = b_rp + b_ri + b_col + b_val + b_out + b_keep;
+  if (ws->rows_bytes < total) {
+    CK(cudaStreamSynchronize(ws->stream));
+    cudaFree(ws->rows_buf); ws->rows_buf = nullptr; ws->rows_bytes = 0;
+    CK(cudaMalloc(&ws->rows_buf, total));
+    ws->rows_bytes = total;
+  }
+  char* base = (char*)ws->rows_buf;
+  int* d_rp = (int*)base; int* d_ri = (int*)(base + b_rp); int* d_col = (int*)(base + b_rp + b_ri);
+  double* d_val = (double*)(base + b_rp + b_ri + b_col);
+  double* d_out = (double*)(base + b_rp + b_ri + b_col + b_val);
+  int* d_keep = (int*)(base + b_rp + b_ri + b_col + b_val + b_out);
+  cudaStream_t st = ws->stream;
+  CK(cudaMemcpyAsync(d_rp, row_ptr, (size_t)(nrows + 1) * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_ri, row_instance, (size_t)nrows * 4, cudaMemcpyHostToDevice, st));
+  if (nnz > 0) {
+    CK(cudaMemcpyAsync(d_col, col, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_val, val, (size_t)nnz * 48, cudaMemcpyHostToDevice, st));
+  }
+  const DevModel& dm = ws->model->dm;
+  RowArgs A{nrows, d_rp, d_ri, d_col, d_val, d_out, d_keep, ws->qcache, ws->capacity};
+  CK(launch_applyJT_rows(dm, ws->tb, A, smem_applyJT(dm), &ws->cfg_rows, st));
+  ws->launches++;
+  CK(cudaMemcpyAsync(out_rows, d_out, (size_t)nrows * nv * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(keep, d_keep, (size_t)nrows * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return RBD_OK;
+}
+

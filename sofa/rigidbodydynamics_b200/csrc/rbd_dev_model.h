@@ -1,0 +1,58 @@
+// rbd_dev_model.h — kinematic-tree constants as the kernels see them.
+//
+// The whole joint table travels as a __grid_constant__ kernel parameter, i.e. it is staged in the constant
+// bank of every launch ("tree constants staged once into constant memory", BASELINE north-star): all threads
+// of a warp read the same joint record at the same time, which is exactly the broadcast access pattern the
+// constant cache serves, and it keeps L1/shared memory free for per-instance state.
+// Replaces the pinocchio::Model the reference shares between loader and mapping
+// (reference KinematicChainMapping.inl:304-311, URDFModelLoader.cpp:263-268).
+#pragma once
+#include <stdint.h>
+
+#ifndef RBD_MAX_JOINTS
+#define RBD_MAX_JOINTS 64 /* joint records that fit the 32 KB kernel-parameter space with room to spare */
+#endif
+
+// joint type codes == include/rbd_b200.h RBD_JOINT_*
+enum : int {
+  JT_UNIVERSE = 0, JT_RX = 1, JT_RY = 2, JT_RZ = 3, JT_RU = 4, JT_PX = 5, JT_PY = 6, JT_PZ = 7, JT_PU = 8,
+  JT_RUBX = 9, JT_RUBY = 10, JT_RUBZ = 11, JT_RUBU = 12, JT_FF = 13
+};
+
+struct DevJoint {
+  double pl[12];    // jointPlacement: R row-major (9), p (3)
+  double axis[3];   // unit axis in the joint frame
+  double Y[10];     // m, c(3), Ic (xx,xy,yy,xz,yz,zz)
+  int parent, type, idx_q, idx_v;
+  int nv;           // dof of this joint (0 universe, 1, or 6)
+  int nchild;       // number of child joints
+  int slot[2];      // shared-memory offset (doubles) of this joint's stack slot: [0] full layout (A|f|Y), [1] lite (A|f)
+  int bidx;         // branch-slot index (joints with >= 2 children), -1 otherwise
+  int out_begin, out_end;  // range of this joint's mapped outputs in DevTables::sorted_*
+  int pad_;
+};
+
+struct DevModel {
+  int njoints, nq, nv, n_out;
+  int slot_total[2];  // doubles of stack slots per instance for the two layouts
+  int nbranch;
+  int has_ff_root;    // joint 1 is a free-flyer attached to the universe
+  int nq_joints, nv_joints;
+  int max_depth, pad_;
+  double gravity[3];
+  DevJoint joint[RBD_MAX_JOINTS];
+};
+
+// Per-output tables (global memory; only the mapping kernels read them).
+struct DevTables {
+  const int* sorted_k;       // [n_out] output index, grouped by parent joint (DevJoint::out_begin/out_end)
+  const double* sorted_pl;   // [n_out][12] frame placement in the parent joint frame, same order
+  const int* outk_parent;    // [n_out] parent joint of output k
+  const double* outk_pl;     // [n_out][12] frame placement of output k
+};
+
+// Stack-slot geometry (doubles): A is 6 wide (1-dof joints: [p x a ; a] world frame) or 12 (free-flyer: R|p).
+#define RBD_SLOT_A(type) ((type) == JT_FF ? 12 : 6)
+#define RBD_BRANCH_EVAL 24 /* R(9) p(3) v(6) a(6) */
+#define RBD_BRANCH_FK 12   /* R(9) p(3) */
+#define RBD_BRANCH_J 18    /* R(9) p(3) V(6) */

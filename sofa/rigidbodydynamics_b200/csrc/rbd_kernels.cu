@@ -1,0 +1,245 @@
+// rbd_kernels.cu — sm_100a kernels of the batched articulated-body back end.
+//
+// Design (DESIGN.md has the numbers):
+//  * one thread = one robot instance; a warp's 32 instances sit side by side in every tiled-SoA field, so each
+//    global load/store instruction moves 32 consecutive doubles (two full 128-byte lines);
+//  * the joint table is a __grid_constant__ parameter -> constant bank, broadcast to the warp;
+//  * per-instance sweep state (depth-indexed stack + branch slots, rbd_sweeps.h) lives in shared memory laid
+//    out [slot][thread] -> bank-conflict free, no __syncthreads anywhere: threads never exchange data;
+//  * FP64 CUDA-core arithmetic only: the path is a tree recursion of 3x3/6x6 products, not a dense
+//    contraction, so tensor cores (tcgen05) do not apply (BASELINE north-star);
+//  * the block size is chosen at run time so that resident warps per SM fill the 227 KB of shared memory.
+#include <cuda_runtime.h>
+
+#include "rbd_kernels.h"
+#include "rbd_sweeps.h"
+
+namespace rbd {
+
+extern __shared__ double rbd_smem[];
+
+// --------------------------------------------------------------------------------------------------------
+// K7 / K5 / K6: fused FK + joint Jacobian (+ CRBA) (+ RNEA)
+template <bool DO_M, bool DO_TAU>
+__global__ void __launch_bounds__(256) eval_kernel(const __grid_constant__ DevModel m, const EvalArgs a) {
+  const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= a.n) return;
+  EvalIO io;
+  io.q = make_field(const_cast<double*>(a.q), inst, m.nq, a.tile);
+  io.v = make_field(const_cast<double*>(a.v), inst, m.nv, a.tile);
+  io.a = make_field(const_cast<double*>(a.a), inst, m.nv, a.tile);
+  io.oMi = make_field(a.oMi, inst, 12 * (m.njoints - 1), a.tile);
+  io.J = make_field(a.J, inst, 6 * m.nv, a.tile);
+  io.M = make_field(a.M, inst, m.nv * (m.nv + 1) / 2, a.tile);
+  io.tau = make_field(a.tau, inst, m.nv, a.tile);
+  Stack S{rbd_smem + threadIdx.x, (int)blockDim.x};
+  eval_instance<DO_M, DO_TAU>(m, io, S);
+}
+
+// K1: apply
+__global__ void __launch_bounds__(256) apply_kernel(const __grid_constant__ DevModel m, const DevTables tb,
+                                                    const MapArgs a) {
+  const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= a.n) return;
+  const int off = a.root ? 7 : 0;
+  SplitQ q{make_field(const_cast<double*>(a.root), inst, 7, a.tile),
+           make_field(const_cast<double*>(a.joints), inst, m.nq - off, a.tile), off};
+  Stack S{rbd_smem + threadIdx.x, (int)blockDim.x};
+  apply_instance(m, tb, q, make_field(a.qcache, a.cache_inst0 + inst, m.nq, a.cache_tile),
+                 make_field(a.out, inst, 7 * m.n_out, a.tile), S);
+}
+
+// K2: applyJ
+__global__ void __launch_bounds__(256) applyJ_kernel(const __grid_constant__ DevModel m, const DevTables tb,
+                                                     const MapArgs a) {
+  const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= a.n) return;
+  const int off = a.root ? 6 : 0;
+  SplitQ dq{make_field(const_cast<double*>(a.root), inst, 6, a.tile),
+            make_field(const_cast<double*>(a.joints), inst, m.nv - off, a.tile), off};
+  Stack S{rbd_smem + threadIdx.x, (int)blockDim.x};
+  applyJ_instance(m, tb, make_field(a.qcache, a.cache_inst0 + inst, m.nq, a.cache_tile), dq,
+                  make_field(a.out, inst, 6 * m.n_out, a.tile), S);
+}
+
+// K3: applyJT (vector).  a.joints / a.root are the ACCUMULATED outputs here, a.in the wrenches.
+__global__ void __launch_bounds__(256) applyJT_kernel(const __grid_constant__ DevModel m, const DevTables tb,
+                                                      const MapArgs a) {
+  const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= a.n) return;
+  const int off = a.root ? 6 : 0;
+  DenseWrenchSrc src{make_field(const_cast<double*>(a.in), inst, 6 * m.n_out, a.tile), &tb};
+  SplitAccumSink sink{make_field(const_cast<double*>(a.root), inst, 6, a.tile),
+                      make_field(const_cast<double*>(a.joints), inst, m.nv - off, a.tile), off};
+  Stack S{rbd_smem + threadIdx.x, (int)blockDim.x};
+  applyJT_instance(m, tb, make_field(a.qcache, a.cache_inst0 + inst, m.nq, a.cache_tile), src, sink, S);
+}
+
+// K4: applyJT (constraint rows): one thread per row
+__global__ void __launch_bounds__(256) applyJT_rows_kernel(const __grid_constant__ DevModel m, const DevTables tb,
+                                                           const RowArgs a) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.nrows) return;
+  const int b = a.row_ptr[r], e = a.row_ptr[r + 1];
+  double n2 = 0.0;
+  RowWrenchSrc src{a.col + b, a.val + 6 * (long long)b, e - b, &tb};
+  RowSink sink{a.out_rows + r * m.nv, &n2};
+  Stack S{rbd_smem + threadIdx.x, (int)blockDim.x};
+  applyJT_instance(m, tb, make_field(a.qcache, a.row_instance[r], m.nq, a.cache_tile), src, sink, S);
+  a.keep[r] = n2 > 1e-12 ? 1 : 0;  // kMinTorqueSqrd, reference KinematicChainMapping.inl:43-45,587,605
+}
+
+// K8: layout adapters.  32 instances x 32 fields per block through a padded shared tile, so both the
+// instance-major side and the tiled-SoA side are accessed with consecutive addresses.
+__global__ void aos_to_soa_kernel(long long n, int K, long long tile, const double* __restrict__ aos,
+                                  double* __restrict__ soa) {
+  __shared__ double t[32][33];
+  const long long i0 = (long long)blockIdx.x * 32;  // instance blocks on x (no 65535 limit)
+  const int k0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const long long i = i0 + r;
+    const int k = k0 + threadIdx.x;
+    if (i < n && k < K) t[r][threadIdx.x] = aos[i * K + k];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int k = k0 + r;
+    const long long i = i0 + threadIdx.x;
+    if (i < n && k < K) soa[(i / tile) * (long long)K * tile + (long long)k * tile + (i % tile)] = t[threadIdx.x][r];
+  }
+}
+__global__ void soa_to_aos_kernel(long long n, int K, long long tile, const double* __restrict__ soa,
+                                  double* __restrict__ aos) {
+  __shared__ double t[32][33];
+  const long long i0 = (long long)blockIdx.x * 32;  // instance blocks on x (no 65535 limit)
+  const int k0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int k = k0 + r;
+    const long long i = i0 + threadIdx.x;
+    if (i < n && k < K) t[threadIdx.x][r] = soa[(i / tile) * (long long)K * tile + (long long)k * tile + (i % tile)];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const long long i = i0 + r;
+    const int k = k0 + threadIdx.x;
+    if (i < n && k < K) aos[i * K + k] = t[r][threadIdx.x];
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// launch helpers
+static const int kMaxSmemOptin = 227 * 1024;
+
+template <class Kern>
+static cudaError_t pick_block(Kern kern, int smem_doubles_per_thread, int forced, LaunchCfg* cfg) {
+  // opt in to the full 227 KB of dynamic shared memory once per kernel
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  const size_t per_thread = (size_t)smem_doubles_per_thread * sizeof(double);
+  int best_threads = 0, best_block = 0, best_blocks_per_sm = 0;
+  const int cand[] = {32, 64, 96, 128, 160, 192, 224, 256};
+  for (int c : cand) {
+    if (forced > 0 && c != forced) continue;
+    const size_t smem = per_thread * c;
+    if (smem > (size_t)kMaxSmemOptin) continue;
+    int nb = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, c, smem);
+    if (e != cudaSuccess) return e;
+    // prefer more resident threads; on ties the larger block (fewer blocks, less per-block reserved smem)
+    if (nb * c > best_threads || (nb * c == best_threads && c > best_block)) {
+      best_threads = nb * c; best_block = c; best_blocks_per_sm = nb;
+    }
+  }
+  if (best_block == 0) return cudaErrorInvalidConfiguration;
+  cfg->block = best_block;
+  cfg->smem_bytes = per_thread * best_block;
+  cfg->blocks_per_sm = best_blocks_per_sm;
+  return cudaSuccess;
+}
+
+#define RBD_GRID(n, block) (unsigned)(((n) + (block)-1) / (block))
+
+cudaError_t launch_eval(const DevModel& m, const EvalArgs& a, int smem_doubles, int forced_block, LaunchCfg* cache,
+                        cudaStream_t st) {
+  const bool do_m = a.M != nullptr, do_tau = a.tau != nullptr;
+  const int v = (do_m ? 2 : 0) | (do_tau ? 1 : 0);
+  LaunchCfg& cfg = cache[v];
+  cudaError_t e = cudaSuccess;
+  if (cfg.block == 0 || cfg.forced != forced_block) {
+    switch (v) {
+      case 3: e = pick_block(eval_kernel<true, true>, smem_doubles, forced_block, &cfg); break;
+      case 2: e = pick_block(eval_kernel<true, false>, smem_doubles, forced_block, &cfg); break;
+      case 1: e = pick_block(eval_kernel<false, true>, smem_doubles, forced_block, &cfg); break;
+      default: e = pick_block(eval_kernel<false, false>, smem_doubles, forced_block, &cfg); break;
+    }
+    if (e != cudaSuccess) return e;
+    cfg.forced = forced_block;
+  }
+  if (a.n <= 0) return cudaSuccess;
+  const unsigned grid = RBD_GRID(a.n, cfg.block);
+  switch (v) {
+    case 3: eval_kernel<true, true><<<grid, cfg.block, cfg.smem_bytes, st>>>(m, a); break;
+    case 2: eval_kernel<true, false><<<grid, cfg.block, cfg.smem_bytes, st>>>(m, a); break;
+    case 1: eval_kernel<false, true><<<grid, cfg.block, cfg.smem_bytes, st>>>(m, a); break;
+    default: eval_kernel<false, false><<<grid, cfg.block, cfg.smem_bytes, st>>>(m, a); break;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_apply(const DevModel& m, const DevTables& tb, const MapArgs& a, int smem_doubles, LaunchCfg* cfg,
+                         cudaStream_t st) {
+  if (cfg->block == 0) {
+    cudaError_t e = pick_block(apply_kernel, smem_doubles, 0, cfg);
+    if (e != cudaSuccess) return e;
+  }
+  if (a.n <= 0) return cudaSuccess;
+  apply_kernel<<<RBD_GRID(a.n, cfg->block), cfg->block, cfg->smem_bytes, st>>>(m, tb, a);
+  return cudaGetLastError();
+}
+cudaError_t launch_applyJ(const DevModel& m, const DevTables& tb, const MapArgs& a, int smem_doubles, LaunchCfg* cfg,
+                          cudaStream_t st) {
+  if (cfg->block == 0) {
+    cudaError_t e = pick_block(applyJ_kernel, smem_doubles, 0, cfg);
+    if (e != cudaSuccess) return e;
+  }
+  if (a.n <= 0) return cudaSuccess;
+  applyJ_kernel<<<RBD_GRID(a.n, cfg->block), cfg->block, cfg->smem_bytes, st>>>(m, tb, a);
+  return cudaGetLastError();
+}
+cudaError_t launch_applyJT(const DevModel& m, const DevTables& tb, const MapArgs& a, int smem_doubles, LaunchCfg* cfg,
+                           cudaStream_t st) {
+  if (cfg->block == 0) {
+    cudaError_t e = pick_block(applyJT_kernel, smem_doubles, 0, cfg);
+    if (e != cudaSuccess) return e;
+  }
+  if (a.n <= 0) return cudaSuccess;
+  applyJT_kernel<<<RBD_GRID(a.n, cfg->block), cfg->block, cfg->smem_bytes, st>>>(m, tb, a);
+  return cudaGetLastError();
+}
+cudaError_t launch_applyJT_rows(const DevModel& m, const DevTables& tb, const RowArgs& a, int smem_doubles,
+                                LaunchCfg* cfg, cudaStream_t st) {
+  if (cfg->block == 0) {
+    cudaError_t e = pick_block(applyJT_rows_kernel, smem_doubles, 0, cfg);
+    if (e != cudaSuccess) return e;
+  }
+  if (a.nrows <= 0) return cudaSuccess;
+  applyJT_rows_kernel<<<RBD_GRID(a.nrows, cfg->block), cfg->block, cfg->smem_bytes, st>>>(m, tb, a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_aos_to_soa(long long n, int K, long long tile, const double* aos, double* soa, cudaStream_t st) {
+  if (n <= 0 || K <= 0) return cudaSuccess;
+  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((K + 31) / 32)), block(32, 8);
+  aos_to_soa_kernel<<<grid, block, 0, st>>>(n, K, tile, aos, soa);
+  return cudaGetLastError();
+}
+cudaError_t launch_soa_to_aos(long long n, int K, long long tile, const double* soa, double* aos, cudaStream_t st) {
+  if (n <= 0 || K <= 0) return cudaSuccess;
+  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((K + 31) / 32)), block(32, 8);
+  soa_to_aos_kernel<<<grid, block, 0, st>>>(n, K, tile, soa, aos);
+  return cudaGetLastError();
+}
+
+}  // namespace rbd

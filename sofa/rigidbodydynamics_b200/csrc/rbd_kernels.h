@@ -1,0 +1,50 @@
+// rbd_kernels.h — launch interface between the C ABI (rbd_capi.cu) and the kernels (rbd_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "rbd_dev_model.h"
+
+namespace rbd {
+
+struct EvalArgs {
+  long long n, tile;
+  const double *q, *v, *a;
+  double *oMi, *J, *M, *tau;
+};
+struct MapArgs {
+  long long n, tile;
+  const double* joints;  // apply: q_joints | applyJ: dq_joints | applyJT: out_tau (accumulated)
+  const double* root;    // apply: root pose (7) | applyJ: root velocity (6) | applyJT: out_root (accumulated) | nullptr
+  const double* in;      // applyJT: wrenches (n_out*6)
+  double* out;           // apply: n_out*7 | applyJ: n_out*6
+  double* qcache;        // workspace copy of the assembled configuration (nq fields)
+  long long cache_tile, cache_inst0;
+};
+struct RowArgs {
+  long long nrows;
+  const int *row_ptr, *row_instance, *col;
+  const double* val;
+  double* out_rows;
+  int* keep;
+  double* qcache;
+  long long cache_tile;
+};
+struct LaunchCfg {
+  int block = 0, forced = 0, blocks_per_sm = 0;
+  size_t smem_bytes = 0;
+};
+
+cudaError_t launch_eval(const DevModel& m, const EvalArgs& a, int smem_doubles, int forced_block, LaunchCfg* cache4,
+                        cudaStream_t st);
+cudaError_t launch_apply(const DevModel& m, const DevTables& tb, const MapArgs& a, int smem_doubles, LaunchCfg* cfg,
+                         cudaStream_t st);
+cudaError_t launch_applyJ(const DevModel& m, const DevTables& tb, const MapArgs& a, int smem_doubles, LaunchCfg* cfg,
+                          cudaStream_t st);
+cudaError_t launch_applyJT(const DevModel& m, const DevTables& tb, const MapArgs& a, int smem_doubles, LaunchCfg* cfg,
+                           cudaStream_t st);
+cudaError_t launch_applyJT_rows(const DevModel& m, const DevTables& tb, const RowArgs& a, int smem_doubles,
+                                LaunchCfg* cfg, cudaStream_t st);
+cudaError_t launch_aos_to_soa(long long n, int K, long long tile, const double* aos, double* soa, cudaStream_t st);
+cudaError_t launch_soa_to_aos(long long n, int K, long long tile, const double* soa, double* aos, cudaStream_t st);
+
+}  // namespace rbd

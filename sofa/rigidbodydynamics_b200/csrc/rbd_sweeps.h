@@ -1,0 +1,879 @@
+// rbd_sweeps.h — per-instance bodies of the sm_100a kernels (one thread = one robot instance).
+//
+// Everything here is written in the WORLD frame: with oMi known, joint motion subspaces become the columns
+// of pinocchio's data.J (A_i = oMi.act(S_i)), spatial velocities/accelerations/forces of all bodies live in
+// one common frame, and the backward passes of RNEA and CRBA reduce to plain additions
+// (f_parent += f_child, Ycrb_parent += Ycrb_child) instead of an SE3 action per joint.  Results equal
+// pinocchio's LOCAL-convention crba/rnea (reference oracle: oracle/rbd_oracle.c) up to rounding.
+//
+// Joints are numbered in DFS pre-order (pinocchio's URDF order; checked by rbd_model_create), so one
+// root-to-leaf sweep with a stack indexed by tree depth visits every joint once; a joint's subtree is
+// complete the moment the sweep leaves it, and its backward step ("pop") runs right then.  Live state per
+// instance is therefore O(depth), not O(njoints): that is what lets a Talos-sized robot keep its whole
+// working set in shared memory ("state budget").
+//
+// The functions are templates over two accessor types so that the identical code is compiled
+//   * by nvcc into the __global__ kernels (rbd_kernels.cu): Stack = shared memory column of this thread,
+//     Field = strided global memory;
+//   * by g++ into tests/emul (CPU unit tests of the kernel logic, never shipped, never a fallback).
+//
+// Reference semantics covered (paths relative to the reference root, KCM.inl =
+// src/sofa/RigidBodyDynamics/KinematicChainMapping.inl):
+//   eval_instance     pinocchio::computeJointJacobians (call site KCM.inl:373) + crba + rnea
+//   apply_instance    KCM.inl:338-396   (computeJointJacobians, updateFramePlacements, se3ToSofaType)
+//   applyJ_instance   KCM.inl:398-448   (getFrameJacobian LOCAL_WORLD_ALIGNED times dq, matrix-free)
+//   applyJT_instance  KCM.inl:450-513 and :515-639 (sum_k J_k^T w_k, matrix-free)
+#pragma once
+#include <math.h>
+
+#include "rbd_dev_model.h"
+
+#if defined(__CUDACC__)
+#define RBD_HD __host__ __device__ __forceinline__
+#else
+#define RBD_HD inline
+#endif
+
+namespace rbd {
+
+// ---------------------------------------------------------------------------------------------------------
+// accessors
+struct Field {  // strided view of one instance's fields in a tiled-SoA array
+  double* p;
+  long long stride;
+  RBD_HD double ld(int k) const { return p[(long long)k * stride]; }
+  RBD_HD void st(int k, double v) const { p[(long long)k * stride] = v; }
+  RBD_HD bool ok() const { return p != nullptr; }
+};
+RBD_HD Field make_field(double* base, long long inst, int K, long long tile) {
+  Field f;
+  f.stride = tile;
+  f.p = base ? base + (inst / tile) * (long long)K * tile + (inst % tile) : nullptr;
+  return f;
+}
+struct Stack {  // this thread's column of the shared-memory state
+  double* p;
+  int stride;
+  RBD_HD double ld(int k) const { return p[k * stride]; }
+  RBD_HD void st(int k, double v) const { p[k * stride] = v; }
+  RBD_HD void add(int k, double v) const { p[k * stride] += v; }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// 3-vector helpers on scalars held in registers
+#define RBD_CROSS(ox, oy, oz, ax, ay, az, bx, by, bz) \
+  do {                                                \
+    ox = (ay) * (bz) - (az) * (by);                   \
+    oy = (az) * (bx) - (ax) * (bz);                   \
+    oz = (ax) * (by) - (ay) * (bx);                   \
+  } while (0)
+
+RBD_HD void sincos_(double x, double* s, double* c) {
+#if defined(__CUDA_ARCH__)
+  sincos(x, s, c);
+#else
+  *s = sin(x);
+  *c = cos(x);
+#endif
+}
+
+// O = A * B (3x3 row-major, O distinct from A and B)
+RBD_HD void mat3_mul(const double* A, const double* B, double* O) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) O[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+  }
+}
+
+// rotate columns (ci, cj) of B by (c, s): col_i' = c col_i + s col_j ; col_j' = -s col_i + c col_j
+#define RBD_ROTCOLS(R, B, ck, ci, cj, c, s)        \
+  do {                                             \
+    _Pragma("unroll") for (int r_ = 0; r_ < 3; ++r_) { \
+      double bi_ = B[3 * r_ + ci], bj_ = B[3 * r_ + cj]; \
+      R[3 * r_ + ck] = B[3 * r_ + ck];             \
+      R[3 * r_ + ci] = c * bi_ + s * bj_;          \
+      R[3 * r_ + cj] = c * bj_ - s * bi_;          \
+    }                                              \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// One forward-kinematics step: (R,p) of the parent joint in, (R,p) of joint `jn` out (world frame), plus the
+// world joint axis aw (1-dof joints).  q0/q1 are the joint's configuration values (angle | displacement |
+// cos,sin); the free-flyer reads its 7 values through `qf`.
+// pinocchio: liMi = jointPlacement * M_joint(q); oMi = oMi[parent] * liMi (JointJacobiansForwardStep).
+template <class QF>
+RBD_HD void fk_joint(const DevJoint& jn, double* R, double* p, double q0, double q1, const QF& qf, double* aw) {
+  double B[9], pn[3];
+  mat3_mul(R, jn.pl, B);
+  pn[0] = R[0] * jn.pl[9] + R[1] * jn.pl[10] + R[2] * jn.pl[11] + p[0];
+  pn[1] = R[3] * jn.pl[9] + R[4] * jn.pl[10] + R[5] * jn.pl[11] + p[1];
+  pn[2] = R[6] * jn.pl[9] + R[7] * jn.pl[10] + R[8] * jn.pl[11] + p[2];
+  const int t = jn.type;
+  double c = q0, s = q1;
+  if (t >= JT_RX && t <= JT_RU) sincos_(q0, &s, &c);
+  switch (t) {
+    case JT_RX: case JT_RUBX:
+      RBD_ROTCOLS(R, B, 0, 1, 2, c, s);
+      aw[0] = B[0]; aw[1] = B[3]; aw[2] = B[6];
+      break;
+    case JT_RY: case JT_RUBY:
+      RBD_ROTCOLS(R, B, 1, 2, 0, c, s);
+      aw[0] = B[1]; aw[1] = B[4]; aw[2] = B[7];
+      break;
+    case JT_RZ: case JT_RUBZ:
+      RBD_ROTCOLS(R, B, 2, 0, 1, c, s);
+      aw[0] = B[2]; aw[1] = B[5]; aw[2] = B[8];
+      break;
+    case JT_RU: case JT_RUBU: {
+      const double ax = jn.axis[0], ay = jn.axis[1], az = jn.axis[2];
+      const double c1 = 1.0 - c, sx = s * ax, sy = s * ay, sz = s * az;
+      double Rj[9];
+      Rj[0] = c1 * ax * ax + c;  Rj[1] = c1 * ax * ay - sz; Rj[2] = c1 * ax * az + sy;
+      Rj[3] = c1 * ay * ax + sz; Rj[4] = c1 * ay * ay + c;  Rj[5] = c1 * ay * az - sx;
+      Rj[6] = c1 * az * ax - sy; Rj[7] = c1 * az * ay + sx; Rj[8] = c1 * az * az + c;
+      mat3_mul(B, Rj, R);
+      aw[0] = B[0] * ax + B[1] * ay + B[2] * az;
+      aw[1] = B[3] * ax + B[4] * ay + B[5] * az;
+      aw[2] = B[6] * ax + B[7] * ay + B[8] * az;
+    } break;
+    case JT_PX: case JT_PY: case JT_PZ: case JT_PU: {
+      const double ax = jn.axis[0], ay = jn.axis[1], az = jn.axis[2];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) R[k] = B[k];
+      aw[0] = B[0] * ax + B[1] * ay + B[2] * az;
+      aw[1] = B[3] * ax + B[4] * ay + B[5] * az;
+      aw[2] = B[6] * ax + B[7] * ay + B[8] * az;
+      pn[0] += q0 * aw[0]; pn[1] += q0 * aw[1]; pn[2] += q0 * aw[2];
+    } break;
+    case JT_FF: {
+      const int o = jn.idx_q;
+      const double px = qf.ld(o), py = qf.ld(o + 1), pz = qf.ld(o + 2);
+      const double x = qf.ld(o + 3), y = qf.ld(o + 4), z = qf.ld(o + 5), w = qf.ld(o + 6);
+      // Eigen toRotationMatrix on raw coefficients (no normalisation), as pinocchio's JointModelFreeFlyer::calc
+      const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+      const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x;
+      const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+      double Rq[9];
+      Rq[0] = 1 - (tyy + tzz); Rq[1] = txy - twz;       Rq[2] = txz + twy;
+      Rq[3] = txy + twz;       Rq[4] = 1 - (txx + tzz); Rq[5] = tyz - twx;
+      Rq[6] = txz - twy;       Rq[7] = tyz + twx;       Rq[8] = 1 - (txx + tyy);
+      mat3_mul(B, Rq, R);
+      pn[0] += B[0] * px + B[1] * py + B[2] * pz;
+      pn[1] += B[3] * px + B[4] * py + B[5] * pz;
+      pn[2] += B[6] * px + B[7] * py + B[8] * pz;
+      aw[0] = aw[1] = aw[2] = 0.0;
+    } break;
+    default:
+#pragma unroll
+      for (int k = 0; k < 9; ++k) R[k] = B[k];
+      aw[0] = aw[1] = aw[2] = 0.0;
+      break;
+  }
+  p[0] = pn[0]; p[1] = pn[1]; p[2] = pn[2];
+}
+
+RBD_HD bool is_prismatic(int t) { return t >= JT_PX && t <= JT_PU; }
+RBD_HD bool is_unbounded(int t) { return t >= JT_RUBX && t <= JT_RUBU; }
+
+// world-frame motion subspace column of a 1-dof joint: revolute [p x a ; a], prismatic [a ; 0]
+RBD_HD void subspace_1dof(int type, const double* p, const double* aw, double* A) {
+  if (is_prismatic(type)) {
+    A[0] = aw[0]; A[1] = aw[1]; A[2] = aw[2];
+    A[3] = A[4] = A[5] = 0.0;
+  } else {
+    RBD_CROSS(A[0], A[1], A[2], p[0], p[1], p[2], aw[0], aw[1], aw[2]);
+    A[3] = aw[0]; A[4] = aw[1]; A[5] = aw[2];
+  }
+}
+// column e (0..5) of the free-flyer subspace oMi.act(I6): e<3 -> [R e ; 0], e>=3 -> [p x R e ; R e]
+#define RBD_FF_COL(A, R, p, e)                                                        \
+  do {                                                                                \
+    const double cx_ = R[(e) % 3], cy_ = R[3 + (e) % 3], cz_ = R[6 + (e) % 3];        \
+    if ((e) < 3) {                                                                    \
+      A[0] = cx_; A[1] = cy_; A[2] = cz_; A[3] = A[4] = A[5] = 0.0;                   \
+    } else {                                                                          \
+      RBD_CROSS(A[0], A[1], A[2], p[0], p[1], p[2], cx_, cy_, cz_);                   \
+      A[3] = cx_; A[4] = cy_; A[5] = cz_;                                             \
+    }                                                                                 \
+  } while (0)
+
+// free-flyer rows of (column F): A_ff^T F = [R^T Fl ; R^T (Fw - p x Fl)]
+RBD_HD void ff_rows(const double* R, const double* p, const double* F, double* out6) {
+  double tx, ty, tz;
+  RBD_CROSS(tx, ty, tz, p[0], p[1], p[2], F[0], F[1], F[2]);
+  tx = F[3] - tx; ty = F[4] - ty; tz = F[5] - tz;
+#pragma unroll
+  for (int e = 0; e < 3; ++e) {
+    out6[e] = R[e] * F[0] + R[3 + e] * F[1] + R[6 + e] * F[2];
+    out6[3 + e] = R[e] * tx + R[3 + e] * ty + R[6 + e] * tz;
+  }
+}
+
+// world spatial inertia about the world origin: Y = (m, h = m c_w, I_O (xx,xy,yy,xz,yz,zz))
+RBD_HD void inertia_world(const DevJoint& jn, const double* R, const double* p, double* Y) {
+  const double m = jn.Y[0];
+  const double cx = R[0] * jn.Y[1] + R[1] * jn.Y[2] + R[2] * jn.Y[3] + p[0];
+  const double cy = R[3] * jn.Y[1] + R[4] * jn.Y[2] + R[5] * jn.Y[3] + p[1];
+  const double cz = R[6] * jn.Y[1] + R[7] * jn.Y[2] + R[8] * jn.Y[3] + p[2];
+  // T = R * Ic
+  const double ixx = jn.Y[4], ixy = jn.Y[5], iyy = jn.Y[6], ixz = jn.Y[7], iyz = jn.Y[8], izz = jn.Y[9];
+  double T[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    T[3 * i + 0] = R[3 * i] * ixx + R[3 * i + 1] * ixy + R[3 * i + 2] * ixz;
+    T[3 * i + 1] = R[3 * i] * ixy + R[3 * i + 1] * iyy + R[3 * i + 2] * iyz;
+    T[3 * i + 2] = R[3 * i] * ixz + R[3 * i + 1] * iyz + R[3 * i + 2] * izz;
+  }
+  const double mcx = m * cx, mcy = m * cy, mcz = m * cz;
+  Y[0] = m; Y[1] = mcx; Y[2] = mcy; Y[3] = mcz;
+  // I_O = R Ic R^T + m (|c|^2 I - c c^T)
+  Y[4] = T[0] * R[0] + T[1] * R[1] + T[2] * R[2] + (mcy * cy + mcz * cz);      // xx
+  Y[5] = T[0] * R[3] + T[1] * R[4] + T[2] * R[5] - mcx * cy;                   // xy
+  Y[6] = T[3] * R[3] + T[4] * R[4] + T[5] * R[5] + (mcx * cx + mcz * cz);      // yy
+  Y[7] = T[0] * R[6] + T[1] * R[7] + T[2] * R[8] - mcx * cz;                   // xz
+  Y[8] = T[3] * R[6] + T[4] * R[7] + T[5] * R[8] - mcy * cz;                   // yz
+  Y[9] = T[6] * R[6] + T[7] * R[7] + T[8] * R[8] + (mcx * cx + mcy * cy);      // zz
+}
+
+// F = Y * motion (both about the world origin): lin = m v + w x h ; ang = I_O w + h x v
+RBD_HD void inertia_mul(const double* Y, const double* mo, double* F) {
+  double ax, ay, az, bx, by, bz;
+  RBD_CROSS(ax, ay, az, mo[3], mo[4], mo[5], Y[1], Y[2], Y[3]);
+  RBD_CROSS(bx, by, bz, Y[1], Y[2], Y[3], mo[0], mo[1], mo[2]);
+  F[0] = Y[0] * mo[0] + ax;
+  F[1] = Y[0] * mo[1] + ay;
+  F[2] = Y[0] * mo[2] + az;
+  F[3] = Y[4] * mo[3] + Y[5] * mo[4] + Y[7] * mo[5] + bx;
+  F[4] = Y[5] * mo[3] + Y[6] * mo[4] + Y[8] * mo[5] + by;
+  F[5] = Y[7] * mo[3] + Y[8] * mo[4] + Y[9] * mo[5] + bz;
+}
+
+RBD_HD double dot6(const double* a, const double* b) {
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+}
+
+// Eigen 3.4 Quaternion(Matrix3) branch order (reference Conversions.h:60), output [x y z w] (Conversions.h:36)
+RBD_HD void rot_to_quat(const double* R, double* q) {
+  double t = R[0] + R[4] + R[8];
+  if (t > 0.0) {
+    t = sqrt(t + 1.0);
+    q[3] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (R[7] - R[5]) * t; q[1] = (R[2] - R[6]) * t; q[2] = (R[3] - R[1]) * t;
+  } else {
+    // i = argmax diag with Eigen's tie order; written branch-wise to keep R in registers
+    if (!(R[4] > R[0]) && !(R[8] > R[0])) {        // i=0, j=1, k=2
+      t = sqrt(R[0] - R[4] - R[8] + 1.0);
+      q[0] = 0.5 * t; t = 0.5 / t;
+      q[3] = (R[7] - R[5]) * t; q[1] = (R[3] + R[1]) * t; q[2] = (R[6] + R[2]) * t;
+    } else if ((R[4] > R[0]) && !(R[8] > R[4])) {  // i=1, j=2, k=0
+      t = sqrt(R[4] - R[8] - R[0] + 1.0);
+      q[1] = 0.5 * t; t = 0.5 / t;
+      q[3] = (R[2] - R[6]) * t; q[2] = (R[7] + R[5]) * t; q[0] = (R[1] + R[3]) * t;
+    } else {                                       // i=2, j=0, k=1
+      t = sqrt(R[8] - R[0] - R[4] + 1.0);
+      q[2] = 0.5 * t; t = 0.5 / t;
+      q[3] = (R[3] - R[1]) * t; q[0] = (R[2] + R[6]) * t; q[1] = (R[5] + R[7]) * t;
+    }
+  }
+}
+
+// =========================================================================================================
+// Fused evaluation: FK + world joint Jacobian (+ CRBA) (+ RNEA)                      [kernel K7 / K5 / K6]
+// =========================================================================================================
+struct EvalIO {
+  Field q, v, a;          // inputs: nq, nv, nv fields
+  Field oMi, J, M, tau;   // outputs (p == nullptr -> not written)
+};
+
+// backward step of joint k: tau_k = A_k^T f_k ; column(s) of M ; accumulate into the parent's slot
+template <bool DO_M, bool DO_TAU>
+RBD_HD void eval_pop(const DevModel& m, int k, const Stack& S, const EvalIO& io) {
+  constexpr int L = DO_M ? 0 : 1;
+  const DevJoint& jn = m.joint[k];
+  const int s = jn.slot[L];
+  const int aw_ = RBD_SLOT_A(jn.type);
+  const int sf = s + aw_, sy = s + aw_ + 6;
+  double f[6], Y[10];
+  if (DO_TAU) {
+#pragma unroll
+    for (int e = 0; e < 6; ++e) f[e] = S.ld(sf + e);
+  }
+  if (DO_M) {
+#pragma unroll
+    for (int e = 0; e < 10; ++e) Y[e] = S.ld(sy + e);
+  }
+  const int par = jn.parent;
+  if (jn.type != JT_FF) {
+    double A[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) A[e] = S.ld(s + e);
+    if (DO_TAU) io.tau.st(jn.idx_v, dot6(A, f));
+    if (DO_M) {
+      double F[6];
+      inertia_mul(Y, A, F);
+      const int col = jn.idx_v;
+      const int base = col * (col + 1) / 2;
+      int next = col + 1;  // rows >= next of this column are done
+      for (int anc = k; anc != 0; anc = m.joint[anc].parent) {
+        const DevJoint& ja = m.joint[anc];
+        const int iv = ja.idx_v;
+        for (int r = iv + ja.nv; r < next; ++r) io.M.st(base + r, 0.0);  // joints off the ancestor chain
+        const int sa = ja.slot[L];
+        if (ja.type == JT_FF) {
+          double Rp[12], o6[6];
+#pragma unroll
+          for (int e = 0; e < 12; ++e) Rp[e] = S.ld(sa + e);
+          ff_rows(Rp, Rp + 9, F, o6);
+#pragma unroll
+          for (int e = 0; e < 6; ++e) io.M.st(base + iv + e, o6[e]);
+        } else {
+          double Aa[6];
+#pragma unroll
+          for (int e = 0; e < 6; ++e) Aa[e] = S.ld(sa + e);
+          io.M.st(base + iv, dot6(Aa, F));
+        }
+        next = iv;
+      }
+      for (int r = 0; r < next; ++r) io.M.st(base + r, 0.0);
+    }
+  } else {
+    double Rp[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) Rp[e] = S.ld(s + e);
+#pragma unroll
+    for (int cc = 0; cc < 6; ++cc) {
+      double A[6];
+      RBD_FF_COL(A, Rp, (Rp + 9), cc);
+      if (DO_TAU) io.tau.st(jn.idx_v + cc, dot6(A, f));
+      if (DO_M) {
+        double F[6], o6[6];
+        inertia_mul(Y, A, F);
+        const int col = jn.idx_v + cc;
+        const int base = col * (col + 1) / 2;
+        ff_rows(Rp, Rp + 9, F, o6);
+#pragma unroll
+        for (int e = 0; e < 6; ++e)
+          if (e <= cc) io.M.st(base + jn.idx_v + e, o6[e]);
+        int next = jn.idx_v;
+        for (int anc = par; anc != 0; anc = m.joint[anc].parent) {
+          const DevJoint& ja = m.joint[anc];
+          const int iv = ja.idx_v;
+          for (int r = iv + ja.nv; r < next; ++r) io.M.st(base + r, 0.0);
+          const int sa = ja.slot[L];
+          if (ja.type == JT_FF) {
+            double Rq[12], p6[6];
+#pragma unroll
+            for (int e = 0; e < 12; ++e) Rq[e] = S.ld(sa + e);
+            ff_rows(Rq, Rq + 9, F, p6);
+#pragma unroll
+            for (int e = 0; e < 6; ++e) io.M.st(base + iv + e, p6[e]);
+          } else {
+            double Aa[6];
+#pragma unroll
+            for (int e = 0; e < 6; ++e) Aa[e] = S.ld(sa + e);
+            io.M.st(base + iv, dot6(Aa, F));
+          }
+          next = iv;
+        }
+        for (int r = 0; r < next; ++r) io.M.st(base + r, 0.0);
+      }
+    }
+  }
+  if (par != 0) {
+    const DevJoint& jp = m.joint[par];
+    const int sp = jp.slot[L] + RBD_SLOT_A(jp.type);
+    if (DO_TAU) {
+#pragma unroll
+      for (int e = 0; e < 6; ++e) S.add(sp + e, f[e]);
+    }
+    if (DO_M) {
+#pragma unroll
+      for (int e = 0; e < 10; ++e) S.add(sp + 6 + e, Y[e]);
+    }
+  }
+}
+
+template <bool DO_M, bool DO_TAU>
+RBD_HD void eval_instance(const DevModel& m, const EvalIO& io, const Stack& S) {
+  constexpr int L = DO_M ? 0 : 1;
+  constexpr bool NEED_STACK = DO_M || DO_TAU;
+  const int nj = m.njoints;
+  const int bbase = NEED_STACK ? m.slot_total[L] : 0;
+  constexpr int BW = DO_TAU ? RBD_BRANCH_EVAL : RBD_BRANCH_FK;
+  double R[9], p[3], vel[6], acc[6];
+#define RBD_RESET_ROOT()                                                   \
+  do {                                                                     \
+    R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1; \
+    p[0] = p[1] = p[2] = 0;                                                \
+    _Pragma("unroll") for (int e_ = 0; e_ < 6; ++e_) { vel[e_] = 0; acc[e_] = 0; } \
+    acc[0] = -m.gravity[0]; acc[1] = -m.gravity[1]; acc[2] = -m.gravity[2]; \
+  } while (0)
+  RBD_RESET_ROOT();
+
+  // one-joint-ahead prefetch of the 1-dof inputs (hides the global-load latency behind the previous joint)
+  double q0n = 0, q1n = 0, vn = 0, an = 0;
+  if (nj > 1 && m.joint[1].type != JT_FF) {
+    const DevJoint& j1 = m.joint[1];
+    q0n = io.q.ld(j1.idx_q);
+    if (is_unbounded(j1.type)) q1n = io.q.ld(j1.idx_q + 1);
+    if (DO_TAU) { vn = io.v.ld(j1.idx_v); an = io.a.ld(j1.idx_v); }
+  }
+
+  for (int i = 1; i < nj; ++i) {
+    const DevJoint& jn = m.joint[i];
+    const int par = jn.parent;
+    if (par != i - 1) {
+      // the sweep leaves the subtree(s) that ended at joint i-1: finish them bottom-up, then resume at `par`
+      if (NEED_STACK)
+        for (int k = i - 1; k != par; k = m.joint[k].parent) eval_pop<DO_M, DO_TAU>(m, k, S, io);
+      if (par == 0) {
+        RBD_RESET_ROOT();
+      } else {
+        const int b = bbase + m.joint[par].bidx * BW;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) R[e] = S.ld(b + e);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) p[e] = S.ld(b + 9 + e);
+        if (DO_TAU) {
+#pragma unroll
+          for (int e = 0; e < 6; ++e) { vel[e] = S.ld(b + 12 + e); acc[e] = S.ld(b + 18 + e); }
+        }
+      }
+    }
+    const double q0 = q0n, q1 = q1n, qd = vn, qdd = an;
+    if (i + 1 < nj && m.joint[i + 1].type != JT_FF) {
+      const DevJoint& jx = m.joint[i + 1];
+      q0n = io.q.ld(jx.idx_q);
+      if (is_unbounded(jx.type)) q1n = io.q.ld(jx.idx_q + 1);
+      if (DO_TAU) { vn = io.v.ld(jx.idx_v); an = io.a.ld(jx.idx_v); }
+    }
+
+    double aw[3];
+    fk_joint(jn, R, p, q0, q1, io.q, aw);
+    if (io.oMi.ok()) {
+      const int o = 12 * (i - 1);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) io.oMi.st(o + e, R[e]);
+#pragma unroll
+      for (int e = 0; e < 3; ++e) io.oMi.st(o + 9 + e, p[e]);
+    }
+    const int s = NEED_STACK ? jn.slot[L] : 0;
+    const int aw_ = RBD_SLOT_A(jn.type);
+    if (jn.type != JT_FF) {
+      double A[6];
+      subspace_1dof(jn.type, p, aw, A);
+      if (io.J.ok()) {
+#pragma unroll
+        for (int e = 0; e < 6; ++e) io.J.st(6 * jn.idx_v + e, A[e]);
+      }
+      if (NEED_STACK) {
+#pragma unroll
+        for (int e = 0; e < 6; ++e) S.st(s + e, A[e]);
+      }
+      if (DO_TAU) {
+        double vj[6], cr[6];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) { vj[e] = A[e] * qd; vel[e] += vj[e]; }
+        // a_i = a_parent + A qdd + v_i x vJ   (joint bias c = 0 for all supported joints)
+        RBD_CROSS(cr[0], cr[1], cr[2], vel[3], vel[4], vel[5], vj[0], vj[1], vj[2]);
+        double tx, ty, tz;
+        RBD_CROSS(tx, ty, tz, vel[0], vel[1], vel[2], vj[3], vj[4], vj[5]);
+        cr[0] += tx; cr[1] += ty; cr[2] += tz;
+        RBD_CROSS(cr[3], cr[4], cr[5], vel[3], vel[4], vel[5], vj[3], vj[4], vj[5]);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) acc[e] += A[e] * qdd + cr[e];
+      }
+    } else {
+      if (io.J.ok()) {
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) {
+          double A[6];
+          RBD_FF_COL(A, R, p, cc);
+#pragma unroll
+          for (int e = 0; e < 6; ++e) io.J.st(6 * (jn.idx_v + cc) + e, A[e]);
+        }
+      }
+      if (NEED_STACK) {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) S.st(s + e, R[e]);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) S.st(s + 9 + e, p[e]);
+      }
+      if (DO_TAU) {
+        // joint velocity / acceleration given in the joint (body) frame: world = oMi.act(.)
+        double vj[6], aj[6], cr[6];
+        {
+          const int o = jn.idx_v;
+          const double l0 = io.v.ld(o), l1 = io.v.ld(o + 1), l2 = io.v.ld(o + 2);
+          const double w0 = io.v.ld(o + 3), w1 = io.v.ld(o + 4), w2 = io.v.ld(o + 5);
+          vj[3] = R[0] * w0 + R[1] * w1 + R[2] * w2;
+          vj[4] = R[3] * w0 + R[4] * w1 + R[5] * w2;
+          vj[5] = R[6] * w0 + R[7] * w1 + R[8] * w2;
+          double tx, ty, tz;
+          RBD_CROSS(tx, ty, tz, p[0], p[1], p[2], vj[3], vj[4], vj[5]);
+          vj[0] = R[0] * l0 + R[1] * l1 + R[2] * l2 + tx;
+          vj[1] = R[3] * l0 + R[4] * l1 + R[5] * l2 + ty;
+          vj[2] = R[6] * l0 + R[7] * l1 + R[8] * l2 + tz;
+        }
+        {
+          const int o = jn.idx_v;
+          const double l0 = io.a.ld(o), l1 = io.a.ld(o + 1), l2 = io.a.ld(o + 2);
+          const double w0 = io.a.ld(o + 3), w1 = io.a.ld(o + 4), w2 = io.a.ld(o + 5);
+          aj[3] = R[0] * w0 + R[1] * w1 + R[2] * w2;
+          aj[4] = R[3] * w0 + R[4] * w1 + R[5] * w2;
+          aj[5] = R[6] * w0 + R[7] * w1 + R[8] * w2;
+          double tx, ty, tz;
+          RBD_CROSS(tx, ty, tz, p[0], p[1], p[2], aj[3], aj[4], aj[5]);
+          aj[0] = R[0] * l0 + R[1] * l1 + R[2] * l2 + tx;
+          aj[1] = R[3] * l0 + R[4] * l1 + R[5] * l2 + ty;
+          aj[2] = R[6] * l0 + R[7] * l1 + R[8] * l2 + tz;
+        }
+#pragma unroll
+        for (int e = 0; e < 6; ++e) vel[e] += vj[e];
+        RBD_CROSS(cr[0], cr[1], cr[2], vel[3], vel[4], vel[5], vj[0], vj[1], vj[2]);
+        double tx, ty, tz;
+        RBD_CROSS(tx, ty, tz, vel[0], vel[1], vel[2], vj[3], vj[4], vj[5]);
+        cr[0] += tx; cr[1] += ty; cr[2] += tz;
+        RBD_CROSS(cr[3], cr[4], cr[5], vel[3], vel[4], vel[5], vj[3], vj[4], vj[5]);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) acc[e] += aj[e] + cr[e];
+      }
+    }
+    if (NEED_STACK) {
+      double Y[10];
+      inertia_world(jn, R, p, Y);
+      if (DO_TAU) {
+        // f = Y a + v x* (Y v)
+        double h[6], f[6];
+        inertia_mul(Y, vel, h);
+        inertia_mul(Y, acc, f);
+        double tx, ty, tz;
+        RBD_CROSS(tx, ty, tz, vel[3], vel[4], vel[5], h[0], h[1], h[2]);
+        f[0] += tx; f[1] += ty; f[2] += tz;
+        RBD_CROSS(tx, ty, tz, vel[3], vel[4], vel[5], h[3], h[4], h[5]);
+        f[3] += tx; f[4] += ty; f[5] += tz;
+        RBD_CROSS(tx, ty, tz, vel[0], vel[1], vel[2], h[0], h[1], h[2]);
+        f[3] += tx; f[4] += ty; f[5] += tz;
+#pragma unroll
+        for (int e = 0; e < 6; ++e) S.st(s + aw_ + e, f[e]);
+      }
+      if (DO_M) {
+#pragma unroll
+        for (int e = 0; e < 10; ++e) S.st(s + aw_ + 6 + e, Y[e]);
+      }
+    }
+    if (jn.nchild >= 2) {
+      const int b = bbase + jn.bidx * BW;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) S.st(b + e, R[e]);
+#pragma unroll
+      for (int e = 0; e < 3; ++e) S.st(b + 9 + e, p[e]);
+      if (DO_TAU) {
+#pragma unroll
+        for (int e = 0; e < 6; ++e) { S.st(b + 12 + e, vel[e]); S.st(b + 18 + e, acc[e]); }
+      }
+    }
+  }
+  if (NEED_STACK)
+    for (int k = nj - 1; k > 0; k = m.joint[k].parent) eval_pop<DO_M, DO_TAU>(m, k, S, io);
+#undef RBD_RESET_ROOT
+}
+
+// =========================================================================================================
+// Mapping path
+// =========================================================================================================
+// Full configuration seen through the SOFA split (root pose | joint dofs): KCM.inl:353-363.
+struct SplitQ {
+  Field root, joints;
+  int off;  // 7 (or 6 for velocities) when a root is supplied, else 0
+  RBD_HD double ld(int k) const { return k < off ? root.ld(k) : joints.ld(k - off); }
+};
+
+// apply: q -> [p, quat] of every mapped output; also copies the assembled q into the workspace cache.
+template <class QF>
+RBD_HD void apply_instance(const DevModel& m, const DevTables& tb, const QF& q, const Field& qcache,
+                           const Field& out, const Stack& S) {
+  const int nj = m.njoints;
+  if (qcache.ok())
+    for (int k = 0; k < m.nq; ++k) qcache.st(k, q.ld(k));
+  // outputs attached to the universe (kSkipUniverse = 0, reference Types.h:32): constant poses
+  {
+    const DevJoint& j0 = m.joint[0];
+    for (int o = j0.out_begin; o < j0.out_end; ++o) {
+      const double* pl = tb.sorted_pl + 12 * o;
+      const int k = tb.sorted_k[o];
+      double qt[4];
+      rot_to_quat(pl, qt);
+      out.st(7 * k + 0, pl[9]); out.st(7 * k + 1, pl[10]); out.st(7 * k + 2, pl[11]);
+      out.st(7 * k + 3, qt[0]); out.st(7 * k + 4, qt[1]); out.st(7 * k + 5, qt[2]); out.st(7 * k + 6, qt[3]);
+    }
+  }
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
+  for (int i = 1; i < nj; ++i) {
+    const DevJoint& jn = m.joint[i];
+    const int par = jn.parent;
+    if (par != i - 1) {
+      if (par == 0) {
+        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+        p[0] = p[1] = p[2] = 0;
+      } else {
+        const int b = m.joint[par].bidx * RBD_BRANCH_FK;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) R[e] = S.ld(b + e);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) p[e] = S.ld(b + 9 + e);
+      }
+    }
+    double aw[3];
+    const double q0 = jn.type == JT_FF ? 0.0 : q.ld(jn.idx_q);
+    const double q1 = is_unbounded(jn.type) ? q.ld(jn.idx_q + 1) : 0.0;
+    fk_joint(jn, R, p, q0, q1, q, aw);
+    for (int o = jn.out_begin; o < jn.out_end; ++o) {
+      // updateFramePlacements: oMf = oMi * placement (KCM.inl:375), then se3ToSofaType (KCM.inl:385,394)
+      const double* pl = tb.sorted_pl + 12 * o;
+      const int k = tb.sorted_k[o];
+      double Rf[9], qt[4];
+      mat3_mul(R, pl, Rf);
+      const double px = R[0] * pl[9] + R[1] * pl[10] + R[2] * pl[11] + p[0];
+      const double py = R[3] * pl[9] + R[4] * pl[10] + R[5] * pl[11] + p[1];
+      const double pz = R[6] * pl[9] + R[7] * pl[10] + R[8] * pl[11] + p[2];
+      rot_to_quat(Rf, qt);
+      out.st(7 * k + 0, px); out.st(7 * k + 1, py); out.st(7 * k + 2, pz);
+      out.st(7 * k + 3, qt[0]); out.st(7 * k + 4, qt[1]); out.st(7 * k + 5, qt[2]); out.st(7 * k + 6, qt[3]);
+    }
+    if (jn.nchild >= 2) {
+      const int b = jn.bidx * RBD_BRANCH_FK;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) S.st(b + e, R[e]);
+#pragma unroll
+      for (int e = 0; e < 3; ++e) S.st(b + 9 + e, p[e]);
+    }
+  }
+}
+
+// applyJ: out_k = J_k(LWA) dq, matrix-free: world twists V_i = V_parent + A_i dq_i, then
+// out_k = [V_lin + V_ang x p_k ; V_ang]  (== [J_lin - p_k x J_ang ; J_ang] dq, getFrameJacobian LWA)
+template <class DQ>
+RBD_HD void applyJ_instance(const DevModel& m, const DevTables& tb, const Field& q, const DQ& dq, const Field& out,
+                            const Stack& S) {
+  const int nj = m.njoints;
+  {
+    const DevJoint& j0 = m.joint[0];
+    for (int o = j0.out_begin; o < j0.out_end; ++o) {
+      const int k = tb.sorted_k[o];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) out.st(6 * k + e, 0.0);  // universe: empty support -> zero Jacobian
+    }
+  }
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0}, V[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 1; i < nj; ++i) {
+    const DevJoint& jn = m.joint[i];
+    const int par = jn.parent;
+    if (par != i - 1) {
+      if (par == 0) {
+        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+        p[0] = p[1] = p[2] = 0;
+#pragma unroll
+        for (int e = 0; e < 6; ++e) V[e] = 0;
+      } else {
+        const int b = m.joint[par].bidx * RBD_BRANCH_J;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) R[e] = S.ld(b + e);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) p[e] = S.ld(b + 9 + e);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) V[e] = S.ld(b + 12 + e);
+      }
+    }
+    double aw[3];
+    const double q0 = jn.type == JT_FF ? 0.0 : q.ld(jn.idx_q);
+    const double q1 = is_unbounded(jn.type) ? q.ld(jn.idx_q + 1) : 0.0;
+    fk_joint(jn, R, p, q0, q1, q, aw);
+    if (jn.type != JT_FF) {
+      double A[6];
+      subspace_1dof(jn.type, p, aw, A);
+      const double d = dq.ld(jn.idx_v);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) V[e] += A[e] * d;
+    } else {
+      const int o = jn.idx_v;
+      const double l0 = dq.ld(o), l1 = dq.ld(o + 1), l2 = dq.ld(o + 2);
+      const double w0 = dq.ld(o + 3), w1 = dq.ld(o + 4), w2 = dq.ld(o + 5);
+      const double wx = R[0] * w0 + R[1] * w1 + R[2] * w2;
+      const double wy = R[3] * w0 + R[4] * w1 + R[5] * w2;
+      const double wz = R[6] * w0 + R[7] * w1 + R[8] * w2;
+      double tx, ty, tz;
+      RBD_CROSS(tx, ty, tz, p[0], p[1], p[2], wx, wy, wz);
+      V[0] += R[0] * l0 + R[1] * l1 + R[2] * l2 + tx;
+      V[1] += R[3] * l0 + R[4] * l1 + R[5] * l2 + ty;
+      V[2] += R[6] * l0 + R[7] * l1 + R[8] * l2 + tz;
+      V[3] += wx; V[4] += wy; V[5] += wz;
+    }
+    for (int o = jn.out_begin; o < jn.out_end; ++o) {
+      const double* pl = tb.sorted_pl + 12 * o;
+      const int k = tb.sorted_k[o];
+      const double px = R[0] * pl[9] + R[1] * pl[10] + R[2] * pl[11] + p[0];
+      const double py = R[3] * pl[9] + R[4] * pl[10] + R[5] * pl[11] + p[1];
+      const double pz = R[6] * pl[9] + R[7] * pl[10] + R[8] * pl[11] + p[2];
+      double tx, ty, tz;
+      RBD_CROSS(tx, ty, tz, V[3], V[4], V[5], px, py, pz);
+      out.st(6 * k + 0, V[0] + tx); out.st(6 * k + 1, V[1] + ty); out.st(6 * k + 2, V[2] + tz);
+      out.st(6 * k + 3, V[3]); out.st(6 * k + 4, V[4]); out.st(6 * k + 5, V[5]);
+    }
+    if (jn.nchild >= 2) {
+      const int b = jn.bidx * RBD_BRANCH_J;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) S.st(b + e, R[e]);
+#pragma unroll
+      for (int e = 0; e < 3; ++e) S.st(b + 9 + e, p[e]);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) S.st(b + 12 + e, V[e]);
+    }
+  }
+}
+
+// applyJT, matrix-free: every wrench w_k = [f; n] given at output k (world-aligned axes) is moved to the
+// world origin, [f ; n + p_k x f], summed per joint, accumulated leaf->root, and projected: tau_i = A_i^T F_i.
+// `Src::gather(i, begin, end, R, p, F)` adds the wrenches attached to joint i; `Sink::put(c, value)` receives
+// the generalized force of velocity index c.
+template <class Src, class Sink>
+RBD_HD void applyJT_instance(const DevModel& m, const DevTables& tb, const Field& q, const Src& src, const Sink& sink,
+                             const Stack& S) {
+  const int nj = m.njoints;
+  const int bbase = m.slot_total[1];
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
+  auto pop = [&](int k) {
+    const DevJoint& jn = m.joint[k];
+    const int s = jn.slot[1];
+    const int aw_ = RBD_SLOT_A(jn.type);
+    double F[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) F[e] = S.ld(s + aw_ + e);
+    if (jn.type != JT_FF) {
+      double A[6];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) A[e] = S.ld(s + e);
+      sink.put(jn.idx_v, dot6(A, F));
+    } else {
+      double Rp[12], o6[6];
+#pragma unroll
+      for (int e = 0; e < 12; ++e) Rp[e] = S.ld(s + e);
+      ff_rows(Rp, Rp + 9, F, o6);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) sink.put(jn.idx_v + e, o6[e]);
+    }
+    if (jn.parent != 0) {
+      const DevJoint& jp = m.joint[jn.parent];
+      const int sp = jp.slot[1] + RBD_SLOT_A(jp.type);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) S.add(sp + e, F[e]);
+    }
+  };
+  for (int i = 1; i < nj; ++i) {
+    const DevJoint& jn = m.joint[i];
+    const int par = jn.parent;
+    if (par != i - 1) {
+      for (int k = i - 1; k != par; k = m.joint[k].parent) pop(k);
+      if (par == 0) {
+        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+        p[0] = p[1] = p[2] = 0;
+      } else {
+        const int b = bbase + m.joint[par].bidx * RBD_BRANCH_FK;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) R[e] = S.ld(b + e);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) p[e] = S.ld(b + 9 + e);
+      }
+    }
+    double aw[3];
+    const double q0 = jn.type == JT_FF ? 0.0 : q.ld(jn.idx_q);
+    const double q1 = is_unbounded(jn.type) ? q.ld(jn.idx_q + 1) : 0.0;
+    fk_joint(jn, R, p, q0, q1, q, aw);
+    const int s = jn.slot[1];
+    const int aw_ = RBD_SLOT_A(jn.type);
+    if (jn.type != JT_FF) {
+      double A[6];
+      subspace_1dof(jn.type, p, aw, A);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) S.st(s + e, A[e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) S.st(s + e, R[e]);
+#pragma unroll
+      for (int e = 0; e < 3; ++e) S.st(s + 9 + e, p[e]);
+    }
+    double F[6] = {0, 0, 0, 0, 0, 0};
+    src.gather(i, jn.out_begin, jn.out_end, R, p, F);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) S.st(s + aw_ + e, F[e]);
+    if (jn.nchild >= 2) {
+      const int b = bbase + jn.bidx * RBD_BRANCH_FK;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) S.st(b + e, R[e]);
+#pragma unroll
+      for (int e = 0; e < 3; ++e) S.st(b + 9 + e, p[e]);
+    }
+  }
+  for (int k = nj - 1; k > 0; k = m.joint[k].parent) pop(k);
+}
+
+// add wrench w (at point pf = R pl_p + p, world-aligned axes) moved to the world origin
+RBD_HD void add_shifted_wrench(const double* R, const double* p, const double* pl, const double* w, double* F) {
+  const double px = R[0] * pl[9] + R[1] * pl[10] + R[2] * pl[11] + p[0];
+  const double py = R[3] * pl[9] + R[4] * pl[10] + R[5] * pl[11] + p[1];
+  const double pz = R[6] * pl[9] + R[7] * pl[10] + R[8] * pl[11] + p[2];
+  double tx, ty, tz;
+  RBD_CROSS(tx, ty, tz, px, py, pz, w[0], w[1], w[2]);
+  F[0] += w[0]; F[1] += w[1]; F[2] += w[2];
+  F[3] += w[3] + tx; F[4] += w[4] + ty; F[5] += w[5] + tz;
+}
+
+// dense wrench source: one wrench per mapped output (KCM.inl:472-492)
+struct DenseWrenchSrc {
+  Field in;  // n_out*6 fields
+  const DevTables* tb;
+  RBD_HD void gather(int, int begin, int end, const double* R, const double* p, double* F) const {
+    for (int o = begin; o < end; ++o) {
+      const int k = tb->sorted_k[o];
+      double w[6];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) w[e] = in.ld(6 * k + e);
+      add_shifted_wrench(R, p, tb->sorted_pl + 12 * o, w, F);
+    }
+  }
+};
+// sparse wrench source: the non-zeros of one constraint row (KCM.inl:558-583)
+struct RowWrenchSrc {
+  const int* col;     // [nnz] mapped-output index
+  const double* val;  // [nnz][6]
+  int nnz;
+  const DevTables* tb;
+  RBD_HD void gather(int joint, int, int, const double* R, const double* p, double* F) const {
+    for (int j = 0; j < nnz; ++j) {
+      const int k = col[j];
+      if (tb->outk_parent[k] == joint) add_shifted_wrench(R, p, tb->outk_pl + 12 * k, val + 6 * j, F);
+    }
+  }
+};
+// += into SOFA's split outputs (root wrench | joint torques): KCM.inl:494-512
+struct SplitAccumSink {
+  Field root, joints;
+  int off;
+  RBD_HD void put(int c, double v) const {
+    if (c < off) {
+      if (root.ok()) root.st(c, root.ld(c) + v);
+    } else {
+      joints.st(c - off, joints.ld(c - off) + v);
+    }
+  }
+};
+// dense row + squared norm (KCM.inl:585-615)
+struct RowSink {
+  double* row;
+  double* n2;
+  RBD_HD void put(int c, double v) const { row[c] = v; *n2 += v * v; }
+};
+
+}  // namespace rbd

@@ -1,0 +1,136 @@
+// emul.cpp — CPU harness around the kernel bodies in sofa/rigidbodydynamics_b200/csrc/rbd_sweeps.h.
+// TEST INFRASTRUCTURE ONLY: lets `pytest -m "not gpu"` exercise the exact per-thread code the sm_100a kernels
+// run (same templates, same stack/branch-slot layout, same tiled addressing), with shared memory emulated by a
+// heap array.  It is never loaded by the product and is not a fallback.
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../sofa/rigidbodydynamics_b200/csrc/rbd_model_build.h"
+#include "../../sofa/rigidbodydynamics_b200/csrc/rbd_sweeps.h"
+
+using namespace rbd;
+
+static std::string g_err;
+extern "C" const char* emul_last_error() { return g_err.c_str(); }
+
+struct Ctx {
+  DevModel m;
+  HostTables ht;
+  DevTables tb;
+};
+static int make_ctx(const rbd_model_desc* d, Ctx* c) {
+  int rc = build_dev_model(d, &c->m, &c->ht, &g_err);
+  if (rc) return rc;
+  c->tb.sorted_k = c->ht.sorted_k.data(); c->tb.sorted_pl = c->ht.sorted_pl.data();
+  c->tb.outk_parent = c->ht.outk_parent.data(); c->tb.outk_pl = c->ht.outk_pl.data();
+  return 0;
+}
+
+extern "C" int emul_model_info(const rbd_model_desc* d, int* out /*[8]*/) {
+  Ctx c;
+  int rc = make_ctx(d, &c);
+  if (rc) return rc;
+  out[0] = c.m.max_depth; out[1] = c.m.nbranch; out[2] = c.m.slot_total[0]; out[3] = c.m.slot_total[1];
+  out[4] = smem_eval(c.m, true, true); out[5] = smem_eval(c.m, false, true); out[6] = smem_applyJT(c.m);
+  out[7] = c.m.has_ff_root;
+  return 0;
+}
+
+extern "C" int emul_eval(const rbd_model_desc* d, long long n, long long tile, int block, double* q, double* v,
+                         double* a, double* oMi, double* J, double* M, double* tau) {
+  Ctx c;
+  int rc = make_ctx(d, &c);
+  if (rc) return rc;
+  const bool do_m = M != nullptr, do_tau = tau != nullptr;
+  const int sd = smem_eval(c.m, do_m, do_tau);
+  std::vector<double> smem((size_t)(sd > 0 ? sd : 1) * block, 1e300);  // poison: reads before writes show up
+  for (long long b0 = 0; b0 < n; b0 += block)
+    for (int t = 0; t < block && b0 + t < n; ++t) {
+      const long long i = b0 + t;
+      EvalIO io;
+      io.q = make_field(q, i, c.m.nq, tile); io.v = make_field(v, i, c.m.nv, tile); io.a = make_field(a, i, c.m.nv, tile);
+      io.oMi = make_field(oMi, i, 12 * (c.m.njoints - 1), tile); io.J = make_field(J, i, 6 * c.m.nv, tile);
+      io.M = make_field(M, i, c.m.nv * (c.m.nv + 1) / 2, tile); io.tau = make_field(tau, i, c.m.nv, tile);
+      Stack S{smem.data() + t, block};
+      if (do_m && do_tau) eval_instance<true, true>(c.m, io, S);
+      else if (do_m) eval_instance<true, false>(c.m, io, S);
+      else if (do_tau) eval_instance<false, true>(c.m, io, S);
+      else eval_instance<false, false>(c.m, io, S);
+    }
+  return 0;
+}
+
+extern "C" int emul_apply(const rbd_model_desc* d, long long n, long long tile, int block, double* q_joints,
+                          double* root, double* qcache, long long cache_tile, double* out) {
+  Ctx c;
+  int rc = make_ctx(d, &c);
+  if (rc) return rc;
+  const int sd = smem_apply(c.m);
+  std::vector<double> smem((size_t)(sd > 0 ? sd : 1) * block, 1e300);
+  const int off = (c.m.has_ff_root && root) ? 7 : 0;
+  for (long long i = 0; i < n; ++i) {
+    const int t = (int)(i % block);
+    SplitQ sq{make_field(root, i, 7, tile), make_field(q_joints, i, c.m.nq - off, tile), off};
+    Stack S{smem.data() + t, block};
+    apply_instance(c.m, c.tb, sq, make_field(qcache, i, c.m.nq, cache_tile), make_field(out, i, 7 * c.m.n_out, tile), S);
+  }
+  return 0;
+}
+
+extern "C" int emul_applyJ(const rbd_model_desc* d, long long n, long long tile, int block, double* qcache,
+                           long long cache_tile, double* dq_joints, double* root_vel, double* out) {
+  Ctx c;
+  int rc = make_ctx(d, &c);
+  if (rc) return rc;
+  const int sd = smem_applyJ(c.m);
+  std::vector<double> smem((size_t)(sd > 0 ? sd : 1) * block, 1e300);
+  const int off = (c.m.has_ff_root && root_vel) ? 6 : 0;
+  for (long long i = 0; i < n; ++i) {
+    const int t = (int)(i % block);
+    SplitQ dq{make_field(root_vel, i, 6, tile), make_field(dq_joints, i, c.m.nv - off, tile), off};
+    Stack S{smem.data() + t, block};
+    applyJ_instance(c.m, c.tb, make_field(qcache, i, c.m.nq, cache_tile), dq, make_field(out, i, 6 * c.m.n_out, tile), S);
+  }
+  return 0;
+}
+
+extern "C" int emul_applyJT(const rbd_model_desc* d, long long n, long long tile, int block, double* qcache,
+                            long long cache_tile, double* in, double* out_tau, double* out_root) {
+  Ctx c;
+  int rc = make_ctx(d, &c);
+  if (rc) return rc;
+  const int sd = smem_applyJT(c.m);
+  std::vector<double> smem((size_t)(sd > 0 ? sd : 1) * block, 1e300);
+  const int off = (c.m.has_ff_root && out_root) ? 6 : 0;
+  for (long long i = 0; i < n; ++i) {
+    const int t = (int)(i % block);
+    DenseWrenchSrc src{make_field(in, i, 6 * c.m.n_out, tile), &c.tb};
+    SplitAccumSink sink{make_field(out_root, i, 6, tile), make_field(out_tau, i, c.m.nv - off, tile), off};
+    Stack S{smem.data() + t, block};
+    applyJT_instance(c.m, c.tb, make_field(qcache, i, c.m.nq, cache_tile), src, sink, S);
+  }
+  return 0;
+}
+
+extern "C" int emul_applyJT_rows(const rbd_model_desc* d, long long nrows, int block, double* qcache,
+                                 long long cache_tile, const int* row_ptr, const int* row_instance, const int* col,
+                                 const double* val, double* out_rows, int* keep) {
+  Ctx c;
+  int rc = make_ctx(d, &c);
+  if (rc) return rc;
+  const int sd = smem_applyJT(c.m);
+  std::vector<double> smem((size_t)(sd > 0 ? sd : 1) * block, 1e300);
+  for (long long r = 0; r < nrows; ++r) {
+    const int t = (int)(r % block);
+    double n2 = 0.0;
+    RowWrenchSrc src{col + row_ptr[r], val + 6 * (size_t)row_ptr[r], row_ptr[r + 1] - row_ptr[r], &c.tb};
+    RowSink sink{out_rows + (size_t)r * c.m.nv, &n2};
+    Stack S{smem.data() + t, block};
+    applyJT_instance(c.m, c.tb, make_field(qcache, row_instance[r], c.m.nq, cache_tile), src, sink, S);
+    keep[r] = n2 > 1e-12 ? 1 : 0;
+  }
+  return 0;
+}
