@@ -16,10 +16,32 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librbd_oracle.so")
 
 
+def _host_id() -> str:
+    """The oracle is compiled with -march=native: rebuild when the snapshot lands on a different host CPU."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    import hashlib
+                    return hashlib.sha1(line.encode()).hexdigest()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "rbd_oracle.c")
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+    stamp = os.path.join(_HERE, "librbd_oracle.hostid")
+    hid = _host_id()
+    try:
+        with open(stamp) as f:
+            same_host = f.read().strip() == hid
+    except OSError:
+        same_host = False
+    if force or not same_host or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
         subprocess.check_call(["make", "-C", _HERE, "-B", "librbd_oracle.so"], stdout=subprocess.DEVNULL)
+        with open(stamp, "w") as f:
+            f.write(hid)
     return LIB_PATH
 
 

@@ -1,0 +1,77 @@
+"""Shared test helpers: tiled-SoA packing, error metric, the CPU emulation shim of the kernel bodies."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLDEN = os.path.join(HERE, "golden")
+
+TOL_FP64 = 1e-10   # BASELINE.json north_star: <= 1e-10 relative error in FP64
+
+
+def to_tiled(x: np.ndarray, tile: int) -> np.ndarray:
+    """[n, K] instance-major -> [ntiles, K, tile] tiled SoA (include/rbd_b200.h 'Memory layouts')."""
+    n, K = x.shape
+    nt = (n + tile - 1) // tile
+    o = np.zeros((nt * tile, K), dtype=x.dtype)
+    o[:n] = x
+    return np.ascontiguousarray(o.reshape(nt, tile, K).transpose(0, 2, 1))
+
+
+def from_tiled(o: np.ndarray, n: int) -> np.ndarray:
+    nt, K, tile = o.shape
+    return np.ascontiguousarray(o.transpose(0, 2, 1).reshape(nt * tile, K)[:n])
+
+
+def rel_err(x, ref) -> float:
+    """SURVEY.md §8(c) metric: max|x - ref| / max(1, max|ref|) over one output block."""
+    x = np.asarray(x, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
+    if ref.size == 0:
+        return 0.0
+    return float(np.max(np.abs(x - ref)) / max(1.0, float(np.max(np.abs(ref)))))
+
+
+def quat_err(qa, qb) -> float:
+    """Quaternion mismatch up to sign (q and -q are the same rotation)."""
+    qa = np.asarray(qa).reshape(-1, 4); qb = np.asarray(qb).reshape(-1, 4)
+    return float(np.max(np.minimum(np.abs(qa - qb).max(axis=1), np.abs(qa + qb).max(axis=1)))) if qa.size else 0.0
+
+
+def load_emul() -> C.CDLL:
+    """tests/emul/libemul.so: the kernel bodies of csrc/rbd_sweeps.h compiled by g++ (test-only)."""
+    src = os.path.join(HERE, "emul", "emul.cpp")
+    out = os.path.join(HERE, "emul", "libemul.so")
+    csrc = os.path.join(ROOT, "sofa", "rigidbodydynamics_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in ("rbd_sweeps.h", "rbd_model_build.h", "rbd_dev_model.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", out, src])
+    lib = C.CDLL(out)
+    vp, ll, i = C.c_void_p, C.c_longlong, C.c_int
+    lib.emul_last_error.restype = C.c_char_p
+    lib.emul_model_info.argtypes = [vp, vp]
+    lib.emul_eval.argtypes = [vp, ll, ll, i] + [vp] * 7
+    lib.emul_apply.argtypes = [vp, ll, ll, i, vp, vp, vp, ll, vp]
+    lib.emul_applyJ.argtypes = [vp, ll, ll, i, vp, ll, vp, vp, vp]
+    lib.emul_applyJT.argtypes = [vp, ll, ll, i, vp, ll, vp, vp, vp]
+    lib.emul_applyJT_rows.argtypes = [vp, ll, i, vp, ll, vp, vp, vp, vp, vp, vp]
+    return lib
+
+
+def P(a):
+    return None if a is None else a.ctypes.data
+
+
+def all_models():
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    ms = [mdl.panda7(), mdl.solo12(), mdl.talos_reduced(),
+          mdl.random_tree(1, 10), mdl.random_tree(2, 12, free_flyer=True),
+          mdl.random_tree(3, 20, branch_prob=0.6), mdl.random_tree(4, 1), mdl.random_tree(5, 6, all_types=False)]
+    for name in ("simple_arm", "schunk_svh_hand_right_regularized_inertia", "schunk_svh_hand_right_ff"):
+        p = os.path.join(GOLDEN, name + ".model.json")
+        if os.path.exists(p):
+            with open(p) as f:
+                ms.append(mdl.ModelDescriptor.from_json(f.read()))
+    return ms

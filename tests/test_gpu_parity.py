@@ -1,0 +1,308 @@
+"""GPU parity tests proper: the sm_100a kernels, called through the C ABI (ctypes -> librbd_b200.so), against the
+CPU oracle on the same seeded inputs, against the committed mpmath golden vectors, and — at BASELINE sizes — through
+size-independent identities.  Tolerance: 1e-10 relative (BASELINE.json north_star, FP64)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from helpers import TOL_FP64, rel_err, to_tiled, from_tiled
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+@pytest.fixture(scope="module")
+def api(rbd_lib):
+    from sofa.rigidbodydynamics_b200 import api as a
+    assert a.device_count() >= 1, "librbd_b200.so sees no CUDA device: the product path has no fallback"
+    return a
+
+
+MODELS = helpers.all_models()
+IDS = [m.name for m in MODELS]
+
+
+def _dev(torch, x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def _eval_gpu(torch, api, d, q, v, a, tile, want=("oMi", "J", "M", "tau"), block=0):
+    n = q.shape[0]
+    m = api.Model(d); ws = api.Workspace(m, max(n, 1))
+    if block:
+        ws.set_eval_block(block)
+    I = m.info
+    nt = (n + tile - 1) // tile
+    K = {"oMi": I.omi_fields, "J": I.jac_fields, "M": I.mass_fields, "tau": I.nv}
+    outs = {k: (torch.full((nt, K[k], tile), float("nan"), dtype=torch.float64, device="cuda") if k in want else None)
+            for k in K}
+    qs, vs, as_ = (_dev(torch, to_tiled(x, tile)) for x in (q, v, a))
+    ws.eval_soa(n, tile, qs, vs, as_, outs["oMi"], outs["J"], outs["M"], outs["tau"])
+    ws.synchronize()
+    res = {k: (from_tiled(o.cpu().numpy(), n) if o is not None else None) for k, o in outs.items()}
+    return res, ws.launch_count
+
+
+@pytest.mark.parametrize("d", MODELS, ids=IDS)
+@pytest.mark.parametrize("tile", [32, 1000])
+def test_eval_matches_oracle(torch_mod, api, d, tile):
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    n = 777
+    q, v, a = mdl.random_state(d, n, seed=11)
+    got, launches = _eval_gpu(torch_mod, api, d, q, v, a, tile)
+    assert launches == 1
+    ref, _ = oracle.eval_batch(d, q, v, a, nthreads=0)
+    for k in ("oMi", "J", "M", "tau"):
+        assert rel_err(got[k], ref[k]) <= TOL_FP64, k
+
+
+@pytest.mark.parametrize("want", [("M",), ("tau",), ("oMi", "J"), ("J", "tau"), ("oMi", "M")])
+def test_eval_partial_outputs(torch_mod, api, want):
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    d = mdl.talos_reduced()
+    q, v, a = mdl.random_state(d, 300, seed=5)
+    got, _ = _eval_gpu(torch_mod, api, d, q, v, a, 64, want=want)
+    ref, _ = oracle.eval_batch(d, q, v, a, nthreads=0)
+    for k in ("oMi", "J", "M", "tau"):
+        if k in want:
+            assert rel_err(got[k], ref[k]) <= TOL_FP64, k
+        else:
+            assert got[k] is None
+
+
+@pytest.mark.parametrize("block", [32, 64, 96, 128])
+def test_eval_block_sizes(torch_mod, api, block):
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    d = mdl.talos_reduced()
+    q, v, a = mdl.random_state(d, 333, seed=6)
+    got, _ = _eval_gpu(torch_mod, api, d, q, v, a, 333, block=block)
+    ref, _ = oracle.eval_batch(d, q, v, a, nthreads=0)
+    for k in ("oMi", "J", "M", "tau"):
+        assert rel_err(got[k], ref[k]) <= TOL_FP64, k
+
+
+def test_golden_vectors(torch_mod, api):
+    """CUDA path against the committed 50-digit mpmath vectors (tests/golden/make_golden.py)."""
+    with open(os.path.join(helpers.GOLDEN, "golden_vectors.json")) as f:
+        G = json.load(f)
+    byname = {m.name: m for m in MODELS}
+    from oracle import unpack_upper
+    checked = 0
+    for name, g in G.items():
+        d = byname[name]
+        q = np.array([s["q"] for s in g["states"]]); v = np.array([s["v"] for s in g["states"]])
+        a = np.array([s["a"] for s in g["states"]])
+        got, _ = _eval_gpu(torch_mod, api, d, q, v, a, 32)
+        for i, s in enumerate(g["states"]):
+            assert rel_err(got["oMi"][i], np.array(s["oMi"]).reshape(-1)) <= TOL_FP64
+            assert rel_err(got["J"][i], np.array(s["J"])) <= TOL_FP64
+            assert rel_err(unpack_upper(got["M"][i], d.nv), np.array(s["M"]).reshape(d.nv, d.nv)) <= TOL_FP64
+            assert rel_err(got["tau"][i], np.array(s["tau"])) <= TOL_FP64
+            checked += 1
+    assert checked >= 20
+
+
+# ---- mapping path -------------------------------------------------------------------------------------------
+def _split(d, q, v):
+    if d.has_freeflyer_root:
+        return (np.ascontiguousarray(q[:, 7:]), np.ascontiguousarray(q[:, :7]),
+                np.ascontiguousarray(v[:, 6:]), np.ascontiguousarray(v[:, :6]))
+    return q, None, v, None
+
+
+@pytest.mark.parametrize("d", MODELS, ids=IDS)
+def test_mapping_soa_matches_oracle(torch_mod, api, d):
+    """apply -> applyJ -> applyJT on device tiled-SoA buffers (the component's call order, KCM.inl:338-513)."""
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    torch = torch_mod
+    n, tile = 200, 64
+    q, v, _ = mdl.random_state(d, n, seed=21)
+    qj, root, dq, rootv = _split(d, q, v)
+    rng = np.random.default_rng(3)
+    w = rng.uniform(-1, 1, (n, d.n_out * 6))
+    tau0 = rng.uniform(-1, 1, (n, d.nv_joints)); root0 = rng.uniform(-1, 1, (n, 6))
+    m = api.Model(d); ws = api.Workspace(m, n)
+    T = lambda x: None if x is None else _dev(torch, to_tiled(x, tile))
+    nt = (n + tile - 1) // tile
+    pos = torch.zeros((nt, 7 * d.n_out, tile), dtype=torch.float64, device="cuda")
+    vel = torch.zeros((nt, 6 * d.n_out, tile), dtype=torch.float64, device="cuda")
+    tau = T(tau0); rt = T(root0) if root is not None else None
+    # if qj has zero fields (1-dof FF-only models do not occur here) the pointer is still valid
+    ws.apply_soa(n, tile, T(qj), T(root), pos)
+    ws.applyJ_soa(n, tile, T(dq), T(rootv), vel)
+    ws.applyJT_soa(n, tile, T(w), tau, rt)
+    ws.synchronize()
+    pos = from_tiled(pos.cpu().numpy(), n).reshape(n, d.n_out, 7)
+    vel = from_tiled(vel.cpu().numpy(), n).reshape(n, d.n_out, 6)
+    tau = from_tiled(tau.cpu().numpy(), n)
+    rt = from_tiled(rt.cpu().numpy(), n) if rt is not None else None
+    orc = oracle.Oracle(d)
+    for i in range(0, n, 7):
+        rp = orc.apply(qj[i], None if root is None else root[i])
+        assert rel_err(pos[i][:, :3], rp[:, :3]) <= TOL_FP64
+        # identical branch order as Eigen's Quaternion(Matrix3): equality, not just up to sign — except when the
+        # trace sits within rounding of the branch point
+        assert helpers.quat_err(pos[i][:, 3:], rp[:, 3:]) <= 1e-9
+        rv = orc.applyJ(dq[i], None if rootv is None else rootv[i])
+        assert rel_err(vel[i], rv) <= TOL_FP64
+        rtau, rroot = orc.applyJT(w[i], tau0[i], root0[i] if root is not None else None)
+        assert rel_err(tau[i], rtau) <= TOL_FP64
+        if root is not None:
+            assert rel_err(rt[i], rroot) <= TOL_FP64
+
+
+def test_applyJ_before_apply_is_an_error(api):
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    import torch
+    d = mdl.panda7()
+    m = api.Model(d); ws = api.Workspace(m, 8)
+    x = torch.zeros((1, d.nv, 8), dtype=torch.float64, device="cuda")
+    o = torch.zeros((1, 6 * d.n_out, 8), dtype=torch.float64, device="cuda")
+    with pytest.raises(api.RbdError) as e:
+        ws.applyJ_soa(8, 8, x, None, o)
+    assert e.value.code == -4   # RBD_ERR_NO_APPLY (KCM.inl:365-372: applyJ relies on the previous apply)
+
+
+@pytest.mark.parametrize("d", [m for m in MODELS if m.name in ("panda7", "solo12", "talos_reduced", "random_2",
+                                                                "schunk_svh_hand_right_regularized_inertia")],
+                         ids=lambda m: m.name)
+def test_component_mirror_host_path(api, d):
+    """KinematicChainMapping mirror over the *_host entry points (SOFA instance-major layout, several chunks)."""
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    from sofa.rigidbodydynamics_b200.mapping import KinematicChainMapping
+    n = 20000 if d.nv < 20 else 17000      # > one 16384-instance chunk: exercises the two-slot pipeline
+    q, v, _ = mdl.random_state(d, n, seed=31)
+    qj, root, dq, rootv = _split(d, q, v)
+    kcm = KinematicChainMapping(d, n_instances=n)
+    pos = np.zeros((n, d.n_out, 7)); vel = np.zeros((n, d.n_out, 6))
+    in2 = [] if root is None else [np.ascontiguousarray(root[:, None, :])]
+    in2v = [] if rootv is None else [np.ascontiguousarray(rootv[:, None, :])]
+    kcm.apply([pos], [qj], in2)
+    kcm.applyJ([vel], [dq], in2v)
+    rng = np.random.default_rng(9)
+    w = rng.uniform(-1, 1, (n, d.n_out, 6))
+    f1 = rng.uniform(-1, 1, (n, d.nv_joints)); f1_0 = f1.copy()
+    f2 = rng.uniform(-1, 1, (n, 1, 6)); f2_0 = f2.copy()
+    kcm.applyJT([f1], [] if root is None else [f2], [w])
+    assert kcm.d_componentState == "Valid"
+    orc = oracle.Oracle(d)
+    for i in list(range(0, n, 1999)) + [16383, 16384, n - 1]:
+        rp = orc.apply(qj[i], None if root is None else root[i])
+        assert rel_err(pos[i][:, :3], rp[:, :3]) <= TOL_FP64
+        assert helpers.quat_err(pos[i][:, 3:], rp[:, 3:]) <= 1e-9
+        assert rel_err(vel[i], orc.applyJ(dq[i], None if rootv is None else rootv[i])) <= TOL_FP64
+        rtau, rroot = orc.applyJT(w[i].reshape(-1), f1_0[i], f2_0[i, 0] if root is not None else None)
+        assert rel_err(f1[i], rtau) <= TOL_FP64
+        if root is not None:
+            assert rel_err(f2[i, 0], rroot) <= TOL_FP64
+    # constraint rows (applyJT MatrixDeriv, KCM.inl:515-639), a handful of instances
+    rows = {}
+    for r in range(40):
+        inst = int(rng.integers(0, n))
+        nnz = int(rng.integers(1, 4))
+        rows[(inst, r)] = [(int(rng.integers(0, d.n_out)), rng.uniform(-1, 1, 6)) for _ in range(nnz)]
+    rows[(5, 40)] = [(0, np.ones(6))]                       # universe output: empty support -> dropped row
+    rows[(6, 41)] = [(d.n_out - 1, np.zeros(6))]            # zero wrench -> dropped row
+    out, out_root = kcm.applyJT_matrix(rows)
+    assert (5, 40) not in out and (6, 41) not in out
+    for key, entries in rows.items():
+        inst = key[0]
+        orc.apply(qj[inst], None if root is None else root[inst])
+        row, keep = orc.applyJT_row([c for c, _ in entries], np.array([x for _, x in entries]))
+        assert keep == (key in out)
+        if keep:
+            full = np.concatenate([out_root[key], out[key]]) if root is not None else out[key]
+            assert rel_err(full, row) <= TOL_FP64
+
+
+def test_eval_host_matches_soa(torch_mod, api):
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    d = mdl.solo12()
+    n = 40000
+    q, v, a = mdl.random_state(d, n, seed=41)
+    m = api.Model(d); ws = api.Workspace(m, n)
+    I = m.info
+    oMi = np.zeros((n, I.omi_fields)); J = np.zeros((n, I.jac_fields)); M = np.zeros((n, I.mass_fields))
+    tau = np.zeros((n, I.nv))
+    ws.eval_host(n, q, v, a, oMi, J, M, tau)
+    ref, _ = oracle.eval_batch(d, q, v, a, nthreads=0)
+    for k, g in (("oMi", oMi), ("J", J), ("M", M), ("tau", tau)):
+        assert rel_err(g, ref[k]) <= TOL_FP64, k
+
+
+# ---- BASELINE sizes: size-independent identities --------------------------------------------------------------
+def test_full_size_identities(torch_mod, api):
+    """Talos at N = 1,048,576 (BASELINE configs[3]): (1) rnea(q,v,a) - rnea(q,v,0) == M(q) a for every instance,
+    (2) M symmetric-positive (diagonal > 0), (3) a strided sample equals the oracle, (4) the chunked result is
+    independent of the tile size (checksum of outputs)."""
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    from sofa.rigidbodydynamics_b200.dynamics import BatchedDynamics
+    torch = torch_mod
+    d = mdl.talos_reduced()
+    n = 1 << 20
+    dyn = BatchedDynamics(d, n)
+    g = torch.Generator(device="cuda"); g.manual_seed(1234)
+    nq, nv = d.nq, d.nv
+    q = (torch.rand((1, nq, n), generator=g, dtype=torch.float64, device="cuda") * 2 - 1) * np.pi
+    q[0, 0:3] = q[0, 0:3] / np.pi
+    quat = torch.randn((4, n), generator=g, dtype=torch.float64, device="cuda")
+    q[0, 3:7] = quat / quat.norm(dim=0, keepdim=True)
+    v = torch.rand((1, nv, n), generator=g, dtype=torch.float64, device="cuda") * 2 - 1
+    a = torch.rand((1, nv, n), generator=g, dtype=torch.float64, device="cuda") * 2 - 1
+    out = dyn.alloc_outputs()
+    dyn.eval(q, v, a, out)
+    tau0 = dyn.empty("tau")
+    dyn.rnea(q, v, torch.zeros_like(a), tau0)
+    torch.cuda.synchronize()
+    # M a from the packed upper triangle
+    Mp = out["M"][0]                                             # [741, n]
+    Ma = torch.zeros((nv, n), dtype=torch.float64, device="cuda")
+    for c in range(nv):
+        base = c * (c + 1) // 2
+        Ma[c] += Mp[base + c] * a[0, c]
+        if c:
+            col = Mp[base:base + c]                              # rows 0..c-1 of column c
+            Ma[:c] += col * a[0, c]
+            Ma[c] += (col * a[0, :c]).sum(dim=0)
+    lhs = out["tau"][0] - tau0[0]
+    scale = max(1.0, float(lhs.abs().max()))
+    assert float((lhs - Ma).abs().max()) / scale <= 1e-9          # two rnea + crba roundings accumulate
+    diag = torch.stack([Mp[c * (c + 1) // 2 + c] for c in range(nv)])
+    assert bool((diag > 0).all())
+    idx = torch.arange(0, n, 8191, device="cuda")
+    qs = q[0][:, idx].T.contiguous().cpu().numpy(); vs = v[0][:, idx].T.contiguous().cpu().numpy()
+    as_ = a[0][:, idx].T.contiguous().cpu().numpy()
+    ref, _ = oracle.eval_batch(d, qs, vs, as_, nthreads=0)
+    for k in ("oMi", "J", "M", "tau"):
+        assert rel_err(out[k][0][:, idx].T.cpu().numpy(), ref[k]) <= TOL_FP64, k
+
+
+def test_layout_adapters_roundtrip(torch_mod, api):
+    torch = torch_mod
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    m = api.Model(mdl.panda7()); ws = api.Workspace(m, 8)
+    for n, K, tile in ((1, 1, 1), (1000, 37, 32), (4097, 100, 4097), (33, 741, 64)):
+        x = torch.randn((n, K), dtype=torch.float64, device="cuda")
+        nt = (n + tile - 1) // tile
+        s = torch.zeros((nt, K, tile), dtype=torch.float64, device="cuda")
+        ws.aos_to_soa(n, K, tile, x, s)
+        assert np.array_equal(from_tiled(s.cpu().numpy(), n), x.cpu().numpy())
+        y = torch.empty_like(x)
+        ws.soa_to_aos(n, K, tile, s, y)
+        assert torch.equal(x, y)
