@@ -56,9 +56,10 @@ struct rbd_workspace {
   int *d_sorted_k = nullptr, *d_outk_parent = nullptr;
   double *d_sorted_pl = nullptr, *d_outk_pl = nullptr;
   DevTables tb{};
+  DevModel* d_model = nullptr;  // device copy of the joint table (staged into shared memory by the eval kernel)
   double* qcache = nullptr;  // [nq][capacity] assembled configuration of the last apply
   long long applied_n = 0;   // instances covered by the cache (0 = apply not called yet)
-  LaunchCfg cfg_eval[4], cfg_apply, cfg_applyJ, cfg_applyJT, cfg_rows;
+  LaunchCfg cfg_eval[8], cfg_apply, cfg_applyJ, cfg_applyJT, cfg_rows;
   int forced_eval_block = 0;
   long long launches = 0;
   // host-path staging
@@ -139,7 +140,7 @@ RBD_API int rbd_model_get_info(const rbd_model* model, rbd_model_info* info) {
 static void ws_free(rbd_workspace* ws) {
   if (!ws) return;
   cudaFree(ws->d_sorted_k); cudaFree(ws->d_outk_parent); cudaFree(ws->d_sorted_pl); cudaFree(ws->d_outk_pl);
-  cudaFree(ws->qcache); cudaFree(ws->rows_buf);
+  cudaFree(ws->qcache); cudaFree(ws->rows_buf); cudaFree(ws->d_model);
   for (int s = 0; s < kSlots; ++s) {
     cudaFree(ws->slot[s].aos); cudaFree(ws->slot[s].soa);
     if (ws->slot[s].st) cudaStreamDestroy(ws->slot[s].st);
@@ -183,6 +184,8 @@ RBD_API int rbd_workspace_create(const rbd_model* model, int device, int64_t cap
   }
   ws->tb.sorted_k = ws->d_sorted_k; ws->tb.sorted_pl = ws->d_sorted_pl;
   ws->tb.outk_parent = ws->d_outk_parent; ws->tb.outk_pl = ws->d_outk_pl;
+  WS_CK(cudaMalloc(&ws->d_model, sizeof(DevModel)));
+  WS_CK(cudaMemcpy(ws->d_model, &model->dm, sizeof(DevModel), cudaMemcpyHostToDevice));
   WS_CK(cudaMalloc(&ws->qcache, (size_t)(model->dm.nq > 0 ? model->dm.nq : 1) * (size_t)capacity * sizeof(double)));
   WS_CK(cudaEventCreateWithFlags(&ws->ev, cudaEventDisableTiming));
 #undef WS_CK
@@ -228,7 +231,7 @@ static int eval_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, 
   if (tau && (!v || !a)) return set_err(RBD_ERR_INVALID_ARG, "rnea needs v and a");
   EvalArgs A{n, tile, q, v, a, oMi, J, M, tau};
   const int sd = smem_eval(dm, M != nullptr, tau != nullptr);
-  CK(launch_eval(dm, A, sd, ws->forced_eval_block, ws->cfg_eval, st));
+  CK(launch_eval(dm, ws->d_model, A, sd, ws->forced_eval_block, ws->cfg_eval, st));
   if (n > 0) ws->launches++;
   return RBD_OK;
 }

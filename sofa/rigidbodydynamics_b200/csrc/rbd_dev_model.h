@@ -7,6 +7,7 @@
 // Replaces the pinocchio::Model the reference shares between loader and mapping
 // (reference KinematicChainMapping.inl:304-311, URDFModelLoader.cpp:263-268).
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #ifndef RBD_MAX_JOINTS
@@ -26,10 +27,12 @@ struct DevJoint {
   int parent, type, idx_q, idx_v;
   int nv;           // dof of this joint (0 universe, 1, or 6)
   int nchild;       // number of child joints
-  int slot[2];      // shared-memory offset (doubles) of this joint's stack slot: [0] full layout (A|f|Y), [1] lite (A|f)
+  int slot[2];      // stack-slot offset (doubles) of a joint that has children: [0] full layout (A|f|Y), [1] lite (A|f);
+                    // leaves never touch the stack (they are emitted from registers)
   int bidx;         // branch-slot index (joints with >= 2 children), -1 otherwise
   int out_begin, out_end;  // range of this joint's mapped outputs in DevTables::sorted_*
-  int pad_;
+  int pl_rot_identity;     // jointPlacement rotation is exactly I (skips one 3x3 product)
+  int depth;               // number of joints on the path universe -> this joint
 };
 
 struct DevModel {
@@ -42,6 +45,11 @@ struct DevModel {
   double gravity[3];
   DevJoint joint[RBD_MAX_JOINTS];
 };
+
+// bytes of a DevModel that are meaningful (header + the first njoints records): what the eval kernel stages
+inline size_t dev_model_bytes(const DevModel& m) {
+  return sizeof(DevModel) - sizeof(DevJoint) * (size_t)(RBD_MAX_JOINTS - m.njoints);
+}
 
 // Per-output tables (global memory; only the mapping kernels read them).
 struct DevTables {

@@ -20,71 +20,83 @@ extern __shared__ double rbd_smem[];
 
 // --------------------------------------------------------------------------------------------------------
 // K7 / K5 / K6: fused FK + joint Jacobian (+ CRBA) (+ RNEA)
-template <bool DO_M, bool DO_TAU>
-__global__ void __launch_bounds__(256) eval_kernel(const __grid_constant__ DevModel m, const EvalArgs a) {
+// The joint table is staged ONCE PER BLOCK from global memory into shared memory (coalesced copy), and the sweep
+// reads it from there: every lane of a warp reads the same record at the same time, which shared memory serves as
+// a single broadcast wavefront at a fixed ~30-cycle latency.  (Round-1 profile r1b: the same table read through
+// the constant bank with run-time indices cost ~40 stall samples per dependent ISETP — the 8.7 KB table does not
+// stay in the small constant L1 while three warps walk it at different phases.)
+template <bool DO_M, bool DO_TAU, int TILE>
+__global__ void __launch_bounds__(256) eval_kernel(const DevModel* __restrict__ gm, const EvalArgs a, const int slots,
+                                                   const int model_words) {
+  {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gm);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(rbd_smem);
+    for (int w = threadIdx.x; w < model_words; w += blockDim.x) dst[w] = src[w];
+  }
+  __syncthreads();
+  const DevModel& m = *reinterpret_cast<const DevModel*>(rbd_smem);
   const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (inst >= a.n) return;
-  EvalIO io;
-  io.q = make_field(const_cast<double*>(a.q), inst, m.nq, a.tile);
-  io.v = make_field(const_cast<double*>(a.v), inst, m.nv, a.tile);
-  io.a = make_field(const_cast<double*>(a.a), inst, m.nv, a.tile);
-  io.oMi = make_field(a.oMi, inst, 12 * (m.njoints - 1), a.tile);
-  io.J = make_field(a.J, inst, 6 * m.nv, a.tile);
-  io.M = make_field(a.M, inst, m.nv * (m.nv + 1) / 2, a.tile);
-  io.tau = make_field(a.tau, inst, m.nv, a.tile);
-  Stack S{rbd_smem + threadIdx.x, (int)blockDim.x};
-  eval_instance<DO_M, DO_TAU>(m, io, S);
+  EvalIOT<TILE> io;
+  io.q = make_field_t<TILE>(const_cast<double*>(a.q), inst, m.nq, a.tile);
+  io.v = make_field_t<TILE>(const_cast<double*>(a.v), inst, m.nv, a.tile);
+  io.a = make_field_t<TILE>(const_cast<double*>(a.a), inst, m.nv, a.tile);
+  io.oMi = make_field_t<TILE>(a.oMi, inst, 12 * (m.njoints - 1), a.tile);
+  io.J = make_field_t<TILE>(a.J, inst, 6 * m.nv, a.tile);
+  io.M = make_field_t<TILE>(a.M, inst, m.nv * (m.nv + 1) / 2, a.tile);
+  io.tau = make_field_t<TILE>(a.tau, inst, m.nv, a.tile);
+  eval_instance<DO_M, DO_TAU, TILE>(m, io, make_stack(rbd_smem + model_words, threadIdx.x, slots));
 }
 
 // K1: apply
 __global__ void __launch_bounds__(256) apply_kernel(const __grid_constant__ DevModel m, const DevTables tb,
-                                                    const MapArgs a) {
+                                                    const MapArgs a, const int slots) {
   const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (inst >= a.n) return;
   const int off = a.root ? 7 : 0;
   SplitQ q{make_field(const_cast<double*>(a.root), inst, 7, a.tile),
            make_field(const_cast<double*>(a.joints), inst, m.nq - off, a.tile), off};
-  Stack S{rbd_smem + threadIdx.x, (int)blockDim.x};
+  Stack S = make_stack(rbd_smem, threadIdx.x, slots);
   apply_instance(m, tb, q, make_field(a.qcache, a.cache_inst0 + inst, m.nq, a.cache_tile),
                  make_field(a.out, inst, 7 * m.n_out, a.tile), S);
 }
 
 // K2: applyJ
 __global__ void __launch_bounds__(256) applyJ_kernel(const __grid_constant__ DevModel m, const DevTables tb,
-                                                     const MapArgs a) {
+                                                     const MapArgs a, const int slots) {
   const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (inst >= a.n) return;
   const int off = a.root ? 6 : 0;
   SplitQ dq{make_field(const_cast<double*>(a.root), inst, 6, a.tile),
             make_field(const_cast<double*>(a.joints), inst, m.nv - off, a.tile), off};
-  Stack S{rbd_smem + threadIdx.x, (int)blockDim.x};
+  Stack S = make_stack(rbd_smem, threadIdx.x, slots);
   applyJ_instance(m, tb, make_field(a.qcache, a.cache_inst0 + inst, m.nq, a.cache_tile), dq,
                   make_field(a.out, inst, 6 * m.n_out, a.tile), S);
 }
 
 // K3: applyJT (vector).  a.joints / a.root are the ACCUMULATED outputs here, a.in the wrenches.
 __global__ void __launch_bounds__(256) applyJT_kernel(const __grid_constant__ DevModel m, const DevTables tb,
-                                                      const MapArgs a) {
+                                                      const MapArgs a, const int slots) {
   const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (inst >= a.n) return;
   const int off = a.root ? 6 : 0;
   DenseWrenchSrc src{make_field(const_cast<double*>(a.in), inst, 6 * m.n_out, a.tile), &tb};
   SplitAccumSink sink{make_field(const_cast<double*>(a.root), inst, 6, a.tile),
                       make_field(const_cast<double*>(a.joints), inst, m.nv - off, a.tile), off};
-  Stack S{rbd_smem + threadIdx.x, (int)blockDim.x};
+  Stack S = make_stack(rbd_smem, threadIdx.x, slots);
   applyJT_instance(m, tb, make_field(a.qcache, a.cache_inst0 + inst, m.nq, a.cache_tile), src, sink, S);
 }
 
 // K4: applyJT (constraint rows): one thread per row
 __global__ void __launch_bounds__(256) applyJT_rows_kernel(const __grid_constant__ DevModel m, const DevTables tb,
-                                                           const RowArgs a) {
+                                                           const RowArgs a, const int slots) {
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= a.nrows) return;
   const int b = a.row_ptr[r], e = a.row_ptr[r + 1];
   double n2 = 0.0;
   RowWrenchSrc src{a.col + b, a.val + 6 * (long long)b, e - b, &tb};
   RowSink sink{a.out_rows + r * m.nv, &n2};
-  Stack S{rbd_smem + threadIdx.x, (int)blockDim.x};
+  Stack S = make_stack(rbd_smem, threadIdx.x, slots);
   applyJT_instance(m, tb, make_field(a.qcache, a.row_instance[r], m.nq, a.cache_tile), src, sink, S);
   a.keep[r] = n2 > 1e-12 ? 1 : 0;  // kMinTorqueSqrd, reference KinematicChainMapping.inl:43-45,587,605
 }
@@ -131,7 +143,8 @@ __global__ void soa_to_aos_kernel(long long n, int K, long long tile, const doub
 static const int kMaxSmemOptin = 227 * 1024;
 
 template <class Kern>
-static cudaError_t pick_block(Kern kern, int smem_doubles_per_thread, int forced, LaunchCfg* cfg) {
+static cudaError_t pick_block(Kern kern, int smem_doubles_per_thread, int forced, LaunchCfg* cfg,
+                              size_t block_fixed_bytes = 0) {
   // opt in to the full 227 KB of dynamic shared memory once per kernel
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin);
   if (e != cudaSuccess) return e;
@@ -142,49 +155,58 @@ static cudaError_t pick_block(Kern kern, int smem_doubles_per_thread, int forced
   const int cand[] = {32, 64, 96, 128, 160, 192, 224, 256};
   for (int c : cand) {
     if (forced > 0 && c != forced) continue;
-    const size_t smem = per_thread * c;
+    const size_t smem = block_fixed_bytes + per_thread * c;
     if (smem > (size_t)kMaxSmemOptin) continue;
     int nb = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, c, smem);
     if (e != cudaSuccess) return e;
-    // prefer more resident threads; on ties the larger block (fewer blocks, less per-block reserved smem)
-    if (nb * c > best_threads || (nb * c == best_threads && c > best_block)) {
+    // prefer more resident threads; on ties the SMALLER block: blocks retire independently, so the tail of a
+    // wave is shorter and the shared-memory allocation granularity wastes less
+    if (nb * c > best_threads) {
       best_threads = nb * c; best_block = c; best_blocks_per_sm = nb;
     }
   }
   if (best_block == 0) return cudaErrorInvalidConfiguration;
   cfg->block = best_block;
-  cfg->smem_bytes = per_thread * best_block;
+  cfg->smem_bytes = block_fixed_bytes + per_thread * best_block;
   cfg->blocks_per_sm = best_blocks_per_sm;
   return cudaSuccess;
 }
 
 #define RBD_GRID(n, block) (unsigned)(((n) + (block)-1) / (block))
 
-cudaError_t launch_eval(const DevModel& m, const EvalArgs& a, int smem_doubles, int forced_block, LaunchCfg* cache,
-                        cudaStream_t st) {
+// variant index: bit 2 = compile-time tile of 32, bit 1 = CRBA, bit 0 = RNEA
+#define RBD_EVAL_DISPATCH(v, CALL)                          \
+  switch (v) {                                              \
+    case 7: CALL((eval_kernel<true, true, 32>)); break;     \
+    case 6: CALL((eval_kernel<true, false, 32>)); break;    \
+    case 5: CALL((eval_kernel<false, true, 32>)); break;    \
+    case 4: CALL((eval_kernel<false, false, 32>)); break;   \
+    case 3: CALL((eval_kernel<true, true, 0>)); break;      \
+    case 2: CALL((eval_kernel<true, false, 0>)); break;     \
+    case 1: CALL((eval_kernel<false, true, 0>)); break;     \
+    default: CALL((eval_kernel<false, false, 0>)); break;   \
+  }
+
+cudaError_t launch_eval(const DevModel& m, const DevModel* d_model, const EvalArgs& a, int smem_doubles,
+                        int forced_block, LaunchCfg* cache, cudaStream_t st) {
   const bool do_m = a.M != nullptr, do_tau = a.tau != nullptr;
-  const int v = (do_m ? 2 : 0) | (do_tau ? 1 : 0);
+  const int v = (a.tile == 32 ? 4 : 0) | (do_m ? 2 : 0) | (do_tau ? 1 : 0);
   LaunchCfg& cfg = cache[v];
+  const int model_words = (int)((dev_model_bytes(m) + 15) / 16) * 2;  // 8-byte words, stacks stay 16-byte aligned
   cudaError_t e = cudaSuccess;
   if (cfg.block == 0 || cfg.forced != forced_block) {
-    switch (v) {
-      case 3: e = pick_block(eval_kernel<true, true>, smem_doubles, forced_block, &cfg); break;
-      case 2: e = pick_block(eval_kernel<true, false>, smem_doubles, forced_block, &cfg); break;
-      case 1: e = pick_block(eval_kernel<false, true>, smem_doubles, forced_block, &cfg); break;
-      default: e = pick_block(eval_kernel<false, false>, smem_doubles, forced_block, &cfg); break;
-    }
+#define RBD_PICK(K) e = pick_block(K, smem_doubles, forced_block, &cfg, (size_t)model_words * 8)
+    RBD_EVAL_DISPATCH(v, RBD_PICK)
+#undef RBD_PICK
     if (e != cudaSuccess) return e;
     cfg.forced = forced_block;
   }
   if (a.n <= 0) return cudaSuccess;
   const unsigned grid = RBD_GRID(a.n, cfg.block);
-  switch (v) {
-    case 3: eval_kernel<true, true><<<grid, cfg.block, cfg.smem_bytes, st>>>(m, a); break;
-    case 2: eval_kernel<true, false><<<grid, cfg.block, cfg.smem_bytes, st>>>(m, a); break;
-    case 1: eval_kernel<false, true><<<grid, cfg.block, cfg.smem_bytes, st>>>(m, a); break;
-    default: eval_kernel<false, false><<<grid, cfg.block, cfg.smem_bytes, st>>>(m, a); break;
-  }
+#define RBD_LAUNCH(K) K<<<grid, cfg.block, cfg.smem_bytes, st>>>(d_model, a, smem_doubles, model_words)
+  RBD_EVAL_DISPATCH(v, RBD_LAUNCH)
+#undef RBD_LAUNCH
   return cudaGetLastError();
 }
 
@@ -195,7 +217,7 @@ cudaError_t launch_apply(const DevModel& m, const DevTables& tb, const MapArgs& 
     if (e != cudaSuccess) return e;
   }
   if (a.n <= 0) return cudaSuccess;
-  apply_kernel<<<RBD_GRID(a.n, cfg->block), cfg->block, cfg->smem_bytes, st>>>(m, tb, a);
+  apply_kernel<<<RBD_GRID(a.n, cfg->block), cfg->block, cfg->smem_bytes, st>>>(m, tb, a, smem_doubles);
   return cudaGetLastError();
 }
 cudaError_t launch_applyJ(const DevModel& m, const DevTables& tb, const MapArgs& a, int smem_doubles, LaunchCfg* cfg,
@@ -205,7 +227,7 @@ cudaError_t launch_applyJ(const DevModel& m, const DevTables& tb, const MapArgs&
     if (e != cudaSuccess) return e;
   }
   if (a.n <= 0) return cudaSuccess;
-  applyJ_kernel<<<RBD_GRID(a.n, cfg->block), cfg->block, cfg->smem_bytes, st>>>(m, tb, a);
+  applyJ_kernel<<<RBD_GRID(a.n, cfg->block), cfg->block, cfg->smem_bytes, st>>>(m, tb, a, smem_doubles);
   return cudaGetLastError();
 }
 cudaError_t launch_applyJT(const DevModel& m, const DevTables& tb, const MapArgs& a, int smem_doubles, LaunchCfg* cfg,
@@ -215,7 +237,7 @@ cudaError_t launch_applyJT(const DevModel& m, const DevTables& tb, const MapArgs
     if (e != cudaSuccess) return e;
   }
   if (a.n <= 0) return cudaSuccess;
-  applyJT_kernel<<<RBD_GRID(a.n, cfg->block), cfg->block, cfg->smem_bytes, st>>>(m, tb, a);
+  applyJT_kernel<<<RBD_GRID(a.n, cfg->block), cfg->block, cfg->smem_bytes, st>>>(m, tb, a, smem_doubles);
   return cudaGetLastError();
 }
 cudaError_t launch_applyJT_rows(const DevModel& m, const DevTables& tb, const RowArgs& a, int smem_doubles,
@@ -225,7 +247,7 @@ cudaError_t launch_applyJT_rows(const DevModel& m, const DevTables& tb, const Ro
     if (e != cudaSuccess) return e;
   }
   if (a.nrows <= 0) return cudaSuccess;
-  applyJT_rows_kernel<<<RBD_GRID(a.nrows, cfg->block), cfg->block, cfg->smem_bytes, st>>>(m, tb, a);
+  applyJT_rows_kernel<<<RBD_GRID(a.nrows, cfg->block), cfg->block, cfg->smem_bytes, st>>>(m, tb, a, smem_doubles);
   return cudaGetLastError();
 }
 

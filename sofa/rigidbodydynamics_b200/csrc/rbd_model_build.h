@@ -77,9 +77,13 @@ inline int build_dev_model(const rbd_model_desc* d, DevModel* m, HostTables* tb,
   m->has_ff_root = (nj > 1 && d->jtype[1] == JT_FF && d->parents[1] == 0) ? 1 : 0;
   m->nq_joints = m->has_ff_root ? d->nq - 7 : d->nq;
   m->nv_joints = m->has_ff_root ? d->nv - 6 : d->nv;
-  // stack slots by depth; branch slots for joints with >= 2 children
-  int maxd = 0;
-  for (int i = 1; i < nj; ++i) maxd = std::max(maxd, depth[i]);
+  // stack slots by depth; branch slots for joints with >= 2 children.  The full layout (fused eval with CRBA) only
+  // needs slots down to the deepest joint that has children: leaves are emitted from registers.
+  int maxd = 0, maxd_internal = 0;
+  for (int i = 1; i < nj; ++i) {
+    maxd = std::max(maxd, depth[i]);
+    if (m->joint[i].nchild > 0) maxd_internal = std::max(maxd_internal, depth[i]);
+  }
   m->max_depth = maxd;
   std::vector<int> aw(maxd + 1, 6);
   for (int i = 1; i < nj; ++i) aw[depth[i]] = std::max(aw[depth[i]], RBD_SLOT_A(d->jtype[i]));
@@ -88,12 +92,16 @@ inline int build_dev_model(const rbd_model_desc* d, DevModel* m, HostTables* tb,
     off_full[dd + 1] = off_full[dd] + aw[dd] + 16;  // A | f(6) | Y(10)
     off_lite[dd + 1] = off_lite[dd] + aw[dd] + 6;   // A | f(6)
   }
-  m->slot_total[0] = off_full[maxd + 1];
+  m->slot_total[0] = off_full[maxd_internal + 1];
   m->slot_total[1] = off_lite[maxd + 1];
   int nb = 0;
   for (int i = 1; i < nj; ++i) {
     m->joint[i].slot[0] = off_full[depth[i]];
     m->joint[i].slot[1] = off_lite[depth[i]];
+    m->joint[i].depth = depth[i];
+    const double* pl = m->joint[i].pl;
+    m->joint[i].pl_rot_identity = (pl[0] == 1.0 && pl[1] == 0.0 && pl[2] == 0.0 && pl[3] == 0.0 && pl[4] == 1.0 &&
+                                   pl[5] == 0.0 && pl[6] == 0.0 && pl[7] == 0.0 && pl[8] == 1.0) ? 1 : 0;
     if (m->joint[i].nchild >= 2) m->joint[i].bidx = nb++;
   }
   m->nbranch = nb;

@@ -38,26 +38,51 @@ namespace rbd {
 
 // ---------------------------------------------------------------------------------------------------------
 // accessors
-struct Field {  // strided view of one instance's fields in a tiled-SoA array
+//
+// FieldT<TILE>: strided view of one instance's fields in a tiled-SoA array.  TILE = 0 reads the tile (= stride
+// between consecutive fields) at run time; TILE = 32 is the AoSoA layout the hot path is tuned for: the 32
+// instances of a warp form one tile, field k of the warp sits at byte offset k*256 from the warp's base, so the
+// stride folds into the immediate offset of every load/store and a warp's whole output is one contiguous block.
+template <int TILE>
+struct FieldT {
   double* p;
   long long stride;
-  RBD_HD double ld(int k) const { return p[(long long)k * stride]; }
-  RBD_HD void st(int k, double v) const { p[(long long)k * stride] = v; }
+  RBD_HD long long off(int k) const { return TILE ? (long long)k * TILE : (long long)k * stride; }
+  RBD_HD double ld(int k) const { return p[off(k)]; }
+  RBD_HD void st(int k, double v) const { p[off(k)] = v; }
   RBD_HD bool ok() const { return p != nullptr; }
 };
-RBD_HD Field make_field(double* base, long long inst, int K, long long tile) {
-  Field f;
-  f.stride = tile;
-  f.p = base ? base + (inst / tile) * (long long)K * tile + (inst % tile) : nullptr;
+using Field = FieldT<0>;
+template <int TILE>
+RBD_HD FieldT<TILE> make_field_t(double* base, long long inst, int K, long long tile) {
+  FieldT<TILE> f;
+  if (TILE) {
+    f.stride = TILE;
+    f.p = base ? base + (inst / TILE) * (long long)K * TILE + (inst % TILE) : nullptr;
+  } else {
+    f.stride = tile;
+    f.p = base ? base + (inst / tile) * (long long)K * tile + (inst % tile) : nullptr;
+  }
   return f;
 }
-struct Stack {  // this thread's column of the shared-memory state
+RBD_HD Field make_field(double* base, long long inst, int K, long long tile) { return make_field_t<0>(base, inst, K, tile); }
+
+// Stack: this thread's column of its warp's shared-memory state.  Every warp owns a contiguous [slots][32]
+// region, so the stride between slots is the compile-time constant 32 (bank-conflict free: the 32 lanes of a
+// warp touch 32 consecutive doubles), whatever the block size.
+#define RBD_WARP 32
+struct Stack {
   double* p;
-  int stride;
-  RBD_HD double ld(int k) const { return p[k * stride]; }
-  RBD_HD void st(int k, double v) const { p[k * stride] = v; }
-  RBD_HD void add(int k, double v) const { p[k * stride] += v; }
+  RBD_HD double ld(int k) const { return p[k * RBD_WARP]; }
+  RBD_HD void st(int k, double v) const { p[k * RBD_WARP] = v; }
+  RBD_HD void add(int k, double v) const { p[k * RBD_WARP] += v; }
 };
+// base of thread t's stack column inside a block-wide region of `slots` doubles per thread
+RBD_HD Stack make_stack(double* smem, int t, int slots) {
+  Stack s;
+  s.p = smem + (long long)(t / RBD_WARP) * slots * RBD_WARP + (t % RBD_WARP);
+  return s;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // 3-vector helpers on scalars held in registers
@@ -68,13 +93,45 @@ struct Stack {  // this thread's column of the shared-memory state
     oz = (ax) * (by) - (ay) * (bx);                   \
   } while (0)
 
+// sin and cos of a joint angle.  Branch-free on the common path so that the compiler can interleave it with the
+// surrounding spatial algebra (the library sincos() carries a Payne-Hanek slow path behind a branch and cost ~120
+// instructions per call in the r1b profile): three-term Cody-Waite reduction by pi/2 (exact products through FMA,
+// good to |x| ~ 1e5), then the fdlibm minimax kernels on [-pi/4, pi/4]; error <= ~1.5 ulp.  Larger or non-finite
+// arguments take the library path.
 RBD_HD void sincos_(double x, double* s, double* c) {
+  if (!(fabs(x) < 1.0e5)) {
 #if defined(__CUDA_ARCH__)
-  sincos(x, s, c);
+    sincos(x, s, c);
 #else
-  *s = sin(x);
-  *c = cos(x);
+    *s = sin(x);
+    *c = cos(x);
 #endif
+    return;
+  }
+  const double q = rint(x * 0.6366197723675814);
+  double r = fma(-q, 1.5707963267948966, x);
+  r = fma(-q, 6.123233995736766e-17, r);
+  r = fma(-q, -1.4973849048591698e-33, r);
+  const double z = r * r;
+  double ps = 1.58969099521155010221e-10;
+  ps = fma(ps, z, -2.50507602534068634195e-08);
+  ps = fma(ps, z, 2.75573137070700676789e-06);
+  ps = fma(ps, z, -1.98412698298579493134e-04);
+  ps = fma(ps, z, 8.33333333332248946124e-03);
+  ps = fma(ps, z, -1.66666666666666324348e-01);
+  const double sr = fma(ps * z, r, r);
+  double pc = -1.13596475577881948265e-11;
+  pc = fma(pc, z, 2.08757232129817482790e-09);
+  pc = fma(pc, z, -2.75573143513906633035e-07);
+  pc = fma(pc, z, 2.48015872894767294178e-05);
+  pc = fma(pc, z, -1.38888888888741095749e-03);
+  pc = fma(pc, z, 4.16666666666666019037e-02);
+  const double cr = fma(pc * z, z, fma(-0.5, z, 1.0));
+  const int n = (int)q;
+  const double a = (n & 1) ? cr : sr;   // quadrant: sin takes cos(r) in odd quadrants
+  const double b = (n & 1) ? sr : cr;
+  *s = (n & 2) ? -a : a;
+  *c = ((n + 1) & 2) ? -b : b;
 }
 
 // O = A * B (3x3 row-major, O distinct from A and B)
@@ -105,7 +162,12 @@ RBD_HD void mat3_mul(const double* A, const double* B, double* O) {
 template <class QF>
 RBD_HD void fk_joint(const DevJoint& jn, double* R, double* p, double q0, double q1, const QF& qf, double* aw) {
   double B[9], pn[3];
-  mat3_mul(R, jn.pl, B);
+  if (jn.pl_rot_identity) {  // uniform branch: most URDF joints have rpy = 0
+#pragma unroll
+    for (int k = 0; k < 9; ++k) B[k] = R[k];
+  } else {
+    mat3_mul(R, jn.pl, B);
+  }
   pn[0] = R[0] * jn.pl[9] + R[1] * jn.pl[10] + R[2] * jn.pl[11] + p[0];
   pn[1] = R[3] * jn.pl[9] + R[4] * jn.pl[10] + R[5] * jn.pl[11] + p[1];
   pn[2] = R[6] * jn.pl[9] + R[7] * jn.pl[10] + R[8] * jn.pl[11] + p[2];
@@ -250,7 +312,7 @@ RBD_HD void inertia_mul(const double* Y, const double* mo, double* F) {
 }
 
 RBD_HD double dot6(const double* a, const double* b) {
-  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+  return (a[0] * b[0] + a[1] * b[1] + a[2] * b[2]) + (a[3] * b[3] + a[4] * b[4] + a[5] * b[5]);
 }
 
 // Eigen 3.4 Quaternion(Matrix3) branch order (reference Conversions.h:60), output [x y z w] (Conversions.h:36)
@@ -282,121 +344,82 @@ RBD_HD void rot_to_quat(const double* R, double* q) {
 // =========================================================================================================
 // Fused evaluation: FK + world joint Jacobian (+ CRBA) (+ RNEA)                      [kernel K7 / K5 / K6]
 // =========================================================================================================
-struct EvalIO {
-  Field q, v, a;          // inputs: nq, nv, nv fields
-  Field oMi, J, M, tau;   // outputs (p == nullptr -> not written)
+template <int TILE>
+struct EvalIOT {
+  FieldT<TILE> q, v, a;          // inputs: nq, nv, nv fields
+  FieldT<TILE> oMi, J, M, tau;   // outputs (p == nullptr -> not written)
 };
+using EvalIO = EvalIOT<0>;
 
-// backward step of joint k: tau_k = A_k^T f_k ; column(s) of M ; accumulate into the parent's slot
-template <bool DO_M, bool DO_TAU>
-RBD_HD void eval_pop(const DevModel& m, int k, const Stack& S, const EvalIO& io) {
+// Rows of packed column `base` above the joint that owns it: one entry per ancestor dof (A_anc . F), zeros for
+// the dofs of joints off the ancestor chain.  `anc` = first ancestor to visit, rows >= `next` are already written.
+template <int L, int TILE>
+RBD_HD void column_tail(const DevModel& m, int anc, int next, int base, const double* F, const Stack& S,
+                        const FieldT<TILE>& M) {
+  for (; anc != 0; anc = m.joint[anc].parent) {
+    const DevJoint& ja = m.joint[anc];
+    const int iv = ja.idx_v;
+    for (int r = iv + ja.nv; r < next; ++r) M.st(base + r, 0.0);
+    const int sa = ja.slot[L];
+    if (ja.type == JT_FF) {
+      double Rq[12], p6[6];
+#pragma unroll
+      for (int e = 0; e < 12; ++e) Rq[e] = S.ld(sa + e);
+      ff_rows(Rq, Rq + 9, F, p6);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) M.st(base + iv + e, p6[e]);
+    } else {
+      double Aa[6];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) Aa[e] = S.ld(sa + e);
+      M.st(base + iv, dot6(Aa, F));
+    }
+    next = iv;
+  }
+  for (int r = 0; r < next; ++r) M.st(base + r, 0.0);
+}
+
+// Everything joint k owes once its subtree is complete: tau_k = A_k^T f_k and its column(s) of M.
+// A = world subspace column (6) of a 1-dof joint, or R|p (12) of a free-flyer; f = total subtree force;
+// Y = composite inertia of the subtree — all three in registers.
+template <bool DO_M, bool DO_TAU, int TILE>
+RBD_HD void emit_joint(const DevModel& m, int k, const double* A, const double* f, const double* Y, const Stack& S,
+                       const EvalIOT<TILE>& io) {
   constexpr int L = DO_M ? 0 : 1;
   const DevJoint& jn = m.joint[k];
-  const int s = jn.slot[L];
-  const int aw_ = RBD_SLOT_A(jn.type);
-  const int sf = s + aw_, sy = s + aw_ + 6;
-  double f[6], Y[10];
-  if (DO_TAU) {
-#pragma unroll
-    for (int e = 0; e < 6; ++e) f[e] = S.ld(sf + e);
-  }
-  if (DO_M) {
-#pragma unroll
-    for (int e = 0; e < 10; ++e) Y[e] = S.ld(sy + e);
-  }
-  const int par = jn.parent;
   if (jn.type != JT_FF) {
-    double A[6];
-#pragma unroll
-    for (int e = 0; e < 6; ++e) A[e] = S.ld(s + e);
     if (DO_TAU) io.tau.st(jn.idx_v, dot6(A, f));
     if (DO_M) {
       double F[6];
       inertia_mul(Y, A, F);
       const int col = jn.idx_v;
       const int base = col * (col + 1) / 2;
-      int next = col + 1;  // rows >= next of this column are done
-      for (int anc = k; anc != 0; anc = m.joint[anc].parent) {
-        const DevJoint& ja = m.joint[anc];
-        const int iv = ja.idx_v;
-        for (int r = iv + ja.nv; r < next; ++r) io.M.st(base + r, 0.0);  // joints off the ancestor chain
-        const int sa = ja.slot[L];
-        if (ja.type == JT_FF) {
-          double Rp[12], o6[6];
-#pragma unroll
-          for (int e = 0; e < 12; ++e) Rp[e] = S.ld(sa + e);
-          ff_rows(Rp, Rp + 9, F, o6);
-#pragma unroll
-          for (int e = 0; e < 6; ++e) io.M.st(base + iv + e, o6[e]);
-        } else {
-          double Aa[6];
-#pragma unroll
-          for (int e = 0; e < 6; ++e) Aa[e] = S.ld(sa + e);
-          io.M.st(base + iv, dot6(Aa, F));
-        }
-        next = iv;
-      }
-      for (int r = 0; r < next; ++r) io.M.st(base + r, 0.0);
+      io.M.st(base + col, dot6(A, F));
+      column_tail<L>(m, jn.parent, col, base, F, S, io.M);
     }
   } else {
-    double Rp[12];
-#pragma unroll
-    for (int e = 0; e < 12; ++e) Rp[e] = S.ld(s + e);
 #pragma unroll
     for (int cc = 0; cc < 6; ++cc) {
-      double A[6];
-      RBD_FF_COL(A, Rp, (Rp + 9), cc);
-      if (DO_TAU) io.tau.st(jn.idx_v + cc, dot6(A, f));
+      double Ac[6];
+      RBD_FF_COL(Ac, A, (A + 9), cc);
+      if (DO_TAU) io.tau.st(jn.idx_v + cc, dot6(Ac, f));
       if (DO_M) {
         double F[6], o6[6];
-        inertia_mul(Y, A, F);
+        inertia_mul(Y, Ac, F);
         const int col = jn.idx_v + cc;
         const int base = col * (col + 1) / 2;
-        ff_rows(Rp, Rp + 9, F, o6);
+        ff_rows(A, A + 9, F, o6);
 #pragma unroll
         for (int e = 0; e < 6; ++e)
           if (e <= cc) io.M.st(base + jn.idx_v + e, o6[e]);
-        int next = jn.idx_v;
-        for (int anc = par; anc != 0; anc = m.joint[anc].parent) {
-          const DevJoint& ja = m.joint[anc];
-          const int iv = ja.idx_v;
-          for (int r = iv + ja.nv; r < next; ++r) io.M.st(base + r, 0.0);
-          const int sa = ja.slot[L];
-          if (ja.type == JT_FF) {
-            double Rq[12], p6[6];
-#pragma unroll
-            for (int e = 0; e < 12; ++e) Rq[e] = S.ld(sa + e);
-            ff_rows(Rq, Rq + 9, F, p6);
-#pragma unroll
-            for (int e = 0; e < 6; ++e) io.M.st(base + iv + e, p6[e]);
-          } else {
-            double Aa[6];
-#pragma unroll
-            for (int e = 0; e < 6; ++e) Aa[e] = S.ld(sa + e);
-            io.M.st(base + iv, dot6(Aa, F));
-          }
-          next = iv;
-        }
-        for (int r = 0; r < next; ++r) io.M.st(base + r, 0.0);
+        column_tail<L>(m, jn.parent, jn.idx_v, base, F, S, io.M);
       }
-    }
-  }
-  if (par != 0) {
-    const DevJoint& jp = m.joint[par];
-    const int sp = jp.slot[L] + RBD_SLOT_A(jp.type);
-    if (DO_TAU) {
-#pragma unroll
-      for (int e = 0; e < 6; ++e) S.add(sp + e, f[e]);
-    }
-    if (DO_M) {
-#pragma unroll
-      for (int e = 0; e < 10; ++e) S.add(sp + 6 + e, Y[e]);
     }
   }
 }
 
-template <bool DO_M, bool DO_TAU>
-RBD_HD void eval_instance(const DevModel& m, const EvalIO& io, const Stack& S) {
+template <bool DO_M, bool DO_TAU, int TILE>
+RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stack& S) {
   constexpr int L = DO_M ? 0 : 1;
   constexpr bool NEED_STACK = DO_M || DO_TAU;
   const int nj = m.njoints;
@@ -425,9 +448,7 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIO& io, const Stack& S) {
     const DevJoint& jn = m.joint[i];
     const int par = jn.parent;
     if (par != i - 1) {
-      // the sweep leaves the subtree(s) that ended at joint i-1: finish them bottom-up, then resume at `par`
-      if (NEED_STACK)
-        for (int k = i - 1; k != par; k = m.joint[k].parent) eval_pop<DO_M, DO_TAU>(m, k, S, io);
+      // joint i starts a new branch below `par` (the subtree that ended at i-1 was unwound already)
       if (par == 0) {
         RBD_RESET_ROOT();
       } else {
@@ -443,6 +464,7 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIO& io, const Stack& S) {
       }
     }
     const double q0 = q0n, q1 = q1n, qd = vn, qdd = an;
+    const int nxt_par = (i + 1 < nj) ? m.joint[i + 1].parent : 0;
     if (i + 1 < nj && m.joint[i + 1].type != JT_FF) {
       const DevJoint& jx = m.joint[i + 1];
       q0n = io.q.ld(jx.idx_q);
@@ -459,23 +481,18 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIO& io, const Stack& S) {
 #pragma unroll
       for (int e = 0; e < 3; ++e) io.oMi.st(o + 9 + e, p[e]);
     }
-    const int s = NEED_STACK ? jn.slot[L] : 0;
-    const int aw_ = RBD_SLOT_A(jn.type);
+    // Ak: world subspace column (1-dof) or R|p (free-flyer) — what the stack keeps for the CRBA/RNEA projections
+    double Ak[12], fk[6], Yk[10];
     if (jn.type != JT_FF) {
-      double A[6];
-      subspace_1dof(jn.type, p, aw, A);
+      subspace_1dof(jn.type, p, aw, Ak);
       if (io.J.ok()) {
 #pragma unroll
-        for (int e = 0; e < 6; ++e) io.J.st(6 * jn.idx_v + e, A[e]);
-      }
-      if (NEED_STACK) {
-#pragma unroll
-        for (int e = 0; e < 6; ++e) S.st(s + e, A[e]);
+        for (int e = 0; e < 6; ++e) io.J.st(6 * jn.idx_v + e, Ak[e]);
       }
       if (DO_TAU) {
         double vj[6], cr[6];
 #pragma unroll
-        for (int e = 0; e < 6; ++e) { vj[e] = A[e] * qd; vel[e] += vj[e]; }
+        for (int e = 0; e < 6; ++e) { vj[e] = Ak[e] * qd; vel[e] += vj[e]; }
         // a_i = a_parent + A qdd + v_i x vJ   (joint bias c = 0 for all supported joints)
         RBD_CROSS(cr[0], cr[1], cr[2], vel[3], vel[4], vel[5], vj[0], vj[1], vj[2]);
         double tx, ty, tz;
@@ -483,9 +500,13 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIO& io, const Stack& S) {
         cr[0] += tx; cr[1] += ty; cr[2] += tz;
         RBD_CROSS(cr[3], cr[4], cr[5], vel[3], vel[4], vel[5], vj[3], vj[4], vj[5]);
 #pragma unroll
-        for (int e = 0; e < 6; ++e) acc[e] += A[e] * qdd + cr[e];
+        for (int e = 0; e < 6; ++e) acc[e] += Ak[e] * qdd + cr[e];
       }
     } else {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Ak[e] = R[e];
+#pragma unroll
+      for (int e = 0; e < 3; ++e) Ak[9 + e] = p[e];
       if (io.J.ok()) {
 #pragma unroll
         for (int cc = 0; cc < 6; ++cc) {
@@ -494,12 +515,6 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIO& io, const Stack& S) {
 #pragma unroll
           for (int e = 0; e < 6; ++e) io.J.st(6 * (jn.idx_v + cc) + e, A[e]);
         }
-      }
-      if (NEED_STACK) {
-#pragma unroll
-        for (int e = 0; e < 9; ++e) S.st(s + e, R[e]);
-#pragma unroll
-        for (int e = 0; e < 3; ++e) S.st(s + 9 + e, p[e]);
       }
       if (DO_TAU) {
         // joint velocity / acceleration given in the joint (body) frame: world = oMi.act(.)
@@ -541,43 +556,102 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIO& io, const Stack& S) {
         for (int e = 0; e < 6; ++e) acc[e] += aj[e] + cr[e];
       }
     }
-    if (NEED_STACK) {
-      double Y[10];
-      inertia_world(jn, R, p, Y);
-      if (DO_TAU) {
-        // f = Y a + v x* (Y v)
-        double h[6], f[6];
-        inertia_mul(Y, vel, h);
-        inertia_mul(Y, acc, f);
-        double tx, ty, tz;
-        RBD_CROSS(tx, ty, tz, vel[3], vel[4], vel[5], h[0], h[1], h[2]);
-        f[0] += tx; f[1] += ty; f[2] += tz;
-        RBD_CROSS(tx, ty, tz, vel[3], vel[4], vel[5], h[3], h[4], h[5]);
-        f[3] += tx; f[4] += ty; f[5] += tz;
-        RBD_CROSS(tx, ty, tz, vel[0], vel[1], vel[2], h[0], h[1], h[2]);
-        f[3] += tx; f[4] += ty; f[5] += tz;
+    if (!NEED_STACK) {
+      if (jn.nchild >= 2) {
+        const int b = bbase + jn.bidx * BW;
 #pragma unroll
-        for (int e = 0; e < 6; ++e) S.st(s + aw_ + e, f[e]);
+        for (int e = 0; e < 9; ++e) S.st(b + e, R[e]);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) S.st(b + 9 + e, p[e]);
+      }
+      continue;
+    }
+    inertia_world(jn, R, p, Yk);
+    if (DO_TAU) {
+      // f = Y a + v x* (Y v)
+      double h[6];
+      inertia_mul(Yk, vel, h);
+      inertia_mul(Yk, acc, fk);
+      double tx, ty, tz;
+      RBD_CROSS(tx, ty, tz, vel[3], vel[4], vel[5], h[0], h[1], h[2]);
+      fk[0] += tx; fk[1] += ty; fk[2] += tz;
+      RBD_CROSS(tx, ty, tz, vel[3], vel[4], vel[5], h[3], h[4], h[5]);
+      fk[3] += tx; fk[4] += ty; fk[5] += tz;
+      RBD_CROSS(tx, ty, tz, vel[0], vel[1], vel[2], h[0], h[1], h[2]);
+      fk[3] += tx; fk[4] += ty; fk[5] += tz;
+    }
+    if (nxt_par == i) {
+      // joint i has children: park A | f | Y in its depth slot; its subtree sums accumulate there
+      const int s = jn.slot[L];
+      const int aw_ = RBD_SLOT_A(jn.type);
+      if (jn.type != JT_FF) {
+#pragma unroll
+        for (int e = 0; e < 6; ++e) S.st(s + e, Ak[e]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 12; ++e) S.st(s + e, Ak[e]);
+      }
+      if (DO_TAU) {
+#pragma unroll
+        for (int e = 0; e < 6; ++e) S.st(s + aw_ + e, fk[e]);
       }
       if (DO_M) {
 #pragma unroll
-        for (int e = 0; e < 10; ++e) S.st(s + aw_ + 6 + e, Y[e]);
+        for (int e = 0; e < 10; ++e) S.st(s + aw_ + 6 + e, Yk[e]);
       }
-    }
-    if (jn.nchild >= 2) {
-      const int b = bbase + jn.bidx * BW;
+      if (jn.nchild >= 2) {
+        const int b = bbase + jn.bidx * BW;
 #pragma unroll
-      for (int e = 0; e < 9; ++e) S.st(b + e, R[e]);
+        for (int e = 0; e < 9; ++e) S.st(b + e, R[e]);
 #pragma unroll
-      for (int e = 0; e < 3; ++e) S.st(b + 9 + e, p[e]);
-      if (DO_TAU) {
+        for (int e = 0; e < 3; ++e) S.st(b + 9 + e, p[e]);
+        if (DO_TAU) {
 #pragma unroll
-        for (int e = 0; e < 6; ++e) { S.st(b + 12 + e, vel[e]); S.st(b + 18 + e, acc[e]); }
+          for (int e = 0; e < 6; ++e) { S.st(b + 12 + e, vel[e]); S.st(b + 18 + e, acc[e]); }
+        }
+      }
+    } else {
+      // joint i is a leaf: its subtree is complete.  Emit it straight from registers, then unwind: every
+      // ancestor whose last child this was is complete too; its sums continue in registers up the chain and
+      // are written back only at the joint that still has children to come (nxt_par).
+      int k = i;
+      while (true) {
+        emit_joint<DO_M, DO_TAU>(m, k, Ak, fk, Yk, S, io);
+        const int pk = m.joint[k].parent;
+        if (pk == 0) break;
+        const DevJoint& jp = m.joint[pk];
+        const int sp = jp.slot[L];
+        const int awp = RBD_SLOT_A(jp.type);
+        if (pk == nxt_par) {
+          if (DO_TAU) {
+#pragma unroll
+            for (int e = 0; e < 6; ++e) S.add(sp + awp + e, fk[e]);
+          }
+          if (DO_M) {
+#pragma unroll
+            for (int e = 0; e < 10; ++e) S.add(sp + awp + 6 + e, Yk[e]);
+          }
+          break;
+        }
+        if (DO_TAU) {
+#pragma unroll
+          for (int e = 0; e < 6; ++e) fk[e] += S.ld(sp + awp + e);
+        }
+        if (DO_M) {
+#pragma unroll
+          for (int e = 0; e < 10; ++e) Yk[e] += S.ld(sp + awp + 6 + e);
+        }
+        if (jp.type != JT_FF) {
+#pragma unroll
+          for (int e = 0; e < 6; ++e) Ak[e] = S.ld(sp + e);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 12; ++e) Ak[e] = S.ld(sp + e);
+        }
+        k = pk;
       }
     }
   }
-  if (NEED_STACK)
-    for (int k = nj - 1; k > 0; k = m.joint[k].parent) eval_pop<DO_M, DO_TAU>(m, k, S, io);
 #undef RBD_RESET_ROOT
 }
 

@@ -29,6 +29,10 @@ static int make_ctx(const rbd_model_desc* d, Ctx* c) {
   return 0;
 }
 
+extern "C" void emul_sincos(long long n, const double* x, double* s, double* c) {
+  for (long long i = 0; i < n; ++i) sincos_(x[i], s + i, c + i);
+}
+
 extern "C" int emul_model_info(const rbd_model_desc* d, int* out /*[8]*/) {
   Ctx c;
   int rc = make_ctx(d, &c);
@@ -39,6 +43,22 @@ extern "C" int emul_model_info(const rbd_model_desc* d, int* out /*[8]*/) {
   return 0;
 }
 
+template <int TILE>
+static void eval_one(const Ctx& c, long long i, long long tile, double* q, double* v, double* a, double* oMi, double* J,
+                     double* M, double* tau, const Stack& S) {
+  const bool do_m = M != nullptr, do_tau = tau != nullptr;
+  EvalIOT<TILE> io;
+  io.q = make_field_t<TILE>(q, i, c.m.nq, tile); io.v = make_field_t<TILE>(v, i, c.m.nv, tile);
+  io.a = make_field_t<TILE>(a, i, c.m.nv, tile);
+  io.oMi = make_field_t<TILE>(oMi, i, 12 * (c.m.njoints - 1), tile); io.J = make_field_t<TILE>(J, i, 6 * c.m.nv, tile);
+  io.M = make_field_t<TILE>(M, i, c.m.nv * (c.m.nv + 1) / 2, tile); io.tau = make_field_t<TILE>(tau, i, c.m.nv, tile);
+  if (do_m && do_tau) eval_instance<true, true, TILE>(c.m, io, S);
+  else if (do_m) eval_instance<true, false, TILE>(c.m, io, S);
+  else if (do_tau) eval_instance<false, true, TILE>(c.m, io, S);
+  else eval_instance<false, false, TILE>(c.m, io, S);
+}
+
+// tile == 32 runs the compile-time-tile instantiation the GPU fast path uses
 extern "C" int emul_eval(const rbd_model_desc* d, long long n, long long tile, int block, double* q, double* v,
                          double* a, double* oMi, double* J, double* M, double* tau) {
   Ctx c;
@@ -46,19 +66,13 @@ extern "C" int emul_eval(const rbd_model_desc* d, long long n, long long tile, i
   if (rc) return rc;
   const bool do_m = M != nullptr, do_tau = tau != nullptr;
   const int sd = smem_eval(c.m, do_m, do_tau);
-  std::vector<double> smem((size_t)(sd > 0 ? sd : 1) * block, 1e300);  // poison: reads before writes show up
+  std::vector<double> smem((size_t)(sd > 0 ? sd : 1) * ((block + 31) / 32) * 32, 1e300);  // poison: reads before writes show up
   for (long long b0 = 0; b0 < n; b0 += block)
     for (int t = 0; t < block && b0 + t < n; ++t) {
       const long long i = b0 + t;
-      EvalIO io;
-      io.q = make_field(q, i, c.m.nq, tile); io.v = make_field(v, i, c.m.nv, tile); io.a = make_field(a, i, c.m.nv, tile);
-      io.oMi = make_field(oMi, i, 12 * (c.m.njoints - 1), tile); io.J = make_field(J, i, 6 * c.m.nv, tile);
-      io.M = make_field(M, i, c.m.nv * (c.m.nv + 1) / 2, tile); io.tau = make_field(tau, i, c.m.nv, tile);
-      Stack S{smem.data() + t, block};
-      if (do_m && do_tau) eval_instance<true, true>(c.m, io, S);
-      else if (do_m) eval_instance<true, false>(c.m, io, S);
-      else if (do_tau) eval_instance<false, true>(c.m, io, S);
-      else eval_instance<false, false>(c.m, io, S);
+      Stack S = make_stack(smem.data(), t, sd);
+      if (tile == 32) eval_one<32>(c, i, tile, q, v, a, oMi, J, M, tau, S);
+      else eval_one<0>(c, i, tile, q, v, a, oMi, J, M, tau, S);
     }
   return 0;
 }
@@ -69,12 +83,12 @@ extern "C" int emul_apply(const rbd_model_desc* d, long long n, long long tile, 
   int rc = make_ctx(d, &c);
   if (rc) return rc;
   const int sd = smem_apply(c.m);
-  std::vector<double> smem((size_t)(sd > 0 ? sd : 1) * block, 1e300);
+  std::vector<double> smem((size_t)(sd > 0 ? sd : 1) * ((block + 31) / 32) * 32, 1e300);
   const int off = (c.m.has_ff_root && root) ? 7 : 0;
   for (long long i = 0; i < n; ++i) {
     const int t = (int)(i % block);
     SplitQ sq{make_field(root, i, 7, tile), make_field(q_joints, i, c.m.nq - off, tile), off};
-    Stack S{smem.data() + t, block};
+    Stack S = make_stack(smem.data(), t, sd);
     apply_instance(c.m, c.tb, sq, make_field(qcache, i, c.m.nq, cache_tile), make_field(out, i, 7 * c.m.n_out, tile), S);
   }
   return 0;
@@ -86,12 +100,12 @@ extern "C" int emul_applyJ(const rbd_model_desc* d, long long n, long long tile,
   int rc = make_ctx(d, &c);
   if (rc) return rc;
   const int sd = smem_applyJ(c.m);
-  std::vector<double> smem((size_t)(sd > 0 ? sd : 1) * block, 1e300);
+  std::vector<double> smem((size_t)(sd > 0 ? sd : 1) * ((block + 31) / 32) * 32, 1e300);
   const int off = (c.m.has_ff_root && root_vel) ? 6 : 0;
   for (long long i = 0; i < n; ++i) {
     const int t = (int)(i % block);
     SplitQ dq{make_field(root_vel, i, 6, tile), make_field(dq_joints, i, c.m.nv - off, tile), off};
-    Stack S{smem.data() + t, block};
+    Stack S = make_stack(smem.data(), t, sd);
     applyJ_instance(c.m, c.tb, make_field(qcache, i, c.m.nq, cache_tile), dq, make_field(out, i, 6 * c.m.n_out, tile), S);
   }
   return 0;
@@ -103,13 +117,13 @@ extern "C" int emul_applyJT(const rbd_model_desc* d, long long n, long long tile
   int rc = make_ctx(d, &c);
   if (rc) return rc;
   const int sd = smem_applyJT(c.m);
-  std::vector<double> smem((size_t)(sd > 0 ? sd : 1) * block, 1e300);
+  std::vector<double> smem((size_t)(sd > 0 ? sd : 1) * ((block + 31) / 32) * 32, 1e300);
   const int off = (c.m.has_ff_root && out_root) ? 6 : 0;
   for (long long i = 0; i < n; ++i) {
     const int t = (int)(i % block);
     DenseWrenchSrc src{make_field(in, i, 6 * c.m.n_out, tile), &c.tb};
     SplitAccumSink sink{make_field(out_root, i, 6, tile), make_field(out_tau, i, c.m.nv - off, tile), off};
-    Stack S{smem.data() + t, block};
+    Stack S = make_stack(smem.data(), t, sd);
     applyJT_instance(c.m, c.tb, make_field(qcache, i, c.m.nq, cache_tile), src, sink, S);
   }
   return 0;
@@ -122,13 +136,13 @@ extern "C" int emul_applyJT_rows(const rbd_model_desc* d, long long nrows, int b
   int rc = make_ctx(d, &c);
   if (rc) return rc;
   const int sd = smem_applyJT(c.m);
-  std::vector<double> smem((size_t)(sd > 0 ? sd : 1) * block, 1e300);
+  std::vector<double> smem((size_t)(sd > 0 ? sd : 1) * ((block + 31) / 32) * 32, 1e300);
   for (long long r = 0; r < nrows; ++r) {
     const int t = (int)(r % block);
     double n2 = 0.0;
     RowWrenchSrc src{col + row_ptr[r], val + 6 * (size_t)row_ptr[r], row_ptr[r + 1] - row_ptr[r], &c.tb};
     RowSink sink{out_rows + (size_t)r * c.m.nv, &n2};
-    Stack S{smem.data() + t, block};
+    Stack S = make_stack(smem.data(), t, sd);
     applyJT_instance(c.m, c.tb, make_field(qcache, row_instance[r], c.m.nq, cache_tile), src, sink, S);
     keep[r] = n2 > 1e-12 ? 1 : 0;
   }

@@ -47,11 +47,14 @@ def load_emul() -> C.CDLL:
     csrc = os.path.join(ROOT, "sofa", "rigidbodydynamics_b200", "csrc")
     deps = [src] + [os.path.join(csrc, f) for f in ("rbd_sweeps.h", "rbd_model_build.h", "rbd_dev_model.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", out, src])
+        subprocess.check_call(["g++", "-O2", "-march=native", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                               "-o", out, src])
     lib = C.CDLL(out)
     vp, ll, i = C.c_void_p, C.c_longlong, C.c_int
     lib.emul_last_error.restype = C.c_char_p
     lib.emul_model_info.argtypes = [vp, vp]
+    lib.emul_sincos.argtypes = [ll, vp, vp, vp]
+    lib.emul_sincos.restype = None
     lib.emul_eval.argtypes = [vp, ll, ll, i] + [vp] * 7
     lib.emul_apply.argtypes = [vp, ll, ll, i, vp, vp, vp, ll, vp]
     lib.emul_applyJ.argtypes = [vp, ll, ll, i, vp, ll, vp, vp, vp]

@@ -1,0 +1,177 @@
+"""CPU tests of the KERNEL BODIES: csrc/rbd_sweeps.h compiled by g++ (tests/emul, test-only shim) against the C oracle.
+Same templates, same stack/branch-slot layout, same tiled addressing as the sm_100a kernels; shared memory is a
+poisoned heap array so that a read-before-write shows up as 1e300 garbage."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import helpers
+from helpers import P, TOL_FP64, from_tiled, rel_err, to_tiled
+
+MODELS = helpers.all_models()
+IDS = [m.name for m in MODELS]
+
+
+def _cdesc(d):
+    from sofa.rigidbodydynamics_b200._capi import make_desc
+    return make_desc(d)
+
+
+def _emul_eval(emul, d, q, v, a, tile, block, want):
+    n = q.shape[0]
+    cd, keep = _cdesc(d)
+    nt = (n + tile - 1) // tile
+    K = {"oMi": 12 * (d.njoints - 1), "J": 6 * d.nv, "M": d.nv * (d.nv + 1) // 2, "tau": d.nv}
+    outs = {k: (np.full((nt, K[k], tile), np.nan) if k in want else None) for k in K}
+    qs, vs, as_ = to_tiled(q, tile), to_tiled(v, tile), to_tiled(a, tile)
+    rc = emul.emul_eval(C.addressof(cd), n, tile, block, P(qs), P(vs), P(as_), P(outs["oMi"]), P(outs["J"]),
+                        P(outs["M"]), P(outs["tau"]))
+    assert rc == 0, emul.emul_last_error()
+    return {k: (from_tiled(o, n) if o is not None else None) for k, o in outs.items()}
+
+
+@pytest.mark.parametrize("d", MODELS, ids=IDS)
+@pytest.mark.parametrize("tile,block", [(32, 64), (7, 32), (100, 96)])
+def test_eval_bodies_match_oracle(emul, d, tile, block):
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    n = 70
+    q, v, a = mdl.random_state(d, n, seed=3)
+    got = _emul_eval(emul, d, q, v, a, tile, block, ("oMi", "J", "M", "tau"))
+    ref, _ = oracle.eval_batch(d, q, v, a, 1)
+    for k in ref:
+        assert rel_err(got[k], ref[k]) <= TOL_FP64, k
+
+
+@pytest.mark.parametrize("want", [("M",), ("tau",), ("oMi", "J"), ("J", "tau"), ("oMi", "M"), ("oMi",)])
+@pytest.mark.parametrize("name", ["talos_reduced", "random_3", "random_2"])
+def test_eval_partial_outputs(emul, name, want):
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    d = [m for m in MODELS if m.name == name][0]
+    q, v, a = mdl.random_state(d, 40, seed=4)
+    got = _emul_eval(emul, d, q, v, a, 32, 64, want)
+    ref, _ = oracle.eval_batch(d, q, v, a, 1)
+    for k in want:
+        assert rel_err(got[k], ref[k]) <= TOL_FP64, k
+
+
+def _split(d, q, v):
+    if d.has_freeflyer_root:
+        return (np.ascontiguousarray(q[:, 7:]), np.ascontiguousarray(q[:, :7]),
+                np.ascontiguousarray(v[:, 6:]), np.ascontiguousarray(v[:, :6]))
+    return q, None, v, None
+
+
+@pytest.mark.parametrize("d", MODELS, ids=IDS)
+def test_mapping_bodies_match_oracle(emul, d):
+    """apply -> applyJ -> applyJT -> applyJT(rows): the component's call order (KCM.inl:338-639)."""
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    n, tile, block, ctile = 45, 16, 64, 64
+    q, v, _ = mdl.random_state(d, n, seed=8)
+    qj, root, dq, rootv = _split(d, q, v)
+    cd, keep = _cdesc(d)
+    T = lambda x: None if x is None else to_tiled(x, tile)
+    nt = (n + tile - 1) // tile
+    qcache = np.full(((n + ctile - 1) // ctile, d.nq, ctile), np.nan)
+    pos = np.full((nt, 7 * d.n_out, tile), np.nan)
+    tq, tr = T(qj), T(root)
+    assert emul.emul_apply(C.addressof(cd), n, tile, block, P(tq), P(tr), P(qcache), ctile, P(pos)) == 0
+    assert rel_err(from_tiled(qcache, n), q) == 0.0
+    vel = np.full((nt, 6 * d.n_out, tile), np.nan)
+    tdq, trv = T(dq), T(rootv)
+    assert emul.emul_applyJ(C.addressof(cd), n, tile, block, P(qcache), ctile, P(tdq), P(trv), P(vel)) == 0
+    rng = np.random.default_rng(5)
+    w = rng.uniform(-1, 1, (n, 6 * d.n_out))
+    tau0 = rng.uniform(-1, 1, (n, d.nv_joints)); root0 = rng.uniform(-1, 1, (n, 6))
+    tw, ttau = T(w), T(tau0)
+    trt = T(root0) if root is not None else None
+    assert emul.emul_applyJT(C.addressof(cd), n, tile, block, P(qcache), ctile, P(tw), P(ttau), P(trt)) == 0
+    pos = from_tiled(pos, n).reshape(n, d.n_out, 7); vel = from_tiled(vel, n).reshape(n, d.n_out, 6)
+    tau = from_tiled(ttau, n); rt = from_tiled(trt, n) if trt is not None else None
+    orc = oracle.Oracle(d)
+    # constraint rows: 2 rows per instance
+    row_ptr = [0]; row_inst = []; cols = []; vals = []
+    for i in range(n):
+        for _ in range(2):
+            nnz = int(rng.integers(0, 4))
+            for _ in range(nnz):
+                cols.append(int(rng.integers(0, d.n_out))); vals.append(rng.uniform(-1, 1, 6))
+            row_ptr.append(len(cols)); row_inst.append(i)
+    row_ptr = np.array(row_ptr, dtype=np.int32); row_inst = np.array(row_inst, dtype=np.int32)
+    cols = np.array(cols, dtype=np.int32); vals = np.array(vals, dtype=np.float64).reshape(-1, 6)
+    nrows = len(row_inst)
+    rows = np.full((nrows, d.nv), np.nan); keepf = np.zeros(nrows, dtype=np.int32)
+    assert emul.emul_applyJT_rows(C.addressof(cd), nrows, block, P(qcache), ctile, P(row_ptr), P(row_inst), P(cols),
+                                  P(vals), P(rows), P(keepf)) == 0
+    for i in range(n):
+        rp = orc.apply(qj[i], None if root is None else root[i])
+        assert rel_err(pos[i][:, :3], rp[:, :3]) <= TOL_FP64
+        assert helpers.quat_err(pos[i][:, 3:], rp[:, 3:]) <= 1e-9
+        assert rel_err(vel[i], orc.applyJ(dq[i], None if rootv is None else rootv[i])) <= TOL_FP64
+        rtau, rroot = orc.applyJT(w[i], tau0[i], root0[i] if root is not None else None)
+        assert rel_err(tau[i], rtau) <= TOL_FP64
+        if root is not None:
+            assert rel_err(rt[i], rroot) <= TOL_FP64
+        for r in (2 * i, 2 * i + 1):
+            b, e = row_ptr[r], row_ptr[r + 1]
+            rrow, rkeep = orc.applyJT_row(cols[b:e], vals[b:e])
+            assert rel_err(rows[r], rrow) <= TOL_FP64
+            assert bool(keepf[r]) == rkeep
+
+
+def test_quaternion_branches(emul):
+    """rot_to_quat follows Eigen's branch order (Conversions.h:60): same quaternion SIGN as the oracle (not just the
+    same rotation) on rotations that hit all four branches.  Not bitwise: the kernels' sincos differs from libm by
+    an ulp."""
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    d = mdl.random_tree(11, 1, all_types=False)   # a single revolute joint: outputs rotate with q
+    rng = np.random.default_rng(2)
+    n = 400
+    q = rng.uniform(-np.pi, np.pi, (n, d.nq))
+    q[:8, 0] = [0.0, np.pi, -np.pi, np.pi / 2, -np.pi / 2, 3.0, -3.0, 1e-9]
+    cd, keep = _cdesc(d)
+    tq = to_tiled(q, 32)
+    pos = np.full((tq.shape[0], 7 * d.n_out, 32), np.nan)
+    assert emul.emul_apply(C.addressof(cd), n, 32, 32, P(tq), None, None, 32, P(pos)) == 0
+    pos = from_tiled(pos, n).reshape(n, d.n_out, 7)
+    orc = oracle.Oracle(d)
+    bad = 0
+    for i in range(n):
+        ref = orc.apply(q[i])
+        assert helpers.quat_err(pos[i][:, 3:], ref[:, 3:]) <= 1e-12
+        if np.max(np.abs(pos[i] - ref)) > 1e-12:
+            bad += 1          # sign flipped: only legitimate exactly on a branch boundary (e.g. q = +-pi)
+    assert bad <= 3
+
+
+def test_stack_budget(emul):
+    """Shared-memory doubles per instance (DESIGN.md 'state budget')."""
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    info = (C.c_int * 8)()
+    for d, max_full in ((mdl.panda7(), 140), (mdl.solo12(), 120), (mdl.talos_reduced(), 280)):
+        cd, keep = _cdesc(d)
+        assert emul.emul_model_info(C.addressof(cd), info) == 0
+        assert info[4] <= max_full, (d.name, list(info))
+
+
+def test_sincos_accuracy(emul):
+    """The kernels' own sincos (Cody-Waite + fdlibm kernels) against 40-digit mpmath over the fast-path range and
+    through the library fallback beyond it."""
+    import mpmath
+    mpmath.mp.dps = 40
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-np.pi, np.pi, 3000), rng.uniform(-1e5, 1e5, 3000), rng.uniform(-1e9, 1e9, 200),
+                        np.array([0.0, -0.0, np.pi / 2, np.pi, -np.pi, 1e-300, 0.7853981633974483, 99999.999, 1e5, 3e5]),
+                        np.arange(-40, 41) * (np.pi / 4)])
+    x = np.ascontiguousarray(x)
+    s = np.zeros_like(x); c = np.zeros_like(x)
+    emul.emul_sincos(x.shape[0], P(x), P(s), P(c))
+    rs = np.array([float(mpmath.sin(mpmath.mpf(float(t)))) for t in x])
+    rc = np.array([float(mpmath.cos(mpmath.mpf(float(t)))) for t in x])
+    assert np.max(np.abs(s - rs)) <= 4.5e-16, np.max(np.abs(s - rs))
+    assert np.max(np.abs(c - rc)) <= 4.5e-16, np.max(np.abs(c - rc))
+    assert np.max(np.abs(s * s + c * c - 1.0)) <= 1e-15
