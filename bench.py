@@ -193,8 +193,9 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="talos", choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=0, help="instances per GPU (default: the BASELINE size of the workload)")
-    ap.add_argument("--tile", type=int, default=0, help="tiled-SoA tile (0 = plain SoA, tile = n)")
+    ap.add_argument("--tile", type=int, default=32, help="tiled-SoA tile (32 = AoSoA fast path, 0 = plain SoA, tile = n)")
     ap.add_argument("--block", type=int, default=0, help="eval kernel block size override (0 = automatic)")
+    ap.add_argument("--no-tmem", action="store_true", help="keep the whole sweep state in shared memory (A/B knob)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -227,6 +228,8 @@ def main():
     dyn = BatchedDynamics(desc, n, device=local, tile=(args.tile or None))
     if args.block:
         dyn.ws.set_eval_block(args.block)
+    if args.no_tmem:
+        dyn.ws.set_eval_tmem(False)
     I = dyn.model.info
     nq, nv = I.nq, I.nv
     bytes_per_eval = int(I.eval_bytes)
@@ -336,6 +339,7 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"{desc.name} N={n} per GPU, fused FK+Jac+CRBA+RNEA, all outputs written",
                            "robot": desc.name, "instances_per_gpu": n, "layout": f"tiled SoA, tile={dyn.tile}",
+                           "eval_storage": dyn.ws.eval_plan(True, True),
                            "l2": f"inputs+outputs {step_bytes / 2**20:.0f} MiB per step > 126 MiB L2, no flush needed",
                            "note": desc.note, "sharding": f"instances, contiguous ranges, {world} rank(s), no collective"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),

@@ -112,6 +112,8 @@ typedef struct rbd_model_info {
   int32_t max_depth;            /* longest joint chain                                                   */
   int32_t eval_smem_doubles;    /* shared-memory doubles per instance used by the fused eval kernel      */
   int64_t eval_bytes;           /* algorithmic bytes per eval                          */
+  int32_t eval_tmem_doubles;    /* tensor-memory doubles per instance used by the fused eval kernel      */
+  int32_t eval_warps_per_sm;    /* resident warps per SM the storage plan of the fused eval reaches      */
 } rbd_model_info;
 
 /* ---------------------------------------------------------------------------------------------------- */
@@ -139,6 +141,14 @@ RBD_API int rbd_workspace_synchronize(rbd_workspace* ws);
 RBD_API int64_t rbd_workspace_launch_count(const rbd_workspace* ws);
 /* Block size override for the fused eval kernel (0 = automatic).  Tuning knob, not part of the contract. */
 RBD_API int rbd_workspace_set_eval_block(rbd_workspace* ws, int threads);
+/* Tensor memory as sweep-state storage of the fused eval kernel: 1 = on (default), 0 = shared memory only.
+ * Tuning / A-B knob, not part of the contract: results are identical either way.                         */
+RBD_API int rbd_workspace_set_eval_tmem(rbd_workspace* ws, int enable);
+/* Storage plan the fused eval kernel uses on this workspace for the output set (with_M, with_tau):
+ * out[0] warps per block, [1] blocks per SM, [2] shared-memory doubles per instance, [3] tensor-memory doubles per
+ * instance, [4] tensor-memory columns per block, [5] 1 if the Y-stack lives in tensor memory, [6] shared-memory
+ * bytes per block, [7] reserved.  Introspection for bench.py / DESIGN.md.                                 */
+RBD_API int rbd_workspace_get_eval_plan(rbd_workspace* ws, int with_M, int with_tau, int32_t out[8]);
 
 /* ---------------------------------------------------------------------------------------------------- */
 /* Mapping path, device SoA.                                                                            */

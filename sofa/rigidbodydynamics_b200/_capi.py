@@ -36,7 +36,7 @@ class RbdModelInfo(C.Structure):
                 ("n_out", C.c_int32), ("has_freeflyer_root", C.c_int32), ("nq_joints", C.c_int32),
                 ("nv_joints", C.c_int32), ("omi_fields", C.c_int32), ("jac_fields", C.c_int32),
                 ("mass_fields", C.c_int32), ("max_depth", C.c_int32), ("eval_smem_doubles", C.c_int32),
-                ("eval_bytes", C.c_int64)]
+                ("eval_bytes", C.c_int64), ("eval_tmem_doubles", C.c_int32), ("eval_warps_per_sm", C.c_int32)]
 
 
 def _dp(a: np.ndarray):
@@ -70,7 +70,7 @@ SYMBOLS = [
     "rbd_version", "rbd_last_error", "rbd_clear_error", "rbd_device_count",
     "rbd_model_create", "rbd_model_destroy", "rbd_model_get_info",
     "rbd_workspace_create", "rbd_workspace_destroy", "rbd_workspace_set_stream", "rbd_workspace_synchronize",
-    "rbd_workspace_launch_count", "rbd_workspace_set_eval_block",
+    "rbd_workspace_launch_count", "rbd_workspace_set_eval_block", "rbd_workspace_set_eval_tmem", "rbd_workspace_get_eval_plan",
     "rbd_apply_soa", "rbd_applyJ_soa", "rbd_applyJT_soa", "rbd_applyJT_rows_dev",
     "rbd_eval_soa", "rbd_crba_soa", "rbd_rnea_soa",
     "rbd_aos_to_soa_dev", "rbd_soa_to_aos_dev",
@@ -105,6 +105,8 @@ def load() -> C.CDLL:
         "rbd_workspace_synchronize": (C.c_int, [vp]),
         "rbd_workspace_launch_count": (i64, [vp]),
         "rbd_workspace_set_eval_block": (C.c_int, [vp, C.c_int]),
+        "rbd_workspace_set_eval_tmem": (C.c_int, [vp, C.c_int]),
+        "rbd_workspace_get_eval_plan": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_int32 * 8)]),
         "rbd_apply_soa": (C.c_int, [vp, i64, i64, vp, vp, vp]),
         "rbd_applyJ_soa": (C.c_int, [vp, i64, i64, vp, vp, vp]),
         "rbd_applyJT_soa": (C.c_int, [vp, i64, i64, vp, vp, vp]),

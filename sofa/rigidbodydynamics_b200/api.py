@@ -108,6 +108,16 @@ class Workspace:
     def set_eval_block(self, threads: int):
         check(self._lib.rbd_workspace_set_eval_block(self._h, int(threads)))
 
+    def set_eval_tmem(self, enable: bool):
+        check(self._lib.rbd_workspace_set_eval_tmem(self._h, 1 if enable else 0))
+
+    def eval_plan(self, with_M: bool = True, with_tau: bool = True) -> dict:
+        out = (C.c_int32 * 8)()
+        check(self._lib.rbd_workspace_get_eval_plan(self._h, int(with_M), int(with_tau), C.byref(out)))
+        keys = ("warps_per_block", "blocks_per_sm", "smem_doubles", "tmem_doubles", "tmem_cols", "y_in_tmem",
+                "smem_bytes_per_block")
+        return {k: int(out[i]) for i, k in enumerate(keys)}
+
     # -- device tiled-SoA entry points ----------------------------------------------------------------------
     def eval_soa(self, n, tile, q, v=None, a=None, oMi=None, J=None, M=None, tau=None):
         check(self._lib.rbd_eval_soa(self._h, n, tile, _dev_ptr(q), _dev_ptr(v), _dev_ptr(a), _dev_ptr(oMi),

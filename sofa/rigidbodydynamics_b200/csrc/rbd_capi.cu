@@ -56,7 +56,11 @@ struct rbd_workspace {
   int *d_sorted_k = nullptr, *d_outk_parent = nullptr;
   double *d_sorted_pl = nullptr, *d_outk_pl = nullptr;
   DevTables tb{};
-  DevModel* d_model = nullptr;  // device copy of the joint table (staged into shared memory by the eval kernel)
+  // fused eval: one planned copy of the joint table per variant (bit 1 = CRBA, bit 0 = RNEA), host + device;
+  // the kernel stages the device copy into shared memory
+  DevModel* h_plan[4] = {nullptr, nullptr, nullptr, nullptr};
+  DevModel* d_plan[4] = {nullptr, nullptr, nullptr, nullptr};
+  int use_tmem = 1;
   double* qcache = nullptr;  // [nq][capacity] assembled configuration of the last apply
   long long applied_n = 0;   // instances covered by the cache (0 = apply not called yet)
   LaunchCfg cfg_eval[8], cfg_apply, cfg_applyJ, cfg_applyJT, cfg_rows;
@@ -71,6 +75,8 @@ struct rbd_workspace {
   void* rows_buf = nullptr;
   size_t rows_bytes = 0;
 };
+
+static void drop_plans(rbd_workspace* ws);
 
 struct DeviceGuard {
   int prev = -1;
@@ -124,7 +130,16 @@ RBD_API int rbd_model_create(const rbd_model_desc* desc, rbd_model** out) {
   I.njoints = d.njoints; I.nq = d.nq; I.nv = d.nv; I.nframes = desc->nframes; I.n_out = d.n_out;
   I.has_freeflyer_root = d.has_ff_root; I.nq_joints = d.nq_joints; I.nv_joints = d.nv_joints;
   I.omi_fields = 12 * (d.njoints - 1); I.jac_fields = 6 * d.nv; I.mass_fields = d.nv * (d.nv + 1) / 2;
-  I.max_depth = d.max_depth; I.eval_smem_doubles = smem_eval(d, true, true);
+  I.max_depth = d.max_depth;
+  {
+    DevModel tmp = d;
+    if (plan_eval(&tmp, true, true, true)) {
+      I.eval_smem_doubles = tmp.plan.smem_doubles; I.eval_tmem_doubles = tmp.plan.tmem_doubles;
+      I.eval_warps_per_sm = tmp.plan.warps * tmp.plan.blocks_per_sm;
+    } else {
+      I.eval_smem_doubles = I.eval_tmem_doubles = I.eval_warps_per_sm = -1;
+    }
+  }
   I.eval_bytes = 8LL * ((d.nq + 2 * d.nv) + I.omi_fields + I.jac_fields + I.mass_fields + d.nv);
   *out = m;
   return RBD_OK;
@@ -140,7 +155,8 @@ RBD_API int rbd_model_get_info(const rbd_model* model, rbd_model_info* info) {
 static void ws_free(rbd_workspace* ws) {
   if (!ws) return;
   cudaFree(ws->d_sorted_k); cudaFree(ws->d_outk_parent); cudaFree(ws->d_sorted_pl); cudaFree(ws->d_outk_pl);
-  cudaFree(ws->qcache); cudaFree(ws->rows_buf); cudaFree(ws->d_model);
+  cudaFree(ws->qcache); cudaFree(ws->rows_buf);
+  for (int k = 0; k < 4; ++k) { cudaFree(ws->d_plan[k]); delete ws->h_plan[k]; }
   for (int s = 0; s < kSlots; ++s) {
     cudaFree(ws->slot[s].aos); cudaFree(ws->slot[s].soa);
     if (ws->slot[s].st) cudaStreamDestroy(ws->slot[s].st);
@@ -184,8 +200,6 @@ RBD_API int rbd_workspace_create(const rbd_model* model, int device, int64_t cap
   }
   ws->tb.sorted_k = ws->d_sorted_k; ws->tb.sorted_pl = ws->d_sorted_pl;
   ws->tb.outk_parent = ws->d_outk_parent; ws->tb.outk_pl = ws->d_outk_pl;
-  WS_CK(cudaMalloc(&ws->d_model, sizeof(DevModel)));
-  WS_CK(cudaMemcpy(ws->d_model, &model->dm, sizeof(DevModel), cudaMemcpyHostToDevice));
   WS_CK(cudaMalloc(&ws->qcache, (size_t)(model->dm.nq > 0 ? model->dm.nq : 1) * (size_t)capacity * sizeof(double)));
   WS_CK(cudaEventCreateWithFlags(&ws->ev, cudaEventDisableTiming));
 #undef WS_CK
@@ -212,7 +226,13 @@ RBD_API int64_t rbd_workspace_launch_count(const rbd_workspace* ws) { return ws 
 RBD_API int rbd_workspace_set_eval_block(rbd_workspace* ws, int threads) {
   if (!ws) return set_err(RBD_ERR_INVALID_ARG, "null workspace");
   if (threads < 0 || threads > 256 || threads % 32 != 0) return set_err(RBD_ERR_INVALID_ARG, "block must be 0 or a multiple of 32 <= 256");
-  ws->forced_eval_block = threads;
+  GUARD(ws);
+  if (ws->forced_eval_block != threads) { ws->forced_eval_block = threads; drop_plans(ws); }
+  return RBD_OK;
+}
+RBD_API int rbd_workspace_set_eval_tmem(rbd_workspace* ws, int enable) {
+  GUARD(ws);
+  if ((ws->use_tmem != 0) != (enable != 0)) { ws->use_tmem = enable ? 1 : 0; drop_plans(ws); }
   return RBD_OK;
 }
 
@@ -224,14 +244,54 @@ static int check_batch(const rbd_workspace* ws, int64_t n, int64_t tile) {
 }
 
 // ---- device SoA entry points (enqueue only) -----------------------------------------------------------------
+// plan (once per variant and tuning-knob setting) + upload of the planned joint table
+static int ensure_plan(rbd_workspace* ws, int pk) {
+  if (ws->h_plan[pk]) return RBD_OK;
+  DevModel* h = new (std::nothrow) DevModel(ws->model->dm);
+  if (!h) return set_err(RBD_ERR_ALLOC, "out of host memory");
+  if (!plan_eval(h, (pk & 2) != 0, (pk & 1) != 0, ws->use_tmem != 0, ws->forced_eval_block / 32)) {
+    delete h;
+    return set_err(RBD_ERR_UNSUPPORTED, "the sweep state of this model does not fit one SM's shared + tensor memory"
+                                        " at the requested block size");
+  }
+  if (!ws->d_plan[pk]) {
+    cudaError_t e = cudaMalloc(&ws->d_plan[pk], sizeof(DevModel));
+    if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaMalloc(plan)"); }
+  }
+  // synchronous copy from a stable host object, ordered before any later launch on any stream of this device
+  cudaError_t e = cudaMemcpy(ws->d_plan[pk], h, sizeof(DevModel), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaMemcpy(plan)"); }
+  ws->h_plan[pk] = h;
+  return RBD_OK;
+}
+static void drop_plans(rbd_workspace* ws) {
+  // kernels still in flight keep reading the device copies: wait for them before the next upload overwrites
+  cudaDeviceSynchronize();
+  for (int k = 0; k < 4; ++k) { delete ws->h_plan[k]; ws->h_plan[k] = nullptr; }
+}
+
+RBD_API int rbd_workspace_get_eval_plan(rbd_workspace* ws, int with_M, int with_tau, int32_t out[8]) {
+  GUARD(ws);
+  if (!out) return set_err(RBD_ERR_INVALID_ARG, "null out");
+  const int pk = (with_M ? 2 : 0) | (with_tau ? 1 : 0);
+  int rc = ensure_plan(ws, pk);
+  if (rc) return rc;
+  const DevModel& h = *ws->h_plan[pk];
+  out[0] = h.plan.warps; out[1] = h.plan.blocks_per_sm; out[2] = h.plan.smem_doubles; out[3] = h.plan.tmem_doubles;
+  out[4] = h.plan.tmem_cols; out[5] = h.plan.y_in_tmem;
+  out[6] = (int32_t)(eval_model_bytes(h) + (size_t)h.plan.warps * 32 * h.plan.smem_doubles * 8); out[7] = 0;
+  return RBD_OK;
+}
+
 static int eval_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, const double* q, const double* v,
                    const double* a, double* oMi, double* J, double* M, double* tau) {
-  const DevModel& dm = ws->model->dm;
   if (!q) return set_err(RBD_ERR_INVALID_ARG, "q is null");
   if (tau && (!v || !a)) return set_err(RBD_ERR_INVALID_ARG, "rnea needs v and a");
+  const int pk = (M ? 2 : 0) | (tau ? 1 : 0);
+  int rc = ensure_plan(ws, pk);
+  if (rc) return rc;
   EvalArgs A{n, tile, q, v, a, oMi, J, M, tau};
-  const int sd = smem_eval(dm, M != nullptr, tau != nullptr);
-  CK(launch_eval(dm, ws->d_model, A, sd, ws->forced_eval_block, ws->cfg_eval, st));
+  CK(launch_eval(*ws->h_plan[pk], ws->d_plan[pk], A, ws->cfg_eval, st));
   if (n > 0) ws->launches++;
   return RBD_OK;
 }

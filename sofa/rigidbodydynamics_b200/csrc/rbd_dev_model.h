@@ -33,7 +33,26 @@ struct DevJoint {
   int out_begin, out_end;  // range of this joint's mapped outputs in DevTables::sorted_*
   int pl_rot_identity;     // jointPlacement rotation is exactly I (skips one 3x3 product)
   int depth;               // number of joints on the path universe -> this joint
+  // fused-eval storage plan (EvalPlan below; filled by plan_eval for one kernel variant):
+  int offA;                // offset of this joint's A record (6 doubles, free-flyer 12) in the shared-memory A-stack
+  int boff;                // branch joints: offset of the saved (R|p)|v|a record; bit 30 set = lives in tensor memory
 };
+
+// Where the fused eval kernel keeps its per-instance sweep state (doubles per instance, DESIGN.md "state budget").
+// Shared memory holds the A-stack and the f-stack; the Y-stack and individual branch records go to TENSOR MEMORY
+// (tcgen05.ld/st, 256 KB per SM that this FP64 path would otherwise leave unused) when that raises the number of
+// resident warps.  All offsets are in doubles from the thread's base in the respective space.
+struct EvalPlan {
+  int fbase;         // shared: f-stack, 6 per internal depth level (RNEA)
+  int ybase;         // Y-stack, 10 per internal depth level (CRBA): shared offset, or tensor-memory offset
+  int y_in_tmem;     // 1 = Y-stack lives in tensor memory
+  int smem_doubles;  // shared-memory doubles per instance
+  int tmem_doubles;  // tensor-memory doubles per instance (0 = tensor memory unused)
+  int warps;         // warps per block
+  int blocks_per_sm; // blocks the plan expects to be resident per SM
+  int tmem_cols;     // columns the block allocates (power of two >= 32, or 0)
+};
+#define RBD_BOFF_TMEM (1 << 30)
 
 struct DevModel {
   int njoints, nq, nv, n_out;
@@ -41,8 +60,9 @@ struct DevModel {
   int nbranch;
   int has_ff_root;    // joint 1 is a free-flyer attached to the universe
   int nq_joints, nv_joints;
-  int max_depth, pad_;
+  int max_depth, max_depth_internal;  // longest joint chain; deepest joint that has children
   double gravity[3];
+  EvalPlan plan;
   DevJoint joint[RBD_MAX_JOINTS];
 };
 
@@ -50,6 +70,10 @@ struct DevModel {
 inline size_t dev_model_bytes(const DevModel& m) {
   return sizeof(DevModel) - sizeof(DevJoint) * (size_t)(RBD_MAX_JOINTS - m.njoints);
 }
+
+// shared-memory bytes the eval kernel reserves in front of the stacks: the staged table rounded to 16 bytes plus two
+// spare 8-byte words (tensor-memory base address)
+inline size_t eval_model_bytes(const DevModel& m) { return (dev_model_bytes(m) + 15) / 16 * 16 + 16; }
 
 // Per-output tables (global memory; only the mapping kernels read them).
 struct DevTables {

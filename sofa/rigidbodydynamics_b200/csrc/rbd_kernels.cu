@@ -25,18 +25,43 @@ extern __shared__ double rbd_smem[];
 // a single broadcast wavefront at a fixed ~30-cycle latency.  (Round-1 profile r1b: the same table read through
 // the constant bank with run-time indices cost ~40 stall samples per dependent ISETP — the 8.7 KB table does not
 // stay in the small constant L1 while three warps walk it at different phases.)
+//
+// Tensor memory: when the plan says so (m.plan.tmem_cols > 0) warp 0 allocates the block's columns, every thread
+// derives its private slice (lane quarter of its warp, column range of its warp group), and warp 0 frees them
+// after the whole block is done.  Lanes past the end of the batch recompute the last instance instead of
+// exiting: tcgen05.ld/st are warp-collective (.sync.aligned) and the duplicate stores write identical values.
 template <bool DO_M, bool DO_TAU, int TILE>
-__global__ void __launch_bounds__(256) eval_kernel(const DevModel* __restrict__ gm, const EvalArgs a, const int slots,
+__global__ void __launch_bounds__(256) eval_kernel(const DevModel* __restrict__ gm, const EvalArgs a,
                                                    const int model_words) {
+  // the last two staged words are spare: the tensor-memory base address lands there (no static shared memory, so
+  // the block can ask for the full 227 KB dynamically)
+  unsigned* const tm_base_p = reinterpret_cast<unsigned*>(rbd_smem + model_words - 2);
   {
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gm);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(rbd_smem);
-    for (int w = threadIdx.x; w < model_words; w += blockDim.x) dst[w] = src[w];
+    for (int w = threadIdx.x; w < model_words - 2; w += blockDim.x) dst[w] = src[w];
   }
   __syncthreads();
   const DevModel& m = *reinterpret_cast<const DevModel*>(rbd_smem);
-  const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (inst >= a.n) return;
+  const int warp = threadIdx.x >> 5;
+  const int tm_cols = m.plan.tmem_cols;
+  TmStack T;
+  T.base = 0;
+  if (tm_cols > 0) {
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"l"(
+                       (unsigned long long)__cvta_generic_to_shared(tm_base_p)),
+                   "r"(tm_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    T.base = *tm_base_p + (((unsigned)(warp & 3) * 32u) << 16) + (unsigned)(warp >> 2) * 2u * (unsigned)m.plan.tmem_doubles;
+  }
+  long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= a.n) inst = a.n - 1;
   EvalIOT<TILE> io;
   io.q = make_field_t<TILE>(const_cast<double*>(a.q), inst, m.nq, a.tile);
   io.v = make_field_t<TILE>(const_cast<double*>(a.v), inst, m.nv, a.tile);
@@ -45,7 +70,13 @@ __global__ void __launch_bounds__(256) eval_kernel(const DevModel* __restrict__ 
   io.J = make_field_t<TILE>(a.J, inst, 6 * m.nv, a.tile);
   io.M = make_field_t<TILE>(a.M, inst, m.nv * (m.nv + 1) / 2, a.tile);
   io.tau = make_field_t<TILE>(a.tau, inst, m.nv, a.tile);
-  eval_instance<DO_M, DO_TAU, TILE>(m, io, make_stack(rbd_smem + model_words, threadIdx.x, slots));
+  eval_instance<DO_M, DO_TAU, TILE>(m, io, make_stack(rbd_smem + model_words, threadIdx.x, m.plan.smem_doubles), T);
+  if (tm_cols > 0) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tm_base_p), "r"(tm_cols) : "memory");
+  }
 }
 
 // K1: apply
@@ -188,23 +219,29 @@ static cudaError_t pick_block(Kern kern, int smem_doubles_per_thread, int forced
     default: CALL((eval_kernel<false, false, 0>)); break;   \
   }
 
-cudaError_t launch_eval(const DevModel& m, const DevModel* d_model, const EvalArgs& a, int smem_doubles,
-                        int forced_block, LaunchCfg* cache, cudaStream_t st) {
+// `hm` is the host copy of the planned model (hm.plan chosen by plan_eval), `d_model` its device copy.
+cudaError_t launch_eval(const DevModel& hm, const DevModel* d_model, const EvalArgs& a, LaunchCfg* cache,
+                        cudaStream_t st) {
   const bool do_m = a.M != nullptr, do_tau = a.tau != nullptr;
   const int v = (a.tile == 32 ? 4 : 0) | (do_m ? 2 : 0) | (do_tau ? 1 : 0);
   LaunchCfg& cfg = cache[v];
-  const int model_words = (int)((dev_model_bytes(m) + 15) / 16) * 2;  // 8-byte words, stacks stay 16-byte aligned
+  const int model_words = (int)(eval_model_bytes(hm) / 8);  // staged joint table + 2 spare words
+  const int block = hm.plan.warps * 32;
+  const size_t smem = (size_t)model_words * 8 + (size_t)block * hm.plan.smem_doubles * 8;
   cudaError_t e = cudaSuccess;
-  if (cfg.block == 0 || cfg.forced != forced_block) {
-#define RBD_PICK(K) e = pick_block(K, smem_doubles, forced_block, &cfg, (size_t)model_words * 8)
-    RBD_EVAL_DISPATCH(v, RBD_PICK)
-#undef RBD_PICK
+  if (cfg.block != block || cfg.smem_bytes != smem) {
+#define RBD_ATTR(K)                                                                                     \
+  e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin);             \
+  if (e == cudaSuccess)                                                                                 \
+    e = cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
+    RBD_EVAL_DISPATCH(v, RBD_ATTR)
+#undef RBD_ATTR
     if (e != cudaSuccess) return e;
-    cfg.forced = forced_block;
+    cfg.block = block; cfg.smem_bytes = smem; cfg.blocks_per_sm = hm.plan.blocks_per_sm;
   }
   if (a.n <= 0) return cudaSuccess;
-  const unsigned grid = RBD_GRID(a.n, cfg.block);
-#define RBD_LAUNCH(K) K<<<grid, cfg.block, cfg.smem_bytes, st>>>(d_model, a, smem_doubles, model_words)
+  const unsigned grid = RBD_GRID(a.n, block);
+#define RBD_LAUNCH(K) K<<<grid, block, smem, st>>>(d_model, a, model_words)
   RBD_EVAL_DISPATCH(v, RBD_LAUNCH)
 #undef RBD_LAUNCH
   return cudaGetLastError();

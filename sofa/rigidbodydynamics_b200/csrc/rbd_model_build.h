@@ -85,6 +85,7 @@ inline int build_dev_model(const rbd_model_desc* d, DevModel* m, HostTables* tb,
     if (m->joint[i].nchild > 0) maxd_internal = std::max(maxd_internal, depth[i]);
   }
   m->max_depth = maxd;
+  m->max_depth_internal = maxd_internal;
   std::vector<int> aw(maxd + 1, 6);
   for (int i = 1; i < nj; ++i) aw[depth[i]] = std::max(aw[depth[i]], RBD_SLOT_A(d->jtype[i]));
   std::vector<int> off_full(maxd + 2, 0), off_lite(maxd + 2, 0);
@@ -99,6 +100,8 @@ inline int build_dev_model(const rbd_model_desc* d, DevModel* m, HostTables* tb,
     m->joint[i].slot[0] = off_full[depth[i]];
     m->joint[i].slot[1] = off_lite[depth[i]];
     m->joint[i].depth = depth[i];
+    m->joint[i].offA = 0;
+    m->joint[i].boff = 0;
     const double* pl = m->joint[i].pl;
     m->joint[i].pl_rot_identity = (pl[0] == 1.0 && pl[1] == 0.0 && pl[2] == 0.0 && pl[3] == 0.0 && pl[4] == 1.0 &&
                                    pl[5] == 0.0 && pl[6] == 0.0 && pl[7] == 0.0 && pl[8] == 1.0) ? 1 : 0;
@@ -127,11 +130,100 @@ inline int build_dev_model(const rbd_model_desc* d, DevModel* m, HostTables* tb,
   return RBD_OK;
 }
 
-// shared-memory doubles per instance of each kernel
-inline int smem_eval(const DevModel& m, bool do_m, bool do_tau) {
-  if (!do_m && !do_tau) return m.nbranch * RBD_BRANCH_FK;
-  return m.slot_total[do_m ? 0 : 1] + m.nbranch * (do_tau ? RBD_BRANCH_EVAL : RBD_BRANCH_FK);
+// ---------------------------------------------------------------------------------------------------------------
+// Storage plan of the fused eval kernel for one variant (do_m = CRBA, do_tau = RNEA).
+//
+// Per-instance sweep state (doubles), D = number of depth levels that hold joints with children:
+//   A-stack   sum of A widths over the D levels (6, free-flyer level 12)        shared memory, read by every column
+//   f-stack   6 D          (RNEA subtree forces)                                  shared memory
+//   Y-stack   10 D         (CRBA composite inertias)                              shared or tensor memory
+//   branch    per joint with >= 2 children: (R|p) 12 [not for a free-flyer: its A record already is R|p] + v|a 12
+//             (RNEA)                                                              shared or tensor memory, per record
+// B200 budget per SM: 227 KB shared memory (minus the staged joint table per block), 512 tensor-memory columns of
+// 128 lanes x 32 bit: a warp owns the 32 lanes of quarter (warp % 4), so a thread owns 512 / ceil(W / 4) columns =
+// 256 / ceil(W / 4) doubles in a block of W warps.  The plan maximises resident warps per SM.
+struct B200Limits {
+  static constexpr int kSmemBytes = 227 * 1024;
+  static constexpr int kSmemReservedPerBlock = 2048;  // 1 KB driver reservation per block + allocation granularity slack
+  static constexpr int kTmemCols = 512;
+  static constexpr int kRegsPerSM = 65536;
+  static constexpr int kRegsPerThread = 192;  // upper bound of what ptxas gives the eval kernels (launch_bounds 256)
+  static constexpr int kMaxWarpsPerBlock = 8;
+};
+
+inline int pow2_cols(int cols) {
+  int c = 32;
+  while (c < cols) c *= 2;
+  return c;
 }
+
+// Fills m->plan and m->joint[*].boff.  forced_warps > 0 pins the block size.  Returns false when nothing fits.
+inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int forced_warps = 0) {
+  const int nj = m->njoints;
+  const bool need_stack = do_m || do_tau;
+  const int D = need_stack ? m->max_depth_internal : 0;
+  int totalA = 0;
+  if (need_stack) {
+    std::vector<int> aw(D + 1, 6);
+    for (int i = 1; i < nj; ++i)
+      if (m->joint[i].nchild > 0) aw[m->joint[i].depth] = std::max(aw[m->joint[i].depth], RBD_SLOT_A(m->joint[i].type));
+    std::vector<int> pre(D + 2, 0);
+    for (int dd = 1; dd <= D; ++dd) pre[dd + 1] = pre[dd] + aw[dd];
+    totalA = pre[D + 1];
+    for (int i = 1; i < nj; ++i) m->joint[i].offA = m->joint[i].depth <= D ? pre[m->joint[i].depth] : 0;
+  }
+  const int fsz = do_tau ? 6 * D : 0, ysz = do_m ? 10 * D : 0;
+  std::vector<int> bj, bw;  // branch joints and record widths
+  for (int i = 1; i < nj; ++i)
+    if (m->joint[i].nchild >= 2) {
+      const bool ff_dedupe = need_stack && m->joint[i].type == JT_FF;
+      bj.push_back(i);
+      bw.push_back((ff_dedupe ? 0 : 12) + (do_tau ? 12 : 0));
+    }
+  const size_t model_bytes = eval_model_bytes(*m);
+  EvalPlan best{};
+  std::vector<int> best_boff;
+  int best_warps_sm = 0;
+  for (int W = 1; W <= B200Limits::kMaxWarpsPerBlock; ++W) {
+    if (forced_warps > 0 && W != forced_warps) continue;
+    const int cap = use_tmem ? (B200Limits::kTmemCols / ((W + 3) / 4)) / 2 : 0;  // doubles per thread
+    // greedy: Y-stack first (one vector access per visit), then the widest branch records that still fit
+    int t_used = 0;
+    EvalPlan pl{};
+    std::vector<int> boff(bj.size(), 0);
+    int s_used = totalA;
+    pl.fbase = s_used; s_used += fsz;
+    if (ysz > 0 && ysz <= cap) { pl.y_in_tmem = 1; pl.ybase = t_used; t_used += ysz; }
+    else { pl.y_in_tmem = 0; pl.ybase = s_used; s_used += ysz; }
+    std::vector<int> order(bj.size());
+    for (size_t k = 0; k < order.size(); ++k) order[k] = (int)k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bw[a] > bw[b]; });
+    for (int k : order) {
+      if (bw[k] > 0 && t_used + bw[k] <= cap) { boff[k] = t_used | RBD_BOFF_TMEM; t_used += bw[k]; }
+      else { boff[k] = s_used; s_used += bw[k]; }
+    }
+    pl.smem_doubles = s_used; pl.tmem_doubles = t_used; pl.warps = W;
+    pl.tmem_cols = t_used > 0 ? pow2_cols(2 * t_used * ((W + 3) / 4)) : 0;
+    const size_t block_bytes = model_bytes + (size_t)W * 32 * s_used * 8;
+    if (block_bytes > (size_t)B200Limits::kSmemBytes) continue;
+    int c = (int)(B200Limits::kSmemBytes / (block_bytes + B200Limits::kSmemReservedPerBlock));
+    if (c < 1) c = 1;
+    if (pl.tmem_cols > 0) c = std::min(c, B200Limits::kTmemCols / pl.tmem_cols);
+    c = std::min(c, B200Limits::kRegsPerSM / (B200Limits::kRegsPerThread * W * 32));
+    c = std::min(c, 32);
+    if (c < 1) continue;
+    pl.blocks_per_sm = c;
+    // more resident warps wins; on ties the LARGER block: the warps of one block spread over the four SM
+    // sub-partitions (warp % 4), whereas many one-warp blocks were measured 3x slower (r1c: 15.8 ms vs 5.2 ms)
+    if (W * c >= best_warps_sm) { best_warps_sm = W * c; best = pl; best_boff = boff; }
+  }
+  if (best_warps_sm == 0) return false;
+  m->plan = best;
+  for (size_t k = 0; k < bj.size(); ++k) m->joint[bj[k]].boff = best_boff[k];
+  return true;
+}
+
+// shared-memory doubles per instance of the mapping kernels
 inline int smem_apply(const DevModel& m) { return m.nbranch * RBD_BRANCH_FK; }
 inline int smem_applyJ(const DevModel& m) { return m.nbranch * RBD_BRANCH_J; }
 inline int smem_applyJT(const DevModel& m) { return m.slot_total[1] + m.nbranch * RBD_BRANCH_FK; }

@@ -56,7 +56,7 @@ using Field = FieldT<0>;
 template <int TILE>
 RBD_HD FieldT<TILE> make_field_t(double* base, long long inst, int K, long long tile) {
   FieldT<TILE> f;
-  if (TILE) {
+  if constexpr (TILE != 0) {
     f.stride = TILE;
     f.p = base ? base + (inst / TILE) * (long long)K * TILE + (inst % TILE) : nullptr;
   } else {
@@ -83,6 +83,91 @@ RBD_HD Stack make_stack(double* smem, int t, int slots) {
   s.p = smem + (long long)(t / RBD_WARP) * slots * RBD_WARP + (t % RBD_WARP);
   return s;
 }
+
+// TmStack: this thread's private slice of TENSOR MEMORY used as scratch (tcgen05.ld / tcgen05.st, shape 32x32b:
+// lane i of the warp <-> TMEM lane 32*(warp%4)+i, one 32-bit column per register; a double takes two columns).
+// `base` already contains the warp's lane quarter (bits 31:16) and the thread's first column (bits 15:0).
+// All lanes of a warp must execute these together (.sync.aligned): the eval sweep is warp-uniform by construction.
+// On the host (tests/emul) the same interface is backed by a plain array.
+#if defined(__CUDACC__)
+struct TmStack {
+  unsigned base;
+  template <int N>
+  __device__ __forceinline__ void issue_ld(unsigned addr, unsigned* r) const {
+#if defined(__CUDA_ARCH__)
+    if constexpr (N >= 8) {
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(addr) : "memory");
+      issue_ld<N - 8>(addr + 16, r + 16);
+    } else if constexpr (N >= 4) {
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                   : "r"(addr) : "memory");
+      issue_ld<N - 4>(addr + 8, r + 8);
+    } else if constexpr (N >= 2) {
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+      issue_ld<N - 2>(addr + 4, r + 4);
+    } else if constexpr (N == 1) {
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr) : "memory");
+    }
+#endif
+  }
+  template <int N>
+  __device__ __forceinline__ void issue_st(unsigned addr, const unsigned* r) const {
+#if defined(__CUDA_ARCH__)
+    if constexpr (N >= 8) {
+      asm volatile(
+          "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+          :: "r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+             "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+      issue_st<N - 8>(addr + 16, r + 16);
+    } else if constexpr (N >= 4) {
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                   :: "r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+      issue_st<N - 4>(addr + 8, r + 8);
+    } else if constexpr (N >= 2) {
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+                   :: "r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+      issue_st<N - 2>(addr + 4, r + 4);
+    } else if constexpr (N == 1) {
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" :: "r"(addr), "r"(r[0]), "r"(r[1]) : "memory");
+    }
+#endif
+  }
+  // v[0..N) <- doubles [k, k+N)
+  template <int N>
+  __host__ __device__ __forceinline__ void ldv(int k, double* v) const {
+    unsigned r[2 * N];
+#if defined(__CUDA_ARCH__)
+    issue_ld<N>(base + 2u * (unsigned)k, r);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]);
+#endif
+  }
+  // doubles [k, k+N) <- v[0..N); complete before returning (a later ldv of the same columns must see it)
+  template <int N>
+  __host__ __device__ __forceinline__ void stv(int k, const double* v) const {
+    unsigned r[2 * N];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int i = 0; i < N; ++i) { r[2 * i] = (unsigned)__double2loint(v[i]); r[2 * i + 1] = (unsigned)__double2hiint(v[i]); }
+    issue_st<N>(base + 2u * (unsigned)k, r);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#endif
+  }
+};
+#else
+struct TmStack {
+  double* p;
+  template <int N> void ldv(int k, double* v) const { for (int i = 0; i < N; ++i) v[i] = p[k + i]; }
+  template <int N> void stv(int k, const double* v) const { for (int i = 0; i < N; ++i) p[k + i] = v[i]; }
+};
+#endif
 
 // ---------------------------------------------------------------------------------------------------------
 // 3-vector helpers on scalars held in registers
@@ -351,27 +436,59 @@ struct EvalIOT {
 };
 using EvalIO = EvalIOT<0>;
 
+// ---- sweep-state storage (EvalPlan): vector accessors over the two spaces ----------------------------------------
+template <int N>
+RBD_HD void s_ldv(const Stack& S, int k, double* v) {
+#pragma unroll
+  for (int e = 0; e < N; ++e) v[e] = S.ld(k + e);
+}
+template <int N>
+RBD_HD void s_stv(const Stack& S, int k, const double* v) {
+#pragma unroll
+  for (int e = 0; e < N; ++e) S.st(k + e, v[e]);
+}
+// load / store / accumulate N doubles at offset k of shared (tm == false) or tensor memory (tm == true)
+template <int N>
+RBD_HD void x_ldv(bool tm, const Stack& S, const TmStack& T, int k, double* v) {
+  if (tm) T.ldv<N>(k, v); else s_ldv<N>(S, k, v);
+}
+template <int N>
+RBD_HD void x_stv(bool tm, const Stack& S, const TmStack& T, int k, const double* v) {
+  if (tm) T.stv<N>(k, v); else s_stv<N>(S, k, v);
+}
+template <int N>
+RBD_HD void x_addv(bool tm, const Stack& S, const TmStack& T, int k, const double* v) {
+  if (tm) {
+    double t[N];
+    T.ldv<N>(k, t);
+#pragma unroll
+    for (int e = 0; e < N; ++e) t[e] += v[e];
+    T.stv<N>(k, t);
+  } else {
+#pragma unroll
+    for (int e = 0; e < N; ++e) S.add(k + e, v[e]);
+  }
+}
+
 // Rows of packed column `base` above the joint that owns it: one entry per ancestor dof (A_anc . F), zeros for
 // the dofs of joints off the ancestor chain.  `anc` = first ancestor to visit, rows >= `next` are already written.
-template <int L, int TILE>
+template <int TILE>
 RBD_HD void column_tail(const DevModel& m, int anc, int next, int base, const double* F, const Stack& S,
                         const FieldT<TILE>& M) {
   for (; anc != 0; anc = m.joint[anc].parent) {
     const DevJoint& ja = m.joint[anc];
     const int iv = ja.idx_v;
     for (int r = iv + ja.nv; r < next; ++r) M.st(base + r, 0.0);
-    const int sa = ja.slot[L];
+    const int sa = ja.offA;
     if (ja.type == JT_FF) {
       double Rq[12], p6[6];
-#pragma unroll
-      for (int e = 0; e < 12; ++e) Rq[e] = S.ld(sa + e);
+      s_ldv<12>(S, sa, Rq);
       ff_rows(Rq, Rq + 9, F, p6);
 #pragma unroll
       for (int e = 0; e < 6; ++e) M.st(base + iv + e, p6[e]);
     } else {
       double Aa[6];
-#pragma unroll
-      for (int e = 0; e < 6; ++e) Aa[e] = S.ld(sa + e);
+      s_ldv<6>(S, sa, Aa);
       M.st(base + iv, dot6(Aa, F));
     }
     next = iv;
@@ -385,7 +502,6 @@ RBD_HD void column_tail(const DevModel& m, int anc, int next, int base, const do
 template <bool DO_M, bool DO_TAU, int TILE>
 RBD_HD void emit_joint(const DevModel& m, int k, const double* A, const double* f, const double* Y, const Stack& S,
                        const EvalIOT<TILE>& io) {
-  constexpr int L = DO_M ? 0 : 1;
   const DevJoint& jn = m.joint[k];
   if (jn.type != JT_FF) {
     if (DO_TAU) io.tau.st(jn.idx_v, dot6(A, f));
@@ -395,7 +511,7 @@ RBD_HD void emit_joint(const DevModel& m, int k, const double* A, const double* 
       const int col = jn.idx_v;
       const int base = col * (col + 1) / 2;
       io.M.st(base + col, dot6(A, F));
-      column_tail<L>(m, jn.parent, col, base, F, S, io.M);
+      column_tail(m, jn.parent, col, base, F, S, io.M);
     }
   } else {
 #pragma unroll
@@ -412,19 +528,20 @@ RBD_HD void emit_joint(const DevModel& m, int k, const double* A, const double* 
 #pragma unroll
         for (int e = 0; e < 6; ++e)
           if (e <= cc) io.M.st(base + jn.idx_v + e, o6[e]);
-        column_tail<L>(m, jn.parent, jn.idx_v, base, F, S, io.M);
+        column_tail(m, jn.parent, jn.idx_v, base, F, S, io.M);
       }
     }
   }
 }
 
+// One instance, one sweep.  S = this thread's shared-memory stack, T = its tensor-memory slice (m.plan says what
+// lives where).  Control flow depends on the model only, so all lanes of a warp stay converged.
 template <bool DO_M, bool DO_TAU, int TILE>
-RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stack& S) {
-  constexpr int L = DO_M ? 0 : 1;
+RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stack& S, const TmStack& T) {
   constexpr bool NEED_STACK = DO_M || DO_TAU;
   const int nj = m.njoints;
-  const int bbase = NEED_STACK ? m.slot_total[L] : 0;
-  constexpr int BW = DO_TAU ? RBD_BRANCH_EVAL : RBD_BRANCH_FK;
+  const int fbase = m.plan.fbase, ybase = m.plan.ybase;
+  const bool ytm = m.plan.y_in_tmem != 0;
   double R[9], p[3], vel[6], acc[6];
 #define RBD_RESET_ROOT()                                                   \
   do {                                                                     \
@@ -452,14 +569,25 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
       if (par == 0) {
         RBD_RESET_ROOT();
       } else {
-        const int b = bbase + m.joint[par].bidx * BW;
+        const DevJoint& jb = m.joint[par];
+        const bool btm = (jb.boff & RBD_BOFF_TMEM) != 0;
+        int b = jb.boff & ~RBD_BOFF_TMEM;
+        double Rp[12];
+        if (NEED_STACK && jb.type == JT_FF) {
+          s_ldv<12>(S, jb.offA, Rp);  // a free-flyer's A record is its R|p
+        } else {
+          x_ldv<12>(btm, S, T, b, Rp);
+          b += 12;
+        }
 #pragma unroll
-        for (int e = 0; e < 9; ++e) R[e] = S.ld(b + e);
+        for (int e = 0; e < 9; ++e) R[e] = Rp[e];
 #pragma unroll
-        for (int e = 0; e < 3; ++e) p[e] = S.ld(b + 9 + e);
+        for (int e = 0; e < 3; ++e) p[e] = Rp[9 + e];
         if (DO_TAU) {
+          double va[12];
+          x_ldv<12>(btm, S, T, b, va);
 #pragma unroll
-          for (int e = 0; e < 6; ++e) { vel[e] = S.ld(b + 12 + e); acc[e] = S.ld(b + 18 + e); }
+          for (int e = 0; e < 6; ++e) { vel[e] = va[e]; acc[e] = va[6 + e]; }
         }
       }
     }
@@ -481,7 +609,7 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
 #pragma unroll
       for (int e = 0; e < 3; ++e) io.oMi.st(o + 9 + e, p[e]);
     }
-    // Ak: world subspace column (1-dof) or R|p (free-flyer) — what the stack keeps for the CRBA/RNEA projections
+    // Ak: world subspace column (1-dof) or R|p (free-flyer) — what the A-stack keeps for the CRBA/RNEA projections
     double Ak[12], fk[6], Yk[10];
     if (jn.type != JT_FF) {
       subspace_1dof(jn.type, p, aw, Ak);
@@ -556,61 +684,50 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
         for (int e = 0; e < 6; ++e) acc[e] += aj[e] + cr[e];
       }
     }
-    if (!NEED_STACK) {
-      if (jn.nchild >= 2) {
-        const int b = bbase + jn.bidx * BW;
-#pragma unroll
-        for (int e = 0; e < 9; ++e) S.st(b + e, R[e]);
-#pragma unroll
-        for (int e = 0; e < 3; ++e) S.st(b + 9 + e, p[e]);
+    if (NEED_STACK) {
+      inertia_world(jn, R, p, Yk);
+      if (DO_TAU) {
+        // f = Y a + v x* (Y v)
+        double h[6];
+        inertia_mul(Yk, vel, h);
+        inertia_mul(Yk, acc, fk);
+        double tx, ty, tz;
+        RBD_CROSS(tx, ty, tz, vel[3], vel[4], vel[5], h[0], h[1], h[2]);
+        fk[0] += tx; fk[1] += ty; fk[2] += tz;
+        RBD_CROSS(tx, ty, tz, vel[3], vel[4], vel[5], h[3], h[4], h[5]);
+        fk[3] += tx; fk[4] += ty; fk[5] += tz;
+        RBD_CROSS(tx, ty, tz, vel[0], vel[1], vel[2], h[0], h[1], h[2]);
+        fk[3] += tx; fk[4] += ty; fk[5] += tz;
       }
-      continue;
-    }
-    inertia_world(jn, R, p, Yk);
-    if (DO_TAU) {
-      // f = Y a + v x* (Y v)
-      double h[6];
-      inertia_mul(Yk, vel, h);
-      inertia_mul(Yk, acc, fk);
-      double tx, ty, tz;
-      RBD_CROSS(tx, ty, tz, vel[3], vel[4], vel[5], h[0], h[1], h[2]);
-      fk[0] += tx; fk[1] += ty; fk[2] += tz;
-      RBD_CROSS(tx, ty, tz, vel[3], vel[4], vel[5], h[3], h[4], h[5]);
-      fk[3] += tx; fk[4] += ty; fk[5] += tz;
-      RBD_CROSS(tx, ty, tz, vel[0], vel[1], vel[2], h[0], h[1], h[2]);
-      fk[3] += tx; fk[4] += ty; fk[5] += tz;
     }
     if (nxt_par == i) {
-      // joint i has children: park A | f | Y in its depth slot; its subtree sums accumulate there
-      const int s = jn.slot[L];
-      const int aw_ = RBD_SLOT_A(jn.type);
-      if (jn.type != JT_FF) {
-#pragma unroll
-        for (int e = 0; e < 6; ++e) S.st(s + e, Ak[e]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 12; ++e) S.st(s + e, Ak[e]);
-      }
-      if (DO_TAU) {
-#pragma unroll
-        for (int e = 0; e < 6; ++e) S.st(s + aw_ + e, fk[e]);
-      }
-      if (DO_M) {
-#pragma unroll
-        for (int e = 0; e < 10; ++e) S.st(s + aw_ + 6 + e, Yk[e]);
+      // joint i has children: park A | f | Y at its depth level; its subtree sums accumulate there
+      if (NEED_STACK) {
+        const int lvl = jn.depth - 1;
+        if (jn.type != JT_FF) s_stv<6>(S, jn.offA, Ak); else s_stv<12>(S, jn.offA, Ak);
+        if (DO_TAU) s_stv<6>(S, fbase + 6 * lvl, fk);
+        if (DO_M) x_stv<10>(ytm, S, T, ybase + 10 * lvl, Yk);
       }
       if (jn.nchild >= 2) {
-        const int b = bbase + jn.bidx * BW;
+        const bool btm = (jn.boff & RBD_BOFF_TMEM) != 0;
+        int b = jn.boff & ~RBD_BOFF_TMEM;
+        if (!(NEED_STACK && jn.type == JT_FF)) {
+          double Rp[12];
 #pragma unroll
-        for (int e = 0; e < 9; ++e) S.st(b + e, R[e]);
+          for (int e = 0; e < 9; ++e) Rp[e] = R[e];
 #pragma unroll
-        for (int e = 0; e < 3; ++e) S.st(b + 9 + e, p[e]);
+          for (int e = 0; e < 3; ++e) Rp[9 + e] = p[e];
+          x_stv<12>(btm, S, T, b, Rp);
+          b += 12;
+        }
         if (DO_TAU) {
+          double va[12];
 #pragma unroll
-          for (int e = 0; e < 6; ++e) { S.st(b + 12 + e, vel[e]); S.st(b + 18 + e, acc[e]); }
+          for (int e = 0; e < 6; ++e) { va[e] = vel[e]; va[6 + e] = acc[e]; }
+          x_stv<12>(btm, S, T, b, va);
         }
       }
-    } else {
+    } else if (NEED_STACK) {
       // joint i is a leaf: its subtree is complete.  Emit it straight from registers, then unwind: every
       // ancestor whose last child this was is complete too; its sums continue in registers up the chain and
       // are written back only at the joint that still has children to come (nxt_par).
@@ -620,34 +737,26 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
         const int pk = m.joint[k].parent;
         if (pk == 0) break;
         const DevJoint& jp = m.joint[pk];
-        const int sp = jp.slot[L];
-        const int awp = RBD_SLOT_A(jp.type);
+        const int lvl = jp.depth - 1;
         if (pk == nxt_par) {
           if (DO_TAU) {
 #pragma unroll
-            for (int e = 0; e < 6; ++e) S.add(sp + awp + e, fk[e]);
+            for (int e = 0; e < 6; ++e) S.add(fbase + 6 * lvl + e, fk[e]);
           }
-          if (DO_M) {
-#pragma unroll
-            for (int e = 0; e < 10; ++e) S.add(sp + awp + 6 + e, Yk[e]);
-          }
+          if (DO_M) x_addv<10>(ytm, S, T, ybase + 10 * lvl, Yk);
           break;
         }
         if (DO_TAU) {
 #pragma unroll
-          for (int e = 0; e < 6; ++e) fk[e] += S.ld(sp + awp + e);
+          for (int e = 0; e < 6; ++e) fk[e] += S.ld(fbase + 6 * lvl + e);
         }
         if (DO_M) {
+          double Yp[10];
+          x_ldv<10>(ytm, S, T, ybase + 10 * lvl, Yp);
 #pragma unroll
-          for (int e = 0; e < 10; ++e) Yk[e] += S.ld(sp + awp + 6 + e);
+          for (int e = 0; e < 10; ++e) Yk[e] += Yp[e];
         }
-        if (jp.type != JT_FF) {
-#pragma unroll
-          for (int e = 0; e < 6; ++e) Ak[e] = S.ld(sp + e);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 12; ++e) Ak[e] = S.ld(sp + e);
-        }
+        if (jp.type != JT_FF) s_ldv<6>(S, jp.offA, Ak); else s_ldv<12>(S, jp.offA, Ak);
         k = pk;
       }
     }

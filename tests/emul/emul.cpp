@@ -37,42 +37,51 @@ extern "C" int emul_model_info(const rbd_model_desc* d, int* out /*[8]*/) {
   Ctx c;
   int rc = make_ctx(d, &c);
   if (rc) return rc;
-  out[0] = c.m.max_depth; out[1] = c.m.nbranch; out[2] = c.m.slot_total[0]; out[3] = c.m.slot_total[1];
-  out[4] = smem_eval(c.m, true, true); out[5] = smem_eval(c.m, false, true); out[6] = smem_applyJT(c.m);
-  out[7] = c.m.has_ff_root;
+  out[0] = c.m.max_depth; out[1] = c.m.nbranch; out[6] = smem_applyJT(c.m); out[7] = c.m.has_ff_root;
+  DevModel t = c.m;
+  if (!plan_eval(&t, true, true, true)) return -100;
+  out[2] = t.plan.smem_doubles; out[3] = t.plan.tmem_doubles; out[4] = t.plan.warps * t.plan.blocks_per_sm;
+  t = c.m;
+  if (!plan_eval(&t, true, true, false)) return -101;
+  out[5] = t.plan.warps * t.plan.blocks_per_sm;
   return 0;
 }
 
 template <int TILE>
-static void eval_one(const Ctx& c, long long i, long long tile, double* q, double* v, double* a, double* oMi, double* J,
-                     double* M, double* tau, const Stack& S) {
+static void eval_one(const DevModel& m, long long i, long long tile, double* q, double* v, double* a, double* oMi,
+                     double* J, double* M, double* tau, const Stack& S, const TmStack& T) {
   const bool do_m = M != nullptr, do_tau = tau != nullptr;
   EvalIOT<TILE> io;
-  io.q = make_field_t<TILE>(q, i, c.m.nq, tile); io.v = make_field_t<TILE>(v, i, c.m.nv, tile);
-  io.a = make_field_t<TILE>(a, i, c.m.nv, tile);
-  io.oMi = make_field_t<TILE>(oMi, i, 12 * (c.m.njoints - 1), tile); io.J = make_field_t<TILE>(J, i, 6 * c.m.nv, tile);
-  io.M = make_field_t<TILE>(M, i, c.m.nv * (c.m.nv + 1) / 2, tile); io.tau = make_field_t<TILE>(tau, i, c.m.nv, tile);
-  if (do_m && do_tau) eval_instance<true, true, TILE>(c.m, io, S);
-  else if (do_m) eval_instance<true, false, TILE>(c.m, io, S);
-  else if (do_tau) eval_instance<false, true, TILE>(c.m, io, S);
-  else eval_instance<false, false, TILE>(c.m, io, S);
+  io.q = make_field_t<TILE>(q, i, m.nq, tile); io.v = make_field_t<TILE>(v, i, m.nv, tile);
+  io.a = make_field_t<TILE>(a, i, m.nv, tile);
+  io.oMi = make_field_t<TILE>(oMi, i, 12 * (m.njoints - 1), tile); io.J = make_field_t<TILE>(J, i, 6 * m.nv, tile);
+  io.M = make_field_t<TILE>(M, i, m.nv * (m.nv + 1) / 2, tile); io.tau = make_field_t<TILE>(tau, i, m.nv, tile);
+  if (do_m && do_tau) eval_instance<true, true, TILE>(m, io, S, T);
+  else if (do_m) eval_instance<true, false, TILE>(m, io, S, T);
+  else if (do_tau) eval_instance<false, true, TILE>(m, io, S, T);
+  else eval_instance<false, false, TILE>(m, io, S, T);
 }
 
-// tile == 32 runs the compile-time-tile instantiation the GPU fast path uses
-extern "C" int emul_eval(const rbd_model_desc* d, long long n, long long tile, int block, double* q, double* v,
-                         double* a, double* oMi, double* J, double* M, double* tau) {
+// tile == 32 runs the compile-time-tile instantiation the GPU fast path uses.  use_tmem selects the storage plan
+// (tensor memory is emulated by a second poisoned array); block = warps * 32 pins the planner's block size (0 = auto).
+extern "C" int emul_eval(const rbd_model_desc* d, long long n, long long tile, int block, int use_tmem, double* q,
+                         double* v, double* a, double* oMi, double* J, double* M, double* tau) {
   Ctx c;
   int rc = make_ctx(d, &c);
   if (rc) return rc;
   const bool do_m = M != nullptr, do_tau = tau != nullptr;
-  const int sd = smem_eval(c.m, do_m, do_tau);
-  std::vector<double> smem((size_t)(sd > 0 ? sd : 1) * ((block + 31) / 32) * 32, 1e300);  // poison: reads before writes show up
-  for (long long b0 = 0; b0 < n; b0 += block)
-    for (int t = 0; t < block && b0 + t < n; ++t) {
+  if (!plan_eval(&c.m, do_m, do_tau, use_tmem != 0, block / 32)) { g_err = "plan_eval failed"; return -100; }
+  const EvalPlan& pl = c.m.plan;
+  const int bt = pl.warps * 32;
+  std::vector<double> smem((size_t)(pl.smem_doubles > 0 ? pl.smem_doubles : 1) * bt, 1e300);  // poison
+  std::vector<double> tmem((size_t)(pl.tmem_doubles > 0 ? pl.tmem_doubles : 1) * bt, 1e300);
+  for (long long b0 = 0; b0 < n; b0 += bt)
+    for (int t = 0; t < bt && b0 + t < n; ++t) {
       const long long i = b0 + t;
-      Stack S = make_stack(smem.data(), t, sd);
-      if (tile == 32) eval_one<32>(c, i, tile, q, v, a, oMi, J, M, tau, S);
-      else eval_one<0>(c, i, tile, q, v, a, oMi, J, M, tau, S);
+      Stack S = make_stack(smem.data(), t, pl.smem_doubles);
+      TmStack T{tmem.data() + (size_t)t * (pl.tmem_doubles > 0 ? pl.tmem_doubles : 1)};
+      if (tile == 32) eval_one<32>(c.m, i, tile, q, v, a, oMi, J, M, tau, S, T);
+      else eval_one<0>(c.m, i, tile, q, v, a, oMi, J, M, tau, S, T);
     }
   return 0;
 }

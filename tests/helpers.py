@@ -55,7 +55,7 @@ def load_emul() -> C.CDLL:
     lib.emul_model_info.argtypes = [vp, vp]
     lib.emul_sincos.argtypes = [ll, vp, vp, vp]
     lib.emul_sincos.restype = None
-    lib.emul_eval.argtypes = [vp, ll, ll, i] + [vp] * 7
+    lib.emul_eval.argtypes = [vp, ll, ll, i, i] + [vp] * 7
     lib.emul_apply.argtypes = [vp, ll, ll, i, vp, vp, vp, ll, vp]
     lib.emul_applyJ.argtypes = [vp, ll, ll, i, vp, ll, vp, vp, vp]
     lib.emul_applyJT.argtypes = [vp, ll, ll, i, vp, ll, vp, vp, vp]

@@ -18,27 +18,29 @@ def _cdesc(d):
     return make_desc(d)
 
 
-def _emul_eval(emul, d, q, v, a, tile, block, want):
+def _emul_eval(emul, d, q, v, a, tile, block, want, use_tmem=1):
     n = q.shape[0]
     cd, keep = _cdesc(d)
     nt = (n + tile - 1) // tile
     K = {"oMi": 12 * (d.njoints - 1), "J": 6 * d.nv, "M": d.nv * (d.nv + 1) // 2, "tau": d.nv}
     outs = {k: (np.full((nt, K[k], tile), np.nan) if k in want else None) for k in K}
     qs, vs, as_ = to_tiled(q, tile), to_tiled(v, tile), to_tiled(a, tile)
-    rc = emul.emul_eval(C.addressof(cd), n, tile, block, P(qs), P(vs), P(as_), P(outs["oMi"]), P(outs["J"]),
+    rc = emul.emul_eval(C.addressof(cd), n, tile, block, use_tmem, P(qs), P(vs), P(as_), P(outs["oMi"]), P(outs["J"]),
                         P(outs["M"]), P(outs["tau"]))
     assert rc == 0, emul.emul_last_error()
     return {k: (from_tiled(o, n) if o is not None else None) for k, o in outs.items()}
 
 
 @pytest.mark.parametrize("d", MODELS, ids=IDS)
-@pytest.mark.parametrize("tile,block", [(32, 64), (7, 32), (100, 96)])
-def test_eval_bodies_match_oracle(emul, d, tile, block):
+@pytest.mark.parametrize("tile,block,use_tmem", [(32, 0, 1), (32, 64, 0), (7, 32, 1), (100, 96, 0), (32, 256, 1)])
+def test_eval_bodies_match_oracle(emul, d, tile, block, use_tmem):
     import oracle
     from sofa.rigidbodydynamics_b200 import model as mdl
     n = 70
     q, v, a = mdl.random_state(d, n, seed=3)
-    got = _emul_eval(emul, d, q, v, a, tile, block, ("oMi", "J", "M", "tau"))
+    if d.name == "talos_reduced" and block == 256 and use_tmem:
+        pytest.skip("state of 256 Talos instances exceeds one SM (planner refuses: covered by test_stack_budget)")
+    got = _emul_eval(emul, d, q, v, a, tile, block, ("oMi", "J", "M", "tau"), use_tmem)
     ref, _ = oracle.eval_batch(d, q, v, a, 1)
     for k in ref:
         assert rel_err(got[k], ref[k]) <= TOL_FP64, k
@@ -46,12 +48,13 @@ def test_eval_bodies_match_oracle(emul, d, tile, block):
 
 @pytest.mark.parametrize("want", [("M",), ("tau",), ("oMi", "J"), ("J", "tau"), ("oMi", "M"), ("oMi",)])
 @pytest.mark.parametrize("name", ["talos_reduced", "random_3", "random_2"])
-def test_eval_partial_outputs(emul, name, want):
+@pytest.mark.parametrize("use_tmem", [0, 1])
+def test_eval_partial_outputs(emul, name, want, use_tmem):
     import oracle
     from sofa.rigidbodydynamics_b200 import model as mdl
     d = [m for m in MODELS if m.name == name][0]
     q, v, a = mdl.random_state(d, 40, seed=4)
-    got = _emul_eval(emul, d, q, v, a, 32, 64, want)
+    got = _emul_eval(emul, d, q, v, a, 32, 0, want, use_tmem)
     ref, _ = oracle.eval_batch(d, q, v, a, 1)
     for k in want:
         assert rel_err(got[k], ref[k]) <= TOL_FP64, k
@@ -149,13 +152,16 @@ def test_quaternion_branches(emul):
 
 
 def test_stack_budget(emul):
-    """Shared-memory doubles per instance (DESIGN.md 'state budget')."""
+    """Storage plan of the fused eval (DESIGN.md 'state budget'): resident warps per SM with and without tensor memory."""
     from sofa.rigidbodydynamics_b200 import model as mdl
     info = (C.c_int * 8)()
-    for d, max_full in ((mdl.panda7(), 140), (mdl.solo12(), 120), (mdl.talos_reduced(), 280)):
+    expect = {"panda7": (8, 6), "solo12": (8, 7), "talos_reduced": (6, 3)}
+    for d in (mdl.panda7(), mdl.solo12(), mdl.talos_reduced()):
         cd, keep = _cdesc(d)
         assert emul.emul_model_info(C.addressof(cd), info) == 0
-        assert info[4] <= max_full, (d.name, list(info))
+        smem_d, tmem_d, warps_tm, warps_sm = info[2], info[3], info[4], info[5]
+        assert warps_tm >= expect[d.name][0] and warps_sm >= expect[d.name][1], (d.name, list(info))
+        assert warps_tm >= warps_sm
 
 
 def test_sincos_accuracy(emul):

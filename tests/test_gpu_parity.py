@@ -35,11 +35,12 @@ def _dev(torch, x):
     return torch.from_numpy(np.ascontiguousarray(x)).cuda()
 
 
-def _eval_gpu(torch, api, d, q, v, a, tile, want=("oMi", "J", "M", "tau"), block=0):
+def _eval_gpu(torch, api, d, q, v, a, tile, want=("oMi", "J", "M", "tau"), block=0, tmem=True):
     n = q.shape[0]
     m = api.Model(d); ws = api.Workspace(m, max(n, 1))
     if block:
         ws.set_eval_block(block)
+    ws.set_eval_tmem(tmem)
     I = m.info
     nt = (n + tile - 1) // tile
     K = {"oMi": I.omi_fields, "J": I.jac_fields, "M": I.mass_fields, "tau": I.nv}
@@ -53,13 +54,13 @@ def _eval_gpu(torch, api, d, q, v, a, tile, want=("oMi", "J", "M", "tau"), block
 
 
 @pytest.mark.parametrize("d", MODELS, ids=IDS)
-@pytest.mark.parametrize("tile", [32, 1000])
-def test_eval_matches_oracle(torch_mod, api, d, tile):
+@pytest.mark.parametrize("tile,tmem", [(32, True), (32, False), (1000, True)])
+def test_eval_matches_oracle(torch_mod, api, d, tile, tmem):
     import oracle
     from sofa.rigidbodydynamics_b200 import model as mdl
     n = 777
     q, v, a = mdl.random_state(d, n, seed=11)
-    got, launches = _eval_gpu(torch_mod, api, d, q, v, a, tile)
+    got, launches = _eval_gpu(torch_mod, api, d, q, v, a, tile, tmem=tmem)
     assert launches == 1
     ref, _ = oracle.eval_batch(d, q, v, a, nthreads=0)
     for k in ("oMi", "J", "M", "tau"):
@@ -81,16 +82,26 @@ def test_eval_partial_outputs(torch_mod, api, want):
             assert got[k] is None
 
 
-@pytest.mark.parametrize("block", [32, 64, 96])
-def test_eval_block_sizes(torch_mod, api, block):
+@pytest.mark.parametrize("block,tmem", [(32, False), (64, False), (96, False), (64, True), (128, True), (192, True)])
+def test_eval_block_sizes(torch_mod, api, block, tmem):
     import oracle
     from sofa.rigidbodydynamics_b200 import model as mdl
     d = mdl.talos_reduced()
     q, v, a = mdl.random_state(d, 333, seed=6)
-    got, _ = _eval_gpu(torch_mod, api, d, q, v, a, 333, block=block)
+    got, _ = _eval_gpu(torch_mod, api, d, q, v, a, 333, block=block, tmem=tmem)
     ref, _ = oracle.eval_batch(d, q, v, a, nthreads=0)
     for k in ("oMi", "J", "M", "tau"):
         assert rel_err(got[k], ref[k]) <= TOL_FP64, k
+
+
+def test_block_too_large_is_an_error(torch_mod, api):
+    """256 Talos instances do not fit one SM: the planner refuses instead of launching something slower."""
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    d = mdl.talos_reduced()
+    q, v, a = mdl.random_state(d, 8, seed=6)
+    with pytest.raises(api.RbdError) as e:
+        _eval_gpu(torch_mod, api, d, q, v, a, 32, block=256, tmem=False)
+    assert e.value.code == -5   # RBD_ERR_UNSUPPORTED
 
 
 def test_golden_vectors(torch_mod, api):
