@@ -38,12 +38,19 @@ MatrixDerivIn = Dict[Tuple[int, int], List[Tuple[int, Sequence[float]]]]
 class KinematicChainMapping:
     def __init__(self, desc: ModelDescriptor, n_instances: int = 1, device: int = 0, index_input2: Optional[int] = None):
         self.m_model = Model(desc)                          # setModel (KinematicChainMapping.inl:304-311)
-        self.m_data = Workspace(self.m_model, max(1, n_instances), device)
+        self._m_data = None                                 # pinocchio::Data analogue, created on first use (needs a GPU)
+        self._device = int(device)
         self.n = int(n_instances)
         self.desc = desc
         self.d_componentState = VALID
         self.d_indexFromRoot = index_input2                 # "indexInput2", default = last index (inl:319-336)
         self.msgs: List[str] = []
+
+    @property
+    def m_data(self) -> Workspace:
+        if self._m_data is None:
+            self._m_data = Workspace(self.m_model, max(1, self.n), self._device)
+        return self._m_data
 
     # ---- helpers ----------------------------------------------------------------------------------------
     def _invalid(self, msg: str) -> None:
