@@ -175,10 +175,10 @@ def run_reference(args, desc, n_cfg):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, len(per_step)),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{desc.name} N={n_cfg} per GPU (bounded CPU sample per step: {n_s} instances)",
+            "config": {"workload": f"{desc.name} N={n_cfg} per GPU (bounded CPU sample per step: {sample})",
                        "robot": desc.name, "note": desc.note},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{len(per_step)} steps x {n_s} instances of the same workload, all outputs"},
+                             "sample": f"{len(per_step)} step(s), each {sample}"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
