@@ -248,7 +248,10 @@ def main():
     q, v, a = dyn.to_soa(q_im), dyn.to_soa(v_im), dyn.to_soa(a_im)
     out = dyn.alloc_outputs()
     step_bytes = n * bytes_per_eval
-    assert step_bytes > L2_BYTES or args.n, "working set must exceed L2 (or flush between iterations)"
+    # timing rule: inputs larger than L2, or flush L2 between timed iterations (a write larger than L2)
+    flush = None
+    if step_bytes <= 2 * L2_BYTES:
+        flush = torch.empty(3 * L2_BYTES // 8, dtype=torch.float64, device=dev)
 
     def barrier():
         if world > 1:
@@ -268,12 +271,15 @@ def main():
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
         for e0, e1 in evs:
+            if flush is not None:
+                flush.fill_(1.0)
             e0.record(); step(); e1.record()
         t1.record()
         barrier()
     launches = dyn.ws.launch_count - l0
-    total_ms = t0.elapsed_time(t1)
     kern_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs) / max(1, len(evs))
+    # with an L2 flush between steps the job time is the sum of the per-step times (the flush is not part of the path)
+    total_ms = t0.elapsed_time(t1) if flush is None else kern_ms * len(evs)
     tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -340,7 +346,9 @@ def main():
                 "config": {"workload": f"{desc.name} N={n} per GPU, fused FK+Jac+CRBA+RNEA, all outputs written",
                            "robot": desc.name, "instances_per_gpu": n, "layout": f"tiled SoA, tile={dyn.tile}",
                            "eval_storage": dyn.ws.eval_plan(True, True),
-                           "l2": f"inputs+outputs {step_bytes / 2**20:.0f} MiB per step > 126 MiB L2, no flush needed",
+                           "l2": (f"inputs+outputs {step_bytes / 2**20:.0f} MiB per step > 126 MiB L2, no flush needed" if flush is None
+                                  else f"inputs+outputs {step_bytes / 2**20:.0f} MiB per step: L2 flushed between timed steps "
+                                       f"by a {3 * L2_BYTES / 2**20:.0f} MiB fill"),
                            "note": desc.note, "sharding": f"instances, contiguous ranges, {world} rank(s), no collective"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -61,6 +61,7 @@ struct rbd_workspace {
   DevModel* h_plan[4] = {nullptr, nullptr, nullptr, nullptr};
   DevModel* d_plan[4] = {nullptr, nullptr, nullptr, nullptr};
   int use_tmem = 1;
+  int num_sms = 0;
   double* qcache = nullptr;  // [nq][capacity] assembled configuration of the last apply
   long long applied_n = 0;   // instances covered by the cache (0 = apply not called yet)
   LaunchCfg cfg_eval[8], cfg_apply, cfg_applyJ, cfg_applyJT, cfg_rows;
@@ -202,6 +203,7 @@ RBD_API int rbd_workspace_create(const rbd_model* model, int device, int64_t cap
   ws->tb.outk_parent = ws->d_outk_parent; ws->tb.outk_pl = ws->d_outk_pl;
   WS_CK(cudaMalloc(&ws->qcache, (size_t)(model->dm.nq > 0 ? model->dm.nq : 1) * (size_t)capacity * sizeof(double)));
   WS_CK(cudaEventCreateWithFlags(&ws->ev, cudaEventDisableTiming));
+  WS_CK(cudaDeviceGetAttribute(&ws->num_sms, cudaDevAttrMultiProcessorCount, device));
 #undef WS_CK
   *out = ws;
   return RBD_OK;
@@ -254,12 +256,14 @@ static int ensure_plan(rbd_workspace* ws, int pk) {
     return set_err(RBD_ERR_UNSUPPORTED, "the sweep state of this model does not fit one SM's shared + tensor memory"
                                         " at the requested block size");
   }
+  const std::vector<unsigned long long> blob = build_eval_blob(h);
   if (!ws->d_plan[pk]) {
-    cudaError_t e = cudaMalloc(&ws->d_plan[pk], sizeof(DevModel));
+    // sized for the largest blob any plan of this model can produce (the ColProg length is plan-independent)
+    cudaError_t e = cudaMalloc(&ws->d_plan[pk], blob.size() * 8);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaMalloc(plan)"); }
   }
-  // synchronous copy from a stable host object, ordered before any later launch on any stream of this device
-  cudaError_t e = cudaMemcpy(ws->d_plan[pk], h, sizeof(DevModel), cudaMemcpyHostToDevice);
+  // synchronous copy, ordered before any later launch on any stream of this device
+  cudaError_t e = cudaMemcpy(ws->d_plan[pk], blob.data(), blob.size() * 8, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaMemcpy(plan)"); }
   ws->h_plan[pk] = h;
   return RBD_OK;
@@ -291,7 +295,7 @@ static int eval_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, 
   int rc = ensure_plan(ws, pk);
   if (rc) return rc;
   EvalArgs A{n, tile, q, v, a, oMi, J, M, tau};
-  CK(launch_eval(*ws->h_plan[pk], ws->d_plan[pk], A, ws->cfg_eval, st));
+  CK(launch_eval(*ws->h_plan[pk], ws->d_plan[pk], A, ws->cfg_eval, ws->num_sms, st));
   if (n > 0) ws->launches++;
   return RBD_OK;
 }

@@ -36,7 +36,17 @@ struct DevJoint {
   // fused-eval storage plan (EvalPlan below; filled by plan_eval for one kernel variant):
   int offA;                // offset of this joint's A record (6 doubles, free-flyer 12) in the shared-memory A-stack
   int boff;                // branch joints: offset of the saved (R|p)|v|a record; bit 30 set = lives in tensor memory
+  // column program of this joint's column(s) of M (ColProg table): depth-1 ancestor entries, then nzseg zero segments
+  int prog_off, nzseg;
 };
+// ColProg entries (int32).  Ancestor entry, root first: row (idx_v of the ancestor) | free-flyer flag | A-stack offset.
+// Zero segment: first row | length.  Rows not covered by either belong to the joint itself.
+#define RBD_PROG_ROW(e) ((e) & 0xffff)
+#define RBD_PROG_FF(e) (((e) >> 16) & 1)
+#define RBD_PROG_OFFA(e) ((e) >> 17)
+#define RBD_PROG_ANC(row, ff, offA) ((row) | ((ff) << 16) | ((offA) << 17))
+#define RBD_PROG_ZSEG(row, len) ((row) | ((len) << 16))
+#define RBD_PROG_ZLEN(e) ((e) >> 16)
 
 // Where the fused eval kernel keeps its per-instance sweep state (doubles per instance, DESIGN.md "state budget").
 // Shared memory holds the A-stack and the f-stack; the Y-stack and individual branch records go to TENSOR MEMORY
@@ -61,6 +71,7 @@ struct DevModel {
   int has_ff_root;    // joint 1 is a free-flyer attached to the universe
   int nq_joints, nv_joints;
   int max_depth, max_depth_internal;  // longest joint chain; deepest joint that has children
+  int prog_words_off, prog_len;       // eval blob: 8-byte-word offset of the ColProg table behind the joint records; ints
   double gravity[3];
   EvalPlan plan;
   DevJoint joint[RBD_MAX_JOINTS];
@@ -73,7 +84,9 @@ inline size_t dev_model_bytes(const DevModel& m) {
 
 // shared-memory bytes the eval kernel reserves in front of the stacks: the staged table rounded to 16 bytes plus two
 // spare 8-byte words (tensor-memory base address)
-inline size_t eval_model_bytes(const DevModel& m) { return (dev_model_bytes(m) + 15) / 16 * 16 + 16; }
+inline size_t eval_model_bytes(const DevModel& m) {
+  return (dev_model_bytes(m) + 15) / 16 * 16 + ((size_t)m.prog_len * 4 + 15) / 16 * 16 + 16;
+}
 
 // Per-output tables (global memory; only the mapping kernels read them).
 struct DevTables {

@@ -60,17 +60,24 @@ __global__ void __launch_bounds__(256) eval_kernel(const DevModel* __restrict__ 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     T.base = *tm_base_p + (((unsigned)(warp & 3) * 32u) << 16) + (unsigned)(warp >> 2) * 2u * (unsigned)m.plan.tmem_doubles;
   }
-  long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (inst >= a.n) inst = a.n - 1;
-  EvalIOT<TILE> io;
-  io.q = make_field_t<TILE>(const_cast<double*>(a.q), inst, m.nq, a.tile);
-  io.v = make_field_t<TILE>(const_cast<double*>(a.v), inst, m.nv, a.tile);
-  io.a = make_field_t<TILE>(const_cast<double*>(a.a), inst, m.nv, a.tile);
-  io.oMi = make_field_t<TILE>(a.oMi, inst, 12 * (m.njoints - 1), a.tile);
-  io.J = make_field_t<TILE>(a.J, inst, 6 * m.nv, a.tile);
-  io.M = make_field_t<TILE>(a.M, inst, m.nv * (m.nv + 1) / 2, a.tile);
-  io.tau = make_field_t<TILE>(a.tau, inst, m.nv, a.tile);
-  eval_instance<DO_M, DO_TAU, TILE>(m, io, make_stack(rbd_smem + model_words, threadIdx.x, m.plan.smem_doubles), T);
+  // persistent: the block's warps stride over the batch's 32-instance tiles independently (no barrier inside),
+  // so the staging, the tensor-memory allocation and the end-of-block wait are paid once per SM, not per tile
+  const Stack S = make_stack(rbd_smem + model_words, threadIdx.x, m.plan.smem_doubles);
+  const long long ntiles = (a.n + 31) / 32;
+  const int wpb = blockDim.x >> 5;
+  for (long long t = (long long)blockIdx.x * wpb + warp; t < ntiles; t += (long long)gridDim.x * wpb) {
+    long long inst = t * 32 + (threadIdx.x & 31);
+    if (inst >= a.n) inst = a.n - 1;
+    EvalIOT<TILE> io;
+    io.q = make_field_t<TILE>(const_cast<double*>(a.q), inst, m.nq, a.tile);
+    io.v = make_field_t<TILE>(const_cast<double*>(a.v), inst, m.nv, a.tile);
+    io.a = make_field_t<TILE>(const_cast<double*>(a.a), inst, m.nv, a.tile);
+    io.oMi = make_field_t<TILE>(a.oMi, inst, 12 * (m.njoints - 1), a.tile);
+    io.J = make_field_t<TILE>(a.J, inst, 6 * m.nv, a.tile);
+    io.M = make_field_t<TILE>(a.M, inst, m.nv * (m.nv + 1) / 2, a.tile);
+    io.tau = make_field_t<TILE>(a.tau, inst, m.nv, a.tile);
+    eval_instance<DO_M, DO_TAU, TILE>(m, io, S, T);
+  }
   if (tm_cols > 0) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -220,7 +227,7 @@ static cudaError_t pick_block(Kern kern, int smem_doubles_per_thread, int forced
   }
 
 // `hm` is the host copy of the planned model (hm.plan chosen by plan_eval), `d_model` its device copy.
-cudaError_t launch_eval(const DevModel& hm, const DevModel* d_model, const EvalArgs& a, LaunchCfg* cache,
+cudaError_t launch_eval(const DevModel& hm, const DevModel* d_model, const EvalArgs& a, LaunchCfg* cache, int num_sms,
                         cudaStream_t st) {
   const bool do_m = a.M != nullptr, do_tau = a.tau != nullptr;
   const int v = (a.tile == 32 ? 4 : 0) | (do_m ? 2 : 0) | (do_tau ? 1 : 0);
@@ -240,7 +247,9 @@ cudaError_t launch_eval(const DevModel& hm, const DevModel* d_model, const EvalA
     cfg.block = block; cfg.smem_bytes = smem; cfg.blocks_per_sm = hm.plan.blocks_per_sm;
   }
   if (a.n <= 0) return cudaSuccess;
-  const unsigned grid = RBD_GRID(a.n, block);
+  unsigned grid = RBD_GRID(a.n, block);
+  const unsigned resident = (unsigned)(num_sms * (hm.plan.blocks_per_sm > 0 ? hm.plan.blocks_per_sm : 1));
+  if (grid > resident) grid = resident;  // persistent blocks: one wave, warps stride over the tiles
 #define RBD_LAUNCH(K) K<<<grid, block, smem, st>>>(d_model, a, model_words)
   RBD_EVAL_DISPATCH(v, RBD_LAUNCH)
 #undef RBD_LAUNCH

@@ -34,8 +34,8 @@ struct LaunchCfg {
   size_t smem_bytes = 0;
 };
 
-cudaError_t launch_eval(const DevModel& planned_host_model, const DevModel* d_model, const EvalArgs& a, LaunchCfg* cache8,
-                        cudaStream_t st);
+cudaError_t launch_eval(const DevModel& planned_host_model, const DevModel* d_eval_blob, const EvalArgs& a,
+                        LaunchCfg* cache8, int num_sms, cudaStream_t st);
 cudaError_t launch_apply(const DevModel& m, const DevTables& tb, const MapArgs& a, int smem_doubles, LaunchCfg* cfg,
                          cudaStream_t st);
 cudaError_t launch_applyJ(const DevModel& m, const DevTables& tb, const MapArgs& a, int smem_doubles, LaunchCfg* cfg,

@@ -19,6 +19,41 @@ struct HostTables {
   std::vector<double> sorted_pl, outk_pl;
 };
 
+// Column programs of M for one planned model (offA values come from plan_eval): see RBD_PROG_* in rbd_dev_model.h.
+// Fills joint[*].prog_off / nzseg and m->prog_len; returns the table.
+inline std::vector<int> build_col_prog(DevModel* m) {
+  std::vector<int> prog;
+  const int nj = m->njoints;
+  for (int k = 1; k < nj; ++k) {
+    DevJoint& jk = m->joint[k];
+    jk.prog_off = (int)prog.size();
+    std::vector<int> chain;  // ancestors, root first
+    for (int a = jk.parent; a != 0; a = m->joint[a].parent) chain.insert(chain.begin(), a);
+    for (int a : chain) prog.push_back(RBD_PROG_ANC(m->joint[a].idx_v, m->joint[a].type == JT_FF ? 1 : 0, m->joint[a].offA));
+    // zero segments: rows below the joint's first dof that no ancestor owns
+    int r = 0, nz = 0;
+    for (int a : chain) {
+      const int iv = m->joint[a].idx_v;
+      if (iv > r) { prog.push_back(RBD_PROG_ZSEG(r, iv - r)); ++nz; }
+      r = iv + m->joint[a].nv;
+    }
+    if (jk.idx_v > r) { prog.push_back(RBD_PROG_ZSEG(r, jk.idx_v - r)); ++nz; }
+    jk.nzseg = nz;
+  }
+  m->prog_len = (int)prog.size();
+  m->prog_words_off = (int)((dev_model_bytes(*m) + 15) / 16 * 2);
+  return prog;
+}
+
+// The blob the eval kernel stages into shared memory: planned DevModel prefix (16-byte rounded) + ColProg table.
+inline std::vector<unsigned long long> build_eval_blob(DevModel* m) {
+  const std::vector<int> prog = build_col_prog(m);
+  std::vector<unsigned long long> blob(eval_model_bytes(*m) / 8 - 2, 0ull);
+  memcpy(blob.data(), m, dev_model_bytes(*m));
+  if (!prog.empty()) memcpy(blob.data() + m->prog_words_off, prog.data(), prog.size() * sizeof(int));
+  return blob;
+}
+
 inline int joint_nq_of(int t) { return t == JT_FF ? 7 : (t >= JT_RUBX && t <= JT_RUBU) ? 2 : (t == JT_UNIVERSE ? 0 : 1); }
 inline int joint_nv_of(int t) { return t == JT_FF ? 6 : (t == JT_UNIVERSE ? 0 : 1); }
 
@@ -147,7 +182,7 @@ struct B200Limits {
   static constexpr int kSmemReservedPerBlock = 2048;  // 1 KB driver reservation per block + allocation granularity slack
   static constexpr int kTmemCols = 512;
   static constexpr int kRegsPerSM = 65536;
-  static constexpr int kRegsPerThread = 192;  // upper bound of what ptxas gives the eval kernels (launch_bounds 256)
+  static constexpr int kRegsPerThread = 255;  // upper bound of what ptxas may give the eval kernels (launch_bounds 256)
   static constexpr int kMaxWarpsPerBlock = 8;
 };
 
@@ -180,6 +215,7 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
       bj.push_back(i);
       bw.push_back((ff_dedupe ? 0 : 12) + (do_tau ? 12 : 0));
     }
+  (void)build_col_prog(m);  // sizes the ColProg table (its length does not depend on the plan)
   const size_t model_bytes = eval_model_bytes(*m);
   EvalPlan best{};
   std::vector<int> best_boff;

@@ -470,30 +470,41 @@ RBD_HD void x_addv(bool tm, const Stack& S, const TmStack& T, int k, const doubl
   }
 }
 
-// Rows of packed column `base` above the joint that owns it: one entry per ancestor dof (A_anc . F), zeros for
-// the dofs of joints off the ancestor chain.  `anc` = first ancestor to visit, rows >= `next` are already written.
+// ColProg table of the staged eval blob (rbd_model_build.h: build_eval_blob): `m` IS the start of the blob.
+RBD_HD const int* col_prog(const DevModel& m) {
+  return reinterpret_cast<const int*>(reinterpret_cast<const unsigned long long*>(&m) + m.prog_words_off);
+}
+
+// Rows of packed column `base` above the joint that owns it, driven by the joint's column program: one entry per
+// ancestor dof (A_anc . F) — independent iterations, so the loads of several ancestors are in flight together —
+// then the zero segments (dofs of joints off the ancestor chain).
 template <int TILE>
-RBD_HD void column_tail(const DevModel& m, int anc, int next, int base, const double* F, const Stack& S,
+RBD_HD void column_rows(const DevModel& m, const DevJoint& jn, int base, const double* F, const Stack& S,
                         const FieldT<TILE>& M) {
-  for (; anc != 0; anc = m.joint[anc].parent) {
-    const DevJoint& ja = m.joint[anc];
-    const int iv = ja.idx_v;
-    for (int r = iv + ja.nv; r < next; ++r) M.st(base + r, 0.0);
-    const int sa = ja.offA;
-    if (ja.type == JT_FF) {
+  const int* pr = col_prog(m) + jn.prog_off;
+  const int na = jn.depth - 1;
+#pragma unroll 2
+  for (int d = 0; d < na; ++d) {
+    const int e = pr[d];
+    const int sa = RBD_PROG_OFFA(e);
+    if (RBD_PROG_FF(e)) {
       double Rq[12], p6[6];
       s_ldv<12>(S, sa, Rq);
       ff_rows(Rq, Rq + 9, F, p6);
 #pragma unroll
-      for (int e = 0; e < 6; ++e) M.st(base + iv + e, p6[e]);
+      for (int k = 0; k < 6; ++k) M.st(base + RBD_PROG_ROW(e) + k, p6[k]);
     } else {
       double Aa[6];
       s_ldv<6>(S, sa, Aa);
-      M.st(base + iv, dot6(Aa, F));
+      M.st(base + RBD_PROG_ROW(e), dot6(Aa, F));
     }
-    next = iv;
   }
-  for (int r = 0; r < next; ++r) M.st(base + r, 0.0);
+  for (int z = 0; z < jn.nzseg; ++z) {
+    const int e = pr[na + z];
+    const int r0 = base + RBD_PROG_ROW(e), len = RBD_PROG_ZLEN(e);
+#pragma unroll 4
+    for (int r = 0; r < len; ++r) M.st(r0 + r, 0.0);
+  }
 }
 
 // Everything joint k owes once its subtree is complete: tau_k = A_k^T f_k and its column(s) of M.
@@ -511,7 +522,7 @@ RBD_HD void emit_joint(const DevModel& m, int k, const double* A, const double* 
       const int col = jn.idx_v;
       const int base = col * (col + 1) / 2;
       io.M.st(base + col, dot6(A, F));
-      column_tail(m, jn.parent, col, base, F, S, io.M);
+      column_rows(m, jn, base, F, S, io.M);
     }
   } else {
 #pragma unroll
@@ -528,7 +539,7 @@ RBD_HD void emit_joint(const DevModel& m, int k, const double* A, const double* 
 #pragma unroll
         for (int e = 0; e < 6; ++e)
           if (e <= cc) io.M.st(base + jn.idx_v + e, o6[e]);
-        column_tail(m, jn.parent, jn.idx_v, base, F, S, io.M);
+        column_rows(m, jn, base, F, S, io.M);
       }
     }
   }

@@ -71,7 +71,10 @@ extern "C" int emul_eval(const rbd_model_desc* d, long long n, long long tile, i
   if (rc) return rc;
   const bool do_m = M != nullptr, do_tau = tau != nullptr;
   if (!plan_eval(&c.m, do_m, do_tau, use_tmem != 0, block / 32)) { g_err = "plan_eval failed"; return -100; }
-  const EvalPlan& pl = c.m.plan;
+  // the sweep reads the model through the staged blob (planned DevModel prefix + ColProg table), as the kernel does
+  const std::vector<unsigned long long> blob = build_eval_blob(&c.m);
+  const DevModel& bm = *reinterpret_cast<const DevModel*>(blob.data());
+  const EvalPlan& pl = bm.plan;
   const int bt = pl.warps * 32;
   std::vector<double> smem((size_t)(pl.smem_doubles > 0 ? pl.smem_doubles : 1) * bt, 1e300);  // poison
   std::vector<double> tmem((size_t)(pl.tmem_doubles > 0 ? pl.tmem_doubles : 1) * bt, 1e300);
@@ -80,8 +83,8 @@ extern "C" int emul_eval(const rbd_model_desc* d, long long n, long long tile, i
       const long long i = b0 + t;
       Stack S = make_stack(smem.data(), t, pl.smem_doubles);
       TmStack T{tmem.data() + (size_t)t * (pl.tmem_doubles > 0 ? pl.tmem_doubles : 1)};
-      if (tile == 32) eval_one<32>(c.m, i, tile, q, v, a, oMi, J, M, tau, S, T);
-      else eval_one<0>(c.m, i, tile, q, v, a, oMi, J, M, tau, S, T);
+      if (tile == 32) eval_one<32>(bm, i, tile, q, v, a, oMi, J, M, tau, S, T);
+      else eval_one<0>(bm, i, tile, q, v, a, oMi, J, M, tau, S, T);
     }
   return 0;
 }
