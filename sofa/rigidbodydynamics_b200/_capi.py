@@ -15,7 +15,8 @@ import numpy as np
 from .model import ModelDescriptor
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librbd_b200.so")
+# RBD_B200_LIB: alternate build of the same library (A/B timing of kernel variants); never a different backend
+LIB_PATH = os.environ.get("RBD_B200_LIB") or os.path.join(_HERE, "librbd_b200.so")
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)

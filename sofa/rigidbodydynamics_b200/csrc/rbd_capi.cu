@@ -58,8 +58,8 @@ struct rbd_workspace {
   DevTables tb{};
   // fused eval: one planned copy of the joint table per variant (bit 1 = CRBA, bit 0 = RNEA), host + device;
   // the kernel stages the device copy into shared memory
-  DevModel* h_plan[4] = {nullptr, nullptr, nullptr, nullptr};
-  DevModel* d_plan[4] = {nullptr, nullptr, nullptr, nullptr};
+  DevModel* h_plan[8] = {};  // index: bit 2 = oMi requested, bit 1 = CRBA, bit 0 = RNEA
+  DevModel* d_plan[8] = {};
   int use_tmem = 1;
   int num_sms = 0;
   double* qcache = nullptr;  // [nq][capacity] assembled configuration of the last apply
@@ -134,7 +134,7 @@ RBD_API int rbd_model_create(const rbd_model_desc* desc, rbd_model** out) {
   I.max_depth = d.max_depth;
   {
     DevModel tmp = d;
-    if (plan_eval(&tmp, true, true, true)) {
+    if (plan_eval(&tmp, true, true, true, 0, true)) {
       I.eval_smem_doubles = tmp.plan.smem_doubles; I.eval_tmem_doubles = tmp.plan.tmem_doubles;
       I.eval_warps_per_sm = tmp.plan.warps * tmp.plan.blocks_per_sm;
     } else {
@@ -157,7 +157,7 @@ static void ws_free(rbd_workspace* ws) {
   if (!ws) return;
   cudaFree(ws->d_sorted_k); cudaFree(ws->d_outk_parent); cudaFree(ws->d_sorted_pl); cudaFree(ws->d_outk_pl);
   cudaFree(ws->qcache); cudaFree(ws->rows_buf);
-  for (int k = 0; k < 4; ++k) { cudaFree(ws->d_plan[k]); delete ws->h_plan[k]; }
+  for (int k = 0; k < 8; ++k) { cudaFree(ws->d_plan[k]); delete ws->h_plan[k]; }
   for (int s = 0; s < kSlots; ++s) {
     cudaFree(ws->slot[s].aos); cudaFree(ws->slot[s].soa);
     if (ws->slot[s].st) cudaStreamDestroy(ws->slot[s].st);
@@ -251,7 +251,7 @@ static int ensure_plan(rbd_workspace* ws, int pk) {
   if (ws->h_plan[pk]) return RBD_OK;
   DevModel* h = new (std::nothrow) DevModel(ws->model->dm);
   if (!h) return set_err(RBD_ERR_ALLOC, "out of host memory");
-  if (!plan_eval(h, (pk & 2) != 0, (pk & 1) != 0, ws->use_tmem != 0, ws->forced_eval_block / 32)) {
+  if (!plan_eval(h, (pk & 2) != 0, (pk & 1) != 0, ws->use_tmem != 0, ws->forced_eval_block / 32, (pk & 4) != 0)) {
     delete h;
     return set_err(RBD_ERR_UNSUPPORTED, "the sweep state of this model does not fit one SM's shared + tensor memory"
                                         " at the requested block size");
@@ -271,13 +271,13 @@ static int ensure_plan(rbd_workspace* ws, int pk) {
 static void drop_plans(rbd_workspace* ws) {
   // kernels still in flight keep reading the device copies: wait for them before the next upload overwrites
   cudaDeviceSynchronize();
-  for (int k = 0; k < 4; ++k) { delete ws->h_plan[k]; ws->h_plan[k] = nullptr; }
+  for (int k = 0; k < 8; ++k) { delete ws->h_plan[k]; ws->h_plan[k] = nullptr; }
 }
 
 RBD_API int rbd_workspace_get_eval_plan(rbd_workspace* ws, int with_M, int with_tau, int32_t out[8]) {
   GUARD(ws);
   if (!out) return set_err(RBD_ERR_INVALID_ARG, "null out");
-  const int pk = (with_M ? 2 : 0) | (with_tau ? 1 : 0);
+  const int pk = 4 | (with_M ? 2 : 0) | (with_tau ? 1 : 0);  // all outputs requested
   int rc = ensure_plan(ws, pk);
   if (rc) return rc;
   const DevModel& h = *ws->h_plan[pk];
@@ -291,7 +291,7 @@ static int eval_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, 
                    const double* a, double* oMi, double* J, double* M, double* tau) {
   if (!q) return set_err(RBD_ERR_INVALID_ARG, "q is null");
   if (tau && (!v || !a)) return set_err(RBD_ERR_INVALID_ARG, "rnea needs v and a");
-  const int pk = (M ? 2 : 0) | (tau ? 1 : 0);
+  const int pk = (oMi ? 4 : 0) | (M ? 2 : 0) | (tau ? 1 : 0);
   int rc = ensure_plan(ws, pk);
   if (rc) return rc;
   EvalArgs A{n, tile, q, v, a, oMi, J, M, tau};

@@ -24,6 +24,8 @@ struct DevJoint {
   double pl[12];    // jointPlacement: R row-major (9), p (3)
   double axis[3];   // unit axis in the joint frame
   double Y[10];     // m, c(3), Ic (xx,xy,yy,xz,yz,zz)
+  double msub;      // mass of the whole subtree below (and including) this joint: the composite-inertia mass is a
+                    // model constant, so the Y-stack carries 9 doubles per level, not 10
   int parent, type, idx_q, idx_v;
   int nv;           // dof of this joint (0 universe, 1, or 6)
   int nchild;       // number of child joints
@@ -53,8 +55,10 @@ struct DevJoint {
 // (tcgen05.ld/st, 256 KB per SM that this FP64 path would otherwise leave unused) when that raises the number of
 // resident warps.  All offsets are in doubles from the thread's base in the respective space.
 struct EvalPlan {
-  int fbase;         // shared: f-stack, 6 per internal depth level (RNEA)
-  int ybase;         // Y-stack, 10 per internal depth level (CRBA): shared offset, or tensor-memory offset
+  int fbase;         // shared: f-stack, 6 per internal depth level (RNEA), levels [0, fsplit)
+  int fsplit;        // first f-stack level that lives in tensor memory (= number of levels when none does)
+  int ftbase;        // tensor memory: f-stack levels [fsplit, D)
+  int ybase;         // Y-stack, 9 per internal depth level (CRBA; the mass is a model constant): shared or tensor offset
   int y_in_tmem;     // 1 = Y-stack lives in tensor memory
   int smem_doubles;  // shared-memory doubles per instance
   int tmem_doubles;  // tensor-memory doubles per instance (0 = tensor memory unused)
@@ -63,6 +67,9 @@ struct EvalPlan {
   int tmem_cols;     // columns the block allocates (power of two >= 32, or 0)
 };
 #define RBD_BOFF_TMEM (1 << 30)
+#define RBD_BOFF_NOVA (1 << 29) /* v|a not saved: recomputed when the sweep returns (joint attached to the universe) */
+#define RBD_BOFF_RPOMI (1 << 28) /* R|p not saved: re-read from the oMi output this thread wrote (oMi requested) */
+#define RBD_BOFF_MASK ((1 << 28) - 1)
 
 struct DevModel {
   int njoints, nq, nv, n_out;

@@ -143,6 +143,8 @@ inline int build_dev_model(const rbd_model_desc* d, DevModel* m, HostTables* tb,
     if (m->joint[i].nchild >= 2) m->joint[i].bidx = nb++;
   }
   m->nbranch = nb;
+  for (int i = 0; i < nj; ++i) m->joint[i].msub = m->joint[i].Y[0];
+  for (int i = nj - 1; i >= 1; --i) m->joint[m->joint[i].parent].msub += m->joint[i].msub;
   // mapped outputs grouped by parent joint (stable: keeps the reference's output order within a joint)
   tb->sorted_k.clear(); tb->sorted_pl.clear(); tb->outk_parent.assign(d->n_out, 0); tb->outk_pl.assign(12 * (size_t)d->n_out, 0.0);
   for (int k = 0; k < d->n_out; ++k) {
@@ -193,7 +195,7 @@ inline int pow2_cols(int cols) {
 }
 
 // Fills m->plan and m->joint[*].boff.  forced_warps > 0 pins the block size.  Returns false when nothing fits.
-inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int forced_warps = 0) {
+inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int forced_warps = 0, bool omi_out = false) {
   const int nj = m->njoints;
   const bool need_stack = do_m || do_tau;
   const int D = need_stack ? m->max_depth_internal : 0;
@@ -207,51 +209,75 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
     totalA = pre[D + 1];
     for (int i = 1; i < nj; ++i) m->joint[i].offA = m->joint[i].depth <= D ? pre[m->joint[i].depth] : 0;
   }
-  const int fsz = do_tau ? 6 * D : 0, ysz = do_m ? 10 * D : 0;
-  std::vector<int> bj, bw;  // branch joints and record widths
-  for (int i = 1; i < nj; ++i)
-    if (m->joint[i].nchild >= 2) {
-      const bool ff_dedupe = need_stack && m->joint[i].type == JT_FF;
-      bj.push_back(i);
-      bw.push_back((ff_dedupe ? 0 : 12) + (do_tau ? 12 : 0));
-    }
+  const int fsz = do_tau ? 6 * D : 0, ysz = do_m ? 9 * D : 0;
   (void)build_col_prog(m);  // sizes the ColProg table (its length does not depend on the plan)
   const size_t model_bytes = eval_model_bytes(*m);
   EvalPlan best{};
-  std::vector<int> best_boff;
+  std::vector<int> best_boff, bj;
+  for (int i = 1; i < nj; ++i)
+    if (m->joint[i].nchild >= 2) bj.push_back(i);
   int best_warps_sm = 0;
   for (int W = 1; W <= B200Limits::kMaxWarpsPerBlock; ++W) {
     if (forced_warps > 0 && W != forced_warps) continue;
     const int cap = use_tmem ? (B200Limits::kTmemCols / ((W + 3) / 4)) / 2 : 0;  // doubles per thread
-    // greedy: Y-stack first (one vector access per visit), then the widest branch records that still fit
-    int t_used = 0;
-    EvalPlan pl{};
-    std::vector<int> boff(bj.size(), 0);
-    int s_used = totalA;
-    pl.fbase = s_used; s_used += fsz;
-    if (ysz > 0 && ysz <= cap) { pl.y_in_tmem = 1; pl.ybase = t_used; t_used += ysz; }
-    else { pl.y_in_tmem = 0; pl.ybase = s_used; s_used += ysz; }
-    std::vector<int> order(bj.size());
-    for (size_t k = 0; k < order.size(); ++k) order[k] = (int)k;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bw[a] > bw[b]; });
-    for (int k : order) {
-      if (bw[k] > 0 && t_used + bw[k] <= cap) { boff[k] = t_used | RBD_BOFF_TMEM; t_used += bw[k]; }
-      else { boff[k] = s_used; s_used += bw[k]; }
+    bool placed = false;
+    // cheapest configuration first: everything saved; then drop the v|a record of branch joints attached to the
+    // universe (recomputed from the A record and the inputs: costs a dozen global re-reads per return)
+    // ...; then re-read R|p of the other branch joints from the oMi output this thread wrote (when oMi is requested)
+    const int ncfg = 1 + (do_tau ? 1 : 0) + ((do_tau && omi_out) ? 1 : 0);
+    for (int cfg = 0; cfg < ncfg && !placed; ++cfg) {
+      const int drop_root_va = cfg >= 1, rp_from_omi = cfg >= 2;
+      std::vector<int> bw(bj.size()), bflag(bj.size(), 0);
+      for (size_t k = 0; k < bj.size(); ++k) {
+        const DevJoint& jb = m->joint[bj[k]];
+        // R|p: not for a free-flyer (its A record already is R|p)
+        const bool ff_dedupe = need_stack && jb.type == JT_FF;
+        const bool nova = drop_root_va && need_stack && jb.parent == 0;
+        const bool rpomi = rp_from_omi && !ff_dedupe;
+        bw[k] = ((ff_dedupe || rpomi) ? 0 : 12) + ((do_tau && !nova) ? 12 : 0);
+        bflag[k] = (nova ? RBD_BOFF_NOVA : 0) | (rpomi ? RBD_BOFF_RPOMI : 0);
+      }
+      // greedy: Y-stack first (one vector access per visit), then the widest branch records that still fit, then
+      // — only as many as shared memory needs to get rid of — the deepest f-stack levels
+      int t_base = 0;
+      EvalPlan pl{};
+      std::vector<int> boff(bj.size(), 0);
+      const int s_base = totalA;
+      const bool y_tm = ysz > 0 && ysz <= cap;
+      if (y_tm) { pl.y_in_tmem = 1; pl.ybase = t_base; t_base += ysz; }
+      std::vector<int> order(bj.size());
+      for (size_t k = 0; k < order.size(); ++k) order[k] = (int)k;
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bw[a] > bw[b]; });
+      std::vector<char> b_tm(bj.size(), 0);
+      for (int k : order)
+        if (bw[k] > 0 && t_base + bw[k] <= cap) { boff[k] = t_base | RBD_BOFF_TMEM; t_base += bw[k]; b_tm[k] = 1; }
+      const int kmax = do_tau ? std::min(D, (cap - t_base) / 6) : 0;
+      for (int kf = 0; kf <= kmax && !placed; ++kf) {
+        int s_used = s_base, t_used = t_base;
+        pl.fbase = s_used; pl.fsplit = do_tau ? D - kf : 0; s_used += do_tau ? 6 * (D - kf) : 0;
+        pl.ftbase = t_used; t_used += 6 * kf;
+        if (!y_tm) { pl.ybase = s_used; s_used += ysz; }
+        for (size_t k = 0; k < bj.size(); ++k)
+          if (!b_tm[k]) { boff[k] = s_used; s_used += bw[k]; }
+        pl.smem_doubles = s_used; pl.tmem_doubles = t_used; pl.warps = W;
+        pl.tmem_cols = t_used > 0 ? pow2_cols(2 * t_used * ((W + 3) / 4)) : 0;
+        const size_t block_bytes = model_bytes + (size_t)W * 32 * s_used * 8;
+        if (block_bytes + B200Limits::kSmemReservedPerBlock > (size_t)B200Limits::kSmemBytes) continue;
+        int c = (int)(B200Limits::kSmemBytes / (block_bytes + B200Limits::kSmemReservedPerBlock));
+        if (pl.tmem_cols > 0) c = std::min(c, B200Limits::kTmemCols / pl.tmem_cols);
+        c = std::min(c, B200Limits::kRegsPerSM / (B200Limits::kRegsPerThread * W * 32));
+        c = std::min(c, 32);
+        if (c < 1) continue;
+        pl.blocks_per_sm = c;
+        placed = true;
+        // more resident warps wins; on ties the LARGER block: the warps of one block spread over the four SM
+        // sub-partitions (warp % 4), whereas many one-warp blocks were measured 3x slower (r1c: 15.8 ms vs 5.2 ms)
+        if (W * c >= best_warps_sm) {
+          best_warps_sm = W * c; best = pl; best_boff = boff;
+          for (size_t k = 0; k < bj.size(); ++k) best_boff[k] |= bflag[k];
+        }
+      }
     }
-    pl.smem_doubles = s_used; pl.tmem_doubles = t_used; pl.warps = W;
-    pl.tmem_cols = t_used > 0 ? pow2_cols(2 * t_used * ((W + 3) / 4)) : 0;
-    const size_t block_bytes = model_bytes + (size_t)W * 32 * s_used * 8;
-    if (block_bytes > (size_t)B200Limits::kSmemBytes) continue;
-    int c = (int)(B200Limits::kSmemBytes / (block_bytes + B200Limits::kSmemReservedPerBlock));
-    if (c < 1) c = 1;
-    if (pl.tmem_cols > 0) c = std::min(c, B200Limits::kTmemCols / pl.tmem_cols);
-    c = std::min(c, B200Limits::kRegsPerSM / (B200Limits::kRegsPerThread * W * 32));
-    c = std::min(c, 32);
-    if (c < 1) continue;
-    pl.blocks_per_sm = c;
-    // more resident warps wins; on ties the LARGER block: the warps of one block spread over the four SM
-    // sub-partitions (warp % 4), whereas many one-warp blocks were measured 3x slower (r1c: 15.8 ms vs 5.2 ms)
-    if (W * c >= best_warps_sm) { best_warps_sm = W * c; best = pl; best_boff = boff; }
   }
   if (best_warps_sm == 0) return false;
   m->plan = best;

@@ -25,6 +25,12 @@
 //   applyJT_instance  KCM.inl:450-513 and :515-639 (sum_k J_k^T w_k, matrix-free)
 #pragma once
 #include <math.h>
+#ifndef RBD_PTR_OMIJ
+#define RBD_PTR_OMIJ 1
+#endif
+#ifndef RBD_PTR_COL
+#define RBD_PTR_COL 0 /* measured slower (A/B r1d: 2.98 vs 2.85 ms): pointer bumps serialise the zero-fill */
+#endif
 
 #include "rbd_dev_model.h"
 
@@ -51,6 +57,11 @@ struct FieldT {
   RBD_HD double ld(int k) const { return p[off(k)]; }
   RBD_HD void st(int k, double v) const { p[off(k)] = v; }
   RBD_HD bool ok() const { return p != nullptr; }
+  // address of field k, and a store at a (small, usually compile-time) field offset e from such an address: with
+  // TILE fixed the offset folds into the instruction's immediate instead of costing one IMAD.WIDE per store
+  RBD_HD double* at(int k) const { return p + off(k); }
+  RBD_HD void st_at(double* a, int e, double v) const { a[TILE ? (long long)e * TILE : (long long)e * stride] = v; }
+  RBD_HD long long step(int e) const { return TILE ? (long long)e * TILE : (long long)e * stride; }
 };
 using Field = FieldT<0>;
 template <int TILE>
@@ -357,6 +368,21 @@ RBD_HD void ff_rows(const double* R, const double* p, const double* F, double* o
   }
 }
 
+// free-flyer joint motion given in the joint (body) frame, 6 fields of `fld` from `o`: world = oMi.act(.)
+template <class FLD>
+RBD_HD void ff_act(const double* R, const double* p, const FLD& fld, int o, double* out) {
+  const double l0 = fld.ld(o), l1 = fld.ld(o + 1), l2 = fld.ld(o + 2);
+  const double w0 = fld.ld(o + 3), w1 = fld.ld(o + 4), w2 = fld.ld(o + 5);
+  out[3] = R[0] * w0 + R[1] * w1 + R[2] * w2;
+  out[4] = R[3] * w0 + R[4] * w1 + R[5] * w2;
+  out[5] = R[6] * w0 + R[7] * w1 + R[8] * w2;
+  double tx, ty, tz;
+  RBD_CROSS(tx, ty, tz, p[0], p[1], p[2], out[3], out[4], out[5]);
+  out[0] = R[0] * l0 + R[1] * l1 + R[2] * l2 + tx;
+  out[1] = R[3] * l0 + R[4] * l1 + R[5] * l2 + ty;
+  out[2] = R[6] * l0 + R[7] * l1 + R[8] * l2 + tz;
+}
+
 // world spatial inertia about the world origin: Y = (m, h = m c_w, I_O (xx,xy,yy,xz,yz,zz))
 RBD_HD void inertia_world(const DevJoint& jn, const double* R, const double* p, double* Y) {
   const double m = jn.Y[0];
@@ -483,6 +509,35 @@ RBD_HD void column_rows(const DevModel& m, const DevJoint& jn, int base, const d
                         const FieldT<TILE>& M) {
   const int* pr = col_prog(m) + jn.prog_off;
   const int na = jn.depth - 1;
+#if RBD_PTR_COL
+  double* const pc = M.at(base);
+#pragma unroll 2
+  for (int d = 0; d < na; ++d) {
+    const int e = pr[d];
+    const int sa = RBD_PROG_OFFA(e);
+    double* const pa = pc + M.step(RBD_PROG_ROW(e));
+    if (RBD_PROG_FF(e)) {
+      double Rq[12], p6[6];
+      s_ldv<12>(S, sa, Rq);
+      ff_rows(Rq, Rq + 9, F, p6);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) M.st_at(pa, k, p6[k]);
+    } else {
+      double Aa[6];
+      s_ldv<6>(S, sa, Aa);
+      *pa = dot6(Aa, F);
+    }
+  }
+  for (int z = 0; z < jn.nzseg; ++z) {
+    const int e = pr[na + z];
+    double* pz = pc + M.step(RBD_PROG_ROW(e));
+    int len = RBD_PROG_ZLEN(e);
+    for (; len >= 4; len -= 4, pz += M.step(4)) {
+      M.st_at(pz, 0, 0.0); M.st_at(pz, 1, 0.0); M.st_at(pz, 2, 0.0); M.st_at(pz, 3, 0.0);
+    }
+    for (; len > 0; --len, pz += M.step(1)) *pz = 0.0;
+  }
+#else
 #pragma unroll 2
   for (int d = 0; d < na; ++d) {
     const int e = pr[d];
@@ -505,6 +560,7 @@ RBD_HD void column_rows(const DevModel& m, const DevJoint& jn, int base, const d
 #pragma unroll 4
     for (int r = 0; r < len; ++r) M.st(r0 + r, 0.0);
   }
+#endif
 }
 
 // Everything joint k owes once its subtree is complete: tau_k = A_k^T f_k and its column(s) of M.
@@ -521,7 +577,7 @@ RBD_HD void emit_joint(const DevModel& m, int k, const double* A, const double* 
       inertia_mul(Y, A, F);
       const int col = jn.idx_v;
       const int base = col * (col + 1) / 2;
-      io.M.st(base + col, dot6(A, F));
+      *io.M.at(base + col) = dot6(A, F);
       column_rows(m, jn, base, F, S, io.M);
     }
   } else {
@@ -536,9 +592,10 @@ RBD_HD void emit_joint(const DevModel& m, int k, const double* A, const double* 
         const int col = jn.idx_v + cc;
         const int base = col * (col + 1) / 2;
         ff_rows(A, A + 9, F, o6);
+        double* const pd = io.M.at(base + jn.idx_v);
 #pragma unroll
         for (int e = 0; e < 6; ++e)
-          if (e <= cc) io.M.st(base + jn.idx_v + e, o6[e]);
+          if (e <= cc) io.M.st_at(pd, e, o6[e]);
         column_rows(m, jn, base, F, S, io.M);
       }
     }
@@ -551,8 +608,11 @@ template <bool DO_M, bool DO_TAU, int TILE>
 RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stack& S, const TmStack& T) {
   constexpr bool NEED_STACK = DO_M || DO_TAU;
   const int nj = m.njoints;
-  const int fbase = m.plan.fbase, ybase = m.plan.ybase;
+  const int fbase = m.plan.fbase, fsplit = m.plan.fsplit, ftbase = m.plan.ftbase, ybase = m.plan.ybase;
   const bool ytm = m.plan.y_in_tmem != 0;
+  // f-stack level -> (space, offset): levels below fsplit in shared memory, the rest in tensor memory
+#define RBD_F_TM(lvl) ((lvl) >= fsplit)
+#define RBD_F_OFF(lvl) ((lvl) >= fsplit ? ftbase + 6 * ((lvl)-fsplit) : fbase + 6 * (lvl))
   double R[9], p[3], vel[6], acc[6];
 #define RBD_RESET_ROOT()                                                   \
   do {                                                                     \
@@ -582,10 +642,14 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
       } else {
         const DevJoint& jb = m.joint[par];
         const bool btm = (jb.boff & RBD_BOFF_TMEM) != 0;
-        int b = jb.boff & ~RBD_BOFF_TMEM;
+        int b = jb.boff & RBD_BOFF_MASK;
         double Rp[12];
         if (NEED_STACK && jb.type == JT_FF) {
           s_ldv<12>(S, jb.offA, Rp);  // a free-flyer's A record is its R|p
+        } else if (jb.boff & RBD_BOFF_RPOMI) {
+          const int o = 12 * (par - 1);  // this thread wrote oMi[par] earlier in the sweep
+#pragma unroll
+          for (int e = 0; e < 12; ++e) Rp[e] = io.oMi.ld(o + e);
         } else {
           x_ldv<12>(btm, S, T, b, Rp);
           b += 12;
@@ -595,10 +659,28 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
 #pragma unroll
         for (int e = 0; e < 3; ++e) p[e] = Rp[9 + e];
         if (DO_TAU) {
-          double va[12];
-          x_ldv<12>(btm, S, T, b, va);
+          if (!(jb.boff & RBD_BOFF_NOVA)) {
+            double va[12];
+            x_ldv<12>(btm, S, T, b, va);
 #pragma unroll
-          for (int e = 0; e < 6; ++e) { vel[e] = va[e]; acc[e] = va[6 + e]; }
+            for (int e = 0; e < 6; ++e) { vel[e] = va[e]; acc[e] = va[6 + e]; }
+          } else {
+            // branch joint attached to the universe: v = A qd, a = -g + A qdd (v x vJ = 0), nothing was saved
+            double vj[6], aj[6];
+            if (jb.type == JT_FF) {
+              ff_act(R, p, io.v, jb.idx_v, vj);
+              ff_act(R, p, io.a, jb.idx_v, aj);
+            } else {
+              double Ab[6];
+              s_ldv<6>(S, jb.offA, Ab);
+              const double qd_b = io.v.ld(jb.idx_v), qdd_b = io.a.ld(jb.idx_v);
+#pragma unroll
+              for (int e = 0; e < 6; ++e) { vj[e] = Ab[e] * qd_b; aj[e] = Ab[e] * qdd_b; }
+            }
+#pragma unroll
+            for (int e = 0; e < 6; ++e) { vel[e] = vj[e]; acc[e] = aj[e]; }
+            acc[0] -= m.gravity[0]; acc[1] -= m.gravity[1]; acc[2] -= m.gravity[2];
+          }
         }
       }
     }
@@ -614,19 +696,33 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
     double aw[3];
     fk_joint(jn, R, p, q0, q1, io.q, aw);
     if (io.oMi.ok()) {
+#if RBD_PTR_OMIJ
+      double* const po = io.oMi.at(12 * (i - 1));
+#pragma unroll
+      for (int e = 0; e < 9; ++e) io.oMi.st_at(po, e, R[e]);
+#pragma unroll
+      for (int e = 0; e < 3; ++e) io.oMi.st_at(po, 9 + e, p[e]);
+#else
       const int o = 12 * (i - 1);
 #pragma unroll
       for (int e = 0; e < 9; ++e) io.oMi.st(o + e, R[e]);
 #pragma unroll
       for (int e = 0; e < 3; ++e) io.oMi.st(o + 9 + e, p[e]);
+#endif
     }
     // Ak: world subspace column (1-dof) or R|p (free-flyer) — what the A-stack keeps for the CRBA/RNEA projections
     double Ak[12], fk[6], Yk[10];
     if (jn.type != JT_FF) {
       subspace_1dof(jn.type, p, aw, Ak);
       if (io.J.ok()) {
+#if RBD_PTR_OMIJ
+        double* const pj = io.J.at(6 * jn.idx_v);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) io.J.st_at(pj, e, Ak[e]);
+#else
 #pragma unroll
         for (int e = 0; e < 6; ++e) io.J.st(6 * jn.idx_v + e, Ak[e]);
+#endif
       }
       if (DO_TAU) {
         double vj[6], cr[6];
@@ -647,43 +743,20 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
 #pragma unroll
       for (int e = 0; e < 3; ++e) Ak[9 + e] = p[e];
       if (io.J.ok()) {
+        double* const pj = io.J.at(6 * jn.idx_v);
 #pragma unroll
         for (int cc = 0; cc < 6; ++cc) {
           double A[6];
           RBD_FF_COL(A, R, p, cc);
 #pragma unroll
-          for (int e = 0; e < 6; ++e) io.J.st(6 * (jn.idx_v + cc) + e, A[e]);
+          for (int e = 0; e < 6; ++e) io.J.st_at(pj, 6 * cc + e, A[e]);
         }
       }
       if (DO_TAU) {
         // joint velocity / acceleration given in the joint (body) frame: world = oMi.act(.)
         double vj[6], aj[6], cr[6];
-        {
-          const int o = jn.idx_v;
-          const double l0 = io.v.ld(o), l1 = io.v.ld(o + 1), l2 = io.v.ld(o + 2);
-          const double w0 = io.v.ld(o + 3), w1 = io.v.ld(o + 4), w2 = io.v.ld(o + 5);
-          vj[3] = R[0] * w0 + R[1] * w1 + R[2] * w2;
-          vj[4] = R[3] * w0 + R[4] * w1 + R[5] * w2;
-          vj[5] = R[6] * w0 + R[7] * w1 + R[8] * w2;
-          double tx, ty, tz;
-          RBD_CROSS(tx, ty, tz, p[0], p[1], p[2], vj[3], vj[4], vj[5]);
-          vj[0] = R[0] * l0 + R[1] * l1 + R[2] * l2 + tx;
-          vj[1] = R[3] * l0 + R[4] * l1 + R[5] * l2 + ty;
-          vj[2] = R[6] * l0 + R[7] * l1 + R[8] * l2 + tz;
-        }
-        {
-          const int o = jn.idx_v;
-          const double l0 = io.a.ld(o), l1 = io.a.ld(o + 1), l2 = io.a.ld(o + 2);
-          const double w0 = io.a.ld(o + 3), w1 = io.a.ld(o + 4), w2 = io.a.ld(o + 5);
-          aj[3] = R[0] * w0 + R[1] * w1 + R[2] * w2;
-          aj[4] = R[3] * w0 + R[4] * w1 + R[5] * w2;
-          aj[5] = R[6] * w0 + R[7] * w1 + R[8] * w2;
-          double tx, ty, tz;
-          RBD_CROSS(tx, ty, tz, p[0], p[1], p[2], aj[3], aj[4], aj[5]);
-          aj[0] = R[0] * l0 + R[1] * l1 + R[2] * l2 + tx;
-          aj[1] = R[3] * l0 + R[4] * l1 + R[5] * l2 + ty;
-          aj[2] = R[6] * l0 + R[7] * l1 + R[8] * l2 + tz;
-        }
+        ff_act(R, p, io.v, jn.idx_v, vj);
+        ff_act(R, p, io.a, jn.idx_v, aj);
 #pragma unroll
         for (int e = 0; e < 6; ++e) vel[e] += vj[e];
         RBD_CROSS(cr[0], cr[1], cr[2], vel[3], vel[4], vel[5], vj[0], vj[1], vj[2]);
@@ -716,13 +789,13 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
       if (NEED_STACK) {
         const int lvl = jn.depth - 1;
         if (jn.type != JT_FF) s_stv<6>(S, jn.offA, Ak); else s_stv<12>(S, jn.offA, Ak);
-        if (DO_TAU) s_stv<6>(S, fbase + 6 * lvl, fk);
-        if (DO_M) x_stv<10>(ytm, S, T, ybase + 10 * lvl, Yk);
+        if (DO_TAU) x_stv<6>(RBD_F_TM(lvl), S, T, RBD_F_OFF(lvl), fk);
+        if (DO_M) x_stv<9>(ytm, S, T, ybase + 9 * lvl, Yk + 1);
       }
       if (jn.nchild >= 2) {
         const bool btm = (jn.boff & RBD_BOFF_TMEM) != 0;
-        int b = jn.boff & ~RBD_BOFF_TMEM;
-        if (!(NEED_STACK && jn.type == JT_FF)) {
+        int b = jn.boff & RBD_BOFF_MASK;
+        if (!(NEED_STACK && jn.type == JT_FF) && !(jn.boff & RBD_BOFF_RPOMI)) {
           double Rp[12];
 #pragma unroll
           for (int e = 0; e < 9; ++e) Rp[e] = R[e];
@@ -731,7 +804,7 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
           x_stv<12>(btm, S, T, b, Rp);
           b += 12;
         }
-        if (DO_TAU) {
+        if (DO_TAU && !(jn.boff & RBD_BOFF_NOVA)) {
           double va[12];
 #pragma unroll
           for (int e = 0; e < 6; ++e) { va[e] = vel[e]; va[6 + e] = acc[e]; }
@@ -750,22 +823,22 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
         const DevJoint& jp = m.joint[pk];
         const int lvl = jp.depth - 1;
         if (pk == nxt_par) {
-          if (DO_TAU) {
-#pragma unroll
-            for (int e = 0; e < 6; ++e) S.add(fbase + 6 * lvl + e, fk[e]);
-          }
-          if (DO_M) x_addv<10>(ytm, S, T, ybase + 10 * lvl, Yk);
+          if (DO_TAU) x_addv<6>(RBD_F_TM(lvl), S, T, RBD_F_OFF(lvl), fk);
+          if (DO_M) x_addv<9>(ytm, S, T, ybase + 9 * lvl, Yk + 1);
           break;
         }
         if (DO_TAU) {
+          double fp[6];
+          x_ldv<6>(RBD_F_TM(lvl), S, T, RBD_F_OFF(lvl), fp);
 #pragma unroll
-          for (int e = 0; e < 6; ++e) fk[e] += S.ld(fbase + 6 * lvl + e);
+          for (int e = 0; e < 6; ++e) fk[e] += fp[e];
         }
         if (DO_M) {
-          double Yp[10];
-          x_ldv<10>(ytm, S, T, ybase + 10 * lvl, Yp);
+          double Yp[9];
+          x_ldv<9>(ytm, S, T, ybase + 9 * lvl, Yp);
 #pragma unroll
-          for (int e = 0; e < 10; ++e) Yk[e] += Yp[e];
+          for (int e = 0; e < 9; ++e) Yk[1 + e] += Yp[e];
+          Yk[0] = jp.msub;  // composite mass of the subtree: model constant
         }
         if (jp.type != JT_FF) s_ldv<6>(S, jp.offA, Ak); else s_ldv<12>(S, jp.offA, Ak);
         k = pk;
@@ -773,6 +846,8 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
     }
   }
 #undef RBD_RESET_ROOT
+#undef RBD_F_TM
+#undef RBD_F_OFF
 }
 
 // =========================================================================================================

@@ -39,7 +39,7 @@ extern "C" int emul_model_info(const rbd_model_desc* d, int* out /*[8]*/) {
   if (rc) return rc;
   out[0] = c.m.max_depth; out[1] = c.m.nbranch; out[6] = smem_applyJT(c.m); out[7] = c.m.has_ff_root;
   DevModel t = c.m;
-  if (!plan_eval(&t, true, true, true)) return -100;
+  if (!plan_eval(&t, true, true, true, 0, true)) return -100;
   out[2] = t.plan.smem_doubles; out[3] = t.plan.tmem_doubles; out[4] = t.plan.warps * t.plan.blocks_per_sm;
   t = c.m;
   if (!plan_eval(&t, true, true, false)) return -101;
@@ -70,7 +70,7 @@ extern "C" int emul_eval(const rbd_model_desc* d, long long n, long long tile, i
   int rc = make_ctx(d, &c);
   if (rc) return rc;
   const bool do_m = M != nullptr, do_tau = tau != nullptr;
-  if (!plan_eval(&c.m, do_m, do_tau, use_tmem != 0, block / 32)) { g_err = "plan_eval failed"; return -100; }
+  if (!plan_eval(&c.m, do_m, do_tau, use_tmem != 0, block / 32, oMi != nullptr)) { g_err = "plan_eval failed"; return -100; }
   // the sweep reads the model through the staged blob (planned DevModel prefix + ColProg table), as the kernel does
   const std::vector<unsigned long long> blob = build_eval_blob(&c.m);
   const DevModel& bm = *reinterpret_cast<const DevModel*>(blob.data());
