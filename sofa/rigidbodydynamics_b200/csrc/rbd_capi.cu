@@ -44,7 +44,7 @@ static const int kSlots = 2;
 struct HostSlot {
   cudaStream_t st = nullptr;
   double* aos = nullptr;  // device, instance-major staging
-  double* soa = nullptr;  // device, tiled-SoA staging (tile = chunk)
+  double* soa = nullptr;  // device, tiled-SoA staging (tile = 32)
 };
 
 struct rbd_workspace {
@@ -53,18 +53,19 @@ struct rbd_workspace {
   long long capacity = 0;
   cudaStream_t stream = nullptr;
   // device copies of the per-output tables
-  int *d_sorted_k = nullptr, *d_outk_parent = nullptr;
+  int *d_sorted_k = nullptr, *d_outk_parent = nullptr, *d_sorted_ident = nullptr;
   double *d_sorted_pl = nullptr, *d_outk_pl = nullptr;
   DevTables tb{};
   // fused eval: one planned copy of the joint table per variant (bit 1 = CRBA, bit 0 = RNEA), host + device;
   // the kernel stages the device copy into shared memory
-  DevModel* h_plan[8] = {};  // index: bit 2 = oMi requested, bit 1 = CRBA, bit 0 = RNEA
-  DevModel* d_plan[8] = {};
+  DevModel* h_plan[9] = {};  // index: bit 2 = oMi requested, bit 1 = CRBA, bit 0 = RNEA; [8] = the applyJT sweep
+  DevModel* d_plan[9] = {};
   int use_tmem = 1;
   int num_sms = 0;
   double* qcache = nullptr;  // [nq][capacity] assembled configuration of the last apply
   long long applied_n = 0;   // instances covered by the cache (0 = apply not called yet)
-  LaunchCfg cfg_eval[8], cfg_apply, cfg_applyJ, cfg_applyJT, cfg_rows;
+  LaunchCfg cfg_eval[8], cfg_apply[2], cfg_applyJ[2], cfg_applyJT[2], cfg_rows;
+  DevModel* d_model = nullptr;  // device copy of the joint table for the mapping kernels
   int forced_eval_block = 0;
   long long launches = 0;
   // host-path staging
@@ -155,9 +156,9 @@ RBD_API int rbd_model_get_info(const rbd_model* model, rbd_model_info* info) {
 // ---- workspace ------------------------------------------------------------------------------------------
 static void ws_free(rbd_workspace* ws) {
   if (!ws) return;
-  cudaFree(ws->d_sorted_k); cudaFree(ws->d_outk_parent); cudaFree(ws->d_sorted_pl); cudaFree(ws->d_outk_pl);
-  cudaFree(ws->qcache); cudaFree(ws->rows_buf);
-  for (int k = 0; k < 8; ++k) { cudaFree(ws->d_plan[k]); delete ws->h_plan[k]; }
+  cudaFree(ws->d_sorted_k); cudaFree(ws->d_outk_parent); cudaFree(ws->d_sorted_ident); cudaFree(ws->d_sorted_pl); cudaFree(ws->d_outk_pl);
+  cudaFree(ws->qcache); cudaFree(ws->rows_buf); cudaFree(ws->d_model);
+  for (int k = 0; k < 9; ++k) { cudaFree(ws->d_plan[k]); delete ws->h_plan[k]; }
   for (int s = 0; s < kSlots; ++s) {
     cudaFree(ws->slot[s].aos); cudaFree(ws->slot[s].soa);
     if (ws->slot[s].st) cudaStreamDestroy(ws->slot[s].st);
@@ -192,6 +193,8 @@ RBD_API int rbd_workspace_create(const rbd_model* model, int device, int64_t cap
   if (no > 0) {
     WS_CK(cudaMalloc(&ws->d_sorted_k, no * sizeof(int)));
     WS_CK(cudaMalloc(&ws->d_outk_parent, no * sizeof(int)));
+    WS_CK(cudaMalloc(&ws->d_sorted_ident, no * sizeof(int)));
+    WS_CK(cudaMemcpy(ws->d_sorted_ident, ht.sorted_ident.data(), no * sizeof(int), cudaMemcpyHostToDevice));
     WS_CK(cudaMalloc(&ws->d_sorted_pl, no * 12 * sizeof(double)));
     WS_CK(cudaMalloc(&ws->d_outk_pl, no * 12 * sizeof(double)));
     WS_CK(cudaMemcpy(ws->d_sorted_k, ht.sorted_k.data(), no * sizeof(int), cudaMemcpyHostToDevice));
@@ -199,9 +202,12 @@ RBD_API int rbd_workspace_create(const rbd_model* model, int device, int64_t cap
     WS_CK(cudaMemcpy(ws->d_sorted_pl, ht.sorted_pl.data(), no * 12 * sizeof(double), cudaMemcpyHostToDevice));
     WS_CK(cudaMemcpy(ws->d_outk_pl, ht.outk_pl.data(), no * 12 * sizeof(double), cudaMemcpyHostToDevice));
   }
-  ws->tb.sorted_k = ws->d_sorted_k; ws->tb.sorted_pl = ws->d_sorted_pl;
+  ws->tb.sorted_k = ws->d_sorted_k; ws->tb.sorted_pl = ws->d_sorted_pl; ws->tb.sorted_ident = ws->d_sorted_ident;
   ws->tb.outk_parent = ws->d_outk_parent; ws->tb.outk_pl = ws->d_outk_pl;
-  WS_CK(cudaMalloc(&ws->qcache, (size_t)(model->dm.nq > 0 ? model->dm.nq : 1) * (size_t)capacity * sizeof(double)));
+  WS_CK(cudaMalloc(&ws->d_model, sizeof(DevModel)));
+  WS_CK(cudaMemcpy(ws->d_model, &model->dm, sizeof(DevModel), cudaMemcpyHostToDevice));
+  // cached configuration of the last apply: tile-32 layout, whole tiles
+  WS_CK(cudaMalloc(&ws->qcache, (size_t)(model->dm.nq > 0 ? model->dm.nq : 1) * (size_t)((capacity + 31) / 32 * 32) * sizeof(double)));
   WS_CK(cudaEventCreateWithFlags(&ws->ev, cudaEventDisableTiming));
   WS_CK(cudaDeviceGetAttribute(&ws->num_sms, cudaDevAttrMultiProcessorCount, device));
 #undef WS_CK
@@ -251,7 +257,10 @@ static int ensure_plan(rbd_workspace* ws, int pk) {
   if (ws->h_plan[pk]) return RBD_OK;
   DevModel* h = new (std::nothrow) DevModel(ws->model->dm);
   if (!h) return set_err(RBD_ERR_ALLOC, "out of host memory");
-  if (!plan_eval(h, (pk & 2) != 0, (pk & 1) != 0, ws->use_tmem != 0, ws->forced_eval_block / 32, (pk & 4) != 0)) {
+  const bool planned = pk == 8 ? plan_eval(h, false, true, ws->use_tmem != 0, 0, false, /*jt=*/true)
+                               : plan_eval(h, (pk & 2) != 0, (pk & 1) != 0, ws->use_tmem != 0,
+                                           ws->forced_eval_block / 32, (pk & 4) != 0);
+  if (!planned) {
     delete h;
     return set_err(RBD_ERR_UNSUPPORTED, "the sweep state of this model does not fit one SM's shared + tensor memory"
                                         " at the requested block size");
@@ -271,7 +280,7 @@ static int ensure_plan(rbd_workspace* ws, int pk) {
 static void drop_plans(rbd_workspace* ws) {
   // kernels still in flight keep reading the device copies: wait for them before the next upload overwrites
   cudaDeviceSynchronize();
-  for (int k = 0; k < 8; ++k) { delete ws->h_plan[k]; ws->h_plan[k] = nullptr; }
+  for (int k = 0; k < 9; ++k) { delete ws->h_plan[k]; ws->h_plan[k] = nullptr; }
 }
 
 RBD_API int rbd_workspace_get_eval_plan(rbd_workspace* ws, int with_M, int with_tau, int32_t out[8]) {
@@ -322,8 +331,8 @@ static int apply_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile,
   const DevModel& dm = ws->model->dm;
   if (!qj || !out) return set_err(RBD_ERR_INVALID_ARG, "null q_joints / out");
   if (root && !dm.has_ff_root) return set_err(RBD_ERR_INVALID_ARG, "root pose given but the model has no free-flyer root");
-  MapArgs A{n, tile, qj, root, nullptr, out, ws->qcache, ws->capacity, inst0};
-  CK(launch_apply(dm, ws->tb, A, smem_apply(dm), &ws->cfg_apply, st));
+  MapArgs A{n, tile, qj, root, nullptr, out, ws->qcache, inst0};
+  CK(launch_apply(dm, ws->d_model, ws->tb, A, smem_apply(dm), ws->cfg_apply, st));
   if (n > 0) ws->launches++;
   return RBD_OK;
 }
@@ -342,8 +351,8 @@ static int applyJ_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile
   const DevModel& dm = ws->model->dm;
   if (!dq || !out) return set_err(RBD_ERR_INVALID_ARG, "null dq_joints / out");
   if (rootv && !dm.has_ff_root) return set_err(RBD_ERR_INVALID_ARG, "root velocity given but the model has no free-flyer root");
-  MapArgs A{n, tile, dq, rootv, nullptr, out, ws->qcache, ws->capacity, inst0};
-  CK(launch_applyJ(dm, ws->tb, A, smem_applyJ(dm), &ws->cfg_applyJ, st));
+  MapArgs A{n, tile, dq, rootv, nullptr, out, ws->qcache, inst0};
+  CK(launch_applyJ(dm, ws->d_model, ws->tb, A, smem_applyJ(dm), ws->cfg_applyJ, st));
   if (n > 0) ws->launches++;
   return RBD_OK;
 }
@@ -361,8 +370,10 @@ static int applyJT_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t til
   const DevModel& dm = ws->model->dm;
   if (!in || !out_tau) return set_err(RBD_ERR_INVALID_ARG, "null in / out_tau");
   if (out_root && !dm.has_ff_root) return set_err(RBD_ERR_INVALID_ARG, "root output given but the model has no free-flyer root");
-  MapArgs A{n, tile, out_tau, out_root, in, nullptr, ws->qcache, ws->capacity, inst0};
-  CK(launch_applyJT(dm, ws->tb, A, smem_applyJT(dm), &ws->cfg_applyJT, st));
+  MapArgs A{n, tile, out_tau, out_root, in, nullptr, ws->qcache, inst0};
+  int rc = ensure_plan(ws, 8);
+  if (rc) return rc;
+  CK(launch_applyJT_plan(*ws->h_plan[8], ws->d_plan[8], ws->tb, A, ws->cfg_applyJT, ws->num_sms, st));
   if (n > 0) ws->launches++;
   return RBD_OK;
 }
@@ -383,8 +394,8 @@ RBD_API int rbd_applyJT_rows_dev(rbd_workspace* ws, int64_t nrows, const int32_t
   if (!row_ptr || !row_instance || !out_rows || !keep) return set_err(RBD_ERR_INVALID_ARG, "null row arrays");
   if (ws->applied_n <= 0) return set_err(RBD_ERR_NO_APPLY, "applyJT(rows) before apply: no cached configuration");
   const DevModel& dm = ws->model->dm;
-  RowArgs A{nrows, row_ptr, row_instance, col, val, out_rows, keep, ws->qcache, ws->capacity};
-  CK(launch_applyJT_rows(dm, ws->tb, A, smem_applyJT(dm), &ws->cfg_rows, ws->stream));
+  RowArgs A{nrows, row_ptr, row_instance, col, val, out_rows, keep, ws->qcache};
+  CK(launch_applyJT_rows(dm, ws->d_model, ws->tb, A, smem_applyJT(dm), &ws->cfg_rows, ws->stream));
   ws->launches++;
   return RBD_OK;
 }
@@ -410,7 +421,7 @@ RBD_API int rbd_soa_to_aos_dev(rbd_workspace* ws, int64_t n, int32_t K, int64_t 
 // Consecutive chunks alternate slots so that the copies of one overlap the kernels of the other.
 static int ensure_slots(rbd_workspace* ws, size_t fields_total) {
   const long long chunk = ws->capacity < kHostChunk ? ws->capacity : kHostChunk;
-  const size_t need = fields_total * (size_t)chunk;
+  const size_t need = fields_total * (size_t)((chunk + 31) / 32 * 32);  // tile-32 staging holds whole tiles
   if (ws->slot[0].st && ws->slot_doubles >= need && ws->chunk == chunk) return RBD_OK;
   for (int s = 0; s < kSlots; ++s) {
     if (!ws->slot[s].st) CK(cudaStreamCreateWithFlags(&ws->slot[s].st, cudaStreamNonBlocking));
@@ -447,6 +458,7 @@ static int run_host_chunks(rbd_workspace* ws, int64_t n, std::vector<Piece>& pie
   CK(cudaEventRecord(ws->ev, ws->stream));
   for (int s = 0; s < kSlots; ++s) CK(cudaStreamWaitEvent(ws->slot[s].st, ws->ev, 0));
   const long long chunk = ws->chunk;
+  const long long cpad = (chunk + 31) / 32 * 32, tile = 32;  // device staging is tile-32 (the kernels' fast path)
   int which = 0;
   for (long long i0 = 0; i0 < n; i0 += chunk, which ^= 1) {
     const long long cn = (n - i0) < chunk ? (n - i0) : chunk;
@@ -455,20 +467,20 @@ static int run_host_chunks(rbd_workspace* ws, int64_t n, std::vector<Piece>& pie
     for (auto& p : pieces) {
       p.d_aos = sl.aos + off;
       p.d_soa = sl.soa + off;
-      off += (size_t)p.K * (size_t)chunk;
+      off += (size_t)p.K * (size_t)cpad;
       const bool present = p.h_in != nullptr || p.h_out != nullptr;
       if (!present) { p.d_aos = p.d_soa = nullptr; continue; }
       if (p.load && p.K > 0) {
         CK(cudaMemcpyAsync(p.d_aos, p.h_in + (size_t)i0 * p.K, (size_t)cn * p.K * sizeof(double), cudaMemcpyHostToDevice, sl.st));
-        CK(launch_aos_to_soa(cn, p.K, chunk, p.d_aos, p.d_soa, sl.st));
+        CK(launch_aos_to_soa(cn, p.K, tile, p.d_aos, p.d_soa, sl.st));
         ws->launches++;
       }
     }
-    rc = kernel(sl.st, i0, cn, chunk);
+    rc = kernel(sl.st, i0, cn, tile);
     if (rc) return rc;
     for (auto& p : pieces) {
       if (p.store && p.h_out && p.K > 0) {
-        CK(launch_soa_to_aos(cn, p.K, chunk, p.d_soa, p.d_aos, sl.st));
+        CK(launch_soa_to_aos(cn, p.K, tile, p.d_soa, p.d_aos, sl.st));
         ws->launches++;
         CK(cudaMemcpyAsync(p.h_out + (size_t)i0 * p.K, p.d_aos, (size_t)cn * p.K * sizeof(double), cudaMemcpyDeviceToHost, sl.st));
       }
@@ -580,8 +592,8 @@ RBD_API int rbd_applyJT_rows_host(rbd_workspace* ws, int64_t nrows, const int32_
     CK(cudaMemcpyAsync(d_val, val, (size_t)nnz * 48, cudaMemcpyHostToDevice, st));
   }
   const DevModel& dm = ws->model->dm;
-  RowArgs A{nrows, d_rp, d_ri, d_col, d_val, d_out, d_keep, ws->qcache, ws->capacity};
-  CK(launch_applyJT_rows(dm, ws->tb, A, smem_applyJT(dm), &ws->cfg_rows, st));
+  RowArgs A{nrows, d_rp, d_ri, d_col, d_val, d_out, d_keep, ws->qcache};
+  CK(launch_applyJT_rows(dm, ws->d_model, ws->tb, A, smem_applyJT(dm), &ws->cfg_rows, st));
   ws->launches++;
   CK(cudaMemcpyAsync(out_rows, d_out, (size_t)nrows * nv * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(keep, d_keep, (size_t)nrows * 4, cudaMemcpyDeviceToHost, st));

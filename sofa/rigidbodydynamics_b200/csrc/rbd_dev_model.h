@@ -95,10 +95,19 @@ inline size_t eval_model_bytes(const DevModel& m) {
   return (dev_model_bytes(m) + 15) / 16 * 16 + ((size_t)m.prog_len * 4 + 15) / 16 * 16 + 16;
 }
 
+// 8-byte words the vector mapping kernels stage behind the joint table for the per-output tables of n_out outputs:
+// placements (12 doubles each), output indices and identity flags (one int each, padded to even counts)
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline int table_words(int n_out) { return 12 * n_out + (n_out + 1) / 2 * 2; }
+
 // Per-output tables (global memory; only the mapping kernels read them).
 struct DevTables {
   const int* sorted_k;       // [n_out] output index, grouped by parent joint (DevJoint::out_begin/out_end)
   const double* sorted_pl;   // [n_out][12] frame placement in the parent joint frame, same order
+  const int* sorted_ident;   // [n_out] 1 when that placement's rotation is exactly I (the output shares the joint's
+                             // rotation: one rotation->quaternion conversion per joint serves all such outputs)
   const int* outk_parent;    // [n_out] parent joint of output k
   const double* outk_pl;     // [n_out][12] frame placement of output k
 };

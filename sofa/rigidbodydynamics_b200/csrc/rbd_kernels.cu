@@ -86,56 +86,147 @@ __global__ void __launch_bounds__(256) eval_kernel(const DevModel* __restrict__ 
   }
 }
 
+// The mapping kernels stage the joint table the same way (one coalesced copy per block, broadcast reads after).
+// The cached configuration of the last apply (workspace) is always tile-32.
+__device__ __forceinline__ const DevModel& stage_model(const DevModel* __restrict__ gm, int model_words) {
+  const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gm);
+  unsigned long long* dst = reinterpret_cast<unsigned long long*>(rbd_smem);
+  for (int w = threadIdx.x; w < model_words; w += blockDim.x) dst[w] = src[w];
+  __syncthreads();
+  return *reinterpret_cast<const DevModel*>(rbd_smem);
+}
+
+// The per-output tables of the vector mapping kernels go to shared memory too: read through the (small, with the
+// maximum shared-memory carve-out) L1 they were evicted by the streaming wrench / pose traffic and every dependent
+// sorted_k -> wrench address chain paid an L2 round trip (r1e: applyJT at 19 % of the HBM roofline).
+// Words (8 bytes) needed behind the staged joint table for n_out outputs:
+// (table_words, rbd_dev_model.h)
+__device__ __forceinline__ DevTables stage_tables(const DevTables& g, int n_out, double* dst) {
+  double* pl = dst;
+  int* k = reinterpret_cast<int*>(dst + 12 * n_out);
+  int* id = k + (n_out + 1) / 2 * 2;
+  for (int w = threadIdx.x; w < 12 * n_out; w += blockDim.x) pl[w] = g.sorted_pl[w];
+  for (int w = threadIdx.x; w < n_out; w += blockDim.x) { k[w] = g.sorted_k[w]; id[w] = g.sorted_ident[w]; }
+  __syncthreads();
+  DevTables t = g;
+  t.sorted_pl = pl; t.sorted_k = k; t.sorted_ident = id;
+  return t;
+}
+
 // K1: apply
-__global__ void __launch_bounds__(256) apply_kernel(const __grid_constant__ DevModel m, const DevTables tb,
-                                                    const MapArgs a, const int slots) {
+template <int TILE>
+__global__ void __launch_bounds__(256) apply_kernel(const DevModel* __restrict__ gm, const int model_words,
+                                                    const DevTables tb, const MapArgs a, const int slots) {
+  const DevModel& m = stage_model(gm, model_words);
+  const DevTables tbs = stage_tables(tb, m.n_out, rbd_smem + model_words);
+  const int tw = table_words(m.n_out);
   const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (inst >= a.n) return;
   const int off = a.root ? 7 : 0;
-  SplitQ q{make_field(const_cast<double*>(a.root), inst, 7, a.tile),
-           make_field(const_cast<double*>(a.joints), inst, m.nq - off, a.tile), off};
-  Stack S = make_stack(rbd_smem, threadIdx.x, slots);
-  apply_instance(m, tb, q, make_field(a.qcache, a.cache_inst0 + inst, m.nq, a.cache_tile),
-                 make_field(a.out, inst, 7 * m.n_out, a.tile), S);
+  SplitQT<FieldT<TILE>> q{make_field_t<TILE>(const_cast<double*>(a.root), inst, 7, a.tile),
+                          make_field_t<TILE>(const_cast<double*>(a.joints), inst, m.nq - off, a.tile), off};
+  Stack S = make_stack(rbd_smem + model_words + tw, threadIdx.x, slots);
+  apply_instance(m, tbs, q, make_field_t<32>(a.qcache, a.cache_inst0 + inst, m.nq, 32),
+                 make_field_t<TILE>(a.out, inst, 7 * m.n_out, a.tile), S);
 }
 
 // K2: applyJ
-__global__ void __launch_bounds__(256) applyJ_kernel(const __grid_constant__ DevModel m, const DevTables tb,
-                                                     const MapArgs a, const int slots) {
+template <int TILE>
+__global__ void __launch_bounds__(256) applyJ_kernel(const DevModel* __restrict__ gm, const int model_words,
+                                                     const DevTables tb, const MapArgs a, const int slots) {
+  const DevModel& m = stage_model(gm, model_words);
+  const DevTables tbs = stage_tables(tb, m.n_out, rbd_smem + model_words);
+  const int tw = table_words(m.n_out);
   const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (inst >= a.n) return;
   const int off = a.root ? 6 : 0;
-  SplitQ dq{make_field(const_cast<double*>(a.root), inst, 6, a.tile),
-            make_field(const_cast<double*>(a.joints), inst, m.nv - off, a.tile), off};
-  Stack S = make_stack(rbd_smem, threadIdx.x, slots);
-  applyJ_instance(m, tb, make_field(a.qcache, a.cache_inst0 + inst, m.nq, a.cache_tile), dq,
-                  make_field(a.out, inst, 6 * m.n_out, a.tile), S);
+  SplitQT<FieldT<TILE>> dq{make_field_t<TILE>(const_cast<double*>(a.root), inst, 6, a.tile),
+                           make_field_t<TILE>(const_cast<double*>(a.joints), inst, m.nv - off, a.tile), off};
+  Stack S = make_stack(rbd_smem + model_words + tw, threadIdx.x, slots);
+  applyJ_instance(m, tbs, make_field_t<32>(a.qcache, a.cache_inst0 + inst, m.nq, 32), dq,
+                  make_field_t<TILE>(a.out, inst, 6 * m.n_out, a.tile), S);
 }
 
 // K3: applyJT (vector).  a.joints / a.root are the ACCUMULATED outputs here, a.in the wrenches.
-__global__ void __launch_bounds__(256) applyJT_kernel(const __grid_constant__ DevModel m, const DevTables tb,
-                                                      const MapArgs a, const int slots) {
+template <int TILE>
+__global__ void __launch_bounds__(256) applyJT_kernel(const DevModel* __restrict__ gm, const int model_words,
+                                                      const DevTables tb, const MapArgs a, const int slots) {
+  const DevModel& m = stage_model(gm, model_words);
   const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (inst >= a.n) return;
   const int off = a.root ? 6 : 0;
-  DenseWrenchSrc src{make_field(const_cast<double*>(a.in), inst, 6 * m.n_out, a.tile), &tb};
-  SplitAccumSink sink{make_field(const_cast<double*>(a.root), inst, 6, a.tile),
-                      make_field(const_cast<double*>(a.joints), inst, m.nv - off, a.tile), off};
-  Stack S = make_stack(rbd_smem, threadIdx.x, slots);
-  applyJT_instance(m, tb, make_field(a.qcache, a.cache_inst0 + inst, m.nq, a.cache_tile), src, sink, S);
+  DenseWrenchSrcT<FieldT<TILE>> src{make_field_t<TILE>(const_cast<double*>(a.in), inst, 6 * m.n_out, a.tile), &tb};
+  SplitAccumSinkT<FieldT<TILE>> sink{make_field_t<TILE>(const_cast<double*>(a.root), inst, 6, a.tile),
+                                     make_field_t<TILE>(const_cast<double*>(a.joints), inst, m.nv - off, a.tile), off};
+  Stack S = make_stack(rbd_smem + model_words, threadIdx.x, slots);
+  applyJT_instance(m, tb, make_field_t<32>(a.qcache, a.cache_inst0 + inst, m.nq, 32), src, sink, S);
+}
+
+// K3 on the storage plan (shared + tensor memory, persistent warps): same prologue / epilogue as eval_kernel.
+template <int TILE>
+__global__ void __launch_bounds__(256) applyJT_plan_kernel(const DevModel* __restrict__ gm, const int model_words,
+                                                              const DevTables tb, const MapArgs a) {
+  unsigned* const tm_base_p = reinterpret_cast<unsigned*>(rbd_smem + model_words - 2);
+  {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gm);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(rbd_smem);
+    for (int w = threadIdx.x; w < model_words - 2; w += blockDim.x) dst[w] = src[w];
+  }
+  __syncthreads();
+  const DevModel& m = *reinterpret_cast<const DevModel*>(rbd_smem);
+  const int warp = threadIdx.x >> 5;
+  const int tm_cols = m.plan.tmem_cols;
+  TmStack T;
+  T.base = 0;
+  if (tm_cols > 0) {
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"l"(
+                       (unsigned long long)__cvta_generic_to_shared(tm_base_p)),
+                   "r"(tm_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    T.base = *tm_base_p + (((unsigned)(warp & 3) * 32u) << 16) + (unsigned)(warp >> 2) * 2u * (unsigned)m.plan.tmem_doubles;
+  }
+  const DevTables tbs = stage_tables(tb, m.n_out, rbd_smem + model_words);
+  const Stack S = make_stack(rbd_smem + model_words + table_words(m.n_out), threadIdx.x, m.plan.smem_doubles);
+  const long long ntiles = (a.n + 31) / 32;
+  const int wpb = blockDim.x >> 5;
+  const int off = a.root ? 6 : 0;
+  for (long long t = (long long)blockIdx.x * wpb + warp; t < ntiles; t += (long long)gridDim.x * wpb) {
+    long long inst = t * 32 + (threadIdx.x & 31);
+    // lanes past the end recompute the last instance but must not accumulate twice: their sink is disabled
+    const bool live = inst < a.n;
+    if (!live) inst = a.n - 1;
+    DenseWrenchSrcT<FieldT<TILE>> src{make_field_t<TILE>(const_cast<double*>(a.in), inst, 6 * m.n_out, a.tile), &tbs};
+    SplitAccumSinkT<FieldT<TILE>> sink{
+        make_field_t<TILE>(live ? const_cast<double*>(a.root) : nullptr, inst, 6, a.tile),
+        make_field_t<TILE>(live ? const_cast<double*>(a.joints) : nullptr, inst, m.nv - off, a.tile), off};
+    applyJT_instance_plan(m, tbs, make_field_t<32>(a.qcache, a.cache_inst0 + inst, m.nq, 32), src, sink, S, T);
+  }
+  if (tm_cols > 0) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tm_base_p), "r"(tm_cols) : "memory");
+  }
 }
 
 // K4: applyJT (constraint rows): one thread per row
-__global__ void __launch_bounds__(256) applyJT_rows_kernel(const __grid_constant__ DevModel m, const DevTables tb,
-                                                           const RowArgs a, const int slots) {
+__global__ void __launch_bounds__(256) applyJT_rows_kernel(const DevModel* __restrict__ gm, const int model_words,
+                                                           const DevTables tb, const RowArgs a, const int slots) {
+  const DevModel& m = stage_model(gm, model_words);
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= a.nrows) return;
   const int b = a.row_ptr[r], e = a.row_ptr[r + 1];
   double n2 = 0.0;
   RowWrenchSrc src{a.col + b, a.val + 6 * (long long)b, e - b, &tb};
   RowSink sink{a.out_rows + r * m.nv, &n2};
-  Stack S = make_stack(rbd_smem, threadIdx.x, slots);
-  applyJT_instance(m, tb, make_field(a.qcache, a.row_instance[r], m.nq, a.cache_tile), src, sink, S);
+  Stack S = make_stack(rbd_smem + model_words, threadIdx.x, slots);
+  applyJT_instance(m, tb, make_field_t<32>(a.qcache, a.row_instance[r], m.nq, 32), src, sink, S);
   a.keep[r] = n2 > 1e-12 ? 1 : 0;  // kMinTorqueSqrd, reference KinematicChainMapping.inl:43-45,587,605
 }
 
@@ -198,9 +289,8 @@ static cudaError_t pick_block(Kern kern, int smem_doubles_per_thread, int forced
     int nb = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, c, smem);
     if (e != cudaSuccess) return e;
-    // prefer more resident threads; on ties the SMALLER block: blocks retire independently, so the tail of a
-    // wave is shorter and the shared-memory allocation granularity wastes less
-    if (nb * c > best_threads) {
+    // prefer more resident threads; on ties the LARGER block (its warps spread over the four SM sub-partitions)
+    if (nb * c >= best_threads) {
       best_threads = nb * c; best_block = c; best_blocks_per_sm = nb;
     }
   }
@@ -249,51 +339,83 @@ cudaError_t launch_eval(const DevModel& hm, const DevModel* d_model, const EvalA
   if (a.n <= 0) return cudaSuccess;
   unsigned grid = RBD_GRID(a.n, block);
   const unsigned resident = (unsigned)(num_sms * (hm.plan.blocks_per_sm > 0 ? hm.plan.blocks_per_sm : 1));
-  if (grid > resident) grid = resident;  // persistent blocks: one wave, warps stride over the tiles
+  // persistent blocks (one wave, warps stride over the tiles) once every warp gets >= 8 tiles; smaller batches run
+  // one block per `block` instances so that the last wave is not half empty
+  if (grid > 8 * resident) grid = resident;
 #define RBD_LAUNCH(K) K<<<grid, block, smem, st>>>(d_model, a, model_words)
   RBD_EVAL_DISPATCH(v, RBD_LAUNCH)
 #undef RBD_LAUNCH
   return cudaGetLastError();
 }
 
-cudaError_t launch_apply(const DevModel& m, const DevTables& tb, const MapArgs& a, int smem_doubles, LaunchCfg* cfg,
-                         cudaStream_t st) {
-  if (cfg->block == 0) {
-    cudaError_t e = pick_block(apply_kernel, smem_doubles, 0, cfg);
+// mapping kernels: cfg[0] = run-time tile, cfg[1] = tile 32
+static inline int map_model_words(const DevModel& m) { return (int)((dev_model_bytes(m) + 15) / 16) * 2; }
+
+#define RBD_MAP_LAUNCH(KERN, n_items)                                                                         \
+  const int mw = map_model_words(m);                                                                          \
+  const size_t fixed = ((size_t)mw + table_words(m.n_out)) * 8;                                               \
+  const int v = a_tile == 32 ? 1 : 0;                                                                         \
+  LaunchCfg& c = cfg[v];                                                                                      \
+  if (c.block == 0) {                                                                                         \
+    cudaError_t e = v ? pick_block(KERN<32>, smem_doubles, 0, &c, fixed)                                      \
+                      : pick_block(KERN<0>, smem_doubles, 0, &c, fixed);                                      \
+    if (e != cudaSuccess) return e;                                                                           \
+  }                                                                                                           \
+  if ((n_items) <= 0) return cudaSuccess;                                                                     \
+  if (v) KERN<32><<<RBD_GRID(n_items, c.block), c.block, c.smem_bytes, st>>>(d_model, mw, tb, a, smem_doubles); \
+  else KERN<0><<<RBD_GRID(n_items, c.block), c.block, c.smem_bytes, st>>>(d_model, mw, tb, a, smem_doubles);  \
+  return cudaGetLastError()
+
+cudaError_t launch_apply(const DevModel& m, const DevModel* d_model, const DevTables& tb, const MapArgs& a,
+                         int smem_doubles, LaunchCfg* cfg, cudaStream_t st) {
+  const long long a_tile = a.tile;
+  RBD_MAP_LAUNCH(apply_kernel, a.n);
+}
+cudaError_t launch_applyJ(const DevModel& m, const DevModel* d_model, const DevTables& tb, const MapArgs& a,
+                          int smem_doubles, LaunchCfg* cfg, cudaStream_t st) {
+  const long long a_tile = a.tile;
+  RBD_MAP_LAUNCH(applyJ_kernel, a.n);
+}
+cudaError_t launch_applyJT(const DevModel& m, const DevModel* d_model, const DevTables& tb, const MapArgs& a,
+                           int smem_doubles, LaunchCfg* cfg, cudaStream_t st) {
+  const long long a_tile = a.tile;
+  RBD_MAP_LAUNCH(applyJT_kernel, a.n);
+}
+// `hm` = host copy of the model planned with plan_eval(..., jt = true), `d_blob` = its staged blob on the device
+cudaError_t launch_applyJT_plan(const DevModel& hm, const DevModel* d_blob, const DevTables& tb, const MapArgs& a,
+                                LaunchCfg* cfg2, int num_sms, cudaStream_t st) {
+  const int v = a.tile == 32 ? 1 : 0;
+  LaunchCfg& c = cfg2[v];
+  const int model_words = (int)(eval_model_bytes(hm) / 8);
+  const int block = hm.plan.warps * 32;
+  const size_t smem = ((size_t)model_words + table_words(hm.n_out)) * 8 + (size_t)block * hm.plan.smem_doubles * 8;
+  if (c.block != block || c.smem_bytes != smem) {
+    cudaError_t e = v ? cudaFuncSetAttribute(applyJT_plan_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin)
+                      : cudaFuncSetAttribute(applyJT_plan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin);
     if (e != cudaSuccess) return e;
+    e = v ? cudaFuncSetAttribute(applyJT_plan_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
+          : cudaFuncSetAttribute(applyJT_plan_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    c.block = block; c.smem_bytes = smem; c.blocks_per_sm = hm.plan.blocks_per_sm;
   }
   if (a.n <= 0) return cudaSuccess;
-  apply_kernel<<<RBD_GRID(a.n, cfg->block), cfg->block, cfg->smem_bytes, st>>>(m, tb, a, smem_doubles);
+  unsigned grid = RBD_GRID(a.n, block);
+  const unsigned resident = (unsigned)(num_sms * (hm.plan.blocks_per_sm > 0 ? hm.plan.blocks_per_sm : 1));
+  if (grid > 8 * resident) grid = resident;  // persistent only when every warp gets >= 8 tiles (else: wave tail)
+  if (v) applyJT_plan_kernel<32><<<grid, block, smem, st>>>(d_blob, model_words, tb, a);
+  else applyJT_plan_kernel<0><<<grid, block, smem, st>>>(d_blob, model_words, tb, a);
   return cudaGetLastError();
 }
-cudaError_t launch_applyJ(const DevModel& m, const DevTables& tb, const MapArgs& a, int smem_doubles, LaunchCfg* cfg,
-                          cudaStream_t st) {
+
+cudaError_t launch_applyJT_rows(const DevModel& m, const DevModel* d_model, const DevTables& tb, const RowArgs& a,
+                                int smem_doubles, LaunchCfg* cfg, cudaStream_t st) {
+  const int mw = map_model_words(m);
   if (cfg->block == 0) {
-    cudaError_t e = pick_block(applyJ_kernel, smem_doubles, 0, cfg);
-    if (e != cudaSuccess) return e;
-  }
-  if (a.n <= 0) return cudaSuccess;
-  applyJ_kernel<<<RBD_GRID(a.n, cfg->block), cfg->block, cfg->smem_bytes, st>>>(m, tb, a, smem_doubles);
-  return cudaGetLastError();
-}
-cudaError_t launch_applyJT(const DevModel& m, const DevTables& tb, const MapArgs& a, int smem_doubles, LaunchCfg* cfg,
-                           cudaStream_t st) {
-  if (cfg->block == 0) {
-    cudaError_t e = pick_block(applyJT_kernel, smem_doubles, 0, cfg);
-    if (e != cudaSuccess) return e;
-  }
-  if (a.n <= 0) return cudaSuccess;
-  applyJT_kernel<<<RBD_GRID(a.n, cfg->block), cfg->block, cfg->smem_bytes, st>>>(m, tb, a, smem_doubles);
-  return cudaGetLastError();
-}
-cudaError_t launch_applyJT_rows(const DevModel& m, const DevTables& tb, const RowArgs& a, int smem_doubles,
-                                LaunchCfg* cfg, cudaStream_t st) {
-  if (cfg->block == 0) {
-    cudaError_t e = pick_block(applyJT_rows_kernel, smem_doubles, 0, cfg);
+    cudaError_t e = pick_block(applyJT_rows_kernel, smem_doubles, 0, cfg, (size_t)mw * 8);
     if (e != cudaSuccess) return e;
   }
   if (a.nrows <= 0) return cudaSuccess;
-  applyJT_rows_kernel<<<RBD_GRID(a.nrows, cfg->block), cfg->block, cfg->smem_bytes, st>>>(m, tb, a, smem_doubles);
+  applyJT_rows_kernel<<<RBD_GRID(a.nrows, cfg->block), cfg->block, cfg->smem_bytes, st>>>(d_model, mw, tb, a, smem_doubles);
   return cudaGetLastError();
 }
 

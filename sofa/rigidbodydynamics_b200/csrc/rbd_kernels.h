@@ -17,8 +17,8 @@ struct MapArgs {
   const double* root;    // apply: root pose (7) | applyJ: root velocity (6) | applyJT: out_root (accumulated) | nullptr
   const double* in;      // applyJT: wrenches (n_out*6)
   double* out;           // apply: n_out*7 | applyJ: n_out*6
-  double* qcache;        // workspace copy of the assembled configuration (nq fields)
-  long long cache_tile, cache_inst0;
+  double* qcache;        // workspace copy of the assembled configuration (nq fields, tile 32)
+  long long cache_inst0;
 };
 struct RowArgs {
   long long nrows;
@@ -26,8 +26,7 @@ struct RowArgs {
   const double* val;
   double* out_rows;
   int* keep;
-  double* qcache;
-  long long cache_tile;
+  double* qcache;  // tile 32
 };
 struct LaunchCfg {
   int block = 0, forced = 0, blocks_per_sm = 0;
@@ -36,14 +35,18 @@ struct LaunchCfg {
 
 cudaError_t launch_eval(const DevModel& planned_host_model, const DevModel* d_eval_blob, const EvalArgs& a,
                         LaunchCfg* cache8, int num_sms, cudaStream_t st);
-cudaError_t launch_apply(const DevModel& m, const DevTables& tb, const MapArgs& a, int smem_doubles, LaunchCfg* cfg,
-                         cudaStream_t st);
-cudaError_t launch_applyJ(const DevModel& m, const DevTables& tb, const MapArgs& a, int smem_doubles, LaunchCfg* cfg,
-                          cudaStream_t st);
-cudaError_t launch_applyJT(const DevModel& m, const DevTables& tb, const MapArgs& a, int smem_doubles, LaunchCfg* cfg,
-                           cudaStream_t st);
-cudaError_t launch_applyJT_rows(const DevModel& m, const DevTables& tb, const RowArgs& a, int smem_doubles,
-                                LaunchCfg* cfg, cudaStream_t st);
+// mapping kernels: `m` = host copy, `d_model` = device copy of the same (unplanned) joint table; cfg2[0] run-time
+// tile, cfg2[1] tile 32
+cudaError_t launch_apply(const DevModel& m, const DevModel* d_model, const DevTables& tb, const MapArgs& a,
+                         int smem_doubles, LaunchCfg* cfg2, cudaStream_t st);
+cudaError_t launch_applyJ(const DevModel& m, const DevModel* d_model, const DevTables& tb, const MapArgs& a,
+                          int smem_doubles, LaunchCfg* cfg2, cudaStream_t st);
+cudaError_t launch_applyJT(const DevModel& m, const DevModel* d_model, const DevTables& tb, const MapArgs& a,
+                           int smem_doubles, LaunchCfg* cfg2, cudaStream_t st);
+cudaError_t launch_applyJT_plan(const DevModel& planned_host_model, const DevModel* d_blob, const DevTables& tb,
+                                const MapArgs& a, LaunchCfg* cfg2, int num_sms, cudaStream_t st);
+cudaError_t launch_applyJT_rows(const DevModel& m, const DevModel* d_model, const DevTables& tb, const RowArgs& a,
+                                int smem_doubles, LaunchCfg* cfg, cudaStream_t st);
 cudaError_t launch_aos_to_soa(long long n, int K, long long tile, const double* aos, double* soa, cudaStream_t st);
 cudaError_t launch_soa_to_aos(long long n, int K, long long tile, const double* soa, double* aos, cudaStream_t st);
 

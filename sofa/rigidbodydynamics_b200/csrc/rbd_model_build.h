@@ -15,7 +15,7 @@
 namespace rbd {
 
 struct HostTables {
-  std::vector<int> sorted_k, outk_parent;
+  std::vector<int> sorted_k, outk_parent, sorted_ident;
   std::vector<double> sorted_pl, outk_pl;
 };
 
@@ -146,7 +146,7 @@ inline int build_dev_model(const rbd_model_desc* d, DevModel* m, HostTables* tb,
   for (int i = 0; i < nj; ++i) m->joint[i].msub = m->joint[i].Y[0];
   for (int i = nj - 1; i >= 1; --i) m->joint[m->joint[i].parent].msub += m->joint[i].msub;
   // mapped outputs grouped by parent joint (stable: keeps the reference's output order within a joint)
-  tb->sorted_k.clear(); tb->sorted_pl.clear(); tb->outk_parent.assign(d->n_out, 0); tb->outk_pl.assign(12 * (size_t)d->n_out, 0.0);
+  tb->sorted_k.clear(); tb->sorted_pl.clear(); tb->sorted_ident.clear(); tb->outk_parent.assign(d->n_out, 0); tb->outk_pl.assign(12 * (size_t)d->n_out, 0.0);
   for (int k = 0; k < d->n_out; ++k) {
     const int f = d->out_frames[k];
     if (f < 0 || f >= d->nframes) return fail(RBD_ERR_MODEL, "out_frames entry out of range");
@@ -160,6 +160,11 @@ inline int build_dev_model(const rbd_model_desc* d, DevModel* m, HostTables* tb,
     for (int k = 0; k < d->n_out; ++k)
       if (tb->outk_parent[k] == j) {
         tb->sorted_k.push_back(k);
+        {
+          const double* pl = &tb->outk_pl[12 * (size_t)k];
+          tb->sorted_ident.push_back((pl[0] == 1.0 && pl[1] == 0.0 && pl[2] == 0.0 && pl[3] == 0.0 && pl[4] == 1.0 &&
+                                      pl[5] == 0.0 && pl[6] == 0.0 && pl[7] == 0.0 && pl[8] == 1.0) ? 1 : 0);
+        }
         tb->sorted_pl.insert(tb->sorted_pl.end(), &tb->outk_pl[12 * (size_t)k], &tb->outk_pl[12 * (size_t)k] + 12);
       }
     m->joint[j].out_end = (int)tb->sorted_k.size();
@@ -195,7 +200,9 @@ inline int pow2_cols(int cols) {
 }
 
 // Fills m->plan and m->joint[*].boff.  forced_warps > 0 pins the block size.  Returns false when nothing fits.
-inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int forced_warps = 0, bool omi_out = false) {
+inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int forced_warps = 0, bool omi_out = false,
+                      bool jt = false, int regs_per_thread = B200Limits::kRegsPerThread) {
+  // jt: the applyJT sweep — stacks of the (no CRBA, RNEA) variant, but branch records hold R|p only (no v|a)
   const int nj = m->njoints;
   const bool need_stack = do_m || do_tau;
   const int D = need_stack ? m->max_depth_internal : 0;
@@ -211,7 +218,8 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
   }
   const int fsz = do_tau ? 6 * D : 0, ysz = do_m ? 9 * D : 0;
   (void)build_col_prog(m);  // sizes the ColProg table (its length does not depend on the plan)
-  const size_t model_bytes = eval_model_bytes(*m);
+  // the applyJT kernel also stages the per-output tables behind the blob
+  const size_t model_bytes = eval_model_bytes(*m) + (jt ? (size_t)table_words(m->n_out) * 8 : 0);
   EvalPlan best{};
   std::vector<int> best_boff, bj;
   for (int i = 1; i < nj; ++i)
@@ -224,7 +232,7 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
     // cheapest configuration first: everything saved; then drop the v|a record of branch joints attached to the
     // universe (recomputed from the A record and the inputs: costs a dozen global re-reads per return)
     // ...; then re-read R|p of the other branch joints from the oMi output this thread wrote (when oMi is requested)
-    const int ncfg = 1 + (do_tau ? 1 : 0) + ((do_tau && omi_out) ? 1 : 0);
+    const int ncfg = jt ? 1 : 1 + (do_tau ? 1 : 0) + ((do_tau && omi_out) ? 1 : 0);
     for (int cfg = 0; cfg < ncfg && !placed; ++cfg) {
       const int drop_root_va = cfg >= 1, rp_from_omi = cfg >= 2;
       std::vector<int> bw(bj.size()), bflag(bj.size(), 0);
@@ -234,7 +242,7 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
         const bool ff_dedupe = need_stack && jb.type == JT_FF;
         const bool nova = drop_root_va && need_stack && jb.parent == 0;
         const bool rpomi = rp_from_omi && !ff_dedupe;
-        bw[k] = ((ff_dedupe || rpomi) ? 0 : 12) + ((do_tau && !nova) ? 12 : 0);
+        bw[k] = ((ff_dedupe || rpomi) ? 0 : 12) + ((do_tau && !nova && !jt) ? 12 : 0);
         bflag[k] = (nova ? RBD_BOFF_NOVA : 0) | (rpomi ? RBD_BOFF_RPOMI : 0);
       }
       // greedy: Y-stack first (one vector access per visit), then the widest branch records that still fit, then
@@ -265,7 +273,7 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
         if (block_bytes + B200Limits::kSmemReservedPerBlock > (size_t)B200Limits::kSmemBytes) continue;
         int c = (int)(B200Limits::kSmemBytes / (block_bytes + B200Limits::kSmemReservedPerBlock));
         if (pl.tmem_cols > 0) c = std::min(c, B200Limits::kTmemCols / pl.tmem_cols);
-        c = std::min(c, B200Limits::kRegsPerSM / (B200Limits::kRegsPerThread * W * 32));
+        c = std::min(c, B200Limits::kRegsPerSM / (regs_per_thread * W * 32));
         c = std::min(c, 32);
         if (c < 1) continue;
         pl.blocks_per_sm = c;

@@ -853,17 +853,31 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
 // =========================================================================================================
 // Mapping path
 // =========================================================================================================
+// one-joint-ahead prefetch of a 1-dof joint's configuration value(s) in the mapping sweeps (`q`, `m`, `nj` in scope)
+#define RBD_Q_PREFETCH(idx)                                              \
+  do {                                                                   \
+    if ((idx) < nj) {                                                    \
+      const DevJoint& jx_ = m.joint[idx];                                \
+      if (jx_.type != JT_FF) {                                           \
+        q0n = q.ld(jx_.idx_q);                                           \
+        if (is_unbounded(jx_.type)) q1n = q.ld(jx_.idx_q + 1);           \
+      }                                                                  \
+    }                                                                    \
+  } while (0)
+
 // Full configuration seen through the SOFA split (root pose | joint dofs): KCM.inl:353-363.
-struct SplitQ {
-  Field root, joints;
+template <class FLD>
+struct SplitQT {
+  FLD root, joints;
   int off;  // 7 (or 6 for velocities) when a root is supplied, else 0
   RBD_HD double ld(int k) const { return k < off ? root.ld(k) : joints.ld(k - off); }
 };
+using SplitQ = SplitQT<Field>;
 
 // apply: q -> [p, quat] of every mapped output; also copies the assembled q into the workspace cache.
-template <class QF>
-RBD_HD void apply_instance(const DevModel& m, const DevTables& tb, const QF& q, const Field& qcache,
-                           const Field& out, const Stack& S) {
+template <class QF, class QC, class OUT>
+RBD_HD void apply_instance(const DevModel& m, const DevTables& tb, const QF& q, const QC& qcache,
+                           const OUT& out, const Stack& S) {
   const int nj = m.njoints;
   if (qcache.ok())
     for (int k = 0; k < m.nq; ++k) qcache.st(k, q.ld(k));
@@ -875,11 +889,14 @@ RBD_HD void apply_instance(const DevModel& m, const DevTables& tb, const QF& q, 
       const int k = tb.sorted_k[o];
       double qt[4];
       rot_to_quat(pl, qt);
-      out.st(7 * k + 0, pl[9]); out.st(7 * k + 1, pl[10]); out.st(7 * k + 2, pl[11]);
-      out.st(7 * k + 3, qt[0]); out.st(7 * k + 4, qt[1]); out.st(7 * k + 5, qt[2]); out.st(7 * k + 6, qt[3]);
+      double* const po = out.at(7 * k);
+      out.st_at(po, 0, pl[9]); out.st_at(po, 1, pl[10]); out.st_at(po, 2, pl[11]);
+      out.st_at(po, 3, qt[0]); out.st_at(po, 4, qt[1]); out.st_at(po, 5, qt[2]); out.st_at(po, 6, qt[3]);
     }
   }
   double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
+  double q0n = 0.0, q1n = 0.0;
+  RBD_Q_PREFETCH(1);
   for (int i = 1; i < nj; ++i) {
     const DevJoint& jn = m.joint[i];
     const int par = jn.parent;
@@ -896,21 +913,31 @@ RBD_HD void apply_instance(const DevModel& m, const DevTables& tb, const QF& q, 
       }
     }
     double aw[3];
-    const double q0 = jn.type == JT_FF ? 0.0 : q.ld(jn.idx_q);
-    const double q1 = is_unbounded(jn.type) ? q.ld(jn.idx_q + 1) : 0.0;
+    const double q0 = q0n, q1 = q1n;
+    RBD_Q_PREFETCH(i + 1);  // next joint's angle: its HBM latency hides behind this joint's work
     fk_joint(jn, R, p, q0, q1, q, aw);
+    // outputs whose placement has an identity rotation share the joint's rotation: convert it once
+    double qj[4];
+    bool have_qj = false;
     for (int o = jn.out_begin; o < jn.out_end; ++o) {
       // updateFramePlacements: oMf = oMi * placement (KCM.inl:375), then se3ToSofaType (KCM.inl:385,394)
       const double* pl = tb.sorted_pl + 12 * o;
       const int k = tb.sorted_k[o];
-      double Rf[9], qt[4];
-      mat3_mul(R, pl, Rf);
+      double qt[4];
+      if (tb.sorted_ident[o]) {
+        if (!have_qj) { rot_to_quat(R, qj); have_qj = true; }
+        qt[0] = qj[0]; qt[1] = qj[1]; qt[2] = qj[2]; qt[3] = qj[3];
+      } else {
+        double Rf[9];
+        mat3_mul(R, pl, Rf);
+        rot_to_quat(Rf, qt);
+      }
       const double px = R[0] * pl[9] + R[1] * pl[10] + R[2] * pl[11] + p[0];
       const double py = R[3] * pl[9] + R[4] * pl[10] + R[5] * pl[11] + p[1];
       const double pz = R[6] * pl[9] + R[7] * pl[10] + R[8] * pl[11] + p[2];
-      rot_to_quat(Rf, qt);
-      out.st(7 * k + 0, px); out.st(7 * k + 1, py); out.st(7 * k + 2, pz);
-      out.st(7 * k + 3, qt[0]); out.st(7 * k + 4, qt[1]); out.st(7 * k + 5, qt[2]); out.st(7 * k + 6, qt[3]);
+      double* const po = out.at(7 * k);
+      out.st_at(po, 0, px); out.st_at(po, 1, py); out.st_at(po, 2, pz);
+      out.st_at(po, 3, qt[0]); out.st_at(po, 4, qt[1]); out.st_at(po, 5, qt[2]); out.st_at(po, 6, qt[3]);
     }
     if (jn.nchild >= 2) {
       const int b = jn.bidx * RBD_BRANCH_FK;
@@ -924,8 +951,8 @@ RBD_HD void apply_instance(const DevModel& m, const DevTables& tb, const QF& q, 
 
 // applyJ: out_k = J_k(LWA) dq, matrix-free: world twists V_i = V_parent + A_i dq_i, then
 // out_k = [V_lin + V_ang x p_k ; V_ang]  (== [J_lin - p_k x J_ang ; J_ang] dq, getFrameJacobian LWA)
-template <class DQ>
-RBD_HD void applyJ_instance(const DevModel& m, const DevTables& tb, const Field& q, const DQ& dq, const Field& out,
+template <class QC, class DQ, class OUT>
+RBD_HD void applyJ_instance(const DevModel& m, const DevTables& tb, const QC& q, const DQ& dq, const OUT& out,
                             const Stack& S) {
   const int nj = m.njoints;
   {
@@ -937,6 +964,8 @@ RBD_HD void applyJ_instance(const DevModel& m, const DevTables& tb, const Field&
     }
   }
   double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0}, V[6] = {0, 0, 0, 0, 0, 0};
+  double q0n = 0.0, q1n = 0.0;
+  RBD_Q_PREFETCH(1);
   for (int i = 1; i < nj; ++i) {
     const DevJoint& jn = m.joint[i];
     const int par = jn.parent;
@@ -957,8 +986,8 @@ RBD_HD void applyJ_instance(const DevModel& m, const DevTables& tb, const Field&
       }
     }
     double aw[3];
-    const double q0 = jn.type == JT_FF ? 0.0 : q.ld(jn.idx_q);
-    const double q1 = is_unbounded(jn.type) ? q.ld(jn.idx_q + 1) : 0.0;
+    const double q0 = q0n, q1 = q1n;
+    RBD_Q_PREFETCH(i + 1);  // next joint's angle: its HBM latency hides behind this joint's work
     fk_joint(jn, R, p, q0, q1, q, aw);
     if (jn.type != JT_FF) {
       double A[6];
@@ -988,8 +1017,9 @@ RBD_HD void applyJ_instance(const DevModel& m, const DevTables& tb, const Field&
       const double pz = R[6] * pl[9] + R[7] * pl[10] + R[8] * pl[11] + p[2];
       double tx, ty, tz;
       RBD_CROSS(tx, ty, tz, V[3], V[4], V[5], px, py, pz);
-      out.st(6 * k + 0, V[0] + tx); out.st(6 * k + 1, V[1] + ty); out.st(6 * k + 2, V[2] + tz);
-      out.st(6 * k + 3, V[3]); out.st(6 * k + 4, V[4]); out.st(6 * k + 5, V[5]);
+      double* const po = out.at(6 * k);
+      out.st_at(po, 0, V[0] + tx); out.st_at(po, 1, V[1] + ty); out.st_at(po, 2, V[2] + tz);
+      out.st_at(po, 3, V[3]); out.st_at(po, 4, V[4]); out.st_at(po, 5, V[5]);
     }
     if (jn.nchild >= 2) {
       const int b = jn.bidx * RBD_BRANCH_J;
@@ -1007,44 +1037,19 @@ RBD_HD void applyJ_instance(const DevModel& m, const DevTables& tb, const Field&
 // world origin, [f ; n + p_k x f], summed per joint, accumulated leaf->root, and projected: tau_i = A_i^T F_i.
 // `Src::gather(i, begin, end, R, p, F)` adds the wrenches attached to joint i; `Sink::put(c, value)` receives
 // the generalized force of velocity index c.
-template <class Src, class Sink>
-RBD_HD void applyJT_instance(const DevModel& m, const DevTables& tb, const Field& q, const Src& src, const Sink& sink,
+template <class QC, class Src, class Sink>
+RBD_HD void applyJT_instance(const DevModel& m, const DevTables& tb, const QC& q, const Src& src, const Sink& sink,
                              const Stack& S) {
   const int nj = m.njoints;
   const int bbase = m.slot_total[1];
   double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
-  auto pop = [&](int k) {
-    const DevJoint& jn = m.joint[k];
-    const int s = jn.slot[1];
-    const int aw_ = RBD_SLOT_A(jn.type);
-    double F[6];
-#pragma unroll
-    for (int e = 0; e < 6; ++e) F[e] = S.ld(s + aw_ + e);
-    if (jn.type != JT_FF) {
-      double A[6];
-#pragma unroll
-      for (int e = 0; e < 6; ++e) A[e] = S.ld(s + e);
-      sink.put(jn.idx_v, dot6(A, F));
-    } else {
-      double Rp[12], o6[6];
-#pragma unroll
-      for (int e = 0; e < 12; ++e) Rp[e] = S.ld(s + e);
-      ff_rows(Rp, Rp + 9, F, o6);
-#pragma unroll
-      for (int e = 0; e < 6; ++e) sink.put(jn.idx_v + e, o6[e]);
-    }
-    if (jn.parent != 0) {
-      const DevJoint& jp = m.joint[jn.parent];
-      const int sp = jp.slot[1] + RBD_SLOT_A(jp.type);
-#pragma unroll
-      for (int e = 0; e < 6; ++e) S.add(sp + e, F[e]);
-    }
-  };
+  double q0n = 0.0, q1n = 0.0;
+  RBD_Q_PREFETCH(1);
   for (int i = 1; i < nj; ++i) {
     const DevJoint& jn = m.joint[i];
     const int par = jn.parent;
     if (par != i - 1) {
-      for (int k = i - 1; k != par; k = m.joint[k].parent) pop(k);
+      // joint i starts a new branch below `par` (the subtree that ended at i-1 was unwound already)
       if (par == 0) {
         R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
         p[0] = p[1] = p[2] = 0;
@@ -1056,36 +1061,168 @@ RBD_HD void applyJT_instance(const DevModel& m, const DevTables& tb, const Field
         for (int e = 0; e < 3; ++e) p[e] = S.ld(b + 9 + e);
       }
     }
+    const int nxt_par = (i + 1 < nj) ? m.joint[i + 1].parent : 0;
     double aw[3];
-    const double q0 = jn.type == JT_FF ? 0.0 : q.ld(jn.idx_q);
-    const double q1 = is_unbounded(jn.type) ? q.ld(jn.idx_q + 1) : 0.0;
+    const double q0 = q0n, q1 = q1n;
+    RBD_Q_PREFETCH(i + 1);  // next joint's angle: its HBM latency hides behind this joint's work
     fk_joint(jn, R, p, q0, q1, q, aw);
-    const int s = jn.slot[1];
-    const int aw_ = RBD_SLOT_A(jn.type);
+    // Ak: world subspace column (1-dof) or R|p (free-flyer); Fk: wrenches attached to this joint, about the origin
+    double Ak[12], Fk[6] = {0, 0, 0, 0, 0, 0};
     if (jn.type != JT_FF) {
-      double A[6];
-      subspace_1dof(jn.type, p, aw, A);
-#pragma unroll
-      for (int e = 0; e < 6; ++e) S.st(s + e, A[e]);
+      subspace_1dof(jn.type, p, aw, Ak);
     } else {
 #pragma unroll
-      for (int e = 0; e < 9; ++e) S.st(s + e, R[e]);
+      for (int e = 0; e < 9; ++e) Ak[e] = R[e];
 #pragma unroll
-      for (int e = 0; e < 3; ++e) S.st(s + 9 + e, p[e]);
+      for (int e = 0; e < 3; ++e) Ak[9 + e] = p[e];
     }
-    double F[6] = {0, 0, 0, 0, 0, 0};
-    src.gather(i, jn.out_begin, jn.out_end, R, p, F);
+    src.gather(i, jn.out_begin, jn.out_end, R, p, Fk);
+    if (nxt_par == i) {
+      // joint i has children: park A | F in its depth slot; the subtree's wrenches accumulate there
+      const int s = jn.slot[1];
+      const int aw_ = RBD_SLOT_A(jn.type);
+      if (jn.type != JT_FF) s_stv<6>(S, s, Ak); else s_stv<12>(S, s, Ak);
+      s_stv<6>(S, s + aw_, Fk);
+      if (jn.nchild >= 2) {
+        const int b = bbase + jn.bidx * RBD_BRANCH_FK;
 #pragma unroll
-    for (int e = 0; e < 6; ++e) S.st(s + aw_ + e, F[e]);
-    if (jn.nchild >= 2) {
-      const int b = bbase + jn.bidx * RBD_BRANCH_FK;
+        for (int e = 0; e < 9; ++e) S.st(b + e, R[e]);
 #pragma unroll
-      for (int e = 0; e < 9; ++e) S.st(b + e, R[e]);
+        for (int e = 0; e < 3; ++e) S.st(b + 9 + e, p[e]);
+      }
+    } else {
+      // leaf: project from registers, then unwind — sums travel up the chain in registers and are written back
+      // only at the joint that still has children to come
+      int k = i;
+      while (true) {
+        const DevJoint& jk = m.joint[k];
+        if (jk.type != JT_FF) {
+          sink.put(jk.idx_v, dot6(Ak, Fk));
+        } else {
+          double o6[6];
+          ff_rows(Ak, Ak + 9, Fk, o6);
 #pragma unroll
-      for (int e = 0; e < 3; ++e) S.st(b + 9 + e, p[e]);
+          for (int e = 0; e < 6; ++e) sink.put(jk.idx_v + e, o6[e]);
+        }
+        const int pk = jk.parent;
+        if (pk == 0) break;
+        const DevJoint& jp = m.joint[pk];
+        const int sp = jp.slot[1];
+        const int awp = RBD_SLOT_A(jp.type);
+        if (pk == nxt_par) {
+#pragma unroll
+          for (int e = 0; e < 6; ++e) S.add(sp + awp + e, Fk[e]);
+          break;
+        }
+#pragma unroll
+        for (int e = 0; e < 6; ++e) Fk[e] += S.ld(sp + awp + e);
+        if (jp.type != JT_FF) s_ldv<6>(S, sp, Ak); else s_ldv<12>(S, sp, Ak);
+        k = pk;
+      }
     }
   }
-  for (int k = nj - 1; k > 0; k = m.joint[k].parent) pop(k);
+}
+
+#define RBD_JT_PREF 4 /* outputs per joint whose wrenches are prefetched one joint ahead */
+RBD_HD void add_shifted_wrench(const double* R, const double* p, const double* pl, const double* w, double* F);
+
+// applyJT on the fused-eval storage plan (plan_eval(..., jt = true)): A-stack in shared memory, F-stack levels and
+// branch R|p records in shared or tensor memory — the batched vector path (K3).  Same sweep as applyJT_instance.
+template <class QC, class Src, class Sink>
+RBD_HD void applyJT_instance_plan(const DevModel& m, const DevTables& tb, const QC& q, const Src& src, const Sink& sink,
+                                  const Stack& S, const TmStack& T) {
+  const int nj = m.njoints;
+  const int fbase = m.plan.fbase, fsplit = m.plan.fsplit, ftbase = m.plan.ftbase;
+#define RBD_F_TM(lvl) ((lvl) >= fsplit)
+#define RBD_F_OFF(lvl) ((lvl) >= fsplit ? ftbase + 6 * ((lvl)-fsplit) : fbase + 6 * (lvl))
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
+  double wn[6 * RBD_JT_PREF];
+#pragma unroll
+  for (int e = 0; e < 6 * RBD_JT_PREF; ++e) wn[e] = 0.0;
+  if (nj > 1) src.prefetch(m.joint[1].out_begin, m.joint[1].out_end, wn);
+  double q0n = 0.0, q1n = 0.0;
+  RBD_Q_PREFETCH(1);
+  for (int i = 1; i < nj; ++i) {
+    const DevJoint& jn = m.joint[i];
+    const int par = jn.parent;
+    // this joint's wrenches arrived while the previous joint was processed; start the next joint's loads now
+    double wc[6 * RBD_JT_PREF];
+#pragma unroll
+    for (int e = 0; e < 6 * RBD_JT_PREF; ++e) wc[e] = wn[e];
+    if (i + 1 < nj) src.prefetch(m.joint[i + 1].out_begin, m.joint[i + 1].out_end, wn);
+    if (par != i - 1) {
+      if (par == 0) {
+        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+        p[0] = p[1] = p[2] = 0;
+      } else {
+        const DevJoint& jb = m.joint[par];
+        double Rp[12];
+        if (jb.type == JT_FF) s_ldv<12>(S, jb.offA, Rp);
+        else x_ldv<12>((jb.boff & RBD_BOFF_TMEM) != 0, S, T, jb.boff & RBD_BOFF_MASK, Rp);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) R[e] = Rp[e];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) p[e] = Rp[9 + e];
+      }
+    }
+    const int nxt_par = (i + 1 < nj) ? m.joint[i + 1].parent : 0;
+    double aw[3];
+    const double q0 = q0n, q1 = q1n;
+    RBD_Q_PREFETCH(i + 1);  // next joint's angle: its HBM latency hides behind this joint's work
+    fk_joint(jn, R, p, q0, q1, q, aw);
+    double Ak[12], Fk[6] = {0, 0, 0, 0, 0, 0};
+    if (jn.type != JT_FF) {
+      subspace_1dof(jn.type, p, aw, Ak);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Ak[e] = R[e];
+#pragma unroll
+      for (int e = 0; e < 3; ++e) Ak[9 + e] = p[e];
+    }
+    src.gather_pref(jn.out_begin, jn.out_end, R, p, wc, Fk);
+    if (nxt_par == i) {
+      const int lvl = jn.depth - 1;
+      if (jn.type != JT_FF) s_stv<6>(S, jn.offA, Ak); else s_stv<12>(S, jn.offA, Ak);
+      x_stv<6>(RBD_F_TM(lvl), S, T, RBD_F_OFF(lvl), Fk);
+      if (jn.nchild >= 2 && jn.type != JT_FF) {
+        double Rp[12];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Rp[e] = R[e];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) Rp[9 + e] = p[e];
+        x_stv<12>((jn.boff & RBD_BOFF_TMEM) != 0, S, T, jn.boff & RBD_BOFF_MASK, Rp);
+      }
+    } else {
+      int k = i;
+      while (true) {
+        const DevJoint& jk = m.joint[k];
+        if (jk.type != JT_FF) {
+          sink.put(jk.idx_v, dot6(Ak, Fk));
+        } else {
+          double o6[6];
+          ff_rows(Ak, Ak + 9, Fk, o6);
+#pragma unroll
+          for (int e = 0; e < 6; ++e) sink.put(jk.idx_v + e, o6[e]);
+        }
+        const int pk = jk.parent;
+        if (pk == 0) break;
+        const DevJoint& jp = m.joint[pk];
+        const int lvl = jp.depth - 1;
+        if (pk == nxt_par) {
+          x_addv<6>(RBD_F_TM(lvl), S, T, RBD_F_OFF(lvl), Fk);
+          break;
+        }
+        double fp[6];
+        x_ldv<6>(RBD_F_TM(lvl), S, T, RBD_F_OFF(lvl), fp);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) Fk[e] += fp[e];
+        if (jp.type != JT_FF) s_ldv<6>(S, jp.offA, Ak); else s_ldv<12>(S, jp.offA, Ak);
+        k = pk;
+      }
+    }
+  }
+#undef RBD_F_TM
+#undef RBD_F_OFF
 }
 
 // add wrench w (at point pf = R pl_p + p, world-aligned axes) moved to the world origin
@@ -1100,10 +1237,32 @@ RBD_HD void add_shifted_wrench(const double* R, const double* p, const double* p
 }
 
 // dense wrench source: one wrench per mapped output (KCM.inl:472-492)
-struct DenseWrenchSrc {
-  Field in;  // n_out*6 fields
+template <class FLD>
+struct DenseWrenchSrcT {
+  FLD in;  // n_out*6 fields
   const DevTables* tb;
+  // Issue the loads of the first RBD_JT_PREF wrenches of outputs [begin, end) (indices past the end are clamped, so
+  // every load is valid; the duplicates are ignored by gather_pref).  The sweep calls this one joint ahead: the HBM
+  // latency of the wrench stream hides behind the previous joint's kinematics.
+  RBD_HD void prefetch(int begin, int end, double* w) const {
+    if (end <= begin) return;
+#pragma unroll
+    for (int j = 0; j < RBD_JT_PREF; ++j) {
+      const int o = begin + j < end ? begin + j : end - 1;
+      const int k = tb->sorted_k[o];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) w[6 * j + e] = in.ld(6 * k + e);
+    }
+  }
+  RBD_HD void gather_pref(int begin, int end, const double* R, const double* p, const double* w, double* F) const {
+#pragma unroll
+    for (int j = 0; j < RBD_JT_PREF; ++j)
+      if (begin + j < end) add_shifted_wrench(R, p, tb->sorted_pl + 12 * (begin + j), w + 6 * j, F);
+    if (end > begin + RBD_JT_PREF) gather(0, begin + RBD_JT_PREF, end, R, p, F);
+  }
   RBD_HD void gather(int, int begin, int end, const double* R, const double* p, double* F) const {
+    // independent iterations: unrolled so that the wrench loads of several outputs are in flight together
+#pragma unroll 4
     for (int o = begin; o < end; ++o) {
       const int k = tb->sorted_k[o];
       double w[6];
@@ -1113,6 +1272,7 @@ struct DenseWrenchSrc {
     }
   }
 };
+using DenseWrenchSrc = DenseWrenchSrcT<Field>;
 // sparse wrench source: the non-zeros of one constraint row (KCM.inl:558-583)
 struct RowWrenchSrc {
   const int* col;     // [nnz] mapped-output index
@@ -1127,17 +1287,19 @@ struct RowWrenchSrc {
   }
 };
 // += into SOFA's split outputs (root wrench | joint torques): KCM.inl:494-512
-struct SplitAccumSink {
-  Field root, joints;
+template <class FLD>
+struct SplitAccumSinkT {
+  FLD root, joints;
   int off;
   RBD_HD void put(int c, double v) const {
     if (c < off) {
       if (root.ok()) root.st(c, root.ld(c) + v);
-    } else {
+    } else if (joints.ok()) {
       joints.st(c - off, joints.ld(c - off) + v);
     }
   }
 };
+using SplitAccumSink = SplitAccumSinkT<Field>;
 // dense row + squared norm (KCM.inl:585-615)
 struct RowSink {
   double* row;

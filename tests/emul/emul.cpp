@@ -25,6 +25,7 @@ static int make_ctx(const rbd_model_desc* d, Ctx* c) {
   int rc = build_dev_model(d, &c->m, &c->ht, &g_err);
   if (rc) return rc;
   c->tb.sorted_k = c->ht.sorted_k.data(); c->tb.sorted_pl = c->ht.sorted_pl.data();
+  c->tb.sorted_ident = c->ht.sorted_ident.data();
   c->tb.outk_parent = c->ht.outk_parent.data(); c->tb.outk_pl = c->ht.outk_pl.data();
   return 0;
 }
@@ -137,6 +138,31 @@ extern "C" int emul_applyJT(const rbd_model_desc* d, long long n, long long tile
     SplitAccumSink sink{make_field(out_root, i, 6, tile), make_field(out_tau, i, c.m.nv - off, tile), off};
     Stack S = make_stack(smem.data(), t, sd);
     applyJT_instance(c.m, c.tb, make_field(qcache, i, c.m.nq, cache_tile), src, sink, S);
+  }
+  return 0;
+}
+
+// applyJT on the shared + tensor memory storage plan (the batched K3 kernel's body)
+extern "C" int emul_applyJT_plan(const rbd_model_desc* d, long long n, long long tile, int use_tmem, double* qcache,
+                                 long long cache_tile, double* in, double* out_tau, double* out_root) {
+  Ctx c;
+  int rc = make_ctx(d, &c);
+  if (rc) return rc;
+  if (!plan_eval(&c.m, false, true, use_tmem != 0, 0, false, true)) { g_err = "plan_eval failed"; return -100; }
+  const std::vector<unsigned long long> blob = build_eval_blob(&c.m);
+  const DevModel& bm = *reinterpret_cast<const DevModel*>(blob.data());
+  const EvalPlan& pl = bm.plan;
+  const int bt = pl.warps * 32;
+  std::vector<double> smem((size_t)(pl.smem_doubles > 0 ? pl.smem_doubles : 1) * bt, 1e300);
+  std::vector<double> tmem((size_t)(pl.tmem_doubles > 0 ? pl.tmem_doubles : 1) * bt, 1e300);
+  const int off = (bm.has_ff_root && out_root) ? 6 : 0;
+  for (long long i = 0; i < n; ++i) {
+    const int t = (int)(i % bt);
+    DenseWrenchSrc src{make_field(in, i, 6 * bm.n_out, tile), &c.tb};
+    SplitAccumSink sink{make_field(out_root, i, 6, tile), make_field(out_tau, i, bm.nv - off, tile), off};
+    Stack S = make_stack(smem.data(), t, pl.smem_doubles);
+    TmStack T{tmem.data() + (size_t)t * (pl.tmem_doubles > 0 ? pl.tmem_doubles : 1)};
+    applyJT_instance_plan(bm, c.tb, make_field(qcache, i, bm.nq, cache_tile), src, sink, S, T);
   }
   return 0;
 }

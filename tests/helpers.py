@@ -59,6 +59,7 @@ def load_emul() -> C.CDLL:
     lib.emul_apply.argtypes = [vp, ll, ll, i, vp, vp, vp, ll, vp]
     lib.emul_applyJ.argtypes = [vp, ll, ll, i, vp, ll, vp, vp, vp]
     lib.emul_applyJT.argtypes = [vp, ll, ll, i, vp, ll, vp, vp, vp]
+    lib.emul_applyJT_plan.argtypes = [vp, ll, ll, i, vp, ll, vp, vp, vp]
     lib.emul_applyJT_rows.argtypes = [vp, ll, i, vp, ll, vp, vp, vp, vp, vp, vp]
     return lib
 

@@ -92,6 +92,13 @@ def test_mapping_bodies_match_oracle(emul, d):
     tw, ttau = T(w), T(tau0)
     trt = T(root0) if root is not None else None
     assert emul.emul_applyJT(C.addressof(cd), n, tile, block, P(qcache), ctile, P(tw), P(ttau), P(trt)) == 0
+    # the same product through the storage-plan sweep (shared-only and shared + tensor memory): identical accumulation
+    for use_tmem in (0, 1):
+        ttau2 = T(tau0); trt2 = T(root0) if root is not None else None
+        assert emul.emul_applyJT_plan(C.addressof(cd), n, tile, use_tmem, P(qcache), ctile, P(tw), P(ttau2), P(trt2)) == 0
+        assert rel_err(from_tiled(ttau2, n), from_tiled(ttau, n)) <= 1e-13
+        if root is not None:
+            assert rel_err(from_tiled(trt2, n), from_tiled(trt, n)) <= 1e-13
     pos = from_tiled(pos, n).reshape(n, d.n_out, 7); vel = from_tiled(vel, n).reshape(n, d.n_out, 6)
     tau = from_tiled(ttau, n); rt = from_tiled(trt, n) if trt is not None else None
     orc = oracle.Oracle(d)
