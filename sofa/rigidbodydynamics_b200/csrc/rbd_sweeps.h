@@ -28,6 +28,17 @@
 #ifndef RBD_PTR_OMIJ
 #define RBD_PTR_OMIJ 1
 #endif
+#ifndef RBD_UNROLL_ANC
+#define RBD_UNROLL_ANC 1 /* A/B r1e: 1 -> 2.45 ms, 2 -> 2.49 ms, 4 -> 2.67 ms (instruction-cache pressure) */
+#endif
+#ifndef RBD_UNROLL_FF
+#define RBD_UNROLL_FF 6 /* rolling this loop indexes A dynamically -> local memory: measured 5 % slower */
+#endif
+#ifndef RBD_UNROLL_ZERO
+#define RBD_UNROLL_ZERO 4
+#endif
+#define RBD_PRAGMA_(x) _Pragma(#x)
+#define RBD_PRAGMA(x) RBD_PRAGMA_(x)
 #ifndef RBD_PTR_COL
 #define RBD_PTR_COL 0 /* measured slower (A/B r1d: 2.98 vs 2.85 ms): pointer bumps serialise the zero-fill */
 #endif
@@ -538,7 +549,7 @@ RBD_HD void column_rows(const DevModel& m, const DevJoint& jn, int base, const d
     for (; len > 0; --len, pz += M.step(1)) *pz = 0.0;
   }
 #else
-#pragma unroll 2
+  RBD_PRAGMA(unroll RBD_UNROLL_ANC)
   for (int d = 0; d < na; ++d) {
     const int e = pr[d];
     const int sa = RBD_PROG_OFFA(e);
@@ -557,7 +568,7 @@ RBD_HD void column_rows(const DevModel& m, const DevJoint& jn, int base, const d
   for (int z = 0; z < jn.nzseg; ++z) {
     const int e = pr[na + z];
     const int r0 = base + RBD_PROG_ROW(e), len = RBD_PROG_ZLEN(e);
-#pragma unroll 4
+    RBD_PRAGMA(unroll RBD_UNROLL_ZERO)
     for (int r = 0; r < len; ++r) M.st(r0 + r, 0.0);
   }
 #endif
@@ -581,7 +592,8 @@ RBD_HD void emit_joint(const DevModel& m, int k, const double* A, const double* 
       column_rows(m, jn, base, F, S, io.M);
     }
   } else {
-#pragma unroll
+    // a real loop (not unrolled): runs once per free-flyer, and the kernel is instruction-cache sensitive
+    RBD_PRAGMA(unroll RBD_UNROLL_FF)
     for (int cc = 0; cc < 6; ++cc) {
       double Ac[6];
       RBD_FF_COL(Ac, A, (A + 9), cc);
