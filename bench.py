@@ -38,6 +38,18 @@ WORKLOADS = {"talos": ("talos_reduced", 1 << 20), "solo": ("solo12", 1 << 18), "
 L2_BYTES = 126 << 20
 
 
+def _traffic(robot: str, n: int, tile: int):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None
+    when no capture exists for this exact workload."""
+    p = os.path.join(ROOT, "profiles", "eval_traffic.json")
+    try:
+        with open(p) as f:
+            rec = json.load(f).get(f"{robot}:{n}:tile{tile}")
+        return (float(rec["dram_bytes_per_launch"]), rec["source"]) if rec else (None, None)
+    except (OSError, ValueError, KeyError):
+        return None, None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -103,7 +115,7 @@ class ClockSampler:
     def _run(self):
         while not self._stop.is_set():
             self._sample()
-            self._stop.wait(0.05)
+            self._stop.wait(0.01)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -340,6 +352,7 @@ def main():
     if rank == 0:
         peak, peak_src = _peaks()
         achieved = step_bytes / (kern_ms * 1e-3) / 1e9
+        traffic, traffic_src = _traffic(desc.name, n, dyn.tile)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -352,8 +365,9 @@ def main():
                            "note": desc.note, "sharding": f"instances, contiguous ranges, {world} rank(s), no collective"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                             "kernel": "rbd::eval_kernel<true,true>", "kernel_ms": kern_ms,
+                             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                             "algorithmic_bytes_per_launch": step_bytes, "peak_source": peak_src,
+                             "kernel": f"rbd::eval_kernel<true,true,{dyn.tile if dyn.tile == 32 else 0}>", "kernel_ms": kern_ms,
                              "bytes_per_eval": bytes_per_eval},
                 "cpu_baseline": cpu, "oracle_check_rel_err": check_err}
         print(json.dumps(line), flush=True)
