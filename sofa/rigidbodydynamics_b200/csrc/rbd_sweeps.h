@@ -644,58 +644,63 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
     if (DO_TAU) { vn = io.v.ld(j1.idx_v); an = io.a.ld(j1.idx_v); }
   }
 
-  for (int i = 1; i < nj; ++i) {
-    const DevJoint& jn = m.joint[i];
-    const int par = jn.parent;
-    if (par != i - 1) {
-      // joint i starts a new branch below `par` (the subtree that ended at i-1 was unwound already)
-      if (par == 0) {
-        RBD_RESET_ROOT();
+  // State of the joint the sweep returns to when a new branch starts below it: R|p (+ v|a).  With a stack
+  // (CRBA / RNEA) this runs at the LEAF that ends the previous branch, BEFORE its unwind — R, p, vel, acc are dead
+  // during the unwind, so the loads (tensor memory, the oMi re-read, the input re-reads) overlap it instead of
+  // stalling the next joint (r1f: the return block was the top stall site, 7.7 % of samples).
+  auto restore = [&](int par) {
+    if (par == 0) {
+      RBD_RESET_ROOT();
+    } else {
+      const DevJoint& jb = m.joint[par];
+      const bool btm = (jb.boff & RBD_BOFF_TMEM) != 0;
+      int b = jb.boff & RBD_BOFF_MASK;
+      double Rp[12];
+      if (NEED_STACK && jb.type == JT_FF) {
+        s_ldv<12>(S, jb.offA, Rp);  // a free-flyer's A record is its R|p
+      } else if (jb.boff & RBD_BOFF_RPOMI) {
+        const int o = 12 * (par - 1);  // this thread wrote oMi[par] earlier in the sweep
+#pragma unroll
+        for (int e = 0; e < 12; ++e) Rp[e] = io.oMi.ld(o + e);
       } else {
-        const DevJoint& jb = m.joint[par];
-        const bool btm = (jb.boff & RBD_BOFF_TMEM) != 0;
-        int b = jb.boff & RBD_BOFF_MASK;
-        double Rp[12];
-        if (NEED_STACK && jb.type == JT_FF) {
-          s_ldv<12>(S, jb.offA, Rp);  // a free-flyer's A record is its R|p
-        } else if (jb.boff & RBD_BOFF_RPOMI) {
-          const int o = 12 * (par - 1);  // this thread wrote oMi[par] earlier in the sweep
+        x_ldv<12>(btm, S, T, b, Rp);
+        b += 12;
+      }
 #pragma unroll
-          for (int e = 0; e < 12; ++e) Rp[e] = io.oMi.ld(o + e);
+      for (int e = 0; e < 9; ++e) R[e] = Rp[e];
+#pragma unroll
+      for (int e = 0; e < 3; ++e) p[e] = Rp[9 + e];
+      if (DO_TAU) {
+        if (!(jb.boff & RBD_BOFF_NOVA)) {
+          double va[12];
+          x_ldv<12>(btm, S, T, b, va);
+#pragma unroll
+          for (int e = 0; e < 6; ++e) { vel[e] = va[e]; acc[e] = va[6 + e]; }
         } else {
-          x_ldv<12>(btm, S, T, b, Rp);
-          b += 12;
-        }
-#pragma unroll
-        for (int e = 0; e < 9; ++e) R[e] = Rp[e];
-#pragma unroll
-        for (int e = 0; e < 3; ++e) p[e] = Rp[9 + e];
-        if (DO_TAU) {
-          if (!(jb.boff & RBD_BOFF_NOVA)) {
-            double va[12];
-            x_ldv<12>(btm, S, T, b, va);
-#pragma unroll
-            for (int e = 0; e < 6; ++e) { vel[e] = va[e]; acc[e] = va[6 + e]; }
+          // branch joint attached to the universe: v = A qd, a = -g + A qdd (v x vJ = 0), nothing was saved
+          double vj[6], aj[6];
+          if (jb.type == JT_FF) {
+            ff_act(R, p, io.v, jb.idx_v, vj);
+            ff_act(R, p, io.a, jb.idx_v, aj);
           } else {
-            // branch joint attached to the universe: v = A qd, a = -g + A qdd (v x vJ = 0), nothing was saved
-            double vj[6], aj[6];
-            if (jb.type == JT_FF) {
-              ff_act(R, p, io.v, jb.idx_v, vj);
-              ff_act(R, p, io.a, jb.idx_v, aj);
-            } else {
-              double Ab[6];
-              s_ldv<6>(S, jb.offA, Ab);
-              const double qd_b = io.v.ld(jb.idx_v), qdd_b = io.a.ld(jb.idx_v);
+            double Ab[6];
+            s_ldv<6>(S, jb.offA, Ab);
+            const double qd_b = io.v.ld(jb.idx_v), qdd_b = io.a.ld(jb.idx_v);
 #pragma unroll
-              for (int e = 0; e < 6; ++e) { vj[e] = Ab[e] * qd_b; aj[e] = Ab[e] * qdd_b; }
-            }
-#pragma unroll
-            for (int e = 0; e < 6; ++e) { vel[e] = vj[e]; acc[e] = aj[e]; }
-            acc[0] -= m.gravity[0]; acc[1] -= m.gravity[1]; acc[2] -= m.gravity[2];
+            for (int e = 0; e < 6; ++e) { vj[e] = Ab[e] * qd_b; aj[e] = Ab[e] * qdd_b; }
           }
+#pragma unroll
+          for (int e = 0; e < 6; ++e) { vel[e] = vj[e]; acc[e] = aj[e]; }
+          acc[0] -= m.gravity[0]; acc[1] -= m.gravity[1]; acc[2] -= m.gravity[2];
         }
       }
     }
+  };
+
+  for (int i = 1; i < nj; ++i) {
+    const DevJoint& jn = m.joint[i];
+    const int par = jn.parent;
+    if (!NEED_STACK && par != i - 1) restore(par);  // FK-only variant: no unwind to hide behind
     const double q0 = q0n, q1 = q1n, qd = vn, qdd = an;
     const int nxt_par = (i + 1 < nj) ? m.joint[i + 1].parent : 0;
     if (i + 1 < nj && m.joint[i + 1].type != JT_FF) {
@@ -827,6 +832,7 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
       // joint i is a leaf: its subtree is complete.  Emit it straight from registers, then unwind: every
       // ancestor whose last child this was is complete too; its sums continue in registers up the chain and
       // are written back only at the joint that still has children to come (nxt_par).
+      if (i + 1 < nj) restore(nxt_par);  // early: see `restore`
       int k = i;
       while (true) {
         emit_joint<DO_M, DO_TAU>(m, k, Ak, fk, Yk, S, io);
