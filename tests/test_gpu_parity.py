@@ -317,3 +317,52 @@ def test_layout_adapters_roundtrip(torch_mod, api):
         y = torch.empty_like(x)
         ws.soa_to_aos(n, K, tile, s, y)
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("name,n,tile", [("talos_reduced", 1000, 32), ("solo12", 77, 32), ("random_3", 333, 100),
+                                         ("panda7", 31, 32)])
+def test_no_out_of_bounds_writes(torch_mod, api, name, n, tile):
+    """compute-sanitizer is closed on this pool, so: every device buffer sits between guard bands of a sentinel value
+    inside one arena; after eval + apply + applyJ + applyJT the bands must be intact (the tail lanes of the last warp
+    recompute the last instance and may only touch the padding INSIDE the last tile)."""
+    torch = torch_mod
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    d = [m for m in MODELS if m.name == name][0]
+    q, v, a = mdl.random_state(d, n, seed=17)
+    m = api.Model(d); ws = api.Workspace(m, n)
+    I = m.info
+    nt = (n + tile - 1) // tile
+    G = 4096                                         # guard doubles
+    sizes = {"q": I.nq, "v": I.nv, "a": I.nv, "oMi": I.omi_fields, "J": I.jac_fields, "M": I.mass_fields, "tau": I.nv,
+             "qj": I.nq_joints, "root": 7, "dq": I.nv_joints, "rootv": 6, "pos": 7 * I.n_out, "vel": 6 * I.n_out,
+             "w": 6 * I.n_out, "tj": I.nv_joints, "tr": 6}
+    total = G + sum(nt * K * tile + G for K in sizes.values())
+    SENT = -7.25e300
+    arena = torch.full((total,), SENT, dtype=torch.float64, device="cuda")
+    views, off = {}, G
+    for k, K in sizes.items():
+        views[k] = arena[off:off + nt * K * tile].view(nt, K, tile)
+        off += nt * K * tile + G
+    views["q"].copy_(_dev(torch, to_tiled(q, tile))); views["v"].copy_(_dev(torch, to_tiled(v, tile)))
+    views["a"].copy_(_dev(torch, to_tiled(a, tile)))
+    ff = bool(I.has_freeflyer_root)
+    views["qj"].copy_(_dev(torch, to_tiled(np.ascontiguousarray(q[:, 7:] if ff else q), tile)))
+    views["dq"].copy_(_dev(torch, to_tiled(np.ascontiguousarray(v[:, 6:] if ff else v), tile)))
+    views["root"].copy_(_dev(torch, to_tiled(np.ascontiguousarray(q[:, :7]), tile)) if ff else torch.zeros_like(views["root"]))
+    views["rootv"].copy_(_dev(torch, to_tiled(np.ascontiguousarray(v[:, :6]), tile)) if ff else torch.zeros_like(views["rootv"]))
+    views["w"].copy_(torch.rand_like(views["w"])); views["tj"].zero_(); views["tr"].zero_()
+    ws.eval_soa(n, tile, views["q"], views["v"], views["a"], views["oMi"], views["J"], views["M"], views["tau"])
+    ws.apply_soa(n, tile, views["qj"], views["root"] if ff else None, views["pos"])
+    ws.applyJ_soa(n, tile, views["dq"], views["rootv"] if ff else None, views["vel"])
+    ws.applyJT_soa(n, tile, views["w"], views["tj"], views["tr"] if ff else None)
+    ws.synchronize()
+    off = 0
+    for k, K in [("", 0)] + list(sizes.items()):
+        off += nt * K * tile
+        band = arena[off:off + G]
+        assert bool((band == SENT).all()), f"guard band after '{k}' was written"
+        off += G
+    # and the live part of every output was written
+    for k in ("oMi", "J", "M", "tau", "pos", "vel"):
+        live = from_tiled(views[k].cpu().numpy(), n)
+        assert not np.any(live == SENT), k
