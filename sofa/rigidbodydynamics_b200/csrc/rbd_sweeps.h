@@ -1141,7 +1141,9 @@ RBD_HD void applyJT_instance(const DevModel& m, const DevTables& tb, const QC& q
   }
 }
 
-#define RBD_JT_PREF 4 /* outputs per joint whose wrenches are prefetched one joint ahead */
+#ifndef RBD_JT_PREF
+#define RBD_JT_PREF 4 /* outputs per joint whose wrenches are prefetched one joint ahead (A/B: 3..6 within 3 %) */
+#endif
 RBD_HD void add_shifted_wrench(const double* R, const double* p, const double* pl, const double* w, double* F);
 
 // applyJT on the fused-eval storage plan (plan_eval(..., jt = true)): A-stack in shared memory, F-stack levels and
