@@ -20,7 +20,9 @@ enum : int {
   JT_RUBX = 9, JT_RUBY = 10, JT_RUBZ = 11, JT_RUBU = 12, JT_FF = 13
 };
 
-struct DevJoint {
+// 16-byte aligned (and the DevModel header padded to a multiple of 16) so that the compiler may read the staged
+// record with 128-bit shared-memory loads
+struct alignas(16) DevJoint {
   double pl[12];    // jointPlacement: R row-major (9), p (3)
   double axis[3];   // unit axis in the joint frame
   double Y[10];     // m, c(3), Ic (xx,xy,yy,xz,yz,zz)
@@ -71,7 +73,7 @@ struct EvalPlan {
 #define RBD_BOFF_RPOMI (1 << 28) /* R|p not saved: re-read from the oMi output this thread wrote (oMi requested) */
 #define RBD_BOFF_MASK ((1 << 28) - 1)
 
-struct DevModel {
+struct alignas(16) DevModel {
   int njoints, nq, nv, n_out;
   int slot_total[2];  // doubles of stack slots per instance for the two layouts
   int nbranch;

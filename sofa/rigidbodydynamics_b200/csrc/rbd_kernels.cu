@@ -16,7 +16,7 @@
 
 namespace rbd {
 
-extern __shared__ double rbd_smem[];
+extern __shared__ __align__(16) double rbd_smem[];
 
 // --------------------------------------------------------------------------------------------------------
 // K7 / K5 / K6: fused FK + joint Jacobian (+ CRBA) (+ RNEA)
