@@ -228,6 +228,29 @@ RBD_API int rbd_applyJT_rows_host(rbd_workspace* ws, int64_t nrows, const int32_
 RBD_API int rbd_eval_host(rbd_workspace* ws, int64_t n, const double* q, const double* v, const double* a,
                           double* oMi, double* J, double* M, double* tau);
 
+/* ---------------------------------------------------------------------------------------------------- */
+/* Multi-robot batching context.  N KinematicChainMapping components of one SOFA scene —
+ * N robots built from the same URDF by N URDFModelLoader instances (URDFModelLoader.cpp:263-282) — share one
+ * workspace of capacity >= N.  Each component binds its instance slot to its own SOFA vectors once per topology
+ * change (the vectors live wherever SOFA allocated them: scattered host memory), and calls rbd_batch_apply /
+ * _applyJ / _applyJT from its worker overload (KinematicChainMapping.h:103-117) with the scene's step counter
+ * (`epoch`).  The FIRST call of an epoch gathers the inputs of ALL bound robots, runs ONE batched launch and
+ * scatters every robot's outputs; the calls of the other components in the same epoch return immediately.
+ * Buffers bound to a slot must stay valid until rebound; sizes are those of the single-robot entry points.    */
+typedef struct rbd_batch rbd_batch;
+RBD_API int rbd_batch_create(rbd_workspace* ws, int64_t n_slots, rbd_batch** out);
+RBD_API void rbd_batch_destroy(rbd_batch* batch);
+RBD_API int rbd_batch_bind_apply(rbd_batch* batch, int64_t slot, const double* q_joints, const double* root_pose,
+                                 double* out);
+RBD_API int rbd_batch_bind_applyJ(rbd_batch* batch, int64_t slot, const double* dq_joints, const double* root_vel,
+                                  double* out);
+RBD_API int rbd_batch_bind_applyJT(rbd_batch* batch, int64_t slot, const double* in, double* out_tau,
+                                   double* out_root);
+/* Return 1 when this call ran the batched launch, 0 when the epoch had already been served, < 0 on error.   */
+RBD_API int rbd_batch_apply(rbd_batch* batch, int64_t slot, int64_t epoch);
+RBD_API int rbd_batch_applyJ(rbd_batch* batch, int64_t slot, int64_t epoch);
+RBD_API int rbd_batch_applyJT(rbd_batch* batch, int64_t slot, int64_t epoch);
+
 #ifdef __cplusplus
 }
 #endif

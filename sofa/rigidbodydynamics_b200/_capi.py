@@ -76,6 +76,8 @@ SYMBOLS = [
     "rbd_eval_soa", "rbd_crba_soa", "rbd_rnea_soa",
     "rbd_aos_to_soa_dev", "rbd_soa_to_aos_dev",
     "rbd_apply_host", "rbd_applyJ_host", "rbd_applyJT_host", "rbd_applyJT_rows_host", "rbd_eval_host",
+    "rbd_batch_create", "rbd_batch_destroy", "rbd_batch_bind_apply", "rbd_batch_bind_applyJ", "rbd_batch_bind_applyJT",
+    "rbd_batch_apply", "rbd_batch_applyJ", "rbd_batch_applyJT",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -122,6 +124,14 @@ def load() -> C.CDLL:
         "rbd_applyJT_host": (C.c_int, [vp, i64, vp, vp, vp]),
         "rbd_applyJT_rows_host": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp]),
         "rbd_eval_host": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp, vp]),
+        "rbd_batch_create": (C.c_int, [vp, i64, C.POINTER(vp)]),
+        "rbd_batch_destroy": (None, [vp]),
+        "rbd_batch_bind_apply": (C.c_int, [vp, i64, vp, vp, vp]),
+        "rbd_batch_bind_applyJ": (C.c_int, [vp, i64, vp, vp, vp]),
+        "rbd_batch_bind_applyJT": (C.c_int, [vp, i64, vp, vp, vp]),
+        "rbd_batch_apply": (C.c_int, [vp, i64, i64]),
+        "rbd_batch_applyJ": (C.c_int, [vp, i64, i64]),
+        "rbd_batch_applyJT": (C.c_int, [vp, i64, i64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)        # AttributeError here = header/library mismatch

@@ -601,3 +601,154 @@ RBD_API int rbd_applyJT_rows_host(rbd_workspace* ws, int64_t nrows, const int32_
   return RBD_OK;
 }
 
+
+
+// ---- multi-robot batching context ---------------------------------------------------------------------------------
+// Host-side gather / scatter around the *_host entry points: the robots' SOFA vectors are scattered host buffers, the
+// library wants one instance-major array per quantity.  Staging is pinned so that the chunked copies run
+// asynchronously.
+struct rbd_batch {
+  rbd_workspace* ws = nullptr;
+  long long n = 0;
+  std::vector<const double*> a_q, a_root, j_dq, j_root, t_in;
+  std::vector<double*> a_out, j_out, t_tau, t_rootout;
+  std::vector<char> a_bound, j_bound, t_bound;
+  double *h_in1 = nullptr, *h_in2 = nullptr, *h_out = nullptr, *h_out2 = nullptr;  // pinned staging
+  long long epoch_apply = -1, epoch_J = -1, epoch_JT = -1;
+  bool any_epoch_apply = false, any_epoch_J = false, any_epoch_JT = false;
+};
+
+RBD_API int rbd_batch_create(rbd_workspace* ws, int64_t n_slots, rbd_batch** out) {
+  if (!out) return set_err(RBD_ERR_INVALID_ARG, "null out");
+  *out = nullptr;
+  GUARD(ws);
+  if (n_slots < 1 || n_slots > ws->capacity) return set_err(RBD_ERR_INVALID_ARG, "n_slots must be in [1, workspace capacity]");
+  rbd_batch* b = new (std::nothrow) rbd_batch();
+  if (!b) return set_err(RBD_ERR_ALLOC, "out of host memory");
+  b->ws = ws; b->n = n_slots;
+  const size_t n = (size_t)n_slots;
+  b->a_q.assign(n, nullptr); b->a_root.assign(n, nullptr); b->j_dq.assign(n, nullptr); b->j_root.assign(n, nullptr);
+  b->t_in.assign(n, nullptr); b->a_out.assign(n, nullptr); b->j_out.assign(n, nullptr); b->t_tau.assign(n, nullptr);
+  b->t_rootout.assign(n, nullptr); b->a_bound.assign(n, 0); b->j_bound.assign(n, 0); b->t_bound.assign(n, 0);
+  const rbd_model_info& I = ws->model->info;
+  const size_t big = (size_t)(7 > 6 ? 7 : 6) * (size_t)I.n_out;  // poses (7) / twists and wrenches (6) per robot
+  const size_t in1 = (size_t)(I.nq > I.nv ? I.nq : I.nv);
+  cudaError_t e = cudaHostAlloc(&b->h_in1, n * (in1 > big ? in1 : big) * sizeof(double), cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaHostAlloc(&b->h_in2, n * 7 * sizeof(double), cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaHostAlloc(&b->h_out, n * big * sizeof(double), cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaHostAlloc(&b->h_out2, n * 7 * sizeof(double), cudaHostAllocDefault);
+  if (e != cudaSuccess) { rbd_batch_destroy(b); return cuda_fail(e, "cudaHostAlloc(batch staging)"); }
+  *out = b;
+  return RBD_OK;
+}
+
+RBD_API void rbd_batch_destroy(rbd_batch* b) {
+  if (!b) return;
+  cudaFreeHost(b->h_in1); cudaFreeHost(b->h_in2); cudaFreeHost(b->h_out); cudaFreeHost(b->h_out2);
+  delete b;
+}
+
+static int batch_slot_ok(const rbd_batch* b, int64_t slot) {
+  if (!b) return set_err(RBD_ERR_INVALID_ARG, "null batch");
+  if (slot < 0 || slot >= b->n) return set_err(RBD_ERR_INVALID_ARG, "slot out of range");
+  return RBD_OK;
+}
+
+RBD_API int rbd_batch_bind_apply(rbd_batch* b, int64_t slot, const double* q_joints, const double* root_pose, double* out) {
+  int rc = batch_slot_ok(b, slot);
+  if (rc) return rc;
+  const rbd_model_info& I = b->ws->model->info;
+  if (!q_joints || !out) return set_err(RBD_ERR_INVALID_ARG, "null q_joints / out");
+  if ((root_pose != nullptr) != (I.has_freeflyer_root != 0))
+    return set_err(RBD_ERR_INVALID_ARG, "root pose must be bound iff the model has a free-flyer root");
+  b->a_q[slot] = q_joints; b->a_root[slot] = root_pose; b->a_out[slot] = out; b->a_bound[slot] = 1;
+  return RBD_OK;
+}
+RBD_API int rbd_batch_bind_applyJ(rbd_batch* b, int64_t slot, const double* dq_joints, const double* root_vel, double* out) {
+  int rc = batch_slot_ok(b, slot);
+  if (rc) return rc;
+  const rbd_model_info& I = b->ws->model->info;
+  if (!dq_joints || !out) return set_err(RBD_ERR_INVALID_ARG, "null dq_joints / out");
+  if ((root_vel != nullptr) != (I.has_freeflyer_root != 0))
+    return set_err(RBD_ERR_INVALID_ARG, "root velocity must be bound iff the model has a free-flyer root");
+  b->j_dq[slot] = dq_joints; b->j_root[slot] = root_vel; b->j_out[slot] = out; b->j_bound[slot] = 1;
+  return RBD_OK;
+}
+RBD_API int rbd_batch_bind_applyJT(rbd_batch* b, int64_t slot, const double* in, double* out_tau, double* out_root) {
+  int rc = batch_slot_ok(b, slot);
+  if (rc) return rc;
+  const rbd_model_info& I = b->ws->model->info;
+  if (!in || !out_tau) return set_err(RBD_ERR_INVALID_ARG, "null in / out_tau");
+  if ((out_root != nullptr) != (I.has_freeflyer_root != 0))
+    return set_err(RBD_ERR_INVALID_ARG, "root output must be bound iff the model has a free-flyer root");
+  b->t_in[slot] = in; b->t_tau[slot] = out_tau; b->t_rootout[slot] = out_root; b->t_bound[slot] = 1;
+  return RBD_OK;
+}
+
+static int batch_all_bound(const std::vector<char>& v, const char* what) {
+  for (char c : v)
+    if (!c) return set_err(RBD_ERR_INVALID_ARG, std::string("not every slot is bound for ") + what);
+  return RBD_OK;
+}
+
+RBD_API int rbd_batch_apply(rbd_batch* b, int64_t slot, int64_t epoch) {
+  int rc = batch_slot_ok(b, slot);
+  if (rc) return rc;
+  if (b->any_epoch_apply && b->epoch_apply == epoch) return 0;
+  if ((rc = batch_all_bound(b->a_bound, "apply"))) return rc;
+  const rbd_model_info& I = b->ws->model->info;
+  const bool ff = I.has_freeflyer_root != 0;
+  const size_t kq = (size_t)I.nq_joints, ko = 7 * (size_t)I.n_out;
+  for (long long i = 0; i < b->n; ++i) {
+    memcpy(b->h_in1 + (size_t)i * kq, b->a_q[i], kq * sizeof(double));
+    if (ff) memcpy(b->h_in2 + (size_t)i * 7, b->a_root[i], 7 * sizeof(double));
+  }
+  rc = rbd_apply_host(b->ws, b->n, b->h_in1, ff ? b->h_in2 : nullptr, b->h_out);
+  if (rc) return rc;
+  for (long long i = 0; i < b->n; ++i) memcpy(b->a_out[i], b->h_out + (size_t)i * ko, ko * sizeof(double));
+  b->epoch_apply = epoch; b->any_epoch_apply = true;
+  return 1;
+}
+
+RBD_API int rbd_batch_applyJ(rbd_batch* b, int64_t slot, int64_t epoch) {
+  int rc = batch_slot_ok(b, slot);
+  if (rc) return rc;
+  if (b->any_epoch_J && b->epoch_J == epoch) return 0;
+  if ((rc = batch_all_bound(b->j_bound, "applyJ"))) return rc;
+  const rbd_model_info& I = b->ws->model->info;
+  const bool ff = I.has_freeflyer_root != 0;
+  const size_t kv = (size_t)I.nv_joints, ko = 6 * (size_t)I.n_out;
+  for (long long i = 0; i < b->n; ++i) {
+    memcpy(b->h_in1 + (size_t)i * kv, b->j_dq[i], kv * sizeof(double));
+    if (ff) memcpy(b->h_in2 + (size_t)i * 6, b->j_root[i], 6 * sizeof(double));
+  }
+  rc = rbd_applyJ_host(b->ws, b->n, b->h_in1, ff ? b->h_in2 : nullptr, b->h_out);
+  if (rc) return rc;
+  for (long long i = 0; i < b->n; ++i) memcpy(b->j_out[i], b->h_out + (size_t)i * ko, ko * sizeof(double));
+  b->epoch_J = epoch; b->any_epoch_J = true;
+  return 1;
+}
+
+RBD_API int rbd_batch_applyJT(rbd_batch* b, int64_t slot, int64_t epoch) {
+  int rc = batch_slot_ok(b, slot);
+  if (rc) return rc;
+  if (b->any_epoch_JT && b->epoch_JT == epoch) return 0;
+  if ((rc = batch_all_bound(b->t_bound, "applyJT"))) return rc;
+  const rbd_model_info& I = b->ws->model->info;
+  const bool ff = I.has_freeflyer_root != 0;
+  const size_t kv = (size_t)I.nv_joints, ki = 6 * (size_t)I.n_out;
+  // the library accumulates (+=) into out_tau / out_root: gather their current contents, scatter the sums back
+  for (long long i = 0; i < b->n; ++i) {
+    memcpy(b->h_in1 + (size_t)i * ki, b->t_in[i], ki * sizeof(double));
+    memcpy(b->h_out + (size_t)i * kv, b->t_tau[i], kv * sizeof(double));
+    if (ff) memcpy(b->h_out2 + (size_t)i * 6, b->t_rootout[i], 6 * sizeof(double));
+  }
+  rc = rbd_applyJT_host(b->ws, b->n, b->h_in1, b->h_out, ff ? b->h_out2 : nullptr);
+  if (rc) return rc;
+  for (long long i = 0; i < b->n; ++i) {
+    memcpy(b->t_tau[i], b->h_out + (size_t)i * kv, kv * sizeof(double));
+    if (ff) memcpy(b->t_rootout[i], b->h_out2 + (size_t)i * 6, 6 * sizeof(double));
+  }
+  b->epoch_JT = epoch; b->any_epoch_JT = true;
+  return 1;
+}

@@ -179,3 +179,96 @@ class KinematicChainMapping:
         out[:, :kv] = tau
         if use_root:
             out_root[:, 0, :] = root
+
+
+class MappingBatch:
+    """N ``KinematicChainMapping`` components of ONE scene — N robots loaded from the same URDF — sharing one workspace
+    (C ABI: ``rbd_batch_*``).  Every component keeps the reference's worker signatures; the first
+    component whose ``apply`` / ``applyJ`` / ``applyJT`` runs in a propagation pass (``epoch``) triggers ONE batched
+    launch for all robots, the others find their output vectors already filled.
+
+    The per-robot state vectors are separate numpy arrays (SOFA allocates every MechanicalObject on its own); they are
+    bound by address, so they must be C-contiguous float64 and stay alive while bound."""
+
+    def __init__(self, desc: ModelDescriptor, n_robots: int, device: int = 0):
+        import ctypes as C
+        from . import _capi
+        self._C = C
+        self.desc = desc
+        self.n = int(n_robots)
+        self.model = Model(desc)
+        self.ws = Workspace(self.model, self.n, device)
+        self._lib = self.model._lib
+        h = C.c_void_p()
+        _capi.check(self._lib.rbd_batch_create(self.ws._h, self.n, C.byref(h)))
+        self._h = h
+        self.epoch = 0
+        self._keep: Dict[Tuple[str, int], tuple] = {}
+        self.components = [_BatchedComponent(self, s) for s in range(self.n)]
+
+    def begin_pass(self) -> None:
+        """A new propagation pass of the scene (SOFA: one visitor traversal)."""
+        self.epoch += 1
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rbd_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _ptr(a: Optional[np.ndarray]):
+        if a is None:
+            return None
+        if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous):
+            raise ValueError("batched components bind C-contiguous float64 arrays by address")
+        return int(a.ctypes.data)
+
+
+class _BatchedComponent:
+    """One robot's mapping inside a :class:`MappingBatch`.  ``bind_*`` is what the component does once in ``init()``
+    (the addresses of its SOFA state vectors); ``apply`` / ``applyJ`` / ``applyJT`` are the protected worker overloads
+    of the reference (KinematicChainMapping.h:103-117) for a single robot, served by the shared batched launch: they
+    return True when this call ran it, False when an earlier component of the same pass already had."""
+
+    def __init__(self, batch: MappingBatch, slot: int):
+        self.batch, self.slot = batch, slot
+
+    def bind_apply(self, out: np.ndarray, in1: np.ndarray, in_root: Optional[np.ndarray]) -> None:
+        from . import _capi
+        b = self.batch
+        b._keep[("a", self.slot)] = (out, in1, in_root)
+        _capi.check(b._lib.rbd_batch_bind_apply(b._h, self.slot, b._ptr(in1), b._ptr(in_root), b._ptr(out)))
+
+    def bind_applyJ(self, out: np.ndarray, in1: np.ndarray, in_root: Optional[np.ndarray]) -> None:
+        from . import _capi
+        b = self.batch
+        b._keep[("j", self.slot)] = (out, in1, in_root)
+        _capi.check(b._lib.rbd_batch_bind_applyJ(b._h, self.slot, b._ptr(in1), b._ptr(in_root), b._ptr(out)))
+
+    def bind_applyJT(self, out: np.ndarray, out_root: Optional[np.ndarray], inp: np.ndarray) -> None:
+        from . import _capi
+        b = self.batch
+        b._keep[("t", self.slot)] = (out, out_root, inp)
+        _capi.check(b._lib.rbd_batch_bind_applyJT(b._h, self.slot, b._ptr(inp), b._ptr(out), b._ptr(out_root)))
+
+    def _call(self, fn) -> bool:
+        from . import _capi
+        rc = fn(self.batch._h, self.slot, self.batch.epoch)
+        if rc < 0:
+            _capi.check(rc)
+        return rc == 1
+
+    def apply(self) -> bool:
+        return self._call(self.batch._lib.rbd_batch_apply)
+
+    def applyJ(self) -> bool:
+        return self._call(self.batch._lib.rbd_batch_applyJ)
+
+    def applyJT(self) -> bool:
+        return self._call(self.batch._lib.rbd_batch_applyJT)
