@@ -302,6 +302,12 @@ static int eval_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, 
   if (tau && (!v || !a)) return set_err(RBD_ERR_INVALID_ARG, "rnea needs v and a");
   const int pk = (oMi ? 4 : 0) | (M ? 2 : 0) | (tau ? 1 : 0);
   int rc = ensure_plan(ws, pk);
+  if (rc == RBD_ERR_UNSUPPORTED && M && tau && ws->forced_eval_block == 0) {
+    // very deep trees: the state of the fused CRBA + RNEA sweep does not fit one SM; the two halves may
+    rc = eval_on(ws, st, n, tile, q, v, a, oMi, J, M, nullptr);
+    if (rc == RBD_OK) rc = eval_on(ws, st, n, tile, q, v, a, nullptr, nullptr, nullptr, tau);
+    return rc;
+  }
   if (rc) return rc;
   EvalArgs A{n, tile, q, v, a, oMi, J, M, tau};
   CK(launch_eval(*ws->h_plan[pk], ws->d_plan[pk], A, ws->cfg_eval, ws->num_sms, st));

@@ -60,8 +60,10 @@ struct EvalPlan {
   int fbase;         // shared: f-stack, 6 per internal depth level (RNEA), levels [0, fsplit)
   int fsplit;        // first f-stack level that lives in tensor memory (= number of levels when none does)
   int ftbase;        // tensor memory: f-stack levels [fsplit, D)
-  int ybase;         // Y-stack, 9 per internal depth level (CRBA; the mass is a model constant): shared or tensor offset
-  int y_in_tmem;     // 1 = Y-stack lives in tensor memory
+  int ybase;         // shared: Y-stack, 9 per internal depth level (CRBA; the mass is a model constant), levels [0, ysplit)
+  int ysplit;        // first Y-stack level that lives in tensor memory (0 = all of it, D = none)
+  int ytbase;        // tensor memory: Y-stack levels [ysplit, D)
+  int y_in_tmem;     // 1 = at least one Y-stack level lives in tensor memory (introspection)
   int smem_doubles;  // shared-memory doubles per instance
   int tmem_doubles;  // tensor-memory doubles per instance (0 = tensor memory unused)
   int warps;         // warps per block

@@ -216,7 +216,6 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
     totalA = pre[D + 1];
     for (int i = 1; i < nj; ++i) m->joint[i].offA = m->joint[i].depth <= D ? pre[m->joint[i].depth] : 0;
   }
-  const int fsz = do_tau ? 6 * D : 0, ysz = do_m ? 9 * D : 0;
   (void)build_col_prog(m);  // sizes the ColProg table (its length does not depend on the plan)
   // the applyJT kernel also stages the per-output tables behind the blob
   const size_t model_bytes = eval_model_bytes(*m) + (jt ? (size_t)table_words(m->n_out) * 8 : 0);
@@ -251,8 +250,11 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
       EvalPlan pl{};
       std::vector<int> boff(bj.size(), 0);
       const int s_base = totalA;
-      const bool y_tm = ysz > 0 && ysz <= cap;
-      if (y_tm) { pl.y_in_tmem = 1; pl.ybase = t_base; t_base += ysz; }
+      // Y-stack: whole if it fits the thread's tensor-memory share, else its deepest levels (long serial chains)
+      const int ky = do_m ? std::min(D, cap / 9) : 0;  // levels in tensor memory
+      pl.ysplit = do_m ? D - ky : 0; pl.ytbase = t_base; pl.y_in_tmem = ky > 0 ? 1 : 0;
+      t_base += 9 * ky;
+      const int ysz_s = do_m ? 9 * (D - ky) : 0;       // levels left in shared memory
       std::vector<int> order(bj.size());
       for (size_t k = 0; k < order.size(); ++k) order[k] = (int)k;
       std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bw[a] > bw[b]; });
@@ -264,7 +266,7 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
         int s_used = s_base, t_used = t_base;
         pl.fbase = s_used; pl.fsplit = do_tau ? D - kf : 0; s_used += do_tau ? 6 * (D - kf) : 0;
         pl.ftbase = t_used; t_used += 6 * kf;
-        if (!y_tm) { pl.ybase = s_used; s_used += ysz; }
+        pl.ybase = s_used; s_used += ysz_s;
         for (size_t k = 0; k < bj.size(); ++k)
           if (!b_tm[k]) { boff[k] = s_used; s_used += bw[k]; }
         pl.smem_doubles = s_used; pl.tmem_doubles = t_used; pl.warps = W;

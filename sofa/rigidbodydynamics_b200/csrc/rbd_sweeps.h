@@ -621,8 +621,10 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
   constexpr bool NEED_STACK = DO_M || DO_TAU;
   const int nj = m.njoints;
   const int fbase = m.plan.fbase, fsplit = m.plan.fsplit, ftbase = m.plan.ftbase, ybase = m.plan.ybase;
-  const bool ytm = m.plan.y_in_tmem != 0;
-  // f-stack level -> (space, offset): levels below fsplit in shared memory, the rest in tensor memory
+  const int ysplit = m.plan.ysplit, ytbase = m.plan.ytbase;
+  // Y- and f-stack level -> (space, offset): levels below the split in shared memory, the rest in tensor memory
+#define RBD_Y_TM(lvl) ((lvl) >= ysplit)
+#define RBD_Y_OFF(lvl) ((lvl) >= ysplit ? ytbase + 9 * ((lvl)-ysplit) : ybase + 9 * (lvl))
 #define RBD_F_TM(lvl) ((lvl) >= fsplit)
 #define RBD_F_OFF(lvl) ((lvl) >= fsplit ? ftbase + 6 * ((lvl)-fsplit) : fbase + 6 * (lvl))
   double R[9], p[3], vel[6], acc[6];
@@ -807,7 +809,7 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
         const int lvl = jn.depth - 1;
         if (jn.type != JT_FF) s_stv<6>(S, jn.offA, Ak); else s_stv<12>(S, jn.offA, Ak);
         if (DO_TAU) x_stv<6>(RBD_F_TM(lvl), S, T, RBD_F_OFF(lvl), fk);
-        if (DO_M) x_stv<9>(ytm, S, T, ybase + 9 * lvl, Yk + 1);
+        if (DO_M) x_stv<9>(RBD_Y_TM(lvl), S, T, RBD_Y_OFF(lvl), Yk + 1);
       }
       if (jn.nchild >= 2) {
         const bool btm = (jn.boff & RBD_BOFF_TMEM) != 0;
@@ -842,7 +844,7 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
         const int lvl = jp.depth - 1;
         if (pk == nxt_par) {
           if (DO_TAU) x_addv<6>(RBD_F_TM(lvl), S, T, RBD_F_OFF(lvl), fk);
-          if (DO_M) x_addv<9>(ytm, S, T, ybase + 9 * lvl, Yk + 1);
+          if (DO_M) x_addv<9>(RBD_Y_TM(lvl), S, T, RBD_Y_OFF(lvl), Yk + 1);
           break;
         }
         if (DO_TAU) {
@@ -853,7 +855,7 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
         }
         if (DO_M) {
           double Yp[9];
-          x_ldv<9>(ytm, S, T, ybase + 9 * lvl, Yp);
+          x_ldv<9>(RBD_Y_TM(lvl), S, T, RBD_Y_OFF(lvl), Yp);
 #pragma unroll
           for (int e = 0; e < 9; ++e) Yk[1 + e] += Yp[e];
           Yk[0] = jp.msub;  // composite mass of the subtree: model constant
@@ -866,6 +868,8 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
 #undef RBD_RESET_ROOT
 #undef RBD_F_TM
 #undef RBD_F_OFF
+#undef RBD_Y_TM
+#undef RBD_Y_OFF
 }
 
 // =========================================================================================================
@@ -1141,6 +1145,9 @@ RBD_HD void applyJT_instance(const DevModel& m, const DevTables& tb, const QC& q
   }
 }
 
+#ifndef RBD_JT_DIST
+#define RBD_JT_DIST 1 /* joints of lookahead of the wrench prefetch (1 or 2) */
+#endif
 #ifndef RBD_JT_PREF
 #define RBD_JT_PREF 4 /* outputs per joint whose wrenches are prefetched one joint ahead (A/B: 3..6 within 3 %) */
 #endif
@@ -1160,16 +1167,29 @@ RBD_HD void applyJT_instance_plan(const DevModel& m, const DevTables& tb, const 
 #pragma unroll
   for (int e = 0; e < 6 * RBD_JT_PREF; ++e) wn[e] = 0.0;
   if (nj > 1) src.prefetch(m.joint[1].out_begin, m.joint[1].out_end, wn);
+#if RBD_JT_DIST == 2
+  double wn2[6 * RBD_JT_PREF];
+#pragma unroll
+  for (int e = 0; e < 6 * RBD_JT_PREF; ++e) wn2[e] = 0.0;
+  if (nj > 2) src.prefetch(m.joint[2].out_begin, m.joint[2].out_end, wn2);
+#endif
   double q0n = 0.0, q1n = 0.0;
   RBD_Q_PREFETCH(1);
   for (int i = 1; i < nj; ++i) {
     const DevJoint& jn = m.joint[i];
     const int par = jn.parent;
-    // this joint's wrenches arrived while the previous joint was processed; start the next joint's loads now
+    // this joint's wrenches arrived while the previous joint(s) were processed; start the loads of the joint
+    // RBD_JT_DIST ahead now (A/B: issuing them only after this joint's gather, without the copy, is 16 % slower)
     double wc[6 * RBD_JT_PREF];
 #pragma unroll
     for (int e = 0; e < 6 * RBD_JT_PREF; ++e) wc[e] = wn[e];
+#if RBD_JT_DIST == 2
+#pragma unroll
+    for (int e = 0; e < 6 * RBD_JT_PREF; ++e) wn[e] = wn2[e];
+    if (i + 2 < nj) src.prefetch(m.joint[i + 2].out_begin, m.joint[i + 2].out_end, wn2);
+#else
     if (i + 1 < nj) src.prefetch(m.joint[i + 1].out_begin, m.joint[i + 1].out_end, wn);
+#endif
     if (par != i - 1) {
       if (par == 0) {
         R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;

@@ -366,3 +366,44 @@ def test_no_out_of_bounds_writes(torch_mod, api, name, n, tile):
     for k in ("oMi", "J", "M", "tau", "pos", "vel"):
         live = from_tiled(views[k].cpu().numpy(), n)
         assert not np.any(live == SENT), k
+
+
+@pytest.mark.parametrize("nmoving,branch_prob,ff", [(40, 0.0, False), (62, 0.0, True), (62, 0.9, False), (50, 0.3, True)])
+def test_deep_and_bushy_trees(torch_mod, api, nmoving, branch_prob, ff):
+    """Storage planner corner cases: long serial chains (sweep state of ~1000 doubles: few resident warps, Y-stack too
+    big for one thread's tensor-memory share) and very bushy trees (many branch records), up to RBD_MAX_JOINTS."""
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    d = mdl.random_tree(1000 + nmoving, nmoving, free_flyer=ff, all_types=True, branch_prob=branch_prob)
+    n = 150
+    q, v, a = mdl.random_state(d, n, seed=23)
+    ref, _ = oracle.eval_batch(d, q, v, a, nthreads=0)
+    for tmem in (True, False):
+        try:
+            got, launches = _eval_gpu(torch_mod, api, d, q, v, a, 32, tmem=tmem)
+        except api.RbdError as e:
+            # without tensor memory the 62-joint chain's state exceeds one SM even for the split sweeps: a clean error
+            assert e.code == -5 and not tmem and nmoving >= 60 and branch_prob == 0.0, str(e)
+            continue
+        assert launches in (1, 2)       # 2 = the fused sweep did not fit and ran as CRBA + RNEA halves
+        for k in ("oMi", "J", "M", "tau"):
+            assert rel_err(got[k], ref[k]) <= TOL_FP64, (k, tmem)
+    # mapping path on the same model
+    torch = torch_mod
+    m = api.Model(d); ws = api.Workspace(m, n)
+    T = lambda x: None if x is None else _dev(torch, to_tiled(x, 32))
+    qj, root, dq, rootv = _split(d, q, v)
+    nt = (n + 31) // 32
+    pos = torch.zeros((nt, 7 * d.n_out, 32), dtype=torch.float64, device="cuda")
+    w = np.random.default_rng(1).uniform(-1, 1, (n, 6 * d.n_out))
+    tau = torch.zeros((nt, d.nv_joints, 32), dtype=torch.float64, device="cuda")
+    rt = torch.zeros((nt, 6, 32), dtype=torch.float64, device="cuda") if ff else None
+    ws.apply_soa(n, 32, T(qj), T(root), pos)
+    ws.applyJT_soa(n, 32, T(w), tau, rt)
+    ws.synchronize()
+    tau = from_tiled(tau.cpu().numpy(), n)
+    orc = oracle.Oracle(d)
+    for i in range(0, n, 29):
+        orc.apply(qj[i], None if root is None else root[i])
+        rtau, _rroot = orc.applyJT(w[i])
+        assert rel_err(tau[i], rtau) <= TOL_FP64
