@@ -208,6 +208,8 @@ def main():
     ap.add_argument("--tile", type=int, default=32, help="tiled-SoA tile (32 = AoSoA fast path, 0 = plain SoA, tile = n)")
     ap.add_argument("--block", type=int, default=0, help="eval kernel block size override (0 = automatic)")
     ap.add_argument("--no-tmem", action="store_true", help="keep the whole sweep state in shared memory (A/B knob)")
+    ap.add_argument("--f32", action="store_true",
+                    help="secondary: also time the optional FP32 mode (1e-4 tolerance) and report it under 'fp32_mode'")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -311,6 +313,32 @@ def main():
             check_err = max(check_err, float(np.max(np.abs(got - ref[k])) / max(1.0, float(np.max(np.abs(ref[k]))))))
         assert check_err <= 1e-10, f"bench outputs differ from the oracle: {check_err:.3e}"
 
+    # ---- optional FP32 mode (secondary; the headline stays FP64) ------------------------------------------------
+    fp32 = None
+    if args.f32:
+        q32, v32, a32 = (x.float() for x in (q, v, a))
+        K32 = {"oMi": I.omi_fields, "J": I.jac_fields, "M": I.mass_fields, "tau": nv}
+        o32 = {k: torch.empty((dyn.ntiles, K32[k], dyn.tile), dtype=torch.float32, device=dev) for k in K32}
+
+        def step32():
+            dyn.ws.eval_soa_f32(n, dyn.tile, q32, v32, a32, o32["oMi"], o32["J"], o32["M"], o32["tau"])
+
+        for _ in range(args.warmup):
+            step32()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(args.steps):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); step32(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms32 = sum(ts) / len(ts)
+        err32 = float((o32["tau"].double() - out["tau"]).abs().max() / max(1.0, float(out["tau"].abs().max())))
+        fp32 = {"ms_per_step": ms32, "evals_per_s": n / (ms32 * 1e-3), "bytes_per_eval": bytes_per_eval // 2,
+                "hbm_frac": (n * (bytes_per_eval // 2) / (ms32 * 1e-3) / 1e9) / _peaks()[0],
+                "max_rel_err_tau_vs_fp64": err32, "tolerance": 1e-4,
+                "eval_storage": dyn.ws.eval_plan(True, True, f32=True)}
+        del q32, v32, a32, o32
+
     # ---- end-to-end leg: host buffers through rbd_eval_host ----------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -370,6 +398,8 @@ def main():
                              "kernel": f"rbd::eval_kernel<true,true,{dyn.tile if dyn.tile == 32 else 0}>", "kernel_ms": kern_ms,
                              "bytes_per_eval": bytes_per_eval},
                 "cpu_baseline": cpu, "oracle_check_rel_err": check_err}
+        if fp32 is not None:
+            line["fp32_mode"] = fp32
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -149,6 +149,8 @@ RBD_API int rbd_workspace_set_eval_tmem(rbd_workspace* ws, int enable);
  * instance, [4] tensor-memory columns per block, [5] 1 if the Y-stack lives in tensor memory, [6] shared-memory
  * bytes per block, [7] reserved.  Introspection for bench.py / DESIGN.md.                                 */
 RBD_API int rbd_workspace_get_eval_plan(rbd_workspace* ws, int with_M, int with_tau, int32_t out[8]);
+/* ... and of the FP32 mode (elements are floats: [2], [3] count floats).                                    */
+RBD_API int rbd_workspace_get_eval_plan_f32(rbd_workspace* ws, int with_M, int with_tau, int32_t out[8]);
 
 /* ---------------------------------------------------------------------------------------------------- */
 /* Mapping path, device SoA.                                                                            */
@@ -199,6 +201,10 @@ RBD_API int rbd_applyJT_rows_dev(rbd_workspace* ws, int64_t nrows, const int32_t
  * Any output pointer may be NULL; the corresponding work is skipped.                                     */
 RBD_API int rbd_eval_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, const double* v,
                          const double* a, double* oMi, double* J, double* M, double* tau);
+/* Optional FP32 mode of the same fused evaluation (BASELINE north-star: tolerance 1e-4 relative instead of 1e-10):
+ * float inputs, float outputs, float sweep state; same layouts (fields are floats), same kernel structure.     */
+RBD_API int rbd_eval_soa_f32(rbd_workspace* ws, int64_t n, int64_t tile, const float* q, const float* v,
+                             const float* a, float* oMi, float* J, float* M, float* tau);
 RBD_API int rbd_crba_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, double* M);
 RBD_API int rbd_rnea_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, const double* v,
                          const double* a, double* tau);

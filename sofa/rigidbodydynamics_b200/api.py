@@ -111,9 +111,10 @@ class Workspace:
     def set_eval_tmem(self, enable: bool):
         check(self._lib.rbd_workspace_set_eval_tmem(self._h, 1 if enable else 0))
 
-    def eval_plan(self, with_M: bool = True, with_tau: bool = True) -> dict:
+    def eval_plan(self, with_M: bool = True, with_tau: bool = True, f32: bool = False) -> dict:
         out = (C.c_int32 * 8)()
-        check(self._lib.rbd_workspace_get_eval_plan(self._h, int(with_M), int(with_tau), C.byref(out)))
+        fn = self._lib.rbd_workspace_get_eval_plan_f32 if f32 else self._lib.rbd_workspace_get_eval_plan
+        check(fn(self._h, int(with_M), int(with_tau), C.byref(out)))
         keys = ("warps_per_block", "blocks_per_sm", "smem_doubles", "tmem_doubles", "tmem_cols", "y_in_tmem",
                 "smem_bytes_per_block")
         return {k: int(out[i]) for i, k in enumerate(keys)}
@@ -122,6 +123,11 @@ class Workspace:
     def eval_soa(self, n, tile, q, v=None, a=None, oMi=None, J=None, M=None, tau=None):
         check(self._lib.rbd_eval_soa(self._h, n, tile, _dev_ptr(q), _dev_ptr(v), _dev_ptr(a), _dev_ptr(oMi),
                                      _dev_ptr(J), _dev_ptr(M), _dev_ptr(tau)))
+
+    def eval_soa_f32(self, n, tile, q, v=None, a=None, oMi=None, J=None, M=None, tau=None):
+        """Optional FP32 mode (tolerance 1e-4): float32 device tensors in the same tiled-SoA layouts."""
+        check(self._lib.rbd_eval_soa_f32(self._h, n, tile, _dev_ptr(q), _dev_ptr(v), _dev_ptr(a), _dev_ptr(oMi),
+                                         _dev_ptr(J), _dev_ptr(M), _dev_ptr(tau)))
 
     def crba_soa(self, n, tile, q, M):
         check(self._lib.rbd_crba_soa(self._h, n, tile, _dev_ptr(q), _dev_ptr(M)))

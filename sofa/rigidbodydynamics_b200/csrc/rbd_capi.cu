@@ -60,6 +60,9 @@ struct rbd_workspace {
   // the kernel stages the device copy into shared memory
   DevModel* h_plan[9] = {};  // index: bit 2 = oMi requested, bit 1 = CRBA, bit 0 = RNEA; [8] = the applyJT sweep
   DevModel* d_plan[9] = {};
+  DevModelT<float>* h_plan32[8] = {};  // FP32 mode of the fused eval
+  DevModelT<float>* d_plan32[8] = {};
+  LaunchCfg cfg_eval32[8];
   int use_tmem = 1;
   int num_sms = 0;
   double* qcache = nullptr;  // [nq][capacity] assembled configuration of the last apply
@@ -159,6 +162,7 @@ static void ws_free(rbd_workspace* ws) {
   cudaFree(ws->d_sorted_k); cudaFree(ws->d_outk_parent); cudaFree(ws->d_sorted_ident); cudaFree(ws->d_sorted_pl); cudaFree(ws->d_outk_pl);
   cudaFree(ws->qcache); cudaFree(ws->rows_buf); cudaFree(ws->d_model);
   for (int k = 0; k < 9; ++k) { cudaFree(ws->d_plan[k]); delete ws->h_plan[k]; }
+  for (int k = 0; k < 8; ++k) { cudaFree(ws->d_plan32[k]); delete ws->h_plan32[k]; }
   for (int s = 0; s < kSlots; ++s) {
     cudaFree(ws->slot[s].aos); cudaFree(ws->slot[s].soa);
     if (ws->slot[s].st) cudaStreamDestroy(ws->slot[s].st);
@@ -281,6 +285,7 @@ static void drop_plans(rbd_workspace* ws) {
   // kernels still in flight keep reading the device copies: wait for them before the next upload overwrites
   cudaDeviceSynchronize();
   for (int k = 0; k < 9; ++k) { delete ws->h_plan[k]; ws->h_plan[k] = nullptr; }
+  for (int k = 0; k < 8; ++k) { delete ws->h_plan32[k]; ws->h_plan32[k] = nullptr; }
 }
 
 RBD_API int rbd_workspace_get_eval_plan(rbd_workspace* ws, int with_M, int with_tau, int32_t out[8]) {
@@ -311,6 +316,59 @@ static int eval_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, 
   if (rc) return rc;
   EvalArgs A{n, tile, q, v, a, oMi, J, M, tau};
   CK(launch_eval(*ws->h_plan[pk], ws->d_plan[pk], A, ws->cfg_eval, ws->num_sms, st));
+  if (n > 0) ws->launches++;
+  return RBD_OK;
+}
+
+// FP32 mode: the plan is made on a double copy of the model (tree structure only) with 4-byte state elements, then
+// the constants are converted to float for the staged blob
+static int ensure_plan32(rbd_workspace* ws, int pk) {
+  if (ws->h_plan32[pk]) return RBD_OK;
+  DevModel* hd = new (std::nothrow) DevModel(ws->model->dm);
+  DevModelT<float>* hf = new (std::nothrow) DevModelT<float>();
+  if (!hd || !hf) { delete hd; delete hf; return set_err(RBD_ERR_ALLOC, "out of host memory"); }
+  if (!plan_eval(hd, (pk & 2) != 0, (pk & 1) != 0, ws->use_tmem != 0, ws->forced_eval_block / 32, (pk & 4) != 0, false,
+                 /*regs=*/128, /*elem_bytes=*/4)) {
+    delete hd; delete hf;
+    return set_err(RBD_ERR_UNSUPPORTED, "the FP32 sweep state of this model does not fit one SM");
+  }
+  const std::vector<unsigned long long> blob = build_eval_blob_f32(hd, hf);
+  delete hd;
+  if (!ws->d_plan32[pk]) {
+    cudaError_t e = cudaMalloc(&ws->d_plan32[pk], blob.size() * 8);
+    if (e != cudaSuccess) { delete hf; return cuda_fail(e, "cudaMalloc(plan32)"); }
+  }
+  cudaError_t e = cudaMemcpy(ws->d_plan32[pk], blob.data(), blob.size() * 8, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { delete hf; return cuda_fail(e, "cudaMemcpy(plan32)"); }
+  ws->h_plan32[pk] = hf;
+  return RBD_OK;
+}
+
+RBD_API int rbd_workspace_get_eval_plan_f32(rbd_workspace* ws, int with_M, int with_tau, int32_t out[8]) {
+  GUARD(ws);
+  if (!out) return set_err(RBD_ERR_INVALID_ARG, "null out");
+  const int pk = 4 | (with_M ? 2 : 0) | (with_tau ? 1 : 0);
+  int rc = ensure_plan32(ws, pk);
+  if (rc) return rc;
+  const DevModelT<float>& h = *ws->h_plan32[pk];
+  out[0] = h.plan.warps; out[1] = h.plan.blocks_per_sm; out[2] = h.plan.smem_doubles; out[3] = h.plan.tmem_doubles;
+  out[4] = h.plan.tmem_cols; out[5] = h.plan.y_in_tmem;
+  out[6] = (int32_t)(eval_model_bytes(h) + (size_t)h.plan.warps * 32 * h.plan.smem_doubles * 4); out[7] = 1;
+  return RBD_OK;
+}
+
+RBD_API int rbd_eval_soa_f32(rbd_workspace* ws, int64_t n, int64_t tile, const float* q, const float* v, const float* a,
+                             float* oMi, float* J, float* M, float* tau) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, tile);
+  if (rc) return rc;
+  if (!q) return set_err(RBD_ERR_INVALID_ARG, "q is null");
+  if (tau && (!v || !a)) return set_err(RBD_ERR_INVALID_ARG, "rnea needs v and a");
+  const int pk = (oMi ? 4 : 0) | (M ? 2 : 0) | (tau ? 1 : 0);
+  rc = ensure_plan32(ws, pk);
+  if (rc) return rc;
+  EvalArgsT<float> A{n, tile, q, v, a, oMi, J, M, tau};
+  CK(launch_eval_f32(*ws->h_plan32[pk], ws->d_plan32[pk], A, ws->cfg_eval32, ws->num_sms, ws->stream));
   if (n > 0) ws->launches++;
   return RBD_OK;
 }

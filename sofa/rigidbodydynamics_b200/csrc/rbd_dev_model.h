@@ -1,11 +1,12 @@
 // rbd_dev_model.h — kinematic-tree constants as the kernels see them.
 //
-// The whole joint table travels as a __grid_constant__ kernel parameter, i.e. it is staged in the constant
-// bank of every launch ("tree constants staged once into constant memory", BASELINE north-star): all threads
-// of a warp read the same joint record at the same time, which is exactly the broadcast access pattern the
-// constant cache serves, and it keeps L1/shared memory free for per-instance state.
-// Replaces the pinocchio::Model the reference shares between loader and mapping
+// The joint table is uploaded once per workspace and staged once per block into shared memory by every kernel
+// ("tree constants staged once into shared/constant memory", BASELINE north-star): all threads of a warp read the
+// same joint record at the same time, which shared memory serves as one broadcast wavefront (DESIGN.md §4.1 explains
+// why not the constant bank).  Replaces the pinocchio::Model the reference shares between loader and mapping
 // (reference KinematicChainMapping.inl:304-311, URDFModelLoader.cpp:263-268).
+// The structs are templates over the scalar type: double (the product's precision) and float (the optional FP32
+// mode of the fused evaluation); the layout differs only in the width of the constants.
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -22,12 +23,13 @@ enum : int {
 
 // 16-byte aligned (and the DevModel header padded to a multiple of 16) so that the compiler may read the staged
 // record with 128-bit shared-memory loads
-struct alignas(16) DevJoint {
-  double pl[12];    // jointPlacement: R row-major (9), p (3)
-  double axis[3];   // unit axis in the joint frame
-  double Y[10];     // m, c(3), Ic (xx,xy,yy,xz,yz,zz)
-  double msub;      // mass of the whole subtree below (and including) this joint: the composite-inertia mass is a
-                    // model constant, so the Y-stack carries 9 doubles per level, not 10
+template <class real>
+struct alignas(16) DevJointT {
+  real pl[12];      // jointPlacement: R row-major (9), p (3)
+  real axis[3];     // unit axis in the joint frame
+  real Y[10];       // m, c(3), Ic (xx,xy,yy,xz,yz,zz)
+  real msub;        // mass of the whole subtree below (and including) this joint: the composite-inertia mass is a
+                    // model constant, so the Y-stack carries 9 values per level, not 10
   int parent, type, idx_q, idx_v;
   int nv;           // dof of this joint (0 universe, 1, or 6)
   int nchild;       // number of child joints
@@ -43,6 +45,7 @@ struct alignas(16) DevJoint {
   // column program of this joint's column(s) of M (ColProg table): depth-1 ancestor entries, then nzseg zero segments
   int prog_off, nzseg;
 };
+using DevJoint = DevJointT<double>;
 // ColProg entries (int32).  Ancestor entry, root first: row (idx_v of the ancestor) | free-flyer flag | A-stack offset.
 // Zero segment: first row | length.  Rows not covered by either belong to the joint itself.
 #define RBD_PROG_ROW(e) ((e) & 0xffff)
@@ -75,7 +78,8 @@ struct EvalPlan {
 #define RBD_BOFF_RPOMI (1 << 28) /* R|p not saved: re-read from the oMi output this thread wrote (oMi requested) */
 #define RBD_BOFF_MASK ((1 << 28) - 1)
 
-struct alignas(16) DevModel {
+template <class real>
+struct alignas(16) DevModelT {
   int njoints, nq, nv, n_out;
   int slot_total[2];  // doubles of stack slots per instance for the two layouts
   int nbranch;
@@ -83,19 +87,45 @@ struct alignas(16) DevModel {
   int nq_joints, nv_joints;
   int max_depth, max_depth_internal;  // longest joint chain; deepest joint that has children
   int prog_words_off, prog_len;       // eval blob: 8-byte-word offset of the ColProg table behind the joint records; ints
-  double gravity[3];
+  real gravity[3];
   EvalPlan plan;
-  DevJoint joint[RBD_MAX_JOINTS];
+  DevJointT<real> joint[RBD_MAX_JOINTS];
 };
+using DevModel = DevModelT<double>;
+
+// the same model with float constants (tree indices and the storage plan are copied verbatim)
+inline void dev_model_to_f32(const DevModel& d, DevModelT<float>* f) {
+  f->njoints = d.njoints; f->nq = d.nq; f->nv = d.nv; f->n_out = d.n_out;
+  f->slot_total[0] = d.slot_total[0]; f->slot_total[1] = d.slot_total[1];
+  f->nbranch = d.nbranch; f->has_ff_root = d.has_ff_root; f->nq_joints = d.nq_joints; f->nv_joints = d.nv_joints;
+  f->max_depth = d.max_depth; f->max_depth_internal = d.max_depth_internal;
+  f->prog_words_off = d.prog_words_off; f->prog_len = d.prog_len;
+  for (int k = 0; k < 3; ++k) f->gravity[k] = (float)d.gravity[k];
+  f->plan = d.plan;
+  for (int i = 0; i < RBD_MAX_JOINTS; ++i) {
+    const DevJoint& a = d.joint[i];
+    DevJointT<float>& b = f->joint[i];
+    for (int k = 0; k < 12; ++k) b.pl[k] = (float)a.pl[k];
+    for (int k = 0; k < 3; ++k) b.axis[k] = (float)a.axis[k];
+    for (int k = 0; k < 10; ++k) b.Y[k] = (float)a.Y[k];
+    b.msub = (float)a.msub;
+    b.parent = a.parent; b.type = a.type; b.idx_q = a.idx_q; b.idx_v = a.idx_v; b.nv = a.nv; b.nchild = a.nchild;
+    b.slot[0] = a.slot[0]; b.slot[1] = a.slot[1]; b.bidx = a.bidx; b.out_begin = a.out_begin; b.out_end = a.out_end;
+    b.pl_rot_identity = a.pl_rot_identity; b.depth = a.depth; b.offA = a.offA; b.boff = a.boff;
+    b.prog_off = a.prog_off; b.nzseg = a.nzseg;
+  }
+}
 
 // bytes of a DevModel that are meaningful (header + the first njoints records): what the eval kernel stages
-inline size_t dev_model_bytes(const DevModel& m) {
-  return sizeof(DevModel) - sizeof(DevJoint) * (size_t)(RBD_MAX_JOINTS - m.njoints);
+template <class real>
+inline size_t dev_model_bytes(const DevModelT<real>& m) {
+  return sizeof(DevModelT<real>) - sizeof(DevJointT<real>) * (size_t)(RBD_MAX_JOINTS - m.njoints);
 }
 
 // shared-memory bytes the eval kernel reserves in front of the stacks: the staged table rounded to 16 bytes plus two
 // spare 8-byte words (tensor-memory base address)
-inline size_t eval_model_bytes(const DevModel& m) {
+template <class real>
+inline size_t eval_model_bytes(const DevModelT<real>& m) {
   return (dev_model_bytes(m) + 15) / 16 * 16 + ((size_t)m.prog_len * 4 + 15) / 16 * 16 + 16;
 }
 

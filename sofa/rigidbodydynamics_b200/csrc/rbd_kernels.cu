@@ -30,61 +30,65 @@ extern __shared__ __align__(16) double rbd_smem[];
 // derives its private slice (lane quarter of its warp, column range of its warp group), and warp 0 frees them
 // after the whole block is done.  Lanes past the end of the batch recompute the last instance instead of
 // exiting: tcgen05.ld/st are warp-collective (.sync.aligned) and the duplicate stores write identical values.
-template <bool DO_M, bool DO_TAU, int TILE>
-__global__ void __launch_bounds__(256) eval_kernel(const DevModel* __restrict__ gm, const EvalArgs a,
-                                                   const int model_words) {
-  // the last two staged words are spare: the tensor-memory base address lands there (no static shared memory, so
-  // the block can ask for the full 227 KB dynamically)
-  unsigned* const tm_base_p = reinterpret_cast<unsigned*>(rbd_smem + model_words - 2);
-  {
-    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gm);
-    unsigned long long* dst = reinterpret_cast<unsigned long long*>(rbd_smem);
-    for (int w = threadIdx.x; w < model_words - 2; w += blockDim.x) dst[w] = src[w];
-  }
-  __syncthreads();
-  const DevModel& m = *reinterpret_cast<const DevModel*>(rbd_smem);
-  const int warp = threadIdx.x >> 5;
-  const int tm_cols = m.plan.tmem_cols;
-  TmStack T;
-  T.base = 0;
-  if (tm_cols > 0) {
-    if (warp == 0) {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"l"(
-                       (unsigned long long)__cvta_generic_to_shared(tm_base_p)),
-                   "r"(tm_cols)
-                   : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    T.base = *tm_base_p + (((unsigned)(warp & 3) * 32u) << 16) + (unsigned)(warp >> 2) * 2u * (unsigned)m.plan.tmem_doubles;
-  }
-  // persistent: the block's warps stride over the batch's 32-instance tiles independently (no barrier inside),
-  // so the staging, the tensor-memory allocation and the end-of-block wait are paid once per SM, not per tile
-  const Stack S = make_stack(rbd_smem + model_words, threadIdx.x, m.plan.smem_doubles);
-  const long long ntiles = (a.n + 31) / 32;
-  const int wpb = blockDim.x >> 5;
-  for (long long t = (long long)blockIdx.x * wpb + warp; t < ntiles; t += (long long)gridDim.x * wpb) {
-    long long inst = t * 32 + (threadIdx.x & 31);
-    if (inst >= a.n) inst = a.n - 1;
-    EvalIOT<TILE> io;
-    io.q = make_field_t<TILE>(const_cast<double*>(a.q), inst, m.nq, a.tile);
-    io.v = make_field_t<TILE>(const_cast<double*>(a.v), inst, m.nv, a.tile);
-    io.a = make_field_t<TILE>(const_cast<double*>(a.a), inst, m.nv, a.tile);
-    io.oMi = make_field_t<TILE>(a.oMi, inst, 12 * (m.njoints - 1), a.tile);
-    io.J = make_field_t<TILE>(a.J, inst, 6 * m.nv, a.tile);
-    io.M = make_field_t<TILE>(a.M, inst, m.nv * (m.nv + 1) / 2, a.tile);
-    io.tau = make_field_t<TILE>(a.tau, inst, m.nv, a.tile);
-    eval_instance<DO_M, DO_TAU, TILE>(m, io, S, T);
-  }
-  if (tm_cols > 0) {
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0)
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tm_base_p), "r"(tm_cols) : "memory");
-  }
+#define RBD_DEFINE_EVAL_KERNEL(NAME, NSQ, REAL) \
+template <bool DO_M, bool DO_TAU, int TILE>                                                                                                             \
+__global__ void __launch_bounds__(256) NAME(const DevModelT<REAL>* __restrict__ gm, const EvalArgsT<REAL> a,                                            \
+                                                   const int model_words) {                                                                             \
+ /* the last two staged words are spare: the tensor-memory base address lands there (no static shared memory, so */                                     \
+ /* the block can ask for the full 227 KB dynamically) */                                                                                               \
+  unsigned* const tm_base_p = reinterpret_cast<unsigned*>(rbd_smem + model_words - 2);                                                                  \
+  {                                                                                                                                                     \
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gm);                                                                    \
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(rbd_smem);                                                                          \
+    for (int w = threadIdx.x; w < model_words - 2; w += blockDim.x) dst[w] = src[w];                                                                    \
+  }                                                                                                                                                     \
+  __syncthreads();                                                                                                                                      \
+  const DevModelT<REAL>& m = *reinterpret_cast<const DevModelT<REAL>*>(rbd_smem);                                                                       \
+  const int warp = threadIdx.x >> 5;                                                                                                                    \
+  const int tm_cols = m.plan.tmem_cols;                                                                                                                 \
+  NSQ::TmStack T;                                                                                                                                       \
+  T.base = 0;                                                                                                                                           \
+  if (tm_cols > 0) {                                                                                                                                    \
+    if (warp == 0) {                                                                                                                                    \
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"l"(                                                           \
+                       (unsigned long long)__cvta_generic_to_shared(tm_base_p)),                                                                        \
+                   "r"(tm_cols)                                                                                                                         \
+                   : "memory");                                                                                                                         \
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");                                                          \
+    }                                                                                                                                                   \
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");                                                                                    \
+    __syncthreads();                                                                                                                                    \
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");                                                                                     \
+    T.base = *tm_base_p + (((unsigned)(warp & 3) * 32u) << 16) + (unsigned)(warp >> 2) * (unsigned)(sizeof(REAL) / 4) * (unsigned)m.plan.tmem_doubles;  \
+  }                                                                                                                                                     \
+ /* persistent: the block's warps stride over the batch's 32-instance tiles independently (no barrier inside), */                                       \
+ /* so the staging, the tensor-memory allocation and the end-of-block wait are paid once per SM, not per tile */                                        \
+  const NSQ::Stack S = NSQ::make_stack(reinterpret_cast<REAL*>(rbd_smem + model_words), threadIdx.x, m.plan.smem_doubles);                              \
+  const long long ntiles = (a.n + 31) / 32;                                                                                                             \
+  const int wpb = blockDim.x >> 5;                                                                                                                      \
+  for (long long t = (long long)blockIdx.x * wpb + warp; t < ntiles; t += (long long)gridDim.x * wpb) {                                                 \
+    long long inst = t * 32 + (threadIdx.x & 31);                                                                                                       \
+    if (inst >= a.n) inst = a.n - 1;                                                                                                                    \
+    NSQ::EvalIOT<TILE> io;                                                                                                                              \
+    io.q = NSQ::make_field_t<TILE>(const_cast<REAL*>(a.q), inst, m.nq, a.tile);                                                                         \
+    io.v = NSQ::make_field_t<TILE>(const_cast<REAL*>(a.v), inst, m.nv, a.tile);                                                                         \
+    io.a = NSQ::make_field_t<TILE>(const_cast<REAL*>(a.a), inst, m.nv, a.tile);                                                                         \
+    io.oMi = NSQ::make_field_t<TILE>(a.oMi, inst, 12 * (m.njoints - 1), a.tile);                                                                        \
+    io.J = NSQ::make_field_t<TILE>(a.J, inst, 6 * m.nv, a.tile);                                                                                        \
+    io.M = NSQ::make_field_t<TILE>(a.M, inst, m.nv * (m.nv + 1) / 2, a.tile);                                                                           \
+    io.tau = NSQ::make_field_t<TILE>(a.tau, inst, m.nv, a.tile);                                                                                        \
+    NSQ::eval_instance<DO_M, DO_TAU, TILE>(m, io, S, T);                                                                                                \
+  }                                                                                                                                                     \
+  if (tm_cols > 0) {                                                                                                                                    \
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");                                                                                    \
+    __syncthreads();                                                                                                                                    \
+    if (warp == 0)                                                                                                                                      \
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tm_base_p), "r"(tm_cols) : "memory");                                 \
+  }                                                                                                                                                     \
 }
+
+RBD_DEFINE_EVAL_KERNEL(eval_kernel, rbd, double)
+RBD_DEFINE_EVAL_KERNEL(eval_kernel_f32, rbd::f32, float)
 
 // The mapping kernels stage the joint table the same way (one coalesced copy per block, broadcast reads after).
 // The cached configuration of the last apply (workspace) is always tile-32.
@@ -304,49 +308,52 @@ static cudaError_t pick_block(Kern kern, int smem_doubles_per_thread, int forced
 #define RBD_GRID(n, block) (unsigned)(((n) + (block)-1) / (block))
 
 // variant index: bit 2 = compile-time tile of 32, bit 1 = CRBA, bit 0 = RNEA
-#define RBD_EVAL_DISPATCH(v, CALL)                          \
-  switch (v) {                                              \
-    case 7: CALL((eval_kernel<true, true, 32>)); break;     \
-    case 6: CALL((eval_kernel<true, false, 32>)); break;    \
-    case 5: CALL((eval_kernel<false, true, 32>)); break;    \
-    case 4: CALL((eval_kernel<false, false, 32>)); break;   \
-    case 3: CALL((eval_kernel<true, true, 0>)); break;      \
-    case 2: CALL((eval_kernel<true, false, 0>)); break;     \
-    case 1: CALL((eval_kernel<false, true, 0>)); break;     \
-    default: CALL((eval_kernel<false, false, 0>)); break;   \
+#define RBD_EVAL_DISPATCH(KERN, v, CALL)             \
+  switch (v) {                                       \
+    case 7: CALL((KERN<true, true, 32>)); break;     \
+    case 6: CALL((KERN<true, false, 32>)); break;    \
+    case 5: CALL((KERN<false, true, 32>)); break;    \
+    case 4: CALL((KERN<false, false, 32>)); break;   \
+    case 3: CALL((KERN<true, true, 0>)); break;      \
+    case 2: CALL((KERN<true, false, 0>)); break;     \
+    case 1: CALL((KERN<false, true, 0>)); break;     \
+    default: CALL((KERN<false, false, 0>)); break;   \
   }
 
-// `hm` is the host copy of the planned model (hm.plan chosen by plan_eval), `d_model` its device copy.
-cudaError_t launch_eval(const DevModel& hm, const DevModel* d_model, const EvalArgs& a, LaunchCfg* cache, int num_sms,
-                        cudaStream_t st) {
-  const bool do_m = a.M != nullptr, do_tau = a.tau != nullptr;
-  const int v = (a.tile == 32 ? 4 : 0) | (do_m ? 2 : 0) | (do_tau ? 1 : 0);
-  LaunchCfg& cfg = cache[v];
-  const int model_words = (int)(eval_model_bytes(hm) / 8);  // staged joint table + 2 spare words
-  const int block = hm.plan.warps * 32;
-  const size_t smem = (size_t)model_words * 8 + (size_t)block * hm.plan.smem_doubles * 8;
-  cudaError_t e = cudaSuccess;
-  if (cfg.block != block || cfg.smem_bytes != smem) {
-#define RBD_ATTR(K)                                                                                     \
-  e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin);             \
-  if (e == cudaSuccess)                                                                                 \
-    e = cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
-    RBD_EVAL_DISPATCH(v, RBD_ATTR)
-#undef RBD_ATTR
-    if (e != cudaSuccess) return e;
-    cfg.block = block; cfg.smem_bytes = smem; cfg.blocks_per_sm = hm.plan.blocks_per_sm;
+// `hm` is the host copy of the planned model (hm.plan chosen by plan_eval), `d_model` its staged blob on the device.
+#define RBD_DEFINE_EVAL_LAUNCH(FN, KERN, REAL)                                                                     \
+  cudaError_t FN(const DevModelT<REAL>& hm, const DevModelT<REAL>* d_model, const EvalArgsT<REAL>& a, LaunchCfg* cache, \
+                 int num_sms, cudaStream_t st) {                                                                   \
+    const bool do_m = a.M != nullptr, do_tau = a.tau != nullptr;                                                   \
+    const int v = (a.tile == 32 ? 4 : 0) | (do_m ? 2 : 0) | (do_tau ? 1 : 0);                                      \
+    LaunchCfg& cfg = cache[v];                                                                                     \
+    const int model_words = (int)(eval_model_bytes(hm) / 8); /* staged joint table + 2 spare words */              \
+    const int block = hm.plan.warps * 32;                                                                          \
+    const size_t smem = (size_t)model_words * 8 + (size_t)block * hm.plan.smem_doubles * sizeof(REAL);             \
+    cudaError_t e = cudaSuccess;                                                                                   \
+    if (cfg.block != block || cfg.smem_bytes != smem) {                                                            \
+      RBD_EVAL_DISPATCH(KERN, v, RBD_ATTR)                                                                         \
+      if (e != cudaSuccess) return e;                                                                              \
+      cfg.block = block; cfg.smem_bytes = smem; cfg.blocks_per_sm = hm.plan.blocks_per_sm;                         \
+    }                                                                                                              \
+    if (a.n <= 0) return cudaSuccess;                                                                              \
+    unsigned grid = RBD_GRID(a.n, block);                                                                          \
+    const unsigned resident = (unsigned)(num_sms * (hm.plan.blocks_per_sm > 0 ? hm.plan.blocks_per_sm : 1));       \
+    /* persistent blocks (one wave, warps stride over the tiles) once every warp gets >= 8 tiles; smaller */      \
+    /* batches run one block per `block` instances so that the last wave is not half empty */                     \
+    if (grid > 8 * resident) grid = resident;                                                                      \
+    RBD_EVAL_DISPATCH(KERN, v, RBD_LAUNCH)                                                                         \
+    return cudaGetLastError();                                                                                     \
   }
-  if (a.n <= 0) return cudaSuccess;
-  unsigned grid = RBD_GRID(a.n, block);
-  const unsigned resident = (unsigned)(num_sms * (hm.plan.blocks_per_sm > 0 ? hm.plan.blocks_per_sm : 1));
-  // persistent blocks (one wave, warps stride over the tiles) once every warp gets >= 8 tiles; smaller batches run
-  // one block per `block` instances so that the last wave is not half empty
-  if (grid > 8 * resident) grid = resident;
+#define RBD_ATTR(K)                                                                                 \
+  e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin);         \
+  if (e == cudaSuccess)                                                                             \
+    e = cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
 #define RBD_LAUNCH(K) K<<<grid, block, smem, st>>>(d_model, a, model_words)
-  RBD_EVAL_DISPATCH(v, RBD_LAUNCH)
+RBD_DEFINE_EVAL_LAUNCH(launch_eval, eval_kernel, double)
+RBD_DEFINE_EVAL_LAUNCH(launch_eval_f32, eval_kernel_f32, float)
+#undef RBD_ATTR
 #undef RBD_LAUNCH
-  return cudaGetLastError();
-}
 
 // mapping kernels: cfg[0] = run-time tile, cfg[1] = tile 32
 static inline int map_model_words(const DevModel& m) { return (int)((dev_model_bytes(m) + 15) / 16) * 2; }

@@ -6,11 +6,13 @@
 
 namespace rbd {
 
-struct EvalArgs {
+template <class real>
+struct EvalArgsT {
   long long n, tile;
-  const double *q, *v, *a;
-  double *oMi, *J, *M, *tau;
+  const real *q, *v, *a;
+  real *oMi, *J, *M, *tau;
 };
+using EvalArgs = EvalArgsT<double>;
 struct MapArgs {
   long long n, tile;
   const double* joints;  // apply: q_joints | applyJ: dq_joints | applyJT: out_tau (accumulated)
@@ -35,6 +37,9 @@ struct LaunchCfg {
 
 cudaError_t launch_eval(const DevModel& planned_host_model, const DevModel* d_eval_blob, const EvalArgs& a,
                         LaunchCfg* cache8, int num_sms, cudaStream_t st);
+// optional FP32 mode of the fused evaluation (float I/O and state, tolerance 1e-4)
+cudaError_t launch_eval_f32(const DevModelT<float>& planned_host_model, const DevModelT<float>* d_eval_blob,
+                            const EvalArgsT<float>& a, LaunchCfg* cache8, int num_sms, cudaStream_t st);
 // mapping kernels: `m` = host copy, `d_model` = device copy of the same (unplanned) joint table; cfg2[0] run-time
 // tile, cfg2[1] tile 32
 cudaError_t launch_apply(const DevModel& m, const DevModel* d_model, const DevTables& tb, const MapArgs& a,

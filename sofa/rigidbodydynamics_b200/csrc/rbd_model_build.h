@@ -53,6 +53,16 @@ inline std::vector<unsigned long long> build_eval_blob(DevModel* m) {
   if (!prog.empty()) memcpy(blob.data() + m->prog_words_off, prog.data(), prog.size() * sizeof(int));
   return blob;
 }
+// ... and its FP32 twin: the same planned model with float constants (`f` receives the converted model)
+inline std::vector<unsigned long long> build_eval_blob_f32(DevModel* m, DevModelT<float>* f) {
+  const std::vector<int> prog = build_col_prog(m);
+  dev_model_to_f32(*m, f);
+  f->prog_words_off = (int)((dev_model_bytes(*f) + 15) / 16 * 2);
+  std::vector<unsigned long long> blob(eval_model_bytes(*f) / 8 - 2, 0ull);
+  memcpy(blob.data(), f, dev_model_bytes(*f));
+  if (!prog.empty()) memcpy(blob.data() + f->prog_words_off, prog.data(), prog.size() * sizeof(int));
+  return blob;
+}
 
 inline int joint_nq_of(int t) { return t == JT_FF ? 7 : (t >= JT_RUBX && t <= JT_RUBU) ? 2 : (t == JT_UNIVERSE ? 0 : 1); }
 inline int joint_nv_of(int t) { return t == JT_FF ? 6 : (t == JT_UNIVERSE ? 0 : 1); }
@@ -201,7 +211,9 @@ inline int pow2_cols(int cols) {
 
 // Fills m->plan and m->joint[*].boff.  forced_warps > 0 pins the block size.  Returns false when nothing fits.
 inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int forced_warps = 0, bool omi_out = false,
-                      bool jt = false, int regs_per_thread = B200Limits::kRegsPerThread) {
+                      bool jt = false, int regs_per_thread = B200Limits::kRegsPerThread, int elem_bytes = 8) {
+  // elem_bytes: 8 = the FP64 product, 4 = the optional FP32 mode (state elements are floats: half the shared-memory
+  // bytes, one tensor-memory column each)
   // jt: the applyJT sweep — stacks of the (no CRBA, RNEA) variant, but branch records hold R|p only (no v|a)
   const int nj = m->njoints;
   const bool need_stack = do_m || do_tau;
@@ -218,7 +230,13 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
   }
   (void)build_col_prog(m);  // sizes the ColProg table (its length does not depend on the plan)
   // the applyJT kernel also stages the per-output tables behind the blob
-  const size_t model_bytes = eval_model_bytes(*m) + (jt ? (size_t)table_words(m->n_out) * 8 : 0);
+  size_t model_bytes = eval_model_bytes(*m) + (jt ? (size_t)table_words(m->n_out) * 8 : 0);
+  if (elem_bytes == 4) {
+    DevModelT<float> probe;
+    probe.njoints = m->njoints; probe.prog_len = m->prog_len;
+    model_bytes = eval_model_bytes(probe);
+  }
+  const int cols_per_elem = elem_bytes / 4;
   EvalPlan best{};
   std::vector<int> best_boff, bj;
   for (int i = 1; i < nj; ++i)
@@ -226,7 +244,7 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
   int best_warps_sm = 0;
   for (int W = 1; W <= B200Limits::kMaxWarpsPerBlock; ++W) {
     if (forced_warps > 0 && W != forced_warps) continue;
-    const int cap = use_tmem ? (B200Limits::kTmemCols / ((W + 3) / 4)) / 2 : 0;  // doubles per thread
+    const int cap = use_tmem ? (B200Limits::kTmemCols / ((W + 3) / 4)) / cols_per_elem : 0;  // elements per thread
     bool placed = false;
     // cheapest configuration first: everything saved; then drop the v|a record of branch joints attached to the
     // universe (recomputed from the A record and the inputs: costs a dozen global re-reads per return)
@@ -270,8 +288,8 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
         for (size_t k = 0; k < bj.size(); ++k)
           if (!b_tm[k]) { boff[k] = s_used; s_used += bw[k]; }
         pl.smem_doubles = s_used; pl.tmem_doubles = t_used; pl.warps = W;
-        pl.tmem_cols = t_used > 0 ? pow2_cols(2 * t_used * ((W + 3) / 4)) : 0;
-        const size_t block_bytes = model_bytes + (size_t)W * 32 * s_used * 8;
+        pl.tmem_cols = t_used > 0 ? pow2_cols(cols_per_elem * t_used * ((W + 3) / 4)) : 0;
+        const size_t block_bytes = model_bytes + (size_t)W * 32 * s_used * elem_bytes;
         if (block_bytes + B200Limits::kSmemReservedPerBlock > (size_t)B200Limits::kSmemBytes) continue;
         int c = (int)(B200Limits::kSmemBytes / (block_bytes + B200Limits::kSmemReservedPerBlock));
         if (pl.tmem_cols > 0) c = std::min(c, B200Limits::kTmemCols / pl.tmem_cols);

@@ -51,1300 +51,19 @@
 #define RBD_HD inline
 #endif
 
+// The bodies live in rbd_sweeps_body.h, written against the scalar type `real` and the model types `DevModel` /
+// `DevJoint`, and are compiled twice: in namespace rbd with real = double (the product), and in namespace rbd::f32
+// with real = float (the optional FP32 mode of the fused evaluation, tolerance 1e-4).
 namespace rbd {
+typedef double real;
+#include "rbd_sweeps_body.h"
 
-// ---------------------------------------------------------------------------------------------------------
-// accessors
-//
-// FieldT<TILE>: strided view of one instance's fields in a tiled-SoA array.  TILE = 0 reads the tile (= stride
-// between consecutive fields) at run time; TILE = 32 is the AoSoA layout the hot path is tuned for: the 32
-// instances of a warp form one tile, field k of the warp sits at byte offset k*256 from the warp's base, so the
-// stride folds into the immediate offset of every load/store and a warp's whole output is one contiguous block.
-template <int TILE>
-struct FieldT {
-  double* p;
-  long long stride;
-  RBD_HD long long off(int k) const { return TILE ? (long long)k * TILE : (long long)k * stride; }
-  RBD_HD double ld(int k) const { return p[off(k)]; }
-  RBD_HD void st(int k, double v) const { p[off(k)] = v; }
-  RBD_HD bool ok() const { return p != nullptr; }
-  // address of field k, and a store at a (small, usually compile-time) field offset e from such an address: with
-  // TILE fixed the offset folds into the instruction's immediate instead of costing one IMAD.WIDE per store
-  RBD_HD double* at(int k) const { return p + off(k); }
-  RBD_HD void st_at(double* a, int e, double v) const { a[TILE ? (long long)e * TILE : (long long)e * stride] = v; }
-  RBD_HD long long step(int e) const { return TILE ? (long long)e * TILE : (long long)e * stride; }
-};
-using Field = FieldT<0>;
-template <int TILE>
-RBD_HD FieldT<TILE> make_field_t(double* base, long long inst, int K, long long tile) {
-  FieldT<TILE> f;
-  if constexpr (TILE != 0) {
-    f.stride = TILE;
-    f.p = base ? base + (inst / TILE) * (long long)K * TILE + (inst % TILE) : nullptr;
-  } else {
-    f.stride = tile;
-    f.p = base ? base + (inst / tile) * (long long)K * tile + (inst % tile) : nullptr;
-  }
-  return f;
-}
-RBD_HD Field make_field(double* base, long long inst, int K, long long tile) { return make_field_t<0>(base, inst, K, tile); }
-
-// Stack: this thread's column of its warp's shared-memory state.  Every warp owns a contiguous [slots][32]
-// region, so the stride between slots is the compile-time constant 32 (bank-conflict free: the 32 lanes of a
-// warp touch 32 consecutive doubles), whatever the block size.
-#define RBD_WARP 32
-struct Stack {
-  double* p;
-  RBD_HD double ld(int k) const { return p[k * RBD_WARP]; }
-  RBD_HD void st(int k, double v) const { p[k * RBD_WARP] = v; }
-  RBD_HD void add(int k, double v) const { p[k * RBD_WARP] += v; }
-};
-// base of thread t's stack column inside a block-wide region of `slots` doubles per thread
-RBD_HD Stack make_stack(double* smem, int t, int slots) {
-  Stack s;
-  s.p = smem + (long long)(t / RBD_WARP) * slots * RBD_WARP + (t % RBD_WARP);
-  return s;
-}
-
-// TmStack: this thread's private slice of TENSOR MEMORY used as scratch (tcgen05.ld / tcgen05.st, shape 32x32b:
-// lane i of the warp <-> TMEM lane 32*(warp%4)+i, one 32-bit column per register; a double takes two columns).
-// `base` already contains the warp's lane quarter (bits 31:16) and the thread's first column (bits 15:0).
-// All lanes of a warp must execute these together (.sync.aligned): the eval sweep is warp-uniform by construction.
-// On the host (tests/emul) the same interface is backed by a plain array.
-#if defined(__CUDACC__)
-struct TmStack {
-  unsigned base;
-  template <int N>
-  __device__ __forceinline__ void issue_ld(unsigned addr, unsigned* r) const {
-#if defined(__CUDA_ARCH__)
-    if constexpr (N >= 8) {
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-          : "r"(addr) : "memory");
-      issue_ld<N - 8>(addr + 16, r + 16);
-    } else if constexpr (N >= 4) {
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                   : "r"(addr) : "memory");
-      issue_ld<N - 4>(addr + 8, r + 8);
-    } else if constexpr (N >= 2) {
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
-                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
-      issue_ld<N - 2>(addr + 4, r + 4);
-    } else if constexpr (N == 1) {
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr) : "memory");
-    }
-#endif
-  }
-  template <int N>
-  __device__ __forceinline__ void issue_st(unsigned addr, const unsigned* r) const {
-#if defined(__CUDA_ARCH__)
-    if constexpr (N >= 8) {
-      asm volatile(
-          "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-          :: "r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-             "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
-      issue_st<N - 8>(addr + 16, r + 16);
-    } else if constexpr (N >= 4) {
-      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                   :: "r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
-      issue_st<N - 4>(addr + 8, r + 8);
-    } else if constexpr (N >= 2) {
-      asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
-                   :: "r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
-      issue_st<N - 2>(addr + 4, r + 4);
-    } else if constexpr (N == 1) {
-      asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" :: "r"(addr), "r"(r[0]), "r"(r[1]) : "memory");
-    }
-#endif
-  }
-  // v[0..N) <- doubles [k, k+N)
-  template <int N>
-  __host__ __device__ __forceinline__ void ldv(int k, double* v) const {
-    unsigned r[2 * N];
-#if defined(__CUDA_ARCH__)
-    issue_ld<N>(base + 2u * (unsigned)k, r);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < N; ++i) v[i] = __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]);
-#endif
-  }
-  // doubles [k, k+N) <- v[0..N); complete before returning (a later ldv of the same columns must see it)
-  template <int N>
-  __host__ __device__ __forceinline__ void stv(int k, const double* v) const {
-    unsigned r[2 * N];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-    for (int i = 0; i < N; ++i) { r[2 * i] = (unsigned)__double2loint(v[i]); r[2 * i + 1] = (unsigned)__double2hiint(v[i]); }
-    issue_st<N>(base + 2u * (unsigned)k, r);
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-#endif
-  }
-};
-#else
-struct TmStack {
-  double* p;
-  template <int N> void ldv(int k, double* v) const { for (int i = 0; i < N; ++i) v[i] = p[k + i]; }
-  template <int N> void stv(int k, const double* v) const { for (int i = 0; i < N; ++i) p[k + i] = v[i]; }
-};
-#endif
-
-// ---------------------------------------------------------------------------------------------------------
-// 3-vector helpers on scalars held in registers
-#define RBD_CROSS(ox, oy, oz, ax, ay, az, bx, by, bz) \
-  do {                                                \
-    ox = (ay) * (bz) - (az) * (by);                   \
-    oy = (az) * (bx) - (ax) * (bz);                   \
-    oz = (ax) * (by) - (ay) * (bx);                   \
-  } while (0)
-
-// sin and cos of a joint angle.  Branch-free on the common path so that the compiler can interleave it with the
-// surrounding spatial algebra (the library sincos() carries a Payne-Hanek slow path behind a branch and cost ~120
-// instructions per call in the r1b profile): three-term Cody-Waite reduction by pi/2 (exact products through FMA,
-// good to |x| ~ 1e5), then the fdlibm minimax kernels on [-pi/4, pi/4]; error <= ~1.5 ulp.  Larger or non-finite
-// arguments take the library path.
-RBD_HD void sincos_(double x, double* s, double* c) {
-  if (!(fabs(x) < 1.0e5)) {
-#if defined(__CUDA_ARCH__)
-    sincos(x, s, c);
-#else
-    *s = sin(x);
-    *c = cos(x);
-#endif
-    return;
-  }
-  const double q = rint(x * 0.6366197723675814);
-  double r = fma(-q, 1.5707963267948966, x);
-  r = fma(-q, 6.123233995736766e-17, r);
-  r = fma(-q, -1.4973849048591698e-33, r);
-  const double z = r * r;
-  double ps = 1.58969099521155010221e-10;
-  ps = fma(ps, z, -2.50507602534068634195e-08);
-  ps = fma(ps, z, 2.75573137070700676789e-06);
-  ps = fma(ps, z, -1.98412698298579493134e-04);
-  ps = fma(ps, z, 8.33333333332248946124e-03);
-  ps = fma(ps, z, -1.66666666666666324348e-01);
-  const double sr = fma(ps * z, r, r);
-  double pc = -1.13596475577881948265e-11;
-  pc = fma(pc, z, 2.08757232129817482790e-09);
-  pc = fma(pc, z, -2.75573143513906633035e-07);
-  pc = fma(pc, z, 2.48015872894767294178e-05);
-  pc = fma(pc, z, -1.38888888888741095749e-03);
-  pc = fma(pc, z, 4.16666666666666019037e-02);
-  const double cr = fma(pc * z, z, fma(-0.5, z, 1.0));
-  const int n = (int)q;
-  const double a = (n & 1) ? cr : sr;   // quadrant: sin takes cos(r) in odd quadrants
-  const double b = (n & 1) ? sr : cr;
-  *s = (n & 2) ? -a : a;
-  *c = ((n + 1) & 2) ? -b : b;
-}
-
-// O = A * B (3x3 row-major, O distinct from A and B)
-RBD_HD void mat3_mul(const double* A, const double* B, double* O) {
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) O[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
-  }
-}
-
-// rotate columns (ci, cj) of B by (c, s): col_i' = c col_i + s col_j ; col_j' = -s col_i + c col_j
-#define RBD_ROTCOLS(R, B, ck, ci, cj, c, s)        \
-  do {                                             \
-    _Pragma("unroll") for (int r_ = 0; r_ < 3; ++r_) { \
-      double bi_ = B[3 * r_ + ci], bj_ = B[3 * r_ + cj]; \
-      R[3 * r_ + ck] = B[3 * r_ + ck];             \
-      R[3 * r_ + ci] = c * bi_ + s * bj_;          \
-      R[3 * r_ + cj] = c * bj_ - s * bi_;          \
-    }                                              \
-  } while (0)
-
-// ---------------------------------------------------------------------------------------------------------
-// One forward-kinematics step: (R,p) of the parent joint in, (R,p) of joint `jn` out (world frame), plus the
-// world joint axis aw (1-dof joints).  q0/q1 are the joint's configuration values (angle | displacement |
-// cos,sin); the free-flyer reads its 7 values through `qf`.
-// pinocchio: liMi = jointPlacement * M_joint(q); oMi = oMi[parent] * liMi (JointJacobiansForwardStep).
-template <class QF>
-RBD_HD void fk_joint(const DevJoint& jn, double* R, double* p, double q0, double q1, const QF& qf, double* aw) {
-  double B[9], pn[3];
-  if (jn.pl_rot_identity) {  // uniform branch: most URDF joints have rpy = 0
-#pragma unroll
-    for (int k = 0; k < 9; ++k) B[k] = R[k];
-  } else {
-    mat3_mul(R, jn.pl, B);
-  }
-  pn[0] = R[0] * jn.pl[9] + R[1] * jn.pl[10] + R[2] * jn.pl[11] + p[0];
-  pn[1] = R[3] * jn.pl[9] + R[4] * jn.pl[10] + R[5] * jn.pl[11] + p[1];
-  pn[2] = R[6] * jn.pl[9] + R[7] * jn.pl[10] + R[8] * jn.pl[11] + p[2];
-  const int t = jn.type;
-  double c = q0, s = q1;
-  if (t >= JT_RX && t <= JT_RU) sincos_(q0, &s, &c);
-  switch (t) {
-    case JT_RX: case JT_RUBX:
-      RBD_ROTCOLS(R, B, 0, 1, 2, c, s);
-      aw[0] = B[0]; aw[1] = B[3]; aw[2] = B[6];
-      break;
-    case JT_RY: case JT_RUBY:
-      RBD_ROTCOLS(R, B, 1, 2, 0, c, s);
-      aw[0] = B[1]; aw[1] = B[4]; aw[2] = B[7];
-      break;
-    case JT_RZ: case JT_RUBZ:
-      RBD_ROTCOLS(R, B, 2, 0, 1, c, s);
-      aw[0] = B[2]; aw[1] = B[5]; aw[2] = B[8];
-      break;
-    case JT_RU: case JT_RUBU: {
-      const double ax = jn.axis[0], ay = jn.axis[1], az = jn.axis[2];
-      const double c1 = 1.0 - c, sx = s * ax, sy = s * ay, sz = s * az;
-      double Rj[9];
-      Rj[0] = c1 * ax * ax + c;  Rj[1] = c1 * ax * ay - sz; Rj[2] = c1 * ax * az + sy;
-      Rj[3] = c1 * ay * ax + sz; Rj[4] = c1 * ay * ay + c;  Rj[5] = c1 * ay * az - sx;
-      Rj[6] = c1 * az * ax - sy; Rj[7] = c1 * az * ay + sx; Rj[8] = c1 * az * az + c;
-      mat3_mul(B, Rj, R);
-      aw[0] = B[0] * ax + B[1] * ay + B[2] * az;
-      aw[1] = B[3] * ax + B[4] * ay + B[5] * az;
-      aw[2] = B[6] * ax + B[7] * ay + B[8] * az;
-    } break;
-    case JT_PX: case JT_PY: case JT_PZ: case JT_PU: {
-      const double ax = jn.axis[0], ay = jn.axis[1], az = jn.axis[2];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) R[k] = B[k];
-      aw[0] = B[0] * ax + B[1] * ay + B[2] * az;
-      aw[1] = B[3] * ax + B[4] * ay + B[5] * az;
-      aw[2] = B[6] * ax + B[7] * ay + B[8] * az;
-      pn[0] += q0 * aw[0]; pn[1] += q0 * aw[1]; pn[2] += q0 * aw[2];
-    } break;
-    case JT_FF: {
-      const int o = jn.idx_q;
-      const double px = qf.ld(o), py = qf.ld(o + 1), pz = qf.ld(o + 2);
-      const double x = qf.ld(o + 3), y = qf.ld(o + 4), z = qf.ld(o + 5), w = qf.ld(o + 6);
-      // Eigen toRotationMatrix on raw coefficients (no normalisation), as pinocchio's JointModelFreeFlyer::calc
-      const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
-      const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x;
-      const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
-      double Rq[9];
-      Rq[0] = 1 - (tyy + tzz); Rq[1] = txy - twz;       Rq[2] = txz + twy;
-      Rq[3] = txy + twz;       Rq[4] = 1 - (txx + tzz); Rq[5] = tyz - twx;
-      Rq[6] = txz - twy;       Rq[7] = tyz + twx;       Rq[8] = 1 - (txx + tyy);
-      mat3_mul(B, Rq, R);
-      pn[0] += B[0] * px + B[1] * py + B[2] * pz;
-      pn[1] += B[3] * px + B[4] * py + B[5] * pz;
-      pn[2] += B[6] * px + B[7] * py + B[8] * pz;
-      aw[0] = aw[1] = aw[2] = 0.0;
-    } break;
-    default:
-#pragma unroll
-      for (int k = 0; k < 9; ++k) R[k] = B[k];
-      aw[0] = aw[1] = aw[2] = 0.0;
-      break;
-  }
-  p[0] = pn[0]; p[1] = pn[1]; p[2] = pn[2];
-}
-
-RBD_HD bool is_prismatic(int t) { return t >= JT_PX && t <= JT_PU; }
-RBD_HD bool is_unbounded(int t) { return t >= JT_RUBX && t <= JT_RUBU; }
-
-// world-frame motion subspace column of a 1-dof joint: revolute [p x a ; a], prismatic [a ; 0]
-RBD_HD void subspace_1dof(int type, const double* p, const double* aw, double* A) {
-  if (is_prismatic(type)) {
-    A[0] = aw[0]; A[1] = aw[1]; A[2] = aw[2];
-    A[3] = A[4] = A[5] = 0.0;
-  } else {
-    RBD_CROSS(A[0], A[1], A[2], p[0], p[1], p[2], aw[0], aw[1], aw[2]);
-    A[3] = aw[0]; A[4] = aw[1]; A[5] = aw[2];
-  }
-}
-// column e (0..5) of the free-flyer subspace oMi.act(I6): e<3 -> [R e ; 0], e>=3 -> [p x R e ; R e]
-#define RBD_FF_COL(A, R, p, e)                                                        \
-  do {                                                                                \
-    const double cx_ = R[(e) % 3], cy_ = R[3 + (e) % 3], cz_ = R[6 + (e) % 3];        \
-    if ((e) < 3) {                                                                    \
-      A[0] = cx_; A[1] = cy_; A[2] = cz_; A[3] = A[4] = A[5] = 0.0;                   \
-    } else {                                                                          \
-      RBD_CROSS(A[0], A[1], A[2], p[0], p[1], p[2], cx_, cy_, cz_);                   \
-      A[3] = cx_; A[4] = cy_; A[5] = cz_;                                             \
-    }                                                                                 \
-  } while (0)
-
-// free-flyer rows of (column F): A_ff^T F = [R^T Fl ; R^T (Fw - p x Fl)]
-RBD_HD void ff_rows(const double* R, const double* p, const double* F, double* out6) {
-  double tx, ty, tz;
-  RBD_CROSS(tx, ty, tz, p[0], p[1], p[2], F[0], F[1], F[2]);
-  tx = F[3] - tx; ty = F[4] - ty; tz = F[5] - tz;
-#pragma unroll
-  for (int e = 0; e < 3; ++e) {
-    out6[e] = R[e] * F[0] + R[3 + e] * F[1] + R[6 + e] * F[2];
-    out6[3 + e] = R[e] * tx + R[3 + e] * ty + R[6 + e] * tz;
-  }
-}
-
-// free-flyer joint motion given in the joint (body) frame, 6 fields of `fld` from `o`: world = oMi.act(.)
-template <class FLD>
-RBD_HD void ff_act(const double* R, const double* p, const FLD& fld, int o, double* out) {
-  const double l0 = fld.ld(o), l1 = fld.ld(o + 1), l2 = fld.ld(o + 2);
-  const double w0 = fld.ld(o + 3), w1 = fld.ld(o + 4), w2 = fld.ld(o + 5);
-  out[3] = R[0] * w0 + R[1] * w1 + R[2] * w2;
-  out[4] = R[3] * w0 + R[4] * w1 + R[5] * w2;
-  out[5] = R[6] * w0 + R[7] * w1 + R[8] * w2;
-  double tx, ty, tz;
-  RBD_CROSS(tx, ty, tz, p[0], p[1], p[2], out[3], out[4], out[5]);
-  out[0] = R[0] * l0 + R[1] * l1 + R[2] * l2 + tx;
-  out[1] = R[3] * l0 + R[4] * l1 + R[5] * l2 + ty;
-  out[2] = R[6] * l0 + R[7] * l1 + R[8] * l2 + tz;
-}
-
-// world spatial inertia about the world origin: Y = (m, h = m c_w, I_O (xx,xy,yy,xz,yz,zz))
-RBD_HD void inertia_world(const DevJoint& jn, const double* R, const double* p, double* Y) {
-  const double m = jn.Y[0];
-  const double cx = R[0] * jn.Y[1] + R[1] * jn.Y[2] + R[2] * jn.Y[3] + p[0];
-  const double cy = R[3] * jn.Y[1] + R[4] * jn.Y[2] + R[5] * jn.Y[3] + p[1];
-  const double cz = R[6] * jn.Y[1] + R[7] * jn.Y[2] + R[8] * jn.Y[3] + p[2];
-  // T = R * Ic
-  const double ixx = jn.Y[4], ixy = jn.Y[5], iyy = jn.Y[6], ixz = jn.Y[7], iyz = jn.Y[8], izz = jn.Y[9];
-  double T[9];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    T[3 * i + 0] = R[3 * i] * ixx + R[3 * i + 1] * ixy + R[3 * i + 2] * ixz;
-    T[3 * i + 1] = R[3 * i] * ixy + R[3 * i + 1] * iyy + R[3 * i + 2] * iyz;
-    T[3 * i + 2] = R[3 * i] * ixz + R[3 * i + 1] * iyz + R[3 * i + 2] * izz;
-  }
-  const double mcx = m * cx, mcy = m * cy, mcz = m * cz;
-  Y[0] = m; Y[1] = mcx; Y[2] = mcy; Y[3] = mcz;
-  // I_O = R Ic R^T + m (|c|^2 I - c c^T)
-  Y[4] = T[0] * R[0] + T[1] * R[1] + T[2] * R[2] + (mcy * cy + mcz * cz);      // xx
-  Y[5] = T[0] * R[3] + T[1] * R[4] + T[2] * R[5] - mcx * cy;                   // xy
-  Y[6] = T[3] * R[3] + T[4] * R[4] + T[5] * R[5] + (mcx * cx + mcz * cz);      // yy
-  Y[7] = T[0] * R[6] + T[1] * R[7] + T[2] * R[8] - mcx * cz;                   // xz
-  Y[8] = T[3] * R[6] + T[4] * R[7] + T[5] * R[8] - mcy * cz;                   // yz
-  Y[9] = T[6] * R[6] + T[7] * R[7] + T[8] * R[8] + (mcx * cx + mcy * cy);      // zz
-}
-
-// F = Y * motion (both about the world origin): lin = m v + w x h ; ang = I_O w + h x v
-RBD_HD void inertia_mul(const double* Y, const double* mo, double* F) {
-  double ax, ay, az, bx, by, bz;
-  RBD_CROSS(ax, ay, az, mo[3], mo[4], mo[5], Y[1], Y[2], Y[3]);
-  RBD_CROSS(bx, by, bz, Y[1], Y[2], Y[3], mo[0], mo[1], mo[2]);
-  F[0] = Y[0] * mo[0] + ax;
-  F[1] = Y[0] * mo[1] + ay;
-  F[2] = Y[0] * mo[2] + az;
-  F[3] = Y[4] * mo[3] + Y[5] * mo[4] + Y[7] * mo[5] + bx;
-  F[4] = Y[5] * mo[3] + Y[6] * mo[4] + Y[8] * mo[5] + by;
-  F[5] = Y[7] * mo[3] + Y[8] * mo[4] + Y[9] * mo[5] + bz;
-}
-
-RBD_HD double dot6(const double* a, const double* b) {
-  return (a[0] * b[0] + a[1] * b[1] + a[2] * b[2]) + (a[3] * b[3] + a[4] * b[4] + a[5] * b[5]);
-}
-
-// Eigen 3.4 Quaternion(Matrix3) branch order (reference Conversions.h:60), output [x y z w] (Conversions.h:36)
-RBD_HD void rot_to_quat(const double* R, double* q) {
-  double t = R[0] + R[4] + R[8];
-  if (t > 0.0) {
-    t = sqrt(t + 1.0);
-    q[3] = 0.5 * t;
-    t = 0.5 / t;
-    q[0] = (R[7] - R[5]) * t; q[1] = (R[2] - R[6]) * t; q[2] = (R[3] - R[1]) * t;
-  } else {
-    // i = argmax diag with Eigen's tie order; written branch-wise to keep R in registers
-    if (!(R[4] > R[0]) && !(R[8] > R[0])) {        // i=0, j=1, k=2
-      t = sqrt(R[0] - R[4] - R[8] + 1.0);
-      q[0] = 0.5 * t; t = 0.5 / t;
-      q[3] = (R[7] - R[5]) * t; q[1] = (R[3] + R[1]) * t; q[2] = (R[6] + R[2]) * t;
-    } else if ((R[4] > R[0]) && !(R[8] > R[4])) {  // i=1, j=2, k=0
-      t = sqrt(R[4] - R[8] - R[0] + 1.0);
-      q[1] = 0.5 * t; t = 0.5 / t;
-      q[3] = (R[2] - R[6]) * t; q[2] = (R[7] + R[5]) * t; q[0] = (R[1] + R[3]) * t;
-    } else {                                       // i=2, j=0, k=1
-      t = sqrt(R[8] - R[0] - R[4] + 1.0);
-      q[2] = 0.5 * t; t = 0.5 / t;
-      q[3] = (R[3] - R[1]) * t; q[0] = (R[2] + R[6]) * t; q[1] = (R[5] + R[7]) * t;
-    }
-  }
-}
-
-// =========================================================================================================
-// Fused evaluation: FK + world joint Jacobian (+ CRBA) (+ RNEA)                      [kernel K7 / K5 / K6]
-// =========================================================================================================
-template <int TILE>
-struct EvalIOT {
-  FieldT<TILE> q, v, a;          // inputs: nq, nv, nv fields
-  FieldT<TILE> oMi, J, M, tau;   // outputs (p == nullptr -> not written)
-};
-using EvalIO = EvalIOT<0>;
-
-// ---- sweep-state storage (EvalPlan): vector accessors over the two spaces ----------------------------------------
-template <int N>
-RBD_HD void s_ldv(const Stack& S, int k, double* v) {
-#pragma unroll
-  for (int e = 0; e < N; ++e) v[e] = S.ld(k + e);
-}
-template <int N>
-RBD_HD void s_stv(const Stack& S, int k, const double* v) {
-#pragma unroll
-  for (int e = 0; e < N; ++e) S.st(k + e, v[e]);
-}
-// load / store / accumulate N doubles at offset k of shared (tm == false) or tensor memory (tm == true)
-template <int N>
-RBD_HD void x_ldv(bool tm, const Stack& S, const TmStack& T, int k, double* v) {
-  if (tm) T.ldv<N>(k, v); else s_ldv<N>(S, k, v);
-}
-template <int N>
-RBD_HD void x_stv(bool tm, const Stack& S, const TmStack& T, int k, const double* v) {
-  if (tm) T.stv<N>(k, v); else s_stv<N>(S, k, v);
-}
-template <int N>
-RBD_HD void x_addv(bool tm, const Stack& S, const TmStack& T, int k, const double* v) {
-  if (tm) {
-    double t[N];
-    T.ldv<N>(k, t);
-#pragma unroll
-    for (int e = 0; e < N; ++e) t[e] += v[e];
-    T.stv<N>(k, t);
-  } else {
-#pragma unroll
-    for (int e = 0; e < N; ++e) S.add(k + e, v[e]);
-  }
-}
-
-// ColProg table of the staged eval blob (rbd_model_build.h: build_eval_blob): `m` IS the start of the blob.
-RBD_HD const int* col_prog(const DevModel& m) {
-  return reinterpret_cast<const int*>(reinterpret_cast<const unsigned long long*>(&m) + m.prog_words_off);
-}
-
-// Rows of packed column `base` above the joint that owns it, driven by the joint's column program: one entry per
-// ancestor dof (A_anc . F) — independent iterations, so the loads of several ancestors are in flight together —
-// then the zero segments (dofs of joints off the ancestor chain).
-template <int TILE>
-RBD_HD void column_rows(const DevModel& m, const DevJoint& jn, int base, const double* F, const Stack& S,
-                        const FieldT<TILE>& M) {
-  const int* pr = col_prog(m) + jn.prog_off;
-  const int na = jn.depth - 1;
-#if RBD_PTR_COL
-  double* const pc = M.at(base);
-#pragma unroll 2
-  for (int d = 0; d < na; ++d) {
-    const int e = pr[d];
-    const int sa = RBD_PROG_OFFA(e);
-    double* const pa = pc + M.step(RBD_PROG_ROW(e));
-    if (RBD_PROG_FF(e)) {
-      double Rq[12], p6[6];
-      s_ldv<12>(S, sa, Rq);
-      ff_rows(Rq, Rq + 9, F, p6);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) M.st_at(pa, k, p6[k]);
-    } else {
-      double Aa[6];
-      s_ldv<6>(S, sa, Aa);
-      *pa = dot6(Aa, F);
-    }
-  }
-  for (int z = 0; z < jn.nzseg; ++z) {
-    const int e = pr[na + z];
-    double* pz = pc + M.step(RBD_PROG_ROW(e));
-    int len = RBD_PROG_ZLEN(e);
-    for (; len >= 4; len -= 4, pz += M.step(4)) {
-      M.st_at(pz, 0, 0.0); M.st_at(pz, 1, 0.0); M.st_at(pz, 2, 0.0); M.st_at(pz, 3, 0.0);
-    }
-    for (; len > 0; --len, pz += M.step(1)) *pz = 0.0;
-  }
-#else
-  RBD_PRAGMA(unroll RBD_UNROLL_ANC)
-  for (int d = 0; d < na; ++d) {
-    const int e = pr[d];
-    const int sa = RBD_PROG_OFFA(e);
-    if (RBD_PROG_FF(e)) {
-      double Rq[12], p6[6];
-      s_ldv<12>(S, sa, Rq);
-      ff_rows(Rq, Rq + 9, F, p6);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) M.st(base + RBD_PROG_ROW(e) + k, p6[k]);
-    } else {
-      double Aa[6];
-      s_ldv<6>(S, sa, Aa);
-      M.st(base + RBD_PROG_ROW(e), dot6(Aa, F));
-    }
-  }
-  for (int z = 0; z < jn.nzseg; ++z) {
-    const int e = pr[na + z];
-    const int r0 = base + RBD_PROG_ROW(e), len = RBD_PROG_ZLEN(e);
-    RBD_PRAGMA(unroll RBD_UNROLL_ZERO)
-    for (int r = 0; r < len; ++r) M.st(r0 + r, 0.0);
-  }
-#endif
-}
-
-// Everything joint k owes once its subtree is complete: tau_k = A_k^T f_k and its column(s) of M.
-// A = world subspace column (6) of a 1-dof joint, or R|p (12) of a free-flyer; f = total subtree force;
-// Y = composite inertia of the subtree — all three in registers.
-template <bool DO_M, bool DO_TAU, int TILE>
-RBD_HD void emit_joint(const DevModel& m, int k, const double* A, const double* f, const double* Y, const Stack& S,
-                       const EvalIOT<TILE>& io) {
-  const DevJoint& jn = m.joint[k];
-  if (jn.type != JT_FF) {
-    if (DO_TAU) io.tau.st(jn.idx_v, dot6(A, f));
-    if (DO_M) {
-      double F[6];
-      inertia_mul(Y, A, F);
-      const int col = jn.idx_v;
-      const int base = col * (col + 1) / 2;
-      *io.M.at(base + col) = dot6(A, F);
-      column_rows(m, jn, base, F, S, io.M);
-    }
-  } else {
-    // a real loop (not unrolled): runs once per free-flyer, and the kernel is instruction-cache sensitive
-    RBD_PRAGMA(unroll RBD_UNROLL_FF)
-    for (int cc = 0; cc < 6; ++cc) {
-      double Ac[6];
-      RBD_FF_COL(Ac, A, (A + 9), cc);
-      if (DO_TAU) io.tau.st(jn.idx_v + cc, dot6(Ac, f));
-      if (DO_M) {
-        double F[6], o6[6];
-        inertia_mul(Y, Ac, F);
-        const int col = jn.idx_v + cc;
-        const int base = col * (col + 1) / 2;
-        ff_rows(A, A + 9, F, o6);
-        double* const pd = io.M.at(base + jn.idx_v);
-#pragma unroll
-        for (int e = 0; e < 6; ++e)
-          if (e <= cc) io.M.st_at(pd, e, o6[e]);
-        column_rows(m, jn, base, F, S, io.M);
-      }
-    }
-  }
-}
-
-// One instance, one sweep.  S = this thread's shared-memory stack, T = its tensor-memory slice (m.plan says what
-// lives where).  Control flow depends on the model only, so all lanes of a warp stay converged.
-template <bool DO_M, bool DO_TAU, int TILE>
-RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stack& S, const TmStack& T) {
-  constexpr bool NEED_STACK = DO_M || DO_TAU;
-  const int nj = m.njoints;
-  const int fbase = m.plan.fbase, fsplit = m.plan.fsplit, ftbase = m.plan.ftbase, ybase = m.plan.ybase;
-  const int ysplit = m.plan.ysplit, ytbase = m.plan.ytbase;
-  // Y- and f-stack level -> (space, offset): levels below the split in shared memory, the rest in tensor memory
-#define RBD_Y_TM(lvl) ((lvl) >= ysplit)
-#define RBD_Y_OFF(lvl) ((lvl) >= ysplit ? ytbase + 9 * ((lvl)-ysplit) : ybase + 9 * (lvl))
-#define RBD_F_TM(lvl) ((lvl) >= fsplit)
-#define RBD_F_OFF(lvl) ((lvl) >= fsplit ? ftbase + 6 * ((lvl)-fsplit) : fbase + 6 * (lvl))
-  double R[9], p[3], vel[6], acc[6];
-#define RBD_RESET_ROOT()                                                   \
-  do {                                                                     \
-    R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1; \
-    p[0] = p[1] = p[2] = 0;                                                \
-    _Pragma("unroll") for (int e_ = 0; e_ < 6; ++e_) { vel[e_] = 0; acc[e_] = 0; } \
-    acc[0] = -m.gravity[0]; acc[1] = -m.gravity[1]; acc[2] = -m.gravity[2]; \
-  } while (0)
-  RBD_RESET_ROOT();
-
-  // one-joint-ahead prefetch of the 1-dof inputs (hides the global-load latency behind the previous joint)
-  double q0n = 0, q1n = 0, vn = 0, an = 0;
-  if (nj > 1 && m.joint[1].type != JT_FF) {
-    const DevJoint& j1 = m.joint[1];
-    q0n = io.q.ld(j1.idx_q);
-    if (is_unbounded(j1.type)) q1n = io.q.ld(j1.idx_q + 1);
-    if (DO_TAU) { vn = io.v.ld(j1.idx_v); an = io.a.ld(j1.idx_v); }
-  }
-
-  // State of the joint the sweep returns to when a new branch starts below it: R|p (+ v|a).  With a stack
-  // (CRBA / RNEA) this runs at the LEAF that ends the previous branch, BEFORE its unwind — R, p, vel, acc are dead
-  // during the unwind, so the loads (tensor memory, the oMi re-read, the input re-reads) overlap it instead of
-  // stalling the next joint (r1f: the return block was the top stall site, 7.7 % of samples).
-  auto restore = [&](int par) {
-    if (par == 0) {
-      RBD_RESET_ROOT();
-    } else {
-      const DevJoint& jb = m.joint[par];
-      const bool btm = (jb.boff & RBD_BOFF_TMEM) != 0;
-      int b = jb.boff & RBD_BOFF_MASK;
-      double Rp[12];
-      if (NEED_STACK && jb.type == JT_FF) {
-        s_ldv<12>(S, jb.offA, Rp);  // a free-flyer's A record is its R|p
-      } else if (jb.boff & RBD_BOFF_RPOMI) {
-        const int o = 12 * (par - 1);  // this thread wrote oMi[par] earlier in the sweep
-#pragma unroll
-        for (int e = 0; e < 12; ++e) Rp[e] = io.oMi.ld(o + e);
-      } else {
-        x_ldv<12>(btm, S, T, b, Rp);
-        b += 12;
-      }
-#pragma unroll
-      for (int e = 0; e < 9; ++e) R[e] = Rp[e];
-#pragma unroll
-      for (int e = 0; e < 3; ++e) p[e] = Rp[9 + e];
-      if (DO_TAU) {
-        if (!(jb.boff & RBD_BOFF_NOVA)) {
-          double va[12];
-          x_ldv<12>(btm, S, T, b, va);
-#pragma unroll
-          for (int e = 0; e < 6; ++e) { vel[e] = va[e]; acc[e] = va[6 + e]; }
-        } else {
-          // branch joint attached to the universe: v = A qd, a = -g + A qdd (v x vJ = 0), nothing was saved
-          double vj[6], aj[6];
-          if (jb.type == JT_FF) {
-            ff_act(R, p, io.v, jb.idx_v, vj);
-            ff_act(R, p, io.a, jb.idx_v, aj);
-          } else {
-            double Ab[6];
-            s_ldv<6>(S, jb.offA, Ab);
-            const double qd_b = io.v.ld(jb.idx_v), qdd_b = io.a.ld(jb.idx_v);
-#pragma unroll
-            for (int e = 0; e < 6; ++e) { vj[e] = Ab[e] * qd_b; aj[e] = Ab[e] * qdd_b; }
-          }
-#pragma unroll
-          for (int e = 0; e < 6; ++e) { vel[e] = vj[e]; acc[e] = aj[e]; }
-          acc[0] -= m.gravity[0]; acc[1] -= m.gravity[1]; acc[2] -= m.gravity[2];
-        }
-      }
-    }
-  };
-
-  for (int i = 1; i < nj; ++i) {
-    const DevJoint& jn = m.joint[i];
-    const int par = jn.parent;
-    if (!NEED_STACK && par != i - 1) restore(par);  // FK-only variant: no unwind to hide behind
-    const double q0 = q0n, q1 = q1n, qd = vn, qdd = an;
-    const int nxt_par = (i + 1 < nj) ? m.joint[i + 1].parent : 0;
-    if (i + 1 < nj && m.joint[i + 1].type != JT_FF) {
-      const DevJoint& jx = m.joint[i + 1];
-      q0n = io.q.ld(jx.idx_q);
-      if (is_unbounded(jx.type)) q1n = io.q.ld(jx.idx_q + 1);
-      if (DO_TAU) { vn = io.v.ld(jx.idx_v); an = io.a.ld(jx.idx_v); }
-    }
-
-    double aw[3];
-    fk_joint(jn, R, p, q0, q1, io.q, aw);
-    if (io.oMi.ok()) {
-#if RBD_PTR_OMIJ
-      double* const po = io.oMi.at(12 * (i - 1));
-#pragma unroll
-      for (int e = 0; e < 9; ++e) io.oMi.st_at(po, e, R[e]);
-#pragma unroll
-      for (int e = 0; e < 3; ++e) io.oMi.st_at(po, 9 + e, p[e]);
-#else
-      const int o = 12 * (i - 1);
-#pragma unroll
-      for (int e = 0; e < 9; ++e) io.oMi.st(o + e, R[e]);
-#pragma unroll
-      for (int e = 0; e < 3; ++e) io.oMi.st(o + 9 + e, p[e]);
-#endif
-    }
-    // Ak: world subspace column (1-dof) or R|p (free-flyer) — what the A-stack keeps for the CRBA/RNEA projections
-    double Ak[12], fk[6], Yk[10];
-    if (jn.type != JT_FF) {
-      subspace_1dof(jn.type, p, aw, Ak);
-      if (io.J.ok()) {
-#if RBD_PTR_OMIJ
-        double* const pj = io.J.at(6 * jn.idx_v);
-#pragma unroll
-        for (int e = 0; e < 6; ++e) io.J.st_at(pj, e, Ak[e]);
-#else
-#pragma unroll
-        for (int e = 0; e < 6; ++e) io.J.st(6 * jn.idx_v + e, Ak[e]);
-#endif
-      }
-      if (DO_TAU) {
-        double vj[6], cr[6];
-#pragma unroll
-        for (int e = 0; e < 6; ++e) { vj[e] = Ak[e] * qd; vel[e] += vj[e]; }
-        // a_i = a_parent + A qdd + v_i x vJ   (joint bias c = 0 for all supported joints)
-        RBD_CROSS(cr[0], cr[1], cr[2], vel[3], vel[4], vel[5], vj[0], vj[1], vj[2]);
-        double tx, ty, tz;
-        RBD_CROSS(tx, ty, tz, vel[0], vel[1], vel[2], vj[3], vj[4], vj[5]);
-        cr[0] += tx; cr[1] += ty; cr[2] += tz;
-        RBD_CROSS(cr[3], cr[4], cr[5], vel[3], vel[4], vel[5], vj[3], vj[4], vj[5]);
-#pragma unroll
-        for (int e = 0; e < 6; ++e) acc[e] += Ak[e] * qdd + cr[e];
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < 9; ++e) Ak[e] = R[e];
-#pragma unroll
-      for (int e = 0; e < 3; ++e) Ak[9 + e] = p[e];
-      if (io.J.ok()) {
-        double* const pj = io.J.at(6 * jn.idx_v);
-#pragma unroll
-        for (int cc = 0; cc < 6; ++cc) {
-          double A[6];
-          RBD_FF_COL(A, R, p, cc);
-#pragma unroll
-          for (int e = 0; e < 6; ++e) io.J.st_at(pj, 6 * cc + e, A[e]);
-        }
-      }
-      if (DO_TAU) {
-        // joint velocity / acceleration given in the joint (body) frame: world = oMi.act(.)
-        double vj[6], aj[6], cr[6];
-        ff_act(R, p, io.v, jn.idx_v, vj);
-        ff_act(R, p, io.a, jn.idx_v, aj);
-#pragma unroll
-        for (int e = 0; e < 6; ++e) vel[e] += vj[e];
-        RBD_CROSS(cr[0], cr[1], cr[2], vel[3], vel[4], vel[5], vj[0], vj[1], vj[2]);
-        double tx, ty, tz;
-        RBD_CROSS(tx, ty, tz, vel[0], vel[1], vel[2], vj[3], vj[4], vj[5]);
-        cr[0] += tx; cr[1] += ty; cr[2] += tz;
-        RBD_CROSS(cr[3], cr[4], cr[5], vel[3], vel[4], vel[5], vj[3], vj[4], vj[5]);
-#pragma unroll
-        for (int e = 0; e < 6; ++e) acc[e] += aj[e] + cr[e];
-      }
-    }
-    if (NEED_STACK) {
-      inertia_world(jn, R, p, Yk);
-      if (DO_TAU) {
-        // f = Y a + v x* (Y v)
-        double h[6];
-        inertia_mul(Yk, vel, h);
-        inertia_mul(Yk, acc, fk);
-        double tx, ty, tz;
-        RBD_CROSS(tx, ty, tz, vel[3], vel[4], vel[5], h[0], h[1], h[2]);
-        fk[0] += tx; fk[1] += ty; fk[2] += tz;
-        RBD_CROSS(tx, ty, tz, vel[3], vel[4], vel[5], h[3], h[4], h[5]);
-        fk[3] += tx; fk[4] += ty; fk[5] += tz;
-        RBD_CROSS(tx, ty, tz, vel[0], vel[1], vel[2], h[0], h[1], h[2]);
-        fk[3] += tx; fk[4] += ty; fk[5] += tz;
-      }
-    }
-    if (nxt_par == i) {
-      // joint i has children: park A | f | Y at its depth level; its subtree sums accumulate there
-      if (NEED_STACK) {
-        const int lvl = jn.depth - 1;
-        if (jn.type != JT_FF) s_stv<6>(S, jn.offA, Ak); else s_stv<12>(S, jn.offA, Ak);
-        if (DO_TAU) x_stv<6>(RBD_F_TM(lvl), S, T, RBD_F_OFF(lvl), fk);
-        if (DO_M) x_stv<9>(RBD_Y_TM(lvl), S, T, RBD_Y_OFF(lvl), Yk + 1);
-      }
-      if (jn.nchild >= 2) {
-        const bool btm = (jn.boff & RBD_BOFF_TMEM) != 0;
-        int b = jn.boff & RBD_BOFF_MASK;
-        if (!(NEED_STACK && jn.type == JT_FF) && !(jn.boff & RBD_BOFF_RPOMI)) {
-          double Rp[12];
-#pragma unroll
-          for (int e = 0; e < 9; ++e) Rp[e] = R[e];
-#pragma unroll
-          for (int e = 0; e < 3; ++e) Rp[9 + e] = p[e];
-          x_stv<12>(btm, S, T, b, Rp);
-          b += 12;
-        }
-        if (DO_TAU && !(jn.boff & RBD_BOFF_NOVA)) {
-          double va[12];
-#pragma unroll
-          for (int e = 0; e < 6; ++e) { va[e] = vel[e]; va[6 + e] = acc[e]; }
-          x_stv<12>(btm, S, T, b, va);
-        }
-      }
-    } else if (NEED_STACK) {
-      // joint i is a leaf: its subtree is complete.  Emit it straight from registers, then unwind: every
-      // ancestor whose last child this was is complete too; its sums continue in registers up the chain and
-      // are written back only at the joint that still has children to come (nxt_par).
-      if (i + 1 < nj) restore(nxt_par);  // early: see `restore`
-      int k = i;
-      while (true) {
-        emit_joint<DO_M, DO_TAU>(m, k, Ak, fk, Yk, S, io);
-        const int pk = m.joint[k].parent;
-        if (pk == 0) break;
-        const DevJoint& jp = m.joint[pk];
-        const int lvl = jp.depth - 1;
-        if (pk == nxt_par) {
-          if (DO_TAU) x_addv<6>(RBD_F_TM(lvl), S, T, RBD_F_OFF(lvl), fk);
-          if (DO_M) x_addv<9>(RBD_Y_TM(lvl), S, T, RBD_Y_OFF(lvl), Yk + 1);
-          break;
-        }
-        if (DO_TAU) {
-          double fp[6];
-          x_ldv<6>(RBD_F_TM(lvl), S, T, RBD_F_OFF(lvl), fp);
-#pragma unroll
-          for (int e = 0; e < 6; ++e) fk[e] += fp[e];
-        }
-        if (DO_M) {
-          double Yp[9];
-          x_ldv<9>(RBD_Y_TM(lvl), S, T, RBD_Y_OFF(lvl), Yp);
-#pragma unroll
-          for (int e = 0; e < 9; ++e) Yk[1 + e] += Yp[e];
-          Yk[0] = jp.msub;  // composite mass of the subtree: model constant
-        }
-        if (jp.type != JT_FF) s_ldv<6>(S, jp.offA, Ak); else s_ldv<12>(S, jp.offA, Ak);
-        k = pk;
-      }
-    }
-  }
-#undef RBD_RESET_ROOT
-#undef RBD_F_TM
-#undef RBD_F_OFF
-#undef RBD_Y_TM
-#undef RBD_Y_OFF
-}
-
-// =========================================================================================================
-// Mapping path
-// =========================================================================================================
-// one-joint-ahead prefetch of a 1-dof joint's configuration value(s) in the mapping sweeps (`q`, `m`, `nj` in scope)
-#define RBD_Q_PREFETCH(idx)                                              \
-  do {                                                                   \
-    if ((idx) < nj) {                                                    \
-      const DevJoint& jx_ = m.joint[idx];                                \
-      if (jx_.type != JT_FF) {                                           \
-        q0n = q.ld(jx_.idx_q);                                           \
-        if (is_unbounded(jx_.type)) q1n = q.ld(jx_.idx_q + 1);           \
-      }                                                                  \
-    }                                                                    \
-  } while (0)
-
-// Full configuration seen through the SOFA split (root pose | joint dofs): KCM.inl:353-363.
-template <class FLD>
-struct SplitQT {
-  FLD root, joints;
-  int off;  // 7 (or 6 for velocities) when a root is supplied, else 0
-  RBD_HD double ld(int k) const { return k < off ? root.ld(k) : joints.ld(k - off); }
-};
-using SplitQ = SplitQT<Field>;
-
-// apply: q -> [p, quat] of every mapped output; also copies the assembled q into the workspace cache.
-template <class QF, class QC, class OUT>
-RBD_HD void apply_instance(const DevModel& m, const DevTables& tb, const QF& q, const QC& qcache,
-                           const OUT& out, const Stack& S) {
-  const int nj = m.njoints;
-  if (qcache.ok())
-    for (int k = 0; k < m.nq; ++k) qcache.st(k, q.ld(k));
-  // outputs attached to the universe (kSkipUniverse = 0, reference Types.h:32): constant poses
-  {
-    const DevJoint& j0 = m.joint[0];
-    for (int o = j0.out_begin; o < j0.out_end; ++o) {
-      const double* pl = tb.sorted_pl + 12 * o;
-      const int k = tb.sorted_k[o];
-      double qt[4];
-      rot_to_quat(pl, qt);
-      double* const po = out.at(7 * k);
-      out.st_at(po, 0, pl[9]); out.st_at(po, 1, pl[10]); out.st_at(po, 2, pl[11]);
-      out.st_at(po, 3, qt[0]); out.st_at(po, 4, qt[1]); out.st_at(po, 5, qt[2]); out.st_at(po, 6, qt[3]);
-    }
-  }
-  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
-  double q0n = 0.0, q1n = 0.0;
-  RBD_Q_PREFETCH(1);
-  for (int i = 1; i < nj; ++i) {
-    const DevJoint& jn = m.joint[i];
-    const int par = jn.parent;
-    if (par != i - 1) {
-      if (par == 0) {
-        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
-        p[0] = p[1] = p[2] = 0;
-      } else {
-        const int b = m.joint[par].bidx * RBD_BRANCH_FK;
-#pragma unroll
-        for (int e = 0; e < 9; ++e) R[e] = S.ld(b + e);
-#pragma unroll
-        for (int e = 0; e < 3; ++e) p[e] = S.ld(b + 9 + e);
-      }
-    }
-    double aw[3];
-    const double q0 = q0n, q1 = q1n;
-    RBD_Q_PREFETCH(i + 1);  // next joint's angle: its HBM latency hides behind this joint's work
-    fk_joint(jn, R, p, q0, q1, q, aw);
-    // outputs whose placement has an identity rotation share the joint's rotation: convert it once
-    double qj[4];
-    bool have_qj = false;
-    for (int o = jn.out_begin; o < jn.out_end; ++o) {
-      // updateFramePlacements: oMf = oMi * placement (KCM.inl:375), then se3ToSofaType (KCM.inl:385,394)
-      const double* pl = tb.sorted_pl + 12 * o;
-      const int k = tb.sorted_k[o];
-      double qt[4];
-      if (tb.sorted_ident[o]) {
-        if (!have_qj) { rot_to_quat(R, qj); have_qj = true; }
-        qt[0] = qj[0]; qt[1] = qj[1]; qt[2] = qj[2]; qt[3] = qj[3];
-      } else {
-        double Rf[9];
-        mat3_mul(R, pl, Rf);
-        rot_to_quat(Rf, qt);
-      }
-      const double px = R[0] * pl[9] + R[1] * pl[10] + R[2] * pl[11] + p[0];
-      const double py = R[3] * pl[9] + R[4] * pl[10] + R[5] * pl[11] + p[1];
-      const double pz = R[6] * pl[9] + R[7] * pl[10] + R[8] * pl[11] + p[2];
-      double* const po = out.at(7 * k);
-      out.st_at(po, 0, px); out.st_at(po, 1, py); out.st_at(po, 2, pz);
-      out.st_at(po, 3, qt[0]); out.st_at(po, 4, qt[1]); out.st_at(po, 5, qt[2]); out.st_at(po, 6, qt[3]);
-    }
-    if (jn.nchild >= 2) {
-      const int b = jn.bidx * RBD_BRANCH_FK;
-#pragma unroll
-      for (int e = 0; e < 9; ++e) S.st(b + e, R[e]);
-#pragma unroll
-      for (int e = 0; e < 3; ++e) S.st(b + 9 + e, p[e]);
-    }
-  }
-}
-
-// applyJ: out_k = J_k(LWA) dq, matrix-free: world twists V_i = V_parent + A_i dq_i, then
-// out_k = [V_lin + V_ang x p_k ; V_ang]  (== [J_lin - p_k x J_ang ; J_ang] dq, getFrameJacobian LWA)
-template <class QC, class DQ, class OUT>
-RBD_HD void applyJ_instance(const DevModel& m, const DevTables& tb, const QC& q, const DQ& dq, const OUT& out,
-                            const Stack& S) {
-  const int nj = m.njoints;
-  {
-    const DevJoint& j0 = m.joint[0];
-    for (int o = j0.out_begin; o < j0.out_end; ++o) {
-      const int k = tb.sorted_k[o];
-#pragma unroll
-      for (int e = 0; e < 6; ++e) out.st(6 * k + e, 0.0);  // universe: empty support -> zero Jacobian
-    }
-  }
-  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0}, V[6] = {0, 0, 0, 0, 0, 0};
-  double q0n = 0.0, q1n = 0.0;
-  RBD_Q_PREFETCH(1);
-  for (int i = 1; i < nj; ++i) {
-    const DevJoint& jn = m.joint[i];
-    const int par = jn.parent;
-    if (par != i - 1) {
-      if (par == 0) {
-        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
-        p[0] = p[1] = p[2] = 0;
-#pragma unroll
-        for (int e = 0; e < 6; ++e) V[e] = 0;
-      } else {
-        const int b = m.joint[par].bidx * RBD_BRANCH_J;
-#pragma unroll
-        for (int e = 0; e < 9; ++e) R[e] = S.ld(b + e);
-#pragma unroll
-        for (int e = 0; e < 3; ++e) p[e] = S.ld(b + 9 + e);
-#pragma unroll
-        for (int e = 0; e < 6; ++e) V[e] = S.ld(b + 12 + e);
-      }
-    }
-    double aw[3];
-    const double q0 = q0n, q1 = q1n;
-    RBD_Q_PREFETCH(i + 1);  // next joint's angle: its HBM latency hides behind this joint's work
-    fk_joint(jn, R, p, q0, q1, q, aw);
-    if (jn.type != JT_FF) {
-      double A[6];
-      subspace_1dof(jn.type, p, aw, A);
-      const double d = dq.ld(jn.idx_v);
-#pragma unroll
-      for (int e = 0; e < 6; ++e) V[e] += A[e] * d;
-    } else {
-      const int o = jn.idx_v;
-      const double l0 = dq.ld(o), l1 = dq.ld(o + 1), l2 = dq.ld(o + 2);
-      const double w0 = dq.ld(o + 3), w1 = dq.ld(o + 4), w2 = dq.ld(o + 5);
-      const double wx = R[0] * w0 + R[1] * w1 + R[2] * w2;
-      const double wy = R[3] * w0 + R[4] * w1 + R[5] * w2;
-      const double wz = R[6] * w0 + R[7] * w1 + R[8] * w2;
-      double tx, ty, tz;
-      RBD_CROSS(tx, ty, tz, p[0], p[1], p[2], wx, wy, wz);
-      V[0] += R[0] * l0 + R[1] * l1 + R[2] * l2 + tx;
-      V[1] += R[3] * l0 + R[4] * l1 + R[5] * l2 + ty;
-      V[2] += R[6] * l0 + R[7] * l1 + R[8] * l2 + tz;
-      V[3] += wx; V[4] += wy; V[5] += wz;
-    }
-    for (int o = jn.out_begin; o < jn.out_end; ++o) {
-      const double* pl = tb.sorted_pl + 12 * o;
-      const int k = tb.sorted_k[o];
-      const double px = R[0] * pl[9] + R[1] * pl[10] + R[2] * pl[11] + p[0];
-      const double py = R[3] * pl[9] + R[4] * pl[10] + R[5] * pl[11] + p[1];
-      const double pz = R[6] * pl[9] + R[7] * pl[10] + R[8] * pl[11] + p[2];
-      double tx, ty, tz;
-      RBD_CROSS(tx, ty, tz, V[3], V[4], V[5], px, py, pz);
-      double* const po = out.at(6 * k);
-      out.st_at(po, 0, V[0] + tx); out.st_at(po, 1, V[1] + ty); out.st_at(po, 2, V[2] + tz);
-      out.st_at(po, 3, V[3]); out.st_at(po, 4, V[4]); out.st_at(po, 5, V[5]);
-    }
-    if (jn.nchild >= 2) {
-      const int b = jn.bidx * RBD_BRANCH_J;
-#pragma unroll
-      for (int e = 0; e < 9; ++e) S.st(b + e, R[e]);
-#pragma unroll
-      for (int e = 0; e < 3; ++e) S.st(b + 9 + e, p[e]);
-#pragma unroll
-      for (int e = 0; e < 6; ++e) S.st(b + 12 + e, V[e]);
-    }
-  }
-}
-
-// applyJT, matrix-free: every wrench w_k = [f; n] given at output k (world-aligned axes) is moved to the
-// world origin, [f ; n + p_k x f], summed per joint, accumulated leaf->root, and projected: tau_i = A_i^T F_i.
-// `Src::gather(i, begin, end, R, p, F)` adds the wrenches attached to joint i; `Sink::put(c, value)` receives
-// the generalized force of velocity index c.
-template <class QC, class Src, class Sink>
-RBD_HD void applyJT_instance(const DevModel& m, const DevTables& tb, const QC& q, const Src& src, const Sink& sink,
-                             const Stack& S) {
-  const int nj = m.njoints;
-  const int bbase = m.slot_total[1];
-  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
-  double q0n = 0.0, q1n = 0.0;
-  RBD_Q_PREFETCH(1);
-  for (int i = 1; i < nj; ++i) {
-    const DevJoint& jn = m.joint[i];
-    const int par = jn.parent;
-    if (par != i - 1) {
-      // joint i starts a new branch below `par` (the subtree that ended at i-1 was unwound already)
-      if (par == 0) {
-        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
-        p[0] = p[1] = p[2] = 0;
-      } else {
-        const int b = bbase + m.joint[par].bidx * RBD_BRANCH_FK;
-#pragma unroll
-        for (int e = 0; e < 9; ++e) R[e] = S.ld(b + e);
-#pragma unroll
-        for (int e = 0; e < 3; ++e) p[e] = S.ld(b + 9 + e);
-      }
-    }
-    const int nxt_par = (i + 1 < nj) ? m.joint[i + 1].parent : 0;
-    double aw[3];
-    const double q0 = q0n, q1 = q1n;
-    RBD_Q_PREFETCH(i + 1);  // next joint's angle: its HBM latency hides behind this joint's work
-    fk_joint(jn, R, p, q0, q1, q, aw);
-    // Ak: world subspace column (1-dof) or R|p (free-flyer); Fk: wrenches attached to this joint, about the origin
-    double Ak[12], Fk[6] = {0, 0, 0, 0, 0, 0};
-    if (jn.type != JT_FF) {
-      subspace_1dof(jn.type, p, aw, Ak);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 9; ++e) Ak[e] = R[e];
-#pragma unroll
-      for (int e = 0; e < 3; ++e) Ak[9 + e] = p[e];
-    }
-    src.gather(i, jn.out_begin, jn.out_end, R, p, Fk);
-    if (nxt_par == i) {
-      // joint i has children: park A | F in its depth slot; the subtree's wrenches accumulate there
-      const int s = jn.slot[1];
-      const int aw_ = RBD_SLOT_A(jn.type);
-      if (jn.type != JT_FF) s_stv<6>(S, s, Ak); else s_stv<12>(S, s, Ak);
-      s_stv<6>(S, s + aw_, Fk);
-      if (jn.nchild >= 2) {
-        const int b = bbase + jn.bidx * RBD_BRANCH_FK;
-#pragma unroll
-        for (int e = 0; e < 9; ++e) S.st(b + e, R[e]);
-#pragma unroll
-        for (int e = 0; e < 3; ++e) S.st(b + 9 + e, p[e]);
-      }
-    } else {
-      // leaf: project from registers, then unwind — sums travel up the chain in registers and are written back
-      // only at the joint that still has children to come
-      int k = i;
-      while (true) {
-        const DevJoint& jk = m.joint[k];
-        if (jk.type != JT_FF) {
-          sink.put(jk.idx_v, dot6(Ak, Fk));
-        } else {
-          double o6[6];
-          ff_rows(Ak, Ak + 9, Fk, o6);
-#pragma unroll
-          for (int e = 0; e < 6; ++e) sink.put(jk.idx_v + e, o6[e]);
-        }
-        const int pk = jk.parent;
-        if (pk == 0) break;
-        const DevJoint& jp = m.joint[pk];
-        const int sp = jp.slot[1];
-        const int awp = RBD_SLOT_A(jp.type);
-        if (pk == nxt_par) {
-#pragma unroll
-          for (int e = 0; e < 6; ++e) S.add(sp + awp + e, Fk[e]);
-          break;
-        }
-#pragma unroll
-        for (int e = 0; e < 6; ++e) Fk[e] += S.ld(sp + awp + e);
-        if (jp.type != JT_FF) s_ldv<6>(S, sp, Ak); else s_ldv<12>(S, sp, Ak);
-        k = pk;
-      }
-    }
-  }
-}
-
-#ifndef RBD_JT_DIST
-#define RBD_JT_DIST 1 /* joints of lookahead of the wrench prefetch (1 or 2) */
-#endif
-#ifndef RBD_JT_PREF
-#define RBD_JT_PREF 4 /* outputs per joint whose wrenches are prefetched one joint ahead (A/B: 3..6 within 3 %) */
-#endif
-RBD_HD void add_shifted_wrench(const double* R, const double* p, const double* pl, const double* w, double* F);
-
-// applyJT on the fused-eval storage plan (plan_eval(..., jt = true)): A-stack in shared memory, F-stack levels and
-// branch R|p records in shared or tensor memory — the batched vector path (K3).  Same sweep as applyJT_instance.
-template <class QC, class Src, class Sink>
-RBD_HD void applyJT_instance_plan(const DevModel& m, const DevTables& tb, const QC& q, const Src& src, const Sink& sink,
-                                  const Stack& S, const TmStack& T) {
-  const int nj = m.njoints;
-  const int fbase = m.plan.fbase, fsplit = m.plan.fsplit, ftbase = m.plan.ftbase;
-#define RBD_F_TM(lvl) ((lvl) >= fsplit)
-#define RBD_F_OFF(lvl) ((lvl) >= fsplit ? ftbase + 6 * ((lvl)-fsplit) : fbase + 6 * (lvl))
-  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
-  double wn[6 * RBD_JT_PREF];
-#pragma unroll
-  for (int e = 0; e < 6 * RBD_JT_PREF; ++e) wn[e] = 0.0;
-  if (nj > 1) src.prefetch(m.joint[1].out_begin, m.joint[1].out_end, wn);
-#if RBD_JT_DIST == 2
-  double wn2[6 * RBD_JT_PREF];
-#pragma unroll
-  for (int e = 0; e < 6 * RBD_JT_PREF; ++e) wn2[e] = 0.0;
-  if (nj > 2) src.prefetch(m.joint[2].out_begin, m.joint[2].out_end, wn2);
-#endif
-  double q0n = 0.0, q1n = 0.0;
-  RBD_Q_PREFETCH(1);
-  for (int i = 1; i < nj; ++i) {
-    const DevJoint& jn = m.joint[i];
-    const int par = jn.parent;
-    // this joint's wrenches arrived while the previous joint(s) were processed; start the loads of the joint
-    // RBD_JT_DIST ahead now (A/B: issuing them only after this joint's gather, without the copy, is 16 % slower)
-    double wc[6 * RBD_JT_PREF];
-#pragma unroll
-    for (int e = 0; e < 6 * RBD_JT_PREF; ++e) wc[e] = wn[e];
-#if RBD_JT_DIST == 2
-#pragma unroll
-    for (int e = 0; e < 6 * RBD_JT_PREF; ++e) wn[e] = wn2[e];
-    if (i + 2 < nj) src.prefetch(m.joint[i + 2].out_begin, m.joint[i + 2].out_end, wn2);
-#else
-    if (i + 1 < nj) src.prefetch(m.joint[i + 1].out_begin, m.joint[i + 1].out_end, wn);
-#endif
-    if (par != i - 1) {
-      if (par == 0) {
-        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
-        p[0] = p[1] = p[2] = 0;
-      } else {
-        const DevJoint& jb = m.joint[par];
-        double Rp[12];
-        if (jb.type == JT_FF) s_ldv<12>(S, jb.offA, Rp);
-        else x_ldv<12>((jb.boff & RBD_BOFF_TMEM) != 0, S, T, jb.boff & RBD_BOFF_MASK, Rp);
-#pragma unroll
-        for (int e = 0; e < 9; ++e) R[e] = Rp[e];
-#pragma unroll
-        for (int e = 0; e < 3; ++e) p[e] = Rp[9 + e];
-      }
-    }
-    const int nxt_par = (i + 1 < nj) ? m.joint[i + 1].parent : 0;
-    double aw[3];
-    const double q0 = q0n, q1 = q1n;
-    RBD_Q_PREFETCH(i + 1);  // next joint's angle: its HBM latency hides behind this joint's work
-    fk_joint(jn, R, p, q0, q1, q, aw);
-    double Ak[12], Fk[6] = {0, 0, 0, 0, 0, 0};
-    if (jn.type != JT_FF) {
-      subspace_1dof(jn.type, p, aw, Ak);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 9; ++e) Ak[e] = R[e];
-#pragma unroll
-      for (int e = 0; e < 3; ++e) Ak[9 + e] = p[e];
-    }
-    src.gather_pref(jn.out_begin, jn.out_end, R, p, wc, Fk);
-    if (nxt_par == i) {
-      const int lvl = jn.depth - 1;
-      if (jn.type != JT_FF) s_stv<6>(S, jn.offA, Ak); else s_stv<12>(S, jn.offA, Ak);
-      x_stv<6>(RBD_F_TM(lvl), S, T, RBD_F_OFF(lvl), Fk);
-      if (jn.nchild >= 2 && jn.type != JT_FF) {
-        double Rp[12];
-#pragma unroll
-        for (int e = 0; e < 9; ++e) Rp[e] = R[e];
-#pragma unroll
-        for (int e = 0; e < 3; ++e) Rp[9 + e] = p[e];
-        x_stv<12>((jn.boff & RBD_BOFF_TMEM) != 0, S, T, jn.boff & RBD_BOFF_MASK, Rp);
-      }
-    } else {
-      int k = i;
-      while (true) {
-        const DevJoint& jk = m.joint[k];
-        if (jk.type != JT_FF) {
-          sink.put(jk.idx_v, dot6(Ak, Fk));
-        } else {
-          double o6[6];
-          ff_rows(Ak, Ak + 9, Fk, o6);
-#pragma unroll
-          for (int e = 0; e < 6; ++e) sink.put(jk.idx_v + e, o6[e]);
-        }
-        const int pk = jk.parent;
-        if (pk == 0) break;
-        const DevJoint& jp = m.joint[pk];
-        const int lvl = jp.depth - 1;
-        if (pk == nxt_par) {
-          x_addv<6>(RBD_F_TM(lvl), S, T, RBD_F_OFF(lvl), Fk);
-          break;
-        }
-        double fp[6];
-        x_ldv<6>(RBD_F_TM(lvl), S, T, RBD_F_OFF(lvl), fp);
-#pragma unroll
-        for (int e = 0; e < 6; ++e) Fk[e] += fp[e];
-        if (jp.type != JT_FF) s_ldv<6>(S, jp.offA, Ak); else s_ldv<12>(S, jp.offA, Ak);
-        k = pk;
-      }
-    }
-  }
-#undef RBD_F_TM
-#undef RBD_F_OFF
-}
-
-// add wrench w (at point pf = R pl_p + p, world-aligned axes) moved to the world origin
-RBD_HD void add_shifted_wrench(const double* R, const double* p, const double* pl, const double* w, double* F) {
-  const double px = R[0] * pl[9] + R[1] * pl[10] + R[2] * pl[11] + p[0];
-  const double py = R[3] * pl[9] + R[4] * pl[10] + R[5] * pl[11] + p[1];
-  const double pz = R[6] * pl[9] + R[7] * pl[10] + R[8] * pl[11] + p[2];
-  double tx, ty, tz;
-  RBD_CROSS(tx, ty, tz, px, py, pz, w[0], w[1], w[2]);
-  F[0] += w[0]; F[1] += w[1]; F[2] += w[2];
-  F[3] += w[3] + tx; F[4] += w[4] + ty; F[5] += w[5] + tz;
-}
-
-// dense wrench source: one wrench per mapped output (KCM.inl:472-492)
-template <class FLD>
-struct DenseWrenchSrcT {
-  FLD in;  // n_out*6 fields
-  const DevTables* tb;
-  // Issue the loads of the first RBD_JT_PREF wrenches of outputs [begin, end) (indices past the end are clamped, so
-  // every load is valid; the duplicates are ignored by gather_pref).  The sweep calls this one joint ahead: the HBM
-  // latency of the wrench stream hides behind the previous joint's kinematics.
-  RBD_HD void prefetch(int begin, int end, double* w) const {
-    if (end <= begin) return;
-#pragma unroll
-    for (int j = 0; j < RBD_JT_PREF; ++j) {
-      const int o = begin + j < end ? begin + j : end - 1;
-      const int k = tb->sorted_k[o];
-#pragma unroll
-      for (int e = 0; e < 6; ++e) w[6 * j + e] = in.ld(6 * k + e);
-    }
-  }
-  RBD_HD void gather_pref(int begin, int end, const double* R, const double* p, const double* w, double* F) const {
-#pragma unroll
-    for (int j = 0; j < RBD_JT_PREF; ++j)
-      if (begin + j < end) add_shifted_wrench(R, p, tb->sorted_pl + 12 * (begin + j), w + 6 * j, F);
-    if (end > begin + RBD_JT_PREF) gather(0, begin + RBD_JT_PREF, end, R, p, F);
-  }
-  RBD_HD void gather(int, int begin, int end, const double* R, const double* p, double* F) const {
-    // independent iterations: unrolled so that the wrench loads of several outputs are in flight together
-#pragma unroll 4
-    for (int o = begin; o < end; ++o) {
-      const int k = tb->sorted_k[o];
-      double w[6];
-#pragma unroll
-      for (int e = 0; e < 6; ++e) w[e] = in.ld(6 * k + e);
-      add_shifted_wrench(R, p, tb->sorted_pl + 12 * o, w, F);
-    }
-  }
-};
-using DenseWrenchSrc = DenseWrenchSrcT<Field>;
-// sparse wrench source: the non-zeros of one constraint row (KCM.inl:558-583)
-struct RowWrenchSrc {
-  const int* col;     // [nnz] mapped-output index
-  const double* val;  // [nnz][6]
-  int nnz;
-  const DevTables* tb;
-  RBD_HD void gather(int joint, int, int, const double* R, const double* p, double* F) const {
-    for (int j = 0; j < nnz; ++j) {
-      const int k = col[j];
-      if (tb->outk_parent[k] == joint) add_shifted_wrench(R, p, tb->outk_pl + 12 * k, val + 6 * j, F);
-    }
-  }
-};
-// += into SOFA's split outputs (root wrench | joint torques): KCM.inl:494-512
-template <class FLD>
-struct SplitAccumSinkT {
-  FLD root, joints;
-  int off;
-  RBD_HD void put(int c, double v) const {
-    if (c < off) {
-      if (root.ok()) root.st(c, root.ld(c) + v);
-    } else if (joints.ok()) {
-      joints.st(c - off, joints.ld(c - off) + v);
-    }
-  }
-};
-using SplitAccumSink = SplitAccumSinkT<Field>;
-// dense row + squared norm (KCM.inl:585-615)
-struct RowSink {
-  double* row;
-  double* n2;
-  RBD_HD void put(int c, double v) const { row[c] = v; *n2 += v * v; }
-};
-
+namespace f32 {
+typedef float real;
+using DevModel = ::DevModelT<float>;
+using DevJoint = ::DevJointT<float>;
+#define RBD_BODY_F32 1
+#include "rbd_sweeps_body.h"
+#undef RBD_BODY_F32
+}  // namespace f32
 }  // namespace rbd

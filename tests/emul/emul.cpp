@@ -90,6 +90,49 @@ extern "C" int emul_eval(const rbd_model_desc* d, long long n, long long tile, i
   return 0;
 }
 
+// FP32 mode of the fused evaluation (namespace rbd::f32): float I/O, float state, the same sweep and storage plan
+template <int TILE>
+static void eval_one_f32(const DevModelT<float>& m, long long i, long long tile, float* q, float* v, float* a, float* oMi,
+                         float* J, float* M, float* tau, const f32::Stack& S, const f32::TmStack& T) {
+  const bool do_m = M != nullptr, do_tau = tau != nullptr;
+  f32::EvalIOT<TILE> io;
+  io.q = f32::make_field_t<TILE>(q, i, m.nq, tile); io.v = f32::make_field_t<TILE>(v, i, m.nv, tile);
+  io.a = f32::make_field_t<TILE>(a, i, m.nv, tile);
+  io.oMi = f32::make_field_t<TILE>(oMi, i, 12 * (m.njoints - 1), tile); io.J = f32::make_field_t<TILE>(J, i, 6 * m.nv, tile);
+  io.M = f32::make_field_t<TILE>(M, i, m.nv * (m.nv + 1) / 2, tile); io.tau = f32::make_field_t<TILE>(tau, i, m.nv, tile);
+  if (do_m && do_tau) f32::eval_instance<true, true, TILE>(m, io, S, T);
+  else if (do_m) f32::eval_instance<true, false, TILE>(m, io, S, T);
+  else if (do_tau) f32::eval_instance<false, true, TILE>(m, io, S, T);
+  else f32::eval_instance<false, false, TILE>(m, io, S, T);
+}
+
+extern "C" int emul_eval_f32(const rbd_model_desc* d, long long n, long long tile, int block, int use_tmem, float* q,
+                             float* v, float* a, float* oMi, float* J, float* M, float* tau) {
+  Ctx c;
+  int rc = make_ctx(d, &c);
+  if (rc) return rc;
+  const bool do_m = M != nullptr, do_tau = tau != nullptr;
+  if (!plan_eval(&c.m, do_m, do_tau, use_tmem != 0, block / 32, oMi != nullptr, false, B200Limits::kRegsPerThread, 4)) {
+    g_err = "plan_eval failed"; return -100;
+  }
+  std::vector<DevModelT<float>> fm(1);
+  const std::vector<unsigned long long> blob = build_eval_blob_f32(&c.m, &fm[0]);
+  const DevModelT<float>& bm = *reinterpret_cast<const DevModelT<float>*>(blob.data());
+  const EvalPlan& pl = bm.plan;
+  const int bt = pl.warps * 32;
+  std::vector<float> smem((size_t)(pl.smem_doubles > 0 ? pl.smem_doubles : 1) * bt, 1e30f);
+  std::vector<float> tmem((size_t)(pl.tmem_doubles > 0 ? pl.tmem_doubles : 1) * bt, 1e30f);
+  for (long long b0 = 0; b0 < n; b0 += bt)
+    for (int t = 0; t < bt && b0 + t < n; ++t) {
+      const long long i = b0 + t;
+      f32::Stack S = f32::make_stack(smem.data(), t, pl.smem_doubles);
+      f32::TmStack T{tmem.data() + (size_t)t * (pl.tmem_doubles > 0 ? pl.tmem_doubles : 1)};
+      if (tile == 32) eval_one_f32<32>(bm, i, tile, q, v, a, oMi, J, M, tau, S, T);
+      else eval_one_f32<0>(bm, i, tile, q, v, a, oMi, J, M, tau, S, T);
+    }
+  return 0;
+}
+
 extern "C" int emul_apply(const rbd_model_desc* d, long long n, long long tile, int block, double* q_joints,
                           double* root, double* qcache, long long cache_tile, double* out) {
   Ctx c;

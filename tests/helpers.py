@@ -10,6 +10,7 @@ ROOT = os.path.dirname(HERE)
 GOLDEN = os.path.join(HERE, "golden")
 
 TOL_FP64 = 1e-10   # BASELINE.json north_star: <= 1e-10 relative error in FP64
+TOL_FP32 = 1e-4    # ... and the optional FP32 mode: <= 1e-4
 
 
 def to_tiled(x: np.ndarray, tile: int) -> np.ndarray:
@@ -45,7 +46,7 @@ def load_emul() -> C.CDLL:
     src = os.path.join(HERE, "emul", "emul.cpp")
     out = os.path.join(HERE, "emul", "libemul.so")
     csrc = os.path.join(ROOT, "sofa", "rigidbodydynamics_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("rbd_sweeps.h", "rbd_model_build.h", "rbd_dev_model.h")]
+    deps = [src] + [os.path.join(csrc, f) for f in ("rbd_sweeps.h", "rbd_sweeps_body.h", "rbd_model_build.h", "rbd_dev_model.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-O2", "-march=native", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
                                "-o", out, src])
@@ -56,6 +57,7 @@ def load_emul() -> C.CDLL:
     lib.emul_sincos.argtypes = [ll, vp, vp, vp]
     lib.emul_sincos.restype = None
     lib.emul_eval.argtypes = [vp, ll, ll, i, i] + [vp] * 7
+    lib.emul_eval_f32.argtypes = [vp, ll, ll, i, i] + [vp] * 7
     lib.emul_apply.argtypes = [vp, ll, ll, i, vp, vp, vp, ll, vp]
     lib.emul_applyJ.argtypes = [vp, ll, ll, i, vp, ll, vp, vp, vp]
     lib.emul_applyJT.argtypes = [vp, ll, ll, i, vp, ll, vp, vp, vp]

@@ -60,6 +60,29 @@ def test_eval_partial_outputs(emul, name, want, use_tmem):
         assert rel_err(got[k], ref[k]) <= TOL_FP64, k
 
 
+@pytest.mark.parametrize("d", MODELS, ids=IDS)
+@pytest.mark.parametrize("use_tmem", [0, 1])
+def test_eval_f32_bodies_within_1e4(emul, d, use_tmem):
+    """Optional FP32 mode (BASELINE north_star: tolerance 1e-4): the same sweep compiled with real = float."""
+    import oracle
+    from helpers import TOL_FP32
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    n, tile = 70, 32
+    q, v, a = mdl.random_state(d, n, seed=3)
+    cd, keep = _cdesc(d)
+    nt = (n + tile - 1) // tile
+    K = {"oMi": 12 * (d.njoints - 1), "J": 6 * d.nv, "M": d.nv * (d.nv + 1) // 2, "tau": d.nv}
+    outs = {k: np.full((nt, K[k], tile), np.nan, dtype=np.float32) for k in K}
+    qs, vs, as_ = (to_tiled(x.astype(np.float32), tile) for x in (q, v, a))
+    rc = emul.emul_eval_f32(C.addressof(cd), n, tile, 0, use_tmem, P(qs), P(vs), P(as_), P(outs["oMi"]), P(outs["J"]),
+                            P(outs["M"]), P(outs["tau"]))
+    assert rc == 0, emul.emul_last_error()
+    ref, _ = oracle.eval_batch(d, q.astype(np.float32).astype(np.float64), v.astype(np.float32).astype(np.float64),
+                               a.astype(np.float32).astype(np.float64), 1)
+    for k in ref:
+        assert rel_err(from_tiled(outs[k], n).astype(np.float64), ref[k]) <= TOL_FP32, k
+
+
 def _split(d, q, v):
     if d.has_freeflyer_root:
         return (np.ascontiguousarray(q[:, 7:]), np.ascontiguousarray(q[:, :7]),

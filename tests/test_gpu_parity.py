@@ -407,3 +407,30 @@ def test_deep_and_bushy_trees(torch_mod, api, nmoving, branch_prob, ff):
         orc.apply(qj[i], None if root is None else root[i])
         rtau, _rroot = orc.applyJT(w[i])
         assert rel_err(tau[i], rtau) <= TOL_FP64
+
+
+@pytest.mark.parametrize("d", MODELS, ids=IDS)
+@pytest.mark.parametrize("tmem", [True, False])
+def test_eval_f32_mode_within_1e4(torch_mod, api, d, tmem):
+    """Optional FP32 mode of the fused evaluation (BASELINE north_star: tolerance 1e-4 relative): float I/O and state,
+    same kernel structure, against the FP64 oracle evaluated on the float-rounded inputs."""
+    import oracle
+    from helpers import TOL_FP32
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    torch = torch_mod
+    n, tile = 1000, 32
+    q, v, a = mdl.random_state(d, n, seed=19)
+    q32, v32, a32 = (x.astype(np.float32) for x in (q, v, a))
+    m = api.Model(d); ws = api.Workspace(m, n)
+    ws.set_eval_tmem(tmem)
+    I = m.info
+    nt = (n + tile - 1) // tile
+    K = {"oMi": I.omi_fields, "J": I.jac_fields, "M": I.mass_fields, "tau": I.nv}
+    outs = {k: torch.full((nt, K[k], tile), float("nan"), dtype=torch.float32, device="cuda") for k in K}
+    qs, vs, as_ = (_dev(torch, to_tiled(x, tile)) for x in (q32, v32, a32))
+    ws.eval_soa_f32(n, tile, qs, vs, as_, outs["oMi"], outs["J"], outs["M"], outs["tau"])
+    ws.synchronize()
+    ref, _ = oracle.eval_batch(d, q32.astype(np.float64), v32.astype(np.float64), a32.astype(np.float64), nthreads=0)
+    for k in K:
+        got = from_tiled(outs[k].cpu().numpy(), n).astype(np.float64)
+        assert rel_err(got, ref[k]) <= TOL_FP32, k
