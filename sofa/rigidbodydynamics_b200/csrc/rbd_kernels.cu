@@ -30,9 +30,9 @@ extern __shared__ __align__(16) double rbd_smem[];
 // derives its private slice (lane quarter of its warp, column range of its warp group), and warp 0 frees them
 // after the whole block is done.  Lanes past the end of the batch recompute the last instance instead of
 // exiting: tcgen05.ld/st are warp-collective (.sync.aligned) and the duplicate stores write identical values.
-#define RBD_DEFINE_EVAL_KERNEL(NAME, NSQ, REAL) \
+#define RBD_DEFINE_EVAL_KERNEL(NAME, NSQ, REAL, MINB) \
 template <bool DO_M, bool DO_TAU, int TILE>                                                                                                             \
-__global__ void __launch_bounds__(256) NAME(const DevModelT<REAL>* __restrict__ gm, const EvalArgsT<REAL> a,                                            \
+__global__ void __launch_bounds__(256, MINB) NAME(const DevModelT<REAL>* __restrict__ gm, const EvalArgsT<REAL> a,                                            \
                                                    const int model_words) {                                                                             \
  /* the last two staged words are spare: the tensor-memory base address lands there (no static shared memory, so */                                     \
  /* the block can ask for the full 227 KB dynamically) */                                                                                               \
@@ -87,8 +87,9 @@ __global__ void __launch_bounds__(256) NAME(const DevModelT<REAL>* __restrict__ 
   }                                                                                                                                                     \
 }
 
-RBD_DEFINE_EVAL_KERNEL(eval_kernel, rbd, double)
-RBD_DEFINE_EVAL_KERNEL(eval_kernel_f32, rbd::f32, float)
+RBD_DEFINE_EVAL_KERNEL(eval_kernel, rbd, double, 1)
+// FP32: 128 registers per thread so that two 8-warp blocks share an SM (the planner counts on it)
+RBD_DEFINE_EVAL_KERNEL(eval_kernel_f32, rbd::f32, float, 2)
 
 // The mapping kernels stage the joint table the same way (one coalesced copy per block, broadcast reads after).
 // The cached configuration of the last apply (workspace) is always tile-32.

@@ -245,12 +245,14 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
   for (int W = 1; W <= B200Limits::kMaxWarpsPerBlock; ++W) {
     if (forced_warps > 0 && W != forced_warps) continue;
     const int cap = use_tmem ? (B200Limits::kTmemCols / ((W + 3) / 4)) / cols_per_elem : 0;  // elements per thread
-    bool placed = false;
+    // per block size: the configuration with the most resident blocks; among equals the cheapest one (everything
+    // saved, fewest f-stack levels in tensor memory)
+    int best_c_w = 0;
     // cheapest configuration first: everything saved; then drop the v|a record of branch joints attached to the
     // universe (recomputed from the A record and the inputs: costs a dozen global re-reads per return)
     // ...; then re-read R|p of the other branch joints from the oMi output this thread wrote (when oMi is requested)
     const int ncfg = jt ? 1 : 1 + (do_tau ? 1 : 0) + ((do_tau && omi_out) ? 1 : 0);
-    for (int cfg = 0; cfg < ncfg && !placed; ++cfg) {
+    for (int cfg = 0; cfg < ncfg; ++cfg) {
       const int drop_root_va = cfg >= 1, rp_from_omi = cfg >= 2;
       std::vector<int> bw(bj.size()), bflag(bj.size(), 0);
       for (size_t k = 0; k < bj.size(); ++k) {
@@ -280,7 +282,7 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
       for (int k : order)
         if (bw[k] > 0 && t_base + bw[k] <= cap) { boff[k] = t_base | RBD_BOFF_TMEM; t_base += bw[k]; b_tm[k] = 1; }
       const int kmax = do_tau ? std::min(D, (cap - t_base) / 6) : 0;
-      for (int kf = 0; kf <= kmax && !placed; ++kf) {
+      for (int kf = 0; kf <= kmax; ++kf) {
         int s_used = s_base, t_used = t_base;
         pl.fbase = s_used; pl.fsplit = do_tau ? D - kf : 0; s_used += do_tau ? 6 * (D - kf) : 0;
         pl.ftbase = t_used; t_used += 6 * kf;
@@ -297,7 +299,8 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
         c = std::min(c, 32);
         if (c < 1) continue;
         pl.blocks_per_sm = c;
-        placed = true;
+        if (c <= best_c_w) continue;  // not better than an earlier (cheaper) configuration of this block size
+        best_c_w = c;
         // more resident warps wins; on ties the LARGER block: the warps of one block spread over the four SM
         // sub-partitions (warp % 4), whereas many one-warp blocks were measured 3x slower (r1c: 15.8 ms vs 5.2 ms)
         if (W * c >= best_warps_sm) {
