@@ -18,6 +18,11 @@
 
 using namespace rbd;
 
+#ifndef RBD_JT_MINB
+#define RBD_JT_MINB 1
+#endif
+#define RBD_JT_REGS (RBD_JT_MINB >= 2 ? 128 : 255)
+
 // --------------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static int set_err(int code, const std::string& msg) { g_err = msg; return code; }
@@ -261,7 +266,7 @@ static int ensure_plan(rbd_workspace* ws, int pk) {
   if (ws->h_plan[pk]) return RBD_OK;
   DevModel* h = new (std::nothrow) DevModel(ws->model->dm);
   if (!h) return set_err(RBD_ERR_ALLOC, "out of host memory");
-  const bool planned = pk == 8 ? plan_eval(h, false, true, ws->use_tmem != 0, 0, false, /*jt=*/true)
+  const bool planned = pk == 8 ? plan_eval(h, false, true, ws->use_tmem != 0, 0, false, /*jt=*/true, RBD_JT_REGS)
                                : plan_eval(h, (pk & 2) != 0, (pk & 1) != 0, ws->use_tmem != 0,
                                            ws->forced_eval_block / 32, (pk & 4) != 0);
   if (!planned) {

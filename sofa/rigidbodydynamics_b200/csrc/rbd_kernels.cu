@@ -168,8 +168,11 @@ __global__ void __launch_bounds__(256) applyJT_kernel(const DevModel* __restrict
 }
 
 // K3 on the storage plan (shared + tensor memory, persistent warps): same prologue / epilogue as eval_kernel.
+#ifndef RBD_JT_MINB
+#define RBD_JT_MINB 1
+#endif
 template <int TILE>
-__global__ void __launch_bounds__(256) applyJT_plan_kernel(const DevModel* __restrict__ gm, const int model_words,
+__global__ void __launch_bounds__(256, RBD_JT_MINB) applyJT_plan_kernel(const DevModel* __restrict__ gm, const int model_words,
                                                               const DevTables tb, const MapArgs a) {
   unsigned* const tm_base_p = reinterpret_cast<unsigned*>(rbd_smem + model_words - 2);
   {
