@@ -28,6 +28,9 @@
 #ifndef RBD_PTR_OMIJ
 #define RBD_PTR_OMIJ 1
 #endif
+#ifndef RBD_IN_DIST
+#define RBD_IN_DIST 1 /* joints of lookahead of the input prefetch in the fused eval (A/B: 2..4 are 0.5 % slower) */
+#endif
 #ifndef RBD_UNROLL_ANC
 #define RBD_UNROLL_ANC 1 /* A/B r1e: 1 -> 2.45 ms, 2 -> 2.49 ms, 4 -> 2.67 ms (instruction-cache pressure) */
 #endif

@@ -19,6 +19,44 @@ struct FieldT {
   RBD_HD real* at(int k) const { return p + off(k); }
   RBD_HD void st_at(real* a, int e, real v) const { a[TILE ? (long long)e * TILE : (long long)e * stride] = v; }
   RBD_HD long long step(int e) const { return TILE ? (long long)e * TILE : (long long)e * stride; }
+  // The same store / load with the L2 eviction priority "evict_last": for the few lines this thread re-reads much
+  // later (R|p of a branch joint out of its own oMi output, the root free-flyer's v / a) — without the hint the
+  // kernel's 5 TB/s write stream evicts them from L2 within ~25 us and the re-read goes to HBM behind that stream
+  // (profile r1g: 10 % of all stall samples on the first consumer of the re-read rotation).
+  RBD_HD void st_at_keep(real* a, int e, real v) const {
+#if defined(__CUDA_ARCH__) && !defined(RBD_NO_L2_KEEP)
+    real* addr = a + step(e);
+    if constexpr (sizeof(real) == 8)
+      asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(addr), "d"((double)v), "l"(l2_keep_policy()) : "memory");
+    else
+      asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(addr), "f"((float)v), "l"(l2_keep_policy()) : "memory");
+#else
+    st_at(a, e, v);
+#endif
+  }
+  RBD_HD real ld_keep(int k) const {
+#if defined(__CUDA_ARCH__) && !defined(RBD_NO_L2_KEEP)
+    const real* addr = p + off(k);
+    if constexpr (sizeof(real) == 8) {
+      double v;
+      asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(addr), "l"(l2_keep_policy()));
+      return (real)v;
+    } else {
+      float v;
+      asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(addr), "l"(l2_keep_policy()));
+      return (real)v;
+    }
+#else
+    return ld(k);
+#endif
+  }
+#if defined(__CUDA_ARCH__)
+  static __device__ __forceinline__ unsigned long long l2_keep_policy() {
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+  }
+#endif
 };
 using Field = FieldT<0>;
 template <int TILE>
@@ -360,10 +398,11 @@ RBD_HD void ff_rows(const real* R, const real* p, const real* F, real* out6) {
 }
 
 // free-flyer joint motion given in the joint (body) frame, 6 fields of `fld` from `o`: world = oMi.act(.)
+// (the six values are read with the L2 "keep" hint: the fused eval re-reads them when the sweep returns to the joint)
 template <class FLD>
 RBD_HD void ff_act(const real* R, const real* p, const FLD& fld, int o, real* out) {
-  const real l0 = fld.ld(o), l1 = fld.ld(o + 1), l2 = fld.ld(o + 2);
-  const real w0 = fld.ld(o + 3), w1 = fld.ld(o + 4), w2 = fld.ld(o + 5);
+  const real l0 = fld.ld_keep(o), l1 = fld.ld_keep(o + 1), l2 = fld.ld_keep(o + 2);
+  const real w0 = fld.ld_keep(o + 3), w1 = fld.ld_keep(o + 4), w2 = fld.ld_keep(o + 5);
   out[3] = R[0] * w0 + R[1] * w1 + R[2] * w2;
   out[4] = R[3] * w0 + R[4] * w1 + R[5] * w2;
   out[5] = R[6] * w0 + R[7] * w1 + R[8] * w2;
@@ -617,14 +656,25 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
   } while (0)
   RBD_RESET_ROOT();
 
-  // one-joint-ahead prefetch of the 1-dof inputs (hides the global-load latency behind the previous joint)
-  real q0n = 0, q1n = 0, vn = 0, an = 0;
-  if (nj > 1 && m.joint[1].type != JT_FF) {
-    const DevJoint& j1 = m.joint[1];
-    q0n = io.q.ld(j1.idx_q);
-    if (is_unbounded(j1.type)) q1n = io.q.ld(j1.idx_q + 1);
-    if (DO_TAU) { vn = io.v.ld(j1.idx_v); an = io.a.ld(j1.idx_v); }
-  }
+  // Prefetch of the 1-dof inputs RBD_IN_DIST joints ahead (a small register ring; 1 = the next joint's values).
+  // In profile r1g the MOV that consumes the prefetched angle at the loop top holds 10.5 % of all stall samples
+  // (long scoreboard), yet a longer distance does not help (A/B): with a ring the shift itself touches the in-flight
+  // register.  Open item for round 2 (unroll the joint loop by two to rotate the ring at compile time).
+  real qn[RBD_IN_DIST], q1n_[RBD_IN_DIST], vn_[RBD_IN_DIST], an_[RBD_IN_DIST];
+#pragma unroll
+  for (int s_ = 0; s_ < RBD_IN_DIST; ++s_) { qn[s_] = 0; q1n_[s_] = 0; vn_[s_] = 0; an_[s_] = 0; }
+  // issue the loads of joint `jidx` into ring slot `slot` (compile-time)
+#define RBD_IN_FETCH(jidx, slot)                                                                   \
+  do {                                                                                             \
+    if ((jidx) < nj && m.joint[jidx].type != JT_FF) {                                              \
+      const DevJoint& jx_ = m.joint[jidx];                                                         \
+      qn[slot] = io.q.ld(jx_.idx_q);                                                               \
+      if (is_unbounded(jx_.type)) q1n_[slot] = io.q.ld(jx_.idx_q + 1);                             \
+      if (DO_TAU) { vn_[slot] = io.v.ld(jx_.idx_v); an_[slot] = io.a.ld(jx_.idx_v); }              \
+    }                                                                                              \
+  } while (0)
+#pragma unroll
+  for (int s_ = 0; s_ < RBD_IN_DIST; ++s_) RBD_IN_FETCH(1 + s_, s_);
 
   // State of the joint the sweep returns to when a new branch starts below it: R|p (+ v|a).  With a stack
   // (CRBA / RNEA) this runs at the LEAF that ends the previous branch, BEFORE its unwind — R, p, vel, acc are dead
@@ -683,24 +733,31 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
     const DevJoint& jn = m.joint[i];
     const int par = jn.parent;
     if (!NEED_STACK && par != i - 1) restore(par);  // FK-only variant: no unwind to hide behind
-    const real q0 = q0n, q1 = q1n, qd = vn, qdd = an;
+    const real q0 = qn[0], q1 = q1n_[0], qd = vn_[0], qdd = an_[0];
     const int nxt_par = (i + 1 < nj) ? m.joint[i + 1].parent : 0;
-    if (i + 1 < nj && m.joint[i + 1].type != JT_FF) {
-      const DevJoint& jx = m.joint[i + 1];
-      q0n = io.q.ld(jx.idx_q);
-      if (is_unbounded(jx.type)) q1n = io.q.ld(jx.idx_q + 1);
-      if (DO_TAU) { vn = io.v.ld(jx.idx_v); an = io.a.ld(jx.idx_v); }
+    // advance the ring and start the loads of joint i + RBD_IN_DIST
+#pragma unroll
+    for (int s_ = 0; s_ + 1 < RBD_IN_DIST; ++s_) {
+      qn[s_] = qn[s_ + 1]; q1n_[s_] = q1n_[s_ + 1]; vn_[s_] = vn_[s_ + 1]; an_[s_] = an_[s_ + 1];
     }
+    RBD_IN_FETCH(i + RBD_IN_DIST, RBD_IN_DIST - 1);
 
     real aw[3];
     fk_joint(jn, R, p, q0, q1, io.q, aw);
     if (io.oMi.ok()) {
 #if RBD_PTR_OMIJ
       real* const po = io.oMi.at(12 * (i - 1));
+      if (jn.boff & RBD_BOFF_RPOMI) {  // this record is re-read when the sweep returns to joint i: keep it in L2
 #pragma unroll
-      for (int e = 0; e < 9; ++e) io.oMi.st_at(po, e, R[e]);
+        for (int e = 0; e < 9; ++e) io.oMi.st_at_keep(po, e, R[e]);
 #pragma unroll
-      for (int e = 0; e < 3; ++e) io.oMi.st_at(po, 9 + e, p[e]);
+        for (int e = 0; e < 3; ++e) io.oMi.st_at_keep(po, 9 + e, p[e]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) io.oMi.st_at(po, e, R[e]);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) io.oMi.st_at(po, 9 + e, p[e]);
+      }
 #else
       const int o = 12 * (i - 1);
 #pragma unroll
@@ -846,6 +903,7 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
     }
   }
 #undef RBD_RESET_ROOT
+#undef RBD_IN_FETCH
 #undef RBD_F_TM
 #undef RBD_F_OFF
 #undef RBD_Y_TM
