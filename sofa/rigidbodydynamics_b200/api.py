@@ -111,6 +111,12 @@ class Workspace:
     def set_eval_tmem(self, enable: bool):
         check(self._lib.rbd_workspace_set_eval_tmem(self._h, 1 if enable else 0))
 
+    def set_applyJT_ring(self, enable: bool) -> int:
+        """A/B knob of the vector applyJT: ring kernel (default) or register path; returns the ring slots per warp."""
+        ns = C.c_int32(0)
+        check(self._lib.rbd_workspace_set_applyJT_ring(self._h, 1 if enable else 0, C.byref(ns)))
+        return int(ns.value)
+
     def eval_plan(self, with_M: bool = True, with_tau: bool = True, f32: bool = False) -> dict:
         out = (C.c_int32 * 8)()
         fn = self._lib.rbd_workspace_get_eval_plan_f32 if f32 else self._lib.rbd_workspace_get_eval_plan

@@ -63,8 +63,11 @@ struct rbd_workspace {
   DevTables tb{};
   // fused eval: one planned copy of the joint table per variant (bit 1 = CRBA, bit 0 = RNEA), host + device;
   // the kernel stages the device copy into shared memory
-  DevModel* h_plan[9] = {};  // index: bit 2 = oMi requested, bit 1 = CRBA, bit 0 = RNEA; [8] = the applyJT sweep
-  DevModel* d_plan[9] = {};
+  DevModel* h_plan[10] = {};  // index: bit 2 = oMi requested, bit 1 = CRBA, bit 0 = RNEA; [8] = the applyJT sweep,
+                              // [9] = its ring variant (full tiles of 32)
+  DevModel* d_plan[10] = {};
+  int jt_ring_slots = -1;     // ring slots per warp of plan [9]; 0 = the ring kernel cannot run this model; -1 = not planned yet
+  int use_jt_ring = 1;
   DevModelT<float>* h_plan32[8] = {};  // FP32 mode of the fused eval
   DevModelT<float>* d_plan32[8] = {};
   LaunchCfg cfg_eval32[8];
@@ -72,7 +75,7 @@ struct rbd_workspace {
   int num_sms = 0;
   double* qcache = nullptr;  // [nq][capacity] assembled configuration of the last apply
   long long applied_n = 0;   // instances covered by the cache (0 = apply not called yet)
-  LaunchCfg cfg_eval[8], cfg_apply[2], cfg_applyJ[2], cfg_applyJT[2], cfg_rows;
+  LaunchCfg cfg_eval[8], cfg_apply[2], cfg_applyJ[2], cfg_applyJT[2], cfg_rows, cfg_jt_ring;
   DevModel* d_model = nullptr;  // device copy of the joint table for the mapping kernels
   int forced_eval_block = 0;
   long long launches = 0;
@@ -166,7 +169,7 @@ static void ws_free(rbd_workspace* ws) {
   if (!ws) return;
   cudaFree(ws->d_sorted_k); cudaFree(ws->d_outk_parent); cudaFree(ws->d_sorted_ident); cudaFree(ws->d_sorted_pl); cudaFree(ws->d_outk_pl);
   cudaFree(ws->qcache); cudaFree(ws->rows_buf); cudaFree(ws->d_model);
-  for (int k = 0; k < 9; ++k) { cudaFree(ws->d_plan[k]); delete ws->h_plan[k]; }
+  for (int k = 0; k < 10; ++k) { cudaFree(ws->d_plan[k]); delete ws->h_plan[k]; }
   for (int k = 0; k < 8; ++k) { cudaFree(ws->d_plan32[k]); delete ws->h_plan32[k]; }
   for (int s = 0; s < kSlots; ++s) {
     cudaFree(ws->slot[s].aos); cudaFree(ws->slot[s].soa);
@@ -253,6 +256,18 @@ RBD_API int rbd_workspace_set_eval_tmem(rbd_workspace* ws, int enable) {
   return RBD_OK;
 }
 
+static int ensure_plan(rbd_workspace* ws, int pk);
+RBD_API int rbd_workspace_set_applyJT_ring(rbd_workspace* ws, int enable, int32_t* ring_slots) {
+  GUARD(ws);
+  ws->use_jt_ring = enable ? 1 : 0;
+  if (ring_slots) {
+    int rc = ensure_plan(ws, 9);
+    if (rc) return rc;
+    *ring_slots = ws->jt_ring_slots;
+  }
+  return RBD_OK;
+}
+
 static int check_batch(const rbd_workspace* ws, int64_t n, int64_t tile) {
   if (n < 0) return set_err(RBD_ERR_INVALID_ARG, "negative batch size");
   if (n > ws->capacity) return set_err(RBD_ERR_INVALID_ARG, "batch size exceeds the workspace capacity");
@@ -264,11 +279,19 @@ static int check_batch(const rbd_workspace* ws, int64_t n, int64_t tile) {
 // plan (once per variant and tuning-knob setting) + upload of the planned joint table
 static int ensure_plan(rbd_workspace* ws, int pk) {
   if (ws->h_plan[pk]) return RBD_OK;
+  if (pk == 9 && ws->jt_ring_slots == 0) return RBD_OK;
   DevModel* h = new (std::nothrow) DevModel(ws->model->dm);
   if (!h) return set_err(RBD_ERR_ALLOC, "out of host memory");
-  const bool planned = pk == 8 ? plan_eval(h, false, true, ws->use_tmem != 0, 0, false, /*jt=*/true, RBD_JT_REGS)
-                               : plan_eval(h, (pk & 2) != 0, (pk & 1) != 0, ws->use_tmem != 0,
-                                           ws->forced_eval_block / 32, (pk & 4) != 0);
+  bool planned;
+  if (pk == 9) {
+    ws->jt_ring_slots = h->njoints > 1 ? plan_jt_ring(h, ws->use_tmem != 0) : 0;
+    if (ws->jt_ring_slots == 0) { delete h; return RBD_OK; }  // not an error: the caller keeps the register path
+    planned = true;
+  } else {
+    planned = pk == 8 ? plan_eval(h, false, true, ws->use_tmem != 0, 0, false, /*jt=*/true, RBD_JT_REGS)
+                      : plan_eval(h, (pk & 2) != 0, (pk & 1) != 0, ws->use_tmem != 0,
+                                  ws->forced_eval_block / 32, (pk & 4) != 0);
+  }
   if (!planned) {
     delete h;
     return set_err(RBD_ERR_UNSUPPORTED, "the sweep state of this model does not fit one SM's shared + tensor memory"
@@ -289,7 +312,8 @@ static int ensure_plan(rbd_workspace* ws, int pk) {
 static void drop_plans(rbd_workspace* ws) {
   // kernels still in flight keep reading the device copies: wait for them before the next upload overwrites
   cudaDeviceSynchronize();
-  for (int k = 0; k < 9; ++k) { delete ws->h_plan[k]; ws->h_plan[k] = nullptr; }
+  for (int k = 0; k < 10; ++k) { delete ws->h_plan[k]; ws->h_plan[k] = nullptr; }
+  ws->jt_ring_slots = -1;
   for (int k = 0; k < 8; ++k) { delete ws->h_plan32[k]; ws->h_plan32[k] = nullptr; }
 }
 
@@ -440,10 +464,30 @@ static int applyJT_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t til
   if (!in || !out_tau) return set_err(RBD_ERR_INVALID_ARG, "null in / out_tau");
   if (out_root && !dm.has_ff_root) return set_err(RBD_ERR_INVALID_ARG, "root output given but the model has no free-flyer root");
   MapArgs A{n, tile, out_tau, out_root, in, nullptr, ws->qcache, inst0};
-  int rc = ensure_plan(ws, 8);
-  if (rc) return rc;
+  int rc;
+  // Full tiles of a tile-32 batch go through the ring kernel (bulk asynchronous copies of the wrench stream into
+  // shared memory); a partial last tile, other tilings and models whose state leaves no room for the ring take the
+  // register path.
+  if (tile == 32 && n >= 32 && ws->use_jt_ring && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    if ((rc = ensure_plan(ws, 9))) return rc;
+    if (ws->jt_ring_slots > 0) {
+      const long long nfull = n / 32 * 32;
+      MapArgs F = A;
+      F.n = nfull;
+      CK(launch_applyJT_ring(*ws->h_plan[9], ws->d_plan[9], ws->tb, F, ws->jt_ring_slots, &ws->cfg_jt_ring, ws->num_sms, st));
+      ws->launches++;
+      if (nfull == n) return RBD_OK;
+      const DevModel& m = ws->model->dm;
+      A.n = n - nfull;
+      A.in = in + nfull * 6 * (long long)m.n_out;
+      A.joints = out_tau + nfull * (long long)(m.nv - (out_root ? 6 : 0));  // field count as the kernels see it
+      A.root = out_root ? out_root + nfull * 6 : nullptr;
+      A.cache_inst0 = inst0 + nfull;
+    }
+  }
+  if ((rc = ensure_plan(ws, 8))) return rc;
   CK(launch_applyJT_plan(*ws->h_plan[8], ws->d_plan[8], ws->tb, A, ws->cfg_applyJT, ws->num_sms, st));
-  if (n > 0) ws->launches++;
+  if (A.n > 0) ws->launches++;
   return RBD_OK;
 }
 RBD_API int rbd_applyJT_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* in, double* out_tau,

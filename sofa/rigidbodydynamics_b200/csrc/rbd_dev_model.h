@@ -51,7 +51,7 @@ using DevJoint = DevJointT<double>;
 #define RBD_PROG_ROW(e) ((e) & 0xffff)
 #define RBD_PROG_FF(e) (((e) >> 16) & 1)
 #define RBD_PROG_OFFA(e) ((e) >> 17)
-#define RBD_PROG_ANC(row, ff, offA) ((row) | ((ff) << 16) | ((offA) << 17))
+#define RBD_PROG_ANC(row, ff, offA) ((row) | ((ff) << 16) | (((offA) & 0x3fff) << 17))
 #define RBD_PROG_ZSEG(row, len) ((row) | ((len) << 16))
 #define RBD_PROG_ZLEN(e) ((e) >> 16)
 
@@ -135,6 +135,20 @@ inline size_t eval_model_bytes(const DevModelT<real>& m) {
 __host__ __device__
 #endif
 inline int table_words(int n_out) { return 12 * n_out + (n_out + 1) / 2 * 2; }
+
+// applyJT ring kernel (rbd_kernels.cu: applyJT_ring_kernel; plan: rbd_model_build.h plan_jt_ring)
+struct JtRing {
+  static constexpr int kWarps = 8;
+  static constexpr int kSlotBytes = 6 * 32 * 8;  // one wrench of the 32 instances of a tile
+  static constexpr int kMaxSlots = 24;  // <= 32: the consumer keeps one phase bit per barrier in a 32-bit mask
+  static constexpr int kMinSlots = 6;
+};
+// 8-byte words the ring kernel stages behind the blob: translations (3 per output), field offsets and the piece
+// program (1 int each per output, each table padded to an even number of words)
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline int jt_table_words(int n_out) { return (3 * n_out + 1) / 2 * 2 + 2 * (((n_out + 1) / 2 + 1) / 2 * 2); }
 
 // Per-output tables (global memory; only the mapping kernels read them).
 struct DevTables {

@@ -223,6 +223,178 @@ __global__ void __launch_bounds__(256, RBD_JT_MINB) applyJT_plan_kernel(const De
   }
 }
 
+// K3, ring variant: full tile-32 batches.  The wrench of mapped output k of a warp's 32 instances is one contiguous
+// 1 536-byte block of the input; lane 0 of every warp streams those blocks with cp.async.bulk into the warp's ring of
+// `ns` slots in shared memory, always as far ahead of the sweep as the ring allows and across tile boundaries, each
+// piece (<= gmax outputs of one joint) completing on its own mbarrier.  The sweep (applyJT_instance_ring) waits for a
+// piece, reads it with conflict-free shared-memory loads and hands the slots back.  Nothing of the 5.6 KB/instance
+// wrench stream passes through a register before it is used, and no load of the stream can stall the sweep for
+// longer than the copy engine is behind.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "RBD_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra RBD_DONE;\n"
+      "bra RBD_WAIT;\n"
+      "RBD_DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+struct WarpRing {
+  const int* okoff;
+  const int* pieces;   // piece program (jt_build_pieces)
+  const double* ring;  // this lane's column of slot 0
+  const char* in;      // wrench array (bytes)
+  long long tile_bytes, ntiles, stride;
+  unsigned ring_s, bar_s;
+  int ns, np, lane;
+  int c_piece, c_slot, c_bar, c_first;
+  unsigned c_phase;
+  long long p_tile;
+  int p_piece, p_slot, p_bar, nfree;
+
+  // issue every piece the free slots allow (warp-uniform bookkeeping, lane 0 talks to the copy engine)
+  __device__ __forceinline__ void produce() {
+    while (p_tile < ntiles) {
+      const int e = pieces[p_piece];
+      const int cnt = e >> 16;
+      if (cnt > nfree) break;
+      if (lane == 0) {
+        const unsigned bar = bar_s + 8u * (unsigned)p_bar;
+        mbar_expect_tx(bar, (unsigned)cnt * (unsigned)JtRing::kSlotBytes);
+        const char* src = in + p_tile * tile_bytes;
+        const int* ko = okoff + (e & 0xffff);
+        int s = p_slot;
+        for (int j = 0; j < cnt; ++j) {
+          bulk_g2s(ring_s + (unsigned)s * (unsigned)JtRing::kSlotBytes, src + (long long)ko[j] * 256, JtRing::kSlotBytes, bar);
+          s = s + 1 == ns ? 0 : s + 1;
+        }
+      }
+      p_slot += cnt; if (p_slot >= ns) p_slot -= ns;
+      p_bar = p_bar + 1 == ns ? 0 : p_bar + 1;
+      nfree -= cnt;
+      if (++p_piece == np) { p_piece = 0; p_tile += stride; }
+    }
+  }
+  __device__ __forceinline__ int acquire() {
+    const int cnt = pieces[c_piece] >> 16;
+    c_piece = c_piece + 1 == np ? 0 : c_piece + 1;
+    mbar_wait(bar_s + 8u * (unsigned)c_bar, (c_phase >> c_bar) & 1u);
+    c_first = c_slot;
+    return cnt;
+  }
+  __device__ __forceinline__ void ld(int j, double* w) const {
+    int s = c_first + j;
+    if (s >= ns) s -= ns;
+    const double* b = ring + s * (JtRing::kSlotBytes / 8);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) w[e] = b[e * 32];
+  }
+  __device__ __forceinline__ void release(int cnt) {
+    c_phase ^= 1u << c_bar;
+    c_bar = c_bar + 1 == ns ? 0 : c_bar + 1;
+    c_slot += cnt; if (c_slot >= ns) c_slot -= ns;
+    __syncwarp();  // every lane has read the piece before lane 0 lets the copy engine overwrite it
+    nfree += cnt;
+    produce();
+  }
+};
+
+__global__ void __launch_bounds__(256, 1) applyJT_ring_kernel(const DevModel* __restrict__ gm, const int model_words,
+                                                              const DevTables tb, const MapArgs a, const int ns) {
+  unsigned* const tm_base_p = reinterpret_cast<unsigned*>(rbd_smem + model_words - 2);
+  {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gm);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(rbd_smem);
+    for (int w = threadIdx.x; w < model_words - 2; w += blockDim.x) dst[w] = src[w];
+  }
+  __syncthreads();
+  const DevModel& m = *reinterpret_cast<const DevModel*>(rbd_smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_out = m.n_out;
+  const int iw = ((n_out + 1) / 2 + 1) / 2 * 2;  // words of one int table
+  double* const opl = rbd_smem + model_words;
+  int* const okoff = reinterpret_cast<int*>(opl + (3 * n_out + 1) / 2 * 2);
+  int* const pieces = okoff + 2 * iw;
+  unsigned long long* const bars = reinterpret_cast<unsigned long long*>(rbd_smem + model_words + jt_table_words(n_out));
+  double* const stacks = reinterpret_cast<double*>(bars + JtRing::kWarps * JtRing::kMaxSlots);
+  double* const rings = stacks + (size_t)blockDim.x * m.plan.smem_doubles;
+  int* const np_p = reinterpret_cast<int*>(tm_base_p) + 1;  // second half of the spare word
+  for (int w = threadIdx.x; w < n_out; w += blockDim.x) {
+    opl[3 * w] = tb.sorted_pl[12 * w + 9]; opl[3 * w + 1] = tb.sorted_pl[12 * w + 10]; opl[3 * w + 2] = tb.sorted_pl[12 * w + 11];
+    okoff[w] = 6 * tb.sorted_k[w];
+  }
+  const int gmax = ns / 2 < 8 ? ns / 2 : 8;
+  if (threadIdx.x == 0) *np_p = jt_build_pieces(m, gmax, pieces);
+  if (lane < ns) mbar_init(smem_u32(bars + warp * JtRing::kMaxSlots + lane), 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  const int tm_cols = m.plan.tmem_cols;
+  TmStack T;
+  T.base = 0;
+  if (tm_cols > 0) {
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"l"(
+                       (unsigned long long)__cvta_generic_to_shared(tm_base_p)),
+                   "r"(tm_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (tm_cols > 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    T.base = *tm_base_p + (((unsigned)(warp & 3) * 32u) << 16) + (unsigned)(warp >> 2) * 2u * (unsigned)m.plan.tmem_doubles;
+  }
+  const int np = *np_p;
+  const long long ntiles = a.n / 32;  // full tiles only (the host sends a partial last tile down the register path)
+  const int wpb = blockDim.x >> 5;
+  if (np > 0) {
+    const Stack S = make_stack(stacks, threadIdx.x, m.plan.smem_doubles);
+    const JtTab jt{opl, okoff};
+    const int off = a.root ? 6 : 0;
+    WarpRing ring;
+    ring.okoff = okoff; ring.pieces = pieces;
+    ring.ring = rings + (size_t)warp * ns * (JtRing::kSlotBytes / 8) + lane;
+    ring.in = reinterpret_cast<const char*>(a.in);
+    ring.tile_bytes = (long long)6 * n_out * 256;
+    ring.ntiles = ntiles; ring.stride = (long long)gridDim.x * wpb;
+    ring.ring_s = smem_u32(rings + (size_t)warp * ns * (JtRing::kSlotBytes / 8));
+    ring.bar_s = smem_u32(bars + warp * JtRing::kMaxSlots);
+    ring.ns = ns; ring.np = np; ring.lane = lane;
+    ring.c_piece = 0; ring.c_slot = 0; ring.c_bar = 0; ring.c_first = 0; ring.c_phase = 0u;
+    ring.p_tile = (long long)blockIdx.x * wpb + warp; ring.p_piece = 0;
+    ring.p_slot = 0; ring.p_bar = 0; ring.nfree = ns;
+    ring.produce();
+    for (long long t = (long long)blockIdx.x * wpb + warp; t < ntiles; t += (long long)gridDim.x * wpb) {
+      const long long inst = t * 32 + lane;
+      SplitRedSinkT<FieldT<32>> sink{make_field_t<32>(const_cast<double*>(a.root), inst, 6, 32),
+                                     make_field_t<32>(const_cast<double*>(a.joints), inst, m.nv - off, 32), off};
+      applyJT_instance_ring(m, jt, make_field_t<32>(a.qcache, a.cache_inst0 + inst, m.nq, 32), ring, sink, S, T);
+    }
+  }
+  if (tm_cols > 0) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tm_base_p), "r"(tm_cols) : "memory");
+  }
+}
+
 // K4: applyJT (constraint rows): one thread per row
 __global__ void __launch_bounds__(256) applyJT_rows_kernel(const DevModel* __restrict__ gm, const int model_words,
                                                            const DevTables tb, const RowArgs a, const int slots) {
@@ -415,6 +587,29 @@ cudaError_t launch_applyJT_plan(const DevModel& hm, const DevModel* d_blob, cons
   if (grid > 8 * resident) grid = resident;  // persistent only when every warp gets >= 8 tiles (else: wave tail)
   if (v) applyJT_plan_kernel<32><<<grid, block, smem, st>>>(d_blob, model_words, tb, a);
   else applyJT_plan_kernel<0><<<grid, block, smem, st>>>(d_blob, model_words, tb, a);
+  return cudaGetLastError();
+}
+
+// `hm` = host copy of the model planned with plan_jt_ring, `d_blob` = its staged blob, ns = ring slots per warp.
+// a.n must be a multiple of 32 and a.tile == 32; a.in 16-byte aligned.
+cudaError_t launch_applyJT_ring(const DevModel& hm, const DevModel* d_blob, const DevTables& tb, const MapArgs& a,
+                                int ns, LaunchCfg* cfg, int num_sms, cudaStream_t st) {
+  const int model_words = (int)(eval_model_bytes(hm) / 8);
+  const int block = JtRing::kWarps * 32;
+  const size_t smem = ((size_t)model_words + jt_table_words(hm.n_out) + (size_t)JtRing::kWarps * JtRing::kMaxSlots) * 8 +
+                      (size_t)block * hm.plan.smem_doubles * 8 + (size_t)JtRing::kWarps * ns * JtRing::kSlotBytes;
+  if (cfg->block != block || cfg->smem_bytes != smem) {
+    cudaError_t e = cudaFuncSetAttribute(applyJT_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(applyJT_ring_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    cfg->block = block; cfg->smem_bytes = smem; cfg->blocks_per_sm = 1;
+  }
+  if (a.n <= 0) return cudaSuccess;
+  const long long ntiles = a.n / 32;
+  unsigned grid = (unsigned)((ntiles + JtRing::kWarps - 1) / JtRing::kWarps);
+  if (grid > (unsigned)num_sms) grid = (unsigned)num_sms;
+  applyJT_ring_kernel<<<grid, block, smem, st>>>(d_blob, model_words, tb, a, ns);
   return cudaGetLastError();
 }
 

@@ -316,6 +316,48 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
   return true;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Storage plan of the applyJT ring kernel (applyJT_instance_ring).  Placement is by record kind, fixed at compile time
+// in the kernel: per depth level of 1-dof joints with children one record [F | A] (12 doubles) and per 1-dof branch
+// joint one R|p record (12) in TENSOR memory; the level record of a free-flyer [R|p | F] (18) in shared memory.  What
+// remains of the SM's shared memory becomes the per-warp wrench ring.
+// Fills m->plan (warps, smem_doubles, tmem_doubles, tmem_cols), joint[*].offA (level record) and joint[*].boff (branch
+// record).  Returns the number of ring slots (1 536-byte wrench blocks) per warp, 0 when the kernel cannot run this
+// model (tensor memory off or too small for the tree's depth: the caller keeps the register path).
+inline int plan_jt_ring(DevModel* m, bool use_tmem) {
+  const int nj = m->njoints, W = JtRing::kWarps;
+  const int D = m->max_depth_internal;
+  if (!use_tmem || nj < 2) return 0;
+  const int cap = B200Limits::kTmemCols / ((W + 3) / 4) / 2;
+  std::vector<int> lvl_t(D + 1, -1), lvl_s(D + 1, -1);
+  int t_used = 0, s_used = 0;
+  for (int i = 1; i < nj; ++i) {
+    DevJoint& j = m->joint[i];
+    j.offA = 0; j.boff = 0;
+    if (j.nchild == 0) continue;
+    if (j.type != JT_FF) {
+      if (lvl_t[j.depth] < 0) { lvl_t[j.depth] = t_used; t_used += 12; }
+      j.offA = lvl_t[j.depth];
+      if (j.nchild >= 2) { j.boff = t_used; t_used += 12; }
+    } else {
+      if (lvl_s[j.depth] < 0) { lvl_s[j.depth] = s_used; s_used += 18; }
+      j.offA = lvl_s[j.depth];
+    }
+  }
+  if (t_used > cap) return 0;
+  (void)build_col_prog(m);
+  EvalPlan pl{};
+  pl.smem_doubles = s_used; pl.tmem_doubles = t_used; pl.warps = W; pl.blocks_per_sm = 1;
+  pl.tmem_cols = t_used > 0 ? pow2_cols(2 * t_used * ((W + 3) / 4)) : 0;
+  m->plan = pl;
+  const size_t fixed = eval_model_bytes(*m) + (size_t)jt_table_words(m->n_out) * 8 + (size_t)W * JtRing::kMaxSlots * 8 +
+                       (size_t)W * 32 * s_used * 8 + B200Limits::kSmemReservedPerBlock;
+  if (fixed >= (size_t)B200Limits::kSmemBytes) return 0;
+  int ns = (int)(((size_t)B200Limits::kSmemBytes - fixed) / ((size_t)W * JtRing::kSlotBytes));
+  ns = std::min(ns, (int)JtRing::kMaxSlots);
+  return ns >= JtRing::kMinSlots ? ns : 0;
+}
+
 // shared-memory doubles per instance of the mapping kernels
 inline int smem_apply(const DevModel& m) { return m.nbranch * RBD_BRANCH_FK; }
 inline int smem_applyJ(const DevModel& m) { return m.nbranch * RBD_BRANCH_J; }

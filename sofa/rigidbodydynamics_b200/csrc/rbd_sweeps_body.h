@@ -166,6 +166,15 @@ struct TmStack {
     }
 #endif
   }
+  // values [k, k+N) += v[0..N)
+  template <int N>
+  __host__ __device__ __forceinline__ void addv(int k, const real* v) const {
+    real t[N];
+    ldv<N>(k, t);
+#pragma unroll
+    for (int i = 0; i < N; ++i) t[i] += v[i];
+    stv<N>(k, t);
+  }
   // values [k, k+N) <- v[0..N); complete before returning (a later ldv of the same columns must see it)
   template <int N>
   __host__ __device__ __forceinline__ void stv(int k, const real* v) const {
@@ -190,6 +199,7 @@ struct TmStack {
   real* p;
   template <int N> void ldv(int k, real* v) const { for (int i = 0; i < N; ++i) v[i] = p[k + i]; }
   template <int N> void stv(int k, const real* v) const { for (int i = 0; i < N; ++i) p[k + i] = v[i]; }
+  template <int N> void addv(int k, const real* v) const { for (int i = 0; i < N; ++i) p[k + i] += v[i]; }
 };
 #endif
 
@@ -1379,10 +1389,200 @@ struct SplitAccumSinkT {
   }
 };
 using SplitAccumSink = SplitAccumSinkT<Field>;
+// the same += as a reduction that returns nothing (device: RED.ADD.F64 — one IEEE add per address and launch, so the
+// result is that of load + add + store, but the sweep never waits for the old value)
+template <class FLD>
+struct SplitRedSinkT {
+  FLD root, joints;
+  int off;
+  static RBD_HD void red(real* a, real v) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(a, v);
+#else
+    *a += v;
+#endif
+  }
+  RBD_HD void put(int c, real v) const {
+    if (c < off) {
+      if (root.ok()) red(root.at(c), v);
+    } else if (joints.ok()) {
+      red(joints.at(c - off), v);
+    }
+  }
+};
 // dense row + squared norm (KCM.inl:585-615)
 struct RowSink {
   real* row;
   real* n2;
   RBD_HD void put(int c, real v) const { row[c] = v; *n2 += v * v; }
 };
+
+// ---------------------------------------------------------------------------------------------------------
+// applyJT, ring variant (K3 on full tile-32 batches): the wrenches do not travel through registers.  A warp's 32
+// instances form one tile, so the wrench of mapped output k is ONE contiguous 1 536-byte block of the input
+// (6 fields x 32 lanes x 8 bytes): the kernel streams those blocks with bulk asynchronous copies
+// (cp.async.bulk, completion on an mbarrier) into a per-warp ring in shared memory, many outputs — and across
+// tile boundaries — ahead of the sweep, and the sweep reads them from there.  `Ring` is that ring on the device
+// (rbd_kernels.cu) and a plain reader of the input array in tests/emul:
+//   int  acquire()         wait for the next piece (<= gmax outputs of one joint, in sweep order); returns its length
+//   void ld(j, w)          wrench of the j-th output of the acquired piece
+//   void release(cnt)      the piece has been consumed: its slots are refilled with the outputs furthest ahead
+// Sweep state (plan_jt_ring), placed at COMPILE time so that the register allocator never has to merge a
+// tensor-memory tuple with a shared-memory load (profile r1h: 22 % of the executed instructions of the first ring
+// kernel were register moves around exactly those merges):
+//   tensor memory   one record [F (6) | A (6)] per depth level of 1-dof joints with children; R|p (12) per 1-dof
+//                   branch joint
+//   shared memory   free-flyer level record [R|p (12) | F (6)]
+// Accumulated outputs go through Sink::put (a fire-and-forget reduction on the device: the += of the reference,
+// KCM.inl:498-511, without a load the sweep would have to wait for).
+struct JtTab {
+  const real* opl;   // [n_out][3] translation of the output's placement in its parent joint frame, sorted order
+  const int* okoff;  // [n_out] 6 * k: first field of output k's wrench, sorted order
+};
+template <class QC, class Ring, class Sink>
+RBD_HD void applyJT_instance_ring(const DevModel& m, const JtTab& tb, const QC& q, Ring& ring, const Sink& sink,
+                                  const Stack& S, const TmStack& T) {
+  const int nj = m.njoints;
+  real R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
+  real q0n = 0.0, q1n = 0.0;
+  RBD_Q_PREFETCH(1);
+  for (int i = 1; i < nj; ++i) {
+    const DevJoint& jn = m.joint[i];
+    const int par = jn.parent;
+    if (par != i - 1) {
+      if (par == 0) {
+        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+        p[0] = p[1] = p[2] = 0;
+      } else {
+        const DevJoint& jb = m.joint[par];
+        real Rp[12];
+        if (jb.type == JT_FF) s_ldv<12>(S, jb.offA, Rp);  // a free-flyer's level record starts with its R|p
+        else T.template ldv<12>(jb.boff, Rp);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) R[e] = Rp[e];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) p[e] = Rp[9 + e];
+      }
+    }
+    const int nxt_par = (i + 1 < nj) ? m.joint[i + 1].parent : 0;
+    real aw[3];
+    const real q0 = q0n, q1 = q1n;
+    RBD_Q_PREFETCH(i + 1);
+    fk_joint(jn, R, p, q0, q1, q, aw);
+    // wrenches attached to this joint, moved to the world origin
+    real Fk[6] = {0, 0, 0, 0, 0, 0};
+    for (int o = jn.out_begin; o < jn.out_end;) {
+      const int cnt = ring.acquire();
+      for (int j = 0; j < cnt; ++j) {
+        real w[6];
+        ring.ld(j, w);
+        const real* pl = tb.opl + 3 * (o + j);
+        const real px = R[0] * pl[0] + R[1] * pl[1] + R[2] * pl[2] + p[0];
+        const real py = R[3] * pl[0] + R[4] * pl[1] + R[5] * pl[2] + p[1];
+        const real pz = R[6] * pl[0] + R[7] * pl[1] + R[8] * pl[2] + p[2];
+        real tx, ty, tz;
+        RBD_CROSS(tx, ty, tz, px, py, pz, w[0], w[1], w[2]);
+        Fk[0] += w[0]; Fk[1] += w[1]; Fk[2] += w[2];
+        Fk[3] += w[3] + tx; Fk[4] += w[4] + ty; Fk[5] += w[5] + tz;
+      }
+      ring.release(cnt);
+      o += cnt;
+    }
+    if (nxt_par == i) {
+      // joint i has children: park F | A at its depth level; the subtree's wrenches accumulate there
+      if (jn.type != JT_FF) {
+        real rec[12];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) rec[e] = Fk[e];
+        subspace_1dof(jn.type, p, aw, rec + 6);
+        T.template stv<12>(jn.offA, rec);
+        if (jn.nchild >= 2) {
+          real Rp[12];
+#pragma unroll
+          for (int e = 0; e < 9; ++e) Rp[e] = R[e];
+#pragma unroll
+          for (int e = 0; e < 3; ++e) Rp[9 + e] = p[e];
+          T.template stv<12>(jn.boff, Rp);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) S.st(jn.offA + e, R[e]);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) S.st(jn.offA + 9 + e, p[e]);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) S.st(jn.offA + 12 + e, Fk[e]);
+      }
+    } else {
+      // leaf: project from registers, then unwind — only the running sum Fk is carried from level to level
+      if (jn.type != JT_FF) {
+        real A[6];
+        subspace_1dof(jn.type, p, aw, A);
+        sink.put(jn.idx_v, dot6(A, Fk));
+      } else {
+        real o6[6];
+        ff_rows(R, p, Fk, o6);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) sink.put(jn.idx_v + e, o6[e]);
+      }
+      int pk = par;
+      while (pk != 0) {
+        const DevJoint& jp = m.joint[pk];
+        if (jp.type != JT_FF) {
+          if (pk == nxt_par) { T.template addv<6>(jp.offA, Fk); break; }
+          real rec[12];
+          T.template ldv<12>(jp.offA, rec);
+#pragma unroll
+          for (int e = 0; e < 6; ++e) Fk[e] += rec[e];
+          sink.put(jp.idx_v, dot6(rec + 6, Fk));
+        } else {
+          if (pk == nxt_par) {
+#pragma unroll
+            for (int e = 0; e < 6; ++e) S.add(jp.offA + 12 + e, Fk[e]);
+            break;
+          }
+          real Rp[12], o6[6];
+          s_ldv<12>(S, jp.offA, Rp);
+#pragma unroll
+          for (int e = 0; e < 6; ++e) Fk[e] += S.ld(jp.offA + 12 + e);
+          ff_rows(Rp, Rp + 9, Fk, o6);
+#pragma unroll
+          for (int e = 0; e < 6; ++e) sink.put(jp.idx_v + e, o6[e]);
+        }
+        pk = jp.parent;
+      }
+    }
+  }
+}
+// reader of the input array with the ring's interface (tests/emul; the device ring lives in rbd_kernels.cu)
+template <class FLD>
+struct DirectRingT {
+  FLD in;
+  const int* okoff;
+  const int* pieces;  // piece program (jt_build_pieces): first sorted index | count << 16, in sweep order
+  int npieces, c;
+  int o0;
+  RBD_HD int acquire() {
+    const int e = pieces[c];
+    c = c + 1 == npieces ? 0 : c + 1;
+    o0 = e & 0xffff;
+    return e >> 16;
+  }
+  RBD_HD void ld(int j, real* w) const {
+#pragma unroll
+    for (int e = 0; e < 6; ++e) w[e] = in.ld(okoff[o0 + j] + e);
+  }
+  RBD_HD void release(int) {}
+};
+// Piece program of the ring: the mapped outputs of joints 1.. in sweep order, cut into pieces of at most gmax outputs
+// that never span two joints.  Returns the number of pieces written (<= n_out).
+RBD_HD int jt_build_pieces(const DevModel& m, int gmax, int* pieces) {
+  int np = 0;
+  for (int i = 1; i < m.njoints; ++i)
+    for (int o = m.joint[i].out_begin; o < m.joint[i].out_end;) {
+      const int cnt = m.joint[i].out_end - o < gmax ? m.joint[i].out_end - o : gmax;
+      pieces[np++] = o | (cnt << 16);
+      o += cnt;
+    }
+  return np;
+}
 #endif  /* !RBD_BODY_F32 */

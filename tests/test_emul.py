@@ -122,6 +122,16 @@ def test_mapping_bodies_match_oracle(emul, d):
         assert rel_err(from_tiled(ttau2, n), from_tiled(ttau, n)) <= 1e-13
         if root is not None:
             assert rel_err(from_tiled(trt2, n), from_tiled(trt, n)) <= 1e-13
+    # ... and through the ring variant (plan_jt_ring; the device ring is replaced by a direct reader)
+    for use_tmem in (0, 1):
+        ttau3 = T(tau0); trt3 = T(root0) if root is not None else None
+        ns = C.c_int(-1)
+        rc = emul.emul_applyJT_ring(C.addressof(cd), n, tile, use_tmem, P(qcache), ctile, P(tw), P(ttau3), P(trt3), C.byref(ns))
+        assert rc in (0, 1) and (rc == 0) == (ns.value > 0)
+        if rc == 0:
+            assert rel_err(from_tiled(ttau3, n), from_tiled(ttau, n)) <= 1e-13
+            if root is not None:
+                assert rel_err(from_tiled(trt3, n), from_tiled(trt, n)) <= 1e-13
     pos = from_tiled(pos, n).reshape(n, d.n_out, 7); vel = from_tiled(vel, n).reshape(n, d.n_out, 6)
     tau = from_tiled(ttau, n); rt = from_tiled(trt, n) if trt is not None else None
     orc = oracle.Oracle(d)
