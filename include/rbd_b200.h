@@ -145,7 +145,7 @@ RBD_API int rbd_workspace_set_eval_block(rbd_workspace* ws, int threads);
  * Tuning / A-B knob, not part of the contract: results are identical either way.                         */
 RBD_API int rbd_workspace_set_eval_tmem(rbd_workspace* ws, int enable);
 /* Ring variant of the vector applyJT (full tiles of a tile-32 batch: the wrench stream is staged in shared memory by
- * bulk asynchronous copies): 1 = on (default), 0 = always the register path; out (may be NULL) receives the ring slots
+ * bulk asynchronous copies): 1 = on (default), 0 = always the register path; out (may be NULL) receives the ring stages
  * per warp the plan found for this model (0 = the ring kernel cannot run it).  Tuning / A-B knob: same results.    */
 RBD_API int rbd_workspace_set_applyJT_ring(rbd_workspace* ws, int enable, int32_t* ring_slots);
 /* Storage plan the fused eval kernel uses on this workspace for the output set (with_M, with_tau):

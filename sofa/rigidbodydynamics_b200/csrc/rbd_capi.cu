@@ -66,7 +66,7 @@ struct rbd_workspace {
   DevModel* h_plan[10] = {};  // index: bit 2 = oMi requested, bit 1 = CRBA, bit 0 = RNEA; [8] = the applyJT sweep,
                               // [9] = its ring variant (full tiles of 32)
   DevModel* d_plan[10] = {};
-  int jt_ring_slots = -1;     // ring slots per warp of plan [9]; 0 = the ring kernel cannot run this model; -1 = not planned yet
+  int jt_ring_slots = -1;     // ring stages per warp of plan [9]; 0 = the ring kernel cannot run this model; -1 = not planned yet
   int use_jt_ring = 1;
   DevModelT<float>* h_plan32[8] = {};  // FP32 mode of the fused eval
   DevModelT<float>* d_plan32[8] = {};
@@ -283,8 +283,9 @@ static int ensure_plan(rbd_workspace* ws, int pk) {
   DevModel* h = new (std::nothrow) DevModel(ws->model->dm);
   if (!h) return set_err(RBD_ERR_ALLOC, "out of host memory");
   bool planned;
+  std::vector<int> jt_prog;
   if (pk == 9) {
-    ws->jt_ring_slots = h->njoints > 1 ? plan_jt_ring(h, ws->use_tmem != 0) : 0;
+    ws->jt_ring_slots = plan_jt_ring(h, ws->model->ht, ws->use_tmem != 0, &jt_prog);
     if (ws->jt_ring_slots == 0) { delete h; return RBD_OK; }  // not an error: the caller keeps the register path
     planned = true;
   } else {
@@ -297,7 +298,7 @@ static int ensure_plan(rbd_workspace* ws, int pk) {
     return set_err(RBD_ERR_UNSUPPORTED, "the sweep state of this model does not fit one SM's shared + tensor memory"
                                         " at the requested block size");
   }
-  const std::vector<unsigned long long> blob = build_eval_blob(h);
+  const std::vector<unsigned long long> blob = pk == 9 ? build_jt_blob(h, jt_prog) : build_eval_blob(h);
   if (!ws->d_plan[pk]) {
     // sized for the largest blob any plan of this model can produce (the ColProg length is plan-independent)
     cudaError_t e = cudaMalloc(&ws->d_plan[pk], blob.size() * 8);
@@ -474,7 +475,7 @@ static int applyJT_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t til
       const long long nfull = n / 32 * 32;
       MapArgs F = A;
       F.n = nfull;
-      CK(launch_applyJT_ring(*ws->h_plan[9], ws->d_plan[9], ws->tb, F, ws->jt_ring_slots, &ws->cfg_jt_ring, ws->num_sms, st));
+      CK(launch_applyJT_ring(*ws->h_plan[9], ws->d_plan[9], F, ws->jt_ring_slots, &ws->cfg_jt_ring, ws->num_sms, st));
       ws->launches++;
       if (nfull == n) return RBD_OK;
       const DevModel& m = ws->model->dm;

@@ -136,19 +136,14 @@ __host__ __device__
 #endif
 inline int table_words(int n_out) { return 12 * n_out + (n_out + 1) / 2 * 2; }
 
-// applyJT ring kernel (rbd_kernels.cu: applyJT_ring_kernel; plan: rbd_model_build.h plan_jt_ring)
+// applyJT ring kernel (rbd_kernels.cu: applyJT_ring_kernel; plan + ring program: rbd_model_build.h plan_jt_ring)
 struct JtRing {
   static constexpr int kWarps = 8;
-  static constexpr int kSlotBytes = 6 * 32 * 8;  // one wrench of the 32 instances of a tile
-  static constexpr int kMaxSlots = 24;  // <= 32: the consumer keeps one phase bit per barrier in a 32-bit mask
-  static constexpr int kMinSlots = 6;
+  static constexpr int kSlotBytes = 6 * 32 * 8;           // one wrench of the 32 instances of a tile
+  static constexpr int kStageBytes = 4 * kSlotBytes;      // one piece: <= RBD_JT_GMAX = 4 outputs of one joint
+  static constexpr int kMaxStages = 8;
+  static constexpr int kMinStages = 2;
 };
-// 8-byte words the ring kernel stages behind the blob: translations (3 per output), field offsets and the piece
-// program (1 int each per output, each table padded to an even number of words)
-#if defined(__CUDACC__)
-__host__ __device__
-#endif
-inline int jt_table_words(int n_out) { return (3 * n_out + 1) / 2 * 2 + 2 * (((n_out + 1) / 2 + 1) / 2 * 2); }
 
 // Per-output tables (global memory; only the mapping kernels read them).
 struct DevTables {

@@ -254,94 +254,73 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
 }
 
 struct WarpRing {
-  const int* okoff;
-  const int* pieces;   // piece program (jt_build_pieces)
-  const double* ring;  // this lane's column of slot 0
+  JtProg prog;
+  const double* ring;  // this lane's column of stage 0
+  const double* cur;   // ... of the acquired stage
   const char* in;      // wrench array (bytes)
   long long tile_bytes, ntiles, stride;
   unsigned ring_s, bar_s;
-  int ns, np, lane;
-  int c_piece, c_slot, c_bar, c_first;
-  unsigned c_phase;
+  int nst, np, lane;
+  int c_piece, stage;
+  unsigned phase;
   long long p_tile;
-  int p_piece, p_slot, p_bar, nfree;
+  int p_piece;
 
-  // issue every piece the free slots allow (warp-uniform bookkeeping, lane 0 talks to the copy engine)
-  __device__ __forceinline__ void produce() {
-    while (p_tile < ntiles) {
-      const int e = pieces[p_piece];
-      const int cnt = e >> 16;
-      if (cnt > nfree) break;
+  // fetch the producer cursor's piece into stage `st` (warp-uniform bookkeeping, lane 0 talks to the copy engine)
+  __device__ __forceinline__ void issue(int st) {
+    if (p_tile < ntiles) {
       if (lane == 0) {
-        const unsigned bar = bar_s + 8u * (unsigned)p_bar;
-        mbar_expect_tx(bar, (unsigned)cnt * (unsigned)JtRing::kSlotBytes);
+        const int4 pe = *reinterpret_cast<const int4*>(prog.piece(p_piece));
+        const unsigned bar = bar_s + 8u * (unsigned)st;
+        mbar_expect_tx(bar, (unsigned)pe.y);
         const char* src = in + p_tile * tile_bytes;
-        const int* ko = okoff + (e & 0xffff);
-        int s = p_slot;
-        for (int j = 0; j < cnt; ++j) {
-          bulk_g2s(ring_s + (unsigned)s * (unsigned)JtRing::kSlotBytes, src + (long long)ko[j] * 256, JtRing::kSlotBytes, bar);
-          s = s + 1 == ns ? 0 : s + 1;
+        const unsigned dst = ring_s + (unsigned)st * (unsigned)JtRing::kStageBytes;
+        const int2* cp = reinterpret_cast<const int2*>(prog.copy(pe.z));
+        for (int c = 0; c < pe.w; ++c) {
+          const int2 ce = cp[c];
+          bulk_g2s(dst + ((unsigned)ce.y & 0xffffu), src + ce.x, (unsigned)ce.y >> 16, bar);
         }
       }
-      p_slot += cnt; if (p_slot >= ns) p_slot -= ns;
-      p_bar = p_bar + 1 == ns ? 0 : p_bar + 1;
-      nfree -= cnt;
       if (++p_piece == np) { p_piece = 0; p_tile += stride; }
     }
   }
   __device__ __forceinline__ int acquire() {
-    const int cnt = pieces[c_piece] >> 16;
+    const int cnt = prog.piece(c_piece)[0] >> 16;
     c_piece = c_piece + 1 == np ? 0 : c_piece + 1;
-    mbar_wait(bar_s + 8u * (unsigned)c_bar, (c_phase >> c_bar) & 1u);
-    c_first = c_slot;
+    cur = ring + stage * (JtRing::kStageBytes / 8);
+    mbar_wait(bar_s + 8u * (unsigned)stage, phase);
     return cnt;
   }
-  __device__ __forceinline__ void ld(int j, double* w) const {
-    int s = c_first + j;
-    if (s >= ns) s -= ns;
-    const double* b = ring + s * (JtRing::kSlotBytes / 8);
+  template <int J>
+  __device__ __forceinline__ void ld(double* w) const {
 #pragma unroll
-    for (int e = 0; e < 6; ++e) w[e] = b[e * 32];
+    for (int e = 0; e < 6; ++e) w[e] = cur[J * (JtRing::kSlotBytes / 8) + e * 32];
   }
-  __device__ __forceinline__ void release(int cnt) {
-    c_phase ^= 1u << c_bar;
-    c_bar = c_bar + 1 == ns ? 0 : c_bar + 1;
-    c_slot += cnt; if (c_slot >= ns) c_slot -= ns;
-    __syncwarp();  // every lane has read the piece before lane 0 lets the copy engine overwrite it
-    nfree += cnt;
-    produce();
+  // the piece has been consumed: its stage receives the piece `nst` ahead
+  __device__ __forceinline__ void release(int) {
+    __syncwarp();  // every lane has read the stage before lane 0 lets the copy engine overwrite it
+    issue(stage);
+    if (++stage == nst) { stage = 0; phase ^= 1u; }
   }
 };
 
 __global__ void __launch_bounds__(256, 1) applyJT_ring_kernel(const DevModel* __restrict__ gm, const int model_words,
-                                                              const DevTables tb, const MapArgs a, const int ns) {
+                                                              const MapArgs a, const int nst) {
   unsigned* const tm_base_p = reinterpret_cast<unsigned*>(rbd_smem + model_words - 2);
   {
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gm);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(rbd_smem);
     for (int w = threadIdx.x; w < model_words - 2; w += blockDim.x) dst[w] = src[w];
   }
-  __syncthreads();
-  const DevModel& m = *reinterpret_cast<const DevModel*>(rbd_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_out = m.n_out;
-  const int iw = ((n_out + 1) / 2 + 1) / 2 * 2;  // words of one int table
-  double* const opl = rbd_smem + model_words;
-  int* const okoff = reinterpret_cast<int*>(opl + (3 * n_out + 1) / 2 * 2);
-  int* const pieces = okoff + 2 * iw;
-  unsigned long long* const bars = reinterpret_cast<unsigned long long*>(rbd_smem + model_words + jt_table_words(n_out));
-  double* const stacks = reinterpret_cast<double*>(bars + JtRing::kWarps * JtRing::kMaxSlots);
-  double* const rings = stacks + (size_t)blockDim.x * m.plan.smem_doubles;
-  int* const np_p = reinterpret_cast<int*>(tm_base_p) + 1;  // second half of the spare word
-  for (int w = threadIdx.x; w < n_out; w += blockDim.x) {
-    opl[3 * w] = tb.sorted_pl[12 * w + 9]; opl[3 * w + 1] = tb.sorted_pl[12 * w + 10]; opl[3 * w + 2] = tb.sorted_pl[12 * w + 11];
-    okoff[w] = 6 * tb.sorted_k[w];
-  }
-  const int gmax = ns / 2 < 8 ? ns / 2 : 8;
-  if (threadIdx.x == 0) *np_p = jt_build_pieces(m, gmax, pieces);
-  if (lane < ns) mbar_init(smem_u32(bars + warp * JtRing::kMaxSlots + lane), 1);
+  unsigned long long* const bars = reinterpret_cast<unsigned long long*>(rbd_smem + model_words);
+  if (lane < nst) mbar_init(smem_u32(bars + warp * JtRing::kMaxStages + lane), 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const DevModel& m = *reinterpret_cast<const DevModel*>(rbd_smem);
+  double* const stacks = reinterpret_cast<double*>(bars + JtRing::kWarps * JtRing::kMaxStages);
+  double* const rings = stacks + (size_t)blockDim.x * m.plan.smem_doubles;
   const int tm_cols = m.plan.tmem_cols;
   TmStack T;
   T.base = 0;
@@ -354,37 +333,36 @@ __global__ void __launch_bounds__(256, 1) applyJT_ring_kernel(const DevModel* __
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  }
-  __syncthreads();
-  if (tm_cols > 0) {
+    __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     T.base = *tm_base_p + (((unsigned)(warp & 3) * 32u) << 16) + (unsigned)(warp >> 2) * 2u * (unsigned)m.plan.tmem_doubles;
   }
-  const int np = *np_p;
+  const JtProg prog{col_prog(m)};
+  const int np = prog.npieces();
   const long long ntiles = a.n / 32;  // full tiles only (the host sends a partial last tile down the register path)
   const int wpb = blockDim.x >> 5;
   if (np > 0) {
     const Stack S = make_stack(stacks, threadIdx.x, m.plan.smem_doubles);
-    const JtTab jt{opl, okoff};
     const int off = a.root ? 6 : 0;
     WarpRing ring;
-    ring.okoff = okoff; ring.pieces = pieces;
-    ring.ring = rings + (size_t)warp * ns * (JtRing::kSlotBytes / 8) + lane;
+    ring.prog = prog;
+    ring.ring = rings + (size_t)warp * nst * (JtRing::kStageBytes / 8) + lane;
+    ring.cur = ring.ring;
     ring.in = reinterpret_cast<const char*>(a.in);
-    ring.tile_bytes = (long long)6 * n_out * 256;
+    ring.tile_bytes = (long long)6 * m.n_out * 256;
     ring.ntiles = ntiles; ring.stride = (long long)gridDim.x * wpb;
-    ring.ring_s = smem_u32(rings + (size_t)warp * ns * (JtRing::kSlotBytes / 8));
-    ring.bar_s = smem_u32(bars + warp * JtRing::kMaxSlots);
-    ring.ns = ns; ring.np = np; ring.lane = lane;
-    ring.c_piece = 0; ring.c_slot = 0; ring.c_bar = 0; ring.c_first = 0; ring.c_phase = 0u;
+    ring.ring_s = smem_u32(rings + (size_t)warp * nst * (JtRing::kStageBytes / 8));
+    ring.bar_s = smem_u32(bars + warp * JtRing::kMaxStages);
+    ring.nst = nst; ring.np = np; ring.lane = lane;
+    ring.c_piece = 0; ring.stage = 0; ring.phase = 0u;
     ring.p_tile = (long long)blockIdx.x * wpb + warp; ring.p_piece = 0;
-    ring.p_slot = 0; ring.p_bar = 0; ring.nfree = ns;
-    ring.produce();
+    for (int st = 0; st < nst; ++st) ring.issue(st);
+    const double* const opl = prog.opl();
     for (long long t = (long long)blockIdx.x * wpb + warp; t < ntiles; t += (long long)gridDim.x * wpb) {
       const long long inst = t * 32 + lane;
       SplitRedSinkT<FieldT<32>> sink{make_field_t<32>(const_cast<double*>(a.root), inst, 6, 32),
                                      make_field_t<32>(const_cast<double*>(a.joints), inst, m.nv - off, 32), off};
-      applyJT_instance_ring(m, jt, make_field_t<32>(a.qcache, a.cache_inst0 + inst, m.nq, 32), ring, sink, S, T);
+      applyJT_instance_ring(m, opl, make_field_t<32>(a.qcache, a.cache_inst0 + inst, m.nq, 32), ring, sink, S, T);
     }
   }
   if (tm_cols > 0) {
@@ -590,14 +568,14 @@ cudaError_t launch_applyJT_plan(const DevModel& hm, const DevModel* d_blob, cons
   return cudaGetLastError();
 }
 
-// `hm` = host copy of the model planned with plan_jt_ring, `d_blob` = its staged blob, ns = ring slots per warp.
-// a.n must be a multiple of 32 and a.tile == 32; a.in 16-byte aligned.
-cudaError_t launch_applyJT_ring(const DevModel& hm, const DevModel* d_blob, const DevTables& tb, const MapArgs& a,
-                                int ns, LaunchCfg* cfg, int num_sms, cudaStream_t st) {
+// `hm` = host copy of the model planned with plan_jt_ring, `d_blob` = its staged blob (build_jt_blob), nst = ring
+// stages per warp.  a.n must be a multiple of 32 and a.tile == 32; a.in 16-byte aligned.
+cudaError_t launch_applyJT_ring(const DevModel& hm, const DevModel* d_blob, const MapArgs& a, int nst, LaunchCfg* cfg,
+                                int num_sms, cudaStream_t st) {
   const int model_words = (int)(eval_model_bytes(hm) / 8);
   const int block = JtRing::kWarps * 32;
-  const size_t smem = ((size_t)model_words + jt_table_words(hm.n_out) + (size_t)JtRing::kWarps * JtRing::kMaxSlots) * 8 +
-                      (size_t)block * hm.plan.smem_doubles * 8 + (size_t)JtRing::kWarps * ns * JtRing::kSlotBytes;
+  const size_t smem = ((size_t)model_words + (size_t)JtRing::kWarps * JtRing::kMaxStages) * 8 +
+                      (size_t)block * hm.plan.smem_doubles * 8 + (size_t)JtRing::kWarps * nst * JtRing::kStageBytes;
   if (cfg->block != block || cfg->smem_bytes != smem) {
     cudaError_t e = cudaFuncSetAttribute(applyJT_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin);
     if (e != cudaSuccess) return e;
@@ -609,7 +587,7 @@ cudaError_t launch_applyJT_ring(const DevModel& hm, const DevModel* d_blob, cons
   const long long ntiles = a.n / 32;
   unsigned grid = (unsigned)((ntiles + JtRing::kWarps - 1) / JtRing::kWarps);
   if (grid > (unsigned)num_sms) grid = (unsigned)num_sms;
-  applyJT_ring_kernel<<<grid, block, smem, st>>>(d_blob, model_words, tb, a, ns);
+  applyJT_ring_kernel<<<grid, block, smem, st>>>(d_blob, model_words, a, nst);
   return cudaGetLastError();
 }
 

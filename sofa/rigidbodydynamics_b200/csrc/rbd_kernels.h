@@ -51,9 +51,9 @@ cudaError_t launch_applyJT(const DevModel& m, const DevModel* d_model, const Dev
 cudaError_t launch_applyJT_plan(const DevModel& planned_host_model, const DevModel* d_blob, const DevTables& tb,
                                 const MapArgs& a, LaunchCfg* cfg2, int num_sms, cudaStream_t st);
 // ring variant of the vector applyJT (full tiles of 32, a.tile == 32, a.n % 32 == 0, a.in 16-byte aligned):
-// `planned_host_model` planned with plan_jt_ring, ns = ring slots per warp it returned
-cudaError_t launch_applyJT_ring(const DevModel& planned_host_model, const DevModel* d_blob, const DevTables& tb,
-                                const MapArgs& a, int ns, LaunchCfg* cfg, int num_sms, cudaStream_t st);
+// `planned_host_model` planned with plan_jt_ring, `d_blob` built by build_jt_blob, nst = ring stages per warp
+cudaError_t launch_applyJT_ring(const DevModel& planned_host_model, const DevModel* d_blob, const MapArgs& a, int nst,
+                                LaunchCfg* cfg, int num_sms, cudaStream_t st);
 cudaError_t launch_applyJT_rows(const DevModel& m, const DevModel* d_model, const DevTables& tb, const RowArgs& a,
                                 int smem_doubles, LaunchCfg* cfg, cudaStream_t st);
 cudaError_t launch_aos_to_soa(long long n, int K, long long tile, const double* aos, double* soa, cudaStream_t st);

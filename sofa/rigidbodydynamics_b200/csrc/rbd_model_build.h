@@ -317,14 +317,15 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Storage plan of the applyJT ring kernel (applyJT_instance_ring).  Placement is by record kind, fixed at compile time
-// in the kernel: per depth level of 1-dof joints with children one record [F | A] (12 doubles) and per 1-dof branch
-// joint one R|p record (12) in TENSOR memory; the level record of a free-flyer [R|p | F] (18) in shared memory.  What
-// remains of the SM's shared memory becomes the per-warp wrench ring.
-// Fills m->plan (warps, smem_doubles, tmem_doubles, tmem_cols), joint[*].offA (level record) and joint[*].boff (branch
-// record).  Returns the number of ring slots (1 536-byte wrench blocks) per warp, 0 when the kernel cannot run this
-// model (tensor memory off or too small for the tree's depth: the caller keeps the register path).
-inline int plan_jt_ring(DevModel* m, bool use_tmem) {
+// Storage plan and ring program of the applyJT ring kernel (applyJT_instance_ring).  Placement is by record kind, fixed
+// at compile time in the kernel: per depth level of 1-dof joints with children one record [F | A] (12 doubles) and per
+// 1-dof branch joint one R|p record (12) in TENSOR memory; the level record of a free-flyer [R|p | F] (18) in shared
+// memory.  What remains of the SM's shared memory becomes the per-warp wrench ring (stages of 4 wrench blocks).
+// Fills m->plan (warps, smem_doubles, tmem_doubles, tmem_cols), joint[*].offA (level record), joint[*].boff (branch
+// record) and m->prog_len / prog_words_off for the ring program `prog` (layout: rbd_sweeps_body.h, JtProg), which takes
+// the place of the ColProg table in the staged blob.  Returns the number of ring stages per warp, 0 when the kernel
+// cannot run this model (tensor memory off or too small for the tree's depth: the caller keeps the register path).
+inline int plan_jt_ring(DevModel* m, const HostTables& tb, bool use_tmem, std::vector<int>* prog) {
   const int nj = m->njoints, W = JtRing::kWarps;
   const int D = m->max_depth_internal;
   if (!use_tmem || nj < 2) return 0;
@@ -345,17 +346,53 @@ inline int plan_jt_ring(DevModel* m, bool use_tmem) {
     }
   }
   if (t_used > cap) return 0;
-  (void)build_col_prog(m);
+  // ring program
+  std::vector<int> pieces, copies;
+  const int gmax = 4;  // RBD_JT_GMAX
+  for (int i = 1; i < nj; ++i)
+    for (int o = m->joint[i].out_begin; o < m->joint[i].out_end;) {
+      const int cnt = std::min(gmax, m->joint[i].out_end - o);
+      const int c0 = (int)copies.size() / 2;
+      for (int j = 0; j < cnt;) {
+        int r = 1;
+        while (j + r < cnt && tb.sorted_k[o + j + r] == tb.sorted_k[o + j] + r) ++r;
+        copies.push_back(6 * tb.sorted_k[o + j] * 256);                                   // source offset in the tile's block
+        copies.push_back((j * JtRing::kSlotBytes) | ((r * JtRing::kSlotBytes) << 16));    // stage offset | bytes
+        j += r;
+      }
+      pieces.push_back(o | (cnt << 16));
+      pieces.push_back(cnt * JtRing::kSlotBytes);
+      pieces.push_back(c0);
+      pieces.push_back((int)copies.size() / 2 - c0);
+      o += cnt;
+    }
+  const int np = (int)pieces.size() / 4, nc = (int)copies.size() / 2;
+  const int off_opl = (4 + 4 * np + 2 * nc + 1) / 2 * 2;
+  prog->assign((size_t)off_opl + 6 * (size_t)m->n_out, 0);
+  (*prog)[0] = np; (*prog)[1] = nc; (*prog)[2] = off_opl; (*prog)[3] = 0;
+  if (np) memcpy(prog->data() + 4, pieces.data(), pieces.size() * sizeof(int));
+  if (nc) memcpy(prog->data() + 4 + 4 * np, copies.data(), copies.size() * sizeof(int));
+  for (int o = 0; o < m->n_out; ++o)
+    memcpy(prog->data() + off_opl + 6 * (size_t)o, &tb.sorted_pl[12 * (size_t)o + 9], 3 * sizeof(double));
+  m->prog_len = (int)prog->size();
+  m->prog_words_off = (int)((dev_model_bytes(*m) + 15) / 16 * 2);
   EvalPlan pl{};
   pl.smem_doubles = s_used; pl.tmem_doubles = t_used; pl.warps = W; pl.blocks_per_sm = 1;
   pl.tmem_cols = t_used > 0 ? pow2_cols(2 * t_used * ((W + 3) / 4)) : 0;
   m->plan = pl;
-  const size_t fixed = eval_model_bytes(*m) + (size_t)jt_table_words(m->n_out) * 8 + (size_t)W * JtRing::kMaxSlots * 8 +
-                       (size_t)W * 32 * s_used * 8 + B200Limits::kSmemReservedPerBlock;
+  const size_t fixed = eval_model_bytes(*m) + (size_t)W * 2 * JtRing::kMaxStages * 8 + (size_t)W * 32 * s_used * 8 +
+                       B200Limits::kSmemReservedPerBlock;
   if (fixed >= (size_t)B200Limits::kSmemBytes) return 0;
-  int ns = (int)(((size_t)B200Limits::kSmemBytes - fixed) / ((size_t)W * JtRing::kSlotBytes));
-  ns = std::min(ns, (int)JtRing::kMaxSlots);
-  return ns >= JtRing::kMinSlots ? ns : 0;
+  int nst = (int)(((size_t)B200Limits::kSmemBytes - fixed) / ((size_t)W * JtRing::kStageBytes));
+  nst = std::min(nst, (int)JtRing::kMaxStages);
+  return nst >= JtRing::kMinStages ? nst : 0;
+}
+// the blob the ring kernel stages: planned DevModel prefix + ring program
+inline std::vector<unsigned long long> build_jt_blob(const DevModel* m, const std::vector<int>& prog) {
+  std::vector<unsigned long long> blob(eval_model_bytes(*m) / 8 - 2, 0ull);
+  memcpy(blob.data(), m, dev_model_bytes(*m));
+  if (!prog.empty()) memcpy(blob.data() + m->prog_words_off, prog.data(), prog.size() * sizeof(int));
+  return blob;
 }
 
 // shared-memory doubles per instance of the mapping kernels

@@ -289,6 +289,16 @@ RBD_HD void mat3_mul(const real* A, const real* B, real* O) {
     }                                              \
   } while (0)
 
+// the same rotation of columns (ci, cj) in place (column ck, the joint axis, is untouched)
+#define RBD_ROTCOLS_IP(R, ci, cj, c, s)             \
+  do {                                              \
+    _Pragma("unroll") for (int r_ = 0; r_ < 3; ++r_) {  \
+      const real bi_ = R[3 * r_ + ci], bj_ = R[3 * r_ + cj]; \
+      R[3 * r_ + ci] = c * bi_ + s * bj_;           \
+      R[3 * r_ + cj] = c * bj_ - s * bi_;           \
+    }                                               \
+  } while (0)
+
 // ---------------------------------------------------------------------------------------------------------
 // One forward-kinematics step: (R,p) of the parent joint in, (R,p) of joint `jn` out (world frame), plus the
 // world joint axis aw (1-dof joints).  q0/q1 are the joint's configuration values (angle | displacement |
@@ -296,52 +306,56 @@ RBD_HD void mat3_mul(const real* A, const real* B, real* O) {
 // pinocchio: liMi = jointPlacement * M_joint(q); oMi = oMi[parent] * liMi (JointJacobiansForwardStep).
 template <class QF>
 RBD_HD void fk_joint(const DevJoint& jn, real* R, real* p, real q0, real q1, const QF& qf, real* aw) {
-  real B[9], pn[3];
-  if (jn.pl_rot_identity) {  // uniform branch: most URDF joints have rpy = 0
-#pragma unroll
-    for (int k = 0; k < 9; ++k) B[k] = R[k];
-  } else {
-    mat3_mul(R, jn.pl, B);
+  // p <- R pl_p + p with the parent's R, then R <- R pl_R IN PLACE: most URDF joints have rpy = 0, and for those the
+  // step is nothing at all (no copy of R into a scratch matrix: profile r1h counted 18 register moves per joint for it)
+  {
+    const real pn0 = R[0] * jn.pl[9] + R[1] * jn.pl[10] + R[2] * jn.pl[11] + p[0];
+    const real pn1 = R[3] * jn.pl[9] + R[4] * jn.pl[10] + R[5] * jn.pl[11] + p[1];
+    const real pn2 = R[6] * jn.pl[9] + R[7] * jn.pl[10] + R[8] * jn.pl[11] + p[2];
+    p[0] = pn0; p[1] = pn1; p[2] = pn2;
   }
-  pn[0] = R[0] * jn.pl[9] + R[1] * jn.pl[10] + R[2] * jn.pl[11] + p[0];
-  pn[1] = R[3] * jn.pl[9] + R[4] * jn.pl[10] + R[5] * jn.pl[11] + p[1];
-  pn[2] = R[6] * jn.pl[9] + R[7] * jn.pl[10] + R[8] * jn.pl[11] + p[2];
+  if (!jn.pl_rot_identity) {  // uniform branch
+    real B[9];
+    mat3_mul(R, jn.pl, B);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = B[k];
+  }
   const int t = jn.type;
   real c = q0, s = q1;
   if (t >= JT_RX && t <= JT_RU) sincos_(q0, &s, &c);
   switch (t) {
     case JT_RX: case JT_RUBX:
-      RBD_ROTCOLS(R, B, 0, 1, 2, c, s);
-      aw[0] = B[0]; aw[1] = B[3]; aw[2] = B[6];
+      aw[0] = R[0]; aw[1] = R[3]; aw[2] = R[6];
+      RBD_ROTCOLS_IP(R, 1, 2, c, s);
       break;
     case JT_RY: case JT_RUBY:
-      RBD_ROTCOLS(R, B, 1, 2, 0, c, s);
-      aw[0] = B[1]; aw[1] = B[4]; aw[2] = B[7];
+      aw[0] = R[1]; aw[1] = R[4]; aw[2] = R[7];
+      RBD_ROTCOLS_IP(R, 2, 0, c, s);
       break;
     case JT_RZ: case JT_RUBZ:
-      RBD_ROTCOLS(R, B, 2, 0, 1, c, s);
-      aw[0] = B[2]; aw[1] = B[5]; aw[2] = B[8];
+      aw[0] = R[2]; aw[1] = R[5]; aw[2] = R[8];
+      RBD_ROTCOLS_IP(R, 0, 1, c, s);
       break;
     case JT_RU: case JT_RUBU: {
       const real ax = jn.axis[0], ay = jn.axis[1], az = jn.axis[2];
       const real c1 = real(1) - c, sx = s * ax, sy = s * ay, sz = s * az;
-      real Rj[9];
+      real Rj[9], B[9];
       Rj[0] = c1 * ax * ax + c;  Rj[1] = c1 * ax * ay - sz; Rj[2] = c1 * ax * az + sy;
       Rj[3] = c1 * ay * ax + sz; Rj[4] = c1 * ay * ay + c;  Rj[5] = c1 * ay * az - sx;
       Rj[6] = c1 * az * ax - sy; Rj[7] = c1 * az * ay + sx; Rj[8] = c1 * az * az + c;
-      mat3_mul(B, Rj, R);
-      aw[0] = B[0] * ax + B[1] * ay + B[2] * az;
-      aw[1] = B[3] * ax + B[4] * ay + B[5] * az;
-      aw[2] = B[6] * ax + B[7] * ay + B[8] * az;
+      aw[0] = R[0] * ax + R[1] * ay + R[2] * az;
+      aw[1] = R[3] * ax + R[4] * ay + R[5] * az;
+      aw[2] = R[6] * ax + R[7] * ay + R[8] * az;
+      mat3_mul(R, Rj, B);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) R[k] = B[k];
     } break;
     case JT_PX: case JT_PY: case JT_PZ: case JT_PU: {
       const real ax = jn.axis[0], ay = jn.axis[1], az = jn.axis[2];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) R[k] = B[k];
-      aw[0] = B[0] * ax + B[1] * ay + B[2] * az;
-      aw[1] = B[3] * ax + B[4] * ay + B[5] * az;
-      aw[2] = B[6] * ax + B[7] * ay + B[8] * az;
-      pn[0] += q0 * aw[0]; pn[1] += q0 * aw[1]; pn[2] += q0 * aw[2];
+      aw[0] = R[0] * ax + R[1] * ay + R[2] * az;
+      aw[1] = R[3] * ax + R[4] * ay + R[5] * az;
+      aw[2] = R[6] * ax + R[7] * ay + R[8] * az;
+      p[0] += q0 * aw[0]; p[1] += q0 * aw[1]; p[2] += q0 * aw[2];
     } break;
     case JT_FF: {
       const int o = jn.idx_q;
@@ -351,23 +365,22 @@ RBD_HD void fk_joint(const DevJoint& jn, real* R, real* p, real q0, real q1, con
       const real tx = 2 * x, ty = 2 * y, tz = 2 * z;
       const real twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x;
       const real tyy = ty * y, tyz = tz * y, tzz = tz * z;
-      real Rq[9];
+      real Rq[9], B[9];
       Rq[0] = 1 - (tyy + tzz); Rq[1] = txy - twz;       Rq[2] = txz + twy;
       Rq[3] = txy + twz;       Rq[4] = 1 - (txx + tzz); Rq[5] = tyz - twx;
       Rq[6] = txz - twy;       Rq[7] = tyz + twx;       Rq[8] = 1 - (txx + tyy);
-      mat3_mul(B, Rq, R);
-      pn[0] += B[0] * px + B[1] * py + B[2] * pz;
-      pn[1] += B[3] * px + B[4] * py + B[5] * pz;
-      pn[2] += B[6] * px + B[7] * py + B[8] * pz;
-      aw[0] = aw[1] = aw[2] = 0.0;
-    } break;
-    default:
+      p[0] += R[0] * px + R[1] * py + R[2] * pz;
+      p[1] += R[3] * px + R[4] * py + R[5] * pz;
+      p[2] += R[6] * px + R[7] * py + R[8] * pz;
+      mat3_mul(R, Rq, B);
 #pragma unroll
       for (int k = 0; k < 9; ++k) R[k] = B[k];
       aw[0] = aw[1] = aw[2] = 0.0;
+    } break;
+    default:
+      aw[0] = aw[1] = aw[2] = 0.0;
       break;
   }
-  p[0] = pn[0]; p[1] = pn[1]; p[2] = pn[2];
 }
 
 RBD_HD bool is_prismatic(int t) { return t >= JT_PX && t <= JT_PU; }
@@ -375,12 +388,12 @@ RBD_HD bool is_unbounded(int t) { return t >= JT_RUBX && t <= JT_RUBU; }
 
 // world-frame motion subspace column of a 1-dof joint: revolute [p x a ; a], prismatic [a ; 0]
 RBD_HD void subspace_1dof(int type, const real* p, const real* aw, real* A) {
+  // revolute first, unconditionally; the (rare, uniform) prismatic case overwrites: no merge of two register sets
+  RBD_CROSS(A[0], A[1], A[2], p[0], p[1], p[2], aw[0], aw[1], aw[2]);
+  A[3] = aw[0]; A[4] = aw[1]; A[5] = aw[2];
   if (is_prismatic(type)) {
     A[0] = aw[0]; A[1] = aw[1]; A[2] = aw[2];
     A[3] = A[4] = A[5] = 0.0;
-  } else {
-    RBD_CROSS(A[0], A[1], A[2], p[0], p[1], p[2], aw[0], aw[1], aw[2]);
-    A[3] = aw[0]; A[4] = aw[1]; A[5] = aw[2];
   }
 }
 // column e (0..5) of the free-flyer subspace oMi.act(I6): e<3 -> [R e ; 0], e>=3 -> [p x R e ; R e]
@@ -1435,12 +1448,8 @@ struct RowSink {
 //   shared memory   free-flyer level record [R|p (12) | F (6)]
 // Accumulated outputs go through Sink::put (a fire-and-forget reduction on the device: the += of the reference,
 // KCM.inl:498-511, without a load the sweep would have to wait for).
-struct JtTab {
-  const real* opl;   // [n_out][3] translation of the output's placement in its parent joint frame, sorted order
-  const int* okoff;  // [n_out] 6 * k: first field of output k's wrench, sorted order
-};
 template <class QC, class Ring, class Sink>
-RBD_HD void applyJT_instance_ring(const DevModel& m, const JtTab& tb, const QC& q, Ring& ring, const Sink& sink,
+RBD_HD void applyJT_instance_ring(const DevModel& m, const real* opl, const QC& q, Ring& ring, const Sink& sink,
                                   const Stack& S, const TmStack& T) {
   const int nj = m.njoints;
   real R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
@@ -1469,25 +1478,46 @@ RBD_HD void applyJT_instance_ring(const DevModel& m, const JtTab& tb, const QC& 
     const real q0 = q0n, q1 = q1n;
     RBD_Q_PREFETCH(i + 1);
     fk_joint(jn, R, p, q0, q1, q, aw);
-    // wrenches attached to this joint, moved to the world origin
+    // wrenches attached to this joint, moved to the world origin.  Pieces hold 1..4 outputs; each size is
+    // straight-line code (four independent shift chains the scheduler can interleave, summed pairwise).
     real Fk[6] = {0, 0, 0, 0, 0, 0};
+#define RBD_JT_W(j, c)                                                                  \
+  real c[6];                                                                            \
+  {                                                                                     \
+    real w[6];                                                                          \
+    ring.template ld<j>(w);                                                             \
+    const real* pl = opl + 3 * (o + j);                                                 \
+    const real px = R[0] * pl[0] + R[1] * pl[1] + R[2] * pl[2] + p[0];                  \
+    const real py = R[3] * pl[0] + R[4] * pl[1] + R[5] * pl[2] + p[1];                  \
+    const real pz = R[6] * pl[0] + R[7] * pl[1] + R[8] * pl[2] + p[2];                  \
+    real tx, ty, tz;                                                                    \
+    RBD_CROSS(tx, ty, tz, px, py, pz, w[0], w[1], w[2]);                                \
+    c[0] = w[0]; c[1] = w[1]; c[2] = w[2];                                              \
+    c[3] = w[3] + tx; c[4] = w[4] + ty; c[5] = w[5] + tz;                               \
+  }
     for (int o = jn.out_begin; o < jn.out_end;) {
       const int cnt = ring.acquire();
-      for (int j = 0; j < cnt; ++j) {
-        real w[6];
-        ring.ld(j, w);
-        const real* pl = tb.opl + 3 * (o + j);
-        const real px = R[0] * pl[0] + R[1] * pl[1] + R[2] * pl[2] + p[0];
-        const real py = R[3] * pl[0] + R[4] * pl[1] + R[5] * pl[2] + p[1];
-        const real pz = R[6] * pl[0] + R[7] * pl[1] + R[8] * pl[2] + p[2];
-        real tx, ty, tz;
-        RBD_CROSS(tx, ty, tz, px, py, pz, w[0], w[1], w[2]);
-        Fk[0] += w[0]; Fk[1] += w[1]; Fk[2] += w[2];
-        Fk[3] += w[3] + tx; Fk[4] += w[4] + ty; Fk[5] += w[5] + tz;
+      if (cnt == 1) {
+        RBD_JT_W(0, c0)
+#pragma unroll
+        for (int e = 0; e < 6; ++e) Fk[e] += c0[e];
+      } else if (cnt == 2) {
+        RBD_JT_W(0, c0) RBD_JT_W(1, c1)
+#pragma unroll
+        for (int e = 0; e < 6; ++e) Fk[e] += c0[e] + c1[e];
+      } else if (cnt == 3) {
+        RBD_JT_W(0, c0) RBD_JT_W(1, c1) RBD_JT_W(2, c2)
+#pragma unroll
+        for (int e = 0; e < 6; ++e) Fk[e] += (c0[e] + c1[e]) + c2[e];
+      } else {
+        RBD_JT_W(0, c0) RBD_JT_W(1, c1) RBD_JT_W(2, c2) RBD_JT_W(3, c3)
+#pragma unroll
+        for (int e = 0; e < 6; ++e) Fk[e] += (c0[e] + c1[e]) + (c2[e] + c3[e]);
       }
       ring.release(cnt);
       o += cnt;
     }
+#undef RBD_JT_W
     if (nxt_par == i) {
       // joint i has children: park F | A at its depth level; the subtree's wrenches accumulate there
       if (jn.type != JT_FF) {
@@ -1553,36 +1583,50 @@ RBD_HD void applyJT_instance_ring(const DevModel& m, const JtTab& tb, const QC& 
     }
   }
 }
-// reader of the input array with the ring's interface (tests/emul; the device ring lives in rbd_kernels.cu)
+// Ring program (host-built by plan_jt_ring, staged with the blob in place of the ColProg table; ints):
+//   [0] pieces  [1] copies  [2] offset (ints, even) of the translation table  [3] reserved
+//   pieces  int4 each: first sorted index | outputs << 16, bytes to expect, first copy, copies
+//   copies  int2 each: source offset within the tile's wrench block (bytes), offset within the stage | bytes << 16
+//   opl     3 doubles per mapped output (sorted order): translation of its placement in the parent joint frame
+// A piece is <= RBD_JT_GMAX outputs of one joint, fetched into one ring stage by one bulk copy per run of consecutive
+// output indices (the frames of one joint usually are consecutive).
+#define RBD_JT_GMAX 4
+struct JtProg {
+  const int* base;
+  RBD_HD int npieces() const { return base[0]; }
+  RBD_HD const int* piece(int i) const { return base + 4 + 4 * i; }
+  RBD_HD const int* copy(int c) const { return base + 4 + 4 * base[0] + 2 * c; }
+  RBD_HD const real* opl() const { return reinterpret_cast<const real*>(base + base[2]); }
+};
+// reader of the input array with the ring's interface (tests/emul; the device ring lives in rbd_kernels.cu): follows
+// the COPY LIST of every piece, i.e. reads exactly the bytes the device's copy engine is told to fetch
 template <class FLD>
 struct DirectRingT {
   FLD in;
-  const int* okoff;
-  const int* pieces;  // piece program (jt_build_pieces): first sorted index | count << 16, in sweep order
-  int npieces, c;
-  int o0;
+  JtProg prog;
+  int c;
+  const int* cur;
   RBD_HD int acquire() {
-    const int e = pieces[c];
-    c = c + 1 == npieces ? 0 : c + 1;
-    o0 = e & 0xffff;
-    return e >> 16;
+    cur = prog.piece(c);
+    c = c + 1 == prog.npieces() ? 0 : c + 1;
+    return cur[0] >> 16;
   }
-  RBD_HD void ld(int j, real* w) const {
+  template <int J>
+  RBD_HD void ld(real* w) const {
+    // locate slot J of the stage in the copy list
+    for (int k = 0; k < cur[3]; ++k) {
+      const int* ce = prog.copy(cur[2] + k);
+      const int dst = ce[1] & 0xffff, bytes = ce[1] >> 16;
+      if (J * 1536 >= dst && J * 1536 < dst + bytes) {
+        const int field0 = (ce[0] + (J * 1536 - dst)) / 256;
 #pragma unroll
-    for (int e = 0; e < 6; ++e) w[e] = in.ld(okoff[o0 + j] + e);
+        for (int e = 0; e < 6; ++e) w[e] = in.ld(field0 + e);
+        return;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 6; ++e) w[e] = real(0) / real(0);  // not covered by any copy: poison
   }
   RBD_HD void release(int) {}
 };
-// Piece program of the ring: the mapped outputs of joints 1.. in sweep order, cut into pieces of at most gmax outputs
-// that never span two joints.  Returns the number of pieces written (<= n_out).
-RBD_HD int jt_build_pieces(const DevModel& m, int gmax, int* pieces) {
-  int np = 0;
-  for (int i = 1; i < m.njoints; ++i)
-    for (int o = m.joint[i].out_begin; o < m.joint[i].out_end;) {
-      const int cnt = m.joint[i].out_end - o < gmax ? m.joint[i].out_end - o : gmax;
-      pieces[np++] = o | (cnt << 16);
-      o += cnt;
-    }
-  return np;
-}
 #endif  /* !RBD_BODY_F32 */

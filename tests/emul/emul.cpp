@@ -210,41 +210,33 @@ extern "C" int emul_applyJT_plan(const rbd_model_desc* d, long long n, long long
   return 0;
 }
 
-// applyJT, ring variant (the batched K3 kernel's body on full tile-32 batches): storage plan of plan_jt_ring, the
-// wrench ring replaced by a direct reader of the input array, the reduction sink by a plain +=
+// applyJT, ring variant (the batched K3 kernel's body on full tile-32 batches): storage plan and ring program of
+// plan_jt_ring, the wrench ring replaced by a reader that follows the program's copy list, the reduction sink by +=
 extern "C" int emul_applyJT_ring(const rbd_model_desc* d, long long n, long long tile, int use_tmem, double* qcache,
-                                 long long cache_tile, double* in, double* out_tau, double* out_root, int* ring_slots) {
+                                 long long cache_tile, double* in, double* out_tau, double* out_root, int* ring_stages) {
   Ctx c;
   int rc = make_ctx(d, &c);
   if (rc) return rc;
-  const int ns = c.m.njoints > 1 ? plan_jt_ring(&c.m, use_tmem != 0) : 0;
-  if (ring_slots) *ring_slots = ns;
-  if (ns == 0) return 1;  // the kernel would not run this model: nothing to emulate
-  const std::vector<unsigned long long> blob = build_eval_blob(&c.m);
+  std::vector<int> prog;
+  const int nst = plan_jt_ring(&c.m, c.ht, use_tmem != 0, &prog);
+  if (ring_stages) *ring_stages = nst;
+  if (nst == 0) return 1;  // the kernel would not run this model: nothing to emulate
+  const std::vector<unsigned long long> blob = build_jt_blob(&c.m, prog);
   const DevModel& bm = *reinterpret_cast<const DevModel*>(blob.data());
   const EvalPlan& pl = bm.plan;
   const int bt = pl.warps * 32;
   std::vector<double> smem((size_t)(pl.smem_doubles > 0 ? pl.smem_doubles : 1) * bt, 1e300);
   std::vector<double> tmem((size_t)(pl.tmem_doubles > 0 ? pl.tmem_doubles : 1) * bt, 1e300);
-  std::vector<double> opl(3 * (size_t)bm.n_out + 1);
-  std::vector<int> okoff((size_t)bm.n_out + 1);
-  for (int o = 0; o < bm.n_out; ++o) {
-    for (int e = 0; e < 3; ++e) opl[3 * o + e] = c.tb.sorted_pl[12 * o + 9 + e];
-    okoff[o] = 6 * c.tb.sorted_k[o];
-  }
-  const JtTab jt{opl.data(), okoff.data()};
+  const JtProg jp{col_prog(bm)};
+  if (jp.npieces() == 0) return 0;  // no wrench reaches a moving joint: the accumulated outputs stay as they are
   const int off = (bm.has_ff_root && out_root) ? 6 : 0;
-  const int gmax = ns / 2 < 8 ? ns / 2 : 8;
-  std::vector<int> pieces((size_t)bm.n_out + 1);
-  const int np = jt_build_pieces(bm, gmax, pieces.data());
-  if (np == 0) return 0;  // no wrench reaches a moving joint: the accumulated outputs stay as they are
   for (long long i = 0; i < n; ++i) {
     const int t = (int)(i % bt);
-    DirectRingT<Field> ring{make_field(in, i, 6 * bm.n_out, tile), okoff.data(), pieces.data(), np, 0, 0};
+    DirectRingT<Field> ring{make_field(in, i, 6 * bm.n_out, tile), jp, 0, nullptr};
     SplitRedSinkT<Field> sink{make_field(out_root, i, 6, tile), make_field(out_tau, i, bm.nv - off, tile), off};
     Stack S = make_stack(smem.data(), t, pl.smem_doubles);
     TmStack T{tmem.data() + (size_t)t * (pl.tmem_doubles > 0 ? pl.tmem_doubles : 1)};
-    applyJT_instance_ring(bm, jt, make_field(qcache, i, bm.nq, cache_tile), ring, sink, S, T);
+    applyJT_instance_ring(bm, jp.opl(), make_field(qcache, i, bm.nq, cache_tile), ring, sink, S, T);
   }
   return 0;
 }
