@@ -248,6 +248,19 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
       "RBD_DONE:\n"
       "}" ::"r"(bar), "r"(parity) : "memory");
 }
+// one lane of the (converged) warp: the compiler knows a single thread runs the guarded code, so operands of the
+// copy-engine instructions move to uniform registers without a per-value waterfall loop (the `lane == 0` test of the
+// first ring kernel cost ~25 instructions per copy for exactly that loop)
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -269,13 +282,14 @@ struct WarpRing {
   // fetch the producer cursor's piece into stage `st` (warp-uniform bookkeeping, lane 0 talks to the copy engine)
   __device__ __forceinline__ void issue(int st) {
     if (p_tile < ntiles) {
-      if (lane == 0) {
+      if (elect_one()) {
         const int4 pe = *reinterpret_cast<const int4*>(prog.piece(p_piece));
         const unsigned bar = bar_s + 8u * (unsigned)st;
         mbar_expect_tx(bar, (unsigned)pe.y);
         const char* src = in + p_tile * tile_bytes;
         const unsigned dst = ring_s + (unsigned)st * (unsigned)JtRing::kStageBytes;
         const int2* cp = reinterpret_cast<const int2*>(prog.copy(pe.z));
+#pragma unroll 1
         for (int c = 0; c < pe.w; ++c) {
           const int2 ce = cp[c];
           bulk_g2s(dst + ((unsigned)ce.y & 0xffffu), src + ce.x, (unsigned)ce.y >> 16, bar);
