@@ -213,6 +213,19 @@ RBD_API int rbd_crba_soa(rbd_workspace* ws, int64_t n, int64_t tile, const doubl
 RBD_API int rbd_rnea_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, const double* v,
                          const double* a, double* tau);
 
+/* Matrix-free Mass / ForceField products in joint space — what the reference's SOFA graph evaluates through the
+ * mapping with one UniformMass<Rigid3> per body (URDFModelLoader.cpp:369-391): Mass::addMDx and ForceField::addForce
+ * reach the joint dofs as applyJT(M_b * applyJ(dx)) and applyJT(m_b g).  Here they are one sweep each, with pinocchio's
+ * exact rigid-body inertias (SURVEY.md §3.5 explains where SOFA's UniformMass deviates for non-isotropic bodies):
+ *   rbd_addMDx_soa    res <- res + factor * M(q) dx                      (Mass::addMDx(res, dx, factor))
+ *   rbd_addForce_soa  f   <- f - (C(q, v) v + g(q)) = f - rnea(q, v, 0)  (ForceField::addForce(f, x, v)); v == NULL
+ *                     leaves the gravity term alone, f <- f + sum_b J_b^T m_b g, which is exactly what the reference
+ *                     computes (applyDJT being a no-op, KinematicChainMapping.h:73-80, it has no velocity term).
+ * q: nq fields; dx, v, res, f: nv fields; both ACCUMULATE as the SOFA methods do.                           */
+RBD_API int rbd_addMDx_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, const double* dx, double factor,
+                           double* res);
+RBD_API int rbd_addForce_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, const double* v, double* f);
+
 /* ---------------------------------------------------------------------------------------------------- */
 /* Layout adapters (Conversions.h:58-119 at batch scale): instance-major [n][K] <-> tiled SoA, on device. */
 RBD_API int rbd_aos_to_soa_dev(rbd_workspace* ws, int64_t n, int32_t K, int64_t tile, const double* aos,

@@ -141,6 +141,14 @@ class Workspace:
     def rnea_soa(self, n, tile, q, v, a, tau):
         check(self._lib.rbd_rnea_soa(self._h, n, tile, _dev_ptr(q), _dev_ptr(v), _dev_ptr(a), _dev_ptr(tau)))
 
+    def addMDx_soa(self, n, tile, q, dx, factor, res):
+        """res += factor * M(q) dx  (SOFA Mass::addMDx in joint space, matrix-free)."""
+        check(self._lib.rbd_addMDx_soa(self._h, n, tile, _dev_ptr(q), _dev_ptr(dx), float(factor), _dev_ptr(res)))
+
+    def addForce_soa(self, n, tile, q, v, f):
+        """f -= rnea(q, v, 0)  (SOFA ForceField::addForce in joint space); v None: gravity only, f += sum_b J_b^T m_b g."""
+        check(self._lib.rbd_addForce_soa(self._h, n, tile, _dev_ptr(q), _dev_ptr(v), _dev_ptr(f)))
+
     def apply_soa(self, n, tile, q_joints, root_pose, out):
         check(self._lib.rbd_apply_soa(self._h, n, tile, _dev_ptr(q_joints), _dev_ptr(root_pose), _dev_ptr(out)))
 

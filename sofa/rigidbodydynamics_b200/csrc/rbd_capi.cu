@@ -327,7 +327,8 @@ RBD_API int rbd_workspace_get_eval_plan(rbd_workspace* ws, int with_M, int with_
   const DevModel& h = *ws->h_plan[pk];
   out[0] = h.plan.warps; out[1] = h.plan.blocks_per_sm; out[2] = h.plan.smem_doubles; out[3] = h.plan.tmem_doubles;
   out[4] = h.plan.tmem_cols; out[5] = h.plan.y_in_tmem;
-  out[6] = (int32_t)(eval_model_bytes(h) + (size_t)h.plan.warps * 32 * h.plan.smem_doubles * 8); out[7] = 0;
+  out[6] = (int32_t)(eval_model_bytes(h) + (size_t)h.plan.warps * 32 * (h.plan.smem_doubles + 3 * h.plan.in_slots) * 8);
+  out[7] = h.plan.in_slots;
   return RBD_OK;
 }
 
@@ -418,6 +419,33 @@ RBD_API int rbd_rnea_soa(rbd_workspace* ws, int64_t n, int64_t tile, const doubl
                          const double* a, double* tau) {
   if (!tau) return set_err(RBD_ERR_INVALID_ARG, "tau is null");
   return rbd_eval_soa(ws, n, tile, q, v, a, nullptr, nullptr, nullptr, tau);
+}
+
+// Mass / ForceField products on the RNEA sweep: out <- out + scale * rnea(q, v | 0, a | 0) with gravity on or off
+static int mass_force_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, const double* q, const double* v,
+                         const double* a, double* out, double scale, int gravity_on) {
+  if (!q || !out) return set_err(RBD_ERR_INVALID_ARG, "null q / output");
+  int rc = ensure_plan(ws, 1);
+  if (rc) return rc;
+  EvalArgs A{n, tile, q, v, a, nullptr, nullptr, nullptr, out};
+  A.tau_scale = scale; A.tau_acc = 1; A.gravity_on = gravity_on;
+  CK(launch_eval(*ws->h_plan[1], ws->d_plan[1], A, ws->cfg_eval, ws->num_sms, st));
+  if (n > 0) ws->launches++;
+  return RBD_OK;
+}
+RBD_API int rbd_addMDx_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, const double* dx, double factor,
+                           double* res) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, tile);
+  if (rc) return rc;
+  if (!dx) return set_err(RBD_ERR_INVALID_ARG, "dx is null");
+  return mass_force_on(ws, ws->stream, n, tile, q, nullptr, dx, res, factor, 0);
+}
+RBD_API int rbd_addForce_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, const double* v, double* f) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, tile);
+  if (rc) return rc;
+  return mass_force_on(ws, ws->stream, n, tile, q, v, nullptr, f, -1.0, 1);
 }
 
 static int apply_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, long long inst0, const double* qj,

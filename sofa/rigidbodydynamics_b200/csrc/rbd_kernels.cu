@@ -66,6 +66,12 @@ __global__ void __launch_bounds__(256, MINB) NAME(const DevModelT<REAL>* __restr
   const NSQ::Stack S = NSQ::make_stack(reinterpret_cast<REAL*>(rbd_smem + model_words), threadIdx.x, m.plan.smem_doubles);                              \
   const long long ntiles = (a.n + 31) / 32;                                                                                                             \
   const int wpb = blockDim.x >> 5;                                                                                                                      \
+ /* asynchronous input ring: per warp [in_slots * 3][32] elements behind the stacks (tile-32 batches only) */                                           \
+  NSQ::InRing inr;                                                                                                                                      \
+  if (TILE != 0 && m.plan.in_slots > 0 && (!DO_TAU || (a.v && a.a)))                                                                                    \
+    inr.p = reinterpret_cast<REAL*>(rbd_smem + model_words) + (size_t)blockDim.x * m.plan.smem_doubles +                                                \
+            (size_t)warp * (3 * m.plan.in_slots * 32) + (threadIdx.x & 31);                                                                             \
+  if (inr.p) inr.ps = (unsigned)__cvta_generic_to_shared(inr.p);                                                                                        \
   for (long long t = (long long)blockIdx.x * wpb + warp; t < ntiles; t += (long long)gridDim.x * wpb) {                                                 \
     long long inst = t * 32 + (threadIdx.x & 31);                                                                                                       \
     if (inst >= a.n) inst = a.n - 1;                                                                                                                    \
@@ -77,7 +83,11 @@ __global__ void __launch_bounds__(256, MINB) NAME(const DevModelT<REAL>* __restr
     io.J = NSQ::make_field_t<TILE>(a.J, inst, 6 * m.nv, a.tile);                                                                                        \
     io.M = NSQ::make_field_t<TILE>(a.M, inst, m.nv * (m.nv + 1) / 2, a.tile);                                                                           \
     io.tau = NSQ::make_field_t<TILE>(a.tau, inst, m.nv, a.tile);                                                                                        \
-    NSQ::eval_instance<DO_M, DO_TAU, TILE>(m, io, S, T);                                                                                                \
+    io.Mtile = (TILE == 32 && a.M && (reinterpret_cast<unsigned long long>(a.M) & 15) == 0)                                                             \
+                   ? a.M + t * (long long)(m.nv * (m.nv + 1) / 2) * 32 : nullptr;                                                                       \
+    io.tau_scale = a.tau_scale; io.tau_acc = a.tau_acc; io.gravity_on = a.gravity_on;                                                                  \
+    io.next = (TILE != 0 && (t + (long long)gridDim.x * wpb + 1) * 32 <= a.n) ? (long long)gridDim.x * wpb : 0; /* full tiles only */                   \
+    NSQ::eval_instance<DO_M, DO_TAU, TILE>(m, io, S, T, inr);                                                                                           \
   }                                                                                                                                                     \
   if (tm_cols > 0) {                                                                                                                                    \
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");                                                                                    \
@@ -497,7 +507,7 @@ static cudaError_t pick_block(Kern kern, int smem_doubles_per_thread, int forced
     LaunchCfg& cfg = cache[v];                                                                                     \
     const int model_words = (int)(eval_model_bytes(hm) / 8); /* staged joint table + 2 spare words */              \
     const int block = hm.plan.warps * 32;                                                                          \
-    const size_t smem = (size_t)model_words * 8 + (size_t)block * hm.plan.smem_doubles * sizeof(REAL);             \
+    const size_t smem = (size_t)model_words * 8 + (size_t)block * (hm.plan.smem_doubles + 3 * hm.plan.in_slots) * sizeof(REAL); \
     cudaError_t e = cudaSuccess;                                                                                   \
     if (cfg.block != block || cfg.smem_bytes != smem) {                                                            \
       RBD_EVAL_DISPATCH(KERN, v, RBD_ATTR)                                                                         \

@@ -9,8 +9,11 @@ namespace rbd {
 template <class real>
 struct EvalArgsT {
   long long n, tile;
-  const real *q, *v, *a;
+  const real *q, *v, *a;  // with tau requested, v or a may be null (zeros): Mass / ForceField products
   real *oMi, *J, *M, *tau;
+  real tau_scale = real(1);  // tau_acc != 0: tau <- tau + tau_scale * rnea(...)
+  int tau_acc = 0;
+  int gravity_on = 1;
 };
 using EvalArgs = EvalArgsT<double>;
 struct MapArgs {

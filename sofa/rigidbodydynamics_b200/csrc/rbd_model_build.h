@@ -203,6 +203,8 @@ struct B200Limits {
   static constexpr int kMaxWarpsPerBlock = 8;
 };
 
+static constexpr int kEvalInSlots = 2;  // == RBD_INR_SLOTS (rbd_sweeps_body.h)
+
 inline int pow2_cols(int cols) {
   int c = 32;
   while (c < cols) c *= 2;
@@ -311,6 +313,15 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
     }
   }
   if (best_warps_sm == 0) return false;
+  // asynchronous input ring (tile-32 batches): 3 elements per slot and instance, if the SM still has room for it next
+  // to the plan (228 KB per SM, 1 KB of it reserved per resident block; 227 KB at most per block)
+  best.in_slots = 0;
+  if (!jt && nj - 1 >= kEvalInSlots) {
+    const size_t blk = model_bytes + (size_t)best.warps * 32 * best.smem_doubles * elem_bytes +
+                       (size_t)best.warps * 32 * 3 * kEvalInSlots * elem_bytes;
+    if (blk <= (size_t)B200Limits::kSmemBytes && (size_t)best.blocks_per_sm * (blk + 1024) <= (size_t)228 * 1024)
+      best.in_slots = kEvalInSlots;
+  }
   m->plan = best;
   for (size_t k = 0; k < bj.size(); ++k) m->joint[bj[k]].boff = best_boff[k];
   return true;

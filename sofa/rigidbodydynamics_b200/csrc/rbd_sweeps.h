@@ -28,8 +28,9 @@
 #ifndef RBD_PTR_OMIJ
 #define RBD_PTR_OMIJ 1
 #endif
-#ifndef RBD_IN_DIST
-#define RBD_IN_DIST 1 /* joints of lookahead of the input prefetch in the fused eval (A/B: 2..4 are 0.5 % slower) */
+#ifndef RBD_COOP_ZERO
+#define RBD_COOP_ZERO 0 /* structural zeros of M written cooperatively with 16-byte stores (tile 32): fewer
+                           instructions, yet measured SLOWER (A/B r1h: 2.361 vs 2.333 ms) -> off */
 #endif
 #ifndef RBD_UNROLL_ANC
 #define RBD_UNROLL_ANC 1 /* A/B r1e: 1 -> 2.45 ms, 2 -> 2.49 ms, 4 -> 2.67 ms (instruction-cache pressure) */

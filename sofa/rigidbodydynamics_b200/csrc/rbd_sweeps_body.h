@@ -12,6 +12,7 @@ struct FieldT {
   long long stride;
   RBD_HD long long off(int k) const { return TILE ? (long long)k * TILE : (long long)k * stride; }
   RBD_HD real ld(int k) const { return p[off(k)]; }
+  RBD_HD real ldz(int k) const { return p ? p[off(k)] : real(0); }  // an absent input array reads as zeros
   RBD_HD void st(int k, real v) const { p[off(k)] = v; }
   RBD_HD bool ok() const { return p != nullptr; }
   // address of field k, and a store at a (small, usually compile-time) field offset e from such an address: with
@@ -19,6 +20,8 @@ struct FieldT {
   RBD_HD real* at(int k) const { return p + off(k); }
   RBD_HD void st_at(real* a, int e, real v) const { a[TILE ? (long long)e * TILE : (long long)e * stride] = v; }
   RBD_HD long long step(int e) const { return TILE ? (long long)e * TILE : (long long)e * stride; }
+  // address `elems` elements behind this lane's field 0 (32-bit offset: one IMAD.WIDE)
+  RBD_HD const real* at_elems(int elems) const { return p + elems; }
   // The same store / load with the L2 eviction priority "evict_last": for the few lines this thread re-reads much
   // later (R|p of a branch joint out of its own oMi output, the root free-flyer's v / a) — without the hint the
   // kernel's 5 TB/s write stream evicts them from L2 within ~25 us and the re-read goes to HBM behind that stream
@@ -423,7 +426,12 @@ RBD_HD void ff_rows(const real* R, const real* p, const real* F, real* out6) {
 // free-flyer joint motion given in the joint (body) frame, 6 fields of `fld` from `o`: world = oMi.act(.)
 // (the six values are read with the L2 "keep" hint: the fused eval re-reads them when the sweep returns to the joint)
 template <class FLD>
-RBD_HD void ff_act(const real* R, const real* p, const FLD& fld, int o, real* out) {
+RBD_HD void ff_act(const real* R, const real* p, const FLD& fld, int o, real* out, bool may_be_absent = false) {
+  if (may_be_absent && !fld.ok()) {  // absent input array (Mass / ForceField products): zero motion
+#pragma unroll
+    for (int e = 0; e < 6; ++e) out[e] = real(0);
+    return;
+  }
   const real l0 = fld.ld_keep(o), l1 = fld.ld_keep(o + 1), l2 = fld.ld_keep(o + 2);
   const real w0 = fld.ld_keep(o + 3), w1 = fld.ld_keep(o + 4), w2 = fld.ld_keep(o + 5);
   out[3] = R[0] * w0 + R[1] * w1 + R[2] * w2;
@@ -512,7 +520,56 @@ template <int TILE>
 struct EvalIOT {
   FieldT<TILE> q, v, a;          // inputs: nq, nv, nv fields
   FieldT<TILE> oMi, J, M, tau;   // outputs (p == nullptr -> not written)
+  real* Mtile = nullptr;         // field 0, lane 0 of this warp's tile of M (tile-32, 16-byte aligned M), else nullptr
+  long long next = 0;            // tiles from this tile to the next one the same warp will process (0 = none): the
+                                 // asynchronous input ring runs on into that tile
+  // Mass / ForceField products (rbd_addMDx_soa, rbd_addForce_soa): v or a may be absent (zeros), gravity may be
+  // switched off, and tau may be accumulated, tau <- tau + tau_scale * rnea(...), as SOFA's addMDx / addForce do
+  real tau_scale = real(1);
+  int tau_acc = 0;
+  int gravity_on = 1;
+  // MF: the instantiation serves the Mass / ForceField products (RNEA without CRBA); the fused kernel compiles the
+  // plain store (the run-time switches cost it 3 % when they were unconditional)
+  template <bool MF>
+  RBD_HD void put_tau(int k, real v) const {
+    if (MF && tau_acc) tau.st(k, tau.ld(k) + tau_scale * v); else tau.st(k, v);
+  }
 };
+// Asynchronous input ring of the fused eval (device, tile-32 batches; the plan says whether it fits): the q | v | a
+// values of the 1-dof joints travel global -> shared memory with cp.async (no destination register, so nothing
+// waits on them until they are read) RBD_INR_SLOTS joints ahead of the sweep, running on into the warp's next tile.
+// Why: under the kernel's own write stream (5.3 TB/s) a global read takes 2 500 cycles on average and 6 000 at the
+// 99th percentile (experiments/load_under_stores.cu) — more than a whole joint's work, which is what a
+// one-joint-ahead register prefetch gives: its consumer held 10 % of all stall samples (profile r1h).  A register
+// ring cannot go further ahead without unrolling the joint loop (shifting the ring reads the in-flight registers).
+#define RBD_INR_SLOTS 2
+struct InRing {
+  real* p = nullptr;  // this thread's column of its warp's [RBD_INR_SLOTS * 3][32] region; nullptr = register prefetch
+  unsigned ps = 0;    // the same address in the shared window (device)
+  int slot = 0;       // slot of the joint the sweep is about to visit
+  int primed = 0;     // the previous tile already started the copies for this tile's first joints
+};
+// element `e` of the ring <- *src, asynchronously
+RBD_HD void cp_async_real(const InRing& r, int e, const real* src) {
+#if defined(__CUDA_ARCH__)
+  const unsigned d = r.ps + (unsigned)e * (unsigned)(RBD_WARP * sizeof(real));
+  if constexpr (sizeof(real) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+#else
+  r.p[e * RBD_WARP] = *src;
+#endif
+}
+RBD_HD void cp_async_commit() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+RBD_HD void cp_async_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
 using EvalIO = EvalIOT<0>;
 
 // ---- sweep-state storage (EvalPlan): vector accessors over the two spaces ----------------------------------------
@@ -559,7 +616,7 @@ RBD_HD const int* col_prog(const DevModel& m) {
 // then the zero segments (dofs of joints off the ancestor chain).
 template <int TILE>
 RBD_HD void column_rows(const DevModel& m, const DevJoint& jn, int base, const real* F, const Stack& S,
-                        const FieldT<TILE>& M) {
+                        const FieldT<TILE>& M, real* Mtile) {
   const int* pr = col_prog(m) + jn.prog_off;
   const int na = jn.depth - 1;
 #if RBD_PTR_COL
@@ -607,6 +664,25 @@ RBD_HD void column_rows(const DevModel& m, const DevJoint& jn, int base, const r
       M.st(base + RBD_PROG_ROW(e), dot6(Aa, F));
     }
   }
+#if defined(__CUDA_ARCH__) && RBD_COOP_ZERO
+  if constexpr (TILE == 32 && sizeof(real) == 8) {
+    // Structural zeros do not depend on the instance, so the warp fills a zero segment (len consecutive 256-byte
+    // fields of its tile) cooperatively with 16-byte stores: one instruction covers two fields instead of one
+    // (r1h: 372 zero stores + 650 loop instructions per tile before).
+    if (Mtile != nullptr) {
+      const int lane = threadIdx.x & 31;
+      for (int z = 0; z < jn.nzseg; ++z) {
+        const int e = pr[na + z];
+        const int r0 = base + RBD_PROG_ROW(e), len = RBD_PROG_ZLEN(e);
+        double2* const pz = reinterpret_cast<double2*>(Mtile + (long long)r0 * 32) + lane;
+        const int pairs = len >> 1;
+        for (int i = 0; i < pairs; ++i) pz[i * 32] = make_double2(0.0, 0.0);
+        if ((len & 1) && lane < 16) pz[pairs * 32] = make_double2(0.0, 0.0);
+      }
+      return;
+    }
+  }
+#endif
   for (int z = 0; z < jn.nzseg; ++z) {
     const int e = pr[na + z];
     const int r0 = base + RBD_PROG_ROW(e), len = RBD_PROG_ZLEN(e);
@@ -624,14 +700,14 @@ RBD_HD void emit_joint(const DevModel& m, int k, const real* A, const real* f, c
                        const EvalIOT<TILE>& io) {
   const DevJoint& jn = m.joint[k];
   if (jn.type != JT_FF) {
-    if (DO_TAU) io.tau.st(jn.idx_v, dot6(A, f));
+    if (DO_TAU) io.template put_tau<(DO_TAU && !DO_M)>(jn.idx_v, dot6(A, f));
     if (DO_M) {
       real F[6];
       inertia_mul(Y, A, F);
       const int col = jn.idx_v;
       const int base = col * (col + 1) / 2;
       *io.M.at(base + col) = dot6(A, F);
-      column_rows(m, jn, base, F, S, io.M);
+      column_rows(m, jn, base, F, S, io.M, io.Mtile);
     }
   } else {
     // a real loop (not unrolled): runs once per free-flyer, and the kernel is instruction-cache sensitive
@@ -639,7 +715,7 @@ RBD_HD void emit_joint(const DevModel& m, int k, const real* A, const real* f, c
     for (int cc = 0; cc < 6; ++cc) {
       real Ac[6];
       RBD_FF_COL(Ac, A, (A + 9), cc);
-      if (DO_TAU) io.tau.st(jn.idx_v + cc, dot6(Ac, f));
+      if (DO_TAU) io.template put_tau<(DO_TAU && !DO_M)>(jn.idx_v + cc, dot6(Ac, f));
       if (DO_M) {
         real F[6], o6[6];
         inertia_mul(Y, Ac, F);
@@ -650,7 +726,7 @@ RBD_HD void emit_joint(const DevModel& m, int k, const real* A, const real* f, c
 #pragma unroll
         for (int e = 0; e < 6; ++e)
           if (e <= cc) io.M.st_at(pd, e, o6[e]);
-        column_rows(m, jn, base, F, S, io.M);
+        column_rows(m, jn, base, F, S, io.M, io.Mtile);
       }
     }
   }
@@ -659,7 +735,7 @@ RBD_HD void emit_joint(const DevModel& m, int k, const real* A, const real* f, c
 // One instance, one sweep.  S = this thread's shared-memory stack, T = its tensor-memory slice (m.plan says what
 // lives where).  Control flow depends on the model only, so all lanes of a warp stay converged.
 template <bool DO_M, bool DO_TAU, int TILE>
-RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stack& S, const TmStack& T) {
+RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stack& S, const TmStack& T, InRing& inr) {
   constexpr bool NEED_STACK = DO_M || DO_TAU;
   const int nj = m.njoints;
   const int fbase = m.plan.fbase, fsplit = m.plan.fsplit, ftbase = m.plan.ftbase, ybase = m.plan.ybase;
@@ -670,34 +746,56 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
 #define RBD_F_TM(lvl) ((lvl) >= fsplit)
 #define RBD_F_OFF(lvl) ((lvl) >= fsplit ? ftbase + 6 * ((lvl)-fsplit) : fbase + 6 * (lvl))
   real R[9], p[3], vel[6], acc[6];
+  constexpr bool MF = DO_TAU && !DO_M;  // Mass / ForceField switches live in the RNEA-only instantiation
+  const real gs_ = (MF && !io.gravity_on) ? real(0) : real(1);
 #define RBD_RESET_ROOT()                                                   \
   do {                                                                     \
     R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1; \
     p[0] = p[1] = p[2] = 0;                                                \
     _Pragma("unroll") for (int e_ = 0; e_ < 6; ++e_) { vel[e_] = 0; acc[e_] = 0; } \
-    acc[0] = -m.gravity[0]; acc[1] = -m.gravity[1]; acc[2] = -m.gravity[2]; \
+    acc[0] = -gs_ * m.gravity[0]; acc[1] = -gs_ * m.gravity[1]; acc[2] = -gs_ * m.gravity[2]; \
   } while (0)
   RBD_RESET_ROOT();
 
-  // Prefetch of the 1-dof inputs RBD_IN_DIST joints ahead (a small register ring; 1 = the next joint's values).
-  // In profile r1g the MOV that consumes the prefetched angle at the loop top holds 10.5 % of all stall samples
-  // (long scoreboard), yet a longer distance does not help (A/B): with a ring the shift itself touches the in-flight
-  // register.  Open item for round 2 (unroll the joint loop by two to rotate the ring at compile time).
-  real qn[RBD_IN_DIST], q1n_[RBD_IN_DIST], vn_[RBD_IN_DIST], an_[RBD_IN_DIST];
-#pragma unroll
-  for (int s_ = 0; s_ < RBD_IN_DIST; ++s_) { qn[s_] = 0; q1n_[s_] = 0; vn_[s_] = 0; an_[s_] = 0; }
-  // issue the loads of joint `jidx` into ring slot `slot` (compile-time)
-#define RBD_IN_FETCH(jidx, slot)                                                                   \
+  // Prefetch of the 1-dof inputs: through the asynchronous ring (see InRing) when the plan has room for it, else one
+  // joint ahead through registers.
+  real qn = 0, q1n = 0, vn = 0, an = 0;
+#define RBD_IN_FETCH(jidx)                                                                         \
   do {                                                                                             \
     if ((jidx) < nj && m.joint[jidx].type != JT_FF) {                                              \
       const DevJoint& jx_ = m.joint[jidx];                                                         \
-      qn[slot] = io.q.ld(jx_.idx_q);                                                               \
-      if (is_unbounded(jx_.type)) q1n_[slot] = io.q.ld(jx_.idx_q + 1);                             \
-      if (DO_TAU) { vn_[slot] = io.v.ld(jx_.idx_v); an_[slot] = io.a.ld(jx_.idx_v); }              \
+      qn = io.q.ld(jx_.idx_q);                                                                     \
+      if (is_unbounded(jx_.type)) q1n = io.q.ld(jx_.idx_q + 1);                                    \
+      if (DO_TAU) {                                                                                \
+        vn = MF ? io.v.ldz(jx_.idx_v) : io.v.ld(jx_.idx_v);                                        \
+        an = MF ? io.a.ldz(jx_.idx_v) : io.a.ld(jx_.idx_v);                                        \
+      }                                                                                            \
     }                                                                                              \
   } while (0)
+  // start the copies of joint `jidx` (`ahead` tiles further on) into ring slot `slot_`; always closes one group
+#define RBD_INR_ISSUE(jidx, ahead, slot_)                                                          \
+  do {                                                                                             \
+    if ((jidx) < nj && m.joint[jidx].type != JT_FF) {                                              \
+      const DevJoint& jx_ = m.joint[jidx];                                                         \
+      const int oq_ = (jx_.idx_q + (ahead) * m.nq) * TILE, ov_ = (jx_.idx_v + (ahead) * m.nv) * TILE; \
+      cp_async_real(inr, 3 * (slot_), io.q.at_elems(oq_));                                         \
+      if (DO_TAU) {                                                                                \
+        cp_async_real(inr, 3 * (slot_) + 1, io.v.at_elems(ov_));                                   \
+        cp_async_real(inr, 3 * (slot_) + 2, io.a.at_elems(ov_));                                   \
+      }                                                                                            \
+    }                                                                                              \
+    cp_async_commit();                                                                             \
+  } while (0)
+  const bool ring = inr.p != nullptr;
+  if (!ring) {
+    RBD_IN_FETCH(1);
+  } else if (!inr.primed) {
 #pragma unroll
-  for (int s_ = 0; s_ < RBD_IN_DIST; ++s_) RBD_IN_FETCH(1 + s_, s_);
+    for (int s_ = 0; s_ < RBD_INR_SLOTS; ++s_) {
+      const int sl_ = inr.slot + s_ >= RBD_INR_SLOTS ? inr.slot + s_ - RBD_INR_SLOTS : inr.slot + s_;
+      RBD_INR_ISSUE(1 + s_, 0, sl_);
+    }
+  }
 
   // State of the joint the sweep returns to when a new branch starts below it: R|p (+ v|a).  With a stack
   // (CRBA / RNEA) this runs at the LEAF that ends the previous branch, BEFORE its unwind — R, p, vel, acc are dead
@@ -735,18 +833,19 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
           // branch joint attached to the universe: v = A qd, a = -g + A qdd (v x vJ = 0), nothing was saved
           real vj[6], aj[6];
           if (jb.type == JT_FF) {
-            ff_act(R, p, io.v, jb.idx_v, vj);
-            ff_act(R, p, io.a, jb.idx_v, aj);
+            ff_act(R, p, io.v, jb.idx_v, vj, MF);
+            ff_act(R, p, io.a, jb.idx_v, aj, MF);
           } else {
             real Ab[6];
             s_ldv<6>(S, jb.offA, Ab);
-            const real qd_b = io.v.ld(jb.idx_v), qdd_b = io.a.ld(jb.idx_v);
+            const real qd_b = MF ? io.v.ldz(jb.idx_v) : io.v.ld(jb.idx_v);
+            const real qdd_b = MF ? io.a.ldz(jb.idx_v) : io.a.ld(jb.idx_v);
 #pragma unroll
             for (int e = 0; e < 6; ++e) { vj[e] = Ab[e] * qd_b; aj[e] = Ab[e] * qdd_b; }
           }
 #pragma unroll
           for (int e = 0; e < 6; ++e) { vel[e] = vj[e]; acc[e] = aj[e]; }
-          acc[0] -= m.gravity[0]; acc[1] -= m.gravity[1]; acc[2] -= m.gravity[2];
+          acc[0] -= gs_ * m.gravity[0]; acc[1] -= gs_ * m.gravity[1]; acc[2] -= gs_ * m.gravity[2];
         }
       }
     }
@@ -756,14 +855,25 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
     const DevJoint& jn = m.joint[i];
     const int par = jn.parent;
     if (!NEED_STACK && par != i - 1) restore(par);  // FK-only variant: no unwind to hide behind
-    const real q0 = qn[0], q1 = q1n_[0], qd = vn_[0], qdd = an_[0];
+    real q0 = qn, q1 = q1n, qd = vn, qdd = an;
     const int nxt_par = (i + 1 < nj) ? m.joint[i + 1].parent : 0;
-    // advance the ring and start the loads of joint i + RBD_IN_DIST
-#pragma unroll
-    for (int s_ = 0; s_ + 1 < RBD_IN_DIST; ++s_) {
-      qn[s_] = qn[s_ + 1]; q1n_[s_] = q1n_[s_ + 1]; vn_[s_] = vn_[s_ + 1]; an_[s_] = an_[s_ + 1];
+    if (!ring) {
+      RBD_IN_FETCH(i + 1);
+    } else {
+      cp_async_wait<RBD_INR_SLOTS - 1>();  // everything but the newest groups has landed: this joint's values are in
+      if (jn.type != JT_FF) {
+        const real* const s_ = inr.p + 3 * inr.slot * RBD_WARP;
+        q0 = s_[0];
+        if (is_unbounded(jn.type)) q1 = io.q.ld(jn.idx_q + 1);
+        if (DO_TAU) { qd = s_[RBD_WARP]; qdd = s_[2 * RBD_WARP]; }
+      }
+      // the slot just read receives the joint RBD_INR_SLOTS positions further on (possibly in the warp's next tile)
+      int pj = i + RBD_INR_SLOTS;
+      int ahead = 0;
+      if (pj >= nj) { pj -= nj - 1; ahead = (int)io.next; if (ahead == 0) pj = nj; }
+      RBD_INR_ISSUE(pj, ahead, inr.slot);
+      inr.slot = inr.slot + 1 == RBD_INR_SLOTS ? 0 : inr.slot + 1;
     }
-    RBD_IN_FETCH(i + RBD_IN_DIST, RBD_IN_DIST - 1);
 
     real aw[3];
     fk_joint(jn, R, p, q0, q1, io.q, aw);
@@ -834,8 +944,8 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
       if (DO_TAU) {
         // joint velocity / acceleration given in the joint (body) frame: world = oMi.act(.)
         real vj[6], aj[6], cr[6];
-        ff_act(R, p, io.v, jn.idx_v, vj);
-        ff_act(R, p, io.a, jn.idx_v, aj);
+        ff_act(R, p, io.v, jn.idx_v, vj, MF);
+        ff_act(R, p, io.a, jn.idx_v, aj, MF);
 #pragma unroll
         for (int e = 0; e < 6; ++e) vel[e] += vj[e];
         RBD_CROSS(cr[0], cr[1], cr[2], vel[3], vel[4], vel[5], vj[0], vj[1], vj[2]);
@@ -925,8 +1035,10 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
       }
     }
   }
+  inr.primed = io.next != 0 ? 1 : 0;
 #undef RBD_RESET_ROOT
 #undef RBD_IN_FETCH
+#undef RBD_INR_ISSUE
 #undef RBD_F_TM
 #undef RBD_F_OFF
 #undef RBD_Y_TM

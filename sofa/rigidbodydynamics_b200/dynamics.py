@@ -67,3 +67,15 @@ class BatchedDynamics:
     def rnea(self, q, v, a, tau):
         self._on_current_stream()
         self.ws.rnea_soa(self.n, self.tile, q, v, a, tau)
+
+    # -- SOFA Mass / ForceField interface in joint space (reference: UniformMass<Rigid3> per body hung under the
+    #    mapping, URDFModelLoader.cpp:369-391; reached there matrix-free through applyJ / applyJT) -------------
+    def addMDx(self, q, dx, factor, res):
+        """Mass::addMDx: res += factor * M(q) dx, one RNEA-shaped sweep (no M is formed)."""
+        self._on_current_stream()
+        self.ws.addMDx_soa(self.n, self.tile, q, dx, factor, res)
+
+    def addForce(self, q, v, f):
+        """ForceField::addForce: f -= C(q, v) v + g(q); v None = gravity only (what the reference computes)."""
+        self._on_current_stream()
+        self.ws.addForce_soa(self.n, self.tile, q, v, f)

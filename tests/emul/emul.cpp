@@ -50,17 +50,18 @@ extern "C" int emul_model_info(const rbd_model_desc* d, int* out /*[8]*/) {
 
 template <int TILE>
 static void eval_one(const DevModel& m, long long i, long long tile, double* q, double* v, double* a, double* oMi,
-                     double* J, double* M, double* tau, const Stack& S, const TmStack& T) {
+                     double* J, double* M, double* tau, const Stack& S, const TmStack& T, InRing& inr, long long next = 0) {
   const bool do_m = M != nullptr, do_tau = tau != nullptr;
   EvalIOT<TILE> io;
+  io.next = next;
   io.q = make_field_t<TILE>(q, i, m.nq, tile); io.v = make_field_t<TILE>(v, i, m.nv, tile);
   io.a = make_field_t<TILE>(a, i, m.nv, tile);
   io.oMi = make_field_t<TILE>(oMi, i, 12 * (m.njoints - 1), tile); io.J = make_field_t<TILE>(J, i, 6 * m.nv, tile);
   io.M = make_field_t<TILE>(M, i, m.nv * (m.nv + 1) / 2, tile); io.tau = make_field_t<TILE>(tau, i, m.nv, tile);
-  if (do_m && do_tau) eval_instance<true, true, TILE>(m, io, S, T);
-  else if (do_m) eval_instance<true, false, TILE>(m, io, S, T);
-  else if (do_tau) eval_instance<false, true, TILE>(m, io, S, T);
-  else eval_instance<false, false, TILE>(m, io, S, T);
+  if (do_m && do_tau) eval_instance<true, true, TILE>(m, io, S, T, inr);
+  else if (do_m) eval_instance<true, false, TILE>(m, io, S, T, inr);
+  else if (do_tau) eval_instance<false, true, TILE>(m, io, S, T, inr);
+  else eval_instance<false, false, TILE>(m, io, S, T, inr);
 }
 
 // tile == 32 runs the compile-time-tile instantiation the GPU fast path uses.  use_tmem selects the storage plan
@@ -79,14 +80,50 @@ extern "C" int emul_eval(const rbd_model_desc* d, long long n, long long tile, i
   const int bt = pl.warps * 32;
   std::vector<double> smem((size_t)(pl.smem_doubles > 0 ? pl.smem_doubles : 1) * bt, 1e300);  // poison
   std::vector<double> tmem((size_t)(pl.tmem_doubles > 0 ? pl.tmem_doubles : 1) * bt, 1e300);
+  // asynchronous input ring (tile-32 batches, when the plan has room): emulated per lane, persisting from one tile to
+  // the next as it does for a warp that strides over the tiles (here: stride 1, a single "warp")
+  const bool use_ring = tile == 32 && pl.in_slots > 0;
+  std::vector<double> ringbuf((size_t)3 * kEvalInSlots * 32 * 32, 1e300);
+  std::vector<InRing> rings(32);
+  for (int l = 0; l < 32; ++l) rings[l].p = use_ring ? ringbuf.data() + (size_t)l * 3 * kEvalInSlots * 32 : nullptr;
   for (long long b0 = 0; b0 < n; b0 += bt)
     for (int t = 0; t < bt && b0 + t < n; ++t) {
       const long long i = b0 + t;
       Stack S = make_stack(smem.data(), t, pl.smem_doubles);
       TmStack T{tmem.data() + (size_t)t * (pl.tmem_doubles > 0 ? pl.tmem_doubles : 1)};
-      if (tile == 32) eval_one<32>(bm, i, tile, q, v, a, oMi, J, M, tau, S, T);
-      else eval_one<0>(bm, i, tile, q, v, a, oMi, J, M, tau, S, T);
+      const long long next = (use_ring && (i / 32 + 2) * 32 <= n) ? 1 : 0;  // the next tile is a full one
+      if (tile == 32) eval_one<32>(bm, i, tile, q, v, a, oMi, J, M, tau, S, T, rings[i % 32], next);
+      else eval_one<0>(bm, i, tile, q, v, a, oMi, J, M, tau, S, T, rings[0]);
     }
+  return 0;
+}
+
+// Mass / ForceField products (rbd_addMDx_soa / rbd_addForce_soa): the RNEA sweep with absent v or a, gravity switch
+// and accumulation out <- out + scale * rnea(...)
+extern "C" int emul_mass_force(const rbd_model_desc* d, long long n, long long tile, double* q, double* v, double* a,
+                               double* out, double scale, int gravity_on) {
+  Ctx c;
+  int rc = make_ctx(d, &c);
+  if (rc) return rc;
+  if (!plan_eval(&c.m, false, true, true, 0, false)) { g_err = "plan_eval failed"; return -100; }
+  const std::vector<unsigned long long> blob = build_eval_blob(&c.m);
+  const DevModel& bm = *reinterpret_cast<const DevModel*>(blob.data());
+  const EvalPlan& pl = bm.plan;
+  const int bt = pl.warps * 32;
+  std::vector<double> smem((size_t)(pl.smem_doubles > 0 ? pl.smem_doubles : 1) * bt, 1e300);
+  std::vector<double> tmem((size_t)(pl.tmem_doubles > 0 ? pl.tmem_doubles : 1) * bt, 1e300);
+  for (long long i = 0; i < n; ++i) {
+    const int t = (int)(i % bt);
+    Stack S = make_stack(smem.data(), t, pl.smem_doubles);
+    TmStack T{tmem.data() + (size_t)t * (pl.tmem_doubles > 0 ? pl.tmem_doubles : 1)};
+    EvalIO io;
+    io.q = make_field(q, i, bm.nq, tile); io.v = make_field(v, i, bm.nv, tile); io.a = make_field(a, i, bm.nv, tile);
+    io.oMi = make_field(nullptr, i, 1, tile); io.J = io.oMi; io.M = io.oMi;
+    io.tau = make_field(out, i, bm.nv, tile);
+    io.tau_scale = scale; io.tau_acc = 1; io.gravity_on = gravity_on;
+    InRing inr;
+    eval_instance<false, true, 0>(bm, io, S, T, inr);
+  }
   return 0;
 }
 
@@ -96,14 +133,15 @@ static void eval_one_f32(const DevModelT<float>& m, long long i, long long tile,
                          float* J, float* M, float* tau, const f32::Stack& S, const f32::TmStack& T) {
   const bool do_m = M != nullptr, do_tau = tau != nullptr;
   f32::EvalIOT<TILE> io;
+  f32::InRing inr;  // register prefetch (the FP32 plan leaves no room for the ring)
   io.q = f32::make_field_t<TILE>(q, i, m.nq, tile); io.v = f32::make_field_t<TILE>(v, i, m.nv, tile);
   io.a = f32::make_field_t<TILE>(a, i, m.nv, tile);
   io.oMi = f32::make_field_t<TILE>(oMi, i, 12 * (m.njoints - 1), tile); io.J = f32::make_field_t<TILE>(J, i, 6 * m.nv, tile);
   io.M = f32::make_field_t<TILE>(M, i, m.nv * (m.nv + 1) / 2, tile); io.tau = f32::make_field_t<TILE>(tau, i, m.nv, tile);
-  if (do_m && do_tau) f32::eval_instance<true, true, TILE>(m, io, S, T);
-  else if (do_m) f32::eval_instance<true, false, TILE>(m, io, S, T);
-  else if (do_tau) f32::eval_instance<false, true, TILE>(m, io, S, T);
-  else f32::eval_instance<false, false, TILE>(m, io, S, T);
+  if (do_m && do_tau) f32::eval_instance<true, true, TILE>(m, io, S, T, inr);
+  else if (do_m) f32::eval_instance<true, false, TILE>(m, io, S, T, inr);
+  else if (do_tau) f32::eval_instance<false, true, TILE>(m, io, S, T, inr);
+  else f32::eval_instance<false, false, TILE>(m, io, S, T, inr);
 }
 
 extern "C" int emul_eval_f32(const rbd_model_desc* d, long long n, long long tile, int block, int use_tmem, float* q,

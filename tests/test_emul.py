@@ -221,3 +221,41 @@ def test_sincos_accuracy(emul):
     assert np.max(np.abs(s - rs)) <= 4.5e-16, np.max(np.abs(s - rs))
     assert np.max(np.abs(c - rc)) <= 4.5e-16, np.max(np.abs(c - rc))
     assert np.max(np.abs(s * s + c * c - 1.0)) <= 1e-15
+
+
+def _unpack_upper(Mp, nv):
+    """packed upper triangle by columns -> full symmetric [n, nv, nv]"""
+    n = Mp.shape[0]
+    M = np.zeros((n, nv, nv))
+    for c in range(nv):
+        for r in range(c + 1):
+            M[:, r, c] = M[:, c, r] = Mp[:, c * (c + 1) // 2 + r]
+    return M
+
+
+@pytest.mark.parametrize("d", MODELS, ids=IDS)
+def test_mass_forcefield_bodies(emul, d):
+    """rbd_addMDx_soa / rbd_addForce_soa bodies (RNEA sweep with absent v or a, gravity switch, accumulation):
+    res += f M(q) dx against the oracle's CRBA matrix; f -= rnea(q, v, 0) and the gravity-only form against its RNEA."""
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    n, tile = 40, 16
+    q, v, dx = mdl.random_state(d, n, seed=8)
+    cd, keep = _cdesc(d)
+    rng = np.random.default_rng(9)
+    r0 = rng.uniform(-1, 1, (n, d.nv))
+    zero = np.zeros_like(v)
+    ref, _ = oracle.eval_batch(d, q, zero, zero, 1)
+    M = _unpack_upper(ref["M"], d.nv)
+    T = lambda x: to_tiled(x, tile)
+    qs = T(q)
+    res = T(r0)
+    assert emul.emul_mass_force(C.addressof(cd), n, tile, P(qs), None, P(T(dx)), P(res), 0.75, 0) == 0
+    assert rel_err(from_tiled(res, n), r0 + 0.75 * np.einsum("nij,nj->ni", M, dx)) <= TOL_FP64
+    f = T(r0)
+    assert emul.emul_mass_force(C.addressof(cd), n, tile, P(qs), P(T(v)), None, P(f), -1.0, 1) == 0
+    bias, _ = oracle.eval_batch(d, q, v, zero, 1)
+    assert rel_err(from_tiled(f, n), r0 - bias["tau"]) <= TOL_FP64
+    g = T(r0)
+    assert emul.emul_mass_force(C.addressof(cd), n, tile, P(qs), None, None, P(g), -1.0, 1) == 0
+    assert rel_err(from_tiled(g, n), r0 - ref["tau"]) <= TOL_FP64

@@ -437,3 +437,36 @@ def test_eval_f32_mode_within_1e4(torch_mod, api, d, tmem):
     for k in K:
         got = from_tiled(outs[k].cpu().numpy(), n).astype(np.float64)
         assert rel_err(got, ref[k]) <= TOL_FP32, k
+
+
+@pytest.mark.parametrize("d", MODELS, ids=IDS)
+@pytest.mark.parametrize("tile", [32, 100])
+def test_mass_forcefield_products(torch_mod, api, d, tile):
+    """SOFA Mass::addMDx / ForceField::addForce in joint space (rbd_addMDx_soa, rbd_addForce_soa): accumulating,
+    matrix-free.  res += f M(q) dx against the oracle's CRBA matrix; f -= rnea(q, v, 0); gravity only: f -= rnea(q, 0, 0),
+    which is what the reference's UniformMass + applyJT path evaluates (URDFModelLoader.cpp:369-391)."""
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    torch = torch_mod
+    n = 500
+    q, v, dx = mdl.random_state(d, n, seed=31)
+    rng = np.random.default_rng(32)
+    r0 = rng.uniform(-1, 1, (n, d.nv))
+    zero = np.zeros_like(v)
+    ref, _ = oracle.eval_batch(d, q, zero, zero, nthreads=0)
+    nv = d.nv
+    M = np.zeros((n, nv, nv))
+    for c in range(nv):
+        for r in range(c + 1):
+            M[:, r, c] = M[:, c, r] = ref["M"][:, c * (c + 1) // 2 + r]
+    m = api.Model(d); ws = api.Workspace(m, n)
+    T = lambda x: _dev(torch, to_tiled(x, tile))
+    qs = T(q)
+    res = T(r0); ws.addMDx_soa(n, tile, qs, T(dx), 0.75, res)
+    f = T(r0); ws.addForce_soa(n, tile, qs, T(v), f)
+    g = T(r0); ws.addForce_soa(n, tile, qs, None, g)
+    ws.synchronize()
+    assert rel_err(from_tiled(res.cpu().numpy(), n), r0 + 0.75 * np.einsum("nij,nj->ni", M, dx)) <= TOL_FP64
+    bias, _ = oracle.eval_batch(d, q, v, zero, nthreads=0)
+    assert rel_err(from_tiled(f.cpu().numpy(), n), r0 - bias["tau"]) <= TOL_FP64
+    assert rel_err(from_tiled(g.cpu().numpy(), n), r0 - ref["tau"]) <= TOL_FP64
