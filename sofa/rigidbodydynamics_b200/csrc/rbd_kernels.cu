@@ -141,8 +141,12 @@ __global__ void __launch_bounds__(256) apply_kernel(const DevModel* __restrict__
   SplitQT<FieldT<TILE>> q{make_field_t<TILE>(const_cast<double*>(a.root), inst, 7, a.tile),
                           make_field_t<TILE>(const_cast<double*>(a.joints), inst, m.nq - off, a.tile), off};
   Stack S = make_stack(rbd_smem + model_words + tw, threadIdx.x, slots);
+  MapRing ring;
+  ring.p = rbd_smem + model_words + tw + (size_t)blockDim.x * slots + (size_t)(threadIdx.x >> 5) * (RBD_MAP_SLOTS * 32) +
+           (threadIdx.x & 31);
+  ring.ps = (unsigned)__cvta_generic_to_shared(ring.p);
   apply_instance(m, tbs, q, make_field_t<32>(a.qcache, a.cache_inst0 + inst, m.nq, 32),
-                 make_field_t<TILE>(a.out, inst, 7 * m.n_out, a.tile), S);
+                 make_field_t<TILE>(a.out, inst, 7 * m.n_out, a.tile), S, ring);
 }
 
 // K2: applyJ
@@ -158,8 +162,12 @@ __global__ void __launch_bounds__(256) applyJ_kernel(const DevModel* __restrict_
   SplitQT<FieldT<TILE>> dq{make_field_t<TILE>(const_cast<double*>(a.root), inst, 6, a.tile),
                            make_field_t<TILE>(const_cast<double*>(a.joints), inst, m.nv - off, a.tile), off};
   Stack S = make_stack(rbd_smem + model_words + tw, threadIdx.x, slots);
+  MapRing ring;
+  ring.p = rbd_smem + model_words + tw + (size_t)blockDim.x * slots +
+           (size_t)(threadIdx.x >> 5) * (2 * RBD_MAP_SLOTS * 32) + (threadIdx.x & 31);
+  ring.ps = (unsigned)__cvta_generic_to_shared(ring.p);
   applyJ_instance(m, tbs, make_field_t<32>(a.qcache, a.cache_inst0 + inst, m.nq, 32), dq,
-                  make_field_t<TILE>(a.out, inst, 6 * m.n_out, a.tile), S);
+                  make_field_t<TILE>(a.out, inst, 6 * m.n_out, a.tile), S, ring);
 }
 
 // K3: applyJT (vector).  a.joints / a.root are the ACCUMULATED outputs here, a.in the wrenches.
@@ -536,14 +544,14 @@ RBD_DEFINE_EVAL_LAUNCH(launch_eval_f32, eval_kernel_f32, float)
 // mapping kernels: cfg[0] = run-time tile, cfg[1] = tile 32
 static inline int map_model_words(const DevModel& m) { return (int)((dev_model_bytes(m) + 15) / 16) * 2; }
 
-#define RBD_MAP_LAUNCH(KERN, n_items)                                                                         \
+#define RBD_MAP_LAUNCH(KERN, n_items, ring_doubles) /* ring_doubles: input ring behind the stacks, per instance */ \
   const int mw = map_model_words(m);                                                                          \
   const size_t fixed = ((size_t)mw + table_words(m.n_out)) * 8;                                               \
   const int v = a_tile == 32 ? 1 : 0;                                                                         \
   LaunchCfg& c = cfg[v];                                                                                      \
   if (c.block == 0) {                                                                                         \
-    cudaError_t e = v ? pick_block(KERN<32>, smem_doubles, 0, &c, fixed)                                      \
-                      : pick_block(KERN<0>, smem_doubles, 0, &c, fixed);                                      \
+    cudaError_t e = v ? pick_block(KERN<32>, smem_doubles + (ring_doubles), 0, &c, fixed)                     \
+                      : pick_block(KERN<0>, smem_doubles + (ring_doubles), 0, &c, fixed);                     \
     if (e != cudaSuccess) return e;                                                                           \
   }                                                                                                           \
   if ((n_items) <= 0) return cudaSuccess;                                                                     \
@@ -554,17 +562,17 @@ static inline int map_model_words(const DevModel& m) { return (int)((dev_model_b
 cudaError_t launch_apply(const DevModel& m, const DevModel* d_model, const DevTables& tb, const MapArgs& a,
                          int smem_doubles, LaunchCfg* cfg, cudaStream_t st) {
   const long long a_tile = a.tile;
-  RBD_MAP_LAUNCH(apply_kernel, a.n);
+  RBD_MAP_LAUNCH(apply_kernel, a.n, RBD_MAP_SLOTS);
 }
 cudaError_t launch_applyJ(const DevModel& m, const DevModel* d_model, const DevTables& tb, const MapArgs& a,
                           int smem_doubles, LaunchCfg* cfg, cudaStream_t st) {
   const long long a_tile = a.tile;
-  RBD_MAP_LAUNCH(applyJ_kernel, a.n);
+  RBD_MAP_LAUNCH(applyJ_kernel, a.n, 2 * RBD_MAP_SLOTS);
 }
 cudaError_t launch_applyJT(const DevModel& m, const DevModel* d_model, const DevTables& tb, const MapArgs& a,
                            int smem_doubles, LaunchCfg* cfg, cudaStream_t st) {
   const long long a_tile = a.tile;
-  RBD_MAP_LAUNCH(applyJT_kernel, a.n);
+  RBD_MAP_LAUNCH(applyJT_kernel, a.n, 0);
 }
 // `hm` = host copy of the model planned with plan_eval(..., jt = true), `d_blob` = its staged blob on the device
 cudaError_t launch_applyJT_plan(const DevModel& hm, const DevModel* d_blob, const DevTables& tb, const MapArgs& a,

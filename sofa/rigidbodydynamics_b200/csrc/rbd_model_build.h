@@ -407,6 +407,8 @@ inline std::vector<unsigned long long> build_jt_blob(const DevModel* m, const st
 }
 
 // shared-memory doubles per instance of the mapping kernels
+// (branch slots; the kernels add their input ring behind them: kMapSlots (apply) / 2 kMapSlots (applyJ) per instance)
+static constexpr int kMapSlots = 4;  // == RBD_MAP_SLOTS (rbd_sweeps_body.h)
 inline int smem_apply(const DevModel& m) { return m.nbranch * RBD_BRANCH_FK; }
 inline int smem_applyJ(const DevModel& m) { return m.nbranch * RBD_BRANCH_J; }
 inline int smem_applyJT(const DevModel& m) { return m.slot_total[1] + m.nbranch * RBD_BRANCH_FK; }

@@ -549,6 +549,21 @@ struct InRing {
   int slot = 0;       // slot of the joint the sweep is about to visit
   int primed = 0;     // the previous tile already started the copies for this tile's first joints
 };
+// Input ring of the mapping kernels (apply, applyJ): NV values per joint (q | q, dq) travel global -> shared memory
+// with cp.async RBD_MAP_SLOTS joints ahead of the sweep.  p: this thread's column of its warp's
+// [RBD_MAP_SLOTS * NV][32] region, nullptr (host, tests/emul) = one joint ahead through registers / direct loads.
+#define RBD_MAP_SLOTS 4
+struct MapRing {
+  real* p = nullptr;
+  unsigned ps = 0;  // the same address in the shared window (device)
+};
+RBD_HD void cp_async_map(const MapRing& r, int e, const real* src) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(r.ps + (unsigned)e * (unsigned)(RBD_WARP * 8)), "l"(src) : "memory");
+#else
+  r.p[e * RBD_WARP] = *src;
+#endif
+}
 // element `e` of the ring <- *src, asynchronously
 RBD_HD void cp_async_real(const InRing& r, int e, const real* src) {
 #if defined(__CUDA_ARCH__)
@@ -1067,16 +1082,29 @@ struct SplitQT {
   FLD root, joints;
   int off;  // 7 (or 6 for velocities) when a root is supplied, else 0
   RBD_HD real ld(int k) const { return k < off ? root.ld(k) : joints.ld(k - off); }
+  RBD_HD const real* at(int k) const { return k < off ? root.at(k) : joints.at(k - off); }
 };
 using SplitQ = SplitQT<Field>;
 
 // apply: q -> [p, quat] of every mapped output; also copies the assembled q into the workspace cache.
 template <class QF, class QC, class OUT>
 RBD_HD void apply_instance(const DevModel& m, const DevTables& tb, const QF& q, const QC& qcache,
-                           const OUT& out, const Stack& S) {
+                           const OUT& out, const Stack& S, const MapRing& ring = MapRing()) {
   const int nj = m.njoints;
-  if (qcache.ok())
-    for (int k = 0; k < m.nq; ++k) qcache.st(k, q.ld(k));
+  // The assembled configuration goes to the workspace cache joint by joint, as the sweep consumes it (a copy loop up
+  // front was 39 dependent load -> store round trips before the first joint: profile r1h, long scoreboard 3.1 / issue)
+  // ring: slot s holds the angle of the joint RBD_MAP_SLOTS positions ahead
+  const bool use_ring = ring.p != nullptr;
+#define RBD_MAP_ISSUE(jidx, slot_)                                                    \
+  do {                                                                                \
+    if ((jidx) < nj && m.joint[jidx].type != JT_FF) cp_async_map(ring, (slot_), q.at(m.joint[jidx].idx_q)); \
+    cp_async_commit();                                                                \
+  } while (0)
+  int slot = 0;
+  if (use_ring) {
+#pragma unroll
+    for (int s_ = 0; s_ < RBD_MAP_SLOTS; ++s_) RBD_MAP_ISSUE(1 + s_, s_);
+  }
   // outputs attached to the universe (kSkipUniverse = 0, reference Types.h:32): constant poses
   {
     const DevJoint& j0 = m.joint[0];
@@ -1092,7 +1120,7 @@ RBD_HD void apply_instance(const DevModel& m, const DevTables& tb, const QF& q, 
   }
   real R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
   real q0n = 0.0, q1n = 0.0;
-  RBD_Q_PREFETCH(1);
+  if (!use_ring) RBD_Q_PREFETCH(1);
   for (int i = 1; i < nj; ++i) {
     const DevJoint& jn = m.joint[i];
     const int par = jn.parent;
@@ -1109,8 +1137,30 @@ RBD_HD void apply_instance(const DevModel& m, const DevTables& tb, const QF& q, 
       }
     }
     real aw[3];
-    const real q0 = q0n, q1 = q1n;
-    RBD_Q_PREFETCH(i + 1);  // next joint's angle: its HBM latency hides behind this joint's work
+    real q0 = q0n, q1 = q1n;
+    if (!use_ring) {
+      RBD_Q_PREFETCH(i + 1);  // next joint's angle: its HBM latency hides behind this joint's work
+    } else {
+      cp_async_wait<RBD_MAP_SLOTS - 1>();
+      if (jn.type != JT_FF) {
+        q0 = ring.p[slot * RBD_WARP];
+        if (is_unbounded(jn.type)) q1 = q.ld(jn.idx_q + 1);
+      }
+      RBD_MAP_ISSUE(i + RBD_MAP_SLOTS, slot);
+      slot = slot + 1 == RBD_MAP_SLOTS ? 0 : slot + 1;
+    }
+    if (qcache.ok()) {
+      if (jn.type == JT_FF) {
+        real t7[7];
+#pragma unroll
+        for (int e = 0; e < 7; ++e) t7[e] = q.ld(jn.idx_q + e);
+#pragma unroll
+        for (int e = 0; e < 7; ++e) qcache.st(jn.idx_q + e, t7[e]);
+      } else {
+        qcache.st(jn.idx_q, q0);
+        if (is_unbounded(jn.type)) qcache.st(jn.idx_q + 1, q1);
+      }
+    }
     fk_joint(jn, R, p, q0, q1, q, aw);
     // outputs whose placement has an identity rotation share the joint's rotation: convert it once
     real qj[4];
@@ -1143,14 +1193,31 @@ RBD_HD void apply_instance(const DevModel& m, const DevTables& tb, const QF& q, 
       for (int e = 0; e < 3; ++e) S.st(b + 9 + e, p[e]);
     }
   }
+#undef RBD_MAP_ISSUE
 }
 
 // applyJ: out_k = J_k(LWA) dq, matrix-free: world twists V_i = V_parent + A_i dq_i, then
 // out_k = [V_lin + V_ang x p_k ; V_ang]  (== [J_lin - p_k x J_ang ; J_ang] dq, getFrameJacobian LWA)
 template <class QC, class DQ, class OUT>
 RBD_HD void applyJ_instance(const DevModel& m, const DevTables& tb, const QC& q, const DQ& dq, const OUT& out,
-                            const Stack& S) {
+                            const Stack& S, const MapRing& ring = MapRing()) {
   const int nj = m.njoints;
+  // ring: slot s holds (angle, joint velocity) of the joint RBD_MAP_SLOTS positions ahead (the velocity used to be
+  // loaded at its point of use: profile r1h, long scoreboard 6.7 / issue)
+  const bool use_ring = ring.p != nullptr;
+#define RBD_MAP_ISSUE(jidx, slot_)                                                    \
+  do {                                                                                \
+    if ((jidx) < nj && m.joint[jidx].type != JT_FF) {                                 \
+      cp_async_map(ring, 2 * (slot_), q.at(m.joint[jidx].idx_q));                     \
+      cp_async_map(ring, 2 * (slot_) + 1, dq.at(m.joint[jidx].idx_v));                \
+    }                                                                                 \
+    cp_async_commit();                                                                \
+  } while (0)
+  int slot = 0;
+  if (use_ring) {
+#pragma unroll
+    for (int s_ = 0; s_ < RBD_MAP_SLOTS; ++s_) RBD_MAP_ISSUE(1 + s_, s_);
+  }
   {
     const DevJoint& j0 = m.joint[0];
     for (int o = j0.out_begin; o < j0.out_end; ++o) {
@@ -1161,7 +1228,7 @@ RBD_HD void applyJ_instance(const DevModel& m, const DevTables& tb, const QC& q,
   }
   real R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0}, V[6] = {0, 0, 0, 0, 0, 0};
   real q0n = 0.0, q1n = 0.0;
-  RBD_Q_PREFETCH(1);
+  if (!use_ring) RBD_Q_PREFETCH(1);
   for (int i = 1; i < nj; ++i) {
     const DevJoint& jn = m.joint[i];
     const int par = jn.parent;
@@ -1182,13 +1249,24 @@ RBD_HD void applyJ_instance(const DevModel& m, const DevTables& tb, const QC& q,
       }
     }
     real aw[3];
-    const real q0 = q0n, q1 = q1n;
-    RBD_Q_PREFETCH(i + 1);  // next joint's angle: its HBM latency hides behind this joint's work
+    real q0 = q0n, q1 = q1n, d = 0.0;
+    if (!use_ring) {
+      RBD_Q_PREFETCH(i + 1);  // next joint's angle: its HBM latency hides behind this joint's work
+      if (jn.type != JT_FF) d = dq.ld(jn.idx_v);
+    } else {
+      cp_async_wait<RBD_MAP_SLOTS - 1>();
+      if (jn.type != JT_FF) {
+        q0 = ring.p[2 * slot * RBD_WARP];
+        d = ring.p[(2 * slot + 1) * RBD_WARP];
+        if (is_unbounded(jn.type)) q1 = q.ld(jn.idx_q + 1);
+      }
+      RBD_MAP_ISSUE(i + RBD_MAP_SLOTS, slot);
+      slot = slot + 1 == RBD_MAP_SLOTS ? 0 : slot + 1;
+    }
     fk_joint(jn, R, p, q0, q1, q, aw);
     if (jn.type != JT_FF) {
       real A[6];
       subspace_1dof(jn.type, p, aw, A);
-      const real d = dq.ld(jn.idx_v);
 #pragma unroll
       for (int e = 0; e < 6; ++e) V[e] += A[e] * d;
     } else {
@@ -1227,6 +1305,7 @@ RBD_HD void applyJ_instance(const DevModel& m, const DevTables& tb, const QC& q,
       for (int e = 0; e < 6; ++e) S.st(b + 12 + e, V[e]);
     }
   }
+#undef RBD_MAP_ISSUE
 }
 
 // applyJT, matrix-free: every wrench w_k = [f; n] given at output k (world-aligned axes) is moved to the
