@@ -487,30 +487,44 @@ RBD_HD real dot6(const real* a, const real* b) {
   return (a[0] * b[0] + a[1] * b[1] + a[2] * b[2]) + (a[3] * b[3] + a[4] * b[4] + a[5] * b[5]);
 }
 
-// Eigen 3.4 Quaternion(Matrix3) branch order (reference Conversions.h:60), output [x y z w] (Conversions.h:36)
+// Eigen 3.4 Quaternion(Matrix3) branch order (reference Conversions.h:60), output [x y z w] (Conversions.h:36).
+// Eigen picks one of four formulas (trace > 0, else the largest diagonal entry with its tie order); which one is
+// data dependent, so neighbouring instances of a warp diverge.  Written with selects instead: the case index is
+// computed first, then ONE square root and ONE division serve whichever case was picked, and every value is the very
+// expression Eigen evaluates in that case (same operations, same order: bit-identical to the branched form, which the
+// profile r1h of the apply kernel showed as 3 600 instructions per tile of mostly register moves behind divergent
+// branches).
 RBD_HD void rot_to_quat(const real* R, real* q) {
-  real t = R[0] + R[4] + R[8];
-  if (t > real(0)) {
-    t = sqrt(t + real(1));
-    q[3] = real(0.5) * t;
-    t = real(0.5) / t;
-    q[0] = (R[7] - R[5]) * t; q[1] = (R[2] - R[6]) * t; q[2] = (R[3] - R[1]) * t;
-  } else {
-    // i = argmax diag with Eigen's tie order; written branch-wise to keep R in registers
-    if (!(R[4] > R[0]) && !(R[8] > R[0])) {        // i=0, j=1, k=2
-      t = sqrt(R[0] - R[4] - R[8] + real(1));
-      q[0] = real(0.5) * t; t = real(0.5) / t;
-      q[3] = (R[7] - R[5]) * t; q[1] = (R[3] + R[1]) * t; q[2] = (R[6] + R[2]) * t;
-    } else if ((R[4] > R[0]) && !(R[8] > R[4])) {  // i=1, j=2, k=0
-      t = sqrt(R[4] - R[8] - R[0] + real(1));
-      q[1] = real(0.5) * t; t = real(0.5) / t;
-      q[3] = (R[2] - R[6]) * t; q[2] = (R[7] + R[5]) * t; q[0] = (R[1] + R[3]) * t;
-    } else {                                       // i=2, j=0, k=1
-      t = sqrt(R[8] - R[0] - R[4] + real(1));
-      q[2] = real(0.5) * t; t = real(0.5) / t;
-      q[3] = (R[3] - R[1]) * t; q[0] = (R[2] + R[6]) * t; q[1] = (R[5] + R[7]) * t;
-    }
-  }
+  const real tr = R[0] + R[4] + R[8];
+  const bool cw = tr > real(0);
+  const bool c0 = !cw && !(R[4] > R[0]) && !(R[8] > R[0]);  // i = 0
+  const bool c1 = !cw && !c0 && (R[4] > R[0]) && !(R[8] > R[4]);  // i = 1; otherwise i = 2
+  // argument of the square root in the four cases
+  const real aw_ = tr + real(1);
+  const real a0_ = R[0] - R[4] - R[8] + real(1);
+  const real a1_ = R[4] - R[8] - R[0] + real(1);
+  const real a2_ = R[8] - R[0] - R[4] + real(1);
+  const real arg = cw ? aw_ : (c0 ? a0_ : (c1 ? a1_ : a2_));
+  const real t = sqrt(arg);
+  const real big = real(0.5) * t;
+  const real f = real(0.5) / t;
+  // antisymmetric and symmetric off-diagonal combinations
+  const real d0 = R[7] - R[5], d1 = R[2] - R[6], d2 = R[3] - R[1];
+  const real s0 = R[7] + R[5], s1 = R[6] + R[2], s2 = R[3] + R[1];  // (R21+R12), (R20+R02), (R10+R01)
+  // case w: x = d0 f, y = d1 f, z = d2 f, w = big
+  // case 0: x = big,  y = s2 f, z = s1 f, w = d0 f
+  // case 1: x = (R[1]+R[3]) f, y = big, z = s0 f, w = d1 f
+  // case 2: x = (R[2]+R[6]) f, y = (R[5]+R[7]) f, z = big, w = d2 f
+  const real s2b = R[1] + R[3], s1b = R[2] + R[6], s0b = R[5] + R[7];  // operand order of Eigen's cases 1 and 2
+  const real nx = cw ? d0 : (c1 ? s2b : s1b);
+  const real ny = cw ? d1 : (c0 ? s2 : s0b);
+  const real nz = cw ? d2 : (c0 ? s1 : s0);
+  const real nw = c0 ? d0 : (c1 ? d1 : d2);
+  const real xv = nx * f, yv = ny * f, zv = nz * f, wv = nw * f;
+  q[0] = c0 ? big : xv;
+  q[1] = c1 ? big : yv;
+  q[2] = (!cw && !c0 && !c1) ? big : zv;
+  q[3] = cw ? big : wv;
 }
 
 // =========================================================================================================
