@@ -815,7 +815,8 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
     }                                                                                              \
     cp_async_commit();                                                                             \
   } while (0)
-  const bool ring = inr.p != nullptr;
+  // (FP64 only: the FP32 mode is capped at 128 registers for two blocks per SM and has no room for the ring's code)
+  const bool ring = sizeof(real) == 8 && inr.p != nullptr;
   if (!ring) {
     RBD_IN_FETCH(1);
   } else if (!inr.primed) {
