@@ -140,7 +140,8 @@ inline int table_words(int n_out) { return 12 * n_out + (n_out + 1) / 2 * 2; }
 
 // applyJT ring kernel (rbd_kernels.cu: applyJT_ring_kernel; plan + ring program: rbd_model_build.h plan_jt_ring)
 struct JtRing {
-  static constexpr int kWarps = 8;
+  static constexpr int kWarps = 8;       // block size when the sweep state needs the whole tensor-memory share ...
+  static constexpr int kWarpsSmall = 12; // ... and when it fits a third less (small robots: three warps per scheduler)
   static constexpr int kSlotBytes = 6 * 32 * 8;           // one wrench of the 32 instances of a tile
   static constexpr int kStageBytes = 4 * kSlotBytes;      // one piece: <= RBD_JT_GMAX = 4 outputs of one joint
   static constexpr int kMaxStages = 8;

@@ -336,8 +336,9 @@ struct WarpRing {
   }
 };
 
-__global__ void __launch_bounds__(256, 1) applyJT_ring_kernel(const DevModel* __restrict__ gm, const int model_words,
-                                                              const MapArgs a, const int nst) {
+template <int W>  // warps per block: JtRing::kWarps, or kWarpsSmall for robots whose state leaves room (<= 170 registers)
+__global__ void __launch_bounds__(W * 32, 1) applyJT_ring_kernel(const DevModel* __restrict__ gm, const int model_words,
+                                                                 const MapArgs a, const int nst) {
   unsigned* const tm_base_p = reinterpret_cast<unsigned*>(rbd_smem + model_words - 2);
   {
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gm);
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(256, 1) applyJT_ring_kernel(const DevModel* __
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
   const DevModel& m = *reinterpret_cast<const DevModel*>(rbd_smem);
-  double* const stacks = reinterpret_cast<double*>(bars + JtRing::kWarps * JtRing::kMaxStages);
+  double* const stacks = reinterpret_cast<double*>(bars + W * JtRing::kMaxStages);
   double* const rings = stacks + (size_t)blockDim.x * m.plan.smem_doubles;
   const int tm_cols = m.plan.tmem_cols;
   TmStack T;
@@ -605,21 +606,27 @@ cudaError_t launch_applyJT_plan(const DevModel& hm, const DevModel* d_blob, cons
 cudaError_t launch_applyJT_ring(const DevModel& hm, const DevModel* d_blob, const MapArgs& a, int nst, LaunchCfg* cfg,
                                 int num_sms, cudaStream_t st) {
   const int model_words = (int)(eval_model_bytes(hm) / 8);
-  const int block = JtRing::kWarps * 32;
-  const size_t smem = ((size_t)model_words + (size_t)JtRing::kWarps * JtRing::kMaxStages) * 8 +
-                      (size_t)block * hm.plan.smem_doubles * 8 + (size_t)JtRing::kWarps * nst * JtRing::kStageBytes;
+  const int W = hm.plan.warps;
+  const int block = W * 32;
+  const size_t smem = ((size_t)model_words + (size_t)W * JtRing::kMaxStages) * 8 + (size_t)block * hm.plan.smem_doubles * 8 +
+                      (size_t)W * nst * JtRing::kStageBytes;
   if (cfg->block != block || cfg->smem_bytes != smem) {
-    cudaError_t e = cudaFuncSetAttribute(applyJT_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin);
+    cudaError_t e = W == JtRing::kWarpsSmall
+        ? cudaFuncSetAttribute(applyJT_ring_kernel<JtRing::kWarpsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin)
+        : cudaFuncSetAttribute(applyJT_ring_kernel<JtRing::kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(applyJT_ring_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = W == JtRing::kWarpsSmall
+        ? cudaFuncSetAttribute(applyJT_ring_kernel<JtRing::kWarpsSmall>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
+        : cudaFuncSetAttribute(applyJT_ring_kernel<JtRing::kWarps>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     cfg->block = block; cfg->smem_bytes = smem; cfg->blocks_per_sm = 1;
   }
   if (a.n <= 0) return cudaSuccess;
   const long long ntiles = a.n / 32;
-  unsigned grid = (unsigned)((ntiles + JtRing::kWarps - 1) / JtRing::kWarps);
+  unsigned grid = (unsigned)((ntiles + W - 1) / W);
   if (grid > (unsigned)num_sms) grid = (unsigned)num_sms;
-  applyJT_ring_kernel<<<grid, block, smem, st>>>(d_blob, model_words, a, nst);
+  if (W == JtRing::kWarpsSmall) applyJT_ring_kernel<JtRing::kWarpsSmall><<<grid, block, smem, st>>>(d_blob, model_words, a, nst);
+  else applyJT_ring_kernel<JtRing::kWarps><<<grid, block, smem, st>>>(d_blob, model_words, a, nst);
   return cudaGetLastError();
 }
 

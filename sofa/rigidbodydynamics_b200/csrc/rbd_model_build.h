@@ -336,8 +336,16 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
 // record) and m->prog_len / prog_words_off for the ring program `prog` (layout: rbd_sweeps_body.h, JtProg), which takes
 // the place of the ColProg table in the staged blob.  Returns the number of ring stages per warp, 0 when the kernel
 // cannot run this model (tensor memory off or too small for the tree's depth: the caller keeps the register path).
+inline int plan_jt_ring_w(DevModel* m, const HostTables& tb, bool use_tmem, std::vector<int>* prog, int W);
 inline int plan_jt_ring(DevModel* m, const HostTables& tb, bool use_tmem, std::vector<int>* prog) {
-  const int nj = m->njoints, W = JtRing::kWarps;
+  // 12 warps per SM (the kernel needs <= 170 registers) when the state fits a third of the tensor memory, else 8
+  const DevModel keep = *m;
+  int nst = plan_jt_ring_w(m, tb, use_tmem, prog, JtRing::kWarpsSmall);
+  if (nst == 0) { *m = keep; nst = plan_jt_ring_w(m, tb, use_tmem, prog, JtRing::kWarps); }
+  return nst;
+}
+inline int plan_jt_ring_w(DevModel* m, const HostTables& tb, bool use_tmem, std::vector<int>* prog, int W) {
+  const int nj = m->njoints;
   const int D = m->max_depth_internal;
   if (!use_tmem || nj < 2) return 0;
   const int cap = B200Limits::kTmemCols / ((W + 3) / 4) / 2;
@@ -391,7 +399,7 @@ inline int plan_jt_ring(DevModel* m, const HostTables& tb, bool use_tmem, std::v
   pl.smem_doubles = s_used; pl.tmem_doubles = t_used; pl.warps = W; pl.blocks_per_sm = 1;
   pl.tmem_cols = t_used > 0 ? pow2_cols(2 * t_used * ((W + 3) / 4)) : 0;
   m->plan = pl;
-  const size_t fixed = eval_model_bytes(*m) + (size_t)W * 2 * JtRing::kMaxStages * 8 + (size_t)W * 32 * s_used * 8 +
+  const size_t fixed = eval_model_bytes(*m) + (size_t)W * JtRing::kMaxStages * 8 + (size_t)W * 32 * s_used * 8 +
                        B200Limits::kSmemReservedPerBlock;
   if (fixed >= (size_t)B200Limits::kSmemBytes) return 0;
   int nst = (int)(((size_t)B200Limits::kSmemBytes - fixed) / ((size_t)W * JtRing::kStageBytes));
