@@ -251,6 +251,11 @@ RBD_API int rbd_applyJT_rows_host(rbd_workspace* ws, int64_t nrows, const int32_
 RBD_API int rbd_eval_host(rbd_workspace* ws, int64_t n, const double* q, const double* v, const double* a,
                           double* oMi, double* J, double* M, double* tau);
 
+/* Mass / ForceField products on host vectors (instance-major q [n][nq]; dx, v, res, f [n][nv]): res and f are
+ * ACCUMULATED in place, as rbd_addMDx_soa / rbd_addForce_soa do on the device.  v may be NULL (gravity only).   */
+RBD_API int rbd_addMDx_host(rbd_workspace* ws, int64_t n, const double* q, const double* dx, double factor, double* res);
+RBD_API int rbd_addForce_host(rbd_workspace* ws, int64_t n, const double* q, const double* v, double* f);
+
 /* ---------------------------------------------------------------------------------------------------- */
 /* Multi-robot batching context.  N KinematicChainMapping components of one SOFA scene —
  * N robots built from the same URDF by N URDFModelLoader instances (URDFModelLoader.cpp:263-282) — share one

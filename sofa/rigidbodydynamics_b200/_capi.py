@@ -75,7 +75,7 @@ SYMBOLS = [
     "rbd_apply_soa", "rbd_applyJ_soa", "rbd_applyJT_soa", "rbd_applyJT_rows_dev",
     "rbd_eval_soa", "rbd_eval_soa_f32", "rbd_crba_soa", "rbd_rnea_soa", "rbd_addMDx_soa", "rbd_addForce_soa",
     "rbd_aos_to_soa_dev", "rbd_soa_to_aos_dev",
-    "rbd_apply_host", "rbd_applyJ_host", "rbd_applyJT_host", "rbd_applyJT_rows_host", "rbd_eval_host",
+    "rbd_apply_host", "rbd_applyJ_host", "rbd_applyJT_host", "rbd_applyJT_rows_host", "rbd_eval_host", "rbd_addMDx_host", "rbd_addForce_host",
     "rbd_batch_create", "rbd_batch_destroy", "rbd_batch_bind_apply", "rbd_batch_bind_applyJ", "rbd_batch_bind_applyJT",
     "rbd_batch_apply", "rbd_batch_applyJ", "rbd_batch_applyJT",
 ]
@@ -122,6 +122,8 @@ def load() -> C.CDLL:
         "rbd_rnea_soa": (C.c_int, [vp, i64, i64, vp, vp, vp, vp]),
         "rbd_addMDx_soa": (C.c_int, [vp, i64, i64, vp, vp, C.c_double, vp]),
         "rbd_addForce_soa": (C.c_int, [vp, i64, i64, vp, vp, vp]),
+        "rbd_addMDx_host": (C.c_int, [vp, i64, vp, vp, C.c_double, vp]),
+        "rbd_addForce_host": (C.c_int, [vp, i64, vp, vp, vp]),
         "rbd_aos_to_soa_dev": (C.c_int, [vp, i64, i32, i64, vp, vp]),
         "rbd_soa_to_aos_dev": (C.c_int, [vp, i64, i32, i64, vp, vp]),
         "rbd_apply_host": (C.c_int, [vp, i64, vp, vp, vp]),

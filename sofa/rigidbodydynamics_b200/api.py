@@ -173,6 +173,14 @@ class Workspace:
         check(self._lib.rbd_eval_host(self._h, n, _host_ptr(q), _host_ptr(v), _host_ptr(a), _host_ptr(oMi),
                                       _host_ptr(J), _host_ptr(M), _host_ptr(tau)))
 
+    def addMDx_host(self, n, q, dx, factor, res):
+        """res += factor * M(q) dx on host vectors (instance-major), in place."""
+        check(self._lib.rbd_addMDx_host(self._h, n, _host_ptr(q), _host_ptr(dx), float(factor), _host_ptr(res)))
+
+    def addForce_host(self, n, q, v, f):
+        """f -= rnea(q, v, 0) on host vectors, in place; v None: gravity only."""
+        check(self._lib.rbd_addForce_host(self._h, n, _host_ptr(q), _host_ptr(v), _host_ptr(f)))
+
     def apply_host(self, n, q_joints, root_pose, out):
         check(self._lib.rbd_apply_host(self._h, n, _host_ptr(q_joints), _host_ptr(root_pose), _host_ptr(out)))
 

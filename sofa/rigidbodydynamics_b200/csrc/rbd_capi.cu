@@ -649,6 +649,30 @@ RBD_API int rbd_eval_host(rbd_workspace* ws, int64_t n, const double* q, const d
   });
 }
 
+// Mass / ForceField products on host vectors: the accumulated vector travels both ways (load, +=, store)
+RBD_API int rbd_addMDx_host(rbd_workspace* ws, int64_t n, const double* q, const double* dx, double factor, double* res) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, 1);
+  if (rc) return rc;
+  if (!q || !dx || !res) return set_err(RBD_ERR_INVALID_ARG, "null q / dx / res");
+  const rbd_model_info& I = ws->model->info;
+  std::vector<Piece> P = {{I.nq, q, nullptr, true, false}, {I.nv, dx, nullptr, true, false}, {I.nv, res, res, true, true}};
+  return run_host_chunks(ws, n, P, [&](cudaStream_t st, long long, long long cn, long long tile) {
+    return mass_force_on(ws, st, cn, tile, P[0].d_soa, nullptr, P[1].d_soa, P[2].d_soa, factor, 0);
+  });
+}
+RBD_API int rbd_addForce_host(rbd_workspace* ws, int64_t n, const double* q, const double* v, double* f) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, 1);
+  if (rc) return rc;
+  if (!q || !f) return set_err(RBD_ERR_INVALID_ARG, "null q / f");
+  const rbd_model_info& I = ws->model->info;
+  std::vector<Piece> P = {{I.nq, q, nullptr, true, false}, {I.nv, v, nullptr, true, false}, {I.nv, f, f, true, true}};
+  return run_host_chunks(ws, n, P, [&](cudaStream_t st, long long, long long cn, long long tile) {
+    return mass_force_on(ws, st, cn, tile, P[0].d_soa, v ? P[1].d_soa : nullptr, nullptr, P[2].d_soa, -1.0, 1);
+  });
+}
+
 RBD_API int rbd_apply_host(rbd_workspace* ws, int64_t n, const double* q_joints, const double* root_pose, double* out) {
   GUARD(ws);
   int rc = check_batch(ws, n, 1);

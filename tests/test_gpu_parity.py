@@ -470,3 +470,31 @@ def test_mass_forcefield_products(torch_mod, api, d, tile):
     bias, _ = oracle.eval_batch(d, q, v, zero, nthreads=0)
     assert rel_err(from_tiled(f.cpu().numpy(), n), r0 - bias["tau"]) <= TOL_FP64
     assert rel_err(from_tiled(g.cpu().numpy(), n), r0 - ref["tau"]) <= TOL_FP64
+
+
+def test_mass_forcefield_host_entry_points(api):
+    """rbd_addMDx_host / rbd_addForce_host: SOFA-side host vectors, accumulated in place through the chunk pipeline
+    (n larger than one chunk, not a multiple of the tile)."""
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    d = mdl.solo12()
+    n = 20000 + 13
+    q, v, dx = mdl.random_state(d, n, seed=41)
+    rng = np.random.default_rng(42)
+    r0 = rng.uniform(-1, 1, (n, d.nv))
+    m = api.Model(d); ws = api.Workspace(m, n)
+    res = r0.copy(); ws.addMDx_host(n, q, dx, -0.5, res)
+    f = r0.copy(); ws.addForce_host(n, q, v, f)
+    g = r0.copy(); ws.addForce_host(n, q, None, g)
+    idx = np.r_[0:40, n - 40:n]
+    zero = np.zeros_like(v[idx])
+    ref, _ = oracle.eval_batch(d, q[idx], zero, zero, nthreads=0)
+    nv = d.nv
+    M = np.zeros((len(idx), nv, nv))
+    for c in range(nv):
+        for r in range(c + 1):
+            M[:, r, c] = M[:, c, r] = ref["M"][:, c * (c + 1) // 2 + r]
+    assert rel_err(res[idx], r0[idx] - 0.5 * np.einsum("nij,nj->ni", M, dx[idx])) <= TOL_FP64
+    bias, _ = oracle.eval_batch(d, q[idx], v[idx], zero, nthreads=0)
+    assert rel_err(f[idx], r0[idx] - bias["tau"]) <= TOL_FP64
+    assert rel_err(g[idx], r0[idx] - ref["tau"]) <= TOL_FP64
