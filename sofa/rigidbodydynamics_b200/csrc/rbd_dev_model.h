@@ -73,7 +73,8 @@ struct EvalPlan {
   int blocks_per_sm; // blocks the plan expects to be resident per SM
   int tmem_cols;     // columns the block allocates (power of two >= 32, or 0)
   int in_slots;      // slots of the asynchronous input ring (rbd_sweeps_body.h InRing; 3 elements each per instance), 0 = none
-  int pad_[3];
+  int jt_fwd;        // applyJT ring kernel: 1 = forward-projection variant (applyJT_instance_fwd)
+  int pad_[2];
 };
 #define RBD_BOFF_TMEM (1 << 30)
 #define RBD_BOFF_NOVA (1 << 29) /* v|a not saved: recomputed when the sweep returns (joint attached to the universe) */

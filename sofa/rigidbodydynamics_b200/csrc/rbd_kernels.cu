@@ -336,7 +336,9 @@ struct WarpRing {
   }
 };
 
-template <int W>  // warps per block: JtRing::kWarps, or kWarpsSmall for robots whose state leaves room (<= 170 registers)
+// W: warps per block (JtRing::kWarps, or kWarpsSmall = 12 when the state leaves room: <= 170 registers);
+// FWD: forward-projection sweep (applyJT_instance_fwd) instead of the depth-stack sweep
+template <int W, bool FWD>
 __global__ void __launch_bounds__(W * 32, 1) applyJT_ring_kernel(const DevModel* __restrict__ gm, const int model_words,
                                                                  const MapArgs a, const int nst) {
   unsigned* const tm_base_p = reinterpret_cast<unsigned*>(rbd_smem + model_words - 2);
@@ -395,7 +397,10 @@ __global__ void __launch_bounds__(W * 32, 1) applyJT_ring_kernel(const DevModel*
       const long long inst = t * 32 + lane;
       SplitRedSinkT<FieldT<32>> sink{make_field_t<32>(const_cast<double*>(a.root), inst, 6, 32),
                                      make_field_t<32>(const_cast<double*>(a.joints), inst, m.nv - off, 32), off};
-      applyJT_instance_ring(m, opl, make_field_t<32>(a.qcache, a.cache_inst0 + inst, m.nq, 32), ring, sink, S, T);
+      if constexpr (FWD)
+        applyJT_instance_fwd(m, opl, prog.anc(), make_field_t<32>(a.qcache, a.cache_inst0 + inst, m.nq, 32), ring, sink, S, T);
+      else
+        applyJT_instance_ring(m, opl, make_field_t<32>(a.qcache, a.cache_inst0 + inst, m.nq, 32), ring, sink, S, T);
     }
   }
   if (tm_cols > 0) {
@@ -603,21 +608,24 @@ cudaError_t launch_applyJT_plan(const DevModel& hm, const DevModel* d_blob, cons
 
 // `hm` = host copy of the model planned with plan_jt_ring, `d_blob` = its staged blob (build_jt_blob), nst = ring
 // stages per warp.  a.n must be a multiple of 32 and a.tile == 32; a.in 16-byte aligned.
+template <class K>
+static cudaError_t jt_ring_attr(K kern) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
 cudaError_t launch_applyJT_ring(const DevModel& hm, const DevModel* d_blob, const MapArgs& a, int nst, LaunchCfg* cfg,
                                 int num_sms, cudaStream_t st) {
   const int model_words = (int)(eval_model_bytes(hm) / 8);
   const int W = hm.plan.warps;
   const int block = W * 32;
+  const int variant = hm.plan.jt_fwd ? 2 : (W == JtRing::kWarpsSmall ? 1 : 0);
   const size_t smem = ((size_t)model_words + (size_t)W * JtRing::kMaxStages) * 8 + (size_t)block * hm.plan.smem_doubles * 8 +
                       (size_t)W * nst * JtRing::kStageBytes;
   if (cfg->block != block || cfg->smem_bytes != smem) {
-    cudaError_t e = W == JtRing::kWarpsSmall
-        ? cudaFuncSetAttribute(applyJT_ring_kernel<JtRing::kWarpsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin)
-        : cudaFuncSetAttribute(applyJT_ring_kernel<JtRing::kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin);
-    if (e != cudaSuccess) return e;
-    e = W == JtRing::kWarpsSmall
-        ? cudaFuncSetAttribute(applyJT_ring_kernel<JtRing::kWarpsSmall>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
-        : cudaFuncSetAttribute(applyJT_ring_kernel<JtRing::kWarps>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaError_t e = variant == 2 ? jt_ring_attr(applyJT_ring_kernel<JtRing::kWarpsSmall, true>)
+                  : variant == 1 ? jt_ring_attr(applyJT_ring_kernel<JtRing::kWarpsSmall, false>)
+                                 : jt_ring_attr(applyJT_ring_kernel<JtRing::kWarps, false>);
     if (e != cudaSuccess) return e;
     cfg->block = block; cfg->smem_bytes = smem; cfg->blocks_per_sm = 1;
   }
@@ -625,8 +633,9 @@ cudaError_t launch_applyJT_ring(const DevModel& hm, const DevModel* d_blob, cons
   const long long ntiles = a.n / 32;
   unsigned grid = (unsigned)((ntiles + W - 1) / W);
   if (grid > (unsigned)num_sms) grid = (unsigned)num_sms;
-  if (W == JtRing::kWarpsSmall) applyJT_ring_kernel<JtRing::kWarpsSmall><<<grid, block, smem, st>>>(d_blob, model_words, a, nst);
-  else applyJT_ring_kernel<JtRing::kWarps><<<grid, block, smem, st>>>(d_blob, model_words, a, nst);
+  if (variant == 2) applyJT_ring_kernel<JtRing::kWarpsSmall, true><<<grid, block, smem, st>>>(d_blob, model_words, a, nst);
+  else if (variant == 1) applyJT_ring_kernel<JtRing::kWarpsSmall, false><<<grid, block, smem, st>>>(d_blob, model_words, a, nst);
+  else applyJT_ring_kernel<JtRing::kWarps, false><<<grid, block, smem, st>>>(d_blob, model_words, a, nst);
   return cudaGetLastError();
 }
 

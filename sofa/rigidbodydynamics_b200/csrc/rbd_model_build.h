@@ -336,21 +336,45 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
 // record) and m->prog_len / prog_words_off for the ring program `prog` (layout: rbd_sweeps_body.h, JtProg), which takes
 // the place of the ColProg table in the staged blob.  Returns the number of ring stages per warp, 0 when the kernel
 // cannot run this model (tensor memory off or too small for the tree's depth: the caller keeps the register path).
-inline int plan_jt_ring_w(DevModel* m, const HostTables& tb, bool use_tmem, std::vector<int>* prog, int W);
-inline int plan_jt_ring(DevModel* m, const HostTables& tb, bool use_tmem, std::vector<int>* prog) {
-  // 12 warps per SM (the kernel needs <= 170 registers) when the state fits a third of the tensor memory, else 8
+inline int plan_jt_ring_w(DevModel* m, const HostTables& tb, bool use_tmem, std::vector<int>* prog, int W, bool fwd);
+static constexpr int kJtMaxDepth = 12;  // == RBD_JT_MAXD (rbd_sweeps_body.h)
+// fwd_mode: 0 = never the forward projection, 1 = automatic (order below), 2 = forward projection first (tests)
+inline int plan_jt_ring(DevModel* m, const HostTables& tb, bool use_tmem, std::vector<int>* prog, int fwd_mode = 1) {
+  // forward projection with 12 warps per SM for shallow trees (applyJT_instance_fwd); else the stack variant with 12
+  // warps when the state fits a third of the tensor memory, else with 8
+  // order: stack sweep with 12 warps (small robots: fewest instructions AND three warps per scheduler), forward
+  // projection with 12 warps (shallow trees whose stack state needs the 8-warp share: Talos), stack sweep with 8
   const DevModel keep = *m;
-  int nst = plan_jt_ring_w(m, tb, use_tmem, prog, JtRing::kWarpsSmall);
-  if (nst == 0) { *m = keep; nst = plan_jt_ring_w(m, tb, use_tmem, prog, JtRing::kWarps); }
+  int nst = fwd_mode == 2 ? plan_jt_ring_w(m, tb, use_tmem, prog, JtRing::kWarpsSmall, true) : 0;
+  if (nst == 0) { *m = keep; nst = plan_jt_ring_w(m, tb, use_tmem, prog, JtRing::kWarpsSmall, false); }
+  if (nst == 0 && fwd_mode == 1) { *m = keep; nst = plan_jt_ring_w(m, tb, use_tmem, prog, JtRing::kWarpsSmall, true); }
+  if (nst == 0) { *m = keep; nst = plan_jt_ring_w(m, tb, use_tmem, prog, JtRing::kWarps, false); }
   return nst;
 }
-inline int plan_jt_ring_w(DevModel* m, const HostTables& tb, bool use_tmem, std::vector<int>* prog, int W) {
+inline int plan_jt_ring_w(DevModel* m, const HostTables& tb, bool use_tmem, std::vector<int>* prog, int W, bool fwd) {
   const int nj = m->njoints;
   const int D = m->max_depth_internal;
   if (!use_tmem || nj < 2) return 0;
   const int cap = B200Limits::kTmemCols / ((W + 3) / 4) / 2;
   std::vector<int> lvl_t(D + 1, -1), lvl_s(D + 1, -1);
   int t_used = 0, s_used = 0;
+  if (fwd) {
+    // forward projection: A column of level L at tensor-memory offset 6 L (compile-time in the kernel), branch R|p
+    // records behind; a free-flyer only as a root joint (level 0), its R|p in shared memory
+    if (m->max_depth > kJtMaxDepth) return 0;
+    for (int i = 1; i < nj; ++i)
+      if (m->joint[i].type == JT_FF && m->joint[i].parent != 0) return 0;
+    t_used = 6 * D;
+    bool any_ff = false;
+    for (int i = 1; i < nj; ++i) {
+      DevJoint& j = m->joint[i];
+      j.offA = 0; j.boff = 0;
+      if (j.type == JT_FF) { any_ff = true; continue; }
+      if (j.nchild > 0) j.offA = 6 * (j.depth - 1);
+      if (j.nchild >= 2) { j.boff = t_used; t_used += 12; }
+    }
+    if (any_ff) s_used = 12;
+  } else
   for (int i = 1; i < nj; ++i) {
     DevJoint& j = m->joint[i];
     j.offA = 0; j.boff = 0;
@@ -387,8 +411,12 @@ inline int plan_jt_ring_w(DevModel* m, const HostTables& tb, bool use_tmem, std:
     }
   const int np = (int)pieces.size() / 4, nc = (int)copies.size() / 2;
   const int off_opl = (4 + 4 * np + 2 * nc + 1) / 2 * 2;
-  prog->assign((size_t)off_opl + 6 * (size_t)m->n_out, 0);
-  (*prog)[0] = np; (*prog)[1] = nc; (*prog)[2] = off_opl; (*prog)[3] = 0;
+  const int off_anc = off_opl + 6 * m->n_out;
+  prog->assign((size_t)off_anc + (fwd ? (size_t)nj * kJtMaxDepth : 0), 0);
+  (*prog)[0] = np; (*prog)[1] = nc; (*prog)[2] = off_opl; (*prog)[3] = fwd ? off_anc : 0;
+  if (fwd)
+    for (int i = 1; i < nj; ++i)
+      for (int a = i; a != 0; a = m->joint[a].parent) (*prog)[(size_t)off_anc + (size_t)i * kJtMaxDepth + (m->joint[a].depth - 1)] = a;
   if (np) memcpy(prog->data() + 4, pieces.data(), pieces.size() * sizeof(int));
   if (nc) memcpy(prog->data() + 4 + 4 * np, copies.data(), copies.size() * sizeof(int));
   for (int o = 0; o < m->n_out; ++o)
@@ -398,6 +426,7 @@ inline int plan_jt_ring_w(DevModel* m, const HostTables& tb, bool use_tmem, std:
   EvalPlan pl{};
   pl.smem_doubles = s_used; pl.tmem_doubles = t_used; pl.warps = W; pl.blocks_per_sm = 1;
   pl.tmem_cols = t_used > 0 ? pow2_cols(2 * t_used * ((W + 3) / 4)) : 0;
+  pl.jt_fwd = fwd ? 1 : 0;
   m->plan = pl;
   const size_t fixed = eval_model_bytes(*m) + (size_t)W * JtRing::kMaxStages * 8 + (size_t)W * 32 * s_used * 8 +
                        B200Limits::kSmemReservedPerBlock;

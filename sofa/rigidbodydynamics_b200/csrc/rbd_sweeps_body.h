@@ -1789,8 +1789,175 @@ RBD_HD void applyJT_instance_ring(const DevModel& m, const real* opl, const QC& 
     }
   }
 }
+// ---------------------------------------------------------------------------------------------------------
+// applyJT, ring variant with FORWARD projection (shallow trees: depth <= RBD_JT_MAXD, a free-flyer only as the
+// root).  Instead of parking the subtree wrench F per depth level and projecting on the way back
+// (tau_i = A_i . sum_k F_k), every joint k projects its own wrench on all its ancestors as it is visited,
+//   tau_i += A_i . F_k   for every ancestor i of k (and k itself),
+// with the running tau of the joint currently occupying depth level L in a REGISTER (the level loop is unrolled, so
+// the index is a compile-time constant).  The sweep state shrinks to the ancestors' A columns (6 per level, tensor
+// memory at compile-time offsets) + R|p of the branch joints: Talos 66 doubles instead of 138, which is what lets 12
+// warps (three per scheduler) share an SM — the kernel is issue-latency-bound, so that is worth more than the extra
+// 6-flop projections (sum of depths = 156 for Talos instead of 33).  Below a free-flyer root the total wrench is
+// summed in registers and projected once.  `anc` (ring program): joint at level L of the chain that ends at joint i.
+#define RBD_JT_MAXD 12
+template <class QC, class Ring, class Sink>
+RBD_HD void applyJT_instance_fwd(const DevModel& m, const real* opl, const int* anc, const QC& q, Ring& ring,
+                                 const Sink& sink, const Stack& S, const TmStack& T) {
+  const int nj = m.njoints;
+  real R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
+  real tacc[RBD_JT_MAXD];
+#pragma unroll
+  for (int L = 0; L < RBD_JT_MAXD; ++L) tacc[L] = 0.0;
+  real Ft[6] = {0, 0, 0, 0, 0, 0};  // total wrench below the free-flyer root
+  int ffroot = 0;                   // the free-flyer occupying level 0 (0 = none)
+  int dprev = 0;                    // depth of the previous joint
+  // the joints at levels [lo, hi) of the chain that ends at joint `last` are complete: hand their tau over
+#define RBD_JT_FLUSH(lo, hi, last)                                                              \
+  _Pragma("unroll") for (int L = 0; L < RBD_JT_MAXD; ++L)                                       \
+    if (L >= (lo) && L < (hi)) {                                                                \
+      if (L == 0 && ffroot != 0) {                                                              \
+        const DevJoint& jf_ = m.joint[ffroot];                                                  \
+        real Rp_[12], o6_[6];                                                                   \
+        s_ldv<12>(S, jf_.offA, Rp_);                                                            \
+        ff_rows(Rp_, Rp_ + 9, Ft, o6_);                                                         \
+        _Pragma("unroll") for (int e = 0; e < 6; ++e) { sink.put(jf_.idx_v + e, o6_[e]); Ft[e] = 0.0; } \
+        ffroot = 0;                                                                             \
+      } else {                                                                                  \
+        sink.put(m.joint[anc[(last) * RBD_JT_MAXD + L]].idx_v, tacc[L]);                        \
+      }                                                                                         \
+    }
+  real q0n = 0.0, q1n = 0.0;
+  RBD_Q_PREFETCH(1);
+  for (int i = 1; i < nj; ++i) {
+    const DevJoint& jn = m.joint[i];
+    const int par = jn.parent;
+    const int d = jn.depth;
+    if (dprev >= d) { RBD_JT_FLUSH(d - 1, dprev, i - 1) }
+    if (par != i - 1) {
+      if (par == 0) {
+        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+        p[0] = p[1] = p[2] = 0;
+      } else {
+        const DevJoint& jb = m.joint[par];
+        real Rp[12];
+        if (jb.type == JT_FF) s_ldv<12>(S, jb.offA, Rp);
+        else T.template ldv<12>(jb.boff, Rp);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) R[e] = Rp[e];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) p[e] = Rp[9 + e];
+      }
+    }
+    real aw[3];
+    const real q0 = q0n, q1 = q1n;
+    RBD_Q_PREFETCH(i + 1);
+    fk_joint(jn, R, p, q0, q1, q, aw);
+    real Fk[6] = {0, 0, 0, 0, 0, 0};
+#define RBD_JT_W(j, c)                                                                  \
+  real c[6];                                                                            \
+  {                                                                                     \
+    real w[6];                                                                          \
+    ring.template ld<j>(w);                                                             \
+    const real* pl = opl + 3 * (o + j);                                                 \
+    const real px = R[0] * pl[0] + R[1] * pl[1] + R[2] * pl[2] + p[0];                  \
+    const real py = R[3] * pl[0] + R[4] * pl[1] + R[5] * pl[2] + p[1];                  \
+    const real pz = R[6] * pl[0] + R[7] * pl[1] + R[8] * pl[2] + p[2];                  \
+    real tx, ty, tz;                                                                    \
+    RBD_CROSS(tx, ty, tz, px, py, pz, w[0], w[1], w[2]);                                \
+    c[0] = w[0]; c[1] = w[1]; c[2] = w[2];                                              \
+    c[3] = w[3] + tx; c[4] = w[4] + ty; c[5] = w[5] + tz;                               \
+  }
+    for (int o = jn.out_begin; o < jn.out_end;) {
+      const int cnt = ring.acquire();
+      if (cnt == 1) {
+        RBD_JT_W(0, c0)
+#pragma unroll
+        for (int e = 0; e < 6; ++e) Fk[e] += c0[e];
+      } else if (cnt == 2) {
+        RBD_JT_W(0, c0) RBD_JT_W(1, c1)
+#pragma unroll
+        for (int e = 0; e < 6; ++e) Fk[e] += c0[e] + c1[e];
+      } else if (cnt == 3) {
+        RBD_JT_W(0, c0) RBD_JT_W(1, c1) RBD_JT_W(2, c2)
+#pragma unroll
+        for (int e = 0; e < 6; ++e) Fk[e] += (c0[e] + c1[e]) + c2[e];
+      } else {
+        RBD_JT_W(0, c0) RBD_JT_W(1, c1) RBD_JT_W(2, c2) RBD_JT_W(3, c3)
+#pragma unroll
+        for (int e = 0; e < 6; ++e) Fk[e] += (c0[e] + c1[e]) + (c2[e] + c3[e]);
+      }
+      ring.release(cnt);
+      o += cnt;
+    }
+#undef RBD_JT_W
+    if (jn.type == JT_FF) {
+      // root free-flyer (level 0): its R|p serves the children's branch returns and the final projection
+#pragma unroll
+      for (int e = 0; e < 9; ++e) S.st(jn.offA + e, R[e]);
+#pragma unroll
+      for (int e = 0; e < 3; ++e) S.st(jn.offA + 9 + e, p[e]);
+      ffroot = i;
+#pragma unroll
+      for (int e = 0; e < 6; ++e) Ft[e] = Fk[e];
+    } else {
+      real A[6];
+      subspace_1dof(jn.type, p, aw, A);
+      const real own = dot6(A, Fk);
+      // own level, then every ancestor level below it: two jump tables on the depth instead of a compare per level
+      // (the second one falls through from level d-2 down to level 0)
+#define RBD_JT_OWN(D_) case D_: tacc[D_ - 1] = own; break;
+      switch (d) {
+        RBD_JT_OWN(1) RBD_JT_OWN(2) RBD_JT_OWN(3) RBD_JT_OWN(4) RBD_JT_OWN(5) RBD_JT_OWN(6)
+        RBD_JT_OWN(7) RBD_JT_OWN(8) RBD_JT_OWN(9) RBD_JT_OWN(10) RBD_JT_OWN(11) RBD_JT_OWN(12)
+        default: break;
+      }
+#undef RBD_JT_OWN
+#define RBD_JT_ANC(L_)                              \
+  {                                                 \
+    real Aa[6];                                     \
+    T.template ldv<6>(6 * (L_), Aa);                \
+    tacc[L_] += dot6(Aa, Fk);                       \
+  }
+      switch (d) {
+        case 12: RBD_JT_ANC(10) [[fallthrough]];
+        case 11: RBD_JT_ANC(9) [[fallthrough]];
+        case 10: RBD_JT_ANC(8) [[fallthrough]];
+        case 9: RBD_JT_ANC(7) [[fallthrough]];
+        case 8: RBD_JT_ANC(6) [[fallthrough]];
+        case 7: RBD_JT_ANC(5) [[fallthrough]];
+        case 6: RBD_JT_ANC(4) [[fallthrough]];
+        case 5: RBD_JT_ANC(3) [[fallthrough]];
+        case 4: RBD_JT_ANC(2) [[fallthrough]];
+        case 3: RBD_JT_ANC(1) [[fallthrough]];
+        case 2:
+          if (ffroot != 0) {
+#pragma unroll
+            for (int e = 0; e < 6; ++e) Ft[e] += Fk[e];
+          } else RBD_JT_ANC(0)
+          break;
+        default: break;
+      }
+#undef RBD_JT_ANC
+      if (jn.nchild > 0) T.template stv<6>(6 * (d - 1), A);
+      if (jn.nchild >= 2) {
+        real Rp[12];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Rp[e] = R[e];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) Rp[9 + e] = p[e];
+        T.template stv<12>(jn.boff, Rp);
+      }
+    }
+    dprev = d;
+  }
+  if (nj > 1) { RBD_JT_FLUSH(0, dprev, nj - 1) }
+#undef RBD_JT_FLUSH
+}
+
 // Ring program (host-built by plan_jt_ring, staged with the blob in place of the ColProg table; ints):
-//   [0] pieces  [1] copies  [2] offset (ints, even) of the translation table  [3] reserved
+//   [0] pieces  [1] copies  [2] offset (ints, even) of the translation table  [3] offset of the ancestor table
+//   (forward-projection variant: joint at level L of the chain ending at joint i, RBD_JT_MAXD ints per joint; 0 = none)
 //   pieces  int4 each: first sorted index | outputs << 16, bytes to expect, first copy, copies
 //   copies  int2 each: source offset within the tile's wrench block (bytes), offset within the stage | bytes << 16
 //   opl     3 doubles per mapped output (sorted order): translation of its placement in the parent joint frame
@@ -1803,6 +1970,7 @@ struct JtProg {
   RBD_HD const int* piece(int i) const { return base + 4 + 4 * i; }
   RBD_HD const int* copy(int c) const { return base + 4 + 4 * base[0] + 2 * c; }
   RBD_HD const real* opl() const { return reinterpret_cast<const real*>(base + base[2]); }
+  RBD_HD const int* anc() const { return base + base[3]; }
 };
 // reader of the input array with the ring's interface (tests/emul; the device ring lives in rbd_kernels.cu): follows
 // the COPY LIST of every piece, i.e. reads exactly the bytes the device's copy engine is told to fetch

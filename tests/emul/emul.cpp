@@ -250,13 +250,17 @@ extern "C" int emul_applyJT_plan(const rbd_model_desc* d, long long n, long long
 
 // applyJT, ring variant (the batched K3 kernel's body on full tile-32 batches): storage plan and ring program of
 // plan_jt_ring, the wrench ring replaced by a reader that follows the program's copy list, the reduction sink by +=
+// allow_fwd: 0 pins the depth-stack sweep, 1 = the planner's automatic choice, 2 = forward projection wherever it fits;
+// *variant receives 1 when the forward-projection body ran
 extern "C" int emul_applyJT_ring(const rbd_model_desc* d, long long n, long long tile, int use_tmem, double* qcache,
-                                 long long cache_tile, double* in, double* out_tau, double* out_root, int* ring_stages) {
+                                 long long cache_tile, double* in, double* out_tau, double* out_root, int* ring_stages,
+                                 int allow_fwd, int* variant) {
   Ctx c;
   int rc = make_ctx(d, &c);
   if (rc) return rc;
   std::vector<int> prog;
-  const int nst = plan_jt_ring(&c.m, c.ht, use_tmem != 0, &prog);
+  const int nst = plan_jt_ring(&c.m, c.ht, use_tmem != 0, &prog, allow_fwd);
+  if (variant) *variant = nst > 0 ? c.m.plan.jt_fwd : 0;
   if (ring_stages) *ring_stages = nst;
   if (nst == 0) return 1;  // the kernel would not run this model: nothing to emulate
   const std::vector<unsigned long long> blob = build_jt_blob(&c.m, prog);
@@ -274,7 +278,8 @@ extern "C" int emul_applyJT_ring(const rbd_model_desc* d, long long n, long long
     SplitRedSinkT<Field> sink{make_field(out_root, i, 6, tile), make_field(out_tau, i, bm.nv - off, tile), off};
     Stack S = make_stack(smem.data(), t, pl.smem_doubles);
     TmStack T{tmem.data() + (size_t)t * (pl.tmem_doubles > 0 ? pl.tmem_doubles : 1)};
-    applyJT_instance_ring(bm, jp.opl(), make_field(qcache, i, bm.nq, cache_tile), ring, sink, S, T);
+    if (bm.plan.jt_fwd) applyJT_instance_fwd(bm, jp.opl(), jp.anc(), make_field(qcache, i, bm.nq, cache_tile), ring, sink, S, T);
+    else applyJT_instance_ring(bm, jp.opl(), make_field(qcache, i, bm.nq, cache_tile), ring, sink, S, T);
   }
   return 0;
 }
