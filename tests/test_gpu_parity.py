@@ -498,3 +498,43 @@ def test_mass_forcefield_host_entry_points(api):
     bias, _ = oracle.eval_batch(d, q[idx], v[idx], zero, nthreads=0)
     assert rel_err(f[idx], r0[idx] - bias["tau"]) <= TOL_FP64
     assert rel_err(g[idx], r0[idx] - ref["tau"]) <= TOL_FP64
+
+
+@pytest.mark.parametrize("name", ["talos_reduced", "solo12", "panda7", "random_2", "random_3"] + [x.name for x in MODELS if x.name.startswith("schunk")])
+def test_applyJT_ring_equals_register_path(torch_mod, api, name):
+    """The three sweeps of the vector applyJT (ring kernel: depth stack or forward projection, chosen by the planner;
+    register path) accumulate the same generalized forces: many tiles per warp so that the ring wraps across tile
+    boundaries, a partial last tile, and a wrench array that is only 8-byte aligned (the ring needs 16: fallback)."""
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    torch = torch_mod
+    cands = [m for m in MODELS if m.name == name]
+    if not cands:
+        pytest.skip(f"no fixture named {name}")
+    d = cands[0]
+    n, tile = 148 * 12 * 32 * 2 + 32 * 5 + 7, 32
+    q, v, _ = mdl.random_state(d, n, seed=51)
+    qj, root, _dq, _rv = _split(d, q, v)
+    rng = np.random.default_rng(52)
+    w = rng.uniform(-1, 1, (n, d.n_out * 6))
+    m = api.Model(d); ws = api.Workspace(m, n)
+    T = lambda x: None if x is None else _dev(torch, to_tiled(x, tile))
+    nt = (n + tile - 1) // tile
+    pos = torch.zeros((nt, 7 * d.n_out, tile), dtype=torch.float64, device="cuda")
+    ws.apply_soa(n, tile, T(qj), T(root), pos)
+    wt = T(w)
+    # the same wrenches at an address that is 8 (mod 16)
+    shifted = torch.empty(wt.numel() + 1, dtype=torch.float64, device="cuda")
+    shifted[1:] = wt.reshape(-1)
+    res = []
+    for ring, src in ((True, wt), (False, wt), (True, shifted[1:])):
+        stages = ws.set_applyJT_ring(ring)
+        tau = torch.zeros((nt, d.nv_joints, tile), dtype=torch.float64, device="cuda")
+        rt = torch.zeros((nt, 6, tile), dtype=torch.float64, device="cuda") if root is not None else None
+        ws.applyJT_soa(n, tile, src, tau, rt)
+        ws.synchronize()
+        res.append((from_tiled(tau.cpu().numpy(), n), None if rt is None else from_tiled(rt.cpu().numpy(), n)))
+    assert stages >= 0
+    for tau_x, rt_x in res[1:]:
+        assert rel_err(tau_x, res[0][0]) <= 1e-12
+        if rt_x is not None:
+            assert rel_err(rt_x, res[0][1]) <= 1e-12
