@@ -68,14 +68,15 @@ __global__ void __launch_bounds__(256, MINB) NAME(const DevModelT<REAL>* __restr
   const int wpb = blockDim.x >> 5;                                                                                                                      \
  /* asynchronous input ring: per warp [in_slots * 3][32] elements behind the stacks (tile-32 batches only) */                                           \
   NSQ::InRing inr;                                                                                                                                      \
-  if (TILE != 0 && m.plan.in_slots > 0 && (!DO_TAU || (a.v && a.a)))                                                                                    \
+  if (TILE != 0 && m.plan.in_slots > 0)                                                                                                                 \
     inr.p = reinterpret_cast<REAL*>(rbd_smem + model_words) + (size_t)blockDim.x * m.plan.smem_doubles +                                                \
             (size_t)warp * (3 * m.plan.in_slots * 32) + (threadIdx.x & 31);                                                                             \
   if (inr.p) inr.ps = (unsigned)__cvta_generic_to_shared(inr.p);                                                                                        \
   for (long long t = (long long)blockIdx.x * wpb + warp; t < ntiles; t += (long long)gridDim.x * wpb) {                                                 \
     long long inst = t * 32 + (threadIdx.x & 31);                                                                                                       \
-    if (inst >= a.n) inst = a.n - 1;                                                                                                                    \
     NSQ::EvalIOT<TILE> io;                                                                                                                              \
+    io.tau_live = inst < a.n ? 1 : 0;                                                                                                                   \
+    if (inst >= a.n) inst = a.n - 1;                                                                                                                    \
     io.q = NSQ::make_field_t<TILE>(const_cast<REAL*>(a.q), inst, m.nq, a.tile);                                                                         \
     io.v = NSQ::make_field_t<TILE>(const_cast<REAL*>(a.v), inst, m.nv, a.tile);                                                                         \
     io.a = NSQ::make_field_t<TILE>(const_cast<REAL*>(a.a), inst, m.nv, a.tile);                                                                         \

@@ -542,11 +542,22 @@ struct EvalIOT {
   real tau_scale = real(1);
   int tau_acc = 0;
   int gravity_on = 1;
+  int tau_live = 1;  // 0 on the lanes past the end of the batch (they recompute the last instance)
   // MF: the instantiation serves the Mass / ForceField products (RNEA without CRBA); the fused kernel compiles the
   // plain store (the run-time switches cost it 3 % when they were unconditional)
   template <bool MF>
   RBD_HD void put_tau(int k, real v) const {
-    if (MF && tau_acc) tau.st(k, tau.ld(k) + tau_scale * v); else tau.st(k, v);
+    if (MF && tau_acc) {
+      // a reduction that returns nothing (RED.ADD.F64: one IEEE add per address and launch = load + add + store),
+      // so the sweep does not wait for the old value (r1i: addMDx 1.87 ms with load + add + store)
+#if defined(__CUDA_ARCH__)
+      if (tau_live) atomicAdd(tau.at(k), tau_scale * v);  // lanes past the end duplicate the last instance: no add
+#else
+      tau.st(k, tau.ld(k) + tau_scale * v);
+#endif
+    } else {
+      tau.st(k, v);
+    }
   }
 };
 // Asynchronous input ring of the fused eval (device, tile-32 batches; the plan says whether it fits): the q | v | a
@@ -809,8 +820,8 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
       const int oq_ = (jx_.idx_q + (ahead) * m.nq) * TILE, ov_ = (jx_.idx_v + (ahead) * m.nv) * TILE; \
       cp_async_real(inr, 3 * (slot_), io.q.at_elems(oq_));                                         \
       if (DO_TAU) {                                                                                \
-        cp_async_real(inr, 3 * (slot_) + 1, io.v.at_elems(ov_));                                   \
-        cp_async_real(inr, 3 * (slot_) + 2, io.a.at_elems(ov_));                                   \
+        if (!MF || io.v.ok()) cp_async_real(inr, 3 * (slot_) + 1, io.v.at_elems(ov_));             \
+        if (!MF || io.a.ok()) cp_async_real(inr, 3 * (slot_) + 2, io.a.at_elems(ov_));             \
       }                                                                                            \
     }                                                                                              \
     cp_async_commit();                                                                             \
@@ -895,7 +906,10 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
         const real* const s_ = inr.p + 3 * inr.slot * RBD_WARP;
         q0 = s_[0];
         if (is_unbounded(jn.type)) q1 = io.q.ld(jn.idx_q + 1);
-        if (DO_TAU) { qd = s_[RBD_WARP]; qdd = s_[2 * RBD_WARP]; }
+        if (DO_TAU) {
+          qd = (!MF || io.v.ok()) ? s_[RBD_WARP] : real(0);
+          qdd = (!MF || io.a.ok()) ? s_[2 * RBD_WARP] : real(0);
+        }
       }
       // the slot just read receives the joint RBD_INR_SLOTS positions further on (possibly in the warp's next tile)
       int pj = i + RBD_INR_SLOTS;
