@@ -32,7 +32,7 @@ extern __shared__ __align__(16) double rbd_smem[];
 // exiting: tcgen05.ld/st are warp-collective (.sync.aligned) and the duplicate stores write identical values.
 #define RBD_DEFINE_EVAL_KERNEL(NAME, NSQ, REAL, MINB) \
 template <bool DO_M, bool DO_TAU, int TILE>                                                                                                             \
-__global__ void __launch_bounds__(256, MINB) NAME(const DevModelT<REAL>* __restrict__ gm, const EvalArgsT<REAL> a,                                            \
+__global__ void __launch_bounds__((MINB == 1 && DO_TAU && !DO_M) ? 384 : 256, MINB) NAME(const DevModelT<REAL>* __restrict__ gm, const EvalArgsT<REAL> a,                                            \
                                                    const int model_words) {                                                                             \
  /* the last two staged words are spare: the tensor-memory base address lands there (no static shared memory, so */                                     \
  /* the block can ask for the full 227 KB dynamically) */                                                                                               \

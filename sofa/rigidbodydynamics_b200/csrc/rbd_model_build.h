@@ -201,6 +201,8 @@ struct B200Limits {
   static constexpr int kRegsPerSM = 65536;
   static constexpr int kRegsPerThread = 255;  // upper bound of what ptxas may give the eval kernels (launch_bounds 256)
   static constexpr int kMaxWarpsPerBlock = 8;
+  static constexpr int kMaxWarpsPerBlockRnea = 12;  // eval_kernel<false, true, *>: __launch_bounds__(384, 1)
+  static constexpr int kRegsPerThreadRnea = 170;
 };
 
 static constexpr int kEvalInSlots = 2;  // == RBD_INR_SLOTS (rbd_sweeps_body.h)
@@ -244,7 +246,12 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
   for (int i = 1; i < nj; ++i)
     if (m->joint[i].nchild >= 2) bj.push_back(i);
   int best_warps_sm = 0;
-  for (int W = 1; W <= B200Limits::kMaxWarpsPerBlock; ++W) {
+  // The RNEA-only instantiation (rnea, Mass / ForceField products) is compiled for blocks of up to 12 warps (<= 170
+  // registers): its state is smaller, and three warps per scheduler hide more of the issue latency that bounds it.
+  const bool wide = elem_bytes == 8 && !jt && do_tau && !do_m && regs_per_thread == B200Limits::kRegsPerThread;
+  const int max_warps = wide ? B200Limits::kMaxWarpsPerBlockRnea : B200Limits::kMaxWarpsPerBlock;
+  if (wide) regs_per_thread = B200Limits::kRegsPerThreadRnea;
+  for (int W = 1; W <= max_warps; ++W) {
     if (forced_warps > 0 && W != forced_warps) continue;
     const int cap = use_tmem ? (B200Limits::kTmemCols / ((W + 3) / 4)) / cols_per_elem : 0;  // elements per thread
     // per block size: the configuration with the most resident blocks; among equals the cheapest one (everything
