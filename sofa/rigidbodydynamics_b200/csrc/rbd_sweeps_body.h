@@ -788,6 +788,7 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
   real R[9], p[3], vel[6], acc[6];
   constexpr bool MF = DO_TAU && !DO_M;  // Mass / ForceField switches live in the RNEA-only instantiation
   const real gs_ = (MF && !io.gravity_on) ? real(0) : real(1);
+  const bool has_v = !MF || io.v.ok();  // (uniform) the Mass / ForceField products without a velocity skip its terms
 #define RBD_RESET_ROOT()                                                   \
   do {                                                                     \
     R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1; \
@@ -958,17 +959,23 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
 #endif
       }
       if (DO_TAU) {
-        real vj[6], cr[6];
+        if (has_v) {
+          real vj[6], cr[6];
 #pragma unroll
-        for (int e = 0; e < 6; ++e) { vj[e] = Ak[e] * qd; vel[e] += vj[e]; }
-        // a_i = a_parent + A qdd + v_i x vJ   (joint bias c = 0 for all supported joints)
-        RBD_CROSS(cr[0], cr[1], cr[2], vel[3], vel[4], vel[5], vj[0], vj[1], vj[2]);
-        real tx, ty, tz;
-        RBD_CROSS(tx, ty, tz, vel[0], vel[1], vel[2], vj[3], vj[4], vj[5]);
-        cr[0] += tx; cr[1] += ty; cr[2] += tz;
-        RBD_CROSS(cr[3], cr[4], cr[5], vel[3], vel[4], vel[5], vj[3], vj[4], vj[5]);
+          for (int e = 0; e < 6; ++e) { vj[e] = Ak[e] * qd; vel[e] += vj[e]; }
+          // a_i = a_parent + A qdd + v_i x vJ   (joint bias c = 0 for all supported joints)
+          RBD_CROSS(cr[0], cr[1], cr[2], vel[3], vel[4], vel[5], vj[0], vj[1], vj[2]);
+          real tx, ty, tz;
+          RBD_CROSS(tx, ty, tz, vel[0], vel[1], vel[2], vj[3], vj[4], vj[5]);
+          cr[0] += tx; cr[1] += ty; cr[2] += tz;
+          RBD_CROSS(cr[3], cr[4], cr[5], vel[3], vel[4], vel[5], vj[3], vj[4], vj[5]);
 #pragma unroll
-        for (int e = 0; e < 6; ++e) acc[e] += Ak[e] * qdd + cr[e];
+          for (int e = 0; e < 6; ++e) acc[e] += Ak[e] * qdd + cr[e];
+        } else {
+          // no velocity (M dx, gravity forces): the velocity-product terms vanish identically
+#pragma unroll
+          for (int e = 0; e < 6; ++e) acc[e] += Ak[e] * qdd;
+        }
       }
     } else {
 #pragma unroll
@@ -1005,16 +1012,18 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
       inertia_world(jn, R, p, Yk);
       if (DO_TAU) {
         // f = Y a + v x* (Y v)
-        real h[6];
-        inertia_mul(Yk, vel, h);
         inertia_mul(Yk, acc, fk);
-        real tx, ty, tz;
-        RBD_CROSS(tx, ty, tz, vel[3], vel[4], vel[5], h[0], h[1], h[2]);
-        fk[0] += tx; fk[1] += ty; fk[2] += tz;
-        RBD_CROSS(tx, ty, tz, vel[3], vel[4], vel[5], h[3], h[4], h[5]);
-        fk[3] += tx; fk[4] += ty; fk[5] += tz;
-        RBD_CROSS(tx, ty, tz, vel[0], vel[1], vel[2], h[0], h[1], h[2]);
-        fk[3] += tx; fk[4] += ty; fk[5] += tz;
+        if (has_v) {
+          real h[6];
+          inertia_mul(Yk, vel, h);
+          real tx, ty, tz;
+          RBD_CROSS(tx, ty, tz, vel[3], vel[4], vel[5], h[0], h[1], h[2]);
+          fk[0] += tx; fk[1] += ty; fk[2] += tz;
+          RBD_CROSS(tx, ty, tz, vel[3], vel[4], vel[5], h[3], h[4], h[5]);
+          fk[3] += tx; fk[4] += ty; fk[5] += tz;
+          RBD_CROSS(tx, ty, tz, vel[0], vel[1], vel[2], h[0], h[1], h[2]);
+          fk[3] += tx; fk[4] += ty; fk[5] += tz;
+        }
       }
     }
     if (nxt_par == i) {
