@@ -12,7 +12,7 @@ from . import model
 from .model import ModelDescriptor, from_urdf, from_urdf_string, panda7, solo12, talos_reduced, random_tree
 
 __all__ = ["model", "ModelDescriptor", "from_urdf", "from_urdf_string", "panda7", "solo12", "talos_reduced",
-           "random_tree", "Model", "Workspace", "KinematicChainMapping", "BatchedDynamics", "shard_range"]
+           "random_tree", "Model", "Workspace", "KinematicChainMapping", "JointSpaceMass", "BatchedDynamics", "shard_range"]
 
 
 def __getattr__(name):  # lazy: keep `import sofa.rigidbodydynamics_b200` free of ctypes loading
@@ -22,6 +22,9 @@ def __getattr__(name):  # lazy: keep `import sofa.rigidbodydynamics_b200` free o
     if name == "KinematicChainMapping":
         from .mapping import KinematicChainMapping
         return KinematicChainMapping
+    if name == "JointSpaceMass":
+        from .mass import JointSpaceMass
+        return JointSpaceMass
     if name in ("BatchedDynamics",):
         from .dynamics import BatchedDynamics
         return BatchedDynamics

@@ -284,6 +284,23 @@ extern "C" int emul_applyJT_ring(const rbd_model_desc* d, long long n, long long
   return 0;
 }
 
+// plan of the applyJT ring kernel for this model: out = {ring stages (0 = register path), forward projection?,
+// warps per block, tensor-memory doubles, shared-memory doubles, shared-memory bytes of the block}
+extern "C" int emul_jt_ring_plan(const rbd_model_desc* d, int use_tmem, int fwd_mode, int* out /*[6]*/) {
+  Ctx c;
+  int rc = make_ctx(d, &c);
+  if (rc) return rc;
+  std::vector<int> prog;
+  const int nst = plan_jt_ring(&c.m, c.ht, use_tmem != 0, &prog, fwd_mode);
+  out[0] = nst;
+  if (nst == 0) { out[1] = out[2] = out[3] = out[4] = out[5] = 0; return 0; }
+  const EvalPlan& pl = c.m.plan;
+  out[1] = pl.jt_fwd; out[2] = pl.warps; out[3] = pl.tmem_doubles; out[4] = pl.smem_doubles;
+  out[5] = (int)(eval_model_bytes(c.m) + (size_t)pl.warps * JtRing::kMaxStages * 8 + (size_t)pl.warps * 32 * pl.smem_doubles * 8 +
+                 (size_t)pl.warps * nst * JtRing::kStageBytes);
+  return 0;
+}
+
 extern "C" int emul_applyJT_rows(const rbd_model_desc* d, long long nrows, int block, double* qcache,
                                  long long cache_tile, const int* row_ptr, const int* row_instance, const int* col,
                                  const double* val, double* out_rows, int* keep) {

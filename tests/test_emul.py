@@ -262,3 +262,28 @@ def test_mass_forcefield_bodies(emul, d):
     g = T(r0)
     assert emul.emul_mass_force(C.addressof(cd), n, tile, P(qs), None, None, P(g), -1.0, 1) == 0
     assert rel_err(from_tiled(g, n), r0 - ref["tau"]) <= TOL_FP64
+
+
+def test_applyJT_ring_planner_choices(emul):
+    """plan_jt_ring: small robots run the depth-stack sweep in 12-warp blocks, Talos needs the forward projection to get
+    12 warps, deep chains fall back to 8 warps or to the register path; every plan respects the SM's budgets (227 KB of
+    shared memory per block, 512 tensor-memory columns, 12 levels for the forward projection)."""
+    from sofa.rigidbodydynamics_b200 import model as mdl
+
+    def plan(d, use_tmem=1, mode=1):
+        cd, keep = _cdesc(d)
+        out = (C.c_int * 6)()
+        assert emul.emul_jt_ring_plan(C.addressof(cd), use_tmem, mode, out) == 0
+        return dict(zip(("stages", "fwd", "warps", "tmem", "smem", "bytes"), list(out)))
+
+    solo, panda, talos = plan(mdl.solo12()), plan(mdl.panda7()), plan(mdl.talos_reduced())
+    assert (solo["fwd"], solo["warps"]) == (0, 12) and solo["stages"] >= 2
+    assert (panda["fwd"], panda["warps"]) == (0, 12)
+    assert (talos["fwd"], talos["warps"]) == (1, 12) and talos["tmem"] <= 85 and talos["stages"] >= 2
+    t8 = plan(mdl.talos_reduced(), mode=0)           # forward projection not allowed: 8 warps, depth stack
+    assert (t8["fwd"], t8["warps"]) == (0, 8) and t8["tmem"] <= 128
+    assert plan(mdl.talos_reduced(), use_tmem=0)["stages"] == 0    # no tensor memory: register path
+    chain = plan(mdl.random_tree(7, 40, branch_prob=0.0))           # 40-joint serial chain: deeper than any plan
+    assert chain["stages"] == 0 or (chain["fwd"] == 0 and chain["tmem"] <= 128)
+    for p in (solo, panda, talos, t8):
+        assert p["bytes"] <= 227 * 1024 and 2 * p["tmem"] * ((p["warps"] + 3) // 4) <= 512

@@ -538,3 +538,37 @@ def test_applyJT_ring_equals_register_path(torch_mod, api, name):
         assert rel_err(tau_x, res[0][0]) <= 1e-12
         if rt_x is not None:
             assert rel_err(rt_x, res[0][1]) <= 1e-12
+
+
+def test_joint_space_mass_mirror(api):
+    """mass.JointSpaceMass (SOFA Mass / ForceField names on the joint dofs) against the oracle, and against the
+    reference's own route for the gravity term: applyJT of m_b g on the body-CoM outputs (URDFModelLoader.cpp:369-391)."""
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    from sofa.rigidbodydynamics_b200.mass import JointSpaceMass
+    from sofa.rigidbodydynamics_b200.mapping import KinematicChainMapping
+    d = mdl.panda7()
+    n = 64
+    q, v, dx = mdl.random_state(d, n, seed=61)
+    mass = JointSpaceMass(d, n)
+    M = mass.getMassMatrix(q)
+    ref, _ = oracle.eval_batch(d, q, np.zeros_like(v), np.zeros_like(v), nthreads=0)
+    res = np.zeros((n, d.nv)); mass.addMDx(res, q, dx, 2.0)
+    assert rel_err(res, 2.0 * np.einsum("nij,nj->ni", M, dx)) <= TOL_FP64
+    assert np.all(np.linalg.eigvalsh(M) > 0)                                   # SPD
+    f = np.zeros((n, d.nv)); mass.addForce(f, q)                               # gravity only
+    assert rel_err(f, -ref["tau"]) <= TOL_FP64
+    fb = np.zeros((n, d.nv)); mass.addForce(fb, q, v)
+    bias, _ = oracle.eval_batch(d, q, v, np.zeros_like(v), nthreads=0)
+    assert rel_err(fb, -bias["tau"]) <= TOL_FP64
+    # the reference's route: gravity wrench m_b g at every body-CoM output, mapped back by applyJT
+    kcm = KinematicChainMapping(d, n)
+    out = np.zeros((n, d.n_out, 7)); kcm.apply([out], [q], [])
+    w = np.zeros((n, d.n_out, 6))
+    for b in range(d.njoints):
+        w[:, b, :3] = np.asarray(d.inertia).reshape(d.njoints, 10)[b, 0] * np.asarray(d.gravity)[:3]
+    tau = np.zeros((n, d.nv)); kcm.applyJT([tau], [], [w])
+    assert kcm.d_componentState == "Valid"
+    assert rel_err(tau, f) <= TOL_FP64
+    with pytest.raises(ValueError):
+        mass.addMDx(res, q, dx[:, :3], 1.0)
