@@ -148,6 +148,11 @@ RBD_API int rbd_workspace_set_eval_tmem(rbd_workspace* ws, int enable);
  * bulk asynchronous copies): 1 = on (default), 0 = always the register path; out (may be NULL) receives the ring stages
  * per warp the plan found for this model (0 = the ring kernel cannot run it).  Tuning / A-B knob: same results.    */
 RBD_API int rbd_workspace_set_applyJT_ring(rbd_workspace* ws, int enable, int32_t* ring_slots);
+/* Constraint-row applyJT on cached Jacobians (default 1): the first row call after an apply fills a cache of the
+ * applied instances' world joint Jacobian and joint placements (what the reference's apply leaves in pinocchio's
+ * data.J / data.oMi, KinematicChainMapping.inl:365-373) — 8 (6 nv + 12 (njoints-1)) bytes per instance of workspace
+ * capacity, allocated on first use — and every row only reads it; 0 = per-row sweep, no cache.  Same results.      */
+RBD_API int rbd_workspace_set_rows_cache(rbd_workspace* ws, int enable);
 /* Storage plan the fused eval kernel uses on this workspace for the output set (with_M, with_tau):
  * out[0] warps per block, [1] blocks per SM, [2] shared-memory doubles per instance, [3] tensor-memory doubles per
  * instance, [4] tensor-memory columns per block, [5] 1 if the Y-stack lives in tensor memory, [6] shared-memory

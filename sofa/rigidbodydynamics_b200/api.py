@@ -111,6 +111,10 @@ class Workspace:
     def set_eval_tmem(self, enable: bool):
         check(self._lib.rbd_workspace_set_eval_tmem(self._h, 1 if enable else 0))
 
+    def set_rows_cache(self, enable: bool):
+        """A/B knob of the constraint-row applyJT: cached Jacobians (default) or one sweep per row."""
+        check(self._lib.rbd_workspace_set_rows_cache(self._h, 1 if enable else 0))
+
     def set_applyJT_ring(self, enable: bool) -> int:
         """A/B knob of the vector applyJT: ring kernel (default) or register path; returns the ring slots per warp."""
         ns = C.c_int32(0)

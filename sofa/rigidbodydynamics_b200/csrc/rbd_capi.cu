@@ -43,6 +43,7 @@ struct rbd_model {
   rbd_model_info info;
 };
 
+static const long long kRowsCacheChunk = 65536;  // instances per fill pass of the row path's Jacobian cache
 static const int kHostChunk = 32768;  // instances per pipelined chunk of the *_host entry points (A/B r1i, e2e M evals/s: 8192 4.54, 16384 4.66, 32768 4.72, 65536 4.74)
 static const int kSlots = 2;
 
@@ -74,6 +75,12 @@ struct rbd_workspace {
   int use_tmem = 1;
   int num_sms = 0;
   double* qcache = nullptr;  // [nq][capacity] assembled configuration of the last apply
+  // Jacobian cache of the constraint-row applyJT (the reference's data.J / data.oMi left behind by apply,
+  // KinematicChainMapping.inl:365-373): world joint Jacobian (6 nv fields) and oMi (12 (njoints-1) fields) of the applied
+  // instances, instance-major; allocated on the first row call, refilled lazily after every apply
+  double *jcache = nullptr, *omicache = nullptr, *jc_scratch = nullptr;  // instance-major caches + tile-32 scratch
+  long long apply_epoch = 0, jc_epoch = -1;
+  int use_rows_cache = 1;
   long long applied_n = 0;   // instances covered by the cache (0 = apply not called yet)
   LaunchCfg cfg_eval[8], cfg_apply[2], cfg_applyJ[2], cfg_applyJT[2], cfg_rows, cfg_jt_ring;
   DevModel* d_model = nullptr;  // device copy of the joint table for the mapping kernels
@@ -168,7 +175,7 @@ RBD_API int rbd_model_get_info(const rbd_model* model, rbd_model_info* info) {
 static void ws_free(rbd_workspace* ws) {
   if (!ws) return;
   cudaFree(ws->d_sorted_k); cudaFree(ws->d_outk_parent); cudaFree(ws->d_sorted_ident); cudaFree(ws->d_sorted_pl); cudaFree(ws->d_outk_pl);
-  cudaFree(ws->qcache); cudaFree(ws->rows_buf); cudaFree(ws->d_model);
+  cudaFree(ws->qcache); cudaFree(ws->rows_buf); cudaFree(ws->d_model); cudaFree(ws->jcache); cudaFree(ws->omicache); cudaFree(ws->jc_scratch);
   for (int k = 0; k < 10; ++k) { cudaFree(ws->d_plan[k]); delete ws->h_plan[k]; }
   for (int k = 0; k < 8; ++k) { cudaFree(ws->d_plan32[k]); delete ws->h_plan32[k]; }
   for (int s = 0; s < kSlots; ++s) {
@@ -456,6 +463,7 @@ static int apply_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile,
   MapArgs A{n, tile, qj, root, nullptr, out, ws->qcache, inst0};
   CK(launch_apply(dm, ws->d_model, ws->tb, A, smem_apply(dm), ws->cfg_apply, st));
   if (n > 0) ws->launches++;
+  ws->apply_epoch++;  // the cached configuration changed: the Jacobian cache of the row path is stale
   return RBD_OK;
 }
 RBD_API int rbd_apply_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q_joints, const double* root_pose,
@@ -528,6 +536,48 @@ RBD_API int rbd_applyJT_soa(rbd_workspace* ws, int64_t n, int64_t tile, const do
   return applyJT_on(ws, ws->stream, n, tile, 0, in, out_tau, out_root);
 }
 
+// constraint rows: refresh the Jacobian cache if an apply happened since it was filled, then one light kernel
+static int rows_on(rbd_workspace* ws, cudaStream_t st, const RowArgs& A) {
+  const DevModel& dm = ws->model->dm;
+  if (!ws->use_rows_cache || dm.njoints < 2) {
+    CK(launch_applyJT_rows(dm, ws->d_model, ws->tb, A, smem_applyJT(dm), &ws->cfg_rows, st));
+    ws->launches++;
+    return RBD_OK;
+  }
+  const int kj = 6 * dm.nv, ko = 12 * (dm.njoints - 1);
+  const long long chunk = std::min<long long>((ws->capacity + 31) / 32 * 32, kRowsCacheChunk);
+  if (!ws->jcache) {
+    const size_t cap = (size_t)((ws->capacity + 31) / 32 * 32);
+    CK(cudaMalloc(&ws->jcache, cap * (size_t)kj * sizeof(double)));
+    CK(cudaMalloc(&ws->omicache, cap * (size_t)ko * sizeof(double)));
+    CK(cudaMalloc(&ws->jc_scratch, (size_t)chunk * (size_t)(kj + ko) * sizeof(double)));
+    ws->jc_epoch = -1;
+  }
+  if (ws->jc_epoch != ws->apply_epoch) {
+    // FK + world joint Jacobian of the applied instances from the cached configuration (eval_kernel<false,false,32>,
+    // tile-32 fast path), transposed chunk by chunk into the instance-major cache the row kernel reads
+    double* sj = ws->jc_scratch;
+    double* so = ws->jc_scratch + (size_t)chunk * kj;
+    for (long long i0 = 0; i0 < ws->applied_n; i0 += chunk) {
+      const long long cn = std::min<long long>(chunk, ws->applied_n - i0);
+      int rc = eval_on(ws, st, cn, 32, ws->qcache + i0 * dm.nq, nullptr, nullptr, so, sj, nullptr, nullptr);
+      if (rc) return rc;
+      CK(launch_soa_to_aos(cn, kj, 32, sj, ws->jcache + i0 * kj, st));
+      CK(launch_soa_to_aos(cn, ko, 32, so, ws->omicache + i0 * ko, st));
+      ws->launches += 2;
+    }
+    ws->jc_epoch = ws->apply_epoch;
+  }
+  CK(launch_applyJT_rows_cached(dm, ws->d_model, ws->tb, A, ws->jcache, ws->omicache, st));
+  ws->launches++;
+  return RBD_OK;
+}
+RBD_API int rbd_workspace_set_rows_cache(rbd_workspace* ws, int enable) {
+  if (!ws) return set_err(RBD_ERR_INVALID_ARG, "null workspace");
+  ws->use_rows_cache = enable ? 1 : 0;
+  return RBD_OK;
+}
+
 RBD_API int rbd_applyJT_rows_dev(rbd_workspace* ws, int64_t nrows, const int32_t* row_ptr, const int32_t* row_instance,
                                  const int32_t* col, const double* val, double* out_rows, int32_t* keep) {
   GUARD(ws);
@@ -537,9 +587,8 @@ RBD_API int rbd_applyJT_rows_dev(rbd_workspace* ws, int64_t nrows, const int32_t
   if (ws->applied_n <= 0) return set_err(RBD_ERR_NO_APPLY, "applyJT(rows) before apply: no cached configuration");
   const DevModel& dm = ws->model->dm;
   RowArgs A{nrows, row_ptr, row_instance, col, val, out_rows, keep, ws->qcache};
-  CK(launch_applyJT_rows(dm, ws->d_model, ws->tb, A, smem_applyJT(dm), &ws->cfg_rows, ws->stream));
-  ws->launches++;
-  return RBD_OK;
+  (void)dm;
+  return rows_on(ws, ws->stream, A);
 }
 
 RBD_API int rbd_aos_to_soa_dev(rbd_workspace* ws, int64_t n, int32_t K, int64_t tile, const double* aos, double* soa) {
@@ -759,8 +808,8 @@ RBD_API int rbd_applyJT_rows_host(rbd_workspace* ws, int64_t nrows, const int32_
   }
   const DevModel& dm = ws->model->dm;
   RowArgs A{nrows, d_rp, d_ri, d_col, d_val, d_out, d_keep, ws->qcache};
-  CK(launch_applyJT_rows(dm, ws->d_model, ws->tb, A, smem_applyJT(dm), &ws->cfg_rows, st));
-  ws->launches++;
+  (void)dm;
+  { int rc2 = rows_on(ws, st, A); if (rc2) return rc2; }
   CK(cudaMemcpyAsync(out_rows, d_out, (size_t)nrows * nv * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(keep, d_keep, (size_t)nrows * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));

@@ -427,6 +427,53 @@ __global__ void __launch_bounds__(256) applyJT_rows_kernel(const DevModel* __res
   a.keep[r] = n2 > 1e-12 ? 1 : 0;  // kMinTorqueSqrd, reference KinematicChainMapping.inl:43-45,587,605
 }
 
+// instance-major record of the Jacobian cache: N consecutive doubles from an even offset with 16-byte loads (a lane's
+// record is contiguous; 6 nv and 12 (njoints-1) are even, so every column / placement starts 16-byte aligned)
+struct AosRec {
+  const double* p;
+  template <int N>
+  __device__ __forceinline__ void ldn(int k, double* v) const {
+    const double2* q2 = reinterpret_cast<const double2*>(p + k);
+#pragma unroll
+    for (int e = 0; e < N / 2; ++e) { const double2 t = __ldg(q2 + e); v[2 * e] = t.x; v[2 * e + 1] = t.y; }
+  }
+};
+
+// K4 on cached Jacobians (rows_cached_row): one thread per row; a warp's 32 rows are accumulated in a padded
+// shared-memory tile [nv][33] (conflict-free both ways) and written out with consecutive addresses — the dense rows
+// are row-major in the caller's array, which one thread per row can only write with a stride of nv doubles.
+__global__ void __launch_bounds__(256) applyJT_rows_cached_kernel(const DevModel* __restrict__ gm, const int model_words,
+                                                                  const DevTables tb, const RowArgs a,
+                                                                  const double* __restrict__ jc,
+                                                                  const double* __restrict__ oc) {
+  const DevModel& m = stage_model(gm, model_words);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nv = m.nv;
+  double* const st = rbd_smem + model_words + (size_t)warp * nv * 33;
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = r < a.nrows;
+  for (int c = 0; c < nv; ++c) st[c * 33 + lane] = 0.0;
+  if (live) {
+    const int b = a.row_ptr[r], e = a.row_ptr[r + 1];
+    const long long inst = a.row_instance[r];
+    // the cache is instance-major: a lane of this kernel reads whole Jacobian columns / placements of ITS instance
+    // (48 / 96 contiguous bytes), not one field of 32 neighbouring instances
+    const AosRec Jc{jc + inst * (long long)(6 * nv)};
+    const AosRec Oc{oc + inst * (long long)(12 * (m.njoints - 1))};
+    rows_cached_row(m, tb, Jc, Oc, a.col + b, a.val + 6 * (long long)b, e - b,
+                    [&](int c, double t) { st[c * 33 + lane] += t; });
+    double n2 = 0.0;
+    for (int c = 0; c < nv; ++c) { const double t = st[c * 33 + lane]; n2 += t * t; }
+    a.keep[r] = n2 > 1e-12 ? 1 : 0;  // kMinTorqueSqrd, reference KinematicChainMapping.inl:43-45,587,605
+  }
+  __syncwarp();
+  const long long row0 = (long long)blockIdx.x * blockDim.x + warp * 32;
+  for (int idx = lane; idx < 32 * nv; idx += 32) {
+    const int rw = idx / nv, c = idx - rw * nv;
+    if (row0 + rw < a.nrows) a.out_rows[(row0 + rw) * nv + c] = st[c * 33 + rw];
+  }
+}
+
 // K8: layout adapters.  32 instances x 32 fields per block through a padded shared tile, so both the
 // instance-major side and the tiled-SoA side are accessed with consecutive addresses.
 __global__ void aos_to_soa_kernel(long long n, int K, long long tile, const double* __restrict__ aos,
@@ -649,6 +696,19 @@ cudaError_t launch_applyJT_rows(const DevModel& m, const DevModel* d_model, cons
   }
   if (a.nrows <= 0) return cudaSuccess;
   applyJT_rows_kernel<<<RBD_GRID(a.nrows, cfg->block), cfg->block, cfg->smem_bytes, st>>>(d_model, mw, tb, a, smem_doubles);
+  return cudaGetLastError();
+}
+
+// rows on the Jacobian cache: `jc` / `oc` = world joint Jacobian and oMi of the applied instances, instance-major
+cudaError_t launch_applyJT_rows_cached(const DevModel& m, const DevModel* d_model, const DevTables& tb, const RowArgs& a,
+                                       const double* jc, const double* oc, cudaStream_t st) {
+  const int mw = map_model_words(m);
+  const int block = 256;
+  const size_t smem = (size_t)mw * 8 + (size_t)(block / 32) * m.nv * 33 * 8;
+  cudaError_t e = cudaFuncSetAttribute(applyJT_rows_cached_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin);
+  if (e != cudaSuccess) return e;
+  if (a.nrows <= 0) return cudaSuccess;
+  applyJT_rows_cached_kernel<<<RBD_GRID(a.nrows, block), block, smem, st>>>(d_model, mw, tb, a, jc, oc);
   return cudaGetLastError();
 }
 

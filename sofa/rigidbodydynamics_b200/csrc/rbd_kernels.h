@@ -59,6 +59,8 @@ cudaError_t launch_applyJT_ring(const DevModel& planned_host_model, const DevMod
                                 LaunchCfg* cfg, int num_sms, cudaStream_t st);
 cudaError_t launch_applyJT_rows(const DevModel& m, const DevModel* d_model, const DevTables& tb, const RowArgs& a,
                                 int smem_doubles, LaunchCfg* cfg, cudaStream_t st);
+cudaError_t launch_applyJT_rows_cached(const DevModel& m, const DevModel* d_model, const DevTables& tb, const RowArgs& a,
+                                       const double* jcache, const double* omicache, cudaStream_t st);
 cudaError_t launch_aos_to_soa(long long n, int K, long long tile, const double* aos, double* soa, cudaStream_t st);
 cudaError_t launch_soa_to_aos(long long n, int K, long long tile, const double* soa, double* aos, cudaStream_t st);
 

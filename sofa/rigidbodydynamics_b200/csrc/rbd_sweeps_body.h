@@ -13,6 +13,11 @@ struct FieldT {
   RBD_HD long long off(int k) const { return TILE ? (long long)k * TILE : (long long)k * stride; }
   RBD_HD real ld(int k) const { return p[off(k)]; }
   RBD_HD real ldz(int k) const { return p ? p[off(k)] : real(0); }  // an absent input array reads as zeros
+  template <int N>
+  RBD_HD void ldn(int k, real* v) const {
+#pragma unroll
+    for (int e = 0; e < N; ++e) v[e] = ld(k + e);
+  }
   RBD_HD void st(int k, real v) const { p[off(k)] = v; }
   RBD_HD bool ok() const { return p != nullptr; }
   // address of field k, and a store at a (small, usually compile-time) field offset e from such an address: with
@@ -1812,6 +1817,43 @@ RBD_HD void applyJT_instance_ring(const DevModel& m, const real* opl, const QC& 
     }
   }
 }
+// ---------------------------------------------------------------------------------------------------------
+// applyJT (MatrixDeriv rows) on CACHED Jacobians — the reference's own structure: apply leaves data.J / data.oMi
+// behind (computeJointJacobians, KinematicChainMapping.inl:365-373) and every constraint row only reads them
+// (getFrameJacobian + J^T w per non-zero, inl:558-583).  Here the cache is the world joint Jacobian J (6 nv fields)
+// and oMi (12 (njoints-1) fields) of the applied instances, filled once per apply by the FK + Jacobian instantiation of
+// the eval kernel; a row then costs, per non-zero, one wrench shift and one 6-flop projection per dof on the path
+// to the root — no kinematics at all.  `acc(c, t)` receives the contribution t to entry c of the dense row.
+template <class JF, class OF, class ACC>
+RBD_HD void rows_cached_row(const DevModel& m, const DevTables& tb, const JF& Jc, const OF& Oc, const int* col,
+                            const real* val, int nnz, const ACC& acc) {
+  for (int j = 0; j < nnz; ++j) {
+    const int k = col[j];
+    const int pj = tb.outk_parent[k];
+    if (pj == 0) continue;  // attached to the universe: empty support, zero Jacobian
+    const real* pl = tb.outk_pl + 12 * k;
+    const real* w = val + 6 * j;
+    real Rp[12];
+    Oc.template ldn<12>(12 * (pj - 1), Rp);
+    const real px = Rp[0] * pl[9] + Rp[1] * pl[10] + Rp[2] * pl[11] + Rp[9];
+    const real py = Rp[3] * pl[9] + Rp[4] * pl[10] + Rp[5] * pl[11] + Rp[10];
+    const real pz = Rp[6] * pl[9] + Rp[7] * pl[10] + Rp[8] * pl[11] + Rp[11];
+    real F[6], tx, ty, tz;
+    RBD_CROSS(tx, ty, tz, px, py, pz, w[0], w[1], w[2]);
+    F[0] = w[0]; F[1] = w[1]; F[2] = w[2];
+    F[3] = w[3] + tx; F[4] = w[4] + ty; F[5] = w[5] + tz;
+    for (int a = pj; a != 0; a = m.joint[a].parent) {
+      const DevJoint& ja = m.joint[a];
+      for (int cc = 0; cc < ja.nv; ++cc) {
+        const int c = ja.idx_v + cc;
+        real A[6];
+        Jc.template ldn<6>(6 * c, A);
+        acc(c, dot6(A, F));
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // applyJT, ring variant with FORWARD projection (shallow trees: depth <= RBD_JT_MAXD, a free-flyer only as the
 // root).  Instead of parking the subtree wrench F per depth level and projecting on the way back

@@ -284,6 +284,41 @@ extern "C" int emul_applyJT_ring(const rbd_model_desc* d, long long n, long long
   return 0;
 }
 
+// constraint rows on cached Jacobians (rows_cached_row): the cache (world joint Jacobian + oMi of every instance) is
+// filled by the FK + Jacobian instantiation of the eval sweep from the cached configuration, as the library does
+extern "C" int emul_applyJT_rows_cached(const rbd_model_desc* d, long long n, double* qcache, long long cache_tile,
+                                        long long nrows, const int* row_ptr, const int* row_instance, const int* col,
+                                        const double* val, double* out_rows, int* keep) {
+  Ctx c;
+  int rc = make_ctx(d, &c);
+  if (rc) return rc;
+  if (!plan_eval(&c.m, false, false, true, 0, true)) { g_err = "plan_eval failed"; return -100; }
+  const std::vector<unsigned long long> blob = build_eval_blob(&c.m);
+  const DevModel& bm = *reinterpret_cast<const DevModel*>(blob.data());
+  const int nj = bm.njoints, nv = bm.nv;
+  const long long nt = (n + cache_tile - 1) / cache_tile;
+  std::vector<double> J((size_t)nt * cache_tile * 6 * nv + 1, 1e300), O((size_t)nt * cache_tile * 12 * (nj - 1) + 1, 1e300);
+  std::vector<double> smem(64, 1e300), tmem(64, 1e300);
+  for (long long i = 0; i < n; ++i) {
+    Stack S = make_stack(smem.data(), 0, 1);
+    TmStack T{tmem.data()};
+    InRing inr;
+    eval_one<0>(bm, i, cache_tile, qcache, nullptr, nullptr, O.data(), J.data(), nullptr, nullptr, S, T, inr);
+  }
+  for (long long r = 0; r < nrows; ++r) {
+    double* row = out_rows + (size_t)r * nv;
+    for (int k = 0; k < nv; ++k) row[k] = 0.0;
+    const Field Jc = make_field(J.data(), row_instance[r], 6 * nv, cache_tile);
+    const Field Oc = make_field(O.data(), row_instance[r], 12 * (nj - 1), cache_tile);
+    rows_cached_row(bm, c.tb, Jc, Oc, col + row_ptr[r], val + 6 * (size_t)row_ptr[r], row_ptr[r + 1] - row_ptr[r],
+                    [&](int cc, double t) { row[cc] += t; });
+    double n2 = 0.0;
+    for (int k = 0; k < nv; ++k) n2 += row[k] * row[k];
+    keep[r] = n2 > 1e-12 ? 1 : 0;
+  }
+  return 0;
+}
+
 // plan of the applyJT ring kernel for this model: out = {ring stages (0 = register path), forward projection?,
 // warps per block, tensor-memory doubles, shared-memory doubles, shared-memory bytes of the block}
 extern "C" int emul_jt_ring_plan(const rbd_model_desc* d, int use_tmem, int fwd_mode, int* out /*[6]*/) {

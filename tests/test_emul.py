@@ -152,6 +152,11 @@ def test_mapping_bodies_match_oracle(emul, d):
     rows = np.full((nrows, d.nv), np.nan); keepf = np.zeros(nrows, dtype=np.int32)
     assert emul.emul_applyJT_rows(C.addressof(cd), nrows, block, P(qcache), ctile, P(row_ptr), P(row_inst), P(cols),
                                   P(vals), P(rows), P(keepf)) == 0
+    # the same rows from cached Jacobians (the library's default row path)
+    rows_c = np.full((nrows, d.nv), np.nan); keep_c = np.zeros(nrows, dtype=np.int32)
+    assert emul.emul_applyJT_rows_cached(C.addressof(cd), n, P(qcache), ctile, nrows, P(row_ptr), P(row_inst), P(cols),
+                                         P(vals), P(rows_c), P(keep_c)) == 0, emul.emul_last_error()
+    assert rel_err(rows_c, rows) <= 1e-13 and np.array_equal(keep_c, keepf)
     for i in range(n):
         rp = orc.apply(qj[i], None if root is None else root[i])
         assert rel_err(pos[i][:, :3], rp[:, :3]) <= TOL_FP64

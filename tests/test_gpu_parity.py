@@ -572,3 +572,50 @@ def test_joint_space_mass_mirror(api):
     assert rel_err(tau, f) <= TOL_FP64
     with pytest.raises(ValueError):
         mass.addMDx(res, q, dx[:, :3], 1.0)
+
+
+@pytest.mark.parametrize("name", ["talos_reduced", "solo12", "random_3"])
+def test_constraint_rows_cached_jacobians(torch_mod, api, name):
+    """rbd_applyJT_rows_dev on the Jacobian cache (default) equals the per-row sweep, follows a new apply (the cache is
+    refilled lazily after every apply, as the reference's data.J is by computeJointJacobians), and matches the oracle."""
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    torch = torch_mod
+    d = [m for m in MODELS if m.name == name][0]
+    n, tile = 300, 32
+    rng = np.random.default_rng(71)
+    nrows = 2 * n + 5
+    row_inst = np.sort(rng.integers(0, n, nrows)).astype(np.int32)
+    nnz_per = rng.integers(0, 4, nrows)
+    row_ptr = np.concatenate([[0], np.cumsum(nnz_per)]).astype(np.int32)
+    nnz = int(row_ptr[-1])
+    col = rng.integers(0, d.n_out, nnz).astype(np.int32)
+    val = rng.uniform(-1, 1, (nnz, 6))
+    m = api.Model(d); ws = api.Workspace(m, n)
+    D = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    d_rp, d_ri, d_col, d_val = D(row_ptr), D(row_inst), D(col), D(val)
+    T = lambda x: None if x is None else _dev(torch, to_tiled(x, tile))
+    nt = (n + tile - 1) // tile
+    pos = torch.zeros((nt, 7 * d.n_out, tile), dtype=torch.float64, device="cuda")
+    results = {}
+    for seed in (81, 82):                                   # two configurations: the second apply must invalidate
+        q, v, _ = mdl.random_state(d, n, seed=seed)
+        qj, root, _dq, _rv = _split(d, q, v)
+        ws.apply_soa(n, tile, T(qj), T(root), pos)
+        for cached in (True, False):
+            ws.set_rows_cache(cached)
+            rows = torch.full((nrows, d.nv), float("nan"), dtype=torch.float64, device="cuda")
+            keep = torch.zeros((nrows,), dtype=torch.int32, device="cuda")
+            ws.applyJT_rows_dev(nrows, d_rp, d_ri, d_col, d_val, rows, keep)
+            ws.synchronize()
+            results[(seed, cached)] = (rows.cpu().numpy(), keep.cpu().numpy())
+        a, b = results[(seed, True)], results[(seed, False)]
+        assert rel_err(a[0], b[0]) <= 1e-12 and np.array_equal(a[1], b[1])
+        orc = oracle.Oracle(d)
+        for r in list(range(0, nrows, 37)) + [nrows - 1]:
+            i = int(row_inst[r])
+            orc.apply(qj[i], None if root is None else root[i])
+            sl = slice(int(row_ptr[r]), int(row_ptr[r + 1]))
+            ref_row, ref_keep = orc.applyJT_row([int(c) for c in col[sl]], val[sl])
+            assert rel_err(a[0][r], ref_row) <= TOL_FP64 and int(a[1][r]) == int(ref_keep)
+    assert rel_err(results[(81, True)][0], results[(82, True)][0]) > 1e-3   # different configurations, different rows
