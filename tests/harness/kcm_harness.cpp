@@ -81,6 +81,11 @@ int main(int argc, char** argv) {
   // Mass / ForceField quantities
   double v[2] = {0.4, -1.1}, a[2] = {0.2, 0.3}, oMi[24], J[12], M[3], tau[2];
   CHECK(rbd_eval_host(ws, 1, in_q.data(), v, a, oMi, J, M, tau));
+  // ... and their matrix-free products on SOFA's own vectors (Mass::addMDx, ForceField::addForce), accumulated in place
+  double res[2] = {10.0, 20.0}, fbias[2] = {0.0, 0.0}, fgrav[2] = {1.0, -1.0};
+  CHECK(rbd_addMDx_host(ws, 1, in_q.data(), a, 2.0, res));          // res += 2 M(q) a
+  CHECK(rbd_addForce_host(ws, 1, in_q.data(), v, fbias));           // f -= C(q, v) v + g(q)
+  CHECK(rbd_addForce_host(ws, 1, in_q.data(), nullptr, fgrav));     // f -= g(q)
 
   for (int k = 0; k < n_out; ++k)
     std::printf("pos %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", k, out_pos[k].p[0], out_pos[k].p[1], out_pos[k].p[2],
@@ -92,6 +97,9 @@ int main(int argc, char** argv) {
   std::printf("rows %d %.17g %.17g %d %.17g %.17g\n", keep[0], rows[0], rows[1], keep[1], rows[2], rows[3]);
   std::printf("M %.17g %.17g %.17g\n", M[0], M[1], M[2]);
   std::printf("tau %.17g %.17g\n", tau[0], tau[1]);
+  std::printf("mdx %.17g %.17g\n", res[0], res[1]);
+  std::printf("fbias %.17g %.17g\n", fbias[0], fbias[1]);
+  std::printf("fgrav %.17g %.17g\n", fgrav[0], fgrav[1]);
   std::printf("launches %lld\n", (long long)rbd_workspace_launch_count(ws));
   rbd_workspace_destroy(ws);
   rbd_model_destroy(model);

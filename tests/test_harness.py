@@ -88,3 +88,10 @@ def test_harness_matches_oracle(rbd_lib):
     assert int(rr[3]) == 0                                             # the all-zero row is dropped (kMinTorque)
     oMi, J, Mp, tau = orc.eval(q, dq, np.array([0.2, 0.3]))
     assert rel_err(np.array(rec["M"][0]), Mp) <= TOL_FP64 and rel_err(np.array(rec["tau"][0]), tau) <= TOL_FP64
+    # Mass / ForceField products on host vectors
+    Mfull = np.array([[Mp[0], Mp[1]], [Mp[1], Mp[2]]])
+    assert rel_err(np.array(rec["mdx"][0]), np.array([10.0, 20.0]) + 2.0 * Mfull @ np.array([0.2, 0.3])) <= TOL_FP64
+    _, _, _, bias = orc.eval(q, dq, np.zeros(2))
+    assert rel_err(np.array(rec["fbias"][0]), -bias) <= TOL_FP64
+    _, _, _, grav = orc.eval(q, np.zeros(2), np.zeros(2))
+    assert rel_err(np.array(rec["fgrav"][0]), np.array([1.0, -1.0]) - grav) <= TOL_FP64
