@@ -637,6 +637,20 @@ template <int N>
 RBD_HD void x_stv(bool tm, const Stack& S, const TmStack& T, int k, const real* v) {
   if (tm) T.stv<N>(k, v); else s_stv<N>(S, k, v);
 }
+// v[0..N) += the N values at offset k: each space adds into v inside its own branch, so that the two load paths do not
+// merge through a temporary (the merge cost ~2 register moves per value: 7 % of the eval kernel's instructions, r1i)
+template <int N>
+RBD_HD void x_accv(bool tm, const Stack& S, const TmStack& T, int k, real* v) {
+  if (tm) {
+    real t[N];
+    T.template ldv<N>(k, t);
+#pragma unroll
+    for (int e = 0; e < N; ++e) v[e] += t[e];
+  } else {
+#pragma unroll
+    for (int e = 0; e < N; ++e) v[e] += S.ld(k + e);
+  }
+}
 template <int N>
 RBD_HD void x_addv(bool tm, const Stack& S, const TmStack& T, int k, const real* v) {
   if (tm) {
@@ -855,27 +869,46 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
       const DevJoint& jb = m.joint[par];
       const bool btm = (jb.boff & RBD_BOFF_TMEM) != 0;
       int b = jb.boff & RBD_BOFF_MASK;
-      real Rp[12];
+      // every source assigns R | p (v | a) inside its own branch: no merge through a temporary
       if (NEED_STACK && jb.type == JT_FF) {
-        s_ldv<12>(S, jb.offA, Rp);  // a free-flyer's A record is its R|p
+        // a free-flyer's A record is its R|p
+#pragma unroll
+        for (int e = 0; e < 9; ++e) R[e] = S.ld(jb.offA + e);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) p[e] = S.ld(jb.offA + 9 + e);
       } else if (jb.boff & RBD_BOFF_RPOMI) {
         const int o = 12 * (par - 1);  // this thread wrote oMi[par] earlier in the sweep
 #pragma unroll
-        for (int e = 0; e < 12; ++e) Rp[e] = io.oMi.ld(o + e);
+        for (int e = 0; e < 9; ++e) R[e] = io.oMi.ld(o + e);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) p[e] = io.oMi.ld(o + 9 + e);
       } else {
-        x_ldv<12>(btm, S, T, b, Rp);
+        if (btm) {
+          real Rp[12];
+          T.template ldv<12>(b, Rp);
+#pragma unroll
+          for (int e = 0; e < 9; ++e) R[e] = Rp[e];
+#pragma unroll
+          for (int e = 0; e < 3; ++e) p[e] = Rp[9 + e];
+        } else {
+#pragma unroll
+          for (int e = 0; e < 9; ++e) R[e] = S.ld(b + e);
+#pragma unroll
+          for (int e = 0; e < 3; ++e) p[e] = S.ld(b + 9 + e);
+        }
         b += 12;
       }
-#pragma unroll
-      for (int e = 0; e < 9; ++e) R[e] = Rp[e];
-#pragma unroll
-      for (int e = 0; e < 3; ++e) p[e] = Rp[9 + e];
       if (DO_TAU) {
         if (!(jb.boff & RBD_BOFF_NOVA)) {
-          real va[12];
-          x_ldv<12>(btm, S, T, b, va);
+          if (btm) {
+            real va[12];
+            T.template ldv<12>(b, va);
 #pragma unroll
-          for (int e = 0; e < 6; ++e) { vel[e] = va[e]; acc[e] = va[6 + e]; }
+            for (int e = 0; e < 6; ++e) { vel[e] = va[e]; acc[e] = va[6 + e]; }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 6; ++e) { vel[e] = S.ld(b + e); acc[e] = S.ld(b + 6 + e); }
+          }
         } else {
           // branch joint attached to the universe: v = A qd, a = -g + A qdd (v x vJ = 0), nothing was saved
           real vj[6], aj[6];
@@ -1075,17 +1108,9 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
           if (DO_M) x_addv<9>(RBD_Y_TM(lvl), S, T, RBD_Y_OFF(lvl), Yk + 1);
           break;
         }
-        if (DO_TAU) {
-          real fp[6];
-          x_ldv<6>(RBD_F_TM(lvl), S, T, RBD_F_OFF(lvl), fp);
-#pragma unroll
-          for (int e = 0; e < 6; ++e) fk[e] += fp[e];
-        }
+        if (DO_TAU) x_accv<6>(RBD_F_TM(lvl), S, T, RBD_F_OFF(lvl), fk);
         if (DO_M) {
-          real Yp[9];
-          x_ldv<9>(RBD_Y_TM(lvl), S, T, RBD_Y_OFF(lvl), Yp);
-#pragma unroll
-          for (int e = 0; e < 9; ++e) Yk[1 + e] += Yp[e];
+          x_accv<9>(RBD_Y_TM(lvl), S, T, RBD_Y_OFF(lvl), Yk + 1);
           Yk[0] = jp.msub;  // composite mass of the subtree: model constant
         }
         if (jp.type != JT_FF) s_ldv<6>(S, jp.offA, Ak); else s_ldv<12>(S, jp.offA, Ak);
