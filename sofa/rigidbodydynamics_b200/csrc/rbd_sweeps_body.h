@@ -1867,14 +1867,30 @@ RBD_HD void rows_cached_row(const DevModel& m, const DevTables& tb, const JF& Jc
     RBD_CROSS(tx, ty, tz, px, py, pz, w[0], w[1], w[2]);
     F[0] = w[0]; F[1] = w[1]; F[2] = w[2];
     F[3] = w[3] + tx; F[4] = w[4] + ty; F[5] = w[5] + tz;
-    for (int a = pj; a != 0; a = m.joint[a].parent) {
-      const DevJoint& ja = m.joint[a];
-      for (int cc = 0; cc < ja.nv; ++cc) {
-        const int c = ja.idx_v + cc;
-        real A[6];
-        Jc.template ldn<6>(6 * c, A);
-        acc(c, dot6(A, F));
+    // walk to the root four dof columns at a time: the column indices come from the staged joint table, then the
+    // four Jacobian columns are loaded together (the row kernel is bound by the latency of these scattered reads:
+    // one column in flight per lane left it at 24 long-scoreboard stall cycles per issue, r1i)
+    int a = pj, cc = 0;  // next dof to visit: dof cc of joint a
+    while (a != 0) {
+      int cidx[4];
+      int ncol = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        cidx[u] = 0;
+        if (a != 0) {
+          const DevJoint& ja = m.joint[a];
+          cidx[u] = ja.idx_v + cc;
+          ncol = u + 1;
+          if (++cc >= ja.nv) { a = ja.parent; cc = 0; }
+        }
       }
+      real A[4][6];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (u < ncol) Jc.template ldn<6>(6 * cidx[u], A[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (u < ncol) acc(cidx[u], dot6(A[u], F));
     }
   }
 }
