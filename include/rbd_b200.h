@@ -196,6 +196,18 @@ RBD_API int rbd_applyJT_rows_dev(rbd_workspace* ws, int64_t nrows, const int32_t
                                  const int32_t* row_instance, const int32_t* col, const double* val,
                                  double* out_rows, int32_t* keep);
 
+/* getFrameJacobian — pinocchio::getFrameJacobian(model, data, frame, LOCAL_WORLD_ALIGNED, J) as the reference
+ * calls it for every mapped output before each J dq / J^T f product (KCM.inl:434,444,480,490,579), here for
+ * explicit (instance, output) pairs: J[p] = dense 6 x nv Jacobian of mapped output out_index[p] (< n_out) of
+ * instance instance[p], column-major ([lin; ang] per column, pinocchio's Matrix6x layout), columns off the path
+ * to the root zero.  Read from the Jacobian cache of the last apply (see rbd_workspace_set_rows_cache); this is
+ * what a real getJ() (KinematicChainMapping.h:83 returns nullptr) would assemble for SOFA's direct solvers.
+ *   _dev: instance, out_index, J are DEVICE pointers, J 16-byte aligned, [npairs][nv][6].   _host: host pointers.  */
+RBD_API int rbd_getFrameJacobian_dev(rbd_workspace* ws, int64_t npairs, const int32_t* instance,
+                                     const int32_t* out_index, double* J);
+RBD_API int rbd_getFrameJacobian_host(rbd_workspace* ws, int64_t npairs, const int32_t* instance,
+                                      const int32_t* out_index, double* J);
+
 /* ---------------------------------------------------------------------------------------------------- */
 /* Mass / ForceField path, device SoA (north-star additions; the reference reaches them matrix-free
  * through UniformMass + applyJ/applyJT, URDFModelLoader.cpp:369-391).                                    */

@@ -166,6 +166,19 @@ class Workspace:
         check(self._lib.rbd_applyJT_rows_dev(self._h, nrows, _dev_ptr(row_ptr), _dev_ptr(row_instance), _dev_ptr(col),
                                              _dev_ptr(val), _dev_ptr(out_rows), _dev_ptr(keep)))
 
+    def frame_jacobians_dev(self, npairs, instance, out_index, J):
+        """Dense LOCAL_WORLD_ALIGNED frame Jacobians of (instance, output) pairs: J [npairs, nv, 6] (device tensors)."""
+        check(self._lib.rbd_getFrameJacobian_dev(self._h, npairs, _dev_ptr(instance), _dev_ptr(out_index), _dev_ptr(J)))
+
+    def frame_jacobians_host(self, instance, out_index) -> np.ndarray:
+        """... on host arrays; returns [npairs, 6, nv] (pinocchio's Matrix6x as numpy sees it)."""
+        inst = np.ascontiguousarray(instance, dtype=np.int32); out = np.ascontiguousarray(out_index, dtype=np.int32)
+        nv = self.model.info.nv
+        J = np.zeros((inst.shape[0], nv, 6))
+        check(self._lib.rbd_getFrameJacobian_host(self._h, inst.shape[0], _host_ptr(inst, np.int32),
+                                                  _host_ptr(out, np.int32), _host_ptr(J)))
+        return np.ascontiguousarray(J.transpose(0, 2, 1))
+
     def aos_to_soa(self, n, K, tile, aos, soa):
         check(self._lib.rbd_aos_to_soa_dev(self._h, n, K, tile, _dev_ptr(aos), _dev_ptr(soa)))
 

@@ -536,6 +536,7 @@ RBD_API int rbd_applyJT_soa(rbd_workspace* ws, int64_t n, int64_t tile, const do
   return applyJT_on(ws, ws->stream, n, tile, 0, in, out_tau, out_root);
 }
 
+static int ensure_jcache(rbd_workspace* ws, cudaStream_t st);
 // constraint rows: refresh the Jacobian cache if an apply happened since it was filled, then one light kernel
 static int rows_on(rbd_workspace* ws, cudaStream_t st, const RowArgs& A) {
   const DevModel& dm = ws->model->dm;
@@ -544,6 +545,15 @@ static int rows_on(rbd_workspace* ws, cudaStream_t st, const RowArgs& A) {
     ws->launches++;
     return RBD_OK;
   }
+  int rc0 = ensure_jcache(ws, st);
+  if (rc0) return rc0;
+  CK(launch_applyJT_rows_cached(dm, ws->d_model, ws->tb, A, ws->jcache, ws->omicache, st));
+  ws->launches++;
+  return RBD_OK;
+}
+// Jacobian cache of the applied instances (see rbd_workspace::jcache): allocate on first use, refill after an apply
+static int ensure_jcache(rbd_workspace* ws, cudaStream_t st) {
+  const DevModel& dm = ws->model->dm;
   const int kj = 6 * dm.nv, ko = 12 * (dm.njoints - 1);
   const long long chunk = std::min<long long>((ws->capacity + 31) / 32 * 32, kRowsCacheChunk);
   if (!ws->jcache) {
@@ -568,8 +578,54 @@ static int rows_on(rbd_workspace* ws, cudaStream_t st, const RowArgs& A) {
     }
     ws->jc_epoch = ws->apply_epoch;
   }
-  CK(launch_applyJT_rows_cached(dm, ws->d_model, ws->tb, A, ws->jcache, ws->omicache, st));
+  return RBD_OK;
+}
+RBD_API int rbd_getFrameJacobian_dev(rbd_workspace* ws, int64_t npairs, const int32_t* instance, const int32_t* out_index,
+                                     double* J) {
+  GUARD(ws);
+  if (npairs < 0) return set_err(RBD_ERR_INVALID_ARG, "negative pair count");
+  if (npairs == 0) return RBD_OK;
+  if (!instance || !out_index || !J) return set_err(RBD_ERR_INVALID_ARG, "null pair arrays");
+  if ((reinterpret_cast<uintptr_t>(J) & 15) != 0) return set_err(RBD_ERR_INVALID_ARG, "J must be 16-byte aligned");
+  if (ws->applied_n <= 0) return set_err(RBD_ERR_NO_APPLY, "getFrameJacobian before apply: no cached configuration");
+  const DevModel& dm = ws->model->dm;
+  if (dm.njoints < 2) { CK(cudaMemsetAsync(J, 0, (size_t)npairs * 6 * dm.nv * sizeof(double), ws->stream)); return RBD_OK; }
+  int rc = ensure_jcache(ws, ws->stream);
+  if (rc) return rc;
+  CK(launch_frame_jacobian(dm, ws->d_model, ws->tb, npairs, instance, out_index, J, ws->jcache, ws->omicache, ws->stream));
   ws->launches++;
+  return RBD_OK;
+}
+RBD_API int rbd_getFrameJacobian_host(rbd_workspace* ws, int64_t npairs, const int32_t* instance, const int32_t* out_index,
+                                      double* J) {
+  GUARD(ws);
+  if (npairs < 0) return set_err(RBD_ERR_INVALID_ARG, "negative pair count");
+  if (npairs == 0) return RBD_OK;
+  if (!instance || !out_index || !J) return set_err(RBD_ERR_INVALID_ARG, "null pair arrays");
+  if (ws->applied_n <= 0) return set_err(RBD_ERR_NO_APPLY, "getFrameJacobian before apply: no cached configuration");
+  const int nv = ws->model->info.nv, n_out = ws->model->info.n_out;
+  for (int64_t p = 0; p < npairs; ++p) {
+    if (instance[p] < 0 || instance[p] >= ws->applied_n) return set_err(RBD_ERR_INVALID_ARG, "instance out of the applied range");
+    if (out_index[p] < 0 || out_index[p] >= n_out) return set_err(RBD_ERR_INVALID_ARG, "output index out of range");
+  }
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t b_i = al((size_t)npairs * 4), b_o = al((size_t)npairs * 4), b_j = al((size_t)npairs * 6 * nv * 8);
+  if (ws->rows_bytes < b_i + b_o + b_j) {
+    CK(cudaStreamSynchronize(ws->stream));
+    cudaFree(ws->rows_buf); ws->rows_buf = nullptr; ws->rows_bytes = 0;
+    CK(cudaMalloc(&ws->rows_buf, b_i + b_o + b_j));
+    ws->rows_bytes = b_i + b_o + b_j;
+  }
+  char* base = (char*)ws->rows_buf;
+  int* d_i = (int*)base; int* d_o = (int*)(base + b_i); double* d_j = (double*)(base + b_i + b_o);
+  cudaStream_t st = ws->stream;
+  CK(cudaMemcpyAsync(d_i, instance, (size_t)npairs * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_o, out_index, (size_t)npairs * 4, cudaMemcpyHostToDevice, st));
+  ws->stream = st;
+  int rc = rbd_getFrameJacobian_dev(ws, npairs, d_i, d_o, d_j);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(J, d_j, (size_t)npairs * 6 * nv * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   return RBD_OK;
 }
 RBD_API int rbd_workspace_set_rows_cache(rbd_workspace* ws, int enable) {

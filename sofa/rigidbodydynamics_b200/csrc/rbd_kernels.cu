@@ -474,6 +474,27 @@ __global__ void __launch_bounds__(256) applyJT_rows_cached_kernel(const DevModel
   }
 }
 
+// getFrameJacobian(LWA) of (instance, output) pairs from the Jacobian cache: one thread per pair writes the columns on
+// the path to the root (the launcher zeroed the array: off-path columns stay 0, as pinocchio leaves them)
+__global__ void __launch_bounds__(256) frame_jacobian_kernel(const DevModel* __restrict__ gm, const int model_words,
+                                                             const DevTables tb, const long long npairs,
+                                                             const int* __restrict__ instance,
+                                                             const int* __restrict__ out_index,
+                                                             double* __restrict__ J, const double* __restrict__ jc,
+                                                             const double* __restrict__ oc) {
+  const DevModel& m = stage_model(gm, model_words);
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= npairs) return;
+  const long long inst = instance[r];
+  const AosRec Jc{jc + inst * (long long)(6 * m.nv)};
+  const AosRec Oc{oc + inst * (long long)(12 * (m.njoints - 1))};
+  double* const Jr = J + r * (long long)(6 * m.nv);
+  frame_jacobian_cached(m, tb, Jc, Oc, out_index[r], [&](int c, const double* o) {
+    double2* q2 = reinterpret_cast<double2*>(Jr + 6 * c);  // 6 nv even, cudaMalloc'ed or 16-byte aligned by contract
+    q2[0] = make_double2(o[0], o[1]); q2[1] = make_double2(o[2], o[3]); q2[2] = make_double2(o[4], o[5]);
+  });
+}
+
 // K8: layout adapters.  32 instances x 32 fields per block through a padded shared tile, so both the
 // instance-major side and the tiled-SoA side are accessed with consecutive addresses.
 __global__ void aos_to_soa_kernel(long long n, int K, long long tile, const double* __restrict__ aos,
@@ -709,6 +730,17 @@ cudaError_t launch_applyJT_rows_cached(const DevModel& m, const DevModel* d_mode
   if (e != cudaSuccess) return e;
   if (a.nrows <= 0) return cudaSuccess;
   applyJT_rows_cached_kernel<<<RBD_GRID(a.nrows, block), block, smem, st>>>(d_model, mw, tb, a, jc, oc);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_frame_jacobian(const DevModel& m, const DevModel* d_model, const DevTables& tb, long long npairs,
+                                  const int* instance, const int* out_index, double* J, const double* jc, const double* oc,
+                                  cudaStream_t st) {
+  if (npairs <= 0) return cudaSuccess;
+  const int mw = map_model_words(m);
+  cudaError_t e = cudaMemsetAsync(J, 0, (size_t)npairs * 6 * m.nv * sizeof(double), st);
+  if (e != cudaSuccess) return e;
+  frame_jacobian_kernel<<<RBD_GRID(npairs, 256), 256, (size_t)mw * 8, st>>>(d_model, mw, tb, npairs, instance, out_index, J, jc, oc);
   return cudaGetLastError();
 }
 

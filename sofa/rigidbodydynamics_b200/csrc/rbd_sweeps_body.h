@@ -1895,6 +1895,35 @@ RBD_HD void rows_cached_row(const DevModel& m, const DevTables& tb, const JF& Jc
   }
 }
 
+// getFrameJacobian(LOCAL_WORLD_ALIGNED) of one mapped output from the same cache — what the reference evaluates per
+// output before every J dq / J^T f product (KinematicChainMapping.inl:434,444,480,490,579):
+//   J_k[:, c] = [J_lin[:, c] - p_k x J_ang[:, c] ; J_ang[:, c]]   for every dof c on the path to the root, else 0,
+// p_k = world position of the output.  `put(c, col6)` receives the non-zero columns (the caller zeroes the rest).
+template <class JF, class OF, class PUT>
+RBD_HD void frame_jacobian_cached(const DevModel& m, const DevTables& tb, const JF& Jc, const OF& Oc, int k,
+                                  const PUT& put) {
+  const int pj = tb.outk_parent[k];
+  if (pj == 0) return;  // attached to the universe: empty support
+  const real* pl = tb.outk_pl + 12 * k;
+  real Rp[12];
+  Oc.template ldn<12>(12 * (pj - 1), Rp);
+  const real px = Rp[0] * pl[9] + Rp[1] * pl[10] + Rp[2] * pl[11] + Rp[9];
+  const real py = Rp[3] * pl[9] + Rp[4] * pl[10] + Rp[5] * pl[11] + Rp[10];
+  const real pz = Rp[6] * pl[9] + Rp[7] * pl[10] + Rp[8] * pl[11] + Rp[11];
+  for (int a = pj; a != 0; a = m.joint[a].parent) {
+    const DevJoint& ja = m.joint[a];
+    for (int cc = 0; cc < ja.nv; ++cc) {
+      const int c = ja.idx_v + cc;
+      real A[6], o[6], tx, ty, tz;
+      Jc.template ldn<6>(6 * c, A);
+      RBD_CROSS(tx, ty, tz, px, py, pz, A[3], A[4], A[5]);
+      o[0] = A[0] - tx; o[1] = A[1] - ty; o[2] = A[2] - tz;
+      o[3] = A[3]; o[4] = A[4]; o[5] = A[5];
+      put(c, o);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // applyJT, ring variant with FORWARD projection (shallow trees: depth <= RBD_JT_MAXD, a free-flyer only as the
 // root).  Instead of parking the subtree wrench F per depth level and projecting on the way back

@@ -319,6 +319,37 @@ extern "C" int emul_applyJT_rows_cached(const rbd_model_desc* d, long long n, do
   return 0;
 }
 
+// dense LOCAL_WORLD_ALIGNED frame Jacobian of (instance, output) pairs from the same cache (frame_jacobian_cached)
+extern "C" int emul_frame_jacobians(const rbd_model_desc* d, long long n, double* qcache, long long cache_tile,
+                                    long long npairs, const int* instance, const int* out_index, double* Jout) {
+  Ctx c;
+  int rc = make_ctx(d, &c);
+  if (rc) return rc;
+  if (!plan_eval(&c.m, false, false, true, 0, true)) { g_err = "plan_eval failed"; return -100; }
+  const std::vector<unsigned long long> blob = build_eval_blob(&c.m);
+  const DevModel& bm = *reinterpret_cast<const DevModel*>(blob.data());
+  const int nj = bm.njoints, nv = bm.nv;
+  const long long nt = (n + cache_tile - 1) / cache_tile;
+  std::vector<double> J((size_t)nt * cache_tile * 6 * nv + 1, 1e300), O((size_t)nt * cache_tile * 12 * (nj - 1) + 1, 1e300);
+  std::vector<double> smem(64, 1e300), tmem(64, 1e300);
+  for (long long i = 0; i < n; ++i) {
+    Stack S = make_stack(smem.data(), 0, 1);
+    TmStack T{tmem.data()};
+    InRing inr;
+    eval_one<0>(bm, i, cache_tile, qcache, nullptr, nullptr, O.data(), J.data(), nullptr, nullptr, S, T, inr);
+  }
+  for (long long p = 0; p < npairs; ++p) {
+    double* Jr = Jout + (size_t)p * 6 * nv;
+    for (int k = 0; k < 6 * nv; ++k) Jr[k] = 0.0;
+    const Field Jc = make_field(J.data(), instance[p], 6 * nv, cache_tile);
+    const Field Oc = make_field(O.data(), instance[p], 12 * (nj - 1), cache_tile);
+    frame_jacobian_cached(bm, c.tb, Jc, Oc, out_index[p], [&](int cc, const double* o) {
+      for (int e = 0; e < 6; ++e) Jr[6 * cc + e] = o[e];
+    });
+  }
+  return 0;
+}
+
 // plan of the applyJT ring kernel for this model: out = {ring stages (0 = register path), forward projection?,
 // warps per block, tensor-memory doubles, shared-memory doubles, shared-memory bytes of the block}
 extern "C" int emul_jt_ring_plan(const rbd_model_desc* d, int use_tmem, int fwd_mode, int* out /*[6]*/) {

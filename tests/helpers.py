@@ -66,6 +66,7 @@ def load_emul() -> C.CDLL:
     lib.emul_mass_force.argtypes = [vp, ll, ll, vp, vp, vp, vp, C.c_double, i]
     lib.emul_jt_ring_plan.argtypes = [vp, i, i, vp]
     lib.emul_applyJT_rows_cached.argtypes = [vp, ll, vp, ll, ll, vp, vp, vp, vp, vp, vp]
+    lib.emul_frame_jacobians.argtypes = [vp, ll, vp, ll, ll, vp, vp, vp]
     lib.emul_applyJT_rows.argtypes = [vp, ll, i, vp, ll, vp, vp, vp, vp, vp, vp]
     return lib
 

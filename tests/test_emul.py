@@ -157,6 +157,18 @@ def test_mapping_bodies_match_oracle(emul, d):
     assert emul.emul_applyJT_rows_cached(C.addressof(cd), n, P(qcache), ctile, nrows, P(row_ptr), P(row_inst), P(cols),
                                          P(vals), P(rows_c), P(keep_c)) == 0, emul.emul_last_error()
     assert rel_err(rows_c, rows) <= 1e-13 and np.array_equal(keep_c, keepf)
+    # dense LOCAL_WORLD_ALIGNED frame Jacobians from the same cache: the oracle's getFrameJacobian, and J_k dq == applyJ
+    pi = np.array([0, 0, n - 1, n // 2], dtype=np.int32)
+    po = np.array([0, d.n_out - 1, d.n_out // 2, min(d.njoints, d.n_out - 1)], dtype=np.int32)
+    Jd = np.full((len(pi), d.nv, 6), np.nan)
+    assert emul.emul_frame_jacobians(C.addressof(cd), n, P(qcache), ctile, len(pi), P(pi), P(po), P(Jd)) == 0
+    for t in range(len(pi)):
+        i, k = int(pi[t]), int(po[t])
+        orc.apply(qj[i], None if root is None else root[i])
+        Jref = orc.frame_jacobian_lwa(int(d.out_frames[k]))
+        assert rel_err(Jd[t].T, Jref) <= TOL_FP64
+        full_dq = dq[i] if rootv is None else np.concatenate([rootv[i], dq[i]])
+        assert rel_err(Jd[t].T @ full_dq, vel[i, k]) <= TOL_FP64
     for i in range(n):
         rp = orc.apply(qj[i], None if root is None else root[i])
         assert rel_err(pos[i][:, :3], rp[:, :3]) <= TOL_FP64

@@ -619,3 +619,43 @@ def test_constraint_rows_cached_jacobians(torch_mod, api, name):
             ref_row, ref_keep = orc.applyJT_row([int(c) for c in col[sl]], val[sl])
             assert rel_err(a[0][r], ref_row) <= TOL_FP64 and int(a[1][r]) == int(ref_keep)
     assert rel_err(results[(81, True)][0], results[(82, True)][0]) > 1e-3   # different configurations, different rows
+
+
+@pytest.mark.parametrize("name", ["talos_reduced", "solo12", "panda7"])
+def test_frame_jacobians_from_cache(torch_mod, api, name):
+    """rbd_getFrameJacobian_* = pinocchio::getFrameJacobian(LOCAL_WORLD_ALIGNED) as the reference calls it per output
+    (KCM.inl:434-490): against the oracle's dense Jacobian, and J_k dq == applyJ, J_k^T w == applyJT (one wrench)."""
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    torch = torch_mod
+    d = [m for m in MODELS if m.name == name][0]
+    n, tile = 100, 32
+    q, v, _ = mdl.random_state(d, n, seed=91)
+    qj, root, dq, rootv = _split(d, q, v)
+    m = api.Model(d); ws = api.Workspace(m, n)
+    T = lambda x: None if x is None else _dev(torch, to_tiled(x, tile))
+    nt = (n + tile - 1) // tile
+    pos = torch.zeros((nt, 7 * d.n_out, tile), dtype=torch.float64, device="cuda")
+    vel = torch.zeros((nt, 6 * d.n_out, tile), dtype=torch.float64, device="cuda")
+    with pytest.raises(api.RbdError):
+        ws.frame_jacobians_host([0], [0])                     # before apply: RBD_ERR_NO_APPLY
+    ws.apply_soa(n, tile, T(qj), T(root), pos)
+    ws.applyJ_soa(n, tile, T(dq), T(rootv), vel)
+    ws.synchronize()
+    vel = from_tiled(vel.cpu().numpy(), n).reshape(n, d.n_out, 6)
+    rng = np.random.default_rng(92)
+    inst = rng.integers(0, n, 40).astype(np.int32); outk = rng.integers(0, d.n_out, 40).astype(np.int32)
+    outk[0] = 0                                               # universe output: zero Jacobian
+    J = ws.frame_jacobians_host(inst, outk)                   # [40, 6, nv]
+    Jdev = torch.full((40, d.nv, 6), float("nan"), dtype=torch.float64, device="cuda")
+    ws.frame_jacobians_dev(40, torch.from_numpy(inst).cuda(), torch.from_numpy(outk).cuda(), Jdev)
+    ws.synchronize()
+    assert np.array_equal(Jdev.cpu().numpy().transpose(0, 2, 1), J)
+    assert np.all(J[0] == 0.0)
+    orc = oracle.Oracle(d)
+    for t in range(40):
+        i, k = int(inst[t]), int(outk[t])
+        orc.apply(qj[i], None if root is None else root[i])
+        assert rel_err(J[t], orc.frame_jacobian_lwa(int(d.out_frames[k]))) <= TOL_FP64
+        full_dq = dq[i] if rootv is None else np.concatenate([rootv[i], dq[i]])
+        assert rel_err(J[t] @ full_dq, vel[i, k]) <= TOL_FP64
