@@ -185,6 +185,19 @@ RBD_API int rbd_applyJ_soa(rbd_workspace* ws, int64_t n, int64_t tile, const dou
 RBD_API int rbd_applyJT_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* in, double* out_tau,
                             double* out_root);
 
+/* applyDJT — OPTIONAL EXTENSION.  The reference's applyDJT is an explicit no-op (KinematicChainMapping.h:73-80), i.e.
+ * the mapping contributes no geometric stiffness; a drop-in keeps it a no-op (the host mirror does).  This entry point
+ * is the real term for callers who want it:  out += kfactor * d/de [ J(q (+) e dq)^T in ] at e = 0  — how the
+ * generalized forces of the FIXED world-aligned wrenches `in` (n_out*6 fields, as in applyJT) change along the
+ * direction dq (dq_joints / root_vel as in applyJ; the root velocity in the free-flyer's joint frame).  Uses the
+ * configuration cached by the last apply; out_tau / out_root are ACCUMULATED; root_vel and out_root go together.
+ * A free-flyer is supported as the root joint only.                                                              */
+RBD_API int rbd_applyDJT_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* dq_joints,
+                             const double* root_vel, const double* in, double kfactor, double* out_tau,
+                             double* out_root);
+RBD_API int rbd_applyDJT_host(rbd_workspace* ws, int64_t n, const double* dq_joints, const double* root_vel,
+                              const double* in, double kfactor, double* out_tau, double* out_root);
+
 /* applyJT (MatrixDeriv) — KCM.inl:515-639: one dense nv-wide row per constraint row.
  *   nrows rows in CSR form: row r owns non-zeros [row_ptr[r], row_ptr[r+1]); row_instance[r] selects the
  *   robot instance (its cached configuration); col[j] is the mapped-output index (< n_out); val is

@@ -73,7 +73,7 @@ SYMBOLS = [
     "rbd_workspace_create", "rbd_workspace_destroy", "rbd_workspace_set_stream", "rbd_workspace_synchronize",
     "rbd_workspace_launch_count", "rbd_workspace_set_eval_block", "rbd_workspace_set_eval_tmem", "rbd_workspace_set_applyJT_ring", "rbd_workspace_set_rows_cache", "rbd_workspace_get_eval_plan", "rbd_workspace_get_eval_plan_f32",
     "rbd_apply_soa", "rbd_applyJ_soa", "rbd_applyJT_soa", "rbd_applyJT_rows_dev",
-    "rbd_getFrameJacobian_dev", "rbd_getFrameJacobian_host",
+    "rbd_getFrameJacobian_dev", "rbd_getFrameJacobian_host", "rbd_applyDJT_soa", "rbd_applyDJT_host",
     "rbd_eval_soa", "rbd_eval_soa_f32", "rbd_crba_soa", "rbd_rnea_soa", "rbd_addMDx_soa", "rbd_addForce_soa",
     "rbd_aos_to_soa_dev", "rbd_soa_to_aos_dev",
     "rbd_apply_host", "rbd_applyJ_host", "rbd_applyJT_host", "rbd_applyJT_rows_host", "rbd_eval_host", "rbd_addMDx_host", "rbd_addForce_host",
@@ -123,6 +123,8 @@ def load() -> C.CDLL:
         "rbd_crba_soa": (C.c_int, [vp, i64, i64, vp, vp]),
         "rbd_rnea_soa": (C.c_int, [vp, i64, i64, vp, vp, vp, vp]),
         "rbd_getFrameJacobian_dev": (C.c_int, [vp, i64, vp, vp, vp]),
+        "rbd_applyDJT_soa": (C.c_int, [vp, i64, i64, vp, vp, vp, C.c_double, vp, vp]),
+        "rbd_applyDJT_host": (C.c_int, [vp, i64, vp, vp, vp, C.c_double, vp, vp]),
         "rbd_getFrameJacobian_host": (C.c_int, [vp, i64, vp, vp, vp]),
         "rbd_addMDx_soa": (C.c_int, [vp, i64, i64, vp, vp, C.c_double, vp]),
         "rbd_addForce_soa": (C.c_int, [vp, i64, i64, vp, vp, vp]),

@@ -162,6 +162,15 @@ class Workspace:
     def applyJT_soa(self, n, tile, wrenches, out_tau, out_root=None):
         check(self._lib.rbd_applyJT_soa(self._h, n, tile, _dev_ptr(wrenches), _dev_ptr(out_tau), _dev_ptr(out_root)))
 
+    def applyDJT_soa(self, n, tile, dq_joints, root_vel, wrenches, kfactor, out_tau, out_root=None):
+        """Optional extension (the reference's applyDJT is a no-op): out += kfactor * d/de [J(q + e dq)^T w]."""
+        check(self._lib.rbd_applyDJT_soa(self._h, n, tile, _dev_ptr(dq_joints), _dev_ptr(root_vel), _dev_ptr(wrenches),
+                                         float(kfactor), _dev_ptr(out_tau), _dev_ptr(out_root)))
+
+    def applyDJT_host(self, n, dq_joints, root_vel, wrenches, kfactor, out_tau, out_root=None):
+        check(self._lib.rbd_applyDJT_host(self._h, n, _host_ptr(dq_joints), _host_ptr(root_vel), _host_ptr(wrenches),
+                                          float(kfactor), _host_ptr(out_tau), _host_ptr(out_root)))
+
     def applyJT_rows_dev(self, nrows, row_ptr, row_instance, col, val, out_rows, keep):
         check(self._lib.rbd_applyJT_rows_dev(self._h, nrows, _dev_ptr(row_ptr), _dev_ptr(row_instance), _dev_ptr(col),
                                              _dev_ptr(val), _dev_ptr(out_rows), _dev_ptr(keep)))

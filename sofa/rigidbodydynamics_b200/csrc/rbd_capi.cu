@@ -82,7 +82,7 @@ struct rbd_workspace {
   long long apply_epoch = 0, jc_epoch = -1;
   int use_rows_cache = 1;
   long long applied_n = 0;   // instances covered by the cache (0 = apply not called yet)
-  LaunchCfg cfg_eval[8], cfg_apply[2], cfg_applyJ[2], cfg_applyJT[2], cfg_rows, cfg_jt_ring;
+  LaunchCfg cfg_eval[8], cfg_apply[2], cfg_applyJ[2], cfg_applyJT[2], cfg_rows, cfg_jt_ring, cfg_djt[2];
   DevModel* d_model = nullptr;  // device copy of the joint table for the mapping kernels
   int forced_eval_block = 0;
   long long launches = 0;
@@ -527,6 +527,31 @@ static int applyJT_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t til
   if (A.n > 0) ws->launches++;
   return RBD_OK;
 }
+// applyDJT: geometric stiffness of the mapping (optional extension: the reference's applyDJT is a no-op)
+static int applyDJT_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, long long inst0, const double* dq,
+                       const double* rootv, const double* in, double kfac, double* out_tau, double* out_root) {
+  const DevModel& dm = ws->model->dm;
+  if (!dq || !in || !out_tau) return set_err(RBD_ERR_INVALID_ARG, "null dq_joints / in / out_tau");
+  if ((rootv || out_root) && !dm.has_ff_root) return set_err(RBD_ERR_INVALID_ARG, "root arrays given but the model has no free-flyer root");
+  if (dm.has_ff_root && (!rootv) != (!out_root)) return set_err(RBD_ERR_INVALID_ARG, "root velocity and root output go together");
+  for (int i = 2; i < dm.njoints; ++i)
+    if (dm.joint[i].type == JT_FF) return set_err(RBD_ERR_UNSUPPORTED, "applyDJT supports a free-flyer only as joint 1");
+  if (dm.njoints > 1 && dm.joint[1].type == JT_FF && dm.joint[1].parent != 0)
+    return set_err(RBD_ERR_UNSUPPORTED, "applyDJT supports a free-flyer only as the root joint");
+  DjtArgs A{n, tile, dq, rootv, in, out_tau, out_root, kfac, ws->qcache, inst0};
+  CK(launch_applyDJT(dm, ws->d_model, ws->tb, A, ws->cfg_djt, st));
+  if (n > 0) ws->launches++;
+  return RBD_OK;
+}
+RBD_API int rbd_applyDJT_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* dq_joints, const double* root_vel,
+                             const double* in, double kfactor, double* out_tau, double* out_root) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, tile);
+  if (rc) return rc;
+  if (n > ws->applied_n) return set_err(RBD_ERR_NO_APPLY, "applyDJT before apply: no cached configuration for these instances");
+  return applyDJT_on(ws, ws->stream, n, tile, 0, dq_joints, root_vel, in, kfactor, out_tau, out_root);
+}
+
 RBD_API int rbd_applyJT_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* in, double* out_tau,
                             double* out_root) {
   GUARD(ws);
@@ -825,6 +850,24 @@ RBD_API int rbd_applyJT_host(rbd_workspace* ws, int64_t n, const double* in, dou
                           {6, out_root, out_root, true, true}};
   return run_host_chunks(ws, n, P, [&](cudaStream_t st, long long i0, long long cn, long long tile) {
     return applyJT_on(ws, st, cn, tile, i0, P[0].d_soa, P[1].d_soa, P[2].d_soa);
+  });
+}
+
+RBD_API int rbd_applyDJT_host(rbd_workspace* ws, int64_t n, const double* dq_joints, const double* root_vel,
+                              const double* in, double kfactor, double* out_tau, double* out_root) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, 1);
+  if (rc) return rc;
+  if (!dq_joints || !in || !out_tau) return set_err(RBD_ERR_INVALID_ARG, "null dq_joints / in / out_tau");
+  if (n > ws->applied_n) return set_err(RBD_ERR_NO_APPLY, "applyDJT before apply: no cached configuration for these instances");
+  const rbd_model_info& I = ws->model->info;
+  if ((root_vel || out_root) && !I.has_freeflyer_root) return set_err(RBD_ERR_INVALID_ARG, "root arrays given but the model has no free-flyer root");
+  const int kv = root_vel ? I.nv - 6 : I.nv;
+  std::vector<Piece> P = {{kv, dq_joints, nullptr, true, false}, {6, root_vel, nullptr, true, false},
+                          {6 * I.n_out, in, nullptr, true, false}, {kv, out_tau, out_tau, true, true},
+                          {6, out_root, out_root, true, true}};
+  return run_host_chunks(ws, n, P, [&](cudaStream_t st, long long i0, long long cn, long long tile) {
+    return applyDJT_on(ws, st, cn, tile, i0, P[0].d_soa, P[1].d_soa, P[2].d_soa, kfactor, P[3].d_soa, P[4].d_soa);
   });
 }
 

@@ -412,6 +412,24 @@ __global__ void __launch_bounds__(W * 32, 1) applyJT_ring_kernel(const DevModel*
   }
 }
 
+// applyDJT (geometric stiffness, optional extension): one thread per instance, shared-memory stack
+template <int TILE>
+__global__ void __launch_bounds__(256) applyDJT_kernel(const DevModel* __restrict__ gm, const int model_words,
+                                                       const DevTables tb, const DjtArgs a, const int slots) {
+  const DevModel& m = stage_model(gm, model_words);
+  const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= a.n) return;
+  const int off = a.dq_root ? 6 : 0;
+  SplitQT<FieldT<TILE>> dq{make_field_t<TILE>(const_cast<double*>(a.dq_root), inst, 6, a.tile),
+                           make_field_t<TILE>(const_cast<double*>(a.dq_joints), inst, m.nv - off, a.tile), off};
+  const int ooff = a.out_root ? 6 : 0;
+  SplitRedSinkT<FieldT<TILE>> sink{make_field_t<TILE>(a.out_root, inst, 6, a.tile),
+                                   make_field_t<TILE>(a.out_joints, inst, m.nv - ooff, a.tile), ooff};
+  Stack S = make_stack(rbd_smem + model_words, threadIdx.x, slots);
+  applyDJT_instance(m, tb, make_field_t<32>(a.qcache, a.cache_inst0 + inst, m.nq, 32), dq,
+                    make_field_t<TILE>(const_cast<double*>(a.in), inst, 6 * m.n_out, a.tile), sink, S, a.kfac);
+}
+
 // K4: applyJT (constraint rows): one thread per row
 __global__ void __launch_bounds__(256) applyJT_rows_kernel(const DevModel* __restrict__ gm, const int model_words,
                                                            const DevTables tb, const RowArgs a, const int slots) {
@@ -705,6 +723,23 @@ cudaError_t launch_applyJT_ring(const DevModel& hm, const DevModel* d_blob, cons
   if (variant == 2) applyJT_ring_kernel<JtRing::kWarpsSmall, true><<<grid, block, smem, st>>>(d_blob, model_words, a, nst);
   else if (variant == 1) applyJT_ring_kernel<JtRing::kWarpsSmall, false><<<grid, block, smem, st>>>(d_blob, model_words, a, nst);
   else applyJT_ring_kernel<JtRing::kWarps, false><<<grid, block, smem, st>>>(d_blob, model_words, a, nst);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_applyDJT(const DevModel& m, const DevModel* d_model, const DevTables& tb, const DjtArgs& a,
+                            LaunchCfg* cfg2, cudaStream_t st) {
+  const int mw = map_model_words(m);
+  const int slots = RBD_DJT_LEVEL * m.max_depth + RBD_DJT_BRANCH * m.nbranch;
+  const int v = a.tile == 32 ? 1 : 0;
+  LaunchCfg& c = cfg2[v];
+  if (c.block == 0) {
+    cudaError_t e = v ? pick_block(applyDJT_kernel<32>, slots, 0, &c, (size_t)mw * 8)
+                      : pick_block(applyDJT_kernel<0>, slots, 0, &c, (size_t)mw * 8);
+    if (e != cudaSuccess) return e;
+  }
+  if (a.n <= 0) return cudaSuccess;
+  if (v) applyDJT_kernel<32><<<RBD_GRID(a.n, c.block), c.block, c.smem_bytes, st>>>(d_model, mw, tb, a, slots);
+  else applyDJT_kernel<0><<<RBD_GRID(a.n, c.block), c.block, c.smem_bytes, st>>>(d_model, mw, tb, a, slots);
   return cudaGetLastError();
 }
 

@@ -25,6 +25,15 @@ struct MapArgs {
   double* qcache;        // workspace copy of the assembled configuration (nq fields, tile 32)
   long long cache_inst0;
 };
+struct DjtArgs {  // applyDJT: geometric stiffness (optional extension; the reference's applyDJT is a no-op)
+  long long n, tile;
+  const double *dq_joints, *dq_root;  // direction (like applyJ's inputs)
+  const double* in;                   // wrenches (n_out*6), like applyJT's input
+  double *out_joints, *out_root;      // accumulated: += kfac * dtau
+  double kfac;
+  double* qcache;
+  long long cache_inst0;
+};
 struct RowArgs {
   long long nrows;
   const int *row_ptr, *row_instance, *col;
@@ -57,6 +66,8 @@ cudaError_t launch_applyJT_plan(const DevModel& planned_host_model, const DevMod
 // `planned_host_model` planned with plan_jt_ring, `d_blob` built by build_jt_blob, nst = ring stages per warp
 cudaError_t launch_applyJT_ring(const DevModel& planned_host_model, const DevModel* d_blob, const MapArgs& a, int nst,
                                 LaunchCfg* cfg, int num_sms, cudaStream_t st);
+cudaError_t launch_applyDJT(const DevModel& m, const DevModel* d_model, const DevTables& tb, const DjtArgs& a,
+                            LaunchCfg* cfg2, cudaStream_t st);
 cudaError_t launch_applyJT_rows(const DevModel& m, const DevModel* d_model, const DevTables& tb, const RowArgs& a,
                                 int smem_doubles, LaunchCfg* cfg, cudaStream_t st);
 cudaError_t launch_applyJT_rows_cached(const DevModel& m, const DevModel* d_model, const DevTables& tb, const RowArgs& a,

@@ -1466,6 +1466,165 @@ RBD_HD void applyJT_instance(const DevModel& m, const DevTables& tb, const QC& q
   }
 }
 
+// applyDJT — the geometric stiffness of the mapping: d/de [ J(q (+) e dq)^T w ] at e = 0, i.e. how the generalized
+// forces of FIXED world-aligned wrenches w_k change when the configuration moves along dq.  The reference leaves it a
+// no-op (KinematicChainMapping.h:73-80: "geometric stiffness absent"); this is the
+// optional real thing (rbd_applyDJT_soa), evaluated matrix-free in one sweep:
+//   tau_i = A_i . F_i,   F_i = sum over the subtree of [f_k ; n_k + p_k x f_k]
+//   dA_i  = dV_parent(i) x A_i            (motion cross product; dV = body twists of applyJ for this dq)
+//   dF_i  = sum over the subtree of [0 ; dp_k x f_k],   dp_k = dV_lin + dV_ang x p_k of the body carrying output k
+//   dtau_i = dA_i . F_i + A_i . dF_i
+// and for a free-flyer ROOT (its velocity is given in the joint frame, so its columns move with its own pose):
+//   dtau_root = ff_rows(R, p, dF) + [ -w_b x tau_l ; -w_b x tau_a - v_b x tau_l ].
+// Stack: per depth level [A (12) | dA (6) | F (6) | dF (6)], per branch joint [R|p (12) | dV (6)], shared memory.
+// sink.put(c, value) receives kfac * dtau_c (accumulated by the caller's sink, like SOFA's parentForce +=).
+#define RBD_DJT_LEVEL 30
+#define RBD_DJT_BRANCH 18
+template <class QC, class DQ, class FLD, class Sink>
+RBD_HD void applyDJT_instance(const DevModel& m, const DevTables& tb, const QC& q, const DQ& dq, const FLD& in,
+                              const Sink& sink, const Stack& S, real kfac) {
+  const int nj = m.njoints;
+  const int bbase = RBD_DJT_LEVEL * m.max_depth;
+  real R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0}, dV[6] = {0, 0, 0, 0, 0, 0};
+  real q0n = 0.0, q1n = 0.0;
+  RBD_Q_PREFETCH(1);
+  for (int i = 1; i < nj; ++i) {
+    const DevJoint& jn = m.joint[i];
+    const int par = jn.parent;
+    if (par != i - 1) {
+      if (par == 0) {
+        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+        p[0] = p[1] = p[2] = 0;
+#pragma unroll
+        for (int e = 0; e < 6; ++e) dV[e] = 0;
+      } else {
+        const int b = bbase + m.joint[par].bidx * RBD_DJT_BRANCH;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) R[e] = S.ld(b + e);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) p[e] = S.ld(b + 9 + e);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) dV[e] = S.ld(b + 12 + e);
+      }
+    }
+    const int nxt_par = (i + 1 < nj) ? m.joint[i + 1].parent : 0;
+    real aw[3];
+    const real q0 = q0n, q1 = q1n;
+    RBD_Q_PREFETCH(i + 1);
+    fk_joint(jn, R, p, q0, q1, q, aw);
+    // rec = [A (12) | dA (6) | F (6) | dF (6)] of this joint
+    real rec[RBD_DJT_LEVEL];
+#pragma unroll
+    for (int e = 0; e < RBD_DJT_LEVEL; ++e) rec[e] = 0;
+    real vb[6] = {0, 0, 0, 0, 0, 0};  // free-flyer: its joint-frame velocity
+    if (jn.type != JT_FF) {
+      subspace_1dof(jn.type, p, aw, rec);
+      // dA = dV_parent x A
+      RBD_CROSS(rec[12], rec[13], rec[14], dV[3], dV[4], dV[5], rec[0], rec[1], rec[2]);
+      real tx, ty, tz;
+      RBD_CROSS(tx, ty, tz, dV[0], dV[1], dV[2], rec[3], rec[4], rec[5]);
+      rec[12] += tx; rec[13] += ty; rec[14] += tz;
+      RBD_CROSS(rec[15], rec[16], rec[17], dV[3], dV[4], dV[5], rec[3], rec[4], rec[5]);
+      const real d = dq.ld(jn.idx_v);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) dV[e] += rec[e] * d;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) rec[e] = R[e];
+#pragma unroll
+      for (int e = 0; e < 3; ++e) rec[9 + e] = p[e];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) vb[e] = dq.ld(jn.idx_v + e);
+      // world twist of the free-flyer body: oMi.act(v_b)
+      const real wx = R[0] * vb[3] + R[1] * vb[4] + R[2] * vb[5];
+      const real wy = R[3] * vb[3] + R[4] * vb[4] + R[5] * vb[5];
+      const real wz = R[6] * vb[3] + R[7] * vb[4] + R[8] * vb[5];
+      real tx, ty, tz;
+      RBD_CROSS(tx, ty, tz, p[0], p[1], p[2], wx, wy, wz);
+      dV[0] += R[0] * vb[0] + R[1] * vb[1] + R[2] * vb[2] + tx;
+      dV[1] += R[3] * vb[0] + R[4] * vb[1] + R[5] * vb[2] + ty;
+      dV[2] += R[6] * vb[0] + R[7] * vb[1] + R[8] * vb[2] + tz;
+      dV[3] += wx; dV[4] += wy; dV[5] += wz;
+      // the joint-frame velocity is needed again when the root is projected: keep it in the dA slot
+#pragma unroll
+      for (int e = 0; e < 6; ++e) rec[12 + e] = vb[e];
+    }
+    // wrenches of this joint's outputs and their first-order change
+    real* const F = rec + 18;
+    real* const dF = rec + 24;
+    for (int o = jn.out_begin; o < jn.out_end; ++o) {
+      const int k = tb.sorted_k[o];
+      const real* pl = tb.sorted_pl + 12 * o;
+      real w[6];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) w[e] = in.ld(6 * k + e);
+      const real px = R[0] * pl[9] + R[1] * pl[10] + R[2] * pl[11] + p[0];
+      const real py = R[3] * pl[9] + R[4] * pl[10] + R[5] * pl[11] + p[1];
+      const real pz = R[6] * pl[9] + R[7] * pl[10] + R[8] * pl[11] + p[2];
+      real tx, ty, tz;
+      RBD_CROSS(tx, ty, tz, px, py, pz, w[0], w[1], w[2]);
+      F[0] += w[0]; F[1] += w[1]; F[2] += w[2];
+      F[3] += w[3] + tx; F[4] += w[4] + ty; F[5] += w[5] + tz;
+      // dp = dV_lin + dV_ang x p_k
+      real dx, dy, dz;
+      RBD_CROSS(dx, dy, dz, dV[3], dV[4], dV[5], px, py, pz);
+      dx += dV[0]; dy += dV[1]; dz += dV[2];
+      RBD_CROSS(tx, ty, tz, dx, dy, dz, w[0], w[1], w[2]);
+      dF[3] += tx; dF[4] += ty; dF[5] += tz;
+    }
+    if (nxt_par == i) {
+      const int s = RBD_DJT_LEVEL * (jn.depth - 1);
+      s_stv<RBD_DJT_LEVEL>(S, s, rec);
+      if (jn.nchild >= 2) {
+        const int b = bbase + jn.bidx * RBD_DJT_BRANCH;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) S.st(b + e, R[e]);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) S.st(b + 9 + e, p[e]);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) S.st(b + 12 + e, dV[e]);
+      }
+    } else {
+      int k = i;
+      while (true) {
+        const DevJoint& jk = m.joint[k];
+        if (jk.type != JT_FF) {
+          sink.put(jk.idx_v, kfac * (dot6(rec + 12, F) + dot6(rec, dF)));
+        } else {
+          // free-flyer root: tau = ff_rows(R, p, F); dtau = ff_rows(R, p, dF) + [-w x tau_l ; -w x tau_a - v x tau_l]
+          real t6[6], d6[6];
+          ff_rows(rec, rec + 9, F, t6);
+          ff_rows(rec, rec + 9, dF, d6);
+          const real* v_b = rec + 12;
+          real ax, ay, az, bx, by, bz, cx, cy, cz;
+          RBD_CROSS(ax, ay, az, v_b[3], v_b[4], v_b[5], t6[0], t6[1], t6[2]);
+          RBD_CROSS(bx, by, bz, v_b[3], v_b[4], v_b[5], t6[3], t6[4], t6[5]);
+          RBD_CROSS(cx, cy, cz, v_b[0], v_b[1], v_b[2], t6[0], t6[1], t6[2]);
+          sink.put(jk.idx_v + 0, kfac * (d6[0] - ax)); sink.put(jk.idx_v + 1, kfac * (d6[1] - ay));
+          sink.put(jk.idx_v + 2, kfac * (d6[2] - az));
+          sink.put(jk.idx_v + 3, kfac * (d6[3] - bx - cx)); sink.put(jk.idx_v + 4, kfac * (d6[4] - by - cy));
+          sink.put(jk.idx_v + 5, kfac * (d6[5] - bz - cz));
+        }
+        const int pk = jk.parent;
+        if (pk == 0) break;
+        const int sp = RBD_DJT_LEVEL * (m.joint[pk].depth - 1);
+        if (pk == nxt_par) {
+#pragma unroll
+          for (int e = 0; e < 12; ++e) S.add(sp + 18 + e, rec[18 + e]);
+          break;
+        }
+        real Fs[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) Fs[e] = rec[18 + e];
+        s_ldv<RBD_DJT_LEVEL>(S, sp, rec);
+#pragma unroll
+        for (int e = 0; e < 12; ++e) rec[18 + e] += Fs[e];
+        k = pk;
+      }
+    }
+  }
+}
+
 #ifndef RBD_JT_DIST
 #define RBD_JT_DIST 1 /* joints of lookahead of the wrench prefetch (1 or 2) */
 #endif

@@ -350,6 +350,26 @@ extern "C" int emul_frame_jacobians(const rbd_model_desc* d, long long n, double
   return 0;
 }
 
+// applyDJT (geometric stiffness, optional extension): out += kfac * d/de [J(q (+) e dq)^T in]
+extern "C" int emul_applyDJT(const rbd_model_desc* d, long long n, long long tile, double* qcache, long long cache_tile,
+                             double* dq_joints, double* dq_root, double* in, double kfac, double* out_tau, double* out_root) {
+  Ctx c;
+  int rc = make_ctx(d, &c);
+  if (rc) return rc;
+  const int sd = RBD_DJT_LEVEL * c.m.max_depth + RBD_DJT_BRANCH * c.m.nbranch;
+  std::vector<double> smem((size_t)(sd > 0 ? sd : 1) * 32, 1e300);
+  const int off = (c.m.has_ff_root && dq_root) ? 6 : 0;
+  const int ooff = (c.m.has_ff_root && out_root) ? 6 : 0;
+  for (long long i = 0; i < n; ++i) {
+    SplitQ dq{make_field(dq_root, i, 6, tile), make_field(dq_joints, i, c.m.nv - off, tile), off};
+    SplitRedSinkT<Field> sink{make_field(out_root, i, 6, tile), make_field(out_tau, i, c.m.nv - ooff, tile), ooff};
+    Stack S = make_stack(smem.data(), (int)(i % 32), sd);
+    applyDJT_instance(c.m, c.tb, make_field(qcache, i, c.m.nq, cache_tile), dq, make_field(in, i, 6 * c.m.n_out, tile), sink, S,
+                      kfac);
+  }
+  return 0;
+}
+
 // plan of the applyJT ring kernel for this model: out = {ring stages (0 = register path), forward projection?,
 // warps per block, tensor-memory doubles, shared-memory doubles, shared-memory bytes of the block}
 extern "C" int emul_jt_ring_plan(const rbd_model_desc* d, int use_tmem, int fwd_mode, int* out /*[6]*/) {

@@ -67,6 +67,7 @@ def load_emul() -> C.CDLL:
     lib.emul_jt_ring_plan.argtypes = [vp, i, i, vp]
     lib.emul_applyJT_rows_cached.argtypes = [vp, ll, vp, ll, ll, vp, vp, vp, vp, vp, vp]
     lib.emul_frame_jacobians.argtypes = [vp, ll, vp, ll, ll, vp, vp, vp]
+    lib.emul_applyDJT.argtypes = [vp, ll, ll, vp, ll, vp, vp, vp, C.c_double, vp, vp]
     lib.emul_applyJT_rows.argtypes = [vp, ll, i, vp, ll, vp, vp, vp, vp, vp, vp]
     return lib
 
@@ -86,3 +87,34 @@ def all_models():
             with open(p) as f:
                 ms.append(mdl.ModelDescriptor.from_json(f.read()))
     return ms
+
+
+def integrate(d, q: np.ndarray, dq: np.ndarray, eps: float) -> np.ndarray:
+    """q (+) eps * dq with pinocchio's conventions ([n, nq], [n, nv]): free-flyer p += R (eps v_b), quat <- quat * exp(eps w_b)
+    (joint-frame velocity); unbounded revolute joints rotate their (cos, sin) pair; the rest is q += eps dq."""
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    out = q.copy()
+    for i in range(1, d.njoints):
+        t, iq, iv = int(d.jtype[i]), int(d.idx_q[i]), int(d.idx_v[i])
+        if t == mdl.J_FF:
+            x, y, z, w = (q[:, iq + 3 + k] for k in range(4))
+            R = np.stack([np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], -1),
+                          np.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], -1),
+                          np.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1)], -2)
+            out[:, iq:iq + 3] = q[:, iq:iq + 3] + eps * np.einsum("nij,nj->ni", R, dq[:, iv:iv + 3])
+            th = eps * dq[:, iv + 3:iv + 6]
+            ang = np.linalg.norm(th, axis=1)
+            s = np.where(ang > 1e-300, np.sin(ang / 2) / np.where(ang > 1e-300, ang, 1.0), 0.5)
+            dx, dy, dz, dw = s * th[:, 0], s * th[:, 1], s * th[:, 2], np.cos(ang / 2)
+            out[:, iq + 3] = w * dx + x * dw + y * dz - z * dy
+            out[:, iq + 4] = w * dy - x * dz + y * dw + z * dx
+            out[:, iq + 5] = w * dz + x * dy - y * dx + z * dw
+            out[:, iq + 6] = w * dw - x * dx - y * dy - z * dz
+        elif mdl.J_RUBX <= t <= mdl.J_RUBU:
+            c, s_ = q[:, iq], q[:, iq + 1]
+            a = eps * dq[:, iv]
+            out[:, iq] = c * np.cos(a) - s_ * np.sin(a)
+            out[:, iq + 1] = s_ * np.cos(a) + c * np.sin(a)
+        else:
+            out[:, iq] = q[:, iq] + eps * dq[:, iv]
+    return out

@@ -304,3 +304,40 @@ def test_applyJT_ring_planner_choices(emul):
     assert chain["stages"] == 0 or (chain["fwd"] == 0 and chain["tmem"] <= 128)
     for p in (solo, panda, talos, t8):
         assert p["bytes"] <= 227 * 1024 and 2 * p["tmem"] * ((p["warps"] + 3) // 4) <= 512
+
+
+@pytest.mark.parametrize("d", MODELS, ids=IDS)
+def test_applyDJT_bodies_match_finite_differences(emul, d):
+    """applyDJT (geometric stiffness, optional extension — the reference's applyDJT is a no-op): the analytic one-sweep
+    derivative equals the central finite difference of applyJT along dq, (J(q+e dq)^T w - J(q-e dq)^T w) / 2e."""
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    if any(int(d.jtype[i]) == mdl.J_FF and int(d.parents[i]) != 0 for i in range(1, d.njoints)):
+        pytest.skip("free-flyer below the root: not supported by applyDJT")
+    n, tile, block, ctile = 12, 4, 32, 4
+    q, v, _ = mdl.random_state(d, n, seed=13)
+    cd, keep = _cdesc(d)
+    rng = np.random.default_rng(14)
+    w = rng.uniform(-1, 1, (n, 6 * d.n_out))
+    T = lambda x: None if x is None else to_tiled(x, tile)
+    ff = bool(d.has_freeflyer_root)
+
+    def jt(qx):
+        qj, root, _, _ = _split(d, qx, v)
+        qcache = np.full(((n + ctile - 1) // ctile, d.nq, ctile), np.nan)
+        pos = np.full(((n + tile - 1) // tile, 7 * d.n_out, tile), np.nan)
+        assert emul.emul_apply(C.addressof(cd), n, tile, block, P(T(qj)), P(T(root)), P(qcache), ctile, P(pos)) == 0
+        tau = T(np.zeros((n, d.nv_joints))); rt = T(np.zeros((n, 6))) if ff else None
+        assert emul.emul_applyJT(C.addressof(cd), n, tile, block, P(qcache), ctile, P(T(w)), P(tau), P(rt)) == 0
+        tj = from_tiled(tau, n)
+        return (np.concatenate([from_tiled(rt, n), tj], axis=1) if ff else tj), qcache
+
+    eps = 1e-6
+    fd = (jt(helpers.integrate(d, q, v, eps))[0] - jt(helpers.integrate(d, q, v, -eps))[0]) / (2 * eps)
+    _, qcache = jt(q)
+    _, _, dq, rootv = _split(d, q, v)
+    out = T(np.ones((n, d.nv_joints))); ort = T(np.ones((n, 6))) if ff else None      # accumulates onto ones
+    assert emul.emul_applyDJT(C.addressof(cd), n, tile, P(qcache), ctile, P(T(dq)), P(T(rootv)), P(T(w)), 0.5, P(out), P(ort)) == 0
+    got = from_tiled(out, n)
+    if ff:
+        got = np.concatenate([from_tiled(ort, n), got], axis=1)
+    assert rel_err(got, 1.0 + 0.5 * fd) <= 1e-6

@@ -659,3 +659,48 @@ def test_frame_jacobians_from_cache(torch_mod, api, name):
         assert rel_err(J[t], orc.frame_jacobian_lwa(int(d.out_frames[k]))) <= TOL_FP64
         full_dq = dq[i] if rootv is None else np.concatenate([rootv[i], dq[i]])
         assert rel_err(J[t] @ full_dq, vel[i, k]) <= TOL_FP64
+
+
+@pytest.mark.parametrize("name,tile", [("talos_reduced", 32), ("solo12", 50), ("random_3", 32), ("panda7", 32)])
+def test_applyDJT_geometric_stiffness(torch_mod, api, name, tile):
+    """rbd_applyDJT_soa / _host (optional extension; the reference's applyDJT is a no-op and the mirror keeps it one):
+    equals the central finite difference of applyJT along dq, accumulates with kfactor, host == device."""
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    torch = torch_mod
+    d = [m for m in MODELS if m.name == name][0]
+    n = 70
+    q, v, _ = mdl.random_state(d, n, seed=101)
+    rng = np.random.default_rng(102)
+    w = rng.uniform(-1, 1, (n, 6 * d.n_out))
+    ff = bool(d.has_freeflyer_root)
+    m = api.Model(d); ws = api.Workspace(m, n)
+    T = lambda x: None if x is None else _dev(torch, to_tiled(x, tile))
+    nt = (n + tile - 1) // tile
+    pos = torch.zeros((nt, 7 * d.n_out, tile), dtype=torch.float64, device="cuda")
+
+    def jt(qx):
+        qj, root, _, _ = _split(d, qx, v)
+        ws.apply_soa(n, tile, T(qj), T(root), pos)
+        tau = torch.zeros((nt, d.nv_joints, tile), dtype=torch.float64, device="cuda")
+        rt = torch.zeros((nt, 6, tile), dtype=torch.float64, device="cuda") if ff else None
+        ws.applyJT_soa(n, tile, T(w), tau, rt)
+        ws.synchronize()
+        tj = from_tiled(tau.cpu().numpy(), n)
+        return np.concatenate([from_tiled(rt.cpu().numpy(), n), tj], axis=1) if ff else tj
+
+    eps = 1e-6
+    fd = (jt(helpers.integrate(d, q, v, eps)) - jt(helpers.integrate(d, q, v, -eps))) / (2 * eps)
+    jt(q)                                                     # the cached configuration is q again
+    _, _, dq, rootv = _split(d, q, v)
+    out = T(np.ones((n, d.nv_joints))); ort = T(np.ones((n, 6))) if ff else None
+    ws.applyDJT_soa(n, tile, T(dq), T(rootv), T(w), -2.0, out, ort)
+    ws.synchronize()
+    got = from_tiled(out.cpu().numpy(), n)
+    if ff:
+        got = np.concatenate([from_tiled(ort.cpu().numpy(), n), got], axis=1)
+    assert rel_err(got, 1.0 - 2.0 * fd) <= 1e-6
+    # host entry point (instance-major, accumulated in place) gives the same numbers
+    h_out = np.ones((n, d.nv_joints)); h_rt = np.ones((n, 6)) if ff else None
+    ws.applyDJT_host(n, dq, rootv, w, -2.0, h_out, h_rt)
+    h = np.concatenate([h_rt, h_out], axis=1) if ff else h_out
+    assert rel_err(h, got) <= 1e-13
