@@ -358,7 +358,32 @@ def test_no_out_of_bounds_writes(torch_mod, api, name, n, tile):
     ws.apply_soa(n, tile, views["qj"], views["root"] if ff else None, views["pos"])
     ws.applyJ_soa(n, tile, views["dq"], views["rootv"] if ff else None, views["vel"])
     ws.applyJT_soa(n, tile, views["w"], views["tj"], views["tr"] if ff else None)
+    # ... and the later entry points on the same arena: Mass / ForceField products, geometric stiffness, constraint rows
+    # and dense frame Jacobians (their row-major outputs get their own guarded arena)
+    ws.addMDx_soa(n, tile, views["q"], views["a"], 0.5, views["tau"])
+    ws.addForce_soa(n, tile, views["q"], views["v"], views["tau"])
+    ws.addForce_soa(n, tile, views["q"], None, views["tau"])
+    mdl_ok = not any(int(d.jtype[i]) == mdl.J_FF and int(d.parents[i]) != 0 for i in range(1, d.njoints))
+    if mdl_ok:
+        ws.applyDJT_soa(n, tile, views["dq"], views["rootv"] if ff else None, views["w"], 1.0, views["tj"],
+                        views["tr"] if ff else None)
+    nrows = n + 3
+    rp = torch.arange(0, 2 * nrows + 1, 2, dtype=torch.int32, device="cuda")
+    ri = (torch.arange(0, nrows, dtype=torch.int32, device="cuda") % n).contiguous()
+    col = torch.randint(0, int(I.n_out), (2 * nrows,), dtype=torch.int32, device="cuda")
+    val = torch.rand((2 * nrows, 6), dtype=torch.float64, device="cuda")
+    arena2 = torch.full((2 * G + nrows * I.nv + G + nrows * 6 * I.nv,), SENT, dtype=torch.float64, device="cuda")
+    rows = arena2[G:G + nrows * I.nv].view(nrows, I.nv)
+    Jd = arena2[2 * G + nrows * I.nv:2 * G + nrows * I.nv + nrows * 6 * I.nv].view(nrows, I.nv, 6)
+    keepf = torch.zeros((nrows,), dtype=torch.int32, device="cuda")
+    for cached in (True, False):
+        ws.set_rows_cache(cached)
+        ws.applyJT_rows_dev(nrows, rp, ri, col, val, rows, keepf)
+    ws.frame_jacobians_dev(nrows, ri, col[:nrows].contiguous(), Jd)
     ws.synchronize()
+    for lo, hi in ((0, G), (G + nrows * I.nv, 2 * G + nrows * I.nv)):
+        assert bool((arena2[lo:hi] == SENT).all()), "guard band of the row / Jacobian arena was written"
+    assert not bool((rows == SENT).any()) and not bool((Jd == SENT).any())
     off = 0
     for k, K in [("", 0)] + list(sizes.items()):
         off += nt * K * tile
