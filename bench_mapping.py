@@ -63,6 +63,7 @@ def main():
              "applyJ": lambda: ws.applyJ_soa(n, tile, dq, rootv, vel),
              "applyJT": lambda: ws.applyJT_soa(n, tile, w, tau, rt),
              "applyJT_rows": lambda: ws.applyJT_rows_dev(nrows, row_ptr, row_inst, col, val, rows, keep),
+             "applyDJT": lambda: ws.applyDJT_soa(n, tile, dq, rootv, w, 1.0, tau, rt),
              "addMDx": lambda: ws.addMDx_soa(n, tile, q, dx, 1.0, res),
              "addForce": lambda: ws.addForce_soa(n, tile, q, v, res),
              "addForce_gravity": lambda: ws.addForce_soa(n, tile, q, None, res),
@@ -73,6 +74,7 @@ def main():
          "applyJ": 8 * (I.nq + I.nv + 6 * I.n_out),
          "applyJT": 8 * (I.nq + 6 * I.n_out + 2 * I.nv),
          "applyJT_rows": 2 * (8 * I.nq + 2 * (4 + 48) + 8 * I.nv + 4 + 8),   # per instance: 2 rows x (q, 2 nnz, row, keep, ptr)
+         "applyDJT": 8 * (I.nq + I.nv + 6 * I.n_out + 2 * I.nv),
          "addMDx": 8 * (I.nq + I.nv + 2 * I.nv),
          "addForce": 8 * (I.nq + I.nv + 2 * I.nv),
          "addForce_gravity": 8 * (I.nq + 2 * I.nv),
