@@ -64,9 +64,10 @@ struct rbd_workspace {
   DevTables tb{};
   // fused eval: one planned copy of the joint table per variant (bit 1 = CRBA, bit 0 = RNEA), host + device;
   // the kernel stages the device copy into shared memory
-  DevModel* h_plan[10] = {};  // index: bit 2 = oMi requested, bit 1 = CRBA, bit 0 = RNEA; [8] = the applyJT sweep,
+  DevModel* h_plan[11] = {};  // index: bit 2 = oMi requested, bit 1 = CRBA, bit 0 = RNEA; [8] = the applyJT sweep,
                               // [9] = its ring variant (full tiles of 32)
-  DevModel* d_plan[10] = {};
+  DevModel* d_plan[11] = {};  // [10] = applyDJT on the ring kernel
+  int djt_ring_slots = -1;    // ... of plan [10]
   int jt_ring_slots = -1;     // ring stages per warp of plan [9]; 0 = the ring kernel cannot run this model; -1 = not planned yet
   int use_jt_ring = 1;
   DevModelT<float>* h_plan32[8] = {};  // FP32 mode of the fused eval
@@ -82,7 +83,7 @@ struct rbd_workspace {
   long long apply_epoch = 0, jc_epoch = -1;
   int use_rows_cache = 1;
   long long applied_n = 0;   // instances covered by the cache (0 = apply not called yet)
-  LaunchCfg cfg_eval[8], cfg_apply[2], cfg_applyJ[2], cfg_applyJT[2], cfg_rows, cfg_jt_ring, cfg_djt[2];
+  LaunchCfg cfg_eval[8], cfg_apply[2], cfg_applyJ[2], cfg_applyJT[2], cfg_rows, cfg_jt_ring, cfg_djt[2], cfg_djt_ring;
   DevModel* d_model = nullptr;  // device copy of the joint table for the mapping kernels
   int forced_eval_block = 0;
   long long launches = 0;
@@ -176,7 +177,7 @@ static void ws_free(rbd_workspace* ws) {
   if (!ws) return;
   cudaFree(ws->d_sorted_k); cudaFree(ws->d_outk_parent); cudaFree(ws->d_sorted_ident); cudaFree(ws->d_sorted_pl); cudaFree(ws->d_outk_pl);
   cudaFree(ws->qcache); cudaFree(ws->rows_buf); cudaFree(ws->d_model); cudaFree(ws->jcache); cudaFree(ws->omicache); cudaFree(ws->jc_scratch);
-  for (int k = 0; k < 10; ++k) { cudaFree(ws->d_plan[k]); delete ws->h_plan[k]; }
+  for (int k = 0; k < 11; ++k) { cudaFree(ws->d_plan[k]); delete ws->h_plan[k]; }
   for (int k = 0; k < 8; ++k) { cudaFree(ws->d_plan32[k]); delete ws->h_plan32[k]; }
   for (int s = 0; s < kSlots; ++s) {
     cudaFree(ws->slot[s].aos); cudaFree(ws->slot[s].soa);
@@ -287,6 +288,7 @@ static int check_batch(const rbd_workspace* ws, int64_t n, int64_t tile) {
 static int ensure_plan(rbd_workspace* ws, int pk) {
   if (ws->h_plan[pk]) return RBD_OK;
   if (pk == 9 && ws->jt_ring_slots == 0) return RBD_OK;
+  if (pk == 10 && ws->djt_ring_slots == 0) return RBD_OK;
   DevModel* h = new (std::nothrow) DevModel(ws->model->dm);
   if (!h) return set_err(RBD_ERR_ALLOC, "out of host memory");
   bool planned;
@@ -294,6 +296,10 @@ static int ensure_plan(rbd_workspace* ws, int pk) {
   if (pk == 9) {
     ws->jt_ring_slots = plan_jt_ring(h, ws->model->ht, ws->use_tmem != 0, &jt_prog);
     if (ws->jt_ring_slots == 0) { delete h; return RBD_OK; }  // not an error: the caller keeps the register path
+    planned = true;
+  } else if (pk == 10) {
+    ws->djt_ring_slots = plan_djt_ring(h, ws->model->ht, ws->use_tmem != 0, &jt_prog);
+    if (ws->djt_ring_slots == 0) { delete h; return RBD_OK; }
     planned = true;
   } else {
     planned = pk == 8 ? plan_eval(h, false, true, ws->use_tmem != 0, 0, false, /*jt=*/true, RBD_JT_REGS)
@@ -305,7 +311,7 @@ static int ensure_plan(rbd_workspace* ws, int pk) {
     return set_err(RBD_ERR_UNSUPPORTED, "the sweep state of this model does not fit one SM's shared + tensor memory"
                                         " at the requested block size");
   }
-  const std::vector<unsigned long long> blob = pk == 9 ? build_jt_blob(h, jt_prog) : build_eval_blob(h);
+  const std::vector<unsigned long long> blob = (pk == 9 || pk == 10) ? build_jt_blob(h, jt_prog) : build_eval_blob(h);
   if (!ws->d_plan[pk]) {
     // sized for the largest blob any plan of this model can produce (the ColProg length is plan-independent)
     cudaError_t e = cudaMalloc(&ws->d_plan[pk], blob.size() * 8);
@@ -320,8 +326,8 @@ static int ensure_plan(rbd_workspace* ws, int pk) {
 static void drop_plans(rbd_workspace* ws) {
   // kernels still in flight keep reading the device copies: wait for them before the next upload overwrites
   cudaDeviceSynchronize();
-  for (int k = 0; k < 10; ++k) { delete ws->h_plan[k]; ws->h_plan[k] = nullptr; }
-  ws->jt_ring_slots = -1;
+  for (int k = 0; k < 11; ++k) { delete ws->h_plan[k]; ws->h_plan[k] = nullptr; }
+  ws->jt_ring_slots = -1; ws->djt_ring_slots = -1;
   for (int k = 0; k < 8; ++k) { delete ws->h_plan32[k]; ws->h_plan32[k] = nullptr; }
 }
 
@@ -539,8 +545,28 @@ static int applyDJT_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t ti
   if (dm.njoints > 1 && dm.joint[1].type == JT_FF && dm.joint[1].parent != 0)
     return set_err(RBD_ERR_UNSUPPORTED, "applyDJT supports a free-flyer only as the root joint");
   DjtArgs A{n, tile, dq, rootv, in, out_tau, out_root, kfac, ws->qcache, inst0};
+  // full tiles of a tile-32 batch: the ring kernel (wrench stream staged by the copy engine, forward projection); a
+  // partial last tile, other tilings and trees too deep for the tensor-memory plan: the shared-memory kernel
+  if (tile == 32 && n >= 32 && ws->use_jt_ring && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    int rc = ensure_plan(ws, 10);
+    if (rc) return rc;
+    if (ws->djt_ring_slots > 0) {
+      const long long nfull = n / 32 * 32;
+      MapArgs F{nfull, tile, out_tau, out_root, in, nullptr, ws->qcache, inst0};
+      F.dq_joints = dq; F.dq_root = rootv; F.kfac = kfac;
+      CK(launch_applyJT_ring(*ws->h_plan[10], ws->d_plan[10], F, ws->djt_ring_slots, &ws->cfg_djt_ring, ws->num_sms, st));
+      ws->launches++;
+      if (nfull == n) return RBD_OK;
+      const long long kj = dm.nv - (out_root ? 6 : 0);
+      A.n = n - nfull;
+      A.in = in + nfull * 6 * (long long)dm.n_out;
+      A.dq_joints = dq + nfull * kj; A.dq_root = rootv ? rootv + nfull * 6 : nullptr;
+      A.out_joints = out_tau + nfull * kj; A.out_root = out_root ? out_root + nfull * 6 : nullptr;
+      A.cache_inst0 = inst0 + nfull;
+    }
+  }
   CK(launch_applyDJT(dm, ws->d_model, ws->tb, A, ws->cfg_djt, st));
-  if (n > 0) ws->launches++;
+  if (A.n > 0) ws->launches++;
   return RBD_OK;
 }
 RBD_API int rbd_applyDJT_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* dq_joints, const double* root_vel,

@@ -338,8 +338,8 @@ struct WarpRing {
 };
 
 // W: warps per block (JtRing::kWarps, or kWarpsSmall = 12 when the state leaves room: <= 170 registers);
-// FWD: forward-projection sweep (applyJT_instance_fwd) instead of the depth-stack sweep
-template <int W, bool FWD>
+// MODE: 0 = depth-stack sweep, 1 = forward-projection sweep (applyJT_instance_fwd), 2 = applyDJT (applyDJT_instance_fwd)
+template <int W, int MODE>
 __global__ void __launch_bounds__(W * 32, 1) applyJT_ring_kernel(const DevModel* __restrict__ gm, const int model_words,
                                                                  const MapArgs a, const int nst) {
   unsigned* const tm_base_p = reinterpret_cast<unsigned*>(rbd_smem + model_words - 2);
@@ -398,7 +398,13 @@ __global__ void __launch_bounds__(W * 32, 1) applyJT_ring_kernel(const DevModel*
       const long long inst = t * 32 + lane;
       SplitRedSinkT<FieldT<32>> sink{make_field_t<32>(const_cast<double*>(a.root), inst, 6, 32),
                                      make_field_t<32>(const_cast<double*>(a.joints), inst, m.nv - off, 32), off};
-      if constexpr (FWD)
+      if constexpr (MODE == 2) {
+        const int doff = a.dq_root ? 6 : 0;
+        SplitQT<FieldT<32>> dq{make_field_t<32>(const_cast<double*>(a.dq_root), inst, 6, 32),
+                               make_field_t<32>(const_cast<double*>(a.dq_joints), inst, m.nv - doff, 32), doff};
+        applyDJT_instance_fwd(m, opl, prog.anc(), make_field_t<32>(a.qcache, a.cache_inst0 + inst, m.nq, 32), dq, ring, sink,
+                              S, T, a.kfac);
+      } else if constexpr (MODE == 1)
         applyJT_instance_fwd(m, opl, prog.anc(), make_field_t<32>(a.qcache, a.cache_inst0 + inst, m.nq, 32), ring, sink, S, T);
       else
         applyJT_instance_ring(m, opl, make_field_t<32>(a.qcache, a.cache_inst0 + inst, m.nq, 32), ring, sink, S, T);
@@ -706,13 +712,15 @@ cudaError_t launch_applyJT_ring(const DevModel& hm, const DevModel* d_blob, cons
   const int model_words = (int)(eval_model_bytes(hm) / 8);
   const int W = hm.plan.warps;
   const int block = W * 32;
-  const int variant = hm.plan.jt_fwd ? 2 : (W == JtRing::kWarpsSmall ? 1 : 0);
+  // 0: stack / 8 warps, 1: stack / 12, 2: forward / 12, 3: applyDJT / 8
+  const int variant = hm.plan.jt_fwd == 2 ? 3 : hm.plan.jt_fwd == 1 ? 2 : (W == JtRing::kWarpsSmall ? 1 : 0);
   const size_t smem = ((size_t)model_words + (size_t)W * JtRing::kMaxStages) * 8 + (size_t)block * hm.plan.smem_doubles * 8 +
                       (size_t)W * nst * JtRing::kStageBytes;
   if (cfg->block != block || cfg->smem_bytes != smem) {
-    cudaError_t e = variant == 2 ? jt_ring_attr(applyJT_ring_kernel<JtRing::kWarpsSmall, true>)
-                  : variant == 1 ? jt_ring_attr(applyJT_ring_kernel<JtRing::kWarpsSmall, false>)
-                                 : jt_ring_attr(applyJT_ring_kernel<JtRing::kWarps, false>);
+    cudaError_t e = variant == 3 ? jt_ring_attr(applyJT_ring_kernel<JtRing::kWarps, 2>)
+                  : variant == 2 ? jt_ring_attr(applyJT_ring_kernel<JtRing::kWarpsSmall, 1>)
+                  : variant == 1 ? jt_ring_attr(applyJT_ring_kernel<JtRing::kWarpsSmall, 0>)
+                                 : jt_ring_attr(applyJT_ring_kernel<JtRing::kWarps, 0>);
     if (e != cudaSuccess) return e;
     cfg->block = block; cfg->smem_bytes = smem; cfg->blocks_per_sm = 1;
   }
@@ -720,9 +728,10 @@ cudaError_t launch_applyJT_ring(const DevModel& hm, const DevModel* d_blob, cons
   const long long ntiles = a.n / 32;
   unsigned grid = (unsigned)((ntiles + W - 1) / W);
   if (grid > (unsigned)num_sms) grid = (unsigned)num_sms;
-  if (variant == 2) applyJT_ring_kernel<JtRing::kWarpsSmall, true><<<grid, block, smem, st>>>(d_blob, model_words, a, nst);
-  else if (variant == 1) applyJT_ring_kernel<JtRing::kWarpsSmall, false><<<grid, block, smem, st>>>(d_blob, model_words, a, nst);
-  else applyJT_ring_kernel<JtRing::kWarps, false><<<grid, block, smem, st>>>(d_blob, model_words, a, nst);
+  if (variant == 3) applyJT_ring_kernel<JtRing::kWarps, 2><<<grid, block, smem, st>>>(d_blob, model_words, a, nst);
+  else if (variant == 2) applyJT_ring_kernel<JtRing::kWarpsSmall, 1><<<grid, block, smem, st>>>(d_blob, model_words, a, nst);
+  else if (variant == 1) applyJT_ring_kernel<JtRing::kWarpsSmall, 0><<<grid, block, smem, st>>>(d_blob, model_words, a, nst);
+  else applyJT_ring_kernel<JtRing::kWarps, 0><<<grid, block, smem, st>>>(d_blob, model_words, a, nst);
   return cudaGetLastError();
 }
 

@@ -24,6 +24,10 @@ struct MapArgs {
   double* out;           // apply: n_out*7 | applyJ: n_out*6
   double* qcache;        // workspace copy of the assembled configuration (nq fields, tile 32)
   long long cache_inst0;
+  // applyDJT on the ring kernel only: direction (as applyJ's inputs) and factor; joints / root are the accumulated outputs
+  const double* dq_joints = nullptr;
+  const double* dq_root = nullptr;
+  double kfac = 1.0;
 };
 struct DjtArgs {  // applyDJT: geometric stiffness (optional extension; the reference's applyDJT is a no-op)
   long long n, tile;

@@ -343,7 +343,7 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
 // record) and m->prog_len / prog_words_off for the ring program `prog` (layout: rbd_sweeps_body.h, JtProg), which takes
 // the place of the ColProg table in the staged blob.  Returns the number of ring stages per warp, 0 when the kernel
 // cannot run this model (tensor memory off or too small for the tree's depth: the caller keeps the register path).
-inline int plan_jt_ring_w(DevModel* m, const HostTables& tb, bool use_tmem, std::vector<int>* prog, int W, bool fwd);
+inline int plan_jt_ring_w(DevModel* m, const HostTables& tb, bool use_tmem, std::vector<int>* prog, int W, int fwd);
 static constexpr int kJtMaxDepth = 12;  // == RBD_JT_MAXD (rbd_sweeps_body.h)
 // fwd_mode: 0 = never the forward projection, 1 = automatic (order below), 2 = forward projection first (tests)
 inline int plan_jt_ring(DevModel* m, const HostTables& tb, bool use_tmem, std::vector<int>* prog, int fwd_mode = 1) {
@@ -352,13 +352,20 @@ inline int plan_jt_ring(DevModel* m, const HostTables& tb, bool use_tmem, std::v
   // order: stack sweep with 12 warps (small robots: fewest instructions AND three warps per scheduler), forward
   // projection with 12 warps (shallow trees whose stack state needs the 8-warp share: Talos), stack sweep with 8
   const DevModel keep = *m;
-  int nst = fwd_mode == 2 ? plan_jt_ring_w(m, tb, use_tmem, prog, JtRing::kWarpsSmall, true) : 0;
-  if (nst == 0) { *m = keep; nst = plan_jt_ring_w(m, tb, use_tmem, prog, JtRing::kWarpsSmall, false); }
-  if (nst == 0 && fwd_mode == 1) { *m = keep; nst = plan_jt_ring_w(m, tb, use_tmem, prog, JtRing::kWarpsSmall, true); }
-  if (nst == 0) { *m = keep; nst = plan_jt_ring_w(m, tb, use_tmem, prog, JtRing::kWarps, false); }
+  int nst = fwd_mode == 2 ? plan_jt_ring_w(m, tb, use_tmem, prog, JtRing::kWarpsSmall, 1) : 0;
+  if (nst == 0) { *m = keep; nst = plan_jt_ring_w(m, tb, use_tmem, prog, JtRing::kWarpsSmall, 0); }
+  if (nst == 0 && fwd_mode == 1) { *m = keep; nst = plan_jt_ring_w(m, tb, use_tmem, prog, JtRing::kWarpsSmall, 1); }
+  if (nst == 0) { *m = keep; nst = plan_jt_ring_w(m, tb, use_tmem, prog, JtRing::kWarps, 0); }
   return nst;
 }
-inline int plan_jt_ring_w(DevModel* m, const HostTables& tb, bool use_tmem, std::vector<int>* prog, int W, bool fwd) {
+// applyDJT on the ring kernel: 8 warps (the sweep carries dV, dA, dF on top of applyJT's state: 226 registers, a
+// 12-warp build spills); 0 = the shared-memory kernel keeps the job
+inline int plan_djt_ring(DevModel* m, const HostTables& tb, bool use_tmem, std::vector<int>* prog) {
+  return plan_jt_ring_w(m, tb, use_tmem, prog, JtRing::kWarps, 2);
+}
+// fwd: 0 = depth-stack sweep, 1 = forward projection (applyJT), 2 = forward projection of applyDJT (level records
+// [A | dA] in tensor memory, branch records [R|p | dV] and the free-flyer root's [R|p | v_b] in shared memory)
+inline int plan_jt_ring_w(DevModel* m, const HostTables& tb, bool use_tmem, std::vector<int>* prog, int W, int fwd) {
   const int nj = m->njoints;
   const int D = m->max_depth_internal;
   if (!use_tmem || nj < 2) return 0;
@@ -371,16 +378,22 @@ inline int plan_jt_ring_w(DevModel* m, const HostTables& tb, bool use_tmem, std:
     if (m->max_depth > kJtMaxDepth) return 0;
     for (int i = 1; i < nj; ++i)
       if (m->joint[i].type == JT_FF && m->joint[i].parent != 0) return 0;
-    t_used = 6 * D;
+    const int lw = fwd == 2 ? 12 : 6;  // level record width
+    t_used = lw * D;
     bool any_ff = false;
     for (int i = 1; i < nj; ++i) {
       DevJoint& j = m->joint[i];
       j.offA = 0; j.boff = 0;
       if (j.type == JT_FF) { any_ff = true; continue; }
-      if (j.nchild > 0) j.offA = 6 * (j.depth - 1);
-      if (j.nchild >= 2) { j.boff = t_used; t_used += 12; }
+      if (j.nchild > 0) j.offA = lw * (j.depth - 1);
     }
-    if (any_ff) s_used = 12;
+    if (any_ff) s_used = fwd == 2 ? 18 : 12;  // a root free-flyer's record sits at shared-memory offset 0
+    for (int i = 1; i < nj; ++i) {
+      DevJoint& j = m->joint[i];
+      if (j.type == JT_FF || j.nchild < 2) continue;
+      if (fwd == 2) { j.boff = s_used; s_used += 18; }   // [R|p | dV] in shared memory
+      else { j.boff = t_used; t_used += 12; }
+    }
   } else
   for (int i = 1; i < nj; ++i) {
     DevJoint& j = m->joint[i];
@@ -433,7 +446,7 @@ inline int plan_jt_ring_w(DevModel* m, const HostTables& tb, bool use_tmem, std:
   EvalPlan pl{};
   pl.smem_doubles = s_used; pl.tmem_doubles = t_used; pl.warps = W; pl.blocks_per_sm = 1;
   pl.tmem_cols = t_used > 0 ? pow2_cols(2 * t_used * ((W + 3) / 4)) : 0;
-  pl.jt_fwd = fwd ? 1 : 0;
+  pl.jt_fwd = fwd;
   m->plan = pl;
   const size_t fixed = eval_model_bytes(*m) + (size_t)W * JtRing::kMaxStages * 8 + (size_t)W * 32 * s_used * 8 +
                        B200Limits::kSmemReservedPerBlock;

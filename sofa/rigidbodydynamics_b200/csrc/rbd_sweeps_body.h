@@ -2249,6 +2249,217 @@ RBD_HD void applyJT_instance_fwd(const DevModel& m, const real* opl, const int* 
 #undef RBD_JT_FLUSH
 }
 
+// applyDJT on the ring kernel: the forward-projection sweep of applyJT_instance_fwd carrying the body twists dV of the
+// direction dq.  Level records [A | dA] (12 doubles) at compile-time tensor-memory offsets, branch records
+// [R|p | dV] (18) and the free-flyer root's [R|p | v_b] (18) in shared memory; per joint k the own wrench F_k and its
+// first-order change dF_k = [0 ; sum dp x f] are projected on every ancestor level:
+//   dtau_L += dA_L . F_k + A_L . dF_k.
+template <class QC, class DQ, class Ring, class Sink>
+RBD_HD void applyDJT_instance_fwd(const DevModel& m, const real* opl, const int* anc, const QC& q, const DQ& dq,
+                                  Ring& ring, const Sink& sink, const Stack& S, const TmStack& T, real kfac) {
+  const int nj = m.njoints;
+  real R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0}, dV[6] = {0, 0, 0, 0, 0, 0};
+  real tacc[RBD_JT_MAXD];
+#pragma unroll
+  for (int L = 0; L < RBD_JT_MAXD; ++L) tacc[L] = 0.0;
+  real Ft[6] = {0, 0, 0, 0, 0, 0}, dFt[3] = {0, 0, 0};  // totals below a free-flyer root
+  int ffroot = 0, dprev = 0;
+#define RBD_DJT_FLUSH(lo, hi, last)                                                             \
+  _Pragma("unroll") for (int L = 0; L < RBD_JT_MAXD; ++L)                                       \
+    if (L >= (lo) && L < (hi)) {                                                                \
+      if (L == 0 && ffroot != 0) {                                                              \
+        const DevJoint& jf_ = m.joint[ffroot];                                                  \
+        real Rp_[18], t6_[6], d6_[6], dF6_[6] = {0, 0, 0, dFt[0], dFt[1], dFt[2]};              \
+        s_ldv<18>(S, jf_.offA, Rp_);                                                            \
+        ff_rows(Rp_, Rp_ + 9, Ft, t6_);                                                         \
+        ff_rows(Rp_, Rp_ + 9, dF6_, d6_);                                                       \
+        const real* vb_ = Rp_ + 12;                                                             \
+        real ax_, ay_, az_, bx_, by_, bz_, cx_, cy_, cz_;                                       \
+        RBD_CROSS(ax_, ay_, az_, vb_[3], vb_[4], vb_[5], t6_[0], t6_[1], t6_[2]);               \
+        RBD_CROSS(bx_, by_, bz_, vb_[3], vb_[4], vb_[5], t6_[3], t6_[4], t6_[5]);               \
+        RBD_CROSS(cx_, cy_, cz_, vb_[0], vb_[1], vb_[2], t6_[0], t6_[1], t6_[2]);               \
+        sink.put(jf_.idx_v + 0, kfac * (d6_[0] - ax_)); sink.put(jf_.idx_v + 1, kfac * (d6_[1] - ay_)); \
+        sink.put(jf_.idx_v + 2, kfac * (d6_[2] - az_));                                         \
+        sink.put(jf_.idx_v + 3, kfac * (d6_[3] - bx_ - cx_)); sink.put(jf_.idx_v + 4, kfac * (d6_[4] - by_ - cy_)); \
+        sink.put(jf_.idx_v + 5, kfac * (d6_[5] - bz_ - cz_));                                   \
+        _Pragma("unroll") for (int e = 0; e < 6; ++e) Ft[e] = 0.0;                              \
+        dFt[0] = dFt[1] = dFt[2] = 0.0;                                                         \
+        ffroot = 0;                                                                             \
+      } else {                                                                                  \
+        sink.put(m.joint[anc[(last) * RBD_JT_MAXD + L]].idx_v, kfac * tacc[L]);                 \
+      }                                                                                         \
+    }
+  real q0n = 0.0, q1n = 0.0, dn = 0.0;
+  RBD_Q_PREFETCH(1);
+  if (nj > 1 && m.joint[1].type != JT_FF) dn = dq.ld(m.joint[1].idx_v);
+  for (int i = 1; i < nj; ++i) {
+    const DevJoint& jn = m.joint[i];
+    const int par = jn.parent;
+    const int d = jn.depth;
+    if (dprev >= d) { RBD_DJT_FLUSH(d - 1, dprev, i - 1) }
+    if (par != i - 1) {
+      if (par == 0) {
+        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+        p[0] = p[1] = p[2] = 0;
+#pragma unroll
+        for (int e = 0; e < 6; ++e) dV[e] = 0;
+      } else {
+        const DevJoint& jb = m.joint[par];
+        if (jb.type == JT_FF) {
+          // free-flyer root: R|p from its record, its world twist recomputed from v_b
+          real Rp[18];
+          s_ldv<18>(S, jb.offA, Rp);
+#pragma unroll
+          for (int e = 0; e < 9; ++e) R[e] = Rp[e];
+#pragma unroll
+          for (int e = 0; e < 3; ++e) p[e] = Rp[9 + e];
+          const real* vb = Rp + 12;
+          const real wx = R[0] * vb[3] + R[1] * vb[4] + R[2] * vb[5];
+          const real wy = R[3] * vb[3] + R[4] * vb[4] + R[5] * vb[5];
+          const real wz = R[6] * vb[3] + R[7] * vb[4] + R[8] * vb[5];
+          real tx, ty, tz;
+          RBD_CROSS(tx, ty, tz, p[0], p[1], p[2], wx, wy, wz);
+          dV[0] = R[0] * vb[0] + R[1] * vb[1] + R[2] * vb[2] + tx;
+          dV[1] = R[3] * vb[0] + R[4] * vb[1] + R[5] * vb[2] + ty;
+          dV[2] = R[6] * vb[0] + R[7] * vb[1] + R[8] * vb[2] + tz;
+          dV[3] = wx; dV[4] = wy; dV[5] = wz;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 9; ++e) R[e] = S.ld(jb.boff + e);
+#pragma unroll
+          for (int e = 0; e < 3; ++e) p[e] = S.ld(jb.boff + 9 + e);
+#pragma unroll
+          for (int e = 0; e < 6; ++e) dV[e] = S.ld(jb.boff + 12 + e);
+        }
+      }
+    }
+    real aw[3];
+    const real q0 = q0n, q1 = q1n, dqi = dn;
+    RBD_Q_PREFETCH(i + 1);
+    if (i + 1 < nj && m.joint[i + 1].type != JT_FF) dn = dq.ld(m.joint[i + 1].idx_v);
+    fk_joint(jn, R, p, q0, q1, q, aw);
+    // A, dA of this joint and the twist of its body
+    real A[6] = {0, 0, 0, 0, 0, 0}, dA[6] = {0, 0, 0, 0, 0, 0};
+    if (jn.type != JT_FF) {
+      subspace_1dof(jn.type, p, aw, A);
+      RBD_CROSS(dA[0], dA[1], dA[2], dV[3], dV[4], dV[5], A[0], A[1], A[2]);
+      real tx, ty, tz;
+      RBD_CROSS(tx, ty, tz, dV[0], dV[1], dV[2], A[3], A[4], A[5]);
+      dA[0] += tx; dA[1] += ty; dA[2] += tz;
+      RBD_CROSS(dA[3], dA[4], dA[5], dV[3], dV[4], dV[5], A[3], A[4], A[5]);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) dV[e] += A[e] * dqi;
+    } else {
+      real vb[6];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) vb[e] = dq.ld(jn.idx_v + e);
+      const real wx = R[0] * vb[3] + R[1] * vb[4] + R[2] * vb[5];
+      const real wy = R[3] * vb[3] + R[4] * vb[4] + R[5] * vb[5];
+      const real wz = R[6] * vb[3] + R[7] * vb[4] + R[8] * vb[5];
+      real tx, ty, tz;
+      RBD_CROSS(tx, ty, tz, p[0], p[1], p[2], wx, wy, wz);
+      dV[0] += R[0] * vb[0] + R[1] * vb[1] + R[2] * vb[2] + tx;
+      dV[1] += R[3] * vb[0] + R[4] * vb[1] + R[5] * vb[2] + ty;
+      dV[2] += R[6] * vb[0] + R[7] * vb[1] + R[8] * vb[2] + tz;
+      dV[3] += wx; dV[4] += wy; dV[5] += wz;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) S.st(jn.offA + e, R[e]);
+#pragma unroll
+      for (int e = 0; e < 3; ++e) S.st(jn.offA + 9 + e, p[e]);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) S.st(jn.offA + 12 + e, vb[e]);
+    }
+    // own wrench about the origin and its first-order change (angular part only)
+    real Fk[6] = {0, 0, 0, 0, 0, 0}, dFk[3] = {0, 0, 0};
+#define RBD_DJT_W(j)                                                                    \
+  {                                                                                     \
+    real w[6];                                                                          \
+    ring.template ld<j>(w);                                                             \
+    const real* pl = opl + 3 * (o + j);                                                 \
+    const real px = R[0] * pl[0] + R[1] * pl[1] + R[2] * pl[2] + p[0];                  \
+    const real py = R[3] * pl[0] + R[4] * pl[1] + R[5] * pl[2] + p[1];                  \
+    const real pz = R[6] * pl[0] + R[7] * pl[1] + R[8] * pl[2] + p[2];                  \
+    real tx, ty, tz, dx, dy, dz;                                                        \
+    RBD_CROSS(tx, ty, tz, px, py, pz, w[0], w[1], w[2]);                                \
+    Fk[0] += w[0]; Fk[1] += w[1]; Fk[2] += w[2];                                        \
+    Fk[3] += w[3] + tx; Fk[4] += w[4] + ty; Fk[5] += w[5] + tz;                         \
+    RBD_CROSS(dx, dy, dz, dV[3], dV[4], dV[5], px, py, pz);                             \
+    dx += dV[0]; dy += dV[1]; dz += dV[2];                                              \
+    RBD_CROSS(tx, ty, tz, dx, dy, dz, w[0], w[1], w[2]);                                \
+    dFk[0] += tx; dFk[1] += ty; dFk[2] += tz;                                           \
+  }
+    for (int o = jn.out_begin; o < jn.out_end;) {
+      const int cnt = ring.acquire();
+      RBD_DJT_W(0)
+      if (cnt > 1) RBD_DJT_W(1)
+      if (cnt > 2) RBD_DJT_W(2)
+      if (cnt > 3) RBD_DJT_W(3)
+      ring.release(cnt);
+      o += cnt;
+    }
+#undef RBD_DJT_W
+    if (jn.type == JT_FF) {
+      ffroot = i;
+#pragma unroll
+      for (int e = 0; e < 6; ++e) Ft[e] = Fk[e];
+      dFt[0] = dFk[0]; dFt[1] = dFk[1]; dFt[2] = dFk[2];
+    } else {
+      const real own = dot6(dA, Fk) + (A[3] * dFk[0] + A[4] * dFk[1] + A[5] * dFk[2]);
+#define RBD_DJT_OWN(D_) case D_: tacc[D_ - 1] = own; break;
+      switch (d) {
+        RBD_DJT_OWN(1) RBD_DJT_OWN(2) RBD_DJT_OWN(3) RBD_DJT_OWN(4) RBD_DJT_OWN(5) RBD_DJT_OWN(6)
+        RBD_DJT_OWN(7) RBD_DJT_OWN(8) RBD_DJT_OWN(9) RBD_DJT_OWN(10) RBD_DJT_OWN(11) RBD_DJT_OWN(12)
+        default: break;
+      }
+#undef RBD_DJT_OWN
+#define RBD_DJT_ANC(L_)                                                                  \
+  {                                                                                      \
+    real rc_[12];                                                                        \
+    T.template ldv<12>(12 * (L_), rc_);                                                  \
+    tacc[L_] += dot6(rc_ + 6, Fk) + (rc_[3] * dFk[0] + rc_[4] * dFk[1] + rc_[5] * dFk[2]); \
+  }
+      switch (d) {
+        case 12: RBD_DJT_ANC(10) [[fallthrough]];
+        case 11: RBD_DJT_ANC(9) [[fallthrough]];
+        case 10: RBD_DJT_ANC(8) [[fallthrough]];
+        case 9: RBD_DJT_ANC(7) [[fallthrough]];
+        case 8: RBD_DJT_ANC(6) [[fallthrough]];
+        case 7: RBD_DJT_ANC(5) [[fallthrough]];
+        case 6: RBD_DJT_ANC(4) [[fallthrough]];
+        case 5: RBD_DJT_ANC(3) [[fallthrough]];
+        case 4: RBD_DJT_ANC(2) [[fallthrough]];
+        case 3: RBD_DJT_ANC(1) [[fallthrough]];
+        case 2:
+          if (ffroot != 0) {
+#pragma unroll
+            for (int e = 0; e < 6; ++e) Ft[e] += Fk[e];
+            dFt[0] += dFk[0]; dFt[1] += dFk[1]; dFt[2] += dFk[2];
+          } else RBD_DJT_ANC(0)
+          break;
+        default: break;
+      }
+#undef RBD_DJT_ANC
+      if (jn.nchild > 0) {
+        real rc[12];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) { rc[e] = A[e]; rc[6 + e] = dA[e]; }
+        T.template stv<12>(12 * (d - 1), rc);
+      }
+      if (jn.nchild >= 2) {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) S.st(jn.boff + e, R[e]);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) S.st(jn.boff + 9 + e, p[e]);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) S.st(jn.boff + 12 + e, dV[e]);
+      }
+    }
+    dprev = d;
+  }
+  if (nj > 1) { RBD_DJT_FLUSH(0, dprev, nj - 1) }
+#undef RBD_DJT_FLUSH
+}
+
 // Ring program (host-built by plan_jt_ring, staged with the blob in place of the ColProg table; ints):
 //   [0] pieces  [1] copies  [2] offset (ints, even) of the translation table  [3] offset of the ancestor table
 //   (forward-projection variant: joint at level L of the chain ending at joint i, RBD_JT_MAXD ints per joint; 0 = none)

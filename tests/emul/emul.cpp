@@ -370,6 +370,39 @@ extern "C" int emul_applyDJT(const rbd_model_desc* d, long long n, long long til
   return 0;
 }
 
+// applyDJT on the ring kernel's forward-projection sweep (applyDJT_instance_fwd; plan_djt_ring); returns 1 when the
+// planner leaves the model to the shared-memory kernel
+extern "C" int emul_applyDJT_ring(const rbd_model_desc* d, long long n, long long tile, double* qcache, long long cache_tile,
+                                  double* dq_joints, double* dq_root, double* in, double kfac, double* out_tau,
+                                  double* out_root) {
+  Ctx c;
+  int rc = make_ctx(d, &c);
+  if (rc) return rc;
+  std::vector<int> prog;
+  const int nst = plan_djt_ring(&c.m, c.ht, true, &prog);
+  if (nst == 0) return 1;
+  const std::vector<unsigned long long> blob = build_jt_blob(&c.m, prog);
+  const DevModel& bm = *reinterpret_cast<const DevModel*>(blob.data());
+  const EvalPlan& pl = bm.plan;
+  const int bt = pl.warps * 32;
+  std::vector<double> smem((size_t)(pl.smem_doubles > 0 ? pl.smem_doubles : 1) * bt, 1e300);
+  std::vector<double> tmem((size_t)(pl.tmem_doubles > 0 ? pl.tmem_doubles : 1) * bt, 1e300);
+  const JtProg jp{col_prog(bm)};
+  if (jp.npieces() == 0) return 0;
+  const int off = (bm.has_ff_root && dq_root) ? 6 : 0;
+  const int ooff = (bm.has_ff_root && out_root) ? 6 : 0;
+  for (long long i = 0; i < n; ++i) {
+    const int t = (int)(i % bt);
+    DirectRingT<Field> ring{make_field(in, i, 6 * bm.n_out, tile), jp, 0, nullptr};
+    SplitQ dq{make_field(dq_root, i, 6, tile), make_field(dq_joints, i, bm.nv - off, tile), off};
+    SplitRedSinkT<Field> sink{make_field(out_root, i, 6, tile), make_field(out_tau, i, bm.nv - ooff, tile), ooff};
+    Stack S = make_stack(smem.data(), t, pl.smem_doubles);
+    TmStack T{tmem.data() + (size_t)t * (pl.tmem_doubles > 0 ? pl.tmem_doubles : 1)};
+    applyDJT_instance_fwd(bm, jp.opl(), jp.anc(), make_field(qcache, i, bm.nq, cache_tile), dq, ring, sink, S, T, kfac);
+  }
+  return 0;
+}
+
 // plan of the applyJT ring kernel for this model: out = {ring stages (0 = register path), forward projection?,
 // warps per block, tensor-memory doubles, shared-memory doubles, shared-memory bytes of the block}
 extern "C" int emul_jt_ring_plan(const rbd_model_desc* d, int use_tmem, int fwd_mode, int* out /*[6]*/) {

@@ -270,10 +270,11 @@ def test_mass_forcefield_bodies(emul, d):
     T = lambda x: to_tiled(x, tile)
     qs = T(q)
     res = T(r0)
-    assert emul.emul_mass_force(C.addressof(cd), n, tile, P(qs), None, P(T(dx)), P(res), 0.75, 0) == 0
+    tdx, tv = T(dx), T(v)   # (P() hands out a raw address: the arrays must outlive the calls)
+    assert emul.emul_mass_force(C.addressof(cd), n, tile, P(qs), None, P(tdx), P(res), 0.75, 0) == 0
     assert rel_err(from_tiled(res, n), r0 + 0.75 * np.einsum("nij,nj->ni", M, dx)) <= TOL_FP64
     f = T(r0)
-    assert emul.emul_mass_force(C.addressof(cd), n, tile, P(qs), P(T(v)), None, P(f), -1.0, 1) == 0
+    assert emul.emul_mass_force(C.addressof(cd), n, tile, P(qs), P(tv), None, P(f), -1.0, 1) == 0
     bias, _ = oracle.eval_batch(d, q, v, zero, 1)
     assert rel_err(from_tiled(f, n), r0 - bias["tau"]) <= TOL_FP64
     g = T(r0)
@@ -320,14 +321,16 @@ def test_applyDJT_bodies_match_finite_differences(emul, d):
     w = rng.uniform(-1, 1, (n, 6 * d.n_out))
     T = lambda x: None if x is None else to_tiled(x, tile)
     ff = bool(d.has_freeflyer_root)
+    tw = T(w)
 
     def jt(qx):
         qj, root, _, _ = _split(d, qx, v)
         qcache = np.full(((n + ctile - 1) // ctile, d.nq, ctile), np.nan)
         pos = np.full(((n + tile - 1) // tile, 7 * d.n_out, tile), np.nan)
-        assert emul.emul_apply(C.addressof(cd), n, tile, block, P(T(qj)), P(T(root)), P(qcache), ctile, P(pos)) == 0
+        tqj, troot = T(qj), T(root)   # (P() hands out a raw address: the arrays must outlive the calls)
+        assert emul.emul_apply(C.addressof(cd), n, tile, block, P(tqj), P(troot), P(qcache), ctile, P(pos)) == 0
         tau = T(np.zeros((n, d.nv_joints))); rt = T(np.zeros((n, 6))) if ff else None
-        assert emul.emul_applyJT(C.addressof(cd), n, tile, block, P(qcache), ctile, P(T(w)), P(tau), P(rt)) == 0
+        assert emul.emul_applyJT(C.addressof(cd), n, tile, block, P(qcache), ctile, P(tw), P(tau), P(rt)) == 0
         tj = from_tiled(tau, n)
         return (np.concatenate([from_tiled(rt, n), tj], axis=1) if ff else tj), qcache
 
@@ -336,8 +339,18 @@ def test_applyDJT_bodies_match_finite_differences(emul, d):
     _, qcache = jt(q)
     _, _, dq, rootv = _split(d, q, v)
     out = T(np.ones((n, d.nv_joints))); ort = T(np.ones((n, 6))) if ff else None      # accumulates onto ones
-    assert emul.emul_applyDJT(C.addressof(cd), n, tile, P(qcache), ctile, P(T(dq)), P(T(rootv)), P(T(w)), 0.5, P(out), P(ort)) == 0
+    tdq, trv = T(dq), T(rootv)
+    assert emul.emul_applyDJT(C.addressof(cd), n, tile, P(qcache), ctile, P(tdq), P(trv), P(tw), 0.5, P(out), P(ort)) == 0
     got = from_tiled(out, n)
     if ff:
         got = np.concatenate([from_tiled(ort, n), got], axis=1)
     assert rel_err(got, 1.0 + 0.5 * fd) <= 1e-6
+    # the ring kernel's forward-projection sweep gives the same numbers (where the planner has a plan for the model)
+    out2 = T(np.ones((n, d.nv_joints))); ort2 = T(np.ones((n, 6))) if ff else None
+    rc = emul.emul_applyDJT_ring(C.addressof(cd), n, tile, P(qcache), ctile, P(tdq), P(trv), P(tw), 0.5, P(out2), P(ort2))
+    assert rc in (0, 1)
+    if rc == 0:
+        got2 = from_tiled(out2, n)
+        if ff:
+            got2 = np.concatenate([from_tiled(ort2, n), got2], axis=1)
+        assert rel_err(got2, got) <= 1e-12
