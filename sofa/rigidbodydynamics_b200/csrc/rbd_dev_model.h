@@ -89,6 +89,8 @@ struct alignas(16) DevModelT {
   int has_ff_root;    // joint 1 is a free-flyer attached to the universe
   int nq_joints, nv_joints;
   int max_depth, max_depth_internal;  // longest joint chain; deepest joint that has children
+  int simple_joints;                  // 1 = every joint is RX / RY / RZ or a free-flyer (rbd::simple kernels apply)
+  int pad0_;
   int prog_words_off, prog_len;       // eval blob: 8-byte-word offset of the ColProg table behind the joint records; ints
   real gravity[3];
   EvalPlan plan;
@@ -101,7 +103,7 @@ inline void dev_model_to_f32(const DevModel& d, DevModelT<float>* f) {
   f->njoints = d.njoints; f->nq = d.nq; f->nv = d.nv; f->n_out = d.n_out;
   f->slot_total[0] = d.slot_total[0]; f->slot_total[1] = d.slot_total[1];
   f->nbranch = d.nbranch; f->has_ff_root = d.has_ff_root; f->nq_joints = d.nq_joints; f->nv_joints = d.nv_joints;
-  f->max_depth = d.max_depth; f->max_depth_internal = d.max_depth_internal;
+  f->max_depth = d.max_depth; f->max_depth_internal = d.max_depth_internal; f->simple_joints = d.simple_joints; f->pad0_ = 0;
   f->prog_words_off = d.prog_words_off; f->prog_len = d.prog_len;
   for (int k = 0; k < 3; ++k) f->gravity[k] = (float)d.gravity[k];
   f->plan = d.plan;

@@ -99,6 +99,8 @@ __global__ void __launch_bounds__((MINB == 1 && DO_TAU && !DO_M) ? 384 : 256, MI
 }
 
 RBD_DEFINE_EVAL_KERNEL(eval_kernel, rbd, double, 1)
+// the same for models with RX / RY / RZ / free-flyer joints only (rbd::simple: rarer joint types not compiled in)
+RBD_DEFINE_EVAL_KERNEL(eval_kernel_simple, rbd::simple, double, 1)
 // FP32: 128 registers per thread so that two 8-warp blocks share an SM (the planner counts on it)
 RBD_DEFINE_EVAL_KERNEL(eval_kernel_f32, rbd::f32, float, 2)
 
@@ -636,6 +638,7 @@ static cudaError_t pick_block(Kern kern, int smem_doubles_per_thread, int forced
     e = cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
 #define RBD_LAUNCH(K) K<<<grid, block, smem, st>>>(d_model, a, model_words)
 RBD_DEFINE_EVAL_LAUNCH(launch_eval, eval_kernel, double)
+RBD_DEFINE_EVAL_LAUNCH(launch_eval_simple, eval_kernel_simple, double)
 RBD_DEFINE_EVAL_LAUNCH(launch_eval_f32, eval_kernel_f32, float)
 #undef RBD_ATTR
 #undef RBD_LAUNCH

@@ -53,6 +53,9 @@ struct LaunchCfg {
 
 cudaError_t launch_eval(const DevModel& planned_host_model, const DevModel* d_eval_blob, const EvalArgs& a,
                         LaunchCfg* cache8, int num_sms, cudaStream_t st);
+// the same for models whose joints are all RX / RY / RZ / free-flyer (DevModel::simple_joints)
+cudaError_t launch_eval_simple(const DevModel& planned_host_model, const DevModel* d_eval_blob, const EvalArgs& a,
+                               LaunchCfg* cache8, int num_sms, cudaStream_t st);
 // optional FP32 mode of the fused evaluation (float I/O and state, tolerance 1e-4)
 cudaError_t launch_eval_f32(const DevModelT<float>& planned_host_model, const DevModelT<float>* d_eval_blob,
                             const EvalArgsT<float>& a, LaunchCfg* cache8, int num_sms, cudaStream_t st);

@@ -130,6 +130,11 @@ inline int build_dev_model(const rbd_model_desc* d, DevModel* m, HostTables* tb,
     if (m->joint[i].nchild > 0) maxd_internal = std::max(maxd_internal, depth[i]);
   }
   m->max_depth = maxd;
+  m->simple_joints = 1;
+  for (int i = 1; i < nj; ++i) {
+    const int t = d->jtype[i];
+    if (!(t == JT_RX || t == JT_RY || t == JT_RZ || t == JT_FF)) m->simple_joints = 0;
+  }
   m->max_depth_internal = maxd_internal;
   std::vector<int> aw(maxd + 1, 6);
   for (int i = 1; i < nj; ++i) aw[depth[i]] = std::max(aw[depth[i]], RBD_SLOT_A(d->jtype[i]));

@@ -62,6 +62,17 @@ namespace rbd {
 typedef double real;
 #include "rbd_sweeps_body.h"
 
+// ... and a third time in namespace rbd::simple for models whose joints are all RX / RY / RZ / free-flyer: the fused
+// evaluation without the code of the rarer joint types (rbd_dev_model.h: DevModelT::simple_joints picks it)
+namespace simple {
+typedef double real;
+#define RBD_SIMPLE_JOINTS 1
+#define RBD_BODY_EVAL_ONLY 1
+#include "rbd_sweeps_body.h"
+#undef RBD_BODY_EVAL_ONLY
+#undef RBD_SIMPLE_JOINTS
+}  // namespace simple
+
 namespace f32 {
 typedef float real;
 using DevModel = ::DevModelT<float>;
