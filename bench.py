@@ -381,6 +381,9 @@ def main():
         cpu = {"value": val, "unit": UNIT, "cores": used, "kind": "port", "sample": sample}
 
     if rank == 0:
+        # models whose joints are all RX / RY / RZ / free-flyer run the rbd::simple instantiation of the same sweep
+        simple = all(int(t) in (mdl.J_RX, mdl.J_RY, mdl.J_RZ, mdl.J_FF) for t in desc.jtype[1:])
+        kname = "eval_kernel_simple" if simple else "eval_kernel"
         peak, peak_src = _peaks()
         achieved = step_bytes / (kern_ms * 1e-3) / 1e9
         traffic, traffic_src = _traffic(desc.name, n, dyn.tile)
@@ -398,7 +401,7 @@ def main():
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                              "algorithmic_bytes_per_launch": step_bytes, "peak_source": peak_src,
-                             "kernel": f"rbd::eval_kernel<true,true,{dyn.tile if dyn.tile == 32 else 0}>", "kernel_ms": kern_ms,
+                             "kernel": f"rbd::{kname}<true,true,{dyn.tile if dyn.tile == 32 else 0}>", "kernel_ms": kern_ms,
                              "bytes_per_eval": bytes_per_eval},
                 "cpu_baseline": cpu, "oracle_check_rel_err": check_err}
         if fp32 is not None:
