@@ -231,13 +231,16 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner to stdout when
+    # the communicator is created), so file descriptor 1 is pointed at stderr for the rest of the run and the JSON line
+    # goes to a private duplicate of the original stdout.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     assert torch.cuda.is_available(), "bench.py (native arm) needs a CUDA device: there is no CPU fallback"
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION on this image) off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
@@ -406,7 +409,7 @@ def main():
                 "cpu_baseline": cpu, "oracle_check_rel_err": check_err}
         if fp32 is not None:
             line["fp32_mode"] = fp32
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
