@@ -610,10 +610,17 @@ static int ensure_jcache(rbd_workspace* ws, cudaStream_t st) {
   const int kj = 6 * dm.nv, ko = 12 * (dm.njoints - 1);
   const long long chunk = std::min<long long>((ws->capacity + 31) / 32 * 32, kRowsCacheChunk);
   if (!ws->jcache) {
+    // all three or none: a failed allocation must not leave a half-built cache behind
     const size_t cap = (size_t)((ws->capacity + 31) / 32 * 32);
-    CK(cudaMalloc(&ws->jcache, cap * (size_t)kj * sizeof(double)));
-    CK(cudaMalloc(&ws->omicache, cap * (size_t)ko * sizeof(double)));
-    CK(cudaMalloc(&ws->jc_scratch, (size_t)chunk * (size_t)(kj + ko) * sizeof(double)));
+    double *j = nullptr, *o = nullptr, *sc = nullptr;
+    cudaError_t e = cudaMalloc(&j, cap * (size_t)kj * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&o, cap * (size_t)ko * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&sc, (size_t)chunk * (size_t)(kj + ko) * sizeof(double));
+    if (e != cudaSuccess) {
+      cudaFree(j); cudaFree(o); cudaFree(sc);
+      return cuda_fail(e, "cudaMalloc(Jacobian cache)");
+    }
+    ws->jcache = j; ws->omicache = o; ws->jc_scratch = sc;
     ws->jc_epoch = -1;
   }
   if (ws->jc_epoch != ws->apply_epoch) {
