@@ -114,6 +114,7 @@ typedef struct rbd_model_info {
   int64_t eval_bytes;           /* algorithmic bytes per eval                          */
   int32_t eval_tmem_doubles;    /* tensor-memory doubles per instance used by the fused eval kernel      */
   int32_t eval_warps_per_sm;    /* resident warps per SM the storage plan of the fused eval reaches      */
+  int32_t mass_support_fields;  /* structurally non-zero entries of M's upper triangle (rbd_model_mass_pattern)  */
 } rbd_model_info;
 
 /* ---------------------------------------------------------------------------------------------------- */
@@ -122,12 +123,22 @@ RBD_API int rbd_version(void);
 RBD_API const char* rbd_last_error(void);
 RBD_API void rbd_clear_error(void);
 RBD_API int rbd_device_count(int* count); /* RBD_ERR_CUDA when no driver / device is present            */
+/* Demangled name of the __global__ function the calling thread launched last through this library ("" = none yet; the
+ * layout adapters are not recorded).  Thread-local like rbd_last_error; bench.py reports the kernel it timed with it. */
+RBD_API const char* rbd_last_kernel_name(void);
 
 /* ---------------------------------------------------------------------------------------------------- */
 /* model: replaces setModel / setBodyCoMFrames / m_extraFrames (KCM.inl:304-317, KCM.h:90-95)            */
 RBD_API int rbd_model_create(const rbd_model_desc* desc, rbd_model** out);
 RBD_API void rbd_model_destroy(rbd_model* model);
 RBD_API int rbd_model_get_info(const rbd_model* model, rbd_model_info* info);
+/* Support pattern of the joint-space mass matrix: M(r, c), r <= c, is structurally non-zero iff the joint that owns dof
+ * r is the joint that owns dof c or one of its ancestors (pinocchio's crba fills exactly these entries of data.M's
+ * upper triangle and leaves the rest 0).  Compressed by columns: col_ptr [nv + 1], row_idx [mass_support_fields], rows
+ * ascending within a column; either pointer may be NULL.  Entry e of the pattern is field e of the `Mval` arrays of
+ * the *_sparse entry points below — the layout a sparse direct solver (the reference's example scenes use
+ * SparseLDLSolver, examples/sofa/RigidBodyDynamics/LoadRobot/robot.py:48) assembles from without scanning zeros.  */
+RBD_API int rbd_model_mass_pattern(const rbd_model* model, int32_t* col_ptr, int32_t* row_idx);
 
 /* ---------------------------------------------------------------------------------------------------- */
 /* workspace: replaces the pinocchio::Data owned by the mapping (KCM.h:121, KCM.inl:310).  `capacity` is  */
@@ -205,6 +216,8 @@ RBD_API int rbd_applyDJT_host(rbd_workspace* ws, int64_t n, const double* dq_joi
  *   out_rows: nrows x nv, row-major (root wrench first when has_freeflyer_root), overwritten.
  *   keep[r] = 1 iff ||row||^2 > 1e-12 (kMinTorque^2, KCM.inl:43-45,587,605): the caller must only emit
  *   kept rows into the SOFA MatrixDeriv.                                                                */
+/* Preconditions of the _dev variant (the _host variant checks them and returns RBD_ERR_INVALID_ARG): row_ptr[0] == 0,
+ * row_ptr non-decreasing, 0 <= col[j] < n_out, 0 <= row_instance[r] < the batch size of the last apply.             */
 RBD_API int rbd_applyJT_rows_dev(rbd_workspace* ws, int64_t nrows, const int32_t* row_ptr,
                                  const int32_t* row_instance, const int32_t* col, const double* val,
                                  double* out_rows, int32_t* keep);
@@ -240,6 +253,12 @@ RBD_API int rbd_eval_soa(rbd_workspace* ws, int64_t n, int64_t tile, const doubl
 RBD_API int rbd_eval_soa_f32(rbd_workspace* ws, int64_t n, int64_t tile, const float* q, const float* v,
                              const float* a, float* oMi, float* J, float* M, float* tau);
 RBD_API int rbd_crba_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, double* M);
+/* The same with M in the support-only format: Mval has mass_support_fields fields per instance, field e = the entry
+ * (row_idx[e], column of e) of rbd_model_mass_pattern; the structural zeros of the packed triangle (Talos: 372 of 741)
+ * are neither computed, stored nor — through rbd_eval_host_sparse — copied over PCIe.  Same kernel, same values.   */
+RBD_API int rbd_eval_soa_sparse(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, const double* v,
+                                const double* a, double* oMi, double* J, double* Mval, double* tau);
+RBD_API int rbd_crba_soa_sparse(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, double* Mval);
 RBD_API int rbd_rnea_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, const double* v,
                          const double* a, double* tau);
 
@@ -280,6 +299,11 @@ RBD_API int rbd_applyJT_rows_host(rbd_workspace* ws, int64_t nrows, const int32_
  * outputs may be NULL.  Processed in pipelined chunks (H2D, kernels and D2H overlap).                    */
 RBD_API int rbd_eval_host(rbd_workspace* ws, int64_t n, const double* q, const double* v, const double* a,
                           double* oMi, double* J, double* M, double* tau);
+/* ... with M in the support-only format, Mval [n][mass_support_fields] (see rbd_eval_soa_sparse).  Only the arrays the
+ * requested outputs need cross PCIe: a NULL output is neither computed nor copied, v and a travel only when tau is
+ * requested (a Mass / ForceField consumer asks for Mval + tau and gets 8 (mass_support_fields + nv) bytes back).    */
+RBD_API int rbd_eval_host_sparse(rbd_workspace* ws, int64_t n, const double* q, const double* v, const double* a,
+                                 double* oMi, double* J, double* Mval, double* tau);
 
 /* Mass / ForceField products on host vectors (instance-major q [n][nq]; dx, v, res, f [n][nv]): res and f are
  * ACCUMULATED in place, as rbd_addMDx_soa / rbd_addForce_soa do on the device.  v may be NULL (gravity only).   */

@@ -37,7 +37,8 @@ class RbdModelInfo(C.Structure):
                 ("n_out", C.c_int32), ("has_freeflyer_root", C.c_int32), ("nq_joints", C.c_int32),
                 ("nv_joints", C.c_int32), ("omi_fields", C.c_int32), ("jac_fields", C.c_int32),
                 ("mass_fields", C.c_int32), ("max_depth", C.c_int32), ("eval_smem_doubles", C.c_int32),
-                ("eval_bytes", C.c_int64), ("eval_tmem_doubles", C.c_int32), ("eval_warps_per_sm", C.c_int32)]
+                ("eval_bytes", C.c_int64), ("eval_tmem_doubles", C.c_int32), ("eval_warps_per_sm", C.c_int32),
+                ("mass_support_fields", C.c_int32)]
 
 
 def _dp(a: np.ndarray):
@@ -68,8 +69,9 @@ def make_desc(d: ModelDescriptor):
 
 # every symbol include/rbd_b200.h declares; tests check the built library exports all of them
 SYMBOLS = [
-    "rbd_version", "rbd_last_error", "rbd_clear_error", "rbd_device_count",
-    "rbd_model_create", "rbd_model_destroy", "rbd_model_get_info",
+    "rbd_version", "rbd_last_error", "rbd_clear_error", "rbd_device_count", "rbd_last_kernel_name",
+    "rbd_model_create", "rbd_model_destroy", "rbd_model_get_info", "rbd_model_mass_pattern",
+    "rbd_eval_soa_sparse", "rbd_crba_soa_sparse", "rbd_eval_host_sparse",
     "rbd_workspace_create", "rbd_workspace_destroy", "rbd_workspace_set_stream", "rbd_workspace_synchronize",
     "rbd_workspace_launch_count", "rbd_workspace_set_eval_block", "rbd_workspace_set_eval_tmem", "rbd_workspace_set_applyJT_ring", "rbd_workspace_set_rows_cache", "rbd_workspace_get_eval_plan", "rbd_workspace_get_eval_plan_f32",
     "rbd_apply_soa", "rbd_applyJ_soa", "rbd_applyJT_soa", "rbd_applyJT_rows_dev",
@@ -100,6 +102,11 @@ def load() -> C.CDLL:
         "rbd_last_error": (C.c_char_p, []),
         "rbd_clear_error": (None, []),
         "rbd_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+        "rbd_last_kernel_name": (C.c_char_p, []),
+        "rbd_model_mass_pattern": (C.c_int, [vp, vp, vp]),
+        "rbd_eval_soa_sparse": (C.c_int, [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp]),
+        "rbd_crba_soa_sparse": (C.c_int, [vp, i64, i64, vp, vp]),
+        "rbd_eval_host_sparse": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp, vp]),
         "rbd_model_create": (C.c_int, [C.POINTER(RbdModelDesc), C.POINTER(vp)]),
         "rbd_model_destroy": (None, [vp]),
         "rbd_model_get_info": (C.c_int, [vp, C.POINTER(RbdModelInfo)]),

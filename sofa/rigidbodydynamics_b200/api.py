@@ -58,6 +58,20 @@ class Model:
         check(self._lib.rbd_model_get_info(self._h, C.byref(info)))
         self.info = info
 
+    def mass_pattern(self):
+        """Support pattern of M's upper triangle by columns: ``(col_ptr [nv + 1], row_idx [nnz])`` int32 arrays; entry
+        ``e`` is field ``e`` of the ``Mval`` arrays of the ``*_sparse`` entry points (``rbd_model_mass_pattern``)."""
+        col_ptr = np.zeros(self.info.nv + 1, dtype=np.int32)
+        row_idx = np.zeros(max(1, self.info.mass_support_fields), dtype=np.int32)
+        check(self._lib.rbd_model_mass_pattern(self._h, col_ptr.ctypes.data, row_idx.ctypes.data))
+        return col_ptr, row_idx[:self.info.mass_support_fields]
+
+    def mass_packed_index(self) -> np.ndarray:
+        """Index of every support entry in the packed upper triangle (``M(r, c)`` at ``c (c + 1) / 2 + r``)."""
+        col_ptr, row_idx = self.mass_pattern()
+        cols = np.repeat(np.arange(self.info.nv), np.diff(col_ptr))
+        return (cols * (cols + 1) // 2 + row_idx).astype(np.int64)
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.rbd_model_destroy(self._h)
@@ -139,6 +153,14 @@ class Workspace:
         check(self._lib.rbd_eval_soa_f32(self._h, n, tile, _dev_ptr(q), _dev_ptr(v), _dev_ptr(a), _dev_ptr(oMi),
                                          _dev_ptr(J), _dev_ptr(M), _dev_ptr(tau)))
 
+    def eval_soa_sparse(self, n, tile, q, v=None, a=None, oMi=None, J=None, Mval=None, tau=None):
+        """The fused evaluation with M in the support-only format (``Model.mass_pattern``)."""
+        check(self._lib.rbd_eval_soa_sparse(self._h, n, tile, _dev_ptr(q), _dev_ptr(v), _dev_ptr(a), _dev_ptr(oMi),
+                                            _dev_ptr(J), _dev_ptr(Mval), _dev_ptr(tau)))
+
+    def crba_soa_sparse(self, n, tile, q, Mval):
+        check(self._lib.rbd_crba_soa_sparse(self._h, n, tile, _dev_ptr(q), _dev_ptr(Mval)))
+
     def crba_soa(self, n, tile, q, M):
         check(self._lib.rbd_crba_soa(self._h, n, tile, _dev_ptr(q), _dev_ptr(M)))
 
@@ -199,6 +221,10 @@ class Workspace:
         check(self._lib.rbd_eval_host(self._h, n, _host_ptr(q), _host_ptr(v), _host_ptr(a), _host_ptr(oMi),
                                       _host_ptr(J), _host_ptr(M), _host_ptr(tau)))
 
+    def eval_host_sparse(self, n, q, v=None, a=None, oMi=None, J=None, Mval=None, tau=None):
+        check(self._lib.rbd_eval_host_sparse(self._h, n, _host_ptr(q), _host_ptr(v), _host_ptr(a), _host_ptr(oMi),
+                                             _host_ptr(J), _host_ptr(Mval), _host_ptr(tau)))
+
     def addMDx_host(self, n, q, dx, factor, res):
         """res += factor * M(q) dx on host vectors (instance-major), in place."""
         check(self._lib.rbd_addMDx_host(self._h, n, _host_ptr(q), _host_ptr(dx), float(factor), _host_ptr(res)))
@@ -222,6 +248,12 @@ class Workspace:
                                               _host_ptr(val), _host_ptr(out_rows), _host_ptr(keep, np.int32)))
 
 
+def last_kernel_name() -> str:
+    """Demangled name of the kernel this thread launched last through the library (``rbd_last_kernel_name``)."""
+    s = _capi.load().rbd_last_kernel_name()
+    return s.decode() if s else ""
+
+
 def device_count() -> int:
     lib = _capi.load()
     n = C.c_int(0)
@@ -229,4 +261,4 @@ def device_count() -> int:
     return int(n.value) if rc == 0 else 0
 
 
-__all__ = ["Model", "Workspace", "RbdError", "device_count"]
+__all__ = ["Model", "Workspace", "RbdError", "device_count", "last_kernel_name"]

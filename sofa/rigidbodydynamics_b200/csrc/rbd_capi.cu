@@ -8,6 +8,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <cxxabi.h>
+#include <stdlib.h>
+
 #include <new>
 #include <string>
 #include <vector>
@@ -64,11 +67,14 @@ struct rbd_workspace {
   DevTables tb{};
   // fused eval: one planned copy of the joint table per variant (bit 1 = CRBA, bit 0 = RNEA), host + device;
   // the kernel stages the device copy into shared memory
-  DevModel* h_plan[11] = {};  // index: bit 2 = oMi requested, bit 1 = CRBA, bit 0 = RNEA; [8] = the applyJT sweep,
-                              // [9] = its ring variant (full tiles of 32)
-  DevModel* d_plan[11] = {};  // [10] = applyDJT on the ring kernel
+  static const int kPlans = 19;
+  DevModel* h_plan[kPlans] = {};  // index: bit 2 = oMi requested, bit 1 = CRBA, bit 0 = RNEA; [8] = the applyJT sweep,
+                                  // [9] = its ring variant (full tiles of 32); [11 + i] = eval variant i with the
+                                  // support-only M format (rbd_eval_soa_sparse)
+  DevModel* d_plan[kPlans] = {};  // [10] = applyDJT on the ring kernel
   int djt_ring_slots = -1;    // ... of plan [10]
   int jt_ring_slots = -1;     // ring stages per warp of plan [9]; 0 = the ring kernel cannot run this model; -1 = not planned yet
+  char plan_failed[kPlans] = {};  // the planner found no configuration for this variant (reset by drop_plans): do not retry per call
   int use_jt_ring = 1;
   DevModelT<float>* h_plan32[8] = {};  // FP32 mode of the fused eval
   DevModelT<float>* d_plan32[8] = {};
@@ -81,9 +87,10 @@ struct rbd_workspace {
   // instances, instance-major; allocated on the first row call, refilled lazily after every apply
   double *jcache = nullptr, *omicache = nullptr, *jc_scratch = nullptr;  // instance-major caches + tile-32 scratch
   long long apply_epoch = 0, jc_epoch = -1;
+  long long jcache_cap = 0;  // instances the Jacobian cache holds
   int use_rows_cache = 1;
   long long applied_n = 0;   // instances covered by the cache (0 = apply not called yet)
-  LaunchCfg cfg_eval[8], cfg_apply[2], cfg_applyJ[2], cfg_applyJT[2], cfg_rows, cfg_jt_ring, cfg_djt[2], cfg_djt_ring;
+  LaunchCfg cfg_eval[8], cfg_eval_sp[8], cfg_apply[2], cfg_applyJ[2], cfg_applyJT[2], cfg_rows, cfg_jt_ring, cfg_djt[2], cfg_djt_ring;
   DevModel* d_model = nullptr;  // device copy of the joint table for the mapping kernels
   int forced_eval_block = 0;
   long long launches = 0;
@@ -130,6 +137,17 @@ RBD_API int rbd_version(void) { return RBD_B200_VERSION; }
 RBD_API const char* rbd_last_error(void) { return g_err.c_str(); }
 RBD_API void rbd_clear_error(void) { g_err.clear(); }
 
+RBD_API const char* rbd_last_kernel_name(void) {
+  static thread_local std::string name;
+  const char* mangled = rbd::last_kernel_mangled();
+  if (!mangled) return "";
+  int status = 0;
+  char* dem = abi::__cxa_demangle(mangled, nullptr, nullptr, &status);
+  name = (status == 0 && dem) ? dem : mangled;
+  free(dem);
+  return name.c_str();
+}
+
 RBD_API int rbd_device_count(int* count) {
   if (!count) return set_err(RBD_ERR_INVALID_ARG, "null count");
   *count = 0;
@@ -162,6 +180,7 @@ RBD_API int rbd_model_create(const rbd_model_desc* desc, rbd_model** out) {
     }
   }
   I.eval_bytes = 8LL * ((d.nq + 2 * d.nv) + I.omi_fields + I.jac_fields + I.mass_fields + d.nv);
+  I.mass_support_fields = mass_support_pattern(d, nullptr, nullptr);
   *out = m;
   return RBD_OK;
 }
@@ -172,12 +191,18 @@ RBD_API int rbd_model_get_info(const rbd_model* model, rbd_model_info* info) {
   return RBD_OK;
 }
 
+RBD_API int rbd_model_mass_pattern(const rbd_model* model, int32_t* col_ptr, int32_t* row_idx) {
+  if (!model) return set_err(RBD_ERR_INVALID_ARG, "null model");
+  (void)mass_support_pattern(model->dm, col_ptr, row_idx);
+  return RBD_OK;
+}
+
 // ---- workspace ------------------------------------------------------------------------------------------
 static void ws_free(rbd_workspace* ws) {
   if (!ws) return;
   cudaFree(ws->d_sorted_k); cudaFree(ws->d_outk_parent); cudaFree(ws->d_sorted_ident); cudaFree(ws->d_sorted_pl); cudaFree(ws->d_outk_pl);
   cudaFree(ws->qcache); cudaFree(ws->rows_buf); cudaFree(ws->d_model); cudaFree(ws->jcache); cudaFree(ws->omicache); cudaFree(ws->jc_scratch);
-  for (int k = 0; k < 11; ++k) { cudaFree(ws->d_plan[k]); delete ws->h_plan[k]; }
+  for (int k = 0; k < rbd_workspace::kPlans; ++k) { cudaFree(ws->d_plan[k]); delete ws->h_plan[k]; }
   for (int k = 0; k < 8; ++k) { cudaFree(ws->d_plan32[k]); delete ws->h_plan32[k]; }
   for (int s = 0; s < kSlots; ++s) {
     cudaFree(ws->slot[s].aos); cudaFree(ws->slot[s].soa);
@@ -287,6 +312,9 @@ static int check_batch(const rbd_workspace* ws, int64_t n, int64_t tile) {
 // plan (once per variant and tuning-knob setting) + upload of the planned joint table
 static int ensure_plan(rbd_workspace* ws, int pk) {
   if (ws->h_plan[pk]) return RBD_OK;
+  if (ws->plan_failed[pk])
+    return set_err(RBD_ERR_UNSUPPORTED, "the sweep state of this model does not fit one SM's shared + tensor memory"
+                                        " at the requested block size");
   if (pk == 9 && ws->jt_ring_slots == 0) return RBD_OK;
   if (pk == 10 && ws->djt_ring_slots == 0) return RBD_OK;
   DevModel* h = new (std::nothrow) DevModel(ws->model->dm);
@@ -302,16 +330,18 @@ static int ensure_plan(rbd_workspace* ws, int pk) {
     if (ws->djt_ring_slots == 0) { delete h; return RBD_OK; }
     planned = true;
   } else {
+    const int ek = pk >= 11 ? pk - 11 : pk;  // eval variant bits (the storage plan does not depend on the M format)
     planned = pk == 8 ? plan_eval(h, false, true, ws->use_tmem != 0, 0, false, /*jt=*/true, RBD_JT_REGS)
-                      : plan_eval(h, (pk & 2) != 0, (pk & 1) != 0, ws->use_tmem != 0,
-                                  ws->forced_eval_block / 32, (pk & 4) != 0);
+                      : plan_eval(h, (ek & 2) != 0, (ek & 1) != 0, ws->use_tmem != 0,
+                                  ws->forced_eval_block / 32, (ek & 4) != 0);
   }
   if (!planned) {
     delete h;
+    ws->plan_failed[pk] = 1;
     return set_err(RBD_ERR_UNSUPPORTED, "the sweep state of this model does not fit one SM's shared + tensor memory"
                                         " at the requested block size");
   }
-  const std::vector<unsigned long long> blob = (pk == 9 || pk == 10) ? build_jt_blob(h, jt_prog) : build_eval_blob(h);
+  const std::vector<unsigned long long> blob = (pk == 9 || pk == 10) ? build_jt_blob(h, jt_prog) : build_eval_blob(h, pk >= 11);
   if (!ws->d_plan[pk]) {
     // sized for the largest blob any plan of this model can produce (the ColProg length is plan-independent)
     cudaError_t e = cudaMalloc(&ws->d_plan[pk], blob.size() * 8);
@@ -326,8 +356,9 @@ static int ensure_plan(rbd_workspace* ws, int pk) {
 static void drop_plans(rbd_workspace* ws) {
   // kernels still in flight keep reading the device copies: wait for them before the next upload overwrites
   cudaDeviceSynchronize();
-  for (int k = 0; k < 11; ++k) { delete ws->h_plan[k]; ws->h_plan[k] = nullptr; }
+  for (int k = 0; k < rbd_workspace::kPlans; ++k) { delete ws->h_plan[k]; ws->h_plan[k] = nullptr; }
   ws->jt_ring_slots = -1; ws->djt_ring_slots = -1;
+  memset(ws->plan_failed, 0, sizeof(ws->plan_failed));
   for (int k = 0; k < 8; ++k) { delete ws->h_plan32[k]; ws->h_plan32[k] = nullptr; }
 }
 
@@ -345,22 +376,26 @@ RBD_API int rbd_workspace_get_eval_plan(rbd_workspace* ws, int with_M, int with_
   return RBD_OK;
 }
 
+// sparse_m: M receives the support-only fields (structural zeros not stored) instead of the packed upper triangle
 static int eval_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, const double* q, const double* v,
-                   const double* a, double* oMi, double* J, double* M, double* tau) {
+                   const double* a, double* oMi, double* J, double* M, double* tau, bool sparse_m = false) {
   if (!q) return set_err(RBD_ERR_INVALID_ARG, "q is null");
   if (tau && (!v || !a)) return set_err(RBD_ERR_INVALID_ARG, "rnea needs v and a");
-  const int pk = (oMi ? 4 : 0) | (M ? 2 : 0) | (tau ? 1 : 0);
+  const int ek = (oMi ? 4 : 0) | (M ? 2 : 0) | (tau ? 1 : 0);
+  const int pk = (sparse_m && M) ? 11 + ek : ek;
   int rc = ensure_plan(ws, pk);
   if (rc == RBD_ERR_UNSUPPORTED && M && tau && ws->forced_eval_block == 0) {
     // very deep trees: the state of the fused CRBA + RNEA sweep does not fit one SM; the two halves may
-    rc = eval_on(ws, st, n, tile, q, v, a, oMi, J, M, nullptr);
+    rc = eval_on(ws, st, n, tile, q, v, a, oMi, J, M, nullptr, sparse_m);
     if (rc == RBD_OK) rc = eval_on(ws, st, n, tile, q, v, a, nullptr, nullptr, nullptr, tau);
+    if (rc == RBD_OK) g_err.clear();  // the "does not fit" message of the fused plan is not an error of this call
     return rc;
   }
   if (rc) return rc;
   EvalArgs A{n, tile, q, v, a, oMi, J, M, tau};
-  if (ws->h_plan[pk]->simple_joints) CK(launch_eval_simple(*ws->h_plan[pk], ws->d_plan[pk], A, ws->cfg_eval, ws->num_sms, st));
-  else CK(launch_eval(*ws->h_plan[pk], ws->d_plan[pk], A, ws->cfg_eval, ws->num_sms, st));
+  LaunchCfg* cfg = pk >= 11 ? ws->cfg_eval_sp : ws->cfg_eval;
+  if (ws->h_plan[pk]->simple_joints) CK(launch_eval_simple(*ws->h_plan[pk], ws->d_plan[pk], A, cfg, ws->num_sms, st));
+  else CK(launch_eval(*ws->h_plan[pk], ws->d_plan[pk], A, cfg, ws->num_sms, st));
   if (n > 0) ws->launches++;
   return RBD_OK;
 }
@@ -424,6 +459,17 @@ RBD_API int rbd_eval_soa(rbd_workspace* ws, int64_t n, int64_t tile, const doubl
   int rc = check_batch(ws, n, tile);
   if (rc) return rc;
   return eval_on(ws, ws->stream, n, tile, q, v, a, oMi, J, M, tau);
+}
+RBD_API int rbd_eval_soa_sparse(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, const double* v,
+                                const double* a, double* oMi, double* J, double* Mval, double* tau) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, tile);
+  if (rc) return rc;
+  return eval_on(ws, ws->stream, n, tile, q, v, a, oMi, J, Mval, tau, true);
+}
+RBD_API int rbd_crba_soa_sparse(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, double* Mval) {
+  if (!Mval) return set_err(RBD_ERR_INVALID_ARG, "Mval is null");
+  return rbd_eval_soa_sparse(ws, n, tile, q, nullptr, nullptr, nullptr, nullptr, Mval, nullptr);
 }
 RBD_API int rbd_crba_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, double* M) {
   if (!M) return set_err(RBD_ERR_INVALID_ARG, "M is null");
@@ -599,28 +645,42 @@ static int rows_on(rbd_workspace* ws, cudaStream_t st, const RowArgs& A) {
     return RBD_OK;
   }
   int rc0 = ensure_jcache(ws, st);
+  if (rc0 == RBD_ERR_ALLOC) {
+    // no room for the cache (a few constraint rows on a very large batch): the per-row sweep needs none
+    g_err.clear();
+    CK(launch_applyJT_rows(dm, ws->d_model, ws->tb, A, smem_applyJT(dm), &ws->cfg_rows, st));
+    ws->launches++;
+    return RBD_OK;
+  }
   if (rc0) return rc0;
   CK(launch_applyJT_rows_cached(dm, ws->d_model, ws->tb, A, ws->jcache, ws->omicache, st));
   ws->launches++;
   return RBD_OK;
 }
-// Jacobian cache of the applied instances (see rbd_workspace::jcache): allocate on first use, refill after an apply
+// Jacobian cache of the applied instances (see rbd_workspace::jcache): sized for the applied instances (grow-only, whole
+// tiles), allocated on first use, refilled after an apply.  RBD_ERR_ALLOC when the device has no room for it.
 static int ensure_jcache(rbd_workspace* ws, cudaStream_t st) {
   const DevModel& dm = ws->model->dm;
   const int kj = 6 * dm.nv, ko = 12 * (dm.njoints - 1);
-  const long long chunk = std::min<long long>((ws->capacity + 31) / 32 * 32, kRowsCacheChunk);
-  if (!ws->jcache) {
+  const long long need = (ws->applied_n + 31) / 32 * 32;
+  const long long chunk = std::min<long long>(need, kRowsCacheChunk);
+  if (!ws->jcache || ws->jcache_cap < need) {
     // all three or none: a failed allocation must not leave a half-built cache behind
-    const size_t cap = (size_t)((ws->capacity + 31) / 32 * 32);
+    if (ws->jcache) {
+      CK(cudaStreamSynchronize(st));
+      cudaFree(ws->jcache); cudaFree(ws->omicache); cudaFree(ws->jc_scratch);
+      ws->jcache = ws->omicache = ws->jc_scratch = nullptr; ws->jcache_cap = 0;
+    }
     double *j = nullptr, *o = nullptr, *sc = nullptr;
-    cudaError_t e = cudaMalloc(&j, cap * (size_t)kj * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&o, cap * (size_t)ko * sizeof(double));
+    cudaError_t e = cudaMalloc(&j, (size_t)need * (size_t)kj * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&o, (size_t)need * (size_t)ko * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&sc, (size_t)chunk * (size_t)(kj + ko) * sizeof(double));
     if (e != cudaSuccess) {
       cudaFree(j); cudaFree(o); cudaFree(sc);
-      return cuda_fail(e, "cudaMalloc(Jacobian cache)");
+      cudaGetLastError();
+      return set_err(RBD_ERR_ALLOC, std::string("cudaMalloc(Jacobian cache): ") + cudaGetErrorString(e));
     }
-    ws->jcache = j; ws->omicache = o; ws->jc_scratch = sc;
+    ws->jcache = j; ws->omicache = o; ws->jc_scratch = sc; ws->jcache_cap = need;
     ws->jc_epoch = -1;
   }
   if (ws->jc_epoch != ws->apply_epoch) {
@@ -755,10 +815,22 @@ struct Piece {  // one array of a host call: K fields, host pointer (may be null
   double* d_aos = nullptr;
 };
 
+// The arrays of one host call: at most kMaxPieces, on the stack (no allocation on the hot path).
+static const int kMaxPieces = 8;
+struct Pieces {
+  Piece p[kMaxPieces];
+  int n = 0;
+  Piece& operator[](int i) { return p[i]; }
+  void add(int K, const double* h_in, double* h_out, bool load, bool store) {
+    Piece& x = p[n++];
+    x.K = K; x.h_in = h_in; x.h_out = h_out; x.load = load; x.store = store; x.d_soa = x.d_aos = nullptr;
+  }
+};
+
 template <class KernelFn>
-static int run_host_chunks(rbd_workspace* ws, int64_t n, std::vector<Piece>& pieces, KernelFn kernel) {
+static int run_host_chunks(rbd_workspace* ws, int64_t n, Pieces& pieces, KernelFn kernel) {
   size_t fields = 0;
-  for (auto& p : pieces) fields += (size_t)p.K;
+  for (int k = 0; k < pieces.n; ++k) fields += (size_t)pieces[k].K;
   int rc = ensure_slots(ws, fields);
   if (rc) return rc;
   // order after whatever the caller queued on the workspace stream
@@ -771,7 +843,8 @@ static int run_host_chunks(rbd_workspace* ws, int64_t n, std::vector<Piece>& pie
     const long long cn = (n - i0) < chunk ? (n - i0) : chunk;
     HostSlot& sl = ws->slot[which];
     size_t off = 0;
-    for (auto& p : pieces) {
+    for (int k = 0; k < pieces.n; ++k) {
+      Piece& p = pieces[k];
       p.d_aos = sl.aos + off;
       p.d_soa = sl.soa + off;
       off += (size_t)p.K * (size_t)cpad;
@@ -785,7 +858,8 @@ static int run_host_chunks(rbd_workspace* ws, int64_t n, std::vector<Piece>& pie
     }
     rc = kernel(sl.st, i0, cn, tile);
     if (rc) return rc;
-    for (auto& p : pieces) {
+    for (int k = 0; k < pieces.n; ++k) {
+      Piece& p = pieces[k];
       if (p.store && p.h_out && p.K > 0) {
         CK(launch_soa_to_aos(cn, p.K, tile, p.d_soa, p.d_aos, sl.st));
         ws->launches++;
@@ -797,21 +871,35 @@ static int run_host_chunks(rbd_workspace* ws, int64_t n, std::vector<Piece>& pie
   return RBD_OK;
 }
 
-RBD_API int rbd_eval_host(rbd_workspace* ws, int64_t n, const double* q, const double* v, const double* a, double* oMi,
-                          double* J, double* M, double* tau) {
+static int eval_host_impl(rbd_workspace* ws, int64_t n, const double* q, const double* v, const double* a, double* oMi,
+                          double* J, double* M, double* tau, bool sparse_m) {
   GUARD(ws);
   int rc = check_batch(ws, n, 1);
   if (rc) return rc;
   if (!q) return set_err(RBD_ERR_INVALID_ARG, "q is null");
   if (tau && (!v || !a)) return set_err(RBD_ERR_INVALID_ARG, "rnea needs v and a");
   const rbd_model_info& I = ws->model->info;
-  std::vector<Piece> P = {{I.nq, q, nullptr, true, false},      {I.nv, v, nullptr, true, false},
-                          {I.nv, a, nullptr, true, false},      {I.omi_fields, nullptr, oMi, false, true},
-                          {I.jac_fields, nullptr, J, false, true}, {I.mass_fields, nullptr, M, false, true},
-                          {I.nv, nullptr, tau, false, true}};
+  // only what the requested outputs need travels: v and a are not copied when tau is not requested
+  Pieces P;
+  P.add(I.nq, q, nullptr, true, false);
+  P.add(I.nv, tau ? v : nullptr, nullptr, true, false);
+  P.add(I.nv, tau ? a : nullptr, nullptr, true, false);
+  P.add(I.omi_fields, nullptr, oMi, false, true);
+  P.add(I.jac_fields, nullptr, J, false, true);
+  P.add(sparse_m ? I.mass_support_fields : I.mass_fields, nullptr, M, false, true);
+  P.add(I.nv, nullptr, tau, false, true);
   return run_host_chunks(ws, n, P, [&](cudaStream_t st, long long, long long cn, long long tile) {
-    return eval_on(ws, st, cn, tile, P[0].d_soa, P[1].d_soa, P[2].d_soa, P[3].d_soa, P[4].d_soa, P[5].d_soa, P[6].d_soa);
+    return eval_on(ws, st, cn, tile, P[0].d_soa, P[1].d_soa, P[2].d_soa, P[3].d_soa, P[4].d_soa, P[5].d_soa, P[6].d_soa,
+                   sparse_m);
   });
+}
+RBD_API int rbd_eval_host(rbd_workspace* ws, int64_t n, const double* q, const double* v, const double* a, double* oMi,
+                          double* J, double* M, double* tau) {
+  return eval_host_impl(ws, n, q, v, a, oMi, J, M, tau, false);
+}
+RBD_API int rbd_eval_host_sparse(rbd_workspace* ws, int64_t n, const double* q, const double* v, const double* a,
+                                 double* oMi, double* J, double* Mval, double* tau) {
+  return eval_host_impl(ws, n, q, v, a, oMi, J, Mval, tau, true);
 }
 
 // Mass / ForceField products on host vectors: the accumulated vector travels both ways (load, +=, store)
@@ -821,7 +909,8 @@ RBD_API int rbd_addMDx_host(rbd_workspace* ws, int64_t n, const double* q, const
   if (rc) return rc;
   if (!q || !dx || !res) return set_err(RBD_ERR_INVALID_ARG, "null q / dx / res");
   const rbd_model_info& I = ws->model->info;
-  std::vector<Piece> P = {{I.nq, q, nullptr, true, false}, {I.nv, dx, nullptr, true, false}, {I.nv, res, res, true, true}};
+  Pieces P;
+  P.add(I.nq, q, nullptr, true, false); P.add(I.nv, dx, nullptr, true, false); P.add(I.nv, res, res, true, true);
   return run_host_chunks(ws, n, P, [&](cudaStream_t st, long long, long long cn, long long tile) {
     return mass_force_on(ws, st, cn, tile, P[0].d_soa, nullptr, P[1].d_soa, P[2].d_soa, factor, 0);
   });
@@ -832,7 +921,8 @@ RBD_API int rbd_addForce_host(rbd_workspace* ws, int64_t n, const double* q, con
   if (rc) return rc;
   if (!q || !f) return set_err(RBD_ERR_INVALID_ARG, "null q / f");
   const rbd_model_info& I = ws->model->info;
-  std::vector<Piece> P = {{I.nq, q, nullptr, true, false}, {I.nv, v, nullptr, true, false}, {I.nv, f, f, true, true}};
+  Pieces P;
+  P.add(I.nq, q, nullptr, true, false); P.add(I.nv, v, nullptr, true, false); P.add(I.nv, f, f, true, true);
   return run_host_chunks(ws, n, P, [&](cudaStream_t st, long long, long long cn, long long tile) {
     return mass_force_on(ws, st, cn, tile, P[0].d_soa, v ? P[1].d_soa : nullptr, nullptr, P[2].d_soa, -1.0, 1);
   });
@@ -846,8 +936,9 @@ RBD_API int rbd_apply_host(rbd_workspace* ws, int64_t n, const double* q_joints,
   const rbd_model_info& I = ws->model->info;
   if (root_pose && !I.has_freeflyer_root) return set_err(RBD_ERR_INVALID_ARG, "root pose given but the model has no free-flyer root");
   const int kq = root_pose ? I.nq - 7 : I.nq;
-  std::vector<Piece> P = {{kq, q_joints, nullptr, true, false}, {7, root_pose, nullptr, true, false},
-                          {7 * I.n_out, nullptr, out, false, true}};
+  Pieces P;
+  P.add(kq, q_joints, nullptr, true, false); P.add(7, root_pose, nullptr, true, false);
+  P.add(7 * I.n_out, nullptr, out, false, true);
   rc = run_host_chunks(ws, n, P, [&](cudaStream_t st, long long i0, long long cn, long long tile) {
     return apply_on(ws, st, cn, tile, i0, P[0].d_soa, P[1].d_soa, P[2].d_soa);
   });
@@ -864,8 +955,9 @@ RBD_API int rbd_applyJ_host(rbd_workspace* ws, int64_t n, const double* dq_joint
   const rbd_model_info& I = ws->model->info;
   if (root_vel && !I.has_freeflyer_root) return set_err(RBD_ERR_INVALID_ARG, "root velocity given but the model has no free-flyer root");
   const int kv = root_vel ? I.nv - 6 : I.nv;
-  std::vector<Piece> P = {{kv, dq_joints, nullptr, true, false}, {6, root_vel, nullptr, true, false},
-                          {6 * I.n_out, nullptr, out, false, true}};
+  Pieces P;
+  P.add(kv, dq_joints, nullptr, true, false); P.add(6, root_vel, nullptr, true, false);
+  P.add(6 * I.n_out, nullptr, out, false, true);
   return run_host_chunks(ws, n, P, [&](cudaStream_t st, long long i0, long long cn, long long tile) {
     return applyJ_on(ws, st, cn, tile, i0, P[0].d_soa, P[1].d_soa, P[2].d_soa);
   });
@@ -881,8 +973,9 @@ RBD_API int rbd_applyJT_host(rbd_workspace* ws, int64_t n, const double* in, dou
   if (out_root && !I.has_freeflyer_root) return set_err(RBD_ERR_INVALID_ARG, "root output given but the model has no free-flyer root");
   const int kv = out_root ? I.nv - 6 : I.nv;
   // out_tau / out_root are accumulated (+=, reference KinematicChainMapping.inl:498-511): load, add, store
-  std::vector<Piece> P = {{6 * I.n_out, in, nullptr, true, false}, {kv, out_tau, out_tau, true, true},
-                          {6, out_root, out_root, true, true}};
+  Pieces P;
+  P.add(6 * I.n_out, in, nullptr, true, false); P.add(kv, out_tau, out_tau, true, true);
+  P.add(6, out_root, out_root, true, true);
   return run_host_chunks(ws, n, P, [&](cudaStream_t st, long long i0, long long cn, long long tile) {
     return applyJT_on(ws, st, cn, tile, i0, P[0].d_soa, P[1].d_soa, P[2].d_soa);
   });
@@ -898,9 +991,10 @@ RBD_API int rbd_applyDJT_host(rbd_workspace* ws, int64_t n, const double* dq_joi
   const rbd_model_info& I = ws->model->info;
   if ((root_vel || out_root) && !I.has_freeflyer_root) return set_err(RBD_ERR_INVALID_ARG, "root arrays given but the model has no free-flyer root");
   const int kv = root_vel ? I.nv - 6 : I.nv;
-  std::vector<Piece> P = {{kv, dq_joints, nullptr, true, false}, {6, root_vel, nullptr, true, false},
-                          {6 * I.n_out, in, nullptr, true, false}, {kv, out_tau, out_tau, true, true},
-                          {6, out_root, out_root, true, true}};
+  Pieces P;
+  P.add(kv, dq_joints, nullptr, true, false); P.add(6, root_vel, nullptr, true, false);
+  P.add(6 * I.n_out, in, nullptr, true, false); P.add(kv, out_tau, out_tau, true, true);
+  P.add(6, out_root, out_root, true, true);
   return run_host_chunks(ws, n, P, [&](cudaStream_t st, long long i0, long long cn, long long tile) {
     return applyDJT_on(ws, st, cn, tile, i0, P[0].d_soa, P[1].d_soa, P[2].d_soa, kfactor, P[3].d_soa, P[4].d_soa);
   });
@@ -916,8 +1010,15 @@ RBD_API int rbd_applyJT_rows_host(rbd_workspace* ws, int64_t nrows, const int32_
   const int nv = ws->model->info.nv;
   const long long nnz = row_ptr[nrows];
   if (nnz < 0 || (nnz > 0 && (!col || !val))) return set_err(RBD_ERR_INVALID_ARG, "bad CSR arrays");
-  for (int64_t r = 0; r < nrows; ++r)
+  // a malformed constraint matrix would index the per-output tables and the Jacobian cache out of bounds on the device
+  if (row_ptr[0] != 0) return set_err(RBD_ERR_INVALID_ARG, "row_ptr[0] must be 0");
+  const int n_out = ws->model->info.n_out;
+  for (int64_t r = 0; r < nrows; ++r) {
     if (row_instance[r] < 0 || row_instance[r] >= ws->applied_n) return set_err(RBD_ERR_INVALID_ARG, "row_instance out of the applied range");
+    if (row_ptr[r + 1] < row_ptr[r]) return set_err(RBD_ERR_INVALID_ARG, "row_ptr is not non-decreasing");
+  }
+  for (long long j = 0; j < nnz; ++j)
+    if (col[j] < 0 || col[j] >= n_out) return set_err(RBD_ERR_INVALID_ARG, "col entry is not a mapped-output index (0 <= col < n_out)");
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
   const size_t b_rp = al((size_t)(nrows + 1) * 4), b_ri = al((size_t)nrows * 4), b_col = al((size_t)nnz * 4),
                b_val = al((size_t)nnz * 48), b_out = al((size_t)nrows * nv * 8), b_keep = al((size_t)nrows * 4);

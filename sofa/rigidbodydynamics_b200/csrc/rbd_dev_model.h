@@ -34,7 +34,9 @@ struct alignas(16) DevJointT {
   int nv;           // dof of this joint (0 universe, 1, or 6)
   int nchild;       // number of child joints
   int slot[2];      // stack-slot offset (doubles) of a joint that has children: [0] full layout (A|f|Y), [1] lite (A|f);
-                    // leaves never touch the stack (they are emitted from registers)
+                    // leaves never touch the stack (they are emitted from registers).  Mapping kernels only: in the
+                    // staged blob of the FUSED EVAL the two words carry the joint's place in the M output instead
+                    // (RBD_MBASE / RBD_MOWN below; the eval sweep never reads stack slots through this table)
   int bidx;         // branch-slot index (joints with >= 2 children), -1 otherwise
   int out_begin, out_end;  // range of this joint's mapped outputs in DevTables::sorted_*
   int pl_rot_identity;     // jointPlacement rotation is exactly I (skips one 3x3 product)
@@ -48,6 +50,15 @@ struct alignas(16) DevJointT {
 using DevJoint = DevJointT<double>;
 // ColProg entries (int32).  Ancestor entry, root first: row (idx_v of the ancestor) | free-flyer flag | A-stack offset.
 // Zero segment: first row | length.  Rows not covered by either belong to the joint itself.
+// Place of joint j's column(s) in the M output (eval blob only, see DevJointT::slot).  Column cc (0 .. nv-1) of the
+// joint starts at field  RBD_MBASE(j) + cc * RBD_MOWN(j) + cc (cc + 1) / 2 ; within it the rows of the ancestors' dofs
+// sit at the offsets the column program gives, the joint's own rows 0 .. cc at offset RBD_MOWN(j) + row.
+//   packed upper triangle (pinocchio data.M):  MBASE = c0 (c0 + 1) / 2, MOWN = c0 (c0 = idx_v), program row = idx_v of
+//     the ancestor, zero segments for the dofs off the ancestor chain;
+//   support-only ("sparse") M:  MBASE = entries before this joint, MOWN = number of ancestor dofs, program row = position
+//     of the ancestor's first dof in the column, no zero segments — the structural zeros are not stored at all.
+#define RBD_MBASE(j) ((j).slot[0])
+#define RBD_MOWN(j) ((j).slot[1])
 #define RBD_PROG_ROW(e) ((e) & 0xffff)
 #define RBD_PROG_FF(e) (((e) >> 16) & 1)
 #define RBD_PROG_OFFA(e) ((e) >> 17)
@@ -90,7 +101,8 @@ struct alignas(16) DevModelT {
   int nq_joints, nv_joints;
   int max_depth, max_depth_internal;  // longest joint chain; deepest joint that has children
   int simple_joints;                  // 1 = every joint is RX / RY / RZ or a free-flyer (rbd::simple kernels apply)
-  int pad0_;
+  int mfields;                        // eval blob: fields per instance of the M output (nv (nv + 1) / 2 packed, or the
+                                      // support-only count); 0 in unplanned models
   int prog_words_off, prog_len;       // eval blob: 8-byte-word offset of the ColProg table behind the joint records; ints
   real gravity[3];
   EvalPlan plan;
@@ -103,7 +115,7 @@ inline void dev_model_to_f32(const DevModel& d, DevModelT<float>* f) {
   f->njoints = d.njoints; f->nq = d.nq; f->nv = d.nv; f->n_out = d.n_out;
   f->slot_total[0] = d.slot_total[0]; f->slot_total[1] = d.slot_total[1];
   f->nbranch = d.nbranch; f->has_ff_root = d.has_ff_root; f->nq_joints = d.nq_joints; f->nv_joints = d.nv_joints;
-  f->max_depth = d.max_depth; f->max_depth_internal = d.max_depth_internal; f->simple_joints = d.simple_joints; f->pad0_ = 0;
+  f->max_depth = d.max_depth; f->max_depth_internal = d.max_depth_internal; f->simple_joints = d.simple_joints; f->mfields = d.mfields;
   f->prog_words_off = d.prog_words_off; f->prog_len = d.prog_len;
   for (int k = 0; k < 3; ++k) f->gravity[k] = (float)d.gravity[k];
   f->plan = d.plan;

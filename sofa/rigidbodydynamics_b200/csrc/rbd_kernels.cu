@@ -82,10 +82,10 @@ __global__ void __launch_bounds__((MINB == 1 && DO_TAU && !DO_M) ? 384 : 256, MI
     io.a = NSQ::make_field_t<TILE>(const_cast<REAL*>(a.a), inst, m.nv, a.tile);                                                                         \
     io.oMi = NSQ::make_field_t<TILE>(a.oMi, inst, 12 * (m.njoints - 1), a.tile);                                                                        \
     io.J = NSQ::make_field_t<TILE>(a.J, inst, 6 * m.nv, a.tile);                                                                                        \
-    io.M = NSQ::make_field_t<TILE>(a.M, inst, m.nv * (m.nv + 1) / 2, a.tile);                                                                           \
+    io.M = NSQ::make_field_t<TILE>(a.M, inst, m.mfields, a.tile);                                                                                       \
     io.tau = NSQ::make_field_t<TILE>(a.tau, inst, m.nv, a.tile);                                                                                        \
     io.Mtile = (TILE == 32 && a.M && (reinterpret_cast<unsigned long long>(a.M) & 15) == 0)                                                             \
-                   ? a.M + t * (long long)(m.nv * (m.nv + 1) / 2) * 32 : nullptr;                                                                       \
+                   ? a.M + t * (long long)m.mfields * 32 : nullptr;                                                                                     \
     io.tau_scale = a.tau_scale; io.tau_acc = a.tau_acc; io.gravity_on = a.gravity_on;                                                                  \
     io.next = (TILE != 0 && (t + (long long)gridDim.x * wpb + 1) * 32 <= a.n) ? (long long)gridDim.x * wpb : 0; /* full tiles only */                   \
     NSQ::eval_instance<DO_M, DO_TAU, TILE>(m, io, S, T, inr);                                                                                           \
@@ -562,6 +562,16 @@ __global__ void soa_to_aos_kernel(long long n, int K, long long tile, const doub
 // launch helpers
 static const int kMaxSmemOptin = 227 * 1024;
 
+// The __global__ function this thread launched last (rbd_last_kernel_name: bench.py reads the name of the timed
+// instantiation back from the launch instead of deriving it from the model).
+static thread_local const void* g_last_kernel = nullptr;
+#define RBD_NOTE(K) (g_last_kernel = reinterpret_cast<const void*>(K))
+const char* last_kernel_mangled() {
+  const char* name = nullptr;
+  if (!g_last_kernel || cudaFuncGetName(&name, g_last_kernel) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return name;
+}
+
 template <class Kern>
 static cudaError_t pick_block(Kern kern, int smem_doubles_per_thread, int forced, LaunchCfg* cfg,
                               size_t block_fixed_bytes = 0) {
@@ -636,7 +646,7 @@ static cudaError_t pick_block(Kern kern, int smem_doubles_per_thread, int forced
   e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin);         \
   if (e == cudaSuccess)                                                                             \
     e = cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
-#define RBD_LAUNCH(K) K<<<grid, block, smem, st>>>(d_model, a, model_words)
+#define RBD_LAUNCH(K) RBD_NOTE(K); K<<<grid, block, smem, st>>>(d_model, a, model_words)
 RBD_DEFINE_EVAL_LAUNCH(launch_eval, eval_kernel, double)
 RBD_DEFINE_EVAL_LAUNCH(launch_eval_simple, eval_kernel_simple, double)
 RBD_DEFINE_EVAL_LAUNCH(launch_eval_f32, eval_kernel_f32, float)
@@ -657,8 +667,8 @@ static inline int map_model_words(const DevModel& m) { return (int)((dev_model_b
     if (e != cudaSuccess) return e;                                                                           \
   }                                                                                                           \
   if ((n_items) <= 0) return cudaSuccess;                                                                     \
-  if (v) KERN<32><<<RBD_GRID(n_items, c.block), c.block, c.smem_bytes, st>>>(d_model, mw, tb, a, smem_doubles); \
-  else KERN<0><<<RBD_GRID(n_items, c.block), c.block, c.smem_bytes, st>>>(d_model, mw, tb, a, smem_doubles);  \
+  if (v) { RBD_NOTE(KERN<32>); KERN<32><<<RBD_GRID(n_items, c.block), c.block, c.smem_bytes, st>>>(d_model, mw, tb, a, smem_doubles); } \
+  else { RBD_NOTE(KERN<0>); KERN<0><<<RBD_GRID(n_items, c.block), c.block, c.smem_bytes, st>>>(d_model, mw, tb, a, smem_doubles); } \
   return cudaGetLastError()
 
 cudaError_t launch_apply(const DevModel& m, const DevModel* d_model, const DevTables& tb, const MapArgs& a,
@@ -697,8 +707,8 @@ cudaError_t launch_applyJT_plan(const DevModel& hm, const DevModel* d_blob, cons
   unsigned grid = RBD_GRID(a.n, block);
   const unsigned resident = (unsigned)(num_sms * (hm.plan.blocks_per_sm > 0 ? hm.plan.blocks_per_sm : 1));
   if (grid > 8 * resident) grid = resident;  // persistent only when every warp gets >= 8 tiles (else: wave tail)
-  if (v) applyJT_plan_kernel<32><<<grid, block, smem, st>>>(d_blob, model_words, tb, a);
-  else applyJT_plan_kernel<0><<<grid, block, smem, st>>>(d_blob, model_words, tb, a);
+  if (v) { RBD_NOTE(applyJT_plan_kernel<32>); applyJT_plan_kernel<32><<<grid, block, smem, st>>>(d_blob, model_words, tb, a); }
+  else { RBD_NOTE(applyJT_plan_kernel<0>); applyJT_plan_kernel<0><<<grid, block, smem, st>>>(d_blob, model_words, tb, a); }
   return cudaGetLastError();
 }
 
@@ -731,10 +741,10 @@ cudaError_t launch_applyJT_ring(const DevModel& hm, const DevModel* d_blob, cons
   const long long ntiles = a.n / 32;
   unsigned grid = (unsigned)((ntiles + W - 1) / W);
   if (grid > (unsigned)num_sms) grid = (unsigned)num_sms;
-  if (variant == 3) applyJT_ring_kernel<JtRing::kWarps, 2><<<grid, block, smem, st>>>(d_blob, model_words, a, nst);
-  else if (variant == 2) applyJT_ring_kernel<JtRing::kWarpsSmall, 1><<<grid, block, smem, st>>>(d_blob, model_words, a, nst);
-  else if (variant == 1) applyJT_ring_kernel<JtRing::kWarpsSmall, 0><<<grid, block, smem, st>>>(d_blob, model_words, a, nst);
-  else applyJT_ring_kernel<JtRing::kWarps, 0><<<grid, block, smem, st>>>(d_blob, model_words, a, nst);
+  if (variant == 3) { RBD_NOTE((applyJT_ring_kernel<JtRing::kWarps, 2>)); applyJT_ring_kernel<JtRing::kWarps, 2><<<grid, block, smem, st>>>(d_blob, model_words, a, nst); }
+  else if (variant == 2) { RBD_NOTE((applyJT_ring_kernel<JtRing::kWarpsSmall, 1>)); applyJT_ring_kernel<JtRing::kWarpsSmall, 1><<<grid, block, smem, st>>>(d_blob, model_words, a, nst); }
+  else if (variant == 1) { RBD_NOTE((applyJT_ring_kernel<JtRing::kWarpsSmall, 0>)); applyJT_ring_kernel<JtRing::kWarpsSmall, 0><<<grid, block, smem, st>>>(d_blob, model_words, a, nst); }
+  else { RBD_NOTE((applyJT_ring_kernel<JtRing::kWarps, 0>)); applyJT_ring_kernel<JtRing::kWarps, 0><<<grid, block, smem, st>>>(d_blob, model_words, a, nst); }
   return cudaGetLastError();
 }
 
@@ -750,8 +760,8 @@ cudaError_t launch_applyDJT(const DevModel& m, const DevModel* d_model, const De
     if (e != cudaSuccess) return e;
   }
   if (a.n <= 0) return cudaSuccess;
-  if (v) applyDJT_kernel<32><<<RBD_GRID(a.n, c.block), c.block, c.smem_bytes, st>>>(d_model, mw, tb, a, slots);
-  else applyDJT_kernel<0><<<RBD_GRID(a.n, c.block), c.block, c.smem_bytes, st>>>(d_model, mw, tb, a, slots);
+  if (v) { RBD_NOTE(applyDJT_kernel<32>); applyDJT_kernel<32><<<RBD_GRID(a.n, c.block), c.block, c.smem_bytes, st>>>(d_model, mw, tb, a, slots); }
+  else { RBD_NOTE(applyDJT_kernel<0>); applyDJT_kernel<0><<<RBD_GRID(a.n, c.block), c.block, c.smem_bytes, st>>>(d_model, mw, tb, a, slots); }
   return cudaGetLastError();
 }
 
@@ -763,6 +773,7 @@ cudaError_t launch_applyJT_rows(const DevModel& m, const DevModel* d_model, cons
     if (e != cudaSuccess) return e;
   }
   if (a.nrows <= 0) return cudaSuccess;
+  RBD_NOTE(applyJT_rows_kernel);
   applyJT_rows_kernel<<<RBD_GRID(a.nrows, cfg->block), cfg->block, cfg->smem_bytes, st>>>(d_model, mw, tb, a, smem_doubles);
   return cudaGetLastError();
 }
@@ -776,6 +787,7 @@ cudaError_t launch_applyJT_rows_cached(const DevModel& m, const DevModel* d_mode
   cudaError_t e = cudaFuncSetAttribute(applyJT_rows_cached_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin);
   if (e != cudaSuccess) return e;
   if (a.nrows <= 0) return cudaSuccess;
+  RBD_NOTE(applyJT_rows_cached_kernel);
   applyJT_rows_cached_kernel<<<RBD_GRID(a.nrows, block), block, smem, st>>>(d_model, mw, tb, a, jc, oc);
   return cudaGetLastError();
 }
@@ -787,6 +799,7 @@ cudaError_t launch_frame_jacobian(const DevModel& m, const DevModel* d_model, co
   const int mw = map_model_words(m);
   cudaError_t e = cudaMemsetAsync(J, 0, (size_t)npairs * 6 * m.nv * sizeof(double), st);
   if (e != cudaSuccess) return e;
+  RBD_NOTE(frame_jacobian_kernel);
   frame_jacobian_kernel<<<RBD_GRID(npairs, 256), 256, (size_t)mw * 8, st>>>(d_model, mw, tb, npairs, instance, out_index, J, jc, oc);
   return cudaGetLastError();
 }

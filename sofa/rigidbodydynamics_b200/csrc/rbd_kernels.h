@@ -86,4 +86,8 @@ cudaError_t launch_frame_jacobian(const DevModel& m, const DevModel* d_model, co
 cudaError_t launch_aos_to_soa(long long n, int K, long long tile, const double* aos, double* soa, cudaStream_t st);
 cudaError_t launch_soa_to_aos(long long n, int K, long long tile, const double* soa, double* aos, cudaStream_t st);
 
+// mangled name of the __global__ function the calling thread launched last through the functions above (the layout
+// adapters are not recorded), or nullptr
+const char* last_kernel_mangled();
+
 }  // namespace rbd

@@ -20,42 +20,75 @@ struct HostTables {
 };
 
 // Column programs of M for one planned model (offA values come from plan_eval): see RBD_PROG_* in rbd_dev_model.h.
-// Fills joint[*].prog_off / nzseg and m->prog_len; returns the table.
-inline std::vector<int> build_col_prog(DevModel* m) {
+// Fills joint[*].prog_off / nzseg, the place of every joint's columns in the M output (RBD_MBASE / RBD_MOWN),
+// m->mfields and m->prog_len; returns the table.  sparse_m = the support-only M format (structural zeros not stored).
+inline std::vector<int> build_col_prog(DevModel* m, bool sparse_m = false) {
   std::vector<int> prog;
   const int nj = m->njoints;
+  int mcount = 0;  // support-only entries before the current joint
   for (int k = 1; k < nj; ++k) {
     DevJoint& jk = m->joint[k];
     jk.prog_off = (int)prog.size();
     std::vector<int> chain;  // ancestors, root first
     for (int a = jk.parent; a != 0; a = m->joint[a].parent) chain.insert(chain.begin(), a);
-    for (int a : chain) prog.push_back(RBD_PROG_ANC(m->joint[a].idx_v, m->joint[a].type == JT_FF ? 1 : 0, m->joint[a].offA));
-    // zero segments: rows below the joint's first dof that no ancestor owns
-    int r = 0, nz = 0;
+    int nanc = 0;  // dofs of the ancestors
     for (int a : chain) {
-      const int iv = m->joint[a].idx_v;
-      if (iv > r) { prog.push_back(RBD_PROG_ZSEG(r, iv - r)); ++nz; }
-      r = iv + m->joint[a].nv;
+      prog.push_back(RBD_PROG_ANC(sparse_m ? nanc : m->joint[a].idx_v, m->joint[a].type == JT_FF ? 1 : 0, m->joint[a].offA));
+      nanc += m->joint[a].nv;
     }
-    if (jk.idx_v > r) { prog.push_back(RBD_PROG_ZSEG(r, jk.idx_v - r)); ++nz; }
+    // zero segments: rows below the joint's first dof that no ancestor owns
+    int nz = 0;
+    if (!sparse_m) {
+      int r = 0;
+      for (int a : chain) {
+        const int iv = m->joint[a].idx_v;
+        if (iv > r) { prog.push_back(RBD_PROG_ZSEG(r, iv - r)); ++nz; }
+        r = iv + m->joint[a].nv;
+      }
+      if (jk.idx_v > r) { prog.push_back(RBD_PROG_ZSEG(r, jk.idx_v - r)); ++nz; }
+    }
     jk.nzseg = nz;
+    RBD_MBASE(jk) = sparse_m ? mcount : jk.idx_v * (jk.idx_v + 1) / 2;
+    RBD_MOWN(jk) = sparse_m ? nanc : jk.idx_v;
+    mcount += jk.nv * nanc + jk.nv * (jk.nv + 1) / 2;
   }
+  m->mfields = sparse_m ? mcount : m->nv * (m->nv + 1) / 2;
   m->prog_len = (int)prog.size();
   m->prog_words_off = (int)((dev_model_bytes(*m) + 15) / 16 * 2);
   return prog;
 }
 
+// Support-only pattern of M (upper triangle, by columns): entry (r, c), r <= c, is structurally non-zero iff the joint
+// owning dof r is the joint owning dof c or one of its ancestors.  col_ptr [nv + 1], row_idx [nnz] (either may be null);
+// returns nnz.  The order is exactly the order of the fields the support-only eval writes (build_col_prog above).
+inline int mass_support_pattern(const DevModel& m, int* col_ptr, int* row_idx) {
+  int nnz = 0;
+  for (int k = 1; k < m.njoints; ++k) {
+    const DevJoint& jk = m.joint[k];
+    std::vector<int> chain;
+    for (int a = jk.parent; a != 0; a = m.joint[a].parent) chain.insert(chain.begin(), a);
+    for (int cc = 0; cc < jk.nv; ++cc) {
+      if (col_ptr) col_ptr[jk.idx_v + cc] = nnz;
+      for (int a : chain)
+        for (int e = 0; e < m.joint[a].nv; ++e) { if (row_idx) row_idx[nnz] = m.joint[a].idx_v + e; ++nnz; }
+      for (int e = 0; e <= cc; ++e) { if (row_idx) row_idx[nnz] = jk.idx_v + e; ++nnz; }
+    }
+  }
+  if (col_ptr) col_ptr[m.nv] = nnz;
+  return nnz;
+}
+
 // The blob the eval kernel stages into shared memory: planned DevModel prefix (16-byte rounded) + ColProg table.
-inline std::vector<unsigned long long> build_eval_blob(DevModel* m) {
-  const std::vector<int> prog = build_col_prog(m);
+inline std::vector<unsigned long long> build_eval_blob(DevModel* m, bool sparse_m = false) {
+  const std::vector<int> prog = build_col_prog(m, sparse_m);
   std::vector<unsigned long long> blob(eval_model_bytes(*m) / 8 - 2, 0ull);
   memcpy(blob.data(), m, dev_model_bytes(*m));
   if (!prog.empty()) memcpy(blob.data() + m->prog_words_off, prog.data(), prog.size() * sizeof(int));
   return blob;
 }
 // ... and its FP32 twin: the same planned model with float constants (`f` receives the converted model)
-inline std::vector<unsigned long long> build_eval_blob_f32(DevModel* m, DevModelT<float>* f) {
-  const std::vector<int> prog = build_col_prog(m);
+inline std::vector<unsigned long long> build_eval_blob_f32(DevModel* m, DevModelT<float>* f, bool sparse_m = false) {
+  const std::vector<int> prog = build_col_prog(m, sparse_m);
   dev_model_to_f32(*m, f);
   f->prog_words_off = (int)((dev_model_bytes(*f) + 15) / 16 * 2);
   std::vector<unsigned long long> blob(eval_model_bytes(*f) / 8 - 2, 0ull);
@@ -237,7 +270,14 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
     totalA = pre[D + 1];
     for (int i = 1; i < nj; ++i) m->joint[i].offA = m->joint[i].depth <= D ? pre[m->joint[i].depth] : 0;
   }
-  (void)build_col_prog(m);  // sizes the ColProg table (its length does not depend on the plan)
+  {
+    // sizes the ColProg table for the staged-blob budget (the packed-M program is the longer one; its length does not
+    // depend on the plan).  On a copy: build_col_prog writes the M placement into the joints' slot words, which the
+    // caller's model may still need as stack slots.
+    DevModel t = *m;
+    (void)build_col_prog(&t);
+    m->prog_len = t.prog_len; m->prog_words_off = t.prog_words_off;
+  }
   // the applyJT kernel also stages the per-output tables behind the blob
   size_t model_bytes = eval_model_bytes(*m) + (jt ? (size_t)table_words(m->n_out) * 8 : 0);
   if (elem_bytes == 4) {

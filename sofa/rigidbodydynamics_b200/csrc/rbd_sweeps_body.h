@@ -777,9 +777,8 @@ RBD_HD void emit_joint(const DevModel& m, int k, const real* A, const real* f, c
     if (DO_M) {
       real F[6];
       inertia_mul(Y, A, F);
-      const int col = jn.idx_v;
-      const int base = col * (col + 1) / 2;
-      *io.M.at(base + col) = dot6(A, F);
+      const int base = RBD_MBASE(jn);  // packed: col (col + 1) / 2, own row at + col; support-only: see rbd_dev_model.h
+      *io.M.at(base + RBD_MOWN(jn)) = dot6(A, F);
       column_rows(m, jn, base, F, S, io.M, io.Mtile);
     }
   } else {
@@ -792,10 +791,9 @@ RBD_HD void emit_joint(const DevModel& m, int k, const real* A, const real* f, c
       if (DO_M) {
         real F[6], o6[6];
         inertia_mul(Y, Ac, F);
-        const int col = jn.idx_v + cc;
-        const int base = col * (col + 1) / 2;
+        const int base = RBD_MBASE(jn) + cc * RBD_MOWN(jn) + cc * (cc + 1) / 2;
         ff_rows(A, A + 9, F, o6);
-        real* const pd = io.M.at(base + jn.idx_v);
+        real* const pd = io.M.at(base + RBD_MOWN(jn));
 #pragma unroll
         for (int e = 0; e < 6; ++e)
           if (e <= cc) io.M.st_at(pd, e, o6[e]);

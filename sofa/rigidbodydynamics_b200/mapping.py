@@ -73,26 +73,32 @@ class KinematicChainMapping:
     def apply(self, out_pos: List[np.ndarray], in1_pos: List[np.ndarray], in2_pos: List[np.ndarray]) -> None:
         if self.d_componentState == INVALID:
             return
-        if len(out_pos) != 1:
-            return self._invalid("apply: exactly one output vector expected")
-        if len(in1_pos) != 1:
-            return self._invalid("apply: exactly one input1 vector expected")
+        if not out_pos or not in1_pos:                      # inl:117-118: empty -> silent return, state untouched
+            return
+        if len(out_pos) > 1:
+            return self._invalid("KinematicChainMapping only supports output vector of size 1")
+        if len(in1_pos) > 1:
+            return self._invalid("KinematicChainMapping only supports input vector of size 1")
         if len(in2_pos) > 1:
-            return self._invalid("apply: at most one input2 vector expected")
+            return self._invalid("KinematicChainMapping only supports input root vector of size 1")
         self._apply(out_pos[0], in1_pos[0], in2_pos[0] if in2_pos else None)
 
     def applyJ(self, out_vel: List[np.ndarray], in1_vel: List[np.ndarray], in2_vel: List[np.ndarray]) -> None:
         if self.d_componentState == INVALID:
             return
-        if len(out_vel) != 1 or len(in1_vel) != 1 or len(in2_vel) > 1:
-            return self._invalid("applyJ: wrong number of state vectors")
+        if not out_vel or not in1_vel:                      # inl:165-166
+            return
+        if len(out_vel) > 1 or len(in1_vel) > 1 or len(in2_vel) > 1:
+            return self._invalid("applyJ: KinematicChainMapping only supports state vectors of size 1")
         self._applyJ(out_vel[0], in1_vel[0], in2_vel[0] if in2_vel else None)
 
     def applyJT(self, out1_force: List[np.ndarray], out2_force: List[np.ndarray], in_force: List[np.ndarray]) -> None:
         if self.d_componentState == INVALID:
             return
-        if len(out1_force) != 1 or len(in_force) != 1 or len(out2_force) > 1:
-            return self._invalid("applyJT: wrong number of state vectors")
+        if not in_force or not out1_force:                  # inl:212-213
+            return
+        if len(in_force) != 1 or len(out1_force) > 1 or len(out2_force) > 1:
+            return self._invalid("applyJT: KinematicChainMapping only supports state vectors of size 1")
         self._applyJT(out1_force[0], out2_force[0] if out2_force else None, in_force[0])
 
     def applyJT_matrix(self, in_const: MatrixDerivIn, with_root: Optional[bool] = None):

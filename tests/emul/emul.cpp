@@ -57,7 +57,7 @@ static void eval_one(const DevModel& m, long long i, long long tile, double* q, 
   io.q = make_field_t<TILE>(q, i, m.nq, tile); io.v = make_field_t<TILE>(v, i, m.nv, tile);
   io.a = make_field_t<TILE>(a, i, m.nv, tile);
   io.oMi = make_field_t<TILE>(oMi, i, 12 * (m.njoints - 1), tile); io.J = make_field_t<TILE>(J, i, 6 * m.nv, tile);
-  io.M = make_field_t<TILE>(M, i, m.nv * (m.nv + 1) / 2, tile); io.tau = make_field_t<TILE>(tau, i, m.nv, tile);
+  io.M = make_field_t<TILE>(M, i, m.mfields, tile); io.tau = make_field_t<TILE>(tau, i, m.nv, tile);
   if (do_m && do_tau) eval_instance<true, true, TILE>(m, io, S, T, inr);
   else if (do_m) eval_instance<true, false, TILE>(m, io, S, T, inr);
   else if (do_tau) eval_instance<false, true, TILE>(m, io, S, T, inr);
@@ -66,15 +66,29 @@ static void eval_one(const DevModel& m, long long i, long long tile, double* q, 
 
 // tile == 32 runs the compile-time-tile instantiation the GPU fast path uses.  use_tmem selects the storage plan
 // (tensor memory is emulated by a second poisoned array); block = warps * 32 pins the planner's block size (0 = auto).
+extern "C" int emul_eval_ex(const rbd_model_desc* d, long long n, long long tile, int block, int use_tmem, double* q,
+                            double* v, double* a, double* oMi, double* J, double* M, double* tau, int sparse_m);
 extern "C" int emul_eval(const rbd_model_desc* d, long long n, long long tile, int block, int use_tmem, double* q,
                          double* v, double* a, double* oMi, double* J, double* M, double* tau) {
+  return emul_eval_ex(d, n, tile, block, use_tmem, q, v, a, oMi, J, M, tau, 0);
+}
+// support-only pattern of M: col_ptr [nv + 1], row_idx [nnz]; returns nnz
+extern "C" int emul_mass_pattern(const rbd_model_desc* d, int* col_ptr, int* row_idx) {
+  Ctx c;
+  int rc = make_ctx(d, &c);
+  if (rc) return rc;
+  return mass_support_pattern(c.m, col_ptr, row_idx);
+}
+// sparse_m != 0: M holds the support-only fields (rbd_eval_soa_sparse)
+extern "C" int emul_eval_ex(const rbd_model_desc* d, long long n, long long tile, int block, int use_tmem, double* q,
+                            double* v, double* a, double* oMi, double* J, double* M, double* tau, int sparse_m) {
   Ctx c;
   int rc = make_ctx(d, &c);
   if (rc) return rc;
   const bool do_m = M != nullptr, do_tau = tau != nullptr;
   if (!plan_eval(&c.m, do_m, do_tau, use_tmem != 0, block / 32, oMi != nullptr)) { g_err = "plan_eval failed"; return -100; }
   // the sweep reads the model through the staged blob (planned DevModel prefix + ColProg table), as the kernel does
-  const std::vector<unsigned long long> blob = build_eval_blob(&c.m);
+  const std::vector<unsigned long long> blob = build_eval_blob(&c.m, sparse_m != 0);
   const DevModel& bm = *reinterpret_cast<const DevModel*>(blob.data());
   const EvalPlan& pl = bm.plan;
   const int bt = pl.warps * 32;
@@ -137,7 +151,7 @@ static void eval_one_f32(const DevModelT<float>& m, long long i, long long tile,
   io.q = f32::make_field_t<TILE>(q, i, m.nq, tile); io.v = f32::make_field_t<TILE>(v, i, m.nv, tile);
   io.a = f32::make_field_t<TILE>(a, i, m.nv, tile);
   io.oMi = f32::make_field_t<TILE>(oMi, i, 12 * (m.njoints - 1), tile); io.J = f32::make_field_t<TILE>(J, i, 6 * m.nv, tile);
-  io.M = f32::make_field_t<TILE>(M, i, m.nv * (m.nv + 1) / 2, tile); io.tau = f32::make_field_t<TILE>(tau, i, m.nv, tile);
+  io.M = f32::make_field_t<TILE>(M, i, m.mfields, tile); io.tau = f32::make_field_t<TILE>(tau, i, m.nv, tile);
   if (do_m && do_tau) f32::eval_instance<true, true, TILE>(m, io, S, T, inr);
   else if (do_m) f32::eval_instance<true, false, TILE>(m, io, S, T, inr);
   else if (do_tau) f32::eval_instance<false, true, TILE>(m, io, S, T, inr);

@@ -57,6 +57,8 @@ def load_emul() -> C.CDLL:
     lib.emul_sincos.argtypes = [ll, vp, vp, vp]
     lib.emul_sincos.restype = None
     lib.emul_eval.argtypes = [vp, ll, ll, i, i] + [vp] * 7
+    lib.emul_eval_ex.argtypes = [vp, ll, ll, i, i] + [vp] * 7 + [i]
+    lib.emul_mass_pattern.argtypes = [vp, vp, vp]
     lib.emul_eval_f32.argtypes = [vp, ll, ll, i, i] + [vp] * 7
     lib.emul_apply.argtypes = [vp, ll, ll, i, vp, vp, vp, ll, vp]
     lib.emul_applyJ.argtypes = [vp, ll, ll, i, vp, ll, vp, vp, vp]
@@ -71,6 +73,31 @@ def load_emul() -> C.CDLL:
     lib.emul_applyDJT_ring.argtypes = [vp, ll, ll, vp, ll, vp, vp, vp, C.c_double, vp, vp]
     lib.emul_applyJT_rows.argtypes = [vp, ll, i, vp, ll, vp, vp, vp, vp, vp, vp]
     return lib
+
+
+def mass_pattern_reference(d):
+    """Support pattern of M's upper triangle straight from the definition (include/rbd_b200.h, rbd_model_mass_pattern):
+    (r, c), r <= c, is kept iff the joint owning dof r is the joint owning dof c or one of its ancestors.  Returns
+    (col_ptr, row_idx, packed index c (c + 1) / 2 + r of every kept entry), column by column, rows ascending."""
+    owner = np.zeros(d.nv, dtype=np.int64)
+    nvj = [0] * d.njoints
+    for j in range(1, d.njoints):
+        nxt = int(d.idx_v[j + 1]) if j + 1 < d.njoints else d.nv
+        nvj[j] = nxt - int(d.idx_v[j])
+        owner[int(d.idx_v[j]):nxt] = j
+    anc = []
+    for j in range(d.njoints):
+        s, k = set(), j
+        while k != 0:
+            s.add(k); k = int(d.parents[k])
+        anc.append(s)
+    col_ptr, rows, packed = [0], [], []
+    for c in range(d.nv):
+        for r in range(c + 1):
+            if owner[r] in anc[owner[c]]:
+                rows.append(r); packed.append(c * (c + 1) // 2 + r)
+        col_ptr.append(len(rows))
+    return np.array(col_ptr, dtype=np.int32), np.array(rows, dtype=np.int32), np.array(packed, dtype=np.int64)
 
 
 def P(a):

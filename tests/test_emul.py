@@ -61,6 +61,39 @@ def test_eval_partial_outputs(emul, name, want, use_tmem):
 
 
 @pytest.mark.parametrize("d", MODELS, ids=IDS)
+@pytest.mark.parametrize("tile,use_tmem,want_tau", [(32, 1, True), (13, 0, False)])
+def test_eval_sparse_mass_format(emul, d, tile, use_tmem, want_tau):
+    """Support-only M (rbd_eval_soa_sparse): the same sweep driven by the compact column programs writes exactly the
+    structurally non-zero entries of the oracle's packed upper triangle, in the order of rbd_model_mass_pattern, and
+    every entry it leaves out is an exact zero of the oracle's M."""
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    n = 50
+    q, v, a = mdl.random_state(d, n, seed=11)
+    cd, keep = _cdesc(d)
+    col_ptr_ref, row_ref, packed = helpers.mass_pattern_reference(d)
+    col_ptr = np.zeros(d.nv + 1, dtype=np.int32); row_idx = np.zeros(max(1, packed.size), dtype=np.int32)
+    nnz = emul.emul_mass_pattern(C.addressof(cd), P(col_ptr), P(row_idx))
+    assert nnz == packed.size
+    assert np.array_equal(col_ptr, col_ptr_ref) and np.array_equal(row_idx[:nnz], row_ref)
+    nt = (n + tile - 1) // tile
+    Mv = np.full((nt, max(1, nnz), tile), np.nan)
+    tau = np.full((nt, d.nv, tile), np.nan) if want_tau else None
+    oMi = np.full((nt, 12 * (d.njoints - 1), tile), np.nan)
+    qs, vs, as_ = to_tiled(q, tile), to_tiled(v, tile), to_tiled(a, tile)
+    rc = emul.emul_eval_ex(C.addressof(cd), n, tile, 0, use_tmem, P(qs), P(vs), P(as_), P(oMi), None, P(Mv), P(tau), 1)
+    assert rc == 0, emul.emul_last_error()
+    ref, _ = oracle.eval_batch(d, q, v, a, 1)
+    got = from_tiled(Mv, n)[:, :nnz]
+    assert rel_err(got, ref["M"][:, packed]) <= TOL_FP64
+    rest = np.ones(d.nv * (d.nv + 1) // 2, dtype=bool); rest[packed] = False
+    assert np.all(ref["M"][:, rest] == 0.0)               # what the format drops is structurally zero
+    assert rel_err(from_tiled(oMi, n), ref["oMi"]) <= TOL_FP64
+    if want_tau:
+        assert rel_err(from_tiled(tau, n), ref["tau"]) <= TOL_FP64
+
+
+@pytest.mark.parametrize("d", MODELS, ids=IDS)
 @pytest.mark.parametrize("use_tmem", [0, 1])
 def test_eval_f32_bodies_within_1e4(emul, d, use_tmem):
     """Optional FP32 mode (BASELINE north_star: tolerance 1e-4): the same sweep compiled with real = float."""

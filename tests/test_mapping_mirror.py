@@ -23,6 +23,22 @@ def test_arity_mismatch_marks_component_invalid(rbd_lib):
     assert kcm.applyJT_matrix({(0, 0): [(1, np.ones(6))]}) == ({}, {})
 
 
+def test_empty_vectors_return_silently_without_invalidating(rbd_lib):
+    """The reference returns early on EMPTY vector lists and leaves the component state alone
+    (KinematicChainMapping.inl:117-118,165-166,212-213); only size > 1 invalidates."""
+    d = mdl.panda7()
+    kcm = KinematicChainMapping(d, n_instances=1)
+    out = np.zeros((1, d.n_out, 7)); in1 = np.zeros((1, d.nq))
+    kcm.apply([], [in1], [])
+    kcm.apply([out], [], [])
+    kcm.applyJ([], [in1], [])
+    kcm.applyJT([], [], [out[..., :6]])
+    kcm.applyJT([in1], [], [])
+    assert kcm.d_componentState == VALID and not kcm.msgs
+    kcm.applyJT([in1], [], [out[..., :6], out[..., :6]])   # inForce.size() != 1 -> Invalid (inl:215-220)
+    assert kcm.d_componentState == INVALID
+
+
 def test_applyDJT_and_getJ(rbd_lib):
     kcm = KinematicChainMapping(mdl.solo12(), n_instances=1)
     assert kcm.applyDJT(None, None, None) is None       # explicit no-op, KinematicChainMapping.h:73-80
