@@ -127,6 +127,11 @@ RBD_API int rbd_device_count(int* count); /* RBD_ERR_CUDA when no driver / devic
  * layout adapters are not recorded).  Thread-local like rbd_last_error; bench.py reports the kernel it timed with it. */
 RBD_API const char* rbd_last_kernel_name(void);
 
+/* Measurement probe (no model, no workspace): peak FP64 throughput of `device` from dependency-free DFMA chains on every
+ * SM, in TFLOP/s (2 flops per DFMA), best of a few repetitions — the measured FP64 roofline denominator bench.py
+ * reports next to the HBM one ("measured DFMA peak").  Takes a few milliseconds.                  */
+RBD_API int rbd_probe_fp64_peak(int device, double* tflops);
+
 /* ---------------------------------------------------------------------------------------------------- */
 /* model: replaces setModel / setBodyCoMFrames / m_extraFrames (KCM.inl:304-317, KCM.h:90-95)            */
 RBD_API int rbd_model_create(const rbd_model_desc* desc, rbd_model** out);

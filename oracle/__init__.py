@@ -39,10 +39,53 @@ def build(force: bool = False) -> str:
     except OSError:
         same_host = False
     if force or not same_host or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "-B", "librbd_oracle.so"], stdout=subprocess.DEVNULL)
+        subprocess.check_call(["make", "-C", _HERE, "-B", "librbd_oracle.so", "librbd_oracle_flops.so"], stdout=subprocess.DEVNULL)
         with open(stamp, "w") as f:
             f.write(hid)
     return LIB_PATH
+
+
+FLOPS_LIB_PATH = os.path.join(_HERE, "librbd_oracle_flops.so")
+_flops_lib = None
+
+
+def flop_counts(desc, q=None, v=None, a=None) -> dict:
+    """Exact FP64 operation counts of ONE evaluation (computeJointJacobians + crba + rnea, all outputs) of the restated
+    reference algorithm, from the ORC_COUNT_FLOPS build (oracle/Makefile: the same source compiled as C++ with a
+    counting scalar).  ``flops`` = add + mul + div + sqrt (one each); ``sincos`` counts sine and cosine evaluations
+    separately.  The counts depend on the model only (the code path has no data-dependent arithmetic branch)."""
+    global _flops_lib
+    if _flops_lib is None:
+        src = os.path.join(_HERE, "rbd_oracle.c")
+        if not os.path.exists(FLOPS_LIB_PATH) or os.path.getmtime(FLOPS_LIB_PATH) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", _HERE, "-B", "librbd_oracle_flops.so"], stdout=subprocess.DEVNULL)
+        _flops_lib = C.CDLL(FLOPS_LIB_PATH)
+        _flops_lib.orc_create.restype = C.c_void_p; _flops_lib.orc_create.argtypes = [C.c_void_p]
+        _flops_lib.orc_destroy.argtypes = [C.c_void_p]
+        _flops_lib.orc_eval.argtypes = [C.c_void_p] * 8
+        _flops_lib.orc_flop_counts.argtypes = [C.c_void_p]
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    from sofa.rigidbodydynamics_b200._capi import make_desc
+    if q is None:
+        q, v, a = (x[0] for x in mdl.random_state(desc, 1, seed=1))
+    q, v, a = _f64(q), _f64(v), _f64(a)
+    cdesc, _keep = make_desc(desc)
+    L = _flops_lib
+    w = L.orc_create(C.addressof(cdesc))
+    oMi = np.zeros(max(1, 12 * (desc.njoints - 1))); J = np.zeros(max(1, 6 * desc.nv))
+    M = np.zeros(max(1, desc.nv * (desc.nv + 1) // 2)); tau = np.zeros(max(1, desc.nv))
+    out = {}
+    parts = {"fk_jacobian": (_p(oMi), _p(J), None, None), "crba": (None, None, _p(M), None),
+             "rnea": (None, None, None, _p(tau)), "eval": (_p(oMi), _p(J), _p(M), _p(tau))}
+    for name, (po, pj, pm, pt) in parts.items():
+        L.orc_flop_reset()
+        L.orc_eval(w, _p(q), _p(v), _p(a), po, pj, pm, pt)
+        c = (C.c_longlong * 6)()
+        L.orc_flop_counts(c)
+        out[name] = {"add": int(c[0]), "mul": int(c[1]), "div": int(c[2]), "sqrt": int(c[3]), "sincos": int(c[4]),
+                     "flops": int(c[0] + c[1] + c[2] + c[3])}
+    L.orc_destroy(w)
+    return out
 
 
 _lib = None

@@ -21,14 +21,23 @@
  *   src/sofa/RigidBodyDynamics/Conversions.h :58-61 se3ToSofaType (Eigen::Quaternion{R}) -> orc_rot_to_quat
  *   north-star additions with no reference call site: pinocchio::crba (LOCAL convention), pinocchio::rnea.
  */
-#include "rbd_oracle.h"
-
 #include <float.h>
 #include <math.h>
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
 #include <unistd.h>
+
+#ifdef ORC_COUNT_FLOPS
+/* Flop-counting build (g++ -x c++ -DORC_COUNT_FLOPS, oracle/Makefile target librbd_oracle_flops.so): from here on
+ * `double` is a counting scalar of the same size and layout, so every arithmetic operation of the restatement below
+ * is tallied (orc_flop_counts) while the C entry points keep their binary interface.  SURVEY.md §8(d). */
+#include "orc_flopcount.hpp"
+thread_local orc_counters orc_cnt = {0, 0, 0, 0, 0, 0};
+#define double orc_counted
+#endif
+#include "rbd_oracle.h"
 
 /* ------------------------------------------------------------------------------------------------ */
 /* small spatial algebra, [linear; angular], SE3 = R row-major + p                                    */
@@ -573,6 +582,17 @@ int orc_eval_batch(const rbd_model_desc* d, long n, const double* q, const doubl
   free(th); free(jobs);
   return nthreads;
 }
+
+#ifdef ORC_COUNT_FLOPS
+#undef double
+/* counts of the calling thread since the last reset: add/sub, mul, div, sqrt, sin+cos evaluations, comparisons */
+extern "C" void orc_flop_reset(void) { orc_counters z = {0, 0, 0, 0, 0, 0}; orc_cnt = z; }
+extern "C" void orc_flop_counts(long long out[6]) {
+  out[0] = orc_cnt.add; out[1] = orc_cnt.mul; out[2] = orc_cnt.div; out[3] = orc_cnt.sqrt_; out[4] = orc_cnt.sincos;
+  out[5] = orc_cnt.cmp;
+}
+#define double orc_counted
+#endif
 
 /* accessors used by the tests */
 const double* orc_data_J(const orc_workspace* w) { return w->J; }

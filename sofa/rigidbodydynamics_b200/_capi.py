@@ -69,7 +69,7 @@ def make_desc(d: ModelDescriptor):
 
 # every symbol include/rbd_b200.h declares; tests check the built library exports all of them
 SYMBOLS = [
-    "rbd_version", "rbd_last_error", "rbd_clear_error", "rbd_device_count", "rbd_last_kernel_name",
+    "rbd_version", "rbd_last_error", "rbd_clear_error", "rbd_device_count", "rbd_last_kernel_name", "rbd_probe_fp64_peak",
     "rbd_model_create", "rbd_model_destroy", "rbd_model_get_info", "rbd_model_mass_pattern",
     "rbd_eval_soa_sparse", "rbd_crba_soa_sparse", "rbd_eval_host_sparse",
     "rbd_workspace_create", "rbd_workspace_destroy", "rbd_workspace_set_stream", "rbd_workspace_synchronize",
@@ -103,6 +103,7 @@ def load() -> C.CDLL:
         "rbd_clear_error": (None, []),
         "rbd_device_count": (C.c_int, [C.POINTER(C.c_int)]),
         "rbd_last_kernel_name": (C.c_char_p, []),
+        "rbd_probe_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
         "rbd_model_mass_pattern": (C.c_int, [vp, vp, vp]),
         "rbd_eval_soa_sparse": (C.c_int, [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp]),
         "rbd_crba_soa_sparse": (C.c_int, [vp, i64, i64, vp, vp]),

@@ -254,6 +254,13 @@ def last_kernel_name() -> str:
     return s.decode() if s else ""
 
 
+def probe_fp64_peak(device: int = 0) -> float:
+    """Measured FP64 peak of `device` in TFLOP/s (``rbd_probe_fp64_peak``: DFMA chains on every SM)."""
+    t = C.c_double(0.0)
+    check(_capi.load().rbd_probe_fp64_peak(int(device), C.byref(t)))
+    return float(t.value)
+
+
 def device_count() -> int:
     lib = _capi.load()
     n = C.c_int(0)

@@ -259,6 +259,93 @@ def test_eval_host_matches_soa(torch_mod, api):
         assert rel_err(g, ref[k]) <= TOL_FP64, k
 
 
+@pytest.mark.parametrize("d", MODELS, ids=IDS)
+@pytest.mark.parametrize("tile", [32, 1000])
+def test_eval_sparse_mass_format(torch_mod, api, d, tile):
+    """rbd_eval_soa_sparse: M in the support-only format equals the structurally non-zero entries of the oracle's packed
+    upper triangle (order of rbd_model_mass_pattern); the other outputs are unchanged; the kernel that ran is the same
+    eval instantiation (read back from the launch)."""
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    torch = torch_mod
+    n = 333
+    q, v, a = mdl.random_state(d, n, seed=12)
+    m = api.Model(d); ws = api.Workspace(m, n)
+    I = m.info
+    col_ptr_ref, row_ref, packed = helpers.mass_pattern_reference(d)
+    col_ptr, row_idx = m.mass_pattern()
+    assert I.mass_support_fields == packed.size
+    assert np.array_equal(col_ptr, col_ptr_ref) and np.array_equal(row_idx, row_ref)
+    assert np.array_equal(m.mass_packed_index(), packed)
+    nt = (n + tile - 1) // tile
+    new = lambda K: torch.full((nt, max(1, K), tile), float("nan"), dtype=torch.float64, device="cuda")
+    oMi, J, Mv, tau = new(I.omi_fields), new(I.jac_fields), new(I.mass_support_fields), new(I.nv)
+    qs, vs, as_ = (_dev(torch, to_tiled(x, tile)) for x in (q, v, a))
+    ws.eval_soa_sparse(n, tile, qs, vs, as_, oMi, J, Mv, tau)
+    ws.synchronize()
+    assert "eval_kernel" in api.last_kernel_name()
+    ref, _ = oracle.eval_batch(d, q, v, a, nthreads=0)
+    assert rel_err(from_tiled(Mv.cpu().numpy(), n)[:, :packed.size], ref["M"][:, packed]) <= TOL_FP64
+    for k, g in (("oMi", oMi), ("J", J), ("tau", tau)):
+        assert rel_err(from_tiled(g.cpu().numpy(), n)[:, :ref[k].shape[1]], ref[k]) <= TOL_FP64, k
+    # crba only, same format
+    Mv2 = new(I.mass_support_fields)
+    ws.crba_soa_sparse(n, tile, qs, Mv2)
+    ws.synchronize()
+    assert torch.equal(Mv, Mv2)
+
+
+def test_eval_host_sparse_and_output_selection(api):
+    """rbd_eval_host_sparse: all outputs, and the Mass / ForceField selection (Mval + tau only) — a NULL output is neither
+    computed nor copied; the values do not depend on the selection."""
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    d = mdl.talos_reduced()
+    n = 40000                                               # two pipelined chunks, the second one partial
+    q, v, a = mdl.random_state(d, n, seed=43)
+    m = api.Model(d); ws = api.Workspace(m, n)
+    I = m.info
+    packed = m.mass_packed_index()
+    oMi = np.zeros((n, I.omi_fields)); J = np.zeros((n, I.jac_fields)); Mv = np.zeros((n, I.mass_support_fields))
+    tau = np.zeros((n, I.nv))
+    ws.eval_host_sparse(n, q, v, a, oMi, J, Mv, tau)
+    ref, _ = oracle.eval_batch(d, q, v, a, nthreads=0)
+    assert rel_err(Mv, ref["M"][:, packed]) <= TOL_FP64
+    for k, g in (("oMi", oMi), ("J", J), ("tau", tau)):
+        assert rel_err(g, ref[k]) <= TOL_FP64, k
+    Mv2 = np.zeros_like(Mv); tau2 = np.zeros_like(tau)
+    ws.eval_host_sparse(n, q, v, a, None, None, Mv2, tau2)
+    assert np.array_equal(Mv, Mv2) and np.array_equal(tau, tau2)
+    Mv3 = np.zeros_like(Mv)
+    ws.eval_host_sparse(n, q, None, None, None, None, Mv3, None)   # crba alone: v and a do not travel
+    assert np.array_equal(Mv, Mv3)
+
+
+def test_rows_host_rejects_malformed_csr(api):
+    """rbd_applyJT_rows_host validates the constraint matrix before anything reaches the device (a bad column index
+    would read the per-output tables and the Jacobian cache out of bounds)."""
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    d = mdl.panda7()
+    n = 4
+    q, v, _ = mdl.random_state(d, n, seed=3)
+    m = api.Model(d); ws = api.Workspace(m, n)
+    pos = np.zeros((n, d.n_out, 7))
+    ws.apply_host(n, np.ascontiguousarray(q), None, pos)
+    rows = np.zeros((2, d.nv)); keep = np.zeros(2, dtype=np.int32)
+    val = np.ones((2, 6))
+    ok = dict(row_ptr=np.array([0, 1, 2], dtype=np.int32), row_instance=np.array([0, 3], dtype=np.int32),
+              col=np.array([1, d.n_out - 1], dtype=np.int32))
+    ws.applyJT_rows_host(2, ok["row_ptr"], ok["row_instance"], ok["col"], val, rows, keep)
+    bad = [dict(ok, col=np.array([1, d.n_out], dtype=np.int32)), dict(ok, col=np.array([-1, 0], dtype=np.int32)),
+           dict(ok, row_ptr=np.array([0, 2, 1], dtype=np.int32)), dict(ok, row_ptr=np.array([1, 1, 2], dtype=np.int32)),
+           dict(ok, row_instance=np.array([0, n], dtype=np.int32))]
+    for b in bad:
+        with pytest.raises(api.RbdError) as e:
+            ws.applyJT_rows_host(2, b["row_ptr"], b["row_instance"], b["col"], val, rows, keep)
+        assert e.value.code == -1
+    ws.applyJT_rows_host(2, ok["row_ptr"], ok["row_instance"], ok["col"], val, rows, keep)   # the workspace is still usable
+
+
 # ---- BASELINE sizes: size-independent identities --------------------------------------------------------------
 def test_full_size_identities(torch_mod, api):
     """Talos at N = 1,048,576 (BASELINE configs[3]): (1) rnea(q,v,a) - rnea(q,v,0) == M(q) a for every instance,

@@ -149,3 +149,20 @@ def test_rot_to_quat_eigen_branches():
         qv = oracle.rot_to_quat(Q)
         assert abs(np.linalg.norm(qv) - 1) < 1e-12
         assert np.max(np.abs(quat_xyzw_to_R(qv) - Q)) < 1e-12
+
+
+def test_flop_counting_build_counts_the_restated_algorithm():
+    """oracle -DORC_COUNT_FLOPS: the same source with a counting scalar.  The counts are a function of
+    the model only, the three algorithms add up to the fused evaluation, and the counting build computes the same
+    numbers as the product oracle."""
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    for d in (mdl.panda7(), mdl.solo12(), mdl.talos_reduced()):
+        q, v, a = mdl.random_state(d, 2, seed=9)
+        c0 = oracle.flop_counts(d, q[0], v[0], a[0]); c1 = oracle.flop_counts(d, q[1], v[1], a[1])
+        assert c0 == c1
+        for k in ("add", "mul", "div", "sqrt", "sincos", "flops"):
+            assert c0["eval"][k] == c0["fk_jacobian"][k] + c0["crba"][k] + c0["rnea"][k]
+        nrev = sum(1 for t in d.jtype[1:] if mdl.J_RX <= int(t) <= mdl.J_RU)
+        assert c0["fk_jacobian"]["sincos"] == 2 * nrev          # one sine + one cosine per revolute joint and FK pass
+        assert c0["eval"]["flops"] > 100 * d.nv
