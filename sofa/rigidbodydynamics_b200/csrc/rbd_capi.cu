@@ -394,8 +394,7 @@ static int eval_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, 
   if (rc) return rc;
   EvalArgs A{n, tile, q, v, a, oMi, J, M, tau};
   LaunchCfg* cfg = pk >= 11 ? ws->cfg_eval_sp : ws->cfg_eval;
-  if (ws->h_plan[pk]->simple_joints) CK(launch_eval_simple(*ws->h_plan[pk], ws->d_plan[pk], A, cfg, ws->num_sms, st));
-  else CK(launch_eval(*ws->h_plan[pk], ws->d_plan[pk], A, cfg, ws->num_sms, st));
+  CK(launch_eval_any(*ws->h_plan[pk], ws->d_plan[pk], A, cfg, ws->num_sms, st));
   if (n > 0) ws->launches++;
   return RBD_OK;
 }
@@ -489,8 +488,7 @@ static int mass_force_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t 
   if (rc) return rc;
   EvalArgs A{n, tile, q, v, a, nullptr, nullptr, nullptr, out};
   A.tau_scale = scale; A.tau_acc = 1; A.gravity_on = gravity_on;
-  if (ws->h_plan[1]->simple_joints) CK(launch_eval_simple(*ws->h_plan[1], ws->d_plan[1], A, ws->cfg_eval, ws->num_sms, st));
-  else CK(launch_eval(*ws->h_plan[1], ws->d_plan[1], A, ws->cfg_eval, ws->num_sms, st));
+  CK(launch_eval_any(*ws->h_plan[1], ws->d_plan[1], A, ws->cfg_eval, ws->num_sms, st));
   if (n > 0) ws->launches++;
   return RBD_OK;
 }

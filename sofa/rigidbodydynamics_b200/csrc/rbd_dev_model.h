@@ -85,8 +85,17 @@ struct EvalPlan {
   int tmem_cols;     // columns the block allocates (power of two >= 32, or 0)
   int in_slots;      // slots of the asynchronous input ring (rbd_sweeps_body.h InRing; 3 elements each per instance), 0 = none
   int jt_fwd;        // applyJT ring kernel: 1 = forward-projection variant (applyJT_instance_fwd)
-  int pad_[2];
+  int kvariant;      // fused eval: the instantiation this plan was made for (RBD_EVAL_*; the 12-warp plans need the
+                     // 168-register chain / ffroot kernels, every other plan runs the generic or simple one)
+  int pad_[1];
 };
+// Instantiations of the fused eval (rbd_sweeps.h compiles the sweep once per namespace):
+#define RBD_EVAL_GENERIC 0 /* any supported joint type                                                              */
+#define RBD_EVAL_SIMPLE 1  /* RX / RY / RZ / free-flyer joints only                                                 */
+#define RBD_EVAL_CHAIN 2   /* fixed-base serial chain of RX / RY / RZ joints (Panda-class arms): no free-flyer, no
+                              branch code -> 166 registers, 12 warps per SM                                         */
+#define RBD_EVAL_FFROOT 3  /* RX / RY / RZ joints below a free-flyer root that is the universe's only child (Solo,
+                              Talos): the root is stepped outside the joint loop -> 168 registers, 12 warps per SM   */
 #define RBD_BOFF_TMEM (1 << 30)
 #define RBD_BOFF_NOVA (1 << 29) /* v|a not saved: recomputed when the sweep returns (joint attached to the universe) */
 #define RBD_BOFF_RPOMI (1 << 28) /* R|p not saved: re-read from the oMi output this thread wrote (oMi requested) */
@@ -100,7 +109,7 @@ struct alignas(16) DevModelT {
   int has_ff_root;    // joint 1 is a free-flyer attached to the universe
   int nq_joints, nv_joints;
   int max_depth, max_depth_internal;  // longest joint chain; deepest joint that has children
-  int simple_joints;                  // 1 = every joint is RX / RY / RZ or a free-flyer (rbd::simple kernels apply)
+  int eval_variant;                   // specialised instantiation of the fused eval this model qualifies for (RBD_EVAL_*)
   int mfields;                        // eval blob: fields per instance of the M output (nv (nv + 1) / 2 packed, or the
                                       // support-only count); 0 in unplanned models
   int prog_words_off, prog_len;       // eval blob: 8-byte-word offset of the ColProg table behind the joint records; ints
@@ -115,7 +124,7 @@ inline void dev_model_to_f32(const DevModel& d, DevModelT<float>* f) {
   f->njoints = d.njoints; f->nq = d.nq; f->nv = d.nv; f->n_out = d.n_out;
   f->slot_total[0] = d.slot_total[0]; f->slot_total[1] = d.slot_total[1];
   f->nbranch = d.nbranch; f->has_ff_root = d.has_ff_root; f->nq_joints = d.nq_joints; f->nv_joints = d.nv_joints;
-  f->max_depth = d.max_depth; f->max_depth_internal = d.max_depth_internal; f->simple_joints = d.simple_joints; f->mfields = d.mfields;
+  f->max_depth = d.max_depth; f->max_depth_internal = d.max_depth_internal; f->eval_variant = d.eval_variant; f->mfields = d.mfields;
   f->prog_words_off = d.prog_words_off; f->prog_len = d.prog_len;
   for (int k = 0; k < 3; ++k) f->gravity[k] = (float)d.gravity[k];
   f->plan = d.plan;

@@ -30,9 +30,19 @@ extern __shared__ __align__(16) double rbd_smem[];
 // derives its private slice (lane quarter of its warp, column range of its warp group), and warp 0 frees them
 // after the whole block is done.  Lanes past the end of the batch recompute the last instance instead of
 // exiting: tcgen05.ld/st are warp-collective (.sync.aligned) and the duplicate stores write identical values.
-#define RBD_DEFINE_EVAL_KERNEL(NAME, NSQ, REAL, MINB) \
+#define RBD_KERNEL_BOUNDS_0(MINB) __launch_bounds__((MINB == 1 && DO_TAU && !DO_M) ? 384 : 256, MINB)
+#define RBD_KERNEL_BOUNDS_1(MINB) __maxnreg__(RBD_CHAIN_REGS)
+#define RBD_KERNEL_BOUNDS_2(MINB) __maxnreg__(RBD_FFROOT_REGS)
+#ifndef RBD_FFROOT_REGS
+#define RBD_FFROOT_REGS 168
+#endif
+#define RBD_KERNEL_BOUNDS(MAXT, MINB) RBD_KERNEL_BOUNDS_##MAXT(MINB)
+#ifndef RBD_CHAIN_REGS
+#define RBD_CHAIN_REGS 168
+#endif
+#define RBD_DEFINE_EVAL_KERNEL(NAME, NSQ, REAL, MINB, MAXT) \
 template <bool DO_M, bool DO_TAU, int TILE>                                                                                                             \
-__global__ void __launch_bounds__((MINB == 1 && DO_TAU && !DO_M) ? 384 : 256, MINB) NAME(const DevModelT<REAL>* __restrict__ gm, const EvalArgsT<REAL> a,                                            \
+__global__ void RBD_KERNEL_BOUNDS(MAXT, MINB) NAME(const DevModelT<REAL>* __restrict__ gm, const EvalArgsT<REAL> a,                                            \
                                                    const int model_words) {                                                                             \
  /* the last two staged words are spare: the tensor-memory base address lands there (no static shared memory, so */                                     \
  /* the block can ask for the full 227 KB dynamically) */                                                                                               \
@@ -98,11 +108,17 @@ __global__ void __launch_bounds__((MINB == 1 && DO_TAU && !DO_M) ? 384 : 256, MI
   }                                                                                                                                                     \
 }
 
-RBD_DEFINE_EVAL_KERNEL(eval_kernel, rbd, double, 1)
+RBD_DEFINE_EVAL_KERNEL(eval_kernel, rbd, double, 1, 0)
 // the same for models with RX / RY / RZ / free-flyer joints only (rbd::simple: rarer joint types not compiled in)
-RBD_DEFINE_EVAL_KERNEL(eval_kernel_simple, rbd::simple, double, 1)
+RBD_DEFINE_EVAL_KERNEL(eval_kernel_simple, rbd::simple, double, 1, 0)
 // FP32: 128 registers per thread so that two 8-warp blocks share an SM (the planner counts on it)
-RBD_DEFINE_EVAL_KERNEL(eval_kernel_f32, rbd::f32, float, 2)
+RBD_DEFINE_EVAL_KERNEL(eval_kernel_f32, rbd::f32, float, 2, 0)
+// fixed-base serial chains (rbd::chain): compiled for blocks of up to RBD_CHAIN_THREADS threads
+#ifndef RBD_CHAIN_THREADS
+#define RBD_CHAIN_THREADS 448
+#endif
+RBD_DEFINE_EVAL_KERNEL(eval_kernel_chain, rbd::chain, double, 1, 1)
+RBD_DEFINE_EVAL_KERNEL(eval_kernel_ffroot, rbd::ffroot, double, 1, 2)
 
 // The mapping kernels stage the joint table the same way (one coalesced copy per block, broadcast reads after).
 // The cached configuration of the last apply (workspace) is always tile-32.
@@ -618,7 +634,7 @@ static cudaError_t pick_block(Kern kern, int smem_doubles_per_thread, int forced
   }
 
 // `hm` is the host copy of the planned model (hm.plan chosen by plan_eval), `d_model` its staged blob on the device.
-#define RBD_DEFINE_EVAL_LAUNCH(FN, KERN, REAL)                                                                     \
+#define RBD_DEFINE_EVAL_LAUNCH(FN, KERN, REAL, TAG)                                                                   \
   cudaError_t FN(const DevModelT<REAL>& hm, const DevModelT<REAL>* d_model, const EvalArgsT<REAL>& a, LaunchCfg* cache, \
                  int num_sms, cudaStream_t st) {                                                                   \
     const bool do_m = a.M != nullptr, do_tau = a.tau != nullptr;                                                   \
@@ -628,10 +644,10 @@ static cudaError_t pick_block(Kern kern, int smem_doubles_per_thread, int forced
     const int block = hm.plan.warps * 32;                                                                          \
     const size_t smem = (size_t)model_words * 8 + (size_t)block * (hm.plan.smem_doubles + 3 * hm.plan.in_slots) * sizeof(REAL); \
     cudaError_t e = cudaSuccess;                                                                                   \
-    if (cfg.block != block || cfg.smem_bytes != smem) {                                                            \
+    if (cfg.block != block || cfg.smem_bytes != smem || cfg.tag != TAG) {                                          \
       RBD_EVAL_DISPATCH(KERN, v, RBD_ATTR)                                                                         \
       if (e != cudaSuccess) return e;                                                                              \
-      cfg.block = block; cfg.smem_bytes = smem; cfg.blocks_per_sm = hm.plan.blocks_per_sm;                         \
+      cfg.block = block; cfg.smem_bytes = smem; cfg.blocks_per_sm = hm.plan.blocks_per_sm; cfg.tag = TAG;          \
     }                                                                                                              \
     if (a.n <= 0) return cudaSuccess;                                                                              \
     unsigned grid = RBD_GRID(a.n, block);                                                                          \
@@ -647,11 +663,22 @@ static cudaError_t pick_block(Kern kern, int smem_doubles_per_thread, int forced
   if (e == cudaSuccess)                                                                             \
     e = cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
 #define RBD_LAUNCH(K) RBD_NOTE(K); K<<<grid, block, smem, st>>>(d_model, a, model_words)
-RBD_DEFINE_EVAL_LAUNCH(launch_eval, eval_kernel, double)
-RBD_DEFINE_EVAL_LAUNCH(launch_eval_simple, eval_kernel_simple, double)
-RBD_DEFINE_EVAL_LAUNCH(launch_eval_f32, eval_kernel_f32, float)
+RBD_DEFINE_EVAL_LAUNCH(launch_eval, eval_kernel, double, RBD_EVAL_GENERIC)
+RBD_DEFINE_EVAL_LAUNCH(launch_eval_simple, eval_kernel_simple, double, RBD_EVAL_SIMPLE)
+RBD_DEFINE_EVAL_LAUNCH(launch_eval_f32, eval_kernel_f32, float, 100)
+RBD_DEFINE_EVAL_LAUNCH(launch_eval_chain, eval_kernel_chain, double, RBD_EVAL_CHAIN)
+RBD_DEFINE_EVAL_LAUNCH(launch_eval_ffroot, eval_kernel_ffroot, double, RBD_EVAL_FFROOT)
 #undef RBD_ATTR
 #undef RBD_LAUNCH
+cudaError_t launch_eval_any(const DevModel& hm, const DevModel* d_model, const EvalArgs& a, LaunchCfg* cache,
+                            int num_sms, cudaStream_t st) {
+  switch (hm.plan.kvariant) {
+    case RBD_EVAL_FFROOT: return launch_eval_ffroot(hm, d_model, a, cache, num_sms, st);
+    case RBD_EVAL_CHAIN: return launch_eval_chain(hm, d_model, a, cache, num_sms, st);
+    case RBD_EVAL_SIMPLE: return launch_eval_simple(hm, d_model, a, cache, num_sms, st);
+    default: return launch_eval(hm, d_model, a, cache, num_sms, st);
+  }
+}
 
 // mapping kernels: cfg[0] = run-time tile, cfg[1] = tile 32
 static inline int map_model_words(const DevModel& m) { return (int)((dev_model_bytes(m) + 15) / 16) * 2; }

@@ -48,6 +48,7 @@ struct RowArgs {
 };
 struct LaunchCfg {
   int block = 0, forced = 0, blocks_per_sm = 0;
+  int tag = -1;  // which __global__ function the cached attributes were set on (eval: RBD_EVAL_* variant)
   size_t smem_bytes = 0;
 };
 
@@ -56,6 +57,9 @@ cudaError_t launch_eval(const DevModel& planned_host_model, const DevModel* d_ev
 // the same for models whose joints are all RX / RY / RZ / free-flyer (DevModel::simple_joints)
 cudaError_t launch_eval_simple(const DevModel& planned_host_model, const DevModel* d_eval_blob, const EvalArgs& a,
                                LaunchCfg* cache8, int num_sms, cudaStream_t st);
+// picks the instantiation the plan was made for (planned_host_model.plan.kvariant: generic, simple, chain, ffroot)
+cudaError_t launch_eval_any(const DevModel& planned_host_model, const DevModel* d_eval_blob, const EvalArgs& a,
+                            LaunchCfg* cache8, int num_sms, cudaStream_t st);
 // optional FP32 mode of the fused evaluation (float I/O and state, tolerance 1e-4)
 cudaError_t launch_eval_f32(const DevModelT<float>& planned_host_model, const DevModelT<float>* d_eval_blob,
                             const EvalArgsT<float>& a, LaunchCfg* cache8, int num_sms, cudaStream_t st);

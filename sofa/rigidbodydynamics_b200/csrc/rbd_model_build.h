@@ -163,10 +163,15 @@ inline int build_dev_model(const rbd_model_desc* d, DevModel* m, HostTables* tb,
     if (m->joint[i].nchild > 0) maxd_internal = std::max(maxd_internal, depth[i]);
   }
   m->max_depth = maxd;
-  m->simple_joints = 1;
-  for (int i = 1; i < nj; ++i) {
-    const int t = d->jtype[i];
-    if (!(t == JT_RX || t == JT_RY || t == JT_RZ || t == JT_FF)) m->simple_joints = 0;
+  {
+    bool simple = true, chain = nj > 1, ffroot = nj > 1 && d->jtype[1] == JT_FF && d->parents[1] == 0;
+    for (int i = 1; i < nj; ++i) {
+      const int t = d->jtype[i];
+      if (!(t == JT_RX || t == JT_RY || t == JT_RZ || t == JT_FF)) simple = false;
+      if (t == JT_FF || d->parents[i] != i - 1) chain = false;
+      if (i >= 2 && (t == JT_FF || d->parents[i] < 1)) ffroot = false;
+    }
+    m->eval_variant = !simple ? RBD_EVAL_GENERIC : chain ? RBD_EVAL_CHAIN : ffroot ? RBD_EVAL_FFROOT : RBD_EVAL_SIMPLE;
   }
   m->max_depth_internal = maxd_internal;
   std::vector<int> aw(maxd + 1, 6);
@@ -241,6 +246,7 @@ struct B200Limits {
   static constexpr int kMaxWarpsPerBlock = 8;
   static constexpr int kMaxWarpsPerBlockRnea = 12;  // eval_kernel<false, true, *>: __launch_bounds__(384, 1)
   static constexpr int kRegsPerThreadRnea = 170;
+  static constexpr int kRegsPerThreadWide = 168;  // eval_kernel_chain / eval_kernel_ffroot: __maxnreg__(168)
 };
 
 static constexpr int kEvalInSlots = 2;  // == RBD_INR_SLOTS (rbd_sweeps_body.h)
@@ -252,8 +258,32 @@ inline int pow2_cols(int cols) {
 }
 
 // Fills m->plan and m->joint[*].boff.  forced_warps > 0 pins the block size.  Returns false when nothing fits.
+inline bool plan_eval_cfg(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int forced_warps, bool omi_out, bool jt,
+                          int regs_per_thread, int elem_bytes, int wide_warps);
 inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int forced_warps = 0, bool omi_out = false,
                       bool jt = false, int regs_per_thread = B200Limits::kRegsPerThread, int elem_bytes = 8) {
+  // Serial chains and free-flyer-rooted trees have 168-register instantiations of the CRBA sweeps (rbd::chain,
+  // rbd::ffroot): try blocks of up to 12 warps first and keep that plan when it really puts more than 8 warps on an SM
+  // (small robots: Panda, Solo); otherwise (Talos: the sweep state caps the SM at 8 warps) the standard plan runs on
+  // the 255-register kernels, which need no spills.
+  if (elem_bytes == 8 && !jt && do_m && forced_warps == 0 && m->eval_variant >= RBD_EVAL_CHAIN &&
+      regs_per_thread == B200Limits::kRegsPerThread) {
+    DevModel t = *m;
+    if (plan_eval_cfg(&t, do_m, do_tau, use_tmem, 0, omi_out, false, B200Limits::kRegsPerThreadWide, 8,
+                      B200Limits::kMaxWarpsPerBlockRnea) &&
+        t.plan.warps * t.plan.blocks_per_sm > B200Limits::kMaxWarpsPerBlock) {
+      *m = t;
+      m->plan.kvariant = m->eval_variant;
+      return true;
+    }
+  }
+  const bool ok = plan_eval_cfg(m, do_m, do_tau, use_tmem, forced_warps, omi_out, jt, regs_per_thread, elem_bytes, 0);
+  if (ok) m->plan.kvariant = m->eval_variant >= RBD_EVAL_SIMPLE ? RBD_EVAL_SIMPLE : RBD_EVAL_GENERIC;
+  return ok;
+}
+// wide_warps > 0: blocks of up to that many warps at regs_per_thread registers (the caller vouches for the kernel)
+inline bool plan_eval_cfg(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int forced_warps, bool omi_out, bool jt,
+                          int regs_per_thread, int elem_bytes, int wide_warps) {
   // elem_bytes: 8 = the FP64 product, 4 = the optional FP32 mode (state elements are floats: half the shared-memory
   // bytes, one tensor-memory column each)
   // jt: the applyJT sweep — stacks of the (no CRBA, RNEA) variant, but branch records hold R|p only (no v|a)
@@ -294,7 +324,7 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
   // The RNEA-only instantiation (rnea, Mass / ForceField products) is compiled for blocks of up to 12 warps (<= 170
   // registers): its state is smaller, and three warps per scheduler hide more of the issue latency that bounds it.
   const bool wide = elem_bytes == 8 && !jt && do_tau && !do_m && regs_per_thread == B200Limits::kRegsPerThread;
-  const int max_warps = wide ? B200Limits::kMaxWarpsPerBlockRnea : B200Limits::kMaxWarpsPerBlock;
+  const int max_warps = wide_warps > 0 ? wide_warps : wide ? B200Limits::kMaxWarpsPerBlockRnea : B200Limits::kMaxWarpsPerBlock;
   if (wide) regs_per_thread = B200Limits::kRegsPerThreadRnea;
   for (int W = 1; W <= max_warps; ++W) {
     if (forced_warps > 0 && W != forced_warps) continue;

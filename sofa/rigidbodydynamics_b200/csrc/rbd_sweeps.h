@@ -43,6 +43,10 @@
 #endif
 #define RBD_PRAGMA_(x) _Pragma(#x)
 #define RBD_PRAGMA(x) RBD_PRAGMA_(x)
+#ifndef RBD_EARLY_RESTORE
+#define RBD_EARLY_RESTORE 1 /* state of the joint a new branch starts from is reloaded before the unwind of the previous
+                               branch (r1f: -3 %); 0 = at the top of the next joint: fewer live registers */
+#endif
 #ifndef RBD_PTR_COL
 #define RBD_PTR_COL 0 /* measured slower (A/B r1d: 2.98 vs 2.85 ms): pointer bumps serialise the zero-fill */
 #endif
@@ -72,6 +76,32 @@ typedef double real;
 #undef RBD_BODY_EVAL_ONLY
 #undef RBD_SIMPLE_JOINTS
 }  // namespace simple
+
+// ... for floating-base robots whose free-flyer root is the universe's only child and the model's only free-flyer
+// (DevModelT::ff_root_only: Solo, Talos): the root is stepped in front of the joint loop and emitted behind it
+namespace ffroot {
+typedef double real;
+#define RBD_SIMPLE_JOINTS 1
+#define RBD_FF_ROOT_ONLY 1
+#define RBD_BODY_EVAL_ONLY 1
+#include "rbd_sweeps_body.h"
+#undef RBD_BODY_EVAL_ONLY
+#undef RBD_FF_ROOT_ONLY
+#undef RBD_SIMPLE_JOINTS
+}  // namespace ffroot
+
+// ... and for fixed-base serial chains of RX / RY / RZ joints (DevModelT::chain_only): additionally without the
+// free-flyer and branch code
+namespace chain {
+typedef double real;
+#define RBD_SIMPLE_JOINTS 1
+#define RBD_CHAIN_ONLY 1
+#define RBD_BODY_EVAL_ONLY 1
+#include "rbd_sweeps_body.h"
+#undef RBD_BODY_EVAL_ONLY
+#undef RBD_CHAIN_ONLY
+#undef RBD_SIMPLE_JOINTS
+}  // namespace chain
 
 namespace f32 {
 typedef float real;

@@ -6,6 +6,38 @@
 // between consecutive fields) at run time; TILE = 32 is the AoSoA layout the hot path is tuned for: the 32
 // instances of a warp form one tile, field k of the warp sits at byte offset k*256 from the warp's base, so the
 // stride folds into the immediate offset of every load/store and a warp's whole output is one contiguous block.
+// rbd::chain instantiation (RBD_CHAIN_ONLY): fixed-base serial chains of RX / RY / RZ joints (Panda-class arms) — no
+// free-flyer code, no branch records, no return-to-branch restores: fewer registers, so more warps fit an SM.
+#undef RBD_T_IS_FF
+#undef RBD_CAN_BRANCH
+#undef RBD_CUR_FF
+#undef RBD_ANC_FF
+#undef RBD_EMIT_CUR
+#undef RBD_EMIT_ANC
+struct FfYes { static constexpr bool value = true; };
+struct FfNo { static constexpr bool value = false; };
+#if defined(RBD_FF_ROOT_ONLY)
+// rbd::ffroot instantiation: joint 1 is a free-flyer attached to the universe, it is the universe's only child and the
+// only free-flyer of the model (Solo, Talos: every floating-base robot).  The root is stepped in front of the joint
+// loop and emitted behind it; inside the loop "the current joint" and "an ancestor being emitted" are never
+// free-flyers, at compile time.
+#define RBD_CUR_FF(ffj, t) (decltype(ffj)::value)
+#define RBD_ANC_FF(t) false
+#define RBD_EMIT_CUR(ffj) (decltype(ffj)::value ? 1 : 2)
+#define RBD_EMIT_ANC 2
+#else
+#define RBD_CUR_FF(ffj, t) RBD_T_IS_FF(t)
+#define RBD_ANC_FF(t) RBD_T_IS_FF(t)
+#define RBD_EMIT_CUR(ffj) 0
+#define RBD_EMIT_ANC 0
+#endif
+#if defined(RBD_CHAIN_ONLY)
+#define RBD_T_IS_FF(t) false
+#define RBD_CAN_BRANCH false
+#else
+#define RBD_T_IS_FF(t) ((t) == JT_FF)
+#define RBD_CAN_BRANCH true
+#endif
 template <int TILE>
 struct FieldT {
   real* p;
@@ -312,7 +344,8 @@ RBD_HD void mat3_mul(const real* A, const real* B, real* O) {
 // world joint axis aw (1-dof joints).  q0/q1 are the joint's configuration values (angle | displacement |
 // cos,sin); the free-flyer reads its 7 values through `qf`.
 // pinocchio: liMi = jointPlacement * M_joint(q); oMi = oMi[parent] * liMi (JointJacobiansForwardStep).
-template <class QF>
+// FFK: 0 = joint type tested at run time, 1 = the joint is a free-flyer, 2 = it is not (free-flyer-root instantiation)
+template <int FFK = 0, class QF>
 RBD_HD void fk_joint(const DevJoint& jn, real* R, real* p, real q0, real q1, const QF& qf, real* aw) {
   // p <- R pl_p + p with the parent's R, then R <- R pl_R IN PLACE: most URDF joints have rpy = 0, and for those the
   // step is nothing at all (no copy of R into a scratch matrix: profile r1h counted 18 register moves per joint for it)
@@ -329,12 +362,35 @@ RBD_HD void fk_joint(const DevJoint& jn, real* R, real* p, real q0, real q1, con
     for (int k = 0; k < 9; ++k) R[k] = B[k];
   }
   const int t = jn.type;
+#if !defined(RBD_CHAIN_ONLY)
+  if (FFK != 2 && (FFK == 1 || t == JT_FF)) {
+    const int o = jn.idx_q;
+    const real px = qf.ld(o), py = qf.ld(o + 1), pz = qf.ld(o + 2);
+    const real x = qf.ld(o + 3), y = qf.ld(o + 4), z = qf.ld(o + 5), w = qf.ld(o + 6);
+    // Eigen toRotationMatrix on raw coefficients (no normalisation), as pinocchio's JointModelFreeFlyer::calc
+    const real tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    const real twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x;
+    const real tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    real Rq[9], B[9];
+    Rq[0] = 1 - (tyy + tzz); Rq[1] = txy - twz;       Rq[2] = txz + twy;
+    Rq[3] = txy + twz;       Rq[4] = 1 - (txx + tzz); Rq[5] = tyz - twx;
+    Rq[6] = txz - twy;       Rq[7] = tyz + twx;       Rq[8] = 1 - (txx + tyy);
+    p[0] += R[0] * px + R[1] * py + R[2] * pz;
+    p[1] += R[3] * px + R[4] * py + R[5] * pz;
+    p[2] += R[6] * px + R[7] * py + R[8] * pz;
+    mat3_mul(R, Rq, B);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = B[k];
+    aw[0] = aw[1] = aw[2] = 0.0;
+    return;
+  }
+#endif
   real c = q0, s = q1;
 #if defined(RBD_SIMPLE_JOINTS)
   // instantiation for models whose joints are all RX / RY / RZ (+ free-flyers) — every URDF robot of the BASELINE
   // configs: the unaligned / prismatic / unbounded cases are not compiled in (A/B r1i: 2.344 -> 2.308 ms; the kernel
   // is instruction-cache sensitive, see RBD_UNROLL_ZERO)
-  if (t != JT_FF) sincos_(q0, &s, &c);
+  sincos_(q0, &s, &c);  // (a free-flyer returned above)
 #else
   if (t >= JT_RX && t <= JT_RU) sincos_(q0, &s, &c);
 #endif
@@ -374,26 +430,6 @@ RBD_HD void fk_joint(const DevJoint& jn, real* R, real* p, real q0, real q1, con
       p[0] += q0 * aw[0]; p[1] += q0 * aw[1]; p[2] += q0 * aw[2];
     } break;
 #endif
-    case JT_FF: {
-      const int o = jn.idx_q;
-      const real px = qf.ld(o), py = qf.ld(o + 1), pz = qf.ld(o + 2);
-      const real x = qf.ld(o + 3), y = qf.ld(o + 4), z = qf.ld(o + 5), w = qf.ld(o + 6);
-      // Eigen toRotationMatrix on raw coefficients (no normalisation), as pinocchio's JointModelFreeFlyer::calc
-      const real tx = 2 * x, ty = 2 * y, tz = 2 * z;
-      const real twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x;
-      const real tyy = ty * y, tyz = tz * y, tzz = tz * z;
-      real Rq[9], B[9];
-      Rq[0] = 1 - (tyy + tzz); Rq[1] = txy - twz;       Rq[2] = txz + twy;
-      Rq[3] = txy + twz;       Rq[4] = 1 - (txx + tzz); Rq[5] = tyz - twx;
-      Rq[6] = txz - twy;       Rq[7] = tyz + twx;       Rq[8] = 1 - (txx + tyy);
-      p[0] += R[0] * px + R[1] * py + R[2] * pz;
-      p[1] += R[3] * px + R[4] * py + R[5] * pz;
-      p[2] += R[6] * px + R[7] * py + R[8] * pz;
-      mat3_mul(R, Rq, B);
-#pragma unroll
-      for (int k = 0; k < 9; ++k) R[k] = B[k];
-      aw[0] = aw[1] = aw[2] = 0.0;
-    } break;
     default:
       aw[0] = aw[1] = aw[2] = 0.0;
       break;
@@ -768,11 +804,14 @@ RBD_HD void column_rows(const DevModel& m, const DevJoint& jn, int base, const r
 // Everything joint k owes once its subtree is complete: tau_k = A_k^T f_k and its column(s) of M.
 // A = world subspace column (6) of a 1-dof joint, or R|p (12) of a free-flyer; f = total subtree force;
 // Y = composite inertia of the subtree — all three in registers.
-template <bool DO_M, bool DO_TAU, int TILE>
+// FFK: 0 = the joint type is tested at run time, 1 = joint k is a free-flyer, 2 = it is not (compile-time knowledge of
+// the free-flyer-root instantiation).
+template <bool DO_M, bool DO_TAU, int TILE, int FFK = 0>
 RBD_HD void emit_joint(const DevModel& m, int k, const real* A, const real* f, const real* Y, const Stack& S,
                        const EvalIOT<TILE>& io) {
   const DevJoint& jn = m.joint[k];
-  if (jn.type != JT_FF) {
+  const bool is_ff = FFK == 1 ? true : (FFK == 2 ? false : RBD_T_IS_FF(jn.type));
+  if (!is_ff) {
     if (DO_TAU) io.template put_tau<(DO_TAU && !DO_M)>(jn.idx_v, dot6(A, f));
     if (DO_M) {
       real F[6];
@@ -834,7 +873,7 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
   real qn = 0, q1n = 0, vn = 0, an = 0;
 #define RBD_IN_FETCH(jidx)                                                                         \
   do {                                                                                             \
-    if ((jidx) < nj && m.joint[jidx].type != JT_FF) {                                              \
+    if ((jidx) < nj && !RBD_T_IS_FF(m.joint[jidx].type)) {                                              \
       const DevJoint& jx_ = m.joint[jidx];                                                         \
       qn = io.q.ld(jx_.idx_q);                                                                     \
       if (is_unbounded(jx_.type)) q1n = io.q.ld(jx_.idx_q + 1);                                    \
@@ -847,7 +886,7 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
   // start the copies of joint `jidx` (`ahead` tiles further on) into ring slot `slot_`; always closes one group
 #define RBD_INR_ISSUE(jidx, ahead, slot_)                                                          \
   do {                                                                                             \
-    if ((jidx) < nj && m.joint[jidx].type != JT_FF) {                                              \
+    if ((jidx) < nj && !RBD_T_IS_FF(m.joint[jidx].type)) {                                              \
       const DevJoint& jx_ = m.joint[jidx];                                                         \
       const int oq_ = (jx_.idx_q + (ahead) * m.nq) * TILE, ov_ = (jx_.idx_v + (ahead) * m.nv) * TILE; \
       cp_async_real(inr, 3 * (slot_), io.q.at_elems(oq_));                                         \
@@ -882,7 +921,7 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
       const bool btm = (jb.boff & RBD_BOFF_TMEM) != 0;
       int b = jb.boff & RBD_BOFF_MASK;
       // every source assigns R | p (v | a) inside its own branch: no merge through a temporary
-      if (NEED_STACK && jb.type == JT_FF) {
+      if (NEED_STACK && RBD_T_IS_FF(jb.type)) {
         // a free-flyer's A record is its R|p
 #pragma unroll
         for (int e = 0; e < 9; ++e) R[e] = S.ld(jb.offA + e);
@@ -924,7 +963,7 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
         } else {
           // branch joint attached to the universe: v = A qd, a = -g + A qdd (v x vJ = 0), nothing was saved
           real vj[6], aj[6];
-          if (jb.type == JT_FF) {
+          if (RBD_T_IS_FF(jb.type)) {
             ff_act(R, p, io.v, jb.idx_v, vj, MF);
             ff_act(R, p, io.a, jb.idx_v, aj, MF);
           } else {
@@ -943,17 +982,24 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
     }
   };
 
-  for (int i = 1; i < nj; ++i) {
+  // Ak: world subspace column (1-dof) or R|p (free-flyer); fk / Yk: this joint's force / inertia, then the running
+  // subtree sums of the unwind.  Declared outside the joint loop: the free-flyer-root instantiation carries fk / Yk of
+  // the root's last subtree out of the loop into its epilogue.
+  real Ak[12], fk[6], Yk[10];
+  // One joint of the sweep.  `ffj` is a compile-time tag in the free-flyer-root instantiation (RBD_FF_ROOT_ONLY: joint 1
+  // is visited by joint_step(FfYes) in front of the loop, every other joint by joint_step(FfNo), so the loop body
+  // carries no free-flyer code and fits 12-warp blocks); elsewhere the joint type is tested at run time.
+  auto joint_step = [&](auto ffj, const int i) {
     const DevJoint& jn = m.joint[i];
     const int par = jn.parent;
-    if (!NEED_STACK && par != i - 1) restore(par);  // FK-only variant: no unwind to hide behind
+    if (RBD_CAN_BRANCH && (!NEED_STACK || !RBD_EARLY_RESTORE) && par != i - 1) restore(par);  // FK-only variant: no unwind to hide behind
     real q0 = qn, q1 = q1n, qd = vn, qdd = an;
     const int nxt_par = (i + 1 < nj) ? m.joint[i + 1].parent : 0;
     if (!ring) {
       RBD_IN_FETCH(i + 1);
     } else {
       cp_async_wait<RBD_INR_SLOTS - 1>();  // everything but the newest groups has landed: this joint's values are in
-      if (jn.type != JT_FF) {
+      if (!RBD_CUR_FF(ffj, jn.type)) {
         const real* const s_ = inr.p + 3 * inr.slot * RBD_WARP;
         q0 = s_[0];
         if (is_unbounded(jn.type)) q1 = io.q.ld(jn.idx_q + 1);
@@ -971,7 +1017,7 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
     }
 
     real aw[3];
-    fk_joint(jn, R, p, q0, q1, io.q, aw);
+    fk_joint<RBD_EMIT_CUR(ffj)>(jn, R, p, q0, q1, io.q, aw);
     if (io.oMi.ok()) {
 #if RBD_PTR_OMIJ
       real* const po = io.oMi.at(12 * (i - 1));
@@ -995,8 +1041,7 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
 #endif
     }
     // Ak: world subspace column (1-dof) or R|p (free-flyer) — what the A-stack keeps for the CRBA/RNEA projections
-    real Ak[12], fk[6], Yk[10];
-    if (jn.type != JT_FF) {
+    if (!RBD_CUR_FF(ffj, jn.type)) {
       subspace_1dof(jn.type, p, aw, Ak);
       if (io.J.ok()) {
 #if RBD_PTR_OMIJ
@@ -1080,14 +1125,14 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
       // joint i has children: park A | f | Y at its depth level; its subtree sums accumulate there
       if (NEED_STACK) {
         const int lvl = jn.depth - 1;
-        if (jn.type != JT_FF) s_stv<6>(S, jn.offA, Ak); else s_stv<12>(S, jn.offA, Ak);
+        if (!RBD_CUR_FF(ffj, jn.type)) s_stv<6>(S, jn.offA, Ak); else s_stv<12>(S, jn.offA, Ak);
         if (DO_TAU) x_stv<6>(RBD_F_TM(lvl), S, T, RBD_F_OFF(lvl), fk);
         if (DO_M) x_stv<9>(RBD_Y_TM(lvl), S, T, RBD_Y_OFF(lvl), Yk + 1);
       }
-      if (jn.nchild >= 2) {
+      if (RBD_CAN_BRANCH && jn.nchild >= 2) {
         const bool btm = (jn.boff & RBD_BOFF_TMEM) != 0;
         int b = jn.boff & RBD_BOFF_MASK;
-        if (!(NEED_STACK && jn.type == JT_FF) && !(jn.boff & RBD_BOFF_RPOMI)) {
+        if (!(NEED_STACK && RBD_CUR_FF(ffj, jn.type)) && !(jn.boff & RBD_BOFF_RPOMI)) {
           real Rp[12];
 #pragma unroll
           for (int e = 0; e < 9; ++e) Rp[e] = R[e];
@@ -1107,10 +1152,10 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
       // joint i is a leaf: its subtree is complete.  Emit it straight from registers, then unwind: every
       // ancestor whose last child this was is complete too; its sums continue in registers up the chain and
       // are written back only at the joint that still has children to come (nxt_par).
-      if (i + 1 < nj) restore(nxt_par);  // early: see `restore`
+      if (RBD_CAN_BRANCH && RBD_EARLY_RESTORE && i + 1 < nj) restore(nxt_par);  // early: see `restore`
       int k = i;
+      emit_joint<DO_M, DO_TAU, TILE, RBD_EMIT_CUR(ffj)>(m, k, Ak, fk, Yk, S, io);
       while (true) {
-        emit_joint<DO_M, DO_TAU>(m, k, Ak, fk, Yk, S, io);
         const int pk = m.joint[k].parent;
         if (pk == 0) break;
         const DevJoint& jp = m.joint[pk];
@@ -1120,16 +1165,38 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
           if (DO_M) x_addv<9>(RBD_Y_TM(lvl), S, T, RBD_Y_OFF(lvl), Yk + 1);
           break;
         }
+#if defined(RBD_FF_ROOT_ONLY)
+        // the free-flyer root is complete (this was the last joint): fk / Yk carry its last subtree to the epilogue
+        if (pk == 1) break;
+#endif
         if (DO_TAU) x_accv<6>(RBD_F_TM(lvl), S, T, RBD_F_OFF(lvl), fk);
         if (DO_M) {
           x_accv<9>(RBD_Y_TM(lvl), S, T, RBD_Y_OFF(lvl), Yk + 1);
           Yk[0] = jp.msub;  // composite mass of the subtree: model constant
         }
-        if (jp.type != JT_FF) s_ldv<6>(S, jp.offA, Ak); else s_ldv<12>(S, jp.offA, Ak);
+        if (!RBD_ANC_FF(jp.type)) s_ldv<6>(S, jp.offA, Ak); else s_ldv<12>(S, jp.offA, Ak);
         k = pk;
+        emit_joint<DO_M, DO_TAU, TILE, RBD_EMIT_ANC>(m, k, Ak, fk, Yk, S, io);
       }
     }
+  };
+#if defined(RBD_FF_ROOT_ONLY)
+  joint_step(FfYes{}, 1);
+  for (int i = 2; i < nj; ++i) joint_step(FfNo{}, i);
+  if (NEED_STACK && m.joint[1].nchild > 0) {
+    // epilogue: the root's subtree sums = its own record + what the last unwind carried here in registers
+    const DevJoint& jr = m.joint[1];
+    if (DO_TAU) x_accv<6>(RBD_F_TM(0), S, T, RBD_F_OFF(0), fk);
+    if (DO_M) {
+      x_accv<9>(RBD_Y_TM(0), S, T, RBD_Y_OFF(0), Yk + 1);
+      Yk[0] = jr.msub;
+    }
+    s_ldv<12>(S, jr.offA, Ak);
+    emit_joint<DO_M, DO_TAU, TILE, 1>(m, 1, Ak, fk, Yk, S, io);
   }
+#else
+  for (int i = 1; i < nj; ++i) joint_step(FfNo{}, i);
+#endif
   inr.primed = io.next != 0 ? 1 : 0;
 #undef RBD_RESET_ROOT
 #undef RBD_IN_FETCH

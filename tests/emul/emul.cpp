@@ -48,29 +48,61 @@ extern "C" int emul_model_info(const rbd_model_desc* d, int* out /*[8]*/) {
   return 0;
 }
 
-template <int TILE>
-static void eval_one(const DevModel& m, long long i, long long tile, double* q, double* v, double* a, double* oMi,
-                     double* J, double* M, double* tau, const Stack& S, const TmStack& T, InRing& inr, long long next = 0) {
-  const bool do_m = M != nullptr, do_tau = tau != nullptr;
-  EvalIOT<TILE> io;
-  io.next = next;
-  io.q = make_field_t<TILE>(q, i, m.nq, tile); io.v = make_field_t<TILE>(v, i, m.nv, tile);
-  io.a = make_field_t<TILE>(a, i, m.nv, tile);
-  io.oMi = make_field_t<TILE>(oMi, i, 12 * (m.njoints - 1), tile); io.J = make_field_t<TILE>(J, i, 6 * m.nv, tile);
-  io.M = make_field_t<TILE>(M, i, m.mfields, tile); io.tau = make_field_t<TILE>(tau, i, m.nv, tile);
-  if (do_m && do_tau) eval_instance<true, true, TILE>(m, io, S, T, inr);
-  else if (do_m) eval_instance<true, false, TILE>(m, io, S, T, inr);
-  else if (do_tau) eval_instance<false, true, TILE>(m, io, S, T, inr);
-  else eval_instance<false, false, TILE>(m, io, S, T, inr);
-}
+// The per-instance eval of one namespace (rbd = generic, rbd::simple, rbd::chain, rbd::ffroot: the sweep compiled with
+// different joint-type knowledge, rbd_sweeps.h) over a whole batch with the storage plan `pl` of the staged blob `bm`.
+#define EMUL_DEFINE_EVAL_RUN(FN, NSQ)                                                                                  \
+  template <int TILE>                                                                                                  \
+  static void FN##_one(const DevModel& m, long long i, long long tile, double* q, double* v, double* a, double* oMi,   \
+                       double* J, double* M, double* tau, const NSQ::Stack& S, const NSQ::TmStack& T, NSQ::InRing& inr, \
+                       long long next) {                                                                               \
+    const bool do_m = M != nullptr, do_tau = tau != nullptr;                                                           \
+    NSQ::EvalIOT<TILE> io;                                                                                             \
+    io.next = next;                                                                                                    \
+    io.q = NSQ::make_field_t<TILE>(q, i, m.nq, tile); io.v = NSQ::make_field_t<TILE>(v, i, m.nv, tile);                \
+    io.a = NSQ::make_field_t<TILE>(a, i, m.nv, tile);                                                                  \
+    io.oMi = NSQ::make_field_t<TILE>(oMi, i, 12 * (m.njoints - 1), tile);                                              \
+    io.J = NSQ::make_field_t<TILE>(J, i, 6 * m.nv, tile);                                                              \
+    io.M = NSQ::make_field_t<TILE>(M, i, m.mfields, tile); io.tau = NSQ::make_field_t<TILE>(tau, i, m.nv, tile);       \
+    if (do_m && do_tau) NSQ::eval_instance<true, true, TILE>(m, io, S, T, inr);                                        \
+    else if (do_m) NSQ::eval_instance<true, false, TILE>(m, io, S, T, inr);                                            \
+    else if (do_tau) NSQ::eval_instance<false, true, TILE>(m, io, S, T, inr);                                          \
+    else NSQ::eval_instance<false, false, TILE>(m, io, S, T, inr);                                                     \
+  }                                                                                                                    \
+  static void FN(const DevModel& bm, long long n, long long tile, double* q, double* v, double* a, double* oMi,        \
+                 double* J, double* M, double* tau) {                                                                  \
+    const EvalPlan& pl = bm.plan;                                                                                      \
+    const int bt = pl.warps * 32;                                                                                      \
+    std::vector<double> smem((size_t)(pl.smem_doubles > 0 ? pl.smem_doubles : 1) * bt, 1e300); /* poison */            \
+    std::vector<double> tmem((size_t)(pl.tmem_doubles > 0 ? pl.tmem_doubles : 1) * bt, 1e300);                         \
+    /* asynchronous input ring (tile-32 batches, when the plan has room): emulated per lane, persisting from one tile */ \
+    /* to the next as it does for a warp that strides over the tiles (here: stride 1, a single "warp") */             \
+    const bool use_ring = tile == 32 && pl.in_slots > 0;                                                               \
+    std::vector<double> ringbuf((size_t)3 * kEvalInSlots * 32 * 32, 1e300);                                            \
+    std::vector<NSQ::InRing> rings(32);                                                                                \
+    for (int l = 0; l < 32; ++l) rings[l].p = use_ring ? ringbuf.data() + (size_t)l * 3 * kEvalInSlots * 32 : nullptr; \
+    for (long long b0 = 0; b0 < n; b0 += bt)                                                                           \
+      for (int t = 0; t < bt && b0 + t < n; ++t) {                                                                     \
+        const long long i = b0 + t;                                                                                    \
+        NSQ::Stack S = NSQ::make_stack(smem.data(), t, pl.smem_doubles);                                               \
+        NSQ::TmStack T{tmem.data() + (size_t)t * (pl.tmem_doubles > 0 ? pl.tmem_doubles : 1)};                         \
+        const long long next = (use_ring && (i / 32 + 2) * 32 <= n) ? 1 : 0; /* the next tile is a full one */         \
+        if (tile == 32) FN##_one<32>(bm, i, tile, q, v, a, oMi, J, M, tau, S, T, rings[i % 32], next);                 \
+        else FN##_one<0>(bm, i, tile, q, v, a, oMi, J, M, tau, S, T, rings[0], 0);                                     \
+      }                                                                                                                \
+  }
+EMUL_DEFINE_EVAL_RUN(run_eval_generic, rbd)
+EMUL_DEFINE_EVAL_RUN(run_eval_simple, rbd::simple)
+EMUL_DEFINE_EVAL_RUN(run_eval_chain, rbd::chain)
+EMUL_DEFINE_EVAL_RUN(run_eval_ffroot, rbd::ffroot)
 
 // tile == 32 runs the compile-time-tile instantiation the GPU fast path uses.  use_tmem selects the storage plan
 // (tensor memory is emulated by a second poisoned array); block = warps * 32 pins the planner's block size (0 = auto).
 extern "C" int emul_eval_ex(const rbd_model_desc* d, long long n, long long tile, int block, int use_tmem, double* q,
-                            double* v, double* a, double* oMi, double* J, double* M, double* tau, int sparse_m);
+                            double* v, double* a, double* oMi, double* J, double* M, double* tau, int sparse_m,
+                            int variant);
 extern "C" int emul_eval(const rbd_model_desc* d, long long n, long long tile, int block, int use_tmem, double* q,
                          double* v, double* a, double* oMi, double* J, double* M, double* tau) {
-  return emul_eval_ex(d, n, tile, block, use_tmem, q, v, a, oMi, J, M, tau, 0);
+  return emul_eval_ex(d, n, tile, block, use_tmem, q, v, a, oMi, J, M, tau, 0, -1);
 }
 // support-only pattern of M: col_ptr [nv + 1], row_idx [nnz]; returns nnz
 extern "C" int emul_mass_pattern(const rbd_model_desc* d, int* col_ptr, int* row_idx) {
@@ -79,36 +111,43 @@ extern "C" int emul_mass_pattern(const rbd_model_desc* d, int* col_ptr, int* row
   if (rc) return rc;
   return mass_support_pattern(c.m, col_ptr, row_idx);
 }
-// sparse_m != 0: M holds the support-only fields (rbd_eval_soa_sparse)
+// which instantiation the planner picks for this model and output set (RBD_EVAL_*), and the warps per SM of its plan
+extern "C" int emul_eval_variant(const rbd_model_desc* d, int do_m, int do_tau, int* warps_per_sm) {
+  Ctx c;
+  int rc = make_ctx(d, &c);
+  if (rc) return rc;
+  if (!plan_eval(&c.m, do_m != 0, do_tau != 0, true, 0, true)) return -100;
+  if (warps_per_sm) *warps_per_sm = c.m.plan.warps * c.m.plan.blocks_per_sm;
+  return c.m.plan.kvariant;
+}
+// sparse_m != 0: M holds the support-only fields (rbd_eval_soa_sparse).  variant: -1 = the generic sweep (namespace
+// rbd) on the planner's plan, -2 = the instantiation the planner picked (what the GPU launches), >= 0 = that
+// instantiation (RBD_EVAL_*; the model must qualify) on a plan made for it.
 extern "C" int emul_eval_ex(const rbd_model_desc* d, long long n, long long tile, int block, int use_tmem, double* q,
-                            double* v, double* a, double* oMi, double* J, double* M, double* tau, int sparse_m) {
+                            double* v, double* a, double* oMi, double* J, double* M, double* tau, int sparse_m,
+                            int variant) {
   Ctx c;
   int rc = make_ctx(d, &c);
   if (rc) return rc;
   const bool do_m = M != nullptr, do_tau = tau != nullptr;
+  if (variant >= 0) {
+    if (variant > c.m.eval_variant && !(variant == RBD_EVAL_SIMPLE && c.m.eval_variant >= RBD_EVAL_SIMPLE)) {
+      g_err = "the model does not qualify for this instantiation"; return -102;
+    }
+    if (variant == RBD_EVAL_SIMPLE && c.m.eval_variant < RBD_EVAL_SIMPLE) { g_err = "not a simple-joint model"; return -102; }
+    if (variant >= RBD_EVAL_CHAIN && variant != c.m.eval_variant) { g_err = "the model does not qualify for this instantiation"; return -102; }
+  }
   if (!plan_eval(&c.m, do_m, do_tau, use_tmem != 0, block / 32, oMi != nullptr)) { g_err = "plan_eval failed"; return -100; }
   // the sweep reads the model through the staged blob (planned DevModel prefix + ColProg table), as the kernel does
   const std::vector<unsigned long long> blob = build_eval_blob(&c.m, sparse_m != 0);
   const DevModel& bm = *reinterpret_cast<const DevModel*>(blob.data());
-  const EvalPlan& pl = bm.plan;
-  const int bt = pl.warps * 32;
-  std::vector<double> smem((size_t)(pl.smem_doubles > 0 ? pl.smem_doubles : 1) * bt, 1e300);  // poison
-  std::vector<double> tmem((size_t)(pl.tmem_doubles > 0 ? pl.tmem_doubles : 1) * bt, 1e300);
-  // asynchronous input ring (tile-32 batches, when the plan has room): emulated per lane, persisting from one tile to
-  // the next as it does for a warp that strides over the tiles (here: stride 1, a single "warp")
-  const bool use_ring = tile == 32 && pl.in_slots > 0;
-  std::vector<double> ringbuf((size_t)3 * kEvalInSlots * 32 * 32, 1e300);
-  std::vector<InRing> rings(32);
-  for (int l = 0; l < 32; ++l) rings[l].p = use_ring ? ringbuf.data() + (size_t)l * 3 * kEvalInSlots * 32 : nullptr;
-  for (long long b0 = 0; b0 < n; b0 += bt)
-    for (int t = 0; t < bt && b0 + t < n; ++t) {
-      const long long i = b0 + t;
-      Stack S = make_stack(smem.data(), t, pl.smem_doubles);
-      TmStack T{tmem.data() + (size_t)t * (pl.tmem_doubles > 0 ? pl.tmem_doubles : 1)};
-      const long long next = (use_ring && (i / 32 + 2) * 32 <= n) ? 1 : 0;  // the next tile is a full one
-      if (tile == 32) eval_one<32>(bm, i, tile, q, v, a, oMi, J, M, tau, S, T, rings[i % 32], next);
-      else eval_one<0>(bm, i, tile, q, v, a, oMi, J, M, tau, S, T, rings[0]);
-    }
+  const int kv = variant == -2 ? bm.plan.kvariant : variant;
+  switch (kv) {
+    case RBD_EVAL_FFROOT: run_eval_ffroot(bm, n, tile, q, v, a, oMi, J, M, tau); break;
+    case RBD_EVAL_CHAIN: run_eval_chain(bm, n, tile, q, v, a, oMi, J, M, tau); break;
+    case RBD_EVAL_SIMPLE: run_eval_simple(bm, n, tile, q, v, a, oMi, J, M, tau); break;
+    default: run_eval_generic(bm, n, tile, q, v, a, oMi, J, M, tau); break;
+  }
   return 0;
 }
 
@@ -317,7 +356,7 @@ extern "C" int emul_applyJT_rows_cached(const rbd_model_desc* d, long long n, do
     Stack S = make_stack(smem.data(), 0, 1);
     TmStack T{tmem.data()};
     InRing inr;
-    eval_one<0>(bm, i, cache_tile, qcache, nullptr, nullptr, O.data(), J.data(), nullptr, nullptr, S, T, inr);
+    run_eval_generic_one<0>(bm, i, cache_tile, qcache, nullptr, nullptr, O.data(), J.data(), nullptr, nullptr, S, T, inr, 0);
   }
   for (long long r = 0; r < nrows; ++r) {
     double* row = out_rows + (size_t)r * nv;
@@ -350,7 +389,7 @@ extern "C" int emul_frame_jacobians(const rbd_model_desc* d, long long n, double
     Stack S = make_stack(smem.data(), 0, 1);
     TmStack T{tmem.data()};
     InRing inr;
-    eval_one<0>(bm, i, cache_tile, qcache, nullptr, nullptr, O.data(), J.data(), nullptr, nullptr, S, T, inr);
+    run_eval_generic_one<0>(bm, i, cache_tile, qcache, nullptr, nullptr, O.data(), J.data(), nullptr, nullptr, S, T, inr, 0);
   }
   for (long long p = 0; p < npairs; ++p) {
     double* Jr = Jout + (size_t)p * 6 * nv;

@@ -57,7 +57,8 @@ def load_emul() -> C.CDLL:
     lib.emul_sincos.argtypes = [ll, vp, vp, vp]
     lib.emul_sincos.restype = None
     lib.emul_eval.argtypes = [vp, ll, ll, i, i] + [vp] * 7
-    lib.emul_eval_ex.argtypes = [vp, ll, ll, i, i] + [vp] * 7 + [i]
+    lib.emul_eval_ex.argtypes = [vp, ll, ll, i, i] + [vp] * 7 + [i, i]
+    lib.emul_eval_variant.argtypes = [vp, i, i, vp]
     lib.emul_mass_pattern.argtypes = [vp, vp, vp]
     lib.emul_eval_f32.argtypes = [vp, ll, ll, i, i] + [vp] * 7
     lib.emul_apply.argtypes = [vp, ll, ll, i, vp, vp, vp, ll, vp]

@@ -81,7 +81,7 @@ def test_eval_sparse_mass_format(emul, d, tile, use_tmem, want_tau):
     tau = np.full((nt, d.nv, tile), np.nan) if want_tau else None
     oMi = np.full((nt, 12 * (d.njoints - 1), tile), np.nan)
     qs, vs, as_ = to_tiled(q, tile), to_tiled(v, tile), to_tiled(a, tile)
-    rc = emul.emul_eval_ex(C.addressof(cd), n, tile, 0, use_tmem, P(qs), P(vs), P(as_), P(oMi), None, P(Mv), P(tau), 1)
+    rc = emul.emul_eval_ex(C.addressof(cd), n, tile, 0, use_tmem, P(qs), P(vs), P(as_), P(oMi), None, P(Mv), P(tau), 1, -2)
     assert rc == 0, emul.emul_last_error()
     ref, _ = oracle.eval_batch(d, q, v, a, 1)
     got = from_tiled(Mv, n)[:, :nnz]
@@ -91,6 +91,67 @@ def test_eval_sparse_mass_format(emul, d, tile, use_tmem, want_tau):
     assert rel_err(from_tiled(oMi, n), ref["oMi"]) <= TOL_FP64
     if want_tau:
         assert rel_err(from_tiled(tau, n), ref["tau"]) <= TOL_FP64
+
+
+def _emul_eval_variant(emul, d, q, v, a, tile, variant, want=("oMi", "J", "M", "tau"), sparse=0):
+    n = q.shape[0]
+    cd, keep = _cdesc(d)
+    nt = (n + tile - 1) // tile
+    col_ptr = np.zeros(d.nv + 1, dtype=np.int32)
+    nnz = emul.emul_mass_pattern(C.addressof(cd), P(col_ptr), None)
+    K = {"oMi": 12 * (d.njoints - 1), "J": 6 * d.nv, "M": nnz if sparse else d.nv * (d.nv + 1) // 2, "tau": d.nv}
+    outs = {k: (np.full((nt, max(1, K[k]), tile), np.nan) if k in want else None) for k in K}
+    qs, vs, as_ = to_tiled(q, tile), to_tiled(v, tile), to_tiled(a, tile)
+    rc = emul.emul_eval_ex(C.addressof(cd), n, tile, 0, 1, P(qs), P(vs), P(as_), P(outs["oMi"]), P(outs["J"]),
+                           P(outs["M"]), P(outs["tau"]), sparse, variant)
+    assert rc == 0, emul.emul_last_error()
+    return {k: (from_tiled(o, n)[:, :K[k]] if o is not None else None) for k, o in outs.items()}
+
+
+VARIANT_NAMES = {0: "generic", 1: "simple", 2: "chain", 3: "ffroot"}
+
+
+@pytest.mark.parametrize("d", MODELS, ids=IDS)
+@pytest.mark.parametrize("tile", [32, 9])
+def test_eval_specialised_instantiations(emul, d, tile):
+    """rbd::simple / rbd::chain / rbd::ffroot (the sweep compiled with joint-type knowledge; rbd_sweeps.h) compute
+    bit-for-bit what the generic sweep computes, for every model that qualifies; the instantiation the planner picks
+    matches the oracle; BASELINE robots get the instantiation they were built for."""
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    n = 70
+    q, v, a = mdl.random_state(d, n, seed=21)
+    cd, keep = _cdesc(d)
+    w = C.c_int(0)
+    picked = emul.emul_eval_variant(C.addressof(cd), 1, 1, C.byref(w))
+    assert picked >= 0
+    expect = {"panda7": (2, 12), "solo12": (3, 12), "talos_reduced": (1, 8)}.get(d.name)
+    if expect:
+        assert (picked, w.value) == expect, (VARIANT_NAMES[picked], w.value)
+    ref, _ = oracle.eval_batch(d, q, v, a, 1)
+    base = _emul_eval_variant(emul, d, q, v, a, tile, -1)
+    got = _emul_eval_variant(emul, d, q, v, a, tile, -2)
+    for k in ref:
+        assert rel_err(got[k], ref[k]) <= TOL_FP64, k
+        assert np.array_equal(got[k], base[k]), k
+    ran = 0
+    for variant in (1, 2, 3):
+        cdv, _k = _cdesc(d)
+        nt = (n + tile - 1) // tile
+        probe = np.full((nt, max(1, d.nv), tile), np.nan)
+        qs, vs, as_ = to_tiled(q, tile), to_tiled(v, tile), to_tiled(a, tile)
+        rc = emul.emul_eval_ex(C.addressof(cdv), n, tile, 0, 1, P(qs), P(vs), P(as_), None, None, None, P(probe), 0, variant)
+        if rc == -102:
+            continue                                        # the model does not qualify for this instantiation
+        assert rc == 0, emul.emul_last_error()
+        ran += 1
+        for want, sparse in ((("oMi", "J", "M", "tau"), 0), (("M",), 1), (("tau",), 0), (("oMi", "M"), 0), (("J",), 0)):
+            g = _emul_eval_variant(emul, d, q, v, a, tile, variant, want, sparse)
+            b = _emul_eval_variant(emul, d, q, v, a, tile, -1, want, sparse)
+            for k in want:
+                assert np.array_equal(g[k], b[k]), (VARIANT_NAMES[variant], want, k)
+    if d.name in ("panda7", "solo12", "talos_reduced"):
+        assert ran >= 2
 
 
 @pytest.mark.parametrize("d", MODELS, ids=IDS)

@@ -292,7 +292,7 @@ def test_eval_sparse_mass_format(torch_mod, api, d, tile):
     Mv2 = new(I.mass_support_fields)
     ws.crba_soa_sparse(n, tile, qs, Mv2)
     ws.synchronize()
-    assert torch.equal(Mv, Mv2)
+    assert np.array_equal(from_tiled(Mv.cpu().numpy(), n), from_tiled(Mv2.cpu().numpy(), n))   # (padding lanes hold NaN)
 
 
 def test_eval_host_sparse_and_output_selection(api):
