@@ -641,7 +641,16 @@ static cudaError_t pick_block(Kern kern, int smem_doubles_per_thread, int forced
     const int v = (a.tile == 32 ? 4 : 0) | (do_m ? 2 : 0) | (do_tau ? 1 : 0);                                      \
     LaunchCfg& cfg = cache[v];                                                                                     \
     const int model_words = (int)(eval_model_bytes(hm) / 8); /* staged joint table + 2 spare words */              \
-    const int block = hm.plan.warps * 32;                                                                          \
+    int warps = hm.plan.warps;                                                                                     \
+    if (warps > 8 && a.n > 0) {                                                                                    \
+      /* 12-warp plans (chain / ffroot kernels; the storage layout holds for any smaller block): a batch that needs */ \
+      /* as many waves of 12-warp blocks as of 8-warp blocks runs the latter — shorter waves (Panda, N = 65 536) */ \
+      const long long tiles = (a.n + 31) / 32;                                                                     \
+      const long long ww = ((tiles + warps - 1) / warps + num_sms - 1) / num_sms;                                  \
+      const long long w8 = ((tiles + 7) / 8 + num_sms - 1) / num_sms;                                              \
+      if (ww >= w8) warps = 8;                                                                                     \
+    }                                                                                                              \
+    const int block = warps * 32;                                                                                  \
     const size_t smem = (size_t)model_words * 8 + (size_t)block * (hm.plan.smem_doubles + 3 * hm.plan.in_slots) * sizeof(REAL); \
     cudaError_t e = cudaSuccess;                                                                                   \
     if (cfg.block != block || cfg.smem_bytes != smem || cfg.tag != TAG) {                                          \

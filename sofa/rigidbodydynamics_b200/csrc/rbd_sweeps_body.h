@@ -10,6 +10,12 @@
 // free-flyer code, no branch records, no return-to-branch restores: fewer registers, so more warps fit an SM.
 #undef RBD_T_IS_FF
 #undef RBD_CAN_BRANCH
+#undef RBD_EARLY_RESTORE_NS
+#if defined(RBD_FF_ROOT_ONLY)
+#define RBD_EARLY_RESTORE_NS 0 /* 12-warp blocks at 168 registers: the early reload would spill (ptxas: 88 bytes) */
+#else
+#define RBD_EARLY_RESTORE_NS RBD_EARLY_RESTORE
+#endif
 #undef RBD_CUR_FF
 #undef RBD_ANC_FF
 #undef RBD_EMIT_CUR
@@ -985,14 +991,19 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
   // Ak: world subspace column (1-dof) or R|p (free-flyer); fk / Yk: this joint's force / inertia, then the running
   // subtree sums of the unwind.  Declared outside the joint loop: the free-flyer-root instantiation carries fk / Yk of
   // the root's last subtree out of the loop into its epilogue.
+#if defined(RBD_FF_ROOT_ONLY)
   real Ak[12], fk[6], Yk[10];
+#define RBD_STEP_STATE
+#else
+#define RBD_STEP_STATE real Ak[12], fk[6], Yk[10];
+#endif
   // One joint of the sweep.  `ffj` is a compile-time tag in the free-flyer-root instantiation (RBD_FF_ROOT_ONLY: joint 1
   // is visited by joint_step(FfYes) in front of the loop, every other joint by joint_step(FfNo), so the loop body
   // carries no free-flyer code and fits 12-warp blocks); elsewhere the joint type is tested at run time.
   auto joint_step = [&](auto ffj, const int i) {
     const DevJoint& jn = m.joint[i];
     const int par = jn.parent;
-    if (RBD_CAN_BRANCH && (!NEED_STACK || !RBD_EARLY_RESTORE) && par != i - 1) restore(par);  // FK-only variant: no unwind to hide behind
+    if (RBD_CAN_BRANCH && (!NEED_STACK || !RBD_EARLY_RESTORE_NS) && par != i - 1) restore(par);  // FK-only variant: no unwind to hide behind
     real q0 = qn, q1 = q1n, qd = vn, qdd = an;
     const int nxt_par = (i + 1 < nj) ? m.joint[i + 1].parent : 0;
     if (!ring) {
@@ -1041,6 +1052,7 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
 #endif
     }
     // Ak: world subspace column (1-dof) or R|p (free-flyer) — what the A-stack keeps for the CRBA/RNEA projections
+    RBD_STEP_STATE
     if (!RBD_CUR_FF(ffj, jn.type)) {
       subspace_1dof(jn.type, p, aw, Ak);
       if (io.J.ok()) {
@@ -1152,8 +1164,11 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
       // joint i is a leaf: its subtree is complete.  Emit it straight from registers, then unwind: every
       // ancestor whose last child this was is complete too; its sums continue in registers up the chain and
       // are written back only at the joint that still has children to come (nxt_par).
-      if (RBD_CAN_BRANCH && RBD_EARLY_RESTORE && i + 1 < nj) restore(nxt_par);  // early: see `restore`
+      if (RBD_CAN_BRANCH && RBD_EARLY_RESTORE_NS && i + 1 < nj) restore(nxt_par);  // early: see `restore`
       int k = i;
+#if defined(RBD_FF_ROOT_ONLY)
+      // (peeled: joint i is of the step's own kind, the ancestors emitted on the way up are never the root; this form
+      // also needs fewer registers than the loop below — 168 without spills)
       emit_joint<DO_M, DO_TAU, TILE, RBD_EMIT_CUR(ffj)>(m, k, Ak, fk, Yk, S, io);
       while (true) {
         const int pk = m.joint[k].parent;
@@ -1165,19 +1180,38 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
           if (DO_M) x_addv<9>(RBD_Y_TM(lvl), S, T, RBD_Y_OFF(lvl), Yk + 1);
           break;
         }
-#if defined(RBD_FF_ROOT_ONLY)
         // the free-flyer root is complete (this was the last joint): fk / Yk carry its last subtree to the epilogue
         if (pk == 1) break;
-#endif
         if (DO_TAU) x_accv<6>(RBD_F_TM(lvl), S, T, RBD_F_OFF(lvl), fk);
         if (DO_M) {
           x_accv<9>(RBD_Y_TM(lvl), S, T, RBD_Y_OFF(lvl), Yk + 1);
           Yk[0] = jp.msub;  // composite mass of the subtree: model constant
         }
-        if (!RBD_ANC_FF(jp.type)) s_ldv<6>(S, jp.offA, Ak); else s_ldv<12>(S, jp.offA, Ak);
+        s_ldv<6>(S, jp.offA, Ak);
         k = pk;
-        emit_joint<DO_M, DO_TAU, TILE, RBD_EMIT_ANC>(m, k, Ak, fk, Yk, S, io);
+        emit_joint<DO_M, DO_TAU, TILE, 2>(m, k, Ak, fk, Yk, S, io);
       }
+#else
+      while (true) {
+        emit_joint<DO_M, DO_TAU, TILE>(m, k, Ak, fk, Yk, S, io);
+        const int pk = m.joint[k].parent;
+        if (pk == 0) break;
+        const DevJoint& jp = m.joint[pk];
+        const int lvl = jp.depth - 1;
+        if (pk == nxt_par) {
+          if (DO_TAU) x_addv<6>(RBD_F_TM(lvl), S, T, RBD_F_OFF(lvl), fk);
+          if (DO_M) x_addv<9>(RBD_Y_TM(lvl), S, T, RBD_Y_OFF(lvl), Yk + 1);
+          break;
+        }
+        if (DO_TAU) x_accv<6>(RBD_F_TM(lvl), S, T, RBD_F_OFF(lvl), fk);
+        if (DO_M) {
+          x_accv<9>(RBD_Y_TM(lvl), S, T, RBD_Y_OFF(lvl), Yk + 1);
+          Yk[0] = jp.msub;  // composite mass of the subtree: model constant
+        }
+        if (!RBD_T_IS_FF(jp.type)) s_ldv<6>(S, jp.offA, Ak); else s_ldv<12>(S, jp.offA, Ak);
+        k = pk;
+      }
+#endif
     }
   };
 #if defined(RBD_FF_ROOT_ONLY)
@@ -1198,6 +1232,7 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
   for (int i = 1; i < nj; ++i) joint_step(FfNo{}, i);
 #endif
   inr.primed = io.next != 0 ? 1 : 0;
+#undef RBD_STEP_STATE
 #undef RBD_RESET_ROOT
 #undef RBD_IN_FETCH
 #undef RBD_INR_ISSUE

@@ -292,7 +292,8 @@ def test_eval_sparse_mass_format(torch_mod, api, d, tile):
     Mv2 = new(I.mass_support_fields)
     ws.crba_soa_sparse(n, tile, qs, Mv2)
     ws.synchronize()
-    assert np.array_equal(from_tiled(Mv.cpu().numpy(), n), from_tiled(Mv2.cpu().numpy(), n))   # (padding lanes hold NaN)
+    # (another instantiation of the sweep: the compiler may contract multiply-adds differently -> last-bit differences)
+    assert rel_err(from_tiled(Mv2.cpu().numpy(), n), from_tiled(Mv.cpu().numpy(), n)) <= 1e-13
 
 
 def test_eval_host_sparse_and_output_selection(api):
@@ -315,10 +316,10 @@ def test_eval_host_sparse_and_output_selection(api):
         assert rel_err(g, ref[k]) <= TOL_FP64, k
     Mv2 = np.zeros_like(Mv); tau2 = np.zeros_like(tau)
     ws.eval_host_sparse(n, q, v, a, None, None, Mv2, tau2)
-    assert np.array_equal(Mv, Mv2) and np.array_equal(tau, tau2)
+    assert rel_err(Mv2, Mv) <= 1e-13 and rel_err(tau2, tau) <= 1e-13   # (other instantiations of the sweep)
     Mv3 = np.zeros_like(Mv)
     ws.eval_host_sparse(n, q, None, None, None, None, Mv3, None)   # crba alone: v and a do not travel
-    assert np.array_equal(Mv, Mv3)
+    assert rel_err(Mv3, Mv) <= 1e-13
 
 
 def test_rows_host_rejects_malformed_csr(api):
