@@ -118,6 +118,22 @@ def all_models():
     return ms
 
 
+def subset_models():
+    """BASELINE robots and the reference's hand with a PERMUTED STRICT SUBSET of the frames as mapped outputs: the
+    reference maps every frame (URDFModelLoader.cpp:159-165, "TODO should be configurable"); rbd_model_desc.out_frames
+    expresses any selection and order."""
+    import dataclasses
+    out = []
+    for k, d in enumerate(m for m in all_models() if m.name in ("talos_reduced", "solo12", "panda7", "random_3",
+                                                                  "schunk_svh_hand_right_ff")):
+        rng = np.random.default_rng(1000 + k)
+        keep = max(3, d.nframes // 3)
+        sel = rng.permutation(d.nframes)[:keep].astype(np.int32)      # permuted, strict subset, universe frame allowed
+        assert keep < d.nframes
+        out.append(dataclasses.replace(d, name=d.name + "_subset", out_frames=np.ascontiguousarray(sel)))
+    return out
+
+
 def integrate(d, q: np.ndarray, dq: np.ndarray, eps: float) -> np.ndarray:
     """q (+) eps * dq with pinocchio's conventions ([n, nq], [n, nv]): free-flyer p += R (eps v_b), quat <- quat * exp(eps w_b)
     (joint-frame velocity); unbounded revolute joints rotate their (cos, sin) pair; the rest is q += eps dq."""
@@ -147,3 +163,42 @@ def integrate(d, q: np.ndarray, dq: np.ndarray, eps: float) -> np.ndarray:
         else:
             out[:, iq] = q[:, iq] + eps * dq[:, iv]
     return out
+
+
+def fd_world_jacobian_error(eval_fn, d, q: np.ndarray, eps: float = 1e-6) -> float:
+    """Central finite differences of the joint placements along every dof (q (+) eps e_c, pinocchio's integrate: the
+    free-flyer moves by a velocity given in ITS OWN frame) against the world joint Jacobian: column c of data.J is the
+    world-frame spatial velocity [v_O; w] (at the world origin) that a unit dq_c gives every body below joint(c), and
+    leaves the other bodies at rest.  eval_fn(q [N, nq]) -> (oMi [N, 12 (nj - 1)], J [N, 6 nv]).  Returns the largest
+    deviation; pins the free-flyer velocity frame and the [lin; ang] ordering independently of any second implementation
+    of the Jacobian."""
+    n, nj, nv = q.shape[0], d.njoints, d.nv
+    owner = np.zeros(nv, dtype=np.int64)
+    for j in range(1, nj):
+        nxt = int(d.idx_v[j + 1]) if j + 1 < nj else nv
+        owner[int(d.idx_v[j]):nxt] = j
+    below = np.zeros((nj, nj), dtype=bool)                 # below[a, i]: joint i is a or a descendant of a
+    for i in range(1, nj):
+        k = i
+        while k != 0:
+            below[k, i] = True; k = int(d.parents[k])
+    qs = [q]
+    for c in range(nv):
+        e = np.zeros((n, nv)); e[:, c] = 1.0
+        qs.append(integrate(d, q, e, eps)); qs.append(integrate(d, q, e, -eps))
+    oMi, J = eval_fn(np.ascontiguousarray(np.concatenate(qs)))
+    oMi = oMi.reshape(2 * nv + 1, n, nj - 1, 12); J0 = J[:n].reshape(n, nv, 6)
+    R0 = oMi[0][..., :9].reshape(n, nj - 1, 3, 3); p0 = oMi[0][..., 9:]
+    worst = 0.0
+    for c in range(nv):
+        P, M = oMi[1 + 2 * c], oMi[2 + 2 * c]
+        dR = (P[..., :9] - M[..., :9]).reshape(n, nj - 1, 3, 3) / (2 * eps)
+        dp = (P[..., 9:] - M[..., 9:]) / (2 * eps)
+        W = np.einsum("nkij,nklj->nkil", dR, R0)           # dR R^T = skew(w)
+        w = np.stack([W[..., 2, 1], W[..., 0, 2], W[..., 1, 0]], -1)
+        v = dp - np.cross(w, p0)                           # velocity of the point at the world origin
+        fd = np.concatenate([v, w], -1)                    # [n, nj - 1, 6]
+        for i in range(1, nj):
+            ref = J0[:, c] if below[owner[c], i] else np.zeros((n, 6))
+            worst = max(worst, float(np.max(np.abs(fd[:, i - 1] - ref))))
+    return worst

@@ -11,6 +11,8 @@ from helpers import P, TOL_FP64, from_tiled, rel_err, to_tiled
 
 MODELS = helpers.all_models()
 IDS = [m.name for m in MODELS]
+MODELS_MAP = MODELS + helpers.subset_models()          # + permuted strict subsets of the frames as mapped outputs
+IDS_MAP = [m.name for m in MODELS_MAP]
 
 
 def _cdesc(d):
@@ -184,7 +186,7 @@ def _split(d, q, v):
     return q, None, v, None
 
 
-@pytest.mark.parametrize("d", MODELS, ids=IDS)
+@pytest.mark.parametrize("d", MODELS_MAP, ids=IDS_MAP)
 def test_mapping_bodies_match_oracle(emul, d):
     """apply -> applyJ -> applyJT -> applyJT(rows): the component's call order (KCM.inl:338-639)."""
     import oracle
@@ -448,3 +450,19 @@ def test_applyDJT_bodies_match_finite_differences(emul, d):
         if ff:
             got2 = np.concatenate([from_tiled(ort2, n), got2], axis=1)
         assert rel_err(got2, got) <= 1e-12
+
+
+@pytest.mark.parametrize("name", ["solo12", "talos_reduced", "random_2", "schunk_svh_hand_right_ff", "panda7"])
+def test_world_jacobian_by_finite_differences(emul, name):
+    """Free-flyer velocity frame, [lin; ang] ordering and column ownership of the world joint Jacobian pinned by central
+    differences of the kernel's own joint placements along pinocchio's integrate (helpers.fd_world_jacobian_error)."""
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    d = [m for m in MODELS if m.name == name][0]
+    q, v, a = mdl.random_state(d, 3, seed=31)
+
+    def eval_fn(qb):
+        zeros = np.zeros((qb.shape[0], d.nv))
+        got = _emul_eval(emul, d, qb, zeros, zeros, 32, 0, ("oMi", "J"))
+        return got["oMi"], got["J"]
+
+    assert helpers.fd_world_jacobian_error(eval_fn, d, q) <= 1e-7

@@ -120,3 +120,81 @@ def test_config2_solo_262144_applyJT():
         qi = Q[i].cpu().numpy()
         ref = orc.apply(qi[7:], qi[:7])
         assert rel_err(P[i, :, :3].cpu().numpy(), ref[:, :3]) <= TOL_FP64
+
+
+@pytest.mark.parametrize("name,n,cols", [("solo12", 262144, None), ("talos_reduced", 1 << 20, (0, 3, 5, 6, 11, 12, 19, 27, 37)),
+                                         ("panda7", 65536, None)])
+def test_mass_matrix_through_the_mapping(name, n, cols):
+    """SURVEY.md §0 fact 3 — the reference's own route to the joint-space mass: one UniformMass<Rigid3> per body hung
+    under the mapping (URDFModelLoader.cpp:369-391), so SOFA evaluates  M e_j = sum_b J_b^T Y_b J_b e_j  matrix-free
+    through applyJ and applyJT.  Here, for EVERY instance of the BASELINE batch: column j of the CRBA kernel's M equals
+    applyJT( diag(m_b I_3, R_b I_c,b R_b^T) applyJ(e_j) ) built from the mapping kernels on the body-CoM outputs, with
+    the rotated body inertias taken from the eval kernel's oMi.  Ties K1/K2/K3 (reference call sites) to K5 (no
+    reference call site) without any second implementation."""
+    import torch
+    from sofa.rigidbodydynamics_b200 import api, model as mdl
+    d = mdl.ROBOTS[name](); nt = n // 32
+    nj, nv, no = d.njoints, d.nv, d.n_out
+    ff = d.has_freeflyer_root
+    m = api.Model(d); ws = api.Workspace(m, n)
+    ws.set_stream(torch.cuda.current_stream().cuda_stream)
+    q, _v, _a = _rand_state(torch, d, n, 17)
+    E = lambda K: torch.empty((nt, K, 32), dtype=torch.float64, device="cuda")
+    Mp, oMi = E(m.info.mass_fields), E(m.info.omi_fields)
+    ws.eval_soa(n, 32, q, None, None, oMi, None, Mp, None)
+    qj, root = (q[:, 7:].contiguous(), q[:, :7].contiguous()) if ff else (q, None)
+    pos = E(7 * no)
+    ws.apply_soa(n, 32, qj, root, pos)
+    # world inertia about the CoM of body b (joint b, b >= 1): R_b Ic_b R_b^T, R_b from the eval kernel's oMi
+    R = oMi.reshape(nt, nj - 1, 12, 32)[:, :, :9].reshape(nt, nj - 1, 3, 3, 32)
+    Ic = torch.zeros((nj - 1, 3, 3), dtype=torch.float64, device="cuda")
+    for b in range(1, nj):
+        xx, xy, yy, xz, yz, zz = (float(x) for x in d.inertia[b, 4:10])
+        Ic[b - 1] = torch.tensor([[xx, xy, xz], [xy, yy, yz], [xz, yz, zz]], dtype=torch.float64)
+    Iw = torch.einsum("tbijl,bjk,tbmkl->tbiml", R, Ic, R)
+    mass = torch.tensor([float(d.inertia[b, 0]) for b in range(1, nj)], dtype=torch.float64, device="cuda")
+    del R, oMi
+    scale = max(1.0, float(Mp.abs().max()))
+    worst = 0.0
+    vel = E(6 * no)
+    for j in (range(nv) if cols is None else cols):
+        dq = torch.zeros((nt, nv, 32), dtype=torch.float64, device="cuda"); dq[:, j] = 1.0
+        dqj, rootv = (dq[:, 6:].contiguous(), dq[:, :6].contiguous()) if ff else (dq, None)
+        ws.applyJ_soa(n, 32, dqj, rootv, vel)
+        V = vel.reshape(nt, no, 6, 32)
+        w = torch.zeros((nt, no, 6, 32), dtype=torch.float64, device="cuda")
+        w[:, 1:nj, :3] = V[:, 1:nj, :3] * mass[None, :, None, None]           # bodies = mapped outputs 1 .. nj-1 (their CoM frames)
+        w[:, 1:nj, 3:] = torch.einsum("tbijl,tbjl->tbil", Iw, V[:, 1:nj, 3:])
+        tau = torch.zeros((nt, d.nv_joints, 32), dtype=torch.float64, device="cuda")
+        rt = torch.zeros((nt, 6, 32), dtype=torch.float64, device="cuda") if ff else None
+        ws.applyJT_soa(n, 32, w.reshape(nt, 6 * no, 32), tau, rt)
+        col = torch.cat([rt, tau], dim=1) if ff else tau                        # [nt, nv, 32]
+        ref = torch.stack([Mp[:, j * (j + 1) // 2 + i] if i <= j else Mp[:, i * (i + 1) // 2 + j] for i in range(nv)], dim=1)
+        worst = max(worst, float((col - ref).abs().max()) / scale)
+        del w, V
+    assert worst <= 1e-10, worst
+
+
+@pytest.mark.parametrize("name", ["solo12", "talos_reduced", "random_2"])
+def test_world_jacobian_by_finite_differences_gpu(name):
+    """The free-flyer velocity frame / [lin; ang] ordering / column ownership of the GPU kernel's world joint Jacobian,
+    pinned by central differences of its OWN joint placements along pinocchio's integrate (helpers.integrate)."""
+    import torch
+    import helpers
+    from sofa.rigidbodydynamics_b200 import api, model as mdl
+    d = [x for x in helpers.all_models() if x.name == name][0]
+    q, _v, _a = mdl.random_state(d, 5, seed=33)
+    m = api.Model(d)
+
+    def eval_fn(qb):
+        N = qb.shape[0]
+        ws = api.Workspace(m, N)
+        qs = torch.from_numpy(helpers.to_tiled(qb, 32)).cuda()
+        nt = qs.shape[0]
+        oMi = torch.zeros((nt, m.info.omi_fields, 32), dtype=torch.float64, device="cuda")
+        J = torch.zeros((nt, m.info.jac_fields, 32), dtype=torch.float64, device="cuda")
+        ws.eval_soa(N, 32, qs, None, None, oMi, J, None, None)
+        ws.synchronize()
+        return helpers.from_tiled(oMi.cpu().numpy(), N), helpers.from_tiled(J.cpu().numpy(), N)
+
+    assert helpers.fd_world_jacobian_error(eval_fn, d, q) <= 1e-7

@@ -29,6 +29,9 @@ def api(rbd_lib):
 
 MODELS = helpers.all_models()
 IDS = [m.name for m in MODELS]
+SUBSETS = helpers.subset_models()                      # permuted strict subsets of the frames as mapped outputs
+MODELS_MAP = MODELS + SUBSETS
+IDS_MAP = [m.name for m in MODELS_MAP]
 
 
 def _dev(torch, x):
@@ -133,7 +136,7 @@ def _split(d, q, v):
     return q, None, v, None
 
 
-@pytest.mark.parametrize("d", MODELS, ids=IDS)
+@pytest.mark.parametrize("d", MODELS_MAP, ids=IDS_MAP)
 @pytest.mark.parametrize("n,tile,ring", [(200, 64, True), (200, 32, True), (200, 32, False), (4000, 32, True)])
 def test_mapping_soa_matches_oracle(torch_mod, api, d, n, tile, ring):
     """apply -> applyJ -> applyJT on device tiled-SoA buffers (the component's call order, KCM.inl:338-513).
@@ -687,14 +690,14 @@ def test_joint_space_mass_mirror(api):
         mass.addMDx(res, q, dx[:, :3], 1.0)
 
 
-@pytest.mark.parametrize("name", ["talos_reduced", "solo12", "random_3"])
+@pytest.mark.parametrize("name", ["talos_reduced", "solo12", "random_3", "talos_reduced_subset", "schunk_svh_hand_right_ff_subset"])
 def test_constraint_rows_cached_jacobians(torch_mod, api, name):
     """rbd_applyJT_rows_dev on the Jacobian cache (default) equals the per-row sweep, follows a new apply (the cache is
     refilled lazily after every apply, as the reference's data.J is by computeJointJacobians), and matches the oracle."""
     import oracle
     from sofa.rigidbodydynamics_b200 import model as mdl
     torch = torch_mod
-    d = [m for m in MODELS if m.name == name][0]
+    d = [m for m in MODELS_MAP if m.name == name][0]
     n, tile = 300, 32
     rng = np.random.default_rng(71)
     nrows = 2 * n + 5
@@ -734,14 +737,14 @@ def test_constraint_rows_cached_jacobians(torch_mod, api, name):
     assert rel_err(results[(81, True)][0], results[(82, True)][0]) > 1e-3   # different configurations, different rows
 
 
-@pytest.mark.parametrize("name", ["talos_reduced", "solo12", "panda7"])
+@pytest.mark.parametrize("name", ["talos_reduced", "solo12", "panda7", "solo12_subset", "panda7_subset"])
 def test_frame_jacobians_from_cache(torch_mod, api, name):
     """rbd_getFrameJacobian_* = pinocchio::getFrameJacobian(LOCAL_WORLD_ALIGNED) as the reference calls it per output
     (KCM.inl:434-490): against the oracle's dense Jacobian, and J_k dq == applyJ, J_k^T w == applyJT (one wrench)."""
     import oracle
     from sofa.rigidbodydynamics_b200 import model as mdl
     torch = torch_mod
-    d = [m for m in MODELS if m.name == name][0]
+    d = [m for m in MODELS_MAP if m.name == name][0]
     n, tile = 100, 32
     q, v, _ = mdl.random_state(d, n, seed=91)
     qj, root, dq, rootv = _split(d, q, v)
