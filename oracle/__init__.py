@@ -104,6 +104,7 @@ def lib() -> C.CDLL:
         l.orc_get_frame_jacobian_lwa.restype = None; l.orc_get_frame_jacobian_lwa.argtypes = [vp, C.c_int, dp]
         l.orc_rot_to_quat.restype = None; l.orc_rot_to_quat.argtypes = [dp, dp]
         l.orc_apply.restype = None; l.orc_apply.argtypes = [vp, dp, dp, dp]
+        l.orc_apply_loop.restype = None; l.orc_apply_loop.argtypes = [vp, C.c_long, dp, dp, dp]
         l.orc_applyJ.restype = None; l.orc_applyJ.argtypes = [vp, dp, dp, dp]
         l.orc_applyJT.restype = None; l.orc_applyJT.argtypes = [vp, dp, dp, dp]
         l.orc_applyJT_row.restype = C.c_int; l.orc_applyJT_row.argtypes = [vp, C.c_int, vp, dp, dp]

@@ -594,6 +594,15 @@ extern "C" void orc_flop_counts(long long out[6]) {
 #define double orc_counted
 #endif
 
+/* The mapping's apply for n robots one after the other on the calling thread (what n KinematicChainMapping components
+ * of one scene cost the reference per propagation pass): experiments/latency_table.py times it next to the batched
+ * back end.  q_joints [n][nq_joints], root_pose [n][7] or NULL, out [n][n_out][7]. */
+void orc_apply_loop(orc_workspace* w, long n, const double* q_joints, const double* root_pose, double* out) {
+  const long kq = has_ff_root(w) && root_pose ? w->nq - 7 : w->nq;
+  for (long i = 0; i < n; ++i)
+    orc_apply(w, q_joints + i * kq, root_pose ? root_pose + i * 7 : NULL, out + i * 7L * w->n_out);
+}
+
 /* accessors used by the tests */
 const double* orc_data_J(const orc_workspace* w) { return w->J; }
 void orc_get_oMi(const orc_workspace* w, int i, double* out12) {

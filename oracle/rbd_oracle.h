@@ -15,6 +15,7 @@ void orc_rot_to_quat(const double* R_rowmajor, double* xyzw);
 void orc_apply(orc_workspace* w, const double* q_joints, const double* root_pose, double* out);
 void orc_applyJ(orc_workspace* w, const double* dq_joints, const double* root_vel, double* out);
 void orc_applyJT(orc_workspace* w, const double* in, double* out_tau, double* out_root);
+void orc_apply_loop(orc_workspace* w, long n, const double* q_joints, const double* root_pose, double* out);
 int orc_applyJT_row(orc_workspace* w, int nnz, const int* col, const double* val, double* row_out);
 void orc_crba(orc_workspace* w, const double* q, double* M_rowmajor);
 void orc_rnea(orc_workspace* w, const double* q, const double* v, const double* a, double* tau);
