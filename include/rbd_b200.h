@@ -239,6 +239,26 @@ RBD_API int rbd_getFrameJacobian_dev(rbd_workspace* ws, int64_t npairs, const in
 RBD_API int rbd_getFrameJacobian_host(rbd_workspace* ws, int64_t npairs, const int32_t* instance,
                                       const int32_t* out_index, double* J);
 
+/* getJ — the ASSEMBLED mapping Jacobian.  The reference's getJ() returns nullptr (KinematicChainMapping.h:82-83), so
+ * SOFA's direct solvers (the example scenes use SparseLDLSolver, examples/sofa/RigidBodyDynamics/LoadRobot/robot.py:48)
+ * cannot see through the mapping.  The matrix has one 6 x nv block row per mapped output, and block row k is
+ * structurally non-zero only in the dofs on the path from the output's parent joint to the root — exactly the columns
+ * getFrameJacobian(LOCAL_WORLD_ALIGNED) fills at KinematicChainMapping.inl:434-490.
+ *   rbd_model_getJ_pattern  the fixed pattern for a selection of n_sel mapped outputs (sel_out == NULL: all n_out, in
+ *                           order): block row s has the dof columns cols[blk_ptr[s] .. blk_ptr[s+1]), ascending;
+ *                           blk_ptr [n_sel + 1]; cols may be NULL (sizing pass).
+ *   rbd_getJ_dev / _host    the values for instances 0 .. n-1 of the last apply: val [n][6 * blk_ptr[n_sel]], block row
+ *                           s of instance i at val[i][6 blk_ptr[s] ...], 6 doubles [lin; ang] per column (pinocchio's
+ *                           Matrix6x column layout).  sel_out is a HOST array in both variants (a per-scene constant);
+ *                           _dev: val is a 16-byte aligned DEVICE pointer, _host: a host pointer.
+ * With one UniformMass per body below the mapping (URDFModelLoader.cpp:369-391) the joint-space matrix SOFA would
+ * assemble through this Jacobian, sum_b J_b^T M_b J_b, is what rbd_crba_soa_sparse returns directly (same support
+ * pattern as rbd_model_mass_pattern; tests/test_gpu_configs.py::test_mass_matrix_through_the_mapping ties the two).  */
+RBD_API int rbd_model_getJ_pattern(const rbd_model* model, int32_t n_sel, const int32_t* sel_out, int32_t* blk_ptr,
+                                   int32_t* cols);
+RBD_API int rbd_getJ_dev(rbd_workspace* ws, int64_t n, int32_t n_sel, const int32_t* sel_out, double* val);
+RBD_API int rbd_getJ_host(rbd_workspace* ws, int64_t n, int32_t n_sel, const int32_t* sel_out, double* val);
+
 /* ---------------------------------------------------------------------------------------------------- */
 /* Mass / ForceField path, device SoA (north-star additions; the reference reaches them matrix-free
  * through UniformMass + applyJ/applyJT, URDFModelLoader.cpp:369-391).                                    */

@@ -66,6 +66,18 @@ class Model:
         check(self._lib.rbd_model_mass_pattern(self._h, col_ptr.ctypes.data, row_idx.ctypes.data))
         return col_ptr, row_idx[:self.info.mass_support_fields]
 
+    def getJ_pattern(self, sel_out=None):
+        """Pattern of the assembled mapping Jacobian for the selected mapped outputs (None: all): ``(blk_ptr [n_sel + 1],
+        cols [nnz])`` — block row ``s`` has the dof columns ``cols[blk_ptr[s]:blk_ptr[s+1]]`` (``rbd_model_getJ_pattern``)."""
+        sel = None if sel_out is None else np.ascontiguousarray(sel_out, dtype=np.int32)
+        n_sel = self.info.n_out if sel is None else int(sel.shape[0])
+        blk = np.zeros(n_sel + 1, dtype=np.int32)
+        sp = None if sel is None else sel.ctypes.data
+        check(self._lib.rbd_model_getJ_pattern(self._h, n_sel, sp, blk.ctypes.data, None))
+        cols = np.zeros(max(1, int(blk[-1])), dtype=np.int32)
+        check(self._lib.rbd_model_getJ_pattern(self._h, n_sel, sp, blk.ctypes.data, cols.ctypes.data))
+        return blk, cols[:int(blk[-1])]
+
     def mass_packed_index(self) -> np.ndarray:
         """Index of every support entry in the packed upper triangle (``M(r, c)`` at ``c (c + 1) / 2 + r``)."""
         col_ptr, row_idx = self.mass_pattern()
@@ -209,6 +221,21 @@ class Workspace:
         check(self._lib.rbd_getFrameJacobian_host(self._h, inst.shape[0], _host_ptr(inst, np.int32),
                                                   _host_ptr(out, np.int32), _host_ptr(J)))
         return np.ascontiguousarray(J.transpose(0, 2, 1))
+
+    def getJ_host(self, n, sel_out=None) -> np.ndarray:
+        """Assembled mapping Jacobian values of instances 0..n-1 for the selected outputs: ``[n, nnz_cols, 6]``, columns in
+        the order of ``Model.getJ_pattern`` (``rbd_getJ_host``)."""
+        blk, cols = self.model.getJ_pattern(sel_out)
+        sel = None if sel_out is None else np.ascontiguousarray(sel_out, dtype=np.int32)
+        n_sel = self.model.info.n_out if sel is None else int(sel.shape[0])
+        val = np.zeros((n, max(1, cols.shape[0]), 6))
+        check(self._lib.rbd_getJ_host(self._h, n, n_sel, None if sel is None else sel.ctypes.data, val.ctypes.data))
+        return val[:, :cols.shape[0]]
+
+    def getJ_dev(self, n, sel_out, val):
+        sel = None if sel_out is None else np.ascontiguousarray(sel_out, dtype=np.int32)
+        n_sel = self.model.info.n_out if sel is None else int(sel.shape[0])
+        check(self._lib.rbd_getJ_dev(self._h, n, n_sel, None if sel is None else sel.ctypes.data, _dev_ptr(val)))
 
     def aos_to_soa(self, n, K, tile, aos, soa):
         check(self._lib.rbd_aos_to_soa_dev(self._h, n, K, tile, _dev_ptr(aos), _dev_ptr(soa)))

@@ -102,6 +102,8 @@ struct rbd_workspace {
   // grow-only buffers for the rows entry point
   void* rows_buf = nullptr;
   size_t rows_bytes = 0;
+  void* sel_buf = nullptr;  // getJ: selection + block pointers
+  size_t sel_bytes = 0;
 };
 
 static void drop_plans(rbd_workspace* ws);
@@ -201,6 +203,7 @@ RBD_API int rbd_model_mass_pattern(const rbd_model* model, int32_t* col_ptr, int
 static void ws_free(rbd_workspace* ws) {
   if (!ws) return;
   cudaFree(ws->d_sorted_k); cudaFree(ws->d_outk_parent); cudaFree(ws->d_sorted_ident); cudaFree(ws->d_sorted_pl); cudaFree(ws->d_outk_pl);
+  cudaFree(ws->sel_buf);
   cudaFree(ws->qcache); cudaFree(ws->rows_buf); cudaFree(ws->d_model); cudaFree(ws->jcache); cudaFree(ws->omicache); cudaFree(ws->jc_scratch);
   for (int k = 0; k < rbd_workspace::kPlans; ++k) { cudaFree(ws->d_plan[k]); delete ws->h_plan[k]; }
   for (int k = 0; k < 8; ++k) { cudaFree(ws->d_plan32[k]); delete ws->h_plan32[k]; }
@@ -746,6 +749,67 @@ RBD_API int rbd_getFrameJacobian_host(rbd_workspace* ws, int64_t npairs, const i
   CK(cudaStreamSynchronize(st));
   return RBD_OK;
 }
+RBD_API int rbd_model_getJ_pattern(const rbd_model* model, int32_t n_sel, const int32_t* sel_out, int32_t* blk_ptr,
+                                   int32_t* cols) {
+  if (!model || !blk_ptr) return set_err(RBD_ERR_INVALID_ARG, "null model / blk_ptr");
+  if (n_sel < 0 || (!sel_out && n_sel > model->info.n_out)) return set_err(RBD_ERR_INVALID_ARG, "bad selection size");
+  if (!getJ_pattern(model->dm, model->ht, n_sel, sel_out, blk_ptr, cols)) return set_err(RBD_ERR_INVALID_ARG, "selected output index out of range");
+  return RBD_OK;
+}
+// selection + block pointers to the device (grow-only buffer of the workspace), then one kernel over the cache
+static int getJ_on(rbd_workspace* ws, int64_t n, int32_t n_sel, const int32_t* sel_out, double* d_val, int64_t* fields) {
+  if (n < 0 || n_sel < 0) return set_err(RBD_ERR_INVALID_ARG, "negative size");
+  if (n > ws->applied_n) return set_err(RBD_ERR_NO_APPLY, "getJ before apply: no cached configuration for these instances");
+  const DevModel& dm = ws->model->dm;
+  std::vector<int> blk((size_t)n_sel + 1), sel((size_t)n_sel);
+  if (!sel_out && n_sel > dm.n_out) return set_err(RBD_ERR_INVALID_ARG, "bad selection size");
+  if (!getJ_pattern(dm, ws->model->ht, n_sel, sel_out, blk.data(), nullptr)) return set_err(RBD_ERR_INVALID_ARG, "selected output index out of range");
+  for (int s = 0; s < n_sel; ++s) sel[s] = sel_out ? sel_out[s] : s;
+  if (fields) *fields = 6LL * blk[n_sel];
+  if (n == 0 || n_sel == 0 || blk[n_sel] == 0 || !d_val) return RBD_OK;
+  const size_t need = ((size_t)2 * n_sel + 1) * sizeof(int);
+  if (ws->sel_bytes < need) {
+    CK(cudaStreamSynchronize(ws->stream));
+    cudaFree(ws->sel_buf); ws->sel_buf = nullptr; ws->sel_bytes = 0;
+    CK(cudaMalloc(&ws->sel_buf, need));
+    ws->sel_bytes = need;
+  }
+  int* d_sel = (int*)ws->sel_buf; int* d_blk = d_sel + n_sel;
+  CK(cudaMemcpyAsync(d_sel, sel.data(), (size_t)n_sel * sizeof(int), cudaMemcpyHostToDevice, ws->stream));
+  CK(cudaMemcpyAsync(d_blk, blk.data(), ((size_t)n_sel + 1) * sizeof(int), cudaMemcpyHostToDevice, ws->stream));
+  CK(cudaStreamSynchronize(ws->stream));  // sel / blk are stack vectors: the copies must have read them
+  int rc = ensure_jcache(ws, ws->stream);
+  if (rc) return rc;
+  CK(launch_getJ(dm, ws->d_model, ws->tb, n, n_sel, d_sel, d_blk, d_val, ws->jcache, ws->omicache, ws->stream));
+  ws->launches++;
+  return RBD_OK;
+}
+RBD_API int rbd_getJ_dev(rbd_workspace* ws, int64_t n, int32_t n_sel, const int32_t* sel_out, double* val) {
+  GUARD(ws);
+  if (!val) return set_err(RBD_ERR_INVALID_ARG, "val is null");
+  if ((reinterpret_cast<uintptr_t>(val) & 15) != 0) return set_err(RBD_ERR_INVALID_ARG, "val must be 16-byte aligned");
+  return getJ_on(ws, n, n_sel, sel_out, val, nullptr);
+}
+RBD_API int rbd_getJ_host(rbd_workspace* ws, int64_t n, int32_t n_sel, const int32_t* sel_out, double* val) {
+  GUARD(ws);
+  if (!val) return set_err(RBD_ERR_INVALID_ARG, "val is null");
+  int64_t fields = 0;
+  int rc = getJ_on(ws, n, n_sel, sel_out, nullptr, &fields);   // validates and sizes
+  if (rc || n == 0 || fields == 0) return rc;
+  const size_t bytes = (size_t)n * (size_t)fields * sizeof(double);
+  if (ws->rows_bytes < bytes) {
+    CK(cudaStreamSynchronize(ws->stream));
+    cudaFree(ws->rows_buf); ws->rows_buf = nullptr; ws->rows_bytes = 0;
+    CK(cudaMalloc(&ws->rows_buf, bytes));
+    ws->rows_bytes = bytes;
+  }
+  rc = getJ_on(ws, n, n_sel, sel_out, (double*)ws->rows_buf, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(val, ws->rows_buf, bytes, cudaMemcpyDeviceToHost, ws->stream));
+  CK(cudaStreamSynchronize(ws->stream));
+  return RBD_OK;
+}
+
 RBD_API int rbd_workspace_set_rows_cache(rbd_workspace* ws, int enable) {
   if (!ws) return set_err(RBD_ERR_INVALID_ARG, "null workspace");
   ws->use_rows_cache = enable ? 1 : 0;

@@ -537,6 +537,21 @@ __global__ void __launch_bounds__(256) frame_jacobian_kernel(const DevModel* __r
   });
 }
 
+// Assembled mapping Jacobian: one thread per (instance, selected output) writes that block row's non-zero columns
+__global__ void __launch_bounds__(256) getJ_kernel(const DevModel* __restrict__ gm, const int model_words, const DevTables tb,
+                                                   const long long n, const int n_sel, const int* __restrict__ sel,
+                                                   const int* __restrict__ blk_ptr, double* __restrict__ val,
+                                                   const double* __restrict__ jc, const double* __restrict__ oc) {
+  const DevModel& m = stage_model(gm, model_words);
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n * n_sel) return;
+  const long long inst = r / n_sel;
+  const int s = (int)(r - inst * n_sel);
+  const AosRec Jc{jc + inst * (long long)(6 * m.nv)};
+  const AosRec Oc{oc + inst * (long long)(12 * (m.njoints - 1))};
+  getJ_block_cached(m, tb, Jc, Oc, sel[s], val + inst * (long long)(6 * blk_ptr[n_sel]) + 6 * (long long)blk_ptr[s]);
+}
+
 // K8: layout adapters.  32 instances x 32 fields per block through a padded shared tile, so both the
 // instance-major side and the tiled-SoA side are accessed with consecutive addresses.
 __global__ void aos_to_soa_kernel(long long n, int K, long long tile, const double* __restrict__ aos,
@@ -837,6 +852,15 @@ cudaError_t launch_frame_jacobian(const DevModel& m, const DevModel* d_model, co
   if (e != cudaSuccess) return e;
   RBD_NOTE(frame_jacobian_kernel);
   frame_jacobian_kernel<<<RBD_GRID(npairs, 256), 256, (size_t)mw * 8, st>>>(d_model, mw, tb, npairs, instance, out_index, J, jc, oc);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_getJ(const DevModel& m, const DevModel* d_model, const DevTables& tb, long long n, int n_sel, const int* sel,
+                        const int* blk_ptr, double* val, const double* jc, const double* oc, cudaStream_t st) {
+  if (n <= 0 || n_sel <= 0) return cudaSuccess;
+  const int mw = map_model_words(m);
+  RBD_NOTE(getJ_kernel);
+  getJ_kernel<<<RBD_GRID(n * n_sel, 256), 256, (size_t)mw * 8, st>>>(d_model, mw, tb, n, n_sel, sel, blk_ptr, val, jc, oc);
   return cudaGetLastError();
 }
 

@@ -87,6 +87,10 @@ cudaError_t launch_applyJT_rows_cached(const DevModel& m, const DevModel* d_mode
 cudaError_t launch_frame_jacobian(const DevModel& m, const DevModel* d_model, const DevTables& tb, long long npairs,
                                   const int* instance, const int* out_index, double* J, const double* jcache,
                                   const double* omicache, cudaStream_t st);
+// assembled mapping Jacobian: block rows of the n_sel selected outputs (device arrays sel [n_sel], blk_ptr [n_sel + 1])
+// of n instances, val [n][6 blk_ptr[n_sel]]
+cudaError_t launch_getJ(const DevModel& m, const DevModel* d_model, const DevTables& tb, long long n, int n_sel, const int* sel,
+                        const int* blk_ptr, double* val, const double* jc, const double* oc, cudaStream_t st);
 cudaError_t launch_aos_to_soa(long long n, int K, long long tile, const double* aos, double* soa, cudaStream_t st);
 cudaError_t launch_soa_to_aos(long long n, int K, long long tile, const double* soa, double* aos, cudaStream_t st);
 

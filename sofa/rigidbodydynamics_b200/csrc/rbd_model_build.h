@@ -58,6 +58,24 @@ inline std::vector<int> build_col_prog(DevModel* m, bool sparse_m = false) {
   return prog;
 }
 
+// Pattern of the assembled mapping Jacobian restricted to n_sel mapped outputs (sel == nullptr: all of them, in order):
+// block row s holds the dofs on the path from output sel[s]'s parent joint to the root, ascending.  blk_ptr
+// [n_sel + 1] counts COLUMNS (6 values each); cols [blk_ptr[n_sel]] may be null.  Returns false on a bad index.
+inline bool getJ_pattern(const DevModel& m, const HostTables& tb, int n_sel, const int* sel, int* blk_ptr, int* cols) {
+  int nnz = 0;
+  for (int s = 0; s < n_sel; ++s) {
+    const int k = sel ? sel[s] : s;
+    if (k < 0 || k >= m.n_out) return false;
+    blk_ptr[s] = nnz;
+    std::vector<int> chain;
+    for (int a = tb.outk_parent[k]; a != 0; a = m.joint[a].parent) chain.insert(chain.begin(), a);
+    for (int a : chain)
+      for (int e = 0; e < m.joint[a].nv; ++e) { if (cols) cols[nnz] = m.joint[a].idx_v + e; ++nnz; }
+  }
+  blk_ptr[n_sel] = nnz;
+  return true;
+}
+
 // Support-only pattern of M (upper triangle, by columns): entry (r, c), r <= c, is structurally non-zero iff the joint
 // owning dof r is the joint owning dof c or one of its ancestors.  col_ptr [nv + 1], row_idx [nnz] (either may be null);
 // returns nnz.  The order is exactly the order of the fields the support-only eval writes (build_col_prog above).

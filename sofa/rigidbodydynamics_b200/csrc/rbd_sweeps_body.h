@@ -2197,6 +2197,36 @@ RBD_HD void frame_jacobian_cached(const DevModel& m, const DevTables& tb, const 
   }
 }
 
+// One block row of the ASSEMBLED mapping Jacobian (what a real getJ() hands SOFA's direct solvers): the non-zero
+// columns of output k's LOCAL_WORLD_ALIGNED frame Jacobian only — the dofs on the path to the root, in ascending dof
+// order — 6 values [lin; ang] each, written back to back at `dst` (16-byte aligned).  Same arithmetic as
+// frame_jacobian_cached; the dof at (joint a, component cc) lands at position (dofs of a's strict ancestors) + cc.
+template <class JF, class OF>
+RBD_HD void getJ_block_cached(const DevModel& m, const DevTables& tb, const JF& Jc, const OF& Oc, int k, real* dst) {
+  const int pj = tb.outk_parent[k];
+  if (pj == 0) return;  // attached to the universe: empty block
+  int pos = 0;
+  for (int a = pj; a != 0; a = m.joint[a].parent) pos += m.joint[a].nv;
+  const real* pl = tb.outk_pl + 12 * k;
+  real Rp[12];
+  Oc.template ldn<12>(12 * (pj - 1), Rp);
+  const real px = Rp[0] * pl[9] + Rp[1] * pl[10] + Rp[2] * pl[11] + Rp[9];
+  const real py = Rp[3] * pl[9] + Rp[4] * pl[10] + Rp[5] * pl[11] + Rp[10];
+  const real pz = Rp[6] * pl[9] + Rp[7] * pl[10] + Rp[8] * pl[11] + Rp[11];
+  for (int a = pj; a != 0; a = m.joint[a].parent) {
+    const DevJoint& ja = m.joint[a];
+    pos -= ja.nv;
+    for (int cc = 0; cc < ja.nv; ++cc) {
+      real A[6], tx, ty, tz;
+      Jc.template ldn<6>(6 * (ja.idx_v + cc), A);
+      RBD_CROSS(tx, ty, tz, px, py, pz, A[3], A[4], A[5]);
+      real* o = dst + 6 * (pos + cc);
+      o[0] = A[0] - tx; o[1] = A[1] - ty; o[2] = A[2] - tz;
+      o[3] = A[3]; o[4] = A[4]; o[5] = A[5];
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // applyJT, ring variant with FORWARD projection (shallow trees: depth <= RBD_JT_MAXD, a free-flyer only as the
 // root).  Instead of parking the subtree wrench F per depth level and projecting on the way back

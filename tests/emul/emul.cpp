@@ -403,6 +403,35 @@ extern "C" int emul_frame_jacobians(const rbd_model_desc* d, long long n, double
   return 0;
 }
 
+// assembled mapping Jacobian (getJ_block_cached) of the selected outputs for every instance; also returns the pattern
+// (blk_ptr [n_sel + 1], cols): val [n][6 blk_ptr[n_sel]]
+extern "C" int emul_getJ(const rbd_model_desc* d, long long n, double* qcache, long long cache_tile, int n_sel,
+                         const int* sel, int* blk_ptr, int* cols, double* val) {
+  Ctx c;
+  int rc = make_ctx(d, &c);
+  if (rc) return rc;
+  if (!getJ_pattern(c.m, c.ht, n_sel, sel, blk_ptr, cols)) { g_err = "bad selection"; return -1; }
+  if (!val) return 0;
+  if (!plan_eval(&c.m, false, false, true, 0, true)) { g_err = "plan_eval failed"; return -100; }
+  const std::vector<unsigned long long> blob = build_eval_blob(&c.m);
+  const DevModel& bm = *reinterpret_cast<const DevModel*>(blob.data());
+  const int nj = bm.njoints, nv = bm.nv;
+  const long long nt = (n + cache_tile - 1) / cache_tile;
+  std::vector<double> J((size_t)nt * cache_tile * 6 * nv + 1, 1e300), O((size_t)nt * cache_tile * 12 * (nj - 1) + 1, 1e300);
+  std::vector<double> smem(64, 1e300), tmem(64, 1e300);
+  for (long long i = 0; i < n; ++i) {
+    Stack S = make_stack(smem.data(), 0, 1);
+    TmStack T{tmem.data()};
+    InRing inr;
+    run_eval_generic_one<0>(bm, i, cache_tile, qcache, nullptr, nullptr, O.data(), J.data(), nullptr, nullptr, S, T, inr, 0);
+    const Field Jc = make_field(J.data(), i, 6 * nv, cache_tile);
+    const Field Oc = make_field(O.data(), i, 12 * (nj - 1), cache_tile);
+    for (int s = 0; s < n_sel; ++s)
+      getJ_block_cached(bm, c.tb, Jc, Oc, sel ? sel[s] : s, val + (size_t)i * 6 * blk_ptr[n_sel] + 6 * (size_t)blk_ptr[s]);
+  }
+  return 0;
+}
+
 // applyDJT (geometric stiffness, optional extension): out += kfac * d/de [J(q (+) e dq)^T in]
 extern "C" int emul_applyDJT(const rbd_model_desc* d, long long n, long long tile, double* qcache, long long cache_tile,
                              double* dq_joints, double* dq_root, double* in, double kfac, double* out_tau, double* out_root) {

@@ -265,6 +265,22 @@ def test_mapping_bodies_match_oracle(emul, d):
         assert rel_err(Jd[t].T, Jref) <= TOL_FP64
         full_dq = dq[i] if rootv is None else np.concatenate([rootv[i], dq[i]])
         assert rel_err(Jd[t].T @ full_dq, vel[i, k]) <= TOL_FP64
+    # the ASSEMBLED mapping Jacobian (rbd_getJ_*): block rows of a permuted selection of outputs, non-zero columns only
+    sel = rng.permutation(d.n_out)[:max(1, d.n_out // 2)].astype(np.int32)
+    blk = np.zeros(len(sel) + 1, dtype=np.int32)
+    assert emul.emul_getJ(C.addressof(cd), n, P(qcache), ctile, len(sel), P(sel), P(blk), None, None) == 0
+    gcols = np.zeros(max(1, int(blk[-1])), dtype=np.int32)
+    gval = np.full((n, max(1, int(blk[-1])), 6), np.nan)
+    assert emul.emul_getJ(C.addressof(cd), n, P(qcache), ctile, len(sel), P(sel), P(blk), P(gcols), P(gval)) == 0
+    for i in (0, n - 1):
+        orc.apply(qj[i], None if root is None else root[i])
+        for s_, k in enumerate(sel):
+            Jref = orc.frame_jacobian_lwa(int(d.out_frames[int(k)]))            # dense 6 x nv
+            cs = gcols[blk[s_]:blk[s_ + 1]]
+            assert np.all(np.diff(cs) > 0)                                       # ascending dof columns
+            assert rel_err(gval[i, blk[s_]:blk[s_ + 1]].T, Jref[:, cs]) <= TOL_FP64
+            rest = np.ones(d.nv, dtype=bool); rest[cs] = False
+            assert np.all(Jref[:, rest] == 0.0)                                  # what the pattern leaves out is zero
     for i in range(n):
         rp = orc.apply(qj[i], None if root is None else root[i])
         assert rel_err(pos[i][:, :3], rp[:, :3]) <= TOL_FP64

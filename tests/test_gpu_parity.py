@@ -778,6 +778,61 @@ def test_frame_jacobians_from_cache(torch_mod, api, name):
         assert rel_err(J[t] @ full_dq, vel[i, k]) <= TOL_FP64
 
 
+@pytest.mark.parametrize("name", ["talos_reduced", "solo12", "panda7", "talos_reduced_subset", "schunk_svh_hand_right_ff_subset"])
+def test_assembled_getJ(torch_mod, api, name):
+    """rbd_getJ_host / _dev: the assembled mapping Jacobian the reference's getJ() does not provide
+    (KinematicChainMapping.h:82-83 returns nullptr) — per selected output the non-zero columns of
+    getFrameJacobian(LOCAL_WORLD_ALIGNED) (KCM.inl:434-490), against the oracle's dense Jacobians; the assembled matrix
+    times dq equals applyJ for every instance."""
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    torch = torch_mod
+    d = [m for m in MODELS_MAP if m.name == name][0]
+    n, tile = 130, 32
+    q, v, _ = mdl.random_state(d, n, seed=93)
+    qj, root, dq, rootv = _split(d, q, v)
+    m = api.Model(d); ws = api.Workspace(m, n)
+    T = lambda x: None if x is None else _dev(torch, to_tiled(x, tile))
+    nt = (n + tile - 1) // tile
+    pos = torch.zeros((nt, 7 * d.n_out, tile), dtype=torch.float64, device="cuda")
+    vel = torch.zeros((nt, 6 * d.n_out, tile), dtype=torch.float64, device="cuda")
+    with pytest.raises(api.RbdError) as e:
+        ws.getJ_host(1)
+    assert e.value.code == -4                                 # RBD_ERR_NO_APPLY
+    ws.apply_soa(n, tile, T(qj), T(root), pos)
+    ws.applyJ_soa(n, tile, T(dq), T(rootv), vel)
+    ws.synchronize()
+    vel = from_tiled(vel.cpu().numpy(), n).reshape(n, d.n_out, 6)
+    full_dq = dq if rootv is None else np.concatenate([rootv, dq], axis=1)
+    # all outputs: J dq == applyJ, instance by instance
+    blk, cols = m.getJ_pattern()
+    val = ws.getJ_host(n)                                      # [n, nnz, 6]
+    for k in range(d.n_out):
+        cs = cols[blk[k]:blk[k + 1]]
+        got = np.einsum("nce,nc->ne", val[:, blk[k]:blk[k + 1]], full_dq[:, cs])
+        assert rel_err(got, vel[:, k]) <= TOL_FP64
+    # a permuted selection, device variant, against the oracle
+    rng = np.random.default_rng(94)
+    sel = rng.permutation(d.n_out)[:max(1, d.n_out // 3)].astype(np.int32)
+    blk, cols = m.getJ_pattern(sel)
+    dval = torch.full((n, max(1, len(cols)), 6), float("nan"), dtype=torch.float64, device="cuda")
+    ws.getJ_dev(n, sel, dval)
+    ws.synchronize()
+    dval = dval.cpu().numpy()
+    assert np.array_equal(dval[:, :len(cols)], ws.getJ_host(n, sel))
+    orc = oracle.Oracle(d)
+    for i in (0, 77, n - 1):
+        orc.apply(qj[i], None if root is None else root[i])
+        for s_, k in enumerate(sel):
+            cs = cols[blk[s_]:blk[s_ + 1]]
+            Jref = orc.frame_jacobian_lwa(int(d.out_frames[int(k)]))
+            assert rel_err(dval[i, blk[s_]:blk[s_ + 1]].T, Jref[:, cs]) <= TOL_FP64
+            rest = np.ones(d.nv, dtype=bool); rest[cs] = False
+            assert np.all(Jref[:, rest] == 0.0)
+    with pytest.raises(api.RbdError):
+        m.getJ_pattern(np.array([d.n_out], dtype=np.int32))   # output index out of range
+
+
 @pytest.mark.parametrize("name,tile", [("talos_reduced", 32), ("solo12", 50), ("random_3", 32), ("panda7", 32)])
 def test_applyDJT_geometric_stiffness(torch_mod, api, name, tile):
     """rbd_applyDJT_soa / _host (optional extension; the reference's applyDJT is a no-op and the mirror keeps it one):
