@@ -287,6 +287,16 @@ RBD_API int rbd_crba_soa_sparse(rbd_workspace* ws, int64_t n, int64_t tile, cons
 RBD_API int rbd_rnea_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, const double* v,
                          const double* a, double* tau);
 
+/* Forward dynamics — pinocchio::aba(model, data, q, v, tau): the joint accelerations ddq [nv fields] of the articulated
+ * body algorithm (not in the reference, which never integrates joint dynamics itself).  Same
+ * conventions as rbd_rnea_soa, of which it is the inverse: rbd_aba(q, v, rbd_rnea(q, v, a)) == a.  A free-flyer is
+ * supported as the root joint only (RBD_ERR_UNSUPPORTED otherwise).  The sweep keeps 45 doubles per joint in a scratch
+ * record per resident warp (allocated in the workspace on first use).                                              */
+RBD_API int rbd_aba_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, const double* v, const double* tau,
+                        double* ddq);
+/* ... on host vectors (instance-major q [n][nq]; v, tau, ddq [n][nv]), chunked and pipelined like rbd_eval_host.      */
+RBD_API int rbd_aba_host(rbd_workspace* ws, int64_t n, const double* q, const double* v, const double* tau, double* ddq);
+
 /* Matrix-free Mass / ForceField products in joint space — what the reference's SOFA graph evaluates through the
  * mapping with one UniformMass<Rigid3> per body (URDFModelLoader.cpp:369-391): Mass::addMDx and ForceField::addForce
  * reach the joint dofs as applyJT(M_b * applyJ(dx)) and applyJT(m_b g).  Here they are one sweep each, with pinocchio's

@@ -110,6 +110,7 @@ def lib() -> C.CDLL:
         l.orc_applyJT_row.restype = C.c_int; l.orc_applyJT_row.argtypes = [vp, C.c_int, vp, dp, dp]
         l.orc_crba.restype = None; l.orc_crba.argtypes = [vp, dp, dp]
         l.orc_rnea.restype = None; l.orc_rnea.argtypes = [vp, dp, dp, dp, dp]
+        l.orc_aba.restype = None; l.orc_aba.argtypes = [vp, dp, dp, dp, dp]
         l.orc_eval.restype = None; l.orc_eval.argtypes = [vp, dp, dp, dp, dp, dp, dp, dp]
         l.orc_eval_batch.restype = C.c_int
         l.orc_eval_batch.argtypes = [vp, C.c_long, dp, dp, dp, dp, dp, dp, dp, C.c_int]
@@ -192,6 +193,12 @@ class Oracle:
         q, v, a = _f64(q), _f64(v), _f64(a); tau = np.zeros(self.d.nv)
         lib().orc_rnea(self._w, _p(q), _p(v), _p(a), _p(tau))
         return tau
+
+    def aba(self, q, v, tau):
+        """pinocchio::aba(q, v, tau) (LOCAL convention): joint accelerations."""
+        q, v, tau = _f64(q), _f64(v), _f64(tau); ddq = np.zeros(self.d.nv)
+        lib().orc_aba(self._w, _p(q), _p(v), _p(tau), _p(ddq))
+        return ddq
 
     def eval(self, q, v, a):
         q, v, a = _f64(q), _f64(v), _f64(a)

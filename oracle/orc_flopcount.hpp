@@ -31,6 +31,7 @@ inline bool operator>(orc_counted a, orc_counted b) { ++orc_cnt.cmp; return a.v 
 inline bool operator<(orc_counted a, orc_counted b) { ++orc_cnt.cmp; return a.v < b.v; }
 inline bool operator>=(orc_counted a, orc_counted b) { ++orc_cnt.cmp; return a.v >= b.v; }
 inline bool operator<=(orc_counted a, orc_counted b) { ++orc_cnt.cmp; return a.v <= b.v; }
+inline orc_counted fabs(orc_counted a) { return orc_counted(::fabs(a.v)); }
 inline orc_counted sqrt(orc_counted a) { ++orc_cnt.sqrt_; return orc_counted(::sqrt(a.v)); }
 inline orc_counted cos(orc_counted a) { ++orc_cnt.sincos; return orc_counted(::cos(a.v)); }
 inline orc_counted sin(orc_counted a) { ++orc_cnt.sincos; return orc_counted(::sin(a.v)); }

@@ -177,7 +177,7 @@ struct orc_workspace {
   int applied;
 };
 
-static int joint_nq(int t) { return t == RBD_JOINT_FF ? 7 : (t >= RBD_JOINT_RUBX && t <= RBD_JOINT_RUBU) ? 2 : (t == RBD_JOINT_UNIVERSE ? 0 : 1); }
+static inline int joint_nq(int t) { return t == RBD_JOINT_FF ? 7 : (t >= RBD_JOINT_RUBX && t <= RBD_JOINT_RUBU) ? 2 : (t == RBD_JOINT_UNIVERSE ? 0 : 1); }
 static int joint_nv(int t) { return t == RBD_JOINT_FF ? 6 : (t == RBD_JOINT_UNIVERSE ? 0 : 1); }
 
 orc_workspace* orc_create(const rbd_model_desc* d) {
@@ -518,6 +518,180 @@ void orc_rnea(orc_workspace* w, const double* q, const double* v, const double* 
       for (int k = 0; k < 6; ++k) w->f[6 * p + k] += t[k];
     }
   }
+}
+
+/* ---- forward dynamics ------------------------------------------------------------------------------------------- */
+/* dense 6x6 helpers (row-major) for the articulated-body inertias */
+static void inertia_to_mat6(const inertia* Y, double* M) {
+  /* InertiaTpl::matrix(): [[m I, -m [c]x], [m [c]x, I_c - m [c]x [c]x]] */
+  const double m = Y->m, *c = Y->c;
+  double cx[9] = {0, -c[2], c[1], c[2], 0, -c[0], -c[1], c[0], 0};
+  double Ic[9] = {Y->I[0], Y->I[1], Y->I[3], Y->I[1], Y->I[2], Y->I[4], Y->I[3], Y->I[4], Y->I[5]};
+  double cc[9];
+  matmul3(cx, cx, cc);
+  for (int r = 0; r < 3; ++r)
+    for (int k = 0; k < 3; ++k) {
+      M[6 * r + k] = r == k ? m : 0.0;
+      M[6 * r + 3 + k] = -m * cx[3 * r + k];
+      M[6 * (3 + r) + k] = m * cx[3 * r + k];
+      M[6 * (3 + r) + 3 + k] = Ic[3 * r + k] - m * cc[3 * r + k];
+    }
+}
+/* X_f of aMb (force transform b -> a): [[R, 0], [[p]x R, R]] */
+static void se3_force_matrix(const se3* M, double* X) {
+  double px[9] = {0, -M->p[2], M->p[1], M->p[2], 0, -M->p[0], -M->p[1], M->p[0], 0}, pR[9];
+  matmul3(px, M->R, pR);
+  for (int r = 0; r < 3; ++r)
+    for (int k = 0; k < 3; ++k) {
+      X[6 * r + k] = M->R[3 * r + k]; X[6 * r + 3 + k] = 0.0;
+      X[6 * (3 + r) + k] = pR[3 * r + k]; X[6 * (3 + r) + 3 + k] = M->R[3 * r + k];
+    }
+}
+/* solve the n x n system A x = b (A symmetric positive definite, row-major, n <= 6) by Gaussian elimination with
+ * partial pivoting; A and b are overwritten */
+static void solve_small(int n, double* A, double* b) {
+  for (int k = 0; k < n; ++k) {
+    int piv = k;
+    for (int r = k + 1; r < n; ++r) if (fabs(A[6 * r + k]) > fabs(A[6 * piv + k])) piv = r;
+    if (piv != k) {
+      for (int c = 0; c < n; ++c) { double t = A[6 * k + c]; A[6 * k + c] = A[6 * piv + c]; A[6 * piv + c] = t; }
+      double t = b[k]; b[k] = b[piv]; b[piv] = t;
+    }
+    for (int r = k + 1; r < n; ++r) {
+      double f = A[6 * r + k] / A[6 * k + k];
+      for (int c = k; c < n; ++c) A[6 * r + c] -= f * A[6 * k + c];
+      b[r] -= f * b[k];
+    }
+  }
+  for (int k = n - 1; k >= 0; --k) {
+    double s = b[k];
+    for (int c = k + 1; c < n; ++c) s -= A[6 * k + c] * b[c];
+    b[k] = s / A[6 * k + k];
+  }
+}
+
+/* pinocchio::aba(model, data, q, v, tau), Convention::LOCAL (algorithm/aba.hxx: AbaLocalConventionForwardStep1,
+ * AbaLocalConventionBackwardStep, AbaLocalConventionForwardStep2; JointModel::calc_aba: U = Ia S, Dinv = (S^T U)^-1,
+ * UDinv = U Dinv, Ia -= UDinv U^T).  North-star extension: no reference call site.
+ * Joint frames, dense 6x6 articulated inertias, SE3 actions between parent and child — a formulation that shares no
+ * code path with the kernels' world-frame sweep.  ddq [nv]. */
+void orc_aba(orc_workspace* w, const double* q, const double* v, const double* tau, double* ddq) {
+  int nj = w->njoints, nv = w->nv;
+  double* Yaba = (double*)calloc((size_t)nj * 36, sizeof(double));
+  double* U = (double*)calloc((size_t)nj * 36, sizeof(double));     /* [joint][6 x nvj] col-major */
+  double* UDinv = (double*)calloc((size_t)nj * 36, sizeof(double));
+  double* Dinv = (double*)calloc((size_t)nj * 36, sizeof(double));  /* [joint][nvj x nvj] row-major, stride 6 */
+  double* u = (double*)calloc((size_t)(nv > 0 ? nv : 1), sizeof(double));
+  memcpy(u, tau, sizeof(double) * (size_t)nv);
+  memset(w->v, 0, 6 * sizeof(double));
+  /* pass 1 */
+  for (int i = 1; i < nj; ++i) {
+    se3 Mj;
+    double* S = w->S + 36 * i;
+    double* vj = w->vj + 6 * i;
+    joint_calc(w, i, q, v, &Mj, S, vj);
+    se3_mul(&w->jplace[i], &Mj, &w->liMi[i]);
+    int p = w->parents[i];
+    double* vi = w->v + 6 * i;
+    memcpy(vi, vj, 6 * sizeof(double));
+    if (p > 0) {
+      double t[6];
+      se3_actinv_motion(&w->liMi[i], w->v + 6 * p, t);
+      for (int k = 0; k < 6; ++k) vi[k] += t[k];
+    }
+    motion_cross(vi, vj, w->a_gf + 6 * i);                       /* joint bias c = 0 */
+    inertia_to_mat6(&w->Y[i], Yaba + 36 * i);
+    inertia_mul_motion(&w->Y[i], vi, w->h + 6 * i);
+    motion_cross_force(vi, w->h + 6 * i, w->f + 6 * i);
+  }
+  /* pass 2 */
+  for (int i = nj - 1; i >= 1; --i) {
+    const double* S = w->S + 36 * i;
+    double* Ia = Yaba + 36 * i;
+    int iv = w->idx_v[i], nvi = w->nvj[i], p = w->parents[i];
+    for (int c = 0; c < nvi; ++c) {
+      double s = 0.0;
+      for (int k = 0; k < 6; ++k) s += S[6 * c + k] * w->f[6 * i + k];
+      u[iv + c] -= s;
+    }
+    double* Ui = U + 36 * i; double* UDi = UDinv + 36 * i; double* Di = Dinv + 36 * i;
+    for (int c = 0; c < nvi; ++c)
+      for (int r = 0; r < 6; ++r) {
+        double s = 0.0;
+        for (int k = 0; k < 6; ++k) s += Ia[6 * r + k] * S[6 * c + k];
+        Ui[6 * c + r] = s;
+      }
+    /* Dinv = (S^T U)^-1, column by column */
+    for (int c = 0; c < nvi; ++c) {
+      double D[36], e[6] = {0, 0, 0, 0, 0, 0};
+      for (int r = 0; r < nvi; ++r)
+        for (int cc = 0; cc < nvi; ++cc) {
+          double s = 0.0;
+          for (int k = 0; k < 6; ++k) s += S[6 * r + k] * Ui[6 * cc + k];
+          D[6 * r + cc] = s;
+        }
+      e[c] = 1.0;
+      solve_small(nvi, D, e);
+      for (int r = 0; r < nvi; ++r) Di[6 * r + c] = e[r];
+    }
+    for (int c = 0; c < nvi; ++c)
+      for (int r = 0; r < 6; ++r) {
+        double s = 0.0;
+        for (int k = 0; k < nvi; ++k) s += Ui[6 * k + r] * Di[6 * k + c];
+        UDi[6 * c + r] = s;
+      }
+    if (p > 0) {
+      for (int r = 0; r < 6; ++r)
+        for (int cc = 0; cc < 6; ++cc) {
+          double s = 0.0;
+          for (int k = 0; k < nvi; ++k) s += UDi[6 * k + r] * Ui[6 * k + cc];
+          Ia[6 * r + cc] -= s;
+        }
+      double pa[6];
+      for (int r = 0; r < 6; ++r) {
+        double s = w->f[6 * i + r];
+        for (int k = 0; k < 6; ++k) s += Ia[6 * r + k] * w->a_gf[6 * i + k];
+        for (int k = 0; k < nvi; ++k) s += UDi[6 * k + r] * u[iv + k];
+        pa[r] = s;
+      }
+      double X[36], XI[36];
+      se3_force_matrix(&w->liMi[i], X);
+      for (int r = 0; r < 6; ++r)
+        for (int cc = 0; cc < 6; ++cc) {
+          double s = 0.0;
+          for (int k = 0; k < 6; ++k) s += X[6 * r + k] * Ia[6 * k + cc];
+          XI[6 * r + cc] = s;
+        }
+      for (int r = 0; r < 6; ++r)
+        for (int cc = 0; cc < 6; ++cc) {
+          double s = 0.0;
+          for (int k = 0; k < 6; ++k) s += XI[6 * r + k] * X[6 * cc + k];
+          Yaba[36 * p + 6 * r + cc] += s;
+        }
+      double t[6];
+      se3_act_force(&w->liMi[i], pa, t);
+      for (int k = 0; k < 6; ++k) w->f[6 * p + k] += t[k];
+    }
+  }
+  /* pass 3 */
+  for (int k = 0; k < 3; ++k) { w->a_gf[k] = -w->gravity[k]; w->a_gf[3 + k] = 0.0; }
+  for (int i = 1; i < nj; ++i) {
+    const double* S = w->S + 36 * i;
+    int iv = w->idx_v[i], nvi = w->nvj[i], p = w->parents[i];
+    double t[6];
+    se3_actinv_motion(&w->liMi[i], w->a_gf + 6 * p, t);
+    for (int k = 0; k < 6; ++k) w->a_gf[6 * i + k] += t[k];
+    const double* UDi = UDinv + 36 * i; const double* Di = Dinv + 36 * i;
+    for (int c = 0; c < nvi; ++c) {
+      double s = 0.0;
+      for (int k = 0; k < nvi; ++k) s += Di[6 * c + k] * u[iv + k];
+      for (int k = 0; k < 6; ++k) s -= UDi[6 * c + k] * w->a_gf[6 * i + k];
+      ddq[iv + c] = s;
+    }
+    for (int c = 0; c < nvi; ++c)
+      for (int k = 0; k < 6; ++k) w->a_gf[6 * i + k] += S[6 * c + k] * ddq[iv + c];
+  }
+  free(Yaba); free(U); free(UDinv); free(Dinv); free(u);
 }
 
 /* One full evaluation in the algorithmic output format of SURVEY.md §8(d):

@@ -19,6 +19,7 @@ void orc_apply_loop(orc_workspace* w, long n, const double* q_joints, const doub
 int orc_applyJT_row(orc_workspace* w, int nnz, const int* col, const double* val, double* row_out);
 void orc_crba(orc_workspace* w, const double* q, double* M_rowmajor);
 void orc_rnea(orc_workspace* w, const double* q, const double* v, const double* a, double* tau);
+void orc_aba(orc_workspace* w, const double* q, const double* v, const double* tau, double* ddq);
 void orc_eval(orc_workspace* w, const double* q, const double* v, const double* a, double* oMi, double* J,
               double* Mpacked, double* tau);
 int orc_eval_batch(const rbd_model_desc* d, long n, const double* q, const double* v, const double* a,

@@ -179,6 +179,10 @@ class Workspace:
     def rnea_soa(self, n, tile, q, v, a, tau):
         check(self._lib.rbd_rnea_soa(self._h, n, tile, _dev_ptr(q), _dev_ptr(v), _dev_ptr(a), _dev_ptr(tau)))
 
+    def aba_soa(self, n, tile, q, v, tau, ddq):
+        """Forward dynamics ddq = aba(q, v, tau) (``rbd_aba_soa``)."""
+        check(self._lib.rbd_aba_soa(self._h, n, tile, _dev_ptr(q), _dev_ptr(v), _dev_ptr(tau), _dev_ptr(ddq)))
+
     def addMDx_soa(self, n, tile, q, dx, factor, res):
         """res += factor * M(q) dx  (SOFA Mass::addMDx in joint space, matrix-free)."""
         check(self._lib.rbd_addMDx_soa(self._h, n, tile, _dev_ptr(q), _dev_ptr(dx), float(factor), _dev_ptr(res)))
@@ -251,6 +255,9 @@ class Workspace:
     def eval_host_sparse(self, n, q, v=None, a=None, oMi=None, J=None, Mval=None, tau=None):
         check(self._lib.rbd_eval_host_sparse(self._h, n, _host_ptr(q), _host_ptr(v), _host_ptr(a), _host_ptr(oMi),
                                              _host_ptr(J), _host_ptr(Mval), _host_ptr(tau)))
+
+    def aba_host(self, n, q, v, tau, ddq):
+        check(self._lib.rbd_aba_host(self._h, n, _host_ptr(q), _host_ptr(v), _host_ptr(tau), _host_ptr(ddq)))
 
     def addMDx_host(self, n, q, dx, factor, res):
         """res += factor * M(q) dx on host vectors (instance-major), in place."""

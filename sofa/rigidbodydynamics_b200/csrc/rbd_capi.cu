@@ -102,6 +102,8 @@ struct rbd_workspace {
   // grow-only buffers for the rows entry point
   void* rows_buf = nullptr;
   size_t rows_bytes = 0;
+  double* aba_scratch[2] = {nullptr, nullptr};  // forward dynamics: one record per resident warp, per chunk stream of the
+                                                // host path ([1]: launches on slot[1].st, which may overlap the others)
   void* sel_buf = nullptr;  // getJ: selection + block pointers
   size_t sel_bytes = 0;
 };
@@ -203,7 +205,7 @@ RBD_API int rbd_model_mass_pattern(const rbd_model* model, int32_t* col_ptr, int
 static void ws_free(rbd_workspace* ws) {
   if (!ws) return;
   cudaFree(ws->d_sorted_k); cudaFree(ws->d_outk_parent); cudaFree(ws->d_sorted_ident); cudaFree(ws->d_sorted_pl); cudaFree(ws->d_outk_pl);
-  cudaFree(ws->sel_buf);
+  cudaFree(ws->sel_buf); cudaFree(ws->aba_scratch[0]); cudaFree(ws->aba_scratch[1]);
   cudaFree(ws->qcache); cudaFree(ws->rows_buf); cudaFree(ws->d_model); cudaFree(ws->jcache); cudaFree(ws->omicache); cudaFree(ws->jc_scratch);
   for (int k = 0; k < rbd_workspace::kPlans; ++k) { cudaFree(ws->d_plan[k]); delete ws->h_plan[k]; }
   for (int k = 0; k < 8; ++k) { cudaFree(ws->d_plan32[k]); delete ws->h_plan32[k]; }
@@ -508,6 +510,36 @@ RBD_API int rbd_addForce_soa(rbd_workspace* ws, int64_t n, int64_t tile, const d
   int rc = check_batch(ws, n, tile);
   if (rc) return rc;
   return mass_force_on(ws, ws->stream, n, tile, q, v, nullptr, f, -1.0, 1);
+}
+
+// forward dynamics (articulated-body algorithm)
+static int aba_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, const double* q, const double* v,
+                  const double* tau, double* ddq) {
+  if (!q || !v || !tau || !ddq) return set_err(RBD_ERR_INVALID_ARG, "null q / v / tau / ddq");
+  const DevModel& dm = ws->model->dm;
+  for (int i = 1; i < dm.njoints; ++i)
+    if (dm.joint[i].type == JT_FF && !(i == 1 && dm.joint[i].parent == 0))
+      return set_err(RBD_ERR_UNSUPPORTED, "aba supports a free-flyer only as the root joint (joint 1 on the universe)");
+  const int sc = (ws->slot[1].st && st == ws->slot[1].st) ? 1 : 0;
+  if (!ws->aba_scratch[sc]) {
+    int warps = 0;
+    AbaArgs S{0, 32, nullptr, nullptr, nullptr, nullptr, nullptr};
+    CK(launch_aba(dm, ws->d_model, S, ws->num_sms, &warps, st));
+    const size_t bytes = (size_t)warps * (size_t)aba_scratch_doubles(dm) * 32 * sizeof(double);
+    cudaError_t e = cudaMalloc(&ws->aba_scratch[sc], bytes > 0 ? bytes : 256);
+    if (e != cudaSuccess) { cudaGetLastError(); return set_err(RBD_ERR_ALLOC, std::string("cudaMalloc(aba scratch): ") + cudaGetErrorString(e)); }
+  }
+  AbaArgs A{n, tile, q, v, tau, ddq, ws->aba_scratch[sc]};
+  CK(launch_aba(dm, ws->d_model, A, ws->num_sms, nullptr, st));
+  if (n > 0) ws->launches++;
+  return RBD_OK;
+}
+RBD_API int rbd_aba_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, const double* v, const double* tau,
+                        double* ddq) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, tile);
+  if (rc) return rc;
+  return aba_on(ws, ws->stream, n, tile, q, v, tau, ddq);
 }
 
 static int apply_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, long long inst0, const double* qj,
@@ -987,6 +1019,21 @@ RBD_API int rbd_addForce_host(rbd_workspace* ws, int64_t n, const double* q, con
   P.add(I.nq, q, nullptr, true, false); P.add(I.nv, v, nullptr, true, false); P.add(I.nv, f, f, true, true);
   return run_host_chunks(ws, n, P, [&](cudaStream_t st, long long, long long cn, long long tile) {
     return mass_force_on(ws, st, cn, tile, P[0].d_soa, v ? P[1].d_soa : nullptr, nullptr, P[2].d_soa, -1.0, 1);
+  });
+}
+
+RBD_API int rbd_aba_host(rbd_workspace* ws, int64_t n, const double* q, const double* v, const double* tau, double* ddq) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, 1);
+  if (rc) return rc;
+  if (!q || !v || !tau || !ddq) return set_err(RBD_ERR_INVALID_ARG, "null q / v / tau / ddq");
+  const rbd_model_info& I = ws->model->info;
+  Pieces P;
+  P.add(I.nq, q, nullptr, true, false); P.add(I.nv, v, nullptr, true, false); P.add(I.nv, tau, nullptr, true, false);
+  P.add(I.nv, nullptr, ddq, false, true);
+  // (each chunk stream has its own scratch records: aba_on)
+  return run_host_chunks(ws, n, P, [&](cudaStream_t st, long long, long long cn, long long tile) {
+    return aba_on(ws, st, cn, tile, P[0].d_soa, P[1].d_soa, P[2].d_soa, P[3].d_soa);
   });
 }
 

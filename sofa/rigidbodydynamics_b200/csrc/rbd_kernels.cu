@@ -537,6 +537,29 @@ __global__ void __launch_bounds__(256) frame_jacobian_kernel(const DevModel* __r
   });
 }
 
+// Forward dynamics (aba_instance): persistent warps over the batch's 32-instance tiles, one scratch record per warp
+struct GlobalScratch {
+  double* p;  // this lane's column of its warp's [E][32] record
+  __device__ __forceinline__ double ld(int e) const { return p[e * 32]; }
+  __device__ __forceinline__ void st(int e, double v) const { p[e * 32] = v; }
+};
+template <int TILE>
+__global__ void __launch_bounds__(256, 1) aba_kernel(const DevModel* __restrict__ gm, const int model_words, const AbaArgs a) {
+  const DevModel& m = stage_model(gm, model_words);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const long long gw = (long long)blockIdx.x * wpb + warp;
+  const GlobalScratch X{a.scratch + gw * (long long)aba_scratch_doubles(m) * 32 + lane};
+  const long long ntiles = (a.n + 31) / 32;
+  for (long long t = gw; t < ntiles; t += (long long)gridDim.x * wpb) {
+    const long long inst = t * 32 + lane;
+    if (inst >= a.n) continue;  // (no warp-collective operation in this sweep)
+    aba_instance(m, make_field_t<TILE>(const_cast<double*>(a.q), inst, m.nq, a.tile),
+                 make_field_t<TILE>(const_cast<double*>(a.v), inst, m.nv, a.tile),
+                 make_field_t<TILE>(const_cast<double*>(a.tau), inst, m.nv, a.tile),
+                 make_field_t<TILE>(a.ddq, inst, m.nv, a.tile), X);
+  }
+}
+
 // Assembled mapping Jacobian: one thread per (instance, selected output) writes that block row's non-zero columns
 __global__ void __launch_bounds__(256) getJ_kernel(const DevModel* __restrict__ gm, const int model_words, const DevTables tb,
                                                    const long long n, const int n_sel, const int* __restrict__ sel,
@@ -852,6 +875,21 @@ cudaError_t launch_frame_jacobian(const DevModel& m, const DevModel* d_model, co
   if (e != cudaSuccess) return e;
   RBD_NOTE(frame_jacobian_kernel);
   frame_jacobian_kernel<<<RBD_GRID(npairs, 256), 256, (size_t)mw * 8, st>>>(d_model, mw, tb, npairs, instance, out_index, J, jc, oc);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_aba(const DevModel& m, const DevModel* d_model, const AbaArgs& a, int num_sms, int* scratch_warps,
+                       cudaStream_t st) {
+  const int mw = map_model_words(m);
+  const int block = 256, wpb = block / 32;
+  const long long ntiles = (a.n + 31) / 32;
+  long long grid = (ntiles + wpb - 1) / wpb;
+  if (grid > num_sms) grid = num_sms;  // one block per SM, warps stride over the tiles
+  if (grid < 1) grid = 1;
+  if (scratch_warps) *scratch_warps = num_sms * wpb;
+  if (!a.scratch || a.n <= 0) return cudaSuccess;
+  if (a.tile == 32) { RBD_NOTE(aba_kernel<32>); aba_kernel<32><<<(unsigned)grid, block, (size_t)mw * 8, st>>>(d_model, mw, a); }
+  else { RBD_NOTE(aba_kernel<0>); aba_kernel<0><<<(unsigned)grid, block, (size_t)mw * 8, st>>>(d_model, mw, a); }
   return cudaGetLastError();
 }
 

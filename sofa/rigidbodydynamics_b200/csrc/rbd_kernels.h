@@ -38,6 +38,12 @@ struct DjtArgs {  // applyDJT: geometric stiffness (optional extension; the refe
   double* qcache;
   long long cache_inst0;
 };
+struct AbaArgs {  // forward dynamics (articulated-body algorithm): q, v, tau -> ddq
+  long long n, tile;
+  const double *q, *v, *tau;
+  double* ddq;
+  double* scratch;  // aba_scratch_doubles(model) * 32 doubles per resident warp
+};
 struct RowArgs {
   long long nrows;
   const int *row_ptr, *row_instance, *col;
@@ -87,6 +93,10 @@ cudaError_t launch_applyJT_rows_cached(const DevModel& m, const DevModel* d_mode
 cudaError_t launch_frame_jacobian(const DevModel& m, const DevModel* d_model, const DevTables& tb, long long npairs,
                                   const int* instance, const int* out_index, double* J, const double* jcache,
                                   const double* omicache, cudaStream_t st);
+// forward dynamics; *scratch_warps receives the number of warp records the launch uses when a.scratch == nullptr
+// (sizing call: nothing is launched)
+cudaError_t launch_aba(const DevModel& m, const DevModel* d_model, const AbaArgs& a, int num_sms, int* scratch_warps,
+                       cudaStream_t st);
 // assembled mapping Jacobian: block rows of the n_sel selected outputs (device arrays sel [n_sel], blk_ptr [n_sel + 1])
 // of n instances, val [n][6 blk_ptr[n_sel]]
 cudaError_t launch_getJ(const DevModel& m, const DevModel* d_model, const DevTables& tb, long long n, int n_sel, const int* sel,

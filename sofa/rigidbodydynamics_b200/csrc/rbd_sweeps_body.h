@@ -2652,4 +2652,291 @@ struct DirectRingT {
   }
   RBD_HD void release(int) {}
 };
+// =========================================================================================================
+// Forward dynamics: the articulated-body algorithm (pinocchio::aba; SURVEY.md §8(f) rank 4 — not in the reference)
+// =========================================================================================================
+// World-frame formulation, like everything else here: with all spatial quantities expressed about the world origin the
+// backward pass needs no transform between child and parent,
+//   pass 1 (root -> leaves)  FK, A_i = oMi.act(S_i), v_i, c_i = v_i x vJ_i, I^A_i = Y_i, p^A_i = v_i x* (Y_i v_i)
+//   pass 2 (leaves -> root)  U_i = I^A_i A_i, D_i = A_i . U_i, u_i = tau_i - A_i . p^A_i;
+//                            I^a = I^A_i - U_i U_i^T / D_i,  p^a = p^A_i + I^a c_i + U_i u_i / D_i,
+//                            I^A_parent += I^a,  p^A_parent += p^a                      (plain additions)
+//   pass 3 (root -> leaves)  a' = a_parent + c_i (a_universe = -g),  qdd_i = (u_i - U_i . a') / D_i,  a_i = a' + A_i qdd_i
+// A free-flyer is supported as the root joint (joint 1 on the universe; the host checks): its 6 x 6 system
+// (X^T I^A X) qdd = tau - X^T (p^A + I^A a') is solved by a Cholesky factorisation in registers at the end of pass 2.
+// Unlike the fused eval, pass 3 needs A, c, U, D, u of EVERY joint after the whole backward pass, so the state is
+// O(njoints), not O(depth): it lives in a per-thread scratch record in global memory (tile-32 interleaved, one record
+// per RESIDENT thread, reused from instance to instance so that it stays in L2), 45 doubles per joint:
+//   [0,6) A (free-flyer root: [0,12) R|p)   [6,12) c   [12,33) I^A (upper triangle, 21) -> after pass 2: U [12,18),
+//   1/D [18], u [19]   [33,39) p^A   [39,45) a_i (pass 3, joints with >= 2 children)
+// plus 18 doubles R|p|v per joint with >= 2 children (the state pass 1 returns to when a new branch starts).
+#define RBD_ABA_REC 45
+#define RBD_ABA_BRANCH 18
+RBD_HD int aba_scratch_doubles(const DevModel& m) { return RBD_ABA_REC * (m.njoints - 1) + RBD_ABA_BRANCH * m.nbranch; }
+
+// index of (r, c) in the row-major upper triangle of a symmetric 6 x 6 matrix
+RBD_HD constexpr int s6(int r, int c) { return r <= c ? 6 * r - r * (r - 1) / 2 + (c - r) : 6 * c - c * (c - 1) / 2 + (r - c); }
+// y = S x
+RBD_HD void sym6_mul(const real* S, const real* x, real* y) {
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    real t = 0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) t += S[s6(r, c)] * x[c];
+    y[r] = t;
+  }
+}
+// the rigid-body inertia Y = (m, h, I_O) as a symmetric 6 x 6 matrix [[m 1, -[h]x], [[h]x, I_O]] ([lin; ang])
+RBD_HD void sym6_from_inertia(const real* Y, real* S) {
+  const real m = Y[0], hx = Y[1], hy = Y[2], hz = Y[3];
+  S[s6(0, 0)] = m; S[s6(0, 1)] = 0; S[s6(0, 2)] = 0; S[s6(0, 3)] = 0;   S[s6(0, 4)] = hz;  S[s6(0, 5)] = -hy;
+  S[s6(1, 1)] = m; S[s6(1, 2)] = 0; S[s6(1, 3)] = -hz; S[s6(1, 4)] = 0; S[s6(1, 5)] = hx;
+  S[s6(2, 2)] = m; S[s6(2, 3)] = hy; S[s6(2, 4)] = -hx; S[s6(2, 5)] = 0;
+  S[s6(3, 3)] = Y[4]; S[s6(3, 4)] = Y[5]; S[s6(3, 5)] = Y[7];
+  S[s6(4, 4)] = Y[6]; S[s6(4, 5)] = Y[8];
+  S[s6(5, 5)] = Y[9];
+}
+
+// X: this thread's scratch record (ld(e) / st(e, v)); q, v, tau, ddq: strided fields of the instance.
+template <class FLD, class SCR>
+RBD_HD void aba_instance(const DevModel& m, const FLD& q, const FLD& v, const FLD& tau, const FLD& ddq, const SCR& X) {
+  const int nj = m.njoints;
+  const int bbase = RBD_ABA_REC * (nj - 1);
+  real R[9], p[3], vel[6];
+#define RBD_ABA_ROOT()                                                                          \
+  do {                                                                                          \
+    R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;   \
+    p[0] = p[1] = p[2] = 0;                                                                     \
+    _Pragma("unroll") for (int e_ = 0; e_ < 6; ++e_) vel[e_] = 0;                               \
+  } while (0)
+  RBD_ABA_ROOT();
+  // ---- pass 1 ----------------------------------------------------------------------------------------------------
+  for (int i = 1; i < nj; ++i) {
+    const DevJoint& jn = m.joint[i];
+    const int par = jn.parent;
+    const int rec = RBD_ABA_REC * (i - 1);
+    if (par != i - 1) {  // a new branch starts below `par`
+      if (par == 0) {
+        RBD_ABA_ROOT();
+      } else {
+        const int b = bbase + RBD_ABA_BRANCH * m.joint[par].bidx;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) R[e] = X.ld(b + e);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) p[e] = X.ld(b + 9 + e);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) vel[e] = X.ld(b + 12 + e);
+      }
+    }
+    real q0 = 0, q1 = 0, aw[3];
+    if (jn.type != JT_FF) {
+      q0 = q.ld(jn.idx_q);
+      if (is_unbounded(jn.type)) q1 = q.ld(jn.idx_q + 1);
+    }
+    fk_joint(jn, R, p, q0, q1, q, aw);
+    real vj[6], cr[6];
+    if (jn.type != JT_FF) {
+      real A[6];
+      subspace_1dof(jn.type, p, aw, A);
+      const real qd = v.ld(jn.idx_v);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) { X.st(rec + e, A[e]); vj[e] = A[e] * qd; }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) X.st(rec + e, R[e]);
+#pragma unroll
+      for (int e = 0; e < 3; ++e) X.st(rec + 9 + e, p[e]);
+      ff_act(R, p, v, jn.idx_v, vj);
+    }
+#pragma unroll
+    for (int e = 0; e < 6; ++e) vel[e] += vj[e];
+    // c = v x vJ
+    {
+      real tx, ty, tz;
+      RBD_CROSS(cr[0], cr[1], cr[2], vel[3], vel[4], vel[5], vj[0], vj[1], vj[2]);
+      RBD_CROSS(tx, ty, tz, vel[0], vel[1], vel[2], vj[3], vj[4], vj[5]);
+      cr[0] += tx; cr[1] += ty; cr[2] += tz;
+      RBD_CROSS(cr[3], cr[4], cr[5], vel[3], vel[4], vel[5], vj[3], vj[4], vj[5]);
+    }
+    if (jn.type != JT_FF) {
+#pragma unroll
+      for (int e = 0; e < 6; ++e) X.st(rec + 6 + e, cr[e]);
+    }  // (a root free-flyer has v = vJ, hence c = 0; its record keeps R|p in [0, 12))
+    real Y[10], IA[21], h[6], pA[6];
+    inertia_world(jn, R, p, Y);
+    sym6_from_inertia(Y, IA);
+#pragma unroll
+    for (int e = 0; e < 21; ++e) X.st(rec + 12 + e, IA[e]);
+    inertia_mul(Y, vel, h);
+    {
+      real tx, ty, tz;
+      RBD_CROSS(pA[0], pA[1], pA[2], vel[3], vel[4], vel[5], h[0], h[1], h[2]);
+      RBD_CROSS(pA[3], pA[4], pA[5], vel[3], vel[4], vel[5], h[3], h[4], h[5]);
+      RBD_CROSS(tx, ty, tz, vel[0], vel[1], vel[2], h[0], h[1], h[2]);
+      pA[3] += tx; pA[4] += ty; pA[5] += tz;
+    }
+#pragma unroll
+    for (int e = 0; e < 6; ++e) X.st(rec + 33 + e, pA[e]);
+    if (jn.nchild >= 2) {
+      const int b = bbase + RBD_ABA_BRANCH * jn.bidx;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) X.st(b + e, R[e]);
+#pragma unroll
+      for (int e = 0; e < 3; ++e) X.st(b + 9 + e, p[e]);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) X.st(b + 12 + e, vel[e]);
+    }
+  }
+  // ---- pass 2 ----------------------------------------------------------------------------------------------------
+  real IA[21], pA[6];
+  bool have = false;  // IA | pA hold what joint i + 1 hands to joint i (its parent)
+  for (int i = nj - 1; i >= 1; --i) {
+    const DevJoint& jn = m.joint[i];
+    const int rec = RBD_ABA_REC * (i - 1);
+    if (have) {
+#pragma unroll
+      for (int e = 0; e < 21; ++e) IA[e] += X.ld(rec + 12 + e);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) pA[e] += X.ld(rec + 33 + e);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 21; ++e) IA[e] = X.ld(rec + 12 + e);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) pA[e] = X.ld(rec + 33 + e);
+    }
+    have = false;
+    if (jn.type != JT_FF) {
+      real A[6], U[6], c[6];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) { A[e] = X.ld(rec + e); c[e] = X.ld(rec + 6 + e); }
+      sym6_mul(IA, A, U);
+      const real dinv = real(1) / dot6(A, U);
+      const real u = tau.ld(jn.idx_v) - dot6(A, pA);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) X.st(rec + 12 + e, U[e]);
+      X.st(rec + 18, dinv);
+      X.st(rec + 19, u);
+      const int par = jn.parent;
+      if (par != 0) {
+        // I^a = I^A - U U^T / D ;  p^a = p^A + I^a c + U u / D
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int cc = r; cc < 6; ++cc) IA[s6(r, cc)] -= U[r] * (U[cc] * dinv);
+        real Ic[6];
+        sym6_mul(IA, c, Ic);
+        const real ud = u * dinv;
+#pragma unroll
+        for (int e = 0; e < 6; ++e) pA[e] += Ic[e] + U[e] * ud;
+        if (par == i - 1) {
+          have = true;  // the parent is visited next: keep the contribution in registers
+        } else {
+          const int pr = RBD_ABA_REC * (par - 1);
+#pragma unroll
+          for (int e = 0; e < 21; ++e) X.st(pr + 12 + e, X.ld(pr + 12 + e) + IA[e]);
+#pragma unroll
+          for (int e = 0; e < 6; ++e) X.st(pr + 33 + e, X.ld(pr + 33 + e) + pA[e]);
+        }
+      }
+    } else {
+      // root free-flyer: (X^T I^A X) qdd = tau - X^T (p^A + I^A a'),  a' = -g  (c = 0)
+      real Rp[12], a0[6], f[6], b[6];
+#pragma unroll
+      for (int e = 0; e < 12; ++e) Rp[e] = X.ld(rec + e);
+      a0[0] = -m.gravity[0]; a0[1] = -m.gravity[1]; a0[2] = -m.gravity[2]; a0[3] = a0[4] = a0[5] = 0;
+      sym6_mul(IA, a0, f);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) f[e] += pA[e];
+      ff_rows(Rp, Rp + 9, f, b);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) b[e] = tau.ld(jn.idx_v + e) - b[e];
+      real D[21];  // upper triangle of X^T I^A X
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) {
+        real Xc[6], F[6], col[6];
+        RBD_FF_COL(Xc, Rp, (Rp + 9), cc);
+        sym6_mul(IA, Xc, F);
+        ff_rows(Rp, Rp + 9, F, col);
+#pragma unroll
+        for (int r = 0; r <= cc; ++r) D[s6(r, cc)] = col[r];
+      }
+      // Cholesky D = L L^T (L stored in D's triangle as its transpose: D[s6(r, c)], r <= c, holds L(c, r)), then two
+      // triangular solves
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        real d = D[s6(k, k)];
+#pragma unroll
+        for (int j = 0; j < k; ++j) d -= D[s6(j, k)] * D[s6(j, k)];
+        d = sqrt(d);
+        D[s6(k, k)] = d;
+        const real di = real(1) / d;
+#pragma unroll
+        for (int r = k + 1; r < 6; ++r) {
+          real t = D[s6(k, r)];
+#pragma unroll
+          for (int j = 0; j < k; ++j) t -= D[s6(j, r)] * D[s6(j, k)];
+          D[s6(k, r)] = t * di;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {  // L y = b
+        real t = b[k];
+#pragma unroll
+        for (int j = 0; j < k; ++j) t -= D[s6(j, k)] * b[j];
+        b[k] = t / D[s6(k, k)];
+      }
+#pragma unroll
+      for (int k = 5; k >= 0; --k) {  // L^T x = y
+        real t = b[k];
+#pragma unroll
+        for (int j = k + 1; j < 6; ++j) t -= D[s6(k, j)] * b[j];
+        b[k] = t / D[s6(k, k)];
+      }
+      // a_1 = a' + X qdd
+      real al[3], aa[3], tx, ty, tz;
+#pragma unroll
+      for (int e = 0; e < 3; ++e) {
+        al[e] = Rp[3 * e] * b[0] + Rp[3 * e + 1] * b[1] + Rp[3 * e + 2] * b[2];
+        aa[e] = Rp[3 * e] * b[3] + Rp[3 * e + 1] * b[4] + Rp[3 * e + 2] * b[5];
+      }
+      RBD_CROSS(tx, ty, tz, Rp[9], Rp[10], Rp[11], aa[0], aa[1], aa[2]);
+      X.st(rec + 39, a0[0] + al[0] + tx); X.st(rec + 40, a0[1] + al[1] + ty); X.st(rec + 41, a0[2] + al[2] + tz);
+      X.st(rec + 42, aa[0]); X.st(rec + 43, aa[1]); X.st(rec + 44, aa[2]);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) ddq.st(jn.idx_v + e, b[e]);
+    }
+  }
+  // ---- pass 3 ----------------------------------------------------------------------------------------------------
+  real acc[6];
+  for (int i = 1; i < nj; ++i) {
+    const DevJoint& jn = m.joint[i];
+    const int par = jn.parent;
+    const int rec = RBD_ABA_REC * (i - 1);
+    if (jn.type == JT_FF) {  // solved at the end of pass 2
+#pragma unroll
+      for (int e = 0; e < 6; ++e) acc[e] = X.ld(rec + 39 + e);
+      continue;
+    }
+    if (par == 0) {
+      acc[0] = -m.gravity[0]; acc[1] = -m.gravity[1]; acc[2] = -m.gravity[2]; acc[3] = acc[4] = acc[5] = 0;
+    } else if (par != i - 1) {  // (else: acc still holds the parent's acceleration)
+      const int pr = RBD_ABA_REC * (par - 1);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) acc[e] = X.ld(pr + 39 + e);
+    }
+    real A[6], U[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) { A[e] = X.ld(rec + e); U[e] = X.ld(rec + 12 + e); acc[e] += X.ld(rec + 6 + e); }
+    const real qdd = (X.ld(rec + 19) - dot6(U, acc)) * X.ld(rec + 18);
+    ddq.st(jn.idx_v, qdd);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) acc[e] += A[e] * qdd;
+    if (jn.nchild >= 2) {
+#pragma unroll
+      for (int e = 0; e < 6; ++e) X.st(rec + 39 + e, acc[e]);
+    }
+  }
+#undef RBD_ABA_ROOT
+}
+
 #endif  /* !RBD_BODY_F32 && !RBD_BODY_EVAL_ONLY */

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -399,6 +400,29 @@ extern "C" int emul_frame_jacobians(const rbd_model_desc* d, long long n, double
     frame_jacobian_cached(bm, c.tb, Jc, Oc, out_index[p], [&](int cc, const double* o) {
       for (int e = 0; e < 6; ++e) Jr[6 * cc + e] = o[e];
     });
+  }
+  return 0;
+}
+
+// forward dynamics (aba_instance): the scratch record is a poisoned heap array per lane
+struct EmulScratch {
+  double* p;
+  double ld(int e) const { return p[e]; }
+  void st(int e, double v) const { p[e] = v; }
+};
+extern "C" int emul_aba(const rbd_model_desc* d, long long n, long long tile, double* q, double* v, double* tau, double* ddq) {
+  Ctx c;
+  int rc = make_ctx(d, &c);
+  if (rc) return rc;
+  for (int i = 1; i < c.m.njoints; ++i)
+    if (c.m.joint[i].type == JT_FF && !(i == 1 && c.m.joint[i].parent == 0)) { g_err = "free-flyer below the root"; return -5; }
+  const int E = aba_scratch_doubles(c.m);
+  std::vector<double> scr((size_t)(E > 0 ? E : 1));
+  for (long long i = 0; i < n; ++i) {
+    std::fill(scr.begin(), scr.end(), 1e300);
+    EmulScratch X{scr.data()};
+    aba_instance(c.m, make_field(q, i, c.m.nq, tile), make_field(v, i, c.m.nv, tile), make_field(tau, i, c.m.nv, tile),
+                 make_field(ddq, i, c.m.nv, tile), X);
   }
   return 0;
 }

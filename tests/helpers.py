@@ -71,6 +71,7 @@ def load_emul() -> C.CDLL:
     lib.emul_applyJT_rows_cached.argtypes = [vp, ll, vp, ll, ll, vp, vp, vp, vp, vp, vp]
     lib.emul_frame_jacobians.argtypes = [vp, ll, vp, ll, ll, vp, vp, vp]
     lib.emul_getJ.argtypes = [vp, ll, vp, ll, i, vp, vp, vp, vp]
+    lib.emul_aba.argtypes = [vp, ll, ll, vp, vp, vp, vp]
     lib.emul_applyDJT.argtypes = [vp, ll, ll, vp, ll, vp, vp, vp, C.c_double, vp, vp]
     lib.emul_applyDJT_ring.argtypes = [vp, ll, ll, vp, ll, vp, vp, vp, C.c_double, vp, vp]
     lib.emul_applyJT_rows.argtypes = [vp, ll, i, vp, ll, vp, vp, vp, vp, vp, vp]

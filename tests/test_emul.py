@@ -482,3 +482,36 @@ def test_world_jacobian_by_finite_differences(emul, name):
         return got["oMi"], got["J"]
 
     assert helpers.fd_world_jacobian_error(eval_fn, d, q) <= 1e-7
+
+
+@pytest.mark.parametrize("d", MODELS, ids=IDS)
+@pytest.mark.parametrize("tile", [32, 11])
+def test_aba_body_matches_oracle_and_golden(emul, d, tile):
+    """aba_instance (world-frame articulated-body sweep, scratch record per thread) against the oracle's ABA (pinocchio's
+    LOCAL-convention algorithm), the mpmath forward-dynamics golden vectors, and the round trip through the oracle's
+    RNEA.  Tolerance 1e-9: the conditioning of M(q) enters (the golden solve is exact to 50 digits)."""
+    import json
+    import os
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    cd, keep = _cdesc(d)
+    with open(os.path.join(helpers.GOLDEN, "golden_aba.json")) as f:
+        gold = json.load(f)[d.name]["states"]
+    n = 40
+    q, v, a = mdl.random_state(d, n, seed=51)
+    rng = np.random.default_rng(52)
+    tau = rng.uniform(-2, 2, (n, d.nv))
+    for s, st in enumerate(gold):                          # the golden states ride along as the first instances
+        q[s], v[s], tau[s] = np.array(st["q"]), np.array(st["v"]), np.array(st["tau"])
+    orc = oracle.Oracle(d)
+    tau[n - 1] = orc.rnea(q[n - 1], v[n - 1], a[n - 1])    # round trip: aba(q, v, rnea(q, v, a)) == a
+    nt = (n + tile - 1) // tile
+    ddq = np.full((nt, max(1, d.nv), tile), np.nan)
+    qs, vs, ts = to_tiled(q, tile), to_tiled(v, tile), to_tiled(tau, tile)
+    assert emul.emul_aba(C.addressof(cd), n, tile, P(qs), P(vs), P(ts), P(ddq)) == 0, emul.emul_last_error()
+    got = from_tiled(ddq, n)[:, :d.nv]
+    ref = np.stack([orc.aba(q[i], v[i], tau[i]) for i in range(n)])
+    assert rel_err(got, ref) <= 1e-9
+    for s, st in enumerate(gold):
+        assert rel_err(got[s], np.array(st["qdd"])) <= 1e-9
+    assert rel_err(got[n - 1], a[n - 1]) <= 1e-9

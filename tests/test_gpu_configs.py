@@ -198,3 +198,26 @@ def test_world_jacobian_by_finite_differences_gpu(name):
         return helpers.from_tiled(oMi.cpu().numpy(), N), helpers.from_tiled(J.cpu().numpy(), N)
 
     assert helpers.fd_world_jacobian_error(eval_fn, d, q) <= 1e-7
+
+
+def test_aba_round_trip_talos_full_size():
+    """Talos at N = 1,048,576: aba(q, v, rnea(q, v, a)) == a for every instance (forward dynamics inverts the inverse
+    dynamics; both kernels on the device), and a strided sample against the oracle's ABA."""
+    import torch
+    import oracle
+    from sofa.rigidbodydynamics_b200 import api, model as mdl
+    d = mdl.talos_reduced(); n = 1 << 20; nt = n // 32
+    m = api.Model(d); ws = api.Workspace(m, n)
+    ws.set_stream(torch.cuda.current_stream().cuda_stream)
+    q, v, a = _rand_state(torch, d, n, 19)
+    tau = torch.empty((nt, d.nv, 32), dtype=torch.float64, device="cuda")
+    ddq = torch.empty((nt, d.nv, 32), dtype=torch.float64, device="cuda")
+    ws.rnea_soa(n, 32, q, v, a, tau)
+    ws.aba_soa(n, 32, q, v, tau, ddq)
+    torch.cuda.synchronize()
+    assert float((ddq - a).abs().max()) <= 1e-8                # |a| <= 1; conditioning of M(q) enters
+    orc = oracle.Oracle(d)
+    im = lambda x, i: x.permute(0, 2, 1).reshape(n, -1)[i].cpu().numpy()
+    for i in range(0, n, 131071):
+        ref = orc.aba(im(q, i), im(v, i), im(tau, i))
+        assert rel_err(im(ddq, i), ref) <= 1e-9

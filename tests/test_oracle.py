@@ -166,3 +166,27 @@ def test_flop_counting_build_counts_the_restated_algorithm():
         nrev = sum(1 for t in d.jtype[1:] if mdl.J_RX <= int(t) <= mdl.J_RU)
         assert c0["fk_jacobian"]["sincos"] == 2 * nrev          # one sine + one cosine per revolute joint and FK pass
         assert c0["eval"]["flops"] > 100 * d.nv
+
+
+def test_aba_matches_independent_forward_dynamics():
+    """orc_aba (pinocchio's articulated-body algorithm, LOCAL convention) against tests/golden/golden_aba.json: forward
+    dynamics solved as M(q)^-1 (tau - nle) in 50-digit arithmetic by the independent implementation (no articulated
+    inertias, no recursion; tests/golden/make_golden_aba.py), and the round trip aba(q, v, rnea(q, v, a)) == a."""
+    import json
+    import os
+    import helpers
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    with open(os.path.join(helpers.GOLDEN, "golden_aba.json")) as f:
+        gold = json.load(f)
+    seen = 0
+    for d in helpers.all_models():
+        orc = oracle.Oracle(d)
+        for st in gold[d.name]["states"]:
+            qdd = orc.aba(np.array(st["q"]), np.array(st["v"]), np.array(st["tau"]))
+            assert helpers.rel_err(qdd, np.array(st["qdd"])) <= 1e-9, d.name   # conditioning of M enters: not 1e-10
+            seen += 1
+        q, v, a = mdl.random_state(d, 3, seed=77)
+        for s in range(3):
+            assert helpers.rel_err(orc.aba(q[s], v[s], orc.rnea(q[s], v[s], a[s])), a[s]) <= 1e-10, d.name
+    assert seen >= 11
