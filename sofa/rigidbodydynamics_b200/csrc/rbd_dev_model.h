@@ -182,6 +182,14 @@ struct DevTables {
   const double* outk_pl;     // [n_out][12] frame placement of output k
 };
 
+// Scratch record of the forward-dynamics sweep (aba_instance, rbd_sweeps_body.h): doubles per joint / per branch joint
+#define RBD_ABA_REC 45
+#define RBD_ABA_BRANCH 18
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline int aba_scratch_doubles(const DevModel& m) { return RBD_ABA_REC * (m.njoints - 1) + RBD_ABA_BRANCH * m.nbranch; }
+
 // Stack-slot geometry (doubles): A is 6 wide (1-dof joints: [p x a ; a] world frame) or 12 (free-flyer: R|p).
 #define RBD_SLOT_A(type) ((type) == JT_FF ? 12 : 6)
 #define RBD_BRANCH_EVAL 24 /* R(9) p(3) v(6) a(6) */

@@ -2670,9 +2670,7 @@ struct DirectRingT {
 //   [0,6) A (free-flyer root: [0,12) R|p)   [6,12) c   [12,33) I^A (upper triangle, 21) -> after pass 2: U [12,18),
 //   1/D [18], u [19]   [33,39) p^A   [39,45) a_i (pass 3, joints with >= 2 children)
 // plus 18 doubles R|p|v per joint with >= 2 children (the state pass 1 returns to when a new branch starts).
-#define RBD_ABA_REC 45
-#define RBD_ABA_BRANCH 18
-RBD_HD int aba_scratch_doubles(const DevModel& m) { return RBD_ABA_REC * (m.njoints - 1) + RBD_ABA_BRANCH * m.nbranch; }
+// (RBD_ABA_REC, RBD_ABA_BRANCH, aba_scratch_doubles: rbd_dev_model.h)
 
 // index of (r, c) in the row-major upper triangle of a symmetric 6 x 6 matrix
 RBD_HD constexpr int s6(int r, int c) { return r <= c ? 6 * r - r * (r - 1) / 2 + (c - r) : 6 * c - c * (c - 1) / 2 + (r - c); }
