@@ -334,6 +334,13 @@ def measure_config(torch, robot: str, n: int, steps: int, dev_index: int, with_e
     for name, fn in calls.items():
         ms, clk, kern = _time_launches(torch, fn, steps, 3, flush, dev_index)
         out[name] = _entry(n, ms, B[name], peak, clk, kern)
+    # layout adapters of the host path (Conversions.h at batch scale): instance-major <-> tile-32, widest array (M)
+    Kw = int(I.mass_fields)
+    aos = torch.empty((n, Kw), dtype=torch.float64, device=dev)
+    for name, fn in (("layout_soa_to_aos_M", lambda: ws.soa_to_aos(n, Kw, tile, Mp, aos)),
+                     ("layout_aos_to_soa_M", lambda: ws.aos_to_soa(n, Kw, tile, aos, Mp))):
+        ms, clk, _ = _time_launches(torch, fn, steps, 3, flush, dev_index)
+        out[name] = _entry(n, ms, 16 * Kw, peak, clk, "rbd::transpose32_kernel" if tile == 32 else "rbd::soa_to_aos / aos_to_soa kernel")
     return {"robot": d.name, "n": n, "tile": tile, "n_out": int(I.n_out), "l2": "flushed between timed launches",
             "note": d.note, "kernels": out}
 

@@ -612,6 +612,54 @@ __global__ void soa_to_aos_kernel(long long n, int K, long long tile, const doub
   }
 }
 
+// tile-32 fast path of the adapters: one block moves the [KC fields] x [32 instances] slab of one instance tile through
+// a padded shared tile — 16 loads in flight per thread before the barrier (the 32 x 32 kernels above keep 4 and pay a
+// block launch per 8 KB: K = 741 ran at 0.39 of the HBM roofline, profiles/r1j_launches_condensed.txt).  In the tiled
+// layout the slab is contiguous (field k of the tile at k * 32), on the instance-major side every instance owns KC
+// consecutive doubles.
+#define RBD_TR_KC 128
+template <bool TO_AOS>
+__global__ void __launch_bounds__(256) transpose32_kernel(long long n, int K, const double* __restrict__ src, double* __restrict__ dst) {
+  __shared__ double t[RBD_TR_KC][33];
+  const long long tile = blockIdx.x;
+  const int k0 = blockIdx.y * RBD_TR_KC;
+  const int kc = min(RBD_TR_KC, K - k0);
+  const long long i0 = tile * 32;
+  const int ni = (int)min(32LL, n - i0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (TO_AOS) {
+    const double* s = src + tile * (long long)K * 32 + (long long)k0 * 32;  // [kc][32] contiguous
+#pragma unroll
+    for (int j = 0; j < RBD_TR_KC * 32 / 256; ++j) {
+      const int idx = tid + 256 * j, k = idx >> 5;
+      if (k < kc) t[k][idx & 31] = s[idx];
+    }
+    __syncthreads();
+    double* d = dst + i0 * K + k0;
+    for (int r = warp; r < ni; r += 8)
+#pragma unroll
+      for (int j = 0; j < RBD_TR_KC / 32; ++j) {
+        const int k = lane + 32 * j;
+        if (k < kc) d[(long long)r * K + k] = t[k][r];
+      }
+  } else {
+    const double* s = src + i0 * K + k0;
+    for (int r = warp; r < ni; r += 8)
+#pragma unroll
+      for (int j = 0; j < RBD_TR_KC / 32; ++j) {
+        const int k = lane + 32 * j;
+        if (k < kc) t[k][r] = s[(long long)r * K + k];
+      }
+    __syncthreads();
+    double* d = dst + tile * (long long)K * 32 + (long long)k0 * 32;
+#pragma unroll
+    for (int j = 0; j < RBD_TR_KC * 32 / 256; ++j) {
+      const int idx = tid + 256 * j, k = idx >> 5;
+      if (k < kc && (idx & 31) < ni) d[idx] = t[k][idx & 31];
+    }
+  }
+}
+
 // --------------------------------------------------------------------------------------------------------
 // launch helpers
 static const int kMaxSmemOptin = 227 * 1024;
@@ -904,12 +952,22 @@ cudaError_t launch_getJ(const DevModel& m, const DevModel* d_model, const DevTab
 
 cudaError_t launch_aos_to_soa(long long n, int K, long long tile, const double* aos, double* soa, cudaStream_t st) {
   if (n <= 0 || K <= 0) return cudaSuccess;
+  if (tile == 32) {
+    dim3 g32((unsigned)((n + 31) / 32), (unsigned)((K + RBD_TR_KC - 1) / RBD_TR_KC));
+    transpose32_kernel<false><<<g32, 256, 0, st>>>(n, K, aos, soa);
+    return cudaGetLastError();
+  }
   dim3 grid((unsigned)((n + 31) / 32), (unsigned)((K + 31) / 32)), block(32, 8);
   aos_to_soa_kernel<<<grid, block, 0, st>>>(n, K, tile, aos, soa);
   return cudaGetLastError();
 }
 cudaError_t launch_soa_to_aos(long long n, int K, long long tile, const double* soa, double* aos, cudaStream_t st) {
   if (n <= 0 || K <= 0) return cudaSuccess;
+  if (tile == 32) {
+    dim3 g32((unsigned)((n + 31) / 32), (unsigned)((K + RBD_TR_KC - 1) / RBD_TR_KC));
+    transpose32_kernel<true><<<g32, 256, 0, st>>>(n, K, soa, aos);
+    return cudaGetLastError();
+  }
   dim3 grid((unsigned)((n + 31) / 32), (unsigned)((K + 31) / 32)), block(32, 8);
   soa_to_aos_kernel<<<grid, block, 0, st>>>(n, K, tile, soa, aos);
   return cudaGetLastError();

@@ -402,7 +402,8 @@ def test_layout_adapters_roundtrip(torch_mod, api):
     torch = torch_mod
     from sofa.rigidbodydynamics_b200 import model as mdl
     m = api.Model(mdl.panda7()); ws = api.Workspace(m, 8)
-    for n, K, tile in ((1, 1, 1), (1000, 37, 32), (4097, 100, 4097), (33, 741, 64)):
+    for n, K, tile in ((1, 1, 1), (1000, 37, 32), (4097, 100, 4097), (33, 741, 64), (4097, 741, 32), (31, 200, 32),
+                       (64, 128, 32), (33, 129, 32), (1, 1, 32), (100, 7, 32)):
         x = torch.randn((n, K), dtype=torch.float64, device="cuda")
         nt = (n + tile - 1) // tile
         s = torch.zeros((nt, K, tile), dtype=torch.float64, device="cuda")
