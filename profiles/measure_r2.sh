@@ -1,0 +1,26 @@
+#!/bin/bash
+# usage (on the GPU box, from the repo root): profiles/measure_r2.sh <tag>
+# Round-2 measurement set: GPU tests, the bench line (with its `secondary` object: every BASELINE config + the Mapping
+# path), the reference arm, the ncu launch list of the bench command, one `ncu --set full` capture per hot kernel and
+# the FP64 instruction counts of the three eval instantiations.  Everything lands in gpurun_out/<tag>_*; the summaries
+# kept under profiles/ are made from these by profiles/ncu_summary.py.
+T="$1"; O=gpurun_out; mkdir -p $O
+nvidia-smi -L > $O/${T}_box.txt; nproc >> $O/${T}_box.txt
+(time python -m pytest tests -m gpu -x -q) > $O/${T}_tests.log 2>&1; tail -2 $O/${T}_tests.log
+python bench.py --steps 20 --warmup 3 --f32 > $O/${T}_bench_1gpu.json 2> $O/${T}_bench.err; cut -c1-300 $O/${T}_bench_1gpu.json
+python bench.py --impl reference --steps 5 --warmup 1 > $O/${T}_bench_reference_arm.json 2>> $O/${T}_bench.err; cut -c1-200 $O/${T}_bench_reference_arm.json
+Q="--steps 2 --warmup 1 --no-e2e --no-cpu --no-secondary"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${T}_launches.csv \
+    python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu --secondary-steps 2 > $O/${T}_launches.log 2>&1
+profiles/capture.sh "eval_kernel_simple" ${T}_eval_talos -- python bench.py $Q
+profiles/capture.sh "eval_kernel_ffroot" ${T}_eval_solo -- python bench.py --workload solo $Q
+profiles/capture.sh "eval_kernel_chain" ${T}_eval_panda -- python bench.py --workload panda $Q
+profiles/capture.sh "aba_kernel" ${T}_aba_talos -- python bench_mapping.py --robot talos_reduced --n 1048576 --steps 3
+profiles/capture.sh "applyJT_rows_cached" ${T}_rows_talos -- python bench_mapping.py --robot talos_reduced --n 1048576 --steps 3
+profiles/capture.sh "transpose32_kernel<\(bool\)1>|transpose32_kernel<true>" ${T}_soa_to_aos -- python bench_mapping.py --robot talos_reduced --n 1048576 --steps 3
+M=smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,gpu__time_duration.sum
+for w in talos solo panda; do
+  ncu --metrics $M --clock-control none --kernel-name-base demangled -k "regex:eval_kernel" -s 2 -c 1 --csv --log-file $O/${T}_fp64_${w}.csv \
+      python bench.py --workload $w $Q > /dev/null 2>&1
+done
+rm -f $O/${T}_*_cuda.csv   # the largest page; the summaries use raw + sass
