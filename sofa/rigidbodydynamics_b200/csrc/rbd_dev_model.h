@@ -96,6 +96,7 @@ struct EvalPlan {
                               branch code -> 166 registers, 12 warps per SM                                         */
 #define RBD_EVAL_FFROOT 3  /* RX / RY / RZ joints below a free-flyer root that is the universe's only child (Solo,
                               Talos): the root is stepped outside the joint loop -> 168 registers, 12 warps per SM   */
+#define RBD_EVAL_FFROOT8 4 /* the ffroot sweep with the full register budget, for plans of <= 8 warps per SM (Talos)       */
 #define RBD_BOFF_TMEM (1 << 30)
 #define RBD_BOFF_NOVA (1 << 29) /* v|a not saved: recomputed when the sweep returns (joint attached to the universe) */
 #define RBD_BOFF_RPOMI (1 << 28) /* R|p not saved: re-read from the oMi output this thread wrote (oMi requested) */

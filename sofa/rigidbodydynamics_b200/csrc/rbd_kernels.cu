@@ -119,6 +119,7 @@ RBD_DEFINE_EVAL_KERNEL(eval_kernel_f32, rbd::f32, float, 2, 0)
 #endif
 RBD_DEFINE_EVAL_KERNEL(eval_kernel_chain, rbd::chain, double, 1, 1)
 RBD_DEFINE_EVAL_KERNEL(eval_kernel_ffroot, rbd::ffroot, double, 1, 2)
+RBD_DEFINE_EVAL_KERNEL(eval_kernel_ffroot8, rbd::ffroot8, double, 1, 0)
 
 // The mapping kernels stage the joint table the same way (one coalesced copy per block, broadcast reads after).
 // The cached configuration of the last apply (workspace) is always tile-32.
@@ -763,12 +764,14 @@ RBD_DEFINE_EVAL_LAUNCH(launch_eval_simple, eval_kernel_simple, double, RBD_EVAL_
 RBD_DEFINE_EVAL_LAUNCH(launch_eval_f32, eval_kernel_f32, float, 100)
 RBD_DEFINE_EVAL_LAUNCH(launch_eval_chain, eval_kernel_chain, double, RBD_EVAL_CHAIN)
 RBD_DEFINE_EVAL_LAUNCH(launch_eval_ffroot, eval_kernel_ffroot, double, RBD_EVAL_FFROOT)
+RBD_DEFINE_EVAL_LAUNCH(launch_eval_ffroot8, eval_kernel_ffroot8, double, RBD_EVAL_FFROOT8)
 #undef RBD_ATTR
 #undef RBD_LAUNCH
 cudaError_t launch_eval_any(const DevModel& hm, const DevModel* d_model, const EvalArgs& a, LaunchCfg* cache,
                             int num_sms, cudaStream_t st) {
   switch (hm.plan.kvariant) {
     case RBD_EVAL_FFROOT: return launch_eval_ffroot(hm, d_model, a, cache, num_sms, st);
+    case RBD_EVAL_FFROOT8: return launch_eval_ffroot8(hm, d_model, a, cache, num_sms, st);
     case RBD_EVAL_CHAIN: return launch_eval_chain(hm, d_model, a, cache, num_sms, st);
     case RBD_EVAL_SIMPLE: return launch_eval_simple(hm, d_model, a, cache, num_sms, st);
     default: return launch_eval(hm, d_model, a, cache, num_sms, st);

@@ -296,7 +296,15 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
     }
   }
   const bool ok = plan_eval_cfg(m, do_m, do_tau, use_tmem, forced_warps, omi_out, jt, regs_per_thread, elem_bytes, 0);
+#ifndef RBD_USE_FFROOT8
+#define RBD_USE_FFROOT8 1
+#endif
   if (ok) m->plan.kvariant = m->eval_variant >= RBD_EVAL_SIMPLE ? RBD_EVAL_SIMPLE : RBD_EVAL_GENERIC;
+  // a floating-base robot on the standard (<= 8-warp) plan: the ffroot sweep with the full register budget — the fused
+  // CRBA + RNEA variant only (A/B r2: Talos 2.29 -> see DESIGN.md §4.1a)
+  if (ok && RBD_USE_FFROOT8 && elem_bytes == 8 && !jt && do_m && do_tau && forced_warps == 0 && m->eval_variant == RBD_EVAL_FFROOT &&
+      regs_per_thread == B200Limits::kRegsPerThread)
+    m->plan.kvariant = RBD_EVAL_FFROOT8;
   return ok;
 }
 // wide_warps > 0: blocks of up to that many warps at regs_per_thread registers (the caller vouches for the kernel)

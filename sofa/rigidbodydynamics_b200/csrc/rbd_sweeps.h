@@ -90,6 +90,21 @@ typedef double real;
 #undef RBD_SIMPLE_JOINTS
 }  // namespace ffroot
 
+// ... the same for plans of <= 8 warps per SM (Talos: the sweep state, not the registers, caps the SM): compiled with
+// the full register budget, so the early reload of the branch state stays in
+namespace ffroot8 {
+typedef double real;
+#define RBD_SIMPLE_JOINTS 1
+#define RBD_FF_ROOT_ONLY 1
+#define RBD_FF_ROOT_WIDE_REGS 1
+#define RBD_BODY_EVAL_ONLY 1
+#include "rbd_sweeps_body.h"
+#undef RBD_BODY_EVAL_ONLY
+#undef RBD_FF_ROOT_WIDE_REGS
+#undef RBD_FF_ROOT_ONLY
+#undef RBD_SIMPLE_JOINTS
+}  // namespace ffroot8
+
 // ... and for fixed-base serial chains of RX / RY / RZ joints (DevModelT::chain_only): additionally without the
 // free-flyer and branch code
 namespace chain {

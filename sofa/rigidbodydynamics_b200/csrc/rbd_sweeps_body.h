@@ -11,7 +11,7 @@
 #undef RBD_T_IS_FF
 #undef RBD_CAN_BRANCH
 #undef RBD_EARLY_RESTORE_NS
-#if defined(RBD_FF_ROOT_ONLY)
+#if defined(RBD_FF_ROOT_ONLY) && !defined(RBD_FF_ROOT_WIDE_REGS)
 #define RBD_EARLY_RESTORE_NS 0 /* 12-warp blocks at 168 registers: the early reload would spill (ptxas: 88 bytes) */
 #else
 #define RBD_EARLY_RESTORE_NS RBD_EARLY_RESTORE

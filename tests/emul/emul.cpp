@@ -95,6 +95,7 @@ EMUL_DEFINE_EVAL_RUN(run_eval_generic, rbd)
 EMUL_DEFINE_EVAL_RUN(run_eval_simple, rbd::simple)
 EMUL_DEFINE_EVAL_RUN(run_eval_chain, rbd::chain)
 EMUL_DEFINE_EVAL_RUN(run_eval_ffroot, rbd::ffroot)
+EMUL_DEFINE_EVAL_RUN(run_eval_ffroot8, rbd::ffroot8)
 
 // tile == 32 runs the compile-time-tile instantiation the GPU fast path uses.  use_tmem selects the storage plan
 // (tensor memory is emulated by a second poisoned array); block = warps * 32 pins the planner's block size (0 = auto).
@@ -132,11 +133,12 @@ extern "C" int emul_eval_ex(const rbd_model_desc* d, long long n, long long tile
   if (rc) return rc;
   const bool do_m = M != nullptr, do_tau = tau != nullptr;
   if (variant >= 0) {
-    if (variant > c.m.eval_variant && !(variant == RBD_EVAL_SIMPLE && c.m.eval_variant >= RBD_EVAL_SIMPLE)) {
+    if (variant > c.m.eval_variant && !(variant == RBD_EVAL_SIMPLE && c.m.eval_variant >= RBD_EVAL_SIMPLE) &&
+        !(variant == RBD_EVAL_FFROOT8 && c.m.eval_variant == RBD_EVAL_FFROOT)) {
       g_err = "the model does not qualify for this instantiation"; return -102;
     }
     if (variant == RBD_EVAL_SIMPLE && c.m.eval_variant < RBD_EVAL_SIMPLE) { g_err = "not a simple-joint model"; return -102; }
-    if (variant >= RBD_EVAL_CHAIN && variant != c.m.eval_variant) { g_err = "the model does not qualify for this instantiation"; return -102; }
+    if (variant >= RBD_EVAL_CHAIN && variant != c.m.eval_variant && !(variant == RBD_EVAL_FFROOT8 && c.m.eval_variant == RBD_EVAL_FFROOT)) { g_err = "the model does not qualify for this instantiation"; return -102; }
   }
   if (!plan_eval(&c.m, do_m, do_tau, use_tmem != 0, block / 32, oMi != nullptr)) { g_err = "plan_eval failed"; return -100; }
   // the sweep reads the model through the staged blob (planned DevModel prefix + ColProg table), as the kernel does
@@ -144,6 +146,7 @@ extern "C" int emul_eval_ex(const rbd_model_desc* d, long long n, long long tile
   const DevModel& bm = *reinterpret_cast<const DevModel*>(blob.data());
   const int kv = variant == -2 ? bm.plan.kvariant : variant;
   switch (kv) {
+    case RBD_EVAL_FFROOT8: run_eval_ffroot8(bm, n, tile, q, v, a, oMi, J, M, tau); break;
     case RBD_EVAL_FFROOT: run_eval_ffroot(bm, n, tile, q, v, a, oMi, J, M, tau); break;
     case RBD_EVAL_CHAIN: run_eval_chain(bm, n, tile, q, v, a, oMi, J, M, tau); break;
     case RBD_EVAL_SIMPLE: run_eval_simple(bm, n, tile, q, v, a, oMi, J, M, tau); break;

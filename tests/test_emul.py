@@ -110,7 +110,7 @@ def _emul_eval_variant(emul, d, q, v, a, tile, variant, want=("oMi", "J", "M", "
     return {k: (from_tiled(o, n)[:, :K[k]] if o is not None else None) for k, o in outs.items()}
 
 
-VARIANT_NAMES = {0: "generic", 1: "simple", 2: "chain", 3: "ffroot"}
+VARIANT_NAMES = {0: "generic", 1: "simple", 2: "chain", 3: "ffroot", 4: "ffroot8"}
 
 
 @pytest.mark.parametrize("d", MODELS, ids=IDS)
@@ -127,7 +127,7 @@ def test_eval_specialised_instantiations(emul, d, tile):
     w = C.c_int(0)
     picked = emul.emul_eval_variant(C.addressof(cd), 1, 1, C.byref(w))
     assert picked >= 0
-    expect = {"panda7": (2, 12), "solo12": (3, 12), "talos_reduced": (1, 8)}.get(d.name)
+    expect = {"panda7": (2, 12), "solo12": (3, 12), "talos_reduced": (4, 8)}.get(d.name)
     if expect:
         assert (picked, w.value) == expect, (VARIANT_NAMES[picked], w.value)
     ref, _ = oracle.eval_batch(d, q, v, a, 1)
@@ -137,7 +137,7 @@ def test_eval_specialised_instantiations(emul, d, tile):
         assert rel_err(got[k], ref[k]) <= TOL_FP64, k
         assert np.array_equal(got[k], base[k]), k
     ran = 0
-    for variant in (1, 2, 3):
+    for variant in (1, 2, 3, 4):
         cdv, _k = _cdesc(d)
         nt = (n + tile - 1) // tile
         probe = np.full((nt, max(1, d.nv), tile), np.nan)
