@@ -368,6 +368,32 @@ RBD_API int rbd_batch_apply(rbd_batch* batch, int64_t slot, int64_t epoch);
 RBD_API int rbd_batch_applyJ(rbd_batch* batch, int64_t slot, int64_t epoch);
 RBD_API int rbd_batch_applyJT(rbd_batch* batch, int64_t slot, int64_t epoch);
 
+/* ---------------------------------------------------------------------------------------------------- */
+/* model ingest (host only): URDF -> descriptor, for callers without pinocchio.
+ * Produces what the reference's loader hands to the mapping: the model pinocchio::urdf::buildModel builds — with a
+ * free-flyer root joint when `free_flyer` != 0 (URDFModelLoader.cpp:126-139) — plus the loader's two frame tables: every
+ * parsed frame as an "extra frame" (URDFModelLoader.cpp:159-165) and one "Body_<j>_CoM" OP_FRAME per joint, universe
+ * included (URDFModelLoader.cpp:175-183); out_frames = CoM frames then extra frames (KCM.inl:382-395).  Joint types:
+ * revolute, continuous (unbounded cos/sin), prismatic (axis-aligned or unaligned), floating, fixed (merged into the
+ * parent joint, inertias aggregated); <mimic> / limits / geometry are ignored; planar -> RBD_ERR_UNSUPPORTED; malformed
+ * XML or trees -> RBD_ERR_MODEL with the reason in rbd_last_error().  Conventions are pinocchio 3.3.1's restated (see
+ * csrc/rbd_urdf.cpp).  The handle owns every array rbd_urdf_desc() points to; pass the descriptor to rbd_model_create
+ * (which copies) and destroy the handle when the names are no longer needed.  Frame types are pinocchio::FrameType
+ * bit values (OP_FRAME 1, JOINT 2, FIXED_JOINT 4, BODY 8).                                                        */
+typedef struct rbd_urdf_model rbd_urdf_model;
+RBD_API int rbd_urdf_load_file(const char* path, int free_flyer, rbd_urdf_model** out);
+RBD_API int rbd_urdf_load_string(const char* xml, int free_flyer, rbd_urdf_model** out);
+RBD_API void rbd_urdf_destroy(rbd_urdf_model* m);
+RBD_API const rbd_model_desc* rbd_urdf_desc(const rbd_urdf_model* m);
+RBD_API int32_t rbd_urdf_nframes0(const rbd_urdf_model* m); /* frames before the CoM frames were appended        */
+RBD_API const char* rbd_urdf_robot_name(const rbd_urdf_model* m);
+RBD_API const char* rbd_urdf_joint_name(const rbd_urdf_model* m, int32_t joint);
+RBD_API const char* rbd_urdf_frame_name(const rbd_urdf_model* m, int32_t frame);
+RBD_API int32_t rbd_urdf_frame_type(const rbd_urdf_model* m, int32_t frame);
+/* first frame called `name` whose type is in `type_mask` (pinocchio Model::getFrameId), joint by name; -1 = none */
+RBD_API int32_t rbd_urdf_find_frame(const rbd_urdf_model* m, const char* name, int32_t type_mask);
+RBD_API int32_t rbd_urdf_find_joint(const rbd_urdf_model* m, const char* name);
+
 #ifdef __cplusplus
 }
 #endif

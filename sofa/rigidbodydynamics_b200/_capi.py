@@ -82,6 +82,9 @@ SYMBOLS = [
     "rbd_apply_host", "rbd_applyJ_host", "rbd_applyJT_host", "rbd_applyJT_rows_host", "rbd_eval_host", "rbd_addMDx_host", "rbd_addForce_host",
     "rbd_batch_create", "rbd_batch_destroy", "rbd_batch_bind_apply", "rbd_batch_bind_applyJ", "rbd_batch_bind_applyJT",
     "rbd_batch_apply", "rbd_batch_applyJ", "rbd_batch_applyJT",
+    "rbd_urdf_load_file", "rbd_urdf_load_string", "rbd_urdf_destroy", "rbd_urdf_desc", "rbd_urdf_nframes0",
+    "rbd_urdf_robot_name", "rbd_urdf_joint_name", "rbd_urdf_frame_name", "rbd_urdf_frame_type", "rbd_urdf_find_frame",
+    "rbd_urdf_find_joint",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -159,6 +162,17 @@ def load() -> C.CDLL:
         "rbd_batch_apply": (C.c_int, [vp, i64, i64]),
         "rbd_batch_applyJ": (C.c_int, [vp, i64, i64]),
         "rbd_batch_applyJT": (C.c_int, [vp, i64, i64]),
+        "rbd_urdf_load_file": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(vp)]),
+        "rbd_urdf_load_string": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(vp)]),
+        "rbd_urdf_destroy": (None, [vp]),
+        "rbd_urdf_desc": (C.POINTER(RbdModelDesc), [vp]),
+        "rbd_urdf_nframes0": (i32, [vp]),
+        "rbd_urdf_robot_name": (C.c_char_p, [vp]),
+        "rbd_urdf_joint_name": (C.c_char_p, [vp, i32]),
+        "rbd_urdf_frame_name": (C.c_char_p, [vp, i32]),
+        "rbd_urdf_frame_type": (i32, [vp, i32]),
+        "rbd_urdf_find_frame": (i32, [vp, C.c_char_p, i32]),
+        "rbd_urdf_find_joint": (i32, [vp, C.c_char_p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)        # AttributeError here = header/library mismatch

@@ -295,6 +295,42 @@ def probe_fp64_peak(device: int = 0) -> float:
     return float(t.value)
 
 
+def load_urdf(source: str, free_flyer: bool = False, is_text: bool = False) -> ModelDescriptor:
+    """URDF file (or text, ``is_text=True``) -> :class:`ModelDescriptor` through the library's own reader
+    (``rbd_urdf_load_file`` / ``rbd_urdf_load_string``, csrc/rbd_urdf.cpp) — what a C++ caller without pinocchio uses
+    in place of ``pinocchio::urdf::buildModel`` + the loader's frame tables (reference URDFModelLoader.cpp:126-183)."""
+    lib = _capi.load()
+    h = C.c_void_p()
+    fn = lib.rbd_urdf_load_string if is_text else lib.rbd_urdf_load_file
+    check(fn(source.encode(), int(bool(free_flyer)), C.byref(h)))
+    try:
+        cd = lib.rbd_urdf_desc(h).contents
+        nj, nf, no = int(cd.njoints), int(cd.nframes), int(cd.n_out)
+
+        def arr(ptr, n, dtype):
+            return np.array(np.ctypeslib.as_array(ptr, shape=(n,)), dtype=dtype, copy=True) if n else np.zeros(0, dtype)
+
+        d = ModelDescriptor(
+            name=(lib.rbd_urdf_robot_name(h) or b"robot").decode(),
+            parents=arr(cd.parents, nj, np.int32), jtype=arr(cd.jtype, nj, np.int32),
+            axis=arr(cd.axis, 3 * nj, np.float64).reshape(nj, 3),
+            placement=arr(cd.placement, 12 * nj, np.float64).reshape(nj, 12),
+            idx_q=arr(cd.idx_q, nj, np.int32), idx_v=arr(cd.idx_v, nj, np.int32),
+            inertia=arr(cd.inertia, 10 * nj, np.float64).reshape(nj, 10),
+            frame_parent=arr(cd.frame_parent, nf, np.int32),
+            frame_placement=arr(cd.frame_placement, 12 * nf, np.float64).reshape(nf, 12),
+            gravity=np.array([cd.gravity[0], cd.gravity[1], cd.gravity[2]], dtype=np.float64),
+            out_frames=arr(cd.out_frames, no, np.int32), nframes0=int(lib.rbd_urdf_nframes0(h)),
+            joint_names=[lib.rbd_urdf_joint_name(h, j).decode() for j in range(nj)],
+            frame_names=[lib.rbd_urdf_frame_name(h, f).decode() for f in range(nf)],
+            frame_types=[int(lib.rbd_urdf_frame_type(h, f)) for f in range(nf)],
+            note="from URDF through rbd_urdf_load (pinocchio 3.3.1 URDF conventions, restated; unpinned)")
+    finally:
+        lib.rbd_urdf_destroy(h)
+    d.validate()
+    return d
+
+
 def device_count() -> int:
     lib = _capi.load()
     n = C.c_int(0)
@@ -302,4 +338,4 @@ def device_count() -> int:
     return int(n.value) if rc == 0 else 0
 
 
-__all__ = ["Model", "Workspace", "RbdError", "device_count", "last_kernel_name"]
+__all__ = ["Model", "Workspace", "RbdError", "device_count", "last_kernel_name", "load_urdf"]

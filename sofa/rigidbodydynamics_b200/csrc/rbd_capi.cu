@@ -29,6 +29,7 @@ using namespace rbd;
 // --------------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static int set_err(int code, const std::string& msg) { g_err = msg; return code; }
+int rbd_internal_set_error(int code, const char* msg) { return set_err(code, msg ? msg : ""); }  // other translation units
 static int cuda_fail(cudaError_t e, const char* what) {
   // cudaGetLastError clears non-sticky launch errors so the next call starts clean
   cudaGetLastError();

@@ -371,13 +371,15 @@ def from_urdf_string(text: str, free_flyer: bool = False, name: Optional[str] = 
         body_frame[root_link] = b.add_frame(root_link, 0, _se3(), F_BODY)
 
     def classify(kind: str, axis: np.ndarray) -> Tuple[int, np.ndarray]:
-        ex = (np.array_equal(axis, [1, 0, 0]), np.array_equal(axis, [0, 1, 0]), np.array_equal(axis, [0, 0, 1]))
+        # pinocchio's extractCartesianAxis: axis.isApprox(Unit{X,Y,Z}) at Eigen's default precision 1e-12
+        n2 = float(axis @ axis)
+        ex = tuple(float((axis - e) @ (axis - e)) <= 1e-24 * min(n2, 1.0) for e in np.eye(3))
         table = {"revolute": (J_RX, J_RY, J_RZ, J_RU), "continuous": (J_RUBX, J_RUBY, J_RUBZ, J_RUBU),
                  "prismatic": (J_PX, J_PY, J_PZ, J_PU)}[kind]
         for k in range(3):
             if ex[k]:
-                return table[k], axis.copy()
-        return table[3], axis / np.linalg.norm(axis)
+                return table[k], np.eye(3)[k].copy()
+        return table[3], axis / math.sqrt(axis[0] * axis[0] + axis[1] * axis[1] + axis[2] * axis[2])
 
     def visit(link: str) -> None:
         for jn in child_of[link]:
