@@ -122,6 +122,20 @@ extern "C" int emul_eval_variant(const rbd_model_desc* d, int do_m, int do_tau, 
   if (warps_per_sm) *warps_per_sm = c.m.plan.warps * c.m.plan.blocks_per_sm;
   return c.m.plan.kvariant;
 }
+// the storage plan of the fused eval: {warps, blocks_per_sm, smem_doubles, tmem_doubles, tmem_cols, in_slots, kvariant,
+// dynamic shared-memory bytes of a full block, ysplit, fsplit}
+extern "C" int emul_eval_plan(const rbd_model_desc* d, int do_m, int do_tau, int* out /*[10]*/) {
+  Ctx c;
+  int rc = make_ctx(d, &c);
+  if (rc) return rc;
+  if (!plan_eval(&c.m, do_m != 0, do_tau != 0, true, 0, true)) return -100;
+  const EvalPlan& p = c.m.plan;
+  out[0] = p.warps; out[1] = p.blocks_per_sm; out[2] = p.smem_doubles; out[3] = p.tmem_doubles; out[4] = p.tmem_cols;
+  out[5] = p.in_slots; out[6] = p.kvariant;
+  out[7] = (int)(eval_model_bytes(c.m) + (size_t)p.warps * 32 * (p.smem_doubles + 3 * p.in_slots) * 8);
+  out[8] = p.ysplit; out[9] = p.fsplit;
+  return 0;
+}
 // sparse_m != 0: M holds the support-only fields (rbd_eval_soa_sparse).  variant: -1 = the generic sweep (namespace
 // rbd) on the planner's plan, -2 = the instantiation the planner picked (what the GPU launches), >= 0 = that
 // instantiation (RBD_EVAL_*; the model must qualify) on a plan made for it.
