@@ -169,6 +169,11 @@ RBD_API int rbd_workspace_set_applyJT_ring(rbd_workspace* ws, int enable, int32_
  * data.J / data.oMi, KinematicChainMapping.inl:365-373) — 8 (6 nv + 12 (njoints-1)) bytes per instance of workspace
  * capacity, allocated on first use — and every row only reads it; 0 = per-row sweep, no cache.  Same results.      */
 RBD_API int rbd_workspace_set_rows_cache(rbd_workspace* ws, int enable);
+/* Forward dynamics (rbd_aba_*): 1 (default) = the fused sweep — passes 1 + 2 of the articulated-body algorithm on on-chip
+ * level records (shared + tensor memory), only the 20 doubles per joint pass 3 needs go through global memory — whenever
+ * its storage plan fits the SM; 0 = always the first version with its whole per-joint state in a global-memory record
+ * (A/B knob; very deep trees take that path anyway).  Same results up to rounding.                              */
+RBD_API int rbd_workspace_set_aba_fused(rbd_workspace* ws, int enable);
 /* Storage plan the fused eval kernel uses on this workspace for the output set (with_M, with_tau):
  * out[0] warps per block, [1] blocks per SM, [2] shared-memory doubles per instance, [3] tensor-memory doubles per
  * instance, [4] tensor-memory columns per block, [5] 1 if the Y-stack lives in tensor memory, [6] shared-memory

@@ -137,6 +137,10 @@ class Workspace:
     def set_eval_tmem(self, enable: bool):
         check(self._lib.rbd_workspace_set_eval_tmem(self._h, 1 if enable else 0))
 
+    def set_aba_fused(self, enable: bool):
+        """A/B knob of forward dynamics: the fused sweep on on-chip level records (default) or the first version."""
+        check(self._lib.rbd_workspace_set_aba_fused(self._h, 1 if enable else 0))
+
     def set_rows_cache(self, enable: bool):
         """A/B knob of the constraint-row applyJT: cached Jacobians (default) or one sweep per row."""
         check(self._lib.rbd_workspace_set_rows_cache(self._h, 1 if enable else 0))

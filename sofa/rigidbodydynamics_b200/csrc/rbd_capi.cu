@@ -105,6 +105,13 @@ struct rbd_workspace {
   size_t rows_bytes = 0;
   double* aba_scratch[2] = {nullptr, nullptr};  // forward dynamics: one record per resident warp, per chunk stream of the
                                                 // host path ([1]: launches on slot[1].st, which may overlap the others)
+  // the fused forward-dynamics sweep (aba2): its planned joint table (host + device), state: 0 = not planned yet, 1 = in
+  // use, -1 = the planner found no configuration (or the knob is off): the global-memory sweep runs
+  DevModel* h_aba2 = nullptr;
+  DevModel* d_aba2 = nullptr;
+  int aba2_state = 0;
+  int use_aba2 = 1;
+  double* aba2_scratch[2] = {nullptr, nullptr};
   void* sel_buf = nullptr;  // getJ: selection + block pointers
   size_t sel_bytes = 0;
 };
@@ -207,6 +214,7 @@ static void ws_free(rbd_workspace* ws) {
   if (!ws) return;
   cudaFree(ws->d_sorted_k); cudaFree(ws->d_outk_parent); cudaFree(ws->d_sorted_ident); cudaFree(ws->d_sorted_pl); cudaFree(ws->d_outk_pl);
   cudaFree(ws->sel_buf); cudaFree(ws->aba_scratch[0]); cudaFree(ws->aba_scratch[1]);
+  cudaFree(ws->aba2_scratch[0]); cudaFree(ws->aba2_scratch[1]); cudaFree(ws->d_aba2); delete ws->h_aba2;
   cudaFree(ws->qcache); cudaFree(ws->rows_buf); cudaFree(ws->d_model); cudaFree(ws->jcache); cudaFree(ws->omicache); cudaFree(ws->jc_scratch);
   for (int k = 0; k < rbd_workspace::kPlans; ++k) { cudaFree(ws->d_plan[k]); delete ws->h_plan[k]; }
   for (int k = 0; k < 8; ++k) { cudaFree(ws->d_plan32[k]); delete ws->h_plan32[k]; }
@@ -295,6 +303,12 @@ RBD_API int rbd_workspace_set_eval_tmem(rbd_workspace* ws, int enable) {
   return RBD_OK;
 }
 
+RBD_API int rbd_workspace_set_aba_fused(rbd_workspace* ws, int enable) {
+  GUARD(ws);
+  if ((ws->use_aba2 != 0) != (enable != 0)) { ws->use_aba2 = enable ? 1 : 0; drop_plans(ws); }
+  return RBD_OK;
+}
+
 static int ensure_plan(rbd_workspace* ws, int pk);
 RBD_API int rbd_workspace_set_applyJT_ring(rbd_workspace* ws, int enable, int32_t* ring_slots) {
   GUARD(ws);
@@ -366,6 +380,8 @@ static void drop_plans(rbd_workspace* ws) {
   ws->jt_ring_slots = -1; ws->djt_ring_slots = -1;
   memset(ws->plan_failed, 0, sizeof(ws->plan_failed));
   for (int k = 0; k < 8; ++k) { delete ws->h_plan32[k]; ws->h_plan32[k] = nullptr; }
+  delete ws->h_aba2; ws->h_aba2 = nullptr; ws->aba2_state = 0;
+  cudaFree(ws->aba2_scratch[0]); cudaFree(ws->aba2_scratch[1]); ws->aba2_scratch[0] = ws->aba2_scratch[1] = nullptr;
 }
 
 RBD_API int rbd_workspace_get_eval_plan(rbd_workspace* ws, int with_M, int with_tau, int32_t out[8]) {
@@ -522,6 +538,36 @@ static int aba_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, c
     if (dm.joint[i].type == JT_FF && !(i == 1 && dm.joint[i].parent == 0))
       return set_err(RBD_ERR_UNSUPPORTED, "aba supports a free-flyer only as the root joint (joint 1 on the universe)");
   const int sc = (ws->slot[1].st && st == ws->slot[1].st) ? 1 : 0;
+  // the fused sweep (passes 1 + 2 on on-chip level records, aba2_instance) whenever its storage plan fits the SM
+  if (ws->aba2_state == 0) {
+    ws->aba2_state = -1;
+    if (ws->use_aba2) {
+      DevModel* h = new (std::nothrow) DevModel(dm);
+      if (!h) return set_err(RBD_ERR_ALLOC, "out of host memory");
+      if (plan_aba2(h, ws->use_tmem != 0)) {
+        if (!ws->d_aba2) CK(cudaMalloc(&ws->d_aba2, sizeof(DevModel)));
+        CK(cudaMemcpyAsync(ws->d_aba2, h, dev_model_bytes(*h), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));  // `h` may be replaced by drop_plans; the upload must not read it later
+        ws->h_aba2 = h; ws->aba2_state = 1;
+      } else {
+        delete h;
+      }
+    }
+  }
+  if (ws->aba2_state == 1) {
+    if (!ws->aba2_scratch[sc]) {
+      int warps = 0;
+      AbaArgs S{0, 32, nullptr, nullptr, nullptr, nullptr, nullptr};
+      CK(launch_aba2(*ws->h_aba2, ws->d_aba2, S, ws->num_sms, &warps, st));
+      const size_t bytes = (size_t)warps * (size_t)(RBD_ABA2_REC * (dm.njoints - 1)) * 32 * sizeof(double);
+      cudaError_t e = cudaMalloc(&ws->aba2_scratch[sc], bytes > 0 ? bytes : 256);
+      if (e != cudaSuccess) { cudaGetLastError(); return set_err(RBD_ERR_ALLOC, std::string("cudaMalloc(aba scratch): ") + cudaGetErrorString(e)); }
+    }
+    AbaArgs A{n, tile, q, v, tau, ddq, ws->aba2_scratch[sc]};
+    CK(launch_aba2(*ws->h_aba2, ws->d_aba2, A, ws->num_sms, nullptr, st));
+    if (n > 0) ws->launches++;
+    return RBD_OK;
+  }
   if (!ws->aba_scratch[sc]) {
     int warps = 0;
     AbaArgs S{0, 32, nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -156,6 +156,10 @@ inline size_t eval_model_bytes(const DevModelT<real>& m) {
   return (dev_model_bytes(m) + 15) / 16 * 16 + ((size_t)m.prog_len * 4 + 15) / 16 * 16 + 16;
 }
 
+#define RBD_ABA2_REC 20 /* doubles per joint of the global pass-3 record of the fused forward-dynamics sweep (rbd_dyn_body.h) */
+// ... and the fused forward-dynamics kernel (aba2_kernel): the joint table rounded to 16 bytes plus the two spare words
+inline size_t aba2_model_bytes(const DevModelT<double>& m) { return (dev_model_bytes(m) + 15) / 16 * 16 + 16; }
+
 // 8-byte words the vector mapping kernels stage behind the joint table for the per-output tables of n_out outputs:
 // placements (12 doubles each), output indices and identity flags (one int each, padded to even counts)
 #if defined(__CUDACC__)

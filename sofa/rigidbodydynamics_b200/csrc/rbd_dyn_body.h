@@ -1,0 +1,317 @@
+// rbd_dyn_body.h — forward dynamics, second version (aba2_instance).  Included from rbd_sweeps_body.h inside namespace
+// rbd (FP64 only); the formulation (world frame, passes 1-3) is the one documented above aba_instance.
+//
+// What changed against aba_instance: passes 1 and 2 are FUSED on the depth-first order of the joints.  The sweep walks
+// root -> leaf keeping, per DEPTH LEVEL that holds a joint with children, one on-chip record
+//     one child :  [h (3) | I_O (6) | p^A (6)]                    15 doubles  (the joint's own inertia and bias force)
+//     >= 2      :  [I^A (21) | p^A (6)] + restart [R | p | v (18)]  45 doubles  (accumulator of the children's I^a, p^a)
+// and at a leaf runs pass 2 upwards at once: U, 1/D, u of the joint, I^a / p^a handed to the parent IN REGISTERS as long
+// as that parent is complete (this was its last child), added to the parent's accumulator record otherwise.  Only one
+// joint per depth level is open at any time, so records are indexed by level: O(depth) on-chip state (shared memory +
+// tensor memory, planned by plan_aba2) instead of the O(njoints) global-memory record of aba_instance.  What pass 3
+// needs of EVERY joint after the whole backward pass — A (6), c (6), U (6), 1/D, u = 20 doubles — is the only thing that
+// still goes through global memory: written once (A, c in pass 1, U, 1/D, u in pass 2), A and c re-read by the unwind,
+// all 20 read by pass 3.  Talos: 10.6 KB + 3.2 KB per instance instead of 29 KB.
+// Pass 3 parks the acceleration of a joint with >= 2 children in that joint's (now free) level record.
+//
+// Level-record offsets: DevJoint::offA (record) / DevJoint::boff (restart record), bit RBD_BOFF_TMEM = tensor memory.
+// All lanes of a warp execute the sweep together (tensor-memory accesses are warp-collective): the kernel lets lanes
+// past the end of the batch recompute the last instance.
+
+// (RBD_ABA2_REC = 20 doubles per joint of the global pass-3 record: rbd_dev_model.h)
+#define RBD_ABA2_LEV1 15 /* level record of a joint with one child                                                */
+#define RBD_ABA2_LEVB 27 /* accumulator record of a joint with >= 2 children ...                                  */
+#define RBD_ABA2_RST 18  /* ... and its restart record                                                            */
+
+template <int N>
+RBD_HD void lev_ld(const Stack& S, const TmStack& T, int off, real* v) {
+  if (off & RBD_BOFF_TMEM) {
+    T.template ldv<N>(off & RBD_BOFF_MASK, v);
+  } else {
+#pragma unroll
+    for (int e = 0; e < N; ++e) v[e] = S.ld(off + e);
+  }
+}
+template <int N>
+RBD_HD void lev_st(const Stack& S, const TmStack& T, int off, const real* v) {
+  if (off & RBD_BOFF_TMEM) {
+    T.template stv<N>(off & RBD_BOFF_MASK, v);
+  } else {
+#pragma unroll
+    for (int e = 0; e < N; ++e) S.st(off + e, v[e]);
+  }
+}
+template <int N>
+RBD_HD void lev_add(const Stack& S, const TmStack& T, int off, const real* v) {
+  if (off & RBD_BOFF_TMEM) {
+    T.template addv<N>(off & RBD_BOFF_MASK, v);
+  } else {
+#pragma unroll
+    for (int e = 0; e < N; ++e) S.add(off + e, v[e]);
+  }
+}
+
+// S += the rigid-body inertia (m, h, I_O) as a symmetric 6 x 6 matrix (sym6_from_inertia, accumulating)
+RBD_HD void sym6_add_inertia(real m, const real* h, const real* I, real* S6) {
+  S6[s6(0, 0)] += m; S6[s6(1, 1)] += m; S6[s6(2, 2)] += m;
+  S6[s6(0, 4)] += h[2]; S6[s6(0, 5)] -= h[1];
+  S6[s6(1, 3)] -= h[2]; S6[s6(1, 5)] += h[0];
+  S6[s6(2, 3)] += h[1]; S6[s6(2, 4)] -= h[0];
+  S6[s6(3, 3)] += I[0]; S6[s6(3, 4)] += I[1]; S6[s6(3, 5)] += I[3];
+  S6[s6(4, 4)] += I[2]; S6[s6(4, 5)] += I[4];
+  S6[s6(5, 5)] += I[5];
+}
+
+// Root free-flyer at the end of the backward pass: (X^T I^A X) qdd = tau - X^T (p^A + I^A a'), a' = -g (c = 0);
+// Cholesky in registers.  Rp = R | p of the joint; returns qdd (6) and the joint's world acceleration a' + X qdd.
+template <class FLD>
+RBD_HD void aba_ff_root_solve(const DevModel& m, const real* Rp, const real* IA, const real* pA, const FLD& tau, int iv,
+                              real* b, real* acc) {
+  real a0[6], f[6];
+  a0[0] = -m.gravity[0]; a0[1] = -m.gravity[1]; a0[2] = -m.gravity[2]; a0[3] = a0[4] = a0[5] = 0;
+  sym6_mul(IA, a0, f);
+#pragma unroll
+  for (int e = 0; e < 6; ++e) f[e] += pA[e];
+  ff_rows(Rp, Rp + 9, f, b);
+#pragma unroll
+  for (int e = 0; e < 6; ++e) b[e] = tau.ld(iv + e) - b[e];
+  real D[21];  // upper triangle of X^T I^A X
+#pragma unroll
+  for (int cc = 0; cc < 6; ++cc) {
+    real Xc[6], F[6], col[6];
+    RBD_FF_COL(Xc, Rp, (Rp + 9), cc);
+    sym6_mul(IA, Xc, F);
+    ff_rows(Rp, Rp + 9, F, col);
+#pragma unroll
+    for (int r = 0; r <= cc; ++r) D[s6(r, cc)] = col[r];
+  }
+  // D = L L^T (D[s6(r, c)], r <= c, holds L(c, r)), then the two triangular solves
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    real d = D[s6(k, k)];
+#pragma unroll
+    for (int j = 0; j < k; ++j) d -= D[s6(j, k)] * D[s6(j, k)];
+    d = sqrt(d);
+    D[s6(k, k)] = d;
+    const real di = real(1) / d;
+#pragma unroll
+    for (int r = k + 1; r < 6; ++r) {
+      real t = D[s6(k, r)];
+#pragma unroll
+      for (int j = 0; j < k; ++j) t -= D[s6(j, r)] * D[s6(j, k)];
+      D[s6(k, r)] = t * di;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    real t = b[k];
+#pragma unroll
+    for (int j = 0; j < k; ++j) t -= D[s6(j, k)] * b[j];
+    b[k] = t / D[s6(k, k)];
+  }
+#pragma unroll
+  for (int k = 5; k >= 0; --k) {
+    real t = b[k];
+#pragma unroll
+    for (int j = k + 1; j < 6; ++j) t -= D[s6(k, j)] * b[j];
+    b[k] = t / D[s6(k, k)];
+  }
+  real al[3], aa[3], tx, ty, tz;
+#pragma unroll
+  for (int e = 0; e < 3; ++e) {
+    al[e] = Rp[3 * e] * b[0] + Rp[3 * e + 1] * b[1] + Rp[3 * e + 2] * b[2];
+    aa[e] = Rp[3 * e] * b[3] + Rp[3 * e + 1] * b[4] + Rp[3 * e + 2] * b[5];
+  }
+  RBD_CROSS(tx, ty, tz, Rp[9], Rp[10], Rp[11], aa[0], aa[1], aa[2]);
+  acc[0] = a0[0] + al[0] + tx; acc[1] = a0[1] + al[1] + ty; acc[2] = a0[2] + al[2] + tz;
+  acc[3] = aa[0]; acc[4] = aa[1]; acc[5] = aa[2];
+}
+
+// X: this thread's global pass-3 record (ld(e) / st(e, v)), RBD_ABA2_REC doubles per joint; S / T: on-chip level records.
+template <class FLD, class SCR>
+RBD_HD void aba2_instance(const DevModel& m, const FLD& q, const FLD& v, const FLD& tau, const FLD& ddq, const SCR& X,
+                          const Stack& S, const TmStack& T) {
+  const int nj = m.njoints;
+  real R[9], p[3], vel[6];
+#define RBD_ABA_ROOT()                                                                          \
+  do {                                                                                          \
+    R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;   \
+    p[0] = p[1] = p[2] = 0;                                                                     \
+    _Pragma("unroll") for (int e_ = 0; e_ < 6; ++e_) vel[e_] = 0;                               \
+  } while (0)
+  RBD_ABA_ROOT();
+  // ---- passes 1 + 2 ---------------------------------------------------------------------------------------------
+  for (int i = 1; i < nj; ++i) {
+    const DevJoint& jn = m.joint[i];
+    const int par = jn.parent;
+    const int rec = RBD_ABA2_REC * (i - 1);
+    if (par != i - 1) {  // a new branch starts below `par`
+      if (par == 0) {
+        RBD_ABA_ROOT();
+      } else {
+        real t[RBD_ABA2_RST];
+        lev_ld<RBD_ABA2_RST>(S, T, m.joint[par].boff, t);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) R[e] = t[e];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) p[e] = t[9 + e];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) vel[e] = t[12 + e];
+      }
+    }
+    const bool ff = jn.type == JT_FF;
+    real q0 = 0, q1 = 0, aw[3];
+    if (!ff) {
+      q0 = q.ld(jn.idx_q);
+      if (is_unbounded(jn.type)) q1 = q.ld(jn.idx_q + 1);
+    }
+    fk_joint(jn, R, p, q0, q1, q, aw);
+    real A[6], cr[6], vj[6];
+    if (!ff) {
+      subspace_1dof(jn.type, p, aw, A);
+      const real qd = v.ld(jn.idx_v);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) { X.st(rec + e, A[e]); vj[e] = A[e] * qd; }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) X.st(rec + e, R[e]);
+#pragma unroll
+      for (int e = 0; e < 3; ++e) X.st(rec + 9 + e, p[e]);
+      ff_act(R, p, v, jn.idx_v, vj);
+    }
+#pragma unroll
+    for (int e = 0; e < 6; ++e) vel[e] += vj[e];
+    if (!ff) {  // c = v x vJ (a root free-flyer has v = vJ, hence c = 0)
+      real tx, ty, tz;
+      RBD_CROSS(cr[0], cr[1], cr[2], vel[3], vel[4], vel[5], vj[0], vj[1], vj[2]);
+      RBD_CROSS(tx, ty, tz, vel[0], vel[1], vel[2], vj[3], vj[4], vj[5]);
+      cr[0] += tx; cr[1] += ty; cr[2] += tz;
+      RBD_CROSS(cr[3], cr[4], cr[5], vel[3], vel[4], vel[5], vj[3], vj[4], vj[5]);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) X.st(rec + 6 + e, cr[e]);
+    }
+    real Y[10], h[6], pA[6];
+    inertia_world(jn, R, p, Y);
+    inertia_mul(Y, vel, h);
+    {
+      real tx, ty, tz;
+      RBD_CROSS(pA[0], pA[1], pA[2], vel[3], vel[4], vel[5], h[0], h[1], h[2]);
+      RBD_CROSS(pA[3], pA[4], pA[5], vel[3], vel[4], vel[5], h[3], h[4], h[5]);
+      RBD_CROSS(tx, ty, tz, vel[0], vel[1], vel[2], h[0], h[1], h[2]);
+      pA[3] += tx; pA[4] += ty; pA[5] += tz;
+    }
+    if (jn.nchild == 1) {
+      real t[RBD_ABA2_LEV1];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) t[e] = Y[1 + e];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) t[9 + e] = pA[e];
+      lev_st<RBD_ABA2_LEV1>(S, T, jn.offA, t);
+      continue;
+    }
+    real IA[21 + 6];  // I^A | p^A
+    sym6_from_inertia(Y, IA);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) IA[21 + e] = pA[e];
+    if (jn.nchild >= 2) {
+      lev_st<RBD_ABA2_LEVB>(S, T, jn.offA, IA);
+      real t[RBD_ABA2_RST];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) t[e] = R[e];
+#pragma unroll
+      for (int e = 0; e < 3; ++e) t[9 + e] = p[e];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) t[12 + e] = vel[e];
+      lev_st<RBD_ABA2_RST>(S, T, jn.boff, t);
+      continue;
+    }
+    // ---- leaf: pass 2 upwards for every joint this leaf completes -----------------------------------------------
+    const int stop_at = (i + 1 < nj) ? m.joint[i + 1].parent : 0;  // the joint that still has a child to come
+    int cur = i;
+    for (;;) {
+      const DevJoint& jc = m.joint[cur];
+      const int rc = RBD_ABA2_REC * (cur - 1);
+      if (jc.type == JT_FF) {  // the root (the host checks that a free-flyer is joint 1 on the universe)
+        real Rp[12], b[6], acc[6];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) Rp[e] = X.ld(rc + e);
+        aba_ff_root_solve(m, Rp, IA, IA + 21, tau, jc.idx_v, b, acc);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) { ddq.st(jc.idx_v + e, b[e]); X.st(rc + 12 + e, acc[e]); }
+        break;
+      }
+      real U[6];
+      sym6_mul(IA, A, U);
+      const real dinv = real(1) / dot6(A, U);
+      const real u = tau.ld(jc.idx_v) - dot6(A, IA + 21);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) X.st(rc + 12 + e, U[e]);
+      X.st(rc + 18, dinv);
+      X.st(rc + 19, u);
+      const int pp = jc.parent;
+      if (pp == 0) break;
+      // I^a = I^A - U U^T / D ;  p^a = p^A + I^a c + U u / D
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int cc = r; cc < 6; ++cc) IA[s6(r, cc)] -= U[r] * (U[cc] * dinv);
+      {
+        real Ic[6];
+        sym6_mul(IA, cr, Ic);
+        const real ud = u * dinv;
+#pragma unroll
+        for (int e = 0; e < 6; ++e) IA[21 + e] += Ic[e] + U[e] * ud;
+      }
+      const DevJoint& jp = m.joint[pp];
+      if (pp == stop_at) {  // the parent has another child to come: park the contribution there
+        lev_add<RBD_ABA2_LEVB>(S, T, jp.offA, IA);
+        break;
+      }
+      // the parent is complete: its own part (one child) or its accumulator (>= 2 children) joins in registers
+      if (jp.nchild >= 2) {
+        real t[RBD_ABA2_LEVB];
+        lev_ld<RBD_ABA2_LEVB>(S, T, jp.offA, t);
+#pragma unroll
+        for (int e = 0; e < RBD_ABA2_LEVB; ++e) IA[e] += t[e];
+      } else {
+        real t[RBD_ABA2_LEV1];
+        lev_ld<RBD_ABA2_LEV1>(S, T, jp.offA, t);
+        sym6_add_inertia(jp.Y[0], t, t + 3, IA);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) IA[21 + e] += t[9 + e];
+      }
+      cur = pp;
+      if (jp.type != JT_FF) {
+        const int rp = RBD_ABA2_REC * (pp - 1);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) { A[e] = X.ld(rp + e); cr[e] = X.ld(rp + 6 + e); }
+      }
+    }
+  }
+  // ---- pass 3 ----------------------------------------------------------------------------------------------------
+  real acc[6];
+  for (int i = 1; i < nj; ++i) {
+    const DevJoint& jn = m.joint[i];
+    const int par = jn.parent;
+    const int rec = RBD_ABA2_REC * (i - 1);
+    if (jn.type == JT_FF) {  // solved at the end of the backward pass
+#pragma unroll
+      for (int e = 0; e < 6; ++e) acc[e] = X.ld(rec + 12 + e);
+    } else {
+      if (par == 0) {
+        acc[0] = -m.gravity[0]; acc[1] = -m.gravity[1]; acc[2] = -m.gravity[2]; acc[3] = acc[4] = acc[5] = 0;
+      } else if (par != i - 1) {  // (else: acc still holds the parent's acceleration)
+        lev_ld<6>(S, T, m.joint[par].offA, acc);
+      }
+      real A[6], U[6];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) { A[e] = X.ld(rec + e); U[e] = X.ld(rec + 12 + e); acc[e] += X.ld(rec + 6 + e); }
+      const real qdd = (X.ld(rec + 19) - dot6(U, acc)) * X.ld(rec + 18);
+      ddq.st(jn.idx_v, qdd);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) acc[e] += A[e] * qdd;
+    }
+    if (jn.nchild >= 2) lev_st<6>(S, T, jn.offA, acc);
+  }
+#undef RBD_ABA_ROOT
+}

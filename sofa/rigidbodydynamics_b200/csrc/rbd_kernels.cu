@@ -669,6 +669,7 @@ static const int kMaxSmemOptin = 227 * 1024;
 // instantiation back from the launch instead of deriving it from the model).
 static thread_local const void* g_last_kernel = nullptr;
 #define RBD_NOTE(K) (g_last_kernel = reinterpret_cast<const void*>(K))
+void note_kernel(const void* fn) { g_last_kernel = fn; }
 const char* last_kernel_mangled() {
   const char* name = nullptr;
   if (!g_last_kernel || cudaFuncGetName(&name, g_last_kernel) != cudaSuccess) { cudaGetLastError(); return nullptr; }

@@ -97,6 +97,12 @@ cudaError_t launch_frame_jacobian(const DevModel& m, const DevModel* d_model, co
 // (sizing call: nothing is launched)
 cudaError_t launch_aba(const DevModel& m, const DevModel* d_model, const AbaArgs& a, int num_sms, int* scratch_warps,
                        cudaStream_t st);
+// the fused variant (aba2_instance; rbd_kernels_dyn.cu): `planned_host_model` planned with plan_aba2, `d_model` its device
+// copy; a.scratch holds RBD_ABA2_REC * (njoints - 1) * 32 doubles per resident warp (sizing call as above)
+cudaError_t launch_aba2(const DevModel& planned_host_model, const DevModel* d_model, const AbaArgs& a, int num_sms,
+                        int* scratch_warps, cudaStream_t st);
+// records the __global__ function a launch_* of another translation unit started (rbd_last_kernel_name)
+void note_kernel(const void* fn);
 // assembled mapping Jacobian: block rows of the n_sel selected outputs (device arrays sel [n_sel], blk_ptr [n_sel + 1])
 // of n instances, val [n][6 blk_ptr[n_sel]]
 cudaError_t launch_getJ(const DevModel& m, const DevModel* d_model, const DevTables& tb, long long n, int n_sel, const int* sel,

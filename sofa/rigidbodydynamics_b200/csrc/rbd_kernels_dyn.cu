@@ -1,0 +1,103 @@
+// rbd_kernels_dyn.cu — forward-dynamics kernels on the depth-first storage plan (aba2_instance, rbd_dyn_body.h).
+//
+// Same launch shape as the fused eval: one persistent block per SM, its warps stride over the batch's 32-instance
+// tiles; the joint table is staged once per block into shared memory; level records of the sweep live in shared memory
+// and — through tcgen05.ld / tcgen05.st, one private column range per thread — in tensor memory (plan_aba2).
+#include <cuda_runtime.h>
+
+#include "rbd_kernels.h"
+#include "rbd_sweeps.h"
+
+namespace rbd {
+
+extern __shared__ __align__(16) double rbd_smem[];
+
+namespace {
+struct GlobalRec {
+  double* p;  // this lane's column of its warp's [E][32] record
+  __device__ __forceinline__ double ld(int e) const { return p[e * 32]; }
+  __device__ __forceinline__ void st(int e, double v) const { p[e * 32] = v; }
+};
+}  // namespace
+
+template <int TILE>
+__global__ void __launch_bounds__(256, 1) aba2_kernel(const DevModel* __restrict__ gm, const int model_words, const AbaArgs a) {
+  // the last two staged words are spare: the tensor-memory base address lands there
+  unsigned* const tm_base_p = reinterpret_cast<unsigned*>(rbd_smem + model_words - 2);
+  {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gm);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(rbd_smem);
+    for (int w = threadIdx.x; w < model_words - 2; w += blockDim.x) dst[w] = src[w];
+  }
+  __syncthreads();
+  const DevModel& m = *reinterpret_cast<const DevModel*>(rbd_smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int tm_cols = m.plan.tmem_cols;
+  TmStack T;
+  T.base = 0;
+  if (tm_cols > 0) {
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"l"(
+                       (unsigned long long)__cvta_generic_to_shared(tm_base_p)),
+                   "r"(tm_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    T.base = *tm_base_p + (((unsigned)(warp & 3) * 32u) << 16) + (unsigned)(warp >> 2) * 2u * (unsigned)m.plan.tmem_doubles;
+  }
+  const Stack S = make_stack(rbd_smem + model_words, threadIdx.x, m.plan.smem_doubles);
+  const long long gw = (long long)blockIdx.x * wpb + warp;
+  const GlobalRec X{a.scratch + gw * (long long)(RBD_ABA2_REC * (m.njoints - 1)) * 32 + lane};
+  const long long ntiles = (a.n + 31) / 32;
+  for (long long t = gw; t < ntiles; t += (long long)gridDim.x * wpb) {
+    long long inst = t * 32 + lane;
+    if (inst >= a.n) inst = a.n - 1;  // lanes past the end recompute the last instance (warp-collective tensor-memory accesses)
+    aba2_instance(m, make_field_t<TILE>(const_cast<double*>(a.q), inst, m.nq, a.tile),
+                  make_field_t<TILE>(const_cast<double*>(a.v), inst, m.nv, a.tile),
+                  make_field_t<TILE>(const_cast<double*>(a.tau), inst, m.nv, a.tile),
+                  make_field_t<TILE>(a.ddq, inst, m.nv, a.tile), X, S, T);
+  }
+  if (tm_cols > 0) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tm_base_p), "r"(tm_cols) : "memory");
+  }
+}
+
+template <class K>
+static cudaError_t dyn_attr(K kern) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
+cudaError_t launch_aba2(const DevModel& hm, const DevModel* d_model, const AbaArgs& a, int num_sms, int* scratch_warps,
+                        cudaStream_t st) {
+  const int mw = (int)(aba2_model_bytes(hm) / 8);
+  const int wpb = hm.plan.warps, block = wpb * 32;
+  const long long ntiles = (a.n + 31) / 32;
+  long long grid = (ntiles + wpb - 1) / wpb;
+  if (grid > num_sms) grid = num_sms;  // one block per SM, warps stride over the tiles
+  if (grid < 1) grid = 1;
+  if (scratch_warps) *scratch_warps = num_sms * wpb;
+  if (!a.scratch || a.n <= 0) return cudaSuccess;
+  const size_t smem = (size_t)mw * 8 + (size_t)block * hm.plan.smem_doubles * 8;
+  static thread_local bool attr_done[2] = {false, false};
+  cudaError_t e = cudaSuccess;
+  if (a.tile == 32) {
+    if (!attr_done[1]) { e = dyn_attr(aba2_kernel<32>); if (e != cudaSuccess) return e; attr_done[1] = true; }
+    note_kernel(reinterpret_cast<const void*>(aba2_kernel<32>));
+    aba2_kernel<32><<<(unsigned)grid, block, smem, st>>>(d_model, mw, a);
+  } else {
+    if (!attr_done[0]) { e = dyn_attr(aba2_kernel<0>); if (e != cudaSuccess) return e; attr_done[0] = true; }
+    note_kernel(reinterpret_cast<const void*>(aba2_kernel<0>));
+    aba2_kernel<0><<<(unsigned)grid, block, smem, st>>>(d_model, mw, a);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace rbd

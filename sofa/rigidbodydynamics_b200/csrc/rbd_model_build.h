@@ -564,6 +564,59 @@ inline std::vector<unsigned long long> build_jt_blob(const DevModel* m, const st
   return blob;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Storage plan of the fused forward-dynamics sweep (aba2_instance, rbd_dyn_body.h): one record per DEPTH LEVEL that
+// holds a joint with children — 15 doubles (one child) or 27 + 18 (>= 2 children: accumulator + restart record), the
+// maximum over the joints at that depth.  Levels are placed whole, largest first, into the thread's share of shared
+// memory and, when that is full, of tensor memory; the plan takes the largest block (<= max_warps warps, one block per
+// SM) for which every level fits.  Fills m->plan (warps, smem_doubles, tmem_doubles, tmem_cols), joint[*].offA (level
+// record) and joint[*].boff (restart record), bit RBD_BOFF_TMEM = tensor memory.  Returns false when nothing fits (very
+// deep trees): the caller keeps the global-memory sweep (aba_instance).
+inline bool plan_aba2(DevModel* m, bool use_tmem, int max_warps = B200Limits::kMaxWarpsPerBlock, int forced_warps = 0) {
+  const int nj = m->njoints;
+  const int D = m->max_depth_internal;
+  std::vector<int> size(D + 1, 0);
+  for (int i = 1; i < nj; ++i) {
+    const DevJoint& j = m->joint[i];
+    if (j.nchild <= 0) continue;
+    if (j.depth > D) return false;
+    size[j.depth] = std::max(size[j.depth], j.nchild >= 2 ? 27 + 18 : 15);
+  }
+  std::vector<int> order;
+  for (int d = 1; d <= D; ++d)
+    if (size[d] > 0) order.push_back(d);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return size[a] > size[b]; });
+  const size_t model_bytes = aba2_model_bytes(*m);
+  for (int W = max_warps; W >= 1; --W) {
+    if (forced_warps > 0 && W != forced_warps) continue;
+    if (model_bytes + B200Limits::kSmemReservedPerBlock >= (size_t)B200Limits::kSmemBytes) return false;
+    const int cap_s = (int)(((size_t)B200Limits::kSmemBytes - model_bytes - B200Limits::kSmemReservedPerBlock) / ((size_t)W * 32 * 8));
+    const int cap_t = use_tmem ? (B200Limits::kTmemCols / ((W + 3) / 4)) / 2 : 0;
+    std::vector<int> off(D + 1, 0);
+    int s_used = 0, t_used = 0;
+    bool ok = true;
+    for (int d : order) {
+      if (s_used + size[d] <= cap_s) { off[d] = s_used; s_used += size[d]; }
+      else if (t_used + size[d] <= cap_t) { off[d] = t_used | RBD_BOFF_TMEM; t_used += size[d]; }
+      else { ok = false; break; }
+    }
+    if (!ok) continue;
+    EvalPlan pl{};
+    pl.smem_doubles = s_used; pl.tmem_doubles = t_used; pl.warps = W; pl.blocks_per_sm = 1;
+    pl.tmem_cols = t_used > 0 ? pow2_cols(2 * t_used * ((W + 3) / 4)) : 0;
+    m->plan = pl;
+    for (int i = 1; i < nj; ++i) {
+      DevJoint& j = m->joint[i];
+      j.offA = 0; j.boff = 0;
+      if (j.nchild <= 0) continue;
+      j.offA = off[j.depth];
+      if (j.nchild >= 2) j.boff = (off[j.depth] & RBD_BOFF_TMEM) | ((off[j.depth] & RBD_BOFF_MASK) + 27);
+    }
+    return true;
+  }
+  return false;
+}
+
 // shared-memory doubles per instance of the mapping kernels
 // (branch slots; the kernels add their input ring behind them: kMapSlots (apply) / 2 kMapSlots (applyJ) per instance)
 static constexpr int kMapSlots = 4;  // == RBD_MAP_SLOTS (rbd_sweeps_body.h)

@@ -2937,4 +2937,5 @@ RBD_HD void aba_instance(const DevModel& m, const FLD& q, const FLD& v, const FL
 #undef RBD_ABA_ROOT
 }
 
+#include "rbd_dyn_body.h"
 #endif  /* !RBD_BODY_F32 && !RBD_BODY_EVAL_ONLY */

@@ -484,12 +484,19 @@ def test_world_jacobian_by_finite_differences(emul, name):
     assert helpers.fd_world_jacobian_error(eval_fn, d, q) <= 1e-7
 
 
+# which forward-dynamics body: the first version (global-memory record), the fused sweep on the planner's plan, the fused
+# sweep without tensor memory, and on blocks of 3 warps (other split of the levels between the two spaces)
+ABA_BODIES = ["v1", "fused", "fused_smem_only", "fused_w3"]
+
+
 @pytest.mark.parametrize("d", MODELS, ids=IDS)
 @pytest.mark.parametrize("tile", [32, 11])
-def test_aba_body_matches_oracle_and_golden(emul, d, tile):
-    """aba_instance (world-frame articulated-body sweep, scratch record per thread) against the oracle's ABA (pinocchio's
-    LOCAL-convention algorithm), the mpmath forward-dynamics golden vectors, and the round trip through the oracle's
-    RNEA.  Tolerance 1e-9: the conditioning of M(q) enters (the golden solve is exact to 50 digits)."""
+@pytest.mark.parametrize("body", ABA_BODIES)
+def test_aba_body_matches_oracle_and_golden(emul, d, tile, body):
+    """aba_instance (world-frame articulated-body sweep, scratch record per thread) and aba2_instance (passes 1 + 2 fused
+    on depth-level records in shared / tensor memory) against the oracle's ABA (pinocchio's LOCAL-convention algorithm),
+    the mpmath forward-dynamics golden vectors, and the round trip through the oracle's RNEA.  Tolerance 1e-9: the
+    conditioning of M(q) enters (the golden solve is exact to 50 digits)."""
     import json
     import os
     import oracle
@@ -508,7 +515,15 @@ def test_aba_body_matches_oracle_and_golden(emul, d, tile):
     nt = (n + tile - 1) // tile
     ddq = np.full((nt, max(1, d.nv), tile), np.nan)
     qs, vs, ts = to_tiled(q, tile), to_tiled(v, tile), to_tiled(tau, tile)
-    assert emul.emul_aba(C.addressof(cd), n, tile, P(qs), P(vs), P(ts), P(ddq)) == 0, emul.emul_last_error()
+    if body == "v1":
+        assert emul.emul_aba(C.addressof(cd), n, tile, P(qs), P(vs), P(ts), P(ddq)) == 0, emul.emul_last_error()
+    else:
+        plan = (C.c_int * 4)()
+        rc = emul.emul_aba2(C.addressof(cd), n, tile, 0 if body == "fused_smem_only" else 1, 3 if body == "fused_w3" else 0,
+                            P(qs), P(vs), P(ts), P(ddq), plan)
+        assert rc == 0, emul.emul_last_error()
+        if body == "fused" and d.name == "talos_reduced":
+            assert list(plan)[:3] == [8, 105, 105]          # 8 warps per SM: 45 + 45 + 15 shared, 7 x 15 tensor memory
     got = from_tiled(ddq, n)[:, :d.nv]
     ref = np.stack([orc.aba(q[i], v[i], tau[i]) for i in range(n)])
     assert rel_err(got, ref) <= 1e-9

@@ -881,10 +881,12 @@ def test_applyDJT_geometric_stiffness(torch_mod, api, name, tile):
 
 @pytest.mark.parametrize("d", MODELS, ids=IDS)
 @pytest.mark.parametrize("tile", [32, 1000])
-def test_aba_matches_oracle(torch_mod, api, d, tile):
+@pytest.mark.parametrize("fused", [1, 0])
+def test_aba_matches_oracle(torch_mod, api, d, tile, fused):
     """rbd_aba_soa (forward dynamics) against the oracle's articulated-body algorithm
     (pinocchio's LOCAL-convention restatement), the mpmath forward-dynamics golden vectors (M^-1 (tau - nle) solved in
-    50 digits by the independent implementation) and the round trip through the GPU's own RNEA."""
+    50 digits by the independent implementation) and the round trip through the GPU's own RNEA.  Both kernels: the fused
+    sweep on on-chip level records (aba2_kernel, the default) and the first version (aba_kernel)."""
     import oracle
     torch = torch_mod
     from sofa.rigidbodydynamics_b200 import model as mdl
@@ -897,13 +899,14 @@ def test_aba_matches_oracle(torch_mod, api, d, tile):
     for s_, st in enumerate(gold):
         q[s_], v[s_], tau[s_] = np.array(st["q"]), np.array(st["v"]), np.array(st["tau"])
     m = api.Model(d); ws = api.Workspace(m, n)
+    ws.set_aba_fused(bool(fused))
     nt = (n + tile - 1) // tile
     new = lambda: torch.full((nt, max(1, d.nv), tile), float("nan"), dtype=torch.float64, device="cuda")
     qs, vs, ts, as_ = (_dev(torch, to_tiled(x, tile)) for x in (q, v, tau, a))
     ddq = new()
     ws.aba_soa(n, tile, qs, vs, ts, ddq)
     ws.synchronize()
-    assert "aba_kernel" in api.last_kernel_name()
+    assert ("aba2_kernel" if fused else "aba_kernel") in api.last_kernel_name()
     got = from_tiled(ddq.cpu().numpy(), n)[:, :d.nv]
     orc = oracle.Oracle(d)
     idx = list(range(len(gold))) + list(range(len(gold), n, 17)) + [n - 1]
