@@ -14,7 +14,10 @@ def main():
     dev = torch.device("cuda:0")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     out = {}
+    only = sys.argv[1] if len(sys.argv) > 1 else None     # optional: one robot (ncu captures)
     for name, n in (("panda7", 65536), ("solo12", 262144), ("talos_reduced", 1 << 20)):
+        if only and name != only:
+            continue
         d = mdl.ROBOTS[name]()
         m = api.Model(d); ws = api.Workspace(m, n)
         ws.set_stream(torch.cuda.current_stream().cuda_stream)

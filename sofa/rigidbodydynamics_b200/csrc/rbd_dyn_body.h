@@ -141,42 +141,37 @@ RBD_HD void aba2_instance(const DevModel& m, const FLD& q, const FLD& v, const F
   } while (0)
   RBD_ABA_ROOT();
   // ---- passes 1 + 2 ---------------------------------------------------------------------------------------------
+  // (joint angle, velocity and torque of 1-dof joints are fetched one joint ahead: a global load under the kernel's own
+  // traffic takes thousands of cycles; record accesses go through a per-joint base with compile-time offsets; R | p | v
+  // of the joint a new branch starts from are restored right behind the unwind that precedes it, so that they are dead
+  // — and their registers free — during the unwind)
+  real nq0 = 0, nqd = 0, ntau = 0;
+#define RBD_ABA_PREFETCH(J)                                                                                  \
+  do {                                                                                                       \
+    const DevJoint& jx_ = m.joint[J];                                                                        \
+    if (jx_.type != JT_FF) { nq0 = q.ld(jx_.idx_q); nqd = v.ld(jx_.idx_v); if (jx_.nchild == 0) ntau = tau.ld(jx_.idx_v); } \
+  } while (0)
+  if (nj > 1) RBD_ABA_PREFETCH(1);
   for (int i = 1; i < nj; ++i) {
     const DevJoint& jn = m.joint[i];
-    const int par = jn.parent;
-    const int rec = RBD_ABA2_REC * (i - 1);
-    if (par != i - 1) {  // a new branch starts below `par`
-      if (par == 0) {
-        RBD_ABA_ROOT();
-      } else {
-        real t[RBD_ABA2_RST];
-        lev_ld<RBD_ABA2_RST>(S, T, m.joint[par].boff, t);
-#pragma unroll
-        for (int e = 0; e < 9; ++e) R[e] = t[e];
-#pragma unroll
-        for (int e = 0; e < 3; ++e) p[e] = t[9 + e];
-#pragma unroll
-        for (int e = 0; e < 6; ++e) vel[e] = t[12 + e];
-      }
-    }
+    const SCR Xi = X.at(RBD_ABA2_REC * (i - 1));
+    const real q0c = nq0, qdc = nqd, tau0 = ntau;
+    if (i + 1 < nj) RBD_ABA_PREFETCH(i + 1);
     const bool ff = jn.type == JT_FF;
-    real q0 = 0, q1 = 0, aw[3];
-    if (!ff) {
-      q0 = q.ld(jn.idx_q);
-      if (is_unbounded(jn.type)) q1 = q.ld(jn.idx_q + 1);
-    }
+    real q0 = q0c, q1 = 0, aw[3];
+    if (!ff && is_unbounded(jn.type)) q1 = q.ld(jn.idx_q + 1);
     fk_joint(jn, R, p, q0, q1, q, aw);
     real A[6], cr[6], vj[6];
     if (!ff) {
       subspace_1dof(jn.type, p, aw, A);
-      const real qd = v.ld(jn.idx_v);
+      const real qd = qdc;
 #pragma unroll
-      for (int e = 0; e < 6; ++e) { X.st(rec + e, A[e]); vj[e] = A[e] * qd; }
+      for (int e = 0; e < 6; ++e) { Xi.st(e, A[e]); vj[e] = A[e] * qd; }
     } else {
 #pragma unroll
-      for (int e = 0; e < 9; ++e) X.st(rec + e, R[e]);
+      for (int e = 0; e < 9; ++e) Xi.st(e, R[e]);
 #pragma unroll
-      for (int e = 0; e < 3; ++e) X.st(rec + 9 + e, p[e]);
+      for (int e = 0; e < 3; ++e) Xi.st(9 + e, p[e]);
       ff_act(R, p, v, jn.idx_v, vj);
     }
 #pragma unroll
@@ -188,7 +183,7 @@ RBD_HD void aba2_instance(const DevModel& m, const FLD& q, const FLD& v, const F
       cr[0] += tx; cr[1] += ty; cr[2] += tz;
       RBD_CROSS(cr[3], cr[4], cr[5], vel[3], vel[4], vel[5], vj[3], vj[4], vj[5]);
 #pragma unroll
-      for (int e = 0; e < 6; ++e) X.st(rec + 6 + e, cr[e]);
+      for (int e = 0; e < 6; ++e) Xi.st(6 + e, cr[e]);
     }
     real Y[10], h[6], pA[6];
     inertia_world(jn, R, p, Y);
@@ -228,27 +223,37 @@ RBD_HD void aba2_instance(const DevModel& m, const FLD& q, const FLD& v, const F
     // ---- leaf: pass 2 upwards for every joint this leaf completes -----------------------------------------------
     const int stop_at = (i + 1 < nj) ? m.joint[i + 1].parent : 0;  // the joint that still has a child to come
     int cur = i;
+    real tauc = tau0;
     for (;;) {
       const DevJoint& jc = m.joint[cur];
-      const int rc = RBD_ABA2_REC * (cur - 1);
+      const SCR Xc = X.at(RBD_ABA2_REC * (cur - 1));
       if (jc.type == JT_FF) {  // the root (the host checks that a free-flyer is joint 1 on the universe)
         real Rp[12], b[6], acc[6];
 #pragma unroll
-        for (int e = 0; e < 12; ++e) Rp[e] = X.ld(rc + e);
+        for (int e = 0; e < 12; ++e) Rp[e] = Xc.ld(e);
         aba_ff_root_solve(m, Rp, IA, IA + 21, tau, jc.idx_v, b, acc);
 #pragma unroll
-        for (int e = 0; e < 6; ++e) { ddq.st(jc.idx_v + e, b[e]); X.st(rc + 12 + e, acc[e]); }
+        for (int e = 0; e < 6; ++e) { ddq.st(jc.idx_v + e, b[e]); Xc.st(12 + e, acc[e]); }
         break;
+      }
+      const int pp = jc.parent;
+      // A, c, tau of the parent are fetched now, a whole joint step ahead of their use (they are in L2 at best)
+      real An[6], cn[6], taun = 0;
+      const bool fetch_parent = pp != 0 && pp != stop_at && m.joint[pp].type != JT_FF;
+      if (fetch_parent) {
+        const SCR Xp = X.at(RBD_ABA2_REC * (pp - 1));
+#pragma unroll
+        for (int e = 0; e < 6; ++e) { An[e] = Xp.ld(e); cn[e] = Xp.ld(6 + e); }
+        taun = tau.ld(m.joint[pp].idx_v);
       }
       real U[6];
       sym6_mul(IA, A, U);
       const real dinv = real(1) / dot6(A, U);
-      const real u = tau.ld(jc.idx_v) - dot6(A, IA + 21);
+      const real u = tauc - dot6(A, IA + 21);
 #pragma unroll
-      for (int e = 0; e < 6; ++e) X.st(rc + 12 + e, U[e]);
-      X.st(rc + 18, dinv);
-      X.st(rc + 19, u);
-      const int pp = jc.parent;
+      for (int e = 0; e < 6; ++e) Xc.st(12 + e, U[e]);
+      Xc.st(18, dinv);
+      Xc.st(19, u);
       if (pp == 0) break;
       // I^a = I^A - U U^T / D ;  p^a = p^A + I^a c + U u / D
 #pragma unroll
@@ -281,37 +286,72 @@ RBD_HD void aba2_instance(const DevModel& m, const FLD& q, const FLD& v, const F
         for (int e = 0; e < 6; ++e) IA[21 + e] += t[9 + e];
       }
       cur = pp;
-      if (jp.type != JT_FF) {
-        const int rp = RBD_ABA2_REC * (pp - 1);
+      if (fetch_parent) {
 #pragma unroll
-        for (int e = 0; e < 6; ++e) { A[e] = X.ld(rp + e); cr[e] = X.ld(rp + 6 + e); }
+        for (int e = 0; e < 6; ++e) { A[e] = An[e]; cr[e] = cn[e]; }
+        tauc = taun;
+      }
+    }
+    // the joint after a leaf starts a new branch: restore R | p | v of its parent (or the universe)
+    if (i + 1 < nj) {
+      if (stop_at == 0) {
+        RBD_ABA_ROOT();
+      } else {
+        real t[RBD_ABA2_RST];
+        lev_ld<RBD_ABA2_RST>(S, T, m.joint[stop_at].boff, t);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) R[e] = t[e];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) p[e] = t[9 + e];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) vel[e] = t[12 + e];
       }
     }
   }
+#undef RBD_ABA_PREFETCH
   // ---- pass 3 ----------------------------------------------------------------------------------------------------
+  // A chain of short dependent steps behind 20 loads each: the record of the next joint is fetched while this one is
+  // stepped (two buffers in ping-pong: the loop is unrolled by two so that no buffer is ever copied).
   real acc[6];
-  for (int i = 1; i < nj; ++i) {
-    const DevJoint& jn = m.joint[i];
-    const int par = jn.parent;
-    const int rec = RBD_ABA2_REC * (i - 1);
-    if (jn.type == JT_FF) {  // solved at the end of the backward pass
-#pragma unroll
-      for (int e = 0; e < 6; ++e) acc[e] = X.ld(rec + 12 + e);
-    } else {
-      if (par == 0) {
-        acc[0] = -m.gravity[0]; acc[1] = -m.gravity[1]; acc[2] = -m.gravity[2]; acc[3] = acc[4] = acc[5] = 0;
-      } else if (par != i - 1) {  // (else: acc still holds the parent's acceleration)
-        lev_ld<6>(S, T, m.joint[par].offA, acc);
-      }
-      real A[6], U[6];
-#pragma unroll
-      for (int e = 0; e < 6; ++e) { A[e] = X.ld(rec + e); U[e] = X.ld(rec + 12 + e); acc[e] += X.ld(rec + 6 + e); }
-      const real qdd = (X.ld(rec + 19) - dot6(U, acc)) * X.ld(rec + 18);
-      ddq.st(jn.idx_v, qdd);
-#pragma unroll
-      for (int e = 0; e < 6; ++e) acc[e] += A[e] * qdd;
+  real b0[RBD_ABA2_REC], b1[RBD_ABA2_REC];
+#define RBD_ABA_FETCH(J, B)                                                                     \
+  do {                                                                                          \
+    const SCR Xn_ = X.at(RBD_ABA2_REC * ((J) - 1));                                             \
+    if (m.joint[J].type != JT_FF) {                                                             \
+      _Pragma("unroll") for (int e_ = 0; e_ < RBD_ABA2_REC; ++e_) B[e_] = Xn_.ld(e_);           \
+    } else { /* the acceleration solved at the end of the backward pass */                      \
+      _Pragma("unroll") for (int e_ = 0; e_ < 6; ++e_) B[e_] = Xn_.ld(12 + e_);                 \
+    }                                                                                           \
+  } while (0)
+#define RBD_ABA_STEP3(I, B)                                                                     \
+  do {                                                                                          \
+    const DevJoint& jn = m.joint[I];                                                            \
+    const int par = jn.parent;                                                                  \
+    if (jn.type == JT_FF) {                                                                     \
+      _Pragma("unroll") for (int e_ = 0; e_ < 6; ++e_) acc[e_] = B[e_];                         \
+    } else {                                                                                    \
+      if (par == 0) {                                                                           \
+        acc[0] = -m.gravity[0]; acc[1] = -m.gravity[1]; acc[2] = -m.gravity[2]; acc[3] = acc[4] = acc[5] = 0; \
+      } else if (par != (I) - 1) { /* (else: acc still holds the parent's acceleration) */      \
+        lev_ld<6>(S, T, m.joint[par].offA, acc);                                                \
+      }                                                                                         \
+      _Pragma("unroll") for (int e_ = 0; e_ < 6; ++e_) acc[e_] += B[6 + e_];                    \
+      const real qdd_ = (B[19] - dot6(B + 12, acc)) * B[18];                                    \
+      ddq.st(jn.idx_v, qdd_);                                                                   \
+      _Pragma("unroll") for (int e_ = 0; e_ < 6; ++e_) acc[e_] += B[e_] * qdd_;                 \
+    }                                                                                           \
+    if (jn.nchild >= 2) lev_st<6>(S, T, jn.offA, acc);                                          \
+  } while (0)
+  if (nj > 1) RBD_ABA_FETCH(1, b0);
+  for (int i = 1; i < nj; i += 2) {
+    if (i + 1 < nj) RBD_ABA_FETCH(i + 1, b1);
+    RBD_ABA_STEP3(i, b0);
+    if (i + 1 < nj) {
+      if (i + 2 < nj) RBD_ABA_FETCH(i + 2, b0);
+      RBD_ABA_STEP3(i + 1, b1);
     }
-    if (jn.nchild >= 2) lev_st<6>(S, T, jn.offA, acc);
   }
+#undef RBD_ABA_STEP3
+#undef RBD_ABA_FETCH
 #undef RBD_ABA_ROOT
 }

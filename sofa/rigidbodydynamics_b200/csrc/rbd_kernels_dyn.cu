@@ -17,6 +17,7 @@ struct GlobalRec {
   double* p;  // this lane's column of its warp's [E][32] record
   __device__ __forceinline__ double ld(int e) const { return p[e * 32]; }
   __device__ __forceinline__ void st(int e, double v) const { p[e * 32] = v; }
+  __device__ __forceinline__ GlobalRec at(int e) const { return GlobalRec{p + e * 32}; }  // base of a joint's record
 };
 }  // namespace
 

@@ -426,6 +426,7 @@ struct EmulScratch {
   double* p;
   double ld(int e) const { return p[e]; }
   void st(int e, double v) const { p[e] = v; }
+  EmulScratch at(int e) const { return EmulScratch{p + e}; }
 };
 extern "C" int emul_aba(const rbd_model_desc* d, long long n, long long tile, double* q, double* v, double* tau, double* ddq) {
   Ctx c;
