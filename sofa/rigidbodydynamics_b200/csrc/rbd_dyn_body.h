@@ -240,7 +240,10 @@ RBD_HD void aba2_instance(const DevModel& m, const FLD& q, const FLD& v, const F
       // A, c, tau of the parent are fetched now, a whole joint step ahead of their use (they are in L2 at best)
       real An[6], cn[6], taun = 0;
       const bool fetch_parent = pp != 0 && pp != stop_at && m.joint[pp].type != JT_FF;
-      if (fetch_parent) {
+#ifndef RBD_ABA2_UNW
+#define RBD_ABA2_UNW 0
+#endif
+      if (RBD_ABA2_UNW && fetch_parent) {
         const SCR Xp = X.at(RBD_ABA2_REC * (pp - 1));
 #pragma unroll
         for (int e = 0; e < 6; ++e) { An[e] = Xp.ld(e); cn[e] = Xp.ld(6 + e); }
@@ -287,9 +290,16 @@ RBD_HD void aba2_instance(const DevModel& m, const FLD& q, const FLD& v, const F
       }
       cur = pp;
       if (fetch_parent) {
+        if (RBD_ABA2_UNW) {
 #pragma unroll
-        for (int e = 0; e < 6; ++e) { A[e] = An[e]; cr[e] = cn[e]; }
-        tauc = taun;
+          for (int e = 0; e < 6; ++e) { A[e] = An[e]; cr[e] = cn[e]; }
+          tauc = taun;
+        } else {
+          const SCR Xp = X.at(RBD_ABA2_REC * (pp - 1));
+#pragma unroll
+          for (int e = 0; e < 6; ++e) { A[e] = Xp.ld(e); cr[e] = Xp.ld(6 + e); }
+          tauc = tau.ld(m.joint[pp].idx_v);
+        }
       }
     }
     // the joint after a leaf starts a new branch: restore R | p | v of its parent (or the universe)
@@ -342,6 +352,10 @@ RBD_HD void aba2_instance(const DevModel& m, const FLD& q, const FLD& v, const F
     }                                                                                           \
     if (jn.nchild >= 2) lev_st<6>(S, T, jn.offA, acc);                                          \
   } while (0)
+#ifndef RBD_ABA2_P3
+#define RBD_ABA2_P3 0
+#endif
+#if RBD_ABA2_P3 == 2
   if (nj > 1) RBD_ABA_FETCH(1, b0);
   for (int i = 1; i < nj; i += 2) {
     if (i + 1 < nj) RBD_ABA_FETCH(i + 1, b1);
@@ -351,6 +365,20 @@ RBD_HD void aba2_instance(const DevModel& m, const FLD& q, const FLD& v, const F
       RBD_ABA_STEP3(i + 1, b1);
     }
   }
+#elif RBD_ABA2_P3 == 1
+  if (nj > 1) RBD_ABA_FETCH(1, b1);
+  for (int i = 1; i < nj; ++i) {
+#pragma unroll
+    for (int e = 0; e < RBD_ABA2_REC; ++e) b0[e] = b1[e];
+    if (i + 1 < nj) RBD_ABA_FETCH(i + 1, b1);
+    RBD_ABA_STEP3(i, b0);
+  }
+#else
+  for (int i = 1; i < nj; ++i) {
+    RBD_ABA_FETCH(i, b0);
+    RBD_ABA_STEP3(i, b0);
+  }
+#endif
 #undef RBD_ABA_STEP3
 #undef RBD_ABA_FETCH
 #undef RBD_ABA_ROOT
