@@ -301,6 +301,14 @@ RBD_API int rbd_aba_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double
                         double* ddq);
 /* ... on host vectors (instance-major q [n][nq]; v, tau, ddq [n][nv]), chunked and pipelined like rbd_eval_host.      */
 RBD_API int rbd_aba_host(rbd_workspace* ws, int64_t n, const double* q, const double* v, const double* tau, double* ddq);
+/* Inverse of the joint-space mass matrix, pinocchio::computeMinverse(model, data, q) (no call site in the reference;
+ * SURVEY.md §8(f) rank 4): Minv = upper triangle of M(q)^-1 packed by columns exactly like M (field c (c + 1) / 2 + r,
+ * r <= c; rbd_model_info::mass_fields fields per instance) — pinocchio fills the upper triangle of data.Minv too.  Computed
+ * without forming M: the articulated-body quantities of the forward-dynamics sweep are shared by all columns (unit torque
+ * per dof, v = 0, no gravity).  A free-flyer is supported as the root joint only; RBD_ERR_UNSUPPORTED for trees whose
+ * level records do not fit an SM.                                                                                */
+RBD_API int rbd_minv_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, double* Minv);
+RBD_API int rbd_minv_host(rbd_workspace* ws, int64_t n, const double* q, double* Minv);
 
 /* Matrix-free Mass / ForceField products in joint space — what the reference's SOFA graph evaluates through the
  * mapping with one UniformMass<Rigid3> per body (URDFModelLoader.cpp:369-391): Mass::addMDx and ForceField::addForce

@@ -200,6 +200,13 @@ class Oracle:
         lib().orc_aba(self._w, _p(q), _p(v), _p(tau), _p(ddq))
         return ddq
 
+    def minv(self, q):
+        """pinocchio::computeMinverse(q) restated as what it equals: the inverse of the CRBA mass matrix (dense, symmetric;
+        numpy LU).  tests/test_oracle.py ties it to the articulated-body restatement: column j == aba(q, 0, e_j) - aba(q, 0, 0)."""
+        M = self.crba(q)
+        M = np.triu(M) + np.triu(M, 1).T
+        return np.linalg.inv(M)
+
     def eval(self, q, v, a):
         q, v, a = _f64(q), _f64(v), _f64(a)
         d = self.d

@@ -187,6 +187,10 @@ class Workspace:
         """Forward dynamics ddq = aba(q, v, tau) (``rbd_aba_soa``)."""
         check(self._lib.rbd_aba_soa(self._h, n, tile, _dev_ptr(q), _dev_ptr(v), _dev_ptr(tau), _dev_ptr(ddq)))
 
+    def minv_soa(self, n, tile, q, Minv):
+        """Packed upper triangle of M(q)^-1 (``rbd_minv_soa``, pinocchio::computeMinverse)."""
+        check(self._lib.rbd_minv_soa(self._h, n, tile, _dev_ptr(q), _dev_ptr(Minv)))
+
     def addMDx_soa(self, n, tile, q, dx, factor, res):
         """res += factor * M(q) dx  (SOFA Mass::addMDx in joint space, matrix-free)."""
         check(self._lib.rbd_addMDx_soa(self._h, n, tile, _dev_ptr(q), _dev_ptr(dx), float(factor), _dev_ptr(res)))
@@ -262,6 +266,9 @@ class Workspace:
 
     def aba_host(self, n, q, v, tau, ddq):
         check(self._lib.rbd_aba_host(self._h, n, _host_ptr(q), _host_ptr(v), _host_ptr(tau), _host_ptr(ddq)))
+
+    def minv_host(self, n, q, Minv):
+        check(self._lib.rbd_minv_host(self._h, n, _host_ptr(q), _host_ptr(Minv)))
 
     def addMDx_host(self, n, q, dx, factor, res):
         """res += factor * M(q) dx on host vectors (instance-major), in place."""

@@ -112,6 +112,11 @@ struct rbd_workspace {
   int aba2_state = 0;
   int use_aba2 = 1;
   double* aba2_scratch[2] = {nullptr, nullptr};
+  // M^-1 sweep (minv): planned joint table, state as aba2_state (-1: the model's level records do not fit an SM)
+  DevModel* h_minv = nullptr;
+  DevModel* d_minv = nullptr;
+  int minv_state = 0;
+  double* minv_scratch[2] = {nullptr, nullptr};
   void* sel_buf = nullptr;  // getJ: selection + block pointers
   size_t sel_bytes = 0;
 };
@@ -215,6 +220,7 @@ static void ws_free(rbd_workspace* ws) {
   cudaFree(ws->d_sorted_k); cudaFree(ws->d_outk_parent); cudaFree(ws->d_sorted_ident); cudaFree(ws->d_sorted_pl); cudaFree(ws->d_outk_pl);
   cudaFree(ws->sel_buf); cudaFree(ws->aba_scratch[0]); cudaFree(ws->aba_scratch[1]);
   cudaFree(ws->aba2_scratch[0]); cudaFree(ws->aba2_scratch[1]); cudaFree(ws->d_aba2); delete ws->h_aba2;
+  cudaFree(ws->minv_scratch[0]); cudaFree(ws->minv_scratch[1]); cudaFree(ws->d_minv); delete ws->h_minv;
   cudaFree(ws->qcache); cudaFree(ws->rows_buf); cudaFree(ws->d_model); cudaFree(ws->jcache); cudaFree(ws->omicache); cudaFree(ws->jc_scratch);
   for (int k = 0; k < rbd_workspace::kPlans; ++k) { cudaFree(ws->d_plan[k]); delete ws->h_plan[k]; }
   for (int k = 0; k < 8; ++k) { cudaFree(ws->d_plan32[k]); delete ws->h_plan32[k]; }
@@ -381,6 +387,8 @@ static void drop_plans(rbd_workspace* ws) {
   memset(ws->plan_failed, 0, sizeof(ws->plan_failed));
   for (int k = 0; k < 8; ++k) { delete ws->h_plan32[k]; ws->h_plan32[k] = nullptr; }
   delete ws->h_aba2; ws->h_aba2 = nullptr; ws->aba2_state = 0;
+  delete ws->h_minv; ws->h_minv = nullptr; ws->minv_state = 0;
+  cudaFree(ws->minv_scratch[0]); cudaFree(ws->minv_scratch[1]); ws->minv_scratch[0] = ws->minv_scratch[1] = nullptr;
   cudaFree(ws->aba2_scratch[0]); cudaFree(ws->aba2_scratch[1]); ws->aba2_scratch[0] = ws->aba2_scratch[1] = nullptr;
 }
 
@@ -587,6 +595,49 @@ RBD_API int rbd_aba_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double
   int rc = check_batch(ws, n, tile);
   if (rc) return rc;
   return aba_on(ws, ws->stream, n, tile, q, v, tau, ddq);
+}
+
+// inverse of the joint-space mass matrix (minv_instance), packed upper triangle
+static int minv_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, const double* q, double* Minv) {
+  if (!q || !Minv) return set_err(RBD_ERR_INVALID_ARG, "null q / Minv");
+  const DevModel& dm = ws->model->dm;
+  for (int i = 1; i < dm.njoints; ++i)
+    if (dm.joint[i].type == JT_FF && !(i == 1 && dm.joint[i].parent == 0))
+      return set_err(RBD_ERR_UNSUPPORTED, "minv supports a free-flyer only as the root joint (joint 1 on the universe)");
+  const int sc = (ws->slot[1].st && st == ws->slot[1].st) ? 1 : 0;
+  if (ws->minv_state == 0) {
+    ws->minv_state = -1;
+    DevModel* h = new (std::nothrow) DevModel(dm);
+    if (!h) return set_err(RBD_ERR_ALLOC, "out of host memory");
+    if (plan_minv(h, ws->use_tmem != 0)) {
+      if (!ws->d_minv) CK(cudaMalloc(&ws->d_minv, sizeof(DevModel)));
+      CK(cudaMemcpyAsync(ws->d_minv, h, dev_model_bytes(*h), cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));
+      ws->h_minv = h; ws->minv_state = 1;
+    } else {
+      delete h;
+    }
+  }
+  if (ws->minv_state != 1)
+    return set_err(RBD_ERR_UNSUPPORTED, "minv: the level records of this tree do not fit the shared + tensor memory of an SM");
+  if (!ws->minv_scratch[sc]) {
+    int warps = 0;
+    MinvArgs S{0, 32, nullptr, nullptr, nullptr};
+    CK(launch_minv(*ws->h_minv, ws->d_minv, S, ws->num_sms, &warps, st));
+    const size_t bytes = (size_t)warps * (size_t)(RBD_MINV_REC * (dm.njoints - 1) + RBD_MINV_ROOT_REC) * 32 * sizeof(double);
+    cudaError_t e = cudaMalloc(&ws->minv_scratch[sc], bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return set_err(RBD_ERR_ALLOC, std::string("cudaMalloc(minv scratch): ") + cudaGetErrorString(e)); }
+  }
+  MinvArgs A{n, tile, q, Minv, ws->minv_scratch[sc]};
+  CK(launch_minv(*ws->h_minv, ws->d_minv, A, ws->num_sms, nullptr, st));
+  if (n > 0) ws->launches++;
+  return RBD_OK;
+}
+RBD_API int rbd_minv_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, double* Minv) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, tile);
+  if (rc) return rc;
+  return minv_on(ws, ws->stream, n, tile, q, Minv);
 }
 
 static int apply_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, long long inst0, const double* qj,
@@ -1081,6 +1132,20 @@ RBD_API int rbd_aba_host(rbd_workspace* ws, int64_t n, const double* q, const do
   // (each chunk stream has its own scratch records: aba_on)
   return run_host_chunks(ws, n, P, [&](cudaStream_t st, long long, long long cn, long long tile) {
     return aba_on(ws, st, cn, tile, P[0].d_soa, P[1].d_soa, P[2].d_soa, P[3].d_soa);
+  });
+}
+
+RBD_API int rbd_minv_host(rbd_workspace* ws, int64_t n, const double* q, double* Minv) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, 1);
+  if (rc) return rc;
+  if (!q || !Minv) return set_err(RBD_ERR_INVALID_ARG, "null q / Minv");
+  const rbd_model_info& I = ws->model->info;
+  Pieces P;
+  P.add(I.nq, q, nullptr, true, false);
+  P.add(I.mass_fields, nullptr, Minv, false, true);
+  return run_host_chunks(ws, n, P, [&](cudaStream_t st, long long, long long cn, long long tile) {
+    return minv_on(ws, st, cn, tile, P[0].d_soa, P[1].d_soa);
   });
 }
 

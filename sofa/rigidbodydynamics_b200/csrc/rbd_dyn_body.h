@@ -383,3 +383,306 @@ RBD_HD void aba2_instance(const DevModel& m, const FLD& q, const FLD& v, const F
 #undef RBD_ABA_FETCH
 #undef RBD_ABA_ROOT
 }
+
+// =========================================================================================================
+// Inverse of the joint-space mass matrix (pinocchio::computeMinverse; SURVEY.md §8(f) rank 4 — not in the reference)
+// =========================================================================================================
+// M^-1 column c is the forward dynamics of a unit torque on dof c with v = 0 and no gravity, so the articulated-body
+// quantities are shared by all columns:
+//   phase 1  passes 1 + 2 of the sweep above restricted to the matrix part (I^A, U = I^A A, 1/D; no bias forces), on the
+//            same depth-level records (one child: the joint's own inertia h | I_O (9); >= 2 children: I^A accumulator (21)
+//            + restart R | p (12)).  Per joint A (6), U (6), 1/D go to the thread's global record (RBD_MINV_REC = 13); a
+//            root free-flyer leaves R | p (12) and (X^T I^A X)^-1 (21, Cholesky) in a 33-double record behind them.
+//   phase 2  columns in blocks of RBD_MINV_CB consecutive dofs.  A unit torque on joint j loads only the path j -> root:
+//            the backward walk p <- U_j / D_j, then u_a = -A_a . p, p += U_a u_a / D_a for every ancestor a, leaves the
+//            partial entries u_a / D_a in the OUTPUT (rows of the ancestors, column c), the root free-flyer closes it
+//            with qdd_root = -(X^T I^A X)^-1 X^T p.  One forward sweep per block then completes the rows:
+//            qdd_i = partial(i, c) - (U_i . a_parent) / D_i,  a_i = a_parent + A_i qdd_i, every joint record (13 doubles)
+//            read once per block; the accelerations of a block at a joint with >= 2 children (6 RBD_MINV_CB doubles) wait
+//            in that joint's level record.  Only the upper triangle is produced (rows <= column, packed by columns like M):
+//            a column is finished as soon as the sweep passes its joint, and the sweep of a block stops at its last joint.
+// Joints other than a root free-flyer have one dof, so dof c belongs to joint c + 1 (fixed base) or c - 4 (c >= 6 below a
+// free-flyer root).  DevJoint::slot[0] of the planned copy holds the end of the joint's subtree (exclusive).
+// (RBD_MINV_CB, RBD_MINV_REC, RBD_MINV_ROOT_REC: rbd_dev_model.h)
+#define RBD_MINV_LEV1 9
+#define RBD_MINV_LEVB 21
+#define RBD_MINV_RST 12
+
+// Mv: packed upper triangle of the output (field c (c + 1) / 2 + r, r <= c); live = 0 for the lanes past the end of the batch
+template <class FLD, class SCR>
+RBD_HD void minv_instance(const DevModel& m, const FLD& q, const FLD& Mv, const SCR& X, const Stack& S, const TmStack& T,
+                          const int live) {
+  const int nj = m.njoints, nv = m.nv;
+  const bool ffroot = nj > 1 && m.joint[1].type == JT_FF;
+  const SCR XR = X.at(RBD_MINV_REC * (nj - 1));
+  real R[9], p[3];
+#define RBD_MINV_ROOT()                                                                         \
+  do {                                                                                          \
+    R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;   \
+    p[0] = p[1] = p[2] = 0;                                                                     \
+  } while (0)
+  RBD_MINV_ROOT();
+  // ---- phase 1 ---------------------------------------------------------------------------------------------------
+  real nq0 = 0;
+  if (nj > 1 && m.joint[1].type != JT_FF) nq0 = q.ld(m.joint[1].idx_q);
+  for (int i = 1; i < nj; ++i) {
+    const DevJoint& jn = m.joint[i];
+    const SCR Xi = X.at(RBD_MINV_REC * (i - 1));
+    const real q0 = nq0;
+    if (i + 1 < nj && m.joint[i + 1].type != JT_FF) nq0 = q.ld(m.joint[i + 1].idx_q);
+    const bool ff = jn.type == JT_FF;
+    real q1 = 0, aw[3];
+    if (!ff && is_unbounded(jn.type)) q1 = q.ld(jn.idx_q + 1);
+    fk_joint(jn, R, p, q0, q1, q, aw);
+    real A[6];
+    if (!ff) {
+      subspace_1dof(jn.type, p, aw, A);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) Xi.st(e, A[e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) XR.st(e, R[e]);
+#pragma unroll
+      for (int e = 0; e < 3; ++e) XR.st(9 + e, p[e]);
+    }
+    real Y[10];
+    inertia_world(jn, R, p, Y);
+    if (jn.nchild == 1) {
+      lev_st<RBD_MINV_LEV1>(S, T, jn.offA, Y + 1);
+      continue;
+    }
+    real IA[21];
+    sym6_from_inertia(Y, IA);
+    if (jn.nchild >= 2) {
+      lev_st<RBD_MINV_LEVB>(S, T, jn.offA, IA);
+      real t[RBD_MINV_RST];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) t[e] = R[e];
+#pragma unroll
+      for (int e = 0; e < 3; ++e) t[9 + e] = p[e];
+      lev_st<RBD_MINV_RST>(S, T, jn.boff, t);
+      continue;
+    }
+    // leaf: backward pass for every joint this leaf completes
+    const int stop_at = (i + 1 < nj) ? m.joint[i + 1].parent : 0;
+    int cur = i;
+    for (;;) {
+      const DevJoint& jc = m.joint[cur];
+      if (jc.type == JT_FF) {  // root: (X^T I^A X)^-1 by Cholesky, upper triangle
+        real Rp[12], D[21], Di[21];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) Rp[e] = XR.ld(e);
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) {
+          real Xc[6], F[6], col[6];
+          RBD_FF_COL(Xc, Rp, (Rp + 9), cc);
+          sym6_mul(IA, Xc, F);
+          ff_rows(Rp, Rp + 9, F, col);
+#pragma unroll
+          for (int r = 0; r <= cc; ++r) D[s6(r, cc)] = col[r];
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {  // D = L L^T, D[s6(r, c)] (r <= c) <- L(c, r)
+          real d = D[s6(k, k)];
+#pragma unroll
+          for (int j = 0; j < k; ++j) d -= D[s6(j, k)] * D[s6(j, k)];
+          d = sqrt(d);
+          D[s6(k, k)] = d;
+          const real di = real(1) / d;
+#pragma unroll
+          for (int r = k + 1; r < 6; ++r) {
+            real t = D[s6(k, r)];
+#pragma unroll
+            for (int j = 0; j < k; ++j) t -= D[s6(j, r)] * D[s6(j, k)];
+            D[s6(k, r)] = t * di;
+          }
+        }
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) {  // column cc of the inverse: L y = e_cc (y_k = 0 for k < cc), L^T x = y
+          real b[6];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            real t = k == cc ? real(1) : real(0);
+#pragma unroll
+            for (int j = cc; j < k; ++j) t -= D[s6(j, k)] * b[j];
+            b[k] = k < cc ? real(0) : t / D[s6(k, k)];
+          }
+#pragma unroll
+          for (int k = 5; k >= 0; --k) {
+            real t = b[k];
+#pragma unroll
+            for (int j = k + 1; j < 6; ++j) t -= D[s6(k, j)] * b[j];
+            b[k] = t / D[s6(k, k)];
+          }
+#pragma unroll
+          for (int r = 0; r <= cc; ++r) Di[s6(r, cc)] = b[r];
+        }
+#pragma unroll
+        for (int e = 0; e < 21; ++e) XR.st(12 + e, Di[e]);
+        break;
+      }
+      const SCR Xc = X.at(RBD_MINV_REC * (cur - 1));
+      real U[6];
+      sym6_mul(IA, A, U);
+      const real dinv = real(1) / dot6(A, U);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) Xc.st(6 + e, U[e]);
+      Xc.st(12, dinv);
+      const int pp = jc.parent;
+      if (pp == 0) break;
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int cc = r; cc < 6; ++cc) IA[s6(r, cc)] -= U[r] * (U[cc] * dinv);
+      const DevJoint& jp = m.joint[pp];
+      if (pp == stop_at) {
+        lev_add<RBD_MINV_LEVB>(S, T, jp.offA, IA);
+        break;
+      }
+      if (jp.nchild >= 2) {
+        real t[RBD_MINV_LEVB];
+        lev_ld<RBD_MINV_LEVB>(S, T, jp.offA, t);
+#pragma unroll
+        for (int e = 0; e < RBD_MINV_LEVB; ++e) IA[e] += t[e];
+      } else {
+        real t[RBD_MINV_LEV1];
+        lev_ld<RBD_MINV_LEV1>(S, T, jp.offA, t);
+        sym6_add_inertia(jp.Y[0], t, t + 3, IA);
+      }
+      cur = pp;
+      if (jp.type != JT_FF) {
+        const SCR Xp = X.at(RBD_MINV_REC * (pp - 1));
+#pragma unroll
+        for (int e = 0; e < 6; ++e) A[e] = Xp.ld(e);
+      }
+    }
+    if (i + 1 < nj) {  // the joint after a leaf starts a new branch
+      if (stop_at == 0) {
+        RBD_MINV_ROOT();
+      } else {
+        real t[RBD_MINV_RST];
+        lev_ld<RBD_MINV_RST>(S, T, m.joint[stop_at].boff, t);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) R[e] = t[e];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) p[e] = t[9 + e];
+      }
+    }
+  }
+#undef RBD_MINV_ROOT
+  // ---- phase 2 ---------------------------------------------------------------------------------------------------
+  real Rp[12];
+  if (ffroot) {
+#pragma unroll
+    for (int e = 0; e < 12; ++e) Rp[e] = XR.ld(e);
+  }
+#define RBD_MINV_JOINT_OF(c) (ffroot ? ((c) < 6 ? 1 : (c) - 4) : (c) + 1)
+#define RBD_MINV_FLD(r, c) ((c) * ((c) + 1) / 2 + (r))
+  for (int c0 = 0; c0 < nv; c0 += RBD_MINV_CB) {
+    const int ncb = nv - c0 < RBD_MINV_CB ? nv - c0 : RBD_MINV_CB;
+    real acc[RBD_MINV_CB][6];
+    // backward walks, column by column
+#pragma unroll
+    for (int k = 0; k < RBD_MINV_CB; ++k) {
+#pragma unroll
+      for (int e = 0; e < 6; ++e) acc[k][e] = 0;
+      if (k < ncb) {
+        const int c = c0 + k;
+        const int j = RBD_MINV_JOINT_OF(c);
+        real qr[6];  // acceleration of the root free-flyer's dofs for this column
+        bool have_root = false;
+        if (ffroot && j == 1) {
+#pragma unroll
+          for (int r = 0; r < 6; ++r) qr[r] = XR.ld(12 + s6(r, c));  // column c of (X^T I^A X)^-1
+          have_root = true;
+        } else {
+          const SCR Xj = X.at(RBD_MINV_REC * (j - 1));
+          real pv[6];
+          const real dj = Xj.ld(12);
+#pragma unroll
+          for (int e = 0; e < 6; ++e) pv[e] = Xj.ld(6 + e) * dj;
+          if (live) Mv.st(RBD_MINV_FLD(c, c), dj);
+          int a = m.joint[j].parent;
+          while (a != 0 && m.joint[a].type != JT_FF) {
+            const SCR Xa = X.at(RBD_MINV_REC * (a - 1));
+            real Aa[6], Ua[6];
+#pragma unroll
+            for (int e = 0; e < 6; ++e) { Aa[e] = Xa.ld(e); Ua[e] = Xa.ld(6 + e); }
+            const real ua = -dot6(Aa, pv) * Xa.ld(12);
+            if (live) Mv.st(RBD_MINV_FLD(m.joint[a].idx_v, c), ua);
+#pragma unroll
+            for (int e = 0; e < 6; ++e) pv[e] += Ua[e] * ua;
+            a = m.joint[a].parent;
+          }
+          if (a != 0) {  // the root free-flyer: qdd_root = -(X^T I^A X)^-1 X^T p
+            real b[6], Di[21];
+            ff_rows(Rp, Rp + 9, pv, b);
+#pragma unroll
+            for (int e = 0; e < 21; ++e) Di[e] = XR.ld(12 + e);
+#pragma unroll
+            for (int e = 0; e < 6; ++e) b[e] = -b[e];
+            sym6_mul(Di, b, qr);
+            have_root = true;
+          }
+        }
+        if (have_root) {
+          const int rmax = c < 5 ? c : 5;
+#pragma unroll
+          for (int r = 0; r < 6; ++r)
+            if (r <= rmax && live) Mv.st(RBD_MINV_FLD(r, c), qr[r]);
+          // a_root = X qdd_root
+          real aa[3], tx, ty, tz;
+#pragma unroll
+          for (int e = 0; e < 3; ++e) {
+            acc[k][e] = Rp[3 * e] * qr[0] + Rp[3 * e + 1] * qr[1] + Rp[3 * e + 2] * qr[2];
+            aa[e] = Rp[3 * e] * qr[3] + Rp[3 * e + 1] * qr[4] + Rp[3 * e + 2] * qr[5];
+          }
+          RBD_CROSS(tx, ty, tz, Rp[9], Rp[10], Rp[11], aa[0], aa[1], aa[2]);
+          acc[k][0] += tx; acc[k][1] += ty; acc[k][2] += tz;
+          acc[k][3] = aa[0]; acc[k][4] = aa[1]; acc[k][5] = aa[2];
+        }
+      }
+    }
+    // forward sweep of the block up to the joint of its last column
+    const int jlast = RBD_MINV_JOINT_OF(c0 + ncb - 1);
+    int i = 1;
+    if (ffroot) {
+      if (m.joint[1].nchild >= 2) lev_st<6 * RBD_MINV_CB>(S, T, m.joint[1].offA, &acc[0][0]);
+      i = 2;
+    }
+    for (; i <= jlast; ++i) {
+      const DevJoint& jn = m.joint[i];
+      const int par = jn.parent;
+      if (par == 0) {
+#pragma unroll
+        for (int k = 0; k < RBD_MINV_CB; ++k)
+#pragma unroll
+          for (int e = 0; e < 6; ++e) acc[k][e] = 0;
+      } else if (par != i - 1) {
+        lev_ld<6 * RBD_MINV_CB>(S, T, m.joint[par].offA, &acc[0][0]);
+      }
+      const SCR Xi = X.at(RBD_MINV_REC * (i - 1));
+      real A[6], U[6];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) { A[e] = Xi.ld(e); U[e] = Xi.ld(6 + e); }
+      const real dinv = Xi.ld(12);
+      const int r = jn.idx_v, send = jn.slot[0];
+#pragma unroll
+      for (int k = 0; k < RBD_MINV_CB; ++k) {
+        const int c = c0 + k;
+        const int jc = RBD_MINV_JOINT_OF(c);
+        if (k < ncb && jc >= i) {  // (a column is finished once the sweep has passed its joint: rows > column)
+          real part = 0;
+          if (jc < send && live) part = Mv.ld(RBD_MINV_FLD(r, c));  // joint i is on the path of column c: u_i / D_i
+          const real qdd = part - dot6(U, acc[k]) * dinv;
+          if (live) Mv.st(RBD_MINV_FLD(r, c), qdd);
+#pragma unroll
+          for (int e = 0; e < 6; ++e) acc[k][e] += A[e] * qdd;
+        }
+      }
+      if (jn.nchild >= 2) lev_st<6 * RBD_MINV_CB>(S, T, jn.offA, &acc[0][0]);
+    }
+  }
+#undef RBD_MINV_JOINT_OF
+#undef RBD_MINV_FLD
+}

@@ -38,6 +38,12 @@ struct DjtArgs {  // applyDJT: geometric stiffness (optional extension; the refe
   double* qcache;
   long long cache_inst0;
 };
+struct MinvArgs {  // inverse of the joint-space mass matrix: q -> packed upper triangle of M^-1
+  long long n, tile;
+  const double* q;
+  double* Minv;
+  double* scratch;  // (RBD_MINV_REC * (njoints - 1) + RBD_MINV_ROOT_REC) * 32 doubles per resident warp
+};
 struct AbaArgs {  // forward dynamics (articulated-body algorithm): q, v, tau -> ddq
   long long n, tile;
   const double *q, *v, *tau;
@@ -100,6 +106,9 @@ cudaError_t launch_aba(const DevModel& m, const DevModel* d_model, const AbaArgs
 // the fused variant (aba2_instance; rbd_kernels_dyn.cu): `planned_host_model` planned with plan_aba2, `d_model` its device
 // copy; a.scratch holds RBD_ABA2_REC * (njoints - 1) * 32 doubles per resident warp (sizing call as above)
 cudaError_t launch_aba2(const DevModel& planned_host_model, const DevModel* d_model, const AbaArgs& a, int num_sms,
+                        int* scratch_warps, cudaStream_t st);
+// inverse of the mass matrix (minv_instance): `planned_host_model` planned with plan_minv; sizing call as launch_aba
+cudaError_t launch_minv(const DevModel& planned_host_model, const DevModel* d_model, const MinvArgs& a, int num_sms,
                         int* scratch_warps, cudaStream_t st);
 // records the __global__ function a launch_* of another translation unit started (rbd_last_kernel_name)
 void note_kernel(const void* fn);

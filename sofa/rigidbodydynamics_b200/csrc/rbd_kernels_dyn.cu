@@ -21,35 +21,58 @@ struct GlobalRec {
 };
 }  // namespace
 
-template <int TILE>
-__global__ void __launch_bounds__(256, 1) aba2_kernel(const DevModel* __restrict__ gm, const int model_words, const AbaArgs a) {
-  // the last two staged words are spare: the tensor-memory base address lands there
-  unsigned* const tm_base_p = reinterpret_cast<unsigned*>(rbd_smem + model_words - 2);
+// Block prologue shared by the kernels of this file: stage the joint table (its last two words are spare: the
+// tensor-memory base address lands there), allocate the block's tensor-memory columns, hand every thread its slices.
+struct DynCtx {
+  const DevModel* m;
+  Stack S;
+  TmStack T;
+  unsigned* tm_base_p;
+  int tm_cols;
+};
+__device__ __forceinline__ DynCtx dyn_prologue(const DevModel* __restrict__ gm, const int model_words) {
+  DynCtx c;
+  c.tm_base_p = reinterpret_cast<unsigned*>(rbd_smem + model_words - 2);
   {
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gm);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(rbd_smem);
     for (int w = threadIdx.x; w < model_words - 2; w += blockDim.x) dst[w] = src[w];
   }
   __syncthreads();
-  const DevModel& m = *reinterpret_cast<const DevModel*>(rbd_smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  const int tm_cols = m.plan.tmem_cols;
-  TmStack T;
-  T.base = 0;
-  if (tm_cols > 0) {
+  c.m = reinterpret_cast<const DevModel*>(rbd_smem);
+  const int warp = threadIdx.x >> 5;
+  c.tm_cols = c.m->plan.tmem_cols;
+  c.T.base = 0;
+  if (c.tm_cols > 0) {
     if (warp == 0) {
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"l"(
-                       (unsigned long long)__cvta_generic_to_shared(tm_base_p)),
-                   "r"(tm_cols)
+                       (unsigned long long)__cvta_generic_to_shared(c.tm_base_p)),
+                   "r"(c.tm_cols)
                    : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    T.base = *tm_base_p + (((unsigned)(warp & 3) * 32u) << 16) + (unsigned)(warp >> 2) * 2u * (unsigned)m.plan.tmem_doubles;
+    c.T.base = *c.tm_base_p + (((unsigned)(warp & 3) * 32u) << 16) + (unsigned)(warp >> 2) * 2u * (unsigned)c.m->plan.tmem_doubles;
   }
-  const Stack S = make_stack(rbd_smem + model_words, threadIdx.x, m.plan.smem_doubles);
+  c.S = make_stack(rbd_smem + model_words, threadIdx.x, c.m->plan.smem_doubles);
+  return c;
+}
+__device__ __forceinline__ void dyn_epilogue(const DynCtx& c) {
+  if (c.tm_cols > 0) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*c.tm_base_p), "r"(c.tm_cols) : "memory");
+  }
+}
+
+template <int TILE>
+__global__ void __launch_bounds__(256, 1) aba2_kernel(const DevModel* __restrict__ gm, const int model_words, const AbaArgs a) {
+  const DynCtx c = dyn_prologue(gm, model_words);
+  const DevModel& m = *c.m;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const long long gw = (long long)blockIdx.x * wpb + warp;
   const GlobalRec X{a.scratch + gw * (long long)(RBD_ABA2_REC * (m.njoints - 1)) * 32 + lane};
   const long long ntiles = (a.n + 31) / 32;
@@ -59,14 +82,29 @@ __global__ void __launch_bounds__(256, 1) aba2_kernel(const DevModel* __restrict
     aba2_instance(m, make_field_t<TILE>(const_cast<double*>(a.q), inst, m.nq, a.tile),
                   make_field_t<TILE>(const_cast<double*>(a.v), inst, m.nv, a.tile),
                   make_field_t<TILE>(const_cast<double*>(a.tau), inst, m.nv, a.tile),
-                  make_field_t<TILE>(a.ddq, inst, m.nv, a.tile), X, S, T);
+                  make_field_t<TILE>(a.ddq, inst, m.nv, a.tile), X, c.S, c.T);
   }
-  if (tm_cols > 0) {
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0)
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tm_base_p), "r"(tm_cols) : "memory");
+  dyn_epilogue(c);
+}
+
+// Inverse of the mass matrix (minv_instance): same launch shape; a.Minv = packed upper triangle, nv (nv + 1) / 2 fields
+template <int TILE>
+__global__ void __launch_bounds__(256, 1) minv_kernel(const DevModel* __restrict__ gm, const int model_words, const MinvArgs a) {
+  const DynCtx c = dyn_prologue(gm, model_words);
+  const DevModel& m = *c.m;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const long long gw = (long long)blockIdx.x * wpb + warp;
+  const GlobalRec X{a.scratch + gw * (long long)(RBD_MINV_REC * (m.njoints - 1) + RBD_MINV_ROOT_REC) * 32 + lane};
+  const long long ntiles = (a.n + 31) / 32;
+  const int mf = m.nv * (m.nv + 1) / 2;
+  for (long long t = gw; t < ntiles; t += (long long)gridDim.x * wpb) {
+    long long inst = t * 32 + lane;
+    const int live = inst < a.n ? 1 : 0;
+    if (!live) inst = a.n - 1;
+    minv_instance(m, make_field_t<TILE>(const_cast<double*>(a.q), inst, m.nq, a.tile),
+                  make_field_t<TILE>(a.Minv, inst, mf, a.tile), X, c.S, c.T, live);
   }
+  dyn_epilogue(c);
 }
 
 template <class K>
@@ -97,6 +135,31 @@ cudaError_t launch_aba2(const DevModel& hm, const DevModel* d_model, const AbaAr
     if (!attr_done[0]) { e = dyn_attr(aba2_kernel<0>); if (e != cudaSuccess) return e; attr_done[0] = true; }
     note_kernel(reinterpret_cast<const void*>(aba2_kernel<0>));
     aba2_kernel<0><<<(unsigned)grid, block, smem, st>>>(d_model, mw, a);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_minv(const DevModel& hm, const DevModel* d_model, const MinvArgs& a, int num_sms, int* scratch_warps,
+                        cudaStream_t st) {
+  const int mw = (int)(aba2_model_bytes(hm) / 8);
+  const int wpb = hm.plan.warps, block = wpb * 32;
+  const long long ntiles = (a.n + 31) / 32;
+  long long grid = (ntiles + wpb - 1) / wpb;
+  if (grid > num_sms) grid = num_sms;
+  if (grid < 1) grid = 1;
+  if (scratch_warps) *scratch_warps = num_sms * wpb;
+  if (!a.scratch || a.n <= 0) return cudaSuccess;
+  const size_t smem = (size_t)mw * 8 + (size_t)block * hm.plan.smem_doubles * 8;
+  static thread_local bool attr_done[2] = {false, false};
+  cudaError_t e = cudaSuccess;
+  if (a.tile == 32) {
+    if (!attr_done[1]) { e = dyn_attr(minv_kernel<32>); if (e != cudaSuccess) return e; attr_done[1] = true; }
+    note_kernel(reinterpret_cast<const void*>(minv_kernel<32>));
+    minv_kernel<32><<<(unsigned)grid, block, smem, st>>>(d_model, mw, a);
+  } else {
+    if (!attr_done[0]) { e = dyn_attr(minv_kernel<0>); if (e != cudaSuccess) return e; attr_done[0] = true; }
+    note_kernel(reinterpret_cast<const void*>(minv_kernel<0>));
+    minv_kernel<0><<<(unsigned)grid, block, smem, st>>>(d_model, mw, a);
   }
   return cudaGetLastError();
 }

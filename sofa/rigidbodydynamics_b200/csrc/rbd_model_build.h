@@ -572,7 +572,24 @@ inline std::vector<unsigned long long> build_jt_blob(const DevModel* m, const st
 // SM) for which every level fits.  Fills m->plan (warps, smem_doubles, tmem_doubles, tmem_cols), joint[*].offA (level
 // record) and joint[*].boff (restart record), bit RBD_BOFF_TMEM = tensor memory.  Returns false when nothing fits (very
 // deep trees): the caller keeps the global-memory sweep (aba_instance).
+inline bool plan_levels(DevModel* m, bool use_tmem, int size_one_child, int size_branch, int restart_off, int max_warps,
+                        int forced_warps, size_t model_bytes);
 inline bool plan_aba2(DevModel* m, bool use_tmem, int max_warps = B200Limits::kMaxWarpsPerBlock, int forced_warps = 0) {
+  return plan_levels(m, use_tmem, 15, 27 + 18, 27, max_warps, forced_warps, aba2_model_bytes(*m));
+}
+// ... and of the M^-1 sweep (minv_instance): one child 9 (own inertia), >= 2 children I^A accumulator (21) + restart R | p
+// (12) in phase 1, the block's accelerations (6 RBD_MINV_CB) in phase 2; DevJoint::slot[0] <- end of the joint's subtree
+inline bool plan_minv(DevModel* m, bool use_tmem, int max_warps = B200Limits::kMaxWarpsPerBlock, int forced_warps = 0) {
+  const int nj = m->njoints;
+  for (int i = nj - 1; i >= 1; --i) m->joint[i].slot[0] = i + 1;
+  for (int i = nj - 1; i >= 1; --i) {  // pre-order: a joint's subtree ends where its last child's subtree ends
+    const int p = m->joint[i].parent;
+    if (p > 0) m->joint[p].slot[0] = std::max(m->joint[p].slot[0], m->joint[i].slot[0]);
+  }
+  return plan_levels(m, use_tmem, 9, std::max(21 + 12, 6 * RBD_MINV_CB), 21, max_warps, forced_warps, aba2_model_bytes(*m));
+}
+inline bool plan_levels(DevModel* m, bool use_tmem, int size_one_child, int size_branch, int restart_off, int max_warps,
+                        int forced_warps, size_t model_bytes) {
   const int nj = m->njoints;
   const int D = m->max_depth_internal;
   std::vector<int> size(D + 1, 0);
@@ -580,13 +597,12 @@ inline bool plan_aba2(DevModel* m, bool use_tmem, int max_warps = B200Limits::kM
     const DevJoint& j = m->joint[i];
     if (j.nchild <= 0) continue;
     if (j.depth > D) return false;
-    size[j.depth] = std::max(size[j.depth], j.nchild >= 2 ? 27 + 18 : 15);
+    size[j.depth] = std::max(size[j.depth], j.nchild >= 2 ? size_branch : size_one_child);
   }
   std::vector<int> order;
   for (int d = 1; d <= D; ++d)
     if (size[d] > 0) order.push_back(d);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return size[a] > size[b]; });
-  const size_t model_bytes = aba2_model_bytes(*m);
   for (int W = max_warps; W >= 1; --W) {
     if (forced_warps > 0 && W != forced_warps) continue;
     if (model_bytes + B200Limits::kSmemReservedPerBlock >= (size_t)B200Limits::kSmemBytes) return false;
@@ -610,7 +626,7 @@ inline bool plan_aba2(DevModel* m, bool use_tmem, int max_warps = B200Limits::kM
       j.offA = 0; j.boff = 0;
       if (j.nchild <= 0) continue;
       j.offA = off[j.depth];
-      if (j.nchild >= 2) j.boff = (off[j.depth] & RBD_BOFF_TMEM) | ((off[j.depth] & RBD_BOFF_MASK) + 27);
+      if (j.nchild >= 2) j.boff = (off[j.depth] & RBD_BOFF_TMEM) | ((off[j.depth] & RBD_BOFF_MASK) + restart_off);
     }
     return true;
   }

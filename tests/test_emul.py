@@ -530,3 +530,46 @@ def test_aba_body_matches_oracle_and_golden(emul, d, tile, body):
     for s, st in enumerate(gold):
         assert rel_err(got[s], np.array(st["qdd"])) <= 1e-9
     assert rel_err(got[n - 1], a[n - 1]) <= 1e-9
+
+
+@pytest.mark.parametrize("d", MODELS, ids=IDS)
+@pytest.mark.parametrize("tile", [32, 11])
+@pytest.mark.parametrize("body", ["planned", "smem_only", "w3"])
+def test_minv_body_matches_oracle(emul, d, tile, body):
+    """minv_instance (M^-1 as forward dynamics of unit torques on the shared articulated-body quantities: backward walks
+    along the path of each column, one forward sweep per block of columns) against the inverse of the oracle's CRBA mass
+    matrix, the oracle's ABA on unit torques, and M^-1 M == I.  Packed upper triangle, like M."""
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    if d.nv == 0:
+        pytest.skip("no dofs")
+    cd, keep = _cdesc(d)
+    n = 37
+    q, _v, _a = mdl.random_state(d, n, seed=77)
+    nt = (n + tile - 1) // tile
+    mf = d.nv * (d.nv + 1) // 2
+    Mv = np.full((nt, mf, tile), np.nan)
+    qs = to_tiled(q, tile)
+    plan = (C.c_int * 4)()
+    rc = emul.emul_minv(C.addressof(cd), n, tile, 0 if body == "smem_only" else 1, 3 if body == "w3" else 0, P(qs), P(Mv), plan)
+    assert rc == 0, emul.emul_last_error()
+    got = from_tiled(Mv, n)[:, :mf]
+    assert np.isfinite(got).all()
+    orc = oracle.Oracle(d)
+    iu = np.triu_indices(d.nv)
+    for i in range(n):
+        G = np.zeros((d.nv, d.nv))
+        for c in range(d.nv):
+            G[:c + 1, c] = got[i, c * (c + 1) // 2: c * (c + 1) // 2 + c + 1]
+        G = np.triu(G) + np.triu(G, 1).T
+        ref = orc.minv(q[i])
+        scale = max(1.0, float(np.max(np.abs(ref))))
+        assert np.max(np.abs(G - ref)) <= 1e-9 * scale, (i, np.max(np.abs(G - ref)) / scale)
+        M = orc.crba(q[i]); M = np.triu(M) + np.triu(M, 1).T
+        assert np.max(np.abs(G @ M - np.eye(d.nv))) <= 1e-8
+        if i < 2:       # the articulated-body restatement on unit torques (v = 0: the gravity term cancels in the difference)
+            z = np.zeros(d.nv)
+            a0 = orc.aba(q[i], z, z)
+            for c in (0, d.nv // 2, d.nv - 1):
+                e = np.zeros(d.nv); e[c] = 1.0
+                assert np.max(np.abs(orc.aba(q[i], z, e) - a0 - G[:, c])) <= 1e-9 * scale

@@ -925,3 +925,64 @@ def test_aba_matches_oracle(torch_mod, api, d, tile, fused):
     hd = np.zeros((n, d.nv))
     ws.aba_host(n, q, v, tau, hd)
     assert rel_err(hd, got) <= 1e-13
+
+
+@pytest.mark.parametrize("d", MODELS, ids=IDS)
+@pytest.mark.parametrize("tile", [32, 1000])
+def test_minv_matches_oracle(torch_mod, api, d, tile):
+    """rbd_minv_soa / rbd_minv_host (pinocchio::computeMinverse, SURVEY.md §8(f) rank 4): the packed upper triangle of
+    M(q)^-1 against the inverse of the oracle's CRBA mass matrix, against M^-1 M == I with the GPU's own CRBA, and as the
+    solution operator of the GPU's forward dynamics (aba(q, 0, tau) - aba(q, 0, 0) == M^-1 tau)."""
+    import oracle
+    torch = torch_mod
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    if d.nv == 0:
+        pytest.skip("no dofs")
+    n = 333
+    q, _v, _a = mdl.random_state(d, n, seed=71)
+    m = api.Model(d); ws = api.Workspace(m, n)
+    nt = (n + tile - 1) // tile
+    mf = d.nv * (d.nv + 1) // 2
+    qs = _dev(torch, to_tiled(q, tile))
+    Mi = torch.full((nt, mf, tile), float("nan"), dtype=torch.float64, device="cuda")
+    ws.minv_soa(n, tile, qs, Mi)
+    ws.synchronize()
+    assert "minv_kernel" in api.last_kernel_name()
+    got = from_tiled(Mi.cpu().numpy(), n)[:, :mf]
+    assert np.isfinite(got).all()
+    iu = np.triu_indices(d.nv)
+
+    def full(packed):
+        G = np.zeros((d.nv, d.nv))
+        for c in range(d.nv):
+            G[:c + 1, c] = packed[c * (c + 1) // 2: c * (c + 1) // 2 + c + 1]
+        return np.triu(G) + np.triu(G, 1).T
+
+    orc = oracle.Oracle(d)
+    for i in list(range(0, n, 23)) + [n - 1]:
+        ref = orc.minv(q[i])
+        assert np.max(np.abs(full(got[i]) - ref)) <= 1e-9 * max(1.0, float(np.max(np.abs(ref))))
+    # M^-1 M == I with the GPU's CRBA, every instance
+    Mp = torch.full((nt, mf, tile), float("nan"), dtype=torch.float64, device="cuda")
+    ws.crba_soa(n, tile, qs, Mp)
+    ws.synchronize()
+    Mg = from_tiled(Mp.cpu().numpy(), n)[:, :mf]
+    worst = 0.0
+    for i in range(n):
+        worst = max(worst, float(np.max(np.abs(full(got[i]) @ full(Mg[i]) - np.eye(d.nv)))))
+    assert worst <= 1e-8
+    # solution operator of the GPU's forward dynamics (gravity cancels in the difference)
+    rng = np.random.default_rng(72)
+    tau = rng.uniform(-1, 1, (n, d.nv)); zero = np.zeros((n, d.nv))
+    new = lambda: torch.full((nt, max(1, d.nv), tile), float("nan"), dtype=torch.float64, device="cuda")
+    zs, ts = _dev(torch, to_tiled(zero, tile)), _dev(torch, to_tiled(tau, tile))
+    a1, a0 = new(), new()
+    ws.aba_soa(n, tile, qs, zs, ts, a1); ws.aba_soa(n, tile, qs, zs, zs, a0)
+    ws.synchronize()
+    da = from_tiled((a1 - a0).cpu().numpy(), n)[:, :d.nv]
+    sol = np.stack([full(got[i]) @ tau[i] for i in range(n)])
+    assert rel_err(da, sol) <= 1e-8
+    # host entry point (instance-major packed upper triangle)
+    hm = np.zeros((n, mf))
+    ws.minv_host(n, q, hm)
+    assert rel_err(hm, got) <= 1e-13

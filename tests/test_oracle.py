@@ -190,3 +190,23 @@ def test_aba_matches_independent_forward_dynamics():
         for s in range(3):
             assert helpers.rel_err(orc.aba(q[s], v[s], orc.rnea(q[s], v[s], a[s])), a[s]) <= 1e-10, d.name
     assert seen >= 11
+
+
+def test_minv_is_the_solution_operator_of_aba():
+    """Oracle.minv (inverse of the CRBA matrix) against the oracle's articulated-body algorithm on unit torques: column j
+    == aba(q, 0, e_j) - aba(q, 0, 0) (v = 0: no Coriolis terms, gravity cancels) — two restatements with no shared code."""
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    for d in helpers.all_models():
+        if d.nv == 0:
+            continue
+        orc = oracle.Oracle(d)
+        q, _v, _a = mdl.random_state(d, 2, seed=9)
+        for s_ in range(2):
+            G = orc.minv(q[s_])
+            z = np.zeros(d.nv)
+            a0 = orc.aba(q[s_], z, z)
+            for c in range(d.nv):
+                e = np.zeros(d.nv); e[c] = 1.0
+                col = orc.aba(q[s_], z, e) - a0
+                assert np.max(np.abs(col - G[:, c])) <= 1e-9 * max(1.0, float(np.max(np.abs(G))))
