@@ -157,7 +157,9 @@ inline size_t eval_model_bytes(const DevModelT<real>& m) {
 }
 
 #define RBD_ABA2_REC 20 /* doubles per joint of the global pass-3 record of the fused forward-dynamics sweep (rbd_dyn_body.h) */
-#define RBD_MINV_CB 8 /* columns of M^-1 the forward sweep of minv_instance completes together                                */
+#ifndef RBD_MINV_CB
+#define RBD_MINV_CB 6 /* columns of M^-1 one backward / forward sweep of minv_instance serves together (A/B r2: 8 spills) */
+#endif
 #define RBD_MINV_REC 13 /* ... of the M^-1 sweep (minv_instance): A (6), U (6), 1 / D; + RBD_MINV_ROOT behind the joints   */
 #define RBD_MINV_ROOT_REC 33 /* root free-flyer: R | p (12), (X^T I^A X)^-1 (21)                                              */
 // ... and the fused forward-dynamics kernel (aba2_kernel): the joint table rounded to 16 bytes plus the two spare words

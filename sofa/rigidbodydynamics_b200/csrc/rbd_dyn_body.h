@@ -404,6 +404,7 @@ RBD_HD void aba2_instance(const DevModel& m, const FLD& q, const FLD& v, const F
 // Joints other than a root free-flyer have one dof, so dof c belongs to joint c + 1 (fixed base) or c - 4 (c >= 6 below a
 // free-flyer root).  DevJoint::slot[0] of the planned copy holds the end of the joint's subtree (exclusive).
 // (RBD_MINV_CB, RBD_MINV_REC, RBD_MINV_ROOT_REC: rbd_dev_model.h)
+static_assert(RBD_MINV_CB >= 6, "the six columns of a root free-flyer must sit in the first block");
 #define RBD_MINV_LEV1 9
 #define RBD_MINV_LEVB 21
 #define RBD_MINV_RST 12
@@ -571,118 +572,173 @@ RBD_HD void minv_instance(const DevModel& m, const FLD& q, const FLD& Mv, const 
   }
 #undef RBD_MINV_ROOT
   // ---- phase 2 ---------------------------------------------------------------------------------------------------
-  real Rp[12];
-  if (ffroot) {
-#pragma unroll
-    for (int e = 0; e < 12; ++e) Rp[e] = XR.ld(e);
-  }
+  // Per block of columns: ONE backward sweep over the joints (descending) serves the walks of all its columns — the
+  // columns of a block are neighbouring dofs and share most of their ancestors, each joint record is read once, and the
+  // steps of different columns are independent —, then the root, then ONE forward sweep.  Records (and, in the forward
+  // sweep, the partial entries) are fetched one joint ahead.
+  const int jlo = ffroot ? 2 : 1;
 #define RBD_MINV_JOINT_OF(c) (ffroot ? ((c) < 6 ? 1 : (c) - 4) : (c) + 1)
 #define RBD_MINV_FLD(r, c) ((c) * ((c) + 1) / 2 + (r))
+// the block's accelerations <-> level record, two columns at a time (a 48-double tensor-memory access would need 96
+// staging registers next to the 96 of acc itself)
+#define RBD_MINV_ACC_LD(OFF)                                                                      \
+  do {                                                                                            \
+    _Pragma("unroll") for (int h_ = 0; h_ < RBD_MINV_CB / 2; ++h_)                                \
+      lev_ld<12>(S, T, (OFF) + 12 * h_, &acc[2 * h_][0]);                                         \
+  } while (0)
+#define RBD_MINV_ACC_ST(OFF)                                                                      \
+  do {                                                                                            \
+    _Pragma("unroll") for (int h_ = 0; h_ < RBD_MINV_CB / 2; ++h_)                                \
+      lev_st<12>(S, T, (OFF) + 12 * h_, &acc[2 * h_][0]);                                         \
+  } while (0)
+#define RBD_MINV_FETCH(J)                                                                         \
+  do {                                                                                            \
+    const SCR Xn_ = X.at(RBD_MINV_REC * ((J) - 1));                                               \
+    _Pragma("unroll") for (int e_ = 0; e_ < RBD_MINV_REC; ++e_) nrec[e_] = Xn_.ld(e_);            \
+  } while (0)
   for (int c0 = 0; c0 < nv; c0 += RBD_MINV_CB) {
     const int ncb = nv - c0 < RBD_MINV_CB ? nv - c0 : RBD_MINV_CB;
-    real acc[RBD_MINV_CB][6];
-    // backward walks, column by column
+    const int jlast = RBD_MINV_JOINT_OF(c0 + ncb - 1);
+    real acc[RBD_MINV_CB][6];  // p of the backward sweep, then the accelerations of the forward sweep
 #pragma unroll
-    for (int k = 0; k < RBD_MINV_CB; ++k) {
+    for (int k = 0; k < RBD_MINV_CB; ++k)
 #pragma unroll
       for (int e = 0; e < 6; ++e) acc[k][e] = 0;
-      if (k < ncb) {
+#ifndef RBD_MINV_PREFETCH
+#define RBD_MINV_PREFETCH 0 /* A/B r2: fetching records one joint ahead costs registers the sweep does not have (spills) */
+#endif
+    real nrec[RBD_MINV_REC];
+    // backward sweep
+    if (RBD_MINV_PREFETCH && jlast >= jlo) RBD_MINV_FETCH(jlast);
+    for (int a = jlast; a >= jlo; --a) {
+#if RBD_MINV_PREFETCH
+      real rec[RBD_MINV_REC];
+#pragma unroll
+      for (int e = 0; e < RBD_MINV_REC; ++e) rec[e] = nrec[e];
+      if (a - 1 >= jlo) RBD_MINV_FETCH(a - 1);
+#else
+      RBD_MINV_FETCH(a);
+      real* const rec = nrec;
+#endif
+      const int r = m.joint[a].idx_v, send = m.joint[a].slot[0];
+      const real dinv = rec[12];
+#pragma unroll
+      for (int k = 0; k < RBD_MINV_CB; ++k) {
         const int c = c0 + k;
-        const int j = RBD_MINV_JOINT_OF(c);
-        real qr[6];  // acceleration of the root free-flyer's dofs for this column
-        bool have_root = false;
-        if (ffroot && j == 1) {
+        const int jc = RBD_MINV_JOINT_OF(c);
+        if (k < ncb) {
+          if (jc == a) {  // the column's own joint: unit torque, p = U / D
 #pragma unroll
-          for (int r = 0; r < 6; ++r) qr[r] = XR.ld(12 + s6(r, c));  // column c of (X^T I^A X)^-1
-          have_root = true;
-        } else {
-          const SCR Xj = X.at(RBD_MINV_REC * (j - 1));
-          real pv[6];
-          const real dj = Xj.ld(12);
+            for (int e = 0; e < 6; ++e) acc[k][e] = rec[6 + e] * dinv;
+            if (live) Mv.st(RBD_MINV_FLD(c, c), dinv);
+          } else if (a < jc && jc < send) {  // an ancestor of the column's joint
+            const real ua = -dot6(rec, acc[k]) * dinv;
+            if (live) Mv.st(RBD_MINV_FLD(r, c), ua);
 #pragma unroll
-          for (int e = 0; e < 6; ++e) pv[e] = Xj.ld(6 + e) * dj;
-          if (live) Mv.st(RBD_MINV_FLD(c, c), dj);
-          int a = m.joint[j].parent;
-          while (a != 0 && m.joint[a].type != JT_FF) {
-            const SCR Xa = X.at(RBD_MINV_REC * (a - 1));
-            real Aa[6], Ua[6];
-#pragma unroll
-            for (int e = 0; e < 6; ++e) { Aa[e] = Xa.ld(e); Ua[e] = Xa.ld(6 + e); }
-            const real ua = -dot6(Aa, pv) * Xa.ld(12);
-            if (live) Mv.st(RBD_MINV_FLD(m.joint[a].idx_v, c), ua);
-#pragma unroll
-            for (int e = 0; e < 6; ++e) pv[e] += Ua[e] * ua;
-            a = m.joint[a].parent;
+            for (int e = 0; e < 6; ++e) acc[k][e] += rec[6 + e] * ua;
           }
-          if (a != 0) {  // the root free-flyer: qdd_root = -(X^T I^A X)^-1 X^T p
-            real b[6], Di[21];
-            ff_rows(Rp, Rp + 9, pv, b);
-#pragma unroll
-            for (int e = 0; e < 21; ++e) Di[e] = XR.ld(12 + e);
-#pragma unroll
-            for (int e = 0; e < 6; ++e) b[e] = -b[e];
-            sym6_mul(Di, b, qr);
-            have_root = true;
-          }
-        }
-        if (have_root) {
-          const int rmax = c < 5 ? c : 5;
-#pragma unroll
-          for (int r = 0; r < 6; ++r)
-            if (r <= rmax && live) Mv.st(RBD_MINV_FLD(r, c), qr[r]);
-          // a_root = X qdd_root
-          real aa[3], tx, ty, tz;
-#pragma unroll
-          for (int e = 0; e < 3; ++e) {
-            acc[k][e] = Rp[3 * e] * qr[0] + Rp[3 * e + 1] * qr[1] + Rp[3 * e + 2] * qr[2];
-            aa[e] = Rp[3 * e] * qr[3] + Rp[3 * e + 1] * qr[4] + Rp[3 * e + 2] * qr[5];
-          }
-          RBD_CROSS(tx, ty, tz, Rp[9], Rp[10], Rp[11], aa[0], aa[1], aa[2]);
-          acc[k][0] += tx; acc[k][1] += ty; acc[k][2] += tz;
-          acc[k][3] = aa[0]; acc[k][4] = aa[1]; acc[k][5] = aa[2];
         }
       }
     }
-    // forward sweep of the block up to the joint of its last column
-    const int jlast = RBD_MINV_JOINT_OF(c0 + ncb - 1);
-    int i = 1;
+    // the root: free-flyer dofs of every column of the block, and the accelerations the forward sweep starts from
+    real Rp[12], Di[21];
     if (ffroot) {
-      if (m.joint[1].nchild >= 2) lev_st<6 * RBD_MINV_CB>(S, T, m.joint[1].offA, &acc[0][0]);
-      i = 2;
+#pragma unroll
+      for (int e = 0; e < 12; ++e) Rp[e] = XR.ld(e);
+#pragma unroll
+      for (int e = 0; e < 21; ++e) Di[e] = XR.ld(12 + e);
     }
-    for (; i <= jlast; ++i) {
+#pragma unroll
+    for (int k = 0; k < RBD_MINV_CB; ++k) {
+      const int c = c0 + k;
+      if (k < ncb && ffroot) {
+        real qr[6];
+        if (c < 6) {
+#pragma unroll
+          for (int r = 0; r < 6; ++r) qr[r] = Di[s6(r, k)];  // (c0 == 0 for these columns: c == k) column c of (X^T I^A X)^-1
+        } else {  // qdd_root = -(X^T I^A X)^-1 X^T p
+          real b[6];
+          ff_rows(Rp, Rp + 9, acc[k], b);
+#pragma unroll
+          for (int e = 0; e < 6; ++e) b[e] = -b[e];
+          sym6_mul(Di, b, qr);
+        }
+        const int rmax = c < 5 ? c : 5;
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+          if (r <= rmax && live) Mv.st(RBD_MINV_FLD(r, c), qr[r]);
+        real aa[3], tx, ty, tz;  // a_root = X qdd_root
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+          acc[k][e] = Rp[3 * e] * qr[0] + Rp[3 * e + 1] * qr[1] + Rp[3 * e + 2] * qr[2];
+          aa[e] = Rp[3 * e] * qr[3] + Rp[3 * e + 1] * qr[4] + Rp[3 * e + 2] * qr[5];
+        }
+        RBD_CROSS(tx, ty, tz, Rp[9], Rp[10], Rp[11], aa[0], aa[1], aa[2]);
+        acc[k][0] += tx; acc[k][1] += ty; acc[k][2] += tz;
+        acc[k][3] = aa[0]; acc[k][4] = aa[1]; acc[k][5] = aa[2];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 6; ++e) acc[k][e] = 0;
+      }
+    }
+    // forward sweep of the block up to the joint of its last column
+    if (ffroot && m.joint[1].nchild >= 2 && jlast >= jlo) RBD_MINV_ACC_ST(m.joint[1].offA);
+    real npart[RBD_MINV_CB];
+#define RBD_MINV_FETCH_PART(J)                                                                    \
+  do {                                                                                            \
+    const int rn_ = m.joint[J].idx_v, sn_ = m.joint[J].slot[0];                                   \
+    _Pragma("unroll") for (int k_ = 0; k_ < RBD_MINV_CB; ++k_) {                                  \
+      const int cn_ = c0 + k_;                                                                    \
+      const int jn_ = RBD_MINV_JOINT_OF(cn_);                                                     \
+      npart[k_] = 0;                                                                              \
+      if (k_ < ncb && jn_ >= (J) && jn_ < sn_ && live) npart[k_] = Mv.ld(RBD_MINV_FLD(rn_, cn_)); \
+    }                                                                                             \
+  } while (0)
+    if (RBD_MINV_PREFETCH && jlast >= jlo) { RBD_MINV_FETCH(jlo); RBD_MINV_FETCH_PART(jlo); }
+    for (int i = jlo; i <= jlast; ++i) {
       const DevJoint& jn = m.joint[i];
       const int par = jn.parent;
+#if RBD_MINV_PREFETCH
+      real rec[RBD_MINV_REC], part[RBD_MINV_CB];
+#pragma unroll
+      for (int e = 0; e < RBD_MINV_REC; ++e) rec[e] = nrec[e];
+#pragma unroll
+      for (int k = 0; k < RBD_MINV_CB; ++k) part[k] = npart[k];
+      if (i + 1 <= jlast) { RBD_MINV_FETCH(i + 1); RBD_MINV_FETCH_PART(i + 1); }
+#else
+      RBD_MINV_FETCH(i);
+      RBD_MINV_FETCH_PART(i);
+      real* const rec = nrec;
+      real* const part = npart;
+#endif
       if (par == 0) {
 #pragma unroll
         for (int k = 0; k < RBD_MINV_CB; ++k)
 #pragma unroll
           for (int e = 0; e < 6; ++e) acc[k][e] = 0;
       } else if (par != i - 1) {
-        lev_ld<6 * RBD_MINV_CB>(S, T, m.joint[par].offA, &acc[0][0]);
+        RBD_MINV_ACC_LD(m.joint[par].offA);
       }
-      const SCR Xi = X.at(RBD_MINV_REC * (i - 1));
-      real A[6], U[6];
-#pragma unroll
-      for (int e = 0; e < 6; ++e) { A[e] = Xi.ld(e); U[e] = Xi.ld(6 + e); }
-      const real dinv = Xi.ld(12);
-      const int r = jn.idx_v, send = jn.slot[0];
+      const real dinv = rec[12];
+      const int r = jn.idx_v;
 #pragma unroll
       for (int k = 0; k < RBD_MINV_CB; ++k) {
         const int c = c0 + k;
         const int jc = RBD_MINV_JOINT_OF(c);
         if (k < ncb && jc >= i) {  // (a column is finished once the sweep has passed its joint: rows > column)
-          real part = 0;
-          if (jc < send && live) part = Mv.ld(RBD_MINV_FLD(r, c));  // joint i is on the path of column c: u_i / D_i
-          const real qdd = part - dot6(U, acc[k]) * dinv;
+          const real qdd = part[k] - dot6(rec + 6, acc[k]) * dinv;
           if (live) Mv.st(RBD_MINV_FLD(r, c), qdd);
 #pragma unroll
-          for (int e = 0; e < 6; ++e) acc[k][e] += A[e] * qdd;
+          for (int e = 0; e < 6; ++e) acc[k][e] += rec[e] * qdd;
         }
       }
-      if (jn.nchild >= 2) lev_st<6 * RBD_MINV_CB>(S, T, jn.offA, &acc[0][0]);
+      if (jn.nchild >= 2) RBD_MINV_ACC_ST(jn.offA);
     }
+#undef RBD_MINV_FETCH_PART
   }
+#undef RBD_MINV_FETCH
+#undef RBD_MINV_ACC_LD
+#undef RBD_MINV_ACC_ST
 #undef RBD_MINV_JOINT_OF
 #undef RBD_MINV_FLD
 }
