@@ -12,10 +12,13 @@ python bench.py --impl reference --steps 5 --warmup 1 > $O/${T}_bench_reference_
 Q="--steps 2 --warmup 1 --no-e2e --no-cpu --no-secondary"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${T}_launches.csv \
     python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu --secondary-steps 2 > $O/${T}_launches.log 2>&1
-profiles/capture.sh "eval_kernel_simple" ${T}_eval_talos -- python bench.py $Q
-profiles/capture.sh "eval_kernel_ffroot" ${T}_eval_solo -- python bench.py --workload solo $Q
+profiles/capture.sh "eval_kernel_ffroot8" ${T}_eval_talos -- python bench.py $Q
+profiles/capture.sh "eval_kernel_ffroot<" ${T}_eval_solo -- python bench.py --workload solo $Q
 profiles/capture.sh "eval_kernel_chain" ${T}_eval_panda -- python bench.py --workload panda $Q
-profiles/capture.sh "aba_kernel" ${T}_aba_talos -- python bench_mapping.py --robot talos_reduced --n 1048576 --steps 3
+profiles/capture.sh "aba2_kernel" ${T}_aba2_talos -- python experiments/time_aba.py talos_reduced
+profiles/capture.sh "minv_kernel" ${T}_minv_talos -- python experiments/time_minv.py talos_reduced
+python experiments/time_aba.py > $O/${T}_time_aba.json 2>&1
+python experiments/time_minv.py > $O/${T}_time_minv.json 2>&1
 profiles/capture.sh "applyJT_rows_cached" ${T}_rows_talos -- python bench_mapping.py --robot talos_reduced --n 1048576 --steps 3
 profiles/capture.sh "transpose32_kernel<\(bool\)1>|transpose32_kernel<true>" ${T}_soa_to_aos -- python bench_mapping.py --robot talos_reduced --n 1048576 --steps 3
 M=smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,gpu__time_duration.sum
