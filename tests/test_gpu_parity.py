@@ -459,6 +459,11 @@ def test_no_out_of_bounds_writes(torch_mod, api, name, n, tile):
     if mdl_ok:
         ws.applyDJT_soa(n, tile, views["dq"], views["rootv"] if ff else None, views["w"], 1.0, views["tj"],
                         views["tr"] if ff else None)
+        # forward dynamics (both kernels) and the inverse mass matrix: outputs land in tau / M of the same arena
+        for fused in (True, False):
+            ws.set_aba_fused(fused)
+            ws.aba_soa(n, tile, views["q"], views["v"], views["a"], views["tau"])
+        ws.minv_soa(n, tile, views["q"], views["M"])
     nrows = n + 3
     rp = torch.arange(0, 2 * nrows + 1, 2, dtype=torch.int32, device="cuda")
     ri = (torch.arange(0, nrows, dtype=torch.int32, device="cuda") % n).contiguous()
