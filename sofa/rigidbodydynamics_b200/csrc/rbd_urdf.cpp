@@ -26,6 +26,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <charconv>
 #include <map>
 #include <memory>
 #include <new>
@@ -349,15 +350,20 @@ struct rbd_urdf_model {
 
 namespace {
 
+// Numbers are parsed with std::from_chars, not strtod: a host application (SOFA's GUI) may have set a LC_NUMERIC locale
+// with a decimal comma, under which strtod("0.5") stops at the dot.
 void parse_floats(const std::string* s, int n, double* out, const char* what) {
   for (int k = 0; k < n; ++k) out[k] = 0.0;
   if (!s) return;
   const char* p = s->c_str();
+  const char* const last = p + s->size();
   for (int k = 0; k < n; ++k) {
-    char* end = nullptr;
-    out[k] = strtod(p, &end);
-    if (end == p) throw UrdfError{RBD_ERR_MODEL, std::string("URDF: ") + what + " needs " + std::to_string(n) + " numbers, got \"" + *s + "\""};
-    p = end;
+    while (p < last && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) ++p;
+    if (p < last && *p == '+') ++p;  // from_chars takes no leading plus sign
+    const std::from_chars_result r = std::from_chars(p, last, out[k]);
+    if (r.ec != std::errc() || r.ptr == p)
+      throw UrdfError{RBD_ERR_MODEL, std::string("URDF: ") + what + " needs " + std::to_string(n) + " numbers, got \"" + *s + "\""};
+    p = r.ptr;
   }
   while (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r') ++p;
   if (*p) throw UrdfError{RBD_ERR_MODEL, std::string("URDF: ") + what + " has trailing text: \"" + *s + "\""};
