@@ -622,8 +622,12 @@ __global__ void soa_to_aos_kernel(long long n, int K, long long tile, const doub
 template <bool TO_AOS>
 __global__ void __launch_bounds__(256) transpose32_kernel(long long n, int K, const double* __restrict__ src, double* __restrict__ dst) {
   __shared__ double t[RBD_TR_KC][33];
-  const long long tile = blockIdx.x;
-  const int k0 = blockIdx.y * RBD_TR_KC;
+  // 1-D grid, field chunk fastest: the blocks that are resident together then cover whole tiles — 32 K contiguous
+  // doubles on either side — instead of one 1 KB piece of many tiles (DRAM page locality: K = 741 ran at 0.75 of the
+  // roofline with the chunk index on grid.y, K = 128, where a block's piece IS the whole tile, at 0.93)
+  const int nchunks = (K + RBD_TR_KC - 1) / RBD_TR_KC;
+  const long long tile = blockIdx.x / nchunks;
+  const int k0 = (int)(blockIdx.x % nchunks) * RBD_TR_KC;
   const int kc = min(RBD_TR_KC, K - k0);
   const long long i0 = tile * 32;
   const int ni = (int)min(32LL, n - i0);
@@ -657,6 +661,130 @@ __global__ void __launch_bounds__(256) transpose32_kernel(long long n, int K, co
     for (int j = 0; j < RBD_TR_KC * 32 / 256; ++j) {
       const int idx = tid + 256 * j, k = idx >> 5;
       if (k < kc && (idx & 31) < ni) d[idx] = t[k][idx & 31];
+    }
+  }
+}
+
+// The same slab with 16-byte accesses on all four legs (global load, shared store, shared load, global store): the
+// kernel above issues four memory instructions per 8 bytes and stalls on the memory-instruction queue (mio / lg throttle
+// 21 + 5 stall cycles per issue, profiles/r2_soa_to_aos_ncu_full.txt).  Every thread moves 2 x 2 blocks — fields (k, k+1)
+// of instances (i, i+1): on the tiled side a block is two 16-byte pieces of two field rows, in the shared tile (kept
+// instance-major, row stride RBD_TRV_S doubles) two 16-byte pieces of two instance rows.  On the instance-major side
+// row r of the slab starts at element (i0 + r) K + k0, whose parity alternates from row to row when K is odd: row r of the
+// shared tile is shifted by that parity, so that a pair which is 16-byte aligned in global memory is 16-byte aligned in
+// shared memory too (a lone head / tail element per row moves as a scalar, and the 2 x 2 blocks of the shifted rows use
+// two 8-byte shared accesses instead of one 16-byte access).  Lane mapping inside a warp: instance pair ip = (lane & 3) +
+// 4 (lane >> 3), field pair bit (lane >> 2) & 1 — a quarter warp's eight 16-byte shared accesses then hit eight different
+// 16-byte bank groups.  Needs 16-byte aligned base pointers (the launcher checks).
+#define RBD_TRV_KC 128
+#define RBD_TRV_S 130
+#ifndef RBD_TR_VEC
+#define RBD_TR_VEC 1 /* A/B knob: 0 = the 8-byte kernel for every launch */
+#endif
+#define RBD_TRV_MINK 96 /* narrower arrays leave most lanes of the row phase idle: the 8-byte kernel is faster there (K = 38) */
+static_assert(RBD_TRV_KC == RBD_TR_KC, "both tile-32 adapters share the launch grid");
+template <bool TO_AOS>
+__global__ void __launch_bounds__(256) transpose32v_kernel(long long n, int K, const double* __restrict__ src, double* __restrict__ dst) {
+  __shared__ __align__(16) double t[32 * RBD_TRV_S];
+  const int nchunks = (K + RBD_TRV_KC - 1) / RBD_TRV_KC;  // 1-D grid, field chunk fastest (see transpose32_kernel)
+  const long long tile = blockIdx.x / nchunks;
+  const int k0 = (int)(blockIdx.x % nchunks) * RBD_TRV_KC;
+  const int kc = min(RBD_TRV_KC, K - k0);
+  const long long i0 = tile * 32;
+  const int ni = (int)min(32LL, n - i0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int par_even = k0 & 1, par_odd = (K + k0) & 1;  // parity of (i0 + r) K + k0 for even / odd r (i0 K is even)
+  const int ip = (lane & 3) + 4 * (lane >> 3);           // instance pair 0 .. 15
+  const int kpbit = (lane >> 2) & 1;
+  const int i = 2 * ip;
+  double* const te = t + i * RBD_TRV_S + par_even;       // row i (even), element k at te[k]
+  double* const to = t + (i + 1) * RBD_TRV_S + par_odd;  // row i + 1
+  if (TO_AOS) {
+    const double* s = src + tile * (long long)K * 32 + (long long)k0 * 32 + i;  // + k * 32: fields k of instances i, i + 1
+    double2 a[4], b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = 2 * (2 * warp + kpbit + 16 * j);
+      a[j] = make_double2(0.0, 0.0); b[j] = a[j];
+      if (k < kc) a[j] = *reinterpret_cast<const double2*>(s + (long long)k * 32);
+      if (k + 1 < kc) b[j] = *reinterpret_cast<const double2*>(s + (long long)(k + 1) * 32);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = 2 * (2 * warp + kpbit + 16 * j);
+      if (k < kc) {
+        if (par_even == 0) *reinterpret_cast<double2*>(te + k) = make_double2(a[j].x, b[j].x);
+        else { te[k] = a[j].x; te[k + 1] = b[j].x; }
+        if (par_odd == 0) *reinterpret_cast<double2*>(to + k) = make_double2(a[j].y, b[j].y);
+        else { to[k] = a[j].y; to[k + 1] = b[j].y; }
+      }
+    }
+    __syncthreads();
+    for (int r = warp; r < ni; r += 8) {
+      const int par = (r & 1) ? par_odd : par_even;
+      const double* tr = t + r * RBD_TRV_S + par;
+      double* gd = dst + (i0 + r) * K + k0;
+      if (par && lane == 0) gd[0] = tr[0];
+      const int npairs = (kc - par) >> 1;
+      for (int m = lane; m < npairs; m += 32)
+        *reinterpret_cast<double2*>(gd + par + 2 * m) = *reinterpret_cast<const double2*>(tr + par + 2 * m);
+      if (((kc - par) & 1) && lane == 31) gd[kc - 1] = tr[kc - 1];
+    }
+  } else {
+    {
+      // all of this thread's loads first (4 rows x 2 pairs + head / tail scalars), then the shared stores
+      double2 v[4][2];
+      double hd[4], tl[4];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int r = warp + 8 * rr;
+        const int par = (r & 1) ? par_odd : par_even;
+        const double* gs = src + (i0 + r) * K + k0;
+        const int npairs = (kc - par) >> 1;
+        hd[rr] = tl[rr] = 0.0;
+#pragma unroll
+        for (int mm = 0; mm < 2; ++mm) {
+          const int m = lane + 32 * mm;
+          v[rr][mm] = make_double2(0.0, 0.0);
+          if (r < ni && m < npairs) v[rr][mm] = *reinterpret_cast<const double2*>(gs + par + 2 * m);
+        }
+        if (r < ni && par && lane == 0) hd[rr] = gs[0];
+        if (r < ni && ((kc - par) & 1) && lane == 31) tl[rr] = gs[kc - 1];
+      }
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int r = warp + 8 * rr;
+        const int par = (r & 1) ? par_odd : par_even;
+        double* tr = t + r * RBD_TRV_S + par;
+        const int npairs = (kc - par) >> 1;
+#pragma unroll
+        for (int mm = 0; mm < 2; ++mm) {
+          const int m = lane + 32 * mm;
+          if (r < ni && m < npairs) *reinterpret_cast<double2*>(tr + par + 2 * m) = v[rr][mm];
+        }
+        if (r < ni && par && lane == 0) tr[0] = hd[rr];
+        if (r < ni && ((kc - par) & 1) && lane == 31) tr[kc - 1] = tl[rr];
+      }
+    }
+    __syncthreads();
+    double* d = dst + tile * (long long)K * 32 + (long long)k0 * 32 + i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = 2 * (2 * warp + kpbit + 16 * j);
+      if (k < kc && i < ni) {
+        double2 x, y;
+        if (par_even == 0) x = *reinterpret_cast<const double2*>(te + k);
+        else { x.x = te[k]; x.y = te[k + 1]; }
+        if (i + 1 < ni) {
+          if (par_odd == 0) y = *reinterpret_cast<const double2*>(to + k);
+          else { y.x = to[k]; y.y = to[k + 1]; }
+          *reinterpret_cast<double2*>(d + (long long)k * 32) = make_double2(x.x, y.x);
+          if (k + 1 < kc) *reinterpret_cast<double2*>(d + (long long)(k + 1) * 32) = make_double2(x.y, y.y);
+        } else {  // the batch ends on an even instance: the padding lane of the last tile is left alone
+          d[(long long)k * 32] = x.x;
+          if (k + 1 < kc) d[(long long)(k + 1) * 32] = x.y;
+        }
+      }
     }
   }
 }
@@ -957,8 +1085,13 @@ cudaError_t launch_getJ(const DevModel& m, const DevModel* d_model, const DevTab
 cudaError_t launch_aos_to_soa(long long n, int K, long long tile, const double* aos, double* soa, cudaStream_t st) {
   if (n <= 0 || K <= 0) return cudaSuccess;
   if (tile == 32) {
-    dim3 g32((unsigned)((n + 31) / 32), (unsigned)((K + RBD_TR_KC - 1) / RBD_TR_KC));
-    transpose32_kernel<false><<<g32, 256, 0, st>>>(n, K, aos, soa);
+    const long long nb32 = ((n + 31) / 32) * ((K + RBD_TR_KC - 1) / RBD_TR_KC);
+    if (nb32 > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    const unsigned g32 = (unsigned)nb32;
+    if (RBD_TR_VEC && K >= RBD_TRV_MINK && ((reinterpret_cast<unsigned long long>(aos) | reinterpret_cast<unsigned long long>(soa)) & 15) == 0)
+      transpose32v_kernel<false><<<g32, 256, 0, st>>>(n, K, aos, soa);
+    else
+      transpose32_kernel<false><<<g32, 256, 0, st>>>(n, K, aos, soa);
     return cudaGetLastError();
   }
   dim3 grid((unsigned)((n + 31) / 32), (unsigned)((K + 31) / 32)), block(32, 8);
@@ -968,8 +1101,13 @@ cudaError_t launch_aos_to_soa(long long n, int K, long long tile, const double* 
 cudaError_t launch_soa_to_aos(long long n, int K, long long tile, const double* soa, double* aos, cudaStream_t st) {
   if (n <= 0 || K <= 0) return cudaSuccess;
   if (tile == 32) {
-    dim3 g32((unsigned)((n + 31) / 32), (unsigned)((K + RBD_TR_KC - 1) / RBD_TR_KC));
-    transpose32_kernel<true><<<g32, 256, 0, st>>>(n, K, soa, aos);
+    const long long nb32 = ((n + 31) / 32) * ((K + RBD_TR_KC - 1) / RBD_TR_KC);
+    if (nb32 > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    const unsigned g32 = (unsigned)nb32;
+    if (RBD_TR_VEC && K >= RBD_TRV_MINK && ((reinterpret_cast<unsigned long long>(aos) | reinterpret_cast<unsigned long long>(soa)) & 15) == 0)
+      transpose32v_kernel<true><<<g32, 256, 0, st>>>(n, K, soa, aos);
+    else
+      transpose32_kernel<true><<<g32, 256, 0, st>>>(n, K, soa, aos);
     return cudaGetLastError();
   }
   dim3 grid((unsigned)((n + 31) / 32), (unsigned)((K + 31) / 32)), block(32, 8);

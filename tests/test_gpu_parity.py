@@ -403,15 +403,22 @@ def test_layout_adapters_roundtrip(torch_mod, api):
     from sofa.rigidbodydynamics_b200 import model as mdl
     m = api.Model(mdl.panda7()); ws = api.Workspace(m, 8)
     for n, K, tile in ((1, 1, 1), (1000, 37, 32), (4097, 100, 4097), (33, 741, 64), (4097, 741, 32), (31, 200, 32),
-                       (64, 128, 32), (33, 129, 32), (1, 1, 32), (100, 7, 32)):
-        x = torch.randn((n, K), dtype=torch.float64, device="cuda")
-        nt = (n + tile - 1) // tile
-        s = torch.zeros((nt, K, tile), dtype=torch.float64, device="cuda")
-        ws.aos_to_soa(n, K, tile, x, s)
-        assert np.array_equal(from_tiled(s.cpu().numpy(), n), x.cpu().numpy())
-        y = torch.empty_like(x)
-        ws.soa_to_aos(n, K, tile, s, y)
-        assert torch.equal(x, y)
+                       (64, 128, 32), (33, 129, 32), (1, 1, 32), (100, 7, 32), (4096, 256, 32), (2049, 255, 32),
+                       (95, 2, 32), (66, 3, 32), (32, 127, 32), (63, 130, 32), (1025, 228, 32), (7, 396, 32)):
+        for shift in (0, 1):        # shift 1: base pointers 8-byte aligned only (the 16-byte kernel must not be picked)
+            xb = torch.randn((n * K + shift,), dtype=torch.float64, device="cuda")
+            x = xb[shift:].view(n, K)
+            nt = (n + tile - 1) // tile
+            sb = torch.zeros((nt * K * tile + shift,), dtype=torch.float64, device="cuda")
+            s = sb[shift:].view(nt, K, tile)
+            ws.aos_to_soa(n, K, tile, x, s)
+            # exact image, padding lanes of the last tile included (they must stay untouched: zeros)
+            assert np.array_equal(s.cpu().numpy(), to_tiled(x.cpu().numpy(), tile)), (n, K, tile, shift)
+            yb = torch.full((n * K + shift + 8,), -7.0, dtype=torch.float64, device="cuda")
+            y = yb[shift:shift + n * K].view(n, K)
+            ws.soa_to_aos(n, K, tile, s, y)
+            assert torch.equal(x, y), (n, K, tile, shift)
+            assert bool((yb[shift + n * K:] == -7.0).all()) and bool((yb[:shift] == -7.0).all())
 
 
 @pytest.mark.parametrize("name,n,tile", [("talos_reduced", 1000, 32), ("solo12", 77, 32), ("random_3", 333, 100),
