@@ -359,6 +359,7 @@ def main():
     ap.add_argument("--tile", type=int, default=32, help="tiled-SoA tile (32 = AoSoA fast path, 0 = plain SoA, tile = n)")
     ap.add_argument("--block", type=int, default=0, help="eval kernel block size override (0 = automatic)")
     ap.add_argument("--no-tmem", action="store_true", help="keep the whole sweep state in shared memory (A/B knob)")
+    ap.add_argument("--no-arm", action="store_true", help="serial chains: the generic chain sweep instead of the unrolled arm kernel (A/B knob)")
     ap.add_argument("--f32", action="store_true",
                     help="secondary: also time the optional FP32 mode (1e-4 tolerance) and report it under 'fp32_mode'")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -404,6 +405,8 @@ def main():
         dyn.ws.set_eval_block(args.block)
     if args.no_tmem:
         dyn.ws.set_eval_tmem(False)
+    if args.no_arm:
+        dyn.ws.set_eval_arm(False)
     I = dyn.model.info
     nq, nv = I.nq, I.nv
     bytes_per_eval = int(I.eval_bytes)

@@ -74,7 +74,7 @@ SYMBOLS = [
     "rbd_eval_soa_sparse", "rbd_crba_soa_sparse", "rbd_eval_host_sparse",
     "rbd_model_getJ_pattern", "rbd_getJ_dev", "rbd_getJ_host", "rbd_aba_soa", "rbd_aba_host", "rbd_minv_soa", "rbd_minv_host",
     "rbd_workspace_create", "rbd_workspace_destroy", "rbd_workspace_set_stream", "rbd_workspace_synchronize",
-    "rbd_workspace_launch_count", "rbd_workspace_set_eval_block", "rbd_workspace_set_eval_tmem", "rbd_workspace_set_applyJT_ring", "rbd_workspace_set_rows_cache", "rbd_workspace_set_aba_fused", "rbd_workspace_get_eval_plan", "rbd_workspace_get_eval_plan_f32",
+    "rbd_workspace_launch_count", "rbd_workspace_set_eval_block", "rbd_workspace_set_eval_tmem", "rbd_workspace_set_applyJT_ring", "rbd_workspace_set_rows_cache", "rbd_workspace_set_aba_fused", "rbd_workspace_set_eval_arm", "rbd_workspace_get_eval_plan", "rbd_workspace_get_eval_plan_f32",
     "rbd_apply_soa", "rbd_applyJ_soa", "rbd_applyJT_soa", "rbd_applyJT_rows_dev",
     "rbd_getFrameJacobian_dev", "rbd_getFrameJacobian_host", "rbd_applyDJT_soa", "rbd_applyDJT_host",
     "rbd_eval_soa", "rbd_eval_soa_f32", "rbd_crba_soa", "rbd_rnea_soa", "rbd_addMDx_soa", "rbd_addForce_soa",
@@ -132,6 +132,7 @@ def load() -> C.CDLL:
         "rbd_workspace_set_applyJT_ring": (C.c_int, [vp, C.c_int, vp]),
         "rbd_workspace_set_rows_cache": (C.c_int, [vp, C.c_int]),
         "rbd_workspace_set_aba_fused": (C.c_int, [vp, C.c_int]),
+        "rbd_workspace_set_eval_arm": (C.c_int, [vp, C.c_int]),
         "rbd_workspace_get_eval_plan": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_int32 * 8)]),
         "rbd_workspace_get_eval_plan_f32": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_int32 * 8)]),
         "rbd_apply_soa": (C.c_int, [vp, i64, i64, vp, vp, vp]),

@@ -137,6 +137,10 @@ class Workspace:
     def set_eval_tmem(self, enable: bool):
         check(self._lib.rbd_workspace_set_eval_tmem(self._h, 1 if enable else 0))
 
+    def set_eval_arm(self, enable: bool):
+        """A/B knob of the fused eval of 6- / 7-joint serial chains: unrolled arm kernel (default) or the generic chain sweep."""
+        check(self._lib.rbd_workspace_set_eval_arm(self._h, 1 if enable else 0))
+
     def set_aba_fused(self, enable: bool):
         """A/B knob of forward dynamics: the fused sweep on on-chip level records (default) or the first version."""
         check(self._lib.rbd_workspace_set_aba_fused(self._h, 1 if enable else 0))

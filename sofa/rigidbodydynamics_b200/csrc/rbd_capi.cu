@@ -111,6 +111,7 @@ struct rbd_workspace {
   DevModel* d_aba2 = nullptr;
   int aba2_state = 0;
   int use_aba2 = 1;
+  int use_arm = 1;  // fused eval of 6- / 7-joint serial chains on the unrolled arm kernel
   double* aba2_scratch[2] = {nullptr, nullptr};
   // M^-1 sweep (minv): planned joint table, state as aba2_state (-1: the model's level records do not fit an SM)
   DevModel* h_minv = nullptr;
@@ -309,6 +310,11 @@ RBD_API int rbd_workspace_set_eval_tmem(rbd_workspace* ws, int enable) {
   return RBD_OK;
 }
 
+RBD_API int rbd_workspace_set_eval_arm(rbd_workspace* ws, int enable) {
+  GUARD(ws);
+  ws->use_arm = enable ? 1 : 0;
+  return RBD_OK;
+}
 RBD_API int rbd_workspace_set_aba_fused(rbd_workspace* ws, int enable) {
   GUARD(ws);
   if ((ws->use_aba2 != 0) != (enable != 0)) { ws->use_aba2 = enable ? 1 : 0; drop_plans(ws); }
@@ -412,6 +418,17 @@ static int eval_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, 
   if (!q) return set_err(RBD_ERR_INVALID_ARG, "q is null");
   if (tau && (!v || !a)) return set_err(RBD_ERR_INVALID_ARG, "rnea needs v and a");
   const int ek = (oMi ? 4 : 0) | (M ? 2 : 0) | (tau ? 1 : 0);
+  // fixed-base serial chains of 6 / 7 joints, M and tau requested: the unrolled sweep with the joint table in the constant
+  // bank (rbd_kernels_arm.cu).  A chain's M has no structural zeros: the support-only format is the same array.
+  if (ws->use_arm && ws->forced_eval_block == 0 && M && tau && v && a) {
+    cudaError_t ce = cudaSuccess;
+    EvalArgs AA{n, tile, q, v, a, oMi, J, M, tau};
+    if (launch_eval_arm(ws->model->dm, AA, ws->num_sms, st, &ce)) {
+      if (ce != cudaSuccess) return cuda_fail(ce, "launch_eval_arm");
+      if (n > 0) ws->launches++;
+      return RBD_OK;
+    }
+  }
   const int pk = (sparse_m && M) ? 11 + ek : ek;
   int rc = ensure_plan(ws, pk);
   if (rc == RBD_ERR_UNSUPPORTED && M && tau && ws->forced_eval_block == 0) {

@@ -110,6 +110,9 @@ cudaError_t launch_aba2(const DevModel& planned_host_model, const DevModel* d_mo
 // inverse of the mass matrix (minv_instance): `planned_host_model` planned with plan_minv; sizing call as launch_aba
 cudaError_t launch_minv(const DevModel& planned_host_model, const DevModel* d_model, const MinvArgs& a, int num_sms,
                         int* scratch_warps, cudaStream_t st);
+// fused eval of fixed-base serial chains with a compile-time joint count (rbd_kernels_arm.cu): returns false when `m` is
+// not such a chain (6 or 7 RX / RY / RZ joints) or the call does not ask for M and tau; else launches and sets *err
+bool launch_eval_arm(const DevModel& m, const EvalArgs& a, int num_sms, cudaStream_t st, cudaError_t* err);
 // records the __global__ function a launch_* of another translation unit started (rbd_last_kernel_name)
 void note_kernel(const void* fn);
 // assembled mapping Jacobian: block rows of the n_sel selected outputs (device arrays sel [n_sel], blk_ptr [n_sel + 1])

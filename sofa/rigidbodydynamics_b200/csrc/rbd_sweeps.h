@@ -113,6 +113,7 @@ typedef double real;
 #define RBD_CHAIN_ONLY 1
 #define RBD_BODY_EVAL_ONLY 1
 #include "rbd_sweeps_body.h"
+#include "rbd_arm_body.h"
 #undef RBD_BODY_EVAL_ONLY
 #undef RBD_CHAIN_ONLY
 #undef RBD_SIMPLE_JOINTS

@@ -122,6 +122,39 @@ extern "C" int emul_eval_variant(const rbd_model_desc* d, int do_m, int do_tau, 
   if (warps_per_sm) *warps_per_sm = c.m.plan.warps * c.m.plan.blocks_per_sm;
   return c.m.plan.kvariant;
 }
+// fused eval of a 6- / 7-joint serial chain on the unrolled arm sweep (rbd::chain::arm_instance); -102 when the model is
+// not such a chain
+template <int NJ>
+static void run_arm(const DevModel& dm, long long n, long long tile, double* q, double* v, double* a, double* oMi, double* J,
+                    double* M, double* tau) {
+  namespace ch = rbd::chain;
+  ch::ArmParams<NJ> P;
+  for (int i = 0; i < NJ; ++i) P.joint[i] = dm.joint[i + 1];
+  for (int k = 0; k < 3; ++k) P.gravity[k] = dm.gravity[k];
+  std::vector<double> smem((size_t)RBD_ARM_LEVEL * (NJ - 1) * 32, 1e300);
+  for (long long i = 0; i < n; ++i) {
+    std::fill(smem.begin(), smem.end(), 1e300);
+    ch::Stack S = ch::make_stack(smem.data(), (int)(i % 32), RBD_ARM_LEVEL * (NJ - 1));
+    std::vector<double> tmem((size_t)6 * NJ, 1e300);
+    ch::TmStack T{tmem.data()};
+    ch::arm_instance<NJ, 0>(P, ch::make_field(q, i, NJ, tile), ch::make_field(v, i, NJ, tile), ch::make_field(a, i, NJ, tile),
+                            ch::make_field(oMi, i, 12 * NJ, tile), ch::make_field(J, i, 6 * NJ, tile),
+                            ch::make_field(M, i, NJ * (NJ + 1) / 2, tile), ch::make_field(tau, i, NJ, tile), S, T);
+  }
+}
+extern "C" int emul_eval_arm(const rbd_model_desc* d, long long n, long long tile, double* q, double* v, double* a,
+                             double* oMi, double* J, double* M, double* tau) {
+  Ctx c;
+  int rc = make_ctx(d, &c);
+  if (rc) return rc;
+  if (c.m.eval_variant != RBD_EVAL_CHAIN) { g_err = "not a fixed-base serial chain of RX / RY / RZ joints"; return -102; }
+  switch (c.m.njoints - 1) {
+    case 6: run_arm<6>(c.m, n, tile, q, v, a, oMi, J, M, tau); return 0;
+    case 7: run_arm<7>(c.m, n, tile, q, v, a, oMi, J, M, tau); return 0;
+    default: g_err = "no arm instantiation for this joint count"; return -102;
+  }
+}
+
 // the storage plan of the fused eval: {warps, blocks_per_sm, smem_doubles, tmem_doubles, tmem_cols, in_slots, kvariant,
 // dynamic shared-memory bytes of a full block, ysplit, fsplit}
 extern "C" int emul_eval_plan(const rbd_model_desc* d, int do_m, int do_tau, int* out /*[10]*/) {

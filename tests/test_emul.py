@@ -573,3 +573,47 @@ def test_minv_body_matches_oracle(emul, d, tile, body):
             for c in (0, d.nv // 2, d.nv - 1):
                 e = np.zeros(d.nv); e[c] = 1.0
                 assert np.max(np.abs(orc.aba(q[i], z, e) - a0 - G[:, c])) <= 1e-9 * scale
+
+
+@pytest.mark.parametrize("tile", [32, 13])
+@pytest.mark.parametrize("nj", [6, 7, 5])
+def test_arm_body_matches_oracle_and_generic_sweep(emul, tile, nj):
+    """rbd::chain::arm_instance (serial chains with a compile-time joint count: both passes unrolled, subspace columns in
+    registers, f | Y stack only) against the oracle and against the generic sweep (same formulas: equal to rounding).  A
+    5-joint chain has no instantiation (-102: the library then runs the generic chain sweep)."""
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    d = mdl.panda7()
+    if nj != 7:     # a shorter arm: the first nj joints of the Panda chain, frames re-derived by the builder
+        b = mdl._Builder(f"arm{nj}")
+        b.add_frame("root_joint", 0, mdl._se3(), mdl.F_FIXED_JOINT)
+        for i in range(1, nj + 1):
+            jid = b.add_joint(i - 1, int(d.jtype[i]), d.placement[i], f"j{i}")
+            b.add_frame(f"j{i}", jid, mdl._se3(), mdl.F_JOINT)
+            b.inertia[jid] = d.inertia[i].copy()
+            b.add_frame(f"b{i}", jid, mdl._se3(), mdl.F_BODY)
+        d = b.finish()
+    n = 45
+    q, v, a = mdl.random_state(d, n, seed=5)
+    cd, keep = _cdesc(d)
+    nt = (n + tile - 1) // tile
+    K = {"oMi": 12 * (d.njoints - 1), "J": 6 * d.nv, "M": d.nv * (d.nv + 1) // 2, "tau": d.nv}
+    outs = {k: np.full((nt, K[k], tile), np.nan) for k in K}
+    qs, vs, as_ = to_tiled(q, tile), to_tiled(v, tile), to_tiled(a, tile)
+    rc = emul.emul_eval_arm(C.addressof(cd), n, tile, P(qs), P(vs), P(as_), P(outs["oMi"]), P(outs["J"]), P(outs["M"]), P(outs["tau"]))
+    if nj == 5:
+        assert rc == -102
+        return
+    assert rc == 0, emul.emul_last_error()
+    ref, _ = oracle.eval_batch(d, q, v, a, 1)
+    base = _emul_eval_variant(emul, d, q, v, a, tile, -1)
+    for k in K:
+        got = from_tiled(outs[k], n)[:, :K[k]]
+        assert np.isfinite(got).all(), k
+        assert rel_err(got, ref[k]) <= TOL_FP64, k
+        assert rel_err(got, base[k]) <= 1e-13, k
+    # oMi and J are optional
+    o2 = {k: np.full((nt, K[k], tile), np.nan) for k in ("M", "tau")}
+    assert emul.emul_eval_arm(C.addressof(cd), n, tile, P(qs), P(vs), P(as_), None, None, P(o2["M"]), P(o2["tau"])) == 0
+    for k in o2:
+        assert np.array_equal(o2[k], outs[k], equal_nan=True), k

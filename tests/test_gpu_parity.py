@@ -286,7 +286,7 @@ def test_eval_sparse_mass_format(torch_mod, api, d, tile):
     qs, vs, as_ = (_dev(torch, to_tiled(x, tile)) for x in (q, v, a))
     ws.eval_soa_sparse(n, tile, qs, vs, as_, oMi, J, Mv, tau)
     ws.synchronize()
-    assert "eval_kernel" in api.last_kernel_name()
+    assert any(k in api.last_kernel_name() for k in ("eval_kernel", "eval_arm_kernel"))
     ref, _ = oracle.eval_batch(d, q, v, a, nthreads=0)
     assert rel_err(from_tiled(Mv.cpu().numpy(), n)[:, :packed.size], ref["M"][:, packed]) <= TOL_FP64
     for k, g in (("oMi", oMi), ("J", J), ("tau", tau)):
@@ -998,3 +998,43 @@ def test_minv_matches_oracle(torch_mod, api, d, tile):
     hm = np.zeros((n, mf))
     ws.minv_host(n, q, hm)
     assert rel_err(hm, got) <= 1e-13
+
+
+@pytest.mark.parametrize("tile", [32, 1000])
+def test_arm_kernel_equals_generic_chain_sweep(torch_mod, api, tile):
+    """Fused eval of the 7-joint Panda chain: the unrolled arm kernel (default for 6- / 7-joint serial chains) against the
+    generic chain instantiation (rbd_workspace_set_eval_arm(0)) and the oracle, all outputs, M in both formats, oMi / J
+    optional; partial last tile."""
+    import oracle
+    torch = torch_mod
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    d = mdl.panda7()
+    n = 1000 + 7
+    q, v, a = mdl.random_state(d, n, seed=91)
+    m = api.Model(d); ws = api.Workspace(m, n)
+    I = m.info
+    nt = (n + tile - 1) // tile
+    new = lambda K: torch.full((nt, K, tile), float("nan"), dtype=torch.float64, device="cuda")
+    qs, vs, as_ = (_dev(torch, to_tiled(x, tile)) for x in (q, v, a))
+    res = {}
+    for arm in (1, 0):
+        ws.set_eval_arm(bool(arm))
+        o = {"oMi": new(I.omi_fields), "J": new(I.jac_fields), "M": new(I.mass_fields), "tau": new(I.nv)}
+        ws.eval_soa(n, tile, qs, vs, as_, o["oMi"], o["J"], o["M"], o["tau"])
+        ws.synchronize()
+        assert ("eval_arm_kernel<7" in api.last_kernel_name()) == bool(arm), api.last_kernel_name()
+        res[arm] = {k: from_tiled(t.cpu().numpy(), n) for k, t in o.items()}
+    ref, _ = oracle.eval_batch(d, q, v, a, nthreads=0)
+    for k in ref:
+        assert rel_err(res[1][k][:, :ref[k].shape[1]], ref[k]) <= TOL_FP64, k
+        assert rel_err(res[1][k], res[0][k]) <= 1e-13, k
+    ws.set_eval_arm(True)
+    Mv, t2 = new(I.mass_support_fields), new(I.nv)
+    assert I.mass_support_fields == I.mass_fields                      # a chain's M has no structural zeros
+    ws.eval_soa_sparse(n, tile, qs, vs, as_, None, None, Mv, t2)
+    ws.synchronize()
+    assert "eval_arm_kernel<7" in api.last_kernel_name()
+    assert np.array_equal(from_tiled(Mv.cpu().numpy(), n), res[1]["M"]) and np.array_equal(from_tiled(t2.cpu().numpy(), n), res[1]["tau"])
+    # M alone / tau alone are not the arm kernel's job
+    ws.crba_soa(n, tile, qs, Mv); ws.synchronize()
+    assert "eval_arm_kernel" not in api.last_kernel_name()
