@@ -111,6 +111,7 @@ def lib() -> C.CDLL:
         l.orc_crba.restype = None; l.orc_crba.argtypes = [vp, dp, dp]
         l.orc_rnea.restype = None; l.orc_rnea.argtypes = [vp, dp, dp, dp, dp]
         l.orc_aba.restype = None; l.orc_aba.argtypes = [vp, dp, dp, dp, dp]
+        l.orc_rnea_derivatives.restype = None; l.orc_rnea_derivatives.argtypes = [vp, dp, dp, dp, dp, dp, dp]
         l.orc_eval.restype = None; l.orc_eval.argtypes = [vp, dp, dp, dp, dp, dp, dp, dp]
         l.orc_eval_batch.restype = C.c_int
         l.orc_eval_batch.argtypes = [vp, C.c_long, dp, dp, dp, dp, dp, dp, dp, C.c_int]
@@ -199,6 +200,14 @@ class Oracle:
         q, v, tau = _f64(q), _f64(v), _f64(tau); ddq = np.zeros(self.d.nv)
         lib().orc_aba(self._w, _p(q), _p(v), _p(tau), _p(ddq))
         return ddq
+
+    def rnea_derivatives(self, q, v, a):
+        """pinocchio::computeRNEADerivatives(q, v, a): (dtau_dq, dtau_dv, M) — nv x nv each, entry (r, c) = d tau_r / d x_c
+        (q: tangent of integrate); M = dtau_da, upper triangle filled."""
+        q, v, a = _f64(q), _f64(v), _f64(a); nv = self.d.nv
+        dq = np.zeros((nv, nv)); dv = np.zeros((nv, nv)); M = np.zeros((nv, nv))
+        lib().orc_rnea_derivatives(self._w, _p(q), _p(v), _p(a), _p(dq), _p(dv), _p(M))
+        return dq, dv, M
 
     def minv(self, q):
         """pinocchio::computeMinverse(q) restated as what it equals: the inverse of the CRBA mass matrix (dense, symmetric;

@@ -694,6 +694,195 @@ void orc_aba(orc_workspace* w, const double* q, const double* v, const double* t
   free(Yaba); free(U); free(UDinv); free(Dinv); free(u);
 }
 
+/* ---- analytical derivatives of inverse dynamics ------------------------------------------------------------------ */
+/* y = A x, A 6x6 row-major */
+static void mat6_mulvec(const double* A, const double* x, double* y) {
+  for (int r = 0; r < 6; ++r) {
+    double s = 0.0;
+    for (int k = 0; k < 6; ++k) s += A[6 * r + k] * x[k];
+    y[r] = s;
+  }
+}
+/* motion cross-product matrix: crm(v) m = v x m, [[w x, v x], [0, w x]] on [lin; ang] */
+static void motion_cross_matrix(const double* v, double* X) {
+  const double vx[9] = {0, -v[2], v[1], v[2], 0, -v[0], -v[1], v[0], 0};
+  const double wx[9] = {0, -v[5], v[4], v[5], 0, -v[3], -v[4], v[3], 0};
+  for (int r = 0; r < 3; ++r)
+    for (int k = 0; k < 3; ++k) {
+      X[6 * r + k] = wx[3 * r + k]; X[6 * r + 3 + k] = vx[3 * r + k];
+      X[6 * (3 + r) + k] = 0.0; X[6 * (3 + r) + 3 + k] = wx[3 * r + k];
+    }
+}
+
+/* pinocchio::computeRNEADerivatives(model, data, q, v, a, dtau_dq, dtau_dv, dtau_da) (algorithm/rnea-derivatives.hxx:
+ * ComputeRNEADerivativesForwardStep / BackwardStep; Carpentier & Mansard, RSS 2018).  North-star extension (SURVEY.md
+ * §8(f) rank 4): no reference call site.  Restated with pinocchio's data layout — every joint's world-frame quantities
+ * kept in arrays, dense 6x6 oYcrb / doYcrb, dense 6 x nv dVdq / dAdq / dAdv / dFdq / dFdv / dFda, a full forward pass
+ * followed by a full backward pass — which shares no code path with the kernels' depth-first sweep on compact forms.
+ * dtau_dq, dtau_dv: nv x nv row-major (pinocchio's RowMatrixXs), entry (r, c) = d tau_r / d q_c (tangent of integrate)
+ * resp. d tau_r / d v_c; structural zeros written.  M (optional): dtau_da, upper triangle filled as by pinocchio, rest 0. */
+void orc_rnea_derivatives(orc_workspace* w, const double* q, const double* v, const double* a, double* dtau_dq,
+                          double* dtau_dv, double* M) {
+  const int nj = w->njoints, nv = w->nv;
+  const size_t snj = (size_t)nj, snv = (size_t)(nv > 0 ? nv : 1);
+  double* ov = (double*)calloc(snj * 6, sizeof(double));
+  double* oa_gf = (double*)calloc(snj * 6, sizeof(double));
+  double* of = (double*)calloc(snj * 6, sizeof(double));
+  double* oY = (double*)calloc(snj * 36, sizeof(double));   /* oYcrb */
+  double* doY = (double*)calloc(snj * 36, sizeof(double));  /* doYcrb */
+  double* dVdq = (double*)calloc(6 * snv, sizeof(double));  /* 6 x nv, column-major like data.J */
+  double* dAdq = (double*)calloc(6 * snv, sizeof(double));
+  double* dAdv = (double*)calloc(6 * snv, sizeof(double));
+  double* dFdq = (double*)calloc(6 * snv, sizeof(double));
+  double* dFdv = (double*)calloc(6 * snv, sizeof(double));
+  double* dFda = (double*)calloc(6 * snv, sizeof(double));
+  memset(dtau_dq, 0, sizeof(double) * snv * snv);
+  memset(dtau_dv, 0, sizeof(double) * snv * snv);
+  if (M) memset(M, 0, sizeof(double) * snv * snv);
+  for (int k = 0; k < 3; ++k) oa_gf[k] = -w->gravity[k];  /* data.oa_gf[0] = -gravity */
+  /* forward step */
+  for (int i = 1; i < nj; ++i) {
+    se3 Mj;
+    double* S = w->S + 36 * i;
+    double* vj = w->vj + 6 * i;
+    joint_calc(w, i, q, v, &Mj, S, vj);
+    se3_mul(&w->jplace[i], &Mj, &w->liMi[i]);
+    const int p = w->parents[i], iv = w->idx_v[i], nvi = w->nvj[i];
+    double* vi = w->v + 6 * i;       /* data.v[i], joint frame */
+    double* ai = w->a_gf + 6 * i;    /* data.a[i], joint frame, WITHOUT gravity */
+    memcpy(vi, vj, 6 * sizeof(double));
+    if (p > 0) {
+      double t[6];
+      se3_mul(&w->oMi[p], &w->liMi[i], &w->oMi[i]);
+      se3_actinv_motion(&w->liMi[i], w->v + 6 * p, t);
+      for (int k = 0; k < 6; ++k) vi[k] += t[k];
+    } else {
+      w->oMi[i] = w->liMi[i];
+    }
+    motion_cross(vi, vj, ai); /* joint bias c = 0 */
+    for (int c = 0; c < nvi; ++c)
+      for (int k = 0; k < 6; ++k) ai[k] += S[6 * c + k] * a[iv + c];
+    if (p > 0) {
+      double t[6];
+      se3_actinv_motion(&w->liMi[i], w->a_gf + 6 * p, t);
+      for (int k = 0; k < 6; ++k) ai[k] += t[k];
+    }
+    inertia Yw;
+    inertia_se3_act(&w->oMi[i], &w->Y[i], &Yw);
+    inertia_to_mat6(&Yw, oY + 36 * i);
+    double oa[6], oh[6], t6[6];
+    se3_act_motion(&w->oMi[i], vi, ov + 6 * i);
+    se3_act_motion(&w->oMi[i], ai, oa);
+    for (int k = 0; k < 6; ++k) oa_gf[6 * i + k] = oa[k];
+    for (int k = 0; k < 3; ++k) oa_gf[6 * i + k] -= w->gravity[k];
+    mat6_mulvec(oY + 36 * i, ov + 6 * i, oh);
+    mat6_mulvec(oY + 36 * i, oa_gf + 6 * i, of + 6 * i);
+    motion_cross_force(ov + 6 * i, oh, t6);
+    for (int k = 0; k < 6; ++k) of[6 * i + k] += t6[k];
+    for (int c = 0; c < nvi; ++c) {
+      double* Jc = w->J + 6 * (iv + c);
+      double dJ[6];
+      se3_act_motion(&w->oMi[i], S + 6 * c, Jc);
+      motion_cross(ov + 6 * i, Jc, dJ);
+      motion_cross(oa_gf + 6 * p, Jc, dAdq + 6 * (iv + c));
+      memcpy(dAdv + 6 * (iv + c), dJ, sizeof dJ);
+      if (p > 0) {
+        double t[6];
+        motion_cross(ov + 6 * p, Jc, dVdq + 6 * (iv + c));
+        motion_cross(ov + 6 * p, dVdq + 6 * (iv + c), t);
+        for (int k = 0; k < 6; ++k) { dAdq[6 * (iv + c) + k] += t[k]; dAdv[6 * (iv + c) + k] += dVdq[6 * (iv + c) + k]; }
+      } else {
+        memset(dVdq + 6 * (iv + c), 0, 6 * sizeof(double));
+      }
+    }
+    /* doYcrb = oYcrb.variation(ov) + forceCrossMatrix(oh):  crf(v) Y - Y crm(v), crf(v) = -crm(v)^T */
+    {
+      double X[36];
+      double* D = doY + 36 * i;
+      const double* Y6 = oY + 36 * i;
+      motion_cross_matrix(ov + 6 * i, X);
+      for (int r = 0; r < 6; ++r)
+        for (int c = 0; c < 6; ++c) {
+          double s = 0.0;
+          for (int k = 0; k < 6; ++k) s += -X[6 * k + r] * Y6[6 * k + c] - Y6[6 * r + k] * X[6 * k + c];
+          D[6 * r + c] = s;
+        }
+      /* addForceCrossMatrix: -[f]x on (lin, ang) and (ang, lin), -[n]x on (ang, ang) */
+      const double fx[9] = {0, -oh[2], oh[1], oh[2], 0, -oh[0], -oh[1], oh[0], 0};
+      const double nx[9] = {0, -oh[5], oh[4], oh[5], 0, -oh[3], -oh[4], oh[3], 0};
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+          D[6 * r + 3 + c] -= fx[3 * r + c];
+          D[6 * (3 + r) + c] -= fx[3 * r + c];
+          D[6 * (3 + r) + 3 + c] -= nx[3 * r + c];
+        }
+    }
+  }
+  /* backward step */
+  for (int i = nj - 1; i >= 1; --i) {
+    const int p = w->parents[i], iv = w->idx_v[i], nvi = w->nvj[i], nsub = w->nv_subtree[i];
+    const double* Y6 = oY + 36 * i;
+    const double* D = doY + 36 * i;
+    for (int c = 0; c < nvi; ++c) {
+      const double* Jc = w->J + 6 * (iv + c);
+      double t[6];
+      /* dtau/dv */
+      mat6_mulvec(D, Jc, dFdv + 6 * (iv + c));
+      mat6_mulvec(Y6, dAdv + 6 * (iv + c), t);
+      for (int k = 0; k < 6; ++k) dFdv[6 * (iv + c) + k] += t[k];
+      /* dtau/dq */
+      if (p > 0) {
+        mat6_mulvec(D, dVdq + 6 * (iv + c), dFdq + 6 * (iv + c));
+        mat6_mulvec(Y6, dAdq + 6 * (iv + c), t);
+        for (int k = 0; k < 6; ++k) dFdq[6 * (iv + c) + k] += t[k];
+      } else {
+        mat6_mulvec(Y6, dAdq + 6 * (iv + c), dFdq + 6 * (iv + c));
+      }
+      mat6_mulvec(Y6, Jc, dFda + 6 * (iv + c));
+    }
+    for (int r = 0; r < nvi; ++r)
+      for (int c = 0; c < nsub; ++c) {
+        double sv = 0.0, sq = 0.0, sa = 0.0;
+        for (int k = 0; k < 6; ++k) {
+          sv += w->J[6 * (iv + r) + k] * dFdv[6 * (iv + c) + k];
+          sq += w->J[6 * (iv + r) + k] * dFdq[6 * (iv + c) + k];
+          sa += w->J[6 * (iv + r) + k] * dFda[6 * (iv + c) + k];
+        }
+        dtau_dv[(size_t)(iv + r) * nv + (iv + c)] = sv;
+        dtau_dq[(size_t)(iv + r) * nv + (iv + c)] = sq;
+        if (M) M[(size_t)(iv + r) * nv + (iv + c)] = sa;
+      }
+    for (int c = 0; c < nvi; ++c) {  /* motionSet::act<ADDTO>(J_cols, of[i], dFdq_cols) */
+      double t[6];
+      motion_cross_force(w->J + 6 * (iv + c), of + 6 * i, t);
+      for (int k = 0; k < 6; ++k) dFdq[6 * (iv + c) + k] += t[k];
+    }
+    /* columns of the ancestors' dofs (parents_fromRow walk) */
+    for (int r = 0; r < nvi; ++r) {
+      double YJ[6], DJ[6];  /* rows of J^T oYcrb and J^T doYcrb */
+      for (int c = 0; c < 6; ++c) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int k = 0; k < 6; ++k) { s1 += w->J[6 * (iv + r) + k] * Y6[6 * k + c]; s2 += w->J[6 * (iv + r) + k] * D[6 * k + c]; }
+        YJ[c] = s1; DJ[c] = s2;
+      }
+      for (int j = w->parent_col[iv]; j >= 0; j = w->parent_col[j]) {
+        double sq = 0.0, sv = 0.0;
+        for (int k = 0; k < 6; ++k) {
+          sq += YJ[k] * dAdq[6 * j + k] + DJ[k] * dVdq[6 * j + k];
+          sv += YJ[k] * dAdv[6 * j + k] + DJ[k] * w->J[6 * j + k];
+        }
+        dtau_dq[(size_t)(iv + r) * nv + j] = sq;
+        dtau_dv[(size_t)(iv + r) * nv + j] = sv;
+      }
+    }
+    if (p > 0) {
+      for (int k = 0; k < 36; ++k) { oY[36 * p + k] += oY[36 * i + k]; doY[36 * p + k] += doY[36 * i + k]; }
+      for (int k = 0; k < 6; ++k) of[6 * p + k] += of[6 * i + k];
+    }
+  }
+  free(ov); free(oa_gf); free(of); free(oY); free(doY); free(dVdq); free(dAdq); free(dAdv); free(dFdq); free(dFdv); free(dFda);
+}
+
 /* One full evaluation in the algorithmic output format of SURVEY.md §8(d):
  * oMi [12(nj-1)], J [6 nv] col-major, M packed upper by columns, tau [nv].  Any output may be NULL. */
 void orc_eval(orc_workspace* w, const double* q, const double* v, const double* a, double* oMi, double* J,

@@ -20,6 +20,8 @@ int orc_applyJT_row(orc_workspace* w, int nnz, const int* col, const double* val
 void orc_crba(orc_workspace* w, const double* q, double* M_rowmajor);
 void orc_rnea(orc_workspace* w, const double* q, const double* v, const double* a, double* tau);
 void orc_aba(orc_workspace* w, const double* q, const double* v, const double* tau, double* ddq);
+void orc_rnea_derivatives(orc_workspace* w, const double* q, const double* v, const double* a, double* dtau_dq_rowmajor,
+                          double* dtau_dv_rowmajor, double* M_rowmajor_or_null);
 void orc_eval(orc_workspace* w, const double* q, const double* v, const double* a, double* oMi, double* J,
               double* Mpacked, double* tau);
 int orc_eval_batch(const rbd_model_desc* d, long n, const double* q, const double* v, const double* a,

@@ -111,6 +111,23 @@ def P(a):
     return None if a is None else a.ctypes.data
 
 
+def support_relation(d) -> np.ndarray:
+    """[nv, nv] bool: dofs r and c belong to joints on one root-to-leaf path (one is the other's ancestor, or the same
+    joint) — the structural non-zero pattern of dtau_dq / dtau_dv (and, upper triangle, of M)."""
+    nj, nv = d.njoints, d.nv
+    owner = np.zeros(nv, dtype=np.int64)
+    for j in range(1, nj):
+        nxt = int(d.idx_v[j + 1]) if j + 1 < nj else nv
+        owner[int(d.idx_v[j]):nxt] = j
+    anc = np.zeros((nj, nj), dtype=bool)                   # anc[a, i]: a is i or an ancestor of i
+    for i in range(1, nj):
+        k = i
+        while k != 0:
+            anc[k, i] = True; k = int(d.parents[k])
+    rel = anc | anc.T
+    return rel[np.ix_(owner, owner)]
+
+
 def all_models():
     from sofa.rigidbodydynamics_b200 import model as mdl
     ms = [mdl.panda7(), mdl.solo12(), mdl.talos_reduced(),

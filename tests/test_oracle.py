@@ -210,3 +210,36 @@ def test_minv_is_the_solution_operator_of_aba():
                 e = np.zeros(d.nv); e[c] = 1.0
                 col = orc.aba(q[s_], z, e) - a0
                 assert np.max(np.abs(col - G[:, c])) <= 1e-9 * max(1.0, float(np.max(np.abs(G))))
+
+
+def test_rnea_derivatives_match_independent_finite_differences():
+    """orc_rnea_derivatives (pinocchio::computeRNEADerivatives restated with dense world-frame matrices) against
+    tests/golden/golden_drnea.json: central differences of the independent Newton-Euler + Kane inverse dynamics in
+    50-digit arithmetic (make_golden_drnea.py), d tau / d q taken along the tangent of integrate; dtau_da == crba; the
+    structural zeros (dofs on different branches) are exact zeros; and, on fresh states, double-precision central
+    differences of the oracle's own rnea."""
+    import json
+    import os
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    with open(os.path.join(helpers.GOLDEN, "golden_drnea.json")) as f:
+        gold = json.load(f)
+    for d in helpers.all_models():
+        orc = oracle.Oracle(d)
+        r = gold[d.name]
+        q, v, a = np.array(r["q"]), np.array(r["v"]), np.array(r["a"])
+        dq, dv, M = orc.rnea_derivatives(q, v, a)
+        assert helpers.rel_err(dq, np.array(r["dtau_dq"])) <= 1e-12, d.name
+        assert helpers.rel_err(dv, np.array(r["dtau_dv"])) <= 1e-12, d.name
+        assert helpers.rel_err(np.triu(M), np.triu(orc.crba(q))) <= 1e-12, d.name
+        related = helpers.support_relation(d)
+        assert np.all(dq[~related] == 0.0) and np.all(dv[~related] == 0.0), d.name
+        q, v, a = mdl.random_state(d, 1, seed=4242)
+        dq, dv, _ = orc.rnea_derivatives(q[0], v[0], a[0])
+        eps = 1e-6
+        for c in range(d.nv):
+            e = np.zeros((1, d.nv)); e[0, c] = 1.0
+            fq = (orc.rnea(helpers.integrate(d, q, e, eps)[0], v[0], a[0]) - orc.rnea(helpers.integrate(d, q, e, -eps)[0], v[0], a[0])) / (2 * eps)
+            fv = (orc.rnea(q[0], v[0] + eps * e[0], a[0]) - orc.rnea(q[0], v[0] - eps * e[0], a[0])) / (2 * eps)
+            assert np.max(np.abs(fq - dq[:, c])) <= 1e-6 * max(1.0, np.max(np.abs(dq))), (d.name, c)
+            assert np.max(np.abs(fv - dv[:, c])) <= 1e-6 * max(1.0, np.max(np.abs(dv))), (d.name, c)
