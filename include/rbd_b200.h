@@ -313,6 +313,20 @@ RBD_API int rbd_aba_host(rbd_workspace* ws, int64_t n, const double* q, const do
  * level records do not fit an SM.                                                                                */
 RBD_API int rbd_minv_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, double* Minv);
 RBD_API int rbd_minv_host(rbd_workspace* ws, int64_t n, const double* q, double* Minv);
+/* Analytical derivatives of inverse dynamics, pinocchio::computeRNEADerivatives(model, data, q, v, a, dtau_dq, dtau_dv,
+ * dtau_da) (no call site in the reference): for tau = rnea(q, v, a),
+ *   dtau_dq [nv * nv fields]  entry (r, c) at field r * nv + c (row-major, as pinocchio's RowMatrixXs) = d tau_r / d q_c,
+ *                             taken along the tangent of pinocchio::integrate (free-flyer: velocity in its own frame);
+ *   dtau_dv [nv * nv fields]  d tau_r / d v_c, same layout;
+ *   M       [mass_fields]     optional (may be NULL): dtau_da = M(q), packed upper triangle exactly like rbd_crba_soa.
+ * Both matrices are written completely, structural zeros (dofs on different branches of the tree) included.  One
+ * depth-first sweep with all state on chip (shared + tensor memory); a free-flyer is supported as the root joint only;
+ * RBD_ERR_UNSUPPORTED for trees whose level records do not fit an SM.                                              */
+RBD_API int rbd_rnea_derivatives_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, const double* v,
+                                     const double* a, double* dtau_dq, double* dtau_dv, double* M);
+/* ... on host vectors (instance-major q [n][nq]; v, a [n][nv]; dtau_dq, dtau_dv [n][nv][nv]; M [n][mass_fields] or NULL) */
+RBD_API int rbd_rnea_derivatives_host(rbd_workspace* ws, int64_t n, const double* q, const double* v, const double* a,
+                                      double* dtau_dq, double* dtau_dv, double* M);
 
 /* Matrix-free Mass / ForceField products in joint space — what the reference's SOFA graph evaluates through the
  * mapping with one UniformMass<Rigid3> per body (URDFModelLoader.cpp:369-391): Mass::addMDx and ForceField::addForce

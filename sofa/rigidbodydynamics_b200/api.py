@@ -191,6 +191,12 @@ class Workspace:
         """Forward dynamics ddq = aba(q, v, tau) (``rbd_aba_soa``)."""
         check(self._lib.rbd_aba_soa(self._h, n, tile, _dev_ptr(q), _dev_ptr(v), _dev_ptr(tau), _dev_ptr(ddq)))
 
+    def rnea_derivatives_soa(self, n, tile, q, v, a, dtau_dq, dtau_dv, M=None):
+        """dtau_dq, dtau_dv [nv * nv fields, row-major] (and M packed upper, optional) of tau = rnea(q, v, a)
+        (``rbd_rnea_derivatives_soa``, pinocchio::computeRNEADerivatives)."""
+        check(self._lib.rbd_rnea_derivatives_soa(self._h, n, tile, _dev_ptr(q), _dev_ptr(v), _dev_ptr(a), _dev_ptr(dtau_dq),
+                                                 _dev_ptr(dtau_dv), _dev_ptr(M)))
+
     def minv_soa(self, n, tile, q, Minv):
         """Packed upper triangle of M(q)^-1 (``rbd_minv_soa``, pinocchio::computeMinverse)."""
         check(self._lib.rbd_minv_soa(self._h, n, tile, _dev_ptr(q), _dev_ptr(Minv)))
@@ -270,6 +276,10 @@ class Workspace:
 
     def aba_host(self, n, q, v, tau, ddq):
         check(self._lib.rbd_aba_host(self._h, n, _host_ptr(q), _host_ptr(v), _host_ptr(tau), _host_ptr(ddq)))
+
+    def rnea_derivatives_host(self, n, q, v, a, dtau_dq, dtau_dv, M=None):
+        check(self._lib.rbd_rnea_derivatives_host(self._h, n, _host_ptr(q), _host_ptr(v), _host_ptr(a), _host_ptr(dtau_dq),
+                                                  _host_ptr(dtau_dv), _host_ptr(M)))
 
     def minv_host(self, n, q, Minv):
         check(self._lib.rbd_minv_host(self._h, n, _host_ptr(q), _host_ptr(Minv)))

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.environ.get("RBD_B200_LIB_OUT") or os.path.join(HERE, "librbd_b200.so")
 SOURCES = ["rbd_kernels.cu", "rbd_kernels_dyn.cu", "rbd_kernels_arm.cu", "rbd_capi.cu", "rbd_probe.cu", "rbd_urdf.cpp"]
-HEADERS = ["rbd_dev_model.h", "rbd_sweeps.h", "rbd_sweeps_body.h", "rbd_dyn_body.h", "rbd_arm_body.h", "rbd_kernels.h", "rbd_model_build.h"]
+HEADERS = ["rbd_dev_model.h", "rbd_sweeps.h", "rbd_sweeps_body.h", "rbd_dyn_body.h", "rbd_deriv_body.h", "rbd_arm_body.h", "rbd_kernels.h", "rbd_model_build.h"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--shared", "-cudart", "static"]
 

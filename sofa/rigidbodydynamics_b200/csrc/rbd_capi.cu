@@ -118,6 +118,10 @@ struct rbd_workspace {
   DevModel* d_minv = nullptr;
   int minv_state = 0;
   double* minv_scratch[2] = {nullptr, nullptr};
+  // derivatives of inverse dynamics (drnea): planned joint table, state as aba2_state; no scratch
+  DevModel* h_drnea = nullptr;
+  DevModel* d_drnea = nullptr;
+  int drnea_state = 0;
   void* sel_buf = nullptr;  // getJ: selection + block pointers
   size_t sel_bytes = 0;
 };
@@ -222,6 +226,7 @@ static void ws_free(rbd_workspace* ws) {
   cudaFree(ws->sel_buf); cudaFree(ws->aba_scratch[0]); cudaFree(ws->aba_scratch[1]);
   cudaFree(ws->aba2_scratch[0]); cudaFree(ws->aba2_scratch[1]); cudaFree(ws->d_aba2); delete ws->h_aba2;
   cudaFree(ws->minv_scratch[0]); cudaFree(ws->minv_scratch[1]); cudaFree(ws->d_minv); delete ws->h_minv;
+  cudaFree(ws->d_drnea); delete ws->h_drnea;
   cudaFree(ws->qcache); cudaFree(ws->rows_buf); cudaFree(ws->d_model); cudaFree(ws->jcache); cudaFree(ws->omicache); cudaFree(ws->jc_scratch);
   for (int k = 0; k < rbd_workspace::kPlans; ++k) { cudaFree(ws->d_plan[k]); delete ws->h_plan[k]; }
   for (int k = 0; k < 8; ++k) { cudaFree(ws->d_plan32[k]); delete ws->h_plan32[k]; }
@@ -394,6 +399,7 @@ static void drop_plans(rbd_workspace* ws) {
   for (int k = 0; k < 8; ++k) { delete ws->h_plan32[k]; ws->h_plan32[k] = nullptr; }
   delete ws->h_aba2; ws->h_aba2 = nullptr; ws->aba2_state = 0;
   delete ws->h_minv; ws->h_minv = nullptr; ws->minv_state = 0;
+  delete ws->h_drnea; ws->h_drnea = nullptr; ws->drnea_state = 0;
   cudaFree(ws->minv_scratch[0]); cudaFree(ws->minv_scratch[1]); ws->minv_scratch[0] = ws->minv_scratch[1] = nullptr;
   cudaFree(ws->aba2_scratch[0]); cudaFree(ws->aba2_scratch[1]); ws->aba2_scratch[0] = ws->aba2_scratch[1] = nullptr;
 }
@@ -655,6 +661,42 @@ RBD_API int rbd_minv_soa(rbd_workspace* ws, int64_t n, int64_t tile, const doubl
   int rc = check_batch(ws, n, tile);
   if (rc) return rc;
   return minv_on(ws, ws->stream, n, tile, q, Minv);
+}
+
+// derivatives of inverse dynamics (drnea_instance): dtau_dq, dtau_dv nv x nv row-major fields, M optional (packed upper)
+static int drnea_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, const double* q, const double* v,
+                    const double* a, double* dq, double* dv, double* M) {
+  if (!q || !v || !a || !dq || !dv) return set_err(RBD_ERR_INVALID_ARG, "null q / v / a / dtau_dq / dtau_dv");
+  const DevModel& dm = ws->model->dm;
+  for (int i = 1; i < dm.njoints; ++i)
+    if (dm.joint[i].type == JT_FF && !(i == 1 && dm.joint[i].parent == 0))
+      return set_err(RBD_ERR_UNSUPPORTED, "rnea_derivatives supports a free-flyer only as the root joint (joint 1 on the universe)");
+  if (ws->drnea_state == 0) {
+    ws->drnea_state = -1;
+    DevModel* h = new (std::nothrow) DevModel(dm);
+    if (!h) return set_err(RBD_ERR_ALLOC, "out of host memory");
+    if (plan_drnea(h, ws->use_tmem != 0)) {
+      if (!ws->d_drnea) CK(cudaMalloc(&ws->d_drnea, sizeof(DevModel)));
+      CK(cudaMemcpyAsync(ws->d_drnea, h, dev_model_bytes(*h), cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));
+      ws->h_drnea = h; ws->drnea_state = 1;
+    } else {
+      delete h;
+    }
+  }
+  if (ws->drnea_state != 1)
+    return set_err(RBD_ERR_UNSUPPORTED, "rnea_derivatives: the level records of this tree do not fit the shared + tensor memory of an SM");
+  DrneaArgs A{n, tile, q, v, a, dq, dv, M};
+  CK(launch_drnea(*ws->h_drnea, ws->d_drnea, A, ws->num_sms, st));
+  if (n > 0) ws->launches++;
+  return RBD_OK;
+}
+RBD_API int rbd_rnea_derivatives_soa(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, const double* v,
+                                     const double* a, double* dtau_dq, double* dtau_dv, double* M) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, tile);
+  if (rc) return rc;
+  return drnea_on(ws, ws->stream, n, tile, q, v, a, dtau_dq, dtau_dv, M);
 }
 
 static int apply_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, long long inst0, const double* qj,
@@ -1163,6 +1205,25 @@ RBD_API int rbd_minv_host(rbd_workspace* ws, int64_t n, const double* q, double*
   P.add(I.mass_fields, nullptr, Minv, false, true);
   return run_host_chunks(ws, n, P, [&](cudaStream_t st, long long, long long cn, long long tile) {
     return minv_on(ws, st, cn, tile, P[0].d_soa, P[1].d_soa);
+  });
+}
+
+RBD_API int rbd_rnea_derivatives_host(rbd_workspace* ws, int64_t n, const double* q, const double* v, const double* a,
+                                      double* dtau_dq, double* dtau_dv, double* M) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, 1);
+  if (rc) return rc;
+  if (!q || !v || !a || !dtau_dq || !dtau_dv) return set_err(RBD_ERR_INVALID_ARG, "null q / v / a / dtau_dq / dtau_dv");
+  const rbd_model_info& I = ws->model->info;
+  Pieces P;
+  P.add(I.nq, q, nullptr, true, false);
+  P.add(I.nv, v, nullptr, true, false);
+  P.add(I.nv, a, nullptr, true, false);
+  P.add(I.nv * I.nv, nullptr, dtau_dq, false, true);
+  P.add(I.nv * I.nv, nullptr, dtau_dv, false, true);
+  P.add(I.mass_fields, nullptr, M, false, true);
+  return run_host_chunks(ws, n, P, [&](cudaStream_t st, long long, long long cn, long long tile) {
+    return drnea_on(ws, st, cn, tile, P[0].d_soa, P[1].d_soa, P[2].d_soa, P[3].d_soa, P[4].d_soa, P[5].d_soa);
   });
 }
 

@@ -1,0 +1,413 @@
+// rbd_deriv_body.h — analytical derivatives of inverse dynamics (drnea_instance): d tau / d q, d tau / d v [, d tau / d a =
+// M] of tau = rnea(q, v, a), pinocchio::computeRNEADerivatives (Carpentier & Mansard, RSS 2018; SURVEY.md §8(f) rank 4 — no
+// call site in the reference).  Included from rbd_sweeps_body.h inside namespace rbd (FP64 only).
+//
+// Formulation.  World frame like every sweep here.  With J_c the world subspace column of dof c, P its joint's parent,
+//     dVdq_c = v_P x J_c          dAdq_c = a_P x J_c + v_P x dVdq_c          dAdv_c = v_joint(c) x J_c + dVdq_c
+// (a includes the -g offset; a_universe = -g, v_universe = 0), and for joint j with the COMPOSITE quantities of its
+// subtree  Y^c = sum Y_k,  B^c = sum (v_k x* Y_k - Y_k v_k x + (Y_k v_k) xbar*),  F^c = sum f_k :
+//     dFdv_c = B^c J_c + Y^c dAdv_c        dFdq_c = B^c dVdq_c + Y^c dAdq_c        (c a dof of j)
+//     row j, column c' of an ancestor:     dtau_dq = (Y^c J_c) . dAdq_c' + (B^c^T J_c) . dVdq_c'
+//                                          dtau_dv = (Y^c J_c) . dAdv_c' + (B^c^T J_c) . J_c'
+//     row of an ancestor-or-self r, column c:  dtau_dv = J_r . dFdv_c,  dtau_dq = J_r . (dFdq_c [+ J_c x* F^c for r != c's joint])
+// which is pinocchio's ComputeRNEADerivativesBackwardStep regrouped per (joint, ancestor) PAIR: every entry that involves
+// joint j and one of its ancestors is produced when the depth-first sweep leaves j, from j's composite quantities and
+// the ancestor's record on the current root-to-leaf path.  Nothing of a finished subtree is kept: O(depth) state, as in
+// the fused eval and aba2.
+//
+// Compact forms.  Y^c is a rigid-body inertia (mass = DevJoint::msub, h, I_O: 9 doubles).  B^c splits into a symmetric
+// part, which is the TIME DERIVATIVE of a rigid-body inertia moving with v (v x* Y - Y v x = dY/dt) and therefore again of
+// inertia form with zero mass rate: (dh, dI_O), 9 doubles — and an antisymmetric part m -> m x* H with H = sum Y_k v_k, 6
+// doubles, linear in the momenta.  15 doubles instead of pinocchio's dense 6 x 6 doYcrb; B m = dY m + m x* H,
+// B^T m = dY m - m x* H.
+//
+// On-chip level records (plan_drnea; DevJoint::offA, bit RBD_BOFF_TMEM = tensor memory), one per DEPTH LEVEL that holds a
+// joint with children:
+//     1-dof joint   [v | a (12) | J (6)     | tail]      tail: one child  -> the joint's own Y (h, I_O: 9)
+//     free-flyer    [v | a (12) | R | p (12) | tail]            >= 2      -> accumulator Y^c (9) | dY^c (9) | H (6) | F (6)
+//     1-dof joints with >= 2 children keep R | p (12) for the restart of the next branch behind the accumulator (boff).
+// dVdq / dAdq of an ancestor are recomputed in the pair loop from its J and its parent's v | a (3 cross products) rather
+// than stored: 27 doubles per level instead of 39 — the sweep state, not the arithmetic, decides how many warps an SM holds.
+//
+// Outputs: DQ, DV: nv x nv, field r nv + c (row-major like pinocchio's RowMatrixXs), structural zeros WRITTEN (dofs on
+// different branches); M (optional): packed upper triangle like rbd_crba_soa.  A free-flyer only as joint 1 on the universe.
+// All lanes of a warp run the sweep together (tensor-memory accesses are warp-collective).
+
+#define RBD_DR_ONE 27      /* 1-dof joint, one child: v | a | J | Y                               */
+#define RBD_DR_BRANCH 60   /* 1-dof joint, >= 2 children: v | a | J | accumulator (30) | R | p     */
+#define RBD_DR_RST 48      /* ... offset of its R | p                                              */
+#define RBD_DR_FF_ONE 33   /* free-flyer, one child: v | a | R | p | Y                             */
+#define RBD_DR_FF_BRANCH 54 /* free-flyer, >= 2 children: v | a | R | p | accumulator (30)         */
+
+// motion x motion: [w_a x v_b + v_a x w_b ; w_a x w_b]
+RBD_HD void mxm(const real* a, const real* b, real* o) {
+  real tx, ty, tz;
+  RBD_CROSS(o[0], o[1], o[2], a[3], a[4], a[5], b[0], b[1], b[2]);
+  RBD_CROSS(tx, ty, tz, a[0], a[1], a[2], b[3], b[4], b[5]);
+  o[0] += tx; o[1] += ty; o[2] += tz;
+  RBD_CROSS(o[3], o[4], o[5], a[3], a[4], a[5], b[3], b[4], b[5]);
+}
+// motion x* force: [w x f ; w x n + v x f]
+RBD_HD void mxf(const real* a, const real* f, real* o) {
+  real tx, ty, tz;
+  RBD_CROSS(o[0], o[1], o[2], a[3], a[4], a[5], f[0], f[1], f[2]);
+  RBD_CROSS(o[3], o[4], o[5], a[3], a[4], a[5], f[3], f[4], f[5]);
+  RBD_CROSS(tx, ty, tz, a[0], a[1], a[2], f[0], f[1], f[2]);
+  o[3] += tx; o[4] += ty; o[5] += tz;
+}
+// time derivative of the world inertia Y = (m, h, I_O) of a body moving with v: dY = v x* Y - Y v x, again of inertia form
+// with zero mass: dY[0] = 0, dh = m v_l + w x h, dI = [w]x I - I [w]x - (h v_l^T + v_l h^T) + 2 (h . v_l) 1
+RBD_HD void inertia_rate(const real* Y, const real* v, real* dY) {
+  const real hx = Y[1], hy = Y[2], hz = Y[3];
+  const real wx = v[3], wy = v[4], wz = v[5];
+  dY[0] = 0;
+  dY[1] = Y[0] * v[0] + (wy * hz - wz * hy);
+  dY[2] = Y[0] * v[1] + (wz * hx - wx * hz);
+  dY[3] = Y[0] * v[2] + (wx * hy - wy * hx);
+  // K = [w]x I, I = [[Y4, Y5, Y7], [Y5, Y6, Y8], [Y7, Y8, Y9]]
+  const real k00 = wy * Y[7] - wz * Y[5], k01 = wy * Y[8] - wz * Y[6], k02 = wy * Y[9] - wz * Y[8];
+  const real k10 = wz * Y[4] - wx * Y[7], k11 = wz * Y[5] - wx * Y[8], k12 = wz * Y[7] - wx * Y[9];
+  const real k20 = wx * Y[5] - wy * Y[4], k21 = wx * Y[6] - wy * Y[5], k22 = wx * Y[8] - wy * Y[7];
+  const real hv = hx * v[0] + hy * v[1] + hz * v[2];
+  dY[4] = 2 * (k00 - hx * v[0] + hv);
+  dY[5] = k01 + k10 - (hx * v[1] + hy * v[0]);
+  dY[6] = 2 * (k11 - hy * v[1] + hv);
+  dY[7] = k02 + k20 - (hx * v[2] + hz * v[0]);
+  dY[8] = k12 + k21 - (hy * v[2] + hz * v[1]);
+  dY[9] = 2 * (k22 - hz * v[2] + hv);
+}
+// own contribution of a body to the composite quantities: Yc[1..9] | dYc[1..9] | H | F  (30 doubles, C[0..29])
+RBD_HD void dr_own(const real* Y, const real* vel, const real* acc, real* C) {
+  real dY[10], h[6], f[6], t[6];
+  inertia_rate(Y, vel, dY);
+  inertia_mul(Y, vel, h);
+  inertia_mul(Y, acc, f);
+  mxf(vel, h, t);
+#pragma unroll
+  for (int e = 0; e < 9; ++e) { C[e] = Y[1 + e]; C[9 + e] = dY[1 + e]; }
+#pragma unroll
+  for (int e = 0; e < 6; ++e) { C[18 + e] = h[e]; C[24 + e] = f[e] + t[e]; }
+}
+
+// Everything joint `cur` (1-dof) contributes when the sweep leaves it: its diagonal entry, the entries it shares with
+// each ancestor (both triangles), the structural zeros it shares with the dofs of earlier branches.
+// A: J of cur; va: v | a of cur's parent; C: composite of cur's subtree (dr_own layout).
+template <class FLD>
+RBD_HD void dr_pop_1dof(const DevModel& m, int cur, const real* A, const real* va, const real* C, const FLD& DQ,
+                        const FLD& DV, const FLD& M, const Stack& S, const TmStack& T) {
+  const DevJoint& jc = m.joint[cur];
+  const int nv = m.nv, iv = jc.idx_v;
+  real Yc[10], dYc[10];
+  Yc[0] = jc.msub; dYc[0] = 0;
+#pragma unroll
+  for (int e = 0; e < 9; ++e) { Yc[1 + e] = C[e]; dYc[1 + e] = C[9 + e]; }
+  const real* H = C + 18;
+  const real* F = C + 24;
+  real dV[6], dA[6], u[6], w[6], dFv[6], dFq[6];
+  {
+    real t[6], cb[6];
+    mxm(va, A, dV);
+    mxm(va + 6, A, dA);
+    mxm(va, dV, t);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) dA[e] += t[e];
+    inertia_mul(Yc, A, u);
+    inertia_mul(dYc, A, w);   // dY J
+    mxf(A, H, cb);            // J x* H
+    inertia_mul(Yc, dV, t);   // Y dVdq  (dAdv = 2 dVdq for a 1-dof joint)
+#pragma unroll
+    for (int e = 0; e < 6; ++e) { dFv[e] = w[e] + cb[e] + 2 * t[e]; w[e] -= cb[e]; }
+    inertia_mul(dYc, dV, dFq);
+    mxf(dV, H, cb);
+    inertia_mul(Yc, dA, t);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) dFq[e] += cb[e] + t[e];
+  }
+  DV.st(iv * nv + iv, dot6(A, dFv));
+  DQ.st(iv * nv + iv, dot6(A, dFq));
+  if (M.ok()) M.st(iv * (iv + 1) / 2 + iv, dot6(A, u));
+  {
+    real t[6];
+    mxf(A, F, t);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) dFq[e] += t[e];
+  }
+  // ancestors, nearest first; the dofs between two consecutive ancestors belong to earlier branches: structural zeros
+  int prev = iv;
+  for (int k = jc.parent; k != 0;) {
+    const DevJoint& jk = m.joint[k];
+    const int ik = jk.idx_v;
+    for (int c = ik + jk.nv; c < prev; ++c) {
+      DQ.st(iv * nv + c, real(0)); DV.st(iv * nv + c, real(0));
+      DQ.st(c * nv + iv, real(0)); DV.st(c * nv + iv, real(0));
+      if (M.ok()) M.st(iv * (iv + 1) / 2 + c, real(0));
+    }
+    prev = ik;
+    if (RBD_T_IS_FF(jk.type)) {  // the root: six columns from R | p; dVdq = 0, dAdq_c = a0 x J_c, dAdv_c = v_root x J_c
+      real Rp[12], vr[6], o[6], t[6];
+      lev_ld<12>(S, T, jk.offA + 12, Rp);
+      lev_ld<6>(S, T, jk.offA, vr);
+      ff_rows(Rp, Rp + 9, dFq, o);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) DQ.st((ik + e) * nv + iv, o[e]);
+      ff_rows(Rp, Rp + 9, dFv, o);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) DV.st((ik + e) * nv + iv, o[e]);
+      if (M.ok()) {
+        ff_rows(Rp, Rp + 9, u, o);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) M.st(iv * (iv + 1) / 2 + ik + e, o[e]);
+      }
+      // u . (a0 x J_c) = -(a0 x* u) . J_c,  a0 = (-g, 0):  -(a0 x* u) = [0 ; g x u_l]
+      t[0] = t[1] = t[2] = 0;
+      RBD_CROSS(t[3], t[4], t[5], m.gravity[0], m.gravity[1], m.gravity[2], u[0], u[1], u[2]);
+      ff_rows(Rp, Rp + 9, t, o);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) DQ.st(iv * nv + ik + e, o[e]);
+      // u . (v_root x J_c) + w . J_c = (w - v_root x* u) . J_c
+      mxf(vr, u, t);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) t[e] = w[e] - t[e];
+      ff_rows(Rp, Rp + 9, t, o);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) DV.st(iv * nv + ik + e, o[e]);
+      k = jk.parent;
+      continue;
+    }
+    real Jk[6], vak[12], dVk[6], dAk[6], t[6];
+    lev_ld<6>(S, T, jk.offA + 12, Jk);
+    const int kp = jk.parent;
+    if (kp == 0) {
+#pragma unroll
+      for (int e = 0; e < 12; ++e) vak[e] = 0;
+      vak[6] = -m.gravity[0]; vak[7] = -m.gravity[1]; vak[8] = -m.gravity[2];
+    } else {
+      lev_ld<12>(S, T, m.joint[kp].offA, vak);
+    }
+    mxm(vak, Jk, dVk);
+    mxm(vak + 6, Jk, dAk);
+    mxm(vak, dVk, t);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) dAk[e] += t[e];
+    DQ.st(ik * nv + iv, dot6(Jk, dFq));
+    DV.st(ik * nv + iv, dot6(Jk, dFv));
+    if (M.ok()) M.st(iv * (iv + 1) / 2 + ik, dot6(Jk, u));
+    DQ.st(iv * nv + ik, dot6(u, dAk) + dot6(w, dVk));
+    DV.st(iv * nv + ik, 2 * dot6(u, dVk) + dot6(w, Jk));
+    k = kp;
+  }
+  for (int c = 0; c < prev; ++c) {
+    DQ.st(iv * nv + c, real(0)); DV.st(iv * nv + c, real(0));
+    DQ.st(c * nv + iv, real(0)); DV.st(c * nv + iv, real(0));
+    if (M.ok()) M.st(iv * (iv + 1) / 2 + c, real(0));
+  }
+}
+
+// ... and the root free-flyer's own 6 x 6 blocks: dVdq = 0, dAdq_c = a0 x J_c, dAdv_c = v x J_c (parent = universe)
+template <class FLD>
+RBD_HD void dr_pop_ff(const DevModel& m, int cur, const real* Rp, const real* vel, const real* C, const FLD& DQ,
+                      const FLD& DV, const FLD& M) {
+  const DevJoint& jc = m.joint[cur];
+  const int nv = m.nv, iv = jc.idx_v;
+  real Yc[10], dYc[10], a0[6];
+  Yc[0] = jc.msub; dYc[0] = 0;
+#pragma unroll
+  for (int e = 0; e < 9; ++e) { Yc[1 + e] = C[e]; dYc[1 + e] = C[9 + e]; }
+  a0[0] = -m.gravity[0]; a0[1] = -m.gravity[1]; a0[2] = -m.gravity[2]; a0[3] = a0[4] = a0[5] = 0;
+  const real* H = C + 18;
+#pragma unroll
+  for (int cc = 0; cc < 6; ++cc) {
+    real Jc[6], t[6], dF[6], o[6];
+    RBD_FF_COL(Jc, Rp, (Rp + 9), cc);
+    // dFdv = dY J + J x* H + Y (v x J)
+    inertia_mul(dYc, Jc, dF);
+    mxf(Jc, H, t);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) dF[e] += t[e];
+    mxm(vel, Jc, t);
+    inertia_mul(Yc, t, o);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) dF[e] += o[e];
+    ff_rows(Rp, Rp + 9, dF, o);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) DV.st((iv + r) * nv + iv + cc, o[r]);
+    // dFdq = Y (a0 x J)
+    mxm(a0, Jc, t);
+    inertia_mul(Yc, t, dF);
+    ff_rows(Rp, Rp + 9, dF, o);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) DQ.st((iv + r) * nv + iv + cc, o[r]);
+    if (M.ok()) {
+      inertia_mul(Yc, Jc, dF);
+      ff_rows(Rp, Rp + 9, dF, o);
+#pragma unroll
+      for (int r = 0; r <= cc; ++r) M.st((iv + cc) * (iv + cc + 1) / 2 + iv + r, o[r]);
+    }
+  }
+}
+
+template <class FLD>
+RBD_HD void drnea_instance(const DevModel& m, const FLD& q, const FLD& v, const FLD& a, const FLD& DQ, const FLD& DV,
+                           const FLD& M, const Stack& S, const TmStack& T) {
+  const int nj = m.njoints;
+  real R[9], p[3], vel[6], acc[6];
+#define RBD_DR_ROOT()                                                                           \
+  do {                                                                                          \
+    R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;   \
+    p[0] = p[1] = p[2] = 0;                                                                     \
+    _Pragma("unroll") for (int e_ = 0; e_ < 6; ++e_) { vel[e_] = 0; acc[e_] = 0; }              \
+    acc[0] = -m.gravity[0]; acc[1] = -m.gravity[1]; acc[2] = -m.gravity[2];                     \
+  } while (0)
+  RBD_DR_ROOT();
+  // (joint angle, velocity and acceleration of 1-dof joints are fetched one joint ahead — in front of the whole unwind of
+  // the current joint: a global load under the kernel's own store stream takes thousands of cycles)
+  real nq0 = 0, nq1 = 0, nqd = 0, nqdd = 0;
+#define RBD_DR_PREFETCH(J)                                                                      \
+  do {                                                                                          \
+    const DevJoint& jx_ = m.joint[J];                                                           \
+    if (!RBD_T_IS_FF(jx_.type)) {                                                               \
+      nq0 = q.ld(jx_.idx_q); nqd = v.ld(jx_.idx_v); nqdd = a.ld(jx_.idx_v);                     \
+      if (is_unbounded(jx_.type)) nq1 = q.ld(jx_.idx_q + 1);                                    \
+    }                                                                                           \
+  } while (0)
+  if (nj > 1) RBD_DR_PREFETCH(1);
+  for (int i = 1; i < nj; ++i) {
+    const DevJoint& jn = m.joint[i];
+    const bool ff = RBD_T_IS_FF(jn.type);
+    const real q0 = nq0, q1 = nq1, qd = nqd, qdd = nqdd;
+    if (i + 1 < nj) RBD_DR_PREFETCH(i + 1);
+    real aw[3], A[6], va[12];
+    fk_joint(jn, R, p, q0, q1, q, aw);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) { va[e] = vel[e]; va[6 + e] = acc[e]; }  // the parent's v | a
+    if (!ff) {
+      subspace_1dof(jn.type, p, aw, A);
+      real vj[6], cr[6];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) { vj[e] = A[e] * qd; vel[e] += vj[e]; }
+      mxm(vel, vj, cr);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) acc[e] += A[e] * qdd + cr[e];
+    } else {  // root free-flyer: v = vJ, hence v x vJ = 0
+      real t[6];
+      ff_act(R, p, v, jn.idx_v, vel);
+      ff_act(R, p, a, jn.idx_v, t);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) acc[e] += t[e];
+    }
+    real Y[10];
+    inertia_world(jn, R, p, Y);
+    if (jn.nchild > 0) {
+      real t[12];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) { t[e] = vel[e]; t[6 + e] = acc[e]; }
+      lev_st<12>(S, T, jn.offA, t);
+      int tail;
+      if (!ff) {
+        lev_st<6>(S, T, jn.offA + 12, A);
+        tail = jn.offA + 18;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) t[e] = R[e];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) t[9 + e] = p[e];
+        lev_st<12>(S, T, jn.offA + 12, t);
+        tail = jn.offA + 24;
+      }
+      if (jn.nchild == 1) {
+        lev_st<9>(S, T, tail, Y + 1);
+      } else {
+        real C[30];
+        dr_own(Y, vel, acc, C);
+        lev_st<30>(S, T, tail, C);
+        if (!ff) {
+#pragma unroll
+          for (int e = 0; e < 9; ++e) t[e] = R[e];
+#pragma unroll
+          for (int e = 0; e < 3; ++e) t[9 + e] = p[e];
+          lev_st<12>(S, T, jn.boff, t);
+        }
+      }
+      continue;
+    }
+    // ---- leaf: every joint this leaf completes is finished now, bottom-up --------------------------------------------
+    const int stop_at = (i + 1 < nj) ? m.joint[i + 1].parent : 0;  // the joint that still has a child to come
+    real C[30];
+    dr_own(Y, vel, acc, C);
+    int cur = i;
+    for (;;) {
+      const DevJoint& jc = m.joint[cur];
+      if (RBD_T_IS_FF(jc.type)) {
+        real Rp[12], vr[6];
+        if (cur == i) {  // a free-flyer leaf: R | p | v are still in registers
+#pragma unroll
+          for (int e = 0; e < 9; ++e) Rp[e] = R[e];
+#pragma unroll
+          for (int e = 0; e < 3; ++e) Rp[9 + e] = p[e];
+#pragma unroll
+          for (int e = 0; e < 6; ++e) vr[e] = vel[e];
+        } else {
+          lev_ld<12>(S, T, jc.offA + 12, Rp);
+          lev_ld<6>(S, T, jc.offA, vr);
+        }
+        dr_pop_ff(m, cur, Rp, vr, C, DQ, DV, M);
+        break;  // (the host checks that a free-flyer is joint 1 on the universe)
+      }
+      dr_pop_1dof(m, cur, A, va, C, DQ, DV, M, S, T);
+      const int pp = jc.parent;
+      if (pp == 0) break;
+      const DevJoint& jp = m.joint[pp];
+      const int ptail = jp.offA + (RBD_T_IS_FF(jp.type) ? 24 : 18);
+      if (pp == stop_at) {  // the parent has another child to come: park the contribution there
+        lev_add<30>(S, T, ptail, C);
+        break;
+      }
+      // the parent is complete: its accumulator (>= 2 children) or its own body (one child) joins in registers; va still
+      // holds the parent's v | a
+      if (jp.nchild >= 2) {
+        real t[30];
+        lev_ld<30>(S, T, ptail, t);
+#pragma unroll
+        for (int e = 0; e < 30; ++e) C[e] += t[e];
+      } else {
+        real Yp[10], t[30];
+        Yp[0] = jp.Y[0];
+        lev_ld<9>(S, T, ptail, Yp + 1);
+        dr_own(Yp, va, va + 6, t);
+#pragma unroll
+        for (int e = 0; e < 30; ++e) C[e] += t[e];
+      }
+      cur = pp;
+      if (!RBD_T_IS_FF(jp.type)) {
+        lev_ld<6>(S, T, jp.offA + 12, A);
+        const int gp = jp.parent;
+        if (gp == 0) {
+#pragma unroll
+          for (int e = 0; e < 12; ++e) va[e] = 0;
+          va[6] = -m.gravity[0]; va[7] = -m.gravity[1]; va[8] = -m.gravity[2];
+        } else {
+          lev_ld<12>(S, T, m.joint[gp].offA, va);
+        }
+      }
+    }
+    // the joint after a leaf starts a new branch: restore R | p | v | a of its parent (or the universe)
+    if (i + 1 < nj) {
+      if (stop_at == 0) {
+        RBD_DR_ROOT();
+      } else {
+        const DevJoint& js = m.joint[stop_at];
+        real t[12];
+        lev_ld<12>(S, T, js.offA, t);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) { vel[e] = t[e]; acc[e] = t[6 + e]; }
+        lev_ld<12>(S, T, RBD_T_IS_FF(js.type) ? js.offA + 12 : js.boff, t);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) R[e] = t[e];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) p[e] = t[9 + e];
+      }
+    }
+  }
+#undef RBD_DR_PREFETCH
+#undef RBD_DR_ROOT
+}

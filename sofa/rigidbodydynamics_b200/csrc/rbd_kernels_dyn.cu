@@ -107,6 +107,28 @@ __global__ void __launch_bounds__(256, 1) minv_kernel(const DevModel* __restrict
   dyn_epilogue(c);
 }
 
+// Derivatives of inverse dynamics (drnea_instance, rbd_deriv_body.h): same launch shape; every level record is on chip,
+// the only global traffic is q, v, a in and the two nv x nv matrices (+ optional packed M) out
+template <int TILE>
+__global__ void __launch_bounds__(256, 1) drnea_kernel(const DevModel* __restrict__ gm, const int model_words, const DrneaArgs a) {
+  const DynCtx c = dyn_prologue(gm, model_words);
+  const DevModel& m = *c.m;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const long long gw = (long long)blockIdx.x * wpb + warp;
+  const long long ntiles = (a.n + 31) / 32;
+  const int nv = m.nv;
+  for (long long t = gw; t < ntiles; t += (long long)gridDim.x * wpb) {
+    long long inst = t * 32 + lane;
+    if (inst >= a.n) inst = a.n - 1;  // lanes past the end recompute the last instance (same values to the same addresses)
+    drnea_instance(m, make_field_t<TILE>(const_cast<double*>(a.q), inst, m.nq, a.tile),
+                   make_field_t<TILE>(const_cast<double*>(a.v), inst, nv, a.tile),
+                   make_field_t<TILE>(const_cast<double*>(a.a), inst, nv, a.tile),
+                   make_field_t<TILE>(a.dtau_dq, inst, nv * nv, a.tile), make_field_t<TILE>(a.dtau_dv, inst, nv * nv, a.tile),
+                   make_field_t<TILE>(a.M, inst, nv * (nv + 1) / 2, a.tile), c.S, c.T);
+  }
+  dyn_epilogue(c);
+}
+
 template <class K>
 static cudaError_t dyn_attr(K kern) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -164,4 +186,28 @@ cudaError_t launch_minv(const DevModel& hm, const DevModel* d_model, const MinvA
   return cudaGetLastError();
 }
 
+}  // namespace rbd
+
+namespace rbd {
+cudaError_t launch_drnea(const DevModel& hm, const DevModel* d_model, const DrneaArgs& a, int num_sms, cudaStream_t st) {
+  const int mw = (int)(aba2_model_bytes(hm) / 8);
+  const int wpb = hm.plan.warps, block = wpb * 32;
+  const long long ntiles = (a.n + 31) / 32;
+  long long grid = (ntiles + wpb - 1) / wpb;
+  if (grid > num_sms) grid = num_sms;  // one block per SM, warps stride over the tiles
+  if (a.n <= 0) return cudaSuccess;
+  const size_t smem = (size_t)mw * 8 + (size_t)block * hm.plan.smem_doubles * 8;
+  static thread_local bool attr_done[2] = {false, false};
+  cudaError_t e = cudaSuccess;
+  if (a.tile == 32) {
+    if (!attr_done[1]) { e = dyn_attr(drnea_kernel<32>); if (e != cudaSuccess) return e; attr_done[1] = true; }
+    note_kernel(reinterpret_cast<const void*>(drnea_kernel<32>));
+    drnea_kernel<32><<<(unsigned)grid, block, smem, st>>>(d_model, mw, a);
+  } else {
+    if (!attr_done[0]) { e = dyn_attr(drnea_kernel<0>); if (e != cudaSuccess) return e; attr_done[0] = true; }
+    note_kernel(reinterpret_cast<const void*>(drnea_kernel<0>));
+    drnea_kernel<0><<<(unsigned)grid, block, smem, st>>>(d_model, mw, a);
+  }
+  return cudaGetLastError();
+}
 }  // namespace rbd

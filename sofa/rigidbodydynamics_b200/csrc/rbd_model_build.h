@@ -588,8 +588,30 @@ inline bool plan_minv(DevModel* m, bool use_tmem, int max_warps = B200Limits::kM
   }
   return plan_levels(m, use_tmem, 9, std::max(21 + 12, 6 * RBD_MINV_CB), 21, max_warps, forced_warps, aba2_model_bytes(*m));
 }
+// ... and of the inverse-dynamics derivatives (drnea_instance, rbd_deriv_body.h): record sizes depend on the joint kind
+// (free-flyer root: R | p instead of J; a 1-dof joint with >= 2 children keeps R | p for the restart behind its accumulator)
+inline bool plan_levels_sized(DevModel* m, bool use_tmem, const std::vector<int>& jsize, const std::vector<int>& jrestart,
+                              int max_warps, int forced_warps, size_t model_bytes);
+inline bool plan_drnea(DevModel* m, bool use_tmem, int max_warps = B200Limits::kMaxWarpsPerBlock, int forced_warps = 0) {
+  std::vector<int> jsize(m->njoints, 0), jrst(m->njoints, 0);
+  for (int i = 1; i < m->njoints; ++i) {
+    const DevJoint& j = m->joint[i];
+    if (j.nchild <= 0) continue;
+    const bool ff = j.type == JT_FF;
+    jsize[i] = ff ? (j.nchild >= 2 ? 54 : 33) : (j.nchild >= 2 ? 60 : 27);  // RBD_DR_* (rbd_deriv_body.h)
+    jrst[i] = ff ? 12 : 48;
+  }
+  return plan_levels_sized(m, use_tmem, jsize, jrst, max_warps, forced_warps, aba2_model_bytes(*m));
+}
 inline bool plan_levels(DevModel* m, bool use_tmem, int size_one_child, int size_branch, int restart_off, int max_warps,
                         int forced_warps, size_t model_bytes) {
+  std::vector<int> jsize(m->njoints, 0), jrst(m->njoints, restart_off);
+  for (int i = 1; i < m->njoints; ++i)
+    if (m->joint[i].nchild > 0) jsize[i] = m->joint[i].nchild >= 2 ? size_branch : size_one_child;
+  return plan_levels_sized(m, use_tmem, jsize, jrst, max_warps, forced_warps, model_bytes);
+}
+inline bool plan_levels_sized(DevModel* m, bool use_tmem, const std::vector<int>& jsize, const std::vector<int>& jrestart,
+                              int max_warps, int forced_warps, size_t model_bytes) {
   const int nj = m->njoints;
   const int D = m->max_depth_internal;
   std::vector<int> size(D + 1, 0);
@@ -597,7 +619,7 @@ inline bool plan_levels(DevModel* m, bool use_tmem, int size_one_child, int size
     const DevJoint& j = m->joint[i];
     if (j.nchild <= 0) continue;
     if (j.depth > D) return false;
-    size[j.depth] = std::max(size[j.depth], j.nchild >= 2 ? size_branch : size_one_child);
+    size[j.depth] = std::max(size[j.depth], jsize[i]);
   }
   std::vector<int> order;
   for (int d = 1; d <= D; ++d)
@@ -626,7 +648,7 @@ inline bool plan_levels(DevModel* m, bool use_tmem, int size_one_child, int size
       j.offA = 0; j.boff = 0;
       if (j.nchild <= 0) continue;
       j.offA = off[j.depth];
-      if (j.nchild >= 2) j.boff = (off[j.depth] & RBD_BOFF_TMEM) | ((off[j.depth] & RBD_BOFF_MASK) + restart_off);
+      if (j.nchild >= 2) j.boff = (off[j.depth] & RBD_BOFF_TMEM) | ((off[j.depth] & RBD_BOFF_MASK) + jrestart[i]);
     }
     return true;
   }

@@ -2938,4 +2938,5 @@ RBD_HD void aba_instance(const DevModel& m, const FLD& q, const FLD& v, const FL
 }
 
 #include "rbd_dyn_body.h"
+#include "rbd_deriv_body.h"
 #endif  /* !RBD_BODY_F32 && !RBD_BODY_EVAL_ONLY */

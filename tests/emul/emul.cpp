@@ -542,6 +542,34 @@ extern "C" int emul_minv(const rbd_model_desc* d, long long n, long long tile, i
   return 0;
 }
 
+// derivatives of inverse dynamics (drnea_instance): DQ, DV nv x nv row-major fields, M (optional) packed upper triangle;
+// level records on the plan of plan_drnea, storage as emul_aba2 (poisoned between instances)
+extern "C" int emul_drnea(const rbd_model_desc* d, long long n, long long tile, int use_tmem, int warps, double* q, double* v,
+                          double* a, double* DQ, double* DV, double* M, int* plan_out) {
+  Ctx c;
+  int rc = make_ctx(d, &c);
+  if (rc) return rc;
+  for (int i = 1; i < c.m.njoints; ++i)
+    if (c.m.joint[i].type == JT_FF && !(i == 1 && c.m.joint[i].parent == 0)) { g_err = "free-flyer below the root"; return -5; }
+  if (!plan_drnea(&c.m, use_tmem != 0, B200Limits::kMaxWarpsPerBlock, warps)) { g_err = "plan_drnea: nothing fits"; return -100; }
+  const EvalPlan& pl = c.m.plan;
+  if (plan_out) { plan_out[0] = pl.warps; plan_out[1] = pl.smem_doubles; plan_out[2] = pl.tmem_doubles; plan_out[3] = pl.tmem_cols; }
+  const int bt = pl.warps * 32;
+  std::vector<double> smem((size_t)(pl.smem_doubles > 0 ? pl.smem_doubles : 1) * bt, 1e300);
+  std::vector<double> tmem((size_t)(pl.tmem_doubles > 0 ? pl.tmem_doubles : 1) * bt, 1e300);
+  const int nv = c.m.nv;
+  for (long long i = 0; i < n; ++i) {
+    const int t = (int)(i % bt);
+    for (int e = 0; e < pl.smem_doubles; ++e) smem[(size_t)(t / 32) * pl.smem_doubles * 32 + (size_t)e * 32 + t % 32] = 1e300;
+    for (int e = 0; e < pl.tmem_doubles; ++e) tmem[(size_t)t * pl.tmem_doubles + e] = 1e300;
+    Stack S = make_stack(smem.data(), t, pl.smem_doubles);
+    TmStack T{tmem.data() + (size_t)t * (pl.tmem_doubles > 0 ? pl.tmem_doubles : 1)};
+    drnea_instance(c.m, make_field(q, i, c.m.nq, tile), make_field(v, i, nv, tile), make_field(a, i, nv, tile),
+                   make_field(DQ, i, nv * nv, tile), make_field(DV, i, nv * nv, tile), make_field(M, i, nv * (nv + 1) / 2, tile), S, T);
+  }
+  return 0;
+}
+
 // assembled mapping Jacobian (getJ_block_cached) of the selected outputs for every instance; also returns the pattern
 // (blk_ptr [n_sel + 1], cols): val [n][6 blk_ptr[n_sel]]
 extern "C" int emul_getJ(const rbd_model_desc* d, long long n, double* qcache, long long cache_tile, int n_sel,

@@ -46,7 +46,7 @@ def load_emul() -> C.CDLL:
     src = os.path.join(HERE, "emul", "emul.cpp")
     out = os.path.join(HERE, "emul", "libemul.so")
     csrc = os.path.join(ROOT, "sofa", "rigidbodydynamics_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("rbd_sweeps.h", "rbd_sweeps_body.h", "rbd_dyn_body.h", "rbd_arm_body.h", "rbd_model_build.h", "rbd_dev_model.h")]
+    deps = [src] + [os.path.join(csrc, f) for f in ("rbd_sweeps.h", "rbd_sweeps_body.h", "rbd_dyn_body.h", "rbd_deriv_body.h", "rbd_arm_body.h", "rbd_model_build.h", "rbd_dev_model.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-O2", "-march=native", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
                                "-o", out, src])
@@ -74,6 +74,7 @@ def load_emul() -> C.CDLL:
     lib.emul_aba.argtypes = [vp, ll, ll, vp, vp, vp, vp]
     lib.emul_aba2.argtypes = [vp, ll, ll, i, i, vp, vp, vp, vp, vp]
     lib.emul_minv.argtypes = [vp, ll, ll, i, i, vp, vp, vp]
+    lib.emul_drnea.argtypes = [vp, ll, ll, i, i, vp, vp, vp, vp, vp, vp, vp]
     lib.emul_eval_arm.argtypes = [vp, ll, ll] + [vp] * 7
     lib.emul_eval_plan.argtypes = [vp, i, i, vp]
     lib.emul_applyDJT.argtypes = [vp, ll, ll, vp, ll, vp, vp, vp, C.c_double, vp, vp]

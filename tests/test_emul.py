@@ -575,6 +575,54 @@ def test_minv_body_matches_oracle(emul, d, tile, body):
                 assert np.max(np.abs(orc.aba(q[i], z, e) - a0 - G[:, c])) <= 1e-9 * scale
 
 
+@pytest.mark.parametrize("d", MODELS, ids=IDS)
+@pytest.mark.parametrize("tile", [32, 11])
+@pytest.mark.parametrize("body", ["planned", "smem_only", "w3"])
+def test_drnea_body_matches_oracle(emul, d, tile, body):
+    """drnea_instance (derivatives of inverse dynamics regrouped per (joint, ancestor) pair on the depth-first sweep,
+    compact composite forms: 9 + 9 + 6 doubles instead of dense 6 x 6 matrices) against the oracle's restatement of
+    pinocchio::computeRNEADerivatives (dense, two full passes), the 50-digit finite-difference golden vectors, and exact
+    structural zeros.  M (dtau_da) in the packed format of the CRBA entry point."""
+    import json
+    import os
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    if d.nv == 0:
+        pytest.skip("no dofs")
+    cd, keep = _cdesc(d)
+    with open(os.path.join(helpers.GOLDEN, "golden_drnea.json")) as f:
+        gold = json.load(f)[d.name]
+    n = 37
+    q, v, a = mdl.random_state(d, n, seed=91)
+    q[0], v[0], a[0] = np.array(gold["q"]), np.array(gold["v"]), np.array(gold["a"])
+    nv = d.nv
+    nt = (n + tile - 1) // tile
+    DQ = np.full((nt, nv * nv, tile), np.nan); DV = np.full((nt, nv * nv, tile), np.nan)
+    Mp = np.full((nt, nv * (nv + 1) // 2, tile), np.nan)
+    qs, vs, as_ = to_tiled(q, tile), to_tiled(v, tile), to_tiled(a, tile)
+    plan = (C.c_int * 4)()
+    rc = emul.emul_drnea(C.addressof(cd), n, tile, 0 if body == "smem_only" else 1, 3 if body == "w3" else 0,
+                         P(qs), P(vs), P(as_), P(DQ), P(DV), P(Mp) if body != "w3" else None, plan)
+    assert rc == 0, emul.emul_last_error()
+    gq = from_tiled(DQ, n)[:, :nv * nv].reshape(n, nv, nv); gv = from_tiled(DV, n)[:, :nv * nv].reshape(n, nv, nv)
+    assert np.isfinite(gq).all() and np.isfinite(gv).all()          # every entry written, structural zeros included
+    orc = oracle.Oracle(d)
+    related = helpers.support_relation(d)
+    for i in range(n):
+        rq, rv, rM = orc.rnea_derivatives(q[i], v[i], a[i])
+        assert rel_err(gq[i], rq) <= 1e-10, (i, rel_err(gq[i], rq))
+        assert rel_err(gv[i], rv) <= 1e-10, (i, rel_err(gv[i], rv))
+        assert np.all(gq[i][~related] == 0.0) and np.all(gv[i][~related] == 0.0)
+        if body != "w3":
+            gM = from_tiled(Mp, n)[i, :nv * (nv + 1) // 2]
+            assert np.isfinite(gM).all()
+            assert rel_err(oracle.unpack_upper(gM, nv), np.triu(rM) + np.triu(rM, 1).T) <= 1e-10
+    assert rel_err(gq[0], np.array(gold["dtau_dq"])) <= 1e-10
+    assert rel_err(gv[0], np.array(gold["dtau_dv"])) <= 1e-10
+    if body == "planned" and d.name == "talos_reduced":
+        assert list(plan)[0] == 4          # the sweep state (54 + 27 + 60 + 7 x 27 doubles) caps the SM at 4 warps
+
+
 @pytest.mark.parametrize("tile", [32, 13])
 @pytest.mark.parametrize("nj", [6, 7, 5])
 def test_arm_body_matches_oracle_and_generic_sweep(emul, tile, nj):

@@ -221,3 +221,65 @@ def test_aba_round_trip_talos_full_size():
     for i in range(0, n, 131071):
         ref = orc.aba(im(q, i), im(v, i), im(tau, i))
         assert rel_err(im(ddq, i), ref) <= 1e-9
+
+
+def _integrate_ff_tree(torch, q, dq, eps):
+    """q (+) eps dq on the device for a free-flyer-rooted tree of revolute / prismatic joints (tiled [nt, nq, 32] /
+    [nt, nv, 32]): p += R (eps v_b), quat <- quat * exp(eps w_b), the rest q += eps dq (pinocchio::integrate)."""
+    out = q.clone()
+    out[:, 7:] = q[:, 7:] + eps * dq[:, 6:]
+    x, y, z, w = q[:, 3], q[:, 4], q[:, 5], q[:, 6]
+    vb = eps * dq[:, 0:3]
+    out[:, 0] = q[:, 0] + (1 - 2 * (y * y + z * z)) * vb[:, 0] + 2 * (x * y - z * w) * vb[:, 1] + 2 * (x * z + y * w) * vb[:, 2]
+    out[:, 1] = q[:, 1] + 2 * (x * y + z * w) * vb[:, 0] + (1 - 2 * (x * x + z * z)) * vb[:, 1] + 2 * (y * z - x * w) * vb[:, 2]
+    out[:, 2] = q[:, 2] + 2 * (x * z - y * w) * vb[:, 0] + 2 * (y * z + x * w) * vb[:, 1] + (1 - 2 * (x * x + y * y)) * vb[:, 2]
+    th = eps * dq[:, 3:6]
+    ang = th.norm(dim=1)
+    s = torch.sin(ang / 2) / ang
+    dx, dy, dz, dw = s * th[:, 0], s * th[:, 1], s * th[:, 2], torch.cos(ang / 2)
+    out[:, 3] = w * dx + x * dw + y * dz - z * dy
+    out[:, 4] = w * dy - x * dz + y * dw + z * dx
+    out[:, 5] = w * dz + x * dy - y * dx + z * dw
+    out[:, 6] = w * dw - x * dx - y * dy - z * dz
+    return out
+
+
+def test_rnea_derivatives_talos_full_size():
+    """Talos at N = 1,048,576 (24 GB of derivative matrices), every instance on the device: tau is QUADRATIC in v, so
+    rnea(q, v + dv, a) - rnea(q, v - dv, a) == 2 dtau_dv dv holds exactly for a finite dv; tau is linear in a with
+    dtau_da = M; and a central difference along q (+) eps dq reproduces dtau_dq dq.  Plus a strided sample against the
+    oracle's restatement of pinocchio::computeRNEADerivatives."""
+    import torch
+    import oracle
+    from sofa.rigidbodydynamics_b200 import api, model as mdl
+    d = mdl.talos_reduced(); n = 1 << 20; nt = n // 32; nv = d.nv
+    m = api.Model(d); ws = api.Workspace(m, n)
+    ws.set_stream(torch.cuda.current_stream().cuda_stream)
+    q, v, a = _rand_state(torch, d, n, 23)
+    _q2, dq, dv = _rand_state(torch, d, n, 29)
+    new = lambda K: torch.empty((nt, K, 32), dtype=torch.float64, device="cuda")
+    DQ, DV, Mp = new(nv * nv), new(nv * nv), new(nv * (nv + 1) // 2)
+    ws.rnea_derivatives_soa(n, 32, q, v, a, DQ, DV, Mp)
+    torch.cuda.synchronize()
+    matvec = lambda D, x: torch.einsum("trcl,tcl->trl", D.view(nt, nv, nv, 32), x)
+    tp, tm = new(nv), new(nv)
+    ws.rnea_soa(n, 32, q, v + dv, a, tp); ws.rnea_soa(n, 32, q, v - dv, a, tm)
+    torch.cuda.synchronize()
+    lin = 2 * matvec(DV, dv)
+    assert float((tp - tm - lin).abs().max()) <= 1e-10 * max(1.0, float(lin.abs().max()))
+    ws.rnea_soa(n, 32, q, v, a + dv, tp); ws.rnea_soa(n, 32, q, v, a, tm)
+    torch.cuda.synchronize()
+    lin = _Ma(torch, Mp, dv, nv)
+    assert float((tp - tm - lin).abs().max()) <= 1e-10 * max(1.0, float(lin.abs().max()))
+    eps = 1e-6
+    ws.rnea_soa(n, 32, _integrate_ff_tree(torch, q, dq, eps), v, a, tp)
+    ws.rnea_soa(n, 32, _integrate_ff_tree(torch, q, dq, -eps), v, a, tm)
+    torch.cuda.synchronize()
+    lin = matvec(DQ, dq)
+    assert float(((tp - tm) / (2 * eps) - lin).abs().max()) <= 2e-6 * max(1.0, float(lin.abs().max()))
+    orc = oracle.Oracle(d)
+    im = lambda x, i: x.permute(0, 2, 1).reshape(n, -1)[i].cpu().numpy()
+    for i in range(0, n, 131071):
+        rq, rv, _ = orc.rnea_derivatives(im(q, i), im(v, i), im(a, i))
+        assert rel_err(im(DQ, i).reshape(nv, nv), rq) <= TOL_FP64
+        assert rel_err(im(DV, i).reshape(nv, nv), rv) <= TOL_FP64

@@ -1000,6 +1000,78 @@ def test_minv_matches_oracle(torch_mod, api, d, tile):
     assert rel_err(hm, got) <= 1e-13
 
 
+@pytest.mark.parametrize("d", MODELS, ids=IDS)
+@pytest.mark.parametrize("tile", [32, 1000])
+def test_rnea_derivatives_match_oracle(torch_mod, api, d, tile):
+    """rbd_rnea_derivatives_soa / _host (pinocchio::computeRNEADerivatives, SURVEY.md §8(f) rank 4): dtau_dq, dtau_dv and
+    the optional M against the oracle's dense restatement, the 50-digit finite-difference golden vectors, exact structural
+    zeros, M against the GPU's own CRBA, and a directional finite difference of the GPU's own rnea for every instance."""
+    import json
+    import os
+    import helpers
+    import oracle
+    torch = torch_mod
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    if d.nv == 0:
+        pytest.skip("no dofs")
+    with open(os.path.join(helpers.GOLDEN, "golden_drnea.json")) as f:
+        gold = json.load(f)[d.name]
+    n = 333
+    nv = d.nv
+    q, v, a = mdl.random_state(d, n, seed=73)
+    q[0], v[0], a[0] = np.array(gold["q"]), np.array(gold["v"]), np.array(gold["a"])
+    m = api.Model(d); ws = api.Workspace(m, n)
+    nt = (n + tile - 1) // tile
+    mf = nv * (nv + 1) // 2
+    new = lambda K: torch.full((nt, K, tile), float("nan"), dtype=torch.float64, device="cuda")
+    qs, vs, as_ = (_dev(torch, to_tiled(x, tile)) for x in (q, v, a))
+    DQ, DV, Mp = new(nv * nv), new(nv * nv), new(mf)
+    ws.rnea_derivatives_soa(n, tile, qs, vs, as_, DQ, DV, Mp)
+    ws.synchronize()
+    assert "drnea_kernel" in api.last_kernel_name()
+    gq = from_tiled(DQ.cpu().numpy(), n)[:, :nv * nv].reshape(n, nv, nv)
+    gv = from_tiled(DV.cpu().numpy(), n)[:, :nv * nv].reshape(n, nv, nv)
+    gM = from_tiled(Mp.cpu().numpy(), n)[:, :mf]
+    assert np.isfinite(gq).all() and np.isfinite(gv).all() and np.isfinite(gM).all()
+    related = helpers.support_relation(d)
+    assert np.all(gq[:, ~related] == 0.0) and np.all(gv[:, ~related] == 0.0)
+    orc = oracle.Oracle(d)
+    for i in list(range(0, n, 23)) + [n - 1]:
+        rq, rv, _ = orc.rnea_derivatives(q[i], v[i], a[i])
+        assert rel_err(gq[i], rq) <= TOL_FP64 and rel_err(gv[i], rv) <= TOL_FP64, i
+    assert rel_err(gq[0], np.array(gold["dtau_dq"])) <= TOL_FP64 and rel_err(gv[0], np.array(gold["dtau_dv"])) <= TOL_FP64
+    # dtau_da == the CRBA kernel's M (same packed format)
+    Mc = new(mf)
+    ws.crba_soa(n, tile, qs, Mc); ws.synchronize()
+    assert rel_err(gM, from_tiled(Mc.cpu().numpy(), n)[:, :mf]) <= 1e-12
+    # without M: same matrices
+    DQ2, DV2 = new(nv * nv), new(nv * nv)
+    ws.rnea_derivatives_soa(n, tile, qs, vs, as_, DQ2, DV2, None); ws.synchronize()
+    assert np.array_equal(from_tiled(DQ2.cpu().numpy(), n), from_tiled(DQ.cpu().numpy(), n))
+    assert np.array_equal(from_tiled(DV2.cpu().numpy(), n), from_tiled(DV.cpu().numpy(), n))
+    # directional central difference of the GPU's own rnea along (dq, dv), every instance
+    rng = np.random.default_rng(74)
+    dq = rng.uniform(-1, 1, (n, nv)); dv = rng.uniform(-1, 1, (n, nv))
+    eps = 1e-6
+    taus = []
+    for sgn in (1.0, -1.0):
+        qe = helpers.integrate(d, q, dq, sgn * eps); ve = v + sgn * eps * dv
+        t = new(max(1, nv))
+        ws.rnea_soa(n, tile, _dev(torch, to_tiled(qe, tile)), _dev(torch, to_tiled(ve, tile)), as_, t)
+        ws.synchronize()
+        taus.append(from_tiled(t.cpu().numpy(), n)[:, :nv])
+    fd = (taus[0] - taus[1]) / (2 * eps)
+    lin = np.einsum("nrc,nc->nr", gq, dq) + np.einsum("nrc,nc->nr", gv, dv)
+    assert np.max(np.abs(fd - lin)) <= 1e-6 * max(1.0, float(np.max(np.abs(lin))))
+    # host entry point (instance-major [n][nv][nv])
+    hq, hv, hM = np.zeros((n, nv, nv)), np.zeros((n, nv, nv)), np.zeros((n, mf))
+    ws.rnea_derivatives_host(n, q, v, a, hq, hv, hM)
+    assert rel_err(hq, gq) <= 1e-13 and rel_err(hv, gv) <= 1e-13 and rel_err(hM, gM) <= 1e-13
+    hq2, hv2 = np.zeros((n, nv, nv)), np.zeros((n, nv, nv))
+    ws.rnea_derivatives_host(n, q, v, a, hq2, hv2, None)
+    assert np.array_equal(hq, hq2) and np.array_equal(hv, hv2)
+
+
 @pytest.mark.parametrize("tile", [32, 1000])
 def test_arm_kernel_equals_generic_chain_sweep(torch_mod, api, tile):
     """Fused eval of the 7-joint Panda chain: the unrolled arm kernel (default for 6- / 7-joint serial chains) against the
