@@ -118,10 +118,11 @@ struct rbd_workspace {
   DevModel* d_minv = nullptr;
   int minv_state = 0;
   double* minv_scratch[2] = {nullptr, nullptr};
-  // derivatives of inverse dynamics (drnea): planned joint table, state as aba2_state; no scratch
+  // derivatives of inverse dynamics (drnea): planned joint table, state as aba2_state; cold level records per resident warp
   DevModel* h_drnea = nullptr;
   DevModel* d_drnea = nullptr;
   int drnea_state = 0;
+  double* drnea_scratch[2] = {nullptr, nullptr};
   void* sel_buf = nullptr;  // getJ: selection + block pointers
   size_t sel_bytes = 0;
 };
@@ -226,7 +227,7 @@ static void ws_free(rbd_workspace* ws) {
   cudaFree(ws->sel_buf); cudaFree(ws->aba_scratch[0]); cudaFree(ws->aba_scratch[1]);
   cudaFree(ws->aba2_scratch[0]); cudaFree(ws->aba2_scratch[1]); cudaFree(ws->d_aba2); delete ws->h_aba2;
   cudaFree(ws->minv_scratch[0]); cudaFree(ws->minv_scratch[1]); cudaFree(ws->d_minv); delete ws->h_minv;
-  cudaFree(ws->d_drnea); delete ws->h_drnea;
+  cudaFree(ws->drnea_scratch[0]); cudaFree(ws->drnea_scratch[1]); cudaFree(ws->d_drnea); delete ws->h_drnea;
   cudaFree(ws->qcache); cudaFree(ws->rows_buf); cudaFree(ws->d_model); cudaFree(ws->jcache); cudaFree(ws->omicache); cudaFree(ws->jc_scratch);
   for (int k = 0; k < rbd_workspace::kPlans; ++k) { cudaFree(ws->d_plan[k]); delete ws->h_plan[k]; }
   for (int k = 0; k < 8; ++k) { cudaFree(ws->d_plan32[k]); delete ws->h_plan32[k]; }
@@ -400,6 +401,7 @@ static void drop_plans(rbd_workspace* ws) {
   delete ws->h_aba2; ws->h_aba2 = nullptr; ws->aba2_state = 0;
   delete ws->h_minv; ws->h_minv = nullptr; ws->minv_state = 0;
   delete ws->h_drnea; ws->h_drnea = nullptr; ws->drnea_state = 0;
+  cudaFree(ws->drnea_scratch[0]); cudaFree(ws->drnea_scratch[1]); ws->drnea_scratch[0] = ws->drnea_scratch[1] = nullptr;
   cudaFree(ws->minv_scratch[0]); cudaFree(ws->minv_scratch[1]); ws->minv_scratch[0] = ws->minv_scratch[1] = nullptr;
   cudaFree(ws->aba2_scratch[0]); cudaFree(ws->aba2_scratch[1]); ws->aba2_scratch[0] = ws->aba2_scratch[1] = nullptr;
 }
@@ -686,8 +688,17 @@ static int drnea_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile,
   }
   if (ws->drnea_state != 1)
     return set_err(RBD_ERR_UNSUPPORTED, "rnea_derivatives: the level records of this tree do not fit the shared + tensor memory of an SM");
-  DrneaArgs A{n, tile, q, v, a, dq, dv, M};
-  CK(launch_drnea(*ws->h_drnea, ws->d_drnea, A, ws->num_sms, st));
+  const int sc = (ws->slot[1].st && st == ws->slot[1].st) ? 1 : 0;
+  if (!ws->drnea_scratch[sc]) {
+    int warps = 0;
+    DrneaArgs S{0, 32, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    CK(launch_drnea(*ws->h_drnea, ws->d_drnea, S, ws->num_sms, &warps, st));
+    const size_t bytes = (size_t)warps * (size_t)(ws->h_drnea->slot_total[0] > 0 ? ws->h_drnea->slot_total[0] : 1) * 32 * sizeof(double);
+    cudaError_t e = cudaMalloc(&ws->drnea_scratch[sc], bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return set_err(RBD_ERR_ALLOC, std::string("cudaMalloc(rnea_derivatives scratch): ") + cudaGetErrorString(e)); }
+  }
+  DrneaArgs A{n, tile, q, v, a, dq, dv, M, ws->drnea_scratch[sc]};
+  CK(launch_drnea(*ws->h_drnea, ws->d_drnea, A, ws->num_sms, nullptr, st));
   if (n > 0) ws->launches++;
   return RBD_OK;
 }

@@ -21,23 +21,29 @@
 // doubles, linear in the momenta.  15 doubles instead of pinocchio's dense 6 x 6 doYcrb; B m = dY m + m x* H,
 // B^T m = dY m - m x* H.
 //
-// On-chip level records (plan_drnea; DevJoint::offA, bit RBD_BOFF_TMEM = tensor memory), one per DEPTH LEVEL that holds a
-// joint with children:
-//     1-dof joint   [v | a (12) | J (6)     | tail]      tail: one child  -> the joint's own Y (h, I_O: 9)
-//     free-flyer    [v | a (12) | R | p (12) | tail]            >= 2      -> accumulator Y^c (9) | dY^c (9) | H (6) | F (6)
-//     1-dof joints with >= 2 children keep R | p (12) for the restart of the next branch behind the accumulator (boff).
+// Sweep state, one record per DEPTH LEVEL that holds a joint with children (plan_drnea), split by how often it is touched:
+//   HOT, on chip (shared / tensor memory; DevJoint::offA, bit RBD_BOFF_TMEM = tensor memory) — read by the pair loop of
+//   every descendant:        1-dof joint [v | a (12) | J (6)]       free-flyer root [v | a (12) | R | p (12)]
+//   COLD, in the thread's global scratch record X (DevJoint::boff; L2-resident: written once, read once or twice):
+//     one child   -> the joint's own Y (h, I_O: 9), re-read when the sweep leaves the joint;
+//     >= 2        -> accumulator Y^c (9) | dY^c (9) | H (6) | F (6), initialised with the joint's own body, the finished
+//                    child subtrees ADD into it without reading it back (red.global.add: nothing waits), + R | p (12) of a
+//                    1-dof joint for the restart of the next branch.
+//   18 doubles per level on chip instead of 27 .. 60: Talos (ten levels) runs 8 warps per SM instead of 4, and it is the
+//   number of warps that hides the issue latency of this sweep (first version, everything on chip: 11.8 ms per 2^20).
 // dVdq / dAdq of an ancestor are recomputed in the pair loop from its J and its parent's v | a (3 cross products) rather
-// than stored: 27 doubles per level instead of 39 — the sweep state, not the arithmetic, decides how many warps an SM holds.
+// than stored.
 //
 // Outputs: DQ, DV: nv x nv, field r nv + c (row-major like pinocchio's RowMatrixXs), structural zeros WRITTEN (dofs on
 // different branches); M (optional): packed upper triangle like rbd_crba_soa.  A free-flyer only as joint 1 on the universe.
 // All lanes of a warp run the sweep together (tensor-memory accesses are warp-collective).
 
-#define RBD_DR_ONE 27      /* 1-dof joint, one child: v | a | J | Y                               */
-#define RBD_DR_BRANCH 60   /* 1-dof joint, >= 2 children: v | a | J | accumulator (30) | R | p     */
-#define RBD_DR_RST 48      /* ... offset of its R | p                                              */
-#define RBD_DR_FF_ONE 33   /* free-flyer, one child: v | a | R | p | Y                             */
-#define RBD_DR_FF_BRANCH 54 /* free-flyer, >= 2 children: v | a | R | p | accumulator (30)         */
+#define RBD_DR_HOT 18       /* on-chip level record of a 1-dof joint: v | a | J                                       */
+#define RBD_DR_HOT_FF 24    /* ... of the free-flyer root: v | a | R | p                                              */
+#define RBD_DR_COLD_ONE 9   /* scratch record, one child: Y                                                          */
+#define RBD_DR_COLD_BRANCH 42 /* ... >= 2 children: accumulator (30) | R | p (12; unused below a free-flyer)           */
+#define RBD_DR_SLOTS 3      /* joints of lookahead of the asynchronous input ring (3 doubles each; == kDrneaSlots);
+                               9 staging doubles for a parent's cold Y sit behind the ring                             */
 
 // motion x motion: [w_a x v_b + v_a x w_b ; w_a x w_b]
 RBD_HD void mxm(const real* a, const real* b, real* o) {
@@ -246,9 +252,9 @@ RBD_HD void dr_pop_ff(const DevModel& m, int cur, const real* Rp, const real* ve
   }
 }
 
-template <class FLD>
+template <class FLD, class SCR>
 RBD_HD void drnea_instance(const DevModel& m, const FLD& q, const FLD& v, const FLD& a, const FLD& DQ, const FLD& DV,
-                           const FLD& M, const Stack& S, const TmStack& T) {
+                           const FLD& M, const SCR& X, const Stack& S, const TmStack& T, const InRing& inr) {
   const int nj = m.njoints;
   real R[9], p[3], vel[6], acc[6];
 #define RBD_DR_ROOT()                                                                           \
@@ -259,23 +265,42 @@ RBD_HD void drnea_instance(const DevModel& m, const FLD& q, const FLD& v, const 
     acc[0] = -m.gravity[0]; acc[1] = -m.gravity[1]; acc[2] = -m.gravity[2];                     \
   } while (0)
   RBD_DR_ROOT();
-  // (joint angle, velocity and acceleration of 1-dof joints are fetched one joint ahead — in front of the whole unwind of
-  // the current joint: a global load under the kernel's own store stream takes thousands of cycles)
-  real nq0 = 0, nq1 = 0, nqd = 0, nqdd = 0;
-#define RBD_DR_PREFETCH(J)                                                                      \
+  // Inputs of the 1-dof joints: through an asynchronous ring in shared memory (cp.async, no destination register)
+  // RBD_DR_SLOTS joints ahead of the sweep when the plan has room for it (InRing, as in the fused eval: under the kernel's
+  // own store stream a global read takes thousands of cycles, and a register prefetch is spilled by ptxas at 255
+  // registers — the spill store then waits for the load: profile s3e); else (tests/emul) read at the point of use.
+  const bool ring = inr.p != nullptr;
+#define RBD_DR_ISSUE(J)                                                                         \
   do {                                                                                          \
-    const DevJoint& jx_ = m.joint[J];                                                           \
-    if (!RBD_T_IS_FF(jx_.type)) {                                                               \
-      nq0 = q.ld(jx_.idx_q); nqd = v.ld(jx_.idx_v); nqdd = a.ld(jx_.idx_v);                     \
-      if (is_unbounded(jx_.type)) nq1 = q.ld(jx_.idx_q + 1);                                    \
+    if ((J) < nj && !RBD_T_IS_FF(m.joint[J].type)) {                                            \
+      const DevJoint& jx_ = m.joint[J];                                                         \
+      const int sl_ = 3 * ((J) % RBD_DR_SLOTS);                                                 \
+      cp_async_real(inr, sl_, q.at(jx_.idx_q));                                                 \
+      cp_async_real(inr, sl_ + 1, v.at(jx_.idx_v));                                             \
+      cp_async_real(inr, sl_ + 2, a.at(jx_.idx_v));                                             \
     }                                                                                           \
+    cp_async_commit();                                                                          \
   } while (0)
-  if (nj > 1) RBD_DR_PREFETCH(1);
+  if (ring) {
+#pragma unroll
+    for (int s_ = 1; s_ <= RBD_DR_SLOTS; ++s_) RBD_DR_ISSUE(s_);
+  }
   for (int i = 1; i < nj; ++i) {
     const DevJoint& jn = m.joint[i];
     const bool ff = RBD_T_IS_FF(jn.type);
-    const real q0 = nq0, q1 = nq1, qd = nqd, qdd = nqdd;
-    if (i + 1 < nj) RBD_DR_PREFETCH(i + 1);
+    real q0 = 0, q1 = 0, qd = 0, qdd = 0;
+    if (ring) {
+      cp_async_wait<RBD_DR_SLOTS - 1>();
+      if (!ff) {
+        const int sl = 3 * (i % RBD_DR_SLOTS);
+        q0 = inr.p[sl * RBD_WARP]; qd = inr.p[(sl + 1) * RBD_WARP]; qdd = inr.p[(sl + 2) * RBD_WARP];
+        if (is_unbounded(jn.type)) q1 = q.ld(jn.idx_q + 1);
+      }
+      RBD_DR_ISSUE(i + RBD_DR_SLOTS);
+    } else if (!ff) {
+      q0 = q.ld(jn.idx_q); qd = v.ld(jn.idx_v); qdd = a.ld(jn.idx_v);
+      if (is_unbounded(jn.type)) q1 = q.ld(jn.idx_q + 1);
+    }
     real aw[3], A[6], va[12];
     fk_joint(jn, R, p, q0, q1, q, aw);
 #pragma unroll
@@ -302,30 +327,24 @@ RBD_HD void drnea_instance(const DevModel& m, const FLD& q, const FLD& v, const 
 #pragma unroll
       for (int e = 0; e < 6; ++e) { t[e] = vel[e]; t[6 + e] = acc[e]; }
       lev_st<12>(S, T, jn.offA, t);
-      int tail;
-      if (!ff) {
-        lev_st<6>(S, T, jn.offA + 12, A);
-        tail = jn.offA + 18;
-      } else {
 #pragma unroll
-        for (int e = 0; e < 9; ++e) t[e] = R[e];
+      for (int e = 0; e < 9; ++e) t[e] = R[e];
 #pragma unroll
-        for (int e = 0; e < 3; ++e) t[9 + e] = p[e];
-        lev_st<12>(S, T, jn.offA + 12, t);
-        tail = jn.offA + 24;
-      }
+      for (int e = 0; e < 3; ++e) t[9 + e] = p[e];
+      if (!ff) lev_st<6>(S, T, jn.offA + 12, A);
+      else lev_st<12>(S, T, jn.offA + 12, t);
+      const SCR Xc = X.at(jn.boff);
       if (jn.nchild == 1) {
-        lev_st<9>(S, T, tail, Y + 1);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Xc.st(e, Y[1 + e]);
       } else {
         real C[30];
         dr_own(Y, vel, acc, C);
-        lev_st<30>(S, T, tail, C);
+#pragma unroll
+        for (int e = 0; e < 30; ++e) Xc.st(e, C[e]);
         if (!ff) {
 #pragma unroll
-          for (int e = 0; e < 9; ++e) t[e] = R[e];
-#pragma unroll
-          for (int e = 0; e < 3; ++e) t[9 + e] = p[e];
-          lev_st<12>(S, T, jn.boff, t);
+          for (int e = 0; e < 12; ++e) Xc.st(30 + e, t[e]);
         }
       }
       continue;
@@ -353,27 +372,43 @@ RBD_HD void drnea_instance(const DevModel& m, const FLD& q, const FLD& v, const 
         dr_pop_ff(m, cur, Rp, vr, C, DQ, DV, M);
         break;  // (the host checks that a free-flyer is joint 1 on the universe)
       }
-      dr_pop_1dof(m, cur, A, va, C, DQ, DV, M, S, T);
       const int pp = jc.parent;
+      // the own inertia of a one-child parent that this pop completes comes back from the scratch record: start the copy
+      // into the staging slots now, behind the pair loop it has arrived (a plain load here would hold 18 registers across
+      // the loop — ptxas spills them, and the spill store waits for the load)
+      const bool merge_own = pp != 0 && pp != stop_at && m.joint[pp].nchild == 1;
+      if (ring && merge_own) {
+        const SCR Xp = X.at(m.joint[pp].boff);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) cp_async_real(inr, 3 * RBD_DR_SLOTS + e, Xp.ptr(e));
+        cp_async_commit();
+      }
+      dr_pop_1dof(m, cur, A, va, C, DQ, DV, M, S, T);
       if (pp == 0) break;
       const DevJoint& jp = m.joint[pp];
-      const int ptail = jp.offA + (RBD_T_IS_FF(jp.type) ? 24 : 18);
-      if (pp == stop_at) {  // the parent has another child to come: park the contribution there
-        lev_add<30>(S, T, ptail, C);
+      const SCR Xp = X.at(jp.boff);
+      if (pp == stop_at) {  // the parent has another child to come: add the contribution to its accumulator (no read back)
+#pragma unroll
+        for (int e = 0; e < 30; ++e) Xp.add(e, C[e]);
         break;
       }
-      // the parent is complete: its accumulator (>= 2 children) or its own body (one child) joins in registers; va still
-      // holds the parent's v | a
+      // the parent is complete: its accumulator (>= 2 children) or its own body (one child) joins in registers
       if (jp.nchild >= 2) {
-        real t[30];
-        lev_ld<30>(S, T, ptail, t);
 #pragma unroll
-        for (int e = 0; e < 30; ++e) C[e] += t[e];
+        for (int e = 0; e < 30; ++e) C[e] += Xp.ld(e);
       } else {
-        real Yp[10], t[30];
+        real Yp[10], t[30], vap[12];
         Yp[0] = jp.Y[0];
-        lev_ld<9>(S, T, ptail, Yp + 1);
-        dr_own(Yp, va, va + 6, t);
+        if (ring) {
+          cp_async_wait<0>();
+#pragma unroll
+          for (int e = 0; e < 9; ++e) Yp[1 + e] = inr.p[(3 * RBD_DR_SLOTS + e) * RBD_WARP];
+        } else {
+#pragma unroll
+          for (int e = 0; e < 9; ++e) Yp[1 + e] = Xp.ld(e);
+        }
+        lev_ld<12>(S, T, jp.offA, vap);  // (re-read: keeping the parent's v | a in registers across the pair loop spills)
+        dr_own(Yp, vap, vap + 6, t);
 #pragma unroll
         for (int e = 0; e < 30; ++e) C[e] += t[e];
       }
@@ -400,7 +435,13 @@ RBD_HD void drnea_instance(const DevModel& m, const FLD& q, const FLD& v, const 
         lev_ld<12>(S, T, js.offA, t);
 #pragma unroll
         for (int e = 0; e < 6; ++e) { vel[e] = t[e]; acc[e] = t[6 + e]; }
-        lev_ld<12>(S, T, RBD_T_IS_FF(js.type) ? js.offA + 12 : js.boff, t);
+        if (RBD_T_IS_FF(js.type)) {
+          lev_ld<12>(S, T, js.offA + 12, t);
+        } else {
+          const SCR Xs = X.at(js.boff);
+#pragma unroll
+          for (int e = 0; e < 12; ++e) t[e] = Xs.ld(30 + e);
+        }
 #pragma unroll
         for (int e = 0; e < 9; ++e) R[e] = t[e];
 #pragma unroll
@@ -408,6 +449,6 @@ RBD_HD void drnea_instance(const DevModel& m, const FLD& q, const FLD& v, const 
       }
     }
   }
-#undef RBD_DR_PREFETCH
+#undef RBD_DR_ISSUE
 #undef RBD_DR_ROOT
 }

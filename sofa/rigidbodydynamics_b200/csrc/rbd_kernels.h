@@ -48,6 +48,7 @@ struct DrneaArgs {  // derivatives of inverse dynamics: q, v, a -> dtau_dq, dtau
   long long n, tile;
   const double *q, *v, *a;
   double *dtau_dq, *dtau_dv, *M;
+  double* scratch;  // planned_model.slot_total[0] * 32 doubles per resident warp (cold level records)
 };
 struct AbaArgs {  // forward dynamics (articulated-body algorithm): q, v, tau -> ddq
   long long n, tile;
@@ -112,9 +113,9 @@ cudaError_t launch_aba(const DevModel& m, const DevModel* d_model, const AbaArgs
 // copy; a.scratch holds RBD_ABA2_REC * (njoints - 1) * 32 doubles per resident warp (sizing call as above)
 cudaError_t launch_aba2(const DevModel& planned_host_model, const DevModel* d_model, const AbaArgs& a, int num_sms,
                         int* scratch_warps, cudaStream_t st);
-// derivatives of inverse dynamics (drnea_instance): `planned_host_model` planned with plan_drnea; no scratch
+// derivatives of inverse dynamics (drnea_instance): `planned_host_model` planned with plan_drnea; sizing call as launch_aba
 cudaError_t launch_drnea(const DevModel& planned_host_model, const DevModel* d_model, const DrneaArgs& a, int num_sms,
-                         cudaStream_t st);
+                         int* scratch_warps, cudaStream_t st);
 // inverse of the mass matrix (minv_instance): `planned_host_model` planned with plan_minv; sizing call as launch_aba
 cudaError_t launch_minv(const DevModel& planned_host_model, const DevModel* d_model, const MinvArgs& a, int num_sms,
                         int* scratch_warps, cudaStream_t st);

@@ -19,6 +19,26 @@ struct GlobalRec {
   __device__ __forceinline__ void st(int e, double v) const { p[e * 32] = v; }
   __device__ __forceinline__ GlobalRec at(int e) const { return GlobalRec{p + e * 32}; }  // base of a joint's record
 };
+// ... the same with the L2 eviction priority "evict_last" on every access (cold level records of drnea_instance: written
+// once, read back tens of microseconds later under a 3 TB/s store stream that would otherwise push them out to HBM), and a
+// += that does not read back (red.global.add.f64: nothing waits on it)
+struct KeepRec {
+  double* p;
+  unsigned long long pol;
+  __device__ __forceinline__ double ld(int e) const {
+    double v;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p + e * 32), "l"(pol));
+    return v;
+  }
+  __device__ __forceinline__ void st(int e, double v) const {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p + e * 32), "d"(v), "l"(pol) : "memory");
+  }
+  __device__ __forceinline__ void add(int e, double v) const {
+    asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p + e * 32), "d"(v), "l"(pol) : "memory");
+  }
+  __device__ __forceinline__ const double* ptr(int e) const { return p + e * 32; }
+  __device__ __forceinline__ KeepRec at(int e) const { return KeepRec{p + e * 32, pol}; }
+};
 }  // namespace
 
 // Block prologue shared by the kernels of this file: stage the joint table (its last two words are spare: the
@@ -117,6 +137,12 @@ __global__ void __launch_bounds__(256, 1) drnea_kernel(const DevModel* __restric
   const long long gw = (long long)blockIdx.x * wpb + warp;
   const long long ntiles = (a.n + 31) / 32;
   const int nv = m.nv;
+  unsigned long long pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  const KeepRec X{a.scratch + gw * (long long)m.slot_total[0] * 32 + lane, pol};
+  InRing inr;  // asynchronous input ring: this thread's column behind its level records
+  inr.p = c.S.p + m.plan.fbase * RBD_WARP;
+  inr.ps = (unsigned)__cvta_generic_to_shared(inr.p);
   for (long long t = gw; t < ntiles; t += (long long)gridDim.x * wpb) {
     long long inst = t * 32 + lane;
     if (inst >= a.n) inst = a.n - 1;  // lanes past the end recompute the last instance (same values to the same addresses)
@@ -124,7 +150,7 @@ __global__ void __launch_bounds__(256, 1) drnea_kernel(const DevModel* __restric
                    make_field_t<TILE>(const_cast<double*>(a.v), inst, nv, a.tile),
                    make_field_t<TILE>(const_cast<double*>(a.a), inst, nv, a.tile),
                    make_field_t<TILE>(a.dtau_dq, inst, nv * nv, a.tile), make_field_t<TILE>(a.dtau_dv, inst, nv * nv, a.tile),
-                   make_field_t<TILE>(a.M, inst, nv * (nv + 1) / 2, a.tile), c.S, c.T);
+                   make_field_t<TILE>(a.M, inst, nv * (nv + 1) / 2, a.tile), X, c.S, c.T, inr);
   }
   dyn_epilogue(c);
 }
@@ -189,13 +215,15 @@ cudaError_t launch_minv(const DevModel& hm, const DevModel* d_model, const MinvA
 }  // namespace rbd
 
 namespace rbd {
-cudaError_t launch_drnea(const DevModel& hm, const DevModel* d_model, const DrneaArgs& a, int num_sms, cudaStream_t st) {
+cudaError_t launch_drnea(const DevModel& hm, const DevModel* d_model, const DrneaArgs& a, int num_sms, int* scratch_warps,
+                         cudaStream_t st) {
   const int mw = (int)(aba2_model_bytes(hm) / 8);
   const int wpb = hm.plan.warps, block = wpb * 32;
   const long long ntiles = (a.n + 31) / 32;
   long long grid = (ntiles + wpb - 1) / wpb;
   if (grid > num_sms) grid = num_sms;  // one block per SM, warps stride over the tiles
-  if (a.n <= 0) return cudaSuccess;
+  if (scratch_warps) *scratch_warps = num_sms * wpb;
+  if (!a.scratch || a.n <= 0) return cudaSuccess;
   const size_t smem = (size_t)mw * 8 + (size_t)block * hm.plan.smem_doubles * 8;
   static thread_local bool attr_done[2] = {false, false};
   cudaError_t e = cudaSuccess;

@@ -591,17 +591,23 @@ inline bool plan_minv(DevModel* m, bool use_tmem, int max_warps = B200Limits::kM
 // ... and of the inverse-dynamics derivatives (drnea_instance, rbd_deriv_body.h): record sizes depend on the joint kind
 // (free-flyer root: R | p instead of J; a 1-dof joint with >= 2 children keeps R | p for the restart behind its accumulator)
 inline bool plan_levels_sized(DevModel* m, bool use_tmem, const std::vector<int>& jsize, const std::vector<int>& jrestart,
-                              int max_warps, int forced_warps, size_t model_bytes);
+                              int max_warps, int forced_warps, size_t model_bytes, int extra_smem = 0);
+static constexpr int kDrneaSlots = 3;  // == RBD_DR_SLOTS (rbd_deriv_body.h): input ring of 3 doubles per slot and instance,
+                                       // behind the level records in shared memory (plan.fbase = its offset, plan.in_slots)
 inline bool plan_drnea(DevModel* m, bool use_tmem, int max_warps = B200Limits::kMaxWarpsPerBlock, int forced_warps = 0) {
   std::vector<int> jsize(m->njoints, 0), jrst(m->njoints, 0);
-  for (int i = 1; i < m->njoints; ++i) {
-    const DevJoint& j = m->joint[i];
-    if (j.nchild <= 0) continue;
-    const bool ff = j.type == JT_FF;
-    jsize[i] = ff ? (j.nchild >= 2 ? 54 : 33) : (j.nchild >= 2 ? 60 : 27);  // RBD_DR_* (rbd_deriv_body.h)
-    jrst[i] = ff ? 12 : 48;
-  }
-  return plan_levels_sized(m, use_tmem, jsize, jrst, max_warps, forced_warps, aba2_model_bytes(*m));
+  for (int i = 1; i < m->njoints; ++i)
+    if (m->joint[i].nchild > 0) jsize[i] = m->joint[i].type == JT_FF ? 24 : 18;  // RBD_DR_HOT_FF / RBD_DR_HOT
+  if (!plan_levels_sized(m, use_tmem, jsize, jrst, max_warps, forced_warps, aba2_model_bytes(*m), 3 * kDrneaSlots + 9)) return false;
+  // cold records (global scratch, per thread): one per depth level, as wide as the widest joint of the level needs
+  const int D = m->max_depth_internal;
+  std::vector<int> csize(D + 2, 0), coff(D + 2, 0);
+  for (int i = 1; i < m->njoints; ++i)
+    if (m->joint[i].nchild > 0) csize[m->joint[i].depth] = std::max(csize[m->joint[i].depth], m->joint[i].nchild >= 2 ? 42 : 9);
+  for (int d = 1; d <= D; ++d) coff[d + 1] = coff[d] + csize[d];
+  for (int i = 1; i < m->njoints; ++i) m->joint[i].boff = m->joint[i].nchild > 0 ? coff[m->joint[i].depth] : 0;
+  m->slot_total[0] = coff[D + 1];  // doubles of scratch per instance in flight
+  return true;
 }
 inline bool plan_levels(DevModel* m, bool use_tmem, int size_one_child, int size_branch, int restart_off, int max_warps,
                         int forced_warps, size_t model_bytes) {
@@ -611,7 +617,7 @@ inline bool plan_levels(DevModel* m, bool use_tmem, int size_one_child, int size
   return plan_levels_sized(m, use_tmem, jsize, jrst, max_warps, forced_warps, model_bytes);
 }
 inline bool plan_levels_sized(DevModel* m, bool use_tmem, const std::vector<int>& jsize, const std::vector<int>& jrestart,
-                              int max_warps, int forced_warps, size_t model_bytes) {
+                              int max_warps, int forced_warps, size_t model_bytes, int extra_smem) {
   const int nj = m->njoints;
   const int D = m->max_depth_internal;
   std::vector<int> size(D + 1, 0);
@@ -628,7 +634,7 @@ inline bool plan_levels_sized(DevModel* m, bool use_tmem, const std::vector<int>
   for (int W = max_warps; W >= 1; --W) {
     if (forced_warps > 0 && W != forced_warps) continue;
     if (model_bytes + B200Limits::kSmemReservedPerBlock >= (size_t)B200Limits::kSmemBytes) return false;
-    const int cap_s = (int)(((size_t)B200Limits::kSmemBytes - model_bytes - B200Limits::kSmemReservedPerBlock) / ((size_t)W * 32 * 8));
+    const int cap_s = (int)(((size_t)B200Limits::kSmemBytes - model_bytes - B200Limits::kSmemReservedPerBlock) / ((size_t)W * 32 * 8)) - extra_smem;
     const int cap_t = use_tmem ? (B200Limits::kTmemCols / ((W + 3) / 4)) / 2 : 0;
     std::vector<int> off(D + 1, 0);
     int s_used = 0, t_used = 0;
@@ -640,7 +646,8 @@ inline bool plan_levels_sized(DevModel* m, bool use_tmem, const std::vector<int>
     }
     if (!ok) continue;
     EvalPlan pl{};
-    pl.smem_doubles = s_used; pl.tmem_doubles = t_used; pl.warps = W; pl.blocks_per_sm = 1;
+    pl.smem_doubles = s_used + extra_smem; pl.tmem_doubles = t_used; pl.warps = W; pl.blocks_per_sm = 1;
+    pl.fbase = s_used; pl.in_slots = extra_smem > 0 ? 1 : 0;  // (input ring + staging behind the level records: drnea only)
     pl.tmem_cols = t_used > 0 ? pow2_cols(2 * t_used * ((W + 3) / 4)) : 0;
     m->plan = pl;
     for (int i = 1; i < nj; ++i) {

@@ -460,6 +460,8 @@ struct EmulScratch {
   double ld(int e) const { return p[e]; }
   void st(int e, double v) const { p[e] = v; }
   EmulScratch at(int e) const { return EmulScratch{p + e}; }
+  void add(int e, double v) const { p[e] += v; }
+  const double* ptr(int e) const { return p + e; }
 };
 extern "C" int emul_aba(const rbd_model_desc* d, long long n, long long tile, double* q, double* v, double* tau, double* ddq) {
   Ctx c;
@@ -558,14 +560,18 @@ extern "C" int emul_drnea(const rbd_model_desc* d, long long n, long long tile, 
   std::vector<double> smem((size_t)(pl.smem_doubles > 0 ? pl.smem_doubles : 1) * bt, 1e300);
   std::vector<double> tmem((size_t)(pl.tmem_doubles > 0 ? pl.tmem_doubles : 1) * bt, 1e300);
   const int nv = c.m.nv;
+  std::vector<double> scr((size_t)(c.m.slot_total[0] > 0 ? c.m.slot_total[0] : 1));
+  if (plan_out) plan_out[3] = c.m.slot_total[0];  // (scratch doubles per instance in place of the column count)
   for (long long i = 0; i < n; ++i) {
     const int t = (int)(i % bt);
+    std::fill(scr.begin(), scr.end(), 1e300);
     for (int e = 0; e < pl.smem_doubles; ++e) smem[(size_t)(t / 32) * pl.smem_doubles * 32 + (size_t)e * 32 + t % 32] = 1e300;
     for (int e = 0; e < pl.tmem_doubles; ++e) tmem[(size_t)t * pl.tmem_doubles + e] = 1e300;
+    EmulScratch X{scr.data()};
     Stack S = make_stack(smem.data(), t, pl.smem_doubles);
     TmStack T{tmem.data() + (size_t)t * (pl.tmem_doubles > 0 ? pl.tmem_doubles : 1)};
     drnea_instance(c.m, make_field(q, i, c.m.nq, tile), make_field(v, i, nv, tile), make_field(a, i, nv, tile),
-                   make_field(DQ, i, nv * nv, tile), make_field(DV, i, nv * nv, tile), make_field(M, i, nv * (nv + 1) / 2, tile), S, T);
+                   make_field(DQ, i, nv * nv, tile), make_field(DV, i, nv * nv, tile), make_field(M, i, nv * (nv + 1) / 2, tile), X, S, T, InRing());
   }
   return 0;
 }
