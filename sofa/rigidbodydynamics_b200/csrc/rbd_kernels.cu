@@ -993,12 +993,14 @@ cudaError_t launch_applyJT_ring(const DevModel& hm, const DevModel* d_blob, cons
   }
   if (a.n <= 0) return cudaSuccess;
   const long long ntiles = a.n / 32;
-  unsigned grid = (unsigned)((ntiles + W - 1) / W);
+  const int wpb = pick_warps_per_block(W, ntiles, num_sms);  // <= W, the size the plan and the tensor-memory shares were made for
+  const int lblock = wpb * 32;
+  unsigned grid = (unsigned)((ntiles + wpb - 1) / wpb);
   if (grid > (unsigned)num_sms) grid = (unsigned)num_sms;
-  if (variant == 3) { RBD_NOTE((applyJT_ring_kernel<JtRing::kWarps, 2>)); applyJT_ring_kernel<JtRing::kWarps, 2><<<grid, block, smem, st>>>(d_blob, model_words, a, nst); }
-  else if (variant == 2) { RBD_NOTE((applyJT_ring_kernel<JtRing::kWarpsSmall, 1>)); applyJT_ring_kernel<JtRing::kWarpsSmall, 1><<<grid, block, smem, st>>>(d_blob, model_words, a, nst); }
-  else if (variant == 1) { RBD_NOTE((applyJT_ring_kernel<JtRing::kWarpsSmall, 0>)); applyJT_ring_kernel<JtRing::kWarpsSmall, 0><<<grid, block, smem, st>>>(d_blob, model_words, a, nst); }
-  else { RBD_NOTE((applyJT_ring_kernel<JtRing::kWarps, 0>)); applyJT_ring_kernel<JtRing::kWarps, 0><<<grid, block, smem, st>>>(d_blob, model_words, a, nst); }
+  if (variant == 3) { RBD_NOTE((applyJT_ring_kernel<JtRing::kWarps, 2>)); applyJT_ring_kernel<JtRing::kWarps, 2><<<grid, lblock, smem, st>>>(d_blob, model_words, a, nst); }
+  else if (variant == 2) { RBD_NOTE((applyJT_ring_kernel<JtRing::kWarpsSmall, 1>)); applyJT_ring_kernel<JtRing::kWarpsSmall, 1><<<grid, lblock, smem, st>>>(d_blob, model_words, a, nst); }
+  else if (variant == 1) { RBD_NOTE((applyJT_ring_kernel<JtRing::kWarpsSmall, 0>)); applyJT_ring_kernel<JtRing::kWarpsSmall, 0><<<grid, lblock, smem, st>>>(d_blob, model_words, a, nst); }
+  else { RBD_NOTE((applyJT_ring_kernel<JtRing::kWarps, 0>)); applyJT_ring_kernel<JtRing::kWarps, 0><<<grid, lblock, smem, st>>>(d_blob, model_words, a, nst); }
   return cudaGetLastError();
 }
 

@@ -165,14 +165,14 @@ static cudaError_t dyn_attr(K kern) {
 cudaError_t launch_aba2(const DevModel& hm, const DevModel* d_model, const AbaArgs& a, int num_sms, int* scratch_warps,
                         cudaStream_t st) {
   const int mw = (int)(aba2_model_bytes(hm) / 8);
-  const int wpb = hm.plan.warps, block = wpb * 32;
   const long long ntiles = (a.n + 31) / 32;
+  const int W = hm.plan.warps, wpb = pick_warps_per_block(W, ntiles, num_sms), block = wpb * 32;
   long long grid = (ntiles + wpb - 1) / wpb;
   if (grid > num_sms) grid = num_sms;  // one block per SM, warps stride over the tiles
   if (grid < 1) grid = 1;
-  if (scratch_warps) *scratch_warps = num_sms * wpb;
+  if (scratch_warps) *scratch_warps = num_sms * W;
   if (!a.scratch || a.n <= 0) return cudaSuccess;
-  const size_t smem = (size_t)mw * 8 + (size_t)block * hm.plan.smem_doubles * 8;
+  const size_t smem = (size_t)mw * 8 + (size_t)W * 32 * hm.plan.smem_doubles * 8;
   static thread_local bool attr_done[2] = {false, false};
   cudaError_t e = cudaSuccess;
   if (a.tile == 32) {
@@ -190,14 +190,14 @@ cudaError_t launch_aba2(const DevModel& hm, const DevModel* d_model, const AbaAr
 cudaError_t launch_minv(const DevModel& hm, const DevModel* d_model, const MinvArgs& a, int num_sms, int* scratch_warps,
                         cudaStream_t st) {
   const int mw = (int)(aba2_model_bytes(hm) / 8);
-  const int wpb = hm.plan.warps, block = wpb * 32;
   const long long ntiles = (a.n + 31) / 32;
+  const int W = hm.plan.warps, wpb = pick_warps_per_block(W, ntiles, num_sms), block = wpb * 32;
   long long grid = (ntiles + wpb - 1) / wpb;
   if (grid > num_sms) grid = num_sms;
   if (grid < 1) grid = 1;
-  if (scratch_warps) *scratch_warps = num_sms * wpb;
+  if (scratch_warps) *scratch_warps = num_sms * W;
   if (!a.scratch || a.n <= 0) return cudaSuccess;
-  const size_t smem = (size_t)mw * 8 + (size_t)block * hm.plan.smem_doubles * 8;
+  const size_t smem = (size_t)mw * 8 + (size_t)W * 32 * hm.plan.smem_doubles * 8;
   static thread_local bool attr_done[2] = {false, false};
   cudaError_t e = cudaSuccess;
   if (a.tile == 32) {
@@ -218,13 +218,13 @@ namespace rbd {
 cudaError_t launch_drnea(const DevModel& hm, const DevModel* d_model, const DrneaArgs& a, int num_sms, int* scratch_warps,
                          cudaStream_t st) {
   const int mw = (int)(aba2_model_bytes(hm) / 8);
-  const int wpb = hm.plan.warps, block = wpb * 32;
   const long long ntiles = (a.n + 31) / 32;
+  const int W = hm.plan.warps, wpb = pick_warps_per_block(W, ntiles, num_sms), block = wpb * 32;
   long long grid = (ntiles + wpb - 1) / wpb;
   if (grid > num_sms) grid = num_sms;  // one block per SM, warps stride over the tiles
-  if (scratch_warps) *scratch_warps = num_sms * wpb;
+  if (scratch_warps) *scratch_warps = num_sms * W;
   if (!a.scratch || a.n <= 0) return cudaSuccess;
-  const size_t smem = (size_t)mw * 8 + (size_t)block * hm.plan.smem_doubles * 8;
+  const size_t smem = (size_t)mw * 8 + (size_t)W * 32 * hm.plan.smem_doubles * 8;
   static thread_local bool attr_done[2] = {false, false};
   cudaError_t e = cudaSuccess;
   if (a.tile == 32) {
