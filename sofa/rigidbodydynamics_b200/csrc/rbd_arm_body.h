@@ -111,3 +111,64 @@ RBD_HD void arm_instance(const ArmParams<NJ>& m, const FieldT<TILE>& q, const Fi
     for (int k = 0; k <= i; ++k) M.st(i * (i + 1) / 2 + k, dot6(A[k], Fc));
   }
 }
+
+// The vector applyJT of the same chains (reference KinematicChainMapping.inl:450-513; the ring kernel's sweep,
+// applyJT_instance_ring, with the tree taken out): tau_i = A_i . sum of the origin-shifted wrenches on joints >= i.  A chain
+// needs no stack for that — with Pre_i the sum over the joints < i, tau_i = A_i . Total - A_i . Pre_i, so the forward pass
+// keeps the NJ columns A_i in registers, one running sum and NJ partial dot products; nothing goes to shared or tensor
+// memory.  Joint constants from the kernel-parameter constant bank, wrenches from the ring (Ring: see rbd_sweeps_body.h).
+#define RBD_ARM_W(j, c)                                                                 \
+  real c[6];                                                                            \
+  {                                                                                     \
+    real w[6];                                                                          \
+    ring.template ld<j>(w);                                                             \
+    const real* pl = opl + 3 * (o + j);                                                 \
+    const real px = R[0] * pl[0] + R[1] * pl[1] + R[2] * pl[2] + p[0];                  \
+    const real py = R[3] * pl[0] + R[4] * pl[1] + R[5] * pl[2] + p[1];                  \
+    const real pz = R[6] * pl[0] + R[7] * pl[1] + R[8] * pl[2] + p[2];                  \
+    real tx, ty, tz;                                                                    \
+    RBD_CROSS(tx, ty, tz, px, py, pz, w[0], w[1], w[2]);                                \
+    c[0] = w[0]; c[1] = w[1]; c[2] = w[2];                                              \
+    c[3] = w[3] + tx; c[4] = w[4] + ty; c[5] = w[5] + tz;                               \
+  }
+template <int NJ, class QC, class Ring, class Sink>
+RBD_HD void applyJT_arm_instance(const ArmParams<NJ>& m, const real* opl, const QC& q, Ring& ring, const Sink& sink) {
+  real R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
+  real A[NJ][6], part[NJ], Pre[6] = {0, 0, 0, 0, 0, 0};
+  real qn = q.ld(0);
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) {
+    const DevJoint& jn = m.joint[i];
+    const real q0 = qn;
+    if (i + 1 < NJ) qn = q.ld(i + 1);  // one joint ahead
+    real aw[3];
+    ::rbd::chain::fk_joint(jn, R, p, q0, real(0), q, aw);  // (qualified: `q` may be a type of namespace rbd, whose fk_joint ADL would find too)
+    subspace_1dof(jn.type, p, aw, A[i]);
+    part[i] = dot6(A[i], Pre);
+    for (int o = jn.out_begin; o < jn.out_end;) {
+      const int cnt = ring.acquire();
+      if (cnt == 1) {
+        RBD_ARM_W(0, c0)
+#pragma unroll
+        for (int e = 0; e < 6; ++e) Pre[e] += c0[e];
+      } else if (cnt == 2) {
+        RBD_ARM_W(0, c0) RBD_ARM_W(1, c1)
+#pragma unroll
+        for (int e = 0; e < 6; ++e) Pre[e] += c0[e] + c1[e];
+      } else if (cnt == 3) {
+        RBD_ARM_W(0, c0) RBD_ARM_W(1, c1) RBD_ARM_W(2, c2)
+#pragma unroll
+        for (int e = 0; e < 6; ++e) Pre[e] += (c0[e] + c1[e]) + c2[e];
+      } else {
+        RBD_ARM_W(0, c0) RBD_ARM_W(1, c1) RBD_ARM_W(2, c2) RBD_ARM_W(3, c3)
+#pragma unroll
+        for (int e = 0; e < 6; ++e) Pre[e] += (c0[e] + c1[e]) + (c2[e] + c3[e]);
+      }
+      ring.release(cnt);
+      o += cnt;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) sink.put(i, dot6(A[i], Pre) - part[i]);
+}
+#undef RBD_ARM_W

@@ -766,7 +766,7 @@ static int applyJT_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t til
       const long long nfull = n / 32 * 32;
       MapArgs F = A;
       F.n = nfull;
-      CK(launch_applyJT_ring(*ws->h_plan[9], ws->d_plan[9], F, ws->jt_ring_slots, &ws->cfg_jt_ring, ws->num_sms, st));
+      CK(launch_applyJT_ring(*ws->h_plan[9], ws->d_plan[9], F, ws->jt_ring_slots, &ws->cfg_jt_ring, ws->num_sms, st, ws->use_arm != 0));
       ws->launches++;
       if (nfull == n) return RBD_OK;
       const DevModel& m = ws->model->dm;

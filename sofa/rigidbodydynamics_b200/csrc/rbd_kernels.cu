@@ -437,6 +437,53 @@ __global__ void __launch_bounds__(W * 32, 1) applyJT_ring_kernel(const DevModel*
   }
 }
 
+// The ring kernel for fixed-base serial chains of NJ joints (chain::applyJT_arm_instance, rbd_arm_body.h): same blob, ring
+// program and shared-memory layout as applyJT_ring_kernel<planW, 0> (planW = the block size the plan was made for), but
+// the sweep is unrolled over the joints, reads their constants from the kernel-parameter constant bank and keeps its whole
+// state in registers: no tensor memory, no level records.
+template <int NJ>
+__global__ void __launch_bounds__(256, 1) applyJT_arm_kernel(const __grid_constant__ chain::ArmParams<NJ> P,
+                                                             const DevModel* __restrict__ gm, const int model_words,
+                                                             const MapArgs a, const int nst, const int planW) {
+  {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gm);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(rbd_smem);
+    for (int w = threadIdx.x; w < model_words - 2; w += blockDim.x) dst[w] = src[w];
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned long long* const bars = reinterpret_cast<unsigned long long*>(rbd_smem + model_words);
+  if (lane < nst) mbar_init(smem_u32(bars + warp * JtRing::kMaxStages + lane), 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const DevModel& m = *reinterpret_cast<const DevModel*>(rbd_smem);
+  double* const rings = reinterpret_cast<double*>(bars + planW * JtRing::kMaxStages);
+  const JtProg prog{col_prog(m)};
+  const int np = prog.npieces();
+  const long long ntiles = a.n / 32;
+  const int wpb = blockDim.x >> 5;
+  if (np <= 0) return;
+  WarpRing ring;
+  ring.prog = prog;
+  ring.ring = rings + (size_t)warp * nst * (JtRing::kStageBytes / 8) + lane;
+  ring.cur = ring.ring;
+  ring.in = reinterpret_cast<const char*>(a.in);
+  ring.tile_bytes = (long long)6 * m.n_out * 256;
+  ring.ntiles = ntiles; ring.stride = (long long)gridDim.x * wpb;
+  ring.ring_s = smem_u32(rings + (size_t)warp * nst * (JtRing::kStageBytes / 8));
+  ring.bar_s = smem_u32(bars + warp * JtRing::kMaxStages);
+  ring.nst = nst; ring.np = np; ring.lane = lane;
+  ring.c_piece = 0; ring.stage = 0; ring.phase = 0u;
+  ring.p_tile = (long long)blockIdx.x * wpb + warp; ring.p_piece = 0;
+  for (int st = 0; st < nst; ++st) ring.issue(st);
+  const double* const opl = prog.opl();
+  for (long long t = (long long)blockIdx.x * wpb + warp; t < ntiles; t += (long long)gridDim.x * wpb) {
+    const long long inst = t * 32 + lane;
+    SplitRedSinkT<FieldT<32>> sink{make_field_t<32>(nullptr, inst, 6, 32), make_field_t<32>(const_cast<double*>(a.joints), inst, NJ, 32), 0};
+    chain::applyJT_arm_instance<NJ>(P, opl, make_field_t<32>(a.qcache, a.cache_inst0 + inst, NJ, 32), ring, sink);
+  }
+}
+
 // applyDJT (geometric stiffness, optional extension): one thread per instance, shared-memory stack
 template <int TILE>
 __global__ void __launch_bounds__(256) applyDJT_kernel(const DevModel* __restrict__ gm, const int model_words,
@@ -975,7 +1022,7 @@ static cudaError_t jt_ring_attr(K kern) {
   return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 cudaError_t launch_applyJT_ring(const DevModel& hm, const DevModel* d_blob, const MapArgs& a, int nst, LaunchCfg* cfg,
-                                int num_sms, cudaStream_t st) {
+                                int num_sms, cudaStream_t st, bool use_arm) {
   const int model_words = (int)(eval_model_bytes(hm) / 8);
   const int W = hm.plan.warps;
   const int block = W * 32;
@@ -993,6 +1040,29 @@ cudaError_t launch_applyJT_ring(const DevModel& hm, const DevModel* d_blob, cons
   }
   if (a.n <= 0) return cudaSuccess;
   const long long ntiles = a.n / 32;
+  // fixed-base serial chains of 6 / 7 joints (stack variants only: the ring program is the same): the unrolled sweep
+  if (use_arm && hm.eval_variant == RBD_EVAL_CHAIN && hm.plan.jt_fwd == 0 && !a.root && (hm.njoints - 1 == 6 || hm.njoints - 1 == 7)) {
+    const int wa = pick_warps_per_block(W < 8 ? W : 8, ntiles, num_sms);
+    unsigned ga = (unsigned)((ntiles + wa - 1) / wa);
+    if (ga > (unsigned)num_sms) ga = (unsigned)num_sms;
+    static thread_local bool attr_done[2] = {false, false};
+    if (hm.njoints - 1 == 7) {
+      if (!attr_done[1]) { cudaError_t e = jt_ring_attr(applyJT_arm_kernel<7>); if (e != cudaSuccess) return e; attr_done[1] = true; }
+      chain::ArmParams<7> P;
+      for (int i = 0; i < 7; ++i) P.joint[i] = hm.joint[i + 1];
+      for (int k = 0; k < 3; ++k) P.gravity[k] = hm.gravity[k];
+      RBD_NOTE(applyJT_arm_kernel<7>);
+      applyJT_arm_kernel<7><<<ga, wa * 32, smem, st>>>(P, d_blob, model_words, a, nst, W);
+    } else {
+      if (!attr_done[0]) { cudaError_t e = jt_ring_attr(applyJT_arm_kernel<6>); if (e != cudaSuccess) return e; attr_done[0] = true; }
+      chain::ArmParams<6> P;
+      for (int i = 0; i < 6; ++i) P.joint[i] = hm.joint[i + 1];
+      for (int k = 0; k < 3; ++k) P.gravity[k] = hm.gravity[k];
+      RBD_NOTE(applyJT_arm_kernel<6>);
+      applyJT_arm_kernel<6><<<ga, wa * 32, smem, st>>>(P, d_blob, model_words, a, nst, W);
+    }
+    return cudaGetLastError();
+  }
   const int wpb = pick_warps_per_block(W, ntiles, num_sms);  // <= W, the size the plan and the tensor-memory shares were made for
   const int lblock = wpb * 32;
   unsigned grid = (unsigned)((ntiles + wpb - 1) / wpb);

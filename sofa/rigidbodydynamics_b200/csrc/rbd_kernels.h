@@ -93,8 +93,9 @@ cudaError_t launch_applyJT_plan(const DevModel& planned_host_model, const DevMod
                                 const MapArgs& a, LaunchCfg* cfg2, int num_sms, cudaStream_t st);
 // ring variant of the vector applyJT (full tiles of 32, a.tile == 32, a.n % 32 == 0, a.in 16-byte aligned):
 // `planned_host_model` planned with plan_jt_ring, `d_blob` built by build_jt_blob, nst = ring stages per warp
+// use_arm: fixed-base serial chains of 6 / 7 joints run applyJT_arm_kernel (unrolled sweep, state in registers)
 cudaError_t launch_applyJT_ring(const DevModel& planned_host_model, const DevModel* d_blob, const MapArgs& a, int nst,
-                                LaunchCfg* cfg, int num_sms, cudaStream_t st);
+                                LaunchCfg* cfg, int num_sms, cudaStream_t st, bool use_arm = false);
 cudaError_t launch_applyDJT(const DevModel& m, const DevModel* d_model, const DevTables& tb, const DjtArgs& a,
                             LaunchCfg* cfg2, cudaStream_t st);
 cudaError_t launch_applyJT_rows(const DevModel& m, const DevModel* d_model, const DevTables& tb, const RowArgs& a,

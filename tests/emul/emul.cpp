@@ -363,6 +363,9 @@ extern "C" int emul_applyJT_ring(const rbd_model_desc* d, long long n, long long
   int rc = make_ctx(d, &c);
   if (rc) return rc;
   std::vector<int> prog;
+  const bool arm = allow_fwd == 3;  // 3: the unrolled chain sweep on the stack variant's ring program (6- / 7-joint chains)
+  if (arm) allow_fwd = 0;
+  if (arm && !(c.m.eval_variant == RBD_EVAL_CHAIN && (c.m.njoints - 1 == 6 || c.m.njoints - 1 == 7))) return 1;
   const int nst = plan_jt_ring(&c.m, c.ht, use_tmem != 0, &prog, allow_fwd);
   if (variant) *variant = nst > 0 ? c.m.plan.jt_fwd : 0;
   if (ring_stages) *ring_stages = nst;
@@ -382,7 +385,17 @@ extern "C" int emul_applyJT_ring(const rbd_model_desc* d, long long n, long long
     SplitRedSinkT<Field> sink{make_field(out_root, i, 6, tile), make_field(out_tau, i, bm.nv - off, tile), off};
     Stack S = make_stack(smem.data(), t, pl.smem_doubles);
     TmStack T{tmem.data() + (size_t)t * (pl.tmem_doubles > 0 ? pl.tmem_doubles : 1)};
-    if (bm.plan.jt_fwd) applyJT_instance_fwd(bm, jp.opl(), jp.anc(), make_field(qcache, i, bm.nq, cache_tile), ring, sink, S, T);
+    if (arm) {  // the unrolled chain sweep (chain::applyJT_arm_instance): joint table as the kernel parameter carries it
+      if (bm.njoints - 1 == 7) {
+        chain::ArmParams<7> P;
+        for (int k = 0; k < 7; ++k) P.joint[k] = bm.joint[k + 1];
+        chain::applyJT_arm_instance<7>(P, jp.opl(), make_field(qcache, i, bm.nq, cache_tile), ring, sink);
+      } else {
+        chain::ArmParams<6> P;
+        for (int k = 0; k < 6; ++k) P.joint[k] = bm.joint[k + 1];
+        chain::applyJT_arm_instance<6>(P, jp.opl(), make_field(qcache, i, bm.nq, cache_tile), ring, sink);
+      }
+    } else if (bm.plan.jt_fwd) applyJT_instance_fwd(bm, jp.opl(), jp.anc(), make_field(qcache, i, bm.nq, cache_tile), ring, sink, S, T);
     else applyJT_instance_ring(bm, jp.opl(), make_field(qcache, i, bm.nq, cache_tile), ring, sink, S, T);
   }
   return 0;

@@ -1110,3 +1110,24 @@ def test_arm_kernel_equals_generic_chain_sweep(torch_mod, api, tile):
     # M alone / tau alone are not the arm kernel's job
     ws.crba_soa(n, tile, qs, Mv); ws.synchronize()
     assert "eval_arm_kernel" not in api.last_kernel_name()
+    # the vector applyJT of the chain: unrolled register sweep (applyJT_arm_kernel, full tiles of a tile-32 batch) against
+    # the generic ring sweep and the oracle, accumulating into a non-zero tau
+    if tile == 32:
+        rng = np.random.default_rng(5)
+        w = rng.uniform(-1, 1, (n, 6 * I.n_out)); tau0 = rng.uniform(-1, 1, (n, I.nv))
+        pos = new(7 * I.n_out)
+        ws.apply_soa(n, tile, qs, None, pos)
+        ws_t = {}
+        for arm in (1, 0):
+            ws.set_eval_arm(bool(arm))
+            t = _dev(torch, to_tiled(tau0, tile))
+            ws.applyJT_soa(n, tile, _dev(torch, to_tiled(w, tile)), t, None)
+            ws.synchronize()
+            ws_t[arm] = from_tiled(t.cpu().numpy(), n)
+        ws.set_eval_arm(True)
+        assert rel_err(ws_t[1], ws_t[0]) <= 1e-12
+        orc = oracle.Oracle(d)
+        for i in (0, 517, n - 1):
+            orc.apply(q[i])
+            ref, _ = orc.applyJT(w[i].reshape(I.n_out, 6), out_tau=tau0[i])
+            assert rel_err(ws_t[1][i], ref) <= TOL_FP64
