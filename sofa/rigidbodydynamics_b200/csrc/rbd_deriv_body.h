@@ -32,7 +32,12 @@
 //   18 doubles per level on chip instead of 27 .. 60: Talos (ten levels) runs 8 warps per SM instead of 4, and it is the
 //   number of warps that hides the issue latency of this sweep (first version, everything on chip: 11.8 ms per 2^20).
 // dVdq / dAdq of an ancestor are recomputed in the pair loop from its J and its parent's v | a (3 cross products) rather
-// than stored.
+// than stored.  Measured alternatives on Talos N = 2^20 (this version: 8.4 ms), all slower:
+//   hot records [J | dVdq | dAdq] with v | a moved to the cold records (21 % fewer FP64 instructions, 12 more doubles of
+//   scratch traffic per joint)                                                                             9.1 ms
+//   row / column base addresses instead of an index multiplication per store (10 more live registers)      9.9 ms
+//   the pair loop as two walks, column entries then row entries (fewer spills, less work in flight per walk) 9.2 ms
+// — at 255 registers per thread every extra live value costs more than the instructions it saves.
 //
 // Outputs: DQ, DV: nv x nv, field r nv + c (row-major like pinocchio's RowMatrixXs), structural zeros WRITTEN (dofs on
 // different branches); M (optional): packed upper triangle like rbd_crba_soa.  A free-flyer only as joint 1 on the universe.
