@@ -169,9 +169,10 @@ RBD_API int rbd_workspace_set_applyJT_ring(rbd_workspace* ws, int enable, int32_
  * data.J / data.oMi, KinematicChainMapping.inl:365-373) — 8 (6 nv + 12 (njoints-1)) bytes per instance of workspace
  * capacity, allocated on first use — and every row only reads it; 0 = per-row sweep, no cache.  Same results.      */
 RBD_API int rbd_workspace_set_rows_cache(rbd_workspace* ws, int enable);
-/* Fused eval of fixed-base serial chains of 6 or 7 RX / RY / RZ joints (arms) with M and tau requested: 1 (default) = the
- * sweep compiled for that joint count (both passes unrolled, joint table in the kernel-parameter constant bank, subspace
- * columns in registers); 0 = the generic chain instantiation (A/B knob).  Same results up to rounding.           */
+/* Fused eval (with M and tau requested) and vector applyJT (full tiles of a tile-32 batch) of fixed-base serial chains of
+ * 6 or 7 RX / RY / RZ joints (arms): 1 (default) = the sweeps compiled for that joint count (unrolled, joint table in the
+ * kernel-parameter constant bank, subspace columns in registers); 0 = the generic instantiations (A/B knob).  Same
+ * results up to rounding.                                                                                         */
 RBD_API int rbd_workspace_set_eval_arm(rbd_workspace* ws, int enable);
 /* Forward dynamics (rbd_aba_*): 1 (default) = the fused sweep — passes 1 + 2 of the articulated-body algorithm on on-chip
  * level records (shared + tensor memory), only the 20 doubles per joint pass 3 needs go through global memory — whenever

@@ -14,16 +14,19 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu --secondary-steps 2 > $O/${T}_launches.log 2>&1
 profiles/capture.sh "eval_kernel_ffroot8" ${T}_eval_talos -- python bench.py $Q
 profiles/capture.sh "eval_kernel_ffroot<" ${T}_eval_solo -- python bench.py --workload solo $Q
-profiles/capture.sh "eval_kernel_chain" ${T}_eval_panda -- python bench.py --workload panda $Q
+profiles/capture.sh "eval_arm_kernel" ${T}_eval_panda -- python bench.py --workload panda $Q
 profiles/capture.sh "aba2_kernel" ${T}_aba2_talos -- python experiments/time_aba.py talos_reduced
 profiles/capture.sh "minv_kernel" ${T}_minv_talos -- python experiments/time_minv.py talos_reduced
+profiles/capture.sh "drnea_kernel" ${T}_drnea_talos -- python experiments/time_drnea.py talos_reduced:262144
+profiles/capture.sh "applyJT_arm_kernel" ${T}_applyJT_panda -- python bench_mapping.py --robot panda7 --n 65536 --steps 3
+python experiments/time_drnea.py > $O/${T}_time_drnea.json 2>&1
 python experiments/time_aba.py > $O/${T}_time_aba.json 2>&1
 python experiments/time_minv.py > $O/${T}_time_minv.json 2>&1
 profiles/capture.sh "applyJT_rows_cached" ${T}_rows_talos -- python bench_mapping.py --robot talos_reduced --n 1048576 --steps 3
-profiles/capture.sh "transpose32_kernel<\(bool\)1>|transpose32_kernel<true>" ${T}_soa_to_aos -- python bench_mapping.py --robot talos_reduced --n 1048576 --steps 3
+profiles/capture.sh "transpose32v_kernel<\(bool\)1>|transpose32v_kernel<true>" ${T}_soa_to_aos -- python bench_mapping.py --robot talos_reduced --n 1048576 --steps 3
 M=smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,gpu__time_duration.sum
 for w in talos solo panda; do
-  ncu --metrics $M --clock-control none --kernel-name-base demangled -k "regex:eval_kernel" -s 2 -c 1 --csv --log-file $O/${T}_fp64_${w}.csv \
+  ncu --metrics $M --clock-control none --kernel-name-base demangled -k "regex:eval_.*kernel" -s 2 -c 1 --csv --log-file $O/${T}_fp64_${w}.csv \
       python bench.py --workload $w $Q > /dev/null 2>&1
 done
 rm -f $O/${T}_*_cuda.csv   # the largest page; the summaries use raw + sass

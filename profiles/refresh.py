@@ -21,7 +21,7 @@ OUT = os.path.join(ROOT, "gpurun_out")
 CAPTURES = {  # tracked name -> scratch name
     "r2_eval_talos": "eval_talos", "r2_eval_solo": "eval_solo", "r2_eval_panda": "eval_panda",
     "r2_aba2_talos": "aba2_talos", "r2_minv_talos": "minv_talos", "r2_rows_talos": "rows_talos",
-    "r2_soa_to_aos": "soa_to_aos",
+    "r2_soa_to_aos": "soa_to_aos", "r2_drnea_talos": "drnea_talos", "r2_applyJT_panda": "applyJT_panda",
 }
 EVALS = {"talos_reduced:1048576:tile32": ("eval_talos", "talos", 1048576),
          "solo12:262144:tile32": ("eval_solo", "solo", 262144),
@@ -42,7 +42,7 @@ def main():
     tag = sys.argv[1]
     for name, src in CAPTURES.items():
         raw = os.path.join(OUT, f"{tag}_{src}_raw.csv"); sass = os.path.join(OUT, f"{tag}_{src}_sass.csv")
-        if not os.path.exists(raw):
+        if not os.path.exists(raw) or os.path.getsize(raw) < 1000:
             print("missing", raw); continue
         r = subprocess.run([sys.executable, os.path.join(HERE, "ncu_summary.py"), raw, sass], capture_output=True, text=True)
         kern = raw_metrics(raw).get("Kernel Name", ("", "?"))[1]
@@ -99,7 +99,8 @@ def main():
             for row in lines:
                 w.writerow([row["Kernel Name"].split("(")[0], row["Metric Name"], row["Metric Unit"], row["Metric Value"]])
     for src, dst in ((f"{tag}_bench_1gpu.json", "r2_bench_1gpu.json"), (f"{tag}_bench_reference_arm.json", "r2_bench_reference_arm.json"),
-                     (f"{tag}_time_aba.json", "r2_time_aba.json"), (f"{tag}_time_minv.json", "r2_time_minv.json")):
+                     (f"{tag}_time_aba.json", "r2_time_aba.json"), (f"{tag}_time_minv.json", "r2_time_minv.json"),
+                     (f"{tag}_time_drnea.json", "r2_time_drnea.json")):
         if os.path.exists(os.path.join(OUT, src)):
             shutil.copy(os.path.join(OUT, src), os.path.join(HERE, dst))
     print("refreshed from", tag)

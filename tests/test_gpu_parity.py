@@ -1063,6 +1063,22 @@ def test_rnea_derivatives_match_oracle(torch_mod, api, d, tile):
     fd = (taus[0] - taus[1]) / (2 * eps)
     lin = np.einsum("nrc,nc->nr", gq, dq) + np.einsum("nrc,nc->nr", gv, dv)
     assert np.max(np.abs(fd - lin)) <= 1e-6 * max(1.0, float(np.max(np.abs(lin))))
+    # derivative of the CRBA mass matrix, contracted with a: d(M(q) a)/dq = dtau_dq(q, 0, a) - dtau_dq(q, 0, 0) (the second
+    # term is pinocchio::computeGeneralizedGravityDerivatives) against a directional central difference of the CRBA kernel
+    zs = _dev(torch, to_tiled(np.zeros((n, nv)), tile))
+    Da, D0, Dv_ = new(nv * nv), new(nv * nv), new(nv * nv)
+    ws.rnea_derivatives_soa(n, tile, qs, zs, as_, Da, Dv_, None)
+    ws.rnea_derivatives_soa(n, tile, qs, zs, zs, D0, Dv_, None)
+    ws.synchronize()
+    dMa = (from_tiled(Da.cpu().numpy(), n)[:, :nv * nv] - from_tiled(D0.cpu().numpy(), n)[:, :nv * nv]).reshape(n, nv, nv)
+    Ms = []
+    for sgn in (1.0, -1.0):
+        Me = new(mf)
+        ws.crba_soa(n, tile, _dev(torch, to_tiled(helpers.integrate(d, q, dq, sgn * eps), tile)), Me); ws.synchronize()
+        Ms.append(np.stack([oracle.unpack_upper(x, nv) for x in from_tiled(Me.cpu().numpy(), n)[:, :mf]]))
+    fdM = np.einsum("nrc,nc->nr", (Ms[0] - Ms[1]) / (2 * eps), a)
+    linM = np.einsum("nrc,nc->nr", dMa, dq)
+    assert np.max(np.abs(fdM - linM)) <= 1e-6 * max(1.0, float(np.max(np.abs(linM))))
     # host entry point (instance-major [n][nv][nv])
     hq, hv, hM = np.zeros((n, nv, nv)), np.zeros((n, nv, nv)), np.zeros((n, mf))
     ws.rnea_derivatives_host(n, q, v, a, hq, hv, hM)
