@@ -347,6 +347,22 @@ def measure_config(torch, robot: str, n: int, steps: int, dev_index: int, with_e
                      ("layout_aos_to_soa_M", lambda: ws.aos_to_soa(n, Kw, tile, aos, Mp))):
         ms, clk, _ = _time_launches(torch, fn, steps, 3, flush, dev_index)
         out[name] = _entry(n, ms, 16 * Kw, peak, clk, "rbd::transpose32_kernel" if tile == 32 else "rbd::soa_to_aos / aos_to_soa kernel")
+    # FP64 roofline next to the HBM one for the entries the flop-counting oracle build covers (the separate CRBA / RNEA
+    # entry points are compute-bound: a fraction of the HBM roofline says little about them)
+    try:
+        import oracle
+        fc = oracle.flop_counts(d)
+        peak_tf = api.probe_fp64_peak(dev_index)
+        for name, part in (("eval", "eval"), ("eval_sparseM", "eval"), ("crba", "crba"), ("rnea", "rnea")):
+            if name in out and peak_tf > 0:
+                ach = fc[part]["flops"] * out[name]["instances_per_s"] / 1e12
+                out[name]["fp64"] = {"flops_per_instance": fc[part]["flops"], "achieved_tflops": ach, "peak_tflops": peak_tf,
+                                     "frac": ach / peak_tf,
+                                     "source": "oracle -DORC_COUNT_FLOPS count of the restated reference algorithm (its own FK "
+                                               "pass included) x measured rate / rbd_probe_fp64_peak"}
+                out[name]["binding"] = "fp64" if ach / peak_tf > out[name]["frac"] else "hbm"
+    except Exception as e:  # the annotation must never cost the measurement
+        out["fp64_annotation_error"] = str(e)
     return {"robot": d.name, "n": n, "tile": tile, "n_out": int(I.n_out), "l2": "flushed between timed launches",
             "note": d.note, "kernels": out}
 

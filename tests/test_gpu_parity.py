@@ -1088,6 +1088,35 @@ def test_rnea_derivatives_match_oracle(torch_mod, api, d, tile):
     assert np.array_equal(hq, hq2) and np.array_equal(hv, hv2)
 
 
+def test_dynamics_entry_points_refuse_a_free_flyer_below_the_root(torch_mod, api):
+    """aba / minv / rnea_derivatives support a free-flyer as joint 1 on the universe only: anything else is
+    RBD_ERR_UNSUPPORTED with a message, not a wrong result (the fused eval and the mapping path do support it)."""
+    torch = torch_mod
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    rng = np.random.default_rng(0)
+    b = mdl._Builder("ff_below_root")
+    b.add_frame("root_joint", 0, mdl._se3(), mdl.F_FIXED_JOINT)
+    j1 = b.add_joint(0, mdl.J_RZ, mdl._se3(), "j1")
+    b.append_body(j1, mdl._synthetic_inertia(rng), mdl._se3())
+    j2 = b.add_joint(j1, mdl.J_FF, mdl._se3(), "j2")
+    b.append_body(j2, mdl._synthetic_inertia(rng), mdl._se3())
+    d = b.finish(gravity=(0.0, 0.0, -9.81), note="test")
+    n, tile = 32, 32
+    q, v, a = mdl.random_state(d, n, seed=1)
+    m = api.Model(d); ws = api.Workspace(m, n)
+    qs, vs, as_ = (_dev(torch, to_tiled(x, tile)) for x in (q, v, a))
+    new = lambda K: torch.zeros((1, K, tile), dtype=torch.float64, device="cuda")
+    for call in (lambda: ws.aba_soa(n, tile, qs, vs, as_, new(d.nv)),
+                 lambda: ws.minv_soa(n, tile, qs, new(d.nv * (d.nv + 1) // 2)),
+                 lambda: ws.rnea_derivatives_soa(n, tile, qs, vs, as_, new(d.nv * d.nv), new(d.nv * d.nv), None)):
+        with pytest.raises(api.RbdError) as e:
+            call()
+        assert e.value.code == -5 and "free-flyer" in str(e.value)   # RBD_ERR_UNSUPPORTED
+    tau = new(d.nv)
+    ws.rnea_soa(n, tile, qs, vs, as_, tau); ws.synchronize()           # the eval path takes the model
+    assert torch.isfinite(tau).all()
+
+
 @pytest.mark.parametrize("tile", [32, 1000])
 def test_arm_kernel_equals_generic_chain_sweep(torch_mod, api, tile):
     """Fused eval of the 7-joint Panda chain: the unrolled arm kernel (default for 6- / 7-joint serial chains) against the
