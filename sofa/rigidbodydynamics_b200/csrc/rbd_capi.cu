@@ -854,7 +854,7 @@ static int rows_on(rbd_workspace* ws, cudaStream_t st, const RowArgs& A) {
     return RBD_OK;
   }
   if (rc0) return rc0;
-  CK(launch_applyJT_rows_cached(dm, ws->d_model, ws->tb, A, ws->jcache, ws->omicache, st));
+  CK(launch_applyJT_rows_cached(dm, ws->d_model, ws->tb, A, ws->jcache, ws->omicache, ws->num_sms, st));
   ws->launches++;
   return RBD_OK;
 }

@@ -564,6 +564,75 @@ __global__ void __launch_bounds__(256) applyJT_rows_cached_kernel(const DevModel
   }
 }
 
+// The same rows with one WARP per row (A/B variant, off: see RBD_ROWS_WARP): lane c owns dof c (and c + 32, c + 64), so the Jacobian columns on the
+// path of a non-zero's output are 32 consecutive 48-byte records of ONE instance — a coalesced 1.5 KB read with 32
+// loads in flight per warp — instead of one lane walking to the root through the joint table four columns at a time
+// (the thread-per-row kernel above: 24 % of the HBM roofline, 10 long-scoreboard stall cycles per issue, r1i / r2).
+// Which dofs lie on the path of a joint is a bit mask per joint, built once per block from the staged table.  The wrench
+// shift and the per-dof accumulation over the non-zeros run in the same order as rows_cached_row (same dot6): the
+// dense row is bit-identical; the squared norm of the 1e-12 filter is summed in dof order through shuffles.
+__global__ void __launch_bounds__(256) applyJT_rows_warp_kernel(const DevModel* __restrict__ gm, const int model_words,
+                                                                const DevTables tb, const RowArgs a,
+                                                                const double* __restrict__ jc,
+                                                                const double* __restrict__ oc) {
+  const DevModel& m = stage_model(gm, model_words);
+  unsigned* const mask = reinterpret_cast<unsigned*>(rbd_smem + model_words);  // [njoints][3]: dofs 0..95 on the path to the root
+  const int nj = m.njoints, nv = m.nv;
+  for (int j = threadIdx.x; j < nj; j += blockDim.x) {
+    unsigned b0 = 0, b1 = 0, b2 = 0;
+    for (int k = j; k != 0; k = m.joint[k].parent)
+      for (int e = 0; e < m.joint[k].nv; ++e) {
+        const int c = m.joint[k].idx_v + e;
+        if (c < 32) b0 |= 1u << c; else if (c < 64) b1 |= 1u << (c - 32); else b2 |= 1u << (c - 64);
+      }
+    mask[3 * j] = b0; mask[3 * j + 1] = b1; mask[3 * j + 2] = b2;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (long long r = (long long)blockIdx.x * wpb + warp; r < a.nrows; r += (long long)gridDim.x * wpb) {
+    const int b = a.row_ptr[r], e = a.row_ptr[r + 1];
+    const long long inst = a.row_instance[r];
+    const double* const Ji = jc + inst * (long long)(6 * nv);
+    const double* const Oi = oc + inst * (long long)(12 * (nj - 1));
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int j = b; j < e; ++j) {
+      const int k = a.col[j];
+      const int pj = tb.outk_parent[k];
+      if (pj == 0) continue;  // attached to the universe: empty support, zero Jacobian
+      const double* pl = tb.outk_pl + 12 * k;
+      const double* w = a.val + 6 * (long long)j;
+      double Rp[12];
+      AosRec{Oi}.ldn<12>(12 * (pj - 1), Rp);
+      const double px = Rp[0] * pl[9] + Rp[1] * pl[10] + Rp[2] * pl[11] + Rp[9];
+      const double py = Rp[3] * pl[9] + Rp[4] * pl[10] + Rp[5] * pl[11] + Rp[10];
+      const double pz = Rp[6] * pl[9] + Rp[7] * pl[10] + Rp[8] * pl[11] + Rp[11];
+      double F[6], tx, ty, tz;
+      RBD_CROSS(tx, ty, tz, px, py, pz, w[0], w[1], w[2]);
+      F[0] = w[0]; F[1] = w[1]; F[2] = w[2];
+      F[3] = w[3] + tx; F[4] = w[4] + ty; F[5] = w[5] + tz;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const int c = lane + 32 * t;
+        if (c < nv && ((mask[3 * pj + t] >> lane) & 1u)) {
+          double A[6];
+          AosRec{Ji}.ldn<6>(6 * c, A);
+          acc[t] += dot6(A, F);
+        }
+      }
+    }
+    double* const row = a.out_rows + r * nv;
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+      if (lane + 32 * t < nv) row[lane + 32 * t] = acc[t];
+    double n2 = 0.0;  // in dof order, as one thread would sum it
+    for (int c = 0; c < nv; ++c) {
+      const double v = __shfl_sync(0xffffffffu, c < 32 ? acc[0] : c < 64 ? acc[1] : acc[2], c & 31);
+      n2 += v * v;
+    }
+    if (lane == 0) a.keep[r] = n2 > 1e-12 ? 1 : 0;  // kMinTorqueSqrd, reference KinematicChainMapping.inl:43-45,587,605
+  }
+}
+
 // getFrameJacobian(LWA) of (instance, output) pairs from the Jacobian cache: one thread per pair writes the columns on
 // the path to the root (the launcher zeroed the array: off-path columns stay 0, as pinocchio leaves them)
 __global__ void __launch_bounds__(256) frame_jacobian_kernel(const DevModel* __restrict__ gm, const int model_words,
@@ -1106,9 +1175,26 @@ cudaError_t launch_applyJT_rows(const DevModel& m, const DevModel* d_model, cons
 
 // rows on the Jacobian cache: `jc` / `oc` = world joint Jacobian and oMi of the applied instances, instance-major
 cudaError_t launch_applyJT_rows_cached(const DevModel& m, const DevModel* d_model, const DevTables& tb, const RowArgs& a,
-                                       const double* jc, const double* oc, cudaStream_t st) {
+                                       const double* jc, const double* oc, int num_sms, cudaStream_t st) {
   const int mw = map_model_words(m);
   const int block = 256;
+#ifndef RBD_ROWS_WARP
+#define RBD_ROWS_WARP 0 /* 1 = one warp per row (applyJT_rows_warp_kernel): coalesced column reads, but measured 2.3x - 3.3x
+                           SLOWER (A/B s3t, 2 rows x 2 non-zeros per instance: Talos 2 M rows 2.19 vs 0.97 ms, Solo 0.47 vs
+                           0.15, Panda 0.147 vs 0.045): the chain row_ptr -> col -> parent -> R|p / J is three dependent
+                           memory round trips per ROW, and a warp then has one row in flight where the thread-per-row
+                           kernel has 32 */
+#endif
+  if (RBD_ROWS_WARP && m.nv <= 96) {
+    if (a.nrows <= 0) return cudaSuccess;
+    const size_t smem = (size_t)mw * 8 + (size_t)m.njoints * 3 * sizeof(unsigned) + 8;
+    long long grid = (a.nrows + block / 32 - 1) / (block / 32);
+    const long long cap = (long long)num_sms * 8 * 16;  // 8 resident blocks per SM, >= 16 rows per warp: the prologue amortised
+    if (grid > cap) grid = cap;
+    RBD_NOTE(applyJT_rows_warp_kernel);
+    applyJT_rows_warp_kernel<<<(unsigned)grid, block, smem, st>>>(d_model, mw, tb, a, jc, oc);
+    return cudaGetLastError();
+  }
   const size_t smem = (size_t)mw * 8 + (size_t)(block / 32) * m.nv * 33 * 8;
   cudaError_t e = cudaFuncSetAttribute(applyJT_rows_cached_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin);
   if (e != cudaSuccess) return e;

@@ -101,7 +101,7 @@ cudaError_t launch_applyDJT(const DevModel& m, const DevModel* d_model, const De
 cudaError_t launch_applyJT_rows(const DevModel& m, const DevModel* d_model, const DevTables& tb, const RowArgs& a,
                                 int smem_doubles, LaunchCfg* cfg, cudaStream_t st);
 cudaError_t launch_applyJT_rows_cached(const DevModel& m, const DevModel* d_model, const DevTables& tb, const RowArgs& a,
-                                       const double* jcache, const double* omicache, cudaStream_t st);
+                                       const double* jcache, const double* omicache, int num_sms, cudaStream_t st);
 // dense getFrameJacobian(LWA) of (instance, output) pairs from the Jacobian cache; J [npairs][nv][6], 16-byte aligned
 cudaError_t launch_frame_jacobian(const DevModel& m, const DevModel* d_model, const DevTables& tb, long long npairs,
                                   const int* instance, const int* out_index, double* J, const double* jcache,
