@@ -117,20 +117,6 @@ RBD_HD void arm_instance(const ArmParams<NJ>& m, const FieldT<TILE>& q, const Fi
 // needs no stack for that — with Pre_i the sum over the joints < i, tau_i = A_i . Total - A_i . Pre_i, so the forward pass
 // keeps the NJ columns A_i in registers, one running sum and NJ partial dot products; nothing goes to shared or tensor
 // memory.  Joint constants from the kernel-parameter constant bank, wrenches from the ring (Ring: see rbd_sweeps_body.h).
-#define RBD_ARM_W(j, c)                                                                 \
-  real c[6];                                                                            \
-  {                                                                                     \
-    real w[6];                                                                          \
-    ring.template ld<j>(w);                                                             \
-    const real* pl = opl + 3 * (o + j);                                                 \
-    const real px = R[0] * pl[0] + R[1] * pl[1] + R[2] * pl[2] + p[0];                  \
-    const real py = R[3] * pl[0] + R[4] * pl[1] + R[5] * pl[2] + p[1];                  \
-    const real pz = R[6] * pl[0] + R[7] * pl[1] + R[8] * pl[2] + p[2];                  \
-    real tx, ty, tz;                                                                    \
-    RBD_CROSS(tx, ty, tz, px, py, pz, w[0], w[1], w[2]);                                \
-    c[0] = w[0]; c[1] = w[1]; c[2] = w[2];                                              \
-    c[3] = w[3] + tx; c[4] = w[4] + ty; c[5] = w[5] + tz;                               \
-  }
 template <int NJ, class QC, class Ring, class Sink>
 RBD_HD void applyJT_arm_instance(const ArmParams<NJ>& m, const real* opl, const QC& q, Ring& ring, const Sink& sink) {
   real R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
@@ -145,24 +131,23 @@ RBD_HD void applyJT_arm_instance(const ArmParams<NJ>& m, const real* opl, const 
     ::rbd::chain::fk_joint(jn, R, p, q0, real(0), q, aw);  // (qualified: `q` may be a type of namespace rbd, whose fk_joint ADL would find too)
     subspace_1dof(jn.type, p, aw, A[i]);
     part[i] = dot6(A[i], Pre);
+    // (one rolled loop over the wrenches of a piece, not the four straight-line cases of the generic ring sweep: with the
+    // joint loop unrolled those made 95 KB of code that every warp runs through once per tile — `no_instruction` was the
+    // largest stall of the first version, 2.0 cycles per issue, profile s3q)
     for (int o = jn.out_begin; o < jn.out_end;) {
       const int cnt = ring.acquire();
-      if (cnt == 1) {
-        RBD_ARM_W(0, c0)
-#pragma unroll
-        for (int e = 0; e < 6; ++e) Pre[e] += c0[e];
-      } else if (cnt == 2) {
-        RBD_ARM_W(0, c0) RBD_ARM_W(1, c1)
-#pragma unroll
-        for (int e = 0; e < 6; ++e) Pre[e] += c0[e] + c1[e];
-      } else if (cnt == 3) {
-        RBD_ARM_W(0, c0) RBD_ARM_W(1, c1) RBD_ARM_W(2, c2)
-#pragma unroll
-        for (int e = 0; e < 6; ++e) Pre[e] += (c0[e] + c1[e]) + c2[e];
-      } else {
-        RBD_ARM_W(0, c0) RBD_ARM_W(1, c1) RBD_ARM_W(2, c2) RBD_ARM_W(3, c3)
-#pragma unroll
-        for (int e = 0; e < 6; ++e) Pre[e] += (c0[e] + c1[e]) + (c2[e] + c3[e]);
+#pragma unroll 1
+      for (int j = 0; j < cnt; ++j) {
+        real w[6];
+        ring.ldr(j, w);
+        const real* pl = opl + 3 * (o + j);
+        const real px = R[0] * pl[0] + R[1] * pl[1] + R[2] * pl[2] + p[0];
+        const real py = R[3] * pl[0] + R[4] * pl[1] + R[5] * pl[2] + p[1];
+        const real pz = R[6] * pl[0] + R[7] * pl[1] + R[8] * pl[2] + p[2];
+        real tx, ty, tz;
+        RBD_CROSS(tx, ty, tz, px, py, pz, w[0], w[1], w[2]);
+        Pre[0] += w[0]; Pre[1] += w[1]; Pre[2] += w[2];
+        Pre[3] += w[3] + tx; Pre[4] += w[4] + ty; Pre[5] += w[5] + tz;
       }
       ring.release(cnt);
       o += cnt;
@@ -171,4 +156,3 @@ RBD_HD void applyJT_arm_instance(const ArmParams<NJ>& m, const real* opl, const 
 #pragma unroll
   for (int i = 0; i < NJ; ++i) sink.put(i, dot6(A[i], Pre) - part[i]);
 }
-#undef RBD_ARM_W

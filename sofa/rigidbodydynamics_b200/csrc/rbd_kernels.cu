@@ -348,6 +348,12 @@ struct WarpRing {
 #pragma unroll
     for (int e = 0; e < 6; ++e) w[e] = cur[J * (JtRing::kSlotBytes / 8) + e * 32];
   }
+  // ... with the slot index at run time (rolled wrench loops)
+  __device__ __forceinline__ void ldr(int j, double* w) const {
+    const double* c = cur + j * (JtRing::kSlotBytes / 8);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) w[e] = c[e * 32];
+  }
   // the piece has been consumed: its stage receives the piece `nst` ahead
   __device__ __forceinline__ void release(int) {
     __syncwarp();  // every lane has read the stage before lane 0 lets the copy engine overwrite it

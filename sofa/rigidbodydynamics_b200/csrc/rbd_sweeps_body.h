@@ -2650,6 +2650,21 @@ struct DirectRingT {
 #pragma unroll
     for (int e = 0; e < 6; ++e) w[e] = real(0) / real(0);  // not covered by any copy: poison
   }
+  // the same with the slot index at run time
+  RBD_HD void ldr(int j, real* w) const {
+    for (int k = 0; k < cur[3]; ++k) {
+      const int* ce = prog.copy(cur[2] + k);
+      const int dst = ce[1] & 0xffff, bytes = ce[1] >> 16;
+      if (j * 1536 >= dst && j * 1536 < dst + bytes) {
+        const int field0 = (ce[0] + (j * 1536 - dst)) / 256;
+#pragma unroll
+        for (int e = 0; e < 6; ++e) w[e] = in.ld(field0 + e);
+        return;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 6; ++e) w[e] = real(0) / real(0);  // not covered by any copy: poison
+  }
   RBD_HD void release(int) {}
 };
 // =========================================================================================================
