@@ -226,7 +226,7 @@ RBD_HD void dr_pop_ff(const DevModel& m, int cur, const real* Rp, const real* ve
   for (int e = 0; e < 9; ++e) { Yc[1 + e] = C[e]; dYc[1 + e] = C[9 + e]; }
   a0[0] = -m.gravity[0]; a0[1] = -m.gravity[1]; a0[2] = -m.gravity[2]; a0[3] = a0[4] = a0[5] = 0;
   const real* H = C + 18;
-#pragma unroll
+#pragma unroll 1  // once per instance: rolled, the six columns are a sixth of the code (instruction-cache pressure)
   for (int cc = 0; cc < 6; ++cc) {
     real Jc[6], t[6], dF[6], o[6];
     RBD_FF_COL(Jc, Rp, (Rp + 9), cc);
