@@ -324,6 +324,7 @@ def measure_config(torch, robot: str, n: int, steps: int, dev_index: int, with_e
     if 16 * I.nv * I.nv * n <= 40 << 30:   # both derivative matrices resident (Talos 2^20: 24 GB)
         DQm, DVm = E(I.nv * I.nv), E(I.nv * I.nv)
         calls["rnea_derivatives"] = lambda: ws.rnea_derivatives_soa(n, tile, q, v, dx, DQm, DVm, None)
+        calls["rnea_derivatives_sparse"] = lambda: ws.rnea_derivatives_soa_sparse(n, tile, q, v, dx, DQm, DVm)
     # algorithmic bytes per instance: inputs read + outputs written (+ cached q for J / JT, += read-modify-write)
     B = {"apply": 8 * (I.nq + 7 * I.n_out + I.nq),            # q in, poses out, q cache out
          "applyJ": 8 * (I.nq + I.nv + 6 * I.n_out),
@@ -336,7 +337,8 @@ def measure_config(torch, robot: str, n: int, steps: int, dev_index: int, with_e
          "crba": 8 * (I.nq + I.mass_fields),
          "aba": 8 * (I.nq + 3 * I.nv),           # q, v, tau in, ddq out (the per-joint scratch records are not algorithmic)
          "minv": 8 * (I.nq + I.mass_fields),     # q in, packed upper triangle of M^-1 out
-         "rnea_derivatives": 8 * (I.nq + 2 * I.nv + 2 * I.nv * I.nv)}   # q, v, a in, dtau_dq and dtau_dv (dense, zeros included) out
+         "rnea_derivatives": 8 * (I.nq + 2 * I.nv + 2 * I.nv * I.nv),   # q, v, a in, dtau_dq and dtau_dv (dense, zeros included) out
+         "rnea_derivatives_sparse": 8 * (I.nq + 2 * I.nv + 2 * len(m.drnea_pattern()[1]))}   # ... structurally non-zero entries only
     for name, fn in calls.items():
         ms, clk, kern = _time_launches(torch, fn, steps, 3, flush, dev_index)
         out[name] = _entry(n, ms, B[name], peak, clk, kern)

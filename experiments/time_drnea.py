@@ -40,8 +40,10 @@ def main():
         DQ = torch.empty((nt, nv * nv, 32), dtype=torch.float64, device=dev)
         DV = torch.empty((nt, nv * nv, 32), dtype=torch.float64, device=dev)
         Mp = torch.empty((nt, mf, 32), dtype=torch.float64, device=dev)
-        res = {}
+        nnz = len(m.drnea_pattern()[1])
+        res = {"support_entries": nnz, "dense_entries": nv * nv}
         for what, fn, fields in (("drnea", lambda: ws.rnea_derivatives_soa(n, 32, q, v, a, DQ, DV, None), d.nq + 2 * nv + 2 * nv * nv),
+                                 ("drnea_sparse", lambda: ws.rnea_derivatives_soa_sparse(n, 32, q, v, a, DQ, DV), d.nq + 2 * nv + 2 * nnz),
                                  ("drnea+M", lambda: ws.rnea_derivatives_soa(n, 32, q, v, a, DQ, DV, Mp), d.nq + 2 * nv + 2 * nv * nv + mf)):
             for _ in range(3):
                 fn()

@@ -328,6 +328,17 @@ RBD_API int rbd_rnea_derivatives_soa(rbd_workspace* ws, int64_t n, int64_t tile,
 /* ... on host vectors (instance-major q [n][nq]; v, a [n][nv]; dtau_dq, dtau_dv [n][nv][nv]; M [n][mass_fields] or NULL) */
 RBD_API int rbd_rnea_derivatives_host(rbd_workspace* ws, int64_t n, const double* q, const double* v, const double* a,
                                       double* dtau_dq, double* dtau_dv, double* M);
+/* The same matrices in a support-only format: entry (r, c) of dtau_dq / dtau_dv is structurally non-zero iff the joints
+ * that own dofs r and c lie on one root-to-leaf path (fewer than half of the entries for a humanoid: Talos 700 of 1 444).
+ *   rbd_model_drnea_pattern   the fixed pattern, compressed by rows: row_ptr [nv + 1], col_idx [nnz], columns ascending
+ *                             within a row; either array may be NULL (sizing pass); *nnz (may be NULL) its size;
+ *   *_sparse                  dq_val / dv_val [nnz fields]: entry e of the pattern is field e.  Same sweep, same values
+ *                             as the dense entry points; the structural zeros are neither written nor copied.        */
+RBD_API int rbd_model_drnea_pattern(const rbd_model* model, int32_t* row_ptr, int32_t* col_idx, int32_t* nnz);
+RBD_API int rbd_rnea_derivatives_soa_sparse(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, const double* v,
+                                            const double* a, double* dq_val, double* dv_val);
+RBD_API int rbd_rnea_derivatives_host_sparse(rbd_workspace* ws, int64_t n, const double* q, const double* v, const double* a,
+                                             double* dq_val, double* dv_val);
 
 /* Matrix-free Mass / ForceField products in joint space — what the reference's SOFA graph evaluates through the
  * mapping with one UniformMass<Rigid3> per body (URDFModelLoader.cpp:369-391): Mass::addMDx and ForceField::addForce

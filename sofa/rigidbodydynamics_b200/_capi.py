@@ -74,6 +74,7 @@ SYMBOLS = [
     "rbd_eval_soa_sparse", "rbd_crba_soa_sparse", "rbd_eval_host_sparse",
     "rbd_model_getJ_pattern", "rbd_getJ_dev", "rbd_getJ_host", "rbd_aba_soa", "rbd_aba_host", "rbd_minv_soa", "rbd_minv_host",
     "rbd_rnea_derivatives_soa", "rbd_rnea_derivatives_host",
+    "rbd_model_drnea_pattern", "rbd_rnea_derivatives_soa_sparse", "rbd_rnea_derivatives_host_sparse",
     "rbd_workspace_create", "rbd_workspace_destroy", "rbd_workspace_set_stream", "rbd_workspace_synchronize",
     "rbd_workspace_launch_count", "rbd_workspace_set_eval_block", "rbd_workspace_set_eval_tmem", "rbd_workspace_set_applyJT_ring", "rbd_workspace_set_rows_cache", "rbd_workspace_set_aba_fused", "rbd_workspace_set_eval_arm", "rbd_workspace_get_eval_plan", "rbd_workspace_get_eval_plan_f32",
     "rbd_apply_soa", "rbd_applyJ_soa", "rbd_applyJT_soa", "rbd_applyJT_rows_dev",
@@ -119,6 +120,9 @@ def load() -> C.CDLL:
         "rbd_minv_host": (C.c_int, [vp, i64, vp, vp]),
         "rbd_rnea_derivatives_soa": (C.c_int, [vp, i64, i64, vp, vp, vp, vp, vp, vp]),
         "rbd_rnea_derivatives_host": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp]),
+        "rbd_model_drnea_pattern": (C.c_int, [vp, vp, vp, vp]),
+        "rbd_rnea_derivatives_soa_sparse": (C.c_int, [vp, i64, i64, vp, vp, vp, vp, vp]),
+        "rbd_rnea_derivatives_host_sparse": (C.c_int, [vp, i64, vp, vp, vp, vp, vp]),
         "rbd_eval_soa_sparse": (C.c_int, [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp]),
         "rbd_crba_soa_sparse": (C.c_int, [vp, i64, i64, vp, vp]),
         "rbd_eval_host_sparse": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp, vp]),

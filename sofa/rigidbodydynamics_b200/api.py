@@ -58,6 +58,16 @@ class Model:
         check(self._lib.rbd_model_get_info(self._h, C.byref(info)))
         self.info = info
 
+    def drnea_pattern(self):
+        """(row_ptr [nv + 1], col_idx [nnz]) of the structurally non-zero entries of dtau_dq / dtau_dv, compressed by rows:
+        entry ``e`` is field ``e`` of the value arrays of ``rnea_derivatives_*_sparse`` (``rbd_model_drnea_pattern``)."""
+        row_ptr = np.zeros(self.info.nv + 1, dtype=np.int32)
+        nnz = C.c_int32(0)
+        check(self._lib.rbd_model_drnea_pattern(self._h, row_ptr.ctypes.data, None, C.addressof(nnz)))
+        col_idx = np.zeros(max(1, nnz.value), dtype=np.int32)
+        check(self._lib.rbd_model_drnea_pattern(self._h, row_ptr.ctypes.data, col_idx.ctypes.data, None))
+        return row_ptr, col_idx[:nnz.value]
+
     def mass_pattern(self):
         """Support pattern of M's upper triangle by columns: ``(col_ptr [nv + 1], row_idx [nnz])`` int32 arrays; entry
         ``e`` is field ``e`` of the ``Mval`` arrays of the ``*_sparse`` entry points (``rbd_model_mass_pattern``)."""
@@ -197,6 +207,11 @@ class Workspace:
         check(self._lib.rbd_rnea_derivatives_soa(self._h, n, tile, _dev_ptr(q), _dev_ptr(v), _dev_ptr(a), _dev_ptr(dtau_dq),
                                                  _dev_ptr(dtau_dv), _dev_ptr(M)))
 
+    def rnea_derivatives_soa_sparse(self, n, tile, q, v, a, dq_val, dv_val):
+        """The same derivatives, structurally non-zero entries only (``Model.drnea_pattern``)."""
+        check(self._lib.rbd_rnea_derivatives_soa_sparse(self._h, n, tile, _dev_ptr(q), _dev_ptr(v), _dev_ptr(a),
+                                                        _dev_ptr(dq_val), _dev_ptr(dv_val)))
+
     def minv_soa(self, n, tile, q, Minv):
         """Packed upper triangle of M(q)^-1 (``rbd_minv_soa``, pinocchio::computeMinverse)."""
         check(self._lib.rbd_minv_soa(self._h, n, tile, _dev_ptr(q), _dev_ptr(Minv)))
@@ -280,6 +295,10 @@ class Workspace:
     def rnea_derivatives_host(self, n, q, v, a, dtau_dq, dtau_dv, M=None):
         check(self._lib.rbd_rnea_derivatives_host(self._h, n, _host_ptr(q), _host_ptr(v), _host_ptr(a), _host_ptr(dtau_dq),
                                                   _host_ptr(dtau_dv), _host_ptr(M)))
+
+    def rnea_derivatives_host_sparse(self, n, q, v, a, dq_val, dv_val):
+        check(self._lib.rbd_rnea_derivatives_host_sparse(self._h, n, _host_ptr(q), _host_ptr(v), _host_ptr(a),
+                                                         _host_ptr(dq_val), _host_ptr(dv_val)))
 
     def minv_host(self, n, q, Minv):
         check(self._lib.rbd_minv_host(self._h, n, _host_ptr(q), _host_ptr(Minv)))

@@ -214,6 +214,12 @@ RBD_API int rbd_model_get_info(const rbd_model* model, rbd_model_info* info) {
   return RBD_OK;
 }
 
+RBD_API int rbd_model_drnea_pattern(const rbd_model* model, int32_t* row_ptr, int32_t* col_idx, int32_t* nnz) {
+  if (!model) return set_err(RBD_ERR_INVALID_ARG, "null model");
+  const int n = drnea_support_pattern(model->dm, row_ptr, col_idx);
+  if (nnz) *nnz = n;
+  return RBD_OK;
+}
 RBD_API int rbd_model_mass_pattern(const rbd_model* model, int32_t* col_ptr, int32_t* row_idx) {
   if (!model) return set_err(RBD_ERR_INVALID_ARG, "null model");
   (void)mass_support_pattern(model->dm, col_ptr, row_idx);
@@ -667,7 +673,7 @@ RBD_API int rbd_minv_soa(rbd_workspace* ws, int64_t n, int64_t tile, const doubl
 
 // derivatives of inverse dynamics (drnea_instance): dtau_dq, dtau_dv nv x nv row-major fields, M optional (packed upper)
 static int drnea_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, const double* q, const double* v,
-                    const double* a, double* dq, double* dv, double* M) {
+                    const double* a, double* dq, double* dv, double* M, bool sparse = false) {
   if (!q || !v || !a || !dq || !dv) return set_err(RBD_ERR_INVALID_ARG, "null q / v / a / dtau_dq / dtau_dv");
   const DevModel& dm = ws->model->dm;
   for (int i = 1; i < dm.njoints; ++i)
@@ -691,13 +697,13 @@ static int drnea_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile,
   const int sc = (ws->slot[1].st && st == ws->slot[1].st) ? 1 : 0;
   if (!ws->drnea_scratch[sc]) {
     int warps = 0;
-    DrneaArgs S{0, 32, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    DrneaArgs S{0, 32, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
     CK(launch_drnea(*ws->h_drnea, ws->d_drnea, S, ws->num_sms, &warps, st));
     const size_t bytes = (size_t)warps * (size_t)(ws->h_drnea->slot_total[0] > 0 ? ws->h_drnea->slot_total[0] : 1) * 32 * sizeof(double);
     cudaError_t e = cudaMalloc(&ws->drnea_scratch[sc], bytes);
     if (e != cudaSuccess) { cudaGetLastError(); return set_err(RBD_ERR_ALLOC, std::string("cudaMalloc(rnea_derivatives scratch): ") + cudaGetErrorString(e)); }
   }
-  DrneaArgs A{n, tile, q, v, a, dq, dv, M, ws->drnea_scratch[sc]};
+  DrneaArgs A{n, tile, q, v, a, dq, dv, M, ws->drnea_scratch[sc], sparse ? 1 : 0};
   CK(launch_drnea(*ws->h_drnea, ws->d_drnea, A, ws->num_sms, nullptr, st));
   if (n > 0) ws->launches++;
   return RBD_OK;
@@ -708,6 +714,14 @@ RBD_API int rbd_rnea_derivatives_soa(rbd_workspace* ws, int64_t n, int64_t tile,
   int rc = check_batch(ws, n, tile);
   if (rc) return rc;
   return drnea_on(ws, ws->stream, n, tile, q, v, a, dtau_dq, dtau_dv, M);
+}
+
+RBD_API int rbd_rnea_derivatives_soa_sparse(rbd_workspace* ws, int64_t n, int64_t tile, const double* q, const double* v,
+                                            const double* a, double* dq_val, double* dv_val) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, tile);
+  if (rc) return rc;
+  return drnea_on(ws, ws->stream, n, tile, q, v, a, dq_val, dv_val, nullptr, true);
 }
 
 static int apply_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, long long inst0, const double* qj,
@@ -1235,6 +1249,25 @@ RBD_API int rbd_rnea_derivatives_host(rbd_workspace* ws, int64_t n, const double
   P.add(I.mass_fields, nullptr, M, false, true);
   return run_host_chunks(ws, n, P, [&](cudaStream_t st, long long, long long cn, long long tile) {
     return drnea_on(ws, st, cn, tile, P[0].d_soa, P[1].d_soa, P[2].d_soa, P[3].d_soa, P[4].d_soa, P[5].d_soa);
+  });
+}
+
+RBD_API int rbd_rnea_derivatives_host_sparse(rbd_workspace* ws, int64_t n, const double* q, const double* v, const double* a,
+                                             double* dq_val, double* dv_val) {
+  GUARD(ws);
+  int rc = check_batch(ws, n, 1);
+  if (rc) return rc;
+  if (!q || !v || !a || !dq_val || !dv_val) return set_err(RBD_ERR_INVALID_ARG, "null q / v / a / dq_val / dv_val");
+  const rbd_model_info& I = ws->model->info;
+  const int nnz = drnea_support_pattern(ws->model->dm, nullptr, nullptr);
+  Pieces P;
+  P.add(I.nq, q, nullptr, true, false);
+  P.add(I.nv, v, nullptr, true, false);
+  P.add(I.nv, a, nullptr, true, false);
+  P.add(nnz, nullptr, dq_val, false, true);
+  P.add(nnz, nullptr, dv_val, false, true);
+  return run_host_chunks(ws, n, P, [&](cudaStream_t st, long long, long long cn, long long tile) {
+    return drnea_on(ws, st, cn, tile, P[0].d_soa, P[1].d_soa, P[2].d_soa, P[3].d_soa, P[4].d_soa, nullptr, true);
   });
 }
 

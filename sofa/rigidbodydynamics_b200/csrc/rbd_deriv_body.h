@@ -40,7 +40,8 @@
 // — at 255 registers per thread every extra live value costs more than the instructions it saves.
 //
 // Outputs: DQ, DV: nv x nv, field r nv + c (row-major like pinocchio's RowMatrixXs), structural zeros WRITTEN (dofs on
-// different branches); M (optional): packed upper triangle like rbd_crba_soa.  A free-flyer only as joint 1 on the universe.
+// different branches) — or, SPARSE, the structurally non-zero entries only, compressed by rows (rbd_model_drnea_pattern:
+// 700 of Talos' 1 444 entries per matrix; no zero fill); M (optional, dense format only): packed upper triangle like rbd_crba_soa.  A free-flyer only as joint 1 on the universe.
 // All lanes of a warp run the sweep together (tensor-memory accesses are warp-collective).
 
 #define RBD_DR_HOT 18       /* on-chip level record of a 1-dof joint: v | a | J                                       */
@@ -103,11 +104,20 @@ RBD_HD void dr_own(const real* Y, const real* vel, const real* acc, real* C) {
 // Everything joint `cur` (1-dof) contributes when the sweep leaves it: its diagonal entry, the entries it shares with
 // each ancestor (both triangles), the structural zeros it shares with the dofs of earlier branches.
 // A: J of cur; va: v | a of cur's parent; C: composite of cur's subtree (dr_own layout).
-template <class FLD>
+// SPARSE: the support-only format (rbd_model_drnea_pattern: compressed by rows, structural zeros not stored).  Row of dof e
+// of joint j starts at RBD_DR_ROWBASE(j) + e RBD_DR_ROWLEN(j) and holds the ancestors' dofs (root first), then the dofs
+// [idx_v(j), idx_v(j) + nv_subtree(j)): entry (row of j, dof e' of ancestor k) sits at offset RBD_DR_NANC(k) + e', entry
+// (row of j, dof c of its subtree) at RBD_DR_NANC(j) + c - idx_v(j).
+#define RBD_DR_ROWBASE(j) ((j).slot[0])
+#define RBD_DR_NANC(j) ((j).slot[1])
+#define RBD_DR_ROWLEN(j) ((j).out_begin)
+template <bool SPARSE, class FLD>
 RBD_HD void dr_pop_1dof(const DevModel& m, int cur, const real* A, const real* va, const real* C, const FLD& DQ,
                         const FLD& DV, const FLD& M, const Stack& S, const TmStack& T) {
   const DevJoint& jc = m.joint[cur];
   const int nv = m.nv, iv = jc.idx_v;
+  // field of entry (iv, column c of ancestor k) / (row r of ancestor k, iv)
+  const int rowj = SPARSE ? RBD_DR_ROWBASE(jc) : iv * nv;
   real Yc[10], dYc[10];
   Yc[0] = jc.msub; dYc[0] = 0;
 #pragma unroll
@@ -134,8 +144,8 @@ RBD_HD void dr_pop_1dof(const DevModel& m, int cur, const real* A, const real* v
 #pragma unroll
     for (int e = 0; e < 6; ++e) dFq[e] += cb[e] + t[e];
   }
-  DV.st(iv * nv + iv, dot6(A, dFv));
-  DQ.st(iv * nv + iv, dot6(A, dFq));
+  DV.st(rowj + (SPARSE ? RBD_DR_NANC(jc) : iv), dot6(A, dFv));
+  DQ.st(rowj + (SPARSE ? RBD_DR_NANC(jc) : iv), dot6(A, dFq));
   if (M.ok()) M.st(iv * (iv + 1) / 2 + iv, dot6(A, u));
   {
     real t[6];
@@ -148,22 +158,28 @@ RBD_HD void dr_pop_1dof(const DevModel& m, int cur, const real* A, const real* v
   for (int k = jc.parent; k != 0;) {
     const DevJoint& jk = m.joint[k];
     const int ik = jk.idx_v;
-    for (int c = ik + jk.nv; c < prev; ++c) {
-      DQ.st(iv * nv + c, real(0)); DV.st(iv * nv + c, real(0));
-      DQ.st(c * nv + iv, real(0)); DV.st(c * nv + iv, real(0));
-      if (M.ok()) M.st(iv * (iv + 1) / 2 + c, real(0));
+    if (!SPARSE) {
+      for (int c = ik + jk.nv; c < prev; ++c) {
+        DQ.st(iv * nv + c, real(0)); DV.st(iv * nv + c, real(0));
+        DQ.st(c * nv + iv, real(0)); DV.st(c * nv + iv, real(0));
+        if (M.ok()) M.st(iv * (iv + 1) / 2 + c, real(0));
+      }
     }
     prev = ik;
+    const int rjk = SPARSE ? RBD_DR_NANC(jk) : ik;  // entry (iv, first dof of k) within row iv
+    // entry (first dof of k, iv), and the distance to the same column in k's next row
+    const int ckj = SPARSE ? RBD_DR_ROWBASE(jk) + RBD_DR_NANC(jk) + (iv - ik) : ik * nv + iv;
+    const int ckstep = SPARSE ? RBD_DR_ROWLEN(jk) : nv;
     if (RBD_T_IS_FF(jk.type)) {  // the root: six columns from R | p; dVdq = 0, dAdq_c = a0 x J_c, dAdv_c = v_root x J_c
       real Rp[12], vr[6], o[6], t[6];
       lev_ld<12>(S, T, jk.offA + 12, Rp);
       lev_ld<6>(S, T, jk.offA, vr);
       ff_rows(Rp, Rp + 9, dFq, o);
 #pragma unroll
-      for (int e = 0; e < 6; ++e) DQ.st((ik + e) * nv + iv, o[e]);
+      for (int e = 0; e < 6; ++e) DQ.st(ckj + e * ckstep, o[e]);
       ff_rows(Rp, Rp + 9, dFv, o);
 #pragma unroll
-      for (int e = 0; e < 6; ++e) DV.st((ik + e) * nv + iv, o[e]);
+      for (int e = 0; e < 6; ++e) DV.st(ckj + e * ckstep, o[e]);
       if (M.ok()) {
         ff_rows(Rp, Rp + 9, u, o);
 #pragma unroll
@@ -174,14 +190,14 @@ RBD_HD void dr_pop_1dof(const DevModel& m, int cur, const real* A, const real* v
       RBD_CROSS(t[3], t[4], t[5], m.gravity[0], m.gravity[1], m.gravity[2], u[0], u[1], u[2]);
       ff_rows(Rp, Rp + 9, t, o);
 #pragma unroll
-      for (int e = 0; e < 6; ++e) DQ.st(iv * nv + ik + e, o[e]);
+      for (int e = 0; e < 6; ++e) DQ.st(rowj + rjk + e, o[e]);
       // u . (v_root x J_c) + w . J_c = (w - v_root x* u) . J_c
       mxf(vr, u, t);
 #pragma unroll
       for (int e = 0; e < 6; ++e) t[e] = w[e] - t[e];
       ff_rows(Rp, Rp + 9, t, o);
 #pragma unroll
-      for (int e = 0; e < 6; ++e) DV.st(iv * nv + ik + e, o[e]);
+      for (int e = 0; e < 6; ++e) DV.st(rowj + rjk + e, o[e]);
       k = jk.parent;
       continue;
     }
@@ -200,26 +216,29 @@ RBD_HD void dr_pop_1dof(const DevModel& m, int cur, const real* A, const real* v
     mxm(vak, dVk, t);
 #pragma unroll
     for (int e = 0; e < 6; ++e) dAk[e] += t[e];
-    DQ.st(ik * nv + iv, dot6(Jk, dFq));
-    DV.st(ik * nv + iv, dot6(Jk, dFv));
+    DQ.st(ckj, dot6(Jk, dFq));
+    DV.st(ckj, dot6(Jk, dFv));
     if (M.ok()) M.st(iv * (iv + 1) / 2 + ik, dot6(Jk, u));
-    DQ.st(iv * nv + ik, dot6(u, dAk) + dot6(w, dVk));
-    DV.st(iv * nv + ik, 2 * dot6(u, dVk) + dot6(w, Jk));
+    DQ.st(rowj + rjk, dot6(u, dAk) + dot6(w, dVk));
+    DV.st(rowj + rjk, 2 * dot6(u, dVk) + dot6(w, Jk));
     k = kp;
   }
-  for (int c = 0; c < prev; ++c) {
-    DQ.st(iv * nv + c, real(0)); DV.st(iv * nv + c, real(0));
-    DQ.st(c * nv + iv, real(0)); DV.st(c * nv + iv, real(0));
-    if (M.ok()) M.st(iv * (iv + 1) / 2 + c, real(0));
+  if (!SPARSE) {
+    for (int c = 0; c < prev; ++c) {
+      DQ.st(iv * nv + c, real(0)); DV.st(iv * nv + c, real(0));
+      DQ.st(c * nv + iv, real(0)); DV.st(c * nv + iv, real(0));
+      if (M.ok()) M.st(iv * (iv + 1) / 2 + c, real(0));
+    }
   }
 }
 
 // ... and the root free-flyer's own 6 x 6 blocks: dVdq = 0, dAdq_c = a0 x J_c, dAdv_c = v x J_c (parent = universe)
-template <class FLD>
+template <bool SPARSE, class FLD>
 RBD_HD void dr_pop_ff(const DevModel& m, int cur, const real* Rp, const real* vel, const real* C, const FLD& DQ,
                       const FLD& DV, const FLD& M) {
   const DevJoint& jc = m.joint[cur];
   const int nv = m.nv, iv = jc.idx_v;
+  const int blk = SPARSE ? RBD_DR_ROWBASE(jc) : iv * nv + iv, rstep = SPARSE ? RBD_DR_ROWLEN(jc) : nv;  // entry (iv + r, iv + cc) at blk + r rstep + cc
   real Yc[10], dYc[10], a0[6];
   Yc[0] = jc.msub; dYc[0] = 0;
 #pragma unroll
@@ -241,13 +260,13 @@ RBD_HD void dr_pop_ff(const DevModel& m, int cur, const real* Rp, const real* ve
     for (int e = 0; e < 6; ++e) dF[e] += o[e];
     ff_rows(Rp, Rp + 9, dF, o);
 #pragma unroll
-    for (int r = 0; r < 6; ++r) DV.st((iv + r) * nv + iv + cc, o[r]);
+    for (int r = 0; r < 6; ++r) DV.st(blk + r * rstep + cc, o[r]);
     // dFdq = Y (a0 x J)
     mxm(a0, Jc, t);
     inertia_mul(Yc, t, dF);
     ff_rows(Rp, Rp + 9, dF, o);
 #pragma unroll
-    for (int r = 0; r < 6; ++r) DQ.st((iv + r) * nv + iv + cc, o[r]);
+    for (int r = 0; r < 6; ++r) DQ.st(blk + r * rstep + cc, o[r]);
     if (M.ok()) {
       inertia_mul(Yc, Jc, dF);
       ff_rows(Rp, Rp + 9, dF, o);
@@ -257,7 +276,7 @@ RBD_HD void dr_pop_ff(const DevModel& m, int cur, const real* Rp, const real* ve
   }
 }
 
-template <class FLD, class SCR>
+template <bool SPARSE, class FLD, class SCR>
 RBD_HD void drnea_instance(const DevModel& m, const FLD& q, const FLD& v, const FLD& a, const FLD& DQ, const FLD& DV,
                            const FLD& M, const SCR& X, const Stack& S, const TmStack& T, const InRing& inr) {
   const int nj = m.njoints;
@@ -374,7 +393,7 @@ RBD_HD void drnea_instance(const DevModel& m, const FLD& q, const FLD& v, const 
           lev_ld<12>(S, T, jc.offA + 12, Rp);
           lev_ld<6>(S, T, jc.offA, vr);
         }
-        dr_pop_ff(m, cur, Rp, vr, C, DQ, DV, M);
+        dr_pop_ff<SPARSE>(m, cur, Rp, vr, C, DQ, DV, M);
         break;  // (the host checks that a free-flyer is joint 1 on the universe)
       }
       const int pp = jc.parent;
@@ -388,7 +407,7 @@ RBD_HD void drnea_instance(const DevModel& m, const FLD& q, const FLD& v, const 
         for (int e = 0; e < 9; ++e) cp_async_real(inr, 3 * RBD_DR_SLOTS + e, Xp.ptr(e));
         cp_async_commit();
       }
-      dr_pop_1dof(m, cur, A, va, C, DQ, DV, M, S, T);
+      dr_pop_1dof<SPARSE>(m, cur, A, va, C, DQ, DV, M, S, T);
       if (pp == 0) break;
       const DevJoint& jp = m.joint[pp];
       const SCR Xp = X.at(jp.boff);

@@ -49,6 +49,7 @@ struct DrneaArgs {  // derivatives of inverse dynamics: q, v, a -> dtau_dq, dtau
   const double *q, *v, *a;
   double *dtau_dq, *dtau_dv, *M;
   double* scratch;  // planned_model.slot_total[0] * 32 doubles per resident warp (cold level records)
+  int sparse = 0;   // 1: dtau_dq / dtau_dv hold the structurally non-zero entries only (planned_model.slot_total[1] fields)
 };
 struct AbaArgs {  // forward dynamics (articulated-body algorithm): q, v, tau -> ddq
   long long n, tile;

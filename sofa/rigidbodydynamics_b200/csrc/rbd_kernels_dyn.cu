@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256, 1) minv_kernel(const DevModel* __restrict
 
 // Derivatives of inverse dynamics (drnea_instance, rbd_deriv_body.h): same launch shape; every level record is on chip,
 // the only global traffic is q, v, a in and the two nv x nv matrices (+ optional packed M) out
-template <int TILE>
+template <int TILE, bool SPARSE>
 __global__ void __launch_bounds__(256, 1) drnea_kernel(const DevModel* __restrict__ gm, const int model_words, const DrneaArgs a) {
   const DynCtx c = dyn_prologue(gm, model_words);
   const DevModel& m = *c.m;
@@ -146,10 +146,11 @@ __global__ void __launch_bounds__(256, 1) drnea_kernel(const DevModel* __restric
   for (long long t = gw; t < ntiles; t += (long long)gridDim.x * wpb) {
     long long inst = t * 32 + lane;
     if (inst >= a.n) inst = a.n - 1;  // lanes past the end recompute the last instance (same values to the same addresses)
-    drnea_instance(m, make_field_t<TILE>(const_cast<double*>(a.q), inst, m.nq, a.tile),
+    const int K = SPARSE ? m.slot_total[1] : nv * nv;
+    drnea_instance<SPARSE>(m, make_field_t<TILE>(const_cast<double*>(a.q), inst, m.nq, a.tile),
                    make_field_t<TILE>(const_cast<double*>(a.v), inst, nv, a.tile),
                    make_field_t<TILE>(const_cast<double*>(a.a), inst, nv, a.tile),
-                   make_field_t<TILE>(a.dtau_dq, inst, nv * nv, a.tile), make_field_t<TILE>(a.dtau_dv, inst, nv * nv, a.tile),
+                   make_field_t<TILE>(a.dtau_dq, inst, K, a.tile), make_field_t<TILE>(a.dtau_dv, inst, K, a.tile),
                    make_field_t<TILE>(a.M, inst, nv * (nv + 1) / 2, a.tile), X, c.S, c.T, inr);
   }
   dyn_epilogue(c);
@@ -225,17 +226,17 @@ cudaError_t launch_drnea(const DevModel& hm, const DevModel* d_model, const Drne
   if (scratch_warps) *scratch_warps = num_sms * W;
   if (!a.scratch || a.n <= 0) return cudaSuccess;
   const size_t smem = (size_t)mw * 8 + (size_t)W * 32 * hm.plan.smem_doubles * 8;
-  static thread_local bool attr_done[2] = {false, false};
+  static thread_local bool attr_done[4] = {false, false, false, false};
   cudaError_t e = cudaSuccess;
-  if (a.tile == 32) {
-    if (!attr_done[1]) { e = dyn_attr(drnea_kernel<32>); if (e != cudaSuccess) return e; attr_done[1] = true; }
-    note_kernel(reinterpret_cast<const void*>(drnea_kernel<32>));
-    drnea_kernel<32><<<(unsigned)grid, block, smem, st>>>(d_model, mw, a);
-  } else {
-    if (!attr_done[0]) { e = dyn_attr(drnea_kernel<0>); if (e != cudaSuccess) return e; attr_done[0] = true; }
-    note_kernel(reinterpret_cast<const void*>(drnea_kernel<0>));
-    drnea_kernel<0><<<(unsigned)grid, block, smem, st>>>(d_model, mw, a);
-  }
+#define RBD_DR_LAUNCH(T_, S_, slot_)                                                                              \
+  do {                                                                                                            \
+    if (!attr_done[slot_]) { e = dyn_attr(drnea_kernel<T_, S_>); if (e != cudaSuccess) return e; attr_done[slot_] = true; } \
+    note_kernel(reinterpret_cast<const void*>(drnea_kernel<T_, S_>));                                             \
+    drnea_kernel<T_, S_><<<(unsigned)grid, block, smem, st>>>(d_model, mw, a);                                    \
+  } while (0)
+  if (a.tile == 32) { if (a.sparse) RBD_DR_LAUNCH(32, true, 3); else RBD_DR_LAUNCH(32, false, 1); }
+  else { if (a.sparse) RBD_DR_LAUNCH(0, true, 2); else RBD_DR_LAUNCH(0, false, 0); }
+#undef RBD_DR_LAUNCH
   return cudaGetLastError();
 }
 }  // namespace rbd

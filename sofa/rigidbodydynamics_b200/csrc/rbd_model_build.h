@@ -607,7 +607,43 @@ inline bool plan_drnea(DevModel* m, bool use_tmem, int max_warps = B200Limits::k
   for (int d = 1; d <= D; ++d) coff[d + 1] = coff[d] + csize[d];
   for (int i = 1; i < m->njoints; ++i) m->joint[i].boff = m->joint[i].nchild > 0 ? coff[m->joint[i].depth] : 0;
   m->slot_total[0] = coff[D + 1];  // doubles of scratch per instance in flight
+  // support-only output format: row base / ancestor dofs / row length of every joint (RBD_DR_ROWBASE / _NANC / _ROWLEN)
+  {
+    const int nj = m->njoints;
+    std::vector<int> nvsub(nj, 0), nanc(nj, 0);
+    for (int i = nj - 1; i >= 1; --i) { nvsub[i] += m->joint[i].nv; nvsub[m->joint[i].parent] += nvsub[i]; }
+    int base = 0;
+    for (int i = 1; i < nj; ++i) {
+      DevJoint& j = m->joint[i];
+      nanc[i] = j.parent ? nanc[j.parent] + m->joint[j.parent].nv : 0;
+      j.slot[0] = base; j.slot[1] = nanc[i]; j.out_begin = nanc[i] + nvsub[i];
+      base += j.nv * j.out_begin;
+    }
+    m->slot_total[1] = base;  // entries of the support pattern
+  }
   return true;
+}
+// Support pattern of dtau_dq / dtau_dv, compressed by rows (the order of the fields the SPARSE sweep writes): row of dof r =
+// the dofs of the ancestors of r's joint (root first), then the dofs [idx_v, idx_v + nv_subtree) of the joint's subtree.
+// row_ptr [nv + 1], col_idx [nnz] (either may be null); returns nnz.
+inline int drnea_support_pattern(const DevModel& m, int* row_ptr, int* col_idx) {
+  const int nj = m.njoints;
+  std::vector<int> nvsub(nj, 0);
+  for (int i = nj - 1; i >= 1; --i) { nvsub[i] += m.joint[i].nv; nvsub[m.joint[i].parent] += nvsub[i]; }
+  int nnz = 0;
+  for (int i = 1; i < nj; ++i) {
+    const DevJoint& j = m.joint[i];
+    std::vector<int> chain;
+    for (int a = j.parent; a != 0; a = m.joint[a].parent) chain.insert(chain.begin(), a);
+    for (int e = 0; e < j.nv; ++e) {
+      if (row_ptr) row_ptr[j.idx_v + e] = nnz;
+      for (int a : chain)
+        for (int k = 0; k < m.joint[a].nv; ++k) { if (col_idx) col_idx[nnz] = m.joint[a].idx_v + k; ++nnz; }
+      for (int c = j.idx_v; c < j.idx_v + nvsub[i]; ++c) { if (col_idx) col_idx[nnz] = c; ++nnz; }
+    }
+  }
+  if (row_ptr) row_ptr[m.nv] = nnz;
+  return nnz;
 }
 inline bool plan_levels(DevModel* m, bool use_tmem, int size_one_child, int size_branch, int restart_off, int max_warps,
                         int forced_warps, size_t model_bytes) {

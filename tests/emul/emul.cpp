@@ -559,8 +559,16 @@ extern "C" int emul_minv(const rbd_model_desc* d, long long n, long long tile, i
 
 // derivatives of inverse dynamics (drnea_instance): DQ, DV nv x nv row-major fields, M (optional) packed upper triangle;
 // level records on the plan of plan_drnea, storage as emul_aba2 (poisoned between instances)
+// sparse != 0: DQ / DV in the support-only format (pattern: row_ptr [nv + 1], col_idx, either may be null; *nnz its size)
+extern "C" int emul_drnea_pattern(const rbd_model_desc* d, int* row_ptr, int* col_idx, int* nnz) {
+  Ctx c;
+  int rc = make_ctx(d, &c);
+  if (rc) return rc;
+  *nnz = drnea_support_pattern(c.m, row_ptr, col_idx);
+  return 0;
+}
 extern "C" int emul_drnea(const rbd_model_desc* d, long long n, long long tile, int use_tmem, int warps, double* q, double* v,
-                          double* a, double* DQ, double* DV, double* M, int* plan_out) {
+                          double* a, double* DQ, double* DV, double* M, int* plan_out, int sparse) {
   Ctx c;
   int rc = make_ctx(d, &c);
   if (rc) return rc;
@@ -583,8 +591,13 @@ extern "C" int emul_drnea(const rbd_model_desc* d, long long n, long long tile, 
     EmulScratch X{scr.data()};
     Stack S = make_stack(smem.data(), t, pl.smem_doubles);
     TmStack T{tmem.data() + (size_t)t * (pl.tmem_doubles > 0 ? pl.tmem_doubles : 1)};
-    drnea_instance(c.m, make_field(q, i, c.m.nq, tile), make_field(v, i, nv, tile), make_field(a, i, nv, tile),
-                   make_field(DQ, i, nv * nv, tile), make_field(DV, i, nv * nv, tile), make_field(M, i, nv * (nv + 1) / 2, tile), X, S, T, InRing());
+    const int K = sparse ? c.m.slot_total[1] : nv * nv;
+    if (sparse)
+      drnea_instance<true>(c.m, make_field(q, i, c.m.nq, tile), make_field(v, i, nv, tile), make_field(a, i, nv, tile),
+                           make_field(DQ, i, K, tile), make_field(DV, i, K, tile), make_field(nullptr, i, 1, tile), X, S, T, InRing());
+    else
+      drnea_instance<false>(c.m, make_field(q, i, c.m.nq, tile), make_field(v, i, nv, tile), make_field(a, i, nv, tile),
+                            make_field(DQ, i, K, tile), make_field(DV, i, K, tile), make_field(M, i, nv * (nv + 1) / 2, tile), X, S, T, InRing());
   }
   return 0;
 }

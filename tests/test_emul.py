@@ -603,7 +603,7 @@ def test_drnea_body_matches_oracle(emul, d, tile, body):
     qs, vs, as_ = to_tiled(q, tile), to_tiled(v, tile), to_tiled(a, tile)
     plan = (C.c_int * 4)()
     rc = emul.emul_drnea(C.addressof(cd), n, tile, 0 if body == "smem_only" else 1, 3 if body == "w3" else 0,
-                         P(qs), P(vs), P(as_), P(DQ), P(DV), P(Mp) if body != "w3" else None, plan)
+                         P(qs), P(vs), P(as_), P(DQ), P(DV), P(Mp) if body != "w3" else None, plan, 0)
     assert rc == 0, emul.emul_last_error()
     gq = from_tiled(DQ, n)[:, :nv * nv].reshape(n, nv, nv); gv = from_tiled(DV, n)[:, :nv * nv].reshape(n, nv, nv)
     assert np.isfinite(gq).all() and np.isfinite(gv).all()          # every entry written, structural zeros included
@@ -620,7 +620,25 @@ def test_drnea_body_matches_oracle(emul, d, tile, body):
             assert rel_err(oracle.unpack_upper(gM, nv), np.triu(rM) + np.triu(rM, 1).T) <= 1e-10
     assert rel_err(gq[0], np.array(gold["dtau_dq"])) <= 1e-10
     assert rel_err(gv[0], np.array(gold["dtau_dv"])) <= 1e-10
+    # support-only format: the pattern is the support relation, row by row with ascending columns, and the values are
+    # the dense entries at the pattern's positions (bit for bit: same sweep, other addresses)
+    row_ptr = np.zeros(nv + 1, dtype=np.int32); nnz = C.c_int(0)
+    assert emul.emul_drnea_pattern(C.addressof(cd), P(row_ptr), None, C.byref(nnz)) == 0
+    col_idx = np.zeros(max(1, nnz.value), dtype=np.int32)
+    assert emul.emul_drnea_pattern(C.addressof(cd), P(row_ptr), P(col_idx), C.byref(nnz)) == 0
+    assert nnz.value == int(related.sum()) == row_ptr[nv]
+    for r in range(nv):
+        cols = col_idx[row_ptr[r]:row_ptr[r + 1]]
+        assert np.all(np.diff(cols) > 0) and np.array_equal(np.flatnonzero(related[r]), cols)
+    SQ = np.full((nt, max(1, nnz.value), tile), np.nan); SV = np.full((nt, max(1, nnz.value), tile), np.nan)
+    rc = emul.emul_drnea(C.addressof(cd), n, tile, 0 if body == "smem_only" else 1, 3 if body == "w3" else 0,
+                         P(qs), P(vs), P(as_), P(SQ), P(SV), None, plan, 1)
+    assert rc == 0, emul.emul_last_error()
+    rows = np.repeat(np.arange(nv), np.diff(row_ptr))
+    assert np.array_equal(from_tiled(SQ, n)[:, :nnz.value], gq[:, rows, col_idx[:nnz.value]])
+    assert np.array_equal(from_tiled(SV, n)[:, :nnz.value], gv[:, rows, col_idx[:nnz.value]])
     if body == "planned" and d.name == "talos_reduced":
+        assert nnz.value == 700          # of 1 444: fewer than half of the entries are structurally non-zero
         # 8 warps per SM: hot records 24 + 9 x 18 doubles on chip (+ input ring and staging: 18), cold ones 42 + 9 + 42 + 7 x 9 in scratch
         assert list(plan) == [8, 96, 108, 156]
 

@@ -1063,6 +1063,21 @@ def test_rnea_derivatives_match_oracle(torch_mod, api, d, tile):
     fd = (taus[0] - taus[1]) / (2 * eps)
     lin = np.einsum("nrc,nc->nr", gq, dq) + np.einsum("nrc,nc->nr", gv, dv)
     assert np.max(np.abs(fd - lin)) <= 1e-6 * max(1.0, float(np.max(np.abs(lin))))
+    # support-only format (rbd_model_drnea_pattern + *_sparse): the pattern is the support relation, the values are the
+    # dense entries at the pattern's positions bit for bit (same sweep, other addresses), device and host entry points
+    row_ptr, col_idx = m.drnea_pattern()
+    nnz = len(col_idx)
+    assert nnz == int(related.sum()) == row_ptr[nv]
+    rows = np.repeat(np.arange(nv), np.diff(row_ptr))
+    assert np.array_equal(np.stack([rows, col_idx], 1), np.argwhere(related))
+    SQ, SV = new(max(1, nnz)), new(max(1, nnz))
+    ws.rnea_derivatives_soa_sparse(n, tile, qs, vs, as_, SQ, SV); ws.synchronize()
+    assert "drnea_kernel" in api.last_kernel_name()
+    assert np.array_equal(from_tiled(SQ.cpu().numpy(), n)[:, :nnz], gq[:, rows, col_idx])
+    assert np.array_equal(from_tiled(SV.cpu().numpy(), n)[:, :nnz], gv[:, rows, col_idx])
+    hsq, hsv = np.zeros((n, nnz)), np.zeros((n, nnz))
+    ws.rnea_derivatives_host_sparse(n, q, v, a, hsq, hsv)
+    assert rel_err(hsq, gq[:, rows, col_idx]) <= 1e-13 and rel_err(hsv, gv[:, rows, col_idx]) <= 1e-13
     # derivative of the CRBA mass matrix, contracted with a: d(M(q) a)/dq = dtau_dq(q, 0, a) - dtau_dq(q, 0, 0) (the second
     # term is pinocchio::computeGeneralizedGravityDerivatives) against a directional central difference of the CRBA kernel
     zs = _dev(torch, to_tiled(np.zeros((n, nv)), tile))
