@@ -598,7 +598,7 @@ static int aba_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, c
       int warps = 0;
       AbaArgs S{0, 32, nullptr, nullptr, nullptr, nullptr, nullptr};
       CK(launch_aba2(*ws->h_aba2, ws->d_aba2, S, ws->num_sms, &warps, st));
-      const size_t bytes = (size_t)warps * (size_t)(RBD_ABA2_REC * (dm.njoints - 1)) * 32 * sizeof(double);
+      const size_t bytes = (size_t)warps * (size_t)aba2_scratch_doubles(dm) * 32 * sizeof(double);
       cudaError_t e = cudaMalloc(&ws->aba2_scratch[sc], bytes > 0 ? bytes : 256);
       if (e != cudaSuccess) { cudaGetLastError(); return set_err(RBD_ERR_ALLOC, std::string("cudaMalloc(aba scratch): ") + cudaGetErrorString(e)); }
     }

@@ -156,7 +156,19 @@ inline size_t eval_model_bytes(const DevModelT<real>& m) {
   return (dev_model_bytes(m) + 15) / 16 * 16 + ((size_t)m.prog_len * 4 + 15) / 16 * 16 + 16;
 }
 
+#ifndef RBD_ABA2_V3
+#define RBD_ABA2_V3 1 /* 1: pass 3 recomputes A and c (FK + velocity recursion once more) instead of re-reading them: the
+                         per-joint record shrinks from 20 to 8 doubles (U, 1 / D, u), A | c of the joints on the current path
+                         wait in a small per-LEVEL record for the unwind (A/B: DESIGN.md §4.5) */
+#endif
+#if RBD_ABA2_V3
+#define RBD_ABA2_REC 8   /* doubles per joint of the global pass-3 record of the fused forward-dynamics sweep: U (6), 1 / D, u
+                            (root free-flyer: its solved acceleration in [0, 6)) */
+#define RBD_ABA2_LREC 12 /* ... and per depth level: A | c of the joint on the current path (root free-flyer: R | p) */
+#else
 #define RBD_ABA2_REC 20 /* doubles per joint of the global pass-3 record of the fused forward-dynamics sweep (rbd_dyn_body.h) */
+#define RBD_ABA2_LREC 0
+#endif
 #ifndef RBD_MINV_CB
 #define RBD_MINV_CB 6 /* columns of M^-1 one backward / forward sweep of minv_instance serves together (A/B r2: 8 spills) */
 #endif
@@ -164,6 +176,11 @@ inline size_t eval_model_bytes(const DevModelT<real>& m) {
 #define RBD_MINV_ROOT_REC 33 /* root free-flyer: R | p (12), (X^T I^A X)^-1 (21)                                              */
 // ... and the fused forward-dynamics kernel (aba2_kernel): the joint table rounded to 16 bytes plus the two spare words
 inline size_t aba2_model_bytes(const DevModelT<double>& m) { return (dev_model_bytes(m) + 15) / 16 * 16 + 16; }
+// doubles of global scratch per instance in flight of aba2_instance
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline int aba2_scratch_doubles(const DevModelT<double>& m) { return RBD_ABA2_REC * (m.njoints - 1) + RBD_ABA2_LREC * (m.max_depth + 1); }
 
 // 8-byte words the vector mapping kernels stage behind the joint table for the per-output tables of n_out outputs:
 // placements (12 doubles each), output indices and identity flags (one int each, padded to even counts)

@@ -154,7 +154,11 @@ RBD_HD void aba2_instance(const DevModel& m, const FLD& q, const FLD& v, const F
   if (nj > 1) RBD_ABA_PREFETCH(1);
   for (int i = 1; i < nj; ++i) {
     const DevJoint& jn = m.joint[i];
+#if RBD_ABA2_V3
+    const SCR Xi = X.at(RBD_ABA2_REC * (nj - 1) + RBD_ABA2_LREC * jn.depth);  // A | c (R | p) of the joint at this depth
+#else
     const SCR Xi = X.at(RBD_ABA2_REC * (i - 1));
+#endif
     const real q0c = nq0, qdc = nqd, tau0 = ntau;
     if (i + 1 < nj) RBD_ABA_PREFETCH(i + 1);
     const bool ff = jn.type == JT_FF;
@@ -229,11 +233,17 @@ RBD_HD void aba2_instance(const DevModel& m, const FLD& q, const FLD& v, const F
       const SCR Xc = X.at(RBD_ABA2_REC * (cur - 1));
       if (jc.type == JT_FF) {  // the root (the host checks that a free-flyer is joint 1 on the universe)
         real Rp[12], b[6], acc[6];
+#if RBD_ABA2_V3
+        const SCR Xl = X.at(RBD_ABA2_REC * (nj - 1) + RBD_ABA2_LREC * jc.depth);
+#pragma unroll
+        for (int e = 0; e < 12; ++e) Rp[e] = Xl.ld(e);
+#else
 #pragma unroll
         for (int e = 0; e < 12; ++e) Rp[e] = Xc.ld(e);
+#endif
         aba_ff_root_solve(m, Rp, IA, IA + 21, tau, jc.idx_v, b, acc);
 #pragma unroll
-        for (int e = 0; e < 6; ++e) { ddq.st(jc.idx_v + e, b[e]); Xc.st(12 + e, acc[e]); }
+        for (int e = 0; e < 6; ++e) { ddq.st(jc.idx_v + e, b[e]); Xc.st((RBD_ABA2_V3 ? 0 : 12) + e, acc[e]); }
         break;
       }
       const int pp = jc.parent;
@@ -244,7 +254,11 @@ RBD_HD void aba2_instance(const DevModel& m, const FLD& q, const FLD& v, const F
 #define RBD_ABA2_UNW 0
 #endif
       if (RBD_ABA2_UNW && fetch_parent) {
+#if RBD_ABA2_V3
+        const SCR Xp = X.at(RBD_ABA2_REC * (nj - 1) + RBD_ABA2_LREC * m.joint[pp].depth);
+#else
         const SCR Xp = X.at(RBD_ABA2_REC * (pp - 1));
+#endif
 #pragma unroll
         for (int e = 0; e < 6; ++e) { An[e] = Xp.ld(e); cn[e] = Xp.ld(6 + e); }
         taun = tau.ld(m.joint[pp].idx_v);
@@ -254,9 +268,9 @@ RBD_HD void aba2_instance(const DevModel& m, const FLD& q, const FLD& v, const F
       const real dinv = real(1) / dot6(A, U);
       const real u = tauc - dot6(A, IA + 21);
 #pragma unroll
-      for (int e = 0; e < 6; ++e) Xc.st(12 + e, U[e]);
-      Xc.st(18, dinv);
-      Xc.st(19, u);
+      for (int e = 0; e < 6; ++e) Xc.st((RBD_ABA2_V3 ? 0 : 12) + e, U[e]);
+      Xc.st(RBD_ABA2_V3 ? 6 : 18, dinv);
+      Xc.st(RBD_ABA2_V3 ? 7 : 19, u);
       if (pp == 0) break;
       // I^a = I^A - U U^T / D ;  p^a = p^A + I^a c + U u / D
 #pragma unroll
@@ -295,7 +309,11 @@ RBD_HD void aba2_instance(const DevModel& m, const FLD& q, const FLD& v, const F
           for (int e = 0; e < 6; ++e) { A[e] = An[e]; cr[e] = cn[e]; }
           tauc = taun;
         } else {
+#if RBD_ABA2_V3
+          const SCR Xp = X.at(RBD_ABA2_REC * (nj - 1) + RBD_ABA2_LREC * m.joint[pp].depth);
+#else
           const SCR Xp = X.at(RBD_ABA2_REC * (pp - 1));
+#endif
 #pragma unroll
           for (int e = 0; e < 6; ++e) { A[e] = Xp.ld(e); cr[e] = Xp.ld(6 + e); }
           tauc = tau.ld(m.joint[pp].idx_v);
@@ -320,6 +338,99 @@ RBD_HD void aba2_instance(const DevModel& m, const FLD& q, const FLD& v, const F
   }
 #undef RBD_ABA_PREFETCH
   // ---- pass 3 ----------------------------------------------------------------------------------------------------
+#if RBD_ABA2_V3
+  // The forward kinematics and the velocity recursion run once more (A, c recomputed: ~150 instructions per joint instead
+  // of 12 doubles written and read twice through a record that does not fit L2), the 8-double record [U | 1 / D | u] is
+  // all that comes back from global memory; joint angle and velocity are fetched one joint ahead as in pass 1.
+  real acc[6];
+  RBD_ABA_ROOT();
+#define RBD_ABA_PREFETCH3(J)                                                                                 \
+  do {                                                                                                       \
+    const DevJoint& jx_ = m.joint[J];                                                                        \
+    if (jx_.type != JT_FF) { nq0 = q.ld(jx_.idx_q); nqd = v.ld(jx_.idx_v); }                                 \
+  } while (0)
+#ifndef RBD_ABA2_P3V3
+#define RBD_ABA2_P3V3 0 /* 1: the record of the next joint is fetched while this one is stepped — measured slower (A/B s4a,
+                           Talos 2^20: 3.44 vs 3.31 ms), like every register prefetch in this sweep */
+#endif
+  real Bn[RBD_ABA2_REC];
+#define RBD_ABA_FETCH3(J)                                                                       \
+  do {                                                                                          \
+    const SCR Xn_ = X.at(RBD_ABA2_REC * ((J) - 1));                                             \
+    _Pragma("unroll") for (int e_ = 0; e_ < RBD_ABA2_REC; ++e_) Bn[e_] = Xn_.ld(e_);            \
+  } while (0)
+  if (nj > 1) { RBD_ABA_PREFETCH3(1); if (RBD_ABA2_P3V3) RBD_ABA_FETCH3(1); }
+  for (int i = 1; i < nj; ++i) {
+    const DevJoint& jn = m.joint[i];
+    const int par = jn.parent;
+    real B[RBD_ABA2_REC];
+    if (!RBD_ABA2_P3V3) RBD_ABA_FETCH3(i);
+#pragma unroll
+    for (int e = 0; e < RBD_ABA2_REC; ++e) B[e] = Bn[e];
+    if (RBD_ABA2_P3V3 && i + 1 < nj) RBD_ABA_FETCH3(i + 1);
+    if (par != i - 1) {  // a new branch: R | p | v of the joint it starts from (or the universe)
+      if (par == 0) {
+        RBD_ABA_ROOT();
+      } else {
+        real t[RBD_ABA2_RST];
+        lev_ld<RBD_ABA2_RST>(S, T, m.joint[par].boff, t);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) R[e] = t[e];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) p[e] = t[9 + e];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) vel[e] = t[12 + e];
+      }
+    }
+    const real q0c = nq0, qdc = nqd;
+    if (i + 1 < nj) RBD_ABA_PREFETCH3(i + 1);
+    const bool ff = jn.type == JT_FF;
+    real q0 = q0c, q1 = 0, aw[3];
+    if (!ff && is_unbounded(jn.type)) q1 = q.ld(jn.idx_q + 1);
+    fk_joint(jn, R, p, q0, q1, q, aw);
+    if (ff) {
+      real vj[6];
+      ff_act(R, p, v, jn.idx_v, vj);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) { vel[e] += vj[e]; acc[e] = B[e]; }
+    } else {
+      real A[6], vj[6], cr[6], tx, ty, tz;
+      subspace_1dof(jn.type, p, aw, A);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) { vj[e] = A[e] * qdc; vel[e] += vj[e]; }
+      RBD_CROSS(cr[0], cr[1], cr[2], vel[3], vel[4], vel[5], vj[0], vj[1], vj[2]);
+      RBD_CROSS(tx, ty, tz, vel[0], vel[1], vel[2], vj[3], vj[4], vj[5]);
+      cr[0] += tx; cr[1] += ty; cr[2] += tz;
+      RBD_CROSS(cr[3], cr[4], cr[5], vel[3], vel[4], vel[5], vj[3], vj[4], vj[5]);
+      if (par == 0) {
+        acc[0] = -m.gravity[0]; acc[1] = -m.gravity[1]; acc[2] = -m.gravity[2]; acc[3] = acc[4] = acc[5] = 0;
+      } else if (par != i - 1) {  // (else: acc still holds the parent's acceleration)
+        lev_ld<6>(S, T, m.joint[par].offA, acc);
+      }
+#pragma unroll
+      for (int e = 0; e < 6; ++e) acc[e] += cr[e];
+      const real qdd = (B[7] - dot6(B, acc)) * B[6];
+      ddq.st(jn.idx_v, qdd);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) acc[e] += A[e] * qdd;
+    }
+    if (jn.nchild >= 2) {
+      // (the restart record is written again: level records are shared by all joints of a depth, and a later joint of
+      // this depth has overwritten what passes 1 + 2 left there)
+      real t[RBD_ABA2_RST];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) t[e] = R[e];
+#pragma unroll
+      for (int e = 0; e < 3; ++e) t[9 + e] = p[e];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) t[12 + e] = vel[e];
+      lev_st<RBD_ABA2_RST>(S, T, jn.boff, t);
+      lev_st<6>(S, T, jn.offA, acc);
+    }
+  }
+#undef RBD_ABA_PREFETCH3
+#undef RBD_ABA_FETCH3
+#else
   // A chain of short dependent steps behind 20 loads each: the record of the next joint is fetched while this one is
   // stepped (two buffers in ping-pong: the loop is unrolled by two so that no buffer is ever copied).
   real acc[6];
@@ -381,6 +492,7 @@ RBD_HD void aba2_instance(const DevModel& m, const FLD& q, const FLD& v, const F
 #endif
 #undef RBD_ABA_STEP3
 #undef RBD_ABA_FETCH
+#endif  /* RBD_ABA2_V3 */
 #undef RBD_ABA_ROOT
 }
 

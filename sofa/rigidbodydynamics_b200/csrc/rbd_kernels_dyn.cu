@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256, 1) aba2_kernel(const DevModel* __restrict
   const DevModel& m = *c.m;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const long long gw = (long long)blockIdx.x * wpb + warp;
-  const GlobalRec X{a.scratch + gw * (long long)(RBD_ABA2_REC * (m.njoints - 1)) * 32 + lane};
+  const GlobalRec X{a.scratch + gw * (long long)aba2_scratch_doubles(m) * 32 + lane};
   const long long ntiles = (a.n + 31) / 32;
   for (long long t = gw; t < ntiles; t += (long long)gridDim.x * wpb) {
     long long inst = t * 32 + lane;

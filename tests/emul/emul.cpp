@@ -510,7 +510,7 @@ extern "C" int emul_aba2(const rbd_model_desc* d, long long n, long long tile, i
   const int bt = pl.warps * 32;
   std::vector<double> smem((size_t)(pl.smem_doubles > 0 ? pl.smem_doubles : 1) * bt, 1e300);
   std::vector<double> tmem((size_t)(pl.tmem_doubles > 0 ? pl.tmem_doubles : 1) * bt, 1e300);
-  const int E = RBD_ABA2_REC * (c.m.njoints - 1);
+  const int E = aba2_scratch_doubles(c.m);
   std::vector<double> scr((size_t)(E > 0 ? E : 1));
   for (long long i = 0; i < n; ++i) {
     const int t = (int)(i % bt);
