@@ -121,12 +121,13 @@ template <int NJ, class QC, class Ring, class Sink>
 RBD_HD void applyJT_arm_instance(const ArmParams<NJ>& m, const real* opl, const QC& q, Ring& ring, const Sink& sink) {
   real R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
   real A[NJ][6], part[NJ], Pre[6] = {0, 0, 0, 0, 0, 0};
-  real qn = q.ld(0);
+  real qv[NJ];  // all joint angles at once: NJ independent loads in flight instead of one round trip per joint
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) qv[i] = q.ld(i);
 #pragma unroll
   for (int i = 0; i < NJ; ++i) {
     const DevJoint& jn = m.joint[i];
-    const real q0 = qn;
-    if (i + 1 < NJ) qn = q.ld(i + 1);  // one joint ahead
+    const real q0 = qv[i];
     real aw[3];
     ::rbd::chain::fk_joint(jn, R, p, q0, real(0), q, aw);  // (qualified: `q` may be a type of namespace rbd, whose fk_joint ADL would find too)
     subspace_1dof(jn.type, p, aw, A[i]);
