@@ -643,6 +643,33 @@ def test_drnea_body_matches_oracle(emul, d, tile, body):
         assert list(plan) == [8, 96, 108, 156]
 
 
+@pytest.mark.parametrize("nmoving,free_flyer", [(40, False), (45, True), (63, False)])
+def test_drnea_deep_chains(emul, nmoving, free_flyer):
+    """Long serial chains: the hot level records no longer fit 8 warps per SM — the planner takes smaller blocks (levels in
+    shared AND tensor memory, more of each per thread) until they fit, and refuses (-100, RBD_ERR_UNSUPPORTED in the
+    library) when even one warp per SM cannot hold them.  Results against the oracle."""
+    import oracle
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    d = mdl.random_tree(100 + nmoving, nmoving, free_flyer=free_flyer, branch_prob=0.0, all_types=False)
+    cd, keep = _cdesc(d)
+    n, tile, nv = 5, 32, d.nv
+    q, v, a = mdl.random_state(d, n, seed=3)
+    DQ = np.full((1, nv * nv, tile), np.nan); DV = np.full((1, nv * nv, tile), np.nan)
+    plan = (C.c_int * 4)()
+    qs, vs, as_ = to_tiled(q, tile), to_tiled(v, tile), to_tiled(a, tile)      # (kept alive across the call)
+    rc = emul.emul_drnea(C.addressof(cd), n, tile, 1, 0, P(qs), P(vs), P(as_), P(DQ), P(DV), None, plan, 0)
+    if nmoving == 63:
+        assert rc == -100          # 62 levels x 18 doubles: more than one warp's share of shared + tensor memory
+        return
+    assert rc == 0, emul.emul_last_error()
+    assert 1 <= list(plan)[0] < 8
+    orc = oracle.Oracle(d)
+    gq = from_tiled(DQ, n)[:, :nv * nv].reshape(n, nv, nv); gv = from_tiled(DV, n)[:, :nv * nv].reshape(n, nv, nv)
+    for i in range(n):
+        rq, rv, _ = orc.rnea_derivatives(q[i], v[i], a[i])
+        assert rel_err(gq[i], rq) <= 1e-9 and rel_err(gv[i], rv) <= 1e-9, (i, rel_err(gq[i], rq), rel_err(gv[i], rv))
+
+
 @pytest.mark.parametrize("tile", [32, 13])
 @pytest.mark.parametrize("nj", [6, 7, 5])
 def test_arm_body_matches_oracle_and_generic_sweep(emul, tile, nj):

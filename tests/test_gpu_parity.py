@@ -1103,6 +1103,37 @@ def test_rnea_derivatives_match_oracle(torch_mod, api, d, tile):
     assert np.array_equal(hq, hq2) and np.array_equal(hv, hv2)
 
 
+@pytest.mark.parametrize("nmoving,free_flyer", [(40, False), (45, True), (63, False)])
+def test_rnea_derivatives_deep_chains(torch_mod, api, nmoving, free_flyer):
+    """Long serial chains through the C ABI: the hot level records force blocks of fewer than 8 warps (more shared and
+    tensor memory per thread); a 63-joint chain fits no block at all: RBD_ERR_UNSUPPORTED, not a wrong result."""
+    import oracle
+    torch = torch_mod
+    from sofa.rigidbodydynamics_b200 import model as mdl
+    d = mdl.random_tree(100 + nmoving, nmoving, free_flyer=free_flyer, branch_prob=0.0, all_types=False)
+    n, tile, nv = 100, 32, d.nv
+    q, v, a = mdl.random_state(d, n, seed=3)
+    m = api.Model(d); ws = api.Workspace(m, n)
+    nt = (n + tile - 1) // tile
+    qs, vs, as_ = (_dev(torch, to_tiled(x, tile)) for x in (q, v, a))
+    DQ = torch.full((nt, nv * nv, tile), float("nan"), dtype=torch.float64, device="cuda")
+    DV = torch.full((nt, nv * nv, tile), float("nan"), dtype=torch.float64, device="cuda")
+    if nmoving == 63:
+        with pytest.raises(api.RbdError) as e:
+            ws.rnea_derivatives_soa(n, tile, qs, vs, as_, DQ, DV, None)
+        assert e.value.code == -5
+        return
+    ws.rnea_derivatives_soa(n, tile, qs, vs, as_, DQ, DV, None)
+    ws.synchronize()
+    gq = from_tiled(DQ.cpu().numpy(), n)[:, :nv * nv].reshape(n, nv, nv)
+    gv = from_tiled(DV.cpu().numpy(), n)[:, :nv * nv].reshape(n, nv, nv)
+    assert np.isfinite(gq).all() and np.isfinite(gv).all()
+    orc = oracle.Oracle(d)
+    for i in (0, 31, 32, n - 1):
+        rq, rv, _ = orc.rnea_derivatives(q[i], v[i], a[i])
+        assert rel_err(gq[i], rq) <= 1e-9 and rel_err(gv[i], rv) <= 1e-9, i
+
+
 def test_dynamics_entry_points_refuse_a_free_flyer_below_the_root(torch_mod, api):
     """aba / minv / rnea_derivatives support a free-flyer as joint 1 on the universe only: anything else is
     RBD_ERR_UNSUPPORTED with a message, not a wrong result (the fused eval and the mapping path do support it)."""
