@@ -437,7 +437,8 @@ def test_no_out_of_bounds_writes(torch_mod, api, name, n, tile):
     G = 4096                                         # guard doubles
     sizes = {"q": I.nq, "v": I.nv, "a": I.nv, "oMi": I.omi_fields, "J": I.jac_fields, "M": I.mass_fields, "tau": I.nv,
              "qj": I.nq_joints, "root": 7, "dq": I.nv_joints, "rootv": 6, "pos": 7 * I.n_out, "vel": 6 * I.n_out,
-             "w": 6 * I.n_out, "tj": I.nv_joints, "tr": 6}
+             "w": 6 * I.n_out, "tj": I.nv_joints, "tr": 6,
+             "DQ": I.nv * I.nv, "DV": I.nv * I.nv, "SQ": max(1, len(m.drnea_pattern()[1])), "SV": max(1, len(m.drnea_pattern()[1]))}
     total = G + sum(nt * K * tile + G for K in sizes.values())
     SENT = -7.25e300
     arena = torch.full((total,), SENT, dtype=torch.float64, device="cuda")
@@ -471,6 +472,10 @@ def test_no_out_of_bounds_writes(torch_mod, api, name, n, tile):
             ws.set_aba_fused(fused)
             ws.aba_soa(n, tile, views["q"], views["v"], views["a"], views["tau"])
         ws.minv_soa(n, tile, views["q"], views["M"])
+        # derivatives of inverse dynamics, dense (with and without M) and support-only
+        ws.rnea_derivatives_soa(n, tile, views["q"], views["v"], views["a"], views["DQ"], views["DV"], views["M"])
+        ws.rnea_derivatives_soa(n, tile, views["q"], views["v"], views["a"], views["DQ"], views["DV"], None)
+        ws.rnea_derivatives_soa_sparse(n, tile, views["q"], views["v"], views["a"], views["SQ"], views["SV"])
     nrows = n + 3
     rp = torch.arange(0, 2 * nrows + 1, 2, dtype=torch.int32, device="cuda")
     ri = (torch.arange(0, nrows, dtype=torch.int32, device="cuda") % n).contiguous()
@@ -495,7 +500,7 @@ def test_no_out_of_bounds_writes(torch_mod, api, name, n, tile):
         assert bool((band == SENT).all()), f"guard band after '{k}' was written"
         off += G
     # and the live part of every output was written
-    for k in ("oMi", "J", "M", "tau", "pos", "vel"):
+    for k in ("oMi", "J", "M", "tau", "pos", "vel") + (("DQ", "DV", "SQ", "SV") if mdl_ok and d.nv > 0 else ()):
         live = from_tiled(views[k].cpu().numpy(), n)
         assert not np.any(live == SENT), k
 
