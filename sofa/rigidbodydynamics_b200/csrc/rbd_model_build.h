@@ -305,6 +305,14 @@ inline bool plan_eval(DevModel* m, bool do_m, bool do_tau, bool use_tmem, int fo
   if (ok && RBD_USE_FFROOT8 && elem_bytes == 8 && !jt && do_m && do_tau && forced_warps == 0 && m->eval_variant == RBD_EVAL_FFROOT &&
       regs_per_thread == B200Limits::kRegsPerThread)
     m->plan.kvariant = RBD_EVAL_FFROOT8;
+#ifndef RBD_RNEA_FFROOT
+#define RBD_RNEA_FFROOT 1
+#endif
+  // the RNEA-only instantiation (rnea, Mass / ForceField products) of a floating-base robot: the ffroot sweep too (168
+  // registers, the same 12-warp blocks as the 170-register simple kernel)
+  if (ok && RBD_RNEA_FFROOT && elem_bytes == 8 && !jt && !do_m && do_tau && forced_warps == 0 && m->eval_variant == RBD_EVAL_FFROOT &&
+      regs_per_thread == B200Limits::kRegsPerThread)
+    m->plan.kvariant = RBD_EVAL_FFROOT;
   return ok;
 }
 // wide_warps > 0: blocks of up to that many warps at regs_per_thread registers (the caller vouches for the kernel)
