@@ -111,7 +111,7 @@ RBD_HD void dr_own(const real* Y, const real* vel, const real* acc, real* C) {
 #define RBD_DR_ROWBASE(j) ((j).slot[0])
 #define RBD_DR_NANC(j) ((j).slot[1])
 #define RBD_DR_ROWLEN(j) ((j).out_begin)
-template <bool SPARSE, class FLD>
+template <bool SPARSE, bool WITH_M, class FLD>
 RBD_HD void dr_pop_1dof(const DevModel& m, int cur, const real* A, const real* va, const real* C, const FLD& DQ,
                         const FLD& DV, const FLD& M, const Stack& S, const TmStack& T) {
   const DevJoint& jc = m.joint[cur];
@@ -146,7 +146,7 @@ RBD_HD void dr_pop_1dof(const DevModel& m, int cur, const real* A, const real* v
   }
   DV.st(rowj + (SPARSE ? RBD_DR_NANC(jc) : iv), dot6(A, dFv));
   DQ.st(rowj + (SPARSE ? RBD_DR_NANC(jc) : iv), dot6(A, dFq));
-  if (M.ok()) M.st(iv * (iv + 1) / 2 + iv, dot6(A, u));
+  if (WITH_M) M.st(iv * (iv + 1) / 2 + iv, dot6(A, u));
   {
     real t[6];
     mxf(A, F, t);
@@ -162,7 +162,7 @@ RBD_HD void dr_pop_1dof(const DevModel& m, int cur, const real* A, const real* v
       for (int c = ik + jk.nv; c < prev; ++c) {
         DQ.st(iv * nv + c, real(0)); DV.st(iv * nv + c, real(0));
         DQ.st(c * nv + iv, real(0)); DV.st(c * nv + iv, real(0));
-        if (M.ok()) M.st(iv * (iv + 1) / 2 + c, real(0));
+        if (WITH_M) M.st(iv * (iv + 1) / 2 + c, real(0));
       }
     }
     prev = ik;
@@ -180,7 +180,7 @@ RBD_HD void dr_pop_1dof(const DevModel& m, int cur, const real* A, const real* v
       ff_rows(Rp, Rp + 9, dFv, o);
 #pragma unroll
       for (int e = 0; e < 6; ++e) DV.st(ckj + e * ckstep, o[e]);
-      if (M.ok()) {
+      if (WITH_M) {
         ff_rows(Rp, Rp + 9, u, o);
 #pragma unroll
         for (int e = 0; e < 6; ++e) M.st(iv * (iv + 1) / 2 + ik + e, o[e]);
@@ -218,7 +218,7 @@ RBD_HD void dr_pop_1dof(const DevModel& m, int cur, const real* A, const real* v
     for (int e = 0; e < 6; ++e) dAk[e] += t[e];
     DQ.st(ckj, dot6(Jk, dFq));
     DV.st(ckj, dot6(Jk, dFv));
-    if (M.ok()) M.st(iv * (iv + 1) / 2 + ik, dot6(Jk, u));
+    if (WITH_M) M.st(iv * (iv + 1) / 2 + ik, dot6(Jk, u));
     DQ.st(rowj + rjk, dot6(u, dAk) + dot6(w, dVk));
     DV.st(rowj + rjk, 2 * dot6(u, dVk) + dot6(w, Jk));
     k = kp;
@@ -227,13 +227,13 @@ RBD_HD void dr_pop_1dof(const DevModel& m, int cur, const real* A, const real* v
     for (int c = 0; c < prev; ++c) {
       DQ.st(iv * nv + c, real(0)); DV.st(iv * nv + c, real(0));
       DQ.st(c * nv + iv, real(0)); DV.st(c * nv + iv, real(0));
-      if (M.ok()) M.st(iv * (iv + 1) / 2 + c, real(0));
+      if (WITH_M) M.st(iv * (iv + 1) / 2 + c, real(0));
     }
   }
 }
 
 // ... and the root free-flyer's own 6 x 6 blocks: dVdq = 0, dAdq_c = a0 x J_c, dAdv_c = v x J_c (parent = universe)
-template <bool SPARSE, class FLD>
+template <bool SPARSE, bool WITH_M, class FLD>
 RBD_HD void dr_pop_ff(const DevModel& m, int cur, const real* Rp, const real* vel, const real* C, const FLD& DQ,
                       const FLD& DV, const FLD& M) {
   const DevJoint& jc = m.joint[cur];
@@ -267,7 +267,7 @@ RBD_HD void dr_pop_ff(const DevModel& m, int cur, const real* Rp, const real* ve
     ff_rows(Rp, Rp + 9, dF, o);
 #pragma unroll
     for (int r = 0; r < 6; ++r) DQ.st(blk + r * rstep + cc, o[r]);
-    if (M.ok()) {
+    if (WITH_M) {
       inertia_mul(Yc, Jc, dF);
       ff_rows(Rp, Rp + 9, dF, o);
 #pragma unroll
@@ -276,7 +276,9 @@ RBD_HD void dr_pop_ff(const DevModel& m, int cur, const real* Rp, const real* ve
   }
 }
 
-template <bool SPARSE, class FLD, class SCR>
+// WITH_M: the M output is requested (dense format only); compiled out otherwise — at 255 registers the dead stores and
+// their addresses cost 10 % (A/B s4h)
+template <bool SPARSE, bool WITH_M, class FLD, class SCR>
 RBD_HD void drnea_instance(const DevModel& m, const FLD& q, const FLD& v, const FLD& a, const FLD& DQ, const FLD& DV,
                            const FLD& M, const SCR& X, const Stack& S, const TmStack& T, const InRing& inr) {
   const int nj = m.njoints;
@@ -393,7 +395,7 @@ RBD_HD void drnea_instance(const DevModel& m, const FLD& q, const FLD& v, const 
           lev_ld<12>(S, T, jc.offA + 12, Rp);
           lev_ld<6>(S, T, jc.offA, vr);
         }
-        dr_pop_ff<SPARSE>(m, cur, Rp, vr, C, DQ, DV, M);
+        dr_pop_ff<SPARSE, WITH_M>(m, cur, Rp, vr, C, DQ, DV, M);
         break;  // (the host checks that a free-flyer is joint 1 on the universe)
       }
       const int pp = jc.parent;
@@ -407,7 +409,7 @@ RBD_HD void drnea_instance(const DevModel& m, const FLD& q, const FLD& v, const 
         for (int e = 0; e < 9; ++e) cp_async_real(inr, 3 * RBD_DR_SLOTS + e, Xp.ptr(e));
         cp_async_commit();
       }
-      dr_pop_1dof<SPARSE>(m, cur, A, va, C, DQ, DV, M, S, T);
+      dr_pop_1dof<SPARSE, WITH_M>(m, cur, A, va, C, DQ, DV, M, S, T);
       if (pp == 0) break;
       const DevJoint& jp = m.joint[pp];
       const SCR Xp = X.at(jp.boff);

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256, 1) minv_kernel(const DevModel* __restrict
 
 // Derivatives of inverse dynamics (drnea_instance, rbd_deriv_body.h): same launch shape; every level record is on chip,
 // the only global traffic is q, v, a in and the two nv x nv matrices (+ optional packed M) out
-template <int TILE, bool SPARSE>
+template <int TILE, bool SPARSE, bool WITH_M>
 __global__ void __launch_bounds__(256, 1) drnea_kernel(const DevModel* __restrict__ gm, const int model_words, const DrneaArgs a) {
   const DynCtx c = dyn_prologue(gm, model_words);
   const DevModel& m = *c.m;
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256, 1) drnea_kernel(const DevModel* __restric
     long long inst = t * 32 + lane;
     if (inst >= a.n) inst = a.n - 1;  // lanes past the end recompute the last instance (same values to the same addresses)
     const int K = SPARSE ? m.slot_total[1] : nv * nv;
-    drnea_instance<SPARSE>(m, make_field_t<TILE>(const_cast<double*>(a.q), inst, m.nq, a.tile),
+    drnea_instance<SPARSE, WITH_M>(m, make_field_t<TILE>(const_cast<double*>(a.q), inst, m.nq, a.tile),
                    make_field_t<TILE>(const_cast<double*>(a.v), inst, nv, a.tile),
                    make_field_t<TILE>(const_cast<double*>(a.a), inst, nv, a.tile),
                    make_field_t<TILE>(a.dtau_dq, inst, K, a.tile), make_field_t<TILE>(a.dtau_dv, inst, K, a.tile),
@@ -226,16 +226,20 @@ cudaError_t launch_drnea(const DevModel& hm, const DevModel* d_model, const Drne
   if (scratch_warps) *scratch_warps = num_sms * W;
   if (!a.scratch || a.n <= 0) return cudaSuccess;
   const size_t smem = (size_t)mw * 8 + (size_t)W * 32 * hm.plan.smem_doubles * 8;
-  static thread_local bool attr_done[4] = {false, false, false, false};
+  static thread_local bool attr_done[6] = {false, false, false, false, false, false};
   cudaError_t e = cudaSuccess;
-#define RBD_DR_LAUNCH(T_, S_, slot_)                                                                              \
+#define RBD_DR_LAUNCH(T_, S_, M_, slot_)                                                                          \
   do {                                                                                                            \
-    if (!attr_done[slot_]) { e = dyn_attr(drnea_kernel<T_, S_>); if (e != cudaSuccess) return e; attr_done[slot_] = true; } \
-    note_kernel(reinterpret_cast<const void*>(drnea_kernel<T_, S_>));                                             \
-    drnea_kernel<T_, S_><<<(unsigned)grid, block, smem, st>>>(d_model, mw, a);                                    \
+    if (!attr_done[slot_]) { e = dyn_attr(drnea_kernel<T_, S_, M_>); if (e != cudaSuccess) return e; attr_done[slot_] = true; } \
+    note_kernel(reinterpret_cast<const void*>(drnea_kernel<T_, S_, M_>));                                         \
+    drnea_kernel<T_, S_, M_><<<(unsigned)grid, block, smem, st>>>(d_model, mw, a);                                \
   } while (0)
-  if (a.tile == 32) { if (a.sparse) RBD_DR_LAUNCH(32, true, 3); else RBD_DR_LAUNCH(32, false, 1); }
-  else { if (a.sparse) RBD_DR_LAUNCH(0, true, 2); else RBD_DR_LAUNCH(0, false, 0); }
+  const bool with_m = a.M != nullptr && !a.sparse;
+  if (a.tile == 32) {
+    if (a.sparse) RBD_DR_LAUNCH(32, true, false, 3); else if (with_m) RBD_DR_LAUNCH(32, false, true, 5); else RBD_DR_LAUNCH(32, false, false, 1);
+  } else {
+    if (a.sparse) RBD_DR_LAUNCH(0, true, false, 2); else if (with_m) RBD_DR_LAUNCH(0, false, true, 4); else RBD_DR_LAUNCH(0, false, false, 0);
+  }
 #undef RBD_DR_LAUNCH
   return cudaGetLastError();
 }

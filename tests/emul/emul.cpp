@@ -593,11 +593,14 @@ extern "C" int emul_drnea(const rbd_model_desc* d, long long n, long long tile, 
     TmStack T{tmem.data() + (size_t)t * (pl.tmem_doubles > 0 ? pl.tmem_doubles : 1)};
     const int K = sparse ? c.m.slot_total[1] : nv * nv;
     if (sparse)
-      drnea_instance<true>(c.m, make_field(q, i, c.m.nq, tile), make_field(v, i, nv, tile), make_field(a, i, nv, tile),
-                           make_field(DQ, i, K, tile), make_field(DV, i, K, tile), make_field(nullptr, i, 1, tile), X, S, T, InRing());
+      drnea_instance<true, false>(c.m, make_field(q, i, c.m.nq, tile), make_field(v, i, nv, tile), make_field(a, i, nv, tile),
+                                  make_field(DQ, i, K, tile), make_field(DV, i, K, tile), make_field(nullptr, i, 1, tile), X, S, T, InRing());
+    else if (M)
+      drnea_instance<false, true>(c.m, make_field(q, i, c.m.nq, tile), make_field(v, i, nv, tile), make_field(a, i, nv, tile),
+                                  make_field(DQ, i, K, tile), make_field(DV, i, K, tile), make_field(M, i, nv * (nv + 1) / 2, tile), X, S, T, InRing());
     else
-      drnea_instance<false>(c.m, make_field(q, i, c.m.nq, tile), make_field(v, i, nv, tile), make_field(a, i, nv, tile),
-                            make_field(DQ, i, K, tile), make_field(DV, i, K, tile), make_field(M, i, nv * (nv + 1) / 2, tile), X, S, T, InRing());
+      drnea_instance<false, false>(c.m, make_field(q, i, c.m.nq, tile), make_field(v, i, nv, tile), make_field(a, i, nv, tile),
+                                   make_field(DQ, i, K, tile), make_field(DV, i, K, tile), make_field(nullptr, i, 1, tile), X, S, T, InRing());
   }
   return 0;
 }
