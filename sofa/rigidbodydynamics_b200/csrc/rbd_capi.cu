@@ -431,6 +431,13 @@ static int eval_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, 
                    const double* a, double* oMi, double* J, double* M, double* tau, bool sparse_m = false) {
   if (!q) return set_err(RBD_ERR_INVALID_ARG, "q is null");
   if (tau && (!v || !a)) return set_err(RBD_ERR_INVALID_ARG, "rnea needs v and a");
+  if (tau && !M && (oMi || J)) {
+    // tau with oMi / J but without M: the RNEA-only instantiation has no oMi / J stores compiled in (rbd_sweeps_body.h,
+    // RBD_MF_NO_OMIJ) — the FK + Jacobian sweep writes them, then the RNEA sweep runs alone
+    int rc2 = eval_on(ws, st, n, tile, q, nullptr, nullptr, oMi, J, nullptr, nullptr);
+    if (rc2 == RBD_OK) rc2 = eval_on(ws, st, n, tile, q, v, a, nullptr, nullptr, nullptr, tau);
+    return rc2;
+  }
   const int ek = (oMi ? 4 : 0) | (M ? 2 : 0) | (tau ? 1 : 0);
   // fixed-base serial chains of 6 / 7 joints, M and tau requested: the unrolled sweep with the joint table in the constant
   // bank (rbd_kernels_arm.cu).  A chain's M has no structural zeros: the support-only format is the same array.
@@ -504,6 +511,11 @@ RBD_API int rbd_eval_soa_f32(rbd_workspace* ws, int64_t n, int64_t tile, const f
   if (rc) return rc;
   if (!q) return set_err(RBD_ERR_INVALID_ARG, "q is null");
   if (tau && (!v || !a)) return set_err(RBD_ERR_INVALID_ARG, "rnea needs v and a");
+  if (tau && !M && (oMi || J)) {  // as in the FP64 path: FK + Jacobian sweep, then the RNEA sweep alone
+    rc = rbd_eval_soa_f32(ws, n, tile, q, nullptr, nullptr, oMi, J, nullptr, nullptr);
+    if (rc == RBD_OK) rc = rbd_eval_soa_f32(ws, n, tile, q, v, a, nullptr, nullptr, nullptr, tau);
+    return rc;
+  }
   const int pk = (oMi ? 4 : 0) | (M ? 2 : 0) | (tau ? 1 : 0);
   rc = ensure_plan32(ws, pk);
   if (rc) return rc;

@@ -863,6 +863,13 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
 #define RBD_F_OFF(lvl) ((lvl) >= fsplit ? ftbase + 6 * ((lvl)-fsplit) : fbase + 6 * (lvl))
   real R[9], p[3], vel[6], acc[6];
   constexpr bool MF = DO_TAU && !DO_M;  // Mass / ForceField switches live in the RNEA-only instantiation
+  // The RNEA-only instantiation never writes oMi / J (the C API serves "tau + oMi / J without M" with two launches): their
+  // stores and addresses are compiled out instead of predicated off — at 168 registers that is worth 4-5 % (A/B s4j:
+  // Talos 2^20 rnea 1.056 -> 1.009 ms, addMDx 0.927 -> 0.879 ms)
+#ifndef RBD_MF_NO_OMIJ
+#define RBD_MF_NO_OMIJ 1
+#endif
+#define RBD_OMIJ(F) ((!RBD_MF_NO_OMIJ || !MF) && (F).ok())
   const real gs_ = (MF && !io.gravity_on) ? real(0) : real(1);
   const bool has_v = !MF || io.v.ok();  // (uniform) the Mass / ForceField products without a velocity skip its terms
 #define RBD_RESET_ROOT()                                                   \
@@ -1029,7 +1036,7 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
 
     real aw[3];
     fk_joint<RBD_EMIT_CUR(ffj)>(jn, R, p, q0, q1, io.q, aw);
-    if (io.oMi.ok()) {
+    if (RBD_OMIJ(io.oMi)) {
 #if RBD_PTR_OMIJ
       real* const po = io.oMi.at(12 * (i - 1));
       if (jn.boff & RBD_BOFF_RPOMI) {  // this record is re-read when the sweep returns to joint i: keep it in L2
@@ -1055,7 +1062,7 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
     RBD_STEP_STATE
     if (!RBD_CUR_FF(ffj, jn.type)) {
       subspace_1dof(jn.type, p, aw, Ak);
-      if (io.J.ok()) {
+      if (RBD_OMIJ(io.J)) {
 #if RBD_PTR_OMIJ
         real* const pj = io.J.at(6 * jn.idx_v);
 #pragma unroll
@@ -1089,7 +1096,7 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
       for (int e = 0; e < 9; ++e) Ak[e] = R[e];
 #pragma unroll
       for (int e = 0; e < 3; ++e) Ak[9 + e] = p[e];
-      if (io.J.ok()) {
+      if (RBD_OMIJ(io.J)) {
         real* const pj = io.J.at(6 * jn.idx_v);
 #pragma unroll
         for (int cc = 0; cc < 6; ++cc) {
