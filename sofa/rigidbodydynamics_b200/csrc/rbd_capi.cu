@@ -431,11 +431,11 @@ static int eval_on(rbd_workspace* ws, cudaStream_t st, int64_t n, int64_t tile, 
                    const double* a, double* oMi, double* J, double* M, double* tau, bool sparse_m = false) {
   if (!q) return set_err(RBD_ERR_INVALID_ARG, "q is null");
   if (tau && (!v || !a)) return set_err(RBD_ERR_INVALID_ARG, "rnea needs v and a");
-  if (tau && !M && (oMi || J)) {
-    // tau with oMi / J but without M: the RNEA-only instantiation has no oMi / J stores compiled in (rbd_sweeps_body.h,
-    // RBD_MF_NO_OMIJ) — the FK + Jacobian sweep writes them, then the RNEA sweep runs alone
+  if ((tau != nullptr) != (M != nullptr) && (oMi || J)) {
+    // tau or M alone with oMi / J: the single-algorithm instantiations have no oMi / J stores compiled in
+    // (rbd_sweeps_body.h, RBD_MF_NO_OMIJ) — the FK + Jacobian sweep writes them, then the RNEA / CRBA sweep runs alone
     int rc2 = eval_on(ws, st, n, tile, q, nullptr, nullptr, oMi, J, nullptr, nullptr);
-    if (rc2 == RBD_OK) rc2 = eval_on(ws, st, n, tile, q, v, a, nullptr, nullptr, nullptr, tau);
+    if (rc2 == RBD_OK) rc2 = eval_on(ws, st, n, tile, q, v, a, nullptr, nullptr, M, tau, sparse_m);
     return rc2;
   }
   const int ek = (oMi ? 4 : 0) | (M ? 2 : 0) | (tau ? 1 : 0);
@@ -511,9 +511,9 @@ RBD_API int rbd_eval_soa_f32(rbd_workspace* ws, int64_t n, int64_t tile, const f
   if (rc) return rc;
   if (!q) return set_err(RBD_ERR_INVALID_ARG, "q is null");
   if (tau && (!v || !a)) return set_err(RBD_ERR_INVALID_ARG, "rnea needs v and a");
-  if (tau && !M && (oMi || J)) {  // as in the FP64 path: FK + Jacobian sweep, then the RNEA sweep alone
+  if ((tau != nullptr) != (M != nullptr) && (oMi || J)) {  // as in the FP64 path: FK + Jacobian sweep, then RNEA / CRBA alone
     rc = rbd_eval_soa_f32(ws, n, tile, q, nullptr, nullptr, oMi, J, nullptr, nullptr);
-    if (rc == RBD_OK) rc = rbd_eval_soa_f32(ws, n, tile, q, v, a, nullptr, nullptr, nullptr, tau);
+    if (rc == RBD_OK) rc = rbd_eval_soa_f32(ws, n, tile, q, v, a, nullptr, nullptr, M, tau);
     return rc;
   }
   const int pk = (oMi ? 4 : 0) | (M ? 2 : 0) | (tau ? 1 : 0);

@@ -863,13 +863,13 @@ RBD_HD void eval_instance(const DevModel& m, const EvalIOT<TILE>& io, const Stac
 #define RBD_F_OFF(lvl) ((lvl) >= fsplit ? ftbase + 6 * ((lvl)-fsplit) : fbase + 6 * (lvl))
   real R[9], p[3], vel[6], acc[6];
   constexpr bool MF = DO_TAU && !DO_M;  // Mass / ForceField switches live in the RNEA-only instantiation
-  // The RNEA-only instantiation never writes oMi / J (the C API serves "tau + oMi / J without M" with two launches): their
-  // stores and addresses are compiled out instead of predicated off — at 168 registers that is worth 4-5 % (A/B s4j:
-  // Talos 2^20 rnea 1.056 -> 1.009 ms, addMDx 0.927 -> 0.879 ms)
+  // The single-algorithm instantiations (RNEA only, CRBA only) never write oMi / J (the C API serves "tau or M alone + oMi /
+  // J" with two launches): their stores and addresses are compiled out instead of predicated off — at 168 registers that
+  // is worth 4-5 % (A/B s4j: Talos 2^20 rnea 1.056 -> 1.009 ms, addMDx 0.927 -> 0.879 ms)
 #ifndef RBD_MF_NO_OMIJ
 #define RBD_MF_NO_OMIJ 1
 #endif
-#define RBD_OMIJ(F) ((!RBD_MF_NO_OMIJ || !MF) && (F).ok())
+#define RBD_OMIJ(F) ((!RBD_MF_NO_OMIJ || (DO_M == DO_TAU)) && (F).ok())
   const real gs_ = (MF && !io.gravity_on) ? real(0) : real(1);
   const bool has_v = !MF || io.v.ok();  // (uniform) the Mass / ForceField products without a velocity skip its terms
 #define RBD_RESET_ROOT()                                                   \

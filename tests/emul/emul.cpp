@@ -175,10 +175,10 @@ extern "C" int emul_eval_plan(const rbd_model_desc* d, int do_m, int do_tau, int
 extern "C" int emul_eval_ex(const rbd_model_desc* d, long long n, long long tile, int block, int use_tmem, double* q,
                             double* v, double* a, double* oMi, double* J, double* M, double* tau, int sparse_m,
                             int variant) {
-  if (tau && !M && (oMi || J)) {
-    // as the library does (rbd_capi.cu eval_on): the RNEA-only instantiation has no oMi / J stores compiled in
+  if ((tau != nullptr) != (M != nullptr) && (oMi || J)) {
+    // as the library does (rbd_capi.cu eval_on): the single-algorithm instantiations have no oMi / J stores compiled in
     int rc2 = emul_eval_ex(d, n, tile, block, use_tmem, q, nullptr, nullptr, oMi, J, nullptr, nullptr, 0, variant);
-    if (rc2 == 0) rc2 = emul_eval_ex(d, n, tile, block, use_tmem, q, v, a, nullptr, nullptr, nullptr, tau, 0, variant);
+    if (rc2 == 0) rc2 = emul_eval_ex(d, n, tile, block, use_tmem, q, v, a, nullptr, nullptr, M, tau, sparse_m, variant);
     return rc2;
   }
   Ctx c;
