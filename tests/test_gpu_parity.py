@@ -522,7 +522,9 @@ def test_deep_and_bushy_trees(torch_mod, api, nmoving, branch_prob, ff):
             # without tensor memory the 62-joint chain's state exceeds one SM even for the split sweeps: a clean error
             assert e.code == -5 and not tmem and nmoving >= 60 and branch_prob == 0.0, str(e)
             continue
-        assert launches in (1, 2)       # 2 = the fused sweep did not fit and ran as CRBA + RNEA halves
+        # 3 = the fused sweep did not fit and ran as FK + Jacobian, CRBA and RNEA sweeps (the single-algorithm
+        # instantiations have no oMi / J stores compiled in)
+        assert launches in (1, 3)
         for k in ("oMi", "J", "M", "tau"):
             assert rel_err(got[k], ref[k]) <= TOL_FP64, (k, tmem)
     # mapping path on the same model
