@@ -222,3 +222,18 @@ inline int aba_scratch_doubles(const DevModel& m) { return RBD_ABA_REC * (m.njoi
 #define RBD_BRANCH_EVAL 24 /* R(9) p(3) v(6) a(6) */
 #define RBD_BRANCH_FK 12   /* R(9) p(3) */
 #define RBD_BRANCH_J 18    /* R(9) p(3) V(6) */
+
+// Warps per block of ONE launch of a persistent one-block-per-SM kernel planned for W warps (<= W): the time of a tile
+// grows almost linearly with the warps sharing the SM (t(w) ~ c + k w, c / k ~ 2.5: measured on the Panda eval,
+// rbd_kernels_arm.cu), so a batch of only a few tiles per warp is fastest with the block size that leaves the fewest warps
+// idle in the last round (N = 65 536 = 2 048 tiles: two full rounds of 7-warp blocks, but 1.15 rounds of 12-warp blocks).
+inline int pick_warps_per_block(int W, long long ntiles, int num_sms) {
+  int wpb = W;
+  double best = 0;
+  for (int w = W; w >= 4; --w) {
+    const long long rounds = (ntiles + (long long)num_sms * w - 1) / ((long long)num_sms * w);
+    const double cost = (double)rounds * (2.5 + w);
+    if (w == W || cost < best - 1e-9) { best = cost; wpb = w; }
+  }
+  return wpb;
+}

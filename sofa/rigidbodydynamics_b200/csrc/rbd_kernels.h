@@ -115,20 +115,6 @@ cudaError_t launch_aba(const DevModel& m, const DevModel* d_model, const AbaArgs
 // copy; a.scratch holds RBD_ABA2_REC * (njoints - 1) * 32 doubles per resident warp (sizing call as above)
 cudaError_t launch_aba2(const DevModel& planned_host_model, const DevModel* d_model, const AbaArgs& a, int num_sms,
                         int* scratch_warps, cudaStream_t st);
-// Warps per block of ONE launch of a persistent one-block-per-SM kernel planned for W warps (<= W): the time of a tile
-// grows almost linearly with the warps sharing the SM (t(w) ~ c + k w, c / k ~ 2.5: measured on the Panda eval,
-// rbd_kernels_arm.cu), so a batch of only a few tiles per warp is fastest with the block size that leaves the fewest warps
-// idle in the last round (N = 65 536 = 2 048 tiles: two full rounds of 7-warp blocks, but 1.15 rounds of 12-warp blocks).
-inline int pick_warps_per_block(int W, long long ntiles, int num_sms) {
-  int wpb = W;
-  double best = 0;
-  for (int w = W; w >= 4; --w) {
-    const long long rounds = (ntiles + (long long)num_sms * w - 1) / ((long long)num_sms * w);
-    const double cost = (double)rounds * (2.5 + w);
-    if (w == W || cost < best - 1e-9) { best = cost; wpb = w; }
-  }
-  return wpb;
-}
 // derivatives of inverse dynamics (drnea_instance): `planned_host_model` planned with plan_drnea; sizing call as launch_aba
 cudaError_t launch_drnea(const DevModel& planned_host_model, const DevModel* d_model, const DrneaArgs& a, int num_sms,
                          int* scratch_warps, cudaStream_t st);

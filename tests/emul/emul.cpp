@@ -563,6 +563,9 @@ extern "C" int emul_minv(const rbd_model_desc* d, long long n, long long tile, i
   return 0;
 }
 
+// block size of one launch of a persistent kernel planned for W warps (rbd_dev_model.h)
+extern "C" int emul_pick_wpb(int W, long long ntiles, int num_sms) { return pick_warps_per_block(W, ntiles, num_sms); }
+
 // derivatives of inverse dynamics (drnea_instance): DQ, DV nv x nv row-major fields, M (optional) packed upper triangle;
 // level records on the plan of plan_drnea, storage as emul_aba2 (poisoned between instances)
 // sparse != 0: DQ / DV in the support-only format (pattern: row_ptr [nv + 1], col_idx, either may be null; *nnz its size)

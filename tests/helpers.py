@@ -76,6 +76,7 @@ def load_emul() -> C.CDLL:
     lib.emul_minv.argtypes = [vp, ll, ll, i, i, vp, vp, vp]
     lib.emul_drnea.argtypes = [vp, ll, ll, i, i, vp, vp, vp, vp, vp, vp, vp, i]
     lib.emul_drnea_pattern.argtypes = [vp, vp, vp, vp]
+    lib.emul_pick_wpb.argtypes = [i, ll, i]
     lib.emul_eval_arm.argtypes = [vp, ll, ll] + [vp] * 7
     lib.emul_eval_plan.argtypes = [vp, i, i, vp]
     lib.emul_applyDJT.argtypes = [vp, ll, ll, vp, ll, vp, vp, vp, C.c_double, vp, vp]

@@ -643,6 +643,22 @@ def test_drnea_body_matches_oracle(emul, d, tile, body):
         assert list(plan) == [8, 96, 108, 156]
 
 
+def test_block_size_per_launch(emul):
+    """pick_warps_per_block: a persistent kernel planned for W warps is launched with the block size that leaves the fewest
+    warps idle in the last round (cost of a round ~ 2.5 + w): Panda's 2 048 tiles on 148 SMs are two full rounds of 7-warp
+    blocks; large batches and the sizing call (no tiles) keep W; never fewer than 4 warps, never more than W."""
+    assert emul.emul_pick_wpb(12, 2048, 148) == 7 and emul.emul_pick_wpb(8, 2048, 148) == 7
+    assert emul.emul_pick_wpb(12, 32768, 148) == 12 and emul.emul_pick_wpb(8, 32768, 148) == 8
+    assert emul.emul_pick_wpb(12, 8192, 148) == 12
+    assert emul.emul_pick_wpb(8, 0, 148) == 8 and emul.emul_pick_wpb(12, 1, 148) == 4
+    for W in (4, 8, 12):
+        for nt in (1, 100, 1183, 1184, 1185, 5000, 100000):
+            w = emul.emul_pick_wpb(W, nt, 148)
+            assert 4 <= w <= W
+            rounds = lambda x: -(-nt // (148 * x))
+            assert rounds(w) * (2.5 + w) <= rounds(W) * (2.5 + W) + 1e-9
+
+
 @pytest.mark.parametrize("nmoving,free_flyer", [(40, False), (45, True), (63, False)])
 def test_drnea_deep_chains(emul, nmoving, free_flyer):
     """Long serial chains: the hot level records no longer fit 8 warps per SM — the planner takes smaller blocks (levels in
